@@ -1,0 +1,627 @@
+// loaders.cpp -- scene loaders above the hot path.
+//
+// PBRTSceneLoader mirrors src/scene_loader.rs:77-315 for the pbrt-v3 subset the path's scenes
+// use: Transform/ConcatTransform/LookAt/Translate/Scale/Rotate/Identity, Film, Camera
+// "perspective", MakeNamedMaterial/NamedMaterial/Material "matte", Shape "trianglemesh",
+// AreaLightSource "diffuse", AttributeBegin/End, TransformBegin/End, ReverseOrientation.
+// The pbrt_rs crate that does the parsing for the reference is not vendored,
+// so the grammar follows the pbrt-v3 file format itself.
+// One labelled extension: material type "phong" (Kd, Ks, exponent) -> BSDFPhong, which the
+// reference can only build through its Mitsuba route (src/bsdfs/mod.rs:509-531).
+//
+// JSONSceneLoader reads the new format documented in DESIGN.md ("scene JSON"); the reference
+// has no JSON loader at this commit.
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <sstream>
+
+#include "rl_host.hpp"
+
+namespace rlh {
+
+static std::string read_file(const std::string &filename) {
+    std::ifstream f(filename, std::ios::binary);
+    if (!f) throw Error("cannot open scene file: " + filename);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+
+// ------------------------------------------------------------------------------------------
+// pbrt tokenizer
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Tok {
+    enum Kind { Ident, Str, Num, LBr, RBr, End } kind = End;
+    std::string s;
+    double v = 0;
+};
+struct Lexer {
+    const std::string &t;
+    size_t p = 0;
+    explicit Lexer(const std::string &text) : t(text) {}
+    Tok next() {
+        for (;;) {
+            while (p < t.size() && std::isspace((unsigned char)t[p])) p++;
+            if (p < t.size() && t[p] == '#') {
+                while (p < t.size() && t[p] != '\n') p++;
+                continue;
+            }
+            break;
+        }
+        Tok k;
+        if (p >= t.size()) return k;
+        char c = t[p];
+        if (c == '[') { p++; k.kind = Tok::LBr; return k; }
+        if (c == ']') { p++; k.kind = Tok::RBr; return k; }
+        if (c == '"') {
+            size_t e = t.find('"', p + 1);
+            if (e == std::string::npos) throw Error("pbrt: unterminated string");
+            k.kind = Tok::Str;
+            k.s = t.substr(p + 1, e - p - 1);
+            p = e + 1;
+            return k;
+        }
+        if (std::isdigit((unsigned char)c) || c == '-' || c == '+' || c == '.') {
+            char *end = nullptr;
+            k.v = std::strtod(t.c_str() + p, &end);
+            if (end == t.c_str() + p) throw Error("pbrt: bad number");
+            k.kind = Tok::Num;
+            p = (size_t)(end - t.c_str());
+            return k;
+        }
+        size_t e = p;
+        while (e < t.size() && (std::isalnum((unsigned char)t[e]) || t[e] == '_')) e++;
+        if (e == p) throw Error(std::string("pbrt: unexpected character '") + c + "'");
+        k.kind = Tok::Ident;
+        k.s = t.substr(p, e - p);
+        p = e;
+        return k;
+    }
+};
+
+struct Param {
+    std::string type, name;
+    std::vector<double> nums;
+    std::vector<std::string> strs;
+};
+struct ParamSet {
+    std::vector<Param> ps;
+    const Param *find(const std::string &name) const {
+        for (auto &p : ps)
+            if (p.name == name) return &p;
+        return nullptr;
+    }
+    std::string str(const std::string &name, const std::string &def = "") const {
+        auto p = find(name);
+        return (p && !p->strs.empty()) ? p->strs[0] : def;
+    }
+    double num(const std::string &name, double def) const {
+        auto p = find(name);
+        return (p && !p->nums.empty()) ? p->nums[0] : def;
+    }
+    Color rgb(const std::string &name, Color def) const {
+        auto p = find(name);
+        if (!p) return def;
+        if (p->type == "texture" || p->type == "spectrum" || p->type == "blackbody")
+            throw Error("pbrt: '" + p->type + " " + name + "' is not supported on this path");
+        if (p->nums.size() == 1) return Color{(float)p->nums[0], (float)p->nums[0], (float)p->nums[0]};
+        if (p->nums.size() < 3) throw Error("pbrt: rgb parameter needs 3 values: " + name);
+        return Color{(float)p->nums[0], (float)p->nums[1], (float)p->nums[2]};
+    }
+};
+
+struct Parser {
+    Lexer lex;
+    Tok cur;
+    explicit Parser(const std::string &text) : lex(text) { cur = lex.next(); }
+    void advance() { cur = lex.next(); }
+    std::string expect_str() {
+        if (cur.kind != Tok::Str) throw Error("pbrt: expected a quoted string");
+        std::string s = cur.s;
+        advance();
+        return s;
+    }
+    double expect_num() {
+        if (cur.kind != Tok::Num) throw Error("pbrt: expected a number");
+        double v = cur.v;
+        advance();
+        return v;
+    }
+    std::vector<double> nums(size_t n) {
+        std::vector<double> r;
+        bool br = cur.kind == Tok::LBr;
+        if (br) advance();
+        for (size_t i = 0; i < n; i++) r.push_back(expect_num());
+        if (br) {
+            if (cur.kind != Tok::RBr) throw Error("pbrt: expected ']'");
+            advance();
+        }
+        return r;
+    }
+    ParamSet params() {
+        ParamSet set;
+        while (cur.kind == Tok::Str) {
+            Param p;
+            std::string decl = cur.s;
+            advance();
+            std::istringstream ds(decl);
+            ds >> p.type >> p.name;
+            if (p.name.empty()) throw Error("pbrt: bad parameter declaration \"" + decl + "\"");
+            auto take = [&]() {
+                if (cur.kind == Tok::Num) p.nums.push_back(cur.v);
+                else if (cur.kind == Tok::Str) p.strs.push_back(cur.s);
+                else if (cur.kind == Tok::Ident && (cur.s == "true" || cur.s == "false")) p.strs.push_back(cur.s);
+                else throw Error("pbrt: bad parameter value for " + p.name);
+                advance();
+            };
+            if (cur.kind == Tok::LBr) {
+                advance();
+                while (cur.kind != Tok::RBr) {
+                    if (cur.kind == Tok::End) throw Error("pbrt: unterminated '['");
+                    take();
+                }
+                advance();
+            } else {
+                take();
+            }
+            set.ps.push_back(std::move(p));
+        }
+        return set;
+    }
+};
+
+struct GState {
+    Mat4 ctm = Mat4::identity();
+    std::string named_material; // current NamedMaterial
+    std::optional<Material> material; // current anonymous Material
+    bool has_area_light = false;
+    Color area_light;
+    bool reverse_orientation = false;
+};
+
+Mat4 mat_from_16(const std::vector<double> &v) {
+    // pbrt lists the matrix column by column, which is also cgmath's storage order
+    Mat4 m{};
+    for (int i = 0; i < 16; i++) m.m[i] = (float)v[i];
+    return m;
+}
+
+Material material_from_params(const std::string &type, const ParamSet &ps) {
+    if (type == "matte") {
+        // pbrt_rs::BSDF::Matte { kd } -> BSDFDiffuse (src/bsdfs/mod.rs:299-306); Kd default 0.5
+        return Material::diffuse(ps.rgb("Kd", Color{0.5f, 0.5f, 0.5f}));
+    }
+    if (type == "phong") { // extension, see file header
+        return Material::phong(ps.rgb("Kd", Color{0.5f, 0.5f, 0.5f}), ps.rgb("Ks", Color{0.5f, 0.5f, 0.5f}),
+                               (float)ps.num("exponent", 30.0));
+    }
+    throw Error("pbrt: material type \"" + type + "\" is outside the hot-path scope (matte, phong)");
+}
+} // namespace
+
+Scene PBRTSceneLoader::load(const std::string &filename, bool use_shading_normal) const {
+    return load_string(read_file(filename), use_shading_normal);
+}
+
+Scene PBRTSceneLoader::load_string(const std::string &text, bool use_shading_normal) const {
+    Parser ps(text);
+    GState gs;
+    std::vector<GState> stack;
+    std::vector<Mat4> tstack;
+    std::map<std::string, Material> materials;
+    Scene scene;
+    uint32_t xres = 512, yres = 512;
+    bool have_camera = false;
+    float fov = 90.0f;
+    Mat4 world_to_camera = Mat4::identity();
+
+    while (ps.cur.kind != Tok::End) {
+        if (ps.cur.kind != Tok::Ident) throw Error("pbrt: expected a directive");
+        std::string d = ps.cur.s;
+        ps.advance();
+        if (d == "Transform") {
+            gs.ctm = mat_from_16(ps.nums(16));
+        } else if (d == "ConcatTransform") {
+            gs.ctm = gs.ctm * mat_from_16(ps.nums(16));
+        } else if (d == "Identity") {
+            gs.ctm = Mat4::identity();
+        } else if (d == "Translate") {
+            auto v = ps.nums(3);
+            gs.ctm = gs.ctm * Mat4::from_translation((float)v[0], (float)v[1], (float)v[2]);
+        } else if (d == "Scale") {
+            auto v = ps.nums(3);
+            gs.ctm = gs.ctm * Mat4::from_nonuniform_scale((float)v[0], (float)v[1], (float)v[2]);
+        } else if (d == "Rotate") {
+            auto v = ps.nums(4);
+            gs.ctm = gs.ctm * Mat4::rotate_deg((float)v[0], Vec3{(float)v[1], (float)v[2], (float)v[3]});
+        } else if (d == "LookAt") {
+            auto v = ps.nums(9);
+            gs.ctm = gs.ctm * Mat4::look_at_pbrt(Vec3{(float)v[0], (float)v[1], (float)v[2]},
+                                                 Vec3{(float)v[3], (float)v[4], (float)v[5]},
+                                                 Vec3{(float)v[6], (float)v[7], (float)v[8]});
+        } else if (d == "Film") {
+            ps.expect_str();
+            ParamSet p = ps.params();
+            xres = (uint32_t)p.num("xresolution", 512);
+            yres = (uint32_t)p.num("yresolution", 512);
+        } else if (d == "Camera") {
+            std::string type = ps.expect_str();
+            ParamSet p = ps.params();
+            if (type != "perspective") throw Error("pbrt: only Camera \"perspective\" is supported");
+            fov = (float)p.num("fov", 90.0);
+            world_to_camera = gs.ctm;
+            have_camera = true;
+        } else if (d == "Integrator" || d == "Sampler" || d == "PixelFilter" || d == "Accelerator") {
+            ps.expect_str();
+            ps.params(); // rendering settings come from the CLI in rustlight, not from the file
+        } else if (d == "WorldBegin") {
+            gs = GState{};
+        } else if (d == "WorldEnd") {
+        } else if (d == "AttributeBegin") {
+            stack.push_back(gs);
+        } else if (d == "AttributeEnd") {
+            if (stack.empty()) throw Error("pbrt: unbalanced AttributeEnd");
+            gs = stack.back();
+            stack.pop_back();
+        } else if (d == "TransformBegin") {
+            tstack.push_back(gs.ctm);
+        } else if (d == "TransformEnd") {
+            if (tstack.empty()) throw Error("pbrt: unbalanced TransformEnd");
+            gs.ctm = tstack.back();
+            tstack.pop_back();
+        } else if (d == "ReverseOrientation") {
+            gs.reverse_orientation = !gs.reverse_orientation;
+        } else if (d == "MakeNamedMaterial") {
+            std::string name = ps.expect_str();
+            ParamSet p = ps.params();
+            materials[name] = material_from_params(p.str("type", "matte"), p);
+        } else if (d == "NamedMaterial") {
+            gs.named_material = ps.expect_str();
+            gs.material.reset();
+        } else if (d == "Material") {
+            std::string type = ps.expect_str();
+            ParamSet p = ps.params();
+            gs.material = material_from_params(type, p);
+            gs.named_material.clear();
+        } else if (d == "AreaLightSource") {
+            std::string type = ps.expect_str();
+            ParamSet p = ps.params();
+            if (type != "diffuse" && type != "area") throw Error("pbrt: only AreaLightSource \"diffuse\"");
+            gs.has_area_light = true;
+            gs.area_light = p.rgb("L", Color{1.0f, 1.0f, 1.0f});
+        } else if (d == "Shape") {
+            std::string type = ps.expect_str();
+            ParamSet p = ps.params();
+            if (type != "trianglemesh")
+                throw Error("pbrt: Shape \"" + type + "\" is outside the hot-path scope (trianglemesh)");
+            const Param *pi = p.find("indices"), *pp = p.find("P"), *pn = p.find("N"), *puv = p.find("uv");
+            if (!puv) puv = p.find("st");
+            if (!pi || !pp) throw Error("pbrt: trianglemesh needs indices and P");
+            if (pi->nums.size() % 3 || pp->nums.size() % 3) throw Error("pbrt: trianglemesh sizes");
+            auto mesh = std::make_shared<Mesh>();
+            mesh->name = "noname"; // scene_loader.rs:137
+            size_t nv = pp->nums.size() / 3;
+            // scene_loader.rs:99-122: points by transform_point, normals by transform_vector
+            for (size_t i = 0; i < nv; i++) {
+                Vec3 q = gs.ctm.transform_point(
+                    Vec3{(float)pp->nums[3 * i], (float)pp->nums[3 * i + 1], (float)pp->nums[3 * i + 2]});
+                mesh->vertices.insert(mesh->vertices.end(), {q.x, q.y, q.z});
+            }
+            for (double v : pi->nums) {
+                if (v < 0 || (size_t)v >= nv) throw Error("pbrt: trianglemesh index out of range");
+                mesh->indices.push_back((uint32_t)v);
+            }
+            if (use_shading_normal && pn) {
+                if (pn->nums.size() != 3 * nv) throw Error("pbrt: N size mismatch");
+                size_t nb_wrong = 0;
+                for (size_t i = 0; i < nv; i++) {
+                    Vec3 n{(float)pn->nums[3 * i], (float)pn->nums[3 * i + 1], (float)pn->nums[3 * i + 2]};
+                    if (gs.reverse_orientation) n = Vec3{-n.x, -n.y, -n.z};
+                    n = gs.ctm.transform_vector(n);
+                    // Mesh::new renormalises, src/geometry.rs:143-153
+                    float l = n.x * n.x + n.y * n.y + n.z * n.z;
+                    if (l == 0.0f) nb_wrong++;
+                    else if (l != 1.0f) {
+                        float s = std::sqrt(l);
+                        n = Vec3{n.x / s, n.y / s, n.z / s};
+                    }
+                    mesh->normals.insert(mesh->normals.end(), {n.x, n.y, n.z});
+                }
+                if (nb_wrong == nv) mesh->normals.clear(); // geometry.rs:159-162
+            }
+            if (puv) {
+                if (puv->nums.size() != 2 * nv) throw Error("pbrt: uv size mismatch");
+                for (double v : puv->nums) mesh->uv.push_back((float)v);
+            }
+            // scene_loader.rs:124-136: unknown / missing material -> diffuse 0.5
+            if (gs.material) mesh->bsdf = *gs.material;
+            else if (!gs.named_material.empty() && materials.count(gs.named_material))
+                mesh->bsdf = materials[gs.named_material];
+            else mesh->bsdf = Material::diffuse(Color{0.5f, 0.5f, 0.5f});
+            if (gs.has_area_light) { // scene_loader.rs:141-145
+                mesh->is_light = true;
+                mesh->emission = gs.area_light;
+            }
+            if (!mesh->indices.empty()) scene.meshes.push_back(mesh); // geometry.rs:165-167
+        } else if (d == "LightSource" || d == "Texture" || d == "MakeNamedMedium" || d == "MediumInterface" ||
+                   d == "ObjectBegin" || d == "ObjectEnd" || d == "ObjectInstance" || d == "Include") {
+            throw Error("pbrt: directive " + d + " is outside the hot-path scope");
+        } else {
+            throw Error("pbrt: unknown directive " + d);
+        }
+    }
+    if (!have_camera) throw Error("The camera is not set!"); // scene_loader.rs:295
+    auto c2w = world_to_camera.invert();                     // scene_loader.rs:288
+    if (!c2w) throw Error("pbrt: camera transform is singular");
+    scene.camera = Camera::create(xres, yres, Fov::Y, fov, *c2w, false); // scene_loader.rs:291
+    return scene;
+}
+
+// ------------------------------------------------------------------------------------------
+// minimal JSON
+// ------------------------------------------------------------------------------------------
+namespace {
+struct JVal {
+    enum T { Null, Bool, Num, Str, Arr, Obj } t = Null;
+    bool b = false;
+    double n = 0;
+    std::string s;
+    std::vector<JVal> a;
+    std::vector<std::pair<std::string, JVal>> o;
+    const JVal *get(const std::string &k) const {
+        for (auto &kv : o)
+            if (kv.first == k) return &kv.second;
+        return nullptr;
+    }
+};
+struct JParser {
+    const std::string &t;
+    size_t p = 0;
+    explicit JParser(const std::string &text) : t(text) {}
+    void ws() {
+        while (p < t.size() && std::isspace((unsigned char)t[p])) p++;
+    }
+    [[noreturn]] void fail(const std::string &m) { throw Error("json: " + m + " at byte " + std::to_string(p)); }
+    JVal parse() {
+        ws();
+        if (p >= t.size()) fail("unexpected end");
+        JVal v;
+        char c = t[p];
+        if (c == '{') {
+            v.t = JVal::Obj;
+            p++;
+            ws();
+            if (p < t.size() && t[p] == '}') { p++; return v; }
+            for (;;) {
+                ws();
+                JVal k = parse();
+                if (k.t != JVal::Str) fail("object key must be a string");
+                ws();
+                if (p >= t.size() || t[p] != ':') fail("expected ':'");
+                p++;
+                v.o.emplace_back(k.s, parse());
+                ws();
+                if (p < t.size() && t[p] == ',') { p++; continue; }
+                if (p < t.size() && t[p] == '}') { p++; break; }
+                fail("expected ',' or '}'");
+            }
+        } else if (c == '[') {
+            v.t = JVal::Arr;
+            p++;
+            ws();
+            if (p < t.size() && t[p] == ']') { p++; return v; }
+            for (;;) {
+                v.a.push_back(parse());
+                ws();
+                if (p < t.size() && t[p] == ',') { p++; continue; }
+                if (p < t.size() && t[p] == ']') { p++; break; }
+                fail("expected ',' or ']'");
+            }
+        } else if (c == '"') {
+            v.t = JVal::Str;
+            p++;
+            while (p < t.size() && t[p] != '"') {
+                if (t[p] == '\\' && p + 1 < t.size()) {
+                    p++;
+                    char e = t[p];
+                    v.s.push_back(e == 'n' ? '\n' : e == 't' ? '\t' : e);
+                } else v.s.push_back(t[p]);
+                p++;
+            }
+            if (p >= t.size()) fail("unterminated string");
+            p++;
+        } else if (t.compare(p, 4, "true") == 0) { v.t = JVal::Bool; v.b = true; p += 4; }
+        else if (t.compare(p, 5, "false") == 0) { v.t = JVal::Bool; v.b = false; p += 5; }
+        else if (t.compare(p, 4, "null") == 0) { p += 4; }
+        else {
+            char *end = nullptr;
+            v.n = std::strtod(t.c_str() + p, &end);
+            if (end == t.c_str() + p) fail("bad value");
+            v.t = JVal::Num;
+            p = (size_t)(end - t.c_str());
+        }
+        return v;
+    }
+};
+std::vector<float> jfloats(const JVal *v, const char *what, size_t expect = 0) {
+    if (!v || v->t != JVal::Arr) throw Error(std::string("json: missing array ") + what);
+    std::vector<float> r;
+    for (auto &e : v->a) {
+        if (e.t != JVal::Num) throw Error(std::string("json: non-number in ") + what);
+        r.push_back((float)e.n);
+    }
+    if (expect && r.size() != expect) throw Error(std::string("json: wrong length for ") + what);
+    return r;
+}
+Color jcolor(const JVal *v, const char *what, Color def) {
+    if (!v) return def;
+    auto f = jfloats(v, what, 3);
+    return Color{f[0], f[1], f[2]};
+}
+Material jmaterial(const JVal &m) {
+    const JVal *ty = m.get("type");
+    std::string type = (ty && ty->t == JVal::Str) ? ty->s : "diffuse";
+    if (type == "diffuse" || type == "matte") return Material::diffuse(jcolor(m.get("kd"), "kd", Color{0.5f, 0.5f, 0.5f}));
+    if (type == "phong") {
+        const JVal *e = m.get("exponent");
+        return Material::phong(jcolor(m.get("kd"), "kd", Color{0.5f, 0.5f, 0.5f}),
+                               jcolor(m.get("ks"), "ks", Color{0.5f, 0.5f, 0.5f}), e ? (float)e->n : 30.0f);
+    }
+    throw Error("json: material type \"" + type + "\" is outside the hot-path scope (diffuse, phong)");
+}
+} // namespace
+
+Scene JSONSceneLoader::load(const std::string &filename, bool use_shading_normal) const {
+    return load_string(read_file(filename), use_shading_normal);
+}
+
+Scene JSONSceneLoader::load_string(const std::string &text, bool use_shading_normal) const {
+    JParser jp(text);
+    JVal root = jp.parse();
+    if (root.t != JVal::Obj) throw Error("json: root must be an object");
+    Scene scene;
+    const JVal *cam = root.get("camera");
+    if (!cam || cam->t != JVal::Obj) throw Error("The camera is not set!");
+    auto num = [](const JVal *v, double def) { return (v && v->t == JVal::Num) ? v->n : def; };
+    uint32_t w = (uint32_t)num(cam->get("width"), 512), h = (uint32_t)num(cam->get("height"), 512);
+    float fov = (float)num(cam->get("fov"), 90.0);
+    const JVal *ax = cam->get("fov_axis");
+    Fov axis = (ax && ax->t == JVal::Str && (ax->s == "x" || ax->s == "X")) ? Fov::X : Fov::Y;
+    const JVal *fl = cam->get("flip");
+    bool flip = fl && fl->t == JVal::Bool && fl->b;
+    Mat4 to_world = Mat4::identity();
+    if (cam->get("to_world")) {
+        auto f = jfloats(cam->get("to_world"), "camera.to_world", 16);
+        for (int i = 0; i < 16; i++) to_world.m[i] = f[i];
+    }
+    scene.camera = Camera::create(w, h, axis, fov, to_world, flip);
+
+    std::map<std::string, Material> materials;
+    if (const JVal *ms = root.get("materials")) {
+        if (ms->t != JVal::Obj) throw Error("json: materials must be an object");
+        for (auto &kv : ms->o) materials[kv.first] = jmaterial(kv.second);
+    }
+    const JVal *meshes = root.get("meshes");
+    if (!meshes || meshes->t != JVal::Arr) throw Error("json: missing meshes array");
+    for (auto &jm : meshes->a) {
+        auto mesh = std::make_shared<Mesh>();
+        const JVal *nm = jm.get("name");
+        mesh->name = (nm && nm->t == JVal::Str) ? nm->s : "noname";
+        mesh->vertices = jfloats(jm.get("P"), "mesh.P");
+        if (mesh->vertices.size() % 3) throw Error("json: mesh.P length must be a multiple of 3");
+        size_t nv = mesh->vertices.size() / 3;
+        const JVal *idx = jm.get("indices");
+        if (!idx || idx->t != JVal::Arr || idx->a.size() % 3) throw Error("json: mesh.indices");
+        for (auto &e : idx->a) {
+            if (e.t != JVal::Num || e.n < 0 || (size_t)e.n >= nv) throw Error("json: mesh index out of range");
+            mesh->indices.push_back((uint32_t)e.n);
+        }
+        if (use_shading_normal && jm.get("N")) {
+            mesh->normals = jfloats(jm.get("N"), "mesh.N", 3 * nv);
+            size_t nb_wrong = 0;
+            for (size_t i = 0; i < nv; i++) { // Mesh::new, geometry.rs:143-153
+                float *n = &mesh->normals[3 * i];
+                float l = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+                if (l == 0.0f) nb_wrong++;
+                else if (l != 1.0f) {
+                    float s = std::sqrt(l);
+                    n[0] /= s, n[1] /= s, n[2] /= s;
+                }
+            }
+            if (nb_wrong == nv) mesh->normals.clear();
+        }
+        if (jm.get("uv")) mesh->uv = jfloats(jm.get("uv"), "mesh.uv", 2 * nv);
+        const JVal *mat = jm.get("material");
+        if (mat && mat->t == JVal::Str) {
+            if (!materials.count(mat->s)) throw Error("json: unknown material " + mat->s);
+            mesh->bsdf = materials[mat->s];
+        } else if (mat && mat->t == JVal::Obj) mesh->bsdf = jmaterial(*mat);
+        else mesh->bsdf = Material::diffuse(Color{0.5f, 0.5f, 0.5f});
+        if (jm.get("emission")) {
+            mesh->is_light = true;
+            mesh->emission = jcolor(jm.get("emission"), "mesh.emission", Color{});
+        }
+        if (!mesh->indices.empty()) scene.meshes.push_back(mesh);
+    }
+    return scene;
+}
+
+static void put_floats(std::ostringstream &o, const float *v, size_t n) {
+    o << "[";
+    char buf[32];
+    for (size_t i = 0; i < n; i++) {
+        std::snprintf(buf, sizeof(buf), "%.9g", (double)v[i]);
+        o << (i ? ", " : "") << buf;
+    }
+    o << "]";
+}
+
+std::string scene_to_json(const Scene &scene) {
+    std::ostringstream o;
+    const Camera &c = scene.camera;
+    o << "{\n  \"camera\": {\"width\": " << c.img_x << ", \"height\": " << c.img_y << ", \"fov\": ";
+    char buf[32];
+    std::snprintf(buf, sizeof(buf), "%.9g", (double)c.fov_deg);
+    o << buf << ", \"fov_axis\": \"" << (c.fov_axis == Fov::X ? "x" : "y") << "\", \"flip\": "
+      << (c.flip ? "true" : "false") << ",\n             \"to_world\": ";
+    put_floats(o, c.to_world.m, 16);
+    o << "},\n  \"meshes\": [\n";
+    for (size_t i = 0; i < scene.meshes.size(); i++) {
+        const Mesh &m = *scene.meshes[i];
+        o << "    {\"name\": \"" << m.name << "\", \"material\": {\"type\": \""
+          << (m.bsdf.m.kind == RL_BSDF_PHONG ? "phong" : "diffuse") << "\", \"kd\": ";
+        put_floats(o, m.bsdf.m.kd, 3);
+        if (m.bsdf.m.kind == RL_BSDF_PHONG) {
+            o << ", \"ks\": ";
+            put_floats(o, m.bsdf.m.ks, 3);
+            o << ", \"exponent\": ";
+            put_floats(o, &m.bsdf.m.exponent, 1);
+        }
+        o << "}";
+        if (m.is_light) {
+            float e[3] = {m.emission.r, m.emission.g, m.emission.b};
+            o << ", \"emission\": ";
+            put_floats(o, e, 3);
+        }
+        o << ",\n     \"indices\": [";
+        for (size_t k = 0; k < m.indices.size(); k++) o << (k ? ", " : "") << m.indices[k];
+        o << "],\n     \"P\": ";
+        put_floats(o, m.vertices.data(), m.vertices.size());
+        if (!m.normals.empty()) {
+            o << ",\n     \"N\": ";
+            put_floats(o, m.normals.data(), m.normals.size());
+        }
+        if (!m.uv.empty()) {
+            o << ",\n     \"uv\": ";
+            put_floats(o, m.uv.data(), m.uv.size());
+        }
+        o << "}" << (i + 1 < scene.meshes.size() ? "," : "") << "\n";
+    }
+    o << "  ]\n}\n";
+    return o.str();
+}
+
+// ------------------------------------------------------------------------------------------
+// SceneLoaderManager, src/scene_loader.rs:21-58
+// ------------------------------------------------------------------------------------------
+SceneLoaderManager::SceneLoaderManager() {
+    loader["pbrt"] = std::make_shared<PBRTSceneLoader>();
+    loader["json"] = std::make_shared<JSONSceneLoader>();
+}
+Scene SceneLoaderManager::load(const std::string &filename, bool use_shading_normal) const {
+    size_t dot = filename.find_last_of('.');
+    size_t slash = filename.find_last_of('/');
+    if (dot == std::string::npos || (slash != std::string::npos && dot < slash))
+        throw Error("No file extension provided"); // scene_loader.rs:34
+    std::string ext = filename.substr(dot + 1);
+    auto it = loader.find(ext);
+    if (it == loader.end())
+        throw Error("Impossible to found scene loader for " + ext + " extension"); // scene_loader.rs:40-43
+    return it->second->load(filename, use_shading_normal);
+}
+
+} // namespace rlh

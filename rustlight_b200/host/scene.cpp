@@ -1,0 +1,278 @@
+// scene.cpp -- Mat4 (cgmath conventions), Camera::new, Scene flattening, Bitmap IO.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+
+#include "rl_host.hpp"
+
+namespace rlh {
+
+// ------------------------------------------------------------------------------------------
+// Mat4: cgmath::Matrix4<f32> conventions (column-major, column vectors).
+// ------------------------------------------------------------------------------------------
+Mat4 Mat4::identity() {
+    Mat4 r{};
+    for (int i = 0; i < 16; i++) r.m[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    return r;
+}
+Mat4 Mat4::from_nonuniform_scale(float x, float y, float z) {
+    Mat4 r = identity();
+    r.at(0, 0) = x;
+    r.at(1, 1) = y;
+    r.at(2, 2) = z;
+    return r;
+}
+Mat4 Mat4::from_translation(float x, float y, float z) {
+    Mat4 r = identity();
+    r.at(3, 0) = x;
+    r.at(3, 1) = y;
+    r.at(3, 2) = z;
+    return r;
+}
+// cgmath 0.18 `perspective(fovy, aspect, near, far)` == PerspectiveFov::into::<Matrix4>():
+//   f = cot(fovy/2); c0r0 = f/aspect; c1r1 = f; c2r2 = (far+near)/(near-far); c2r3 = -1;
+//   c3r2 = 2*far*near/(near-far)
+Mat4 Mat4::perspective(float fovy_rad, float aspect, float near, float far) {
+    Mat4 r{};
+    std::memset(r.m, 0, sizeof(r.m));
+    float f = 1.0f / std::tan(fovy_rad / 2.0f);
+    r.at(0, 0) = f / aspect;
+    r.at(1, 1) = f;
+    r.at(2, 2) = (far + near) / (near - far);
+    r.at(2, 3) = -1.0f;
+    r.at(3, 2) = (2.0f * far * near) / (near - far);
+    return r;
+}
+Mat4 Mat4::operator*(const Mat4 &rhs) const {
+    Mat4 r{};
+    for (int c = 0; c < 4; c++)
+        for (int row = 0; row < 4; row++) {
+            // self[0]*v.x + self[1]*v.y + self[2]*v.z + self[3]*v.w, left to right
+            float acc = at(0, row) * rhs.at(c, 0);
+            acc = acc + at(1, row) * rhs.at(c, 1);
+            acc = acc + at(2, row) * rhs.at(c, 2);
+            acc = acc + at(3, row) * rhs.at(c, 3);
+            r.at(c, row) = acc;
+        }
+    return r;
+}
+static float det3(float a, float b, float c, float d, float e, float f, float g, float h, float i) {
+    // columns (a,b,c) (d,e,f) (g,h,i)
+    return a * (e * i - h * f) - d * (b * i - h * c) + g * (b * f - e * c);
+}
+std::optional<Mat4> Mat4::invert() const {
+    // cofactor inverse; cgmath's invert() has the same structure (determinant, transposed
+    // cofactors times 1/det).  Host-only: last-bit differences are tolerated.
+    float cof[16];
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) {
+            float s[9];
+            int k = 0;
+            for (int cc = 0; cc < 4; cc++) {
+                if (cc == c) continue;
+                for (int rr = 0; rr < 4; rr++) {
+                    if (rr == r) continue;
+                    s[k++] = at(cc, rr);
+                }
+            }
+            float d = det3(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8]);
+            cof[4 * c + r] = ((c + r) & 1) ? -d : d;
+        }
+    float det = at(0, 0) * cof[0] + at(0, 1) * cof[1] + at(0, 2) * cof[2] + at(0, 3) * cof[3];
+    if (det == 0.0f) return std::nullopt;
+    float inv_det = 1.0f / det;
+    Mat4 out{};
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) out.at(c, r) = cof[4 * r + c] * inv_det; // adjugate = cof^T
+    return out;
+}
+Vec3 Mat4::transform_point(Vec3 p) const {
+    float h[4];
+    for (int row = 0; row < 4; row++) {
+        float acc = at(0, row) * p.x;
+        acc = acc + at(1, row) * p.y;
+        acc = acc + at(2, row) * p.z;
+        acc = acc + at(3, row) * 1.0f;
+        h[row] = acc;
+    }
+    float iw = 1.0f / h[3];
+    return Vec3{h[0] * iw, h[1] * iw, h[2] * iw};
+}
+Vec3 Mat4::transform_vector(Vec3 v) const {
+    float h[3];
+    for (int row = 0; row < 3; row++) {
+        float acc = at(0, row) * v.x;
+        acc = acc + at(1, row) * v.y;
+        acc = acc + at(2, row) * v.z;
+        acc = acc + at(3, row) * 0.0f;
+        h[row] = acc;
+    }
+    return Vec3{h[0], h[1], h[2]};
+}
+static Vec3 sub(Vec3 a, Vec3 b) { return Vec3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+static Vec3 cross(Vec3 a, Vec3 b) {
+    return Vec3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+static Vec3 normalize(Vec3 a) {
+    float l = std::sqrt(a.x * a.x + a.y * a.y + a.z * a.z);
+    return Vec3{a.x / l, a.y / l, a.z / l};
+}
+// pbrt-v3 LookAt: left-handed camera space, +z forward.  Returns world_to_camera.
+Mat4 Mat4::look_at_pbrt(Vec3 eye, Vec3 at_, Vec3 up) {
+    Vec3 dir = normalize(sub(at_, eye));
+    Vec3 right = normalize(cross(normalize(up), dir));
+    Vec3 new_up = cross(dir, right);
+    Mat4 c2w = identity();
+    c2w.at(0, 0) = right.x, c2w.at(0, 1) = right.y, c2w.at(0, 2) = right.z;
+    c2w.at(1, 0) = new_up.x, c2w.at(1, 1) = new_up.y, c2w.at(1, 2) = new_up.z;
+    c2w.at(2, 0) = dir.x, c2w.at(2, 1) = dir.y, c2w.at(2, 2) = dir.z;
+    c2w.at(3, 0) = eye.x, c2w.at(3, 1) = eye.y, c2w.at(3, 2) = eye.z;
+    return *c2w.invert();
+}
+Mat4 Mat4::rotate_deg(float angle, Vec3 axis) {
+    Vec3 a = normalize(axis);
+    float rad = angle * 3.14159265358979323846f / 180.0f;
+    float s = std::sin(rad), c = std::cos(rad);
+    Mat4 r = identity();
+    r.at(0, 0) = a.x * a.x + (1 - a.x * a.x) * c;
+    r.at(1, 0) = a.x * a.y * (1 - c) - a.z * s;
+    r.at(2, 0) = a.x * a.z * (1 - c) + a.y * s;
+    r.at(0, 1) = a.x * a.y * (1 - c) + a.z * s;
+    r.at(1, 1) = a.y * a.y + (1 - a.y * a.y) * c;
+    r.at(2, 1) = a.y * a.z * (1 - c) - a.x * s;
+    r.at(0, 2) = a.x * a.z * (1 - c) - a.y * s;
+    r.at(1, 2) = a.y * a.z * (1 - c) + a.x * s;
+    r.at(2, 2) = a.z * a.z + (1 - a.z * a.z) * c;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Camera::new, src/camera.rs:31-67
+// ------------------------------------------------------------------------------------------
+Camera Camera::create(uint32_t w, uint32_t h, Fov axis, float fov_deg, const Mat4 &mat, bool flip) {
+    if (w == 0 || h == 0) throw Error("Camera: empty image");
+    Camera cam;
+    cam.img_x = w;
+    cam.img_y = h;
+    cam.fov_axis = axis;
+    cam.fov_deg = fov_deg;
+    cam.flip = flip;
+    cam.to_world = mat;
+    auto inv = mat.invert();
+    if (!inv) throw Error("Camera: to_world is singular");
+    cam.to_local = *inv;
+    float x_v = flip ? 1.0f : -1.0f;
+    float aspect_ratio = (float)w / (float)h;
+    const float PI = 3.14159265358979323846f;
+    // Fov::Y(v) is converted as v*aspect (not through tan): src/camera.rs:41-44
+    float fov_rad = (axis == Fov::X) ? fov_deg * PI / 180.0f : fov_deg * aspect_ratio * PI / 180.0f;
+    cam.camera_to_sample = Mat4::from_nonuniform_scale(-0.5f, -0.5f * aspect_ratio, 1.0f) *
+                           Mat4::from_translation(-1.0f, -1.0f / aspect_ratio, 0.0f) *
+                           Mat4::perspective(fov_rad, 1.0f, 1e-2f, 1000.0f) *
+                           Mat4::from_nonuniform_scale(x_v, 1.0f, -1.0f);
+    auto s2c = cam.camera_to_sample.invert();
+    if (!s2c) throw Error("Camera: camera_to_sample is singular");
+    cam.sample_to_camera = *s2c;
+    return cam;
+}
+void Camera::scale_image(float s) {
+    uint32_t nx = (uint32_t)(s * (float)img_x), ny = (uint32_t)(s * (float)img_y);
+    // the reference only rewrites `img` (camera.rs:73-78): matrices keep the original aspect
+    img_x = nx;
+    img_y = ny;
+}
+
+// ------------------------------------------------------------------------------------------
+// Materials
+// ------------------------------------------------------------------------------------------
+Material Material::diffuse(Color kd) {
+    Material r;
+    r.m.kind = RL_BSDF_DIFFUSE;
+    r.m.kd[0] = kd.r, r.m.kd[1] = kd.g, r.m.kd[2] = kd.b;
+    r.m.ks[0] = r.m.ks[1] = r.m.ks[2] = 0.0f;
+    r.m.exponent = 0.0f;
+    r.m.weight_specular = 0.0f;
+    return r;
+}
+Material Material::phong(Color kd, Color ks, float exponent) {
+    Material r;
+    r.m.kind = RL_BSDF_PHONG;
+    r.m.kd[0] = kd.r, r.m.kd[1] = kd.g, r.m.kd[2] = kd.b;
+    r.m.ks[0] = ks.r, r.m.ks[1] = ks.g, r.m.ks[2] = ks.b;
+    r.m.exponent = exponent;
+    float d_avg = kd.luminance(), s_avg = ks.luminance();
+    if (d_avg + s_avg == 0.0f) throw Error("Phong: kd and ks are both black (bsdfs/mod.rs:521)");
+    r.m.weight_specular = s_avg / (d_avg + s_avg);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Scene
+// ------------------------------------------------------------------------------------------
+size_t Scene::nb_triangles() const {
+    size_t n = 0;
+    for (auto &m : meshes) n += m->indices.size() / 3;
+    return n;
+}
+const rl_scene_desc *Scene::desc() {
+    mesh_descs_.clear();
+    for (auto &mp : meshes) {
+        const Mesh &m = *mp;
+        rl_mesh_desc d{};
+        d.P = m.vertices.data();
+        d.nverts = (uint32_t)(m.vertices.size() / 3);
+        d.idx = m.indices.data();
+        d.ntris = (uint32_t)(m.indices.size() / 3);
+        d.N = m.normals.empty() ? nullptr : m.normals.data();
+        d.UV = m.uv.empty() ? nullptr : m.uv.data();
+        d.mat = m.bsdf.m;
+        d.emission_kind = m.is_light ? 1u : 0u;
+        d.emission[0] = m.emission.r, d.emission[1] = m.emission.g, d.emission[2] = m.emission.b;
+        mesh_descs_.push_back(d);
+    }
+    desc_.nmeshes = (uint32_t)mesh_descs_.size();
+    desc_.meshes = mesh_descs_.data();
+    desc_.camera.width = camera.img_x;
+    desc_.camera.height = camera.img_y;
+    std::memcpy(desc_.camera.sample_to_camera, camera.sample_to_camera.m, sizeof(float) * 16);
+    std::memcpy(desc_.camera.to_world, camera.to_world.m, sizeof(float) * 16);
+    desc_.has_volume = has_volume ? 1u : 0u;
+    desc_.has_environment = has_environment ? 1u : 0u;
+    return &desc_;
+}
+
+// ------------------------------------------------------------------------------------------
+// Bitmap::save_pfm, src/structure.rs:547-560
+// ------------------------------------------------------------------------------------------
+void Bitmap::save_pfm(const std::string &path) const {
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw Error("cannot open " + path);
+    char header[64];
+    int n = std::snprintf(header, sizeof(header), "PF\n%u %u\n-1.0\n", size_x, size_y);
+    f.write(header, n);
+    std::vector<float> row(3 * (size_t)size_x);
+    for (uint32_t y = 0; y < size_y; y++) {
+        const float *src = &colors[3 * (size_t)(size_y - y - 1) * size_x];
+        for (size_t i = 0; i < row.size(); i++) row[i] = std::fabs(src[i]);
+        f.write(reinterpret_cast<const char *>(row.data()), (std::streamsize)(row.size() * sizeof(float)));
+    }
+}
+Bitmap Bitmap::read_pfm(const std::string &path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw Error("cannot open " + path);
+    std::string magic;
+    uint32_t w, h;
+    float scale;
+    f >> magic >> w >> h >> scale;
+    f.get(); // single whitespace after the scale
+    if (magic != "PF") throw Error("not a colour PFM: " + path);
+    Bitmap b;
+    b.size_x = w, b.size_y = h;
+    b.colors.resize(3 * (size_t)w * h);
+    for (uint32_t y = 0; y < h; y++)
+        f.read(reinterpret_cast<char *>(&b.colors[3 * (size_t)(h - y - 1) * w]), (std::streamsize)(3 * w * sizeof(float)));
+    return b;
+}
+
+} // namespace rlh
