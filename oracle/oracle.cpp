@@ -1,0 +1,1808 @@
+// oracle.cpp -- CPU restatement of rustlight@864df34's `path` / `direct` hot path.
+//
+// TEST INFRASTRUCTURE, NOT PRODUCT.  PARITY UNPINNED (see oracle.h).
+//
+// Every section names the reference file:line it follows.  The layout deliberately mirrors
+// the reference (AoS records, recursive BVH, explicit path graph, trait-like virtual calls),
+// which is the opposite of the GPU implementation, so that agreement between the two is
+// evidence and not tautology.  Build with -O2 -ffp-contract=off -fno-fast-math: every f32
+// operation below is a single IEEE-754 operation in the order written.
+//
+//   structure.rs  : PDF 20-58,71-94 | Color 106-380 | Ray 697-732 | AABB 760-878 | Intersection 924-1059
+//   math.rs       : sampling 37-72 | Frame 357-384 | uniform_sample_triangle 388-394 | Distribution1D 398-487
+//   geometry.rs   : Mesh::new 122-182 | emit 184-206 | pdf 223-225 | sample_tri/sample 261-348
+//                   intersection_tri 358-410 | compute_aabb_tri 423-439
+//   accel.rs      : NaiveAcceleration 22-77 | BVHAccel build 107-240, traversal 243-288, trace/visible 292-343
+//   bsdfs/        : diffuse.rs 10-87 | phong.rs 14-136 | mod.rs 124-161
+//   emitter.rs    : LightSampling 10-44 | impl Emitter for Mesh 570-688 | EmitterSampler 1491-1647
+//   scene.rs      : build_emitters 53-123
+//   camera.rs     : Camera::new 31-67 | generate 81-91
+//   samplers/     : mod.rs 3-9 | independent.rs 5-34  (+ rand 0.8.5 SmallRng, restated from its published algorithm)
+//   paths/        : path.rs 56-73 | vertex.rs 61-82 | edge.rs 27-210 | strategies/{mod,directional,emitters}.rs
+//   integrators/  : mod.rs 351-478 | explicit/path.rs 27-238 | direct.rs 20-233
+#include "oracle.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+constexpr float EPSILON = 0.0001f;                     // lib.rs:51
+constexpr float F32_MAX = std::numeric_limits<float>::max();
+constexpr float PI = 3.14159265358979323846264338327950288f;
+constexpr float FRAC_PI_2 = 1.57079632679489661923132169163975144f;
+constexpr float FRAC_PI_4 = 0.785398163397448309615660845819875721f;
+constexpr float FRAC_1_PI = 0.318309886183790671537767526745028724f;
+
+// ============================================================================================
+// cgmath 0.18 vector arithmetic (crate not vendored; restated: SURVEY.md §8c)
+// ============================================================================================
+struct V3 {
+    float x, y, z;
+};
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+inline float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; } // (xx + yy) + zz
+inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline float magnitude2(V3 a) { return dot(a, a); }
+inline float magnitude(V3 a) { return std::sqrt(dot(a, a)); }
+inline V3 normalize(V3 a) { return a * (1.0f / magnitude(a)); } // normalize_to(1): v * (1/|v|)
+inline float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+inline V3 load3(const float *p) { return {p[0], p[1], p[2]}; }
+inline void store3(float *p, V3 v) { p[0] = v.x, p[1] = v.y, p[2] = v.z; }
+// Rust f32::max / f32::min: if one operand is NaN the other is returned == fmaxf / fminf
+inline float rmax(float a, float b) { return std::fmax(a, b); }
+inline float rmin(float a, float b) { return std::fmin(a, b); }
+
+struct M4 { // column-major, m[4*c+r]
+    float m[16];
+    float at(int c, int r) const { return m[4 * c + r]; }
+};
+// Matrix4 * Vector4 = c0*x + c1*y + c2*z + c3*w
+inline void m4_mul_v4(const M4 &m, const float v[4], float out[4]) {
+    for (int r = 0; r < 4; r++) out[r] = ((m.at(0, r) * v[0] + m.at(1, r) * v[1]) + m.at(2, r) * v[2]) + m.at(3, r) * v[3];
+}
+inline V3 transform_point(const M4 &m, V3 p) { // Point3::from_homogeneous(m * p.to_homogeneous())
+    float v[4] = {p.x, p.y, p.z, 1.0f}, h[4];
+    m4_mul_v4(m, v, h);
+    float iw = 1.0f / h[3];
+    return {h[0] * iw, h[1] * iw, h[2] * iw};
+}
+inline V3 transform_vector(const M4 &m, V3 d) { // (m * d.extend(0)).truncate()
+    float v[4] = {d.x, d.y, d.z, 0.0f}, h[4];
+    m4_mul_v4(m, v, h);
+    return {h[0], h[1], h[2]};
+}
+
+// ============================================================================================
+// "spec" transcendental functions: f64 polynomials, identical op sequence on
+// the GPU.  Used when math_mode == ORC_MATH_SPEC; ORC_MATH_LIBM calls glibc like Rust does.
+// ============================================================================================
+inline void spec_sincos(float xf, float *s, float *c) {
+    const double TWO_OVER_PI = 0.63661977236758134308;
+    const double PIO2_HI = 1.57079632673412561417e+00; // first 33 bits of pi/2
+    const double PIO2_LO = 6.07710050650619224932e-11; // pi/2 - PIO2_HI
+    double x = (double)xf;
+    double fn = std::floor(x * TWO_OVER_PI + 0.5);
+    int n = (int)fn;
+    double y = (x - fn * PIO2_HI) - fn * PIO2_LO;
+    double y2 = y * y;
+    // Taylor coefficients 1/3!, 1/5!, ... and 1/2!, 1/4!, ...
+    double ps = 1.0 / 6227020800.0;                // +1/13!
+    ps = ps * y2 + -1.0 / 39916800.0;              // -1/11!
+    ps = ps * y2 + 1.0 / 362880.0;                 // +1/9!
+    ps = ps * y2 + -1.0 / 5040.0;                  // -1/7!
+    ps = ps * y2 + 1.0 / 120.0;                    // +1/5!
+    ps = ps * y2 + -1.0 / 6.0;                     // -1/3!
+    double sy = y + y * (y2 * ps);
+    double pc = -1.0 / 87178291200.0;              // -1/14!
+    pc = pc * y2 + 1.0 / 479001600.0;              // +1/12!
+    pc = pc * y2 + -1.0 / 3628800.0;               // -1/10!
+    pc = pc * y2 + 1.0 / 40320.0;                  // +1/8!
+    pc = pc * y2 + -1.0 / 720.0;                   // -1/6!
+    pc = pc * y2 + 1.0 / 24.0;                     // +1/4!
+    pc = pc * y2 + -0.5;                           // -1/2!
+    double cy = 1.0 + y2 * pc;
+    double rs, rc;
+    switch (n & 3) {
+    case 0: rs = sy, rc = cy; break;
+    case 1: rs = cy, rc = -sy; break;
+    case 2: rs = -sy, rc = -cy; break;
+    default: rs = -cy, rc = sy; break;
+    }
+    *s = (float)rs;
+    *c = (float)rc;
+}
+inline double spec_log2(double x) { // x > 0, normal
+    uint64_t bits;
+    std::memcpy(&bits, &x, 8);
+    int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    uint64_t mb = (bits & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
+    double m;
+    std::memcpy(&m, &mb, 8);
+    if (m > 1.4142135623730951) {
+        m = m * 0.5;
+        e = e + 1;
+    }
+    double f = (m - 1.0) / (m + 1.0);
+    double f2 = f * f;
+    double p = 1.0 / 21.0;
+    p = p * f2 + 1.0 / 19.0;
+    p = p * f2 + 1.0 / 17.0;
+    p = p * f2 + 1.0 / 15.0;
+    p = p * f2 + 1.0 / 13.0;
+    p = p * f2 + 1.0 / 11.0;
+    p = p * f2 + 1.0 / 9.0;
+    p = p * f2 + 1.0 / 7.0;
+    p = p * f2 + 1.0 / 5.0;
+    p = p * f2 + 1.0 / 3.0;
+    double ln_m = 2.0 * (f + f * (f2 * p));
+    return (double)e + ln_m * 1.4426950408889634074;
+}
+inline double spec_exp2(double t) {
+    if (t < -1000.0) return 0.0;
+    if (t > 1000.0) return std::numeric_limits<double>::infinity();
+    double k = std::floor(t + 0.5);
+    double r = (t - k) * 0.69314718055994530942; // |r| <= 0.3466
+    double p = 1.0 / 6227020800.0;               // 1/13!
+    p = p * r + 1.0 / 479001600.0;
+    p = p * r + 1.0 / 39916800.0;
+    p = p * r + 1.0 / 3628800.0;
+    p = p * r + 1.0 / 362880.0;
+    p = p * r + 1.0 / 40320.0;
+    p = p * r + 1.0 / 5040.0;
+    p = p * r + 1.0 / 720.0;
+    p = p * r + 1.0 / 120.0;
+    p = p * r + 1.0 / 24.0;
+    p = p * r + 1.0 / 6.0;
+    p = p * r + 0.5;
+    p = p * r + 1.0;
+    p = p * r + 1.0;
+    int ki = (int)k;
+    // scale by 2^ki in two steps so that subnormal results round once
+    int k1 = ki / 2, k2 = ki - k1;
+    uint64_t b1 = (uint64_t)(k1 + 1023) << 52, b2 = (uint64_t)(k2 + 1023) << 52;
+    double s1, s2;
+    std::memcpy(&s1, &b1, 8);
+    std::memcpy(&s2, &b2, 8);
+    return (p * s1) * s2;
+}
+inline float spec_powf(float x, float y) { // x >= 0
+    if (y == 0.0f) return 1.0f;
+    if (x == 0.0f) return y > 0.0f ? 0.0f : std::numeric_limits<float>::infinity();
+    if (x == 1.0f) return 1.0f;
+    if (!(x > 0.0f)) return std::numeric_limits<float>::quiet_NaN();
+    return (float)spec_exp2((double)y * spec_log2((double)x));
+}
+struct Math {
+    uint32_t mode;
+    void sincos(float x, float *s, float *c) const {
+        if (mode == ORC_MATH_LIBM) {
+            *s = std::sin(x);
+            *c = std::cos(x);
+        } else spec_sincos(x, s, c);
+    }
+    float powf(float x, float y) const { return mode == ORC_MATH_LIBM ? std::pow(x, y) : spec_powf(x, y); }
+};
+
+// ============================================================================================
+// structure.rs: PDF, Color
+// ============================================================================================
+struct PDF { // structure.rs:19-24
+    enum Kind { SolidAngle, Area, Discrete } kind;
+    float v;
+    bool is_zero() const { return v == 0.0f; }                  // :72-76
+    float value() const { return v; }                           // :78-82
+    PDF operator*(float o) const { return PDF{kind, v * o}; }   // :85-94
+    PDF as_solid_angle_geom(float g_ad) const {                 // :27-39
+        if (kind == SolidAngle) return *this;
+        if (g_ad == 0.0f) return PDF{SolidAngle, 0.0f};
+        return PDF{SolidAngle, v / g_ad};
+    }
+};
+struct Color { // structure.rs:105-110
+    float r, g, b;
+    static Color zero() { return {0, 0, 0}; }
+    static Color one() { return {1, 1, 1}; }
+    bool is_zero() const { return r == 0.0f && g == 0.0f && b == 0.0f; }     // :153-155
+    float channel_max() const { return rmax(r, rmax(g, b)); }                // :169-171
+    void scale(float v) { r *= v, g *= v, b *= v; }                          // :185-191
+};
+inline Color operator*(Color a, float o) { // :278-292 (zero if the scalar is not finite)
+    if (std::isfinite(o)) return {a.r * o, a.g * o, a.b * o};
+    return Color::zero();
+}
+inline Color operator*(float s, Color o) { return {o.r * s, o.g * s, o.b * s}; } // :294-303
+inline Color operator*(Color a, Color b) { return {a.r * b.r, a.g * b.g, a.b * b.b}; } // :338-347
+inline Color operator+(Color a, Color b) { return {a.r + b.r, a.g + b.g, a.b + b.b}; } // :360-369
+inline Color operator/(Color a, float o) { // :249-265
+    if (o == 0.0f || !std::isfinite(o)) return Color::zero();
+    return {a.r / o, a.g / o, a.b / o};
+}
+inline void div_assign(Color &a, float o) { a.r /= o, a.g /= o, a.b /= o; } // :201-207 (no guard)
+
+// ============================================================================================
+// structure.rs: Ray, AABB
+// ============================================================================================
+struct Ray { // :697-702
+    V3 o, d;
+    float tnear, tfar;
+};
+inline Ray ray_new(V3 o, V3 d) { return Ray{o, d, EPSILON, F32_MAX}; } // :705-715 (assert on |d| omitted)
+
+struct AABB { // :760-763
+    V3 p_min{F32_MAX, F32_MAX, F32_MAX}, p_max{-F32_MAX, -F32_MAX, -F32_MAX}; // Default :765-772 (f32::MIN == -MAX)
+    AABB union_aabb(const AABB &b) const { // :779-784
+        AABB r;
+        r.p_min = {rmin(p_min.x, b.p_min.x), rmin(p_min.y, b.p_min.y), rmin(p_min.z, b.p_min.z)};
+        r.p_max = {rmax(p_max.x, b.p_max.x), rmax(p_max.y, b.p_max.y), rmax(p_max.z, b.p_max.z)};
+        return r;
+    }
+    AABB union_vec(V3 v) const { // :786-791
+        AABB r;
+        r.p_min = {rmin(p_min.x, v.x), rmin(p_min.y, v.y), rmin(p_min.z, v.z)};
+        r.p_max = {rmax(p_max.x, v.x), rmax(p_max.y, v.y), rmax(p_max.z, v.z)};
+        return r;
+    }
+    V3 size() const { return p_max - p_min; }           // :839-841
+    V3 center() const { return size() * 0.5f + p_min; } // :844-846
+    float surface_area() const {                        // :822-836 (half the true area)
+        V3 d = size();
+        float s = 0.0f;
+        for (int i = 0; i < 3; i++) {
+            float v = 1.0f;
+            for (int j = 0; j < 3; j++) {
+                if (i == j) continue;
+                v *= comp(d, j);
+            }
+            s += v;
+        }
+        return s;
+    }
+    bool intersect(const Ray &r, float *t_out) const { // :849-869
+        float t_max = r.tfar, t_min = r.tnear;
+        for (int d = 0; d < 3; d++) {
+            float inv_d = 1.0f / comp(r.d, d);
+            float t0 = (comp(p_min, d) - comp(r.o, d)) * inv_d;
+            float t1 = (comp(p_max, d) - comp(r.o, d)) * inv_d;
+            if (inv_d < 0.0f) std::swap(t0, t1);
+            t_min = t0 > t_min ? t0 : t_min;
+            t_max = t1 < t_max ? t1 : t_max;
+            if (t_max <= t_min) return false;
+        }
+        *t_out = t_min;
+        return true;
+    }
+};
+
+// ============================================================================================
+// math.rs
+// ============================================================================================
+struct P2 {
+    float x, y;
+};
+P2 concentric_sample_disk(const Math &m, P2 u) { // :37-59
+    P2 u_offset{u.x * 2.0f - 1.0f, u.y * 2.0f - 1.0f};
+    if (u_offset.x == 0.0f && u_offset.y == 0.0f) return P2{0.0f, 0.0f};
+    float theta, r;
+    if (std::fabs(u_offset.x) > std::fabs(u_offset.y)) {
+        r = u_offset.x;
+        theta = FRAC_PI_4 * (u_offset.y / u_offset.x);
+    } else {
+        r = u_offset.y;
+        theta = FRAC_PI_2 - FRAC_PI_4 * (u_offset.x / u_offset.y);
+    }
+    float s, c;
+    m.sincos(theta, &s, &c);
+    return P2{c * r, s * r};
+}
+V3 cosine_sample_hemisphere(const Math &m, P2 u) { // :61-65
+    P2 d = concentric_sample_disk(m, u);
+    float z = std::sqrt(rmax(0.0f, 1.0f - d.x * d.x - d.y * d.y));
+    return V3{d.x, d.y, z};
+}
+struct Frame { // :357-384 (Matrix3 columns x, y, z)
+    V3 x, y, z;
+    explicit Frame(V3 n) {
+        float sign = std::copysign(1.0f, n.z); // f32::signum: +1 for +0.0, -1 for -0.0 (NaN -> NaN, not reachable)
+        float a = -1.0f / (sign + n.z);
+        float b = n.x * n.y * a;
+        x = V3{1.0f + sign * n.x * n.x * a, sign * b, -sign * n.x};
+        y = V3{b, sign + n.y * n.y * a, -n.y};
+        z = n;
+    }
+    Frame() : x{1, 0, 0}, y{0, 1, 0}, z{0, 0, 1} {}
+    V3 to_world(V3 v) const { return x * v.x + y * v.y + z * v.z; }
+    V3 to_local(V3 v) const { return V3{dot(v, x), dot(v, y), dot(v, z)}; }
+};
+P2 uniform_sample_triangle(P2 u) { // :388-394
+    float su0 = std::sqrt(u.x);
+    return P2{1.0f - su0, u.y * su0};
+}
+struct Distribution1D { // :402-406
+    std::vector<float> cdf, func;
+    float func_int = 0;
+    static Distribution1D normalize(const std::vector<float> &elements) { // :418-441
+        Distribution1D d;
+        float cur = 0.0f;
+        for (float e : elements) {
+            d.cdf.push_back(cur);
+            cur += e / (float)elements.size();
+        }
+        d.cdf.push_back(cur);
+        if (cur != 0.0f)
+            for (float &x : d.cdf) x /= cur;
+        d.cdf.back() = 1.0f;
+        d.func = elements;
+        d.func_int = cur;
+        return d;
+    }
+    // :447-457.  Rust's binary_search_by returns Ok(i) for cdf[i]==v, else Err(insertion)->insertion-1;
+    // both equal "last index with cdf[i] <= v" when the cdf has no repeated entries.
+    size_t sample_discrete(float v) const {
+        size_t ub = (size_t)(std::upper_bound(cdf.begin(), cdf.end(), v) - cdf.begin());
+        return ub - 1;
+    }
+    float pdf(size_t i) const { return cdf[i + 1] - cdf[i]; }            // :480-482
+    float total() const { return func_int * (float)(cdf.size() - 1); }   // :484-486
+};
+
+// ============================================================================================
+// bsdfs
+// ============================================================================================
+struct SampledDirection { // bsdfs/mod.rs:129-137
+    Color weight;
+    V3 d;
+    PDF pdf;
+};
+inline V3 reflect(V3 d) { return V3{-d.x, -d.y, d.z}; } // bsdfs/mod.rs:124-126
+
+struct BSDF { // trait BSDF, bsdfs/mod.rs:163-199
+    virtual ~BSDF() = default;
+    virtual bool sample(const Math &m, V3 d_in, P2 sample, SampledDirection *out) const = 0;
+    virtual PDF pdf(const Math &m, V3 d_in, V3 d_out) const = 0;
+    virtual Color eval(const Math &m, V3 d_in, V3 d_out) const = 0;
+    virtual bool is_twosided() const = 0;
+    virtual bool is_smooth() const = 0; // bsdf_type().is_smooth(), bsdfs/mod.rs:157-161
+};
+struct BSDFDiffuse : BSDF { // bsdfs/diffuse.rs
+    Color diffuse;
+    bool sample(const Math &m, V3 d_in, P2 s, SampledDirection *out) const override { // :11-31
+        if (d_in.z <= 0.0f) return false;
+        V3 d_out = cosine_sample_hemisphere(m, s);
+        *out = SampledDirection{diffuse, d_out, PDF{PDF::SolidAngle, d_out.z * FRAC_1_PI}};
+        return true;
+    }
+    PDF pdf(const Math &, V3 d_in, V3 d_out) const override { // :33-51
+        if (d_in.z <= 0.0f) return PDF{PDF::SolidAngle, 0.0f};
+        if (d_out.z <= 0.0f) return PDF{PDF::SolidAngle, 0.0f};
+        return PDF{PDF::SolidAngle, d_out.z * FRAC_1_PI};
+    }
+    Color eval(const Math &, V3 d_in, V3 d_out) const override { // :53-71
+        if (d_in.z <= 0.0f) return Color::zero();
+        if (d_out.z > 0.0f) return diffuse * d_out.z * FRAC_1_PI;
+        return Color::zero();
+    }
+    bool is_twosided() const override { return true; }
+    bool is_smooth() const override { return false; }
+};
+struct BSDFPhong : BSDF { // bsdfs/phong.rs
+    Color diffuse, specular;
+    float exponent, weight_specular;
+    bool sample(const Math &m, V3 d_in, P2 s, SampledDirection *out) const override { // :14-63
+        if (d_in.z <= 0.0f) return false;
+        V3 d_out;
+        if (s.x < weight_specular) {
+            s.x /= weight_specular;
+            float sin_alpha = std::sqrt(1.0f - m.powf(s.y, 2.0f / (exponent + 1.0f)));
+            float cos_alpha = m.powf(s.y, 1.0f / (exponent + 1.0f));
+            float phi = 2.0f * PI * s.x;
+            float sp, cp;
+            m.sincos(phi, &sp, &cp);
+            V3 local_dir{sin_alpha * cp, sin_alpha * sp, cos_alpha};
+            Frame frame(reflect(d_in));
+            d_out = frame.to_world(local_dir);
+            if (d_out.z <= 0.0f) return false;
+        } else {
+            s.x = (s.x - weight_specular) / (1.0f - weight_specular);
+            d_out = cosine_sample_hemisphere(m, s);
+        }
+        PDF p = pdf(m, d_in, d_out);
+        if (p.value() == 0.0f) return false;
+        *out = SampledDirection{eval(m, d_in, d_out) / p.value(), d_out, p};
+        return true;
+    }
+    PDF pdf(const Math &m, V3 d_in, V3 d_out) const override { // :65-91
+        if (d_in.z <= 0.0f || d_out.z <= 0.0f) return PDF{PDF::SolidAngle, 0.0f};
+        float pdf_specular;
+        float alpha = dot(reflect(d_in), d_out);
+        if (alpha > 0.0f) pdf_specular = weight_specular * m.powf(alpha, exponent) * (exponent + 1.0f) / (2.0f * PI);
+        else pdf_specular = 0.0f;
+        float pdf_diffuse = (1.0f - weight_specular) * d_out.z * FRAC_1_PI;
+        return PDF{PDF::SolidAngle, pdf_specular + pdf_diffuse};
+    }
+    Color eval(const Math &m, V3 d_in, V3 d_out) const override { // :93-119
+        if (d_in.z <= 0.0f || d_out.z <= 0.0f) return Color::zero();
+        Color specular_value;
+        float alpha = dot(reflect(d_in), d_out);
+        if (alpha > 0.0f) specular_value = specular * (m.powf(alpha, exponent) * (exponent + 2.0f) / (2.0f * PI));
+        else specular_value = Color::zero();
+        Color diffuse_value = diffuse * d_out.z * FRAC_1_PI;
+        return specular_value + diffuse_value;
+    }
+    bool is_twosided() const override { return true; }
+    bool is_smooth() const override { return false; }
+};
+std::unique_ptr<BSDF> make_bsdf(const rl_material &m) {
+    if (m.kind == RL_BSDF_PHONG) {
+        auto b = std::make_unique<BSDFPhong>();
+        b->diffuse = Color{m.kd[0], m.kd[1], m.kd[2]};
+        b->specular = Color{m.ks[0], m.ks[1], m.ks[2]};
+        b->exponent = m.exponent;
+        b->weight_specular = m.weight_specular;
+        return b;
+    }
+    auto b = std::make_unique<BSDFDiffuse>();
+    b->diffuse = Color{m.kd[0], m.kd[1], m.kd[2]};
+    return b;
+}
+
+// ============================================================================================
+// geometry.rs: Mesh
+// ============================================================================================
+struct IntersectionUV { // structure.rs:924-930
+    float t;
+    V3 p, n;
+    float u, v;
+};
+struct SampledPosition { // structure.rs:96-102
+    V3 p, n;
+    PDF pdf;
+    size_t primitive_id;
+};
+struct Idx3 {
+    uint32_t x, y, z;
+};
+struct Mesh { // geometry.rs:107-119
+    std::vector<V3> vertices;
+    std::vector<Idx3> indices;
+    bool has_normals = false;
+    std::vector<V3> normals;
+    std::unique_ptr<BSDF> bsdf;
+    bool light = false; // emission != EmissionType::Zero
+    Color emission = Color::zero();
+    Distribution1D cdf;
+    uint32_t first_prim = 0; // global index of triangle 0 (mesh-major numbering)
+
+    void build_cdf() { // Mesh::new, :130-138
+        std::vector<float> areas;
+        for (auto id : indices) {
+            V3 v0 = vertices[id.x], v1 = vertices[id.y], v2 = vertices[id.z];
+            areas.push_back(magnitude(cross(v1 - v0, v2 - v0)) * 0.5f);
+        }
+        cdf = Distribution1D::normalize(areas);
+    }
+    Color emit() const { return light ? emission : Color::zero(); } // :184-206 (Zero | Color)
+    bool is_light() const { return light; }                         // :412-417
+    float pdf() const { return 1.0f / cdf.total(); }                // :223-225
+
+    bool intersection_tri(size_t i, V3 p_c, V3 d_c, IntersectionUV &its) const { // :358-410
+        Idx3 id = indices[i];
+        V3 v0 = vertices[id.x], v1 = vertices[id.y], v2 = vertices[id.z];
+        V3 e1 = v1 - v0, e2 = v2 - v0;
+        V3 n_geo = normalize(cross(e1, e2));
+        float denom = dot(d_c, n_geo);
+        if (denom == 0.0f) return false;
+        float t = -dot(p_c - v0, n_geo) / denom;
+        if (t < 0.0f) return false;
+        V3 p = p_c + t * d_c;
+        float det = magnitude(cross(e1, e2));
+        V3 u0 = cross(e1, p - v0);
+        V3 v0c = cross(p - v0, e2);
+        if (dot(u0, n_geo) < 0.0f || dot(v0c, n_geo) < 0.0f) return false;
+        float v = magnitude(u0) / det;
+        float u = magnitude(v0c) / det;
+        if (u < 0.0f || v < 0.0f || u > 1.0f || v > 1.0f) return false;
+        if (u + v <= 1.0f) {
+            if (t < its.t && t > 0.00001f) {
+                its.t = t, its.u = u, its.v = v, its.p = p, its.n = n_geo;
+                return true;
+            }
+        }
+        return false;
+    }
+    AABB compute_aabb_tri(size_t i) const { // :423-439
+        Idx3 id = indices[i];
+        AABB aabb;
+        aabb = aabb.union_vec(vertices[id.x]);
+        aabb = aabb.union_vec(vertices[id.y]);
+        aabb = aabb.union_vec(vertices[id.z]);
+        V3 s = aabb.size();
+        if (s.x < EPSILON) aabb.p_max.x += EPSILON, aabb.p_min.x -= EPSILON;
+        if (s.y < EPSILON) aabb.p_max.y += EPSILON, aabb.p_min.y -= EPSILON;
+        if (s.z < EPSILON) aabb.p_max.z += EPSILON, aabb.p_min.z -= EPSILON;
+        return aabb;
+    }
+    SampledPosition sample_tri(size_t primitive_id, P2 v) const { // :261-337
+        Idx3 id = indices[primitive_id];
+        V3 v0 = vertices[id.x], v1 = vertices[id.y], v2 = vertices[id.z];
+        P2 b = uniform_sample_triangle(v);
+        V3 pos = v0 * b.x + v1 * b.y + v2 * (1.0f - b.x - b.y);
+        V3 n_g;
+        {
+            V3 u = v1 - v0, w = v2 - v0;
+            n_g = normalize(cross(w, u));
+        }
+        if (has_normals) {
+            V3 n0 = normals[id.x], n1 = normals[id.y], n2 = normals[id.z];
+            V3 n = n0 * b.x + n1 * b.y + n2 * (1.0f - b.x - b.y);
+            float n_l = magnitude2(n);
+            if (n_l == 0.0f) n = n_g;
+            else if (n_l != 1.0f) n = n / std::sqrt(n_l);
+            if (dot(n_g, n) < 0.0f) n_g = -n_g;
+        }
+        float area_tri = magnitude(cross(v1 - v0, v2 - v0)) * 0.5f;
+        return SampledPosition{pos, n_g, PDF{PDF::Area, 1.0f / area_tri}, primitive_id};
+    }
+    SampledPosition sample(float s, P2 v) const { // :340-348
+        size_t primitive_id = cdf.sample_discrete(s);
+        SampledPosition res = sample_tri(primitive_id, v);
+        res.pdf = PDF{PDF::Area, 1.0f / cdf.total()};
+        return res;
+    }
+    Color flux() const { return cdf.total() * emit() * PI; } // emitter.rs:591-599 (f32*Color then Color*f32)
+};
+
+// ============================================================================================
+// structure.rs: Intersection::fill_intersection :965-1059
+// ============================================================================================
+struct Intersection {
+    float dist;
+    V3 n_g, n_s, p;
+    const Mesh *mesh;
+    Frame frame;
+    V3 wi;
+    size_t primitive_id;
+    float cos_theta() const { return wi.z; }
+};
+Intersection fill_intersection(const Mesh *mesh, size_t tri_id, float hit_u, float hit_v, const Ray &ray, V3 n_g, float dist, V3 p) {
+    Idx3 index = mesh->indices[tri_id];
+    V3 n_s;
+    if (mesh->has_normals) {
+        V3 d0 = mesh->normals[index.x], d1 = mesh->normals[index.y], d2 = mesh->normals[index.z];
+        V3 ns = d0 * (1.0f - hit_u - hit_v) + d1 * hit_u + d2 * hit_v;
+        if (dot(n_g, ns) < 0.0f) n_g = -n_g;
+        float l = dot(ns, ns);
+        if (l == 0.0f) n_s = n_g;
+        else if (l != 1.0f) n_s = ns / std::sqrt(l);
+        else n_s = ns;
+    } else n_s = n_g;
+    if (mesh->bsdf->is_twosided() && !mesh->is_light() && dot(ray.d, n_s) > 0.0f) {
+        n_s = V3{-n_s.x, -n_s.y, -n_s.z};
+        n_g = V3{-n_g.x, -n_g.y, -n_g.z};
+    }
+    Intersection its;
+    its.dist = dist, its.n_g = n_g, its.n_s = n_s, its.p = p, its.mesh = mesh;
+    its.frame = Frame(n_s);
+    its.wi = its.frame.to_local(-ray.d);
+    its.primitive_id = tri_id;
+    return its;
+}
+inline Ray spawn_ray(const Intersection &its, V3 d_out) { return Ray{its.p, d_out, EPSILON, F32_MAX}; } // structure.rs:717-731
+
+// ============================================================================================
+// emitter.rs: impl Emitter for Mesh :570-688, EmitterSampler :1491-1647
+// ============================================================================================
+struct LightSampling { // :10-24
+    const Mesh *emitter;
+    PDF pdf;
+    V3 p, n, d;
+    size_t primitive_id;
+    Color weight;
+    bool is_valid() const { return !pdf.is_zero(); }
+};
+struct LightSamplingPDF { // :26-44
+    V3 o, p, n, dir;
+};
+PDF mesh_direct_pdf(const Mesh &m, const LightSamplingPDF &ls) { // :571-579
+    float cos_light = rmax(dot(ls.n, -ls.dir), 0.0f);
+    if (cos_light == 0.0f) return PDF{PDF::SolidAngle, 0.0f};
+    float geom = cos_light / magnitude2(ls.p - ls.o);
+    return PDF{PDF::SolidAngle, m.pdf() / geom};
+}
+LightSampling mesh_direct_sample(const Mesh &m, V3 p, float r, P2 uv) { // :652-688
+    SampledPosition sp = m.sample(r, uv);
+    V3 d = sp.p - p;
+    float dist = magnitude(d);
+    if (dist != 0.0f) d = d / dist;
+    float geom = dist != 0.0f ? rmax(dot(sp.n, -d), 0.0f) / (dist * dist) : 0.0f;
+    float pdf_area = sp.pdf.value();
+    PDF pdf = sp.pdf.as_solid_angle_geom(geom);
+    Color weight = pdf.is_zero() ? Color::zero() : m.emit() * geom / pdf_area;
+    return LightSampling{&m, pdf, sp.p, sp.n, d, sp.primitive_id, weight};
+}
+struct EmitterSampler { // :1491-1495 (ats == None on this path)
+    std::vector<const Mesh *> emitters;
+    Distribution1D emitters_cdf;
+    float pdf(const Mesh *e) const { // :1510-1526 (pointer identity)
+        for (size_t i = 0; i < emitters.size(); i++)
+            if (emitters[i] == e) return emitters_cdf.pdf(i);
+        return 0.0f; // the reference panics here; unreachable (only light meshes are queried)
+    }
+    PDF direct_pdf(const Mesh *e, const LightSamplingPDF &ls) const { return mesh_direct_pdf(*e, ls) * pdf(e); } // :1566-1575
+    LightSampling sample_light(V3 p, float r_sel, float r, P2 uv) const { // :1604-1620, :1641-1647
+        size_t id_light = emitters_cdf.sample_discrete(r_sel);
+        float pdf_sel = emitters_cdf.pdf(id_light);
+        LightSampling res = mesh_direct_sample(*emitters[id_light], p, r, uv);
+        div_assign(res.weight, pdf_sel);
+        res.pdf = res.pdf * pdf_sel;
+        return res;
+    }
+};
+
+// ============================================================================================
+// camera.rs
+// ============================================================================================
+struct Camera {
+    uint32_t img_x, img_y;
+    M4 sample_to_camera, to_world;
+    V3 position() const { return transform_point(to_world, V3{0, 0, 0}); } // :140-142
+    Ray generate(P2 px) const {                                            // :81-91
+        V3 near_p = transform_point(sample_to_camera, V3{px.x / (float)img_x, px.y / (float)img_y, 0.0f});
+        V3 d = normalize(near_p);
+        return ray_new(position(), transform_vector(to_world, d));
+    }
+};
+M4 m4_mul(const M4 &a, const M4 &b) {
+    M4 r;
+    for (int c = 0; c < 4; c++) {
+        float v[4] = {b.at(c, 0), b.at(c, 1), b.at(c, 2), b.at(c, 3)}, o[4];
+        m4_mul_v4(a, v, o);
+        for (int k = 0; k < 4; k++) r.m[4 * c + k] = o[k];
+    }
+    return r;
+}
+bool m4_invert(const M4 &a, M4 *out) { // cgmath SquareMatrix::invert: adjugate / determinant (host-only)
+    auto det3 = [](float a0, float a1, float a2, float b0, float b1, float b2, float c0, float c1, float c2) {
+        return a0 * (b1 * c2 - c1 * b2) - b0 * (a1 * c2 - c1 * a2) + c0 * (a1 * b2 - b1 * a2);
+    };
+    float cof[16];
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) {
+            float s[9];
+            int k = 0;
+            for (int cc = 0; cc < 4; cc++) {
+                if (cc == c) continue;
+                for (int rr = 0; rr < 4; rr++) {
+                    if (rr == r) continue;
+                    s[k++] = a.at(cc, rr);
+                }
+            }
+            float d = det3(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8]);
+            cof[4 * c + r] = ((c + r) & 1) ? -d : d;
+        }
+    float det = a.at(0, 0) * cof[0] + a.at(0, 1) * cof[1] + a.at(0, 2) * cof[2] + a.at(0, 3) * cof[3];
+    if (det == 0.0f) return false;
+    float inv = 1.0f / det;
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) out->m[4 * c + r] = cof[4 * r + c] * inv;
+    return true;
+}
+bool camera_new(uint32_t w, uint32_t h, int fov_axis, float fov_deg, const M4 &to_world, bool flip, M4 *s2c) { // :31-67
+    float x_v = flip ? 1.0f : -1.0f;
+    float aspect_ratio = (float)w / (float)h;
+    float fov_rad = fov_axis ? fov_deg * PI / 180.0f : fov_deg * aspect_ratio * PI / 180.0f;
+    auto diag = [](float a, float b, float c) {
+        M4 m{};
+        m.m[0] = a, m.m[5] = b, m.m[10] = c, m.m[15] = 1.0f;
+        return m;
+    };
+    M4 trans = diag(1, 1, 1);
+    trans.m[12] = -1.0f, trans.m[13] = -1.0f / aspect_ratio, trans.m[14] = 0.0f;
+    M4 persp{};
+    float f = 1.0f / std::tan(fov_rad / 2.0f); // Rad::cot(fovy / 2)
+    float near = 1e-2f, far = 1000.0f, aspect = 1.0f;
+    persp.m[0] = f / aspect, persp.m[5] = f, persp.m[10] = (far + near) / (near - far), persp.m[11] = -1.0f;
+    persp.m[14] = (2.0f * far * near) / (near - far);
+    M4 camera_to_sample = m4_mul(m4_mul(m4_mul(diag(-0.5f, -0.5f * aspect_ratio, 1.0f), trans), persp), diag(x_v, 1.0f, -1.0f));
+    (void)to_world;
+    return m4_invert(camera_to_sample, s2c);
+}
+
+// ============================================================================================
+// samplers: trait Sampler (samplers/mod.rs:3-9); IndependentSampler (independent.rs) over
+// rand 0.8.5 SmallRng == xoshiro256++ on 64-bit targets (crate not vendored: restated from
+// the published algorithm; seeding variant selectable, see oracle.h).
+// ============================================================================================
+inline uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+struct Xoshiro256PP {
+    uint64_t s[4];
+    uint64_t next_u64() {
+        uint64_t result = rotl64(s[0] + s[3], 23) + s[0];
+        uint64_t t = s[1] << 17;
+        s[2] ^= s[0], s[3] ^= s[1], s[1] ^= s[2], s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl64(s[3], 45);
+        return result;
+    }
+    uint32_t next_u32() { return (uint32_t)(next_u64() >> 32); }
+    // rand::distributions::Standard for f32: 24 random bits scaled by 2^-24
+    float gen_f32() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }
+    static Xoshiro256PP seed_from_u64(uint64_t state, uint32_t seeding) {
+        Xoshiro256PP r;
+        if (seeding == ORC_SEED_SPLITMIX64) {
+            for (int i = 0; i < 4; i++) {
+                state += 0x9e3779b97f4a7c15ULL;
+                uint64_t z = state;
+                z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+                z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+                r.s[i] = z ^ (z >> 31);
+            }
+        } else { // rand_core 0.6 SeedableRng::seed_from_u64: PCG32 stream fills the 32-byte seed (LE)
+            uint32_t w[8];
+            for (int i = 0; i < 8; i++) {
+                state = state * 6364136223846793005ULL + 11634580027462260723ULL;
+                uint32_t xorshifted = (uint32_t)(((state >> 18) ^ state) >> 27);
+                uint32_t rot = (uint32_t)(state >> 59);
+                w[i] = (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31));
+            }
+            for (int i = 0; i < 4; i++) r.s[i] = (uint64_t)w[2 * i] | ((uint64_t)w[2 * i + 1] << 32);
+        }
+        if ((r.s[0] | r.s[1] | r.s[2] | r.s[3]) == 0) return seed_from_u64(0, ORC_SEED_SPLITMIX64);
+        return r;
+    }
+};
+struct Sampler {
+    virtual ~Sampler() = default;
+    virtual float next() = 0;
+    P2 next2d() { // x then y, independent.rs:13-17
+        float x = next();
+        float y = next();
+        return P2{x, y};
+    }
+    uint32_t draws = 0;
+};
+struct IndependentSampler : Sampler { // mode A
+    Xoshiro256PP rnd;
+    uint32_t seeding;
+    float next() override {
+        draws++;
+        return rnd.gen_f32();
+    }
+    IndependentSampler clone_box() { // independent.rs:18-22
+        IndependentSampler c;
+        c.seeding = seeding;
+        c.rnd = Xoshiro256PP::seed_from_u64(rnd.next_u64(), seeding);
+        return c;
+    }
+};
+// mode B: counter-based stream per (seed, pixel, sample); DESIGN.md §rng.  Same on the GPU.
+inline uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+struct CounterSampler : Sampler {
+    uint64_t key;
+    uint32_t n = 0;
+    CounterSampler(uint64_t seed, uint32_t pixel, uint32_t sample) {
+        uint64_t h = mix64(seed + 0x9e3779b97f4a7c15ULL);
+        key = mix64(h ^ (((uint64_t)pixel << 32) | (uint64_t)sample));
+    }
+    float next() override {
+        draws++;
+        n++;
+        uint64_t z = mix64(key + (uint64_t)n * 0x9e3779b97f4a7c15ULL);
+        return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+    }
+};
+
+// ============================================================================================
+// Scene (scene.rs) + accel.rs
+// ============================================================================================
+struct Counters {
+    uint64_t segments = 0, shadow_rays = 0, shadow_visible = 0, hits = 0, max_depth = 0;
+};
+struct TriRef {
+    uint32_t id_mesh, id_tri;
+};
+struct BVHNode { // accel.rs:79-88
+    AABB aabb;
+    size_t info, count;
+    bool is_leaf() const { return count != 0; }
+};
+struct CachedAABB {
+    AABB aabb;
+    TriRef info;
+};
+struct Scene {
+    Camera camera;
+    std::vector<std::unique_ptr<Mesh>> meshes;
+    EmitterSampler emitters;
+    // BVHAccel
+    std::vector<TriRef> primitives;
+    std::vector<BVHNode> nodes;
+
+    void build_emitters() { // scene.rs:53-123 (mesh emitters only; no env map, no ATS)
+        emitters.emitters.clear();
+        for (auto &m : meshes)
+            if (m->is_light()) emitters.emitters.push_back(m.get());
+        if (emitters.emitters.empty()) return;
+        std::vector<float> fl;
+        for (auto e : emitters.emitters) fl.push_back(e->flux().channel_max());
+        emitters.emitters_cdf = Distribution1D::normalize(fl);
+    }
+
+    // ---- BVHAccel::new, accel.rs:201-240 -----------------------------------------------
+    static AABB compute_aabb(const std::vector<CachedAABB> &aabbs, size_t start, size_t count) { // :107-113
+        AABB a;
+        for (size_t i = 0; i < count; i++) a = a.union_aabb(aabbs[i + start].aabb);
+        return a;
+    }
+    void subdivide_node(size_t id_node, std::vector<CachedAABB> &aabbs) { // :115-199
+        if (nodes[id_node].count <= 2) return;
+        size_t nb_prim = nodes[id_node].count, first_prim = nodes[id_node].info;
+        nodes[id_node].count = 0;
+        nodes[id_node].info = nodes.size();
+        size_t best_pos = 0;
+        float best_cost = std::numeric_limits<float>::infinity();
+        int best_axis = 3;
+        auto by_axis = [&](int o) {
+            // Rust's sort_by is a stable merge sort that only asks `compare(a,b) == Less`; the
+            // reference comparator (never Equal) therefore acts as a stable sort on `<`.
+            std::stable_sort(aabbs.begin() + first_prim, aabbs.begin() + first_prim + nb_prim,
+                             [o](const CachedAABB &a, const CachedAABB &b) { return comp(a.aabb.center(), o) < comp(b.aabb.center(), o); });
+        };
+        {
+            std::vector<float> scores(nb_prim - 1, 0.0f);
+            for (int o = 0; o < 3; o++) {
+                by_axis(o);
+                AABB tmp;
+                for (size_t id = 0; id < nb_prim - 1; id++) {
+                    size_t id_left = nb_prim - id - 1;
+                    tmp = tmp.union_aabb(aabbs[id_left + first_prim].aabb);
+                    scores[id_left - 1] = tmp.surface_area() * (float)(id + 1);
+                }
+                tmp = AABB();
+                for (size_t id = 0; id < nb_prim - 1; id++) {
+                    tmp = tmp.union_aabb(aabbs[id + first_prim].aabb);
+                    scores[id] += tmp.surface_area() * (float)(id + 1);
+                    if (scores[id] < best_cost) {
+                        best_cost = scores[id];
+                        best_axis = o;
+                        best_pos = id + 1;
+                    }
+                }
+            }
+        }
+        if (best_axis < 3) by_axis(best_axis);
+        size_t offset;
+        if (best_pos == nb_prim || best_pos == 0) offset = std::max<size_t>((size_t)((float)nb_prim * 0.5f), 1);
+        else offset = best_pos;
+        BVHNode left{compute_aabb(aabbs, first_prim, offset), first_prim, offset};
+        BVHNode right{compute_aabb(aabbs, first_prim + offset, nb_prim - offset), first_prim + offset, nb_prim - offset};
+        size_t id_left = nodes.size();
+        nodes.push_back(left);
+        nodes.push_back(right);
+        subdivide_node(id_left, aabbs);
+        subdivide_node(id_left + 1, aabbs);
+    }
+    void build_bvh() {
+        AABB root_aabb;
+        std::vector<CachedAABB> cached;
+        for (size_t m = 0; m < meshes.size(); m++)
+            for (size_t i = 0; i < meshes[m]->indices.size(); i++) {
+                cached.push_back(CachedAABB{meshes[m]->compute_aabb_tri(i), TriRef{(uint32_t)m, (uint32_t)i}});
+                root_aabb = root_aabb.union_aabb(cached.back().aabb);
+            }
+        nodes.clear();
+        nodes.push_back(BVHNode{root_aabb, 0, cached.size()});
+        subdivide_node(0, cached);
+        primitives.clear();
+        for (auto &c : cached) primitives.push_back(c.info);
+    }
+
+    // ---- BVHAccel::intersect, accel.rs:243-288 ------------------------------------------
+    bool bvh_intersect(size_t id_node, const Ray &ray, IntersectionUV &its, TriRef *res) const {
+        const BVHNode &node = nodes[id_node];
+        if (node.is_leaf()) {
+            bool found = false;
+            for (size_t k = 0; k < node.count; k++) {
+                const TriRef &e = primitives[node.info + k];
+                if (meshes[e.id_mesh]->intersection_tri(e.id_tri, ray.o, ray.d, its)) {
+                    *res = e;
+                    found = true;
+                }
+            }
+            return found;
+        }
+        size_t id1 = node.info, id2 = node.info + 1;
+        float d1, d2;
+        if (!nodes[id1].aabb.intersect(ray, &d1)) d1 = std::numeric_limits<float>::infinity();
+        if (!nodes[id2].aabb.intersect(ray, &d2)) d2 = std::numeric_limits<float>::infinity();
+        if (d1 > d2) {
+            std::swap(d1, d2);
+            std::swap(id1, id2);
+        }
+        bool found = false;
+        if (d1 < its.t) found = bvh_intersect(id1, ray, its, res);
+        if (d2 < its.t) {
+            TriRef r2;
+            if (bvh_intersect(id2, ray, its, &r2)) {
+                *res = r2;
+                found = true;
+            }
+        }
+        return found;
+    }
+
+    // ---- Acceleration::trace ---------------------------------------------------------------
+    // BVH: accel.rs:292-315.  NAIVE: the brute-force loop of accel.rs:23-51 (mesh-major, strict
+    // `t < its.t`, so the lowest (mesh,tri) wins exact ties) behind BVHAccel's root-box test.
+    bool trace_uv(const Ray &ray, uint32_t accel_mode, IntersectionUV &its, TriRef *res) const {
+        float t0;
+        if (!nodes[0].aabb.intersect(ray, &t0)) return false;
+        its = IntersectionUV{F32_MAX, V3{0, 0, 0}, V3{0, 0, 0}, 0.0f, 0.0f};
+        if (accel_mode == ORC_ACCEL_NAIVE) {
+            for (size_t m = 0; m < meshes.size(); m++)
+                for (size_t i = 0; i < meshes[m]->indices.size(); i++)
+                    if (meshes[m]->intersection_tri(i, ray.o, ray.d, its)) *res = TriRef{(uint32_t)m, (uint32_t)i};
+        } else {
+            bvh_intersect(0, ray, its, res);
+        }
+        return its.t != F32_MAX;
+    }
+    bool trace(const Ray &ray, uint32_t accel_mode, Counters &c, Intersection *out) const {
+        c.segments++;
+        IntersectionUV its;
+        TriRef res{0, 0};
+        if (!trace_uv(ray, accel_mode, its, &res)) return false;
+        c.hits++;
+        *out = fill_intersection(meshes[res.id_mesh].get(), res.id_tri, its.u, its.v, ray, its.n, its.t, its.p);
+        return true;
+    }
+    // ---- Acceleration::visible, accel.rs:316-343 (NAIVE: loop of :52-76 behind the root test) --
+    bool visible(V3 p0, V3 p1, uint32_t accel_mode, Counters &c) const {
+        c.shadow_rays++;
+        const float SHADOW_EPS = 0.00001f;
+        V3 d = p1 - p0;
+        float length = magnitude(d);
+        d = d / length;
+        IntersectionUV its{length * (1.0f - SHADOW_EPS), V3{0, 0, 0}, V3{0, 0, 0}, 0.0f, 0.0f};
+        Ray ray{p0, d, EPSILON, length * (1.0f - SHADOW_EPS)};
+        float t0;
+        if (!nodes[0].aabb.intersect(ray, &t0)) return false;
+        bool vis;
+        if (accel_mode == ORC_ACCEL_NAIVE) {
+            vis = true;
+            for (size_t m = 0; m < meshes.size() && vis; m++)
+                for (size_t i = 0; i < meshes[m]->indices.size(); i++)
+                    if (meshes[m]->intersection_tri(i, p0, d, its)) {
+                        vis = false;
+                        break;
+                    }
+        } else {
+            TriRef r;
+            vis = !bvh_intersect(0, ray, its, &r);
+        }
+        if (vis) c.shadow_visible++;
+        return vis;
+    }
+};
+
+// ============================================================================================
+// paths/: Vertex (vertex.rs:9-39), Edge (edge.rs:11-24), Path (path.rs:15-18)
+// ============================================================================================
+struct Ctx { // what the reference threads through as (accel, scene, sampler)
+    const Scene *scene;
+    uint32_t accel_mode;
+    Math math;
+    Counters *counters;
+};
+struct Vertex {
+    enum Kind { Sensor, Surface, Light } kind;
+    // Sensor
+    P2 uv{};
+    V3 pos{};
+    // Surface
+    Intersection its{};
+    // Light
+    V3 n{};
+    const Mesh *emitter = nullptr;
+    // edges
+    int edge_in = -1;
+    std::vector<int> edge_out; // Sensor/Light hold at most one
+    V3 position() const { return kind == Surface ? its.p : pos; }                                   // vertex.rs:46-53
+    bool on_light_source() const { return kind == Surface ? its.mesh->is_light() : kind == Light; } // :60-66
+};
+struct Edge {
+    bool has_dist = false;
+    float dist = 0;
+    V3 d{};
+    int v0 = -1, v1 = -1; // vertices: (VertexID, Option<VertexID>)
+    PDF pdf_direction{PDF::SolidAngle, 0};
+    Color weight{};
+    bool has_contrib = false;
+    Color contrib{};
+    float rr_weight = 1;
+    size_t id_sampling = 0;
+};
+struct Path {
+    std::vector<Vertex> vertices;
+    std::vector<Edge> edges;
+    int register_vertex(Vertex v) {
+        vertices.push_back(std::move(v));
+        return (int)vertices.size() - 1;
+    }
+    int register_edge(Edge e) {
+        edges.push_back(e);
+        return (int)edges.size() - 1;
+    }
+};
+// Vertex::contribution, vertex.rs:69-82
+Color vertex_contribution(const Vertex &v, const Edge &edge) {
+    if (v.kind == Vertex::Surface) {
+        if (dot(v.its.n_s, -edge.d) >= 0.0f) return v.its.mesh->emit();
+        return Color::zero();
+    }
+    if (v.kind == Vertex::Light) return v.emitter->emit(); // emitter.eval(-edge.d, uv), emitter.rs:605-607
+    return Color::zero();
+}
+// Edge::contribution, edge.rs:201-210 (environment luminance is zero on this path)
+Color edge_contribution(const Edge &e, const Path &path) {
+    if (e.v1 >= 0) {
+        if (e.has_contrib) return e.contrib * e.weight * e.rr_weight;
+        return e.weight * e.rr_weight * vertex_contribution(path.vertices[e.v1], e);
+    }
+    return e.weight * e.rr_weight * Color::zero();
+}
+bool edge_next_on_light_source(const Edge &e, const Path &path) { // edge.rs:191-197
+    if (e.v1 >= 0) return path.vertices[e.v1].on_light_source();
+    return false; // no environment emitter
+}
+// Edge::from_ray, edge.rs:65-189 (medium == None)
+std::pair<int, int> edge_from_ray(Path &path, const Ray &ray, int org, PDF pdf_direction, Color weight, float rr_weight, const Ctx &cx, size_t id_sampling) {
+    Edge e;
+    e.d = ray.d, e.v0 = org, e.pdf_direction = pdf_direction, e.weight = weight, e.rr_weight = rr_weight, e.id_sampling = id_sampling;
+    int eid = path.register_edge(e);
+    Intersection its;
+    if (!cx.scene->trace(ray, cx.accel_mode, *cx.counters, &its)) return {eid, -1};
+    Vertex nv;
+    nv.kind = Vertex::Surface;
+    nv.its = its;
+    nv.edge_in = eid;
+    int vid = path.register_vertex(nv);
+    path.edges[eid].has_dist = true;
+    path.edges[eid].dist = its.dist;
+    path.edges[eid].v1 = vid;
+    return {eid, vid};
+}
+// Edge::from_vertex, edge.rs:27-63
+int edge_from_vertex(Path &path, int org, PDF pdf_direction, Color weight, Color contrib, float rr_weight, int next, size_t id_sampling) {
+    V3 d = path.vertices[next].position() - path.vertices[org].position();
+    float dist = magnitude(d);
+    d = d / dist;
+    Edge e;
+    e.has_dist = true, e.dist = dist, e.d = d, e.v0 = org, e.v1 = next, e.pdf_direction = pdf_direction, e.weight = weight;
+    e.has_contrib = true, e.contrib = contrib, e.rr_weight = rr_weight, e.id_sampling = id_sampling;
+    int eid = path.register_edge(e);
+    path.vertices[next].edge_in = eid;
+    return eid;
+}
+
+// ============================================================================================
+// paths/strategies
+// ============================================================================================
+struct SamplingStrategy { // strategies/mod.rs:11-33
+    virtual ~SamplingStrategy() = default;
+    // returns true and fills (new_vertex, new_throughput) for Some(..)
+    virtual bool sample(Path &path, int vertex_id, const Ctx &cx, Color throughput, Sampler &sampler, size_t id_strategy, uint32_t depth, int *new_vertex, Color *new_throughput) const = 0;
+    virtual bool pdf(const Path &path, const Ctx &cx, int vertex_id, int edge_id, float *out) const = 0;
+};
+struct DirectionalSamplingStrategy : SamplingStrategy { // strategies/directional.rs
+    int32_t rr_depth; // Option<u32>, -1 = None
+    // bounce, :13-210 (Sensor and Surface arms; transport == Importance)
+    void bounce(Path &path, int vertex_id, const Ctx &cx, Color &throughput, Sampler &sampler, size_t id_strategy, uint32_t depth, int *edge, int *new_vertex) const {
+        *edge = -1, *new_vertex = -1;
+        const Vertex &v = path.vertices[vertex_id];
+        if (v.kind == Vertex::Sensor) { // :26-43
+            Ray ray = cx.scene->camera.generate(v.uv);
+            auto r = edge_from_ray(path, ray, vertex_id, PDF{PDF::SolidAngle, 1.0f}, Color::one(), 1.0f, cx, id_strategy);
+            *edge = r.first, *new_vertex = r.second;
+            return;
+        }
+        if (v.kind == Vertex::Surface) { // :44-107
+            Intersection its = v.its; // copy: `path` is mutated below
+            SampledDirection sb;
+            P2 s2 = sampler.next2d();
+            if (!its.mesh->bsdf->sample(cx.math, its.wi, s2, &sb)) return;
+            V3 d_out_global = its.frame.to_world(sb.d);
+            throughput = throughput * sb.weight; // *throughput *= &weight
+            if (throughput.is_zero()) return;
+            bool do_rr = rr_depth < 0 ? true : (uint32_t)rr_depth <= depth;
+            float rr_weight;
+            if (do_rr) {
+                float q = rmin(throughput.channel_max(), 0.95f);
+                if (q < sampler.next()) return;
+                rr_weight = 1.0f / q;
+            } else rr_weight = 1.0f;
+            throughput.scale(rr_weight);
+            Ray ray = spawn_ray(its, d_out_global);
+            auto r = edge_from_ray(path, ray, vertex_id, sb.pdf, sb.weight, rr_weight, cx, id_strategy);
+            *edge = r.first, *new_vertex = r.second;
+            return;
+        }
+        // Vertex::Light arm (light tracing) is not reachable from the sensor
+    }
+    bool sample(Path &path, int vertex_id, const Ctx &cx, Color throughput, Sampler &sampler, size_t id_strategy, uint32_t depth, int *new_vertex, Color *new_throughput) const override { // :211-257
+        int edge, nv;
+        bounce(path, vertex_id, cx, throughput, sampler, id_strategy, depth, &edge, &nv);
+        if (edge >= 0) {
+            Vertex &v = path.vertices[vertex_id];
+            if (v.kind == Vertex::Sensor || v.kind == Vertex::Light) {
+                v.edge_out.clear();
+                v.edge_out.push_back(edge);
+            } else v.edge_out.push_back(edge);
+        }
+        if (nv >= 0) {
+            *new_vertex = nv;
+            *new_throughput = throughput;
+            return true;
+        }
+        return false;
+    }
+    bool pdf(const Path &path, const Ctx &cx, int vertex_id, int edge_id, float *out) const override { // :258-304
+        const Edge &edge = path.edges[edge_id];
+        if (!edge_next_on_light_source(edge, path)) return false;
+        const Vertex &v = path.vertices[vertex_id];
+        if (v.kind == Vertex::Surface) {
+            if (v.its.mesh->bsdf->is_smooth()) return false;
+            *out = v.its.mesh->bsdf->pdf(cx.math, v.its.wi, v.its.frame.to_local(edge.d)).value();
+            return true;
+        }
+        if (v.kind == Vertex::Sensor) {
+            *out = 1.0f;
+            return true;
+        }
+        return false;
+    }
+};
+struct LightSamplingStrategy : SamplingStrategy { // strategies/emitters.rs
+    bool sample(Path &path, int vertex_id, const Ctx &cx, Color, Sampler &sampler, size_t id_strategy, uint32_t, int *, Color *) const override { // :95-248
+        if (path.vertices[vertex_id].kind != Vertex::Surface) return false;
+        Intersection its = path.vertices[vertex_id].its;
+        if (its.mesh->bsdf->is_smooth()) return false;
+        float r_sel = sampler.next();
+        float r = sampler.next();
+        P2 uv = sampler.next2d();
+        LightSampling rec = cx.scene->emitters.sample_light(its.p, r_sel, r, uv);
+        bool visible = cx.scene->visible(its.p, rec.p, cx.accel_mode, *cx.counters); // evaluated before the && (:125-126)
+        if (rec.is_valid() && visible) {
+            Vertex nv;
+            nv.kind = Vertex::Light;
+            nv.pos = rec.p, nv.n = rec.n, nv.emitter = rec.emitter;
+            Color weight = its.mesh->bsdf->eval(cx.math, its.wi, its.frame.to_local(rec.d));
+            int nvid = path.register_vertex(nv);
+            int eid = edge_from_vertex(path, vertex_id, rec.pdf, weight, rec.weight, 1.0f, nvid, id_strategy);
+            path.vertices[vertex_id].edge_out.push_back(eid);
+        }
+        return false; // "Finish the sampling here"
+    }
+    bool pdf_emitter(const Path &path, const Ctx &cx, const Ray &ray, int next_vertex_id, float *out) const { // :10-92
+        if (next_vertex_id < 0) return false;
+        const Vertex &nv = path.vertices[next_vertex_id];
+        if (nv.kind == Vertex::Surface) {
+            PDF p = cx.scene->emitters.direct_pdf(nv.its.mesh, LightSamplingPDF{ray.o, nv.its.p, nv.its.n_g, ray.d});
+            *out = p.value();
+            return true;
+        }
+        if (nv.kind == Vertex::Light) {
+            PDF p = cx.scene->emitters.direct_pdf(nv.emitter, LightSamplingPDF{ray.o, nv.pos, nv.n, ray.d});
+            *out = p.value();
+            return true;
+        }
+        return false;
+    }
+    bool pdf(const Path &path, const Ctx &cx, int vertex_id, int edge_id, float *out) const override { // :250-282
+        const Edge &edge = path.edges[edge_id];
+        if (!edge_next_on_light_source(edge, path)) return false;
+        const Vertex &v = path.vertices[vertex_id];
+        if (v.kind == Vertex::Surface) {
+            if (v.its.mesh->bsdf->is_smooth()) return false;
+            Ray ray = ray_new(v.position(), edge.d);
+            return pdf_emitter(path, cx, ray, edge.v1, out);
+        }
+        return false;
+    }
+};
+
+// generate, strategies/mod.rs:35-80
+struct TechniquePathTracing { // path.rs:22-35
+    int32_t max_depth; // Option<u32>
+    std::vector<const SamplingStrategy *> samplings;
+    bool single_scattering;
+    bool expand(uint32_t depth) const { return max_depth < 0 ? true : depth < (uint32_t)max_depth; }
+};
+void generate(Path &path, int root, const Ctx &cx, Sampler &sampler, const TechniquePathTracing &technique) {
+    std::vector<std::pair<int, Color>> curr{{root, Color::one()}}, next;
+    uint32_t depth = 1;
+    while (!curr.empty()) {
+        next.clear();
+        for (auto &cv : curr) {
+            if (technique.expand(depth)) {
+                for (size_t id_sampling = 0; id_sampling < technique.samplings.size(); id_sampling++) {
+                    int nv;
+                    Color nt;
+                    if (technique.samplings[id_sampling]->sample(path, cv.first, cx, cv.second, sampler, id_sampling, depth, &nv, &nt)) next.push_back({nv, nt});
+                }
+            }
+        }
+        std::swap(curr, next);
+        if (depth > cx.counters->max_depth) cx.counters->max_depth = depth;
+        depth++;
+    }
+}
+
+// TechniquePathTracing::evalute_edge / evaluate, path.rs:37-185
+Color evalute_edge(const TechniquePathTracing &tq, uint32_t curr_depth, int32_t min_depth, const Path &path, const Ctx &cx, int vertex_id, int edge_id, uint32_t strategy) {
+    const Edge &edge = path.edges[edge_id];
+    Color contrib = edge_contribution(edge, path);
+    if (strategy == RL_STRATEGY_BSDF && edge.id_sampling != 0) contrib = Color::zero();
+    if (strategy == RL_STRATEGY_EMITTER && edge.id_sampling != 1) contrib = Color::zero();
+    bool add_contrib = min_depth < 0 ? true : curr_depth >= (uint32_t)min_depth;
+    if (!contrib.is_zero() && add_contrib) {
+        float weight = 1.0f;
+        if (strategy == RL_STRATEGY_ALL) {
+            if (edge.pdf_direction.kind == PDF::SolidAngle) { // balance heuristic
+                float v = edge.pdf_direction.v;
+                float total = 0.0f;
+                for (size_t id = 0; id < tq.samplings.size(); id++) {
+                    float pdf;
+                    if (id == edge.id_sampling) pdf = v;
+                    else if (!tq.samplings[id]->pdf(path, cx, vertex_id, edge_id, &pdf)) pdf = 0.0f;
+                    total += pdf;
+                }
+                weight = v / total;
+            }
+        }
+        return contrib * weight;
+    }
+    return Color::zero();
+}
+Color evaluate(const TechniquePathTracing &tq, uint32_t curr_depth, int32_t min_depth, const Path &path, const Ctx &cx, int vertex_id, uint32_t strategy) {
+    const Vertex &v = path.vertices[vertex_id];
+    if (tq.single_scattering && (v.kind == Vertex::Surface || v.kind == Vertex::Light)) return Color::zero();
+    Color l_i = Color::zero();
+    if (v.kind == Vertex::Surface) {
+        for (int edge_id : v.edge_out) {
+            l_i = l_i + evalute_edge(tq, curr_depth, min_depth, path, cx, vertex_id, edge_id, strategy);
+            const Edge &edge = path.edges[edge_id];
+            if (edge.v1 >= 0) l_i = l_i + edge.weight * edge.rr_weight * evaluate(tq, curr_depth + 1, min_depth, path, cx, edge.v1, strategy);
+        }
+    } else if (v.kind == Vertex::Sensor) {
+        const Edge &edge = path.edges[v.edge_out.at(0)];
+        bool add_contrib = min_depth < 0 ? true : curr_depth >= (uint32_t)min_depth;
+        Color contrib = edge_contribution(edge, path);
+        if (!contrib.is_zero() && add_contrib) l_i = l_i + contrib;
+        if (edge.v1 >= 0) l_i = l_i + edge.weight * edge.rr_weight * evaluate(tq, curr_depth + 1, min_depth, path, cx, edge.v1, strategy);
+    }
+    return l_i;
+}
+
+// ============================================================================================
+// integrators
+// ============================================================================================
+float mis_weight(float pdf_a, float pdf_b) { // integrators/mod.rs:462-478
+    if (pdf_a == 0.0f) return 0.0f;
+    if (!std::isfinite(pdf_a) || !std::isfinite(pdf_b)) return 0.0f;
+    float w = (pdf_a * pdf_a) / ((pdf_a * pdf_a) + (pdf_b * pdf_b)); // powi(2) == x*x
+    return std::isfinite(w) ? w : 0.0f;
+}
+
+// IntegratorPathTracing::compute_pixel, explicit/path.rs:197-238
+Color path_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy, const Ctx &cx, Sampler &sampler) {
+    DirectionalSamplingStrategy dir;
+    dir.rr_depth = I.rr_depth;
+    LightSamplingStrategy light;
+    TechniquePathTracing technique;
+    technique.max_depth = I.max_depth;
+    technique.single_scattering = I.single_scattering != 0;
+    technique.samplings.push_back(&dir);
+    if (I.strategy == RL_STRATEGY_ALL || I.strategy == RL_STRATEGY_EMITTER) technique.samplings.push_back(&light);
+    Path path;
+    Vertex root; // Path::from_sensor, paths/path.rs:56-73
+    root.kind = Vertex::Sensor;
+    float jx = sampler.next();
+    float jy = sampler.next();
+    root.uv = P2{(float)ix + jx, (float)iy + jy};
+    root.pos = cx.scene->camera.position();
+    int rid = path.register_vertex(root);
+    generate(path, rid, cx, sampler, technique);
+    return evaluate(technique, 0, I.min_depth, path, cx, rid, I.strategy);
+}
+
+// The same estimator written as a forward accumulation (throughput carried along the path), in
+// the operation order of the GPU kernels.  Identical random numbers,
+// rays and discrete decisions as the graph version; radiance differs only by f32 rounding of
+// the re-associated products.
+Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32_t iy, const Ctx &cx, Sampler &sampler) {
+    const Scene &sc = *cx.scene;
+    const bool use_nee = (I.strategy == RL_STRATEGY_ALL || I.strategy == RL_STRATEGY_EMITTER);
+    auto expand = [&](uint32_t depth) { return I.max_depth < 0 ? true : depth < (uint32_t)I.max_depth; };
+    auto add_ok = [&](uint32_t curr_depth) { return I.min_depth < 0 ? true : curr_depth >= (uint32_t)I.min_depth; };
+    Color L = Color::zero();
+    float jx = sampler.next();
+    float jy = sampler.next();
+    uint32_t depth = 1;
+    if (depth > cx.counters->max_depth) cx.counters->max_depth = depth;
+    if (!expand(depth)) return L;
+    Ray ray = sc.camera.generate(P2{(float)ix + jx, (float)iy + jy});
+    Intersection its;
+    if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) return L;
+    // sensor edge: emission un-weighted (path.rs:152-165)
+    if (add_ok(0) && dot(its.n_s, -ray.d) >= 0.0f) {
+        Color c = its.mesh->emit();
+        if (!c.is_zero()) L = L + c;
+    }
+    const bool mute = I.single_scattering != 0; // evaluate() returns zero for every surface vertex (path.rs:122-124)
+    Color T = Color::one(); // throughput entering the current vertex
+    for (uint32_t k = 1;; k++) { // k-th surface vertex, handled at generate() depth k+1
+        depth = k + 1;
+        if (depth > cx.counters->max_depth) cx.counters->max_depth = depth;
+        if (!expand(depth)) break;
+        const BSDF &bsdf = *its.mesh->bsdf;
+        // ---- directional strategy (bounce) ----
+        bool alive = false;
+        Intersection next_its;
+        Ray next_ray{};
+        Color Tn = T;
+        float bsdf_pdf = 0.0f;
+        {
+            SampledDirection sb;
+            P2 s2 = sampler.next2d();
+            if (bsdf.sample(cx.math, its.wi, s2, &sb)) {
+                V3 d_out_global = its.frame.to_world(sb.d);
+                Tn = T * sb.weight;
+                if (!Tn.is_zero()) {
+                    bool do_rr = I.rr_depth < 0 ? true : (uint32_t)I.rr_depth <= depth;
+                    bool survive = true;
+                    float rr_weight = 1.0f;
+                    if (do_rr) {
+                        float q = rmin(Tn.channel_max(), 0.95f);
+                        if (q < sampler.next()) survive = false;
+                        else rr_weight = 1.0f / q;
+                    }
+                    if (survive) {
+                        Tn.scale(rr_weight);
+                        next_ray = spawn_ray(its, d_out_global);
+                        bsdf_pdf = sb.pdf.value();
+                        alive = sc.trace(next_ray, cx.accel_mode, *cx.counters, &next_its);
+                        if (alive && !mute && add_ok(k) && I.strategy != RL_STRATEGY_EMITTER) {
+                            // emission seen through the BSDF-sampled edge, MIS against light sampling
+                            if (dot(next_its.n_s, -next_ray.d) >= 0.0f) {
+                                Color le = next_its.mesh->emit();
+                                Color contrib = Tn * le;
+                                if (!contrib.is_zero()) {
+                                    float w = 1.0f;
+                                    if (I.strategy == RL_STRATEGY_ALL && use_nee && next_its.mesh->is_light() && !bsdf.is_smooth()) {
+                                        float pl = sc.emitters.direct_pdf(next_its.mesh, LightSamplingPDF{next_ray.o, next_its.p, next_its.n_g, next_ray.d}).value();
+                                        w = bsdf_pdf / (bsdf_pdf + pl);
+                                    }
+                                    L = L + contrib * w;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // ---- light sampling strategy (runs even if the bounce died) ----
+        if (use_nee && !bsdf.is_smooth()) {
+            float r_sel = sampler.next();
+            float r = sampler.next();
+            P2 uv = sampler.next2d();
+            LightSampling rec = sc.emitters.sample_light(its.p, r_sel, r, uv);
+            bool visible = sc.visible(its.p, rec.p, cx.accel_mode, *cx.counters);
+            if (rec.is_valid() && visible && !mute && add_ok(k) && I.strategy != RL_STRATEGY_BSDF) {
+                V3 wo = its.frame.to_local(rec.d);
+                Color f = bsdf.eval(cx.math, its.wi, wo);
+                Color contrib = T * (rec.weight * f);
+                if (!contrib.is_zero()) {
+                    float w = 1.0f;
+                    if (I.strategy == RL_STRATEGY_ALL) {
+                        float pb = bsdf.pdf(cx.math, its.wi, wo).value();
+                        float pl = rec.pdf.value();
+                        w = pl / (pb + pl);
+                    }
+                    L = L + contrib * w;
+                }
+            }
+        }
+        if (!alive) break;
+        T = Tn;
+        its = next_its;
+        ray = next_ray;
+    }
+    return L;
+}
+
+// IntegratorDirect::compute_pixel, direct.rs:21-233 (no environment map)
+Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy, const Ctx &cx, Sampler &sampler) {
+    const Scene &sc = *cx.scene;
+    float jx = sampler.next();
+    float jy = sampler.next();
+    Ray ray = sc.camera.generate(P2{(float)ix + jx, (float)iy + jy});
+    Color l_i = Color::zero();
+    if (1 > cx.counters->max_depth) cx.counters->max_depth = 1;
+    Intersection its;
+    if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) return Color::zero();
+    if (its.cos_theta() <= 0.0f) return l_i;
+    l_i = l_i + its.mesh->emit();
+    float weight_nb_bsdf = I.nb_bsdf_samples == 0 ? 0.0f : 1.0f / (float)I.nb_bsdf_samples;
+    float weight_nb_light = I.nb_light_samples == 0 ? 0.0f : 1.0f / (float)I.nb_light_samples;
+    const BSDF &bsdf = *its.mesh->bsdf;
+    for (uint32_t i = 0; i < I.nb_light_samples; i++) { // :63-129
+        float r_sel = sampler.next();
+        float r = sampler.next();
+        P2 uv = sampler.next2d();
+        LightSampling rec = sc.emitters.sample_light(its.p, r_sel, r, uv);
+        V3 d_out_local = its.frame.to_local(rec.d);
+        if (rec.is_valid() && sc.visible(its.p, rec.p, cx.accel_mode, *cx.counters) && !bsdf.is_smooth()) {
+            float pdf_bsdf = bsdf.pdf(cx.math, its.wi, d_out_local).value();
+            float weight_light = mis_weight(rec.pdf.value() * weight_nb_light, pdf_bsdf * weight_nb_bsdf);
+            l_i = l_i + weight_light * bsdf.eval(cx.math, its.wi, d_out_local) * weight_nb_light * rec.weight;
+        }
+    }
+    for (uint32_t i = 0; i < I.nb_bsdf_samples; i++) { // :135-230
+        SampledDirection sb;
+        P2 s2 = sampler.next2d();
+        if (!bsdf.sample(cx.math, its.wi, s2, &sb)) continue;
+        V3 d_out_world = its.frame.to_world(sb.d);
+        Ray r2 = spawn_ray(its, d_out_world);
+        Intersection next_its;
+        if (sc.trace(r2, cx.accel_mode, *cx.counters, &next_its)) {
+            if (next_its.mesh->is_light() && dot(next_its.n_g, -r2.d) > 0.0f) {
+                float light_pdf = sc.emitters.direct_pdf(next_its.mesh, LightSamplingPDF{r2.o, next_its.p, next_its.n_g, r2.d}).value();
+                float weight_bsdf = mis_weight(sb.pdf.value() * weight_nb_bsdf, light_pdf * weight_nb_light);
+                l_i = l_i + weight_bsdf * sb.weight * next_its.mesh->emit() * weight_nb_bsdf;
+            }
+        }
+    }
+    return l_i;
+}
+
+Color compute_pixel(const rl_integrator_desc &I, uint32_t estimator, uint32_t ix, uint32_t iy, const Ctx &cx, Sampler &sampler) {
+    if (I.kind == RL_INTEGRATOR_DIRECT) return direct_compute_pixel(I, ix, iy, cx, sampler);
+    if (estimator == ORC_EST_STREAM) return path_compute_pixel_stream(I, ix, iy, cx, sampler);
+    return path_compute_pixel(I, ix, iy, cx, sampler);
+}
+
+// Image-tile ownership shared with the GPU library: 16x16 tiles,
+// tile (tx,ty) belongs to rank (tx + ty) % nranks.
+inline bool tile_owned(uint32_t tx, uint32_t ty, uint32_t rank, uint32_t nranks) { return nranks <= 1 || ((tx + ty) % nranks) == rank; }
+
+} // namespace
+
+// ================================================================================================
+// C entry points
+// ================================================================================================
+struct orc_scene {
+    Scene scene;
+};
+
+extern "C" {
+
+orc_scene *orc_scene_create(const rl_scene_desc *desc, char *err, size_t errlen) {
+    auto fail = [&](const char *m) -> orc_scene * {
+        if (err && errlen) {
+            std::strncpy(err, m, errlen - 1);
+            err[errlen - 1] = 0;
+        }
+        return nullptr;
+    };
+    if (!desc || !desc->meshes || desc->nmeshes == 0) return fail("empty scene");
+    if (desc->has_volume || desc->has_environment) return fail("volume / environment map are outside the hot path");
+    auto *os = new orc_scene;
+    Scene &s = os->scene;
+    s.camera.img_x = desc->camera.width, s.camera.img_y = desc->camera.height;
+    std::memcpy(s.camera.sample_to_camera.m, desc->camera.sample_to_camera, 64);
+    std::memcpy(s.camera.to_world.m, desc->camera.to_world, 64);
+    uint32_t first = 0;
+    for (uint32_t i = 0; i < desc->nmeshes; i++) {
+        const rl_mesh_desc &md = desc->meshes[i];
+        auto m = std::make_unique<Mesh>();
+        for (uint32_t v = 0; v < md.nverts; v++) m->vertices.push_back(load3(md.P + 3 * v));
+        for (uint32_t t = 0; t < md.ntris; t++) m->indices.push_back(Idx3{md.idx[3 * t], md.idx[3 * t + 1], md.idx[3 * t + 2]});
+        if (md.N) {
+            m->has_normals = true;
+            for (uint32_t v = 0; v < md.nverts; v++) m->normals.push_back(load3(md.N + 3 * v));
+        }
+        m->bsdf = make_bsdf(md.mat);
+        m->light = md.emission_kind != 0;
+        m->emission = Color{md.emission[0], md.emission[1], md.emission[2]};
+        m->first_prim = first;
+        first += md.ntris;
+        m->build_cdf();
+        s.meshes.push_back(std::move(m));
+    }
+    s.build_emitters();
+    s.build_bvh();
+    return os;
+}
+void orc_scene_destroy(orc_scene *s) { delete s; }
+
+void orc_bvh_info(const orc_scene *s, uint32_t *nnodes, uint32_t *nprims, float root_min[3], float root_max[3]) {
+    if (nnodes) *nnodes = (uint32_t)s->scene.nodes.size();
+    if (nprims) *nprims = (uint32_t)s->scene.primitives.size();
+    if (root_min) store3(root_min, s->scene.nodes[0].aabb.p_min);
+    if (root_max) store3(root_max, s->scene.nodes[0].aabb.p_max);
+}
+
+int orc_render(const orc_scene *os, const rl_integrator_desc *integ, uint32_t spp, uint64_t seed, uint32_t sampler_mode,
+               const orc_config *cfg, float *out_rgb, orc_stats *stats) {
+    if (!os || !integ || !cfg || !out_rgb || spp == 0) return RL_ERR_INVALID; // assert_ne!(nb_samples, 0), mod.rs:410
+    const Scene &sc = os->scene;
+    const uint32_t W = sc.camera.img_x, H = sc.camera.img_y;
+    if (integ->kind == RL_INTEGRATOR_PATH) {
+        // max_depth < 2: the sensor vertex is never expanded and evaluate() unwraps a None edge (path.rs:154) -> panic
+        if (integ->max_depth >= 0 && integ->max_depth < 2) return RL_ERR_INVALID;
+        if (sc.emitters.emitters.empty() && integ->strategy != RL_STRATEGY_BSDF) return RL_ERR_INVALID; // scene.rs:97-100
+    } else if (integ->kind == RL_INTEGRATOR_DIRECT) {
+        if (sc.emitters.emitters.empty() && integ->nb_light_samples > 0) return RL_ERR_INVALID;
+    } else return RL_ERR_INVALID;
+    // generate_img_blocks, mod.rs:351-374: x-major block order, one cloned sampler per block
+    struct Block {
+        uint32_t px, py, sx, sy;
+        IndependentSampler sampler;
+        std::vector<Color> colors;
+    };
+    std::vector<Block> blocks;
+    IndependentSampler master;
+    master.seeding = cfg->seeding;
+    master.rnd = Xoshiro256PP::seed_from_u64(seed, cfg->seeding); // cli.rs:886-890
+    for (uint32_t ix = 0; ix < W; ix += 16)
+        for (uint32_t iy = 0; iy < H; iy += 16) {
+            Block b;
+            b.px = ix, b.py = iy, b.sx = std::min(16u, W - ix), b.sy = std::min(16u, H - iy);
+            b.sampler = master.clone_box();
+            blocks.push_back(std::move(b));
+        }
+    uint32_t nthreads = cfg->nthreads ? cfg->nthreads : std::max(1u, std::thread::hardware_concurrency());
+    nthreads = std::min<uint32_t>(nthreads, (uint32_t)blocks.size());
+    std::vector<Counters> counters(nthreads);
+    std::atomic<size_t> next_block{0};
+    auto t0 = std::chrono::steady_clock::now();
+    auto worker = [&](uint32_t tid) {
+        Ctx cx{&sc, cfg->accel_mode, Math{cfg->math_mode}, &counters[tid]};
+        for (;;) {
+            size_t bi = next_block.fetch_add(1);
+            if (bi >= blocks.size()) break;
+            Block &b = blocks[bi];
+            b.colors.assign((size_t)b.sx * b.sy, Color::zero());
+            if (!tile_owned(b.px / 16, b.py / 16, cfg->rank, cfg->nranks)) continue;
+            for (uint32_t iy = 0; iy < b.sy; iy++)
+                for (uint32_t ix = 0; ix < b.sx; ix++) {
+                    Color &acc = b.colors[(size_t)iy * b.sx + ix];
+                    for (uint32_t s = 0; s < spp; s++) {
+                        uint32_t gx = ix + b.px, gy = iy + b.py;
+                        Color c;
+                        if (sampler_mode == RL_SAMPLER_COUNTER) {
+                            CounterSampler cs(seed, gy * W + gx, s);
+                            c = compute_pixel(*integ, cfg->estimator, gx, gy, cx, cs);
+                        } else c = compute_pixel(*integ, cfg->estimator, gx, gy, cx, b.sampler);
+                        acc = acc + c; // Bitmap::accumulate, structure.rs:397-402
+                    }
+                }
+            float f = 1.0f / (float)spp; // im_block.scale(1/spp), mod.rs:436
+            for (Color &c : b.colors) c.scale(f);
+        }
+    };
+    if (nthreads == 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (uint32_t t = 0; t < nthreads; t++) th.emplace_back(worker, t);
+        for (auto &t : th) t.join();
+    }
+    // image.accumulate_bitmap(block), mod.rs:445-449
+    std::memset(out_rgb, 0, sizeof(float) * 3 * (size_t)W * H);
+    for (auto &b : blocks)
+        for (uint32_t y = 0; y < b.sy; y++)
+            for (uint32_t x = 0; x < b.sx; x++) {
+                size_t idx = (size_t)(b.py + y) * W + (b.px + x);
+                const Color &c = b.colors[(size_t)y * b.sx + x];
+                out_rgb[3 * idx] += c.r, out_rgb[3 * idx + 1] += c.g, out_rgb[3 * idx + 2] += c.b;
+            }
+    auto t1 = std::chrono::steady_clock::now();
+    if (stats) {
+        *stats = orc_stats{};
+        for (auto &c : counters) {
+            stats->segments += c.segments, stats->shadow_rays += c.shadow_rays, stats->shadow_visible += c.shadow_visible;
+            stats->hits += c.hits;
+            stats->max_depth_seen = std::max<uint64_t>(stats->max_depth_seen, c.max_depth);
+        }
+        uint64_t npix = 0;
+        for (auto &b : blocks)
+            if (tile_owned(b.px / 16, b.py / 16, cfg->rank, cfg->nranks)) npix += (uint64_t)b.sx * b.sy;
+        stats->samples = npix * spp;
+        stats->seconds = std::chrono::duration<double>(t1 - t0).count();
+        stats->threads_used = nthreads;
+    }
+    return RL_OK;
+}
+
+void orc_path_sample(const orc_scene *os, const rl_integrator_desc *integ, uint64_t seed, uint32_t px, uint32_t py, uint32_t sample,
+                     const orc_config *cfg, float rgb[3], uint32_t *n_segments, uint32_t *n_shadow, uint32_t *n_draws) {
+    Counters c;
+    Ctx cx{&os->scene, cfg->accel_mode, Math{cfg->math_mode}, &c};
+    CounterSampler cs(seed, py * os->scene.camera.img_x + px, sample);
+    Color r = compute_pixel(*integ, cfg->estimator, px, py, cx, cs);
+    rgb[0] = r.r, rgb[1] = r.g, rgb[2] = r.b;
+    if (n_segments) *n_segments = (uint32_t)c.segments;
+    if (n_shadow) *n_shadow = (uint32_t)c.shadow_rays;
+    if (n_draws) *n_draws = cs.draws;
+}
+
+int orc_trace(const orc_scene *os, uint32_t accel_mode, size_t n, const float *o, const float *d, uint32_t *prim, float *tuv,
+              float *p, float *n_g, float *n_s, float *wi) {
+    const Scene &sc = os->scene;
+    for (size_t i = 0; i < n; i++) {
+        Ray ray = ray_new(load3(o + 3 * i), load3(d + 3 * i));
+        IntersectionUV its;
+        TriRef res{0, 0};
+        if (!sc.trace_uv(ray, accel_mode, its, &res)) {
+            prim[i] = 0xFFFFFFFFu;
+            if (tuv) tuv[3 * i] = tuv[3 * i + 1] = tuv[3 * i + 2] = 0.0f;
+            continue;
+        }
+        prim[i] = sc.meshes[res.id_mesh]->first_prim + res.id_tri;
+        if (tuv) tuv[3 * i] = its.t, tuv[3 * i + 1] = its.u, tuv[3 * i + 2] = its.v;
+        if (p || n_g || n_s || wi) {
+            Intersection f = fill_intersection(sc.meshes[res.id_mesh].get(), res.id_tri, its.u, its.v, ray, its.n, its.t, its.p);
+            if (p) store3(p + 3 * i, f.p);
+            if (n_g) store3(n_g + 3 * i, f.n_g);
+            if (n_s) store3(n_s + 3 * i, f.n_s);
+            if (wi) store3(wi + 3 * i, f.wi);
+        }
+    }
+    return RL_OK;
+}
+int orc_visible(const orc_scene *os, uint32_t accel_mode, size_t n, const float *p0, const float *p1, uint8_t *out) {
+    Counters c;
+    for (size_t i = 0; i < n; i++) out[i] = os->scene.visible(load3(p0 + 3 * i), load3(p1 + 3 * i), accel_mode, c) ? 1 : 0;
+    return RL_OK;
+}
+int orc_primary_hits(const orc_scene *os, uint32_t accel_mode, uint32_t *prim, float *tuv) {
+    const Scene &sc = os->scene;
+    uint32_t W = sc.camera.img_x, H = sc.camera.img_y;
+    for (uint32_t y = 0; y < H; y++)
+        for (uint32_t x = 0; x < W; x++) {
+            Ray ray = sc.camera.generate(P2{(float)x + 0.5f, (float)y + 0.5f});
+            size_t i = (size_t)y * W + x;
+            orc_trace(os, accel_mode, 1, &ray.o.x, &ray.d.x, prim + i, tuv ? tuv + 3 * i : nullptr, nullptr, nullptr, nullptr, nullptr);
+        }
+    return RL_OK;
+}
+
+int orc_intersect_tri(const float v0[3], const float v1[3], const float v2[3], const float o[3], const float d[3], float *t_io,
+                      float *u, float *v, float p[3], float n[3]) {
+    Mesh m;
+    m.vertices = {load3(v0), load3(v1), load3(v2)};
+    m.indices = {Idx3{0, 1, 2}};
+    IntersectionUV its{*t_io, V3{0, 0, 0}, V3{0, 0, 0}, 0, 0};
+    bool hit = m.intersection_tri(0, load3(o), load3(d), its);
+    if (hit) {
+        *t_io = its.t;
+        if (u) *u = its.u;
+        if (v) *v = its.v;
+        if (p) store3(p, its.p);
+        if (n) store3(n, its.n);
+    }
+    return hit ? 1 : 0;
+}
+int orc_aabb_intersect(const float pmin[3], const float pmax[3], const float o[3], const float d[3], float tnear, float tfar, float *t) {
+    AABB a;
+    a.p_min = load3(pmin), a.p_max = load3(pmax);
+    Ray r{load3(o), load3(d), tnear, tfar};
+    float tt;
+    if (!a.intersect(r, &tt)) return 0;
+    if (t) *t = tt;
+    return 1;
+}
+void orc_frame(const float n[3], float out9[9]) {
+    Frame f(load3(n));
+    store3(out9, f.x), store3(out9 + 3, f.y), store3(out9 + 6, f.z);
+}
+void orc_cosine_sample_hemisphere(uint32_t math_mode, float u0, float u1, float out[3]) { store3(out, cosine_sample_hemisphere(Math{math_mode}, P2{u0, u1})); }
+void orc_uniform_sample_triangle(float u0, float u1, float out[2]) {
+    P2 b = uniform_sample_triangle(P2{u0, u1});
+    out[0] = b.x, out[1] = b.y;
+}
+float orc_dist1d_normalize(const float *elements, uint32_t n, float *cdf) {
+    Distribution1D d = Distribution1D::normalize(std::vector<float>(elements, elements + n));
+    std::memcpy(cdf, d.cdf.data(), sizeof(float) * (n + 1));
+    return d.func_int;
+}
+uint32_t orc_dist1d_sample_discrete(const float *cdf, uint32_t n_plus_1, float v) {
+    Distribution1D d;
+    d.cdf.assign(cdf, cdf + n_plus_1);
+    return (uint32_t)d.sample_discrete(v);
+}
+float orc_mis_weight(float a, float b) { return mis_weight(a, b); }
+int orc_bsdf_sample(uint32_t math_mode, const rl_material *m, const float wi[3], float s0, float s1, float weight[3], float d[3], float *pdf) {
+    auto b = make_bsdf(*m);
+    SampledDirection sd;
+    if (!b->sample(Math{math_mode}, load3(wi), P2{s0, s1}, &sd)) return 0;
+    weight[0] = sd.weight.r, weight[1] = sd.weight.g, weight[2] = sd.weight.b;
+    store3(d, sd.d);
+    *pdf = sd.pdf.value();
+    return 1;
+}
+float orc_bsdf_pdf(uint32_t math_mode, const rl_material *m, const float wi[3], const float wo[3]) {
+    return make_bsdf(*m)->pdf(Math{math_mode}, load3(wi), load3(wo)).value();
+}
+void orc_bsdf_eval(uint32_t math_mode, const rl_material *m, const float wi[3], const float wo[3], float out[3]) {
+    Color c = make_bsdf(*m)->eval(Math{math_mode}, load3(wi), load3(wo));
+    out[0] = c.r, out[1] = c.g, out[2] = c.b;
+}
+int orc_sample_light(const orc_scene *os, const float x[3], float r_sel, float r, float u0, float u1, float p[3], float n[3], float d[3],
+                     float weight[3], float *pdf) {
+    const Scene &sc = os->scene;
+    if (sc.emitters.emitters.empty()) return -1;
+    LightSampling rec = sc.emitters.sample_light(load3(x), r_sel, r, P2{u0, u1});
+    store3(p, rec.p), store3(n, rec.n), store3(d, rec.d);
+    weight[0] = rec.weight.r, weight[1] = rec.weight.g, weight[2] = rec.weight.b;
+    *pdf = rec.pdf.value();
+    for (size_t i = 0; i < sc.meshes.size(); i++)
+        if (sc.meshes[i].get() == rec.emitter) return (int)i;
+    return -1;
+}
+float orc_direct_pdf(const orc_scene *os, uint32_t mesh, const float o[3], const float p[3], const float n[3], const float dir[3]) {
+    const Scene &sc = os->scene;
+    return sc.emitters.direct_pdf(sc.meshes[mesh].get(), LightSamplingPDF{load3(o), load3(p), load3(n), load3(dir)}).value();
+}
+int orc_camera_new(uint32_t w, uint32_t h, int fov_axis, float fov_deg, const float to_world[16], int flip, float sample_to_camera[16]) {
+    M4 tw, s2c;
+    std::memcpy(tw.m, to_world, 64);
+    if (!camera_new(w, h, fov_axis, fov_deg, tw, flip != 0, &s2c)) return -1;
+    std::memcpy(sample_to_camera, s2c.m, 64);
+    return 0;
+}
+void orc_camera_generate(const orc_scene *os, float px, float py, float o[3], float d[3]) {
+    Ray r = os->scene.camera.generate(P2{px, py});
+    store3(o, r.o), store3(d, r.d);
+}
+void orc_sampler_block_stream(uint64_t seed, uint32_t seeding, uint32_t block, uint32_t n, float *out) {
+    IndependentSampler master;
+    master.seeding = seeding;
+    master.rnd = Xoshiro256PP::seed_from_u64(seed, seeding);
+    IndependentSampler b = master.clone_box();
+    for (uint32_t i = 0; i < block; i++) b = master.clone_box();
+    for (uint32_t i = 0; i < n; i++) out[i] = b.next();
+}
+void orc_sampler_counter(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float *out) {
+    CounterSampler cs(seed, pixel, sample);
+    for (uint32_t i = 0; i < n; i++) out[i] = cs.next();
+}
+uint64_t orc_xoshiro_next_u64(uint64_t state[4]) {
+    Xoshiro256PP x;
+    std::memcpy(x.s, state, 32);
+    uint64_t r = x.next_u64();
+    std::memcpy(state, x.s, 32);
+    return r;
+}
+void orc_spec_sincos(float x, float *s, float *c) { spec_sincos(x, s, c); }
+float orc_spec_powf(float x, float y) { return spec_powf(x, y); }
+
+} // extern "C"

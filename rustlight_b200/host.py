@@ -1,0 +1,170 @@
+"""Python face of the C++ host layer (librl_host.so): scene loading and camera construction.
+
+Mirrors the reference names: SceneLoaderManager.load (src/scene_loader.rs:28-45),
+Scene.nb_samples/output_img (src/scene.rs:33-44), Camera.scale_image (src/camera.rs:73-78).
+No rendering happens here.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "librl_host.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(path)
+        L.rlh_load_scene.restype = C.c_void_p
+        L.rlh_load_scene.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+        L.rlh_load_scene_string.restype = C.c_void_p
+        L.rlh_load_scene_string.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+        L.rlh_scene_free.argtypes = [C.c_void_p]
+        L.rlh_scene_desc.restype = C.POINTER(_abi.rl_scene_desc)
+        L.rlh_scene_desc.argtypes = [C.c_void_p]
+        L.rlh_scene_nb_meshes.restype = C.c_uint32
+        L.rlh_scene_nb_meshes.argtypes = [C.c_void_p]
+        L.rlh_scene_nb_triangles.restype = C.c_uint64
+        L.rlh_scene_nb_triangles.argtypes = [C.c_void_p]
+        L.rlh_scene_scale_image.argtypes = [C.c_void_p, C.c_float]
+        L.rlh_scene_set_resolution.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]
+        L.rlh_scene_set_material.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_abi.rl_material)]
+        L.rlh_material_phong.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
+                                         C.POINTER(_abi.rl_material)]
+        L.rlh_scene_to_json.restype = C.c_size_t
+        L.rlh_scene_to_json.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+        L.rlh_camera_create.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_float, C.POINTER(C.c_float),
+                                        C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.rlh_save_pfm.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+        L.rlh_read_pfm.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                   C.POINTER(C.c_float), C.c_size_t]
+        _lib = L
+    return _lib
+
+
+class SceneError(RuntimeError):
+    pass
+
+
+class Scene:
+    """src/scene.rs:16-30 -- owns the C++ Scene; `desc` is the flat rl_scene_desc view of it."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self.nb_samples = 1
+        self.output_img_path = "out.pfm"
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().rlh_scene_free(self._h)
+            self._h = None
+
+    @property
+    def desc(self):
+        return lib().rlh_scene_desc(self._h)
+
+    @property
+    def size(self):
+        d = self.desc.contents.camera
+        return int(d.width), int(d.height)
+
+    @property
+    def nb_meshes(self):
+        return int(lib().rlh_scene_nb_meshes(self._h))
+
+    @property
+    def nb_triangles(self):
+        return int(lib().rlh_scene_nb_triangles(self._h))
+
+    def scale_image(self, s):
+        """CLI `-s`: Camera::scale_image (truncating, matrices untouched)."""
+        lib().rlh_scene_scale_image(self._h, float(s))
+        return self
+
+    def set_resolution(self, w, h):
+        """Edit the Film resolution and rebuild the camera (NOT the `-s` flag)."""
+        err = C.create_string_buffer(512)
+        if lib().rlh_scene_set_resolution(self._h, int(w), int(h), err, 512) != 0:
+            raise SceneError(err.value.decode())
+        return self
+
+    def set_material(self, mesh, material):
+        if lib().rlh_scene_set_material(self._h, int(mesh), C.byref(material)) != 0:
+            raise SceneError("bad mesh index")
+        return self
+
+    def mesh_is_light(self, mesh):
+        return bool(self.desc.contents.meshes[mesh].emission_kind)
+
+    def to_json(self):
+        n = lib().rlh_scene_to_json(self._h, None, 0)
+        buf = C.create_string_buffer(n)
+        lib().rlh_scene_to_json(self._h, buf, n)
+        return buf.value.decode()
+
+
+class SceneLoaderManager:
+    """src/scene_loader.rs:21-58: extension -> loader ("pbrt", plus the new "json")."""
+
+    def load(self, filename, use_shading_normal=True):
+        err = C.create_string_buffer(1024)
+        h = lib().rlh_load_scene(os.fsencode(filename), 1 if use_shading_normal else 0, err, 1024)
+        if not h:
+            raise SceneError(err.value.decode())
+        return Scene(h)
+
+    def load_string(self, text, fmt, use_shading_normal=True):
+        err = C.create_string_buffer(1024)
+        h = lib().rlh_load_scene_string(text.encode(), fmt.encode(), 1 if use_shading_normal else 0, err, 1024)
+        if not h:
+            raise SceneError(err.value.decode())
+        return Scene(h)
+
+
+def material_phong(kd, ks, exponent):
+    m = _abi.rl_material()
+    a = (C.c_float * 3)(*kd)
+    b = (C.c_float * 3)(*ks)
+    if lib().rlh_material_phong(a, b, float(exponent), C.byref(m)) != 0:
+        raise SceneError("Phong: kd and ks are both black")
+    return m
+
+
+def material_diffuse(kd):
+    m = _abi.rl_material()
+    m.kind = _abi.RL_BSDF_DIFFUSE
+    m.kd[:] = kd
+    return m
+
+
+def camera_create(w, h, fov_deg, to_world, fov_axis="y", flip=False):
+    """Camera::new -> (sample_to_camera, camera_to_sample) as 16-float column-major arrays."""
+    tw = (C.c_float * 16)(*np.asarray(to_world, dtype=np.float32).ravel())
+    s2c = (C.c_float * 16)()
+    c2s = (C.c_float * 16)()
+    if lib().rlh_camera_create(w, h, 1 if fov_axis == "x" else 0, float(fov_deg), tw, 1 if flip else 0, s2c, c2s) != 0:
+        raise SceneError("Camera::new failed")
+    return np.array(s2c, dtype=np.float32), np.array(c2s, dtype=np.float32)
+
+
+def save_pfm(path, img):
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    h, w, _ = img.shape
+    if lib().rlh_save_pfm(os.fsencode(path), w, h, img.ctypes.data_as(C.POINTER(C.c_float))) != 0:
+        raise SceneError(f"cannot write {path}")
+
+
+def read_pfm(path):
+    w, h = C.c_uint32(), C.c_uint32()
+    if lib().rlh_read_pfm(os.fsencode(path), C.byref(w), C.byref(h), None, 0) != 0:
+        raise SceneError(f"cannot read {path}")
+    img = np.zeros((h.value, w.value, 3), dtype=np.float32)
+    lib().rlh_read_pfm(os.fsencode(path), C.byref(w), C.byref(h), img.ctypes.data_as(C.POINTER(C.c_float)), img.size)
+    return img
