@@ -28,7 +28,7 @@ class orc_config(C.Structure):
 class orc_stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("segments", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("shadow_visible", C.c_uint64), ("hits", C.c_uint64), ("max_depth_seen", C.c_uint64),
-                ("seconds", C.c_double), ("threads_used", C.c_uint32)]
+                ("nee_added", C.c_uint64), ("seconds", C.c_double), ("threads_used", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

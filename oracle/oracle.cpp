@@ -813,7 +813,7 @@ struct CounterSampler : Sampler {
 // Scene (scene.rs) + accel.rs
 // ============================================================================================
 struct Counters {
-    uint64_t segments = 0, shadow_rays = 0, shadow_visible = 0, hits = 0, max_depth = 0;
+    uint64_t segments = 0, shadow_rays = 0, shadow_visible = 0, hits = 0, max_depth = 0, nee_added = 0;
 };
 struct TriRef {
     uint32_t id_mesh, id_tri;
@@ -1340,32 +1340,44 @@ Color path_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy, 
 Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32_t iy, const Ctx &cx, Sampler &sampler) {
     const Scene &sc = *cx.scene;
     const bool use_nee = (I.strategy == RL_STRATEGY_ALL || I.strategy == RL_STRATEGY_EMITTER);
+    const bool mute = I.single_scattering != 0; // evaluate() returns zero for every surface vertex (path.rs:122-124)
     auto expand = [&](uint32_t depth) { return I.max_depth < 0 ? true : depth < (uint32_t)I.max_depth; };
     auto add_ok = [&](uint32_t curr_depth) { return I.min_depth < 0 ? true : curr_depth >= (uint32_t)I.min_depth; };
     Color L = Color::zero();
     float jx = sampler.next();
     float jy = sampler.next();
-    uint32_t depth = 1;
+    uint32_t depth = 1; // generate() depth at which the current ray was sampled
     if (depth > cx.counters->max_depth) cx.counters->max_depth = depth;
     if (!expand(depth)) return L;
     Ray ray = sc.camera.generate(P2{(float)ix + jx, (float)iy + jy});
-    Intersection its;
-    if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) return L;
-    // sensor edge: emission un-weighted (path.rs:152-165)
-    if (add_ok(0) && dot(its.n_s, -ray.d) >= 0.0f) {
-        Color c = its.mesh->emit();
-        if (!c.is_zero()) L = L + c;
-    }
-    const bool mute = I.single_scattering != 0; // evaluate() returns zero for every surface vertex (path.rs:122-124)
-    Color T = Color::one(); // throughput entering the current vertex
-    for (uint32_t k = 1;; k++) { // k-th surface vertex, handled at generate() depth k+1
-        depth = k + 1;
+    Color T = Color::one(); // throughput carried by `ray`
+    float pdf_prev = 1.0f;  // solid-angle pdf of the direction of `ray`
+    for (;;) {
+        Intersection its;
+        if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) break;
+        const BSDF &bsdf = *its.mesh->bsdf;
+        // ---- emission carried by the arriving edge ----
+        if (depth == 1) { // sensor edge: un-weighted (path.rs:152-165)
+            if (add_ok(0) && dot(its.n_s, -ray.d) >= 0.0f && its.mesh->is_light() && !its.mesh->emit().is_zero()) L = L + its.mesh->emit();
+        } else if (!mute && add_ok(depth - 1) && I.strategy != RL_STRATEGY_EMITTER) {
+            if (dot(its.n_s, -ray.d) >= 0.0f && its.mesh->is_light()) {
+                Color contrib = T * its.mesh->emit();
+                if (!contrib.is_zero()) {
+                    float w = 1.0f;
+                    if (I.strategy == RL_STRATEGY_ALL) { // balance heuristic (path.rs:78-99)
+                        float pl = sc.emitters.direct_pdf(its.mesh, LightSamplingPDF{ray.o, its.p, its.n_g, ray.d}).value();
+                        w = pdf_prev / (pdf_prev + pl);
+                    }
+                    L = L + contrib * w;
+                }
+            }
+        }
+        // ---- expand this vertex ----
+        uint32_t vdepth = depth; // == curr_depth of this vertex in evaluate()
+        depth = depth + 1;
         if (depth > cx.counters->max_depth) cx.counters->max_depth = depth;
         if (!expand(depth)) break;
-        const BSDF &bsdf = *its.mesh->bsdf;
-        // ---- directional strategy (bounce) ----
         bool alive = false;
-        Intersection next_its;
         Ray next_ray{};
         Color Tn = T;
         float bsdf_pdf = 0.0f;
@@ -1388,22 +1400,7 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
                         Tn.scale(rr_weight);
                         next_ray = spawn_ray(its, d_out_global);
                         bsdf_pdf = sb.pdf.value();
-                        alive = sc.trace(next_ray, cx.accel_mode, *cx.counters, &next_its);
-                        if (alive && !mute && add_ok(k) && I.strategy != RL_STRATEGY_EMITTER) {
-                            // emission seen through the BSDF-sampled edge, MIS against light sampling
-                            if (dot(next_its.n_s, -next_ray.d) >= 0.0f) {
-                                Color le = next_its.mesh->emit();
-                                Color contrib = Tn * le;
-                                if (!contrib.is_zero()) {
-                                    float w = 1.0f;
-                                    if (I.strategy == RL_STRATEGY_ALL && use_nee && next_its.mesh->is_light() && !bsdf.is_smooth()) {
-                                        float pl = sc.emitters.direct_pdf(next_its.mesh, LightSamplingPDF{next_ray.o, next_its.p, next_its.n_g, next_ray.d}).value();
-                                        w = bsdf_pdf / (bsdf_pdf + pl);
-                                    }
-                                    L = L + contrib * w;
-                                }
-                            }
-                        }
+                        alive = true;
                     }
                 }
             }
@@ -1415,7 +1412,7 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
             P2 uv = sampler.next2d();
             LightSampling rec = sc.emitters.sample_light(its.p, r_sel, r, uv);
             bool visible = sc.visible(its.p, rec.p, cx.accel_mode, *cx.counters);
-            if (rec.is_valid() && visible && !mute && add_ok(k) && I.strategy != RL_STRATEGY_BSDF) {
+            if (rec.is_valid() && !mute && add_ok(vdepth) && I.strategy != RL_STRATEGY_BSDF) {
                 V3 wo = its.frame.to_local(rec.d);
                 Color f = bsdf.eval(cx.math, its.wi, wo);
                 Color contrib = T * (rec.weight * f);
@@ -1426,13 +1423,16 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
                         float pl = rec.pdf.value();
                         w = pl / (pb + pl);
                     }
-                    L = L + contrib * w;
+                    if (visible) {
+                        L = L + contrib * w;
+                        cx.counters->nee_added++;
+                    }
                 }
             }
         }
         if (!alive) break;
         T = Tn;
-        its = next_its;
+        pdf_prev = bsdf_pdf;
         ray = next_ray;
     }
     return L;
@@ -1630,6 +1630,7 @@ int orc_render(const orc_scene *os, const rl_integrator_desc *integ, uint32_t sp
         for (auto &c : counters) {
             stats->segments += c.segments, stats->shadow_rays += c.shadow_rays, stats->shadow_visible += c.shadow_visible;
             stats->hits += c.hits;
+            stats->nee_added += c.nee_added;
             stats->max_depth_seen = std::max<uint64_t>(stats->max_depth_seen, c.max_depth);
         }
         uint64_t npix = 0;

@@ -44,6 +44,7 @@ typedef struct orc_config {
 
 typedef struct orc_stats {
     uint64_t samples, segments, shadow_rays, shadow_visible, hits, max_depth_seen;
+    uint64_t nee_added; /* ORC_EST_STREAM only: light-sampling contributions actually added (== GPU shadow_visible) */
     double seconds; /* wall clock of the block loop + merge == "Elapsed Integrator" region, mod.rs:323-334 */
     uint32_t threads_used;
 } orc_stats;

@@ -1,0 +1,714 @@
+// rl_b200.cu -- implementation of include/rl_b200.h: context, scene upload + device LBVH build,
+// and the wavefront render loop.  Everything that touches a pixel sample runs in the kernels
+// of rl_kernels.cuh; there is no CPU path (calls fail with RL_ERR_CUDA when no device exists).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "rl_b200.h"
+#include "rl_kernels.cuh"
+#include "rl_scene_host.hpp"
+
+using namespace rl;
+
+// ---- minimal NCCL surface, resolved at run time so the library has no link-time dependency -----
+namespace {
+typedef struct ncclComm *ncclComm_t;
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, char[128], int) = nullptr; // ncclUniqueId is passed by value (128-byte struct)
+    int (*Reduce)(const void *, void *, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+struct NcclId {
+    char internal[128];
+};
+NcclApi g_nccl;
+bool load_nccl(std::string &err) {
+    if (g_nccl.handle) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) {
+        err = "libnccl.so.2 not found (dlopen)";
+        return false;
+    }
+    g_nccl.GetUniqueId = (int (*)(void *))dlsym(g_nccl.handle, "ncclGetUniqueId");
+    *(void **)&g_nccl.CommInitRank = dlsym(g_nccl.handle, "ncclCommInitRank");
+    *(void **)&g_nccl.Reduce = dlsym(g_nccl.handle, "ncclReduce");
+    *(void **)&g_nccl.CommDestroy = dlsym(g_nccl.handle, "ncclCommDestroy");
+    *(void **)&g_nccl.GetErrorString = dlsym(g_nccl.handle, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Reduce || !g_nccl.CommDestroy) {
+        err = "libnccl.so.2 lacks the expected symbols";
+        return false;
+    }
+    return true;
+}
+std::string g_create_error;
+} // namespace
+
+struct rl_ctx {
+    int device = 0, nranks = 1, rank = 0, sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool profiling = false;
+    ncclComm_t comm = nullptr;
+    // wavefront buffers (grown on demand)
+    size_t cap_paths = 0;
+    float4 *ray_o[2] = {nullptr, nullptr}, *ray_d[2] = {nullptr, nullptr}, *state[2] = {nullptr, nullptr};
+    float4 *hit = nullptr, *sh_a = nullptr, *sh_b = nullptr, *sh_c = nullptr, *lacc = nullptr;
+    // per-image buffers
+    size_t cap_pix = 0, cap_frame = 0;
+    float4 *img_sum = nullptr;
+    uint32_t *pixel_list = nullptr;
+    float *frame = nullptr; // W*H*3 mean image of this rank (zeros outside its tiles)
+    uint32_t pl_w = 0, pl_h = 0, pl_npix = 0;
+    uint32_t *d_counts = nullptr; // [cur/next ping-pong x2, shadow, pad]
+    Counters *d_counters = nullptr;
+    uint32_t *h_counts = nullptr; // pinned
+    Counters *h_counters = nullptr;
+    cudaEvent_t ev[8] = {};
+    uint64_t launches = 0;
+};
+
+struct rl_scene {
+    HostScene hs;
+    SceneView sv{};
+    float4 *d_trav = nullptr, *d_nodes = nullptr, *d_shade = nullptr, *d_verts = nullptr, *d_mats = nullptr, *d_emit_info = nullptr;
+    float *d_emit_cdf = nullptr, *d_area_cdf = nullptr;
+    uint32_t n_node_f4 = 0, n_trav_f4 = 0;
+    size_t smem_bytes = 0;
+    bool smem_ok = false;
+    rl_bvh_info info{};
+};
+
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) {                                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                         \
+            return RL_ERR_CUDA;                                                                                    \
+        }                                                                                                          \
+    } while (0)
+
+static constexpr size_t kMaxSmemScene = 96 * 1024;
+
+static int grid_for(const rl_ctx *ctx, size_t n, int per_sm) {
+    size_t blocks = (n + kBlock - 1) / kBlock;
+    size_t cap = (size_t)ctx->sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// The definitions below take C linkage from their declarations in rl_b200.h.
+
+int rl_abi_version(void) { return RL_B200_ABI_VERSION; }
+
+const char *rl_last_error(const rl_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rl_nccl_unique_id(void *out_128_bytes) {
+    if (!out_128_bytes) return RL_ERR_INVALID;
+    if (!load_nccl(g_create_error)) return RL_ERR_NCCL;
+    int rc = g_nccl.GetUniqueId(out_128_bytes);
+    if (rc != 0) {
+        g_create_error = std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+        return RL_ERR_NCCL;
+    }
+    return RL_OK;
+}
+
+int rl_create(rl_ctx **out, int device, int nranks, int rank, const void *nccl_unique_id) {
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks) {
+        g_create_error = "rl_create: bad arguments";
+        return RL_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)";
+        return RL_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        g_create_error = "rl_create: device ordinal out of range";
+        return RL_ERR_INVALID;
+    }
+    rl_ctx *ctx = new rl_ctx;
+    ctx->device = device, ctx->nranks = nranks, ctx->rank = rank;
+    auto fail = [&](int code) {
+        g_create_error = ctx->err;
+        delete ctx;
+        return code;
+    };
+#define CKC(call)                                                                                                  \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) {                                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                         \
+            return fail(RL_ERR_CUDA);                                                                              \
+        }                                                                                                          \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKC(cudaMalloc(&ctx->d_counts, 4 * sizeof(uint32_t)));
+    CKC(cudaMalloc(&ctx->d_counters, sizeof(Counters)));
+    CKC(cudaMallocHost(&ctx->h_counts, 4 * sizeof(uint32_t)));
+    CKC(cudaMallocHost(&ctx->h_counters, sizeof(Counters)));
+    for (auto &ev : ctx->ev) CKC(cudaEventCreate(&ev));
+    CKC(cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemScene));
+    CKC(cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemScene));
+#undef CKC
+    if (nranks > 1 && nccl_unique_id) {
+        if (!load_nccl(ctx->err)) return fail(RL_ERR_NCCL);
+        NcclId id;
+        std::memcpy(id.internal, nccl_unique_id, 128);
+        // ncclCommInitRank(ncclComm_t*, int nranks, ncclUniqueId commId /*by value*/, int rank)
+        typedef int (*init_fn)(ncclComm_t *, int, NcclId, int);
+        int rc = ((init_fn)g_nccl.CommInitRank)(&ctx->comm, nranks, id, rank);
+        if (rc != 0) {
+            ctx->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+            return fail(RL_ERR_NCCL);
+        }
+    }
+    *out = ctx;
+    return RL_OK;
+}
+
+void rl_destroy(rl_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    for (int i = 0; i < 2; i++) {
+        cudaFree(ctx->ray_o[i]);
+        cudaFree(ctx->ray_d[i]);
+        cudaFree(ctx->state[i]);
+    }
+    cudaFree(ctx->hit), cudaFree(ctx->sh_a), cudaFree(ctx->sh_b), cudaFree(ctx->sh_c), cudaFree(ctx->lacc);
+    cudaFree(ctx->img_sum), cudaFree(ctx->pixel_list), cudaFree(ctx->frame);
+    cudaFree(ctx->d_counts), cudaFree(ctx->d_counters);
+    cudaFreeHost(ctx->h_counts), cudaFreeHost(ctx->h_counters);
+    for (auto &ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int rl_set_profiling(rl_ctx *ctx, int on) {
+    if (!ctx) return RL_ERR_INVALID;
+    ctx->profiling = on != 0;
+    return RL_OK;
+}
+
+int rl_layout(rl_ctx *ctx, rl_layout_info *out) {
+    if (!ctx || !out) return RL_ERR_INVALID;
+    out->ray_bytes = 32, out->hit_bytes = 16, out->state_bytes = 16, out->shadow_bytes = 48, out->accum_bytes = 16;
+    out->max_paths_in_flight = ctx->cap_paths;
+    return RL_OK;
+}
+
+// ---- scene -------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t upload(T **dst, const std::vector<T> &src, cudaStream_t st) {
+    cudaError_t e = cudaMalloc(dst, std::max<size_t>(src.size(), 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (!src.empty()) e = cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    return e;
+}
+
+void rl_scene_destroy(rl_ctx *ctx, rl_scene *s) {
+    if (!s) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    cudaFree(s->d_trav), cudaFree(s->d_nodes), cudaFree(s->d_shade), cudaFree(s->d_verts), cudaFree(s->d_mats);
+    cudaFree(s->d_emit_info), cudaFree(s->d_emit_cdf), cudaFree(s->d_area_cdf);
+    delete s;
+}
+
+int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
+    if (!ctx || !desc || !out) return RL_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    rl_scene *s = new rl_scene;
+    std::string err;
+    if (!build_host_scene(desc, s->hs, err)) {
+        ctx->err = "rl_scene_create: " + err;
+        bool unsupported = desc && (desc->has_volume || desc->has_environment);
+        delete s;
+        return unsupported ? RL_ERR_UNSUPPORTED : RL_ERR_INVALID;
+    }
+    HostScene &hs = s->hs;
+    const uint32_t n = hs.ntris;
+    cudaStream_t st = ctx->stream;
+    uint64_t *d_keys = nullptr, *d_keys_sorted = nullptr;
+    int2 *d_children = nullptr;
+    int *d_parent_node = nullptr, *d_parent_leaf = nullptr, *d_flags = nullptr;
+    float4 *d_leaf_lo = nullptr, *d_leaf_hi = nullptr, *d_node_lo = nullptr, *d_node_hi = nullptr;
+    void *d_tmp = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_keys), cudaFree(d_keys_sorted), cudaFree(d_children), cudaFree(d_parent_node), cudaFree(d_parent_leaf);
+        cudaFree(d_flags), cudaFree(d_leaf_lo), cudaFree(d_leaf_hi), cudaFree(d_node_lo), cudaFree(d_node_hi), cudaFree(d_tmp);
+    };
+#define CKS(call)                                                                                                  \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) {                                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                         \
+            cleanup();                                                                                             \
+            rl_scene_destroy(ctx, s);                                                                              \
+            return RL_ERR_CUDA;                                                                                    \
+        }                                                                                                          \
+    } while (0)
+    CKS(upload(&s->d_verts, hs.verts, st));
+    CKS(upload(&s->d_shade, hs.shade, st));
+    CKS(upload(&s->d_mats, hs.mats, st));
+    CKS(upload(&s->d_emit_info, hs.emit_info, st));
+    CKS(upload(&s->d_emit_cdf, hs.emit_cdf, st));
+    CKS(upload(&s->d_area_cdf, hs.area_cdf, st));
+    const uint32_t n_nodes = n > 1 ? n - 1 : 1;
+    CKS(cudaMalloc(&s->d_trav, (size_t)n * 4 * sizeof(float4)));
+    CKS(cudaMalloc(&s->d_nodes, (size_t)n_nodes * 4 * sizeof(float4)));
+    CKS(cudaMalloc(&d_keys, (size_t)n * 8));
+    CKS(cudaMalloc(&d_keys_sorted, (size_t)n * 8));
+    CKS(cudaMalloc(&d_leaf_lo, (size_t)n * sizeof(float4)));
+    CKS(cudaMalloc(&d_leaf_hi, (size_t)n * sizeof(float4)));
+    // Morton keys over the raw vertex bounds
+    V3 smin = V3{hs.raw_min[0], hs.raw_min[1], hs.raw_min[2]};
+    V3 ext = V3{hs.raw_max[0] - hs.raw_min[0], hs.raw_max[1] - hs.raw_min[1], hs.raw_max[2] - hs.raw_min[2]};
+    V3 sinv = V3{ext.x > 0.0f ? 1.0f / ext.x : 0.0f, ext.y > 0.0f ? 1.0f / ext.y : 0.0f, ext.z > 0.0f ? 1.0f / ext.z : 0.0f};
+    k_morton<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(s->d_verts, n, smin, sinv, d_keys);
+    CKS(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CKS(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_keys_sorted, (int)n, 0, 64, st));
+    CKS(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+    CKS(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_keys_sorted, (int)n, 0, 64, st));
+    k_tri_setup<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(s->d_verts, d_keys_sorted, n, s->d_trav, s->d_shade, d_leaf_lo, d_leaf_hi);
+    CKS(cudaGetLastError());
+    std::vector<int2> h_children;
+    if (n > 1) {
+        CKS(cudaMalloc(&d_children, (size_t)(n - 1) * sizeof(int2)));
+        CKS(cudaMalloc(&d_parent_node, (size_t)(n - 1) * sizeof(int)));
+        CKS(cudaMalloc(&d_parent_leaf, (size_t)n * sizeof(int)));
+        CKS(cudaMalloc(&d_flags, (size_t)(n - 1) * sizeof(int)));
+        CKS(cudaMalloc(&d_node_lo, (size_t)(n - 1) * sizeof(float4)));
+        CKS(cudaMalloc(&d_node_hi, (size_t)(n - 1) * sizeof(float4)));
+        CKS(cudaMemsetAsync(d_flags, 0, (size_t)(n - 1) * sizeof(int), st));
+        k_karras<<<grid_for(ctx, n - 1, 8), kBlock, 0, st>>>(d_keys_sorted, (int)n, d_children, d_parent_node, d_parent_leaf);
+        CKS(cudaGetLastError());
+        k_fit<<<grid_for(ctx, n, 8), kBlock, 0, st>>>((int)n, d_children, d_parent_node, d_parent_leaf, d_leaf_lo, d_leaf_hi, d_node_lo, d_node_hi,
+                                                        d_flags, s->d_nodes);
+        CKS(cudaGetLastError());
+        h_children.resize(n - 1);
+        CKS(cudaMemcpyAsync(h_children.data(), d_children, (size_t)(n - 1) * sizeof(int2), cudaMemcpyDeviceToHost, st));
+    } else {
+        // single triangle: one node whose first child is the leaf and whose second child box is empty
+        float4 lo, hi;
+        CKS(cudaStreamSynchronize(st));
+        CKS(cudaMemcpy(&lo, d_leaf_lo, sizeof(float4), cudaMemcpyDeviceToHost));
+        CKS(cudaMemcpy(&hi, d_leaf_hi, sizeof(float4), cudaMemcpyDeviceToHost));
+        float4 node[4];
+        const float inf = RL_F32_MAX;
+        node[0] = f4(lo.x, lo.y, lo.z, hi.x);
+        node[1] = f4(hi.y, hi.z, inf, inf);
+        node[2] = f4(inf, -inf, -inf, -inf);
+        node[3] = f4(u2f((uint32_t)~0), u2f((uint32_t)~0), 0.0f, 0.0f);
+        CKS(cudaMemcpy(s->d_nodes, node, sizeof(node), cudaMemcpyHostToDevice));
+    }
+    CKS(cudaStreamSynchronize(st));
+    cleanup();
+#undef CKS
+    // tree statistics (and the traversal-stack bound)
+    uint32_t max_depth = 1;
+    if (n > 1) {
+        std::vector<std::pair<int, uint32_t>> stack{{0, 1u}};
+        while (!stack.empty()) {
+            auto [node, depth] = stack.back();
+            stack.pop_back();
+            max_depth = std::max(max_depth, depth);
+            int2 ch = h_children[node];
+            if (ch.x >= 0) stack.push_back({ch.x, depth + 1});
+            if (ch.y >= 0) stack.push_back({ch.y, depth + 1});
+        }
+    }
+    if (max_depth + 1 > RL_STACK_SIZE) {
+        ctx->err = "rl_scene_create: LBVH deeper than the traversal stack";
+        rl_scene_destroy(ctx, s);
+        return RL_ERR_UNSUPPORTED;
+    }
+    s->n_node_f4 = n_nodes * 4;
+    s->n_trav_f4 = n * 4;
+    s->smem_bytes = (size_t)(s->n_node_f4 + s->n_trav_f4) * sizeof(float4);
+    s->smem_ok = s->smem_bytes <= kMaxSmemScene;
+    SceneView &sv = s->sv;
+    sv.trav = s->d_trav, sv.nodes = s->d_nodes, sv.shade = s->d_shade, sv.verts = s->d_verts, sv.mats = s->d_mats;
+    sv.emit_info = s->d_emit_info, sv.emit_cdf = s->d_emit_cdf, sv.area_cdf = s->d_area_cdf;
+    sv.ntris = n, sv.n_emitters = hs.n_emitters;
+    sv.root_min = V3{hs.root_min[0], hs.root_min[1], hs.root_min[2]};
+    sv.root_max = V3{hs.root_max[0], hs.root_max[1], hs.root_max[2]};
+    sv.abs_max = hs.abs_max;
+    std::memcpy(sv.s2c, hs.s2c, 64);
+    std::memcpy(sv.c2w, hs.c2w, 64);
+    sv.cam_pos = V3{hs.cam_pos[0], hs.cam_pos[1], hs.cam_pos[2]};
+    sv.img_w = (float)hs.img_w, sv.img_h = (float)hs.img_h;
+    s->info.ntris = n, s->info.nnodes = n_nodes, s->info.nleaves = n, s->info.max_depth = max_depth;
+    std::memcpy(s->info.root_min, hs.root_min, 12);
+    std::memcpy(s->info.root_max, hs.root_max, 12);
+    s->info.smem_resident = s->smem_ok ? 1u : 0u;
+    *out = s;
+    return RL_OK;
+}
+
+int rl_scene_bvh_info(rl_ctx *ctx, const rl_scene *scene, rl_bvh_info *out) {
+    if (!ctx || !scene || !out) return RL_ERR_INVALID;
+    *out = scene->info;
+    return RL_OK;
+}
+
+// ---- buffers -----------------------------------------------------------------------------------------
+static int ensure_paths(rl_ctx *ctx, size_t n) {
+    if (n <= ctx->cap_paths) return RL_OK;
+    for (int i = 0; i < 2; i++) {
+        cudaFree(ctx->ray_o[i]), cudaFree(ctx->ray_d[i]), cudaFree(ctx->state[i]);
+        ctx->ray_o[i] = ctx->ray_d[i] = ctx->state[i] = nullptr;
+    }
+    cudaFree(ctx->hit), cudaFree(ctx->sh_a), cudaFree(ctx->sh_b), cudaFree(ctx->sh_c), cudaFree(ctx->lacc);
+    ctx->hit = ctx->sh_a = ctx->sh_b = ctx->sh_c = ctx->lacc = nullptr;
+    ctx->cap_paths = 0;
+    size_t bytes = n * sizeof(float4);
+    for (int i = 0; i < 2; i++) {
+        CK(cudaMalloc(&ctx->ray_o[i], bytes));
+        CK(cudaMalloc(&ctx->ray_d[i], bytes));
+        CK(cudaMalloc(&ctx->state[i], bytes));
+    }
+    CK(cudaMalloc(&ctx->hit, bytes));
+    CK(cudaMalloc(&ctx->sh_a, bytes));
+    CK(cudaMalloc(&ctx->sh_b, bytes));
+    CK(cudaMalloc(&ctx->sh_c, bytes));
+    CK(cudaMalloc(&ctx->lacc, bytes));
+    ctx->cap_paths = n;
+    return RL_OK;
+}
+
+// Pixels owned by this rank, in 16x16 tile order (tile (tx,ty) -> rank (tx+ty) % nranks).
+static int ensure_pixels(rl_ctx *ctx, uint32_t w, uint32_t h) {
+    if (ctx->pl_w == w && ctx->pl_h == h && ctx->pixel_list) return RL_OK;
+    std::vector<uint32_t> list;
+    uint32_t tiles_x = (w + 15) / 16, tiles_y = (h + 15) / 16;
+    for (uint32_t ty = 0; ty < tiles_y; ty++)
+        for (uint32_t tx = 0; tx < tiles_x; tx++) {
+            if (ctx->nranks > 1 && (int)((tx + ty) % (uint32_t)ctx->nranks) != ctx->rank) continue;
+            for (uint32_t y = ty * 16; y < std::min(h, ty * 16 + 16); y++)
+                for (uint32_t x = tx * 16; x < std::min(w, tx * 16 + 16); x++) list.push_back(y * w + x);
+        }
+    size_t frame = (size_t)w * h * 3;
+    if (list.size() > ctx->cap_pix) {
+        cudaFree(ctx->img_sum), cudaFree(ctx->pixel_list);
+        ctx->img_sum = nullptr, ctx->pixel_list = nullptr, ctx->cap_pix = 0;
+        CK(cudaMalloc(&ctx->img_sum, std::max<size_t>(list.size(), 1) * sizeof(float4)));
+        CK(cudaMalloc(&ctx->pixel_list, std::max<size_t>(list.size(), 1) * sizeof(uint32_t)));
+        ctx->cap_pix = list.size();
+    }
+    if (frame > ctx->cap_frame) {
+        cudaFree(ctx->frame);
+        ctx->frame = nullptr, ctx->cap_frame = 0;
+        CK(cudaMalloc(&ctx->frame, frame * sizeof(float)));
+        ctx->cap_frame = frame;
+    }
+    if (!list.empty()) CK(cudaMemcpy(ctx->pixel_list, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ctx->pl_w = w, ctx->pl_h = h, ctx->pl_npix = (uint32_t)list.size();
+    return RL_OK;
+}
+
+static int validate(rl_ctx *ctx, const rl_scene *scene, const rl_integrator_desc *I, const rl_render_opts *o) {
+    if (!scene || !I || !o) {
+        ctx->err = "rl_render: null argument";
+        return RL_ERR_INVALID;
+    }
+    if (o->struct_size != sizeof(rl_render_opts)) {
+        ctx->err = "rl_render: rl_render_opts.struct_size mismatch";
+        return RL_ERR_INVALID;
+    }
+    if (o->spp == 0) { // assert_ne!(scene.nb_samples, 0), integrators/mod.rs:410
+        ctx->err = "rl_render: nb_samples must not be 0";
+        return RL_ERR_INVALID;
+    }
+    if (o->sampler_mode != RL_SAMPLER_COUNTER) {
+        ctx->err = "rl_render: only RL_SAMPLER_COUNTER runs on the GPU (mode A is the oracle's)";
+        return RL_ERR_UNSUPPORTED;
+    }
+    if (I->kind == RL_INTEGRATOR_PATH) {
+        if (I->strategy > RL_STRATEGY_EMITTER) {
+            ctx->err = "rl_render: bad strategy";
+            return RL_ERR_INVALID;
+        }
+        if (I->max_depth >= 0 && I->max_depth < 2) { // evaluate() unwraps a missing sensor edge: path.rs:154
+            ctx->err = "rl_render: max_depth < 2 panics in the reference (path.rs:154)";
+            return RL_ERR_INVALID;
+        }
+        if (scene->hs.n_emitters == 0 && I->strategy != RL_STRATEGY_BSDF) { // scene.rs:97-100
+            ctx->err = "rl_render: no emitter in the scene but light sampling requested";
+            return RL_ERR_INVALID;
+        }
+    } else if (I->kind == RL_INTEGRATOR_DIRECT) {
+        ctx->err = "rl_render: direct integrator not built yet";
+        return RL_ERR_UNSUPPORTED;
+    } else {
+        ctx->err = "rl_render: unknown integrator kind";
+        return RL_ERR_INVALID;
+    }
+    return RL_OK;
+}
+
+template <bool SMEM>
+static void launch_trace(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_t n, const float4 *ro, const float4 *rd, float4 *hit) {
+    k_trace<SMEM><<<grid_for(ctx, n, 8), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sc->sv, count, ro, rd, hit, sc->n_node_f4, sc->n_trav_f4);
+    ctx->launches++;
+}
+template <bool SMEM>
+static void launch_shadow(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_t n) {
+    k_shadow<SMEM><<<grid_for(ctx, n, 8), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sc->sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc,
+                                                                                             ctx->d_counters, sc->n_node_f4, sc->n_trav_f4);
+    ctx->launches++;
+}
+
+static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, const rl_render_opts *o, rl_stats *stats) {
+    int rc = validate(ctx, sc, I, o);
+    if (rc != RL_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t W = sc->hs.img_w, H = sc->hs.img_h;
+    rc = ensure_pixels(ctx, W, H);
+    if (rc != RL_OK) return rc;
+    const uint32_t npix = ctx->pl_npix;
+    cudaStream_t st = ctx->stream;
+    rl_stats S{};
+    ctx->launches = 0;
+    CK(cudaMemsetAsync(ctx->frame, 0, (size_t)W * H * 3 * sizeof(float), st));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), st));
+    CK(cudaEventRecord(ctx->ev[0], st));
+    if (npix > 0) {
+        uint32_t batch = o->batch_spp;
+        if (batch == 0) batch = (uint32_t)std::max<size_t>(1, ((size_t)1 << 24) / npix);
+        batch = std::min(batch, o->spp);
+        rc = ensure_paths(ctx, (size_t)npix * batch);
+        if (rc != RL_OK) return rc;
+        IntegParams ip{};
+        ip.kind = I->kind, ip.min_depth = I->min_depth, ip.max_depth = I->max_depth, ip.rr_depth = I->rr_depth;
+        ip.strategy = I->strategy, ip.single_scattering = I->single_scattering;
+        ip.nb_bsdf_samples = I->nb_bsdf_samples, ip.nb_light_samples = I->nb_light_samples;
+        ip.seed_h = seed_hash(o->seed);
+        ip.npix = npix, ip.img_w = W;
+        const bool prof = ctx->profiling;
+        float ms;
+        for (uint32_t s0 = 0; s0 < o->spp; s0 += batch) {
+            const uint32_t nb = std::min(batch, o->spp - s0);
+            const size_t n_paths = (size_t)npix * nb;
+            ip.sample_base = s0;
+            if (prof) CK(cudaEventRecord(ctx->ev[2], st));
+            k_raygen<<<grid_for(ctx, n_paths, 8), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, (uint32_t)n_paths, ctx->ray_o[0], ctx->ray_d[0],
+                                                                   ctx->state[0], ctx->lacc);
+            ctx->launches++;
+            if (prof) {
+                CK(cudaEventRecord(ctx->ev[3], st));
+                CK(cudaEventSynchronize(ctx->ev[3]));
+                CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+                S.ms_raygen += ms;
+            }
+            uint32_t init[4] = {(uint32_t)n_paths, 0, 0, 0};
+            CK(cudaMemcpyAsync(ctx->d_counts, init, sizeof(init), cudaMemcpyHostToDevice, st));
+            size_t n = n_paths;
+            int cur = 0;
+            uint64_t iter = 0;
+            while (n > 0) {
+                uint32_t *c_in = ctx->d_counts + cur, *c_out = ctx->d_counts + (cur ^ 1), *c_sh = ctx->d_counts + 2;
+                CK(cudaMemsetAsync(c_out, 0, sizeof(uint32_t), st));
+                CK(cudaMemsetAsync(c_sh, 0, sizeof(uint32_t), st));
+                if (prof) CK(cudaEventRecord(ctx->ev[2], st));
+                if (sc->smem_ok) launch_trace<true>(ctx, sc, c_in, n, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit);
+                else launch_trace<false>(ctx, sc, c_in, n, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit);
+                if (prof) CK(cudaEventRecord(ctx->ev[3], st));
+                k_shade<<<grid_for(ctx, n, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, c_in, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur],
+                                                                ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1], ctx->state[cur ^ 1], c_out, ctx->sh_a,
+                                                                ctx->sh_b, ctx->sh_c, c_sh, ctx->lacc, ctx->d_counters);
+                ctx->launches++;
+                if (prof) CK(cudaEventRecord(ctx->ev[4], st));
+                // the shadow queue can never be longer than the input queue: size the grid from n
+                if (sc->smem_ok) launch_shadow<true>(ctx, sc, c_sh, n);
+                else launch_shadow<false>(ctx, sc, c_sh, n);
+                if (prof) CK(cudaEventRecord(ctx->ev[5], st));
+                CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                CK(cudaGetLastError());
+                if (prof) {
+                    CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+                    S.ms_trace += ms;
+                    CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
+                    S.ms_shade += ms;
+                    CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+                    S.ms_shadow += ms;
+                }
+                S.segments += n;
+                iter++;
+                n = ctx->h_counts[cur ^ 1];
+                cur ^= 1;
+            }
+            S.max_depth_seen = std::max<uint64_t>(S.max_depth_seen, iter);
+            if (prof) CK(cudaEventRecord(ctx->ev[2], st));
+            k_accum<<<grid_for(ctx, npix, 8), kBlock, 0, st>>>(ctx->lacc, npix, nb, ctx->img_sum, s0 == 0 ? 1 : 0);
+            ctx->launches++;
+            if (prof) {
+                CK(cudaEventRecord(ctx->ev[3], st));
+                CK(cudaEventSynchronize(ctx->ev[3]));
+                CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+                S.ms_accum += ms;
+            }
+        }
+        k_finish<<<grid_for(ctx, npix, 8), kBlock, 0, st>>>(ctx->img_sum, ctx->pixel_list, npix, 1.0f / (float)o->spp, ctx->frame);
+        ctx->launches++;
+    }
+    CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[1], st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    float ms_total = 0;
+    CK(cudaEventElapsedTime(&ms_total, ctx->ev[0], ctx->ev[1]));
+    S.ms_total = ms_total;
+    S.samples = (uint64_t)npix * o->spp;
+    S.hits = ctx->h_counters->hits;
+    S.shadow_rays = ctx->h_counters->nee_sampled;
+    S.shadow_visible = ctx->h_counters->shadow_visible;
+    S.kernel_launches = ctx->launches;
+    if (stats) *stats = S;
+    return RL_OK;
+}
+
+int rl_render_device(rl_ctx *ctx, rl_scene *scene, const rl_integrator_desc *integrator, const rl_render_opts *opts, float *out_rgb_device,
+                     rl_stats *stats) {
+    if (!ctx) return RL_ERR_INVALID;
+    rl_stats S{};
+    int rc = render_impl(ctx, scene, integrator, opts, &S);
+    if (rc != RL_OK) return rc;
+    if (out_rgb_device) {
+        size_t bytes = (size_t)scene->hs.img_w * scene->hs.img_h * 3 * sizeof(float);
+        CK(cudaMemcpyAsync(out_rgb_device, ctx->frame, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (stats) *stats = S;
+    return RL_OK;
+}
+
+int rl_render(rl_ctx *ctx, rl_scene *scene, const rl_integrator_desc *integrator, const rl_render_opts *opts, float *out_rgb, rl_stats *stats) {
+    if (!ctx) return RL_ERR_INVALID;
+    rl_stats S{};
+    int rc = render_impl(ctx, scene, integrator, opts, &S);
+    if (rc != RL_OK) return rc;
+    const size_t count = (size_t)scene->hs.img_w * scene->hs.img_h * 3;
+    float ms = 0;
+    if (ctx->nranks > 1 && ctx->comm) {
+        // one ncclReduce(sum, f32) of the framebuffer: tiles are disjoint, so the sum is exact
+        CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+        int nrc = g_nccl.Reduce(ctx->frame, ctx->frame, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, 0, ctx->comm, ctx->stream);
+        if (nrc != 0) {
+            ctx->err = std::string("ncclReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error");
+            return RL_ERR_NCCL;
+        }
+        CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev[7]));
+        CK(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]));
+        S.ms_reduce = ms;
+    }
+    if (out_rgb && (ctx->rank == 0 || !ctx->comm)) {
+        CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+        CK(cudaMemcpyAsync(out_rgb, ctx->frame, count * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev[7]));
+        CK(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]));
+        S.ms_d2h = ms;
+    }
+    if (stats) *stats = S;
+    return RL_OK;
+}
+
+// ---- Acceleration::{trace, visible} batches -----------------------------------------------------------
+static int trace_device_rays(rl_ctx *ctx, rl_scene *sc, size_t n, uint32_t *prim, float *tuv) {
+    uint32_t cnt = (uint32_t)n;
+    CK(cudaMemcpyAsync(ctx->d_counts, &cnt, sizeof(cnt), cudaMemcpyHostToDevice, ctx->stream));
+    if (sc->smem_ok) launch_trace<true>(ctx, sc, ctx->d_counts, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit);
+    else launch_trace<false>(ctx, sc, ctx->d_counts, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit);
+    CK(cudaGetLastError());
+    std::vector<float4> h(n);
+    CK(cudaMemcpyAsync(h.data(), ctx->hit, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < n; i++) {
+        uint32_t p = f2u(h[i].w);
+        prim[i] = p;
+        if (tuv) {
+            tuv[3 * i] = p == RL_MISS ? 0.0f : h[i].x;
+            tuv[3 * i + 1] = p == RL_MISS ? 0.0f : h[i].y;
+            tuv[3 * i + 2] = p == RL_MISS ? 0.0f : h[i].z;
+        }
+    }
+    return RL_OK;
+}
+
+int rl_trace(rl_ctx *ctx, rl_scene *sc, size_t n, const float *o, const float *d, uint32_t *prim, float *tuv) {
+    if (!ctx || !sc || !o || !d || !prim) return RL_ERR_INVALID;
+    if (n == 0) return RL_OK;
+    if (n > 0x7fffffffu) return RL_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_paths(ctx, n);
+    if (rc != RL_OK) return rc;
+    float *d_o = nullptr, *d_d = nullptr;
+    CK(cudaMalloc(&d_o, n * 12));
+    CK(cudaMalloc(&d_d, n * 12));
+    cudaMemcpyAsync(d_o, o, n * 12, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_d, d, n * 12, cudaMemcpyHostToDevice, ctx->stream);
+    k_pack_rays<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(d_o, d_d, (uint32_t)n, ctx->ray_o[0], ctx->ray_d[0]);
+    rc = trace_device_rays(ctx, sc, n, prim, tuv);
+    cudaFree(d_o), cudaFree(d_d);
+    return rc;
+}
+
+int rl_primary_hits(rl_ctx *ctx, rl_scene *sc, uint32_t *prim, float *tuv) {
+    if (!ctx || !sc || !prim) return RL_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    size_t n = (size_t)sc->hs.img_w * sc->hs.img_h;
+    int rc = ensure_paths(ctx, n);
+    if (rc != RL_OK) return rc;
+    k_primary_rays<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(sc->sv, sc->hs.img_w, sc->hs.img_h, ctx->ray_o[0], ctx->ray_d[0]);
+    return trace_device_rays(ctx, sc, n, prim, tuv);
+}
+
+int rl_visible(rl_ctx *ctx, rl_scene *sc, size_t n, const float *p0, const float *p1, uint8_t *out) {
+    if (!ctx || !sc || !p0 || !p1 || !out) return RL_ERR_INVALID;
+    if (n == 0) return RL_OK;
+    if (n > 0x7fffffffu) return RL_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    float *d_a = nullptr, *d_b = nullptr;
+    unsigned char *d_out = nullptr;
+    CK(cudaMalloc(&d_a, n * 12));
+    CK(cudaMalloc(&d_b, n * 12));
+    CK(cudaMalloc(&d_out, n));
+    cudaMemcpyAsync(d_a, p0, n * 12, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(d_b, p1, n * 12, cudaMemcpyHostToDevice, ctx->stream);
+    k_visible_batch<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(sc->sv, d_a, d_b, (uint32_t)n, d_out);
+    cudaError_t e = cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_a), cudaFree(d_b), cudaFree(d_out);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("rl_visible: ") + cudaGetErrorString(e);
+        return RL_ERR_CUDA;
+    }
+    return RL_OK;
+}
+

@@ -1,0 +1,844 @@
+// rl_device.cuh -- per-thread arithmetic of the wavefront path tracer.
+//
+// Everything here is a plain inline function over registers and read-only scene tables, so
+// the same source is compiled (a) by nvcc for the kernels in rl_kernels.cu (-fmad=false:
+// every f32/f64 operation is one IEEE-754 operation in source order) and (b) by g++ for the
+// serial emulator in tests/emu (RL_HD expands to nothing) that lets the CPU test-suite check
+// the device arithmetic against the oracle without a GPU.  It is NOT a CPU fallback: the
+// product library only ever calls these from __global__ kernels.
+//
+// Operation order follows the reference so that discrete decisions (hit / miss, visible /
+// occluded, Russian roulette, lobe choice) are bit-identical to the CPU restatement:
+//   Mesh::intersection_tri           src/geometry.rs:358-410
+//   AABB::intersect                  src/structure.rs:849-869   (root test only)
+//   Intersection::fill_intersection  src/structure.rs:965-1059
+//   Frame                            src/math.rs:357-384
+//   concentric/cosine sampling       src/math.rs:37-65
+//   BSDFDiffuse / BSDFPhong          src/bsdfs/diffuse.rs, src/bsdfs/phong.rs
+//   Mesh::sample_tri/sample, direct_sample, direct_pdf   src/geometry.rs:261-348, src/emitter.rs:571-688
+//   EmitterSampler::sample_light/direct_pdf              src/emitter.rs:1566-1647
+//   Camera::generate                 src/camera.rs:81-91
+//   Color ops                        src/structure.rs:106-380
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define RL_HD __host__ __device__ __forceinline__
+#else
+#define RL_HD inline
+struct float4 {
+    float x, y, z, w;
+};
+struct float2 {
+    float x, y;
+};
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+#endif
+
+namespace rl {
+
+#define RL_EPSILON 0.0001f
+#define RL_F32_MAX 3.402823466e+38f
+#define RL_PI 3.14159265358979323846264338327950288f
+#define RL_FRAC_PI_2 1.57079632679489661923132169163975144f
+#define RL_FRAC_PI_4 0.785398163397448309615660845819875721f
+#define RL_FRAC_1_PI 0.318309886183790671537767526745028724f
+#define RL_MISS 0xFFFFFFFFu
+
+RL_HD uint32_t f2u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
+RL_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+RL_HD uint64_t d2u(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t u;
+    memcpy(&u, &d, 8);
+    return u;
+#endif
+}
+RL_HD double u2d(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double d;
+    memcpy(&d, &u, 8);
+    return d;
+#endif
+}
+RL_HD bool finite_f(float x) { return (f2u(x) & 0x7f800000u) != 0x7f800000u; }
+
+// ---- vectors (cgmath op order: dot = (xx+yy)+zz, normalize = v * (1/|v|)) ------------------
+struct V3 {
+    float x, y, z;
+};
+RL_HD V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+RL_HD V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+RL_HD V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+RL_HD V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }
+RL_HD V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
+RL_HD V3 operator*(float s, V3 a) { return V3{s * a.x, s * a.y, s * a.z}; }
+RL_HD V3 operator/(V3 a, float s) { return V3{a.x / s, a.y / s, a.z / s}; }
+RL_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+RL_HD V3 cross(V3 a, V3 b) { return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+RL_HD float magnitude(V3 a) { return sqrtf(dot(a, a)); }
+RL_HD V3 normalize(V3 a) { return a * (1.0f / magnitude(a)); }
+RL_HD V3 xyz(float4 f) { return V3{f.x, f.y, f.z}; }
+
+// ---- Color (structure.rs:106-380) -----------------------------------------------------------
+struct Col {
+    float r, g, b;
+};
+RL_HD Col col(float r, float g, float b) { return Col{r, g, b}; }
+RL_HD bool is_zero(Col c) { return c.r == 0.0f && c.g == 0.0f && c.b == 0.0f; }
+RL_HD float channel_max(Col c) { return fmaxf(c.r, fmaxf(c.g, c.b)); }
+RL_HD Col operator*(Col a, Col b) { return Col{a.r * b.r, a.g * b.g, a.b * b.b}; }
+RL_HD Col operator+(Col a, Col b) { return Col{a.r + b.r, a.g + b.g, a.b + b.b}; }
+// Color * f32 returns zero when the scalar is not finite (structure.rs:278-292)
+RL_HD Col mul_checked(Col a, float s) { return finite_f(s) ? Col{a.r * s, a.g * s, a.b * s} : Col{0.0f, 0.0f, 0.0f}; }
+// f32 * Color has no such check (structure.rs:294-303)
+RL_HD Col mul_plain(float s, Col a) { return Col{a.r * s, a.g * s, a.b * s}; }
+// Color / f32 returns zero on a zero or non-finite divisor (structure.rs:249-265)
+RL_HD Col div_checked(Col a, float s) { return (s == 0.0f || !finite_f(s)) ? Col{0.0f, 0.0f, 0.0f} : Col{a.r / s, a.g / s, a.b / s}; }
+RL_HD Col xyz_col(float4 f) { return Col{f.x, f.y, f.z}; }
+
+// ---- "spec" transcendental functions: DESIGN.md §math.  f64 polynomials; the oracle carries
+// an independently typed copy with the same operation sequence (oracle.cpp spec_*). ----------
+RL_HD void spec_sincos(float xf, float *s, float *c) {
+    const double TWO_OVER_PI = 0.63661977236758134308;
+    const double PIO2_HI = 1.57079632673412561417e+00;
+    const double PIO2_LO = 6.07710050650619224932e-11;
+    double x = (double)xf;
+    double fn = floor(x * TWO_OVER_PI + 0.5);
+    int n = (int)fn;
+    double y = (x - fn * PIO2_HI) - fn * PIO2_LO;
+    double y2 = y * y;
+    double ps = 1.0 / 6227020800.0;
+    ps = ps * y2 + -1.0 / 39916800.0;
+    ps = ps * y2 + 1.0 / 362880.0;
+    ps = ps * y2 + -1.0 / 5040.0;
+    ps = ps * y2 + 1.0 / 120.0;
+    ps = ps * y2 + -1.0 / 6.0;
+    double sy = y + y * (y2 * ps);
+    double pc = -1.0 / 87178291200.0;
+    pc = pc * y2 + 1.0 / 479001600.0;
+    pc = pc * y2 + -1.0 / 3628800.0;
+    pc = pc * y2 + 1.0 / 40320.0;
+    pc = pc * y2 + -1.0 / 720.0;
+    pc = pc * y2 + 1.0 / 24.0;
+    pc = pc * y2 + -0.5;
+    double cy = 1.0 + y2 * pc;
+    double rs, rc;
+    int q = n & 3;
+    if (q == 0) { rs = sy; rc = cy; }
+    else if (q == 1) { rs = cy; rc = -sy; }
+    else if (q == 2) { rs = -sy; rc = -cy; }
+    else { rs = -cy; rc = sy; }
+    *s = (float)rs;
+    *c = (float)rc;
+}
+RL_HD double spec_log2(double x) {
+    uint64_t bits = d2u(x);
+    int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    double m = u2d((bits & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL);
+    if (m > 1.4142135623730951) {
+        m = m * 0.5;
+        e = e + 1;
+    }
+    double f = (m - 1.0) / (m + 1.0);
+    double f2 = f * f;
+    double p = 1.0 / 21.0;
+    p = p * f2 + 1.0 / 19.0;
+    p = p * f2 + 1.0 / 17.0;
+    p = p * f2 + 1.0 / 15.0;
+    p = p * f2 + 1.0 / 13.0;
+    p = p * f2 + 1.0 / 11.0;
+    p = p * f2 + 1.0 / 9.0;
+    p = p * f2 + 1.0 / 7.0;
+    p = p * f2 + 1.0 / 5.0;
+    p = p * f2 + 1.0 / 3.0;
+    double ln_m = 2.0 * (f + f * (f2 * p));
+    return (double)e + ln_m * 1.4426950408889634074;
+}
+RL_HD double spec_exp2(double t) {
+    if (t < -1000.0) return 0.0;
+    if (t > 1000.0) return u2d(0x7ff0000000000000ULL);
+    double k = floor(t + 0.5);
+    double r = (t - k) * 0.69314718055994530942;
+    double p = 1.0 / 6227020800.0;
+    p = p * r + 1.0 / 479001600.0;
+    p = p * r + 1.0 / 39916800.0;
+    p = p * r + 1.0 / 3628800.0;
+    p = p * r + 1.0 / 362880.0;
+    p = p * r + 1.0 / 40320.0;
+    p = p * r + 1.0 / 5040.0;
+    p = p * r + 1.0 / 720.0;
+    p = p * r + 1.0 / 120.0;
+    p = p * r + 1.0 / 24.0;
+    p = p * r + 1.0 / 6.0;
+    p = p * r + 0.5;
+    p = p * r + 1.0;
+    p = p * r + 1.0;
+    int ki = (int)k;
+    int k1 = ki / 2, k2 = ki - k1;
+    double s1 = u2d((uint64_t)(k1 + 1023) << 52), s2 = u2d((uint64_t)(k2 + 1023) << 52);
+    return (p * s1) * s2;
+}
+RL_HD float spec_powf(float x, float y) {
+    if (y == 0.0f) return 1.0f;
+    if (x == 0.0f) return y > 0.0f ? 0.0f : u2f(0x7f800000u);
+    if (x == 1.0f) return 1.0f;
+    if (!(x > 0.0f)) return u2f(0x7fc00000u);
+    return (float)spec_exp2((double)y * spec_log2((double)x));
+}
+
+// ---- counter-based sampler (mode B) -----------------------------------------
+RL_HD uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+RL_HD uint64_t seed_hash(uint64_t seed) { return mix64(seed + 0x9e3779b97f4a7c15ULL); }
+struct Sampler {
+    uint64_t key;
+    uint32_t n;
+    RL_HD float next() {
+        n++;
+        uint64_t z = mix64(key + (uint64_t)n * 0x9e3779b97f4a7c15ULL);
+        return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+    }
+};
+RL_HD Sampler make_sampler(uint64_t seed_h, uint32_t pixel, uint32_t sample, uint32_t n) {
+    Sampler s;
+    s.key = mix64(seed_h ^ (((uint64_t)pixel << 32) | (uint64_t)sample));
+    s.n = n;
+    return s;
+}
+
+// ---- Frame (math.rs:357-384) ------------------------------------------------------------------
+struct Frame {
+    V3 x, y, z;
+};
+RL_HD Frame make_frame(V3 n) {
+    float sign = copysignf(1.0f, n.z);
+    float a = -1.0f / (sign + n.z);
+    float b = n.x * n.y * a;
+    Frame f;
+    f.x = V3{1.0f + sign * n.x * n.x * a, sign * b, -sign * n.x};
+    f.y = V3{b, sign + n.y * n.y * a, -n.y};
+    f.z = n;
+    return f;
+}
+RL_HD V3 to_world(const Frame &f, V3 v) { return f.x * v.x + f.y * v.y + f.z * v.z; }
+RL_HD V3 to_local(const Frame &f, V3 v) { return V3{dot(v, f.x), dot(v, f.y), dot(v, f.z)}; }
+
+// ---- sampling (math.rs:37-65, 388-394) -------------------------------------------------------
+RL_HD V3 cosine_sample_hemisphere(float ux, float uy) {
+    float ox = ux * 2.0f - 1.0f, oy = uy * 2.0f - 1.0f;
+    float dx, dy;
+    if (ox == 0.0f && oy == 0.0f) {
+        dx = 0.0f;
+        dy = 0.0f;
+    } else {
+        float theta, r;
+        if (fabsf(ox) > fabsf(oy)) {
+            r = ox;
+            theta = RL_FRAC_PI_4 * (oy / ox);
+        } else {
+            r = oy;
+            theta = RL_FRAC_PI_2 - RL_FRAC_PI_4 * (ox / oy);
+        }
+        float s, c;
+        spec_sincos(theta, &s, &c);
+        dx = c * r;
+        dy = s * r;
+    }
+    float z = sqrtf(fmaxf(0.0f, 1.0f - dx * dx - dy * dy));
+    return V3{dx, dy, z};
+}
+
+// ---- scene tables ------------------------------------------------------------------------------
+// All tables are arrays of float4 so that every access is one 128-bit load.
+//   trav[4*s+0..3]   (Morton order s): {v0.xyz, det} {e1.xyz, prim} {e2.xyz, -} {n_geo.xyz, -}
+//   nodes[4*j+0..3]  wide LBVH node:   {lo0.xyz, hi0.x} {hi0.yz, lo1.xy} {lo1.z, hi1.xyz} {child0, child1, -, -}
+//   shade[4*p+0..3]  (original order p): {n_geo.xyz, mesh} {n0.xyz, has_normals} {n1.xyz, -} {n2.xyz, -}
+//   verts[3*p+0..2]  (original order p): {v.xyz, -}
+//   mats[4*m+0..3]   {kd.rgb, kind} {ks.rgb, exponent} {Le.rgb, is_light} {weight_specular, 1/area, pdf_sel, -}
+//   emit_info[e]     {mesh, first_prim, ntris, cdf_offset} (as uint bits)
+struct SceneView {
+    const float4 *trav;
+    const float4 *nodes;
+    const float4 *shade;
+    const float4 *verts;
+    const float4 *mats;
+    const float4 *emit_info;
+    const float *emit_cdf; // n_emitters+1
+    const float *area_cdf; // concatenated per-emitter triangle-area cdfs (ntris+1 each)
+    uint32_t ntris, n_emitters;
+    // BVHAccel nodes[0].aabb (union of compute_aabb_tri boxes), for the reference's root test
+    V3 root_min, root_max;
+    float abs_max; // max |coordinate| of the scene, scales the conservative-culling epsilon
+    // camera
+    float s2c[16], c2w[16];
+    V3 cam_pos;
+    float img_w, img_h;
+};
+
+// ---- AABB::intersect (structure.rs:849-869), used verbatim for the root box -------------------
+RL_HD bool aabb_intersect_ref(V3 pmin, V3 pmax, V3 o, V3 d, float tnear, float tfar) {
+    float t_max = tfar, t_min = tnear;
+    {
+        float inv_d = 1.0f / d.x;
+        float t0 = (pmin.x - o.x) * inv_d, t1 = (pmax.x - o.x) * inv_d;
+        if (inv_d < 0.0f) { float t = t0; t0 = t1; t1 = t; }
+        t_min = t0 > t_min ? t0 : t_min;
+        t_max = t1 < t_max ? t1 : t_max;
+        if (t_max <= t_min) return false;
+    }
+    {
+        float inv_d = 1.0f / d.y;
+        float t0 = (pmin.y - o.y) * inv_d, t1 = (pmax.y - o.y) * inv_d;
+        if (inv_d < 0.0f) { float t = t0; t0 = t1; t1 = t; }
+        t_min = t0 > t_min ? t0 : t_min;
+        t_max = t1 < t_max ? t1 : t_max;
+        if (t_max <= t_min) return false;
+    }
+    {
+        float inv_d = 1.0f / d.z;
+        float t0 = (pmin.z - o.z) * inv_d, t1 = (pmax.z - o.z) * inv_d;
+        if (inv_d < 0.0f) { float t = t0; t0 = t1; t1 = t; }
+        t_min = t0 > t_min ? t0 : t_min;
+        t_max = t1 < t_max ? t1 : t_max;
+        if (t_max <= t_min) return false;
+    }
+    return true;
+}
+
+// ---- Mesh::intersection_tri with the ray-independent terms (e1, e2, n_geo, det) precomputed ---
+// Returns true when the triangle accepts the ray at parameter *t (all of the reference's
+// rejections applied except the final `t < its.t && t > 1e-5` which the caller owns).
+RL_HD bool tri_test(float4 r0, float4 r1, float4 r2, float4 r3, V3 o, V3 d, float *t_out, float *u_out, float *v_out) {
+    V3 v0 = xyz(r0), e1 = xyz(r1), e2 = xyz(r2), n_geo = xyz(r3);
+    float det = r0.w;
+    float denom = dot(d, n_geo);
+    if (denom == 0.0f) return false;
+    float t = -dot(o - v0, n_geo) / denom;
+    if (t < 0.0f) return false;
+    V3 p = o + t * d;
+    V3 pv = p - v0;
+    V3 u0 = cross(e1, pv);
+    V3 v0c = cross(pv, e2);
+    if (dot(u0, n_geo) < 0.0f || dot(v0c, n_geo) < 0.0f) return false;
+    float v = magnitude(u0) / det;
+    float u = magnitude(v0c) / det;
+    if (u < 0.0f || v < 0.0f || u > 1.0f || v > 1.0f) return false;
+    if (!(u + v <= 1.0f)) return false;
+    *t_out = t;
+    *u_out = u;
+    *v_out = v;
+    return true;
+}
+
+// Per-ray constants of the conservative slab test used for LBVH culling.  The reference's
+// BVH shape is not reproduced; instead culling is made strictly
+// conservative (boxes grown by eps around the ray) so that the result equals the brute-force
+// NaiveAcceleration loop: the closest accepted triangle, lowest (mesh,tri) on exact ties.
+struct RaySlab {
+    V3 inv_d;
+    V3 o_near, o_far; // origin shifted by +-eps toward the side that widens the interval
+    uint32_t neg;     // bit a set when d[a] < 0
+};
+RL_HD RaySlab make_slab(V3 o, V3 d, float abs_max) {
+    RaySlab s;
+    s.inv_d = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    float m = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), abs_max));
+    float eps = 1e-5f * m + 1e-30f;
+    s.neg = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    // entering plane uses o shifted forward (smaller t), leaving plane uses o shifted back
+    s.o_near = V3{d.x < 0.0f ? o.x - eps : o.x + eps, d.y < 0.0f ? o.y - eps : o.y + eps, d.z < 0.0f ? o.z - eps : o.z + eps};
+    s.o_far = V3{d.x < 0.0f ? o.x + eps : o.x - eps, d.y < 0.0f ? o.y + eps : o.y - eps, d.z < 0.0f ? o.z + eps : o.z - eps};
+    return s;
+}
+// Returns conservative entry distance, or a negative value on a miss, for t in [0, tmax].
+RL_HD float slab_test(const RaySlab &s, V3 lo, V3 hi, float tmax) {
+    float nx = (s.neg & 1u) ? hi.x : lo.x, fx = (s.neg & 1u) ? lo.x : hi.x;
+    float ny = (s.neg & 2u) ? hi.y : lo.y, fy = (s.neg & 2u) ? lo.y : hi.y;
+    float nz = (s.neg & 4u) ? hi.z : lo.z, fz = (s.neg & 4u) ? lo.z : hi.z;
+    float t0x = (nx - s.o_near.x) * s.inv_d.x, t1x = (fx - s.o_far.x) * s.inv_d.x;
+    float t0y = (ny - s.o_near.y) * s.inv_d.y, t1y = (fy - s.o_far.y) * s.inv_d.y;
+    float t0z = (nz - s.o_near.z) * s.inv_d.z, t1z = (fz - s.o_far.z) * s.inv_d.z;
+    // fmaxf/fminf drop NaNs (0*inf on a degenerate axis), which keeps the test conservative
+    float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
+    float tend = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
+    return tmin <= tend ? tmin : -1.0f;
+}
+
+struct HitRec {
+    float t, u, v;
+    uint32_t prim;
+};
+
+#ifndef RL_STACK_SIZE
+#define RL_STACK_SIZE 64
+#endif
+
+// Acceleration::trace (accel.rs:292-315) without fill_intersection: closest accepted triangle.
+RL_HD HitRec trace_closest(const SceneView &sv, const float4 *nodes, const float4 *trav, V3 o, V3 d) {
+    HitRec best;
+    best.t = RL_F32_MAX;
+    best.u = 0.0f;
+    best.v = 0.0f;
+    best.prim = RL_MISS;
+    if (!aabb_intersect_ref(sv.root_min, sv.root_max, o, d, RL_EPSILON, RL_F32_MAX)) return best;
+    RaySlab sl = make_slab(o, d, sv.abs_max);
+    int stack[RL_STACK_SIZE];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        int node = stack[--sp];
+        float4 a = nodes[4 * node + 0], b = nodes[4 * node + 1], c = nodes[4 * node + 2], k = nodes[4 * node + 3];
+        float d0 = slab_test(sl, V3{a.x, a.y, a.z}, V3{a.w, b.x, b.y}, best.t);
+        float d1 = slab_test(sl, V3{b.z, b.w, c.x}, V3{c.y, c.z, c.w}, best.t);
+        int c0 = (int)f2u(k.x), c1 = (int)f2u(k.y);
+        if (d1 >= 0.0f && (d0 < 0.0f || d1 < d0)) { // visit the nearer child first
+            float td = d0; d0 = d1; d1 = td;
+            int tc = c0; c0 = c1; c1 = tc;
+        }
+#define RL_VISIT(child, dist)                                                                      \
+    if ((dist) >= 0.0f && (dist) <= best.t) {                                                      \
+        if ((child) < 0) {                                                                         \
+            int s_ = ~(child);                                                                     \
+            float4 r0 = trav[4 * s_], r1 = trav[4 * s_ + 1], r2 = trav[4 * s_ + 2], r3 = trav[4 * s_ + 3]; \
+            float t_, u_, v_;                                                                      \
+            if (tri_test(r0, r1, r2, r3, o, d, &t_, &u_, &v_)) {                                   \
+                uint32_t prim_ = f2u(r1.w);                                                        \
+                if ((t_ < best.t || (t_ == best.t && best.prim != RL_MISS && prim_ < best.prim)) && t_ > 0.00001f) {       \
+                    best.t = t_; best.u = u_; best.v = v_; best.prim = prim_;                      \
+                }                                                                                  \
+            }                                                                                      \
+        } else if (sp < RL_STACK_SIZE) {                                                           \
+            stack[sp++] = (child);                                                                 \
+        }                                                                                          \
+    }
+        // leaves are tested immediately; inner nodes: push far then near so near pops first
+        if (c0 < 0) {
+            RL_VISIT(c0, d0)
+            RL_VISIT(c1, d1)
+        } else {
+            RL_VISIT(c1, d1)
+            RL_VISIT(c0, d0)
+        }
+#undef RL_VISIT
+    }
+    return best;
+}
+
+// Acceleration::visible (accel.rs:316-343): true when no triangle accepts the segment.
+RL_HD bool trace_visible(const SceneView &sv, const float4 *nodes, const float4 *trav, V3 p0, V3 p1) {
+    const float SHADOW_EPS = 0.00001f;
+    V3 d = p1 - p0;
+    float length = magnitude(d);
+    d = d / length;
+    float thr = length * (1.0f - SHADOW_EPS);
+    if (!aabb_intersect_ref(sv.root_min, sv.root_max, p0, d, RL_EPSILON, thr)) return false;
+    RaySlab sl = make_slab(p0, d, sv.abs_max);
+    int stack[RL_STACK_SIZE];
+    int sp = 0;
+    stack[sp++] = 0;
+    while (sp > 0) {
+        int node = stack[--sp];
+        float4 a = nodes[4 * node + 0], b = nodes[4 * node + 1], c = nodes[4 * node + 2], k = nodes[4 * node + 3];
+        float d0 = slab_test(sl, V3{a.x, a.y, a.z}, V3{a.w, b.x, b.y}, thr);
+        float d1 = slab_test(sl, V3{b.z, b.w, c.x}, V3{c.y, c.z, c.w}, thr);
+        int ch[2] = {(int)f2u(k.x), (int)f2u(k.y)};
+        float dd[2] = {d0, d1};
+        for (int q = 0; q < 2; q++) {
+            if (dd[q] < 0.0f) continue;
+            if (ch[q] < 0) {
+                int s_ = ~ch[q];
+                float t_, u_, v_;
+                if (tri_test(trav[4 * s_], trav[4 * s_ + 1], trav[4 * s_ + 2], trav[4 * s_ + 3], p0, d, &t_, &u_, &v_)) {
+                    if (t_ < thr && t_ > 0.00001f) return false;
+                }
+            } else if (sp < RL_STACK_SIZE) {
+                stack[sp++] = ch[q];
+            }
+        }
+    }
+    return true;
+}
+
+// ---- Camera::generate (camera.rs:81-91) -------------------------------------------------------
+RL_HD void m4_mul_v4(const float *m, float x, float y, float z, float w, float *out) {
+    for (int r = 0; r < 4; r++) out[r] = ((m[r] * x + m[4 + r] * y) + m[8 + r] * z) + m[12 + r] * w;
+}
+RL_HD void camera_generate(const SceneView &sv, float px, float py, V3 *o, V3 *d) {
+    float h[4];
+    m4_mul_v4(sv.s2c, px / sv.img_w, py / sv.img_h, 0.0f, 1.0f, h);
+    float iw = 1.0f / h[3];
+    V3 near_p = V3{h[0] * iw, h[1] * iw, h[2] * iw};
+    V3 dl = normalize(near_p);
+    float g[4];
+    m4_mul_v4(sv.c2w, dl.x, dl.y, dl.z, 0.0f, g);
+    *o = sv.cam_pos;
+    *d = V3{g[0], g[1], g[2]};
+}
+
+// ---- materials ---------------------------------------------------------------------------------
+struct Material {
+    Col kd, ks, le;
+    float exponent, weight_specular, inv_area, pdf_sel;
+    uint32_t kind;
+    bool is_light;
+};
+RL_HD Material load_material(const float4 *mats, uint32_t mesh) {
+    float4 a = mats[4 * mesh], b = mats[4 * mesh + 1], c = mats[4 * mesh + 2], e = mats[4 * mesh + 3];
+    Material m;
+    m.kd = xyz_col(a);
+    m.kind = f2u(a.w);
+    m.ks = xyz_col(b);
+    m.exponent = b.w;
+    m.le = xyz_col(c);
+    m.is_light = f2u(c.w) != 0u;
+    m.weight_specular = e.x;
+    m.inv_area = e.y;
+    m.pdf_sel = e.z;
+    return m;
+}
+RL_HD V3 reflect_local(V3 d) { return V3{-d.x, -d.y, d.z}; }
+
+// BSDF::pdf (diffuse.rs:33-51, phong.rs:65-91)
+RL_HD float bsdf_pdf(const Material &m, V3 wi, V3 wo) {
+    if (m.kind == 0u) {
+        if (wi.z <= 0.0f) return 0.0f;
+        if (wo.z <= 0.0f) return 0.0f;
+        return wo.z * RL_FRAC_1_PI;
+    }
+    if (wi.z <= 0.0f || wo.z <= 0.0f) return 0.0f;
+    float pdf_specular;
+    float alpha = dot(reflect_local(wi), wo);
+    if (alpha > 0.0f) pdf_specular = m.weight_specular * spec_powf(alpha, m.exponent) * (m.exponent + 1.0f) / (2.0f * RL_PI);
+    else pdf_specular = 0.0f;
+    float pdf_diffuse = (1.0f - m.weight_specular) * wo.z * RL_FRAC_1_PI;
+    return pdf_specular + pdf_diffuse;
+}
+// BSDF::eval (diffuse.rs:53-71, phong.rs:93-119); includes the cosine for the diffuse lobe
+RL_HD Col bsdf_eval(const Material &m, V3 wi, V3 wo) {
+    if (m.kind == 0u) {
+        if (wi.z <= 0.0f) return Col{0.0f, 0.0f, 0.0f};
+        if (wo.z > 0.0f) return mul_checked(mul_checked(m.kd, wo.z), RL_FRAC_1_PI);
+        return Col{0.0f, 0.0f, 0.0f};
+    }
+    if (wi.z <= 0.0f || wo.z <= 0.0f) return Col{0.0f, 0.0f, 0.0f};
+    Col specular_value;
+    float alpha = dot(reflect_local(wi), wo);
+    if (alpha > 0.0f) specular_value = mul_checked(m.ks, spec_powf(alpha, m.exponent) * (m.exponent + 2.0f) / (2.0f * RL_PI));
+    else specular_value = Col{0.0f, 0.0f, 0.0f};
+    Col diffuse_value = mul_checked(mul_checked(m.kd, wo.z), RL_FRAC_1_PI);
+    return specular_value + diffuse_value;
+}
+// BSDF::sample (diffuse.rs:11-31, phong.rs:14-63)
+RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight, V3 *wo, float *pdf) {
+    if (wi.z <= 0.0f) return false;
+    if (m.kind == 0u) {
+        V3 d_out = cosine_sample_hemisphere(sx, sy);
+        *weight = m.kd;
+        *wo = d_out;
+        *pdf = d_out.z * RL_FRAC_1_PI;
+        return true;
+    }
+    V3 d_out;
+    if (sx < m.weight_specular) {
+        sx = sx / m.weight_specular;
+        float sin_alpha = sqrtf(1.0f - spec_powf(sy, 2.0f / (m.exponent + 1.0f)));
+        float cos_alpha = spec_powf(sy, 1.0f / (m.exponent + 1.0f));
+        float phi = 2.0f * RL_PI * sx;
+        float sp, cp;
+        spec_sincos(phi, &sp, &cp);
+        V3 local_dir = V3{sin_alpha * cp, sin_alpha * sp, cos_alpha};
+        Frame fr = make_frame(reflect_local(wi));
+        d_out = to_world(fr, local_dir);
+        if (d_out.z <= 0.0f) return false;
+    } else {
+        sx = (sx - m.weight_specular) / (1.0f - m.weight_specular);
+        d_out = cosine_sample_hemisphere(sx, sy);
+    }
+    float p = bsdf_pdf(m, wi, d_out);
+    if (p == 0.0f) return false;
+    *weight = div_checked(bsdf_eval(m, wi, d_out), p);
+    *wo = d_out;
+    *pdf = p;
+    return true;
+}
+
+// ---- surface interaction (fill_intersection, structure.rs:965-1059) ---------------------------
+struct Surface {
+    V3 p, n_g, n_s, wi;
+    Frame frame;
+    uint32_t mesh;
+};
+RL_HD Surface fill_intersection(const SceneView &sv, const Material &mat, uint32_t prim, uint32_t mesh, float4 s0, float4 s1,
+                                float4 s2, float4 s3, float t, float hit_u, float hit_v, V3 o, V3 d) {
+    Surface s;
+    s.mesh = mesh;
+    s.p = o + t * d; // its.p as computed inside intersection_tri (geometry.rs:382)
+    V3 n_g = xyz(s0);
+    V3 n_s;
+    if (f2u(s1.w) != 0u) {
+        V3 d0 = xyz(s1), d1 = xyz(s2), d2 = xyz(s3);
+        V3 ns = d0 * (1.0f - hit_u - hit_v) + d1 * hit_u + d2 * hit_v;
+        if (dot(n_g, ns) < 0.0f) n_g = -n_g;
+        float l = dot(ns, ns);
+        if (l == 0.0f) n_s = n_g;
+        else if (l != 1.0f) n_s = ns / sqrtf(l);
+        else n_s = ns;
+    } else n_s = n_g;
+    // both supported BSDFs are two-sided; lights are never flipped (structure.rs:1006)
+    if (!mat.is_light && dot(d, n_s) > 0.0f) {
+        n_s = V3{-n_s.x, -n_s.y, -n_s.z};
+        n_g = V3{-n_g.x, -n_g.y, -n_g.z};
+    }
+    s.n_g = n_g;
+    s.n_s = n_s;
+    s.frame = make_frame(n_s);
+    s.wi = to_local(s.frame, -d);
+    (void)sv;
+    (void)prim;
+    return s;
+}
+
+// ---- emitters -----------------------------------------------------------------------------------
+// Distribution1D::sample_discrete (math.rs:447-457): last index with cdf[i] <= v
+RL_HD uint32_t cdf_sample_discrete(const float *cdf, uint32_t n_plus_1, float v) {
+    uint32_t lo = 0, hi = n_plus_1; // first index with cdf[i] > v
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (cdf[mid] <= v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo - 1;
+}
+struct LightSample {
+    V3 p, n, d;
+    Col weight;
+    float pdf;
+    bool valid;
+};
+// EmitterSampler::sample_light -> Mesh::direct_sample -> Mesh::sample -> sample_tri
+// (emitter.rs:1604-1620, 652-688; geometry.rs:340-348, 261-337; math.rs:388-394)
+RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, float ux, float uy) {
+    uint32_t id_light = cdf_sample_discrete(sv.emit_cdf, sv.n_emitters + 1, r_sel);
+    float pdf_sel = sv.emit_cdf[id_light + 1] - sv.emit_cdf[id_light];
+    float4 info = sv.emit_info[id_light];
+    uint32_t mesh = f2u(info.x), first_prim = f2u(info.y), ntris = f2u(info.z), cdf_off = f2u(info.w);
+    Material mat = load_material(sv.mats, mesh);
+    uint32_t tri = cdf_sample_discrete(sv.area_cdf + cdf_off, ntris + 1, r);
+    uint32_t prim = first_prim + tri;
+    V3 v0 = xyz(sv.verts[3 * prim]), v1 = xyz(sv.verts[3 * prim + 1]), v2 = xyz(sv.verts[3 * prim + 2]);
+    float su0 = sqrtf(ux);
+    float b0 = 1.0f - su0, b1 = uy * su0;
+    V3 pos = v0 * b0 + v1 * b1 + v2 * (1.0f - b0 - b1);
+    V3 n_g = normalize(cross(v2 - v0, v1 - v0));
+    float4 s1 = sv.shade[4 * prim + 1];
+    if (f2u(s1.w) != 0u) {
+        V3 n0 = xyz(s1), n1 = xyz(sv.shade[4 * prim + 2]), n2 = xyz(sv.shade[4 * prim + 3]);
+        V3 n = n0 * b0 + n1 * b1 + n2 * (1.0f - b0 - b1);
+        float n_l = dot(n, n);
+        if (n_l == 0.0f) n = n_g;
+        else if (n_l != 1.0f) n = n / sqrtf(n_l);
+        if (dot(n_g, n) < 0.0f) n_g = -n_g;
+    }
+    float pdf_area = mat.inv_area; // 1 / cdf.total()
+    V3 dd = pos - x;
+    float dist = magnitude(dd);
+    if (dist != 0.0f) dd = dd / dist;
+    float geom = dist != 0.0f ? fmaxf(dot(n_g, -dd), 0.0f) / (dist * dist) : 0.0f;
+    float pdf = geom == 0.0f ? 0.0f : pdf_area / geom;
+    Col weight = pdf == 0.0f ? Col{0.0f, 0.0f, 0.0f} : div_checked(mul_checked(mat.le, geom), pdf_area);
+    LightSample ls;
+    ls.p = pos;
+    ls.n = n_g;
+    ls.d = dd;
+    ls.weight = Col{weight.r / pdf_sel, weight.g / pdf_sel, weight.b / pdf_sel};
+    ls.pdf = pdf * pdf_sel;
+    ls.valid = ls.pdf != 0.0f;
+    return ls;
+}
+// EmitterSampler::direct_pdf (emitter.rs:1566-1575) -> Mesh::direct_pdf (emitter.rs:571-579)
+RL_HD float direct_pdf(const Material &light_mat, V3 o, V3 p, V3 n, V3 dir) {
+    float cos_light = fmaxf(dot(n, -dir), 0.0f);
+    float v;
+    if (cos_light == 0.0f) v = 0.0f;
+    else {
+        V3 po = p - o;
+        float geom = cos_light / dot(po, po);
+        v = light_mat.inv_area / geom;
+    }
+    return v * light_mat.pdf_sel;
+}
+
+// mis_weight, integrators/mod.rs:462-478 (power heuristic, `direct` only)
+RL_HD float mis_weight_power(float pdf_a, float pdf_b) {
+    if (pdf_a == 0.0f) return 0.0f;
+    if (!finite_f(pdf_a) || !finite_f(pdf_b)) return 0.0f;
+    float w = (pdf_a * pdf_a) / ((pdf_a * pdf_a) + (pdf_b * pdf_b));
+    return finite_f(w) ? w : 0.0f;
+}
+
+// ---- integrator parameters ------------------------------------------------------------------------
+struct IntegParams {
+    uint32_t kind;     // 0 path, 1 direct
+    int32_t min_depth, max_depth, rr_depth;
+    uint32_t strategy; // 0 all, 1 bsdf, 2 emitter
+    uint32_t single_scattering;
+    uint32_t nb_bsdf_samples, nb_light_samples;
+    uint64_t seed_h;   // seed_hash(seed)
+    uint32_t sample_base; // first sample index of this batch
+    uint32_t npix;        // pixels owned by this rank
+    uint32_t img_w;
+};
+
+// ---- one wavefront step of the `path` integrator for one path ------------------------------------
+// Input: the ray that was traced (o, d), its hit, the path state.  Output: radiance to add
+// now (arrival emission), an optional next ray + state, an optional shadow segment + the
+// radiance it carries.  Mirrors generate()/evaluate() of the reference in streaming form
+// (identical to oracle.cpp path_compute_pixel_stream).
+struct PathState {
+    Col T;            // throughput entering the vertex that this ray hits
+    float pdf_prev;   // solid-angle pdf of the direction that produced this ray
+    uint32_t path_id; // s_local * npix + local pixel
+    uint32_t depth;   // generate() depth at which this ray was sampled (1 = sensor)
+    uint32_t rng_n;   // random numbers consumed so far
+};
+struct StepOut {
+    Col add;          // arrival emission (already throughput- and MIS-weighted)
+    bool has_add;
+    bool alive;       // next ray valid
+    V3 next_o, next_d;
+    PathState next;
+    bool nee_sampled; // the reference would call Acceleration::visible here
+    bool shadow;      // a shadow segment must be traced
+    V3 sh_p0, sh_p1;
+    Col sh_contrib;
+};
+RL_HD bool ip_expand(const IntegParams &ip, uint32_t depth) { return ip.max_depth < 0 ? true : depth < (uint32_t)ip.max_depth; }
+RL_HD bool ip_add_ok(const IntegParams &ip, uint32_t curr_depth) { return ip.min_depth < 0 ? true : curr_depth >= (uint32_t)ip.min_depth; }
+
+RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, const HitRec &hit, const PathState &st, uint32_t pixel,
+                     uint32_t sample, StepOut *out) {
+    out->has_add = false;
+    out->alive = false;
+    out->shadow = false;
+    out->nee_sampled = false;
+    out->add = Col{0.0f, 0.0f, 0.0f};
+    if (hit.prim == RL_MISS) return;
+    float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
+    uint32_t mesh = f2u(s0.w);
+    Material mat = load_material(sv.mats, mesh);
+    Surface its = fill_intersection(sv, mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
+    const bool mute = ip.single_scattering != 0u;
+    const bool use_nee = (ip.strategy == 0u || ip.strategy == 2u);
+    // ---- emission carried by the arriving edge --------------------------------------------------
+    if (st.depth == 1u) { // sensor edge: un-weighted (path.rs:152-165)
+        if (ip_add_ok(ip, 0u) && dot(its.n_s, -d) >= 0.0f && mat.is_light && !is_zero(mat.le)) {
+            out->add = mat.le;
+            out->has_add = true;
+        }
+    } else if (!mute && ip_add_ok(ip, st.depth - 1u) && ip.strategy != 2u) {
+        if (dot(its.n_s, -d) >= 0.0f && mat.is_light) {
+            Col contrib = st.T * mat.le;
+            if (!is_zero(contrib)) {
+                float w = 1.0f;
+                if (ip.strategy == 0u) { // balance heuristic against light sampling (path.rs:78-99)
+                    float pl = direct_pdf(mat, o, its.p, its.n_g, d);
+                    w = st.pdf_prev / (st.pdf_prev + pl);
+                }
+                out->add = mul_checked(contrib, w);
+                out->has_add = true;
+            }
+        }
+    }
+    // ---- expand this vertex ----------------------------------------------------------------------
+    uint32_t depth = st.depth + 1u;
+    if (!ip_expand(ip, depth)) return;
+    Sampler smp = make_sampler(ip.seed_h, pixel, sample, st.rng_n);
+    // directional strategy: BSDF sample + Russian roulette (directional.rs:44-107)
+    {
+        float sx = smp.next();
+        float sy = smp.next();
+        Col bw;
+        V3 wo;
+        float bpdf;
+        if (bsdf_sample(mat, its.wi, sx, sy, &bw, &wo, &bpdf)) {
+            V3 d_out = to_world(its.frame, wo);
+            Col Tn = st.T * bw;
+            if (!is_zero(Tn)) {
+                bool do_rr = ip.rr_depth < 0 ? true : (uint32_t)ip.rr_depth <= depth;
+                bool survive = true;
+                float rr_weight = 1.0f;
+                if (do_rr) {
+                    float q = fminf(channel_max(Tn), 0.95f);
+                    if (q < smp.next()) survive = false;
+                    else rr_weight = 1.0f / q;
+                }
+                if (survive) {
+                    Tn.r *= rr_weight;
+                    Tn.g *= rr_weight;
+                    Tn.b *= rr_weight;
+                    out->alive = true;
+                    out->next_o = its.p;
+                    out->next_d = d_out;
+                    out->next.T = Tn;
+                    out->next.pdf_prev = bpdf;
+                    out->next.path_id = st.path_id;
+                    out->next.depth = depth;
+                }
+            }
+        }
+    }
+    // light sampling strategy (emitters.rs:108-175); runs even when the bounce died
+    if (use_nee) {
+        float r_sel = smp.next();
+        float r = smp.next();
+        float ux = smp.next();
+        float uy = smp.next();
+        out->nee_sampled = true;
+        LightSample ls = sample_light(sv, its.p, r_sel, r, ux, uy);
+        if (ls.valid && !mute && ip_add_ok(ip, st.depth) && ip.strategy != 1u) {
+            V3 wo = to_local(its.frame, ls.d);
+            Col f = bsdf_eval(mat, its.wi, wo);
+            Col contrib = st.T * (ls.weight * f);
+            if (!is_zero(contrib)) {
+                float w = 1.0f;
+                if (ip.strategy == 0u) {
+                    float pb = bsdf_pdf(mat, its.wi, wo);
+                    w = ls.pdf / (pb + ls.pdf);
+                }
+                out->shadow = true;
+                out->sh_p0 = its.p;
+                out->sh_p1 = ls.p;
+                out->sh_contrib = mul_checked(contrib, w);
+            }
+        }
+    }
+    out->next.rng_n = smp.n;
+}
+
+} // namespace rl

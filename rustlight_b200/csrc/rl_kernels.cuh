@@ -1,0 +1,308 @@
+// rl_kernels.cuh -- the wavefront kernels (sm_100a).
+//
+// One stage per kernel over SoA queues in HBM, every record a 16-byte float4 so each access
+// is one coalesced 128-bit load/store:
+//   ray_o[i]  = {o.xyz, path_id}          ray_d[i] = {d.xyz, pdf of the sampled direction}
+//   state[i]  = {throughput.rgb, depth<<16 | rng_n}
+//   hit[i]    = {t, u, v, prim}
+//   shadow queue: sh_a[k] = {p0.xyz, path_id}  sh_b[k] = {p1.xyz, -}  sh_c[k] = {radiance.rgb, -}
+//   lacc[path_id] = {radiance.rgb, -}     per-path radiance accumulator (fixed slot)
+// Kernels are persistent: the grid is a multiple of the SM count and each CTA walks tiles of
+// 256 records; queue lengths are read from device memory.  Survivors and shadow segments are
+// stream-compacted with warp ballots + one atomicAdd per CTA tile.  The BVH and the triangle
+// records are staged in shared memory when they fit (Cornell box: 4.5 KB).
+//
+// Stages <- reference:  k_raygen  <- Path::from_sensor + Camera::generate (paths/path.rs:56-73, camera.rs:81-91)
+//                       k_trace   <- Acceleration::trace   (accel.rs:292-315)
+//                       k_shade   <- DirectionalSamplingStrategy::bounce + LightSamplingStrategy::sample
+//                                    + evalute_edge MIS (directional.rs:44-107, emitters.rs:108-175, path.rs:37-111)
+//                       k_shadow  <- Acceleration::visible (accel.rs:316-343) + edge contribution
+//                       k_accum / k_finish <- Bitmap::accumulate, scale(1/spp) (structure.rs:397-425, mod.rs:431-436)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rl_build.cuh"
+#include "rl_device.cuh"
+
+namespace rl {
+
+constexpr int kBlock = 256;
+
+struct Counters { // device-side statistics, 64-bit
+    unsigned long long hits, nee_sampled, shadow_visible, pad;
+};
+
+__device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+
+// ---- scene staging -------------------------------------------------------------------------------
+// Copies the wide nodes and the traversal records to dynamic shared memory (128-bit copies).
+__device__ __forceinline__ void stage_scene(const SceneView &sv, float4 *smem, uint32_t n_node_f4, uint32_t n_trav_f4) {
+    for (uint32_t i = threadIdx.x; i < n_node_f4; i += blockDim.x) smem[i] = ldg4(sv.nodes + i);
+    for (uint32_t i = threadIdx.x; i < n_trav_f4; i += blockDim.x) smem[n_node_f4 + i] = ldg4(sv.trav + i);
+    __syncthreads();
+}
+
+// ---- ray generation ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list, uint32_t n_paths,
+                                                   float4 *__restrict__ ray_o, float4 *__restrict__ ray_d, float4 *__restrict__ state,
+                                                   float4 *__restrict__ lacc) {
+    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n_paths; id += gridDim.x * blockDim.x) {
+        uint32_t s_local = id / ip.npix, lp = id - s_local * ip.npix;
+        uint32_t pixel = __ldg(pixel_list + lp);
+        uint32_t px = pixel % ip.img_w, py = pixel / ip.img_w;
+        Sampler smp = make_sampler(ip.seed_h, pixel, ip.sample_base + s_local, 0u);
+        float jx = smp.next();
+        float jy = smp.next();
+        V3 o, d;
+        camera_generate(sv, (float)px + jx, (float)py + jy, &o, &d);
+        ray_o[id] = make_float4(o.x, o.y, o.z, u2f(id));
+        ray_d[id] = make_float4(d.x, d.y, d.z, 1.0f);
+        state[id] = make_float4(1.0f, 1.0f, 1.0f, u2f((1u << 16) | smp.n));
+        lacc[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
+// ---- closest-hit traversal ------------------------------------------------------------------------
+template <bool SMEM>
+__global__ void __launch_bounds__(kBlock) k_trace(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
+                                                  const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t n_node_f4,
+                                                  uint32_t n_trav_f4) {
+    extern __shared__ float4 smem[];
+    const float4 *nodes = sv.nodes, *trav = sv.trav;
+    if (SMEM) {
+        stage_scene(sv, smem, n_node_f4, n_trav_f4);
+        nodes = smem;
+        trav = smem + n_node_f4;
+    }
+    const uint32_t n = *count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 ro = ray_o[i], rd = ray_d[i];
+        HitRec h = trace_closest(sv, nodes, trav, xyz(ro), xyz(rd));
+        hit[i] = make_float4(h.t, h.u, h.v, u2f(h.prim));
+    }
+}
+
+// ---- block-level compaction helper ---------------------------------------------------------------
+// Returns this thread's slot in the output queue (valid when flag), reserving the CTA's range
+// with one atomicAdd.  `scratch` is 2*(kBlock/32)+2 uint32 of shared memory.
+__device__ __forceinline__ uint32_t block_compact(bool flag, uint32_t *global_count, uint32_t *warp_tot, uint32_t *base_slot) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned m = __ballot_sync(0xffffffffu, flag);
+    uint32_t in_warp = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < kBlock / 32; w++) {
+            uint32_t c = warp_tot[w];
+            warp_tot[w] = tot;
+            tot += c;
+        }
+        *base_slot = tot ? atomicAdd(global_count, tot) : 0u;
+    }
+    __syncthreads();
+    uint32_t slot = *base_slot + warp_tot[warp] + in_warp;
+    __syncthreads(); // scratch is reused by the next call
+    return slot;
+}
+
+// ---- shade: surface interaction, arrival emission, BSDF sample + RR, NEE sample ------------------
+__global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
+                                                  const uint32_t *__restrict__ count_in, const float4 *__restrict__ ray_o,
+                                                  const float4 *__restrict__ ray_d, const float4 *__restrict__ state,
+                                                  const float4 *__restrict__ hit, float4 *__restrict__ out_o, float4 *__restrict__ out_d,
+                                                  float4 *__restrict__ out_state, uint32_t *count_out, float4 *__restrict__ sh_a,
+                                                  float4 *__restrict__ sh_b, float4 *__restrict__ sh_c, uint32_t *count_shadow,
+                                                  float4 *__restrict__ lacc, Counters *counters) {
+    __shared__ uint32_t s_warp[kBlock / 32];
+    __shared__ uint32_t s_base;
+    const uint32_t n = *count_in;
+    const uint32_t n_tiles = (n + kBlock - 1) / kBlock;
+    uint32_t c_hits = 0, c_nee = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t i = tile * kBlock + threadIdx.x;
+        StepOut so;
+        so.alive = false;
+        so.shadow = false;
+        uint32_t pid = 0;
+        if (i < n) {
+            float4 ro = ray_o[i], rd = ray_d[i], st4 = state[i], h4 = hit[i];
+            HitRec h;
+            h.t = h4.x, h.u = h4.y, h.v = h4.z, h.prim = f2u(h4.w);
+            PathState st;
+            st.T = Col{st4.x, st4.y, st4.z};
+            st.pdf_prev = rd.w;
+            st.path_id = f2u(ro.w);
+            pid = st.path_id;
+            uint32_t packed = f2u(st4.w);
+            st.depth = packed >> 16;
+            st.rng_n = packed & 0xffffu;
+            uint32_t s_local = st.path_id / ip.npix, lp = st.path_id - s_local * ip.npix;
+            uint32_t pixel = __ldg(pixel_list + lp);
+            path_step(sv, ip, xyz(ro), xyz(rd), h, st, pixel, ip.sample_base + s_local, &so);
+            if (h.prim != RL_MISS) c_hits++;
+            if (so.nee_sampled) c_nee++;
+            if (so.has_add) {
+                float4 l = lacc[st.path_id];
+                l.x += so.add.r, l.y += so.add.g, l.z += so.add.b;
+                lacc[st.path_id] = l;
+            }
+            if (so.alive && (so.next.depth >= 0xfff0u || so.next.rng_n >= 0xfff0u)) so.alive = false; // packing guard
+        }
+        uint32_t slot = block_compact(so.alive, count_out, s_warp, &s_base);
+        if (so.alive) {
+            out_o[slot] = make_float4(so.next_o.x, so.next_o.y, so.next_o.z, u2f(so.next.path_id));
+            out_d[slot] = make_float4(so.next_d.x, so.next_d.y, so.next_d.z, so.next.pdf_prev);
+            out_state[slot] = make_float4(so.next.T.r, so.next.T.g, so.next.T.b, u2f((so.next.depth << 16) | so.next.rng_n));
+        }
+        uint32_t sslot = block_compact(so.shadow, count_shadow, s_warp, &s_base);
+        if (so.shadow) {
+            sh_a[sslot] = make_float4(so.sh_p0.x, so.sh_p0.y, so.sh_p0.z, u2f(pid));
+            sh_b[sslot] = make_float4(so.sh_p1.x, so.sh_p1.y, so.sh_p1.z, 0.0f);
+            sh_c[sslot] = make_float4(so.sh_contrib.r, so.sh_contrib.g, so.sh_contrib.b, 0.0f);
+        }
+    }
+    // per-CTA statistics: warp reduce, one atomic per warp
+    for (int off = 16; off > 0; off >>= 1) {
+        c_hits += __shfl_down_sync(0xffffffffu, c_hits, off);
+        c_nee += __shfl_down_sync(0xffffffffu, c_nee, off);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        if (c_hits) atomicAdd(&counters->hits, (unsigned long long)c_hits);
+        if (c_nee) atomicAdd(&counters->nee_sampled, (unsigned long long)c_nee);
+    }
+}
+
+// ---- shadow rays + NEE resolve ---------------------------------------------------------------------
+template <bool SMEM>
+__global__ void __launch_bounds__(kBlock) k_shadow(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ sh_a,
+                                                   const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c,
+                                                   float4 *__restrict__ lacc, Counters *counters, uint32_t n_node_f4, uint32_t n_trav_f4) {
+    extern __shared__ float4 smem[];
+    const float4 *nodes = sv.nodes, *trav = sv.trav;
+    if (SMEM) {
+        stage_scene(sv, smem, n_node_f4, n_trav_f4);
+        nodes = smem;
+        trav = smem + n_node_f4;
+    }
+    const uint32_t n = *count;
+    uint32_t c_vis = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 a = sh_a[i], b = sh_b[i];
+        if (trace_visible(sv, nodes, trav, xyz(a), xyz(b))) {
+            float4 c = sh_c[i];
+            uint32_t pid = f2u(a.w);
+            float4 l = lacc[pid];
+            l.x += c.x, l.y += c.y, l.z += c.z;
+            lacc[pid] = l;
+            c_vis++;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) c_vis += __shfl_down_sync(0xffffffffu, c_vis, off);
+    if ((threadIdx.x & 31u) == 0 && c_vis) atomicAdd(&counters->shadow_visible, (unsigned long long)c_vis);
+}
+
+// ---- per-pixel accumulation in sample order (Bitmap::accumulate, structure.rs:397-402) ------------
+__global__ void __launch_bounds__(kBlock) k_accum(const float4 *__restrict__ lacc, uint32_t npix, uint32_t n_samples, float4 *__restrict__ img_sum,
+                                                  int first_batch) {
+    for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < npix; lp += gridDim.x * blockDim.x) {
+        float4 s = first_batch ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : img_sum[lp];
+        for (uint32_t k = 0; k < n_samples; k++) {
+            float4 l = lacc[(size_t)k * npix + lp];
+            s.x += l.x, s.y += l.y, s.z += l.z;
+        }
+        img_sum[lp] = s;
+    }
+}
+// im_block.scale(1/spp) (integrators/mod.rs:436) + scatter into the full frame
+__global__ void __launch_bounds__(kBlock) k_finish(const float4 *__restrict__ img_sum, const uint32_t *__restrict__ pixel_list, uint32_t npix,
+                                                   float inv_spp, float *__restrict__ out_rgb) {
+    for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < npix; lp += gridDim.x * blockDim.x) {
+        float4 s = img_sum[lp];
+        uint32_t pixel = pixel_list[lp];
+        out_rgb[3 * (size_t)pixel + 0] = s.x * inv_spp;
+        out_rgb[3 * (size_t)pixel + 1] = s.y * inv_spp;
+        out_rgb[3 * (size_t)pixel + 2] = s.z * inv_spp;
+    }
+}
+
+// ---- Acceleration::{trace, visible} on caller-provided rays (rl_trace / rl_visible) ---------------
+__global__ void __launch_bounds__(kBlock) k_pack_rays(const float *__restrict__ o, const float *__restrict__ d, uint32_t n, float4 *ray_o, float4 *ray_d) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        ray_o[i] = make_float4(o[3 * i], o[3 * i + 1], o[3 * i + 2], u2f(i));
+        ray_d[i] = make_float4(d[3 * i], d[3 * i + 1], d[3 * i + 2], 1.0f);
+    }
+}
+__global__ void __launch_bounds__(kBlock) k_primary_rays(SceneView sv, uint32_t w, uint32_t h, float4 *ray_o, float4 *ray_d) {
+    uint32_t n = w * h;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t px = i % w, py = i / w;
+        V3 o, d;
+        camera_generate(sv, (float)px + 0.5f, (float)py + 0.5f, &o, &d);
+        ray_o[i] = make_float4(o.x, o.y, o.z, u2f(i));
+        ray_d[i] = make_float4(d.x, d.y, d.z, 1.0f);
+    }
+}
+__global__ void __launch_bounds__(kBlock) k_visible_batch(SceneView sv, const float *__restrict__ p0, const float *__restrict__ p1, uint32_t n,
+                                                          unsigned char *out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        V3 a = V3{p0[3 * i], p0[3 * i + 1], p0[3 * i + 2]}, b = V3{p1[3 * i], p1[3 * i + 1], p1[3 * i + 2]};
+        out[i] = trace_visible(sv, sv.nodes, sv.trav, a, b) ? 1 : 0;
+    }
+}
+
+// ---- LBVH build -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_morton(const float4 *__restrict__ verts, uint32_t ntris, V3 smin, V3 sinv, uint64_t *keys) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < ntris; p += gridDim.x * blockDim.x) {
+        V3 lo, hi;
+        tri_bounds(verts, p, &lo, &hi);
+        keys[p] = morton_key(lo, hi, smin, sinv, p);
+    }
+}
+__global__ void __launch_bounds__(kBlock) k_tri_setup(const float4 *__restrict__ verts, const uint64_t *__restrict__ keys, uint32_t ntris, float4 *trav,
+                                                      float4 *shade, float4 *leaf_lo, float4 *leaf_hi) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < ntris; s += gridDim.x * blockDim.x) {
+        uint32_t prim = (uint32_t)(keys[s] & 0xffffffffull);
+        tri_setup(verts, prim, s, trav, shade);
+        V3 lo, hi;
+        tri_bounds(verts, prim, &lo, &hi);
+        leaf_lo[s] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+        leaf_hi[s] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    }
+}
+__global__ void __launch_bounds__(kBlock) k_karras(const uint64_t *__restrict__ keys, int ntris, int2 *children, int *parent_of_node, int *parent_of_leaf) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntris - 1; i += gridDim.x * blockDim.x) {
+        int l, r;
+        karras_node(keys, ntris, i, &l, &r);
+        children[i] = make_int2(l, r);
+        if (l < 0) parent_of_leaf[~l] = i;
+        else parent_of_node[l] = i;
+        if (r < 0) parent_of_leaf[~r] = i;
+        else parent_of_node[r] = i;
+        if (i == 0) parent_of_node[0] = -1;
+    }
+}
+// Bottom-up fit: the second thread to reach a node owns it (atomic flag), merges the two child
+// boxes, writes the wide node and continues to the parent.
+__global__ void __launch_bounds__(kBlock) k_fit(int ntris, const int2 *__restrict__ children, const int *__restrict__ parent_of_node,
+                                                const int *__restrict__ parent_of_leaf, const float4 *__restrict__ leaf_lo,
+                                                const float4 *__restrict__ leaf_hi, float4 *node_lo, float4 *node_hi, int *flags, float4 *nodes) {
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < ntris; s += gridDim.x * blockDim.x) {
+        int node = parent_of_leaf[s];
+        while (node >= 0) {
+            if (atomicAdd(&flags[node], 1) == 0) break; // first arrival: the sibling subtree is not ready yet
+            __threadfence();
+            int2 ch = children[node];
+            // boxes written by other SMs: read through L2 (__ldcg), L1 may hold a stale line
+            float4 lo0 = ch.x < 0 ? leaf_lo[~ch.x] : __ldcg(&node_lo[ch.x]), hi0 = ch.x < 0 ? leaf_hi[~ch.x] : __ldcg(&node_hi[ch.x]);
+            float4 lo1 = ch.y < 0 ? leaf_lo[~ch.y] : __ldcg(&node_lo[ch.y]), hi1 = ch.y < 0 ? leaf_hi[~ch.y] : __ldcg(&node_hi[ch.y]);
+            write_wide_node(nodes, node, xyz(lo0), xyz(hi0), xyz(lo1), xyz(hi1), ch.x, ch.y);
+            node_lo[node] = make_float4(fminf(lo0.x, lo1.x), fminf(lo0.y, lo1.y), fminf(lo0.z, lo1.z), 0.0f);
+            node_hi[node] = make_float4(fmaxf(hi0.x, hi1.x), fmaxf(hi0.y, hi1.y), fmaxf(hi0.z, hi1.z), 0.0f);
+            __threadfence();
+            node = parent_of_node[node];
+        }
+    }
+}
+
+} // namespace rl

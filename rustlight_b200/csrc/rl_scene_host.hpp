@@ -1,0 +1,189 @@
+// rl_scene_host.hpp -- flattens an rl_scene_desc into the float4 tables of rl_device.cuh.
+//
+// Host-side, once per scene (the reference does the same work in Mesh::new, geometry.rs:122-182,
+// and Scene::build_emitters, scene.rs:53-123).  Sequential f32 accumulations (the area CDFs)
+// are done here in the reference's order; compile with -ffp-contract=off.  The per-triangle
+// traversal records and the LBVH are built on the device (rl_build.cuh / rl_kernels.cu).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rl_b200.h"
+#include "rl_device.cuh"
+
+namespace rl {
+
+struct HostScene {
+    uint32_t ntris = 0, nmeshes = 0, n_emitters = 0;
+    std::vector<float4> verts;     // 3 per prim
+    std::vector<float4> shade;     // 4 per prim; [0].xyz (n_geo) filled by the device setup kernel
+    std::vector<float4> mats;      // 4 per mesh
+    std::vector<float4> emit_info; // 1 per emitter
+    std::vector<float> emit_cdf;   // n_emitters + 1
+    std::vector<float> area_cdf;   // concatenated
+    float root_min[3], root_max[3]; // reference root box (padded per-triangle boxes, geometry.rs:423-439)
+    float raw_min[3], raw_max[3];   // plain vertex bounds (Morton normalisation)
+    float abs_max = 0;
+    float s2c[16], c2w[16], cam_pos[3];
+    uint32_t img_w = 0, img_h = 0;
+};
+
+inline float4 f4(float x, float y, float z, float w) {
+    float4 r;
+    r.x = x, r.y = y, r.z = z, r.w = w;
+    return r;
+}
+
+// Distribution1DConstruct::normalize, math.rs:418-441
+inline float dist1d_normalize(const std::vector<float> &elements, std::vector<float> &cdf) {
+    cdf.clear();
+    float cur = 0.0f;
+    for (float e : elements) {
+        cdf.push_back(cur);
+        cur += e / (float)elements.size();
+    }
+    cdf.push_back(cur);
+    if (cur != 0.0f)
+        for (float &x : cdf) x /= cur;
+    cdf.back() = 1.0f;
+    return cur; // func_int
+}
+
+inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::string &err) {
+    if (!desc || !desc->meshes || desc->nmeshes == 0) {
+        err = "empty scene";
+        return false;
+    }
+    if (desc->has_volume) {
+        err = "scene.volume must be None on this path";
+        return false;
+    }
+    if (desc->has_environment) {
+        err = "environment emitters are outside the hot path";
+        return false;
+    }
+    if (desc->camera.width == 0 || desc->camera.height == 0) {
+        err = "empty image";
+        return false;
+    }
+    hs = HostScene();
+    hs.nmeshes = desc->nmeshes;
+    hs.img_w = desc->camera.width;
+    hs.img_h = desc->camera.height;
+    std::memcpy(hs.s2c, desc->camera.sample_to_camera, 64);
+    std::memcpy(hs.c2w, desc->camera.to_world, 64);
+    { // Camera::position = to_world.transform_point(0,0,0), camera.rs:140-142
+        float h[4];
+        m4_mul_v4(hs.c2w, 0.0f, 0.0f, 0.0f, 1.0f, h);
+        float iw = 1.0f / h[3];
+        hs.cam_pos[0] = h[0] * iw, hs.cam_pos[1] = h[1] * iw, hs.cam_pos[2] = h[2] * iw;
+    }
+    for (int a = 0; a < 3; a++) {
+        hs.root_min[a] = hs.raw_min[a] = RL_F32_MAX;
+        hs.root_max[a] = hs.raw_max[a] = -RL_F32_MAX;
+    }
+    struct EmitterTmp {
+        uint32_t mesh, first_prim, ntris, cdf_off;
+        float flux_max;
+    };
+    std::vector<EmitterTmp> emitters;
+    std::vector<float> mesh_inv_area(desc->nmeshes, 0.0f);
+    uint32_t first = 0;
+    for (uint32_t mi = 0; mi < desc->nmeshes; mi++) {
+        const rl_mesh_desc &m = desc->meshes[mi];
+        if (!m.P || !m.idx || m.ntris == 0 || m.nverts == 0) {
+            err = "mesh without geometry";
+            return false;
+        }
+        if (m.mat.kind != RL_BSDF_DIFFUSE && m.mat.kind != RL_BSDF_PHONG) {
+            err = "unsupported BSDF kind";
+            return false;
+        }
+        std::vector<float> areas;
+        for (uint32_t t = 0; t < m.ntris; t++) {
+            uint32_t id[3] = {m.idx[3 * t], m.idx[3 * t + 1], m.idx[3 * t + 2]};
+            V3 v[3];
+            for (int k = 0; k < 3; k++) {
+                if (id[k] >= m.nverts) {
+                    err = "triangle index out of range";
+                    return false;
+                }
+                v[k] = V3{m.P[3 * id[k]], m.P[3 * id[k] + 1], m.P[3 * id[k] + 2]};
+                hs.verts.push_back(f4(v[k].x, v[k].y, v[k].z, 0.0f));
+            }
+            // shading record: n_geo slot (device fills xyz), mesh id, vertex normals
+            hs.shade.push_back(f4(0.0f, 0.0f, 0.0f, u2f(mi)));
+            for (int k = 0; k < 3; k++) {
+                if (m.N) hs.shade.push_back(f4(m.N[3 * id[k]], m.N[3 * id[k] + 1], m.N[3 * id[k] + 2], k == 0 ? u2f(1u) : 0.0f));
+                else hs.shade.push_back(f4(0.0f, 0.0f, 0.0f, 0.0f));
+            }
+            // bounds: compute_aabb_tri (geometry.rs:423-439) for the reference root box
+            float lo[3], hi[3];
+            for (int a = 0; a < 3; a++) {
+                float c0 = a == 0 ? v[0].x : (a == 1 ? v[0].y : v[0].z);
+                float c1 = a == 0 ? v[1].x : (a == 1 ? v[1].y : v[1].z);
+                float c2 = a == 0 ? v[2].x : (a == 1 ? v[2].y : v[2].z);
+                lo[a] = fminf(fminf(c0, c1), c2);
+                hi[a] = fmaxf(fmaxf(c0, c1), c2);
+                hs.raw_min[a] = fminf(hs.raw_min[a], lo[a]);
+                hs.raw_max[a] = fmaxf(hs.raw_max[a], hi[a]);
+                if (hi[a] - lo[a] < RL_EPSILON) {
+                    hi[a] += RL_EPSILON;
+                    lo[a] -= RL_EPSILON;
+                }
+                hs.root_min[a] = fminf(hs.root_min[a], lo[a]);
+                hs.root_max[a] = fmaxf(hs.root_max[a], hi[a]);
+            }
+            areas.push_back(magnitude(cross(v[1] - v[0], v[2] - v[0])) * 0.5f); // Mesh::new, geometry.rs:136
+        }
+        // Mesh.cdf, total(), pdf() = 1/total  (geometry.rs:179,223-225; math.rs:484-486)
+        std::vector<float> cdf;
+        float func_int = dist1d_normalize(areas, cdf);
+        float total = func_int * (float)(cdf.size() - 1);
+        mesh_inv_area[mi] = 1.0f / total;
+        if (m.emission_kind != 0) {
+            EmitterTmp e;
+            e.mesh = mi, e.first_prim = first, e.ntris = m.ntris, e.cdf_off = (uint32_t)hs.area_cdf.size();
+            // Mesh::flux = total * Le * PI, emitter.rs:591-599; channel_max for the emitter CDF, scene.rs:103-111
+            float fr = (m.emission[0] * total), fg = (m.emission[1] * total), fb = (m.emission[2] * total);
+            Col fl = mul_checked(Col{fr, fg, fb}, RL_PI);
+            e.flux_max = channel_max(fl);
+            emitters.push_back(e);
+            hs.area_cdf.insert(hs.area_cdf.end(), cdf.begin(), cdf.end());
+        }
+        first += m.ntris;
+    }
+    hs.ntris = first;
+    hs.n_emitters = (uint32_t)emitters.size();
+    std::vector<float> pdf_sel(desc->nmeshes, 0.0f);
+    if (!emitters.empty()) {
+        std::vector<float> fl;
+        for (auto &e : emitters) fl.push_back(e.flux_max);
+        dist1d_normalize(fl, hs.emit_cdf);
+        for (size_t i = 0; i < emitters.size(); i++) {
+            pdf_sel[emitters[i].mesh] = hs.emit_cdf[i + 1] - hs.emit_cdf[i];
+            hs.emit_info.push_back(f4(u2f(emitters[i].mesh), u2f(emitters[i].first_prim), u2f(emitters[i].ntris), u2f(emitters[i].cdf_off)));
+        }
+    } else {
+        hs.emit_cdf = {0.0f, 1.0f};
+        hs.emit_info.push_back(f4(0, 0, 0, 0));
+        hs.area_cdf = {0.0f, 1.0f};
+    }
+    for (uint32_t mi = 0; mi < desc->nmeshes; mi++) {
+        const rl_mesh_desc &m = desc->meshes[mi];
+        hs.mats.push_back(f4(m.mat.kd[0], m.mat.kd[1], m.mat.kd[2], u2f(m.mat.kind)));
+        hs.mats.push_back(f4(m.mat.ks[0], m.mat.ks[1], m.mat.ks[2], m.mat.exponent));
+        hs.mats.push_back(f4(m.emission_kind ? m.emission[0] : 0.0f, m.emission_kind ? m.emission[1] : 0.0f,
+                             m.emission_kind ? m.emission[2] : 0.0f, u2f(m.emission_kind ? 1u : 0u)));
+        hs.mats.push_back(f4(m.mat.weight_specular, mesh_inv_area[mi], pdf_sel[mi], 0.0f));
+    }
+    float am = 0.0f;
+    for (int a = 0; a < 3; a++) am = fmaxf(am, fmaxf(fabsf(hs.raw_min[a]), fabsf(hs.raw_max[a])));
+    hs.abs_max = am;
+    return true;
+}
+
+} // namespace rl

@@ -1,0 +1,236 @@
+// emu.cpp -- serial CPU emulator of the device arithmetic (TEST INFRASTRUCTURE).
+//
+// Compiles rustlight_b200/csrc/rl_device.cuh, rl_build.cuh and rl_scene_host.hpp with g++
+// (RL_HD expands to `inline`) and drives them in the same order as the kernels of
+// rl_kernels.cuh: Morton keys -> sort -> triangle records -> Karras tree -> box fit, then per
+// path: raygen -> trace_closest -> path_step -> trace_visible, radiance accumulated per path
+// and summed per pixel in sample order.  It lets `pytest -m "not gpu"` verify on a CPU box
+// that the device code takes the same discrete decisions as the oracle.  It is never built
+// into or loaded by the product library.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rl_b200.h"
+#include "rl_build.cuh"
+#include "rl_device.cuh"
+#include "rl_scene_host.hpp"
+
+using namespace rl;
+
+struct emu_scene {
+    HostScene hs;
+    std::vector<float4> trav, nodes;
+    SceneView sv{};
+    uint32_t max_depth = 0;
+};
+
+extern "C" {
+
+emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen) {
+    auto *s = new emu_scene;
+    std::string e;
+    if (!build_host_scene(desc, s->hs, e)) {
+        if (err && errlen) {
+            std::strncpy(err, e.c_str(), errlen - 1);
+            err[errlen - 1] = 0;
+        }
+        delete s;
+        return nullptr;
+    }
+    HostScene &hs = s->hs;
+    const int n = (int)hs.ntris;
+    // k_morton
+    V3 smin = V3{hs.raw_min[0], hs.raw_min[1], hs.raw_min[2]};
+    V3 ext = V3{hs.raw_max[0] - hs.raw_min[0], hs.raw_max[1] - hs.raw_min[1], hs.raw_max[2] - hs.raw_min[2]};
+    V3 sinv = V3{ext.x > 0.0f ? 1.0f / ext.x : 0.0f, ext.y > 0.0f ? 1.0f / ext.y : 0.0f, ext.z > 0.0f ? 1.0f / ext.z : 0.0f};
+    std::vector<uint64_t> keys(n);
+    for (int p = 0; p < n; p++) {
+        V3 lo, hi;
+        tri_bounds(hs.verts.data(), p, &lo, &hi);
+        keys[p] = morton_key(lo, hi, smin, sinv, (uint32_t)p);
+    }
+    std::sort(keys.begin(), keys.end()); // cub::DeviceRadixSort on the device
+    // k_tri_setup
+    s->trav.resize((size_t)4 * n);
+    std::vector<V3> leaf_lo(n), leaf_hi(n);
+    for (int i = 0; i < n; i++) {
+        uint32_t prim = (uint32_t)(keys[i] & 0xffffffffull);
+        tri_setup(hs.verts.data(), prim, i, s->trav.data(), hs.shade.data());
+        tri_bounds(hs.verts.data(), prim, &leaf_lo[i], &leaf_hi[i]);
+    }
+    // k_karras + k_fit
+    int n_nodes = n > 1 ? n - 1 : 1;
+    s->nodes.resize((size_t)4 * n_nodes);
+    if (n > 1) {
+        std::vector<int> cl(n - 1), cr(n - 1);
+        for (int i = 0; i < n - 1; i++) karras_node(keys.data(), n, i, &cl[i], &cr[i]);
+        std::vector<V3> nlo(n - 1), nhi(n - 1);
+        struct Rec {
+            static uint32_t fit(int node, const std::vector<int> &cl, const std::vector<int> &cr, const std::vector<V3> &llo, const std::vector<V3> &lhi,
+                                std::vector<V3> &nlo, std::vector<V3> &nhi, float4 *nodes) {
+                uint32_t d0 = 0, d1 = 0;
+                int a = cl[node], b = cr[node];
+                if (a >= 0) d0 = fit(a, cl, cr, llo, lhi, nlo, nhi, nodes);
+                if (b >= 0) d1 = fit(b, cl, cr, llo, lhi, nlo, nhi, nodes);
+                V3 lo0 = a < 0 ? llo[~a] : nlo[a], hi0 = a < 0 ? lhi[~a] : nhi[a];
+                V3 lo1 = b < 0 ? llo[~b] : nlo[b], hi1 = b < 0 ? lhi[~b] : nhi[b];
+                write_wide_node(nodes, node, lo0, hi0, lo1, hi1, a, b);
+                nlo[node] = V3{fminf(lo0.x, lo1.x), fminf(lo0.y, lo1.y), fminf(lo0.z, lo1.z)};
+                nhi[node] = V3{fmaxf(hi0.x, hi1.x), fmaxf(hi0.y, hi1.y), fmaxf(hi0.z, hi1.z)};
+                return 1 + std::max(d0, d1);
+            }
+        };
+        s->max_depth = Rec::fit(0, cl, cr, leaf_lo, leaf_hi, nlo, nhi, s->nodes.data());
+    } else {
+        const float inf = RL_F32_MAX;
+        s->nodes[0] = f4(leaf_lo[0].x, leaf_lo[0].y, leaf_lo[0].z, leaf_hi[0].x);
+        s->nodes[1] = f4(leaf_hi[0].y, leaf_hi[0].z, inf, inf);
+        s->nodes[2] = f4(inf, -inf, -inf, -inf);
+        s->nodes[3] = f4(u2f((uint32_t)~0), u2f((uint32_t)~0), 0.0f, 0.0f);
+        s->max_depth = 1;
+    }
+    SceneView &sv = s->sv;
+    sv.trav = s->trav.data(), sv.nodes = s->nodes.data(), sv.shade = hs.shade.data(), sv.verts = hs.verts.data(), sv.mats = hs.mats.data();
+    sv.emit_info = hs.emit_info.data(), sv.emit_cdf = hs.emit_cdf.data(), sv.area_cdf = hs.area_cdf.data();
+    sv.ntris = hs.ntris, sv.n_emitters = hs.n_emitters;
+    sv.root_min = V3{hs.root_min[0], hs.root_min[1], hs.root_min[2]};
+    sv.root_max = V3{hs.root_max[0], hs.root_max[1], hs.root_max[2]};
+    sv.abs_max = hs.abs_max;
+    std::memcpy(sv.s2c, hs.s2c, 64);
+    std::memcpy(sv.c2w, hs.c2w, 64);
+    sv.cam_pos = V3{hs.cam_pos[0], hs.cam_pos[1], hs.cam_pos[2]};
+    sv.img_w = (float)hs.img_w, sv.img_h = (float)hs.img_h;
+    return s;
+}
+void emu_scene_destroy(emu_scene *s) { delete s; }
+uint32_t emu_bvh_max_depth(const emu_scene *s) { return s->max_depth; }
+
+// Checks the tree: every triangle is referenced by exactly one leaf and every child box
+// contains its subtree.  Returns 0 when valid.
+int emu_bvh_validate(const emu_scene *s) {
+    const int n = (int)s->hs.ntris;
+    if (n < 2) return 0;
+    std::vector<int> seen(n, 0);
+    struct Rec {
+        static bool walk(const emu_scene *s, int node, V3 *lo, V3 *hi, std::vector<int> &seen) {
+            const float4 *nd = &s->nodes[4 * node];
+            int ch[2] = {(int)f2u(nd[3].x), (int)f2u(nd[3].y)};
+            V3 blo[2] = {V3{nd[0].x, nd[0].y, nd[0].z}, V3{nd[1].z, nd[1].w, nd[2].x}};
+            V3 bhi[2] = {V3{nd[0].w, nd[1].x, nd[1].y}, V3{nd[2].y, nd[2].z, nd[2].w}};
+            for (int q = 0; q < 2; q++) {
+                V3 clo, chi;
+                if (ch[q] < 0) {
+                    int leaf = ~ch[q];
+                    seen[leaf]++;
+                    uint32_t prim = f2u(s->trav[4 * leaf + 1].w);
+                    tri_bounds(s->hs.verts.data(), prim, &clo, &chi);
+                } else if (!walk(s, ch[q], &clo, &chi, seen)) return false;
+                if (clo.x < blo[q].x || clo.y < blo[q].y || clo.z < blo[q].z || chi.x > bhi[q].x || chi.y > bhi[q].y || chi.z > bhi[q].z) return false;
+            }
+            *lo = V3{fminf(blo[0].x, blo[1].x), fminf(blo[0].y, blo[1].y), fminf(blo[0].z, blo[1].z)};
+            *hi = V3{fmaxf(bhi[0].x, bhi[1].x), fmaxf(bhi[0].y, bhi[1].y), fmaxf(bhi[0].z, bhi[1].z)};
+            return true;
+        }
+    };
+    V3 lo, hi;
+    if (!Rec::walk(s, 0, &lo, &hi, seen)) return 1;
+    for (int i = 0; i < n; i++)
+        if (seen[i] != 1) return 2;
+    return 0;
+}
+
+int emu_trace(const emu_scene *s, size_t n, const float *o, const float *d, uint32_t *prim, float *tuv) {
+    for (size_t i = 0; i < n; i++) {
+        HitRec h = trace_closest(s->sv, s->sv.nodes, s->sv.trav, V3{o[3 * i], o[3 * i + 1], o[3 * i + 2]}, V3{d[3 * i], d[3 * i + 1], d[3 * i + 2]});
+        prim[i] = h.prim;
+        if (tuv) {
+            bool miss = h.prim == RL_MISS;
+            tuv[3 * i] = miss ? 0.0f : h.t, tuv[3 * i + 1] = miss ? 0.0f : h.u, tuv[3 * i + 2] = miss ? 0.0f : h.v;
+        }
+    }
+    return 0;
+}
+int emu_visible(const emu_scene *s, size_t n, const float *p0, const float *p1, uint8_t *out) {
+    for (size_t i = 0; i < n; i++)
+        out[i] = trace_visible(s->sv, s->sv.nodes, s->sv.trav, V3{p0[3 * i], p0[3 * i + 1], p0[3 * i + 2]}, V3{p1[3 * i], p1[3 * i + 1], p1[3 * i + 2]}) ? 1 : 0;
+    return 0;
+}
+int emu_primary_hits(const emu_scene *s, uint32_t *prim, float *tuv) {
+    uint32_t W = s->hs.img_w, H = s->hs.img_h;
+    for (uint32_t y = 0; y < H; y++)
+        for (uint32_t x = 0; x < W; x++) {
+            V3 o, d;
+            camera_generate(s->sv, (float)x + 0.5f, (float)y + 0.5f, &o, &d);
+            size_t i = (size_t)y * W + x;
+            emu_trace(s, 1, &o.x, &d.x, prim + i, tuv ? tuv + 3 * i : nullptr);
+        }
+    return 0;
+}
+
+struct emu_stats {
+    uint64_t samples, segments, shadow_rays, shadow_traced, shadow_visible, hits, max_depth_seen;
+};
+
+// The wavefront of rl_render, executed one path at a time (each path is independent).
+int emu_render(const emu_scene *s, const rl_integrator_desc *I, uint32_t spp, uint64_t seed, uint32_t rank, uint32_t nranks, float *out_rgb,
+               emu_stats *stats) {
+    if (!s || !I || spp == 0 || I->kind != RL_INTEGRATOR_PATH) return RL_ERR_INVALID;
+    const SceneView &sv = s->sv;
+    const uint32_t W = s->hs.img_w, H = s->hs.img_h;
+    IntegParams ip{};
+    ip.kind = I->kind, ip.min_depth = I->min_depth, ip.max_depth = I->max_depth, ip.rr_depth = I->rr_depth;
+    ip.strategy = I->strategy, ip.single_scattering = I->single_scattering;
+    ip.nb_bsdf_samples = I->nb_bsdf_samples, ip.nb_light_samples = I->nb_light_samples;
+    ip.seed_h = seed_hash(seed);
+    ip.sample_base = 0, ip.npix = W * H, ip.img_w = W;
+    emu_stats S{};
+    std::memset(out_rgb, 0, sizeof(float) * 3 * (size_t)W * H);
+    const float inv_spp = 1.0f / (float)spp;
+    for (uint32_t py = 0; py < H; py++)
+        for (uint32_t px = 0; px < W; px++) {
+            if (nranks > 1 && ((px / 16 + py / 16) % nranks) != rank) continue;
+            uint32_t pixel = py * W + px;
+            float sum[3] = {0.0f, 0.0f, 0.0f};
+            for (uint32_t sidx = 0; sidx < spp; sidx++) {
+                // k_raygen
+                Sampler smp = make_sampler(ip.seed_h, pixel, sidx, 0u);
+                float jx = smp.next();
+                float jy = smp.next();
+                V3 o, d;
+                camera_generate(sv, (float)px + jx, (float)py + jy, &o, &d);
+                PathState st;
+                st.T = Col{1.0f, 1.0f, 1.0f}, st.pdf_prev = 1.0f, st.path_id = 0, st.depth = 1, st.rng_n = smp.n;
+                float L[3] = {0.0f, 0.0f, 0.0f};
+                uint64_t iter = 0;
+                for (;;) {
+                    iter++;
+                    S.segments++;
+                    HitRec h = trace_closest(sv, sv.nodes, sv.trav, o, d); // k_trace
+                    if (h.prim != RL_MISS) S.hits++;
+                    StepOut so;
+                    path_step(sv, ip, o, d, h, st, pixel, sidx, &so); // k_shade
+                    if (so.has_add) L[0] += so.add.r, L[1] += so.add.g, L[2] += so.add.b;
+                    if (so.nee_sampled) S.shadow_rays++;
+                    if (so.shadow) { // k_shadow
+                        S.shadow_traced++;
+                        if (trace_visible(sv, sv.nodes, sv.trav, so.sh_p0, so.sh_p1)) {
+                            S.shadow_visible++;
+                            L[0] += so.sh_contrib.r, L[1] += so.sh_contrib.g, L[2] += so.sh_contrib.b;
+                        }
+                    }
+                    if (!so.alive) break;
+                    o = so.next_o, d = so.next_d, st = so.next;
+                }
+                S.max_depth_seen = std::max(S.max_depth_seen, iter);
+                sum[0] += L[0], sum[1] += L[1], sum[2] += L[2]; // k_accum
+                S.samples++;
+            }
+            out_rgb[3 * (size_t)pixel] = sum[0] * inv_spp, out_rgb[3 * (size_t)pixel + 1] = sum[1] * inv_spp, out_rgb[3 * (size_t)pixel + 2] = sum[2] * inv_spp; // k_finish
+        }
+    if (stats) *stats = S;
+    return 0;
+}
+
+} // extern "C"

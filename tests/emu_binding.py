@@ -1,0 +1,96 @@
+"""ctypes binding of tests/emu (serial CPU emulation of the device arithmetic; test-only)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from rustlight_b200 import _abi
+
+_HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+_SO = os.path.join(_HERE, "_build", "libemu.so")
+FP = C.POINTER(C.c_float)
+_lib = None
+
+
+class emu_stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("samples", "segments", "shadow_rays", "shadow_traced", "shadow_visible",
+                                          "hits", "max_depth_seen")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        L = C.CDLL(_SO)
+        L.emu_scene_create.restype = C.c_void_p
+        L.emu_scene_create.argtypes = [C.POINTER(_abi.rl_scene_desc), C.c_char_p, C.c_size_t]
+        L.emu_scene_destroy.argtypes = [C.c_void_p]
+        L.emu_bvh_max_depth.restype = C.c_uint32
+        L.emu_bvh_max_depth.argtypes = [C.c_void_p]
+        L.emu_bvh_validate.argtypes = [C.c_void_p]
+        L.emu_trace.argtypes = [C.c_void_p, C.c_size_t, FP, FP, C.POINTER(C.c_uint32), FP]
+        L.emu_visible.argtypes = [C.c_void_p, C.c_size_t, FP, FP, C.POINTER(C.c_uint8)]
+        L.emu_primary_hits.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), FP]
+        L.emu_render.argtypes = [C.c_void_p, C.POINTER(_abi.rl_integrator_desc), C.c_uint32, C.c_uint64, C.c_uint32,
+                                 C.c_uint32, FP, C.POINTER(emu_stats)]
+        _lib = L
+    return _lib
+
+
+def _f(a):
+    return a.ctypes.data_as(FP)
+
+
+class EmuScene:
+    def __init__(self, scene):
+        self._scene = scene
+        err = C.create_string_buffer(512)
+        self._h = lib().emu_scene_create(scene.desc, err, 512)
+        if not self._h:
+            raise RuntimeError("emu: " + err.value.decode())
+        self.width, self.height = scene.size
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().emu_scene_destroy(self._h)
+            self._h = None
+
+    def bvh_max_depth(self):
+        return lib().emu_bvh_max_depth(self._h)
+
+    def bvh_validate(self):
+        return lib().emu_bvh_validate(self._h)
+
+    def trace(self, o, d):
+        o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+        prim = np.zeros(o.shape[0], np.uint32)
+        tuv = np.zeros((o.shape[0], 3), np.float32)
+        lib().emu_trace(self._h, o.shape[0], _f(o), _f(d), prim.ctypes.data_as(C.POINTER(C.c_uint32)), _f(tuv))
+        return prim, tuv
+
+    def visible(self, p0, p1):
+        p0 = np.ascontiguousarray(p0, np.float32).reshape(-1, 3)
+        p1 = np.ascontiguousarray(p1, np.float32).reshape(-1, 3)
+        out = np.zeros(p0.shape[0], np.uint8)
+        lib().emu_visible(self._h, p0.shape[0], _f(p0), _f(p1), out.ctypes.data_as(C.POINTER(C.c_uint8)))
+        return out
+
+    def primary_hits(self):
+        n = self.width * self.height
+        prim = np.zeros(n, np.uint32)
+        tuv = np.zeros((n, 3), np.float32)
+        lib().emu_primary_hits(self._h, prim.ctypes.data_as(C.POINTER(C.c_uint32)), _f(tuv))
+        return prim.reshape(self.height, self.width), tuv.reshape(self.height, self.width, 3)
+
+    def render(self, integ, spp, seed=0, rank=0, nranks=1):
+        img = np.zeros((self.height, self.width, 3), np.float32)
+        st = emu_stats()
+        rc = lib().emu_render(self._h, C.byref(integ), spp, seed, rank, nranks, _f(img), C.byref(st))
+        if rc != 0:
+            raise ValueError(f"emu_render failed: {rc}")
+        return img, st
