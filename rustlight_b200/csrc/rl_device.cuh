@@ -370,10 +370,12 @@ RL_HD RaySlab make_slab(V3 o, V3 d, float abs_max) {
     s.inv_d = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
     float m = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), abs_max));
     float eps = 1e-5f * m + 1e-30f;
-    s.neg = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    // direction signs are taken from 1/d like AABB::intersect does (structure.rs:857): d = -0.0 gives -inf
+    const bool nx = s.inv_d.x < 0.0f, ny = s.inv_d.y < 0.0f, nz = s.inv_d.z < 0.0f;
+    s.neg = (nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u);
     // entering plane uses o shifted forward (smaller t), leaving plane uses o shifted back
-    s.o_near = V3{d.x < 0.0f ? o.x - eps : o.x + eps, d.y < 0.0f ? o.y - eps : o.y + eps, d.z < 0.0f ? o.z - eps : o.z + eps};
-    s.o_far = V3{d.x < 0.0f ? o.x + eps : o.x - eps, d.y < 0.0f ? o.y + eps : o.y - eps, d.z < 0.0f ? o.z + eps : o.z - eps};
+    s.o_near = V3{nx ? o.x - eps : o.x + eps, ny ? o.y - eps : o.y + eps, nz ? o.z - eps : o.z + eps};
+    s.o_far = V3{nx ? o.x + eps : o.x - eps, ny ? o.y + eps : o.y - eps, nz ? o.z + eps : o.z - eps};
     return s;
 }
 // Returns conservative entry distance, or a negative value on a miss, for t in [0, tmax].

@@ -1,0 +1,116 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+DATA = os.path.join(ROOT, "data")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _ensure_built():
+    """Build the CPU-side libraries once per session (host layer, oracle, emulator)."""
+    import __graft_entry__ as g
+    import subprocess
+    pkg = os.path.join(ROOT, "rustlight_b200")
+    if not os.path.exists(os.path.join(pkg, "librl_host.so")) or not os.path.exists(os.path.join(pkg, "librl_b200.so")):
+        g.build()
+    else:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "emu")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+_ensure_built()
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device in this container (GPU tests run under gpurun)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def loader():
+    from rustlight_b200 import SceneLoaderManager
+    return SceneLoaderManager()
+
+
+def load_cbox(w=None, h=None, name="cbox.pbrt"):
+    from rustlight_b200 import SceneLoaderManager
+    sc = SceneLoaderManager().load(os.path.join(DATA, name))
+    if w is not None:
+        sc.set_resolution(w, h or w)
+    return sc
+
+
+@pytest.fixture(scope="session")
+def cbox():
+    return load_cbox()
+
+
+@pytest.fixture(scope="session")
+def cbox_oracle(cbox):
+    from oracle import binding as ob
+    return ob.OracleScene(cbox)
+
+
+@pytest.fixture(scope="session")
+def cbox64():
+    return load_cbox(64, 64)
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    from rustlight_b200.device import Context
+    ctx = Context(0)
+    yield ctx
+    ctx.close()
+
+
+def soup_scene(ntris, seed=0, w=64, h=64, emissive_first=True):
+    """Random triangle soup inside the unit cube + one emissive quad, as scene JSON text."""
+    import json
+    rng = np.random.default_rng(seed)
+    meshes = []
+    per = 50
+    nm = max(1, ntris // per)
+    for m in range(nm):
+        c = rng.uniform(-0.8, 0.8, (per, 1, 3))
+        tri = c + rng.normal(scale=0.15, size=(per, 3, 3))
+        P = tri.reshape(-1, 3).astype(np.float32)
+        idx = np.arange(per * 3)
+        kd = rng.uniform(0.2, 0.8, 3)
+        meshes.append({"name": f"soup{m}", "material": {"type": "diffuse", "kd": [float(x) for x in kd]},
+                       "indices": [int(i) for i in idx], "P": [float(x) for x in P.ravel()]})
+    if emissive_first:
+        meshes.append({"name": "light", "material": {"type": "diffuse", "kd": [0, 0, 0]}, "emission": [10, 10, 10],
+                       "indices": [0, 1, 2, 0, 2, 3],
+                       "P": [-0.5, 0.95, -0.5, 0.5, 0.95, -0.5, 0.5, 0.95, 0.5, -0.5, 0.95, 0.5],
+                       "N": [0, -1, 0] * 4})
+    cam = {"width": w, "height": h, "fov": 40.0, "fov_axis": "y", "flip": False,
+           "to_world": [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 0, 0, 3.5, 1]}
+    return json.dumps({"camera": cam, "meshes": meshes})
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(np.linalg.norm(b.astype(np.float64)), 1e-30))

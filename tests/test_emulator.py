@@ -1,0 +1,124 @@
+"""Device arithmetic (rl_device.cuh / rl_build.cuh compiled for the CPU by tests/emu) vs the oracle.
+
+This is the CPU-side half of the parity argument: the functions the kernels call take the same
+discrete decisions, and produce the same radiance bits, as the oracle's stream estimator.  The
+GPU half (tests/test_gpu.py) checks that the kernels around them move the records correctly.
+"""
+import numpy as np
+import pytest
+
+import emu_binding as eb
+from conftest import load_cbox, soup_scene
+from oracle import binding as ob
+from rustlight_b200 import SceneLoaderManager, _abi
+from rustlight_b200.host import material_phong
+
+STREAM = dict(estimator=ob.EST_STREAM, accel_mode=ob.ACCEL_NAIVE)
+
+
+def _rays(n, seed, lo=-0.99, hi=0.99, shift=(0, 1, 0)):
+    rng = np.random.default_rng(seed)
+    o = (rng.uniform(lo, hi, (n, 3)) + shift).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    p1 = (rng.uniform(lo, hi, (n, 3)) + shift).astype(np.float32)
+    return o, d, p1
+
+
+def test_lbvh_is_valid(cbox):
+    esc = eb.EmuScene(cbox)
+    assert esc.bvh_validate() == 0 and 6 <= esc.bvh_max_depth() <= 36
+
+
+def test_primary_hits_exact(cbox, cbox_oracle):
+    pe, te = eb.EmuScene(cbox).primary_hits()
+    po, to = cbox_oracle.primary_hits(ob.ACCEL_NAIVE)
+    assert np.array_equal(pe, po) and np.array_equal(te, to)
+
+
+def test_random_rays_and_segments_exact(cbox, cbox_oracle):
+    esc = eb.EmuScene(cbox)
+    o, d, p1 = _rays(30000, 1)
+    pe, te = esc.trace(o, d)
+    po, to = cbox_oracle.trace(o, d, ob.ACCEL_NAIVE)
+    assert np.array_equal(pe, po) and np.array_equal(te, to)
+    assert np.array_equal(esc.visible(o, p1), cbox_oracle.visible(o, p1, ob.ACCEL_NAIVE))
+
+
+@pytest.mark.parametrize("ntris,seed", [(50, 0), (600, 1), (3000, 2)])
+def test_soup_lbvh_equals_brute_force(ntris, seed):
+    """Conservative culling: the LBVH never loses a triangle the exact test accepts."""
+    sc = SceneLoaderManager().load_string(soup_scene(ntris, seed), "json")
+    esc, osc = eb.EmuScene(sc), ob.OracleScene(sc)
+    assert esc.bvh_validate() == 0
+    o, d, p1 = _rays(6000, seed + 10, -1.2, 1.2, (0, 0, 0))
+    pe, te = esc.trace(o, d)
+    po, to = osc.trace(o, d, ob.ACCEL_NAIVE)
+    assert np.array_equal(pe, po) and np.array_equal(te, to)
+    assert np.array_equal(esc.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))
+
+
+def test_far_origin_rays_exact(cbox, cbox_oracle):
+    # origins far from the scene stress the culling epsilon (scaled by |o|)
+    esc = eb.EmuScene(cbox)
+    rng = np.random.default_rng(7)
+    tgt = (rng.uniform(-1, 1, (4000, 3)) + [0, 1, 0])
+    o = (tgt + rng.normal(size=(4000, 3)) * 300).astype(np.float32)
+    d = tgt - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    pe, te = esc.trace(o, d)
+    po, to = cbox_oracle.trace(o, d, ob.ACCEL_NAIVE)
+    assert np.array_equal(pe, po) and np.array_equal(te, to)
+
+
+def test_axis_aligned_rays_exact(cbox, cbox_oracle):
+    # zero direction components: 1/0 = inf in the slab tests
+    esc = eb.EmuScene(cbox)
+    rng = np.random.default_rng(8)
+    o = (rng.uniform(-0.9, 0.9, (3000, 3)) + [0, 1, 0]).astype(np.float32)
+    axes = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 3000)] * rng.choice([-1, 1], (3000, 1)).astype(np.float32)
+    pe, te = esc.trace(o, axes)
+    po, to = cbox_oracle.trace(o, axes, ob.ACCEL_NAIVE)
+    assert np.array_equal(pe, po) and np.array_equal(te, to)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(strategy=_abi.RL_STRATEGY_BSDF), dict(strategy=_abi.RL_STRATEGY_EMITTER),
+                                dict(max_depth=2), dict(max_depth=4, min_depth=2), dict(rr_depth=4, max_depth=9),
+                                dict(rr_depth=None), dict(single_scattering=True)])
+def test_path_render_bit_exact(kw):
+    sc = load_cbox(96, 96)
+    integ = _abi.path_desc(**kw)
+    ie, se = eb.EmuScene(sc).render(integ, 6, seed=5)
+    io, so = ob.OracleScene(sc).render(integ, 6, seed=5, cfg=ob.config(**STREAM))
+    assert (se.segments, se.hits, se.shadow_rays, se.shadow_visible) == (so.segments, so.hits, so.shadow_rays, so.nee_added)
+    assert np.array_equal(ie, io)
+
+
+def test_phong_render_bit_exact():
+    sc = load_cbox(64, 64)
+    kds = [(0.63, 0.065, 0.05), (0.14, 0.45, 0.091), (0.725, 0.71, 0.68)]
+    for mesh, kd in [(0, kds[2]), (1, kds[2]), (2, kds[2]), (3, kds[1]), (4, kds[0])]:
+        sc.set_material(mesh, material_phong([0.5 * c for c in kd], (0.3, 0.3, 0.3), 50.0))
+    integ = _abi.path_desc()
+    ie, se = eb.EmuScene(sc).render(integ, 8, seed=2)
+    io, so = ob.OracleScene(sc).render(integ, 8, seed=2, cfg=ob.config(**STREAM))
+    assert (se.segments, se.hits, se.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+    assert np.array_equal(ie, io)
+
+
+def test_soup_render_bit_exact():
+    sc = SceneLoaderManager().load_string(soup_scene(400, 4, 48, 48), "json")
+    integ = _abi.path_desc(max_depth=6)
+    ie, se = eb.EmuScene(sc).render(integ, 4, seed=1)
+    io, so = ob.OracleScene(sc).render(integ, 4, seed=1, cfg=ob.config(**STREAM))
+    assert (se.segments, se.hits, se.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+    assert np.array_equal(ie, io)
+
+
+def test_tile_partition(cbox64):
+    esc = eb.EmuScene(cbox64)
+    integ = _abi.path_desc()
+    full, _ = esc.render(integ, 3)
+    parts = [esc.render(integ, 3, rank=r, nranks=2)[0] for r in range(2)]
+    assert np.array_equal(parts[0] + parts[1], full)
+    assert not (parts[0].astype(bool) & parts[1].astype(bool)).any()

@@ -1,0 +1,255 @@
+"""GPU parity tests: everything goes through the C ABI (librl_b200.so) and is compared with the
+oracle on the same seeded inputs, with the committed golden fixtures, and -- at BASELINE.json's
+full sizes -- through size-independent properties.  Integer/index results must be identical;
+radiance must be bit-identical to the oracle's stream estimator and within 1e-3 relative L2
+(north_star tolerance) of the reference-faithful configuration."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_cbox, rel_l2, soup_scene
+from oracle import binding as ob
+from rustlight_b200 import SceneLoaderManager, _abi
+from rustlight_b200.device import Context, DeviceError, DeviceScene, IndependentSampler, IntegratorPathTracing, lib
+from rustlight_b200.host import material_phong
+
+pytestmark = pytest.mark.gpu
+
+STREAM = dict(estimator=ob.EST_STREAM, accel_mode=ob.ACCEL_NAIVE)
+TOL = 1e-3  # north_star: image within 1e-3 relative L2 of the CPU reference at matched spp
+
+
+def _rays(n, seed, lo=-0.99, hi=0.99, shift=(0, 1, 0)):
+    rng = np.random.default_rng(seed)
+    o = (rng.uniform(lo, hi, (n, 3)) + shift).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    p1 = (rng.uniform(lo, hi, (n, 3)) + shift).astype(np.float32)
+    return o, d, p1
+
+
+@pytest.fixture(scope="module")
+def cbox_dev(gpu_ctx, cbox):
+    d = DeviceScene(gpu_ctx, cbox)
+    yield d
+    d.close()
+
+
+# ---- traversal kernel: exact hit indices ------------------------------------------------------------
+def test_native_library_is_the_one_running(gpu_ctx, cbox_dev):
+    assert lib()._name.endswith("rustlight_b200/librl_b200.so")
+    bi = cbox_dev.bvh_info()
+    assert (bi.ntris, bi.nnodes, bi.nleaves, bi.smem_resident) == (36, 35, 36, 1) and bi.max_depth <= 36
+
+
+def test_primary_ray_grid_exact(cbox_dev, cbox_oracle):
+    """north_star: exact match on ray/triangle hit indices for the fixed primary-ray test."""
+    pg, tg = cbox_dev.primary_hits()
+    po, to = cbox_oracle.primary_hits(ob.ACCEL_NAIVE)
+    assert np.array_equal(pg, po) and np.array_equal(tg, to)
+    g = np.load(os.path.join(GOLDEN, "cbox512_primary_hits.npz"))
+    assert np.array_equal(np.where(pg == 0xFFFFFFFF, 255, pg).astype(np.uint8), g["prim"])
+    assert np.array_equal(tg[::8, ::8, 0], g["t_sub8"])
+    # vs the reference's own BVH order: identical except on exact ties in t (wall seams)
+    pb, tb = cbox_oracle.primary_hits(ob.ACCEL_BVH)
+    diff = pg != pb
+    assert diff.sum() < 200 and np.array_equal(tg[..., 0], tb[..., 0])
+
+
+def test_random_rays_exact(cbox_dev, cbox_oracle):
+    o, d, p1 = _rays(300000, 1)
+    pg, tg = cbox_dev.trace(o, d)
+    po, to = cbox_oracle.trace(o, d, ob.ACCEL_NAIVE)
+    assert np.array_equal(pg, po) and np.array_equal(tg, to)
+    assert np.array_equal(cbox_dev.visible(o, p1), cbox_oracle.visible(o, p1, ob.ACCEL_NAIVE))
+
+
+def test_edge_case_rays(cbox_dev, cbox_oracle):
+    rng = np.random.default_rng(3)
+    o = (rng.uniform(-0.9, 0.9, (5000, 3)) + [0, 1, 0]).astype(np.float32)
+    axes = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 5000)] * rng.choice([-1, 1], (5000, 1)).astype(np.float32)  # +-0 components
+    tgt = (rng.uniform(-1, 1, (5000, 3)) + [0, 1, 0])
+    far = (tgt + rng.normal(size=(5000, 3)) * 300).astype(np.float32)
+    dfar = tgt - far
+    dfar = (dfar / np.linalg.norm(dfar, axis=1, keepdims=True)).astype(np.float32)
+    for oo, dd in ((o, axes), (far, dfar)):
+        pg, tg = cbox_dev.trace(oo, dd)
+        po, to = cbox_oracle.trace(oo, dd, ob.ACCEL_NAIVE)
+        assert np.array_equal(pg, po) and np.array_equal(tg, to)
+    # empty input, zero-length segment, segment shorter than tnear
+    assert cbox_dev.trace(np.zeros((0, 3)), np.zeros((0, 3)))[0].size == 0
+    p = np.float32([[0, 1, 0], [0, 1, 0]])
+    q = np.float32([[0, 1, 0], [0, 1, 5e-5]])
+    assert np.array_equal(cbox_dev.visible(p, q), cbox_oracle.visible(p, q, ob.ACCEL_NAIVE))
+
+
+@pytest.mark.parametrize("ntris,seed", [(1, 0), (2, 1), (50, 2), (600, 3), (4000, 4)])
+def test_soup_scenes_exact(gpu_ctx, ntris, seed):
+    """Ragged sizes incl. a single triangle; 4000 triangles do not fit shared memory (global-memory path)."""
+    if ntris <= 2:
+        import json
+        tris = [[0, 0, 0, 1, 0, 0, 0, 1, 0], [0.2, 0.2, -0.5, 1.2, 0.2, -0.5, 0.2, 1.2, -0.5]][:ntris]
+        meshes = [{"material": {"type": "diffuse", "kd": [0.5] * 3}, "emission": [1, 1, 1], "indices": [0, 1, 2], "P": t} for t in tris]
+        txt = json.dumps({"camera": {"width": 16, "height": 16, "fov": 40, "to_world": [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 0.3, 0.3, 3, 1]}, "meshes": meshes})
+    else:
+        txt = soup_scene(ntris, seed)
+    sc = SceneLoaderManager().load_string(txt, "json")
+    dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
+    bi = dev.bvh_info()
+    assert bi.ntris == sc.nb_triangles and bi.smem_resident == (1 if ntris < 700 else 0)
+    o, d, p1 = _rays(50000, seed + 20, -1.2, 1.2, (0, 0, 0))
+    pg, tg = dev.trace(o, d)
+    po, to = osc.trace(o, d, ob.ACCEL_NAIVE)
+    assert np.array_equal(pg, po) and np.array_equal(tg, to)
+    assert np.array_equal(dev.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))
+    pg, tg = dev.primary_hits()
+    po, to = osc.primary_hits(ob.ACCEL_NAIVE)
+    assert np.array_equal(pg, po) and np.array_equal(tg, to)
+    dev.close()
+
+
+# ---- the wavefront: radiance parity ---------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [dict(), dict(strategy=_abi.RL_STRATEGY_BSDF), dict(strategy=_abi.RL_STRATEGY_EMITTER),
+                                dict(max_depth=2), dict(max_depth=4, min_depth=2), dict(rr_depth=4, max_depth=9),
+                                dict(rr_depth=None), dict(single_scattering=True)])
+def test_path_render_bit_exact_vs_oracle(gpu_ctx, kw):
+    sc = load_cbox(200, 136)  # ragged: neither dimension is a multiple of the 16x16 tile
+    dev = DeviceScene(gpu_ctx, sc)
+    integ = _abi.path_desc(**kw)
+    img, st = dev.render(integ, 6, seed=5, batch_spp=4)  # 2 batches, the second one ragged
+    ref, so = ob.OracleScene(sc).render(integ, 6, seed=5, cfg=ob.config(**STREAM))
+    assert (st.samples, st.segments, st.hits, st.shadow_rays, st.shadow_visible) == (so.samples, so.segments, so.hits, so.shadow_rays, so.nee_added)
+    assert np.array_equal(img, ref)
+    dev.close()
+
+
+def test_cbox_512_spp16_vs_faithful_oracle(cbox_dev, cbox_oracle):
+    """BASELINE configs[0]: path -n 16, 512x512.  GPU vs the reference-faithful oracle configuration
+    (graph estimator, BVHAccel order, glibc math) on the same counter-based stream."""
+    integ = _abi.path_desc()
+    img, st = cbox_dev.render(integ, 16, seed=0)
+    ref, so = cbox_oracle.render(integ, 16, seed=0, cfg=ob.config(math_mode=ob.MATH_LIBM, accel_mode=ob.ACCEL_BVH, estimator=ob.EST_GRAPH))
+    r = rel_l2(img, ref)
+    assert r < TOL, r
+    assert abs(int(st.segments) - int(so.segments)) <= 32 and abs(int(st.shadow_rays) - int(so.shadow_rays)) <= 32
+    ex, se = cbox_oracle.render(integ, 16, seed=0, cfg=ob.config(**STREAM))
+    assert np.array_equal(img, ex) and st.segments == se.segments
+
+
+def test_golden_fixture(gpu_ctx):
+    g = np.load(os.path.join(GOLDEN, "cbox64_spp16_seed0.npz"))
+    dev = DeviceScene(gpu_ctx, load_cbox(64, 64))
+    for name, integ in [("path", _abi.path_desc()), ("path_bsdf", _abi.path_desc(strategy=_abi.RL_STRATEGY_BSDF)), ("path_d4", _abi.path_desc(max_depth=4))]:
+        img, st = dev.render(integ, 16, seed=0)
+        assert rel_l2(img, g[name]) < TOL
+        assert abs(int(st.segments) - int(g[name + "_counts"][0])) <= 4
+    dev.close()
+
+
+def test_phong_walls_bit_exact(gpu_ctx):
+    """BASELINE configs[2]: Cornell box with glossy Phong walls (kd = 0.5*wall colour, ks = 0.3, exponent 50)."""
+    sc = load_cbox(128, 128)
+    kds = [(0.63, 0.065, 0.05), (0.14, 0.45, 0.091), (0.725, 0.71, 0.68)]
+    for mesh, kd in [(0, kds[2]), (1, kds[2]), (2, kds[2]), (3, kds[1]), (4, kds[0])]:
+        sc.set_material(mesh, material_phong([0.5 * c for c in kd], (0.3, 0.3, 0.3), 50.0))
+    dev = DeviceScene(gpu_ctx, sc)
+    integ = _abi.path_desc()
+    img, st = dev.render(integ, 8, seed=2)
+    ref, so = ob.OracleScene(sc).render(integ, 8, seed=2, cfg=ob.config(**STREAM))
+    assert (st.segments, st.hits, st.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+    assert np.array_equal(img, ref)
+    faithful, _ = ob.OracleScene(sc).render(integ, 8, seed=2, cfg=ob.config(math_mode=ob.MATH_LIBM))
+    assert rel_l2(img, faithful) < TOL
+    dev.close()
+
+
+def test_soup_render_bit_exact(gpu_ctx):
+    sc = SceneLoaderManager().load_string(soup_scene(1500, 4, 64, 64), "json")
+    dev = DeviceScene(gpu_ctx, sc)
+    integ = _abi.path_desc(max_depth=6)
+    img, st = dev.render(integ, 4, seed=1)
+    ref, so = ob.OracleScene(sc).render(integ, 4, seed=1, cfg=ob.config(**STREAM))
+    assert (st.segments, st.hits, st.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+    assert np.array_equal(img, ref)
+    dev.close()
+
+
+# ---- properties at BASELINE.json's full size (configs[1]: 1024x1024, 128 spp) ---------------------------------
+@pytest.fixture(scope="module")
+def c2(gpu_ctx):
+    sc = load_cbox().scale_image(2.0)  # CLI `-s 2`: 1024x1024, matrices untouched
+    dev = DeviceScene(gpu_ctx, sc)
+    yield sc, dev
+    dev.close()
+
+
+def test_full_size_deterministic_and_batch_independent(c2):
+    sc, dev = c2
+    integ = _abi.path_desc()
+    a, sa = dev.render(integ, 128, seed=0)
+    b, sb = dev.render(integ, 128, seed=0, batch_spp=5)  # different wavefront batching, ragged last batch
+    assert np.array_equal(a, b) and sa.segments == sb.segments and sa.shadow_visible == sb.shadow_visible
+    assert sa.samples == 1024 * 1024 * 128 and sa.hits <= sa.segments and sa.shadow_visible <= sa.shadow_rays == sa.hits
+    assert np.isfinite(a).all() and (a >= 0).all()
+    # the same pixels at 1/64 of the work agree within Monte-Carlo noise; the estimate is consistent
+    c, _ = dev.render(integ, 2, seed=7)
+    assert a.mean(axis=(0, 1)) == pytest.approx(c.mean(axis=(0, 1)), rel=0.01)
+    # against the oracle on a sub-sample of rows (bit-exact, same stream)
+    osc = ob.OracleScene(sc)
+    for px, py in [(5, 7), (512, 512), (1000, 30), (300, 900)]:
+        acc = np.zeros(3, np.float32)
+        for s in range(128):
+            rgb, *_ = osc.path_sample(integ, 0, px, py, s, ob.config(**STREAM))
+            acc = (acc + rgb).astype(np.float32)
+        assert np.array_equal(acc * np.float32(1.0 / 128.0), a[py, px])
+
+
+def test_full_size_strategies_are_unbiased(c2):
+    _, dev = c2
+    m = [dev.render(_abi.path_desc(strategy=s), 8, seed=s)[0].mean(axis=(0, 1)) for s in (0, 1, 2)]
+    assert np.allclose(m[0], m[1], rtol=0.01) and np.allclose(m[0], m[2], rtol=0.01)
+
+
+def test_tile_partition_sums_to_the_full_image(cbox):
+    """Multi-GPU decomposition on one device: rank images are disjoint and add up exactly."""
+    integ = _abi.path_desc()
+    full_ctx = Context(0)
+    full, sf = DeviceScene(full_ctx, cbox).render(integ, 4, seed=9)
+    parts, segs = [], 0
+    for r in range(3):
+        ctx = Context(0, nranks=3, rank=r)
+        img, st = DeviceScene(ctx, cbox).render(integ, 4, seed=9)
+        parts.append(img)
+        segs += st.segments
+        ctx.close()
+    assert np.array_equal(parts[0] + parts[1] + parts[2], full) and segs == sf.segments
+    assert not (parts[0].astype(bool) & parts[1].astype(bool)).any()
+    full_ctx.close()
+
+
+def test_integrator_mirror_api(gpu_ctx, cbox64):
+    cbox64.nb_samples = 4
+    bc = IntegratorPathTracing().compute(IndependentSampler(3), DeviceScene(gpu_ctx, cbox64))
+    ref, _ = ob.OracleScene(cbox64).render(_abi.path_desc(), 4, seed=3, cfg=ob.config(**STREAM))
+    assert np.array_equal(bc.values["primal"], ref)
+
+
+# ---- error behaviour (the reference panics; the C ABI returns codes) ---------------------------------------------
+def test_error_codes(gpu_ctx, cbox_dev, cbox):
+    with pytest.raises(DeviceError) as e:
+        cbox_dev.render(_abi.path_desc(), 0)                 # assert_ne!(nb_samples, 0)
+    assert e.value.code == _abi.RL_ERR_INVALID
+    with pytest.raises(DeviceError) as e:
+        cbox_dev.render(_abi.path_desc(max_depth=1), 1)      # path.rs:154 unwrap
+    assert e.value.code == _abi.RL_ERR_INVALID
+    desc = cbox.desc.contents
+    bad = _abi.rl_scene_desc(desc.nmeshes, desc.meshes, desc.camera, 1, 0)  # scene.volume = Some(..)
+    h = C.c_void_p()
+    assert lib().rl_scene_create(gpu_ctx._h, C.byref(bad), C.byref(h)) == _abi.RL_ERR_UNSUPPORTED
+    assert b"volume" in lib().rl_last_error(gpu_ctx._h)
+    opts = _abi.rl_render_opts(C.sizeof(_abi.rl_render_opts), 1, 0, _abi.RL_SAMPLER_BLOCK_STREAM, 0, 0, 0)
+    st = _abi.rl_stats()
+    integ = _abi.path_desc()
+    assert lib().rl_render(gpu_ctx._h, cbox_dev._h, C.byref(integ), C.byref(opts), None, C.byref(st)) == _abi.RL_ERR_UNSUPPORTED

@@ -1,0 +1,157 @@
+"""Host layer (C++ loaders, camera, PFM) and the C-ABI surface; no GPU needed."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import DATA, ROOT, load_cbox
+from rustlight_b200 import SceneError, SceneLoaderManager, _abi
+from rustlight_b200.host import read_pfm, save_pfm
+
+
+def test_cbox_pbrt_contents(cbox):
+    d = cbox.desc.contents
+    assert d.nmeshes == 8 and cbox.nb_triangles == 36 and cbox.size == (512, 512)
+    assert [d.meshes[i].ntris for i in range(8)] == [2, 2, 2, 2, 2, 12, 12, 2]
+    assert [d.meshes[i].emission_kind for i in range(8)] == [0] * 7 + [1]
+    assert list(d.meshes[7].emission) == [17.0, 12.0, 4.0]
+    assert np.allclose(list(d.meshes[4].mat.kd), [0.63, 0.065, 0.05])   # LeftWall: red
+    assert np.allclose(list(d.meshes[3].mat.kd), [0.14, 0.45, 0.091])   # RightWall: green
+    assert all(d.meshes[i].mat.kind == _abi.RL_BSDF_DIFFUSE for i in range(8))
+    assert d.meshes[0].N and d.meshes[0].UV
+    # light area 0.47 x 0.38 = 0.1786
+    P = np.ctypeslib.as_array(d.meshes[7].P, (12,)).reshape(4, 3)
+    assert np.ptp(P[:, 0]) * np.ptp(P[:, 2]) == pytest.approx(0.1786, rel=1e-6)
+
+
+def test_json_is_a_faithful_transcription(cbox):
+    js = SceneLoaderManager().load(os.path.join(DATA, "cbox.json"))
+    a, b = cbox.desc.contents, js.desc.contents
+    assert a.nmeshes == b.nmeshes
+    assert bytes(a.camera) == bytes(b.camera)
+    for i in range(a.nmeshes):
+        ma, mb = a.meshes[i], b.meshes[i]
+        assert (ma.nverts, ma.ntris, ma.emission_kind) == (mb.nverts, mb.ntris, mb.emission_kind)
+        for f, n in (("P", 3 * ma.nverts), ("N", 3 * ma.nverts), ("UV", 2 * ma.nverts)):
+            assert np.array_equal(np.ctypeslib.as_array(getattr(ma, f), (n,)), np.ctypeslib.as_array(getattr(mb, f), (n,)))
+        assert np.array_equal(np.ctypeslib.as_array(ma.idx, (3 * ma.ntris,)), np.ctypeslib.as_array(mb.idx, (3 * ma.ntris,)))
+        assert bytes(ma.mat) == bytes(mb.mat) and list(ma.emission) == list(mb.emission)
+    # and the writer round-trips
+    again = SceneLoaderManager().load_string(js.to_json(), "json")
+    assert bytes(again.desc.contents.camera) == bytes(a.camera)
+
+
+def test_use_shading_normal_flag():
+    sc = SceneLoaderManager().load(os.path.join(DATA, "cbox.pbrt"), use_shading_normal=False)
+    assert not sc.desc.contents.meshes[0].N  # `-x no-shading`: normals dropped (scene_loader.rs:101-118)
+
+
+def test_loader_errors():
+    m = SceneLoaderManager()
+    with pytest.raises(SceneError, match="extension"):
+        m.load("scene.xml")            # no such loader registered (scene_loader.rs:40-43)
+    with pytest.raises(SceneError, match="No file extension"):
+        m.load("scene")
+    with pytest.raises(SceneError, match="camera"):
+        m.load_string('WorldBegin Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0] WorldEnd', "pbrt")
+    with pytest.raises(SceneError, match="scope"):
+        m.load_string('Camera "perspective" WorldBegin MakeNamedMaterial "g" "string type" ["glass"] WorldEnd', "pbrt")
+    with pytest.raises(SceneError, match="out of range"):
+        m.load_string('Camera "perspective" WorldBegin Shape "trianglemesh" "integer indices" [0 1 5] "point P" [0 0 0 1 0 0 0 1 0] WorldEnd', "pbrt")
+
+
+def test_pbrt_transforms_and_defaults():
+    txt = '''LookAt 0 0 5  0 0 0  0 1 0
+    Camera "perspective" "float fov" [30]
+    Film "image" "integer xresolution" [32] "integer yresolution" [16]
+    WorldBegin
+      AttributeBegin
+        Translate 1 2 3  Scale 2 2 2
+        Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]
+      AttributeEnd
+      Material "phong" "rgb Kd" [0.2 0.2 0.2] "rgb Ks" [0.6 0.6 0.6] "float exponent" [10]
+      Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]
+    WorldEnd'''
+    sc = SceneLoaderManager().load_string(txt, "pbrt")
+    d = sc.desc.contents
+    assert sc.size == (32, 16) and d.nmeshes == 2
+    P0 = np.ctypeslib.as_array(d.meshes[0].P, (9,)).reshape(3, 3)
+    assert np.array_equal(P0, [[1, 2, 3], [3, 2, 3], [1, 4, 3]])
+    assert np.allclose(list(d.meshes[0].mat.kd), [0.5] * 3)          # no material: diffuse 0.5 (scene_loader.rs:132-135)
+    P1 = np.ctypeslib.as_array(d.meshes[1].P, (9,)).reshape(3, 3)
+    assert np.array_equal(P1, [[0, 0, 0], [1, 0, 0], [0, 1, 0]])     # AttributeEnd restored the CTM
+    assert d.meshes[1].mat.kind == _abi.RL_BSDF_PHONG and d.meshes[1].mat.weight_specular == pytest.approx(0.75)
+    tw = np.array(d.camera.to_world, np.float32).reshape(4, 4).T
+    assert np.allclose(tw[:3, 3], [0, 0, 5], atol=1e-6) and np.allclose(tw[:3, 2], [0, 0, -1], atol=1e-6)
+
+
+def test_scale_image_truncates_and_keeps_matrices():
+    sc = load_cbox()
+    before = bytes(sc.desc.contents.camera)[8:]
+    sc.scale_image(0.3)                       # CLI -s (camera.rs:73-78)
+    assert sc.size == (153, 153) and bytes(sc.desc.contents.camera)[8:] == before
+
+
+def test_pfm_roundtrip_and_layout(tmp_path):
+    img = np.arange(2 * 3 * 3, dtype=np.float32).reshape(2, 3, 3) - 4.0
+    p = str(tmp_path / "a.pfm")
+    save_pfm(p, img)
+    raw = open(p, "rb").read()
+    assert raw.startswith(b"PF\n3 2\n-1.0\n")                           # structure.rs:550
+    body = np.frombuffer(raw[len(b"PF\n3 2\n-1.0\n"):], "<f4").reshape(2, 3, 3)
+    assert np.array_equal(body, np.abs(img[::-1]))                        # bottom-to-top rows of abs() (:552-558)
+    assert np.array_equal(read_pfm(p), np.abs(img))
+
+
+HEADER = open(os.path.join(ROOT, "include", "rl_b200.h")).read()
+DECLARED = sorted(set(re.findall(r"\b(rl_[a-z_0-9]+)\s*\(", HEADER)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The CUDA library loads without a GPU and exports exactly the entry points of rl_b200.h."""
+    path = os.path.join(ROOT, "rustlight_b200", "librl_b200.so")
+    assert os.path.exists(path), "CUDA extension not built: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = C.CDLL(path)
+    assert len(DECLARED) >= 14
+    for name in DECLARED:
+        assert hasattr(lib, name), name
+    lib.rl_abi_version.restype = C.c_int
+    assert lib.rl_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """sizeof() from the C compiler vs the ctypes mirror in rustlight_b200/_abi.py."""
+    import subprocess
+    names = ["rl_material", "rl_mesh_desc", "rl_camera_desc", "rl_scene_desc", "rl_integrator_desc", "rl_render_opts",
+             "rl_stats", "rl_bvh_info", "rl_layout_info"]
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "rl_b200.h"\nint main(void){' +
+                   "".join(f'printf("%zu\\n", sizeof({n}));' for n in names) + "return 0;}")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [C.sizeof(getattr(_abi, n)) for n in names]
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    from conftest import has_gpu
+    if has_gpu():
+        pytest.skip("GPU present")
+    from rustlight_b200.device import Context, DeviceError
+    with pytest.raises(DeviceError, match="no CUDA device"):
+        Context(0)
+
+
+def test_product_never_touches_the_oracle():
+    """The product tree must not import, link or mention oracle/ or tests/emu."""
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "rustlight_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"(from|import)\s+oracle|oracle/|liboracle|libemu|emu_binding", txt):
+                    bad.append(f)
+    assert not bad, bad
