@@ -18,15 +18,9 @@ def pytest_configure(config):
 
 
 def _ensure_built():
-    """Build the CPU-side libraries once per session (host layer, oracle, emulator)."""
+    """(Re)build every native piece whose sources changed: CUDA library, host layer, oracle, emulator."""
     import __graft_entry__ as g
-    import subprocess
-    pkg = os.path.join(ROOT, "rustlight_b200")
-    if not os.path.exists(os.path.join(pkg, "librl_host.so")) or not os.path.exists(os.path.join(pkg, "librl_b200.so")):
-        g.build()
-    else:
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "emu")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    g.build()
 
 
 _ensure_built()
