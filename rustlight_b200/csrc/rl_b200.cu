@@ -293,7 +293,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     CKS(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_keys_sorted, (int)n, 0, 64, st));
     CKS(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
     CKS(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_keys_sorted, (int)n, 0, 64, st));
-    k_tri_setup<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(s->d_verts, d_keys_sorted, n, s->d_trav, s->d_shade, d_leaf_lo, d_leaf_hi);
+    k_tri_setup<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(s->d_verts, d_keys_sorted, n, bvh_box_eps(hs.abs_max), s->d_trav, s->d_shade, d_leaf_lo, d_leaf_hi);
     CKS(cudaGetLastError());
     std::vector<int2> h_children;
     if (n > 1) {

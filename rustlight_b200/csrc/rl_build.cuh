@@ -37,6 +37,15 @@ RL_HD void tri_bounds(const float4 *verts, uint32_t prim, V3 *lo, V3 *hi) {
     *hi = V3{fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z)};
 }
 
+// Leaf box used by the LBVH: the raw bounds grown by `eps` (3e-5 * abs_max) so that the
+// fma-based slab test of rl_device.cuh stays conservative.
+RL_HD float bvh_box_eps(float abs_max) { return 3e-5f * abs_max + 1e-30f; }
+RL_HD void tri_bounds_inflated(const float4 *verts, uint32_t prim, float eps, V3 *lo, V3 *hi) {
+    tri_bounds(verts, prim, lo, hi);
+    *lo = V3{lo->x - eps, lo->y - eps, lo->z - eps};
+    *hi = V3{hi->x + eps, hi->y + eps, hi->z + eps};
+}
+
 // Ray-independent part of Mesh::intersection_tri (geometry.rs:365-372, 383): e1, e2,
 // n_geo = normalize(e1 x e2), det = |e1 x e2|.  Written to Morton slot s; n_geo also goes to
 // the shading table.
@@ -48,7 +57,7 @@ RL_HD void tri_setup(const float4 *verts, uint32_t prim, uint32_t s, float4 *tra
     float det = magnitude(cr);
     trav[4 * s + 0] = make_float4(v0.x, v0.y, v0.z, det);
     trav[4 * s + 1] = make_float4(e1.x, e1.y, e1.z, u2f(prim));
-    trav[4 * s + 2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+    trav[4 * s + 2] = make_float4(e2.x, e2.y, e2.z, det * det * 1.0001f); // prefilter bound, see tri_test
     trav[4 * s + 3] = make_float4(n_geo.x, n_geo.y, n_geo.z, 0.0f);
     float4 s0 = shade[4 * prim];
     shade[4 * prim] = make_float4(n_geo.x, n_geo.y, n_geo.z, s0.w);

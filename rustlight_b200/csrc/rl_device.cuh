@@ -332,22 +332,33 @@ RL_HD bool aabb_intersect_ref(V3 pmin, V3 pmax, V3 o, V3 d, float tnear, float t
 }
 
 // ---- Mesh::intersection_tri with the ray-independent terms (e1, e2, n_geo, det) precomputed ---
-// Returns true when the triangle accepts the ray at parameter *t (all of the reference's
-// rejections applied except the final `t < its.t && t > 1e-5` which the caller owns).
-RL_HD bool tri_test(float4 r0, float4 r1, float4 r2, float4 r3, V3 o, V3 d, float *t_out, float *u_out, float *v_out) {
+// Exactly the reference's accept/reject decision and (t,u,v) values, with the tests re-ordered
+// (every test is a pure function of the inputs, so order cannot change the outcome) and two
+// conservative shortcuts in front of the sqrt/div pairs:
+//   * `t` is compared with the caller's bound first (the reference does it last, geometry.rs:398);
+//   * u = |a|/det > 1  <=>  |a| > det  (both roundings are monotonic), so |a|^2 > det^2 (1+1e-4)
+//     rejects without the sqrt and the divide; likewise u^2 + v^2 > 1 implies u + v > 1.
+// `t_bound` semantics: closest hit passes best.t and accepts t <= t_bound here (the caller
+// resolves the t == best.t tie by triangle index); shadow rays pass thr and the caller checks <.
+RL_HD bool tri_test(float4 r0, float4 r1, float4 r2, float4 r3, V3 o, V3 d, float t_bound, float *t_out, float *u_out, float *v_out) {
     V3 v0 = xyz(r0), e1 = xyz(r1), e2 = xyz(r2), n_geo = xyz(r3);
     float det = r0.w;
     float denom = dot(d, n_geo);
     if (denom == 0.0f) return false;
     float t = -dot(o - v0, n_geo) / denom;
     if (t < 0.0f) return false;
+    if (!(t <= t_bound) || !(t > 0.00001f)) return false;
     V3 p = o + t * d;
     V3 pv = p - v0;
     V3 u0 = cross(e1, pv);
+    if (dot(u0, n_geo) < 0.0f) return false;
     V3 v0c = cross(pv, e2);
-    if (dot(u0, n_geo) < 0.0f || dot(v0c, n_geo) < 0.0f) return false;
-    float v = magnitude(u0) / det;
-    float u = magnitude(v0c) / det;
+    if (dot(v0c, n_geo) < 0.0f) return false;
+    float a2 = dot(u0, u0), b2 = dot(v0c, v0c);
+    float det2m = r2.w; // det*det*(1+1e-4), written by tri_setup
+    if (a2 > det2m || b2 > det2m || a2 + b2 > det2m) return false;
+    float v = sqrtf(a2) / det;
+    float u = sqrtf(b2) / det;
     if (u < 0.0f || v < 0.0f || u > 1.0f || v > 1.0f) return false;
     if (!(u + v <= 1.0f)) return false;
     *t_out = t;
@@ -356,133 +367,173 @@ RL_HD bool tri_test(float4 r0, float4 r1, float4 r2, float4 r3, V3 o, V3 d, floa
     return true;
 }
 
-// Per-ray constants of the conservative slab test used for LBVH culling.  The reference's
-// BVH shape is not reproduced; instead culling is made strictly
-// conservative (boxes grown by eps around the ray) so that the result equals the brute-force
-// NaiveAcceleration loop: the closest accepted triangle, lowest (mesh,tri) on exact ties.
-struct RaySlab {
-    V3 inv_d;
-    V3 o_near, o_far; // origin shifted by +-eps toward the side that widens the interval
-    uint32_t neg;     // bit a set when d[a] < 0
-};
-RL_HD RaySlab make_slab(V3 o, V3 d, float abs_max) {
-    RaySlab s;
-    s.inv_d = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
-    float m = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), abs_max));
-    float eps = 1e-5f * m + 1e-30f;
-    // direction signs are taken from 1/d like AABB::intersect does (structure.rs:857): d = -0.0 gives -inf
-    const bool nx = s.inv_d.x < 0.0f, ny = s.inv_d.y < 0.0f, nz = s.inv_d.z < 0.0f;
-    s.neg = (nx ? 1u : 0u) | (ny ? 2u : 0u) | (nz ? 4u : 0u);
-    // entering plane uses o shifted forward (smaller t), leaving plane uses o shifted back
-    s.o_near = V3{nx ? o.x - eps : o.x + eps, ny ? o.y - eps : o.y + eps, nz ? o.z - eps : o.z + eps};
-    s.o_far = V3{nx ? o.x + eps : o.x - eps, ny ? o.y + eps : o.y - eps, nz ? o.z + eps : o.z - eps};
-    return s;
-}
-// Returns conservative entry distance, or a negative value on a miss, for t in [0, tmax].
-RL_HD float slab_test(const RaySlab &s, V3 lo, V3 hi, float tmax) {
-    float nx = (s.neg & 1u) ? hi.x : lo.x, fx = (s.neg & 1u) ? lo.x : hi.x;
-    float ny = (s.neg & 2u) ? hi.y : lo.y, fy = (s.neg & 2u) ? lo.y : hi.y;
-    float nz = (s.neg & 4u) ? hi.z : lo.z, fz = (s.neg & 4u) ? lo.z : hi.z;
-    float t0x = (nx - s.o_near.x) * s.inv_d.x, t1x = (fx - s.o_far.x) * s.inv_d.x;
-    float t0y = (ny - s.o_near.y) * s.inv_d.y, t1y = (fy - s.o_far.y) * s.inv_d.y;
-    float t0z = (nz - s.o_near.z) * s.inv_d.z, t1z = (fz - s.o_far.z) * s.inv_d.z;
-    // fmaxf/fminf drop NaNs (0*inf on a degenerate axis), which keeps the test conservative
-    float tmin = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.0f));
-    float tend = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-    return tmin <= tend ? tmin : -1.0f;
-}
+// ---- LBVH traversal state -----------------------------------------------------------------------
+// The reference's BVH shape is not reproduced.  Culling is conservative:
+// node boxes are pre-inflated by 3e-5*abs_max at build time (rl_build.cuh), far more than the
+// rounding of the fma-based slab test below, and rays whose origin lies far outside the scene
+// add a per-ray term.  A culling test that is merely conservative cannot change the result,
+// which is fixed by the exact triangle test + the tie rule: closest accepted triangle, lowest
+// (mesh,tri) index on exact ties == the brute-force loop of NaiveAcceleration (accel.rs:22-51).
+#ifndef RL_STACK_SIZE
+#define RL_STACK_SIZE 64
+#endif
+#define RL_TRAV_DONE 0x7fffffff
 
 struct HitRec {
     float t, u, v;
     uint32_t prim;
 };
-
-#ifndef RL_STACK_SIZE
-#define RL_STACK_SIZE 64
-#endif
-
-// Acceleration::trace (accel.rs:292-315) without fill_intersection: closest accepted triangle.
-RL_HD HitRec trace_closest(const SceneView &sv, const float4 *nodes, const float4 *trav, V3 o, V3 d) {
-    HitRec best;
-    best.t = RL_F32_MAX;
-    best.u = 0.0f;
-    best.v = 0.0f;
-    best.prim = RL_MISS;
-    if (!aabb_intersect_ref(sv.root_min, sv.root_max, o, d, RL_EPSILON, RL_F32_MAX)) return best;
-    RaySlab sl = make_slab(o, d, sv.abs_max);
-    int stack[RL_STACK_SIZE];
-    int sp = 0;
-    stack[sp++] = 0;
-    while (sp > 0) {
-        int node = stack[--sp];
-        float4 a = nodes[4 * node + 0], b = nodes[4 * node + 1], c = nodes[4 * node + 2], k = nodes[4 * node + 3];
-        float d0 = slab_test(sl, V3{a.x, a.y, a.z}, V3{a.w, b.x, b.y}, best.t);
-        float d1 = slab_test(sl, V3{b.z, b.w, c.x}, V3{c.y, c.z, c.w}, best.t);
-        int c0 = (int)f2u(k.x), c1 = (int)f2u(k.y);
-        if (d1 >= 0.0f && (d0 < 0.0f || d1 < d0)) { // visit the nearer child first
-            float td = d0; d0 = d1; d1 = td;
-            int tc = c0; c0 = c1; c1 = tc;
-        }
-#define RL_VISIT(child, dist)                                                                      \
-    if ((dist) >= 0.0f && (dist) <= best.t) {                                                      \
-        if ((child) < 0) {                                                                         \
-            int s_ = ~(child);                                                                     \
-            float4 r0 = trav[4 * s_], r1 = trav[4 * s_ + 1], r2 = trav[4 * s_ + 2], r3 = trav[4 * s_ + 3]; \
-            float t_, u_, v_;                                                                      \
-            if (tri_test(r0, r1, r2, r3, o, d, &t_, &u_, &v_)) {                                   \
-                uint32_t prim_ = f2u(r1.w);                                                        \
-                if ((t_ < best.t || (t_ == best.t && best.prim != RL_MISS && prim_ < best.prim)) && t_ > 0.00001f) {       \
-                    best.t = t_; best.u = u_; best.v = v_; best.prim = prim_;                      \
-                }                                                                                  \
-            }                                                                                      \
-        } else if (sp < RL_STACK_SIZE) {                                                           \
-            stack[sp++] = (child);                                                                 \
-        }                                                                                          \
+struct Trav {
+    V3 o, d;
+    V3 inv, ood;   // 1/d (clamped away from 0) and o/d for t = fma(plane, inv, -ood)
+    V3 et;         // extra widening in t for far origins (0 otherwise)
+    bool far;
+    float tmax;    // closest: best t so far; shadow: the segment's threshold
+    float u, v;
+    uint32_t prim;
+    int cur;       // >= 0 inner node, < 0 leaf ~cur, RL_TRAV_DONE
+    int sp;        // entries in the caller's stack array (kept outside the struct so the state stays in registers)
+};
+RL_HD float clamp_inv(float d) {
+    // |d| < 1e-18 would give inf (and NaN in the fma form); a finite 1e18 keeps every product finite
+    float ad = fabsf(d);
+    float inv = 1.0f / (ad < 1e-18f ? 1e-18f : ad);
+    return copysignf(inv, d);
+}
+RL_HD void trav_begin(Trav &tr, const SceneView &sv, V3 o, V3 d, float tmax) {
+    tr.o = o;
+    tr.d = d;
+    tr.inv = V3{clamp_inv(d.x), clamp_inv(d.y), clamp_inv(d.z)};
+    tr.ood = V3{o.x * tr.inv.x, o.y * tr.inv.y, o.z * tr.inv.z};
+    float m = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+    tr.far = m > 8.0f * sv.abs_max;
+    float eps = tr.far ? 1e-5f * m : 0.0f;
+    tr.et = V3{eps * fabsf(tr.inv.x), eps * fabsf(tr.inv.y), eps * fabsf(tr.inv.z)};
+    tr.tmax = tmax;
+    tr.u = 0.0f;
+    tr.v = 0.0f;
+    tr.prim = RL_MISS;
+    tr.cur = 0;
+    tr.sp = 0;
+}
+// Conservative entry distance of the ray into box (lo,hi) for t in [0, tmax], or -1 on a miss.
+RL_HD float box_entry(const Trav &tr, float lox, float loy, float loz, float hix, float hiy, float hiz) {
+    float ax = fmaf(lox, tr.inv.x, -tr.ood.x), bx = fmaf(hix, tr.inv.x, -tr.ood.x);
+    float ay = fmaf(loy, tr.inv.y, -tr.ood.y), by = fmaf(hiy, tr.inv.y, -tr.ood.y);
+    float az = fmaf(loz, tr.inv.z, -tr.ood.z), bz = fmaf(hiz, tr.inv.z, -tr.ood.z);
+    float nx = fminf(ax, bx), fx = fmaxf(ax, bx);
+    float ny = fminf(ay, by), fy = fmaxf(ay, by);
+    float nz = fminf(az, bz), fz = fmaxf(az, bz);
+    if (tr.far) {
+        nx -= tr.et.x, ny -= tr.et.y, nz -= tr.et.z;
+        fx += tr.et.x, fy += tr.et.y, fz += tr.et.z;
     }
-        // leaves are tested immediately; inner nodes: push far then near so near pops first
-        if (c0 < 0) {
-            RL_VISIT(c0, d0)
-            RL_VISIT(c1, d1)
-        } else {
-            RL_VISIT(c1, d1)
-            RL_VISIT(c0, d0)
+    float tmin = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
+    float tend = fminf(fminf(fx, fy), fminf(fz, tr.tmax));
+    return tmin <= tend ? tmin : -1.0f;
+}
+RL_HD int trav_pop(Trav &tr, const int *stack) { return tr.sp > 0 ? stack[--tr.sp] : RL_TRAV_DONE; }
+// Phase A: one inner-node step (tr.cur >= 0).  Leaves tr.cur at a child, a popped entry or DONE.
+RL_HD void trav_node_step(Trav &tr, int *stack, const float4 *nodes) {
+    const int node = tr.cur;
+    float4 a = nodes[4 * node + 0], b = nodes[4 * node + 1], c = nodes[4 * node + 2], k = nodes[4 * node + 3];
+    float d0 = box_entry(tr, a.x, a.y, a.z, a.w, b.x, b.y);
+    float d1 = box_entry(tr, b.z, b.w, c.x, c.y, c.z, c.w);
+    int c0 = (int)f2u(k.x), c1 = (int)f2u(k.y);
+    if (d0 >= 0.0f && d1 >= 0.0f) {
+        bool swap = d1 < d0;
+        int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
+        if (tr.sp < RL_STACK_SIZE) stack[tr.sp++] = farc;
+        tr.cur = nearc;
+    } else if (d0 >= 0.0f) tr.cur = c0;
+    else if (d1 >= 0.0f) tr.cur = c1;
+    else tr.cur = trav_pop(tr, stack);
+}
+// Phase B (closest hit): tr.cur is a leaf.
+RL_HD void trav_leaf_closest(Trav &tr, const int *stack, const float4 *trav) {
+    int s_ = ~tr.cur;
+    float4 r0 = trav[4 * s_], r1 = trav[4 * s_ + 1], r2 = trav[4 * s_ + 2], r3 = trav[4 * s_ + 3];
+    float t_, u_, v_;
+    if (tri_test(r0, r1, r2, r3, tr.o, tr.d, tr.tmax, &t_, &u_, &v_)) {
+        uint32_t prim_ = f2u(r1.w);
+        // reference: strict `t < its.t` in mesh-major order => on exact ties the lowest index wins
+        if (t_ < tr.tmax || (tr.prim != RL_MISS && prim_ < tr.prim)) {
+            tr.tmax = t_;
+            tr.u = u_;
+            tr.v = v_;
+            tr.prim = prim_;
         }
-#undef RL_VISIT
     }
-    return best;
+    tr.cur = trav_pop(tr, stack);
+}
+// Phase B (any hit): returns true when the segment is blocked.
+RL_HD bool trav_leaf_any(Trav &tr, const int *stack, const float4 *trav) {
+    int s_ = ~tr.cur;
+    float t_, u_, v_;
+    bool blocked = false;
+    if (tri_test(trav[4 * s_], trav[4 * s_ + 1], trav[4 * s_ + 2], trav[4 * s_ + 3], tr.o, tr.d, tr.tmax, &t_, &u_, &v_)) blocked = t_ < tr.tmax;
+    tr.cur = blocked ? RL_TRAV_DONE : trav_pop(tr, stack);
+    return blocked;
 }
 
-// Acceleration::visible (accel.rs:316-343): true when no triangle accepts the segment.
-RL_HD bool trace_visible(const SceneView &sv, const float4 *nodes, const float4 *trav, V3 p0, V3 p1) {
+// Acceleration::trace (accel.rs:292-315) without fill_intersection.  Returns false when the
+// reference's root-box test rejects the ray (no traversal needed).
+RL_HD bool closest_begin(Trav &tr, const SceneView &sv, V3 o, V3 d) {
+    trav_begin(tr, sv, o, d, RL_F32_MAX);
+    if (!aabb_intersect_ref(sv.root_min, sv.root_max, o, d, RL_EPSILON, RL_F32_MAX)) {
+        tr.cur = RL_TRAV_DONE;
+        return false;
+    }
+    return true;
+}
+RL_HD HitRec closest_result(const Trav &tr) {
+    HitRec h;
+    h.t = tr.prim == RL_MISS ? RL_F32_MAX : tr.tmax;
+    h.u = tr.u;
+    h.v = tr.v;
+    h.prim = tr.prim;
+    return h;
+}
+// Acceleration::visible (accel.rs:316-343): segment setup.  *decided is set when the root test
+// already answers (then *vis holds the answer).
+RL_HD void visible_begin(Trav &tr, const SceneView &sv, V3 p0, V3 p1, bool *decided, bool *vis) {
     const float SHADOW_EPS = 0.00001f;
     V3 d = p1 - p0;
     float length = magnitude(d);
     d = d / length;
     float thr = length * (1.0f - SHADOW_EPS);
-    if (!aabb_intersect_ref(sv.root_min, sv.root_max, p0, d, RL_EPSILON, thr)) return false;
-    RaySlab sl = make_slab(p0, d, sv.abs_max);
+    trav_begin(tr, sv, p0, d, thr);
+    *decided = false;
+    *vis = true;
+    if (!aabb_intersect_ref(sv.root_min, sv.root_max, p0, d, RL_EPSILON, thr)) {
+        tr.cur = RL_TRAV_DONE;
+        *decided = true;
+        *vis = false; // accel.rs:338-340
+    }
+}
+
+// Serial drivers (used by the CPU emulator and the small batch kernels; the wavefront kernels
+// run the same steps inside a persistent while-while loop, rl_kernels.cuh).
+RL_HD HitRec trace_closest(const SceneView &sv, const float4 *nodes, const float4 *trav, V3 o, V3 d) {
+    Trav tr;
     int stack[RL_STACK_SIZE];
-    int sp = 0;
-    stack[sp++] = 0;
-    while (sp > 0) {
-        int node = stack[--sp];
-        float4 a = nodes[4 * node + 0], b = nodes[4 * node + 1], c = nodes[4 * node + 2], k = nodes[4 * node + 3];
-        float d0 = slab_test(sl, V3{a.x, a.y, a.z}, V3{a.w, b.x, b.y}, thr);
-        float d1 = slab_test(sl, V3{b.z, b.w, c.x}, V3{c.y, c.z, c.w}, thr);
-        int ch[2] = {(int)f2u(k.x), (int)f2u(k.y)};
-        float dd[2] = {d0, d1};
-        for (int q = 0; q < 2; q++) {
-            if (dd[q] < 0.0f) continue;
-            if (ch[q] < 0) {
-                int s_ = ~ch[q];
-                float t_, u_, v_;
-                if (tri_test(trav[4 * s_], trav[4 * s_ + 1], trav[4 * s_ + 2], trav[4 * s_ + 3], p0, d, &t_, &u_, &v_)) {
-                    if (t_ < thr && t_ > 0.00001f) return false;
-                }
-            } else if (sp < RL_STACK_SIZE) {
-                stack[sp++] = ch[q];
-            }
+    if (closest_begin(tr, sv, o, d)) {
+        while (tr.cur != RL_TRAV_DONE) {
+            if (tr.cur >= 0) trav_node_step(tr, stack, nodes);
+            else trav_leaf_closest(tr, stack, trav);
         }
+    }
+    return closest_result(tr);
+}
+RL_HD bool trace_visible(const SceneView &sv, const float4 *nodes, const float4 *trav, V3 p0, V3 p1) {
+    Trav tr;
+    int stack[RL_STACK_SIZE];
+    bool decided, vis;
+    visible_begin(tr, sv, p0, p1, &decided, &vis);
+    if (decided) return vis;
+    while (tr.cur != RL_TRAV_DONE) {
+        if (tr.cur >= 0) trav_node_step(tr, stack, nodes);
+        else if (trav_leaf_any(tr, stack, trav)) return false;
     }
     return true;
 }

@@ -63,6 +63,29 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, IntegParams ip,
 }
 
 // ---- closest-hit traversal ------------------------------------------------------------------------
+// Persistent while-while traversal with in-warp ray refill (Aila & Laine 2009): every warp owns a
+// contiguous chunk of the queue; lanes whose ray has finished pull the next rays of the chunk
+// once at least kRefillIdle lanes are idle (measured best on B200: 32 = refill when the whole warp is
+// idle; partial refills pay the per-ray setup at low lane occupancy), so that the descend phase and the leaf
+// phase (exact triangle test) each run with most lanes active although rays are incoherent.
+#ifndef RL_REFILL_IDLE
+#define RL_REFILL_IDLE 32
+#endif
+#ifndef RL_WHILE_WHILE
+#define RL_WHILE_WHILE 1
+#endif
+constexpr int kRefillIdle = RL_REFILL_IDLE;
+
+__device__ __forceinline__ void warp_chunk(uint32_t n, uint32_t *begin, uint32_t *end) {
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t per = (n + warps - 1) / warps;
+    per = (per + 31u) & ~31u;
+    uint64_t b = (uint64_t)w * per;
+    *begin = b < n ? (uint32_t)b : n;
+    *end = (b + per) < n ? (uint32_t)(b + per) : n;
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(kBlock) k_trace(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
                                                   const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t n_node_f4,
@@ -74,11 +97,40 @@ __global__ void __launch_bounds__(kBlock) k_trace(SceneView sv, const uint32_t *
         nodes = smem;
         trav = smem + n_node_f4;
     }
-    const uint32_t n = *count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 ro = ray_o[i], rd = ray_d[i];
-        HitRec h = trace_closest(sv, nodes, trav, xyz(ro), xyz(rd));
-        hit[i] = make_float4(h.t, h.u, h.v, u2f(h.prim));
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t cursor, chunk_end;
+    warp_chunk(*count, &cursor, &chunk_end);
+    Trav tr;
+    int stack[RL_STACK_SIZE];
+    tr.cur = RL_TRAV_DONE;
+    uint32_t my = RL_MISS; // queue index of the ray this lane is tracing
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, tr.cur == RL_TRAV_DONE);
+        if (cursor < chunk_end && (__popc(idle) >= kRefillIdle)) {
+            if (tr.cur == RL_TRAV_DONE) {
+                uint32_t i = cursor + __popc(idle & ((1u << lane) - 1u));
+                if (i < chunk_end) {
+                    float4 ro = ray_o[i], rd = ray_d[i];
+                    if (closest_begin(tr, sv, xyz(ro), xyz(rd))) my = i;
+                    else hit[i] = make_float4(RL_F32_MAX, 0.0f, 0.0f, u2f(RL_MISS)); // root box missed
+                }
+            }
+            cursor += __popc(idle);
+            continue; // re-evaluate: lanes whose new ray missed the root box are still idle
+        }
+        if (idle == 0xffffffffu) break; // chunk exhausted and every lane finished
+#if RL_WHILE_WHILE
+        while ((uint32_t)tr.cur < (uint32_t)RL_TRAV_DONE) trav_node_step(tr, stack, nodes); // descend: inner nodes
+        if (tr.cur < 0) trav_leaf_closest(tr, stack, trav);                                  // one leaf
+#else
+        if ((uint32_t)tr.cur < (uint32_t)RL_TRAV_DONE) trav_node_step(tr, stack, nodes);
+        else if (tr.cur < 0) trav_leaf_closest(tr, stack, trav);
+#endif
+        if (tr.cur == RL_TRAV_DONE && my != RL_MISS) {
+            HitRec h = closest_result(tr);
+            hit[my] = make_float4(h.t, h.u, h.v, u2f(h.prim));
+            my = RL_MISS;
+        }
     }
 }
 
@@ -185,21 +237,53 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneView sv, const uint32_t 
         nodes = smem;
         trav = smem + n_node_f4;
     }
-    const uint32_t n = *count;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t cursor, chunk_end;
+    warp_chunk(*count, &cursor, &chunk_end);
+    Trav tr;
+    int stack[RL_STACK_SIZE];
+    tr.cur = RL_TRAV_DONE;
+    uint32_t my = RL_MISS;
+    bool blocked = false;
     uint32_t c_vis = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float4 a = sh_a[i], b = sh_b[i];
-        if (trace_visible(sv, nodes, trav, xyz(a), xyz(b))) {
-            float4 c = sh_c[i];
-            uint32_t pid = f2u(a.w);
-            float4 l = lacc[pid];
-            l.x += c.x, l.y += c.y, l.z += c.z;
-            lacc[pid] = l;
-            c_vis++;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, tr.cur == RL_TRAV_DONE);
+        if (cursor < chunk_end && (__popc(idle) >= kRefillIdle)) {
+            if (tr.cur == RL_TRAV_DONE) {
+                uint32_t i = cursor + __popc(idle & ((1u << lane) - 1u));
+                if (i < chunk_end) {
+                    float4 a = sh_a[i], b = sh_b[i];
+                    bool decided, vis;
+                    visible_begin(tr, sv, xyz(a), xyz(b), &decided, &vis);
+                    blocked = false;
+                    if (!decided) my = i; // else: the root test says "not visible" (accel.rs:338-340): nothing to add
+                }
+            }
+            cursor += __popc(idle);
+            continue;
+        }
+        if (idle == 0xffffffffu) break;
+#if RL_WHILE_WHILE
+        while ((uint32_t)tr.cur < (uint32_t)RL_TRAV_DONE) trav_node_step(tr, stack, nodes);
+        if (tr.cur < 0) blocked = trav_leaf_any(tr, stack, trav) || blocked;
+#else
+        if ((uint32_t)tr.cur < (uint32_t)RL_TRAV_DONE) trav_node_step(tr, stack, nodes);
+        else if (tr.cur < 0) blocked = trav_leaf_any(tr, stack, trav) || blocked;
+#endif
+        if (tr.cur == RL_TRAV_DONE && my != RL_MISS) {
+            if (!blocked) { // visible: add the light-sampling contribution to the path's accumulator
+                float4 c = sh_c[my];
+                uint32_t pid = f2u(sh_a[my].w);
+                float4 l = lacc[pid];
+                l.x += c.x, l.y += c.y, l.z += c.z;
+                lacc[pid] = l;
+                c_vis++;
+            }
+            my = RL_MISS;
         }
     }
     for (int off = 16; off > 0; off >>= 1) c_vis += __shfl_down_sync(0xffffffffu, c_vis, off);
-    if ((threadIdx.x & 31u) == 0 && c_vis) atomicAdd(&counters->shadow_visible, (unsigned long long)c_vis);
+    if (lane == 0 && c_vis) atomicAdd(&counters->shadow_visible, (unsigned long long)c_vis);
 }
 
 // ---- per-pixel accumulation in sample order (Bitmap::accumulate, structure.rs:397-402) ------------
@@ -259,13 +343,13 @@ __global__ void __launch_bounds__(kBlock) k_morton(const float4 *__restrict__ ve
         keys[p] = morton_key(lo, hi, smin, sinv, p);
     }
 }
-__global__ void __launch_bounds__(kBlock) k_tri_setup(const float4 *__restrict__ verts, const uint64_t *__restrict__ keys, uint32_t ntris, float4 *trav,
+__global__ void __launch_bounds__(kBlock) k_tri_setup(const float4 *__restrict__ verts, const uint64_t *__restrict__ keys, uint32_t ntris, float box_eps, float4 *trav,
                                                       float4 *shade, float4 *leaf_lo, float4 *leaf_hi) {
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < ntris; s += gridDim.x * blockDim.x) {
         uint32_t prim = (uint32_t)(keys[s] & 0xffffffffull);
         tri_setup(verts, prim, s, trav, shade);
         V3 lo, hi;
-        tri_bounds(verts, prim, &lo, &hi);
+        tri_bounds_inflated(verts, prim, box_eps, &lo, &hi);
         leaf_lo[s] = make_float4(lo.x, lo.y, lo.z, 0.0f);
         leaf_hi[s] = make_float4(hi.x, hi.y, hi.z, 0.0f);
     }

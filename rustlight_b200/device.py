@@ -30,7 +30,7 @@ class DeviceError(RuntimeError):
 def lib():
     global _lib
     if _lib is None:
-        path = os.path.join(_HERE, "librl_b200.so")
+        path = os.environ.get("RL_B200_LIB") or os.path.join(_HERE, "librl_b200.so")  # override: kernel A/B experiments only
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: the CUDA extension is not built "
                                "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")

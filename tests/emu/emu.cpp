@@ -58,7 +58,7 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
     for (int i = 0; i < n; i++) {
         uint32_t prim = (uint32_t)(keys[i] & 0xffffffffull);
         tri_setup(hs.verts.data(), prim, i, s->trav.data(), hs.shade.data());
-        tri_bounds(hs.verts.data(), prim, &leaf_lo[i], &leaf_hi[i]);
+        tri_bounds_inflated(hs.verts.data(), prim, bvh_box_eps(hs.abs_max), &leaf_lo[i], &leaf_hi[i]);
     }
     // k_karras + k_fit
     int n_nodes = n > 1 ? n - 1 : 1;
