@@ -65,7 +65,7 @@ struct rl_ctx {
     bool profiling = false;
     ncclComm_t comm = nullptr;
     // wavefront buffers (grown on demand)
-    size_t cap_paths = 0;
+    size_t cap_paths = 0, cap_shadow = 0, cap_lacc = 0; // ray/hit queues, shadow queues, radiance slots (records)
     float4 *ray_o[2] = {nullptr, nullptr}, *ray_d[2] = {nullptr, nullptr}, *state[2] = {nullptr, nullptr};
     float4 *hit = nullptr, *sh_a = nullptr, *sh_b = nullptr, *sh_c = nullptr, *lacc = nullptr;
     // per-image buffers
@@ -376,27 +376,42 @@ int rl_scene_bvh_info(rl_ctx *ctx, const rl_scene *scene, rl_bvh_info *out) {
 }
 
 // ---- buffers -----------------------------------------------------------------------------------------
-static int ensure_paths(rl_ctx *ctx, size_t n) {
-    if (n <= ctx->cap_paths) return RL_OK;
-    for (int i = 0; i < 2; i++) {
-        cudaFree(ctx->ray_o[i]), cudaFree(ctx->ray_d[i]), cudaFree(ctx->state[i]);
-        ctx->ray_o[i] = ctx->ray_d[i] = ctx->state[i] = nullptr;
+static int ensure_paths(rl_ctx *ctx, size_t n_ray, size_t n_shadow = 0, size_t n_lacc = 0) {
+    if (n_shadow == 0) n_shadow = n_ray;
+    if (n_lacc == 0) n_lacc = n_ray;
+    if (n_ray > ctx->cap_paths) {
+        for (int i = 0; i < 2; i++) {
+            cudaFree(ctx->ray_o[i]), cudaFree(ctx->ray_d[i]), cudaFree(ctx->state[i]);
+            ctx->ray_o[i] = ctx->ray_d[i] = ctx->state[i] = nullptr;
+        }
+        cudaFree(ctx->hit);
+        ctx->hit = nullptr;
+        ctx->cap_paths = 0;
+        size_t bytes = n_ray * sizeof(float4);
+        for (int i = 0; i < 2; i++) {
+            CK(cudaMalloc(&ctx->ray_o[i], bytes));
+            CK(cudaMalloc(&ctx->ray_d[i], bytes));
+            CK(cudaMalloc(&ctx->state[i], bytes));
+        }
+        CK(cudaMalloc(&ctx->hit, bytes));
+        ctx->cap_paths = n_ray;
     }
-    cudaFree(ctx->hit), cudaFree(ctx->sh_a), cudaFree(ctx->sh_b), cudaFree(ctx->sh_c), cudaFree(ctx->lacc);
-    ctx->hit = ctx->sh_a = ctx->sh_b = ctx->sh_c = ctx->lacc = nullptr;
-    ctx->cap_paths = 0;
-    size_t bytes = n * sizeof(float4);
-    for (int i = 0; i < 2; i++) {
-        CK(cudaMalloc(&ctx->ray_o[i], bytes));
-        CK(cudaMalloc(&ctx->ray_d[i], bytes));
-        CK(cudaMalloc(&ctx->state[i], bytes));
+    if (n_shadow > ctx->cap_shadow) {
+        cudaFree(ctx->sh_a), cudaFree(ctx->sh_b), cudaFree(ctx->sh_c);
+        ctx->sh_a = ctx->sh_b = ctx->sh_c = nullptr;
+        ctx->cap_shadow = 0;
+        CK(cudaMalloc(&ctx->sh_a, n_shadow * sizeof(float4)));
+        CK(cudaMalloc(&ctx->sh_b, n_shadow * sizeof(float4)));
+        CK(cudaMalloc(&ctx->sh_c, n_shadow * sizeof(float4)));
+        ctx->cap_shadow = n_shadow;
     }
-    CK(cudaMalloc(&ctx->hit, bytes));
-    CK(cudaMalloc(&ctx->sh_a, bytes));
-    CK(cudaMalloc(&ctx->sh_b, bytes));
-    CK(cudaMalloc(&ctx->sh_c, bytes));
-    CK(cudaMalloc(&ctx->lacc, bytes));
-    ctx->cap_paths = n;
+    if (n_lacc > ctx->cap_lacc) {
+        cudaFree(ctx->lacc);
+        ctx->lacc = nullptr;
+        ctx->cap_lacc = 0;
+        CK(cudaMalloc(&ctx->lacc, n_lacc * sizeof(float4)));
+        ctx->cap_lacc = n_lacc;
+    }
     return RL_OK;
 }
 
@@ -461,8 +476,14 @@ static int validate(rl_ctx *ctx, const rl_scene *scene, const rl_integrator_desc
             return RL_ERR_INVALID;
         }
     } else if (I->kind == RL_INTEGRATOR_DIRECT) {
-        ctx->err = "rl_render: direct integrator not built yet";
-        return RL_ERR_UNSUPPORTED;
+        if (scene->hs.n_emitters == 0 && I->nb_light_samples > 0) {
+            ctx->err = "rl_render: no emitter in the scene but light samples requested";
+            return RL_ERR_INVALID;
+        }
+        if (I->nb_bsdf_samples > 64 || I->nb_light_samples > 64) {
+            ctx->err = "rl_render: more than 64 bsdf/light samples per pixel sample";
+            return RL_ERR_INVALID;
+        }
     } else {
         ctx->err = "rl_render: unknown integrator kind";
         return RL_ERR_INVALID;
@@ -497,10 +518,15 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
     CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), st));
     CK(cudaEventRecord(ctx->ev[0], st));
     if (npix > 0) {
+        const bool direct = I->kind == RL_INTEGRATOR_DIRECT;
+        const uint32_t nl = direct ? I->nb_light_samples : 1u, nbs = direct ? I->nb_bsdf_samples : 1u;
+        const uint32_t n_slots = direct ? 1u + nl + nbs : 1u;
+        const uint32_t widest = std::max(std::max(nl, nbs), n_slots);
         uint32_t batch = o->batch_spp;
-        if (batch == 0) batch = (uint32_t)std::max<size_t>(1, ((size_t)1 << 24) / npix);
+        if (batch == 0) batch = (uint32_t)std::max<size_t>(1, ((size_t)1 << 24) / ((size_t)npix * widest));
         batch = std::min(batch, o->spp);
-        rc = ensure_paths(ctx, (size_t)npix * batch);
+        const size_t batch_paths = (size_t)npix * batch;
+        rc = ensure_paths(ctx, batch_paths * std::max(1u, nbs), batch_paths * std::max(1u, nl), batch_paths * n_slots);
         if (rc != RL_OK) return rc;
         IntegParams ip{};
         ip.kind = I->kind, ip.min_depth = I->min_depth, ip.max_depth = I->max_depth, ip.rr_depth = I->rr_depth;
@@ -516,7 +542,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
             ip.sample_base = s0;
             if (prof) CK(cudaEventRecord(ctx->ev[2], st));
             k_raygen<<<grid_for(ctx, n_paths, 8), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, (uint32_t)n_paths, ctx->ray_o[0], ctx->ray_d[0],
-                                                                   ctx->state[0], ctx->lacc);
+                                                                   ctx->state[0], ctx->lacc, n_slots);
             ctx->launches++;
             if (prof) {
                 CK(cudaEventRecord(ctx->ev[3], st));
@@ -529,6 +555,56 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
             size_t n = n_paths;
             int cur = 0;
             uint64_t iter = 0;
+            if (direct) {
+                // primary rays -> stage 1 (emission, light samples, BSDF samples) -> shadow rays -> extension rays -> stage 2
+                uint32_t *c_in = ctx->d_counts, *c_out = ctx->d_counts + 1, *c_sh = ctx->d_counts + 2;
+                if (prof) CK(cudaEventRecord(ctx->ev[2], st));
+                if (sc->smem_ok) launch_trace<true>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit);
+                else launch_trace<false>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit);
+                if (prof) CK(cudaEventRecord(ctx->ev[3], st));
+                k_shade_direct1<<<grid_for(ctx, n, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, c_in, (uint32_t)n_paths, ctx->ray_o[0], ctx->ray_d[0],
+                                                                        ctx->state[0], ctx->hit, ctx->ray_o[1], ctx->ray_d[1], ctx->state[1], c_out, ctx->sh_a,
+                                                                        ctx->sh_b, ctx->sh_c, c_sh, ctx->lacc, ctx->d_counters);
+                ctx->launches++;
+                if (prof) CK(cudaEventRecord(ctx->ev[4], st));
+                if (sc->smem_ok) launch_shadow<true>(ctx, sc, c_sh, n * std::max(1u, nl));
+                else launch_shadow<false>(ctx, sc, c_sh, n * std::max(1u, nl));
+                if (prof) CK(cudaEventRecord(ctx->ev[5], st));
+                CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                CK(cudaGetLastError());
+                if (prof) {
+                    CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+                    S.ms_trace += ms;
+                    CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
+                    S.ms_shade += ms;
+                    CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+                    S.ms_shadow += ms;
+                }
+                S.segments += n;
+                iter = 1;
+                const size_t n2 = ctx->h_counts[1];
+                if (n2 > 0) {
+                    if (prof) CK(cudaEventRecord(ctx->ev[2], st));
+                    if (sc->smem_ok) launch_trace<true>(ctx, sc, c_out, n2, ctx->ray_o[1], ctx->ray_d[1], ctx->hit);
+                    else launch_trace<false>(ctx, sc, c_out, n2, ctx->ray_o[1], ctx->ray_d[1], ctx->hit);
+                    if (prof) CK(cudaEventRecord(ctx->ev[3], st));
+                    k_shade_direct2<<<grid_for(ctx, n2, 8), kBlock, 0, st>>>(sc->sv, ip, c_out, ctx->ray_o[1], ctx->ray_d[1], ctx->state[1], ctx->hit, ctx->lacc,
+                                                                             ctx->d_counters);
+                    ctx->launches++;
+                    if (prof) {
+                        CK(cudaEventRecord(ctx->ev[4], st));
+                        CK(cudaEventSynchronize(ctx->ev[4]));
+                        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+                        S.ms_trace += ms;
+                        CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
+                        S.ms_shade += ms;
+                    }
+                    S.segments += n2;
+                    iter = 2;
+                }
+                n = 0;
+            }
             while (n > 0) {
                 uint32_t *c_in = ctx->d_counts + cur, *c_out = ctx->d_counts + (cur ^ 1), *c_sh = ctx->d_counts + 2;
                 CK(cudaMemsetAsync(c_out, 0, sizeof(uint32_t), st));
@@ -564,7 +640,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
             }
             S.max_depth_seen = std::max<uint64_t>(S.max_depth_seen, iter);
             if (prof) CK(cudaEventRecord(ctx->ev[2], st));
-            k_accum<<<grid_for(ctx, npix, 8), kBlock, 0, st>>>(ctx->lacc, npix, nb, ctx->img_sum, s0 == 0 ? 1 : 0);
+            k_accum<<<grid_for(ctx, npix, 8), kBlock, 0, st>>>(ctx->lacc, npix, nb, n_slots, ctx->img_sum, s0 == 0 ? 1 : 0);
             ctx->launches++;
             if (prof) {
                 CK(cudaEventRecord(ctx->ev[3], st));

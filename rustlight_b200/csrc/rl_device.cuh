@@ -894,4 +894,78 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
     out->next.rng_n = smp.n;
 }
 
+// ---- `direct` integrator (IntegratorDirect::compute_pixel, direct.rs:21-233) ------------------------
+// Stage 1 runs on the primary hit: emission, then nb_light_samples shadow segments and
+// nb_bsdf_samples extension rays.  Stage 2 runs on the hit of an extension ray.  Every
+// contribution of one pixel sample goes to its own radiance slot (0 = emission, 1..nl = light
+// samples, nl+1.. = BSDF samples) and the slots are summed in that order, which is the order of
+// the reference's `l_i +=` statements.
+struct DirectCtx {
+    Surface its;
+    Material mat;
+    Sampler smp;
+    float wb, wl; // weight_nb_bsdf, weight_nb_light (direct.rs:48-57)
+    bool ok;      // primary ray hit a surface seen from its front side
+    Col emit;
+};
+RL_HD void direct_begin(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, const HitRec &hit, uint32_t rng_n, uint32_t pixel, uint32_t sample,
+                        DirectCtx *cx) {
+    cx->ok = false;
+    cx->emit = Col{0.0f, 0.0f, 0.0f};
+    if (hit.prim == RL_MISS) return; // environment luminance is zero on this path (direct.rs:35)
+    float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
+    uint32_t mesh = f2u(s0.w);
+    cx->mat = load_material(sv.mats, mesh);
+    cx->its = fill_intersection(sv, cx->mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
+    if (cx->its.wi.z <= 0.0f) return; // its.cos_theta() <= 0 (direct.rs:40-42)
+    cx->ok = true;
+    if (cx->mat.is_light) cx->emit = cx->mat.le;
+    cx->wb = ip.nb_bsdf_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_bsdf_samples;
+    cx->wl = ip.nb_light_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_light_samples;
+    cx->smp = make_sampler(ip.seed_h, pixel, sample, rng_n);
+}
+// One light sample (direct.rs:63-129).  Returns true when a shadow segment must be traced;
+// *valid tells whether the reference would have called Acceleration::visible.
+RL_HD bool direct_light_sample(const SceneView &sv, DirectCtx *cx, V3 *p1, Col *contrib, bool *valid) {
+    float r_sel = cx->smp.next();
+    float r = cx->smp.next();
+    float ux = cx->smp.next();
+    float uy = cx->smp.next();
+    LightSample ls = sample_light(sv, cx->its.p, r_sel, r, ux, uy);
+    *valid = ls.valid;
+    if (!ls.valid) return false;
+    V3 wo = to_local(cx->its.frame, ls.d);
+    float pdf_bsdf = bsdf_pdf(cx->mat, cx->its.wi, wo);
+    float weight_light = mis_weight_power(ls.pdf * cx->wl, pdf_bsdf * cx->wb);
+    Col c = mul_checked(mul_plain(weight_light, bsdf_eval(cx->mat, cx->its.wi, wo)), cx->wl) * ls.weight;
+    *p1 = ls.p;
+    *contrib = c;
+    return !is_zero(c);
+}
+// One BSDF sample (direct.rs:135-144): the extension ray and what stage 2 needs (weight, pdf).
+RL_HD bool direct_bsdf_sample(DirectCtx *cx, V3 *dir, Col *weight, float *pdf) {
+    float sx = cx->smp.next();
+    float sy = cx->smp.next();
+    V3 wo;
+    if (!bsdf_sample(cx->mat, cx->its.wi, sx, sy, weight, &wo, pdf)) return false;
+    *dir = to_world(cx->its.frame, wo);
+    return true;
+}
+// Stage 2 (direct.rs:145-181): the extension ray hit something; contribution if it is a light.
+RL_HD bool direct_finish(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, const HitRec &hit, Col bsdf_weight, float bsdf_pdf_v, Col *contrib) {
+    if (hit.prim == RL_MISS) return false;
+    float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
+    uint32_t mesh = f2u(s0.w);
+    Material mat = load_material(sv.mats, mesh);
+    if (!mat.is_light) return false;
+    Surface nx = fill_intersection(sv, mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
+    if (!(dot(nx.n_g, -d) > 0.0f)) return false;
+    float wb = ip.nb_bsdf_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_bsdf_samples;
+    float wl = ip.nb_light_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_light_samples;
+    float light_pdf = direct_pdf(mat, o, nx.p, nx.n_g, d);
+    float weight_bsdf = mis_weight_power(bsdf_pdf_v * wb, light_pdf * wl);
+    *contrib = mul_checked(mul_plain(weight_bsdf, bsdf_weight) * mat.le, wb);
+    return true;
+}
+
 } // namespace rl

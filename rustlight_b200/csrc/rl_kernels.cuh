@@ -45,7 +45,7 @@ __device__ __forceinline__ void stage_scene(const SceneView &sv, float4 *smem, u
 // ---- ray generation ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list, uint32_t n_paths,
                                                    float4 *__restrict__ ray_o, float4 *__restrict__ ray_d, float4 *__restrict__ state,
-                                                   float4 *__restrict__ lacc) {
+                                                   float4 *__restrict__ lacc, uint32_t n_slots) {
     for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n_paths; id += gridDim.x * blockDim.x) {
         uint32_t s_local = id / ip.npix, lp = id - s_local * ip.npix;
         uint32_t pixel = __ldg(pixel_list + lp);
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, IntegParams ip,
         ray_o[id] = make_float4(o.x, o.y, o.z, u2f(id));
         ray_d[id] = make_float4(d.x, d.y, d.z, 1.0f);
         state[id] = make_float4(1.0f, 1.0f, 1.0f, u2f((1u << 16) | smp.n));
-        lacc[id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (uint32_t sl = 0; sl < n_slots; sl++) lacc[(size_t)sl * n_paths + id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 
@@ -225,6 +225,88 @@ __global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, IntegParams ip, 
     }
 }
 
+// ---- `direct` integrator, stage 1: primary hit -> emission, light samples, BSDF samples ---------------
+__global__ void __launch_bounds__(kBlock) k_shade_direct1(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
+                                                          const uint32_t *__restrict__ count_in, uint32_t n_paths, const float4 *__restrict__ ray_o,
+                                                          const float4 *__restrict__ ray_d, const float4 *__restrict__ state,
+                                                          const float4 *__restrict__ hit, float4 *__restrict__ out_o, float4 *__restrict__ out_d,
+                                                          float4 *__restrict__ out_state, uint32_t *count_out, float4 *__restrict__ sh_a,
+                                                          float4 *__restrict__ sh_b, float4 *__restrict__ sh_c, uint32_t *count_shadow,
+                                                          float4 *__restrict__ lacc, Counters *counters) {
+    __shared__ uint32_t s_warp[kBlock / 32];
+    __shared__ uint32_t s_base;
+    const uint32_t n = *count_in;
+    const uint32_t n_tiles = (n + kBlock - 1) / kBlock;
+    uint32_t c_hits = 0, c_nee = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t i = tile * kBlock + threadIdx.x;
+        DirectCtx cx;
+        cx.ok = false;
+        uint32_t pid = 0;
+        if (i < n) {
+            float4 ro = ray_o[i], rd = ray_d[i], st4 = state[i], h4 = hit[i];
+            HitRec h;
+            h.t = h4.x, h.u = h4.y, h.v = h4.z, h.prim = f2u(h4.w);
+            pid = f2u(ro.w);
+            uint32_t s_local = pid / ip.npix, lp = pid - s_local * ip.npix;
+            direct_begin(sv, ip, xyz(ro), xyz(rd), h, f2u(st4.w) & 0xffffu, __ldg(pixel_list + lp), ip.sample_base + s_local, &cx);
+            if (h.prim != RL_MISS) c_hits++;
+            if (cx.ok && !is_zero(cx.emit)) lacc[pid] = make_float4(cx.emit.r, cx.emit.g, cx.emit.b, 0.0f);
+        }
+        for (uint32_t j = 0; j < ip.nb_light_samples; j++) {
+            V3 p1 = V3{0.0f, 0.0f, 0.0f};
+            Col c = Col{0.0f, 0.0f, 0.0f};
+            bool valid = false;
+            bool emit_sh = cx.ok && direct_light_sample(sv, &cx, &p1, &c, &valid);
+            if (valid) c_nee++;
+            uint32_t slot = block_compact(emit_sh, count_shadow, s_warp, &s_base);
+            if (emit_sh) {
+                sh_a[slot] = make_float4(cx.its.p.x, cx.its.p.y, cx.its.p.z, u2f((1u + j) * n_paths + pid));
+                sh_b[slot] = make_float4(p1.x, p1.y, p1.z, 0.0f);
+                sh_c[slot] = make_float4(c.r, c.g, c.b, 0.0f);
+            }
+        }
+        for (uint32_t k = 0; k < ip.nb_bsdf_samples; k++) {
+            V3 dir = V3{0.0f, 0.0f, 0.0f};
+            Col w = Col{0.0f, 0.0f, 0.0f};
+            float pdf = 0.0f;
+            bool go = cx.ok && direct_bsdf_sample(&cx, &dir, &w, &pdf);
+            uint32_t slot = block_compact(go, count_out, s_warp, &s_base);
+            if (go) {
+                out_o[slot] = make_float4(cx.its.p.x, cx.its.p.y, cx.its.p.z, u2f(pid));
+                out_d[slot] = make_float4(dir.x, dir.y, dir.z, pdf);
+                out_state[slot] = make_float4(w.r, w.g, w.b, u2f((1u + ip.nb_light_samples + k) * n_paths + pid));
+            }
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        c_hits += __shfl_down_sync(0xffffffffu, c_hits, off);
+        c_nee += __shfl_down_sync(0xffffffffu, c_nee, off);
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        if (c_hits) atomicAdd(&counters->hits, (unsigned long long)c_hits);
+        if (c_nee) atomicAdd(&counters->nee_sampled, (unsigned long long)c_nee);
+    }
+}
+// stage 2: the BSDF-sampled ray hit something; MIS-weighted emission if it is a light (direct.rs:145-181)
+__global__ void __launch_bounds__(kBlock) k_shade_direct2(SceneView sv, IntegParams ip, const uint32_t *__restrict__ count_in,
+                                                          const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d,
+                                                          const float4 *__restrict__ state, const float4 *__restrict__ hit, float4 *__restrict__ lacc,
+                                                          Counters *counters) {
+    const uint32_t n = *count_in;
+    uint32_t c_hits = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 ro = ray_o[i], rd = ray_d[i], st4 = state[i], h4 = hit[i];
+        HitRec h;
+        h.t = h4.x, h.u = h4.y, h.v = h4.z, h.prim = f2u(h4.w);
+        if (h.prim != RL_MISS) c_hits++;
+        Col c;
+        if (direct_finish(sv, ip, xyz(ro), xyz(rd), h, Col{st4.x, st4.y, st4.z}, rd.w, &c)) lacc[f2u(st4.w)] = make_float4(c.r, c.g, c.b, 0.0f);
+    }
+    for (int off = 16; off > 0; off >>= 1) c_hits += __shfl_down_sync(0xffffffffu, c_hits, off);
+    if ((threadIdx.x & 31u) == 0 && c_hits) atomicAdd(&counters->hits, (unsigned long long)c_hits);
+}
+
 // ---- shadow rays + NEE resolve ---------------------------------------------------------------------
 template <bool SMEM>
 __global__ void __launch_bounds__(kBlock) k_shadow(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ sh_a,
@@ -287,13 +369,20 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneView sv, const uint32_t 
 }
 
 // ---- per-pixel accumulation in sample order (Bitmap::accumulate, structure.rs:397-402) ------------
-__global__ void __launch_bounds__(kBlock) k_accum(const float4 *__restrict__ lacc, uint32_t npix, uint32_t n_samples, float4 *__restrict__ img_sum,
-                                                  int first_batch) {
+__global__ void __launch_bounds__(kBlock) k_accum(const float4 *__restrict__ lacc, uint32_t npix, uint32_t n_samples, uint32_t n_slots,
+                                                  float4 *__restrict__ img_sum, int first_batch) {
+    const size_t n_paths = (size_t)npix * n_samples;
     for (uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x; lp < npix; lp += gridDim.x * blockDim.x) {
         float4 s = first_batch ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : img_sum[lp];
         for (uint32_t k = 0; k < n_samples; k++) {
-            float4 l = lacc[(size_t)k * npix + lp];
-            s.x += l.x, s.y += l.y, s.z += l.z;
+            // one pixel sample: its slots in the order of the reference's `l_i +=` statements, then
+            // Bitmap::accumulate of the sample (structure.rs:397-402)
+            float4 c = lacc[(size_t)k * npix + lp];
+            for (uint32_t sl = 1; sl < n_slots; sl++) {
+                float4 l = lacc[sl * n_paths + (size_t)k * npix + lp];
+                c.x += l.x, c.y += l.y, c.z += l.z;
+            }
+            s.x += c.x, s.y += c.y, s.z += c.z;
         }
         img_sum[lp] = s;
     }

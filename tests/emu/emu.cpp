@@ -176,7 +176,7 @@ struct emu_stats {
 // The wavefront of rl_render, executed one path at a time (each path is independent).
 int emu_render(const emu_scene *s, const rl_integrator_desc *I, uint32_t spp, uint64_t seed, uint32_t rank, uint32_t nranks, float *out_rgb,
                emu_stats *stats) {
-    if (!s || !I || spp == 0 || I->kind != RL_INTEGRATOR_PATH) return RL_ERR_INVALID;
+    if (!s || !I || spp == 0) return RL_ERR_INVALID;
     const SceneView &sv = s->sv;
     const uint32_t W = s->hs.img_w, H = s->hs.img_h;
     IntegParams ip{};
@@ -204,6 +204,47 @@ int emu_render(const emu_scene *s, const rl_integrator_desc *I, uint32_t spp, ui
                 st.T = Col{1.0f, 1.0f, 1.0f}, st.pdf_prev = 1.0f, st.path_id = 0, st.depth = 1, st.rng_n = smp.n;
                 float L[3] = {0.0f, 0.0f, 0.0f};
                 uint64_t iter = 0;
+                if (I->kind == RL_INTEGRATOR_DIRECT) {
+                    // k_trace -> k_shade_direct1 -> k_shadow -> k_trace -> k_shade_direct2; slots summed in order (k_accum)
+                    std::vector<Col> slots(1 + ip.nb_light_samples + ip.nb_bsdf_samples, Col{0.0f, 0.0f, 0.0f});
+                    S.segments++;
+                    HitRec h = trace_closest(sv, sv.nodes, sv.trav, o, d);
+                    if (h.prim != RL_MISS) S.hits++;
+                    DirectCtx cx;
+                    direct_begin(sv, ip, o, d, h, st.rng_n, pixel, sidx, &cx);
+                    if (cx.ok) slots[0] = cx.emit;
+                    for (uint32_t j = 0; j < ip.nb_light_samples && cx.ok; j++) {
+                        V3 p1;
+                        Col c;
+                        bool valid;
+                        bool sh = direct_light_sample(sv, &cx, &p1, &c, &valid);
+                        if (valid) S.shadow_rays++;
+                        if (sh) {
+                            S.shadow_traced++;
+                            if (trace_visible(sv, sv.nodes, sv.trav, cx.its.p, p1)) {
+                                S.shadow_visible++;
+                                slots[1 + j] = c;
+                            }
+                        }
+                    }
+                    for (uint32_t k = 0; k < ip.nb_bsdf_samples && cx.ok; k++) {
+                        V3 dir;
+                        Col w;
+                        float pdf;
+                        if (!direct_bsdf_sample(&cx, &dir, &w, &pdf)) continue;
+                        S.segments++;
+                        HitRec h2 = trace_closest(sv, sv.nodes, sv.trav, cx.its.p, dir);
+                        if (h2.prim != RL_MISS) S.hits++;
+                        Col c;
+                        if (direct_finish(sv, ip, cx.its.p, dir, h2, w, pdf, &c)) slots[1 + ip.nb_light_samples + k] = c;
+                    }
+                    Col tot = slots[0];
+                    for (size_t q = 1; q < slots.size(); q++) tot = tot + slots[q];
+                    sum[0] += tot.r, sum[1] += tot.g, sum[2] += tot.b;
+                    S.max_depth_seen = std::max<uint64_t>(S.max_depth_seen, 2);
+                    S.samples++;
+                    continue;
+                }
                 for (;;) {
                     iter++;
                     S.segments++;

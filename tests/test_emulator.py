@@ -122,3 +122,13 @@ def test_tile_partition(cbox64):
     parts = [esc.render(integ, 3, rank=r, nranks=2)[0] for r in range(2)]
     assert np.array_equal(parts[0] + parts[1], full)
     assert not (parts[0].astype(bool) & parts[1].astype(bool)).any()
+
+
+@pytest.mark.parametrize("nb,nl", [(1, 1), (2, 3), (0, 2), (3, 0)])
+def test_direct_render_bit_exact(nb, nl):
+    sc = load_cbox(96, 80)
+    integ = _abi.direct_desc(nb, nl)
+    ie, se = eb.EmuScene(sc).render(integ, 5, seed=4)
+    io, so = ob.OracleScene(sc).render(integ, 5, seed=4, cfg=ob.config(accel_mode=ob.ACCEL_NAIVE))
+    assert (se.segments, se.hits, se.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+    assert np.array_equal(ie, io)

@@ -253,3 +253,36 @@ def test_error_codes(gpu_ctx, cbox_dev, cbox):
     st = _abi.rl_stats()
     integ = _abi.path_desc()
     assert lib().rl_render(gpu_ctx._h, cbox_dev._h, C.byref(integ), C.byref(opts), None, C.byref(st)) == _abi.RL_ERR_UNSUPPORTED
+
+
+# ---- `direct` integrator (BASELINE configs[3]) ----------------------------------------------------------------------
+@pytest.mark.parametrize("nb,nl", [(1, 1), (2, 3), (0, 2), (3, 0)])
+def test_direct_render_bit_exact_vs_oracle(gpu_ctx, nb, nl):
+    sc = load_cbox(200, 136)
+    dev = DeviceScene(gpu_ctx, sc)
+    integ = _abi.direct_desc(nb, nl)
+    img, st = dev.render(integ, 6, seed=4, batch_spp=4)
+    ref, so = ob.OracleScene(sc).render(integ, 6, seed=4, cfg=ob.config(accel_mode=ob.ACCEL_NAIVE))
+    assert (st.samples, st.segments, st.hits, st.shadow_rays) == (so.samples, so.segments, so.hits, so.shadow_rays)
+    assert np.array_equal(img, ref)
+    faithful, _ = ob.OracleScene(sc).render(integ, 6, seed=4, cfg=ob.config(math_mode=ob.MATH_LIBM, accel_mode=ob.ACCEL_BVH))
+    assert rel_l2(img, faithful) < TOL
+    dev.close()
+
+
+def test_direct_golden_and_full_size_property(gpu_ctx):
+    g = np.load(os.path.join(GOLDEN, "cbox64_spp16_seed0.npz"))
+    dev = DeviceScene(gpu_ctx, load_cbox(64, 64))
+    img, st = dev.render(_abi.direct_desc(1, 1), 16, seed=0)
+    assert rel_l2(img, g["direct"]) < TOL and abs(int(st.segments) - int(g["direct_counts"][0])) <= 4
+    dev.close()
+    # configs[3] size: 2048x2048 (`-s 4`), direct -n 64 is 3 rays per sample; here 4 spp of it
+    big = DeviceScene(gpu_ctx, load_cbox().scale_image(4.0))
+    a, sa = big.render(_abi.direct_desc(1, 1), 4, seed=1)
+    b, sb = big.render(_abi.direct_desc(1, 1), 4, seed=1, batch_spp=1)
+    assert np.array_equal(a, b) and sa.segments == sb.segments
+    assert sa.samples == 2048 * 2048 * 4 and sa.segments <= 2 * sa.samples and sa.shadow_rays <= sa.samples
+    # direct lighting is the depth-2 truncation of the path integrator: same expectation
+    p, _ = big.render(_abi.path_desc(max_depth=3), 4, seed=2)
+    assert a.mean(axis=(0, 1)) == pytest.approx(p.mean(axis=(0, 1)), rel=0.02)
+    big.close()
