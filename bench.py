@@ -261,10 +261,13 @@ def main():
     # ---- roofline of the dominant kernel (closest-hit traversal), per-stage CUDA events ----
     roof = None
     stage_ms = None
+    # every rank runs the profiled step: rl_render contains the collective (ncclReduce)
+    barrier()
+    ctx.set_profiling(True)
+    st = step_device()
+    ctx.set_profiling(False)
+    barrier()
     if rank == 0:
-        ctx.set_profiling(True)
-        st = step_device()
-        ctx.set_profiling(False)
         peak, peak_src = measured_peaks()
         n_trace = int(st.max_depth_seen) if st.max_depth_seen else 1
         launches_trace = max(1, (st.kernel_launches - 1) // 3) if st.kernel_launches else 1
