@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -74,7 +75,8 @@ struct rl_ctx {
     uint32_t *pixel_list = nullptr;
     float *frame = nullptr; // W*H*3 mean image of this rank (zeros outside its tiles)
     uint32_t pl_w = 0, pl_h = 0, pl_npix = 0;
-    uint32_t *d_counts = nullptr; // [cur/next ping-pong x2, shadow, pad]
+    uint32_t *d_counts = nullptr; // [cur/next ping-pong x2, shadow, pad] (direct integrator, rl_trace)
+    uint32_t *d_hist = nullptr, *h_hist = nullptr; // queue length per wavefront iteration [0,kMaxIters) and shadow-queue length [kMaxIters, 2*kMaxIters)
     Counters *d_counters = nullptr;
     uint32_t *h_counts = nullptr; // pinned
     Counters *h_counters = nullptr;
@@ -103,6 +105,10 @@ struct rl_scene {
     } while (0)
 
 static constexpr size_t kMaxSmemScene = 96 * 1024;
+static constexpr uint32_t kMaxIters = 4096; // wavefront iterations per batch (path depth); 0.95^4096 ~ 1e-91
+#ifndef RL_SYNC_GROUP
+#define RL_SYNC_GROUP 4
+#endif
 
 static int grid_for(const rl_ctx *ctx, size_t n, int per_sm) {
     size_t blocks = (n + kBlock - 1) / kBlock;
@@ -166,6 +172,8 @@ int rl_create(rl_ctx **out, int device, int nranks, int rank, const void *nccl_u
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CKC(cudaMalloc(&ctx->d_counts, 4 * sizeof(uint32_t)));
     CKC(cudaMalloc(&ctx->d_counters, sizeof(Counters)));
+    CKC(cudaMalloc(&ctx->d_hist, 2 * kMaxIters * sizeof(uint32_t)));
+    CKC(cudaMallocHost(&ctx->h_hist, 2 * kMaxIters * sizeof(uint32_t)));
     CKC(cudaMallocHost(&ctx->h_counts, 4 * sizeof(uint32_t)));
     CKC(cudaMallocHost(&ctx->h_counters, sizeof(Counters)));
     for (auto &ev : ctx->ev) CKC(cudaEventCreate(&ev));
@@ -199,7 +207,8 @@ void rl_destroy(rl_ctx *ctx) {
     }
     cudaFree(ctx->hit), cudaFree(ctx->sh_a), cudaFree(ctx->sh_b), cudaFree(ctx->sh_c), cudaFree(ctx->lacc);
     cudaFree(ctx->img_sum), cudaFree(ctx->pixel_list), cudaFree(ctx->frame);
-    cudaFree(ctx->d_counts), cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_counts), cudaFree(ctx->d_counters), cudaFree(ctx->d_hist);
+    cudaFreeHost(ctx->h_hist);
     cudaFreeHost(ctx->h_counts), cudaFreeHost(ctx->h_counters);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
@@ -253,11 +262,12 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     cudaStream_t st = ctx->stream;
     uint64_t *d_keys = nullptr, *d_keys_sorted = nullptr;
     int2 *d_children = nullptr;
+    int2v *d_ranges = nullptr;
     int *d_parent_node = nullptr, *d_parent_leaf = nullptr, *d_flags = nullptr;
     float4 *d_leaf_lo = nullptr, *d_leaf_hi = nullptr, *d_node_lo = nullptr, *d_node_hi = nullptr;
     void *d_tmp = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_keys), cudaFree(d_keys_sorted), cudaFree(d_children), cudaFree(d_parent_node), cudaFree(d_parent_leaf);
+        cudaFree(d_keys), cudaFree(d_keys_sorted), cudaFree(d_children), cudaFree(d_ranges), cudaFree(d_parent_node), cudaFree(d_parent_leaf);
         cudaFree(d_flags), cudaFree(d_leaf_lo), cudaFree(d_leaf_hi), cudaFree(d_node_lo), cudaFree(d_node_hi), cudaFree(d_tmp);
     };
 #define CKS(call)                                                                                                  \
@@ -277,7 +287,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     CKS(upload(&s->d_emit_cdf, hs.emit_cdf, st));
     CKS(upload(&s->d_area_cdf, hs.area_cdf, st));
     const uint32_t n_nodes = n > 1 ? n - 1 : 1;
-    CKS(cudaMalloc(&s->d_trav, (size_t)n * 4 * sizeof(float4)));
+    CKS(cudaMalloc(&s->d_trav, (size_t)n * RL_TRAV_F4 * sizeof(float4)));
     CKS(cudaMalloc(&s->d_nodes, (size_t)n_nodes * 4 * sizeof(float4)));
     CKS(cudaMalloc(&d_keys, (size_t)n * 8));
     CKS(cudaMalloc(&d_keys_sorted, (size_t)n * 8));
@@ -295,50 +305,59 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     CKS(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_keys_sorted, (int)n, 0, 64, st));
     k_tri_setup<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(s->d_verts, d_keys_sorted, n, bvh_box_eps(hs.abs_max), s->d_trav, s->d_shade, d_leaf_lo, d_leaf_hi);
     CKS(cudaGetLastError());
+    // Leaf size: scenes of up to 64 triangles become ONE leaf (every lane scans the same triangles in
+    // lockstep: no SIMT divergence, shared-memory broadcasts); larger scenes collapse subtrees of <= 4.
+    int leaf_max = n <= (uint32_t)RL_LEAF_MAX_CAP ? RL_LEAF_MAX_CAP : 4;
+    if (const char *e = getenv("RL_LEAF_MAX")) leaf_max = std::max(1, std::min(RL_LEAF_MAX_CAP, atoi(e)));
+    if (n >= (1u << 25)) {
+        ctx->err = "rl_scene_create: more than 2^25 triangles";
+        cleanup();
+        rl_scene_destroy(ctx, s);
+        return RL_ERR_UNSUPPORTED;
+    }
     std::vector<int2> h_children;
+    std::vector<int2v> h_ranges;
     if (n > 1) {
         CKS(cudaMalloc(&d_children, (size_t)(n - 1) * sizeof(int2)));
+        CKS(cudaMalloc(&d_ranges, (size_t)(n - 1) * sizeof(int2v)));
         CKS(cudaMalloc(&d_parent_node, (size_t)(n - 1) * sizeof(int)));
         CKS(cudaMalloc(&d_parent_leaf, (size_t)n * sizeof(int)));
         CKS(cudaMalloc(&d_flags, (size_t)(n - 1) * sizeof(int)));
         CKS(cudaMalloc(&d_node_lo, (size_t)(n - 1) * sizeof(float4)));
         CKS(cudaMalloc(&d_node_hi, (size_t)(n - 1) * sizeof(float4)));
         CKS(cudaMemsetAsync(d_flags, 0, (size_t)(n - 1) * sizeof(int), st));
-        k_karras<<<grid_for(ctx, n - 1, 8), kBlock, 0, st>>>(d_keys_sorted, (int)n, d_children, d_parent_node, d_parent_leaf);
+        k_karras<<<grid_for(ctx, n - 1, 8), kBlock, 0, st>>>(d_keys_sorted, (int)n, d_children, d_ranges, d_parent_node, d_parent_leaf);
         CKS(cudaGetLastError());
-        k_fit<<<grid_for(ctx, n, 8), kBlock, 0, st>>>((int)n, d_children, d_parent_node, d_parent_leaf, d_leaf_lo, d_leaf_hi, d_node_lo, d_node_hi,
-                                                        d_flags, s->d_nodes);
+        k_fit<<<grid_for(ctx, n, 8), kBlock, 0, st>>>((int)n, leaf_max, d_children, d_ranges, d_parent_node, d_parent_leaf, d_leaf_lo, d_leaf_hi, d_node_lo,
+                                                        d_node_hi, d_flags, s->d_nodes);
         CKS(cudaGetLastError());
         h_children.resize(n - 1);
+        h_ranges.resize(n - 1);
         CKS(cudaMemcpyAsync(h_children.data(), d_children, (size_t)(n - 1) * sizeof(int2), cudaMemcpyDeviceToHost, st));
-    } else {
-        // single triangle: one node whose first child is the leaf and whose second child box is empty
-        float4 lo, hi;
-        CKS(cudaStreamSynchronize(st));
-        CKS(cudaMemcpy(&lo, d_leaf_lo, sizeof(float4), cudaMemcpyDeviceToHost));
-        CKS(cudaMemcpy(&hi, d_leaf_hi, sizeof(float4), cudaMemcpyDeviceToHost));
-        float4 node[4];
-        const float inf = RL_F32_MAX;
-        node[0] = f4(lo.x, lo.y, lo.z, hi.x);
-        node[1] = f4(hi.y, hi.z, inf, inf);
-        node[2] = f4(inf, -inf, -inf, -inf);
-        node[3] = f4(u2f((uint32_t)~0), u2f((uint32_t)~0), 0.0f, 0.0f);
-        CKS(cudaMemcpy(s->d_nodes, node, sizeof(node), cudaMemcpyHostToDevice));
+        CKS(cudaMemcpyAsync(h_ranges.data(), d_ranges, (size_t)(n - 1) * sizeof(int2v), cudaMemcpyDeviceToHost, st));
     }
     CKS(cudaStreamSynchronize(st));
     cleanup();
 #undef CKS
-    // tree statistics (and the traversal-stack bound)
-    uint32_t max_depth = 1;
-    if (n > 1) {
+    // tree statistics over the live part of the tree (and the traversal-stack bound)
+    uint32_t max_depth = 1, live_nodes = 0, live_leaves = 0;
+    int root_ref;
+    if (n <= (uint32_t)leaf_max) {
+        root_ref = leaf_ref(0u, n);
+        live_leaves = 1;
+    } else {
+        root_ref = 0;
         std::vector<std::pair<int, uint32_t>> stack{{0, 1u}};
         while (!stack.empty()) {
             auto [node, depth] = stack.back();
             stack.pop_back();
+            live_nodes++;
             max_depth = std::max(max_depth, depth);
             int2 ch = h_children[node];
-            if (ch.x >= 0) stack.push_back({ch.x, depth + 1});
-            if (ch.y >= 0) stack.push_back({ch.y, depth + 1});
+            for (int c : {ch.x, ch.y}) {
+                if (c >= 0 && h_ranges[c].y - h_ranges[c].x + 1 > leaf_max) stack.push_back({c, depth + 1});
+                else live_leaves++;
+            }
         }
     }
     if (max_depth + 1 > RL_STACK_SIZE) {
@@ -347,13 +366,14 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
         return RL_ERR_UNSUPPORTED;
     }
     s->n_node_f4 = n_nodes * 4;
-    s->n_trav_f4 = n * 4;
+    s->n_trav_f4 = n * RL_TRAV_F4;
     s->smem_bytes = (size_t)(s->n_node_f4 + s->n_trav_f4) * sizeof(float4);
     s->smem_ok = s->smem_bytes <= kMaxSmemScene;
     SceneView &sv = s->sv;
     sv.trav = s->d_trav, sv.nodes = s->d_nodes, sv.shade = s->d_shade, sv.verts = s->d_verts, sv.mats = s->d_mats;
     sv.emit_info = s->d_emit_info, sv.emit_cdf = s->d_emit_cdf, sv.area_cdf = s->d_area_cdf;
     sv.ntris = n, sv.n_emitters = hs.n_emitters;
+    sv.root_ref = root_ref;
     sv.root_min = V3{hs.root_min[0], hs.root_min[1], hs.root_min[2]};
     sv.root_max = V3{hs.root_max[0], hs.root_max[1], hs.root_max[2]};
     sv.abs_max = hs.abs_max;
@@ -361,7 +381,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     std::memcpy(sv.c2w, hs.c2w, 64);
     sv.cam_pos = V3{hs.cam_pos[0], hs.cam_pos[1], hs.cam_pos[2]};
     sv.img_w = (float)hs.img_w, sv.img_h = (float)hs.img_h;
-    s->info.ntris = n, s->info.nnodes = n_nodes, s->info.nleaves = n, s->info.max_depth = max_depth;
+    s->info.ntris = n, s->info.nnodes = live_nodes, s->info.nleaves = live_leaves, s->info.max_depth = max_depth;
     std::memcpy(s->info.root_min, hs.root_min, 12);
     std::memcpy(s->info.root_max, hs.root_max, 12);
     s->info.smem_resident = s->smem_ok ? 1u : 0u;
@@ -605,38 +625,57 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                 }
                 n = 0;
             }
-            while (n > 0) {
-                uint32_t *c_in = ctx->d_counts + cur, *c_out = ctx->d_counts + (cur ^ 1), *c_sh = ctx->d_counts + 2;
-                CK(cudaMemsetAsync(c_out, 0, sizeof(uint32_t), st));
-                CK(cudaMemsetAsync(c_sh, 0, sizeof(uint32_t), st));
-                if (prof) CK(cudaEventRecord(ctx->ev[2], st));
-                if (sc->smem_ok) launch_trace<true>(ctx, sc, c_in, n, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit);
-                else launch_trace<false>(ctx, sc, c_in, n, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit);
-                if (prof) CK(cudaEventRecord(ctx->ev[3], st));
-                k_shade<<<grid_for(ctx, n, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, c_in, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur],
-                                                                ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1], ctx->state[cur ^ 1], c_out, ctx->sh_a,
-                                                                ctx->sh_b, ctx->sh_c, c_sh, ctx->lacc, ctx->d_counters);
-                ctx->launches++;
-                if (prof) CK(cudaEventRecord(ctx->ev[4], st));
-                // the shadow queue can never be longer than the input queue: size the grid from n
-                if (sc->smem_ok) launch_shadow<true>(ctx, sc, c_sh, n);
-                else launch_shadow<false>(ctx, sc, c_sh, n);
-                if (prof) CK(cudaEventRecord(ctx->ev[5], st));
-                CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                CK(cudaGetLastError());
-                if (prof) {
-                    CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-                    S.ms_trace += ms;
-                    CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
-                    S.ms_shade += ms;
-                    CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
-                    S.ms_shadow += ms;
+            if (n > 0) {
+                // Queue lengths live in a per-iteration history on the device (iteration k reads hist[k] and
+                // appends to hist[k+1]), so the host launches RL_SYNC_GROUP iterations back to back and only
+                // then reads the lengths; launches past the end of the longest path see empty queues.
+                uint32_t *qc = ctx->d_hist, *shc = ctx->d_hist + kMaxIters;
+                CK(cudaMemsetAsync(ctx->d_hist, 0, 2 * kMaxIters * sizeof(uint32_t), st));
+                k_set_u32<<<1, 1, 0, st>>>(qc, (uint32_t)n_paths);
+                uint32_t k = 0, k_read = 0;
+                size_t n_ub = n_paths; // upper bound of the current queue length (lengths never grow)
+                const uint32_t group = prof ? 1u : (uint32_t)RL_SYNC_GROUP;
+                while (n_ub > 0) {
+                    if (k + group >= kMaxIters) {
+                        ctx->err = "rl_render: a path exceeded 4095 wavefront iterations (no Russian roulette in a closed scene?)";
+                        return RL_ERR_UNSUPPORTED;
+                    }
+                    for (uint32_t g = 0; g < group; g++, k++) {
+                        if (prof) CK(cudaEventRecord(ctx->ev[2], st));
+                        if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit);
+                        else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit);
+                        if (prof) CK(cudaEventRecord(ctx->ev[3], st));
+                        k_shade<<<grid_for(ctx, n_ub, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur],
+                                                                           ctx->state[cur], ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1],
+                                                                           ctx->state[cur ^ 1], qc + k + 1, ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc,
+                                                                           ctx->d_counters);
+                        ctx->launches++;
+                        if (prof) CK(cudaEventRecord(ctx->ev[4], st));
+                        // the shadow queue can never be longer than the input queue: size the grid from n_ub
+                        if (sc->smem_ok) launch_shadow<true>(ctx, sc, shc + k, n_ub);
+                        else launch_shadow<false>(ctx, sc, shc + k, n_ub);
+                        if (prof) CK(cudaEventRecord(ctx->ev[5], st));
+                        cur ^= 1;
+                    }
+                    CK(cudaMemcpyAsync(ctx->h_hist + k_read, qc + k_read, (k + 1 - k_read) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                    CK(cudaGetLastError());
+                    if (prof) {
+                        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+                        S.ms_trace += ms;
+                        CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
+                        S.ms_shade += ms;
+                        CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+                        S.ms_shadow += ms;
+                    }
+                    for (uint32_t j = k_read; j < k; j++) {
+                        if (ctx->h_hist[j] == 0) break;
+                        S.segments += ctx->h_hist[j];
+                        iter++;
+                    }
+                    k_read = k;
+                    n_ub = ctx->h_hist[k];
                 }
-                S.segments += n;
-                iter++;
-                n = ctx->h_counts[cur ^ 1];
-                cur ^= 1;
             }
             S.max_depth_seen = std::max<uint64_t>(S.max_depth_seen, iter);
             if (prof) CK(cudaEventRecord(ctx->ev[2], st));

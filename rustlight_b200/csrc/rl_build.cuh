@@ -47,18 +47,26 @@ RL_HD void tri_bounds_inflated(const float4 *verts, uint32_t prim, float eps, V3
 }
 
 // Ray-independent part of Mesh::intersection_tri (geometry.rs:365-372, 383): e1, e2,
-// n_geo = normalize(e1 x e2), det = |e1 x e2|.  Written to Morton slot s; n_geo also goes to
-// the shading table.
+// n_geo = normalize(e1 x e2), det = |e1 x e2| with the reference's operations, plus the data of
+// the conservative prefilter (rl_device.cuh: tri_prefilter): plane offset pn = v0.n and the
+// affine barycentric functionals u(p) = Mu.p + cu, v(p) = Mv.p + cv.  Six float4 per triangle,
+// written to Morton slot s; n_geo also goes to the shading table.
+#define RL_TRAV_F4 6
 RL_HD void tri_setup(const float4 *verts, uint32_t prim, uint32_t s, float4 *trav, float4 *shade) {
     V3 v0 = xyz(verts[3 * prim]), v1 = xyz(verts[3 * prim + 1]), v2 = xyz(verts[3 * prim + 2]);
     V3 e1 = v1 - v0, e2 = v2 - v0;
     V3 cr = cross(e1, e2);
     V3 n_geo = normalize(cr);
     float det = magnitude(cr);
-    trav[4 * s + 0] = make_float4(v0.x, v0.y, v0.z, det);
-    trav[4 * s + 1] = make_float4(e1.x, e1.y, e1.z, u2f(prim));
-    trav[4 * s + 2] = make_float4(e2.x, e2.y, e2.z, det * det * 1.0001f); // prefilter bound, see tri_test
-    trav[4 * s + 3] = make_float4(n_geo.x, n_geo.y, n_geo.z, 0.0f);
+    float idet = 1.0f / det;
+    V3 mu = cross(e2, n_geo) * idet, mv = cross(n_geo, e1) * idet;
+    float mn = fmaxf(magnitude(mu), magnitude(mv));
+    trav[RL_TRAV_F4 * s + 0] = make_float4(v0.x, v0.y, v0.z, det);
+    trav[RL_TRAV_F4 * s + 1] = make_float4(e1.x, e1.y, e1.z, u2f(prim));
+    trav[RL_TRAV_F4 * s + 2] = make_float4(e2.x, e2.y, e2.z, mn);
+    trav[RL_TRAV_F4 * s + 3] = make_float4(n_geo.x, n_geo.y, n_geo.z, dot(v0, n_geo));
+    trav[RL_TRAV_F4 * s + 4] = make_float4(mu.x, mu.y, mu.z, -dot(v0, mu));
+    trav[RL_TRAV_F4 * s + 5] = make_float4(mv.x, mv.y, mv.z, -dot(v0, mv));
     float4 s0 = shade[4 * prim];
     shade[4 * prim] = make_float4(n_geo.x, n_geo.y, n_geo.z, s0.w);
 }
@@ -76,7 +84,7 @@ RL_HD int karras_delta(const uint64_t *keys, int n, int i, int j) {
     return clz64(keys[i] ^ keys[j]);
 }
 // Internal node i of n-1: children as node refs (>=0 internal, ~leaf for leaves).
-RL_HD void karras_node(const uint64_t *keys, int n, int i, int *left, int *right) {
+RL_HD void karras_node(const uint64_t *keys, int n, int i, int *left, int *right, int *first, int *last) {
     int d = (karras_delta(keys, n, i, i + 1) - karras_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
     int dmin = karras_delta(keys, n, i, i - d);
     int lmax = 2;
@@ -94,10 +102,20 @@ RL_HD void karras_node(const uint64_t *keys, int n, int i, int *left, int *right
     } while (t > 1);
     int gamma = i + s * d + (d < 0 ? -1 : 0);
     int lo = i < j ? i : j, hi = i < j ? j : i;
+    *first = lo;
+    *last = hi;
     *left = (lo == gamma) ? ~gamma : gamma;
     *right = (hi == gamma + 1) ? ~(gamma + 1) : (gamma + 1);
 }
 
+// Child reference of a wide node: >= 0 inner node index; bit 31 set = leaf covering `count`
+// consecutive triangles of the Morton order starting at `first` (subtrees with at most
+// leaf_max triangles are collapsed into one leaf).
+RL_HD int make_child_ref(int child, const int2v *ranges, int leaf_max) {
+    if (child < 0) return leaf_ref((uint32_t)~child, 1u);
+    int size = ranges[child].y - ranges[child].x + 1;
+    return size <= leaf_max ? leaf_ref((uint32_t)ranges[child].x, (uint32_t)size) : child;
+}
 // Write the wide node: child boxes + child refs.
 RL_HD void write_wide_node(float4 *nodes, int i, V3 lo0, V3 hi0, V3 lo1, V3 hi1, int c0, int c1) {
     nodes[4 * i + 0] = make_float4(lo0.x, lo0.y, lo0.z, hi0.x);

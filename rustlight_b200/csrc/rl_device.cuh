@@ -292,6 +292,7 @@ struct SceneView {
     const float *emit_cdf; // n_emitters+1
     const float *area_cdf; // concatenated per-emitter triangle-area cdfs (ntris+1 each)
     uint32_t ntris, n_emitters;
+    int root_ref; // inner node 0, or a leaf reference when the whole scene is one leaf
     // BVHAccel nodes[0].aabb (union of compute_aabb_tri boxes), for the reference's root test
     V3 root_min, root_max;
     float abs_max; // max |coordinate| of the scene, scales the conservative-culling epsilon
@@ -302,28 +303,27 @@ struct SceneView {
 };
 
 // ---- AABB::intersect (structure.rs:849-869), used verbatim for the root box -------------------
-RL_HD bool aabb_intersect_ref(V3 pmin, V3 pmax, V3 o, V3 d, float tnear, float tfar) {
+// `inv` must be the IEEE quotients 1.0f/d.{x,y,z} (the reference computes them inside the loop;
+// they are hoisted so that the LBVH slab test can reuse them).
+RL_HD bool aabb_intersect_ref(V3 pmin, V3 pmax, V3 o, V3 inv, float tnear, float tfar) {
     float t_max = tfar, t_min = tnear;
     {
-        float inv_d = 1.0f / d.x;
-        float t0 = (pmin.x - o.x) * inv_d, t1 = (pmax.x - o.x) * inv_d;
-        if (inv_d < 0.0f) { float t = t0; t0 = t1; t1 = t; }
+        float t0 = (pmin.x - o.x) * inv.x, t1 = (pmax.x - o.x) * inv.x;
+        if (inv.x < 0.0f) { float t = t0; t0 = t1; t1 = t; }
         t_min = t0 > t_min ? t0 : t_min;
         t_max = t1 < t_max ? t1 : t_max;
         if (t_max <= t_min) return false;
     }
     {
-        float inv_d = 1.0f / d.y;
-        float t0 = (pmin.y - o.y) * inv_d, t1 = (pmax.y - o.y) * inv_d;
-        if (inv_d < 0.0f) { float t = t0; t0 = t1; t1 = t; }
+        float t0 = (pmin.y - o.y) * inv.y, t1 = (pmax.y - o.y) * inv.y;
+        if (inv.y < 0.0f) { float t = t0; t0 = t1; t1 = t; }
         t_min = t0 > t_min ? t0 : t_min;
         t_max = t1 < t_max ? t1 : t_max;
         if (t_max <= t_min) return false;
     }
     {
-        float inv_d = 1.0f / d.z;
-        float t0 = (pmin.z - o.z) * inv_d, t1 = (pmax.z - o.z) * inv_d;
-        if (inv_d < 0.0f) { float t = t0; t0 = t1; t1 = t; }
+        float t0 = (pmin.z - o.z) * inv.z, t1 = (pmax.z - o.z) * inv.z;
+        if (inv.z < 0.0f) { float t = t0; t0 = t1; t1 = t; }
         t_min = t0 > t_min ? t0 : t_min;
         t_max = t1 < t_max ? t1 : t_max;
         if (t_max <= t_min) return false;
@@ -333,11 +333,8 @@ RL_HD bool aabb_intersect_ref(V3 pmin, V3 pmax, V3 o, V3 d, float tnear, float t
 
 // ---- Mesh::intersection_tri with the ray-independent terms (e1, e2, n_geo, det) precomputed ---
 // Exactly the reference's accept/reject decision and (t,u,v) values, with the tests re-ordered
-// (every test is a pure function of the inputs, so order cannot change the outcome) and two
-// conservative shortcuts in front of the sqrt/div pairs:
-//   * `t` is compared with the caller's bound first (the reference does it last, geometry.rs:398);
-//   * u = |a|/det > 1  <=>  |a| > det  (both roundings are monotonic), so |a|^2 > det^2 (1+1e-4)
-//     rejects without the sqrt and the divide; likewise u^2 + v^2 > 1 implies u + v > 1.
+// (every test is a pure function of the inputs, so order cannot change the outcome): `t` is
+// compared with the caller's bound first (the reference does it last, geometry.rs:398).
 // `t_bound` semantics: closest hit passes best.t and accepts t <= t_bound here (the caller
 // resolves the t == best.t tie by triangle index); shadow rays pass thr and the caller checks <.
 RL_HD bool tri_test(float4 r0, float4 r1, float4 r2, float4 r3, V3 o, V3 d, float t_bound, float *t_out, float *u_out, float *v_out) {
@@ -354,11 +351,8 @@ RL_HD bool tri_test(float4 r0, float4 r1, float4 r2, float4 r3, V3 o, V3 d, floa
     if (dot(u0, n_geo) < 0.0f) return false;
     V3 v0c = cross(pv, e2);
     if (dot(v0c, n_geo) < 0.0f) return false;
-    float a2 = dot(u0, u0), b2 = dot(v0c, v0c);
-    float det2m = r2.w; // det*det*(1+1e-4), written by tri_setup
-    if (a2 > det2m || b2 > det2m || a2 + b2 > det2m) return false;
-    float v = sqrtf(a2) / det;
-    float u = sqrtf(b2) / det;
+    float v = magnitude(u0) / det;
+    float u = magnitude(v0c) / det;
     if (u < 0.0f || v < 0.0f || u > 1.0f || v > 1.0f) return false;
     if (!(u + v <= 1.0f)) return false;
     *t_out = t;
@@ -378,6 +372,14 @@ RL_HD bool tri_test(float4 r0, float4 r1, float4 r2, float4 r3, V3 o, V3 d, floa
 #define RL_STACK_SIZE 64
 #endif
 #define RL_TRAV_DONE 0x7fffffff
+#define RL_LEAF_MAX_CAP 64
+struct int2v {
+    int x, y;
+};
+// leaf reference: bit 31 | (count-1) << 25 | first   (first < 2^25 triangles, count <= 64)
+RL_HD int leaf_ref(uint32_t first, uint32_t count) { return (int)(0x80000000u | ((count - 1u) << 25) | first); }
+RL_HD uint32_t leaf_first(int ref) { return (uint32_t)ref & 0x01ffffffu; }
+RL_HD uint32_t leaf_count(int ref) { return (((uint32_t)ref >> 25) & 63u) + 1u; }
 
 struct HitRec {
     float t, u, v;
@@ -388,22 +390,21 @@ struct Trav {
     V3 inv, ood;   // 1/d (clamped away from 0) and o/d for t = fma(plane, inv, -ood)
     V3 et;         // extra widening in t for far origins (0 otherwise)
     bool far;
+    float rs;      // coordinate scale of this ray (prefilter margins)
     float tmax;    // closest: best t so far; shadow: the segment's threshold
     float u, v;
     uint32_t prim;
     int cur;       // >= 0 inner node, < 0 leaf ~cur, RL_TRAV_DONE
     int sp;        // entries in the caller's stack array (kept outside the struct so the state stays in registers)
 };
-RL_HD float clamp_inv(float d) {
-    // |d| < 1e-18 would give inf (and NaN in the fma form); a finite 1e18 keeps every product finite
-    float ad = fabsf(d);
-    float inv = 1.0f / (ad < 1e-18f ? 1e-18f : ad);
-    return copysignf(inv, d);
+RL_HD float clamp_inv(float inv) {
+    // |1/d| > 1e18 (incl. +-inf for d = +-0) would give NaN in the fma form; a finite 1e18 keeps every product finite
+    return fabsf(inv) <= 1e18f ? inv : copysignf(1e18f, inv);
 }
-RL_HD void trav_begin(Trav &tr, const SceneView &sv, V3 o, V3 d, float tmax) {
+RL_HD void trav_begin(Trav &tr, const SceneView &sv, V3 o, V3 d, V3 inv, float tmax) {
     tr.o = o;
     tr.d = d;
-    tr.inv = V3{clamp_inv(d.x), clamp_inv(d.y), clamp_inv(d.z)};
+    tr.inv = V3{clamp_inv(inv.x), clamp_inv(inv.y), clamp_inv(inv.z)};
     tr.ood = V3{o.x * tr.inv.x, o.y * tr.inv.y, o.z * tr.inv.z};
     float m = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
     tr.far = m > 8.0f * sv.abs_max;
@@ -413,8 +414,9 @@ RL_HD void trav_begin(Trav &tr, const SceneView &sv, V3 o, V3 d, float tmax) {
     tr.u = 0.0f;
     tr.v = 0.0f;
     tr.prim = RL_MISS;
-    tr.cur = 0;
+    tr.cur = sv.root_ref;
     tr.sp = 0;
+    tr.rs = 4.0f * fmaxf(m, sv.abs_max);
 }
 // Conservative entry distance of the ray into box (lo,hi) for t in [0, tmax], or -1 on a miss.
 RL_HD float box_entry(const Trav &tr, float lox, float loy, float loz, float hix, float hiy, float hiz) {
@@ -449,38 +451,100 @@ RL_HD void trav_node_step(Trav &tr, int *stack, const float4 *nodes) {
     else if (d1 >= 0.0f) tr.cur = c1;
     else tr.cur = trav_pop(tr, stack);
 }
-// Phase B (closest hit): tr.cur is a leaf.
+// Conservative prefilter in front of the exact triangle test: approximate hit parameter and
+// barycentrics from the precomputed plane / affine functionals (fma, reciprocal), with error
+// margins that dominate every rounding term of both this estimate and the reference's own
+// arithmetic.  Returns false only when the exact test is certain to reject.
+// NaNs (degenerate triangles, d.n == 0) fall through to the exact test.
+RL_HD float rcp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); // one MUFU.RCP; 1 ulp, covered by the margins
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+RL_HD int ffs64(uint64_t m) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)m);
+#else
+    return __builtin_ffsll((long long)m);
+#endif
+}
+RL_HD bool tri_prefilter(const Trav &tr, float4 r2, float4 r3, float4 r4, float4 r5) {
+    float den = fmaf(tr.d.x, r3.x, fmaf(tr.d.y, r3.y, tr.d.z * r3.z));
+    float on = fmaf(tr.o.x, r3.x, fmaf(tr.o.y, r3.y, tr.o.z * r3.z));
+    float num = r3.w - on;
+    float rden = rcp_fast(den);
+    float tp = num * rden;
+    float mt = (tr.rs * 2e-6f + fabsf(num) * 4e-6f + fabsf(tp) * 1e-6f) * fabsf(rden);
+    if (tp < -mt || tp > tr.tmax + mt) return false;
+    float px = fmaf(tp, tr.d.x, tr.o.x), py = fmaf(tp, tr.d.y, tr.o.y), pz = fmaf(tp, tr.d.z, tr.o.z);
+    float up = fmaf(px, r4.x, fmaf(py, r4.y, fmaf(pz, r4.z, r4.w)));
+    float vp = fmaf(px, r5.x, fmaf(py, r5.y, fmaf(pz, r5.z, r5.w)));
+    float m = r2.w * (4.0f * mt + 8e-6f * tr.rs + 2e-6f * fabsf(tp)) + 1e-6f;
+    if (up < -m || vp < -m || up + vp > 1.0f + m) return false;
+    return true;
+}
+// Phase B (closest hit): tr.cur is a leaf reference.  Two uniform loops: the scan runs only the
+// prefilter and records the survivors in a bit mask (a leaf holds at most 64 triangles); the
+// exact tests then run back to back, so that the long exact path is not executed once per scan
+// iteration for the one or two lanes that need it.
+RL_HD uint64_t leaf_scan(const Trav &tr, const float4 *trav, uint32_t first, uint32_t count) {
+    uint64_t mask = 0;
+    for (uint32_t k = 0; k < count; k++) {
+        const float4 *r = trav + 6 * (first + k);
+        if (tri_prefilter(tr, r[2], r[3], r[4], r[5])) mask |= 1ull << k;
+    }
+    return mask;
+}
 RL_HD void trav_leaf_closest(Trav &tr, const int *stack, const float4 *trav) {
-    int s_ = ~tr.cur;
-    float4 r0 = trav[4 * s_], r1 = trav[4 * s_ + 1], r2 = trav[4 * s_ + 2], r3 = trav[4 * s_ + 3];
-    float t_, u_, v_;
-    if (tri_test(r0, r1, r2, r3, tr.o, tr.d, tr.tmax, &t_, &u_, &v_)) {
-        uint32_t prim_ = f2u(r1.w);
-        // reference: strict `t < its.t` in mesh-major order => on exact ties the lowest index wins
-        if (t_ < tr.tmax || (tr.prim != RL_MISS && prim_ < tr.prim)) {
-            tr.tmax = t_;
-            tr.u = u_;
-            tr.v = v_;
-            tr.prim = prim_;
+    const uint32_t first = leaf_first(tr.cur), count = leaf_count(tr.cur);
+    uint64_t mask = leaf_scan(tr, trav, first, count);
+    while (mask) {
+        const uint32_t k = (uint32_t)ffs64(mask) - 1u;
+        mask &= mask - 1;
+        const float4 *r = trav + 6 * (first + k);
+        float4 r1 = r[1];
+        float t_, u_, v_;
+        if (tri_test(r[0], r1, r[2], r[3], tr.o, tr.d, tr.tmax, &t_, &u_, &v_)) {
+            uint32_t prim_ = f2u(r1.w);
+            // reference: strict `t < its.t` in mesh-major order => on exact ties the lowest index wins
+            if (t_ < tr.tmax || (tr.prim != RL_MISS && prim_ < tr.prim)) {
+                tr.tmax = t_;
+                tr.u = u_;
+                tr.v = v_;
+                tr.prim = prim_;
+            }
         }
     }
     tr.cur = trav_pop(tr, stack);
 }
 // Phase B (any hit): returns true when the segment is blocked.
 RL_HD bool trav_leaf_any(Trav &tr, const int *stack, const float4 *trav) {
-    int s_ = ~tr.cur;
-    float t_, u_, v_;
-    bool blocked = false;
-    if (tri_test(trav[4 * s_], trav[4 * s_ + 1], trav[4 * s_ + 2], trav[4 * s_ + 3], tr.o, tr.d, tr.tmax, &t_, &u_, &v_)) blocked = t_ < tr.tmax;
-    tr.cur = blocked ? RL_TRAV_DONE : trav_pop(tr, stack);
-    return blocked;
+    const uint32_t first = leaf_first(tr.cur), count = leaf_count(tr.cur);
+    uint64_t mask = leaf_scan(tr, trav, first, count);
+    while (mask) {
+        const uint32_t k = (uint32_t)ffs64(mask) - 1u;
+        mask &= mask - 1;
+        const float4 *r = trav + 6 * (first + k);
+        float t_, u_, v_;
+        if (tri_test(r[0], r[1], r[2], r[3], tr.o, tr.d, tr.tmax, &t_, &u_, &v_) && t_ < tr.tmax) {
+            tr.cur = RL_TRAV_DONE;
+            return true;
+        }
+    }
+    tr.cur = trav_pop(tr, stack);
+    return false;
 }
 
 // Acceleration::trace (accel.rs:292-315) without fill_intersection.  Returns false when the
 // reference's root-box test rejects the ray (no traversal needed).
 RL_HD bool closest_begin(Trav &tr, const SceneView &sv, V3 o, V3 d) {
-    trav_begin(tr, sv, o, d, RL_F32_MAX);
-    if (!aabb_intersect_ref(sv.root_min, sv.root_max, o, d, RL_EPSILON, RL_F32_MAX)) {
+    V3 inv = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    trav_begin(tr, sv, o, d, inv, RL_F32_MAX);
+    if (!aabb_intersect_ref(sv.root_min, sv.root_max, o, inv, RL_EPSILON, RL_F32_MAX)) {
         tr.cur = RL_TRAV_DONE;
         return false;
     }
@@ -502,10 +566,11 @@ RL_HD void visible_begin(Trav &tr, const SceneView &sv, V3 p0, V3 p1, bool *deci
     float length = magnitude(d);
     d = d / length;
     float thr = length * (1.0f - SHADOW_EPS);
-    trav_begin(tr, sv, p0, d, thr);
+    V3 inv = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    trav_begin(tr, sv, p0, d, inv, thr);
     *decided = false;
     *vis = true;
-    if (!aabb_intersect_ref(sv.root_min, sv.root_max, p0, d, RL_EPSILON, thr)) {
+    if (!aabb_intersect_ref(sv.root_min, sv.root_max, p0, inv, RL_EPSILON, thr)) {
         tr.cur = RL_TRAV_DONE;
         *decided = true;
         *vis = false; // accel.rs:338-340

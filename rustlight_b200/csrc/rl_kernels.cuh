@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, IntegParams ip,
 // idle; partial refills pay the per-ray setup at low lane occupancy), so that the descend phase and the leaf
 // phase (exact triangle test) each run with most lanes active although rays are incoherent.
 #ifndef RL_REFILL_IDLE
-#define RL_REFILL_IDLE 32
+#define RL_REFILL_IDLE 24
 #endif
 #ifndef RL_WHILE_WHILE
 #define RL_WHILE_WHILE 1
@@ -159,7 +159,10 @@ __device__ __forceinline__ uint32_t block_compact(bool flag, uint32_t *global_co
 }
 
 // ---- shade: surface interaction, arrival emission, BSDF sample + RR, NEE sample ------------------
-__global__ void __launch_bounds__(kBlock) k_shade(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
+#ifndef RL_SHADE_MINBLOCKS
+#define RL_SHADE_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kBlock, RL_SHADE_MINBLOCKS) k_shade(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
                                                   const uint32_t *__restrict__ count_in, const float4 *__restrict__ ray_o,
                                                   const float4 *__restrict__ ray_d, const float4 *__restrict__ state,
                                                   const float4 *__restrict__ hit, float4 *__restrict__ out_o, float4 *__restrict__ out_d,
@@ -399,6 +402,8 @@ __global__ void __launch_bounds__(kBlock) k_finish(const float4 *__restrict__ im
     }
 }
 
+__global__ void k_set_u32(uint32_t *p, uint32_t v) { *p = v; }
+
 // ---- Acceleration::{trace, visible} on caller-provided rays (rl_trace / rl_visible) ---------------
 __global__ void __launch_bounds__(kBlock) k_pack_rays(const float *__restrict__ o, const float *__restrict__ d, uint32_t n, float4 *ray_o, float4 *ray_d) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -443,11 +448,14 @@ __global__ void __launch_bounds__(kBlock) k_tri_setup(const float4 *__restrict__
         leaf_hi[s] = make_float4(hi.x, hi.y, hi.z, 0.0f);
     }
 }
-__global__ void __launch_bounds__(kBlock) k_karras(const uint64_t *__restrict__ keys, int ntris, int2 *children, int *parent_of_node, int *parent_of_leaf) {
+__global__ void __launch_bounds__(kBlock) k_karras(const uint64_t *__restrict__ keys, int ntris, int2 *children, int2v *ranges, int *parent_of_node,
+                                                   int *parent_of_leaf) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntris - 1; i += gridDim.x * blockDim.x) {
-        int l, r;
-        karras_node(keys, ntris, i, &l, &r);
+        int l, r, first, last;
+        karras_node(keys, ntris, i, &l, &r, &first, &last);
         children[i] = make_int2(l, r);
+        ranges[i].x = first;
+        ranges[i].y = last;
         if (l < 0) parent_of_leaf[~l] = i;
         else parent_of_node[l] = i;
         if (r < 0) parent_of_leaf[~r] = i;
@@ -456,10 +464,12 @@ __global__ void __launch_bounds__(kBlock) k_karras(const uint64_t *__restrict__ 
     }
 }
 // Bottom-up fit: the second thread to reach a node owns it (atomic flag), merges the two child
-// boxes, writes the wide node and continues to the parent.
-__global__ void __launch_bounds__(kBlock) k_fit(int ntris, const int2 *__restrict__ children, const int *__restrict__ parent_of_node,
-                                                const int *__restrict__ parent_of_leaf, const float4 *__restrict__ leaf_lo,
-                                                const float4 *__restrict__ leaf_hi, float4 *node_lo, float4 *node_hi, int *flags, float4 *nodes) {
+// boxes, writes the wide node (children with at most leaf_max triangles become leaf references)
+// and continues to the parent.
+__global__ void __launch_bounds__(kBlock) k_fit(int ntris, int leaf_max, const int2 *__restrict__ children, const int2v *__restrict__ ranges,
+                                                const int *__restrict__ parent_of_node, const int *__restrict__ parent_of_leaf,
+                                                const float4 *__restrict__ leaf_lo, const float4 *__restrict__ leaf_hi, float4 *node_lo, float4 *node_hi,
+                                                int *flags, float4 *nodes) {
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < ntris; s += gridDim.x * blockDim.x) {
         int node = parent_of_leaf[s];
         while (node >= 0) {
@@ -469,7 +479,8 @@ __global__ void __launch_bounds__(kBlock) k_fit(int ntris, const int2 *__restric
             // boxes written by other SMs: read through L2 (__ldcg), L1 may hold a stale line
             float4 lo0 = ch.x < 0 ? leaf_lo[~ch.x] : __ldcg(&node_lo[ch.x]), hi0 = ch.x < 0 ? leaf_hi[~ch.x] : __ldcg(&node_hi[ch.x]);
             float4 lo1 = ch.y < 0 ? leaf_lo[~ch.y] : __ldcg(&node_lo[ch.y]), hi1 = ch.y < 0 ? leaf_hi[~ch.y] : __ldcg(&node_hi[ch.y]);
-            write_wide_node(nodes, node, xyz(lo0), xyz(hi0), xyz(lo1), xyz(hi1), ch.x, ch.y);
+            write_wide_node(nodes, node, xyz(lo0), xyz(hi0), xyz(lo1), xyz(hi1), make_child_ref(ch.x, ranges, leaf_max),
+                            make_child_ref(ch.y, ranges, leaf_max));
             node_lo[node] = make_float4(fminf(lo0.x, lo1.x), fminf(lo0.y, lo1.y), fminf(lo0.z, lo1.z), 0.0f);
             node_hi[node] = make_float4(fmaxf(hi0.x, hi1.x), fmaxf(hi0.y, hi1.y), fmaxf(hi0.z, hi1.z), 0.0f);
             __threadfence();

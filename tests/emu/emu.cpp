@@ -8,6 +8,7 @@
 // that the device code takes the same discrete decisions as the oracle.  It is never built
 // into or loaded by the product library.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -24,6 +25,7 @@ struct emu_scene {
     std::vector<float4> trav, nodes;
     SceneView sv{};
     uint32_t max_depth = 0;
+    int root_ref = 0, leaf_max = 1;
 };
 
 extern "C" {
@@ -53,7 +55,7 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
     }
     std::sort(keys.begin(), keys.end()); // cub::DeviceRadixSort on the device
     // k_tri_setup
-    s->trav.resize((size_t)4 * n);
+    s->trav.resize((size_t)RL_TRAV_F4 * n);
     std::vector<V3> leaf_lo(n), leaf_hi(n);
     for (int i = 0; i < n; i++) {
         uint32_t prim = (uint32_t)(keys[i] & 0xffffffffull);
@@ -61,40 +63,38 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         tri_bounds_inflated(hs.verts.data(), prim, bvh_box_eps(hs.abs_max), &leaf_lo[i], &leaf_hi[i]);
     }
     // k_karras + k_fit
+    int leaf_max = n <= RL_LEAF_MAX_CAP ? RL_LEAF_MAX_CAP : 4;
+    if (const char *e = getenv("RL_LEAF_MAX")) leaf_max = std::max(1, std::min(RL_LEAF_MAX_CAP, atoi(e)));
+    s->leaf_max = leaf_max;
     int n_nodes = n > 1 ? n - 1 : 1;
     s->nodes.resize((size_t)4 * n_nodes);
+    s->root_ref = n <= leaf_max ? leaf_ref(0u, (uint32_t)n) : 0;
+    s->max_depth = 1;
     if (n > 1) {
         std::vector<int> cl(n - 1), cr(n - 1);
-        for (int i = 0; i < n - 1; i++) karras_node(keys.data(), n, i, &cl[i], &cr[i]);
+        std::vector<int2v> ranges(n - 1);
+        for (int i = 0; i < n - 1; i++) karras_node(keys.data(), n, i, &cl[i], &cr[i], &ranges[i].x, &ranges[i].y);
         std::vector<V3> nlo(n - 1), nhi(n - 1);
         struct Rec {
-            static uint32_t fit(int node, const std::vector<int> &cl, const std::vector<int> &cr, const std::vector<V3> &llo, const std::vector<V3> &lhi,
-                                std::vector<V3> &nlo, std::vector<V3> &nhi, float4 *nodes) {
-                uint32_t d0 = 0, d1 = 0;
+            static void fit(int node, const std::vector<int> &cl, const std::vector<int> &cr, const std::vector<int2v> &ranges, int leaf_max,
+                            const std::vector<V3> &llo, const std::vector<V3> &lhi, std::vector<V3> &nlo, std::vector<V3> &nhi, float4 *nodes) {
                 int a = cl[node], b = cr[node];
-                if (a >= 0) d0 = fit(a, cl, cr, llo, lhi, nlo, nhi, nodes);
-                if (b >= 0) d1 = fit(b, cl, cr, llo, lhi, nlo, nhi, nodes);
+                if (a >= 0) fit(a, cl, cr, ranges, leaf_max, llo, lhi, nlo, nhi, nodes);
+                if (b >= 0) fit(b, cl, cr, ranges, leaf_max, llo, lhi, nlo, nhi, nodes);
                 V3 lo0 = a < 0 ? llo[~a] : nlo[a], hi0 = a < 0 ? lhi[~a] : nhi[a];
                 V3 lo1 = b < 0 ? llo[~b] : nlo[b], hi1 = b < 0 ? lhi[~b] : nhi[b];
-                write_wide_node(nodes, node, lo0, hi0, lo1, hi1, a, b);
+                write_wide_node(nodes, node, lo0, hi0, lo1, hi1, make_child_ref(a, ranges.data(), leaf_max), make_child_ref(b, ranges.data(), leaf_max));
                 nlo[node] = V3{fminf(lo0.x, lo1.x), fminf(lo0.y, lo1.y), fminf(lo0.z, lo1.z)};
                 nhi[node] = V3{fmaxf(hi0.x, hi1.x), fmaxf(hi0.y, hi1.y), fmaxf(hi0.z, hi1.z)};
-                return 1 + std::max(d0, d1);
             }
         };
-        s->max_depth = Rec::fit(0, cl, cr, leaf_lo, leaf_hi, nlo, nhi, s->nodes.data());
-    } else {
-        const float inf = RL_F32_MAX;
-        s->nodes[0] = f4(leaf_lo[0].x, leaf_lo[0].y, leaf_lo[0].z, leaf_hi[0].x);
-        s->nodes[1] = f4(leaf_hi[0].y, leaf_hi[0].z, inf, inf);
-        s->nodes[2] = f4(inf, -inf, -inf, -inf);
-        s->nodes[3] = f4(u2f((uint32_t)~0), u2f((uint32_t)~0), 0.0f, 0.0f);
-        s->max_depth = 1;
+        Rec::fit(0, cl, cr, ranges, leaf_max, leaf_lo, leaf_hi, nlo, nhi, s->nodes.data());
     }
     SceneView &sv = s->sv;
     sv.trav = s->trav.data(), sv.nodes = s->nodes.data(), sv.shade = hs.shade.data(), sv.verts = hs.verts.data(), sv.mats = hs.mats.data();
     sv.emit_info = hs.emit_info.data(), sv.emit_cdf = hs.emit_cdf.data(), sv.area_cdf = hs.area_cdf.data();
     sv.ntris = hs.ntris, sv.n_emitters = hs.n_emitters;
+    sv.root_ref = s->root_ref;
     sv.root_min = V3{hs.root_min[0], hs.root_min[1], hs.root_min[2]};
     sv.root_max = V3{hs.root_max[0], hs.root_max[1], hs.root_max[2]};
     sv.abs_max = hs.abs_max;
@@ -111,10 +111,24 @@ uint32_t emu_bvh_max_depth(const emu_scene *s) { return s->max_depth; }
 // contains its subtree.  Returns 0 when valid.
 int emu_bvh_validate(const emu_scene *s) {
     const int n = (int)s->hs.ntris;
-    if (n < 2) return 0;
     std::vector<int> seen(n, 0);
     struct Rec {
-        static bool walk(const emu_scene *s, int node, V3 *lo, V3 *hi, std::vector<int> &seen) {
+        static bool leaf(const emu_scene *s, int ref, V3 *lo, V3 *hi, std::vector<int> &seen) {
+            *lo = V3{RL_F32_MAX, RL_F32_MAX, RL_F32_MAX};
+            *hi = V3{-RL_F32_MAX, -RL_F32_MAX, -RL_F32_MAX};
+            for (uint32_t k = 0; k < leaf_count(ref); k++) {
+                uint32_t slot = leaf_first(ref) + k;
+                if (slot >= s->hs.ntris) return false;
+                seen[slot]++;
+                V3 a, b;
+                tri_bounds(s->hs.verts.data(), f2u(s->trav[RL_TRAV_F4 * slot + 1].w), &a, &b);
+                *lo = V3{fminf(lo->x, a.x), fminf(lo->y, a.y), fminf(lo->z, a.z)};
+                *hi = V3{fmaxf(hi->x, b.x), fmaxf(hi->y, b.y), fmaxf(hi->z, b.z)};
+            }
+            return true;
+        }
+        static bool walk(const emu_scene *s, int node, V3 *lo, V3 *hi, std::vector<int> &seen, uint32_t depth, uint32_t *max_depth) {
+            *max_depth = std::max(*max_depth, depth);
             const float4 *nd = &s->nodes[4 * node];
             int ch[2] = {(int)f2u(nd[3].x), (int)f2u(nd[3].y)};
             V3 blo[2] = {V3{nd[0].x, nd[0].y, nd[0].z}, V3{nd[1].z, nd[1].w, nd[2].x}};
@@ -122,11 +136,8 @@ int emu_bvh_validate(const emu_scene *s) {
             for (int q = 0; q < 2; q++) {
                 V3 clo, chi;
                 if (ch[q] < 0) {
-                    int leaf = ~ch[q];
-                    seen[leaf]++;
-                    uint32_t prim = f2u(s->trav[4 * leaf + 1].w);
-                    tri_bounds(s->hs.verts.data(), prim, &clo, &chi);
-                } else if (!walk(s, ch[q], &clo, &chi, seen)) return false;
+                    if (!leaf(s, ch[q], &clo, &chi, seen)) return false;
+                } else if (!walk(s, ch[q], &clo, &chi, seen, depth + 1, max_depth)) return false;
                 if (clo.x < blo[q].x || clo.y < blo[q].y || clo.z < blo[q].z || chi.x > bhi[q].x || chi.y > bhi[q].y || chi.z > bhi[q].z) return false;
             }
             *lo = V3{fminf(blo[0].x, blo[1].x), fminf(blo[0].y, blo[1].y), fminf(blo[0].z, blo[1].z)};
@@ -135,7 +146,10 @@ int emu_bvh_validate(const emu_scene *s) {
         }
     };
     V3 lo, hi;
-    if (!Rec::walk(s, 0, &lo, &hi, seen)) return 1;
+    uint32_t md = 1;
+    bool ok = s->root_ref < 0 ? Rec::leaf(s, s->root_ref, &lo, &hi, seen) : Rec::walk(s, s->root_ref, &lo, &hi, seen, 1, &md);
+    const_cast<emu_scene *>(s)->max_depth = md;
+    if (!ok) return 1;
     for (int i = 0; i < n; i++)
         if (seen[i] != 1) return 2;
     return 0;

@@ -27,7 +27,7 @@ def _rays(n, seed, lo=-0.99, hi=0.99, shift=(0, 1, 0)):
 
 def test_lbvh_is_valid(cbox):
     esc = eb.EmuScene(cbox)
-    assert esc.bvh_validate() == 0 and 6 <= esc.bvh_max_depth() <= 36
+    assert esc.bvh_validate() == 0 and 1 <= esc.bvh_max_depth() <= 36
 
 
 def test_primary_hits_exact(cbox, cbox_oracle):
