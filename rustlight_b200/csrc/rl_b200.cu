@@ -93,6 +93,8 @@ struct rl_scene {
     size_t smem_bytes = 0;
     bool smem_ok = false;
     rl_bvh_info info{};
+    // roots: the tree (coherent rays) and, for scenes of <= 64 triangles, the whole scene as one leaf
+    int root_tree = 0, root_flat = 0, coherent_tree = 2;
 };
 
 #define CK(call)                                                                                                   \
@@ -307,8 +309,12 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     CKS(cudaGetLastError());
     // Leaf size: scenes of up to 64 triangles become ONE leaf (every lane scans the same triangles in
     // lockstep: no SIMT divergence, shared-memory broadcasts); larger scenes collapse subtrees of <= 4.
-    int leaf_max = n <= (uint32_t)RL_LEAF_MAX_CAP ? RL_LEAF_MAX_CAP : 4;
+    // The tree itself collapses subtrees of <= 2 (tiny scenes) or <= 4 triangles; scenes of <= 64 triangles
+    // additionally get a "flat" root (the whole scene as one leaf) used for incoherent rays.
+    int leaf_max = n <= (uint32_t)RL_LEAF_MAX_CAP ? 2 : 4;
     if (const char *e = getenv("RL_LEAF_MAX")) leaf_max = std::max(1, std::min(RL_LEAF_MAX_CAP, atoi(e)));
+    bool flat_ok = n <= (uint32_t)RL_LEAF_MAX_CAP;
+    if (const char *e = getenv("RL_FLAT")) flat_ok = flat_ok && atoi(e) != 0;
     if (n >= (1u << 25)) {
         ctx->err = "rl_scene_create: more than 2^25 triangles";
         cleanup();
@@ -374,6 +380,10 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     sv.emit_info = s->d_emit_info, sv.emit_cdf = s->d_emit_cdf, sv.area_cdf = s->d_area_cdf;
     sv.ntris = n, sv.n_emitters = hs.n_emitters;
     sv.root_ref = root_ref;
+    s->root_tree = root_ref;
+    s->root_flat = flat_ok ? leaf_ref(0u, n) : root_ref;
+    s->coherent_tree = 2; // camera rays and the shadow rays of the first hits walk the tree; everything else scans the flat leaf
+    if (const char *e = getenv("RL_COHERENT_TREE")) s->coherent_tree = atoi(e);
     sv.root_min = V3{hs.root_min[0], hs.root_min[1], hs.root_min[2]};
     sv.root_max = V3{hs.root_max[0], hs.root_max[1], hs.root_max[2]};
     sv.abs_max = hs.abs_max;
@@ -512,13 +522,18 @@ static int validate(rl_ctx *ctx, const rl_scene *scene, const rl_integrator_desc
 }
 
 template <bool SMEM>
-static void launch_trace(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_t n, const float4 *ro, const float4 *rd, float4 *hit) {
-    k_trace<SMEM><<<grid_for(ctx, n, 8), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sc->sv, count, ro, rd, hit, sc->n_node_f4, sc->n_trav_f4);
+static void launch_trace(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_t n, const float4 *ro, const float4 *rd, float4 *hit,
+                         bool coherent = false) {
+    SceneView sv = sc->sv;
+    sv.root_ref = (coherent && sc->coherent_tree >= 1) ? sc->root_tree : sc->root_flat;
+    k_trace<SMEM><<<grid_for(ctx, n, 8), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_node_f4, sc->n_trav_f4);
     ctx->launches++;
 }
 template <bool SMEM>
-static void launch_shadow(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_t n) {
-    k_shadow<SMEM><<<grid_for(ctx, n, 8), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sc->sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc,
+static void launch_shadow(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_t n, bool coherent = false) {
+    SceneView sv = sc->sv;
+    sv.root_ref = (coherent && sc->coherent_tree >= 2) ? sc->root_tree : sc->root_flat;
+    k_shadow<SMEM><<<grid_for(ctx, n, 8), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc,
                                                                                              ctx->d_counters, sc->n_node_f4, sc->n_trav_f4);
     ctx->launches++;
 }
@@ -579,16 +594,16 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                 // primary rays -> stage 1 (emission, light samples, BSDF samples) -> shadow rays -> extension rays -> stage 2
                 uint32_t *c_in = ctx->d_counts, *c_out = ctx->d_counts + 1, *c_sh = ctx->d_counts + 2;
                 if (prof) CK(cudaEventRecord(ctx->ev[2], st));
-                if (sc->smem_ok) launch_trace<true>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit);
-                else launch_trace<false>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit);
+                if (sc->smem_ok) launch_trace<true>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, true);
+                else launch_trace<false>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, true);
                 if (prof) CK(cudaEventRecord(ctx->ev[3], st));
                 k_shade_direct1<<<grid_for(ctx, n, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, c_in, (uint32_t)n_paths, ctx->ray_o[0], ctx->ray_d[0],
                                                                         ctx->state[0], ctx->hit, ctx->ray_o[1], ctx->ray_d[1], ctx->state[1], c_out, ctx->sh_a,
                                                                         ctx->sh_b, ctx->sh_c, c_sh, ctx->lacc, ctx->d_counters);
                 ctx->launches++;
                 if (prof) CK(cudaEventRecord(ctx->ev[4], st));
-                if (sc->smem_ok) launch_shadow<true>(ctx, sc, c_sh, n * std::max(1u, nl));
-                else launch_shadow<false>(ctx, sc, c_sh, n * std::max(1u, nl));
+                if (sc->smem_ok) launch_shadow<true>(ctx, sc, c_sh, n * std::max(1u, nl), true);
+                else launch_shadow<false>(ctx, sc, c_sh, n * std::max(1u, nl), true);
                 if (prof) CK(cudaEventRecord(ctx->ev[5], st));
                 CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
@@ -642,8 +657,8 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                     }
                     for (uint32_t g = 0; g < group; g++, k++) {
                         if (prof) CK(cudaEventRecord(ctx->ev[2], st));
-                        if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit);
-                        else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit);
+                        if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
+                        else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
                         if (prof) CK(cudaEventRecord(ctx->ev[3], st));
                         k_shade<<<grid_for(ctx, n_ub, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur],
                                                                            ctx->state[cur], ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1],
@@ -652,8 +667,8 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                         ctx->launches++;
                         if (prof) CK(cudaEventRecord(ctx->ev[4], st));
                         // the shadow queue can never be longer than the input queue: size the grid from n_ub
-                        if (sc->smem_ok) launch_shadow<true>(ctx, sc, shc + k, n_ub);
-                        else launch_shadow<false>(ctx, sc, shc + k, n_ub);
+                        if (sc->smem_ok) launch_shadow<true>(ctx, sc, shc + k, n_ub, k == 0);
+                        else launch_shadow<false>(ctx, sc, shc + k, n_ub, k == 0);
                         if (prof) CK(cudaEventRecord(ctx->ev[5], st));
                         cur ^= 1;
                     }
@@ -755,11 +770,11 @@ int rl_render(rl_ctx *ctx, rl_scene *scene, const rl_integrator_desc *integrator
 }
 
 // ---- Acceleration::{trace, visible} batches -----------------------------------------------------------
-static int trace_device_rays(rl_ctx *ctx, rl_scene *sc, size_t n, uint32_t *prim, float *tuv) {
+static int trace_device_rays(rl_ctx *ctx, rl_scene *sc, size_t n, uint32_t *prim, float *tuv, bool coherent = false) {
     uint32_t cnt = (uint32_t)n;
     CK(cudaMemcpyAsync(ctx->d_counts, &cnt, sizeof(cnt), cudaMemcpyHostToDevice, ctx->stream));
-    if (sc->smem_ok) launch_trace<true>(ctx, sc, ctx->d_counts, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit);
-    else launch_trace<false>(ctx, sc, ctx->d_counts, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit);
+    if (sc->smem_ok) launch_trace<true>(ctx, sc, ctx->d_counts, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, coherent);
+    else launch_trace<false>(ctx, sc, ctx->d_counts, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, coherent);
     CK(cudaGetLastError());
     std::vector<float4> h(n);
     CK(cudaMemcpyAsync(h.data(), ctx->hit, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
@@ -801,7 +816,7 @@ int rl_primary_hits(rl_ctx *ctx, rl_scene *sc, uint32_t *prim, float *tuv) {
     int rc = ensure_paths(ctx, n);
     if (rc != RL_OK) return rc;
     k_primary_rays<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(sc->sv, sc->hs.img_w, sc->hs.img_h, ctx->ray_o[0], ctx->ray_d[0]);
-    return trace_device_rays(ctx, sc, n, prim, tuv);
+    return trace_device_rays(ctx, sc, n, prim, tuv, true); // camera rays: the tree root
 }
 
 int rl_visible(rl_ctx *ctx, rl_scene *sc, size_t n, const float *p0, const float *p1, uint8_t *out) {

@@ -390,7 +390,7 @@ struct Trav {
     V3 inv, ood;   // 1/d (clamped away from 0) and o/d for t = fma(plane, inv, -ood)
     V3 et;         // extra widening in t for far origins (0 otherwise)
     bool far;
-    float rs;      // coordinate scale of this ray (prefilter margins)
+    float rs2, rs8; // 2e-6 and 8e-6 times the coordinate scale of this ray (prefilter margins)
     float tmax;    // closest: best t so far; shadow: the segment's threshold
     float u, v;
     uint32_t prim;
@@ -416,7 +416,9 @@ RL_HD void trav_begin(Trav &tr, const SceneView &sv, V3 o, V3 d, V3 inv, float t
     tr.prim = RL_MISS;
     tr.cur = sv.root_ref;
     tr.sp = 0;
-    tr.rs = 4.0f * fmaxf(m, sv.abs_max);
+    const float rs = 4.0f * fmaxf(m, sv.abs_max);
+    tr.rs2 = 2e-6f * rs;
+    tr.rs8 = 8e-6f * rs;
 }
 // Conservative entry distance of the ray into box (lo,hi) for t in [0, tmax], or -1 on a miss.
 RL_HD float box_entry(const Trav &tr, float lox, float loy, float loz, float hix, float hiy, float hiz) {
@@ -473,19 +475,23 @@ RL_HD int ffs64(uint64_t m) {
 #endif
 }
 RL_HD bool tri_prefilter(const Trav &tr, float4 r2, float4 r3, float4 r4, float4 r5) {
+    // plane: t' = (pn - o.n) / (d.n); |t' - t| <= mt covers the roundings of both this estimate and
+    // the exact path (|d.n| <= 1, so |1/(d.n)| >= 1 and mt >= 1e-6 |t'|)
     float den = fmaf(tr.d.x, r3.x, fmaf(tr.d.y, r3.y, tr.d.z * r3.z));
     float on = fmaf(tr.o.x, r3.x, fmaf(tr.o.y, r3.y, tr.o.z * r3.z));
     float num = r3.w - on;
     float rden = rcp_fast(den);
     float tp = num * rden;
-    float mt = (tr.rs * 2e-6f + fabsf(num) * 4e-6f + fabsf(tp) * 1e-6f) * fabsf(rden);
-    if (tp < -mt || tp > tr.tmax + mt) return false;
+    float ard = fabsf(rden);
+    float mt = ard * fmaf(fabsf(num), fmaf(ard, 1e-6f, 4e-6f), tr.rs2);
+    // barycentrics at p' = o + t' d from the affine functionals; margin m >= |Mu| (4 mt + 8e-6 rs + 2e-6 |t'|)
     float px = fmaf(tp, tr.d.x, tr.o.x), py = fmaf(tp, tr.d.y, tr.o.y), pz = fmaf(tp, tr.d.z, tr.o.z);
     float up = fmaf(px, r4.x, fmaf(py, r4.y, fmaf(pz, r4.z, r4.w)));
     float vp = fmaf(px, r5.x, fmaf(py, r5.y, fmaf(pz, r5.z, r5.w)));
-    float m = r2.w * (4.0f * mt + 8e-6f * tr.rs + 2e-6f * fabsf(tp)) + 1e-6f;
-    if (up < -m || vp < -m || up + vp > 1.0f + m) return false;
-    return true;
+    float m = fmaf(r2.w, fmaf(mt, 6.0f, tr.rs8), 1e-6f);
+    // branch-free: every comparison is false for NaN, so degenerate cases fall through to the exact test
+    bool reject = (tp < -mt) | (tp > tr.tmax + mt) | (fminf(up, vp) < -m) | (up + vp > 1.0f + m);
+    return !reject;
 }
 // Phase B (closest hit): tr.cur is a leaf reference.  Two uniform loops: the scan runs only the
 // prefilter and records the survivors in a bit mask (a leaf holds at most 64 triangles); the
