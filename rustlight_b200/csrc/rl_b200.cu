@@ -660,10 +660,16 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                         if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
                         else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
                         if (prof) CK(cudaEventRecord(ctx->ev[3], st));
-                        k_shade<<<grid_for(ctx, n_ub, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur],
-                                                                           ctx->state[cur], ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1],
-                                                                           ctx->state[cur ^ 1], qc + k + 1, ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc,
-                                                                           ctx->d_counters);
+                        if (o->material_sort)
+                            k_shade<true><<<grid_for(ctx, n_ub, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur],
+                                                                                     ctx->state[cur], ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1],
+                                                                                     ctx->state[cur ^ 1], qc + k + 1, ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k,
+                                                                                     ctx->lacc, ctx->d_counters);
+                        else
+                            k_shade<false><<<grid_for(ctx, n_ub, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur],
+                                                                                      ctx->state[cur], ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1],
+                                                                                      ctx->state[cur ^ 1], qc + k + 1, ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k,
+                                                                                      ctx->lacc, ctx->d_counters);
                         ctx->launches++;
                         if (prof) CK(cudaEventRecord(ctx->ev[4], st));
                         // the shadow queue can never be longer than the input queue: size the grid from n_ub

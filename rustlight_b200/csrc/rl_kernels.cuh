@@ -158,10 +158,70 @@ __device__ __forceinline__ uint32_t block_compact(bool flag, uint32_t *global_co
     return slot;
 }
 
+// Two queues at once (survivors and shadow segments): one pair of barriers instead of three per queue.
+__device__ __forceinline__ void block_compact2(bool fa, bool fb, uint32_t *count_a, uint32_t *count_b, uint32_t *scratch /* 2*(kBlock/32)+2 */,
+                                               uint32_t *slot_a, uint32_t *slot_b) {
+    constexpr int W = kBlock / 32;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned ma = __ballot_sync(0xffffffffu, fa), mb = __ballot_sync(0xffffffffu, fb);
+    const uint32_t lt = (1u << lane) - 1u;
+    if (lane == 0) {
+        scratch[warp] = __popc(ma);
+        scratch[W + warp] = __popc(mb);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) { // thread 0 scans queue a, thread 1 queue b
+        uint32_t *w = scratch + threadIdx.x * W;
+        uint32_t tot = 0;
+        for (int k = 0; k < W; k++) {
+            uint32_t c = w[k];
+            w[k] = tot;
+            tot += c;
+        }
+        scratch[2 * W + threadIdx.x] = tot ? atomicAdd(threadIdx.x == 0 ? count_a : count_b, tot) : 0u;
+    }
+    __syncthreads();
+    *slot_a = scratch[2 * W] + scratch[warp] + __popc(ma & lt);
+    *slot_b = scratch[2 * W + 1] + scratch[W + warp] + __popc(mb & lt);
+    // no trailing barrier: the next call writes scratch only after its own ballots, and every thread
+    // reads its slots before it can reach the next call's first barrier... but a fast warp could
+    // overwrite scratch[warp] of the NEXT tile before a slow warp has read this tile's values:
+    __syncthreads();
+}
+
 // ---- shade: surface interaction, arrival emission, BSDF sample + RR, NEE sample ------------------
+// ---- material sort inside a CTA tile ------------------------------------------------------------
+// Counting sort of the tile's 256 records by key (0 diffuse, 1 phong, 2 miss, 3 = past the end of the
+// queue) with warp ballots + per-warp prefix sums in shared memory.  Returns the tile-local index of
+// the record this thread should process, so that every warp shades one material kind (and rays that
+// missed are grouped into whole warps that exit at once).  `perm` is kBlock uint16, `cnt` 4*(kBlock/32).
+__device__ __forceinline__ uint32_t tile_sort_by_key(uint32_t key, unsigned short *perm, uint32_t *cnt) {
+    constexpr int W = kBlock / 32;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+    unsigned m[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) m[k] = __ballot_sync(0xffffffffu, key == (uint32_t)k);
+    if (lane < 4) cnt[lane * W + warp] = __popc(m[lane]);
+    __syncthreads();
+    if (threadIdx.x == 0) { // exclusive scan in key-major, warp-minor order (32 entries)
+        uint32_t tot = 0;
+        for (int q = 0; q < 4 * W; q++) {
+            uint32_t c = cnt[q];
+            cnt[q] = tot;
+            tot += c;
+        }
+    }
+    __syncthreads();
+    uint32_t rank = cnt[key * W + warp] + __popc(m[key] & lt);
+    perm[rank] = (unsigned short)threadIdx.x;
+    __syncthreads();
+    return perm[threadIdx.x];
+}
+
 #ifndef RL_SHADE_MINBLOCKS
 #define RL_SHADE_MINBLOCKS 4
 #endif
+template <bool SORT>
 __global__ void __launch_bounds__(kBlock, RL_SHADE_MINBLOCKS) k_shade(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
                                                   const uint32_t *__restrict__ count_in, const float4 *__restrict__ ray_o,
                                                   const float4 *__restrict__ ray_d, const float4 *__restrict__ state,
@@ -169,13 +229,22 @@ __global__ void __launch_bounds__(kBlock, RL_SHADE_MINBLOCKS) k_shade(SceneView 
                                                   float4 *__restrict__ out_state, uint32_t *count_out, float4 *__restrict__ sh_a,
                                                   float4 *__restrict__ sh_b, float4 *__restrict__ sh_c, uint32_t *count_shadow,
                                                   float4 *__restrict__ lacc, Counters *counters) {
-    __shared__ uint32_t s_warp[kBlock / 32];
-    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_scratch[2 * (kBlock / 32) + 2];
+    __shared__ unsigned short s_perm[SORT ? kBlock : 1];
+    __shared__ uint32_t s_cnt[SORT ? 4 * (kBlock / 32) : 1];
     const uint32_t n = *count_in;
     const uint32_t n_tiles = (n + kBlock - 1) / kBlock;
     uint32_t c_hits = 0, c_nee = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint32_t i = tile * kBlock + threadIdx.x;
+        uint32_t i = tile * kBlock + threadIdx.x;
+        if (SORT) {
+            uint32_t key = 3u;
+            if (i < n) {
+                const uint32_t prim = f2u(hit[i].w);
+                key = prim == RL_MISS ? 2u : (f2u(__ldg(&sv.mats[4 * f2u(__ldg(&sv.shade[4 * prim]).w)]).w) != 0u ? 1u : 0u);
+            }
+            i = tile * kBlock + tile_sort_by_key(key, s_perm, s_cnt);
+        }
         StepOut so;
         so.alive = false;
         so.shadow = false;
@@ -204,13 +273,13 @@ __global__ void __launch_bounds__(kBlock, RL_SHADE_MINBLOCKS) k_shade(SceneView 
             }
             if (so.alive && (so.next.depth >= 0xfff0u || so.next.rng_n >= 0xfff0u)) so.alive = false; // packing guard
         }
-        uint32_t slot = block_compact(so.alive, count_out, s_warp, &s_base);
+        uint32_t slot, sslot;
+        block_compact2(so.alive, so.shadow, count_out, count_shadow, s_scratch, &slot, &sslot);
         if (so.alive) {
             out_o[slot] = make_float4(so.next_o.x, so.next_o.y, so.next_o.z, u2f(so.next.path_id));
             out_d[slot] = make_float4(so.next_d.x, so.next_d.y, so.next_d.z, so.next.pdf_prev);
             out_state[slot] = make_float4(so.next.T.r, so.next.T.g, so.next.T.b, u2f((so.next.depth << 16) | so.next.rng_n));
         }
-        uint32_t sslot = block_compact(so.shadow, count_shadow, s_warp, &s_base);
         if (so.shadow) {
             sh_a[sslot] = make_float4(so.sh_p0.x, so.sh_p0.y, so.sh_p0.z, u2f(pid));
             sh_b[sslot] = make_float4(so.sh_p1.x, so.sh_p1.y, so.sh_p1.z, 0.0f);

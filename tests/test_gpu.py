@@ -287,3 +287,20 @@ def test_direct_golden_and_full_size_property(gpu_ctx):
     p, _ = big.render(_abi.path_desc(max_depth=3), 4, seed=2)
     assert a.mean(axis=(0, 1)) == pytest.approx(p.mean(axis=(0, 1)), rel=0.02)
     big.close()
+
+
+# ---- material sort (BASELINE configs[4]: "with per-bounce material sort") -----------------------------------------------
+def test_material_sort_changes_nothing_but_the_schedule(gpu_ctx):
+    sc = load_cbox(200, 136)
+    kds = [(0.63, 0.065, 0.05), (0.14, 0.45, 0.091), (0.725, 0.71, 0.68)]
+    for mesh, kd in [(0, kds[2]), (2, kds[2]), (4, kds[0])]:  # floor, back wall, left wall become Phong: two BSDF kinds
+        sc.set_material(mesh, material_phong([0.5 * c for c in kd], (0.3, 0.3, 0.3), 50.0))
+    dev = DeviceScene(gpu_ctx, sc)
+    integ = _abi.path_desc()
+    a, sa = dev.render(integ, 6, seed=8)
+    b, sb = dev.render(integ, 6, seed=8, material_sort=1)
+    assert np.array_equal(a, b)
+    assert (sa.segments, sa.hits, sa.shadow_rays, sa.shadow_visible) == (sb.segments, sb.hits, sb.shadow_rays, sb.shadow_visible)
+    ref, so = ob.OracleScene(sc).render(integ, 6, seed=8, cfg=ob.config(**STREAM))
+    assert np.array_equal(b, ref) and sb.segments == so.segments
+    dev.close()
