@@ -269,17 +269,23 @@ def main():
     barrier()
     if rank == 0:
         peak, peak_src = measured_peaks()
-        n_trace = int(st.max_depth_seen) if st.max_depth_seen else 1
-        launches_trace = max(1, (st.kernel_launches - 1) // 3) if st.kernel_launches else 1
+        # per profiled step: 1 k_finish + per batch (1 k_raygen + 1 k_set_u32-free count + 1 k_accum) + 3 kernels per wavefront iteration
+        launches_trace = max(1, (int(st.kernel_launches) - 1) // 3)
         bytes_total = st.segments * TRACE_BYTES_PER_SEGMENT
         achieved = bytes_total / (st.ms_trace * 1e-3) / 1e9 if st.ms_trace > 0 else 0.0
         stage_ms = {k: getattr(st, k) for k in ("ms_total", "ms_raygen", "ms_trace", "ms_shade", "ms_shadow", "ms_accum")}
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per k_trace launch from the committed ncu --set full capture
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("k_trace_dram_bytes_per_launch"), tj.get("source")
         roof = {"kernel": "k_trace (closest-hit LBVH traversal)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_unit": TRACE_BYTES_PER_SEGMENT, "units": "path segments", "units_per_step": int(st.segments),
                 "launches_per_step": launches_trace, "avg_launch_ms": st.ms_trace / launches_trace,
                 "share_of_step": st.ms_trace / st.ms_total if st.ms_total else None,
-                "note": "BVH+triangles (4.5 KB) are shared-memory resident: the kernel is issue/latency bound, not HBM bound (SURVEY.md F9)"}
+                "algorithmic_bytes_per_launch": bytes_total / launches_trace,
+                "note": "BVH+triangles (7 KB) are shared-memory resident: the kernel is instruction-issue bound, not HBM bound (SURVEY.md F9; profiles/)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
