@@ -106,5 +106,50 @@ def soup_scene(ntris, seed=0, w=64, h=64, emissive_first=True):
     return json.dumps({"camera": cam, "meshes": meshes})
 
 
+def adversarial_case(seed):
+    """Scene + rays that stress culling and the leaf prefilter: tiny / huge / sliver / far-away triangles,
+    rays aimed at vertices and edges, grazing directions, origins from 1e-3 to 1e2 scene units away."""
+    import json
+    from rustlight_b200 import SceneLoaderManager
+    rng = np.random.default_rng(100 + seed)
+    scale = [1e-3, 1.0, 50.0, 1.0, 1.0, 1e3][seed]
+    shift = np.array([[0, 0, 0], [0, 0, 0], [0, 0, 0], [300, -200, 100], [0, 0, 0], [0, 0, 0]][seed], np.float64)
+    meshes = []
+    for m in range(6):
+        n = 8
+        c = rng.uniform(-1, 1, (n, 1, 3)) * scale + shift
+        ext = scale * 10.0 ** rng.uniform(-3, 0, (n, 1, 1))
+        tri = c + rng.normal(size=(n, 3, 3)) * ext
+        if m % 2 == 0:  # slivers: third vertex almost on the first edge
+            tri[:, 2] = tri[:, 0] + (tri[:, 1] - tri[:, 0]) * rng.uniform(0.2, 0.8, (n, 1)) + rng.normal(size=(n, 3)) * ext[:, 0] * 1e-3
+        meshes.append({"material": {"type": "diffuse", "kd": [0.5] * 3}, "indices": list(range(3 * n)),
+                       "P": [float(x) for x in tri.astype(np.float32).ravel()]})
+    meshes[0]["emission"] = [1, 1, 1]
+    txt = json.dumps({"camera": {"width": 8, "height": 8, "fov": 40, "to_world": [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 0, 0, 3, 1]}, "meshes": meshes})
+    sc = SceneLoaderManager().load_string(txt, "json")
+    d = sc.desc.contents
+    verts = np.concatenate([np.ctypeslib.as_array(d.meshes[i].P, (3 * d.meshes[i].nverts,)).reshape(-1, 3) for i in range(d.nmeshes)])
+    tris = verts.reshape(-1, 3, 3).astype(np.float64)
+    nr = 4000
+    pick = rng.integers(0, len(tris), nr)
+    bary = rng.dirichlet([0.3, 0.3, 0.3], nr)                      # clustered toward edges and vertices
+    bary[::5] = np.eye(3)[rng.integers(0, 3, len(bary[::5]))]      # exactly at a vertex
+    bary[1::5, 2] = 0.0
+    bary[1::5, :2] = rng.dirichlet([1, 1], len(bary[1::5]))        # exactly on an edge
+    tgt = (tris[pick] * bary[:, :, None]).sum(axis=1)
+    nrm = np.cross(tris[pick, 1] - tris[pick, 0], tris[pick, 2] - tris[pick, 0])
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-30)
+    dirs = rng.normal(size=(nr, 3))
+    g = dirs[::2]
+    dirs[::2] = g - (g * nrm[::2]).sum(axis=1, keepdims=True) * nrm[::2] * (1 - 10.0 ** rng.uniform(-6, -1, (len(g), 1)))  # grazing
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    dist = scale * 10.0 ** rng.uniform(-3, 2, (nr, 1))
+    o = (tgt - dirs * dist).astype(np.float32)
+    dd = dirs.astype(np.float32)
+    dd /= np.linalg.norm(dd.astype(np.float64), axis=1, keepdims=True).astype(np.float32)
+    p1 = (tgt + rng.normal(size=(nr, 3)) * scale * 1e-2).astype(np.float32)
+    return sc, o, dd, p1
+
+
 def rel_l2(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(np.linalg.norm(b.astype(np.float64)), 1e-30))

@@ -132,3 +132,17 @@ def test_direct_render_bit_exact(nb, nl):
     io, so = ob.OracleScene(sc).render(integ, 5, seed=4, cfg=ob.config(accel_mode=ob.ACCEL_NAIVE))
     assert (se.segments, se.hits, se.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
     assert np.array_equal(ie, io)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_prefilter_is_conservative_on_adversarial_scenes(seed):
+    """Tiny, huge, sliver and far-away triangles; grazing, edge-on and vertex-on rays.  The leaf prefilter
+    (fma, approximate reciprocal, margins) must never reject what the exact test accepts."""
+    from conftest import adversarial_case
+    sc, o, dd, p1 = adversarial_case(seed)
+    esc, osc = eb.EmuScene(sc), ob.OracleScene(sc)
+    pe, te = esc.trace(o, dd)
+    po, to = osc.trace(o, dd, ob.ACCEL_NAIVE)
+    assert np.array_equal(pe, po) and np.array_equal(te, to)
+    assert (po != 0xFFFFFFFF).mean() > 0.2  # the rays do hit things
+    assert np.array_equal(esc.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))

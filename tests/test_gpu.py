@@ -304,3 +304,37 @@ def test_material_sort_changes_nothing_but_the_schedule(gpu_ctx):
     ref, so = ob.OracleScene(sc).render(integ, 6, seed=8, cfg=ob.config(**STREAM))
     assert np.array_equal(b, ref) and sb.segments == so.segments
     dev.close()
+
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_adversarial_scenes_exact(gpu_ctx, seed):
+    """Same stress set as the CPU emulator test, on the device (approximate reciprocal in the prefilter)."""
+    from conftest import adversarial_case
+    sc, o, dd, p1 = adversarial_case(seed)
+    dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
+    pg, tg = dev.trace(o, dd)
+    po, to = osc.trace(o, dd, ob.ACCEL_NAIVE)
+    assert np.array_equal(pg, po) and np.array_equal(tg, to)
+    assert np.array_equal(dev.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))
+    dev.close()
+
+
+def test_config_shapes_c3_c5(gpu_ctx):
+    """BASELINE configs[2] (Phong walls, 512x512) and configs[4] (1920x1080, Fov::Y quirk, ragged 16x16 tiles,
+    material sort on): sub-sampled spp, bit-exact against the oracle on the same stream."""
+    sc = load_cbox()
+    kds = [(0.63, 0.065, 0.05), (0.14, 0.45, 0.091), (0.725, 0.71, 0.68)]
+    for mesh, kd in [(0, kds[2]), (1, kds[2]), (2, kds[2]), (3, kds[1]), (4, kds[0])]:
+        sc.set_material(mesh, material_phong([0.5 * c for c in kd], (0.3, 0.3, 0.3), 50.0))
+    dev = DeviceScene(gpu_ctx, sc)
+    img, st = dev.render(_abi.path_desc(), 2, seed=0)
+    ref, so = ob.OracleScene(sc).render(_abi.path_desc(), 2, seed=0, cfg=ob.config(**STREAM))
+    assert np.array_equal(img, ref) and st.segments == so.segments
+    dev.close()
+    wide = load_cbox(1920, 1080)
+    dev = DeviceScene(gpu_ctx, wide)
+    img, st = dev.render(_abi.path_desc(), 1, seed=0, material_sort=1)
+    ref, so = ob.OracleScene(wide).render(_abi.path_desc(), 1, seed=0, cfg=ob.config(**STREAM))
+    assert img.shape == (1080, 1920, 3) and np.array_equal(img, ref) and st.segments == so.segments
+    dev.close()
