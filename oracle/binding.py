@@ -22,7 +22,8 @@ SEED_PCG32, SEED_SPLITMIX64 = 0, 1
 
 class orc_config(C.Structure):
     _fields_ = [("math_mode", C.c_uint32), ("accel_mode", C.c_uint32), ("estimator", C.c_uint32),
-                ("seeding", C.c_uint32), ("nthreads", C.c_uint32), ("rank", C.c_uint32), ("nranks", C.c_uint32)]
+                ("seeding", C.c_uint32), ("nthreads", C.c_uint32), ("rank", C.c_uint32), ("nranks", C.c_uint32),
+                ("sample_offset", C.c_uint32)]
 
 
 class orc_stats(C.Structure):
@@ -104,8 +105,8 @@ def f32(x):
 
 
 def config(math_mode=MATH_SPEC, accel_mode=ACCEL_BVH, estimator=EST_GRAPH, seeding=SEED_PCG32, nthreads=0, rank=0,
-           nranks=1):
-    return orc_config(math_mode, accel_mode, estimator, seeding, nthreads, rank, nranks)
+           nranks=1, sample_offset=0):
+    return orc_config(math_mode, accel_mode, estimator, seeding, nthreads, rank, nranks, sample_offset)
 
 
 class OracleScene:

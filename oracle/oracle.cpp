@@ -1599,7 +1599,7 @@ int orc_render(const orc_scene *os, const rl_integrator_desc *integ, uint32_t sp
                         uint32_t gx = ix + b.px, gy = iy + b.py;
                         Color c;
                         if (sampler_mode == RL_SAMPLER_COUNTER) {
-                            CounterSampler cs(seed, gy * W + gx, s);
+                            CounterSampler cs(seed, gy * W + gx, cfg->sample_offset + s);
                             c = compute_pixel(*integ, cfg->estimator, gx, gy, cx, cs);
                         } else c = compute_pixel(*integ, cfg->estimator, gx, gy, cx, b.sampler);
                         acc = acc + c; // Bitmap::accumulate, structure.rs:397-402

@@ -40,6 +40,7 @@ typedef struct orc_config {
     uint32_t math_mode, accel_mode, estimator, seeding;
     uint32_t nthreads; /* 0 = all hardware threads */
     uint32_t rank, nranks; /* image-tile partition identical to the GPU's; nranks<=1 = whole image */
+    uint32_t sample_offset; /* mode B: index of the first sample (rl_render_opts.sample_offset) */
 } orc_config;
 
 typedef struct orc_stats {

@@ -55,7 +55,7 @@ class rl_integrator_desc(C.Structure):
 class rl_render_opts(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("spp", C.c_uint32), ("seed", C.c_uint64),
                 ("sampler_mode", C.c_uint32), ("batch_spp", C.c_uint32),
-                ("material_sort", C.c_uint32), ("reserved", C.c_uint32)]
+                ("material_sort", C.c_uint32), ("sample_offset", C.c_uint32)]
 
 
 class rl_stats(C.Structure):

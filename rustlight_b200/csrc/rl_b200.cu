@@ -574,7 +574,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
         for (uint32_t s0 = 0; s0 < o->spp; s0 += batch) {
             const uint32_t nb = std::min(batch, o->spp - s0);
             const size_t n_paths = (size_t)npix * nb;
-            ip.sample_base = s0;
+            ip.sample_base = o->sample_offset + s0;
             if (prof) CK(cudaEventRecord(ctx->ev[2], st));
             k_raygen<<<grid_for(ctx, n_paths, 8), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, (uint32_t)n_paths, ctx->ray_o[0], ctx->ray_d[0],
                                                                    ctx->state[0], ctx->lacc, n_slots);

@@ -25,7 +25,7 @@ pub struct rl_mesh_desc {
     pub kind: u32, pub min_depth: i32, pub max_depth: i32, pub rr_depth: i32, pub strategy: u32,
     pub single_scattering: u32, pub nb_bsdf_samples: u32, pub nb_light_samples: u32,
 }
-#[repr(C)] pub struct rl_render_opts { pub struct_size: u32, pub spp: u32, pub seed: u64, pub sampler_mode: u32, pub batch_spp: u32, pub material_sort: u32, pub reserved: u32 }
+#[repr(C)] pub struct rl_render_opts { pub struct_size: u32, pub spp: u32, pub seed: u64, pub sampler_mode: u32, pub batch_spp: u32, pub material_sort: u32, pub sample_offset: u32 }
 #[repr(C)] #[derive(Default)]
 pub struct rl_stats {
     pub samples: u64, pub segments: u64, pub shadow_rays: u64, pub shadow_visible: u64, pub hits: u64, pub max_depth_seen: u64,
@@ -100,7 +100,7 @@ fn render(scene: &Scene, integ: rl_integrator_desc, seed: u64) -> BufferCollecti
         let size = *scene.camera.size();
         let mut rgb = vec![0f32; (size.x * size.y * 3) as usize];
         let opts = rl_render_opts { struct_size: std::mem::size_of::<rl_render_opts>() as u32, spp: scene.nb_samples as u32,
-            seed, sampler_mode: 1, batch_spp: 0, material_sort: 0, reserved: 0 };
+            seed, sampler_mode: 1, batch_spp: 0, material_sort: 0, sample_offset: 0 };
         let mut st = rl_stats::default();
         if rl_render(ctx, dev, &integ, &opts, rgb.as_mut_ptr(), &mut st) != 0 { panic!("{:?}", CStr::from_ptr(rl_last_error(ctx))); }
         info!("Elapsed Integrator: {} ms", st.ms_total as u64);   // same log line as integrators/mod.rs:334
