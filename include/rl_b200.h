@@ -163,6 +163,9 @@ typedef struct rl_bvh_info {
     uint32_t ntris, nnodes, nleaves, max_depth;
     float root_min[3], root_max[3]; /* == BVHAccel nodes[0].aabb (accel.rs:204-217)            */
     uint32_t smem_resident;         /* 1 if BVH+triangles are staged in shared memory          */
+    /* group table of small scenes (incoherent rays scan it instead of walking the tree): 0 groups = absent */
+    uint32_t flat_groups, flat_pairs, flat_singles;
+    float flat_delta;               /* largest plane mismatch inside a triangle pair           */
 } rl_bvh_info;
 int rl_scene_bvh_info(rl_ctx *ctx, const rl_scene *scene, rl_bvh_info *out);
 

@@ -73,7 +73,8 @@ class rl_stats(C.Structure):
 class rl_bvh_info(C.Structure):
     _fields_ = [("ntris", C.c_uint32), ("nnodes", C.c_uint32), ("nleaves", C.c_uint32),
                 ("max_depth", C.c_uint32), ("root_min", C.c_float * 3), ("root_max", C.c_float * 3),
-                ("smem_resident", C.c_uint32)]
+                ("smem_resident", C.c_uint32), ("flat_groups", C.c_uint32), ("flat_pairs", C.c_uint32),
+                ("flat_singles", C.c_uint32), ("flat_delta", C.c_float)]
 
 
 class rl_layout_info(C.Structure):

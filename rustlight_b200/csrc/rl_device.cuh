@@ -292,6 +292,11 @@ struct SceneView {
     const float *emit_cdf; // n_emitters+1
     const float *area_cdf; // concatenated per-emitter triangle-area cdfs (ntris+1 each)
     uint32_t ntris, n_emitters;
+    // flat group table (rl_build.cuh: build_flat_table) for scenes of a few dozen triangles: n_groups == 0 when absent
+    const float4 *flat;
+    uint32_t n_groups;
+    uint32_t flat_valid[2]; // candidate bits that refer to real triangles (bit order of flat_scan)
+    float flat_delta;       // largest plane mismatch inside a triangle pair (world units), added to the t margin
     int root_ref; // inner node 0, or a leaf reference when the whole scene is one leaf
     // BVHAccel nodes[0].aabb (union of compute_aabb_tri boxes), for the reference's root test
     V3 root_min, root_max;
@@ -545,6 +550,203 @@ RL_HD bool trav_leaf_any(Trav &tr, const int *stack, const float4 *trav) {
     return false;
 }
 
+// ---- flat group scan (scenes of a few dozen triangles) ----------------------------------------------
+// Incoherent rays gain nothing from a hierarchy over ~36 triangles (every lane of a warp walks a different
+// branch), so they run the conservative prefilter over ALL triangles in lockstep and the exact test only on
+// the survivors.  To make the scan cheap the triangles are grouped at build time (rl_build.cuh):
+//   pair record  = two triangles A, B lying in one plane (a quad face): the ray/plane part of the prefilter
+//                  is computed once, with A's plane (B's vertices are within flat_delta of it; unpaired
+//                  triangles get a dummy B whose candidate bit is masked by flat_valid);
+//   group        = two pair records P, Q interleaved component-wise, so that every arithmetic step is one
+//                  packed fma.rn.f32x2 / add / mul (FFMA2 / FADD2 / FMUL2 on sm_100) over (P, Q).
+// Eleven float4 per group (four triangles):
+//   [0] {n.x P,Q  n.y P,Q}   [1] {n.z P,Q  pn P,Q}            plane of A: n.p = pn
+//   [2] {MuA.x P,Q MuA.y P,Q} [3] {MuA.z P,Q cuA P,Q}          u_A(p) = MuA.p + cuA        [4],[5] the same for v_A
+//   [6],[7] u_B   [8],[9] v_B
+//   [10] {mn P, mn Q, slots P, slots Q}   mn = largest gradient norm of the four functionals of the pair,
+//                                         slots = Morton slot of A | slot of B << 8 (index into trav[])
+// The result is one REJECT bit per triangle, shifted into the mask in scan order (first triangle ends in the
+// highest bit).  Rejection is decided by the sign of min(min(u,v,w) + m, tp + mt, tmax + mt - tp): FMNMX drops
+// NaN operands and an all-NaN minimum is the canonical (positive) NaN, so degenerate cases (d.n == 0, inf
+// arithmetic) stay candidates exactly like in tri_prefilter.
+#define RL_FLAT_F4 11
+#define RL_FLAT_MAX_GROUPS 16
+#ifndef RL_FLAT_MARGIN_SCALE
+#define RL_FLAT_MARGIN_SCALE 1.0f // test hook: tests/ shrink the margins to measure how much slack they carry
+#endif
+struct F2 {
+    float x, y;
+};
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ unsigned long long f2_pack(F2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ F2 f2_unpack(unsigned long long v) {
+    F2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+#endif
+RL_HD F2 f2(float x, float y) { return F2{x, y}; }
+RL_HD F2 f2b(float x) { return F2{x, x}; }
+RL_HD F2 fma2(F2 a, F2 b, F2 c) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+    return f2_unpack(r);
+#else
+    return F2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)};
+#endif
+}
+RL_HD F2 mul2(F2 a, F2 b) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(r);
+#else
+    return F2{a.x * b.x, a.y * b.y};
+#endif
+}
+RL_HD F2 add2(F2 a, F2 b) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(r);
+#else
+    return F2{a.x + b.x, a.y + b.y};
+#endif
+}
+RL_HD F2 sub2(F2 a, F2 b) {
+#if defined(__CUDA_ARCH__)
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+    return f2_unpack(r);
+#else
+    return F2{a.x - b.x, a.y - b.y};
+#endif
+}
+// min of three that ignores NaN operands (FMNMX3 on sm_100)
+RL_HD float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
+// (mask << 1) | reject, reject = "s is negative and not NaN"
+RL_HD uint32_t push_reject(uint32_t mask, float s) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(__float_as_uint(s), mask, 1); // NaN results are the canonical 0x7fffffff: sign clear
+#else
+    return (mask << 1) | ((s < 0.0f) ? 1u : 0u);
+#endif
+}
+struct FlatRay {
+    V3 o, d;
+    float tmax;
+    float rs2, rs8; // margins scaled by the coordinate magnitude of this ray (as in trav_begin) + flat_delta
+};
+RL_HD FlatRay flat_ray(const SceneView &sv, V3 o, V3 d, float tmax) {
+    FlatRay fr;
+    fr.o = o, fr.d = d, fr.tmax = tmax;
+    float m = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+    const float rs = 4.0f * fmaxf(m, sv.abs_max);
+    fr.rs2 = RL_FLAT_MARGIN_SCALE * (3e-6f * rs + 2.0f * sv.flat_delta);
+    fr.rs8 = RL_FLAT_MARGIN_SCALE * 8e-6f * rs;
+    return fr;
+}
+// Scan groups [g0, g1): returns the reject bits (4 per group, scan order from the top).
+RL_HD uint32_t flat_scan(const FlatRay &fr, const float4 *flat, uint32_t g0, uint32_t g1) {
+    uint32_t mask = 0;
+    const F2 dx = f2b(fr.d.x), dy = f2b(fr.d.y), dz = f2b(fr.d.z);
+    const F2 ox = f2b(fr.o.x), oy = f2b(fr.o.y), oz = f2b(fr.o.z);
+    const F2 nox = f2b(-fr.o.x), noy = f2b(-fr.o.y), noz = f2b(-fr.o.z);
+    for (uint32_t gi = g0; gi < g1; gi++) {
+        const float4 *g = flat + RL_FLAT_F4 * gi;
+        const float4 a0 = g[0], a1 = g[1];
+        const F2 nx = f2(a0.x, a0.y), ny = f2(a0.z, a0.w), nz = f2(a1.x, a1.y), pn = f2(a1.z, a1.w);
+        // plane: t' = (pn - o.n) / (d.n)
+        const F2 den = fma2(dx, nx, fma2(dy, ny, mul2(dz, nz)));
+        const F2 num = fma2(nox, nx, fma2(noy, ny, fma2(noz, nz, pn)));
+        const F2 rden = f2(rcp_fast(den.x), rcp_fast(den.y));
+        const F2 tp = mul2(num, rden);
+        const float ard0 = fabsf(rden.x), ard1 = fabsf(rden.y);
+        const F2 mt = f2(ard0 * fmaf(fabsf(num.x), fmaf(ard0, RL_FLAT_MARGIN_SCALE * 2e-6f, RL_FLAT_MARGIN_SCALE * 8e-6f), fr.rs2), ard1 * fmaf(fabsf(num.y), fmaf(ard1, RL_FLAT_MARGIN_SCALE * 2e-6f, RL_FLAT_MARGIN_SCALE * 8e-6f), fr.rs2));
+        const F2 px = fma2(tp, dx, ox), py = fma2(tp, dy, oy), pz = fma2(tp, dz, oz);
+        const float4 c10 = g[10];
+        const F2 m = fma2(f2(c10.x, c10.y), fma2(mt, f2b(6.0f), f2b(fr.rs8)), f2b(RL_FLAT_MARGIN_SCALE * 2e-6f));
+        const F2 q1 = add2(tp, mt), q2 = sub2(add2(f2b(fr.tmax), mt), tp);
+        const float4 b0 = g[2], b1 = g[3], b2 = g[4], b3 = g[5];
+        const F2 uA = fma2(px, f2(b0.x, b0.y), fma2(py, f2(b0.z, b0.w), fma2(pz, f2(b1.x, b1.y), f2(b1.z, b1.w))));
+        const F2 vA = fma2(px, f2(b2.x, b2.y), fma2(py, f2(b2.z, b2.w), fma2(pz, f2(b3.x, b3.y), f2(b3.z, b3.w))));
+        const F2 wA = sub2(sub2(f2b(1.0f), uA), vA);
+        const float4 b4 = g[6], b5 = g[7], b6 = g[8], b7 = g[9];
+        const F2 uB = fma2(px, f2(b4.x, b4.y), fma2(py, f2(b4.z, b4.w), fma2(pz, f2(b5.x, b5.y), f2(b5.z, b5.w))));
+        const F2 vB = fma2(px, f2(b6.x, b6.y), fma2(py, f2(b6.z, b6.w), fma2(pz, f2(b7.x, b7.y), f2(b7.z, b7.w))));
+        const F2 wB = sub2(sub2(f2b(1.0f), uB), vB);
+        mask = push_reject(mask, min3f(min3f(uA.x, vA.x, wA.x) + m.x, q1.x, q2.x)); // P.A
+        mask = push_reject(mask, min3f(min3f(uB.x, vB.x, wB.x) + m.x, q1.x, q2.x)); // P.B
+        mask = push_reject(mask, min3f(min3f(uA.y, vA.y, wA.y) + m.y, q1.y, q2.y)); // Q.A
+        mask = push_reject(mask, min3f(min3f(uB.y, vB.y, wB.y) + m.y, q1.y, q2.y)); // Q.B
+    }
+    return mask;
+}
+// Candidate bits of one half (groups [g0, g1)): valid and not rejected.  Bit b <-> scan index 4*(g1-g0)-1-b.
+RL_HD uint32_t flat_candidates(const FlatRay &fr, const SceneView &sv, const float4 *flat, int half) {
+    const uint32_t g0 = half ? 8u : 0u, g1 = half ? sv.n_groups : (sv.n_groups < 8u ? sv.n_groups : 8u);
+    if (g0 >= g1) return 0u;
+    return ~flat_scan(fr, flat, g0, g1) & sv.flat_valid[half];
+}
+RL_HD int clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+// Morton slot of the triangle behind candidate bit `b` of half `half`.
+RL_HD uint32_t flat_slot(const SceneView &sv, const float4 *flat, int half, uint32_t b) {
+    const uint32_t g0 = half ? 8u : 0u, g1 = half ? sv.n_groups : (sv.n_groups < 8u ? sv.n_groups : 8u);
+    const uint32_t idx = 4u * (g1 - g0) - 1u - b; // scan index inside this half
+    const float4 c10 = flat[RL_FLAT_F4 * (g0 + (idx >> 2)) + 10];
+    const uint32_t word = f2u((idx & 2u) ? c10.w : c10.z);
+    return (word >> ((idx & 1u) * 8u)) & 0xffu;
+}
+// Closest hit over the flat table: same result rule as trav_leaf_closest.
+RL_HD HitRec flat_closest(const SceneView &sv, const float4 *flat, const float4 *trav, V3 o, V3 d) {
+    FlatRay fr = flat_ray(sv, o, d, RL_F32_MAX);
+    HitRec h;
+    h.t = RL_F32_MAX, h.u = 0.0f, h.v = 0.0f, h.prim = RL_MISS;
+    uint32_t c0 = flat_candidates(fr, sv, flat, 0), c1 = flat_candidates(fr, sv, flat, 1);
+    for (int half = 0; half < 2; half++) {
+        uint32_t c = half ? c1 : c0;
+        while (c) {
+            const uint32_t b = 31u - (uint32_t)clz32(c);
+            c &= ~(1u << b);
+            const float4 *r = trav + 6 * flat_slot(sv, flat, half, b);
+            float4 r1 = r[1];
+            float t_, u_, v_;
+            if (tri_test(r[0], r1, r[2], r[3], o, d, h.t, &t_, &u_, &v_)) {
+                uint32_t prim_ = f2u(r1.w);
+                if (t_ < h.t || (h.prim != RL_MISS && prim_ < h.prim)) h.t = t_, h.u = u_, h.v = v_, h.prim = prim_;
+            }
+        }
+    }
+    return h;
+}
+// Any hit with t < thr over the flat table (Acceleration::visible): true when the segment is blocked.
+RL_HD bool flat_any(const SceneView &sv, const float4 *flat, const float4 *trav, V3 o, V3 d, float thr) {
+    FlatRay fr = flat_ray(sv, o, d, thr);
+    uint32_t c0 = flat_candidates(fr, sv, flat, 0), c1 = flat_candidates(fr, sv, flat, 1);
+    for (int half = 0; half < 2; half++) {
+        uint32_t c = half ? c1 : c0;
+        while (c) {
+            const uint32_t b = 31u - (uint32_t)clz32(c);
+            c &= ~(1u << b);
+            const float4 *r = trav + 6 * flat_slot(sv, flat, half, b);
+            float t_, u_, v_;
+            if (tri_test(r[0], r[1], r[2], r[3], o, d, thr, &t_, &u_, &v_) && t_ < thr) return true;
+        }
+    }
+    return false;
+}
+
 // Acceleration::trace (accel.rs:292-315) without fill_intersection.  Returns false when the
 // reference's root-box test rejects the ray (no traversal needed).
 RL_HD bool closest_begin(Trav &tr, const SceneView &sv, V3 o, V3 d) {
@@ -566,6 +768,18 @@ RL_HD HitRec closest_result(const Trav &tr) {
 }
 // Acceleration::visible (accel.rs:316-343): segment setup.  *decided is set when the root test
 // already answers (then *vis holds the answer).
+// Segment direction, threshold and the reference's root test; false = "not visible" without traversal.
+RL_HD bool visible_setup(const SceneView &sv, V3 p0, V3 p1, V3 *d_out, float *thr_out) {
+    const float SHADOW_EPS = 0.00001f;
+    V3 d = p1 - p0;
+    float length = magnitude(d);
+    d = d / length;
+    float thr = length * (1.0f - SHADOW_EPS);
+    V3 inv = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    *d_out = d;
+    *thr_out = thr;
+    return aabb_intersect_ref(sv.root_min, sv.root_max, p0, inv, RL_EPSILON, thr);
+}
 RL_HD void visible_begin(Trav &tr, const SceneView &sv, V3 p0, V3 p1, bool *decided, bool *vis) {
     const float SHADOW_EPS = 0.00001f;
     V3 d = p1 - p0;
@@ -588,6 +802,15 @@ RL_HD void visible_begin(Trav &tr, const SceneView &sv, V3 p0, V3 p1, bool *deci
 RL_HD HitRec trace_closest(const SceneView &sv, const float4 *nodes, const float4 *trav, V3 o, V3 d) {
     Trav tr;
     int stack[RL_STACK_SIZE];
+    if (sv.n_groups) { // flat group table: root test, then scan + exact tests
+        V3 inv = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+        if (!aabb_intersect_ref(sv.root_min, sv.root_max, o, inv, RL_EPSILON, RL_F32_MAX)) {
+            HitRec h;
+            h.t = RL_F32_MAX, h.u = 0.0f, h.v = 0.0f, h.prim = RL_MISS;
+            return h;
+        }
+        return flat_closest(sv, sv.flat, trav, o, d);
+    }
     if (closest_begin(tr, sv, o, d)) {
         while (tr.cur != RL_TRAV_DONE) {
             if (tr.cur >= 0) trav_node_step(tr, stack, nodes);
@@ -600,6 +823,12 @@ RL_HD bool trace_visible(const SceneView &sv, const float4 *nodes, const float4 
     Trav tr;
     int stack[RL_STACK_SIZE];
     bool decided, vis;
+    if (sv.n_groups) {
+        V3 d;
+        float thr;
+        if (!visible_setup(sv, p0, p1, &d, &thr)) return false; // accel.rs:338-340
+        return !flat_any(sv, sv.flat, trav, p0, d, thr);
+    }
     visible_begin(tr, sv, p0, p1, &decided, &vis);
     if (decided) return vis;
     while (tr.cur != RL_TRAV_DONE) {

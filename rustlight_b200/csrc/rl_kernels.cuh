@@ -134,6 +134,59 @@ __global__ void __launch_bounds__(kBlock) k_trace(SceneView sv, const uint32_t *
     }
 }
 
+// ---- group-table variants (scenes of a few dozen triangles, incoherent rays) ------------------------
+// One ray per thread, grid-stride, no traversal state: the reference's root-box test, the lockstep scan of the
+// flat group table (rl_device.cuh: flat_scan, packed f32x2 arithmetic, no divergence), then the exact triangle
+// test on the few survivors.  The group table and the exact-test records are staged in shared memory.
+__device__ __forceinline__ void stage_flat(const SceneView &sv, float4 *smem, uint32_t n_flat_f4, uint32_t n_trav_f4) {
+    for (uint32_t i = threadIdx.x; i < n_flat_f4; i += blockDim.x) smem[i] = ldg4(sv.flat + i);
+    for (uint32_t i = threadIdx.x; i < n_trav_f4; i += blockDim.x) smem[n_flat_f4 + i] = ldg4(sv.trav + i);
+    __syncthreads();
+}
+__global__ void __launch_bounds__(kBlock) k_trace_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
+                                                       const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t n_trav_f4) {
+    extern __shared__ float4 smem[];
+    const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
+    stage_flat(sv, smem, n_flat_f4, n_trav_f4);
+    const float4 *flat = smem, *trav = smem + n_flat_f4;
+    const uint32_t n = *count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 ro = ray_o[i], rd = ray_d[i];
+        const V3 o = xyz(ro), d = xyz(rd);
+        const V3 inv = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+        HitRec h;
+        h.t = RL_F32_MAX, h.u = 0.0f, h.v = 0.0f, h.prim = RL_MISS;
+        if (aabb_intersect_ref(sv.root_min, sv.root_max, o, inv, RL_EPSILON, RL_F32_MAX)) h = flat_closest(sv, flat, trav, o, d);
+        hit[i] = make_float4(h.t, h.u, h.v, u2f(h.prim));
+    }
+}
+__global__ void __launch_bounds__(kBlock) k_shadow_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ sh_a,
+                                                        const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c, float4 *__restrict__ lacc,
+                                                        Counters *counters, uint32_t n_trav_f4) {
+    extern __shared__ float4 smem[];
+    const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
+    stage_flat(sv, smem, n_flat_f4, n_trav_f4);
+    const float4 *flat = smem, *trav = smem + n_flat_f4;
+    const uint32_t n = *count;
+    uint32_t c_vis = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = sh_a[i], b = sh_b[i];
+        V3 d;
+        float thr;
+        // root test failed => "not visible" (accel.rs:338-340): nothing to add
+        if (visible_setup(sv, xyz(a), xyz(b), &d, &thr) && !flat_any(sv, flat, trav, xyz(a), d, thr)) {
+            const float4 c = sh_c[i];
+            const uint32_t pid = f2u(a.w);
+            float4 l = lacc[pid];
+            l.x += c.x, l.y += c.y, l.z += c.z;
+            lacc[pid] = l;
+            c_vis++;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) c_vis += __shfl_down_sync(0xffffffffu, c_vis, off);
+    if ((threadIdx.x & 31u) == 0 && c_vis) atomicAdd(&counters->shadow_visible, (unsigned long long)c_vis);
+}
+
 // ---- block-level compaction helper ---------------------------------------------------------------
 // Returns this thread's slot in the output queue (valid when flag), reserving the CTA's range
 // with one atomicAdd.  `scratch` is 2*(kBlock/32)+2 uint32 of shared memory.

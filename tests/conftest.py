@@ -151,5 +151,65 @@ def adversarial_case(seed):
     return sc, o, dd, p1
 
 
+def adversarial_pairs_case(seed):
+    """Scene of quads (two triangles each) that stresses the PAIR records of the flat group table: the fourth
+    vertex sits 1e-9..3e-6 quad sizes off the plane of the first triangle (straddling the pairing thresholds:
+    normals equal to 4e-7, mismatch below 1e-6 * abs_max), quads are parallelograms, kites or slivers, the second triangle is wound either way;
+    rays aim at the shared diagonal, at edges and vertices, half of them grazing."""
+    import json
+    from rustlight_b200 import SceneLoaderManager
+    rng = np.random.default_rng(500 + seed)
+    scale = [1.0, 1e-3, 200.0, 1.0][seed]
+    shift = np.array([[0, 0, 0], [0, 0, 0], [0, 0, 0], [40, -25, 10]][seed], np.float64)
+    nq = [14, 12, 10, 14][seed]
+    meshes, quads = [], []
+    for q in range(nq):
+        c = rng.uniform(-1, 1, 3) * scale + shift
+        e1 = rng.normal(size=3)
+        e1 /= np.linalg.norm(e1)
+        e2 = np.cross(e1, rng.normal(size=3))
+        e2 /= np.linalg.norm(e2)
+        nrm = np.cross(e1, e2)
+        if q % 4 == 0:  # axis-aligned face
+            e1, e2, nrm = np.eye(3)[[q % 3, (q + 1) % 3, (q + 2) % 3]]
+        s1, s2 = scale * 10.0 ** rng.uniform(-2, 0, 2)
+        if q % 5 == 1:
+            s2 = s1 * 1e-3  # sliver quad
+        a, b, d = c, c + e1 * s1, c + e2 * s2
+        cc = c + e1 * s1 * rng.uniform(0.6, 1.4) + e2 * s2 * rng.uniform(0.6, 1.4) if q % 2 else c + e1 * s1 + e2 * s2
+        cc = cc + nrm * min(s1, s2) * 10.0 ** rng.uniform(-9, -5.5) * rng.choice([-1, 1])
+        P = np.array([a, b, cc, d], np.float32)
+        idx = [0, 1, 2, 0, 2, 3] if q % 3 else [0, 1, 2, 0, 3, 2]
+        quads.append(P.astype(np.float64))
+        meshes.append({"material": {"type": "diffuse", "kd": [0.5] * 3}, "indices": idx, "P": [float(x) for x in P.ravel()]})
+    meshes[0]["emission"] = [1, 1, 1]
+    txt = json.dumps({"camera": {"width": 8, "height": 8, "fov": 40, "to_world": [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 0, 0, 3, 1]}, "meshes": meshes})
+    sc = SceneLoaderManager().load_string(txt, "json")
+    nr = 6000
+    pick = rng.integers(0, nq, nr)
+    Q = np.array(quads)[pick]                                     # nr x 4 x 3
+    w = rng.dirichlet([0.4, 0.4, 0.4, 0.4], nr)
+    w[::6] = 0.0
+    w[::6, 0] = rng.uniform(0, 1, len(w[::6]))                    # on the shared diagonal (vertices 0 and 2)
+    w[::6, 2] = 1.0 - w[::6, 0]
+    w[1::6] = np.eye(4)[rng.integers(0, 4, len(w[1::6]))]         # exactly at a vertex
+    k = rng.integers(0, 4, len(w[2::6]))                          # on an outer edge
+    t = rng.uniform(0, 1, len(k))
+    w[2::6] = np.eye(4)[k] * t[:, None] + np.eye(4)[(k + 1) % 4] * (1 - t[:, None])
+    tgt = (Q * w[:, :, None]).sum(axis=1)
+    nrm = np.cross(Q[:, 1] - Q[:, 0], Q[:, 3] - Q[:, 0])
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-300)
+    dirs = rng.normal(size=(nr, 3))
+    g = dirs[::2]
+    dirs[::2] = g - (g * nrm[::2]).sum(axis=1, keepdims=True) * nrm[::2] * (1 - 10.0 ** rng.uniform(-7, -1, (len(g), 1)))  # grazing
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    dist = scale * 10.0 ** rng.uniform(-3, 2, (nr, 1))
+    o = (tgt - dirs * dist).astype(np.float32)
+    dd = dirs.astype(np.float32)
+    dd /= np.linalg.norm(dd.astype(np.float64), axis=1, keepdims=True).astype(np.float32)
+    p1 = (tgt + rng.normal(size=(nr, 3)) * scale * 1e-2).astype(np.float32)
+    return sc, o, dd, p1
+
+
 def rel_l2(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(np.linalg.norm(b.astype(np.float64)), 1e-30))

@@ -16,6 +16,7 @@
 #include "rl_b200.h"
 #include "rl_build.cuh"
 #include "rl_device.cuh"
+#include "rl_flat_host.hpp"
 #include "rl_scene_host.hpp"
 
 using namespace rl;
@@ -23,6 +24,7 @@ using namespace rl;
 struct emu_scene {
     HostScene hs;
     std::vector<float4> trav, nodes;
+    FlatTable flat;
     SceneView sv{};
     uint32_t max_depth = 0;
     int root_ref = 0, leaf_max = 1;
@@ -62,8 +64,17 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         tri_setup(hs.verts.data(), prim, i, s->trav.data(), hs.shade.data());
         tri_bounds_inflated(hs.verts.data(), prim, bvh_box_eps(hs.abs_max), &leaf_lo[i], &leaf_hi[i]);
     }
+    // Traversal mode (the device uses all three: group table for incoherent rays of small scenes, tree otherwise;
+    // the single big leaf is the pre-group-table flat path, kept as a cross-check): RL_EMU_ACCEL = flat | leaf | tree
+    std::string mode = "flat";
+    if (const char *e = getenv("RL_EMU_ACCEL")) mode = e;
+    if (mode == "flat" && n <= RL_LEAF_MAX_CAP) {
+        std::vector<uint32_t> prim_of_slot(n);
+        for (int i = 0; i < n; i++) prim_of_slot[i] = (uint32_t)(keys[i] & 0xffffffffull);
+        if (!build_flat_table(hs, prim_of_slot, s->flat)) s->flat = FlatTable{};
+    }
     // k_karras + k_fit
-    int leaf_max = n <= RL_LEAF_MAX_CAP ? RL_LEAF_MAX_CAP : 4;
+    int leaf_max = n <= RL_LEAF_MAX_CAP ? (mode == "leaf" ? RL_LEAF_MAX_CAP : 2) : 4;
     if (const char *e = getenv("RL_LEAF_MAX")) leaf_max = std::max(1, std::min(RL_LEAF_MAX_CAP, atoi(e)));
     s->leaf_max = leaf_max;
     int n_nodes = n > 1 ? n - 1 : 1;
@@ -95,6 +106,8 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
     sv.emit_info = hs.emit_info.data(), sv.emit_cdf = hs.emit_cdf.data(), sv.area_cdf = hs.area_cdf.data();
     sv.ntris = hs.ntris, sv.n_emitters = hs.n_emitters;
     sv.root_ref = s->root_ref;
+    sv.flat = s->flat.f4.data(), sv.n_groups = s->flat.n_groups, sv.flat_valid[0] = s->flat.valid[0], sv.flat_valid[1] = s->flat.valid[1];
+    sv.flat_delta = s->flat.delta;
     sv.root_min = V3{hs.root_min[0], hs.root_min[1], hs.root_min[2]};
     sv.root_max = V3{hs.root_max[0], hs.root_max[1], hs.root_max[2]};
     sv.abs_max = hs.abs_max;
@@ -106,6 +119,13 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
 }
 void emu_scene_destroy(emu_scene *s) { delete s; }
 uint32_t emu_bvh_max_depth(const emu_scene *s) { return s->max_depth; }
+// group table statistics: groups, pairs, singles; delta in *delta
+uint32_t emu_flat_info(const emu_scene *s, uint32_t *pairs, uint32_t *singles, float *delta) {
+    if (pairs) *pairs = s->flat.n_pairs;
+    if (singles) *singles = s->flat.n_singles;
+    if (delta) *delta = s->flat.delta;
+    return s->flat.n_groups;
+}
 
 // Checks the tree: every triangle is referenced by exactly one leaf and every child box
 // contains its subtree.  Returns 0 when valid.

@@ -32,6 +32,8 @@ def lib():
         L.emu_bvh_max_depth.restype = C.c_uint32
         L.emu_bvh_max_depth.argtypes = [C.c_void_p]
         L.emu_bvh_validate.argtypes = [C.c_void_p]
+        L.emu_flat_info.restype = C.c_uint32
+        L.emu_flat_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), FP]
         L.emu_trace.argtypes = [C.c_void_p, C.c_size_t, FP, FP, C.POINTER(C.c_uint32), FP]
         L.emu_visible.argtypes = [C.c_void_p, C.c_size_t, FP, FP, C.POINTER(C.c_uint8)]
         L.emu_primary_hits.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), FP]
@@ -46,10 +48,22 @@ def _f(a):
 
 
 class EmuScene:
-    def __init__(self, scene):
+    def __init__(self, scene, accel=None):
+        """accel: None/"flat" (group table when the scene is small enough, the device default for incoherent rays),
+        "leaf" (whole scene as one leaf of single-triangle records), "tree" (LBVH with small leaves)."""
         self._scene = scene
         err = C.create_string_buffer(512)
-        self._h = lib().emu_scene_create(scene.desc, err, 512)
+        old = os.environ.get("RL_EMU_ACCEL")
+        if accel:
+            os.environ["RL_EMU_ACCEL"] = accel
+        try:
+            self._h = lib().emu_scene_create(scene.desc, err, 512)
+        finally:
+            if accel:
+                if old is None:
+                    del os.environ["RL_EMU_ACCEL"]
+                else:
+                    os.environ["RL_EMU_ACCEL"] = old
         if not self._h:
             raise RuntimeError("emu: " + err.value.decode())
         self.width, self.height = scene.size
@@ -61,6 +75,11 @@ class EmuScene:
 
     def bvh_max_depth(self):
         return lib().emu_bvh_max_depth(self._h)
+
+    def flat_info(self):
+        pairs, singles, delta = C.c_uint32(), C.c_uint32(), C.c_float()
+        g = lib().emu_flat_info(self._h, C.byref(pairs), C.byref(singles), C.byref(delta))
+        return dict(groups=g, pairs=pairs.value, singles=singles.value, delta=delta.value)
 
     def bvh_validate(self):
         return lib().emu_bvh_validate(self._h)

@@ -53,23 +53,24 @@ def test_cli_matches_library(tmp_path, gpu_ctx):
 
 @pytest.mark.gpu
 def test_average_wrapper(tmp_path, gpu_ctx):
-    """`-a 3`: three passes of 2 spp over sample indices [0,2), [2,4), [4,6), running mean like avg.rs:58-62,
-    one dump per iteration + _time.csv (avg.rs:69-106)."""
+    """`-a 3`: three passes of 2 spp over sample indices [0,2), [2,4), [4,6), combined exactly like avg.rs:51-62 --
+    `iteration` is already 2 on the second pass, so the reference computes (2a+b)/3, then (2a+b+c)/4: the first
+    pass keeps a double weight (a quirk of the reference, mirrored) -- one dump per iteration + _time.csv (avg.rs:69-106)."""
     from rustlight_b200.device import DeviceScene
     out = str(tmp_path / "avg.pfm")
     assert run("-n", "2", "-a", "3", "-s", "0.125", "-o", out, CBOX, "path").returncode == 0
     dev = DeviceScene(gpu_ctx, load_cbox().scale_image(0.125))
     passes = [dev.render(_abi.path_desc(), 2, seed=0, sample_offset=2 * p)[0] for p in range(3)]
     acc = passes[0].copy()
-    for it, nb in enumerate(passes[1:], start=1):
-        acc = ((acc * np.float32(it)) + nb) * np.float32(1.0 / (it + 1))
+    for it, nb in enumerate(passes[1:], start=2):
+        acc = ((acc * np.float32(it)) + nb) * np.float32(np.float32(1.0) / np.float32(it + 1))
     assert np.array_equal(read_pfm(out), np.abs(acc))
     for it in (1, 2, 3):
         assert os.path.exists(str(tmp_path / f"avg_{it}.pfm"))
     assert len(open(str(tmp_path / "avg_time.csv")).read().strip().splitlines()) == 3
-    # the passes are disjoint sample sets of one 6-spp render: same expectation, nearly the same image
-    six, _ = dev.render(_abi.path_desc(), 6, seed=0)
-    assert np.allclose(acc, six, rtol=2e-5, atol=1e-6)
+    # a convex combination (weights 2:1:1) of disjoint sample sets of one 6-spp render
+    want = (2.0 * passes[0].astype(np.float64) + passes[1] + passes[2]) / 4.0
+    assert np.allclose(acc, want, rtol=2e-5, atol=1e-6)
 
 
 @pytest.mark.gpu

@@ -30,6 +30,48 @@ def test_lbvh_is_valid(cbox):
     assert esc.bvh_validate() == 0 and 1 <= esc.bvh_max_depth() <= 36
 
 
+def test_cbox_group_table_pairs_every_quad(cbox):
+    """36 triangles = 18 planar quads -> 18 pair records in 9 groups; the plane mismatch inside a pair is rounding noise."""
+    info = eb.EmuScene(cbox).flat_info()
+    assert info["groups"] == 9 and info["pairs"] == 18 and info["singles"] == 0 and info["delta"] < 1e-6
+
+
+@pytest.mark.parametrize("accel", ["flat", "leaf", "tree"])
+def test_accel_modes_agree_with_the_oracle(cbox, cbox_oracle, accel):
+    """The three traversal modes of the device (group table, one big leaf, LBVH) give the oracle's hits bit for bit."""
+    esc = eb.EmuScene(cbox, accel)
+    assert (esc.flat_info()["groups"] > 0) == (accel == "flat")
+    o, d, p1 = _rays(20000, 3)
+    pe, te = esc.trace(o, d)
+    po, to = cbox_oracle.trace(o, d, ob.ACCEL_NAIVE)
+    assert np.array_equal(pe, po) and np.array_equal(te, to)
+    assert np.array_equal(esc.visible(o, p1), cbox_oracle.visible(o, p1, ob.ACCEL_NAIVE))
+    # rays that start ON the surfaces (what the path tracer actually traces), incl. toward the light
+    hit = po != 0xFFFFFFFF
+    o2 = (o[hit] + d[hit] * to[hit, :1]).astype(np.float32)
+    d2 = _rays(len(o2), 4)[1]
+    pe, te = esc.trace(o2, d2)
+    po2, to2 = cbox_oracle.trace(o2, d2, ob.ACCEL_NAIVE)
+    assert np.array_equal(pe, po2) and np.array_equal(te, to2)
+    light = np.tile(np.array([[0.0, 1.98, 0.0]], np.float32), (len(o2), 1)) + _rays(len(o2), 5)[0] * np.float32(0.2) * [1, 0, 1]
+    light = light.astype(np.float32)
+    assert np.array_equal(esc.visible(o2, light), cbox_oracle.visible(o2, light, ob.ACCEL_NAIVE))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_pair_records_are_conservative_on_adversarial_quads(seed):
+    from conftest import adversarial_pairs_case
+    sc, o, dd, p1 = adversarial_pairs_case(seed)
+    esc, osc = eb.EmuScene(sc), ob.OracleScene(sc)
+    info = esc.flat_info()
+    assert info["groups"] > 0 and info["pairs"] >= 3, info
+    pe, te = esc.trace(o, dd)
+    po, to = osc.trace(o, dd, ob.ACCEL_NAIVE)
+    assert (po != 0xFFFFFFFF).mean() > 0.3
+    assert np.array_equal(pe, po) and np.array_equal(te, to)
+    assert np.array_equal(esc.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))
+
+
 def test_primary_hits_exact(cbox, cbox_oracle):
     pe, te = eb.EmuScene(cbox).primary_hits()
     po, to = cbox_oracle.primary_hits(ob.ACCEL_NAIVE)

@@ -41,8 +41,10 @@ def cbox_dev(gpu_ctx, cbox):
 def test_native_library_is_the_one_running(gpu_ctx, cbox_dev):
     assert lib()._name.endswith("rustlight_b200/librl_b200.so")
     bi = cbox_dev.bvh_info()
-    # tree with leaves of <= 2 triangles (coherent rays) + the flat whole-scene leaf (incoherent rays), all in shared memory
+    # tree with leaves of <= 2 triangles (coherent rays) + the group table (incoherent rays: 18 planar quads -> 18 pair
+    # records in 9 groups), all in shared memory
     assert (bi.ntris, bi.smem_resident) == (36, 1) and 18 <= bi.nleaves <= 36 and bi.nnodes == bi.nleaves - 1 and bi.max_depth <= 36
+    assert (bi.flat_groups, bi.flat_pairs, bi.flat_singles) == (9, 18, 0) and bi.flat_delta < 1e-6
 
 
 def test_primary_ray_grid_exact(cbox_dev, cbox_oracle):
@@ -318,6 +320,40 @@ def test_adversarial_scenes_exact(gpu_ctx, seed):
     assert np.array_equal(pg, po) and np.array_equal(tg, to)
     assert np.array_equal(dev.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))
     dev.close()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_adversarial_quads_exact(gpu_ctx, seed):
+    """Pair records of the group table (packed f32x2 scan, sign-bit reject mask) on near-coplanar quads: rl_trace runs
+    k_trace_flat, rl_visible runs flat_any."""
+    from conftest import adversarial_pairs_case
+    sc, o, dd, p1 = adversarial_pairs_case(seed)
+    dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
+    bi = dev.bvh_info()
+    assert bi.flat_groups > 0 and bi.flat_pairs >= 3
+    pg, tg = dev.trace(o, dd)
+    po, to = osc.trace(o, dd, ob.ACCEL_NAIVE)
+    assert np.array_equal(pg, po) and np.array_equal(tg, to)
+    assert np.array_equal(dev.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))
+    dev.close()
+
+
+def test_group_table_on_surface_rays_and_degenerate_directions(cbox_dev, cbox_oracle):
+    """What the wavefront actually traces: rays leaving the surfaces (origins ON planes of the table: num == 0 for the
+    own quad), axis-parallel directions (d.n == 0: inf/NaN arithmetic in the scan must stay a candidate), segments to the light."""
+    o, d, _ = _rays(300000, 21)
+    po, to = cbox_oracle.trace(o, d, ob.ACCEL_NAIVE)
+    hit = po != 0xFFFFFFFF
+    o2 = (o[hit] + d[hit] * to[hit, :1]).astype(np.float32)
+    d2 = _rays(len(o2), 22)[1]
+    axes = np.eye(3, dtype=np.float32)[np.arange(len(o2)) % 3] * np.where(np.arange(len(o2)) % 2, 1, -1).astype(np.float32)[:, None]
+    d2[::7] = axes[::7]
+    pg, tg = cbox_dev.trace(o2, d2)
+    po2, to2 = cbox_oracle.trace(o2, d2, ob.ACCEL_NAIVE)
+    assert np.array_equal(pg, po2) and np.array_equal(tg, to2)
+    light = (np.array([[0.0, 1.98, -0.03]]) + (_rays(len(o2), 23)[0] - [0, 1, 0]) * [0.24, 0, 0.2]).astype(np.float32)
+    vg = cbox_dev.visible(o2, light)
+    assert np.array_equal(vg, cbox_oracle.visible(o2, light, ob.ACCEL_NAIVE)) and 0.2 < vg.mean() < 0.9
 
 
 def test_config_shapes_c3_c5(gpu_ctx):
