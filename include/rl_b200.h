@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RL_B200_ABI_VERSION 1
+#define RL_B200_ABI_VERSION 2
 
 typedef struct rl_ctx rl_ctx;     /* one per GPU / per rank; single-owner, not thread-safe */
 typedef struct rl_scene rl_scene; /* device-resident scene: geometry, LBVH, emitters, camera */
@@ -45,16 +45,35 @@ typedef enum rl_status {
 
 /* ---- materials: src/bsdfs/mod.rs:163-199 (trait BSDF) ------------------------------------ */
 typedef enum rl_bsdf_kind {
-    RL_BSDF_DIFFUSE = 0, /* BSDFDiffuse  src/bsdfs/diffuse.rs:6-87  */
-    RL_BSDF_PHONG = 1    /* BSDFPhong    src/bsdfs/phong.rs:6-136   */
+    RL_BSDF_DIFFUSE = 0,   /* BSDFDiffuse   src/bsdfs/diffuse.rs:6-87                                     */
+    RL_BSDF_PHONG = 1,     /* BSDFPhong     src/bsdfs/phong.rs:6-136                                      */
+    RL_BSDF_METAL = 2,     /* BSDFMetal     src/bsdfs/metal.rs:6-177 (microfacet == NONE: pbrt "mirror")  */
+    RL_BSDF_GLASS = 3,     /* BSDFGlass     src/bsdfs/glass.rs:35-192 (DELTA, not two-sided)              */
+    RL_BSDF_SUBSTRATE = 4  /* BSDFSubstrate src/bsdfs/substrate.rs:8-225                                  */
 } rl_bsdf_kind;
+typedef enum rl_microfacet { /* MicrofacetDistributionBSDF, src/bsdfs/distribution.rs:5-17; isotropic only (:62) */
+    RL_MICROFACET_NONE = 0, /* distribution: None -> pure specular lobe (BSDFType::DELTA)                */
+    RL_MICROFACET_GGX = 1,  /* what the PBRT route builds (bsdfs/mod.rs:260-291)                          */
+    RL_MICROFACET_BECKMANN = 2
+} rl_microfacet;
 
+/* All colours are BSDFColor::Constant (bsdfs/mod.rs:11-41).  Fields used per kind:
+ *   DIFFUSE   kd
+ *   PHONG     kd, ks, exponent, weight_specular
+ *   METAL     ks = specular, eta, k, microfacet, alpha
+ *   GLASS     ks = specular_reflectance, kt = specular_transmittance, ior = int_ior / ext_ior (BSDFGlass::eta)
+ *   SUBSTRATE kd = diffuse, ks = specular, microfacet, alpha */
 typedef struct rl_material {
     uint32_t kind;         /* rl_bsdf_kind                                                    */
-    float kd[3];           /* BSDFColor::Constant diffuse reflectance                         */
-    float ks[3];           /* Phong specular reflectance                                      */
+    float kd[3];           /* diffuse reflectance                                             */
+    float ks[3];           /* specular reflectance                                            */
     float exponent;        /* Phong exponent                                                  */
     float weight_specular; /* lum(ks)/(lum(kd)+lum(ks)), src/bsdfs/mod.rs:518-523             */
+    float kt[3];           /* glass: specular transmittance                                   */
+    float eta[3], k[3];    /* metal: real and imaginary part of the index of refraction       */
+    float ior;             /* glass: relative index of refraction (!= 0, glass.rs:43-48)      */
+    float alpha;           /* microfacet roughness alpha_u == alpha_v                          */
+    uint32_t microfacet;   /* rl_microfacet                                                   */
 } rl_material;
 
 /* ---- geometry: Mesh, src/geometry.rs:107-119 ---------------------------------------------- */

@@ -250,6 +250,20 @@ def bsdf_sample(mat, wi, s0, s1, math_mode=MATH_SPEC):
     return (bool(ok), w, d, pdf.value)
 
 
+def bsdf_sample_ex(mat, wi, s0, s1, math_mode=MATH_SPEC):
+    """(ok, weight, d, pdf, discrete): discrete <=> the sampled pdf is PDF::Discrete."""
+    wi = f32(wi)
+    w, d = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    pdf = C.c_float()
+    rc = lib().orc_bsdf_sample(math_mode, C.byref(mat), _f(wi), s0, s1, _f(w), _f(d), C.byref(pdf))
+    return (rc != 0, w, d, pdf.value, rc == 2)
+
+
+def bsdf_flags(mat):
+    f = lib().orc_bsdf_flags(C.byref(mat))
+    return dict(twosided=bool(f & 1), smooth=bool(f & 2))
+
+
 def bsdf_pdf(mat, wi, wo, math_mode=MATH_SPEC):
     wi, wo = f32(wi), f32(wo)
     return lib().orc_bsdf_pdf(math_mode, C.byref(mat), _f(wi), _f(wo))

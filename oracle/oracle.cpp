@@ -195,6 +195,14 @@ struct Math {
         } else spec_sincos(x, s, c);
     }
     float powf(float x, float y) const { return mode == ORC_MATH_LIBM ? std::pow(x, y) : spec_powf(x, y); }
+    float exp(float x) const { return mode == ORC_MATH_LIBM ? std::exp(x) : (float)spec_exp2((double)x * 1.4426950408889634074); }
+    float ln(float x) const {
+        if (mode == ORC_MATH_LIBM) return std::log(x);
+        if (x == 0.0f) return -std::numeric_limits<float>::infinity();
+        if (!(x > 0.0f)) return std::numeric_limits<float>::quiet_NaN();
+        if (!std::isfinite(x)) return x;
+        return (float)(spec_log2((double)x) * 0.69314718055994530942);
+    }
 };
 
 // ============================================================================================
@@ -232,6 +240,10 @@ inline Color operator/(Color a, float o) { // :249-265
     return {a.r / o, a.g / o, a.b / o};
 }
 inline void div_assign(Color &a, float o) { a.r /= o, a.g /= o, a.b /= o; } // :201-207 (no guard)
+inline Color operator-(Color a, Color b) { return {a.r - b.r, a.g - b.g, a.b - b.b}; } // :349-358
+inline Color operator/(Color a, Color b) { return {a.r / b.r, a.g / b.g, a.b / b.b}; } // :266-275 (no guard)
+inline Color color_value(float v) { return {v, v, v}; }                                 // :122-124
+inline Color safe_sqrt(Color c) { return {std::sqrt(rmax(c.r, 0.0f)), std::sqrt(rmax(c.g, 0.0f)), std::sqrt(rmax(c.b, 0.0f))}; } // :132-138
 
 // ============================================================================================
 // structure.rs: Ray, AABB
@@ -445,7 +457,276 @@ struct BSDFPhong : BSDF { // bsdfs/phong.rs
     bool is_twosided() const override { return true; }
     bool is_smooth() const override { return false; }
 };
+// f32::powi(n): llvm.powi / compiler-rt __powisf2 = binary exponentiation (r = 1; loop { if b&1 { r *= a } b /= 2; a *= a })
+inline float powi(float a, int b) {
+    float r = 1.0f;
+    for (;;) {
+        if (b & 1) r *= a;
+        b /= 2;
+        if (b == 0) break;
+        a *= a;
+    }
+    return r;
+}
+// bsdfs/utils.rs
+namespace bu {
+inline float cos_theta(V3 w) { return w.z; }                                            // :5-7
+inline float cos_2_theta(V3 w) { return w.z * w.z; }                                    // :8-10
+inline float abs_cos_theta(V3 w) { return std::fabs(w.z); }                             // :11-13
+inline float sin_2_theta(V3 w) { return rmax(1.0f - cos_2_theta(w), 0.0f); }            // :14-16
+inline float sin_theta(V3 w) { return std::sqrt(sin_2_theta(w)); }                      // :17-19
+inline float tan_theta(V3 w) { return sin_theta(w) / cos_theta(w); }                    // :20-22
+inline float hypot2(float a, float b) {                                                 // :50-60
+    if (std::fabs(a) > std::fabs(b)) {
+        float r = b / a;
+        return std::fabs(a) * std::sqrt(1.0f + r * r);
+    } else if (b != 0.0f) {
+        float r = a / b;
+        return std::fabs(b) * std::sqrt(1.0f + r * r);
+    } else return 0.0f;
+}
+inline V3 reflect_vector(V3 wo, V3 n) { return -(wo) + n * 2.0f * dot(wo, n); }          // :62-64
+inline bool check_reflection_condition(V3 wi, V3 wo) {                                  // :65-67
+    return std::fabs(wi.z * wo.z - wi.x * wo.x - wi.y * wo.y - 1.0f) < 0.0001f;
+}
+Color fresnel_conductor(float cos_theta, Color eta, Color k) {                          // :78-100
+    float cos_theta_2 = cos_theta * cos_theta;
+    float sin_theta_2 = 1.0f - cos_theta_2;
+    float sin_theta_4 = sin_theta_2 * sin_theta_2;
+    Color temp1 = eta * eta - k * k - color_value(sin_theta_2);
+    Color a2pb2 = safe_sqrt(temp1 * temp1 + k * k * eta * eta * 4.0f);
+    Color a = safe_sqrt((a2pb2 + temp1) * 0.5f);
+    Color term1 = a2pb2 + color_value(cos_theta_2);
+    Color term2 = a * (2.0f * cos_theta_2);
+    Color rs2 = (term1 - term2) / (term1 + term2);
+    Color term3 = a2pb2 * cos_theta_2 + color_value(sin_theta_4);
+    Color term4 = term2 * sin_theta_2;
+    Color rp2 = rs2 * (term3 - term4) / (term3 + term4);
+    return 0.5f * (rp2 + rs2);
+}
+std::pair<float, float> fresnel_dielectric(float cos_theta_i_, float eta) {             // :103-130 -> (fresnel, cosThetaT)
+    if (eta == 1.0f) return {0.0f, -cos_theta_i_};
+    float scale = cos_theta_i_ > 0.0f ? 1.0f / eta : eta;
+    float cos_theta_t_sqr = 1.0f - (1.0f - cos_theta_i_ * cos_theta_i_) * (scale * scale);
+    if (cos_theta_t_sqr <= 0.0f) return {1.0f, 0.0f};
+    float cos_theta_i = std::fabs(cos_theta_i_);
+    float cos_theta_t = std::sqrt(cos_theta_t_sqr);
+    float rs = (cos_theta_i - eta * cos_theta_t) / (cos_theta_i + eta * cos_theta_t);
+    float rp = (eta * cos_theta_i - cos_theta_t) / (eta * cos_theta_i + cos_theta_t);
+    float ct = cos_theta_i_ > 0.0f ? -cos_theta_t : cos_theta_t;
+    return {0.5f * (rs * rs + rp * rp), ct};
+}
+} // namespace bu
+
+// bsdfs/distribution.rs
+struct MicrofacetDistribution {
+    enum Type { Beckmann, GGX } microfacet_type;
+    float alpha_u, alpha_v;
+    float eval(const Math &mm, V3 m) const { // :27-56
+        if (bu::cos_theta(m) <= 0.0f) return 0.0f;
+        float cos_theta_2 = bu::cos_2_theta(m);
+        float beckmann_exp = ((m.x * m.x) / (alpha_u * alpha_u) + (m.y * m.y) / (alpha_v * alpha_v)) / cos_theta_2;
+        float res;
+        if (microfacet_type == Beckmann) res = mm.exp(-beckmann_exp) / (PI * alpha_u * alpha_v * cos_theta_2 * cos_theta_2);
+        else {
+            float root = (1.0f + beckmann_exp) * cos_theta_2;
+            res = 1.0f / (PI * alpha_u * alpha_v * root * root);
+        }
+        if (res * bu::cos_theta(m) < 1e-20f) return 0.0f;
+        return res;
+    }
+    float pdf(const Math &mm, V3 m) const { return eval(mm, m) * bu::cos_theta(m); } // :58-60
+    std::pair<V3, float> sample(const Math &mm, P2 sample) const { // :63-111 (asserts alpha_u == alpha_v)
+        float sin_phi_m, cos_phi_m;
+        mm.sincos(2.0f * PI * sample.y, &sin_phi_m, &cos_phi_m);
+        float alpha_sqr = alpha_u * alpha_v;
+        float cos_theta_m, pdf;
+        if (microfacet_type == Beckmann) {
+            float tan_theta_m_sqr = alpha_sqr * -mm.ln(1.0f - sample.x);
+            cos_theta_m = 1.0f / std::sqrt(1.0f + tan_theta_m_sqr);
+            pdf = (1.0f - sample.x) / (PI * alpha_u * alpha_v * powi(cos_theta_m, 3));
+        } else {
+            float tan_theta_m_sqr = alpha_sqr * sample.x / (1.0f - sample.x);
+            cos_theta_m = 1.0f / std::sqrt(1.0f + tan_theta_m_sqr);
+            float tmp = 1.0f + tan_theta_m_sqr / alpha_sqr;
+            pdf = FRAC_1_PI / (alpha_u * alpha_v * powi(cos_theta_m, 3) * powi(tmp, 2));
+        }
+        if (pdf < 1e-20f) pdf = 0.0f;
+        float sin_theta_m = std::sqrt(rmax(1.0f - powi(cos_theta_m, 2), 0.0f));
+        return {V3{sin_theta_m * cos_phi_m, sin_theta_m * sin_phi_m, cos_theta_m}, pdf};
+    }
+    float smith_g1(V3 v, V3 m) const { // :117-144
+        if (dot(v, m) * bu::cos_theta(v) <= 0.0f) return 0.0f;
+        float tan_theta = std::fabs(bu::tan_theta(v));
+        if (tan_theta == 0.0f) return 1.0f;
+        float alpha = alpha_u;
+        if (microfacet_type == Beckmann) {
+            float a = 1.0f / (alpha * tan_theta);
+            if (a >= 1.6f) return 1.0f;
+            float a_sqr = powi(a, 2);
+            return (3.535f * a + 2.181f * a_sqr) / (1.0f + 2.276f * a + 2.577f * a_sqr);
+        }
+        float root = alpha * tan_theta;
+        return 2.0f / (1.0f + bu::hypot2(1.0f, root));
+    }
+    float g(V3 wi, V3 wo, V3 m) const { return smith_g1(wi, m) * smith_g1(wo, m); } // :113-115
+};
+
+struct BSDFMetal : BSDF { // bsdfs/metal.rs
+    Color specular, eta, k;
+    bool has_distribution;
+    MicrofacetDistribution distr;
+    bool sample(const Math &mm, V3 d_in, P2 s, SampledDirection *out) const override { // :15-73
+        if (d_in.z <= 0.0f) return false;
+        if (!has_distribution) {
+            *out = SampledDirection{specular * bu::fresnel_conductor(d_in.z, eta, k), reflect(d_in), PDF{PDF::Discrete, 1.0f}};
+            return true;
+        }
+        auto [m, pdf] = distr.sample(mm, s);
+        if (pdf == 0.0f) return false;
+        V3 wo = bu::reflect_vector(d_in, m);
+        if (bu::cos_theta(wo) <= 0.0f) return false;
+        Color f = bu::fresnel_conductor(dot(d_in, m), eta, k) * specular;
+        float w = distr.eval(mm, m) * distr.g(d_in, wo, m) * dot(d_in, m) / (pdf * bu::cos_theta(d_in));
+        *out = SampledDirection{w * f, wo, PDF{PDF::SolidAngle, pdf}};
+        return true;
+    }
+    PDF pdf(const Math &mm, V3 wi, V3 wo) const override { // :75-110 (Domain::SolidAngle; the Discrete arm is never asked)
+        V3 h = normalize(wi + wo);
+        return PDF{PDF::SolidAngle, distr.pdf(mm, h) / (4.0f * std::fabs(dot(wo, h)))};
+    }
+    Color eval(const Math &mm, V3 wi, V3 wo) const override { // :112-156
+        V3 h = normalize(wi + wo);
+        float d = distr.eval(mm, h);
+        if (d == 0.0f) return Color::zero();
+        Color f = specular * bu::fresnel_conductor(dot(wi, h), eta, k);
+        float g = distr.g(wi, wo, h);
+        float model = d * g / (4.0f * bu::cos_theta(wi));
+        return f * model;
+    }
+    bool is_twosided() const override { return true; }
+    bool is_smooth() const override { return !has_distribution; } // DELTA without a distribution, GLOSSY with one (:166-171)
+};
+struct BSDFGlass : BSDF { // bsdfs/glass.rs
+    Color specular_transmittance, specular_reflectance;
+    float eta, inv_eta;
+    V3 refract(V3 wi, float cos_theta_t) const { // :50-58
+        float scale = cos_theta_t < 0.0f ? -inv_eta : -eta;
+        return V3{scale * wi.x, scale * wi.y, cos_theta_t};
+    }
+    bool sample(const Math &, V3 d_in, P2 s, SampledDirection *out) const override { // :75-121, transport == Importance
+        auto [fresnel, cos_theta_trans] = bu::fresnel_dielectric(d_in.z, eta);
+        if (s.x <= fresnel) {
+            *out = SampledDirection{specular_reflectance, reflect(d_in), PDF{PDF::Discrete, fresnel}};
+        } else {
+            float factor = 1.0f;
+            *out = SampledDirection{specular_transmittance * factor * factor, refract(d_in, cos_theta_trans), PDF{PDF::Discrete, fresnel}};
+        }
+        return true;
+    }
+    // pdf() is todo!() and eval() asserts Domain::Discrete in the reference (:123-176): never reached because the BSDF is smooth
+    PDF pdf(const Math &, V3, V3) const override { std::abort(); }
+    Color eval(const Math &, V3, V3) const override { std::abort(); }
+    bool is_twosided() const override { return false; }
+    bool is_smooth() const override { return true; }
+};
+struct BSDFSubstrate : BSDF { // bsdfs/substrate.rs
+    Color specular, diffuse;
+    bool has_distribution;
+    MicrofacetDistribution distr;
+    Color schlick_fresnel(float cos_theta) const { // :15-18
+        Color rs = specular;
+        return rs + (Color::one() - rs) * powi(1.0f - cos_theta, 5);
+    }
+    PDF pdf_domain(const Math &mm, V3 wi, V3 wo, PDF::Kind domain) const { // :92-147
+        if (wi.z <= 0.0f || wo.z <= 0.0f) return PDF{domain, 0.0f};
+        V3 m = wi + wo;
+        if (m.x == 0.0f && m.y == 0.0f && m.z == 0.0f) return PDF{domain, 0.0f};
+        m = normalize(m);
+        if (domain == PDF::Discrete) {
+            if (bu::check_reflection_condition(wi, wo)) return PDF{PDF::Discrete, 0.5f};
+            std::abort(); // unimplemented!()
+        }
+        float pdf_diffuse = wo.z * FRAC_1_PI;
+        float pdf_specular = has_distribution ? distr.pdf(mm, m) / (4.0f * std::fabs(dot(wo, m))) : 0.0f;
+        return PDF{PDF::SolidAngle, 0.5f * (pdf_diffuse + pdf_specular)};
+    }
+    Color eval_domain(const Math &mm, V3 d_in, V3 d_out, PDF::Kind domain) const { // :149-206
+        if (d_in.z <= 0.0f || d_out.z <= 0.0f) return Color::zero();
+        V3 m = d_in + d_out;
+        if (m.x == 0.0f && m.y == 0.0f && m.z == 0.0f) return Color::zero();
+        m = normalize(m);
+        if (domain == PDF::SolidAngle) {
+            Color diff = diffuse * (Color::one() - specular) * (28.0f / (23.0f * PI)) * (1.0f - powi(1.0f - 0.5f * bu::abs_cos_theta(d_in), 5)) *
+                         (1.0f - powi(1.0f - 0.5f * bu::abs_cos_theta(d_out), 5));
+            Color spec = Color::zero();
+            if (has_distribution) {
+                float model = distr.eval(mm, m) / (4.0f * std::fabs(dot(d_in, m)) * rmax(std::fabs(bu::cos_theta(d_in)), std::fabs(bu::cos_theta(d_out))));
+                spec = model * schlick_fresnel(dot(d_in, m));
+            }
+            return (diff + spec) * d_out.z;
+        }
+        if (bu::check_reflection_condition(d_in, d_out)) return schlick_fresnel(dot(d_in, m));
+        std::abort(); // unimplemented!()
+    }
+    bool sample(const Math &mm, V3 d_in, P2 s, SampledDirection *out) const override { // :22-90
+        if (d_in.z <= 0.0f) return false;
+        V3 d_out;
+        PDF::Kind domain;
+        if (s.x < 0.5f) {
+            s.x *= 2.0f;
+            d_out = cosine_sample_hemisphere(mm, s);
+            domain = PDF::SolidAngle;
+        } else {
+            s.x = (s.x - 0.5f) * 2.0f;
+            V3 m;
+            if (!has_distribution) {
+                m = V3{0.0f, 0.0f, 1.0f};
+                domain = PDF::Discrete;
+            } else {
+                auto r = distr.sample(mm, s);
+                if (r.second == 0.0f) return false;
+                m = r.first;
+                domain = PDF::SolidAngle;
+            }
+            d_out = bu::reflect_vector(d_in, m);
+            if (bu::cos_theta(d_out) <= 0.0f) return false;
+        }
+        PDF p = pdf_domain(mm, d_in, d_out, domain);
+        if (p.value() == 0.0f) return false;
+        Color f = eval_domain(mm, d_in, d_out, domain);
+        *out = SampledDirection{f / p.value(), d_out, p};
+        return true;
+    }
+    PDF pdf(const Math &mm, V3 wi, V3 wo) const override { return pdf_domain(mm, wi, wo, PDF::SolidAngle); }
+    Color eval(const Math &mm, V3 wi, V3 wo) const override { return eval_domain(mm, wi, wo, PDF::SolidAngle); }
+    bool is_twosided() const override { return true; }
+    bool is_smooth() const override { return !has_distribution; } // DELTA | DIFFUSE without a distribution (:216-221)
+};
 std::unique_ptr<BSDF> make_bsdf(const rl_material &m) {
+    auto distribution = [&](bool *has) {
+        *has = m.microfacet != RL_MICROFACET_NONE;
+        return MicrofacetDistribution{m.microfacet == RL_MICROFACET_BECKMANN ? MicrofacetDistribution::Beckmann : MicrofacetDistribution::GGX, m.alpha, m.alpha};
+    };
+    if (m.kind == RL_BSDF_METAL) {
+        auto b = std::make_unique<BSDFMetal>();
+        b->specular = Color{m.ks[0], m.ks[1], m.ks[2]}, b->eta = Color{m.eta[0], m.eta[1], m.eta[2]}, b->k = Color{m.k[0], m.k[1], m.k[2]};
+        b->distr = distribution(&b->has_distribution);
+        return b;
+    }
+    if (m.kind == RL_BSDF_GLASS) {
+        auto b = std::make_unique<BSDFGlass>();
+        b->specular_reflectance = Color{m.ks[0], m.ks[1], m.ks[2]}, b->specular_transmittance = Color{m.kt[0], m.kt[1], m.kt[2]};
+        b->eta = m.ior;
+        b->inv_eta = 1.0f / b->eta; // glass.rs:46
+        return b;
+    }
+    if (m.kind == RL_BSDF_SUBSTRATE) {
+        auto b = std::make_unique<BSDFSubstrate>();
+        b->diffuse = Color{m.kd[0], m.kd[1], m.kd[2]}, b->specular = Color{m.ks[0], m.ks[1], m.ks[2]};
+        b->distr = distribution(&b->has_distribution);
+        return b;
+    }
     if (m.kind == RL_BSDF_PHONG) {
         auto b = std::make_unique<BSDFPhong>();
         b->diffuse = Color{m.kd[0], m.kd[1], m.kd[2]};
@@ -1352,6 +1633,7 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
     Ray ray = sc.camera.generate(P2{(float)ix + jx, (float)iy + jy});
     Color T = Color::one(); // throughput carried by `ray`
     float pdf_prev = 1.0f;  // solid-angle pdf of the direction of `ray`
+    bool mis_prev = true;   // false: the edge is PDF::Discrete, or was sampled at a smooth vertex (the light strategy's pdf is None: v / (v + 0))
     for (;;) {
         Intersection its;
         if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) break;
@@ -1364,7 +1646,7 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
                 Color contrib = T * its.mesh->emit();
                 if (!contrib.is_zero()) {
                     float w = 1.0f;
-                    if (I.strategy == RL_STRATEGY_ALL) { // balance heuristic (path.rs:78-99)
+                    if (I.strategy == RL_STRATEGY_ALL && mis_prev) { // balance heuristic (path.rs:78-99)
                         float pl = sc.emitters.direct_pdf(its.mesh, LightSamplingPDF{ray.o, its.p, its.n_g, ray.d}).value();
                         w = pdf_prev / (pdf_prev + pl);
                     }
@@ -1381,6 +1663,7 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
         Ray next_ray{};
         Color Tn = T;
         float bsdf_pdf = 0.0f;
+        bool mis_next = true;
         {
             SampledDirection sb;
             P2 s2 = sampler.next2d();
@@ -1400,6 +1683,7 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
                         Tn.scale(rr_weight);
                         next_ray = spawn_ray(its, d_out_global);
                         bsdf_pdf = sb.pdf.value();
+                        mis_next = sb.pdf.kind == PDF::SolidAngle && !bsdf.is_smooth();
                         alive = true;
                     }
                 }
@@ -1433,6 +1717,7 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
         if (!alive) break;
         T = Tn;
         pdf_prev = bsdf_pdf;
+        mis_prev = mis_next;
         ray = next_ray;
     }
     return L;
@@ -1474,8 +1759,11 @@ Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy
         Intersection next_its;
         if (sc.trace(r2, cx.accel_mode, *cx.counters, &next_its)) {
             if (next_its.mesh->is_light() && dot(next_its.n_g, -r2.d) > 0.0f) {
-                float light_pdf = sc.emitters.direct_pdf(next_its.mesh, LightSamplingPDF{r2.o, next_its.p, next_its.n_g, r2.d}).value();
-                float weight_bsdf = mis_weight(sb.pdf.value() * weight_nb_bsdf, light_pdf * weight_nb_light);
+                float weight_bsdf = 1.0f; // PDF::Discrete(_v) => 1.0 (direct.rs:170)
+                if (sb.pdf.kind == PDF::SolidAngle) {
+                    float light_pdf = sc.emitters.direct_pdf(next_its.mesh, LightSamplingPDF{r2.o, next_its.p, next_its.n_g, r2.d}).value();
+                    weight_bsdf = mis_weight(sb.pdf.value() * weight_nb_bsdf, light_pdf * weight_nb_light);
+                }
                 l_i = l_i + weight_bsdf * sb.weight * next_its.mesh->emit() * weight_nb_bsdf;
             }
         }
@@ -1748,7 +2036,11 @@ int orc_bsdf_sample(uint32_t math_mode, const rl_material *m, const float wi[3],
     weight[0] = sd.weight.r, weight[1] = sd.weight.g, weight[2] = sd.weight.b;
     store3(d, sd.d);
     *pdf = sd.pdf.value();
-    return 1;
+    return sd.pdf.kind == PDF::Discrete ? 2 : 1; // 2: PDF::Discrete
+}
+int orc_bsdf_flags(const rl_material *m) { // bit 0: is_twosided, bit 1: bsdf_type().is_smooth()
+    auto b = make_bsdf(*m);
+    return (b->is_twosided() ? 1 : 0) | (b->is_smooth() ? 2 : 0);
 }
 float orc_bsdf_pdf(uint32_t math_mode, const rl_material *m, const float wi[3], const float wo[3]) {
     return make_bsdf(*m)->pdf(Math{math_mode}, load3(wi), load3(wo)).value();

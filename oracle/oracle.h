@@ -83,6 +83,7 @@ float orc_mis_weight(float pdf_a, float pdf_b);                                 
 int orc_bsdf_sample(uint32_t math_mode, const rl_material *m, const float wi[3], float s0, float s1,
                     float weight[3], float d[3], float *pdf);
 float orc_bsdf_pdf(uint32_t math_mode, const rl_material *m, const float wi[3], const float wo[3]);
+int orc_bsdf_flags(const rl_material *m); /* bit 0 is_twosided, bit 1 is_smooth */
 void orc_bsdf_eval(uint32_t math_mode, const rl_material *m, const float wi[3], const float wo[3], float out[3]);
 /* EmitterSampler::sample_light (emitter.rs:1604-1620).  Outputs: p[3], n[3], d[3], weight[3], pdf; returns emitter mesh index. */
 int orc_sample_light(const orc_scene *s, const float x[3], float r_sel, float r, float u0, float u1, float p[3],

@@ -10,6 +10,12 @@ RL_ERR_NOMEM = -5
 
 RL_BSDF_DIFFUSE = 0
 RL_BSDF_PHONG = 1
+RL_BSDF_METAL = 2
+RL_BSDF_GLASS = 3
+RL_BSDF_SUBSTRATE = 4
+RL_MICROFACET_NONE = 0
+RL_MICROFACET_GGX = 1
+RL_MICROFACET_BECKMANN = 2
 
 RL_INTEGRATOR_PATH = 0
 RL_INTEGRATOR_DIRECT = 1
@@ -26,7 +32,9 @@ RL_MISS = 0xFFFFFFFF
 
 class rl_material(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("kd", C.c_float * 3), ("ks", C.c_float * 3),
-                ("exponent", C.c_float), ("weight_specular", C.c_float)]
+                ("exponent", C.c_float), ("weight_specular", C.c_float), ("kt", C.c_float * 3),
+                ("eta", C.c_float * 3), ("k", C.c_float * 3), ("ior", C.c_float), ("alpha", C.c_float),
+                ("microfacet", C.c_uint32)]
 
 
 class rl_mesh_desc(C.Structure):

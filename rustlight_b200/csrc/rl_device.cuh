@@ -209,6 +209,15 @@ RL_HD float spec_powf(float x, float y) {
     return (float)spec_exp2((double)y * spec_log2((double)x));
 }
 
+// e^x and ln x (Beckmann distribution only), same construction: f64 kernels, one rounding to f32
+RL_HD float spec_expf(float x) { return (float)spec_exp2((double)x * 1.4426950408889634074); }
+RL_HD float spec_logf(float x) {
+    if (x == 0.0f) return -u2f(0x7f800000u);
+    if (!(x > 0.0f)) return u2f(0x7fc00000u);
+    if (!finite_f(x)) return x;
+    return (float)(spec_log2((double)x) * 0.69314718055994530942);
+}
+
 // ---- counter-based sampler (mode B) -----------------------------------------
 RL_HD uint64_t mix64(uint64_t z) {
     z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
@@ -280,7 +289,8 @@ RL_HD V3 cosine_sample_hemisphere(float ux, float uy) {
 //   nodes[4*j+0..3]  wide LBVH node:   {lo0.xyz, hi0.x} {hi0.yz, lo1.xy} {lo1.z, hi1.xyz} {child0, child1, -, -}
 //   shade[4*p+0..3]  (original order p): {n_geo.xyz, mesh} {n0.xyz, has_normals} {n1.xyz, -} {n2.xyz, -}
 //   verts[3*p+0..2]  (original order p): {v.xyz, -}
-//   mats[4*m+0..3]   {kd.rgb, kind} {ks.rgb, exponent} {Le.rgb, is_light} {weight_specular, 1/area, pdf_sel, -}
+//   mats[5*m+0..4]   {kd.rgb | metal eta | glass kt, kind} {ks.rgb, phong exponent | microfacet alpha} {Le.rgb, is_light}
+//                    {phong weight_specular | glass eta, 1/area, pdf_sel, microfacet} {metal k.rgb, glass 1/eta}
 //   emit_info[e]     {mesh, first_prim, ntris, cdf_offset} (as uint bits)
 struct SceneView {
     const float4 *trav;
@@ -855,14 +865,19 @@ RL_HD void camera_generate(const SceneView &sv, float px, float py, V3 *o, V3 *d
 }
 
 // ---- materials ---------------------------------------------------------------------------------
+#define RL_MAT_F4 5
 struct Material {
-    Col kd, ks, le;
-    float exponent, weight_specular, inv_area, pdf_sel;
-    uint32_t kind;
+    Col kd, ks, le;       // kd: diffuse | metal eta | glass transmittance;  ks: specular / reflectance
+    float exponent;       // phong exponent | microfacet alpha
+    float weight_specular; // phong lobe weight | glass eta
+    float inv_area, pdf_sel;
+    uint32_t kind, microfacet;
     bool is_light;
+    const float4 *ext;    // {metal k.rgb, glass 1/eta}: read only by the metal and glass branches
 };
 RL_HD Material load_material(const float4 *mats, uint32_t mesh) {
-    float4 a = mats[4 * mesh], b = mats[4 * mesh + 1], c = mats[4 * mesh + 2], e = mats[4 * mesh + 3];
+    const float4 *row = mats + RL_MAT_F4 * mesh;
+    float4 a = row[0], b = row[1], c = row[2], e = row[3];
     Material m;
     m.kd = xyz_col(a);
     m.kind = f2u(a.w);
@@ -873,12 +888,178 @@ RL_HD Material load_material(const float4 *mats, uint32_t mesh) {
     m.weight_specular = e.x;
     m.inv_area = e.y;
     m.pdf_sel = e.z;
+    m.microfacet = f2u(e.w);
+    m.ext = row + 4;
     return m;
 }
+// bsdf_type().is_smooth() (bsdfs/mod.rs:157-161): DELTA in the type -> no light sampling, no MIS at this vertex
+RL_HD bool mat_is_smooth(const Material &m) { return m.kind == 3u || ((m.kind == 2u || m.kind == 4u) && m.microfacet == 0u); }
+RL_HD bool mat_is_twosided(const Material &m) { return m.kind != 3u; } // glass.rs:181-183
 RL_HD V3 reflect_local(V3 d) { return V3{-d.x, -d.y, d.z}; }
+
+// ---- bsdfs/utils.rs -------------------------------------------------------------------------------
+RL_HD Col operator-(Col a, Col b) { return Col{a.r - b.r, a.g - b.g, a.b - b.b}; }     // structure.rs:349-358
+RL_HD Col col_div(Col a, Col b) { return Col{a.r / b.r, a.g / b.g, a.b / b.b}; }       // Div<Color>, :266-275
+RL_HD Col col_value(float v) { return Col{v, v, v}; }
+RL_HD Col col_safe_sqrt(Col c) { return Col{sqrtf(fmaxf(c.r, 0.0f)), sqrtf(fmaxf(c.g, 0.0f)), sqrtf(fmaxf(c.b, 0.0f))}; } // :132-138
+RL_HD float powi2(float x) { return x * x; }
+RL_HD float powi3(float x) { return x * (x * x); }
+RL_HD float powi5(float x) { // llvm.powi / __powisf2: binary exponentiation, x * ((x^2)^2)
+    float x2 = x * x;
+    return x * (x2 * x2);
+}
+RL_HD float sin_2_theta(V3 w) { return fmaxf(1.0f - w.z * w.z, 0.0f); }   // utils.rs:14-16
+RL_HD float tan_theta(V3 w) { return sqrtf(sin_2_theta(w)) / w.z; }       // :20-22
+RL_HD float hypot2(float a, float b) {                                    // :50-60
+    if (fabsf(a) > fabsf(b)) {
+        float r = b / a;
+        return fabsf(a) * sqrtf(1.0f + r * r);
+    } else if (b != 0.0f) {
+        float r = a / b;
+        return fabsf(b) * sqrtf(1.0f + r * r);
+    }
+    return 0.0f;
+}
+RL_HD V3 reflect_vector(V3 wo, V3 n) { return -(wo) + n * 2.0f * dot(wo, n); } // :62-64
+RL_HD bool check_reflection_condition(V3 wi, V3 wo) { return fabsf(wi.z * wo.z - wi.x * wo.x - wi.y * wo.y - 1.0f) < 0.0001f; } // :65-67
+// fresnel_conductor, utils.rs:78-100
+RL_HD Col fresnel_conductor(float cos_theta, Col eta, Col k) {
+    float cos_theta_2 = cos_theta * cos_theta;
+    float sin_theta_2 = 1.0f - cos_theta_2;
+    float sin_theta_4 = sin_theta_2 * sin_theta_2;
+    Col temp1 = eta * eta - k * k - col_value(sin_theta_2);
+    Col a2pb2 = col_safe_sqrt(temp1 * temp1 + mul_checked(k * k * eta * eta, 4.0f));
+    Col a = col_safe_sqrt(mul_checked(a2pb2 + temp1, 0.5f));
+    Col term1 = a2pb2 + col_value(cos_theta_2);
+    Col term2 = mul_checked(a, 2.0f * cos_theta_2);
+    Col rs2 = col_div(term1 - term2, term1 + term2);
+    Col term3 = mul_checked(a2pb2, cos_theta_2) + col_value(sin_theta_4);
+    Col term4 = mul_checked(term2, sin_theta_2);
+    Col rp2 = col_div(rs2 * (term3 - term4), term3 + term4);
+    return mul_plain(0.5f, rp2 + rs2);
+}
+// fresnel_dielectric, utils.rs:103-130: (fresnel, cos_theta_t)
+RL_HD void fresnel_dielectric(float cos_theta_i_, float eta, float *fresnel, float *cos_theta_t_out) {
+    if (eta == 1.0f) {
+        *fresnel = 0.0f;
+        *cos_theta_t_out = -cos_theta_i_;
+        return;
+    }
+    float scale = cos_theta_i_ > 0.0f ? 1.0f / eta : eta;
+    float cos_theta_t_sqr = 1.0f - (1.0f - cos_theta_i_ * cos_theta_i_) * (scale * scale);
+    if (cos_theta_t_sqr <= 0.0f) {
+        *fresnel = 1.0f;
+        *cos_theta_t_out = 0.0f;
+        return;
+    }
+    float cos_theta_i = fabsf(cos_theta_i_);
+    float cos_theta_t = sqrtf(cos_theta_t_sqr);
+    float rs = (cos_theta_i - eta * cos_theta_t) / (cos_theta_i + eta * cos_theta_t);
+    float rp = (eta * cos_theta_i - cos_theta_t) / (eta * cos_theta_i + cos_theta_t);
+    *cos_theta_t_out = cos_theta_i_ > 0.0f ? -cos_theta_t : cos_theta_t;
+    *fresnel = 0.5f * (rs * rs + rp * rp);
+}
+
+// ---- MicrofacetDistribution (bsdfs/distribution.rs:26-144), isotropic: alpha_u == alpha_v == alpha -----
+// kind: 1 GGX, 2 Beckmann (rl_microfacet)
+RL_HD float mf_eval(uint32_t kind, float alpha, V3 m) { // :27-56
+    if (m.z <= 0.0f) return 0.0f;
+    float cos_theta_2 = m.z * m.z;
+    float beckmann_exp = ((m.x * m.x) / (alpha * alpha) + (m.y * m.y) / (alpha * alpha)) / cos_theta_2;
+    float res;
+    if (kind == 2u) res = spec_expf(-beckmann_exp) / (RL_PI * alpha * alpha * cos_theta_2 * cos_theta_2);
+    else {
+        float root = (1.0f + beckmann_exp) * cos_theta_2;
+        res = 1.0f / (RL_PI * alpha * alpha * root * root);
+    }
+    return res * m.z < 1e-20f ? 0.0f : res;
+}
+RL_HD float mf_pdf(uint32_t kind, float alpha, V3 m) { return mf_eval(kind, alpha, m) * m.z; } // :58-60
+RL_HD V3 mf_sample(uint32_t kind, float alpha, float sx, float sy, float *pdf_out) { // :63-111
+    float sin_phi_m, cos_phi_m;
+    spec_sincos(2.0f * RL_PI * sy, &sin_phi_m, &cos_phi_m);
+    float alpha_sqr = alpha * alpha;
+    float cos_theta_m, pdf;
+    if (kind == 2u) {
+        float tan_theta_m_sqr = alpha_sqr * -spec_logf(1.0f - sx);
+        cos_theta_m = 1.0f / sqrtf(1.0f + tan_theta_m_sqr);
+        pdf = (1.0f - sx) / (RL_PI * alpha * alpha * powi3(cos_theta_m));
+    } else {
+        float tan_theta_m_sqr = alpha_sqr * sx / (1.0f - sx);
+        cos_theta_m = 1.0f / sqrtf(1.0f + tan_theta_m_sqr);
+        float tmp = 1.0f + tan_theta_m_sqr / alpha_sqr;
+        pdf = RL_FRAC_1_PI / (alpha * alpha * powi3(cos_theta_m) * powi2(tmp));
+    }
+    if (pdf < 1e-20f) pdf = 0.0f;
+    float sin_theta_m = sqrtf(fmaxf(1.0f - powi2(cos_theta_m), 0.0f));
+    *pdf_out = pdf;
+    return V3{sin_theta_m * cos_phi_m, sin_theta_m * sin_phi_m, cos_theta_m};
+}
+RL_HD float mf_smith_g1(uint32_t kind, float alpha, V3 v, V3 m) { // :117-144
+    if (dot(v, m) * v.z <= 0.0f) return 0.0f;
+    float tan_t = fabsf(tan_theta(v));
+    if (tan_t == 0.0f) return 1.0f;
+    if (kind == 2u) {
+        float a = 1.0f / (alpha * tan_t);
+        if (a >= 1.6f) return 1.0f;
+        float a_sqr = powi2(a);
+        return (3.535f * a + 2.181f * a_sqr) / (1.0f + 2.276f * a + 2.577f * a_sqr);
+    }
+    float root = alpha * tan_t;
+    return 2.0f / (1.0f + hypot2(1.0f, root));
+}
+RL_HD float mf_g(uint32_t kind, float alpha, V3 wi, V3 wo, V3 m) { return mf_smith_g1(kind, alpha, wi, m) * mf_smith_g1(kind, alpha, wo, m); } // :113-115
+
+// ---- BSDFMetal with a distribution (bsdfs/metal.rs:37-70, 95-109, 128-155): GLOSSY, SolidAngle pdfs ------
+RL_HD float metal_pdf(const Material &mt, V3 wi, V3 wo) {
+    V3 h = normalize(wi + wo);
+    return mf_pdf(mt.microfacet, mt.exponent, h) / (4.0f * fabsf(dot(wo, h)));
+}
+RL_HD Col metal_eval(const Material &mt, V3 wi, V3 wo) {
+    V3 h = normalize(wi + wo);
+    float d = mf_eval(mt.microfacet, mt.exponent, h);
+    if (d == 0.0f) return Col{0.0f, 0.0f, 0.0f};
+    Col f = mt.ks * fresnel_conductor(dot(wi, h), mt.kd, xyz_col(mt.ext[0]));
+    float g = mf_g(mt.microfacet, mt.exponent, wi, wo, h);
+    float model = d * g / (4.0f * wi.z);
+    return mul_checked(f, model);
+}
+// ---- BSDFSubstrate (bsdfs/substrate.rs): pdf / eval per domain ---------------------------------------
+RL_HD Col substrate_schlick(const Material &mt, float cos_theta) { // :15-18
+    Col rs = mt.ks;
+    return rs + mul_checked(col_value(1.0f) - rs, powi5(1.0f - cos_theta));
+}
+RL_HD float substrate_pdf(const Material &mt, V3 wi, V3 wo, bool discrete) { // :92-147
+    if (wi.z <= 0.0f || wo.z <= 0.0f) return 0.0f;
+    V3 m = wi + wo;
+    if (m.x == 0.0f && m.y == 0.0f && m.z == 0.0f) return 0.0f;
+    m = normalize(m);
+    if (discrete) return 0.5f; // reached only with wo = reflect(wi): check_reflection_condition holds
+    float pdf_diffuse = wo.z * RL_FRAC_1_PI;
+    float pdf_specular = mt.microfacet == 0u ? 0.0f : mf_pdf(mt.microfacet, mt.exponent, m) / (4.0f * fabsf(dot(wo, m)));
+    return 0.5f * (pdf_diffuse + pdf_specular);
+}
+RL_HD Col substrate_eval(const Material &mt, V3 d_in, V3 d_out, bool discrete) { // :149-206
+    if (d_in.z <= 0.0f || d_out.z <= 0.0f) return Col{0.0f, 0.0f, 0.0f};
+    V3 m = d_in + d_out;
+    if (m.x == 0.0f && m.y == 0.0f && m.z == 0.0f) return Col{0.0f, 0.0f, 0.0f};
+    m = normalize(m);
+    if (discrete) return substrate_schlick(mt, dot(d_in, m));
+    Col diffuse = mul_checked(mul_checked(mul_checked(mt.kd * (col_value(1.0f) - mt.ks), 28.0f / (23.0f * RL_PI)),
+                                          1.0f - powi5(1.0f - 0.5f * fabsf(d_in.z))),
+                              1.0f - powi5(1.0f - 0.5f * fabsf(d_out.z)));
+    Col specular = Col{0.0f, 0.0f, 0.0f};
+    if (mt.microfacet != 0u) {
+        float model = mf_eval(mt.microfacet, mt.exponent, m) / (4.0f * fabsf(dot(d_in, m)) * fmaxf(fabsf(d_in.z), fabsf(d_out.z)));
+        specular = mul_plain(model, substrate_schlick(mt, dot(d_in, m)));
+    }
+    return mul_checked(diffuse + specular, d_out.z);
+}
 
 // BSDF::pdf (diffuse.rs:33-51, phong.rs:65-91)
 RL_HD float bsdf_pdf(const Material &m, V3 wi, V3 wo) {
+    if (m.kind == 2u) return metal_pdf(m, wi, wo);               // only reached with a distribution (not smooth)
+    if (m.kind == 4u) return substrate_pdf(m, wi, wo, false);
     if (m.kind == 0u) {
         if (wi.z <= 0.0f) return 0.0f;
         if (wo.z <= 0.0f) return 0.0f;
@@ -894,6 +1075,8 @@ RL_HD float bsdf_pdf(const Material &m, V3 wi, V3 wo) {
 }
 // BSDF::eval (diffuse.rs:53-71, phong.rs:93-119); includes the cosine for the diffuse lobe
 RL_HD Col bsdf_eval(const Material &m, V3 wi, V3 wo) {
+    if (m.kind == 2u) return metal_eval(m, wi, wo);
+    if (m.kind == 4u) return substrate_eval(m, wi, wo, false);
     if (m.kind == 0u) {
         if (wi.z <= 0.0f) return Col{0.0f, 0.0f, 0.0f};
         if (wo.z > 0.0f) return mul_checked(mul_checked(m.kd, wo.z), RL_FRAC_1_PI);
@@ -907,9 +1090,75 @@ RL_HD Col bsdf_eval(const Material &m, V3 wi, V3 wo) {
     Col diffuse_value = mul_checked(mul_checked(m.kd, wo.z), RL_FRAC_1_PI);
     return specular_value + diffuse_value;
 }
-// BSDF::sample (diffuse.rs:11-31, phong.rs:14-63)
-RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight, V3 *wo, float *pdf) {
+// BSDF::sample (diffuse.rs:11-31, phong.rs:14-63, metal.rs:15-73, glass.rs:75-121, substrate.rs:22-90).
+// *discrete: the sampled pdf is PDF::Discrete (delta lobe) -- no MIS for the edge it creates.
+RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight, V3 *wo, float *pdf, bool *discrete) {
+    *discrete = false;
+    if (m.kind == 3u) { // glass: no wi.z test (not two-sided), transport == Importance -> factor 1
+        float fresnel, cos_theta_trans;
+        fresnel_dielectric(wi.z, m.weight_specular, &fresnel, &cos_theta_trans);
+        *discrete = true;
+        *pdf = fresnel;
+        if (sx <= fresnel) {
+            *weight = m.ks;
+            *wo = reflect_local(wi);
+        } else {
+            *weight = mul_checked(mul_checked(m.kd, 1.0f), 1.0f);
+            float scale = cos_theta_trans < 0.0f ? -m.ext[0].w : -m.weight_specular;
+            *wo = V3{scale * wi.x, scale * wi.y, cos_theta_trans};
+        }
+        return true;
+    }
     if (wi.z <= 0.0f) return false;
+    if (m.kind == 2u) { // metal
+        Col k = xyz_col(m.ext[0]);
+        if (m.microfacet == 0u) {
+            *weight = m.ks * fresnel_conductor(wi.z, m.kd, k);
+            *wo = reflect_local(wi);
+            *pdf = 1.0f;
+            *discrete = true;
+            return true;
+        }
+        float p;
+        V3 mm = mf_sample(m.microfacet, m.exponent, sx, sy, &p);
+        if (p == 0.0f) return false;
+        V3 d_out = reflect_vector(wi, mm);
+        if (d_out.z <= 0.0f) return false;
+        Col f = fresnel_conductor(dot(wi, mm), m.kd, k) * m.ks;
+        float w = mf_eval(m.microfacet, m.exponent, mm) * mf_g(m.microfacet, m.exponent, wi, d_out, mm) * dot(wi, mm) / (p * wi.z);
+        *weight = mul_plain(w, f);
+        *wo = d_out;
+        *pdf = p; // the microfacet-normal pdf, as the reference returns it (metal.rs:64)
+        return true;
+    }
+    if (m.kind == 4u) { // substrate
+        V3 d_out;
+        bool disc = false;
+        if (sx < 0.5f) {
+            sx = sx * 2.0f;
+            d_out = cosine_sample_hemisphere(sx, sy);
+        } else {
+            sx = (sx - 0.5f) * 2.0f;
+            V3 mm;
+            if (m.microfacet == 0u) {
+                mm = V3{0.0f, 0.0f, 1.0f};
+                disc = true;
+            } else {
+                float p;
+                mm = mf_sample(m.microfacet, m.exponent, sx, sy, &p);
+                if (p == 0.0f) return false;
+            }
+            d_out = reflect_vector(wi, mm);
+            if (d_out.z <= 0.0f) return false;
+        }
+        float p = substrate_pdf(m, wi, d_out, disc);
+        if (p == 0.0f) return false;
+        *weight = div_checked(substrate_eval(m, wi, d_out, disc), p);
+        *wo = d_out;
+        *pdf = p;
+        *discrete = disc;
+        return true;
+    }
     if (m.kind == 0u) {
         V3 d_out = cosine_sample_hemisphere(sx, sy);
         *weight = m.kd;
@@ -963,8 +1212,8 @@ RL_HD Surface fill_intersection(const SceneView &sv, const Material &mat, uint32
         else if (l != 1.0f) n_s = ns / sqrtf(l);
         else n_s = ns;
     } else n_s = n_g;
-    // both supported BSDFs are two-sided; lights are never flipped (structure.rs:1006)
-    if (!mat.is_light && dot(d, n_s) > 0.0f) {
+    // bsdf.is_twosided() && !is_light (structure.rs:1006): every BSDF but glass is two-sided; lights are never flipped
+    if (mat_is_twosided(mat) && !mat.is_light && dot(d, n_s) > 0.0f) {
         n_s = V3{-n_s.x, -n_s.y, -n_s.z};
         n_g = V3{-n_g.x, -n_g.y, -n_g.z};
     }
@@ -1119,7 +1368,8 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
     Material mat = load_material(sv.mats, mesh);
     Surface its = fill_intersection(sv, mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
     const bool mute = ip.single_scattering != 0u;
-    const bool use_nee = (ip.strategy == 0u || ip.strategy == 2u);
+    const bool smooth = mat_is_smooth(mat); // no light sampling at this vertex (emitters.rs:110-112), no draws either
+    const bool use_nee = (ip.strategy == 0u || ip.strategy == 2u) && !smooth;
     // ---- emission carried by the arriving edge --------------------------------------------------
     if (st.depth == 1u) { // sensor edge: un-weighted (path.rs:152-165)
         if (ip_add_ok(ip, 0u) && dot(its.n_s, -d) >= 0.0f && mat.is_light && !is_zero(mat.le)) {
@@ -1131,7 +1381,9 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
             Col contrib = st.T * mat.le;
             if (!is_zero(contrib)) {
                 float w = 1.0f;
-                if (ip.strategy == 0u) { // balance heuristic against light sampling (path.rs:78-99)
+                // balance heuristic against light sampling (path.rs:78-99); a negative pdf_prev marks an edge without
+                // MIS: PDF::Discrete (delta lobe), or sampled at a smooth vertex where the light strategy has no pdf
+                if (ip.strategy == 0u && !(f2u(st.pdf_prev) >> 31)) {
                     float pl = direct_pdf(mat, o, its.p, its.n_g, d);
                     w = st.pdf_prev / (st.pdf_prev + pl);
                 }
@@ -1151,7 +1403,8 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
         Col bw;
         V3 wo;
         float bpdf;
-        if (bsdf_sample(mat, its.wi, sx, sy, &bw, &wo, &bpdf)) {
+        bool discrete;
+        if (bsdf_sample(mat, its.wi, sx, sy, &bw, &wo, &bpdf, &discrete)) {
             V3 d_out = to_world(its.frame, wo);
             Col Tn = st.T * bw;
             if (!is_zero(Tn)) {
@@ -1171,7 +1424,7 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
                     out->next_o = its.p;
                     out->next_d = d_out;
                     out->next.T = Tn;
-                    out->next.pdf_prev = bpdf;
+                    out->next.pdf_prev = (discrete || smooth) ? u2f(f2u(bpdf) | 0x80000000u) : bpdf;
                     out->next.path_id = st.path_id;
                     out->next.depth = depth;
                 }
@@ -1246,6 +1499,7 @@ RL_HD bool direct_light_sample(const SceneView &sv, DirectCtx *cx, V3 *p1, Col *
     LightSample ls = sample_light(sv, cx->its.p, r_sel, r, ux, uy);
     *valid = ls.valid;
     if (!ls.valid) return false;
+    if (mat_is_smooth(cx->mat)) return false; // direct.rs:74-77: visible() is still called (valid stays true), nothing is added
     V3 wo = to_local(cx->its.frame, ls.d);
     float pdf_bsdf = bsdf_pdf(cx->mat, cx->its.wi, wo);
     float weight_light = mis_weight_power(ls.pdf * cx->wl, pdf_bsdf * cx->wb);
@@ -1259,7 +1513,9 @@ RL_HD bool direct_bsdf_sample(DirectCtx *cx, V3 *dir, Col *weight, float *pdf) {
     float sx = cx->smp.next();
     float sy = cx->smp.next();
     V3 wo;
-    if (!bsdf_sample(cx->mat, cx->its.wi, sx, sy, weight, &wo, pdf)) return false;
+    bool discrete;
+    if (!bsdf_sample(cx->mat, cx->its.wi, sx, sy, weight, &wo, pdf, &discrete)) return false;
+    if (discrete) *pdf = u2f(f2u(*pdf) | 0x80000000u); // PDF::Discrete -> weight_bsdf = 1 in stage 2 (direct.rs:170)
     *dir = to_world(cx->its.frame, wo);
     return true;
 }
@@ -1274,8 +1530,11 @@ RL_HD bool direct_finish(const SceneView &sv, const IntegParams &ip, V3 o, V3 d,
     if (!(dot(nx.n_g, -d) > 0.0f)) return false;
     float wb = ip.nb_bsdf_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_bsdf_samples;
     float wl = ip.nb_light_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_light_samples;
-    float light_pdf = direct_pdf(mat, o, nx.p, nx.n_g, d);
-    float weight_bsdf = mis_weight_power(bsdf_pdf_v * wb, light_pdf * wl);
+    float weight_bsdf = 1.0f;
+    if (!(f2u(bsdf_pdf_v) >> 31)) {
+        float light_pdf = direct_pdf(mat, o, nx.p, nx.n_g, d);
+        weight_bsdf = mis_weight_power(bsdf_pdf_v * wb, light_pdf * wl);
+    }
     *contrib = mul_checked(mul_plain(weight_bsdf, bsdf_weight) * mat.le, wb);
     return true;
 }

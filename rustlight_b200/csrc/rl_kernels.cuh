@@ -244,28 +244,31 @@ __device__ __forceinline__ void block_compact2(bool fa, bool fb, uint32_t *count
 
 // ---- shade: surface interaction, arrival emission, BSDF sample + RR, NEE sample ------------------
 // ---- material sort inside a CTA tile ------------------------------------------------------------
-// Counting sort of the tile's 256 records by key (0 diffuse, 1 phong, 2 miss, 3 = past the end of the
-// queue) with warp ballots + per-warp prefix sums in shared memory.  Returns the tile-local index of
+// Counting sort of the tile's 256 records by key (0..4 = rl_bsdf_kind of the surface hit, 5 miss, 6 = past the end
+// of the queue) with warp ballots + per-warp prefix sums in shared memory.  Returns the tile-local index of
 // the record this thread should process, so that every warp shades one material kind (and rays that
-// missed are grouped into whole warps that exit at once).  `perm` is kBlock uint16, `cnt` 4*(kBlock/32).
+// missed are grouped into whole warps that exit at once).  `perm` is kBlock uint16, `cnt` kSortKeys*(kBlock/32).
+constexpr int kSortKeys = 8;
 __device__ __forceinline__ uint32_t tile_sort_by_key(uint32_t key, unsigned short *perm, uint32_t *cnt) {
     constexpr int W = kBlock / 32;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
-    unsigned m[4];
+    const unsigned mine = __match_any_sync(0xffffffffu, key); // lanes of this warp with my key
 #pragma unroll
-    for (int k = 0; k < 4; k++) m[k] = __ballot_sync(0xffffffffu, key == (uint32_t)k);
-    if (lane < 4) cnt[lane * W + warp] = __popc(m[lane]);
+    for (int k = 0; k < kSortKeys; k++) {
+        const unsigned mk = __ballot_sync(0xffffffffu, key == (uint32_t)k);
+        if (lane == (uint32_t)k) cnt[k * W + warp] = __popc(mk);
+    }
     __syncthreads();
-    if (threadIdx.x == 0) { // exclusive scan in key-major, warp-minor order (32 entries)
+    if (threadIdx.x == 0) { // exclusive scan in key-major, warp-minor order (64 entries)
         uint32_t tot = 0;
-        for (int q = 0; q < 4 * W; q++) {
+        for (int q = 0; q < kSortKeys * W; q++) {
             uint32_t c = cnt[q];
             cnt[q] = tot;
             tot += c;
         }
     }
     __syncthreads();
-    uint32_t rank = cnt[key * W + warp] + __popc(m[key] & lt);
+    uint32_t rank = cnt[key * W + warp] + __popc(mine & lt);
     perm[rank] = (unsigned short)threadIdx.x;
     __syncthreads();
     return perm[threadIdx.x];
@@ -284,17 +287,17 @@ __global__ void __launch_bounds__(kBlock, RL_SHADE_MINBLOCKS) k_shade(SceneView 
                                                   float4 *__restrict__ lacc, Counters *counters) {
     __shared__ uint32_t s_scratch[2 * (kBlock / 32) + 2];
     __shared__ unsigned short s_perm[SORT ? kBlock : 1];
-    __shared__ uint32_t s_cnt[SORT ? 4 * (kBlock / 32) : 1];
+    __shared__ uint32_t s_cnt[SORT ? kSortKeys * (kBlock / 32) : 1];
     const uint32_t n = *count_in;
     const uint32_t n_tiles = (n + kBlock - 1) / kBlock;
     uint32_t c_hits = 0, c_nee = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint32_t i = tile * kBlock + threadIdx.x;
         if (SORT) {
-            uint32_t key = 3u;
+            uint32_t key = 6u;
             if (i < n) {
                 const uint32_t prim = f2u(hit[i].w);
-                key = prim == RL_MISS ? 2u : (f2u(__ldg(&sv.mats[4 * f2u(__ldg(&sv.shade[4 * prim]).w)]).w) != 0u ? 1u : 0u);
+                key = prim == RL_MISS ? 5u : min(f2u(__ldg(&sv.mats[RL_MAT_F4 * f2u(__ldg(&sv.shade[4 * prim]).w)]).w), 4u);
             }
             i = tile * kBlock + tile_sort_by_key(key, s_perm, s_cnt);
         }

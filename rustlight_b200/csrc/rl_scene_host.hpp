@@ -98,8 +98,10 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
             err = "mesh without geometry";
             return false;
         }
-        if (m.mat.kind != RL_BSDF_DIFFUSE && m.mat.kind != RL_BSDF_PHONG) {
-            err = "unsupported BSDF kind";
+        const bool has_mf = m.mat.kind == RL_BSDF_METAL || m.mat.kind == RL_BSDF_SUBSTRATE;
+        if (m.mat.kind > RL_BSDF_SUBSTRATE || (has_mf && m.mat.microfacet > RL_MICROFACET_BECKMANN) ||
+            (has_mf && m.mat.microfacet != RL_MICROFACET_NONE && !(m.mat.alpha > 0.0f)) || (m.mat.kind == RL_BSDF_GLASS && m.mat.ior == 0.0f)) {
+            err = "unsupported BSDF kind or parameters";
             return false;
         }
         std::vector<float> areas;
@@ -174,11 +176,16 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
     }
     for (uint32_t mi = 0; mi < desc->nmeshes; mi++) {
         const rl_mesh_desc &m = desc->meshes[mi];
-        hs.mats.push_back(f4(m.mat.kd[0], m.mat.kd[1], m.mat.kd[2], u2f(m.mat.kind)));
-        hs.mats.push_back(f4(m.mat.ks[0], m.mat.ks[1], m.mat.ks[2], m.mat.exponent));
+        // rows of rl_device.cuh: load_material
+        const rl_material &mt = m.mat;
+        const float *ca = mt.kind == RL_BSDF_METAL ? mt.eta : (mt.kind == RL_BSDF_GLASS ? mt.kt : mt.kd);
+        const bool has_mf = mt.kind == RL_BSDF_METAL || mt.kind == RL_BSDF_SUBSTRATE;
+        hs.mats.push_back(f4(ca[0], ca[1], ca[2], u2f(mt.kind)));
+        hs.mats.push_back(f4(mt.ks[0], mt.ks[1], mt.ks[2], has_mf ? mt.alpha : mt.exponent));
         hs.mats.push_back(f4(m.emission_kind ? m.emission[0] : 0.0f, m.emission_kind ? m.emission[1] : 0.0f,
                              m.emission_kind ? m.emission[2] : 0.0f, u2f(m.emission_kind ? 1u : 0u)));
-        hs.mats.push_back(f4(m.mat.weight_specular, mesh_inv_area[mi], pdf_sel[mi], 0.0f));
+        hs.mats.push_back(f4(mt.kind == RL_BSDF_GLASS ? mt.ior : mt.weight_specular, mesh_inv_area[mi], pdf_sel[mi], u2f(has_mf ? mt.microfacet : 0u)));
+        hs.mats.push_back(f4(mt.k[0], mt.k[1], mt.k[2], mt.kind == RL_BSDF_GLASS ? 1.0f / mt.ior : 0.0f)); // BSDFGlass::eta(): inv_eta = 1.0 / eta
     }
     float am = 0.0f;
     for (int a = 0; a < 3; a++) am = fmaxf(am, fmaxf(fabsf(hs.raw_min[a]), fabsf(hs.raw_max[a])));

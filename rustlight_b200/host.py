@@ -35,6 +35,12 @@ def lib():
         L.rlh_scene_nb_triangles.argtypes = [C.c_void_p]
         L.rlh_scene_scale_image.argtypes = [C.c_void_p, C.c_float]
         L.rlh_scene_set_resolution.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p, C.c_size_t]
+        f3 = C.c_float * 3
+        L.rlh_material_metal.argtypes = [f3, f3, f3, C.c_uint32, C.c_float, C.POINTER(_abi.rl_material)]
+        L.rlh_material_glass.argtypes = [f3, f3, C.c_float, C.c_float, C.POINTER(_abi.rl_material)]
+        L.rlh_material_substrate.argtypes = [f3, f3, C.c_uint32, C.c_float, C.POINTER(_abi.rl_material)]
+        L.rlh_remap_roughness.restype = C.c_float
+        L.rlh_remap_roughness.argtypes = [C.c_float, C.c_int]
         L.rlh_scene_set_material.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_abi.rl_material)]
         L.rlh_material_phong.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
                                          C.POINTER(_abi.rl_material)]
@@ -135,6 +141,47 @@ def material_phong(kd, ks, exponent):
     if lib().rlh_material_phong(a, b, float(exponent), C.byref(m)) != 0:
         raise SceneError("Phong: kd and ks are both black")
     return m
+
+
+_MICROFACET = {None: _abi.RL_MICROFACET_NONE, "none": _abi.RL_MICROFACET_NONE, "ggx": _abi.RL_MICROFACET_GGX,
+               "beckmann": _abi.RL_MICROFACET_BECKMANN}
+
+
+def _f3(v):
+    return (C.c_float * 3)(*v)
+
+
+def material_metal(specular=(1, 1, 1), eta=(0.2004, 0.9240, 1.1022), k=(3.9129, 2.4528, 2.1421), microfacet="ggx", alpha=0.1):
+    """BSDFMetal (bsdfs/metal.rs); microfacet=None is the pure specular lobe."""
+    m = _abi.rl_material()
+    if lib().rlh_material_metal(_f3(specular), _f3(eta), _f3(k), _MICROFACET[microfacet], float(alpha), C.byref(m)) != 0:
+        raise SceneError("metal: bad parameters")
+    return m
+
+
+def material_mirror(kr=(0.9, 0.9, 0.9)):
+    """pbrt "mirror" = BSDFMetal{specular: Kr, eta: 1, k: 0, distribution: None} (bsdfs/mod.rs:349-357)."""
+    return material_metal(kr, (1, 1, 1), (0, 0, 0), None, 0.0)
+
+
+def material_glass(reflectance=(1, 1, 1), transmittance=(1, 1, 1), int_ior=1.5046, ext_ior=1.000277):
+    """BSDFGlass.eta(int_ior, ext_ior) (bsdfs/glass.rs:43-72)."""
+    m = _abi.rl_material()
+    if lib().rlh_material_glass(_f3(reflectance), _f3(transmittance), float(int_ior), float(ext_ior), C.byref(m)) != 0:
+        raise SceneError("glass: eta must not be 0")
+    return m
+
+
+def material_substrate(diffuse=(0.5, 0.5, 0.5), specular=(0.5, 0.5, 0.5), microfacet="ggx", alpha=0.1):
+    """BSDFSubstrate (bsdfs/substrate.rs)."""
+    m = _abi.rl_material()
+    if lib().rlh_material_substrate(_f3(diffuse), _f3(specular), _MICROFACET[microfacet], float(alpha), C.byref(m)) != 0:
+        raise SceneError("substrate: bad parameters")
+    return m
+
+
+def remap_roughness(v, remap=True):
+    return lib().rlh_remap_roughness(float(v), 1 if remap else 0)
 
 
 def material_diffuse(kd):

@@ -89,6 +89,33 @@ int rlh_material_phong(const float kd[3], const float ks[3], float exponent, rl_
     }
 }
 
+// Material::metal / glass / substrate (bsdfs/metal.rs, glass.rs, substrate.rs); microfacet is an rl_microfacet
+int rlh_material_metal(const float specular[3], const float eta[3], const float k[3], uint32_t microfacet, float alpha, rl_material *out) {
+    try {
+        *out = Material::metal(Color{specular[0], specular[1], specular[2]}, Color{eta[0], eta[1], eta[2]}, Color{k[0], k[1], k[2]}, microfacet, alpha).m;
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+int rlh_material_glass(const float reflectance[3], const float transmittance[3], float int_ior, float ext_ior, rl_material *out) {
+    try {
+        *out = Material::glass(Color{reflectance[0], reflectance[1], reflectance[2]}, Color{transmittance[0], transmittance[1], transmittance[2]}, int_ior, ext_ior).m;
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+int rlh_material_substrate(const float diffuse[3], const float specular[3], uint32_t microfacet, float alpha, rl_material *out) {
+    try {
+        *out = Material::substrate(Color{diffuse[0], diffuse[1], diffuse[2]}, Color{specular[0], specular[1], specular[2]}, microfacet, alpha).m;
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+float rlh_remap_roughness(float v, int remap) { return remap_roughness(v, remap != 0); }
+
 // Returns the number of bytes needed (including the terminator); writes at most buflen.
 size_t rlh_scene_to_json(const rlh_scene *s, char *buf, size_t buflen) {
     std::string j = scene_to_json(s->scene);

@@ -103,6 +103,11 @@ struct ParamSet {
         auto p = find(name);
         return (p && !p->nums.empty()) ? p->nums[0] : def;
     }
+    bool boolean(const std::string &name, bool def) const {
+        auto p = find(name);
+        if (!p || p->strs.empty()) return def;
+        return p->strs[0] == "true";
+    }
     Color rgb(const std::string &name, Color def) const {
         auto p = find(name);
         if (!p) return def;
@@ -199,7 +204,24 @@ Material material_from_params(const std::string &type, const ParamSet &ps) {
         return Material::phong(ps.rgb("Kd", Color{0.5f, 0.5f, 0.5f}), ps.rgb("Ks", Color{0.5f, 0.5f, 0.5f}),
                                (float)ps.num("exponent", 30.0));
     }
-    throw Error("pbrt: material type \"" + type + "\" is outside the hot-path scope (matte, phong)");
+    // distribution_pbrt (bsdfs/mod.rs:260-291): always GGX; isotropic only (distribution.rs:62 asserts alpha_u == alpha_v)
+    auto ggx_alpha = [&](double def_roughness) {
+        bool remap = ps.boolean("remaproughness", true);
+        double r = ps.num("roughness", def_roughness);
+        double u = ps.num("uroughness", r), v = ps.num("vroughness", r);
+        if (u != v) throw Error("pbrt: anisotropic roughness panics in the reference (distribution.rs:62)");
+        return remap_roughness((float)u, remap);
+    };
+    if (type == "mirror") // bsdfs/mod.rs:349-357
+        return Material::metal(ps.rgb("Kr", Color{0.9f, 0.9f, 0.9f}), Color{1.0f, 1.0f, 1.0f}, Color{0.0f, 0.0f, 0.0f}, RL_MICROFACET_NONE, 0.0f);
+    if (type == "metal") // bsdfs/mod.rs:334-348; defaults: pbrt-v3's copper as RGB (pbrt_rs is not vendored: unpinned)
+        return Material::metal(Color{1.0f, 1.0f, 1.0f}, ps.rgb("eta", Color{0.2004f, 0.9240f, 1.1022f}), ps.rgb("k", Color{3.9129f, 2.4528f, 2.1421f}),
+                               RL_MICROFACET_GGX, ggx_alpha(0.01));
+    if (type == "glass") // bsdfs/mod.rs:307-333: the distribution is ignored ("Pure glass instead"), .eta(eta, 1.0)
+        return Material::glass(ps.rgb("Kr", Color{1.0f, 1.0f, 1.0f}), ps.rgb("Kt", Color{1.0f, 1.0f, 1.0f}), (float)ps.num("eta", ps.num("index", 1.5)), 1.0f);
+    if (type == "substrate") // bsdfs/mod.rs:358-374
+        return Material::substrate(ps.rgb("Kd", Color{0.5f, 0.5f, 0.5f}), ps.rgb("Ks", Color{0.5f, 0.5f, 0.5f}), RL_MICROFACET_GGX, ggx_alpha(0.1));
+    throw Error("pbrt: material type \"" + type + "\" is not supported (matte, mirror, metal, glass, substrate, phong)");
 }
 } // namespace
 
@@ -471,7 +493,30 @@ Material jmaterial(const JVal &m) {
         return Material::phong(jcolor(m.get("kd"), "kd", Color{0.5f, 0.5f, 0.5f}),
                                jcolor(m.get("ks"), "ks", Color{0.5f, 0.5f, 0.5f}), e ? (float)e->n : 30.0f);
     }
-    throw Error("json: material type \"" + type + "\" is outside the hot-path scope (diffuse, phong)");
+    auto jnum = [&](const char *k, double def) {
+        const JVal *v = m.get(k);
+        return (v && v->t == JVal::Num) ? v->n : def;
+    };
+    auto jmicrofacet = [&]() -> uint32_t {
+        const JVal *v = m.get("microfacet");
+        std::string d = (v && v->t == JVal::Str) ? v->s : "ggx";
+        if (d == "none") return RL_MICROFACET_NONE;
+        if (d == "ggx") return RL_MICROFACET_GGX;
+        if (d == "beckmann") return RL_MICROFACET_BECKMANN;
+        throw Error("json: unknown microfacet \"" + d + "\"");
+    };
+    if (type == "mirror") return Material::metal(jcolor(m.get("ks"), "ks", Color{0.9f, 0.9f, 0.9f}), Color{1.0f, 1.0f, 1.0f}, Color{0.0f, 0.0f, 0.0f}, RL_MICROFACET_NONE, 0.0f);
+    if (type == "metal")
+        return Material::metal(jcolor(m.get("ks"), "ks", Color{1.0f, 1.0f, 1.0f}), jcolor(m.get("eta"), "eta", Color{0.2004f, 0.9240f, 1.1022f}),
+                               jcolor(m.get("k"), "k", Color{3.9129f, 2.4528f, 2.1421f}), jmicrofacet(), (float)jnum("alpha", 0.1));
+    if (type == "glass") { // "ior" = the relative index directly; else int_ior / ext_ior with BSDFGlass::default()'s bk7 / air (glass.rs:60-72)
+        const bool rel = m.get("ior") != nullptr;
+        return Material::glass(jcolor(m.get("ks"), "ks", Color{1.0f, 1.0f, 1.0f}), jcolor(m.get("kt"), "kt", Color{1.0f, 1.0f, 1.0f}),
+                               (float)(rel ? jnum("ior", 1.5) : jnum("int_ior", 1.5046)), (float)(rel ? 1.0 : jnum("ext_ior", 1.000277)));
+    }
+    if (type == "substrate")
+        return Material::substrate(jcolor(m.get("kd"), "kd", Color{0.5f, 0.5f, 0.5f}), jcolor(m.get("ks"), "ks", Color{0.5f, 0.5f, 0.5f}), jmicrofacet(), (float)jnum("alpha", 0.1));
+    throw Error("json: material type \"" + type + "\" is not supported (diffuse, phong, mirror, metal, glass, substrate)");
 }
 } // namespace
 
@@ -572,14 +617,26 @@ std::string scene_to_json(const Scene &scene) {
     o << "},\n  \"meshes\": [\n";
     for (size_t i = 0; i < scene.meshes.size(); i++) {
         const Mesh &m = *scene.meshes[i];
-        o << "    {\"name\": \"" << m.name << "\", \"material\": {\"type\": \""
-          << (m.bsdf.m.kind == RL_BSDF_PHONG ? "phong" : "diffuse") << "\", \"kd\": ";
-        put_floats(o, m.bsdf.m.kd, 3);
-        if (m.bsdf.m.kind == RL_BSDF_PHONG) {
-            o << ", \"ks\": ";
-            put_floats(o, m.bsdf.m.ks, 3);
-            o << ", \"exponent\": ";
-            put_floats(o, &m.bsdf.m.exponent, 1);
+        const rl_material &mt = m.bsdf.m;
+        static const char *kinds[] = {"diffuse", "phong", "metal", "glass", "substrate"};
+        static const char *mfs[] = {"none", "ggx", "beckmann"};
+        o << "    {\"name\": \"" << m.name << "\", \"material\": {\"type\": \"" << kinds[mt.kind <= RL_BSDF_SUBSTRATE ? mt.kind : 0] << "\"";
+        auto put = [&](const char *key, const float *v, size_t n) {
+            o << ", \"" << key << "\": ";
+            if (n == 1) { // scalars are bare numbers
+                char b1[32];
+                std::snprintf(b1, sizeof(b1), "%.9g", (double)v[0]);
+                o << b1;
+            } else put_floats(o, v, n);
+        };
+        if (mt.kind == RL_BSDF_DIFFUSE || mt.kind == RL_BSDF_PHONG || mt.kind == RL_BSDF_SUBSTRATE) put("kd", mt.kd, 3);
+        if (mt.kind != RL_BSDF_DIFFUSE) put("ks", mt.ks, 3);
+        if (mt.kind == RL_BSDF_PHONG) put("exponent", &mt.exponent, 1);
+        if (mt.kind == RL_BSDF_METAL) put("eta", mt.eta, 3), put("k", mt.k, 3);
+        if (mt.kind == RL_BSDF_GLASS) put("kt", mt.kt, 3), put("ior", &mt.ior, 1);
+        if (mt.kind == RL_BSDF_METAL || mt.kind == RL_BSDF_SUBSTRATE) {
+            o << ", \"microfacet\": \"" << mfs[mt.microfacet <= RL_MICROFACET_BECKMANN ? mt.microfacet : 0] << "\"";
+            put("alpha", &mt.alpha, 1);
         }
         o << "}";
         if (m.is_light) {

@@ -73,7 +73,16 @@ struct Material {
     static Material diffuse(Color kd);
     // weight_specular per src/bsdfs/mod.rs:518-523
     static Material phong(Color kd, Color ks, float exponent);
+    // BSDFMetal (bsdfs/metal.rs); microfacet == RL_MICROFACET_NONE is the pure specular case ("mirror" in bsdf_pbrt,
+    // bsdfs/mod.rs:349-357: specular = Kr, eta = 1, k = 0)
+    static Material metal(Color specular, Color eta, Color k, uint32_t microfacet, float alpha);
+    // BSDFGlass with .eta(int_ior, ext_ior) (bsdfs/glass.rs:43-48)
+    static Material glass(Color reflectance, Color transmittance, float int_ior, float ext_ior);
+    // BSDFSubstrate (bsdfs/substrate.rs)
+    static Material substrate(Color diffuse, Color specular, uint32_t microfacet, float alpha);
 };
+// distribution_pbrt's roughness remapping (bsdfs/mod.rs:265-276)
+float remap_roughness(float v, bool remap);
 
 // src/geometry.rs:107-119
 struct Mesh {

@@ -207,6 +207,39 @@ Material Material::phong(Color kd, Color ks, float exponent) {
     return r;
 }
 
+static void set3(float *dst, Color c) { dst[0] = c.r, dst[1] = c.g, dst[2] = c.b; }
+Material Material::metal(Color specular, Color eta, Color k, uint32_t microfacet, float alpha) {
+    if (microfacet > RL_MICROFACET_BECKMANN) throw Error("metal: unknown microfacet distribution");
+    Material r;
+    r.m.kind = RL_BSDF_METAL;
+    set3(r.m.ks, specular), set3(r.m.eta, eta), set3(r.m.k, k);
+    r.m.microfacet = microfacet;
+    r.m.alpha = microfacet == RL_MICROFACET_NONE ? 0.0f : alpha;
+    return r;
+}
+Material Material::glass(Color reflectance, Color transmittance, float int_ior, float ext_ior) {
+    Material r;
+    r.m.kind = RL_BSDF_GLASS;
+    set3(r.m.ks, reflectance), set3(r.m.kt, transmittance);
+    r.m.ior = int_ior / ext_ior;
+    if (r.m.ior == 0.0f) throw Error("glass: eta must not be 0 (bsdfs/glass.rs:45)");
+    return r;
+}
+Material Material::substrate(Color diffuse, Color specular, uint32_t microfacet, float alpha) {
+    if (microfacet > RL_MICROFACET_BECKMANN) throw Error("substrate: unknown microfacet distribution");
+    Material r;
+    r.m.kind = RL_BSDF_SUBSTRATE;
+    set3(r.m.kd, diffuse), set3(r.m.ks, specular);
+    r.m.microfacet = microfacet;
+    r.m.alpha = microfacet == RL_MICROFACET_NONE ? 0.0f : alpha;
+    return r;
+}
+float remap_roughness(float v, bool remap) {
+    if (!remap) return v;
+    float x = std::log(std::max(v, 1e-3f));
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+
 // ------------------------------------------------------------------------------------------
 // Scene
 // ------------------------------------------------------------------------------------------

@@ -13,7 +13,10 @@ use std::os::raw::{c_char, c_int, c_void};
 #[repr(C)] pub struct rl_scene { _p: [u8; 0] }
 
 #[repr(C)] #[derive(Clone, Copy)]
-pub struct rl_material { pub kind: u32, pub kd: [f32; 3], pub ks: [f32; 3], pub exponent: f32, pub weight_specular: f32 }
+pub struct rl_material {
+    pub kind: u32, pub kd: [f32; 3], pub ks: [f32; 3], pub exponent: f32, pub weight_specular: f32,
+    pub kt: [f32; 3], pub eta: [f32; 3], pub k: [f32; 3], pub ior: f32, pub alpha: f32, pub microfacet: u32,
+}
 #[repr(C)]
 pub struct rl_mesh_desc {
     pub p: *const f32, pub nverts: u32, pub idx: *const u32, pub ntris: u32,

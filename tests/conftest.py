@@ -211,5 +211,21 @@ def adversarial_pairs_case(seed):
     return sc, o, dd, p1
 
 
+def mixed_cbox(w=48, h=48):
+    """Cornell box with every material kind: floor substrate (GGX), ceiling phong, back wall rough gold (GGX), right wall
+    mirror, left wall substrate without a distribution (delta + diffuse), short box glass (closed mesh), tall box
+    Beckmann aluminium."""
+    from rustlight_b200.host import material_glass, material_metal, material_mirror, material_phong, material_substrate
+    sc = load_cbox(w, h)
+    sc.set_material(0, material_substrate((0.4, 0.25, 0.1), (0.05, 0.05, 0.05), "ggx", 0.1))
+    sc.set_material(1, material_phong((0.4, 0.4, 0.4), (0.3, 0.3, 0.3), 40.0))
+    sc.set_material(2, material_metal((1, 1, 1), (0.143, 0.375, 1.442), (3.983, 2.386, 1.603), "ggx", 0.12))
+    sc.set_material(3, material_mirror((0.9, 0.8, 0.7)))
+    sc.set_material(4, material_substrate((0.5, 0.5, 0.5), (0.04, 0.04, 0.04), None, 0.0))
+    sc.set_material(5, material_glass((1, 1, 1), (0.95, 0.97, 1.0), 1.5046, 1.000277))
+    sc.set_material(6, material_metal((0.9, 0.9, 0.9), (1.657, 0.880, 0.521), (9.224, 6.270, 4.837), "beckmann", 0.25))
+    return sc
+
+
 def rel_l2(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(np.linalg.norm(b.astype(np.float64)), 1e-30))

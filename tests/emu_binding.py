@@ -39,8 +39,38 @@ def lib():
         L.emu_primary_hits.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), FP]
         L.emu_render.argtypes = [C.c_void_p, C.POINTER(_abi.rl_integrator_desc), C.c_uint32, C.c_uint64, C.c_uint32,
                                  C.c_uint32, FP, C.POINTER(emu_stats)]
+        L.emu_bsdf_sample.argtypes = [C.POINTER(_abi.rl_material), FP, C.c_float, C.c_float, FP, FP, FP]
+        L.emu_bsdf_pdf.restype = C.c_float
+        L.emu_bsdf_pdf.argtypes = [C.POINTER(_abi.rl_material), FP, FP]
+        L.emu_bsdf_eval.argtypes = [C.POINTER(_abi.rl_material), FP, FP, FP]
+        L.emu_bsdf_flags.argtypes = [C.POINTER(_abi.rl_material)]
         _lib = L
     return _lib
+
+
+def bsdf_sample_ex(mat, wi, s0, s1):
+    wi = np.ascontiguousarray(wi, np.float32)
+    w, d = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    pdf = C.c_float()
+    rc = lib().emu_bsdf_sample(C.byref(mat), _f(wi), s0, s1, _f(w), _f(d), C.byref(pdf))
+    return (rc != 0, w, d, pdf.value, rc == 2)
+
+
+def bsdf_pdf(mat, wi, wo):
+    wi, wo = np.ascontiguousarray(wi, np.float32), np.ascontiguousarray(wo, np.float32)
+    return lib().emu_bsdf_pdf(C.byref(mat), _f(wi), _f(wo))
+
+
+def bsdf_eval(mat, wi, wo):
+    wi, wo = np.ascontiguousarray(wi, np.float32), np.ascontiguousarray(wo, np.float32)
+    out = np.zeros(3, np.float32)
+    lib().emu_bsdf_eval(C.byref(mat), _f(wi), _f(wo), _f(out))
+    return out
+
+
+def bsdf_flags(mat):
+    f = lib().emu_bsdf_flags(C.byref(mat))
+    return dict(twosided=bool(f & 1), smooth=bool(f & 2))
 
 
 def _f(a):

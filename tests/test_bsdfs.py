@@ -1,0 +1,221 @@
+"""BSDFMetal / BSDFGlass / BSDFSubstrate + MicrofacetDistribution (bsdfs/{metal,glass,substrate,distribution,utils}.rs).
+
+Three layers, like the rest of the suite: (1) the oracle against closed forms and identities of the model,
+(2) the device arithmetic (tests/emu) against the oracle, bit for bit, (3) whole renders of a Cornell box that
+mixes every material kind: emulator == oracle (stream estimator) bit for bit, stream ~= graph estimator."""
+import math
+
+import numpy as np
+import pytest
+
+import emu_binding as eb
+from conftest import load_cbox, mixed_cbox, rel_l2
+from oracle import binding as ob
+from rustlight_b200 import _abi
+from rustlight_b200.host import (material_glass, material_metal, material_mirror, material_phong, material_substrate)
+
+STREAM = dict(estimator=ob.EST_STREAM, accel_mode=ob.ACCEL_NAIVE)
+
+MIRROR = material_mirror((0.9, 0.8, 0.7))
+GOLD = material_metal((1, 1, 1), (0.143, 0.375, 1.442), (3.983, 2.386, 1.603), "ggx", 0.12)
+ALU_B = material_metal((0.9, 0.9, 0.9), (1.657, 0.880, 0.521), (9.224, 6.270, 4.837), "beckmann", 0.25)
+GLASS = material_glass((1, 1, 1), (0.95, 0.97, 1.0), 1.5046, 1.000277)
+COAT = material_substrate((0.4, 0.25, 0.1), (0.05, 0.05, 0.05), "ggx", 0.1)
+COAT_B = material_substrate((0.2, 0.3, 0.4), (0.08, 0.08, 0.08), "beckmann", 0.3)
+COAT_DELTA = material_substrate((0.5, 0.5, 0.5), (0.04, 0.04, 0.04), None, 0.0)
+ALL = [MIRROR, GOLD, ALU_B, GLASS, COAT, COAT_B, COAT_DELTA]
+NAMES = ["mirror", "gold_ggx", "alu_beckmann", "glass", "substrate_ggx", "substrate_beckmann", "substrate_delta"]
+
+
+def _dir(theta, phi):
+    return np.float32([math.sin(theta) * math.cos(phi), math.sin(theta) * math.sin(phi), math.cos(theta)])
+
+
+# ---- (1) oracle vs the model -------------------------------------------------------------------------
+def test_flags():
+    want = {"mirror": (True, True), "gold_ggx": (True, False), "alu_beckmann": (True, False), "glass": (False, True),
+            "substrate_ggx": (True, False), "substrate_beckmann": (True, False), "substrate_delta": (True, True)}
+    for m, n in zip(ALL, NAMES):
+        f = ob.bsdf_flags(m)
+        assert (f["twosided"], f["smooth"]) == want[n], n
+        assert eb.bsdf_flags(m) == f, n
+
+
+def test_mirror_is_a_conductor_with_eta_1_k_0():
+    """pbrt "mirror" -> BSDFMetal{eta: 1, k: 0} (bsdfs/mod.rs:349-357): fresnel_conductor degenerates to
+    Rs = (1-c)/(1+c), Rp = Rs ((1-c)/(1+c))... evaluated here in float64 from utils.rs:78-100; the lobe is the mirror direction."""
+    for c in (0.1, 0.5, 0.9, 1.0):
+        wi = _dir(math.acos(c), 0.7)
+        ok, w, d, pdf, disc = ob.bsdf_sample_ex(MIRROR, wi, 0.3, 0.6)
+        assert ok and disc and pdf == 1.0 and np.allclose(d, [-wi[0], -wi[1], wi[2]])
+        c = float(wi[2])
+        c2, s2 = c * c, 1 - c * c
+        a2pb2 = math.sqrt(c2 * c2)
+        a = math.sqrt(0.5 * (a2pb2 + c2))
+        t1, t2 = a2pb2 + c2, a * 2 * c2
+        rs = (t1 - t2) / (t1 + t2)
+        t3, t4 = a2pb2 * c2 + s2 * s2, t2 * s2
+        rp = rs * (t3 - t4) / (t3 + t4)
+        assert np.allclose(w, np.float32([0.9, 0.8, 0.7]) * 0.5 * (rp + rs), rtol=2e-5, atol=1e-7)
+
+
+def test_glass_fresnel_and_snell():
+    eta = GLASS.ior
+    n_refl = 0
+    rng = np.random.default_rng(1)
+    for ct in (0.05, 0.3, 0.7, 1.0, -0.05, -0.5, -0.9):
+        wi = _dir(math.acos(ct), 1.1)
+        # Fresnel (unpolarised) in float64
+        scale = 1 / eta if ct > 0 else eta
+        ct2 = 1 - (1 - wi[2] ** 2) * scale * scale
+        if ct2 <= 0:
+            F = 1.0
+        else:
+            ci, cT = abs(float(wi[2])), math.sqrt(ct2)
+            rs = (ci - eta * cT) / (ci + eta * cT)
+            rp = (eta * ci - cT) / (eta * ci + cT)
+            F = 0.5 * (rs * rs + rp * rp)
+        for s0 in rng.random(20):
+            ok, w, d, pdf, disc = ob.bsdf_sample_ex(GLASS, wi, float(s0), 0.5)
+            assert ok and disc and pdf == pytest.approx(F, rel=2e-5, abs=1e-7)
+            if s0 <= pdf:
+                n_refl += 1
+                assert np.allclose(d, [-wi[0], -wi[1], wi[2]]) and np.array_equal(w, np.float32([1, 1, 1]))
+            else:
+                assert np.array_equal(w, np.float32(list(GLASS.kt)))  # Importance transport: factor 1 (glass.rs:95-105)
+                assert d[2] * wi[2] < 0 and abs(np.linalg.norm(d) - 1) < 1e-5
+                # Snell: sin_t = sin_i * (1/eta entering, eta leaving)
+                assert math.hypot(d[0], d[1]) == pytest.approx(math.hypot(wi[0], wi[1]) * scale, rel=1e-5)
+    assert n_refl > 5
+    # total internal reflection from inside at a grazing angle
+    ok, w, d, pdf, disc = ob.bsdf_sample_ex(GLASS, _dir(math.radians(100), 0.0), 0.999, 0.5)
+    assert ok and pdf == 1.0 and d[2] < 0
+
+
+@pytest.mark.parametrize("mat", [GOLD, ALU_B])
+def test_microfacet_normal_distribution(mat):
+    """D(m) cos(theta_m) integrates to 1; sample() returns exactly pdf(m) = D(m) cos(theta_m) of the normal it
+    draws -- seen through BSDFMetal: the sampled `pdf` is the pdf of the NORMAL (metal.rs:64, a quirk that is kept),
+    while BSDFMetal::pdf() is D cos / (4 |wo.h|)."""
+    wi = _dir(0.4, 0.3)
+    for s0, s1 in np.random.default_rng(2).random((200, 2)):
+        ok, w, d, pdf, disc = ob.bsdf_sample_ex(mat, wi, float(s0), float(s1))
+        if not ok:
+            continue
+        assert not disc and d[2] > 0
+        h = (wi + d) / np.linalg.norm(wi + d)
+        assert np.allclose(d, -wi + 2 * np.dot(wi, h) * h, atol=2e-6)  # reflect_vector
+        p_wo = ob.bsdf_pdf(mat, wi, d)
+        assert p_wo == pytest.approx(pdf / (4 * abs(float(np.dot(d, h)))), rel=2e-4)
+    # hemispherical integral of pdf(wo) for normal incidence equals 1 minus the mass reflected below the horizon (none here)
+    nt, nph = 600, 64
+    tot = 0.0
+    wi = np.float32([0, 0, 1])
+    for t in (np.arange(nt) + 0.5) * (math.pi / 2) / nt:
+        tot += sum(ob.bsdf_pdf(mat, wi, _dir(t, p)) for p in (np.arange(nph) + 0.5) * 2 * math.pi / nph) * math.sin(t)
+    tot *= (math.pi / 2 / nt) * (2 * math.pi / nph)
+    assert tot == pytest.approx(1.0, abs=2e-2)
+
+
+@pytest.mark.parametrize("mat", [COAT, COAT_B, COAT_DELTA])
+def test_substrate_weight_is_eval_over_pdf_and_lobes(mat):
+    wi = _dir(0.6, -0.4)
+    n_spec = 0
+    for s0, s1 in np.random.default_rng(3).random((300, 2)):
+        ok, w, d, pdf, disc = ob.bsdf_sample_ex(mat, wi, float(s0), float(s1))
+        if not ok:
+            continue
+        assert d[2] > 0 and pdf > 0
+        if disc:  # only the distribution-less substrate has a delta lobe: pdf 1/2, weight = schlick / (1/2)
+            n_spec += 1
+            assert mat.microfacet == _abi.RL_MICROFACET_NONE and s0 >= 0.5 and pdf == 0.5
+            rs = np.float32(list(mat.ks))
+            assert np.allclose(w, (rs + (1 - rs) * (1 - wi[2]) ** 5) / 0.5, rtol=1e-5)
+        else:
+            assert pdf == pytest.approx(ob.bsdf_pdf(mat, wi, d), rel=1e-6)
+            assert np.allclose(w, ob.bsdf_eval(mat, wi, d) / np.float32(pdf), rtol=1e-6)
+    assert (n_spec > 50) == (mat.microfacet == _abi.RL_MICROFACET_NONE)
+
+
+def test_math_modes_agree_on_the_new_lobes():
+    wi = _dir(0.5, 0.2)
+    for mat in (GOLD, ALU_B, COAT, COAT_B):
+        for s0, s1 in np.random.default_rng(5).random((50, 2)):
+            a = ob.bsdf_sample_ex(mat, wi, float(s0), float(s1), ob.MATH_LIBM)
+            b = ob.bsdf_sample_ex(mat, wi, float(s0), float(s1), ob.MATH_SPEC)
+            assert a[0] == b[0]
+            if a[0]:
+                assert np.allclose(a[1], b[1], rtol=2e-5) and np.allclose(a[2], b[2], atol=2e-6) and a[3] == pytest.approx(b[3], rel=2e-5)
+
+
+# ---- (2) device arithmetic == oracle, bit for bit ----------------------------------------------------------
+@pytest.mark.parametrize("mat,name", list(zip(ALL, NAMES)))
+def test_device_bsdf_bit_exact(mat, name):
+    rng = np.random.default_rng(11)
+    n_ok = 0
+    for i in range(600):
+        wi = _dir(math.acos(rng.uniform(-1 if name == "glass" else -0.2, 1)), rng.uniform(0, 2 * math.pi))
+        if i % 50 == 0:
+            wi = np.float32([0, 0, 1])
+        s0, s1 = float(np.float32(rng.random())), float(np.float32(rng.random()))
+        a = ob.bsdf_sample_ex(mat, wi, s0, s1)
+        b = eb.bsdf_sample_ex(mat, wi, s0, s1)
+        assert a[0] == b[0], (name, wi, s0, s1)
+        if not a[0]:
+            continue
+        n_ok += 1
+        assert a[4] == b[4] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3], (name, wi, s0, s1)
+        if not ob.bsdf_flags(mat)["smooth"]:
+            wo = _dir(math.acos(rng.uniform(-0.1, 1)), rng.uniform(0, 2 * math.pi))
+            for o in (a[2], wo):
+                pa, pb = ob.bsdf_pdf(mat, wi, o), eb.bsdf_pdf(mat, wi, o)
+                assert pa == pb or (math.isnan(pa) and math.isnan(pb)), (name, wi, o)
+                assert np.array_equal(ob.bsdf_eval(mat, wi, o), eb.bsdf_eval(mat, wi, o), equal_nan=True), (name, wi, o)
+    assert n_ok > 300
+
+
+# ---- (3) renders ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kw", [dict(), dict(strategy=_abi.RL_STRATEGY_BSDF), dict(strategy=_abi.RL_STRATEGY_EMITTER), dict(max_depth=5, rr_depth=3)])
+def test_mixed_scene_path_bit_exact(kw):
+    sc = mixed_cbox()
+    integ = _abi.path_desc(**kw)
+    ie, se = eb.EmuScene(sc).render(integ, 6, seed=4)
+    io, so = ob.OracleScene(sc).render(integ, 6, seed=4, cfg=ob.config(**STREAM))
+    assert np.isfinite(io).all() and io.mean() > 0.01
+    assert (se.segments, se.hits, se.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+    assert np.array_equal(ie, io)
+
+
+@pytest.mark.parametrize("nb,nl", [(1, 1), (2, 0), (0, 2)])
+def test_mixed_scene_direct_bit_exact(nb, nl):
+    sc = mixed_cbox()
+    integ = _abi.direct_desc(nb, nl)
+    ie, se = eb.EmuScene(sc).render(integ, 4, seed=9)
+    io, so = ob.OracleScene(sc).render(integ, 4, seed=9, cfg=ob.config(**STREAM))
+    assert (se.segments, se.hits, se.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+    assert np.array_equal(ie, io)
+
+
+def test_mixed_scene_stream_estimator_equals_graph():
+    """path.rs builds the vertex/edge graph and recurses; the streaming form must take the same decisions (same ray
+    counts) and differ only by re-association of products -- now including PDF::Discrete edges and smooth vertices."""
+    sc = mixed_cbox(40, 40)
+    osc = ob.OracleScene(sc)
+    for kw in (dict(), dict(strategy=_abi.RL_STRATEGY_BSDF), dict(strategy=_abi.RL_STRATEGY_EMITTER)):
+        integ = _abi.path_desc(**kw)
+        a, sa = osc.render(integ, 8, seed=2, cfg=ob.config(estimator=ob.EST_GRAPH, accel_mode=ob.ACCEL_NAIVE))
+        b, sb = osc.render(integ, 8, seed=2, cfg=ob.config(**STREAM))
+        assert (sa.segments, sa.shadow_rays) == (sb.segments, sb.shadow_rays)
+        assert rel_l2(b, a) < 1e-6
+
+
+def test_strategies_agree_statistically_on_glossy_scene():
+    """BSDF-only, emitter-only and MIS estimators of a scene WITHOUT delta lobes converge to the same image."""
+    sc = load_cbox(24, 24)
+    for i, m in enumerate([COAT, COAT_B, GOLD, ALU_B, COAT]):
+        sc.set_material(i, m)
+    osc = ob.OracleScene(sc)
+    imgs = [osc.render(_abi.path_desc(strategy=s, max_depth=4), 600, seed=1, cfg=ob.config(**STREAM))[0]
+            for s in (_abi.RL_STRATEGY_ALL, _abi.RL_STRATEGY_BSDF, _abi.RL_STRATEGY_EMITTER)]
+    m = [float(i.mean()) for i in imgs]
+    assert m[1] == pytest.approx(m[0], rel=0.06) and m[2] == pytest.approx(m[0], rel=0.06)

@@ -356,6 +356,29 @@ def test_group_table_on_surface_rays_and_degenerate_directions(cbox_dev, cbox_or
     assert np.array_equal(vg, cbox_oracle.visible(o2, light, ob.ACCEL_NAIVE)) and 0.2 < vg.mean() < 0.9
 
 
+@pytest.mark.parametrize("sort", [0, 1])
+def test_mixed_material_scene_bit_exact(gpu_ctx, sort):
+    """Every BSDF kind in one scene (metal GGX / Beckmann, mirror, glass, substrate with and without a distribution, phong,
+    diffuse): PDF::Discrete edges, smooth vertices without light sampling, the non-two-sided glass box -- with and
+    without the per-bounce material sort (7 keys)."""
+    from conftest import mixed_cbox
+    sc = mixed_cbox(96, 96)
+    dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
+    for kw in (dict(), dict(strategy=_abi.RL_STRATEGY_BSDF), dict(max_depth=6, rr_depth=2)):
+        integ = _abi.path_desc(**kw)
+        img, st = dev.render(integ, 8, seed=12, material_sort=sort)
+        ref, so = osc.render(integ, 8, seed=12, cfg=ob.config(**STREAM))
+        assert (st.segments, st.hits, st.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+        assert np.array_equal(img, ref)
+    if sort == 0:
+        for nb, nl in ((1, 1), (2, 2)):
+            integ = _abi.direct_desc(nb, nl)
+            img, st = dev.render(integ, 4, seed=5)
+            ref, so = osc.render(integ, 4, seed=5, cfg=ob.config(**STREAM))
+            assert np.array_equal(img, ref) and st.segments == so.segments
+    dev.close()
+
+
 def test_config_shapes_c3_c5(gpu_ctx):
     """BASELINE configs[2] (Phong walls, 512x512) and configs[4] (1920x1080, Fov::Y quirk, ragged 16x16 tiles,
     material sort on): sub-sampled spp, bit-exact against the oracle on the same stream."""

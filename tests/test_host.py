@@ -57,10 +57,56 @@ def test_loader_errors():
         m.load("scene")
     with pytest.raises(SceneError, match="camera"):
         m.load_string('WorldBegin Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0] WorldEnd', "pbrt")
-    with pytest.raises(SceneError, match="scope"):
-        m.load_string('Camera "perspective" WorldBegin MakeNamedMaterial "g" "string type" ["glass"] WorldEnd', "pbrt")
+    with pytest.raises(SceneError, match="not supported"):
+        m.load_string('Camera "perspective" WorldBegin MakeNamedMaterial "g" "string type" ["uber"] WorldEnd', "pbrt")
+    with pytest.raises(SceneError, match="anisotropic"):  # distribution.rs:62 asserts alpha_u == alpha_v
+        m.load_string('Camera "perspective" WorldBegin Material "metal" "float uroughness" [0.1] "float vroughness" [0.2] WorldEnd', "pbrt")
     with pytest.raises(SceneError, match="out of range"):
         m.load_string('Camera "perspective" WorldBegin Shape "trianglemesh" "integer indices" [0 1 5] "point P" [0 0 0 1 0 0 0 1 0] WorldEnd', "pbrt")
+
+
+def test_pbrt_material_mapping():
+    """bsdf_pbrt (bsdfs/mod.rs:294-386): mirror -> BSDFMetal without a distribution, metal / substrate -> GGX with the
+    remapped roughness (distribution_pbrt, :260-291), glass -> BSDFGlass.eta(eta, 1.0), distribution ignored."""
+    import math
+    from rustlight_b200.host import remap_roughness
+    tri = 'Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]'
+    txt = f'''Camera "perspective" WorldBegin
+      Material "mirror" "rgb Kr" [0.8 0.7 0.6] {tri}
+      Material "metal" "rgb eta" [0.2 0.9 1.1] "rgb k" [3.9 2.4 2.1] "float roughness" [0.05] {tri}
+      Material "metal" "float roughness" [0.3] "bool remaproughness" ["false"] {tri}
+      Material "glass" "float eta" [1.33] "rgb Kt" [0.9 0.9 1.0] "float uroughness" [0.2] "float vroughness" [0.2] {tri}
+      Material "substrate" "rgb Kd" [0.3 0.2 0.1] "rgb Ks" [0.04 0.04 0.04] "float uroughness" [0.02] "float vroughness" [0.02] {tri}
+      Material "substrate" {tri}
+    WorldEnd'''
+    d = SceneLoaderManager().load_string(txt, "pbrt").desc.contents
+    mats = [d.meshes[i].mat for i in range(6)]
+    assert [m.kind for m in mats] == [_abi.RL_BSDF_METAL, _abi.RL_BSDF_METAL, _abi.RL_BSDF_METAL, _abi.RL_BSDF_GLASS, _abi.RL_BSDF_SUBSTRATE, _abi.RL_BSDF_SUBSTRATE]
+    assert mats[0].microfacet == _abi.RL_MICROFACET_NONE and list(mats[0].ks) == pytest.approx([0.8, 0.7, 0.6]) and list(mats[0].eta) == [1, 1, 1] and list(mats[0].k) == [0, 0, 0]
+    x = math.log(0.05)
+    want = 1.62142 + 0.819955 * x + 0.1734 * x * x + 0.0171201 * x ** 3 + 0.000640711 * x ** 4
+    assert mats[1].microfacet == _abi.RL_MICROFACET_GGX and mats[1].alpha == pytest.approx(want, rel=1e-5) == pytest.approx(remap_roughness(0.05), rel=1e-6)
+    assert list(mats[1].ks) == [1, 1, 1] and list(mats[1].eta) == pytest.approx([0.2, 0.9, 1.1])
+    assert mats[2].alpha == pytest.approx(0.3) and remap_roughness(1e-9) == pytest.approx(remap_roughness(1e-3))  # v.max(1e-3)
+    assert mats[3].ior == pytest.approx(1.33) and list(mats[3].kt) == pytest.approx([0.9, 0.9, 1.0]) and list(mats[3].ks) == [1, 1, 1]
+    assert mats[4].alpha == pytest.approx(remap_roughness(0.02)) and list(mats[4].kd) == pytest.approx([0.3, 0.2, 0.1])
+    assert list(mats[5].kd) == [0.5] * 3 and list(mats[5].ks) == [0.5] * 3 and mats[5].alpha == pytest.approx(remap_roughness(0.1))
+
+
+def test_json_materials_round_trip():
+    import json
+    from rustlight_b200.host import material_glass, material_metal, material_mirror, material_substrate
+    sc = load_cbox(16, 16)
+    mats = [material_mirror((0.9, 0.8, 0.7)), material_metal(alpha=0.07), material_metal(microfacet="beckmann", alpha=0.2),
+            material_glass(int_ior=1.5046, ext_ior=1.000277), material_substrate((0.4, 0.3, 0.2), (0.05, 0.05, 0.05), "ggx", 0.15),
+            material_substrate(microfacet=None)]
+    for i, m in enumerate(mats):
+        sc.set_material(i, m)
+    back = SceneLoaderManager().load_string(sc.to_json(), "json").desc.contents
+    for i, m in enumerate(mats):
+        got = back.meshes[i].mat
+        assert bytes(got) == bytes(m), i
+    assert json.loads(sc.to_json())["meshes"][3]["material"]["type"] == "glass"
 
 
 def test_pbrt_transforms_and_defaults():
@@ -119,7 +165,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in DECLARED:
         assert hasattr(lib, name), name
     lib.rl_abi_version.restype = C.c_int
-    assert lib.rl_abi_version() == 1
+    assert lib.rl_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(tmp_path):
