@@ -204,7 +204,7 @@ def main():
     import ctypes as C
     from rustlight_b200.device import lib
     L = lib()
-    opts = _abi.rl_render_opts(C.sizeof(_abi.rl_render_opts), spp, seed, _abi.RL_SAMPLER_COUNTER, args.batch_spp, 0, 0)
+    opts = _abi.rl_render_opts(C.sizeof(_abi.rl_render_opts), spp, seed, _abi.RL_SAMPLER_COUNTER, args.batch_spp, 2, 0)  # material_sort = auto (off: one BSDF kind)
     FP = C.POINTER(C.c_float)
 
     def step_device():

@@ -141,7 +141,9 @@ typedef struct rl_render_opts {
     uint64_t seed;          /* `-r independent:<seed>` (cli.rs:886-890)                        */
     uint32_t sampler_mode;  /* rl_sampler_mode; only RL_SAMPLER_COUNTER on the GPU             */
     uint32_t batch_spp;     /* samples per pixel in flight per wavefront batch; 0 = auto       */
-    uint32_t material_sort; /* 0 = off, 1 = sort hits by material inside each CTA tile         */
+    uint32_t material_sort; /* 0 = off, 1 = sort hits by material inside each CTA tile, 2 = auto: on when the scene
+                               holds more than one BSDF kind (measured: 1.57x on the shade kernel of a 7-kind scene,
+                               a few % slower on a single-kind scene)                         */
     uint32_t sample_offset; /* index of the first sample: pass p of an averaging wrapper (avg.rs, equal_time.rs)
                                renders samples [p*spp, (p+1)*spp) so that passes never repeat a stream        */
 } rl_render_opts;

@@ -98,6 +98,7 @@ struct rl_scene {
     rl_bvh_info info{};
     // roots: the tree (coherent rays) and, for scenes of <= 64 triangles, the whole scene as one leaf
     int root_tree = 0, root_flat = 0, coherent_tree = 2;
+    uint32_t n_bsdf_kinds = 1; // distinct rl_bsdf_kind values over the meshes (material sort: auto)
     bool flat_ok = false; // group table present: incoherent rays use k_trace_flat / k_shadow_flat
     size_t smem_flat_bytes = 0;
 };
@@ -421,6 +422,11 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     s->info.ntris = n, s->info.nnodes = live_nodes, s->info.nleaves = live_leaves, s->info.max_depth = max_depth;
     std::memcpy(s->info.root_min, hs.root_min, 12);
     std::memcpy(s->info.root_max, hs.root_max, 12);
+    {
+        uint32_t seen = 0;
+        for (uint32_t mi = 0; mi < desc->nmeshes; mi++) seen |= 1u << (desc->meshes[mi].mat.kind & 31u);
+        s->n_bsdf_kinds = (uint32_t)__builtin_popcount(seen);
+    }
     s->info.smem_resident = s->smem_ok ? 1u : 0u;
     s->info.flat_groups = s->flat_ok ? s->flat.n_groups : 0u, s->info.flat_pairs = s->flat.n_pairs, s->info.flat_singles = s->flat.n_singles;
     s->info.flat_delta = s->flat.delta;
@@ -614,6 +620,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
         ip.seed_h = seed_hash(o->seed);
         ip.npix = npix, ip.img_w = W;
         const bool prof = ctx->profiling;
+        const bool sort_on = o->material_sort == 1u || (o->material_sort >= 2u && sc->n_bsdf_kinds > 1u);
         float ms;
         for (uint32_t s0 = 0; s0 < o->spp; s0 += batch) {
             const uint32_t nb = std::min(batch, o->spp - s0);
@@ -704,7 +711,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                         if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
                         else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
                         if (prof) CK(cudaEventRecord(ctx->ev[3], st));
-                        if (o->material_sort)
+                        if (sort_on)
                             k_shade<true><<<grid_for(ctx, n_ub, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur],
                                                                                      ctx->state[cur], ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1],
                                                                                      ctx->state[cur ^ 1], qc + k + 1, ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k,

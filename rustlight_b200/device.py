@@ -145,7 +145,7 @@ class DeviceScene:
         self.ctx._check(lib().rl_primary_hits(self.ctx._h, self._h, prim.ctypes.data_as(U32P), tuv.ctypes.data_as(FP)))
         return prim.reshape(self.height, self.width), tuv.reshape(self.height, self.width, 3)
 
-    def render(self, integ, spp, seed=0, out=None, batch_spp=0, material_sort=0, device_out=None, want_image=True, sample_offset=0):
+    def render(self, integ, spp, seed=0, out=None, batch_spp=0, material_sort=2, device_out=None, want_image=True, sample_offset=0):
         """rl_render: returns (image HxWx3 float32 or None, rl_stats)."""
         opts = _abi.rl_render_opts(C.sizeof(_abi.rl_render_opts), int(spp), int(seed), _abi.RL_SAMPLER_COUNTER,
                                    int(batch_spp), int(material_sort), int(sample_offset))

@@ -57,6 +57,7 @@ inline BufferCollection render_primal(Device &dev, Scene &scene, const rl_integr
     opts.spp = (uint32_t)scene.nb_samples;
     opts.seed = sampler.seed;
     opts.sampler_mode = RL_SAMPLER_COUNTER;
+    opts.material_sort = 2; // auto: on when the scene mixes BSDF kinds
     opts.sample_offset = sampler.passes * (uint32_t)scene.nb_samples;
     Bitmap bmp;
     bmp.size_x = scene.camera.img_x, bmp.size_y = scene.camera.img_y;
