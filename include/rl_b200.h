@@ -108,7 +108,8 @@ typedef struct rl_scene_desc {
 /* ---- integrators --------------------------------------------------------------------------- */
 typedef enum rl_integrator_kind {
     RL_INTEGRATOR_PATH = 0,  /* IntegratorPathTracing  src/integrators/explicit/path.rs:14-20 */
-    RL_INTEGRATOR_DIRECT = 1 /* IntegratorDirect       src/integrators/direct.rs:5-8          */
+    RL_INTEGRATOR_DIRECT = 1, /* IntegratorDirect      src/integrators/direct.rs:5-8          */
+    RL_INTEGRATOR_AO = 2      /* IntegratorAO          src/integrators/ao.rs:4-7              */
 } rl_integrator_kind;
 
 typedef enum rl_path_strategy { /* IntegratorPathTracingStrategies, path.rs:9-13 */
@@ -126,6 +127,8 @@ typedef struct rl_integrator_desc {
     uint32_t single_scattering; /* path.rs:19                                                  */
     uint32_t nb_bsdf_samples;   /* direct.rs:6, CLI default 1                                  */
     uint32_t nb_light_samples;  /* direct.rs:7, CLI default 1                                  */
+    float ao_max_distance;      /* ao.rs:5 Option<f32>: < 0 = None (`-d inf`); CLI default 1.0 */
+    uint32_t ao_normal_correction; /* ao.rs:6                                                  */
 } rl_integrator_desc;
 
 /* Sampler streams.  Mode A is the reference's own: one sequential SmallRng per 16x16 block,

@@ -1771,7 +1771,29 @@ Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy
     return l_i;
 }
 
+// IntegratorAO::compute_pixel, ao.rs:20-72
+Color ao_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy, const Ctx &cx, Sampler &sampler) {
+    const Scene &sc = *cx.scene;
+    float jx = sampler.next();
+    float jy = sampler.next();
+    Ray ray = sc.camera.generate(P2{(float)ix + jx, (float)iy + jy});
+    if (1 > cx.counters->max_depth) cx.counters->max_depth = 1;
+    Intersection its;
+    if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) return Color::zero();
+    const bool normal_correction = I.ao_normal_correction != 0;
+    if (!normal_correction && its.cos_theta() <= 0.0f) return Color::zero();
+    bool flipped = normal_correction && its.cos_theta() <= 0.0f;
+    V3 d_local = cosine_sample_hemisphere(cx.math, sampler.next2d());
+    V3 d_world = flipped ? its.frame.to_world(-d_local) : its.frame.to_world(d_local);
+    Ray r2 = spawn_ray(its, d_world);
+    Intersection new_its;
+    if (!sc.trace(r2, cx.accel_mode, *cx.counters, &new_its)) return Color::one();
+    if (I.ao_max_distance < 0.0f) return Color::zero(); // max_distance: None
+    return new_its.dist > I.ao_max_distance ? Color::one() : Color::zero();
+}
+
 Color compute_pixel(const rl_integrator_desc &I, uint32_t estimator, uint32_t ix, uint32_t iy, const Ctx &cx, Sampler &sampler) {
+    if (I.kind == RL_INTEGRATOR_AO) return ao_compute_pixel(I, ix, iy, cx, sampler);
     if (I.kind == RL_INTEGRATOR_DIRECT) return direct_compute_pixel(I, ix, iy, cx, sampler);
     if (estimator == ORC_EST_STREAM) return path_compute_pixel_stream(I, ix, iy, cx, sampler);
     return path_compute_pixel(I, ix, iy, cx, sampler);
@@ -1849,6 +1871,8 @@ int orc_render(const orc_scene *os, const rl_integrator_desc *integ, uint32_t sp
         if (sc.emitters.emitters.empty() && integ->strategy != RL_STRATEGY_BSDF) return RL_ERR_INVALID; // scene.rs:97-100
     } else if (integ->kind == RL_INTEGRATOR_DIRECT) {
         if (sc.emitters.emitters.empty() && integ->nb_light_samples > 0) return RL_ERR_INVALID;
+    } else if (integ->kind == RL_INTEGRATOR_AO) {
+        if (integ->ao_max_distance != integ->ao_max_distance) return RL_ERR_INVALID;
     } else return RL_ERR_INVALID;
     // generate_img_blocks, mod.rs:351-374: x-major block order, one cloned sampler per block
     struct Block {

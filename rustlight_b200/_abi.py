@@ -19,6 +19,7 @@ RL_MICROFACET_BECKMANN = 2
 
 RL_INTEGRATOR_PATH = 0
 RL_INTEGRATOR_DIRECT = 1
+RL_INTEGRATOR_AO = 2
 
 RL_STRATEGY_ALL = 0
 RL_STRATEGY_BSDF = 1
@@ -57,7 +58,8 @@ class rl_scene_desc(C.Structure):
 class rl_integrator_desc(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("min_depth", C.c_int32), ("max_depth", C.c_int32),
                 ("rr_depth", C.c_int32), ("strategy", C.c_uint32), ("single_scattering", C.c_uint32),
-                ("nb_bsdf_samples", C.c_uint32), ("nb_light_samples", C.c_uint32)]
+                ("nb_bsdf_samples", C.c_uint32), ("nb_light_samples", C.c_uint32),
+                ("ao_max_distance", C.c_float), ("ao_normal_correction", C.c_uint32)]
 
 
 class rl_render_opts(C.Structure):
@@ -96,6 +98,12 @@ def path_desc(min_depth=0, max_depth=None, rr_depth=0, strategy=RL_STRATEGY_ALL,
     opt = lambda v: -1 if v is None else int(v)
     return rl_integrator_desc(RL_INTEGRATOR_PATH, opt(min_depth), opt(max_depth), opt(rr_depth),
                               strategy, 1 if single_scattering else 0, 1, 1)
+
+
+def ao_desc(max_distance=1.0, normal_correction=False):
+    """IntegratorAO with the CLI defaults of examples/cli.rs:150-155 (`-d inf` = None)."""
+    return rl_integrator_desc(RL_INTEGRATOR_AO, 0, -1, 0, RL_STRATEGY_ALL, 0, 1, 0,
+                              -1.0 if max_distance is None else float(max_distance), 1 if normal_correction else 0)
 
 
 def direct_desc(nb_bsdf_samples=1, nb_light_samples=1):

@@ -99,6 +99,7 @@ struct rl_scene {
     // roots: the tree (coherent rays) and, for scenes of <= 64 triangles, the whole scene as one leaf
     int root_tree = 0, root_flat = 0, coherent_tree = 2;
     uint32_t n_bsdf_kinds = 1; // distinct rl_bsdf_kind values over the meshes (material sort: auto)
+    uint32_t kind_mask = 1;    // bit k: some mesh has rl_bsdf_kind k (selects the k_shade specialisation)
     bool flat_ok = false; // group table present: incoherent rays use k_trace_flat / k_shadow_flat
     size_t smem_flat_bytes = 0;
 };
@@ -426,6 +427,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
         uint32_t seen = 0;
         for (uint32_t mi = 0; mi < desc->nmeshes; mi++) seen |= 1u << (desc->meshes[mi].mat.kind & 31u);
         s->n_bsdf_kinds = (uint32_t)__builtin_popcount(seen);
+        s->kind_mask = seen;
     }
     s->info.smem_resident = s->smem_ok ? 1u : 0u;
     s->info.flat_groups = s->flat_ok ? s->flat.n_groups : 0u, s->info.flat_pairs = s->flat.n_pairs, s->info.flat_singles = s->flat.n_singles;
@@ -549,6 +551,11 @@ static int validate(rl_ctx *ctx, const rl_scene *scene, const rl_integrator_desc
             ctx->err = "rl_render: more than 64 bsdf/light samples per pixel sample";
             return RL_ERR_INVALID;
         }
+    } else if (I->kind == RL_INTEGRATOR_AO) {
+        if (I->ao_max_distance != I->ao_max_distance) {
+            ctx->err = "rl_render: ao max_distance is NaN";
+            return RL_ERR_INVALID;
+        }
     } else {
         ctx->err = "rl_render: unknown integrator kind";
         return RL_ERR_INVALID;
@@ -603,8 +610,9 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
     CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), st));
     CK(cudaEventRecord(ctx->ev[0], st));
     if (npix > 0) {
-        const bool direct = I->kind == RL_INTEGRATOR_DIRECT;
-        const uint32_t nl = direct ? I->nb_light_samples : 1u, nbs = direct ? I->nb_bsdf_samples : 1u;
+        const bool ao = I->kind == RL_INTEGRATOR_AO; // runs on the two stages of `direct`: no light samples, one extension ray
+        const bool direct = I->kind == RL_INTEGRATOR_DIRECT || ao;
+        const uint32_t nl = ao ? 0u : (direct ? I->nb_light_samples : 1u), nbs = ao ? 1u : (direct ? I->nb_bsdf_samples : 1u);
         const uint32_t n_slots = direct ? 1u + nl + nbs : 1u;
         const uint32_t widest = std::max(std::max(nl, nbs), n_slots);
         uint32_t batch = o->batch_spp;
@@ -616,7 +624,8 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
         IntegParams ip{};
         ip.kind = I->kind, ip.min_depth = I->min_depth, ip.max_depth = I->max_depth, ip.rr_depth = I->rr_depth;
         ip.strategy = I->strategy, ip.single_scattering = I->single_scattering;
-        ip.nb_bsdf_samples = I->nb_bsdf_samples, ip.nb_light_samples = I->nb_light_samples;
+        ip.nb_bsdf_samples = ao ? 1u : I->nb_bsdf_samples, ip.nb_light_samples = ao ? 0u : I->nb_light_samples;
+        ip.ao_max_distance = I->ao_max_distance, ip.ao_normal_correction = I->ao_normal_correction;
         ip.seed_h = seed_hash(o->seed);
         ip.npix = npix, ip.img_w = W;
         const bool prof = ctx->profiling;
@@ -711,16 +720,20 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                         if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
                         else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
                         if (prof) CK(cudaEventRecord(ctx->ev[3], st));
-                        if (sort_on)
-                            k_shade<true><<<grid_for(ctx, n_ub, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur],
-                                                                                     ctx->state[cur], ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1],
-                                                                                     ctx->state[cur ^ 1], qc + k + 1, ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k,
-                                                                                     ctx->lacc, ctx->d_counters);
-                        else
-                            k_shade<false><<<grid_for(ctx, n_ub, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur],
-                                                                                      ctx->state[cur], ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1],
-                                                                                      ctx->state[cur ^ 1], qc + k + 1, ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k,
-                                                                                      ctx->lacc, ctx->d_counters);
+#define RL_LAUNCH_SHADE(SORT, KM)                                                                                                                   \
+    k_shade<SORT, KM><<<grid_for(ctx, n_ub, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], \
+                                                                 ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1], ctx->state[cur ^ 1], qc + k + 1,     \
+                                                                 ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc, ctx->d_counters)
+                        // kernel specialised for the BSDF kinds of the scene: {diffuse}, {diffuse, phong}, everything
+                        if (sc->kind_mask == 0x1u) RL_LAUNCH_SHADE(false, 0x1u);
+                        else if ((sc->kind_mask & ~0x3u) == 0u) {
+                            if (sort_on) RL_LAUNCH_SHADE(true, 0x3u);
+                            else RL_LAUNCH_SHADE(false, 0x3u);
+                        } else {
+                            if (sort_on) RL_LAUNCH_SHADE(true, RL_KM_ALL);
+                            else RL_LAUNCH_SHADE(false, RL_KM_ALL);
+                        }
+#undef RL_LAUNCH_SHADE
                         ctx->launches++;
                         if (prof) CK(cudaEventRecord(ctx->ev[4], st));
                         // the shadow queue can never be longer than the input queue: size the grid from n_ub

@@ -893,8 +893,17 @@ RL_HD Material load_material(const float4 *mats, uint32_t mesh) {
     return m;
 }
 // bsdf_type().is_smooth() (bsdfs/mod.rs:157-161): DELTA in the type -> no light sampling, no MIS at this vertex
-RL_HD bool mat_is_smooth(const Material &m) { return m.kind == 3u || ((m.kind == 2u || m.kind == 4u) && m.microfacet == 0u); }
-RL_HD bool mat_is_twosided(const Material &m) { return m.kind != 3u; } // glass.rs:181-183
+// KM (here and below): compile-time mask of the rl_bsdf_kind values present in the scene (bit k = kind k).  The shade
+// kernel is instantiated for the masks {diffuse}, {diffuse, phong} and "all", so that a Cornell box does not carry the
+// microfacet / Fresnel code (registers, instruction cache) it never runs; every other caller uses the default "all".
+#define RL_KM_ALL 0xffu
+#define RL_HAS(KM, k) (((KM) >> (k)) & 1u)
+template <uint32_t KM = RL_KM_ALL>
+RL_HD bool mat_is_smooth(const Material &m) {
+    return (RL_HAS(KM, 3) && m.kind == 3u) || (((RL_HAS(KM, 2) && m.kind == 2u) || (RL_HAS(KM, 4) && m.kind == 4u)) && m.microfacet == 0u);
+}
+template <uint32_t KM = RL_KM_ALL>
+RL_HD bool mat_is_twosided(const Material &m) { return !(RL_HAS(KM, 3) && m.kind == 3u); } // glass.rs:181-183
 RL_HD V3 reflect_local(V3 d) { return V3{-d.x, -d.y, d.z}; }
 
 // ---- bsdfs/utils.rs -------------------------------------------------------------------------------
@@ -1057,10 +1066,11 @@ RL_HD Col substrate_eval(const Material &mt, V3 d_in, V3 d_out, bool discrete) {
 }
 
 // BSDF::pdf (diffuse.rs:33-51, phong.rs:65-91)
+template <uint32_t KM = RL_KM_ALL>
 RL_HD float bsdf_pdf(const Material &m, V3 wi, V3 wo) {
-    if (m.kind == 2u) return metal_pdf(m, wi, wo);               // only reached with a distribution (not smooth)
-    if (m.kind == 4u) return substrate_pdf(m, wi, wo, false);
-    if (m.kind == 0u) {
+    if (RL_HAS(KM, 2) && m.kind == 2u) return metal_pdf(m, wi, wo);               // only reached with a distribution (not smooth)
+    if (RL_HAS(KM, 4) && m.kind == 4u) return substrate_pdf(m, wi, wo, false);
+    if (!RL_HAS(KM, 1) || m.kind == 0u) {
         if (wi.z <= 0.0f) return 0.0f;
         if (wo.z <= 0.0f) return 0.0f;
         return wo.z * RL_FRAC_1_PI;
@@ -1074,10 +1084,11 @@ RL_HD float bsdf_pdf(const Material &m, V3 wi, V3 wo) {
     return pdf_specular + pdf_diffuse;
 }
 // BSDF::eval (diffuse.rs:53-71, phong.rs:93-119); includes the cosine for the diffuse lobe
+template <uint32_t KM = RL_KM_ALL>
 RL_HD Col bsdf_eval(const Material &m, V3 wi, V3 wo) {
-    if (m.kind == 2u) return metal_eval(m, wi, wo);
-    if (m.kind == 4u) return substrate_eval(m, wi, wo, false);
-    if (m.kind == 0u) {
+    if (RL_HAS(KM, 2) && m.kind == 2u) return metal_eval(m, wi, wo);
+    if (RL_HAS(KM, 4) && m.kind == 4u) return substrate_eval(m, wi, wo, false);
+    if (!RL_HAS(KM, 1) || m.kind == 0u) {
         if (wi.z <= 0.0f) return Col{0.0f, 0.0f, 0.0f};
         if (wo.z > 0.0f) return mul_checked(mul_checked(m.kd, wo.z), RL_FRAC_1_PI);
         return Col{0.0f, 0.0f, 0.0f};
@@ -1092,9 +1103,10 @@ RL_HD Col bsdf_eval(const Material &m, V3 wi, V3 wo) {
 }
 // BSDF::sample (diffuse.rs:11-31, phong.rs:14-63, metal.rs:15-73, glass.rs:75-121, substrate.rs:22-90).
 // *discrete: the sampled pdf is PDF::Discrete (delta lobe) -- no MIS for the edge it creates.
+template <uint32_t KM = RL_KM_ALL>
 RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight, V3 *wo, float *pdf, bool *discrete) {
     *discrete = false;
-    if (m.kind == 3u) { // glass: no wi.z test (not two-sided), transport == Importance -> factor 1
+    if (RL_HAS(KM, 3) && m.kind == 3u) { // glass: no wi.z test (not two-sided), transport == Importance -> factor 1
         float fresnel, cos_theta_trans;
         fresnel_dielectric(wi.z, m.weight_specular, &fresnel, &cos_theta_trans);
         *discrete = true;
@@ -1110,7 +1122,7 @@ RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight
         return true;
     }
     if (wi.z <= 0.0f) return false;
-    if (m.kind == 2u) { // metal
+    if (RL_HAS(KM, 2) && m.kind == 2u) { // metal
         Col k = xyz_col(m.ext[0]);
         if (m.microfacet == 0u) {
             *weight = m.ks * fresnel_conductor(wi.z, m.kd, k);
@@ -1131,7 +1143,7 @@ RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight
         *pdf = p; // the microfacet-normal pdf, as the reference returns it (metal.rs:64)
         return true;
     }
-    if (m.kind == 4u) { // substrate
+    if (RL_HAS(KM, 4) && m.kind == 4u) { // substrate
         V3 d_out;
         bool disc = false;
         if (sx < 0.5f) {
@@ -1159,7 +1171,7 @@ RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight
         *discrete = disc;
         return true;
     }
-    if (m.kind == 0u) {
+    if (!RL_HAS(KM, 1) || m.kind == 0u) {
         V3 d_out = cosine_sample_hemisphere(sx, sy);
         *weight = m.kd;
         *wo = d_out;
@@ -1182,9 +1194,9 @@ RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight
         sx = (sx - m.weight_specular) / (1.0f - m.weight_specular);
         d_out = cosine_sample_hemisphere(sx, sy);
     }
-    float p = bsdf_pdf(m, wi, d_out);
+    float p = bsdf_pdf<KM>(m, wi, d_out);
     if (p == 0.0f) return false;
-    *weight = div_checked(bsdf_eval(m, wi, d_out), p);
+    *weight = div_checked(bsdf_eval<KM>(m, wi, d_out), p);
     *wo = d_out;
     *pdf = p;
     return true;
@@ -1196,6 +1208,7 @@ struct Surface {
     Frame frame;
     uint32_t mesh;
 };
+template <uint32_t KM = RL_KM_ALL>
 RL_HD Surface fill_intersection(const SceneView &sv, const Material &mat, uint32_t prim, uint32_t mesh, float4 s0, float4 s1,
                                 float4 s2, float4 s3, float t, float hit_u, float hit_v, V3 o, V3 d) {
     Surface s;
@@ -1213,7 +1226,7 @@ RL_HD Surface fill_intersection(const SceneView &sv, const Material &mat, uint32
         else n_s = ns;
     } else n_s = n_g;
     // bsdf.is_twosided() && !is_light (structure.rs:1006): every BSDF but glass is two-sided; lights are never flipped
-    if (mat_is_twosided(mat) && !mat.is_light && dot(d, n_s) > 0.0f) {
+    if (mat_is_twosided<KM>(mat) && !mat.is_light && dot(d, n_s) > 0.0f) {
         n_s = V3{-n_s.x, -n_s.y, -n_s.z};
         n_g = V3{-n_g.x, -n_g.y, -n_g.z};
     }
@@ -1318,7 +1331,9 @@ RL_HD float mis_weight_power(float pdf_a, float pdf_b) {
 
 // ---- integrator parameters ------------------------------------------------------------------------
 struct IntegParams {
-    uint32_t kind;     // 0 path, 1 direct
+    uint32_t kind;     // 0 path, 1 direct, 2 ao
+    float ao_max_distance;         // < 0: None
+    uint32_t ao_normal_correction;
     int32_t min_depth, max_depth, rr_depth;
     uint32_t strategy; // 0 all, 1 bsdf, 2 emitter
     uint32_t single_scattering;
@@ -1355,6 +1370,7 @@ struct StepOut {
 RL_HD bool ip_expand(const IntegParams &ip, uint32_t depth) { return ip.max_depth < 0 ? true : depth < (uint32_t)ip.max_depth; }
 RL_HD bool ip_add_ok(const IntegParams &ip, uint32_t curr_depth) { return ip.min_depth < 0 ? true : curr_depth >= (uint32_t)ip.min_depth; }
 
+template <uint32_t KM = RL_KM_ALL>
 RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, const HitRec &hit, const PathState &st, uint32_t pixel,
                      uint32_t sample, StepOut *out) {
     out->has_add = false;
@@ -1366,9 +1382,9 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
     uint32_t mesh = f2u(s0.w);
     Material mat = load_material(sv.mats, mesh);
-    Surface its = fill_intersection(sv, mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
+    Surface its = fill_intersection<KM>(sv, mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
     const bool mute = ip.single_scattering != 0u;
-    const bool smooth = mat_is_smooth(mat); // no light sampling at this vertex (emitters.rs:110-112), no draws either
+    const bool smooth = mat_is_smooth<KM>(mat); // no light sampling at this vertex (emitters.rs:110-112), no draws either
     const bool use_nee = (ip.strategy == 0u || ip.strategy == 2u) && !smooth;
     // ---- emission carried by the arriving edge --------------------------------------------------
     if (st.depth == 1u) { // sensor edge: un-weighted (path.rs:152-165)
@@ -1404,7 +1420,7 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
         V3 wo;
         float bpdf;
         bool discrete;
-        if (bsdf_sample(mat, its.wi, sx, sy, &bw, &wo, &bpdf, &discrete)) {
+        if (bsdf_sample<KM>(mat, its.wi, sx, sy, &bw, &wo, &bpdf, &discrete)) {
             V3 d_out = to_world(its.frame, wo);
             Col Tn = st.T * bw;
             if (!is_zero(Tn)) {
@@ -1441,12 +1457,12 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
         LightSample ls = sample_light(sv, its.p, r_sel, r, ux, uy);
         if (ls.valid && !mute && ip_add_ok(ip, st.depth) && ip.strategy != 1u) {
             V3 wo = to_local(its.frame, ls.d);
-            Col f = bsdf_eval(mat, its.wi, wo);
+            Col f = bsdf_eval<KM>(mat, its.wi, wo);
             Col contrib = st.T * (ls.weight * f);
             if (!is_zero(contrib)) {
                 float w = 1.0f;
                 if (ip.strategy == 0u) {
-                    float pb = bsdf_pdf(mat, its.wi, wo);
+                    float pb = bsdf_pdf<KM>(mat, its.wi, wo);
                     w = ls.pdf / (pb + ls.pdf);
                 }
                 out->shadow = true;
@@ -1507,6 +1523,34 @@ RL_HD bool direct_light_sample(const SceneView &sv, DirectCtx *cx, V3 *p1, Col *
     *p1 = ls.p;
     *contrib = c;
     return !is_zero(c);
+}
+// ---- IntegratorAO::compute_pixel (ao.rs:20-72) on the same two stages: stage 1 = primary hit -> one cosine-distributed
+// extension ray (flipped when normal_correction and the surface is seen from behind), stage 2 = 1 when the ray escapes
+// or, with a max_distance, when the next surface is further away.
+RL_HD void ao_begin(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, const HitRec &hit, uint32_t rng_n, uint32_t pixel, uint32_t sample, DirectCtx *cx) {
+    cx->ok = false;
+    cx->emit = Col{0.0f, 0.0f, 0.0f};
+    if (hit.prim == RL_MISS) return;
+    float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
+    uint32_t mesh = f2u(s0.w);
+    cx->mat = load_material(sv.mats, mesh);
+    cx->its = fill_intersection(sv, cx->mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
+    if (ip.ao_normal_correction == 0u && cx->its.wi.z <= 0.0f) return;
+    cx->ok = true;
+    cx->smp = make_sampler(ip.seed_h, pixel, sample, rng_n);
+}
+RL_HD bool ao_sample(const IntegParams &ip, DirectCtx *cx, V3 *dir) {
+    const bool flipped = ip.ao_normal_correction != 0u && cx->its.wi.z <= 0.0f;
+    float sx = cx->smp.next();
+    float sy = cx->smp.next();
+    V3 d_local = cosine_sample_hemisphere(sx, sy);
+    *dir = to_world(cx->its.frame, flipped ? -d_local : d_local);
+    return true;
+}
+RL_HD bool ao_finish(const IntegParams &ip, const HitRec &hit, Col *contrib) {
+    const bool open = hit.prim == RL_MISS || (ip.ao_max_distance >= 0.0f && hit.t > ip.ao_max_distance);
+    *contrib = Col{1.0f, 1.0f, 1.0f};
+    return open;
 }
 // One BSDF sample (direct.rs:135-144): the extension ray and what stage 2 needs (weight, pdf).
 RL_HD bool direct_bsdf_sample(DirectCtx *cx, V3 *dir, Col *weight, float *pdf) {

@@ -277,7 +277,7 @@ __device__ __forceinline__ uint32_t tile_sort_by_key(uint32_t key, unsigned shor
 #ifndef RL_SHADE_MINBLOCKS
 #define RL_SHADE_MINBLOCKS 4
 #endif
-template <bool SORT>
+template <bool SORT, uint32_t KM>
 __global__ void __launch_bounds__(kBlock, RL_SHADE_MINBLOCKS) k_shade(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
                                                   const uint32_t *__restrict__ count_in, const float4 *__restrict__ ray_o,
                                                   const float4 *__restrict__ ray_d, const float4 *__restrict__ state,
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(kBlock, RL_SHADE_MINBLOCKS) k_shade(SceneView 
             st.rng_n = packed & 0xffffu;
             uint32_t s_local = st.path_id / ip.npix, lp = st.path_id - s_local * ip.npix;
             uint32_t pixel = __ldg(pixel_list + lp);
-            path_step(sv, ip, xyz(ro), xyz(rd), h, st, pixel, ip.sample_base + s_local, &so);
+            path_step<KM>(sv, ip, xyz(ro), xyz(rd), h, st, pixel, ip.sample_base + s_local, &so);
             if (h.prim != RL_MISS) c_hits++;
             if (so.nee_sampled) c_nee++;
             if (so.has_add) {
@@ -377,7 +377,8 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct1(SceneView sv, IntegPar
             h.t = h4.x, h.u = h4.y, h.v = h4.z, h.prim = f2u(h4.w);
             pid = f2u(ro.w);
             uint32_t s_local = pid / ip.npix, lp = pid - s_local * ip.npix;
-            direct_begin(sv, ip, xyz(ro), xyz(rd), h, f2u(st4.w) & 0xffffu, __ldg(pixel_list + lp), ip.sample_base + s_local, &cx);
+            if (ip.kind == 2u) ao_begin(sv, ip, xyz(ro), xyz(rd), h, f2u(st4.w) & 0xffffu, __ldg(pixel_list + lp), ip.sample_base + s_local, &cx);
+            else direct_begin(sv, ip, xyz(ro), xyz(rd), h, f2u(st4.w) & 0xffffu, __ldg(pixel_list + lp), ip.sample_base + s_local, &cx);
             if (h.prim != RL_MISS) c_hits++;
             if (cx.ok && !is_zero(cx.emit)) lacc[pid] = make_float4(cx.emit.r, cx.emit.g, cx.emit.b, 0.0f);
         }
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct1(SceneView sv, IntegPar
             V3 dir = V3{0.0f, 0.0f, 0.0f};
             Col w = Col{0.0f, 0.0f, 0.0f};
             float pdf = 0.0f;
-            bool go = cx.ok && direct_bsdf_sample(&cx, &dir, &w, &pdf);
+            bool go = cx.ok && (ip.kind == 2u ? ao_sample(ip, &cx, &dir) : direct_bsdf_sample(&cx, &dir, &w, &pdf));
             uint32_t slot = block_compact(go, count_out, s_warp, &s_base);
             if (go) {
                 out_o[slot] = make_float4(cx.its.p.x, cx.its.p.y, cx.its.p.z, u2f(pid));
@@ -429,7 +430,8 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct2(SceneView sv, IntegPar
         h.t = h4.x, h.u = h4.y, h.v = h4.z, h.prim = f2u(h4.w);
         if (h.prim != RL_MISS) c_hits++;
         Col c;
-        if (direct_finish(sv, ip, xyz(ro), xyz(rd), h, Col{st4.x, st4.y, st4.z}, rd.w, &c)) lacc[f2u(st4.w)] = make_float4(c.r, c.g, c.b, 0.0f);
+        const bool add = ip.kind == 2u ? ao_finish(ip, h, &c) : direct_finish(sv, ip, xyz(ro), xyz(rd), h, Col{st4.x, st4.y, st4.z}, rd.w, &c);
+        if (add) lacc[f2u(st4.w)] = make_float4(c.r, c.g, c.b, 0.0f);
     }
     for (int off = 16; off > 0; off >>= 1) c_hits += __shfl_down_sync(0xffffffffu, c_hits, off);
     if ((threadIdx.x & 31u) == 0 && c_hits) atomicAdd(&counters->hits, (unsigned long long)c_hits);

@@ -203,6 +203,16 @@ class IntegratorPathTracing(_IntegratorBase):
         return _abi.path_desc(self.min_depth, self.max_depth, self.rr_depth, self.strategy, self.single_scattering)
 
 
+class IntegratorAO(_IntegratorBase):
+    """ao.rs:4-7 with the CLI defaults (cli.rs:150-155); max_distance=None is `-d inf`."""
+
+    def __init__(self, max_distance=1.0, normal_correction=False):
+        self.max_distance, self.normal_correction = max_distance, normal_correction
+
+    def desc(self):
+        return _abi.ao_desc(self.max_distance, self.normal_correction)
+
+
 class IntegratorDirect(_IntegratorBase):
     """direct.rs:5-8 with the CLI defaults (cli.rs:157-160)."""
 

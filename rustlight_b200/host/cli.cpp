@@ -1,12 +1,13 @@
 // cli.cpp -- `rustlight-b200`: the reference's command line (examples/cli.rs:106-275, wiring 277-924) for the
-// two integrators that run on the GPU.
+// integrators that run on the GPU.
 //
 //   rustlight-b200 [-n spp] [-a passes|inf|<secs>s] [-e secs] [-r independent[:seed]] [-s scale] -o out.pfm
 //                  [-t threads] [-m density] [-l logfile] [-x no-shading]... <scene.{pbrt,json}>
 //                  path   [-m max_depth|inf] [-n min_depth] [-r rr_depth|inf] [-x] [-s all|bsdf|emitter]
 //                | direct [-b nb_bsdf_samples] [-l nb_light_samples]
+//                | ao     [-d distance|inf] [-n]
 //
-// Differences from the reference, all forced by scope: only `path` and `direct`; `-m` must be 0
+// Differences from the reference, all forced by scope: only `path`, `direct` and `ao`; `-m` must be 0
 // (no medium); `-x ats|hvs-light|texture-light` are rejected; `-t` is accepted and ignored (the GPU replaces
 // the Rayon pool); output must be .pfm.  `-a N` averages N passes (the reference's argument is a time-out in
 // seconds or `inf`; both spellings are accepted: `-a 30s` / `-a inf` / `-a 8`).
@@ -26,7 +27,7 @@ static std::optional<uint32_t> match_infinity(const std::string &s) { // cli.rs:
 }
 [[noreturn]] static void usage(const char *msg) {
     std::fprintf(stderr, "error: %s\nusage: rustlight-b200 [-n N] [-a A] [-e SECS] [-r independent[:SEED]] [-s SCALE] -o OUT.pfm [-x no-shading] SCENE "
-                         "(path [-m MAX] [-n MIN] [-r RR] [-x] [-s all|bsdf|emitter] | direct [-b NB] [-l NL])\n", msg);
+                         "(path [-m MAX] [-n MIN] [-r RR] [-x] [-s all|bsdf|emitter] | direct [-b NB] [-l NL] | ao [-d DIST|inf] [-n])\n", msg);
     std::exit(2);
 }
 
@@ -45,7 +46,7 @@ int main(int argc, char **argv) {
     std::string command;
     for (; i < a.size(); i++) {
         const std::string &t = a[i];
-        if (t == "path" || t == "direct") {
+        if (t == "path" || t == "direct" || t == "ao") {
             command = t;
             i++;
             break;
@@ -66,7 +67,7 @@ int main(int argc, char **argv) {
         else if (!t.empty() && t[0] == '-') usage(("unknown option " + t).c_str());
         else scene_path = t;
     }
-    if (command.empty()) usage("missing subcommand (path | direct)");
+    if (command.empty()) usage("missing subcommand (path | direct | ao)");
     if (scene_path.empty()) usage("missing scene file");
     if (output.empty()) usage("missing -o output");
     if (std::stof(medium) != 0.0f) usage("participating media are outside the GPU path (-m must be 0)");
@@ -88,6 +89,18 @@ int main(int argc, char **argv) {
                 else if (s == "emitter") p->strategy = IntegratorPathTracingStrategies::Emitter;
                 else usage("invalid strategy: [all, bsdf, emitter]"); // cli.rs:536-541
             } else usage(("unknown path option " + t).c_str());
+        }
+        integ = std::move(p);
+    } else if (command == "ao") { // cli.rs:150-155, 856-865
+        auto p = std::make_unique<IntegratorAO>();
+        for (; i < a.size(); i++) {
+            const std::string &t = a[i];
+            if (t == "-d" || t == "--distance") {
+                std::string v = need("-d");
+                if (v == "inf") p->max_distance = std::nullopt;
+                else p->max_distance = std::stof(v);
+            } else if (t == "-n" || t == "--normal-correction") p->normal_correction = true;
+            else usage(("unknown ao option " + t).c_str());
         }
         integ = std::move(p);
     } else {

@@ -101,6 +101,22 @@ struct IntegratorDirect : Integrator {
     }
 };
 
+// ao.rs:4-72 (`ao -d <distance|inf> -n`, cli.rs:150-155)
+struct IntegratorAO : Integrator {
+    std::optional<float> max_distance = 1.0f;
+    bool normal_correction = false;
+    rl_stats last_stats{};
+    BufferCollection compute(IndependentSampler &sampler, Device &dev, Scene &scene) override {
+        rl_integrator_desc d{};
+        d.kind = RL_INTEGRATOR_AO;
+        d.min_depth = 0, d.max_depth = -1, d.rr_depth = 0;
+        d.nb_bsdf_samples = 1, d.nb_light_samples = 0;
+        d.ao_max_distance = max_distance ? *max_distance : -1.0f;
+        d.ao_normal_correction = normal_correction ? 1u : 0u;
+        return render_primal(dev, scene, d, sampler, &last_stats);
+    }
+};
+
 inline void bitmap_scale(Bitmap &b, float f) { // Bitmap::scale, structure.rs:423-425
     for (float &c : b.colors) c *= f;
 }

@@ -27,6 +27,7 @@ pub struct rl_mesh_desc {
 #[repr(C)] pub struct rl_integrator_desc {
     pub kind: u32, pub min_depth: i32, pub max_depth: i32, pub rr_depth: i32, pub strategy: u32,
     pub single_scattering: u32, pub nb_bsdf_samples: u32, pub nb_light_samples: u32,
+    pub ao_max_distance: f32, pub ao_normal_correction: u32,
 }
 #[repr(C)] pub struct rl_render_opts { pub struct_size: u32, pub spp: u32, pub seed: u64, pub sampler_mode: u32, pub batch_spp: u32, pub material_sort: u32, pub sample_offset: u32 }
 #[repr(C)] #[derive(Default)]
@@ -125,13 +126,23 @@ impl Integrator for IntegratorPathTracing {
         let strategy = match self.strategy { IntegratorPathTracingStrategies::All => 0, IntegratorPathTracingStrategies::BSDF => 1,
                                              IntegratorPathTracingStrategies::Emitter => 2 };
         render(scene, rl_integrator_desc { kind: 0, min_depth: opt(self.min_depth), max_depth: opt(self.max_depth), rr_depth: opt(self.rr_depth),
-            strategy, single_scattering: self.single_scattering as u32, nb_bsdf_samples: 1, nb_light_samples: 1 }, sampler.seed())
+            strategy, single_scattering: self.single_scattering as u32, nb_bsdf_samples: 1, nb_light_samples: 1,
+            ao_max_distance: -1.0, ao_normal_correction: 0 }, sampler.seed())
     }
 }
 #[cfg(feature = "b200")]
 impl Integrator for IntegratorDirect {
     fn compute(&mut self, sampler: &mut dyn Sampler, _accel: &dyn Acceleration, scene: &Scene) -> BufferCollection {
         render(scene, rl_integrator_desc { kind: 1, min_depth: 0, max_depth: -1, rr_depth: 0, strategy: 0, single_scattering: 0,
-            nb_bsdf_samples: self.nb_bsdf_samples as u32, nb_light_samples: self.nb_light_samples as u32 }, sampler.seed())
+            nb_bsdf_samples: self.nb_bsdf_samples as u32, nb_light_samples: self.nb_light_samples as u32,
+            ao_max_distance: -1.0, ao_normal_correction: 0 }, sampler.seed())
+    }
+}
+#[cfg(feature = "b200")]
+impl Integrator for crate::integrators::ao::IntegratorAO {
+    fn compute(&mut self, sampler: &mut dyn Sampler, _accel: &dyn Acceleration, scene: &Scene) -> BufferCollection {
+        render(scene, rl_integrator_desc { kind: 2, min_depth: 0, max_depth: -1, rr_depth: 0, strategy: 0, single_scattering: 0,
+            nb_bsdf_samples: 1, nb_light_samples: 0, ao_max_distance: self.max_distance.unwrap_or(-1.0),
+            ao_normal_correction: self.normal_correction as u32 }, sampler.seed())
     }
 }

@@ -258,6 +258,7 @@ int emu_render(const emu_scene *s, const rl_integrator_desc *I, uint32_t spp, ui
     ip.kind = I->kind, ip.min_depth = I->min_depth, ip.max_depth = I->max_depth, ip.rr_depth = I->rr_depth;
     ip.strategy = I->strategy, ip.single_scattering = I->single_scattering;
     ip.nb_bsdf_samples = I->nb_bsdf_samples, ip.nb_light_samples = I->nb_light_samples;
+    ip.ao_max_distance = I->ao_max_distance, ip.ao_normal_correction = I->ao_normal_correction;
     ip.seed_h = seed_hash(seed);
     ip.sample_base = 0, ip.npix = W * H, ip.img_w = W;
     emu_stats S{};
@@ -279,6 +280,27 @@ int emu_render(const emu_scene *s, const rl_integrator_desc *I, uint32_t spp, ui
                 st.T = Col{1.0f, 1.0f, 1.0f}, st.pdf_prev = 1.0f, st.path_id = 0, st.depth = 1, st.rng_n = smp.n;
                 float L[3] = {0.0f, 0.0f, 0.0f};
                 uint64_t iter = 0;
+                if (I->kind == RL_INTEGRATOR_AO) {
+                    // k_trace -> k_shade_direct1 (ao_begin / ao_sample) -> k_trace -> k_shade_direct2 (ao_finish)
+                    S.segments++;
+                    HitRec h = trace_closest(sv, sv.nodes, sv.trav, o, d);
+                    if (h.prim != RL_MISS) S.hits++;
+                    DirectCtx cx;
+                    ao_begin(sv, ip, o, d, h, st.rng_n, pixel, sidx, &cx);
+                    Col tot = Col{0.0f, 0.0f, 0.0f};
+                    V3 dir;
+                    if (cx.ok && ao_sample(ip, &cx, &dir)) {
+                        S.segments++;
+                        HitRec h2 = trace_closest(sv, sv.nodes, sv.trav, cx.its.p, dir);
+                        if (h2.prim != RL_MISS) S.hits++;
+                        Col c;
+                        if (ao_finish(ip, h2, &c)) tot = tot + c;
+                    }
+                    sum[0] += tot.r, sum[1] += tot.g, sum[2] += tot.b;
+                    S.max_depth_seen = std::max<uint64_t>(S.max_depth_seen, 2);
+                    S.samples++;
+                    continue;
+                }
                 if (I->kind == RL_INTEGRATOR_DIRECT) {
                     // k_trace -> k_shade_direct1 -> k_shadow -> k_trace -> k_shade_direct2; slots summed in order (k_accum)
                     std::vector<Col> slots(1 + ip.nb_light_samples + ip.nb_bsdf_samples, Col{0.0f, 0.0f, 0.0f});

@@ -24,6 +24,7 @@ def test_cli_argument_errors():
     assert run("-o", "x.pfm", "-m", "0.5", CBOX, "path").returncode == 2  # media are out of scope
     assert run("-o", "x.pfm", "-x", "ats", CBOX, "path").returncode == 2
     assert run("-o", "x.pfm", CBOX, "path", "-s", "nope").returncode == 2  # "invalid strategy", cli.rs:536-541
+    assert run("-o", "x.pfm", CBOX, "ao", "-q").returncode == 2
     r = run("-o", "x.pfm", "nothing.xml", "path")
     assert r.returncode == 1 and "scene loader" in r.stderr               # scene_loader.rs:40-43
 
@@ -45,6 +46,10 @@ def test_cli_matches_library(tmp_path, gpu_ctx):
     sc = load_cbox().scale_image(0.25)
     img, _ = DeviceScene(gpu_ctx, sc).render(_abi.path_desc(max_depth=6), 4, seed=5)
     assert np.array_equal(read_pfm(out), np.abs(img))
+    out3 = str(tmp_path / "ao.pfm")
+    assert run("-n", "2", "-s", "0.25", "-o", out3, CBOX, "ao", "-d", "0.5", "-n").returncode == 0
+    img, _ = DeviceScene(gpu_ctx, sc).render(_abi.ao_desc(0.5, True), 2, seed=0)
+    assert np.array_equal(read_pfm(out3), img)
     out2 = str(tmp_path / "d.pfm")
     assert run("-n", "2", "-s", "0.25", "-o", out2, os.path.join(DATA, "cbox.json"), "direct", "-b", "2", "-l", "1").returncode == 0
     img, _ = DeviceScene(gpu_ctx, sc).render(_abi.direct_desc(2, 1), 2, seed=0)

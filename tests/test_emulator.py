@@ -188,3 +188,15 @@ def test_prefilter_is_conservative_on_adversarial_scenes(seed):
     assert np.array_equal(pe, po) and np.array_equal(te, to)
     assert (po != 0xFFFFFFFF).mean() > 0.2  # the rays do hit things
     assert np.array_equal(esc.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))
+
+
+@pytest.mark.parametrize("dist,nc", [(1.0, False), (None, False), (0.3, True)])
+def test_ao_render_bit_exact(dist, nc):
+    """IntegratorAO (ao.rs): values are 0 or 1 per sample, so the images agree exactly iff every hit/miss and every
+    distance comparison does."""
+    sc = load_cbox(64, 64)
+    integ = _abi.ao_desc(dist, nc)
+    ie, se = eb.EmuScene(sc).render(integ, 8, seed=3)
+    io, so = ob.OracleScene(sc).render(integ, 8, seed=3, cfg=ob.config(**STREAM))
+    assert se.segments == so.segments and np.array_equal(ie, io)
+    assert 0.05 < io.mean() < 0.95 and set(np.unique(io * 8).tolist()) <= set(range(9))

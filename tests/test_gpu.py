@@ -379,6 +379,16 @@ def test_mixed_material_scene_bit_exact(gpu_ctx, sort):
     dev.close()
 
 
+@pytest.mark.parametrize("dist,nc", [(1.0, False), (None, True), (0.25, False)])
+def test_ao_bit_exact(gpu_ctx, cbox, dist, nc):
+    dev, osc = DeviceScene(gpu_ctx, cbox), ob.OracleScene(cbox)
+    integ = _abi.ao_desc(dist, nc)
+    img, st = dev.render(integ, 4, seed=6)
+    ref, so = osc.render(integ, 4, seed=6, cfg=ob.config(**STREAM))
+    assert st.segments == so.segments and np.array_equal(img, ref)
+    dev.close()
+
+
 def test_config_shapes_c3_c5(gpu_ctx):
     """BASELINE configs[2] (Phong walls, 512x512) and configs[4] (1920x1080, Fov::Y quirk, ragged 16x16 tiles,
     material sort on): sub-sampled spp, bit-exact against the oracle on the same stream."""
