@@ -127,6 +127,31 @@ static int grid_for(const rl_ctx *ctx, size_t n, int per_sm) {
     return (int)blocks;
 }
 
+// Grid sizes (measured on B200, cbox 1024^2 x 32 spp, per-stage CUDA events; tools/ab_env.py RL_GRID_PER_SM):
+//   traversal kernels: grid-stride over the queue with kTravPerSm CTAs per SM.  Rays differ in cost, so MORE CTAs than
+//   are resident (5 per SM for k_trace_flat) balance better through the hardware block scheduler: 4/SM 5.01 ms,
+//   resident (5) 4.93, 8 4.77, 16 4.68, 32 4.60, 64 4.56 ms -- 32 keeps the per-CTA scene staging (5 KB) negligible.
+//   k_shade: one wave of resident CTAs (4 per SM at 64 registers); 6/SM 5.52 ms vs 4.81 ms.
+static constexpr int kTravPerSm = 32;
+template <typename K>
+static int resident_per_sm(K kernel, size_t smem) {
+    static std::vector<std::pair<size_t, int>> cache; // one static per kernel type
+    for (auto &c : cache)
+        if (c.first == smem) return c.second;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kBlock, smem) != cudaSuccess || nb < 1) nb = 1;
+    cache.push_back({smem, nb});
+    return nb;
+}
+static int trav_per_sm() {
+    static int v = 0;
+    if (!v) {
+        v = kTravPerSm;
+        if (const char *e = getenv("RL_GRID_PER_SM")) v = std::max(1, atoi(e)); // A/B hook
+    }
+    return v;
+}
+
 // The definitions below take C linkage from their declarations in rl_b200.h.
 
 int rl_abi_version(void) { return RL_B200_ABI_VERSION; }
@@ -570,12 +595,12 @@ static void launch_trace(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_
     const bool tree = coherent && sc->coherent_tree >= 1;
     if (!tree && sc->flat_ok) {
         sv.n_groups = sc->flat.n_groups;
-        k_trace_flat<<<grid_for(ctx, n, 8), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_trav_f4);
+        k_trace_flat<<<grid_for(ctx, n, trav_per_sm()), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_trav_f4);
         ctx->launches++;
         return;
     }
     sv.root_ref = tree ? sc->root_tree : sc->root_flat;
-    k_trace<SMEM><<<grid_for(ctx, n, 8), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_node_f4, sc->n_trav_f4);
+    k_trace<SMEM><<<grid_for(ctx, n, trav_per_sm()), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_node_f4, sc->n_trav_f4);
     ctx->launches++;
 }
 template <bool SMEM>
@@ -584,13 +609,13 @@ static void launch_shadow(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size
     const bool tree = coherent && sc->coherent_tree >= 2;
     if (!tree && sc->flat_ok) {
         sv.n_groups = sc->flat.n_groups;
-        k_shadow_flat<<<grid_for(ctx, n, 8), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc, ctx->d_counters,
+        k_shadow_flat<<<grid_for(ctx, n, trav_per_sm()), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc, ctx->d_counters,
                                                                                           sc->n_trav_f4);
         ctx->launches++;
         return;
     }
     sv.root_ref = tree ? sc->root_tree : sc->root_flat;
-    k_shadow<SMEM><<<grid_for(ctx, n, 8), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc,
+    k_shadow<SMEM><<<grid_for(ctx, n, trav_per_sm()), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc,
                                                                                              ctx->d_counters, sc->n_node_f4, sc->n_trav_f4);
     ctx->launches++;
 }
@@ -721,7 +746,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                         else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
                         if (prof) CK(cudaEventRecord(ctx->ev[3], st));
 #define RL_LAUNCH_SHADE(SORT, KM)                                                                                                                   \
-    k_shade<SORT, KM><<<grid_for(ctx, n_ub, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], \
+    k_shade<SORT, KM><<<grid_for(ctx, n_ub, resident_per_sm(k_shade<SORT, KM>, 0)), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], \
                                                                  ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1], ctx->state[cur ^ 1], qc + k + 1,     \
                                                                  ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc, ctx->d_counters)
                         // kernel specialised for the BSDF kinds of the scene: {diffuse}, {diffuse, phong}, everything
