@@ -128,7 +128,8 @@ static int grid_for(const rl_ctx *ctx, size_t n, int per_sm) {
 }
 
 // Grid sizes (measured on B200, cbox 1024^2 x 32 spp, per-stage CUDA events; tools/ab_env.py RL_GRID_PER_SM):
-//   traversal kernels: grid-stride over the queue with kTravPerSm CTAs per SM.  Rays differ in cost, so MORE CTAs than
+//   group-table traversal kernels: grid-stride over the queue with kTravPerSm CTAs per SM (the tree kernels, which
+//   stage up to 96 KB per CTA, stay at 8).  Rays differ in cost, so MORE CTAs than
 //   are resident (5 per SM for k_trace_flat) balance better through the hardware block scheduler: 4/SM 5.01 ms,
 //   resident (5) 4.93, 8 4.77, 16 4.68, 32 4.60, 64 4.56 ms -- 32 keeps the per-CTA scene staging (5 KB) negligible.
 //   k_shade: one wave of resident CTAs (4 per SM at 64 registers); 6/SM 5.52 ms vs 4.81 ms.
@@ -600,7 +601,7 @@ static void launch_trace(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_
         return;
     }
     sv.root_ref = tree ? sc->root_tree : sc->root_flat;
-    k_trace<SMEM><<<grid_for(ctx, n, trav_per_sm()), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_node_f4, sc->n_trav_f4);
+    k_trace<SMEM><<<grid_for(ctx, n, 8), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_node_f4, sc->n_trav_f4);
     ctx->launches++;
 }
 template <bool SMEM>
@@ -615,7 +616,7 @@ static void launch_shadow(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size
         return;
     }
     sv.root_ref = tree ? sc->root_tree : sc->root_flat;
-    k_shadow<SMEM><<<grid_for(ctx, n, trav_per_sm()), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc,
+    k_shadow<SMEM><<<grid_for(ctx, n, 8), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc,
                                                                                              ctx->d_counters, sc->n_node_f4, sc->n_trav_f4);
     ctx->launches++;
 }
