@@ -279,13 +279,13 @@ def main():
         if os.path.exists(tp):
             tj = json.load(open(tp))
             traffic, traffic_src = tj.get("k_trace_dram_bytes_per_launch"), tj.get("source")
-        roof = {"kernel": "k_trace (closest-hit LBVH traversal)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roof = {"kernel": "k_trace_flat (closest hit: group-table scan + exact triangle tests)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_unit": TRACE_BYTES_PER_SEGMENT, "units": "path segments", "units_per_step": int(st.segments),
                 "launches_per_step": launches_trace, "avg_launch_ms": st.ms_trace / launches_trace,
                 "share_of_step": st.ms_trace / st.ms_total if st.ms_total else None,
                 "algorithmic_bytes_per_launch": bytes_total / launches_trace,
-                "note": "BVH+triangles (7 KB) are shared-memory resident: the kernel is instruction-issue bound, not HBM bound (SURVEY.md F9; profiles/)"}
+                "note": "group table + triangle records (5 KB) are shared-memory resident: the kernel is instruction-issue bound, not HBM bound (SURVEY.md F9; profiles/)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -55,7 +55,7 @@ with open(os.path.join(out, f"{tag}_ncu_full_summary.md"), "w") as f:
         txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rr = list(csv.reader(txt.splitlines()))
         h, u = rr[0], rr[1]
-        f.write(f"## k_{k}\n\n| metric | unit | launch 1 | launch 2 | launch 3 |\n|---|---|---:|---:|---:|\n")
+        f.write(f"## k_{k}{'' if k == 'shade' else '_flat'}\n\n| metric | unit | launch 1 | launch 2 | launch 3 |\n|---|---|---:|---:|---:|\n")
         for w in want:
             if w in h:
                 i = h.index(w)
