@@ -96,6 +96,18 @@ typedef struct rl_camera_desc {
     float to_world[16];
 } rl_camera_desc;
 
+/* ---- non-mesh emitters: what PBRTSceneLoader turns `LightSource "point" / "distant"` into (scene_loader.rs:207-240) -- */
+typedef enum rl_light_kind {
+    RL_LIGHT_POINT = 0,      /* PointEmitter      src/emitter.rs:186-250: intensity, position       */
+    RL_LIGHT_DIRECTIONAL = 1 /* DirectionalLight  src/emitter.rs:96-190:  intensity, direction (light -> world, unit);
+                                its bounding sphere comes from Scene::build_emitters (scene.rs:54-60), radius x 1.1 */
+} rl_light_kind;
+typedef struct rl_light_desc {
+    uint32_t kind;
+    float intensity[3];
+    float v[3]; /* position (point) or direction (directional) */
+} rl_light_desc;
+
 /* ---- scene: src/scene.rs:16-30 ------------------------------------------------------------ */
 typedef struct rl_scene_desc {
     uint32_t nmeshes;
@@ -103,6 +115,8 @@ typedef struct rl_scene_desc {
     rl_camera_desc camera;
     uint32_t has_volume;      /* must be 0: scene.volume == None on this path                 */
     uint32_t has_environment; /* must be 0: emitter_environment == None on this path          */
+    uint32_t nlights;         /* Scene.emitters (EmittersState::Unbuild): sampled after the mesh lights, in this order */
+    const rl_light_desc *lights;
 } rl_scene_desc;
 
 /* ---- integrators --------------------------------------------------------------------------- */

@@ -886,8 +886,9 @@ inline Ray spawn_ray(const Intersection &its, V3 d_out) { return Ray{its.p, d_ou
 // ============================================================================================
 // emitter.rs: impl Emitter for Mesh :570-688, EmitterSampler :1491-1647
 // ============================================================================================
+struct Emitter;
 struct LightSampling { // :10-24
-    const Mesh *emitter;
+    const Emitter *emitter;
     PDF pdf;
     V3 p, n, d;
     size_t primitive_id;
@@ -897,36 +898,89 @@ struct LightSampling { // :10-24
 struct LightSamplingPDF { // :26-44
     V3 o, p, n, dir;
 };
-PDF mesh_direct_pdf(const Mesh &m, const LightSamplingPDF &ls) { // :571-579
-    float cos_light = rmax(dot(ls.n, -ls.dir), 0.0f);
-    if (cos_light == 0.0f) return PDF{PDF::SolidAngle, 0.0f};
-    float geom = cos_light / magnitude2(ls.p - ls.o);
-    return PDF{PDF::SolidAngle, m.pdf() / geom};
-}
-LightSampling mesh_direct_sample(const Mesh &m, V3 p, float r, P2 uv) { // :652-688
-    SampledPosition sp = m.sample(r, uv);
-    V3 d = sp.p - p;
-    float dist = magnitude(d);
-    if (dist != 0.0f) d = d / dist;
-    float geom = dist != 0.0f ? rmax(dot(sp.n, -d), 0.0f) / (dist * dist) : 0.0f;
-    float pdf_area = sp.pdf.value();
-    PDF pdf = sp.pdf.as_solid_angle_geom(geom);
-    Color weight = pdf.is_zero() ? Color::zero() : m.emit() * geom / pdf_area;
-    return LightSampling{&m, pdf, sp.p, sp.n, d, sp.primitive_id, weight};
-}
-struct EmitterSampler { // :1491-1495 (ats == None on this path)
-    std::vector<const Mesh *> emitters;
-    Distribution1D emitters_cdf;
-    float pdf(const Mesh *e) const { // :1510-1526 (pointer identity)
-        for (size_t i = 0; i < emitters.size(); i++)
-            if (emitters[i] == e) return emitters_cdf.pdf(i);
-        return 0.0f; // the reference panics here; unreachable (only light meshes are queried)
+struct BoundingSphere { // structure.rs:880-884
+    V3 center;
+    float radius;
+};
+struct Emitter { // trait Emitter, emitter.rs:46-94 (the methods this path calls)
+    virtual ~Emitter() = default;
+    virtual PDF direct_pdf(const LightSamplingPDF &ls) const = 0;
+    virtual LightSampling direct_sample(V3 p, float r, P2 uv) const = 0;
+    virtual Color flux() const = 0;
+    virtual Color eval() const = 0; // eval(d, uv) with constant emission
+};
+struct MeshEmitter : Emitter { // impl Emitter for Mesh, emitter.rs:570-688
+    const Mesh *m;
+    explicit MeshEmitter(const Mesh *mesh) : m(mesh) {}
+    PDF direct_pdf(const LightSamplingPDF &ls) const override { // :571-579
+        float cos_light = rmax(dot(ls.n, -ls.dir), 0.0f);
+        if (cos_light == 0.0f) return PDF{PDF::SolidAngle, 0.0f};
+        float geom = cos_light / magnitude2(ls.p - ls.o);
+        return PDF{PDF::SolidAngle, m->pdf() / geom};
     }
-    PDF direct_pdf(const Mesh *e, const LightSamplingPDF &ls) const { return mesh_direct_pdf(*e, ls) * pdf(e); } // :1566-1575
+    LightSampling direct_sample(V3 p, float r, P2 uv) const override { // :652-688
+        SampledPosition sp = m->sample(r, uv);
+        V3 d = sp.p - p;
+        float dist = magnitude(d);
+        if (dist != 0.0f) d = d / dist;
+        float geom = dist != 0.0f ? rmax(dot(sp.n, -d), 0.0f) / (dist * dist) : 0.0f;
+        float pdf_area = sp.pdf.value();
+        PDF pdf = sp.pdf.as_solid_angle_geom(geom);
+        Color weight = pdf.is_zero() ? Color::zero() : m->emit() * geom / pdf_area;
+        return LightSampling{this, pdf, sp.p, sp.n, d, sp.primitive_id, weight};
+    }
+    Color flux() const override { return m->flux(); }
+    Color eval() const override { return m->emit(); }
+};
+struct PointEmitter : Emitter { // emitter.rs:186-250
+    Color intensity;
+    V3 position;
+    PDF direct_pdf(const LightSamplingPDF &) const override { return PDF{PDF::Discrete, 1.0f}; }
+    LightSampling direct_sample(V3 v, float, P2) const override { // :197-215
+        V3 p = position;
+        V3 d = p - v;
+        float dist = magnitude(d);
+        d = d / dist;
+        return LightSampling{this, PDF{PDF::Discrete, 1.0f}, p, V3{0.0f, 0.0f, 0.0f}, d, 0, intensity / powi(dist, 2)};
+    }
+    Color flux() const override { return intensity * 4.0f * PI; } // :239-241
+    Color eval() const override { return intensity; }
+};
+struct DirectionalLight : Emitter { // emitter.rs:96-190
+    V3 direction; // from the light to the world
+    Color intensity;
+    BoundingSphere bsphere{}; // preprocess(): scene.bsphere with radius * 1.1 (:106-109)
+    PDF direct_pdf(const LightSamplingPDF &) const override { return PDF{PDF::Discrete, 1.0f}; }
+    LightSampling direct_sample(V3 v, float, P2) const override { // :115-133
+        V3 p = v - bsphere.radius * direction;
+        return LightSampling{this, PDF{PDF::Discrete, 1.0f}, p, direction, -direction, 0, intensity};
+    }
+    Color flux() const override { // :164-168
+        float area = PI * powi(bsphere.radius, 2);
+        return area * intensity;
+    }
+    Color eval() const override { return intensity; }
+};
+struct EmitterSampler { // :1491-1495 (ats == None on this path)
+    std::vector<std::unique_ptr<Emitter>> emitters;
+    std::vector<const Mesh *> emitter_mesh; // the mesh behind emitters[i], or null
+    Distribution1D emitters_cdf;
+    const Emitter *of_mesh(const Mesh *m) const {
+        for (size_t i = 0; i < emitters.size(); i++)
+            if (emitter_mesh[i] == m) return emitters[i].get();
+        return nullptr;
+    }
+    float pdf(const Emitter *e) const { // :1510-1526 (pointer identity)
+        for (size_t i = 0; i < emitters.size(); i++)
+            if (emitters[i].get() == e) return emitters_cdf.pdf(i);
+        return 0.0f; // the reference panics here; unreachable (only listed emitters are queried)
+    }
+    PDF direct_pdf(const Emitter *e, const LightSamplingPDF &ls) const { return e->direct_pdf(ls) * pdf(e); } // :1566-1575
+    PDF direct_pdf(const Mesh *m, const LightSamplingPDF &ls) const { return direct_pdf(of_mesh(m), ls); }
     LightSampling sample_light(V3 p, float r_sel, float r, P2 uv) const { // :1604-1620, :1641-1647
         size_t id_light = emitters_cdf.sample_discrete(r_sel);
         float pdf_sel = emitters_cdf.pdf(id_light);
-        LightSampling res = mesh_direct_sample(*emitters[id_light], p, r, uv);
+        LightSampling res = emitters[id_light]->direct_sample(p, r, uv);
         div_assign(res.weight, pdf_sel);
         res.pdf = res.pdf * pdf_sel;
         return res;
@@ -1116,13 +1170,47 @@ struct Scene {
     std::vector<TriRef> primitives;
     std::vector<BVHNode> nodes;
 
-    void build_emitters() { // scene.rs:53-123 (mesh emitters only; no env map, no ATS)
+    std::vector<rl_light_desc> lights; // Scene.emitters: EmittersState::Unbuild (point / directional), in file order
+    BoundingSphere bsphere{};
+    void build_emitters() { // scene.rs:53-123 (no env map, no ATS)
+        // bounding sphere: union of Mesh::compute_aabb (all vertices, geometry.rs:441-456) and the camera position
+        AABB aabb;
+        for (auto &m : meshes) {
+            AABB a;
+            for (auto &v : m->vertices) a = a.union_vec(v);
+            V3 sz = a.size();
+            if (sz.x < EPSILON) a.p_max.x += EPSILON, a.p_min.x -= EPSILON;
+            if (sz.y < EPSILON) a.p_max.y += EPSILON, a.p_min.y -= EPSILON;
+            if (sz.z < EPSILON) a.p_max.z += EPSILON, a.p_min.z -= EPSILON;
+            aabb = aabb.union_aabb(a);
+        }
+        aabb = aabb.union_vec(camera.position());
+        V3 c = aabb.center();
+        bsphere = BoundingSphere{c, magnitude(c - aabb.p_max)}; // AABB::to_sphere, structure.rs:871-877
         emitters.emitters.clear();
+        emitters.emitter_mesh.clear();
         for (auto &m : meshes)
-            if (m->is_light()) emitters.emitters.push_back(m.get());
+            if (m->is_light()) {
+                emitters.emitters.push_back(std::make_unique<MeshEmitter>(m.get()));
+                emitters.emitter_mesh.push_back(m.get());
+            }
+        for (auto &l : lights) { // e.preprocess(self); emitters.push(e)  (scene.rs:85-96)
+            if (l.kind == RL_LIGHT_POINT) {
+                auto e = std::make_unique<PointEmitter>();
+                e->intensity = Color{l.intensity[0], l.intensity[1], l.intensity[2]}, e->position = V3{l.v[0], l.v[1], l.v[2]};
+                emitters.emitters.push_back(std::move(e));
+            } else {
+                auto e = std::make_unique<DirectionalLight>();
+                e->intensity = Color{l.intensity[0], l.intensity[1], l.intensity[2]}, e->direction = V3{l.v[0], l.v[1], l.v[2]};
+                e->bsphere = bsphere;
+                e->bsphere.radius *= 1.1f;
+                emitters.emitters.push_back(std::move(e));
+            }
+            emitters.emitter_mesh.push_back(nullptr);
+        }
         if (emitters.emitters.empty()) return;
         std::vector<float> fl;
-        for (auto e : emitters.emitters) fl.push_back(e->flux().channel_max());
+        for (auto &e : emitters.emitters) fl.push_back(e->flux().channel_max());
         emitters.emitters_cdf = Distribution1D::normalize(fl);
     }
 
@@ -1301,7 +1389,7 @@ struct Vertex {
     Intersection its{};
     // Light
     V3 n{};
-    const Mesh *emitter = nullptr;
+    const Emitter *emitter = nullptr;
     // edges
     int edge_in = -1;
     std::vector<int> edge_out; // Sensor/Light hold at most one
@@ -1338,7 +1426,7 @@ Color vertex_contribution(const Vertex &v, const Edge &edge) {
         if (dot(v.its.n_s, -edge.d) >= 0.0f) return v.its.mesh->emit();
         return Color::zero();
     }
-    if (v.kind == Vertex::Light) return v.emitter->emit(); // emitter.eval(-edge.d, uv), emitter.rs:605-607
+    if (v.kind == Vertex::Light) return v.emitter->eval(); // emitter.eval(-edge.d, uv), emitter.rs:605-607
     return Color::zero();
 }
 // Edge::contribution, edge.rs:201-210 (environment luminance is zero on this path)
@@ -1702,7 +1790,7 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
                 Color contrib = T * (rec.weight * f);
                 if (!contrib.is_zero()) {
                     float w = 1.0f;
-                    if (I.strategy == RL_STRATEGY_ALL) {
+                    if (I.strategy == RL_STRATEGY_ALL && rec.pdf.kind == PDF::SolidAngle) { // a Discrete light edge has no MIS (path.rs:80)
                         float pb = bsdf.pdf(cx.math, its.wi, wo).value();
                         float pl = rec.pdf.value();
                         w = pl / (pb + pl);
@@ -1746,7 +1834,8 @@ Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy
         V3 d_out_local = its.frame.to_local(rec.d);
         if (rec.is_valid() && sc.visible(its.p, rec.p, cx.accel_mode, *cx.counters) && !bsdf.is_smooth()) {
             float pdf_bsdf = bsdf.pdf(cx.math, its.wi, d_out_local).value();
-            float weight_light = mis_weight(rec.pdf.value() * weight_nb_light, pdf_bsdf * weight_nb_bsdf);
+            float weight_light = rec.pdf.kind == PDF::Discrete ? 1.0f // (PDF::Discrete(_), _) => 1.0, direct.rs:110
+                                                               : mis_weight(rec.pdf.value() * weight_nb_light, pdf_bsdf * weight_nb_bsdf);
             l_i = l_i + weight_light * bsdf.eval(cx.math, its.wi, d_out_local) * weight_nb_light * rec.weight;
         }
     }
@@ -1846,6 +1935,10 @@ orc_scene *orc_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         first += md.ntris;
         m->build_cdf();
         s.meshes.push_back(std::move(m));
+    }
+    for (uint32_t li = 0; li < desc->nlights; li++) {
+        if (desc->lights[li].kind > RL_LIGHT_DIRECTIONAL) return fail("unknown light kind");
+        s.lights.push_back(desc->lights[li]);
     }
     s.build_emitters();
     s.build_bvh();
@@ -2082,8 +2175,8 @@ int orc_sample_light(const orc_scene *os, const float x[3], float r_sel, float r
     weight[0] = rec.weight.r, weight[1] = rec.weight.g, weight[2] = rec.weight.b;
     *pdf = rec.pdf.value();
     for (size_t i = 0; i < sc.meshes.size(); i++)
-        if (sc.meshes[i].get() == rec.emitter) return (int)i;
-    return -1;
+        if (sc.emitters.of_mesh(sc.meshes[i].get()) == rec.emitter) return (int)i;
+    return -2 - (rec.pdf.kind == PDF::Discrete ? 1 : 0); // a non-mesh emitter (-3: PDF::Discrete)
 }
 float orc_direct_pdf(const orc_scene *os, uint32_t mesh, const float o[3], const float p[3], const float n[3], const float dir[3]) {
     const Scene &sc = os->scene;

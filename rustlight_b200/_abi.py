@@ -45,6 +45,14 @@ class rl_mesh_desc(C.Structure):
                 ("mat", rl_material), ("emission_kind", C.c_uint32), ("emission", C.c_float * 3)]
 
 
+RL_LIGHT_POINT = 0
+RL_LIGHT_DIRECTIONAL = 1
+
+
+class rl_light_desc(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("intensity", C.c_float * 3), ("v", C.c_float * 3)]
+
+
 class rl_camera_desc(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32),
                 ("sample_to_camera", C.c_float * 16), ("to_world", C.c_float * 16)]
@@ -52,7 +60,8 @@ class rl_camera_desc(C.Structure):
 
 class rl_scene_desc(C.Structure):
     _fields_ = [("nmeshes", C.c_uint32), ("meshes", C.POINTER(rl_mesh_desc)),
-                ("camera", rl_camera_desc), ("has_volume", C.c_uint32), ("has_environment", C.c_uint32)]
+                ("camera", rl_camera_desc), ("has_volume", C.c_uint32), ("has_environment", C.c_uint32),
+                ("nlights", C.c_uint32), ("lights", C.POINTER(rl_light_desc))]
 
 
 class rl_integrator_desc(C.Structure):

@@ -291,7 +291,8 @@ RL_HD V3 cosine_sample_hemisphere(float ux, float uy) {
 //   verts[3*p+0..2]  (original order p): {v.xyz, -}
 //   mats[5*m+0..4]   {kd.rgb | metal eta | glass kt, kind} {ks.rgb, phong exponent | microfacet alpha} {Le.rgb, is_light}
 //                    {phong weight_specular | glass eta, 1/area, pdf_sel, microfacet} {metal k.rgb, glass 1/eta}
-//   emit_info[e]     {mesh, first_prim, ntris, cdf_offset} (as uint bits)
+//   emit_info[2e..]  mesh light {mesh, first_prim, ntris, cdf_offset} {-};  point / directional light
+//                    {0xfffffff0 | rl_light_kind, intensity.rgb} {position | direction, bounding-sphere radius}
 struct SceneView {
     const float4 *trav;
     const float4 *nodes;
@@ -1255,6 +1256,7 @@ struct LightSample {
     Col weight;
     float pdf;
     bool valid;
+    bool discrete; // PDF::Discrete: point and directional lights (no MIS against BSDF sampling)
 };
 // EmitterSampler::sample_light -> Mesh::direct_sample -> Mesh::sample -> sample_tri
 // (emitter.rs:1604-1620, 652-688; geometry.rs:340-348, 261-337; math.rs:388-394)
@@ -1262,7 +1264,32 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, 
     // one emitter: the cdf is {0, 1} and r_sel < 1, so the search returns 0
     uint32_t id_light = sv.n_emitters == 1u ? 0u : cdf_sample_discrete(sv.emit_cdf, sv.n_emitters + 1, r_sel);
     float pdf_sel = sv.emit_cdf[id_light + 1] - sv.emit_cdf[id_light];
-    float4 info = sv.emit_info[id_light];
+    float4 info = sv.emit_info[2 * id_light];
+    if (f2u(info.x) >= 0xfffffff0u) { // PointEmitter / DirectionalLight::direct_sample (emitter.rs:197-215, 115-133)
+        float4 geo = sv.emit_info[2 * id_light + 1];
+        Col intensity = Col{info.y, info.z, info.w};
+        LightSample ls;
+        Col weight;
+        if ((f2u(info.x) & 0xfu) == 0u) {
+            ls.p = xyz(geo);
+            V3 dd = ls.p - x;
+            float dist = magnitude(dd);
+            ls.d = dd / dist;
+            ls.n = V3{0.0f, 0.0f, 0.0f};
+            weight = div_checked(intensity, dist * dist); // intensity / dist.powi(2)
+        } else {
+            V3 dir = xyz(geo);
+            ls.p = x - geo.w * dir; // v - bsphere.radius * direction
+            ls.n = dir;
+            ls.d = -dir;
+            weight = intensity;
+        }
+        ls.weight = Col{weight.r / pdf_sel, weight.g / pdf_sel, weight.b / pdf_sel}; // res.weight /= pdf_sel (no guard)
+        ls.pdf = 1.0f * pdf_sel;                                                      // PDF::Discrete(1.0) * pdf_sel
+        ls.valid = ls.pdf != 0.0f;
+        ls.discrete = true;
+        return ls;
+    }
     uint32_t mesh = f2u(info.x), first_prim = f2u(info.y), ntris = f2u(info.z), cdf_off = f2u(info.w);
     Material mat = load_material(sv.mats, mesh);
     uint32_t tri = cdf_sample_discrete(sv.area_cdf + cdf_off, ntris + 1, r);
@@ -1289,6 +1316,7 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, 
     ls.p = pos;
     ls.n = n_g;
     ls.d = dd;
+    ls.discrete = false;
     const float cosl = dist != 0.0f ? fmaxf(dot(n_g, -dd), 0.0f) : 0.0f;
     const float d2 = dist * dist;
     if ((dist == 0.0f || (cosl == 0.0f && d2 > 0.0f)) && pdf_sel > 0.0f) {
@@ -1461,7 +1489,7 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
             Col contrib = st.T * (ls.weight * f);
             if (!is_zero(contrib)) {
                 float w = 1.0f;
-                if (ip.strategy == 0u) {
+                if (ip.strategy == 0u && !ls.discrete) { // a PDF::Discrete light edge has no MIS (path.rs:80)
                     float pb = bsdf_pdf<KM>(mat, its.wi, wo);
                     w = ls.pdf / (pb + ls.pdf);
                 }
@@ -1518,7 +1546,7 @@ RL_HD bool direct_light_sample(const SceneView &sv, DirectCtx *cx, V3 *p1, Col *
     if (mat_is_smooth(cx->mat)) return false; // direct.rs:74-77: visible() is still called (valid stays true), nothing is added
     V3 wo = to_local(cx->its.frame, ls.d);
     float pdf_bsdf = bsdf_pdf(cx->mat, cx->its.wi, wo);
-    float weight_light = mis_weight_power(ls.pdf * cx->wl, pdf_bsdf * cx->wb);
+    float weight_light = ls.discrete ? 1.0f : mis_weight_power(ls.pdf * cx->wl, pdf_bsdf * cx->wb); // direct.rs:106-110
     Col c = mul_checked(mul_plain(weight_light, bsdf_eval(cx->mat, cx->its.wi, wo)), cx->wl) * ls.weight;
     *p1 = ls.p;
     *contrib = c;

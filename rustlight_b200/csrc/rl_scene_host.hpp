@@ -86,8 +86,10 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
         hs.root_max[a] = hs.raw_max[a] = -RL_F32_MAX;
     }
     struct EmitterTmp {
-        uint32_t mesh, first_prim, ntris, cdf_off;
+        uint32_t mesh, first_prim, ntris, cdf_off; // mesh lights
         float flux_max;
+        uint32_t light_kind = 0xffffffffu; // rl_light_kind for non-mesh emitters
+        float intensity[3] = {0, 0, 0}, v[3] = {0, 0, 0}, radius = 0.0f;
     };
     std::vector<EmitterTmp> emitters;
     std::vector<float> mesh_inv_area(desc->nmeshes, 0.0f);
@@ -159,18 +161,70 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
         first += m.ntris;
     }
     hs.ntris = first;
+    // Non-mesh emitters follow the mesh lights (scene.rs:85-96).  Scene.bsphere (scene.rs:54-60): union of
+    // Mesh::compute_aabb over ALL vertices of every mesh (geometry.rs:441-456) and the camera position, to_sphere
+    // (structure.rs:871-877); DirectionalLight::preprocess enlarges the radius by 1.1 (emitter.rs:106-109).
+    if (desc->nlights > 0) {
+        if (!desc->lights) {
+            err = "nlights > 0 but lights is null";
+            return false;
+        }
+        float bmin[3] = {RL_F32_MAX, RL_F32_MAX, RL_F32_MAX}, bmax[3] = {-RL_F32_MAX, -RL_F32_MAX, -RL_F32_MAX};
+        for (uint32_t mi = 0; mi < desc->nmeshes; mi++) {
+            const rl_mesh_desc &m = desc->meshes[mi];
+            float lo[3] = {RL_F32_MAX, RL_F32_MAX, RL_F32_MAX}, hi[3] = {-RL_F32_MAX, -RL_F32_MAX, -RL_F32_MAX};
+            for (uint32_t k = 0; k < m.nverts; k++)
+                for (int a = 0; a < 3; a++) lo[a] = fminf(lo[a], m.P[3 * k + a]), hi[a] = fmaxf(hi[a], m.P[3 * k + a]);
+            for (int a = 0; a < 3; a++) {
+                if (hi[a] - lo[a] < RL_EPSILON) hi[a] += RL_EPSILON, lo[a] -= RL_EPSILON;
+                bmin[a] = fminf(bmin[a], lo[a]), bmax[a] = fmaxf(bmax[a], hi[a]);
+            }
+        }
+        for (int a = 0; a < 3; a++) bmin[a] = fminf(bmin[a], hs.cam_pos[a]), bmax[a] = fmaxf(bmax[a], hs.cam_pos[a]);
+        V3 size = V3{bmax[0] - bmin[0], bmax[1] - bmin[1], bmax[2] - bmin[2]};
+        V3 c = size * 0.5f + V3{bmin[0], bmin[1], bmin[2]}; // AABB::center, structure.rs:844-846
+        float radius = magnitude(c - V3{bmax[0], bmax[1], bmax[2]});
+        for (uint32_t li = 0; li < desc->nlights; li++) {
+            const rl_light_desc &l = desc->lights[li];
+            EmitterTmp e{};
+            e.light_kind = l.kind;
+            for (int a = 0; a < 3; a++) e.intensity[a] = l.intensity[a], e.v[a] = l.v[a];
+            Col I = Col{l.intensity[0], l.intensity[1], l.intensity[2]};
+            if (l.kind == RL_LIGHT_POINT) {
+                e.flux_max = channel_max(mul_checked(mul_checked(I, 4.0f), RL_PI)); // emitter.rs:239-241
+            } else if (l.kind == RL_LIGHT_DIRECTIONAL) {
+                e.radius = radius * 1.1f;
+                float area = RL_PI * (e.radius * e.radius);
+                e.flux_max = channel_max(mul_plain(area, I)); // emitter.rs:164-168
+            } else {
+                err = "unknown light kind";
+                return false;
+            }
+            emitters.push_back(e);
+        }
+    }
     hs.n_emitters = (uint32_t)emitters.size();
     std::vector<float> pdf_sel(desc->nmeshes, 0.0f);
     if (!emitters.empty()) {
         std::vector<float> fl;
         for (auto &e : emitters) fl.push_back(e.flux_max);
         dist1d_normalize(fl, hs.emit_cdf);
+        // two float4 per emitter.  Mesh light: {mesh, first_prim, ntris, cdf_offset} {-}.
+        // Point / directional: {0xfffffff0 | rl_light_kind, intensity.rgb} {position | direction, bounding-sphere radius}
         for (size_t i = 0; i < emitters.size(); i++) {
-            pdf_sel[emitters[i].mesh] = hs.emit_cdf[i + 1] - hs.emit_cdf[i];
-            hs.emit_info.push_back(f4(u2f(emitters[i].mesh), u2f(emitters[i].first_prim), u2f(emitters[i].ntris), u2f(emitters[i].cdf_off)));
+            const EmitterTmp &e = emitters[i];
+            if (e.light_kind == 0xffffffffu) {
+                pdf_sel[e.mesh] = hs.emit_cdf[i + 1] - hs.emit_cdf[i];
+                hs.emit_info.push_back(f4(u2f(e.mesh), u2f(e.first_prim), u2f(e.ntris), u2f(e.cdf_off)));
+                hs.emit_info.push_back(f4(0, 0, 0, 0));
+            } else {
+                hs.emit_info.push_back(f4(u2f(0xfffffff0u | e.light_kind), e.intensity[0], e.intensity[1], e.intensity[2]));
+                hs.emit_info.push_back(f4(e.v[0], e.v[1], e.v[2], e.radius));
+            }
         }
     } else {
         hs.emit_cdf = {0.0f, 1.0f};
+        hs.emit_info.push_back(f4(0, 0, 0, 0));
         hs.emit_info.push_back(f4(0, 0, 0, 0));
         hs.area_cdf = {0.0f, 1.0f};
     }

@@ -41,6 +41,7 @@ def lib():
         L.rlh_material_substrate.argtypes = [f3, f3, C.c_uint32, C.c_float, C.POINTER(_abi.rl_material)]
         L.rlh_remap_roughness.restype = C.c_float
         L.rlh_remap_roughness.argtypes = [C.c_float, C.c_int]
+        L.rlh_scene_add_light.argtypes = [C.c_void_p, C.c_uint32, C.c_float * 3, C.c_float * 3]
         L.rlh_scene_set_material.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_abi.rl_material)]
         L.rlh_material_phong.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
                                          C.POINTER(_abi.rl_material)]
@@ -104,6 +105,18 @@ class Scene:
     def set_material(self, mesh, material):
         if lib().rlh_scene_set_material(self._h, int(mesh), C.byref(material)) != 0:
             raise SceneError("bad mesh index")
+        return self
+
+    def add_point_light(self, intensity, position):
+        """PointEmitter (emitter.rs:186-250), appended to Scene.emitters."""
+        if lib().rlh_scene_add_light(self._h, _abi.RL_LIGHT_POINT, (C.c_float * 3)(*intensity), (C.c_float * 3)(*position)) != 0:
+            raise SceneError("bad light")
+        return self
+
+    def add_directional_light(self, intensity, direction):
+        """DirectionalLight (emitter.rs:96-190); `direction` points from the light into the scene and is normalised."""
+        if lib().rlh_scene_add_light(self._h, _abi.RL_LIGHT_DIRECTIONAL, (C.c_float * 3)(*intensity), (C.c_float * 3)(*direction)) != 0:
+            raise SceneError("bad light")
         return self
 
     def mesh_is_light(self, mesh):

@@ -89,6 +89,19 @@ int rlh_material_phong(const float kd[3], const float ks[3], float exponent, rl_
     }
 }
 
+// Scene.emitters: kind is an rl_light_kind; v = position (point) or direction (directional, normalised here)
+int rlh_scene_add_light(rlh_scene *s, uint32_t kind, const float intensity[3], const float v[3]) {
+    try {
+        Color I{intensity[0], intensity[1], intensity[2]};
+        if (kind == RL_LIGHT_POINT) s->scene.add_point_light(I, v[0], v[1], v[2]);
+        else if (kind == RL_LIGHT_DIRECTIONAL) s->scene.add_directional_light(I, v[0], v[1], v[2]);
+        else return -1;
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+
 // Material::metal / glass / substrate (bsdfs/metal.rs, glass.rs, substrate.rs); microfacet is an rl_microfacet
 int rlh_material_metal(const float specular[3], const float eta[3], const float k[3], uint32_t microfacet, float alpha, rl_material *out) {
     try {

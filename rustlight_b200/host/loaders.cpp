@@ -369,7 +369,25 @@ Scene PBRTSceneLoader::load_string(const std::string &text, bool use_shading_nor
                 mesh->emission = gs.area_light;
             }
             if (!mesh->indices.empty()) scene.meshes.push_back(mesh); // geometry.rs:165-167
-        } else if (d == "LightSource" || d == "Texture" || d == "MakeNamedMedium" || d == "MediumInterface" ||
+        } else if (d == "LightSource") { // scene_loader.rs:207-240 (pbrt_rs::Light::{Point, Distant}); positions in world space
+            std::string type = ps.expect_str();
+            ParamSet p = ps.params();
+            Color scale = p.rgb("scale", Color{1.0f, 1.0f, 1.0f});
+            auto pt = [&](const char *name, float dx, float dy, float dz) {
+                auto q = p.find(name);
+                Vec3 v = (q && q->nums.size() >= 3) ? Vec3{(float)q->nums[0], (float)q->nums[1], (float)q->nums[2]} : Vec3{dx, dy, dz};
+                return gs.ctm.transform_point(v);
+            };
+            if (type == "point") {
+                Color I = p.rgb("I", Color{1.0f, 1.0f, 1.0f});
+                Vec3 from = pt("from", 0, 0, 0);
+                scene.add_point_light(Color{I.r * scale.r, I.g * scale.g, I.b * scale.b}, from.x, from.y, from.z);
+            } else if (type == "distant") {
+                Color L = p.rgb("L", Color{1.0f, 1.0f, 1.0f});
+                Vec3 from = pt("from", 0, 0, 0), to = pt("to", 0, 0, 1);
+                scene.add_directional_light(Color{L.r * scale.r, L.g * scale.g, L.b * scale.b}, to.x - from.x, to.y - from.y, to.z - from.z);
+            } else throw Error("pbrt: LightSource \"" + type + "\" is outside the hot-path scope (point, distant)");
+        } else if (d == "Texture" || d == "MakeNamedMedium" || d == "MediumInterface" ||
                    d == "ObjectBegin" || d == "ObjectEnd" || d == "ObjectInstance" || d == "Include") {
             throw Error("pbrt: directive " + d + " is outside the hot-path scope");
         } else {
@@ -550,6 +568,21 @@ Scene JSONSceneLoader::load_string(const std::string &text, bool use_shading_nor
         if (ms->t != JVal::Obj) throw Error("json: materials must be an object");
         for (auto &kv : ms->o) materials[kv.first] = jmaterial(kv.second);
     }
+    if (const JVal *ls = root.get("lights")) { // [{"type": "point", "intensity": [r,g,b], "position": [x,y,z]}, {"type": "directional", "intensity", "direction"}]
+        if (ls->t != JVal::Arr) throw Error("json: lights must be an array");
+        for (auto &l : ls->a) {
+            const JVal *ty = l.get("type");
+            std::string type = (ty && ty->t == JVal::Str) ? ty->s : "";
+            Color I = jcolor(l.get("intensity"), "intensity", Color{1.0f, 1.0f, 1.0f});
+            if (type == "point") {
+                auto p = jfloats(l.get("position"), "position", 3);
+                scene.add_point_light(I, p[0], p[1], p[2]);
+            } else if (type == "directional") {
+                auto d = jfloats(l.get("direction"), "direction", 3);
+                scene.add_directional_light(I, d[0], d[1], d[2]);
+            } else throw Error("json: unknown light type \"" + type + "\"");
+        }
+    }
     const JVal *meshes = root.get("meshes");
     if (!meshes || meshes->t != JVal::Arr) throw Error("json: missing meshes array");
     for (auto &jm : meshes->a) {
@@ -614,7 +647,20 @@ std::string scene_to_json(const Scene &scene) {
     o << buf << ", \"fov_axis\": \"" << (c.fov_axis == Fov::X ? "x" : "y") << "\", \"flip\": "
       << (c.flip ? "true" : "false") << ",\n             \"to_world\": ";
     put_floats(o, c.to_world.m, 16);
-    o << "},\n  \"meshes\": [\n";
+    o << "},\n";
+    if (!scene.lights.empty()) {
+        o << "  \"lights\": [";
+        for (size_t i = 0; i < scene.lights.size(); i++) {
+            const rl_light_desc &l = scene.lights[i];
+            o << (i ? ", " : "") << "{\"type\": \"" << (l.kind == RL_LIGHT_POINT ? "point" : "directional") << "\", \"intensity\": ";
+            put_floats(o, l.intensity, 3);
+            o << ", \"" << (l.kind == RL_LIGHT_POINT ? "position" : "direction") << "\": ";
+            put_floats(o, l.v, 3);
+            o << "}";
+        }
+        o << "],\n";
+    }
+    o << "  \"meshes\": [\n";
     for (size_t i = 0; i < scene.meshes.size(); i++) {
         const Mesh &m = *scene.meshes[i];
         const rl_material &mt = m.bsdf.m;

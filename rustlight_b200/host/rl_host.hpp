@@ -104,6 +104,10 @@ struct Scene {
     std::optional<size_t> nb_threads;
     std::string output_img_path = "out.pfm";
     bool has_volume = false, has_environment = false;
+    // Scene.emitters before build_emitters (EmittersState::Unbuild): PointEmitter / DirectionalLight (scene_loader.rs:207-240)
+    std::vector<rl_light_desc> lights;
+    void add_point_light(Color intensity, float x, float y, float z);
+    void add_directional_light(Color intensity, float dx, float dy, float dz); // direction = normalize(to - from)
 
     // Flatten to the C-ABI description.  The returned struct points into `this` and into
     // the scratch vector kept alive inside the Scene.

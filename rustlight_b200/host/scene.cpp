@@ -248,6 +248,23 @@ size_t Scene::nb_triangles() const {
     for (auto &m : meshes) n += m->indices.size() / 3;
     return n;
 }
+void Scene::add_point_light(Color intensity, float x, float y, float z) {
+    rl_light_desc l{};
+    l.kind = RL_LIGHT_POINT;
+    l.intensity[0] = intensity.r, l.intensity[1] = intensity.g, l.intensity[2] = intensity.b;
+    l.v[0] = x, l.v[1] = y, l.v[2] = z;
+    lights.push_back(l);
+}
+void Scene::add_directional_light(Color intensity, float dx, float dy, float dz) {
+    float len = std::sqrt(dx * dx + dy * dy + dz * dz);
+    if (!(len > 0.0f)) throw Error("directional light: zero direction");
+    float inv = 1.0f / len; // cgmath normalize: v * (1 / |v|)
+    rl_light_desc l{};
+    l.kind = RL_LIGHT_DIRECTIONAL;
+    l.intensity[0] = intensity.r, l.intensity[1] = intensity.g, l.intensity[2] = intensity.b;
+    l.v[0] = dx * inv, l.v[1] = dy * inv, l.v[2] = dz * inv;
+    lights.push_back(l);
+}
 const rl_scene_desc *Scene::desc() {
     mesh_descs_.clear();
     for (auto &mp : meshes) {
@@ -272,6 +289,8 @@ const rl_scene_desc *Scene::desc() {
     std::memcpy(desc_.camera.to_world, camera.to_world.m, sizeof(float) * 16);
     desc_.has_volume = has_volume ? 1u : 0u;
     desc_.has_environment = has_environment ? 1u : 0u;
+    desc_.nlights = (uint32_t)lights.size();
+    desc_.lights = lights.empty() ? nullptr : lights.data();
     return &desc_;
 }
 

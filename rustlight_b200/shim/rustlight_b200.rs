@@ -23,7 +23,11 @@ pub struct rl_mesh_desc {
     pub n: *const f32, pub uv: *const f32, pub mat: rl_material, pub emission_kind: u32, pub emission: [f32; 3],
 }
 #[repr(C)] pub struct rl_camera_desc { pub width: u32, pub height: u32, pub sample_to_camera: [f32; 16], pub to_world: [f32; 16] }
-#[repr(C)] pub struct rl_scene_desc { pub nmeshes: u32, pub meshes: *const rl_mesh_desc, pub camera: rl_camera_desc, pub has_volume: u32, pub has_environment: u32 }
+#[repr(C)] pub struct rl_light_desc { pub kind: u32, pub intensity: [f32; 3], pub v: [f32; 3] }
+#[repr(C)] pub struct rl_scene_desc {
+    pub nmeshes: u32, pub meshes: *const rl_mesh_desc, pub camera: rl_camera_desc, pub has_volume: u32, pub has_environment: u32,
+    pub nlights: u32, pub lights: *const rl_light_desc,
+}
 #[repr(C)] pub struct rl_integrator_desc {
     pub kind: u32, pub min_depth: i32, pub max_depth: i32, pub rr_depth: i32, pub strategy: u32,
     pub single_scattering: u32, pub nb_bsdf_samples: u32, pub nb_light_samples: u32,
@@ -60,10 +64,10 @@ use cgmath::{Matrix, Point2};
 fn opt(v: Option<u32>) -> i32 { v.map_or(-1, |x| x as i32) }
 
 /// Scene -> flat description.  Vectors are kept alive in `Flat` for the duration of the call.
-struct Flat { p: Vec<Vec<f32>>, n: Vec<Vec<f32>>, idx: Vec<Vec<u32>>, meshes: Vec<rl_mesh_desc> }
+struct Flat { p: Vec<Vec<f32>>, n: Vec<Vec<f32>>, idx: Vec<Vec<u32>>, meshes: Vec<rl_mesh_desc>, lights: Vec<rl_light_desc> }
 fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
     assert!(scene.volume.is_none(), "scene.volume must be None on the GPU path");
-    let mut f = Flat { p: vec![], n: vec![], idx: vec![], meshes: vec![] };
+    let mut f = Flat { p: vec![], n: vec![], idx: vec![], meshes: vec![], lights: vec![] };
     for m in &scene.meshes {
         f.p.push(m.vertices.iter().flat_map(|v| [v.x, v.y, v.z]).collect());
         f.n.push(m.normals.as_ref().map_or(vec![], |ns| ns.iter().flat_map(|v| [v.x, v.y, v.z]).collect()));
@@ -90,7 +94,10 @@ fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
     c2w.copy_from_slice(AsRef::<[f32; 16]>::as_ref(cam.to_world()));
     let desc = rl_scene_desc { nmeshes: f.meshes.len() as u32, meshes: f.meshes.as_ptr(),
         camera: rl_camera_desc { width: cam.size().x, height: cam.size().y, sample_to_camera: s2c, to_world: c2w },
-        has_volume: 0, has_environment: scene.emitter_environment.is_some() as u32 };
+        has_volume: 0, has_environment: scene.emitter_environment.is_some() as u32,
+        // PointEmitter / DirectionalLight of EmittersState::Unbuild need a `describe() -> Option<rl_light_desc>` on the Emitter
+        // trait; `f.lights` keeps them alive like the mesh vectors
+        nlights: f.lights.len() as u32, lights: f.lights.as_ptr() };
     (f, desc)
 }
 

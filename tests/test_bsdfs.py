@@ -219,3 +219,78 @@ def test_strategies_agree_statistically_on_glossy_scene():
             for s in (_abi.RL_STRATEGY_ALL, _abi.RL_STRATEGY_BSDF, _abi.RL_STRATEGY_EMITTER)]
     m = [float(i.mean()) for i in imgs]
     assert m[1] == pytest.approx(m[0], rel=0.06) and m[2] == pytest.approx(m[0], rel=0.06)
+
+
+# ---- non-mesh emitters (PointEmitter, DirectionalLight: emitter.rs:96-250) ------------------------------------
+def lit_cbox(w=48, h=48, keep_area_light=True):
+    sc = load_cbox(w, h)
+    sc.add_point_light((0.6, 0.5, 0.4), (0.3, 1.2, 0.4))
+    sc.add_directional_light((0.8, 0.8, 1.0), (0.3, -1.0, -0.2))
+    return sc
+
+
+def test_point_and_directional_light_sampling():
+    """sample_light over [area light, point, directional]: selection by flux (scene.rs:103-111), PDF::Discrete(1) * pdf_sel,
+    point weight I / d^2 / pdf_sel, directional p = x - 1.1 R dir with R from Scene.bsphere (meshes + camera)."""
+    sc = lit_cbox()
+    osc = ob.OracleScene(sc)
+    x = np.float32([0.1, 0.5, 0.2])
+    seen = set()
+    for r_sel in np.linspace(0.001, 0.999, 40):
+        rec = osc.sample_light(x, float(r_sel), 0.3, 0.4, 0.6)
+        e, p, n, d, w, pdf = rec["mesh"], rec["p"], rec["n"], rec["d"], rec["weight"], rec["pdf"]
+        seen.add(e)
+        if e == -3 and not n.any():  # point light
+            dist2 = float(((np.float32([0.3, 1.2, 0.4]) - x) ** 2).sum())
+            assert np.allclose(p, [0.3, 1.2, 0.4]) and np.allclose(w * pdf, np.float32([0.6, 0.5, 0.4]) / dist2, rtol=1e-5)
+        elif e == -3:  # directional
+            dn = np.float32([0.3, -1.0, -0.2]) / np.linalg.norm([0.3, -1.0, -0.2])
+            assert np.allclose(n, dn, atol=1e-6) and np.allclose(d, -dn, atol=1e-6) and np.allclose(w * pdf, [0.8, 0.8, 1.0], rtol=1e-5)
+            # bounding sphere of the box [-1,1]x[0,2]x[-1,1] united with the camera at z = 6.8: centre (0,1,2.9), R = |(1,1,3.9)|
+            R = 1.1 * math.sqrt(1 + 1 + 3.9 ** 2)
+            assert np.linalg.norm(p - x) == pytest.approx(R, rel=1e-4)
+    assert -3 in seen and any(e >= 0 for e in seen)
+
+
+@pytest.mark.parametrize("integ", [_abi.path_desc(), _abi.path_desc(strategy=_abi.RL_STRATEGY_EMITTER, max_depth=3), _abi.direct_desc(1, 2)])
+def test_delta_lights_render_bit_exact(integ):
+    sc = lit_cbox()
+    ie, se = eb.EmuScene(sc).render(integ, 6, seed=7)
+    io, so = ob.OracleScene(sc).render(integ, 6, seed=7, cfg=ob.config(**STREAM))
+    assert (se.segments, se.hits, se.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+    assert np.array_equal(ie, io) and io.mean() > 0.05
+    if integ.kind == _abi.RL_INTEGRATOR_PATH:
+        ig, sg = ob.OracleScene(sc).render(integ, 6, seed=7, cfg=ob.config(estimator=ob.EST_GRAPH, accel_mode=ob.ACCEL_NAIVE))
+        assert rel_l2(io, ig) < 1e-6 and sg.segments == so.segments
+
+
+def test_point_light_only_scene_matches_inverse_square_law():
+    """No emissive mesh: a diffuse floor under one point light, `direct -b 0 -l 1`: radiance = kd/pi * I cos / d^2, a
+    closed form per pixel (the light is a delta; only the pixel jitter moves the hit point)."""
+    import json
+    from rustlight_b200 import SceneLoaderManager
+    kd, I, hgt = 0.6, 3.0, 1.5
+    txt = json.dumps({"camera": {"width": 16, "height": 16, "fov": 30, "to_world": [1, 0, 0, 0, 0, 0, -1, 0, 0, -1, 0, 0, 0, 4, 0, 1]},
+                      "lights": [{"type": "point", "intensity": [I, I, I], "position": [0.0, hgt, 0.0]}],
+                      "meshes": [{"material": {"type": "diffuse", "kd": [kd] * 3}, "indices": [0, 1, 2, 0, 2, 3],
+                                  "P": [-5, 0, -5, -5, 0, 5, 5, 0, 5, 5, 0, -5]},
+                                 # a far-away sliver that lifts the root box above the light: BVHAccel::visible answers "occluded"
+                                 # for any segment that leaves the root box within tnear (accel.rs:338-340), which a flat scene
+                                 # would hit for the near-vertical shadow rays under the light
+                                 {"material": {"type": "diffuse", "kd": [0.5] * 3}, "indices": [0, 1, 2], "P": [40, 5, 40, 41, 5, 40, 40, 5, 41]}]})
+    sc = SceneLoaderManager().load_string(txt, "json")
+    assert sc.desc.contents.nlights == 1
+    osc = ob.OracleScene(sc)
+    img, st = osc.render(_abi.direct_desc(0, 1), 64, seed=1, cfg=ob.config(**STREAM))
+    pg, tg = osc.primary_hits(ob.ACCEL_NAIVE)
+    assert (pg != 0xFFFFFFFF).all()
+    # hit points of the pixel centres: camera at (0,4,0) looking down
+    o = np.float32([0, 4, 0])
+    ys, xs = np.mgrid[0:16, 0:16]
+    rays = np.array([osc.camera_generate(float(x) + 0.5, float(y) + 0.5)[1] for y, x in zip(ys.ravel(), xs.ravel())])
+    hit = o + rays * tg.reshape(-1, 3)[:, :1]
+    d2 = (hit[:, 0] ** 2 + hgt ** 2 + hit[:, 2] ** 2)
+    want = kd / math.pi * I * (hgt / np.sqrt(d2)) / d2
+    assert np.allclose(img[..., 0].ravel(), want, rtol=0.03)
+    ie, _ = eb.EmuScene(sc).render(_abi.direct_desc(0, 1), 64, seed=1)
+    assert np.array_equal(ie, img)

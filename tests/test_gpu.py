@@ -389,6 +389,21 @@ def test_ao_bit_exact(gpu_ctx, cbox, dist, nc):
     dev.close()
 
 
+def test_point_and_directional_lights_bit_exact(gpu_ctx):
+    """PointEmitter / DirectionalLight next to the area light: flux-weighted selection over three emitters, PDF::Discrete
+    light edges (no MIS), shadow segments that end outside the scene (directional)."""
+    sc = load_cbox(96, 96)
+    sc.add_point_light((0.6, 0.5, 0.4), (0.3, 1.2, 0.4))
+    sc.add_directional_light((0.8, 0.8, 1.0), (0.3, -1.0, -0.2))
+    dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
+    for integ in (_abi.path_desc(), _abi.path_desc(strategy=_abi.RL_STRATEGY_EMITTER, max_depth=3), _abi.direct_desc(1, 2)):
+        img, st = dev.render(integ, 6, seed=7)
+        ref, so = osc.render(integ, 6, seed=7, cfg=ob.config(**STREAM))
+        assert (st.segments, st.hits, st.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+        assert np.array_equal(img, ref)
+    dev.close()
+
+
 def test_config_shapes_c3_c5(gpu_ctx):
     """BASELINE configs[2] (Phong walls, 512x512) and configs[4] (1920x1080, Fov::Y quirk, ragged 16x16 tiles,
     material sort on): sub-sampled spp, bit-exact against the oracle on the same stream."""

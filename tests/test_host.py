@@ -93,6 +93,28 @@ def test_pbrt_material_mapping():
     assert list(mats[5].kd) == [0.5] * 3 and list(mats[5].ks) == [0.5] * 3 and mats[5].alpha == pytest.approx(remap_roughness(0.1))
 
 
+def test_pbrt_light_sources():
+    """LightSource "point" / "distant" -> PointEmitter / DirectionalLight (scene_loader.rs:207-240): intensity * scale,
+    direction = normalize(to - from), positions through the current transform; "infinite" stays outside the path."""
+    tri = 'Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]'
+    txt = f'''Camera "perspective" WorldBegin
+      LightSource "point" "rgb I" [1 2 3] "rgb scale" [2 2 2] "point from" [0 1 0]
+      AttributeBegin Translate 0 0 5 LightSource "point" "point from" [1 0 0] AttributeEnd
+      LightSource "distant" "rgb L" [4 4 4] "point from" [0 10 0] "point to" [0 0 10]
+      {tri} WorldEnd'''
+    sc = SceneLoaderManager().load_string(txt, "pbrt")
+    d = sc.desc.contents
+    assert d.nlights == 3
+    assert (d.lights[0].kind, list(d.lights[0].intensity), list(d.lights[0].v)) == (_abi.RL_LIGHT_POINT, [2, 4, 6], [0, 1, 0])
+    assert list(d.lights[1].v) == [1, 0, 5] and list(d.lights[1].intensity) == [1, 1, 1]
+    assert d.lights[2].kind == _abi.RL_LIGHT_DIRECTIONAL and list(d.lights[2].v) == pytest.approx([0, -2 ** -0.5, 2 ** -0.5])
+    back = SceneLoaderManager().load_string(sc.to_json(), "json").desc.contents
+    assert back.nlights == 3 and all(bytes(back.lights[i]) == bytes(d.lights[i]) for i in range(2))
+    assert list(back.lights[2].v) == pytest.approx(list(d.lights[2].v), abs=1e-7)  # re-normalised on load
+    with pytest.raises(SceneError, match="scope"):
+        SceneLoaderManager().load_string('Camera "perspective" WorldBegin LightSource "infinite" WorldEnd', "pbrt")
+
+
 def test_json_materials_round_trip():
     import json
     from rustlight_b200.host import material_glass, material_metal, material_mirror, material_substrate
