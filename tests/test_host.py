@@ -79,7 +79,8 @@ def test_pbrt_material_mapping():
       Material "substrate" "rgb Kd" [0.3 0.2 0.1] "rgb Ks" [0.04 0.04 0.04] "float uroughness" [0.02] "float vroughness" [0.02] {tri}
       Material "substrate" {tri}
     WorldEnd'''
-    d = SceneLoaderManager().load_string(txt, "pbrt").desc.contents
+    sc = SceneLoaderManager().load_string(txt, "pbrt")
+    d = sc.desc.contents
     mats = [d.meshes[i].mat for i in range(6)]
     assert [m.kind for m in mats] == [_abi.RL_BSDF_METAL, _abi.RL_BSDF_METAL, _abi.RL_BSDF_METAL, _abi.RL_BSDF_GLASS, _abi.RL_BSDF_SUBSTRATE, _abi.RL_BSDF_SUBSTRATE]
     assert mats[0].microfacet == _abi.RL_MICROFACET_NONE and list(mats[0].ks) == pytest.approx([0.8, 0.7, 0.6]) and list(mats[0].eta) == [1, 1, 1] and list(mats[0].k) == [0, 0, 0]
@@ -108,7 +109,8 @@ def test_pbrt_light_sources():
     assert (d.lights[0].kind, list(d.lights[0].intensity), list(d.lights[0].v)) == (_abi.RL_LIGHT_POINT, [2, 4, 6], [0, 1, 0])
     assert list(d.lights[1].v) == [1, 0, 5] and list(d.lights[1].intensity) == [1, 1, 1]
     assert d.lights[2].kind == _abi.RL_LIGHT_DIRECTIONAL and list(d.lights[2].v) == pytest.approx([0, -2 ** -0.5, 2 ** -0.5])
-    back = SceneLoaderManager().load_string(sc.to_json(), "json").desc.contents
+    back_scene = SceneLoaderManager().load_string(sc.to_json(), "json")  # keep the owner alive: desc points into it
+    back = back_scene.desc.contents
     assert back.nlights == 3 and all(bytes(back.lights[i]) == bytes(d.lights[i]) for i in range(2))
     assert list(back.lights[2].v) == pytest.approx(list(d.lights[2].v), abs=1e-7)  # re-normalised on load
     with pytest.raises(SceneError, match="scope"):
@@ -124,7 +126,8 @@ def test_json_materials_round_trip():
             material_substrate(microfacet=None)]
     for i, m in enumerate(mats):
         sc.set_material(i, m)
-    back = SceneLoaderManager().load_string(sc.to_json(), "json").desc.contents
+    back_scene = SceneLoaderManager().load_string(sc.to_json(), "json")  # keep the owner alive: desc points into it
+    back = back_scene.desc.contents
     for i, m in enumerate(mats):
         got = back.meshes[i].mat
         assert bytes(got) == bytes(m), i
