@@ -2,8 +2,9 @@
 //
 // PBRTSceneLoader mirrors src/scene_loader.rs:77-315 for the pbrt-v3 subset the path's scenes
 // use: Transform/ConcatTransform/LookAt/Translate/Scale/Rotate/Identity, Film, Camera
-// "perspective", MakeNamedMaterial/NamedMaterial/Material "matte", Shape "trianglemesh",
-// AreaLightSource "diffuse", AttributeBegin/End, TransformBegin/End, ReverseOrientation.
+// "perspective", MakeNamedMaterial/NamedMaterial/Material "matte" | "mirror" | "metal" | "glass" | "substrate",
+// Shape "trianglemesh" | "plymesh", ObjectBegin/ObjectEnd/ObjectInstance, AreaLightSource "diffuse",
+// LightSource "point" | "distant", AttributeBegin/End, TransformBegin/End, ReverseOrientation.
 // The pbrt_rs crate that does the parsing for the reference is not vendored,
 // so the grammar follows the pbrt-v3 file format itself.
 // One labelled extension: material type "phong" (Kd, Ks, exponent) -> BSDFPhong, which the
@@ -15,7 +16,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
+#include <map>
 #include <sstream>
 
 #include "rl_host.hpp"
@@ -195,6 +198,173 @@ Mat4 mat_from_16(const std::vector<double> &v) {
     return m;
 }
 
+// pbrt_rs::ShapeInfo after to_trimesh(): object-space data + the CTM, orientation, material and emission at definition
+struct RawShape {
+    std::vector<float> P, N, uv;
+    std::vector<uint32_t> idx;
+    Mat4 matrix = Mat4::identity();
+    bool reverse_orientation = false;
+    Material bsdf;
+    bool is_light = false;
+    Color emission;
+};
+// PBRTSceneLoader::transform_mesh, scene_loader.rs:80-157: mat = matrix * m.matrix; points by transform_point, normals by
+// transform_vector (negated first under ReverseOrientation); Mesh::new renormalises the normals (geometry.rs:143-162)
+void emit_mesh(Scene &scene, const RawShape &rs, const Mat4 &matrix, bool use_shading_normal) {
+    Mat4 mat = matrix * rs.matrix;
+    auto mesh = std::make_shared<Mesh>();
+    mesh->name = "noname"; // scene_loader.rs:137
+    size_t nv = rs.P.size() / 3;
+    for (size_t i = 0; i < nv; i++) {
+        Vec3 q = mat.transform_point(Vec3{rs.P[3 * i], rs.P[3 * i + 1], rs.P[3 * i + 2]});
+        mesh->vertices.insert(mesh->vertices.end(), {q.x, q.y, q.z});
+    }
+    mesh->indices = rs.idx;
+    if (use_shading_normal && !rs.N.empty()) {
+        size_t nb_wrong = 0;
+        for (size_t i = 0; i < nv; i++) {
+            Vec3 n{rs.N[3 * i], rs.N[3 * i + 1], rs.N[3 * i + 2]};
+            if (rs.reverse_orientation) n = Vec3{-n.x, -n.y, -n.z};
+            n = mat.transform_vector(n);
+            float l = n.x * n.x + n.y * n.y + n.z * n.z;
+            if (l == 0.0f) nb_wrong++;
+            else if (l != 1.0f) {
+                float s = std::sqrt(l);
+                n = Vec3{n.x / s, n.y / s, n.z / s};
+            }
+            mesh->normals.insert(mesh->normals.end(), {n.x, n.y, n.z});
+        }
+        if (nb_wrong == nv) mesh->normals.clear(); // geometry.rs:159-162
+    }
+    mesh->uv = rs.uv;
+    mesh->bsdf = rs.bsdf;
+    if (rs.is_light) {
+        mesh->is_light = true;
+        mesh->emission = rs.emission;
+    }
+    if (!mesh->indices.empty()) scene.meshes.push_back(mesh); // geometry.rs:165-167
+}
+
+// Minimal PLY reader (ascii 1.0 / binary_little_endian 1.0): vertex x y z [nx ny nz] [u v | s t], faces as index lists,
+// polygons fanned into triangles.  Stands in for pbrt_rs::ply::read_ply(..).to_trimesh() (crate not vendored: unpinned).
+void read_ply(const std::string &filename, RawShape &out) {
+    std::ifstream f(filename, std::ios::binary);
+    if (!f) throw Error("ply: cannot open " + filename);
+    std::string line;
+    if (!std::getline(f, line) || line.substr(0, 3) != "ply") throw Error("ply: bad magic in " + filename);
+    struct Prop {
+        std::string name, type, count_type, item_type;
+        bool list = false;
+    };
+    struct Elem {
+        std::string name;
+        size_t count = 0;
+        std::vector<Prop> props;
+    };
+    std::vector<Elem> elems;
+    bool binary = false;
+    while (std::getline(f, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        std::istringstream ls(line);
+        std::string w;
+        ls >> w;
+        if (w == "format") {
+            std::string fmt;
+            ls >> fmt;
+            if (fmt == "binary_little_endian") binary = true;
+            else if (fmt != "ascii") throw Error("ply: unsupported format " + fmt);
+        } else if (w == "element") {
+            Elem e;
+            ls >> e.name >> e.count;
+            elems.push_back(e);
+        } else if (w == "property") {
+            if (elems.empty()) throw Error("ply: property before element");
+            Prop p;
+            ls >> p.type;
+            if (p.type == "list") {
+                p.list = true;
+                ls >> p.count_type >> p.item_type >> p.name;
+            } else ls >> p.name;
+            elems.back().props.push_back(p);
+        } else if (w == "end_header") break;
+    }
+    auto size_of = [](const std::string &t) -> size_t {
+        if (t == "char" || t == "uchar" || t == "int8" || t == "uint8") return 1;
+        if (t == "short" || t == "ushort" || t == "int16" || t == "uint16") return 2;
+        if (t == "int" || t == "uint" || t == "float" || t == "int32" || t == "uint32" || t == "float32") return 4;
+        if (t == "double" || t == "float64") return 8;
+        throw Error("ply: unknown type " + t);
+    };
+    auto read_num = [&](const std::string &t) -> double {
+        if (!binary) {
+            double v;
+            if (!(f >> v)) throw Error("ply: truncated ascii data");
+            return v;
+        }
+        unsigned char b[8];
+        size_t n = size_of(t);
+        f.read(reinterpret_cast<char *>(b), (std::streamsize)n);
+        if (!f) throw Error("ply: truncated binary data");
+        if (t == "float" || t == "float32") { float v; std::memcpy(&v, b, 4); return v; }
+        if (t == "double" || t == "float64") { double v; std::memcpy(&v, b, 8); return v; }
+        if (t == "char" || t == "int8") return (signed char)b[0];
+        if (t == "uchar" || t == "uint8") return b[0];
+        if (t == "short" || t == "int16") { int16_t v; std::memcpy(&v, b, 2); return v; }
+        if (t == "ushort" || t == "uint16") { uint16_t v; std::memcpy(&v, b, 2); return v; }
+        if (t == "int" || t == "int32") { int32_t v; std::memcpy(&v, b, 4); return v; }
+        uint32_t v;
+        std::memcpy(&v, b, 4);
+        return v;
+    };
+    bool have_n = false, have_uv = false;
+    for (auto &e : elems) {
+        if (e.name == "vertex") {
+            int ix = -1, iy = -1, iz = -1, inx = -1, iny = -1, inz = -1, iu = -1, iv = -1;
+            for (size_t k = 0; k < e.props.size(); k++) {
+                const std::string &n = e.props[k].name;
+                if (e.props[k].list) throw Error("ply: list property on vertices");
+                if (n == "x") ix = (int)k; else if (n == "y") iy = (int)k; else if (n == "z") iz = (int)k;
+                else if (n == "nx") inx = (int)k; else if (n == "ny") iny = (int)k; else if (n == "nz") inz = (int)k;
+                else if (n == "u" || n == "s") iu = (int)k; else if (n == "v" || n == "t") iv = (int)k;
+            }
+            if (ix < 0 || iy < 0 || iz < 0) throw Error("ply: vertex needs x y z");
+            have_n = inx >= 0 && iny >= 0 && inz >= 0, have_uv = iu >= 0 && iv >= 0;
+            std::vector<double> row(e.props.size());
+            for (size_t i = 0; i < e.count; i++) {
+                for (size_t k = 0; k < e.props.size(); k++) row[k] = read_num(e.props[k].type);
+                out.P.insert(out.P.end(), {(float)row[ix], (float)row[iy], (float)row[iz]});
+                if (have_n) out.N.insert(out.N.end(), {(float)row[inx], (float)row[iny], (float)row[inz]});
+                if (have_uv) out.uv.insert(out.uv.end(), {(float)row[iu], (float)row[iv]});
+            }
+        } else if (e.name == "face") {
+            for (size_t i = 0; i < e.count; i++)
+                for (auto &p : e.props) {
+                    if (!p.list) {
+                        read_num(p.type);
+                        continue;
+                    }
+                    size_t n = (size_t)read_num(p.count_type);
+                    std::vector<uint32_t> poly(n);
+                    for (size_t k = 0; k < n; k++) poly[k] = (uint32_t)read_num(p.item_type);
+                    if (p.name != "vertex_indices" && p.name != "vertex_index") continue;
+                    for (size_t k = 2; k < n; k++) out.idx.insert(out.idx.end(), {poly[0], poly[k - 1], poly[k]});
+                }
+        } else {
+            for (size_t i = 0; i < e.count; i++)
+                for (auto &p : e.props) {
+                    if (!p.list) read_num(p.type);
+                    else {
+                        size_t n = (size_t)read_num(p.count_type);
+                        for (size_t k = 0; k < n; k++) read_num(p.item_type);
+                    }
+                }
+        }
+    }
+    size_t nv = out.P.size() / 3;
+    for (uint32_t v : out.idx)
+        if (v >= nv) throw Error("ply: face index out of range in " + filename);
+}
+
 Material material_from_params(const std::string &type, const ParamSet &ps) {
     if (type == "matte") {
         // pbrt_rs::BSDF::Matte { kd } -> BSDFDiffuse (src/bsdfs/mod.rs:299-306); Kd default 0.5
@@ -226,15 +396,20 @@ Material material_from_params(const std::string &type, const ParamSet &ps) {
 } // namespace
 
 Scene PBRTSceneLoader::load(const std::string &filename, bool use_shading_normal) const {
-    return load_string(read_file(filename), use_shading_normal);
+    size_t slash = filename.find_last_of('/');
+    return load_string(read_file(filename), use_shading_normal, slash == std::string::npos ? "" : filename.substr(0, slash));
 }
 
-Scene PBRTSceneLoader::load_string(const std::string &text, bool use_shading_normal) const {
+Scene PBRTSceneLoader::load_string(const std::string &text, bool use_shading_normal, const std::string &base_dir) const {
     Parser ps(text);
     GState gs;
     std::vector<GState> stack;
     std::vector<Mat4> tstack;
     std::map<std::string, Material> materials;
+    std::vector<RawShape> top_shapes;                       // pbrt_rs::Scene::shapes
+    std::map<std::string, std::vector<RawShape>> objects;   // pbrt_rs::Scene::objects
+    std::vector<std::pair<std::string, Mat4>> instances;    // pbrt_rs::Scene::instances {name, matrix}
+    std::string current_object;
     Scene scene;
     uint32_t xres = 512, yres = 512;
     bool have_camera = false;
@@ -318,57 +493,56 @@ Scene PBRTSceneLoader::load_string(const std::string &text, bool use_shading_nor
         } else if (d == "Shape") {
             std::string type = ps.expect_str();
             ParamSet p = ps.params();
-            if (type != "trianglemesh")
-                throw Error("pbrt: Shape \"" + type + "\" is outside the hot-path scope (trianglemesh)");
-            const Param *pi = p.find("indices"), *pp = p.find("P"), *pn = p.find("N"), *puv = p.find("uv");
-            if (!puv) puv = p.find("st");
-            if (!pi || !pp) throw Error("pbrt: trianglemesh needs indices and P");
-            if (pi->nums.size() % 3 || pp->nums.size() % 3) throw Error("pbrt: trianglemesh sizes");
-            auto mesh = std::make_shared<Mesh>();
-            mesh->name = "noname"; // scene_loader.rs:137
-            size_t nv = pp->nums.size() / 3;
-            // scene_loader.rs:99-122: points by transform_point, normals by transform_vector
-            for (size_t i = 0; i < nv; i++) {
-                Vec3 q = gs.ctm.transform_point(
-                    Vec3{(float)pp->nums[3 * i], (float)pp->nums[3 * i + 1], (float)pp->nums[3 * i + 2]});
-                mesh->vertices.insert(mesh->vertices.end(), {q.x, q.y, q.z});
-            }
-            for (double v : pi->nums) {
-                if (v < 0 || (size_t)v >= nv) throw Error("pbrt: trianglemesh index out of range");
-                mesh->indices.push_back((uint32_t)v);
-            }
-            if (use_shading_normal && pn) {
-                if (pn->nums.size() != 3 * nv) throw Error("pbrt: N size mismatch");
-                size_t nb_wrong = 0;
-                for (size_t i = 0; i < nv; i++) {
-                    Vec3 n{(float)pn->nums[3 * i], (float)pn->nums[3 * i + 1], (float)pn->nums[3 * i + 2]};
-                    if (gs.reverse_orientation) n = Vec3{-n.x, -n.y, -n.z};
-                    n = gs.ctm.transform_vector(n);
-                    // Mesh::new renormalises, src/geometry.rs:143-153
-                    float l = n.x * n.x + n.y * n.y + n.z * n.z;
-                    if (l == 0.0f) nb_wrong++;
-                    else if (l != 1.0f) {
-                        float s = std::sqrt(l);
-                        n = Vec3{n.x / s, n.y / s, n.z / s};
-                    }
-                    mesh->normals.insert(mesh->normals.end(), {n.x, n.y, n.z});
+            RawShape rs;
+            if (type == "trianglemesh") {
+                const Param *pi = p.find("indices"), *pp = p.find("P"), *pn = p.find("N"), *puv = p.find("uv");
+                if (!puv) puv = p.find("st");
+                if (!pi || !pp) throw Error("pbrt: trianglemesh needs indices and P");
+                if (pi->nums.size() % 3 || pp->nums.size() % 3) throw Error("pbrt: trianglemesh sizes");
+                for (double v : pp->nums) rs.P.push_back((float)v);
+                for (double v : pi->nums) {
+                    if (v < 0 || (size_t)v >= pp->nums.size() / 3) throw Error("pbrt: trianglemesh index out of range");
+                    rs.idx.push_back((uint32_t)v);
                 }
-                if (nb_wrong == nv) mesh->normals.clear(); // geometry.rs:159-162
-            }
-            if (puv) {
-                if (puv->nums.size() != 2 * nv) throw Error("pbrt: uv size mismatch");
-                for (double v : puv->nums) mesh->uv.push_back((float)v);
-            }
+                if (pn) {
+                    if (pn->nums.size() != pp->nums.size()) throw Error("pbrt: N size mismatch");
+                    for (double v : pn->nums) rs.N.push_back((float)v);
+                }
+                if (puv) {
+                    if (puv->nums.size() != 2 * (pp->nums.size() / 3)) throw Error("pbrt: uv size mismatch");
+                    for (double v : puv->nums) rs.uv.push_back((float)v);
+                }
+            } else if (type == "plymesh") { // pbrt_rs::ply::read_ply(..).to_trimesh(), scene_loader.rs:88-92
+                std::string fn = p.str("filename");
+                if (fn.empty()) throw Error("pbrt: plymesh needs a filename");
+                if (fn[0] != '/' && !base_dir.empty()) fn = base_dir + "/" + fn;
+                read_ply(fn, rs);
+            } else throw Error("pbrt: Shape \"" + type + "\" is outside the hot-path scope (trianglemesh, plymesh)");
+            rs.matrix = gs.ctm;
+            rs.reverse_orientation = gs.reverse_orientation;
             // scene_loader.rs:124-136: unknown / missing material -> diffuse 0.5
-            if (gs.material) mesh->bsdf = *gs.material;
-            else if (!gs.named_material.empty() && materials.count(gs.named_material))
-                mesh->bsdf = materials[gs.named_material];
-            else mesh->bsdf = Material::diffuse(Color{0.5f, 0.5f, 0.5f});
-            if (gs.has_area_light) { // scene_loader.rs:141-145
-                mesh->is_light = true;
-                mesh->emission = gs.area_light;
-            }
-            if (!mesh->indices.empty()) scene.meshes.push_back(mesh); // geometry.rs:165-167
+            if (gs.material) rs.bsdf = *gs.material;
+            else if (!gs.named_material.empty() && materials.count(gs.named_material)) rs.bsdf = materials[gs.named_material];
+            else rs.bsdf = Material::diffuse(Color{0.5f, 0.5f, 0.5f});
+            rs.is_light = gs.has_area_light, rs.emission = gs.area_light; // scene_loader.rs:141-145
+            if (!current_object.empty()) objects[current_object].push_back(std::move(rs));
+            else top_shapes.push_back(std::move(rs));
+        } else if (d == "ObjectBegin") { // pbrt_rs::Scene::objects (scene_loader.rs:183-203)
+            if (!current_object.empty()) throw Error("pbrt: nested ObjectBegin");
+            current_object = ps.expect_str();
+            objects[current_object];
+            stack.push_back(gs); // ObjectBegin implies AttributeBegin
+            tstack.push_back(gs.ctm);
+        } else if (d == "ObjectEnd") {
+            if (current_object.empty() || stack.empty()) throw Error("pbrt: unbalanced ObjectEnd");
+            current_object.clear();
+            gs = stack.back();
+            stack.pop_back();
+            tstack.pop_back();
+        } else if (d == "ObjectInstance") {
+            std::string name = ps.expect_str();
+            if (!objects.count(name)) throw Error("pbrt: ObjectInstance of unknown object " + name);
+            instances.push_back({name, gs.ctm});
         } else if (d == "LightSource") { // scene_loader.rs:207-240 (pbrt_rs::Light::{Point, Distant}); positions in world space
             std::string type = ps.expect_str();
             ParamSet p = ps.params();
@@ -387,13 +561,16 @@ Scene PBRTSceneLoader::load_string(const std::string &text, bool use_shading_nor
                 Vec3 from = pt("from", 0, 0, 0), to = pt("to", 0, 0, 1);
                 scene.add_directional_light(Color{L.r * scale.r, L.g * scale.g, L.b * scale.b}, to.x - from.x, to.y - from.y, to.z - from.z);
             } else throw Error("pbrt: LightSource \"" + type + "\" is outside the hot-path scope (point, distant)");
-        } else if (d == "Texture" || d == "MakeNamedMedium" || d == "MediumInterface" ||
-                   d == "ObjectBegin" || d == "ObjectEnd" || d == "ObjectInstance" || d == "Include") {
+        } else if (d == "Texture" || d == "MakeNamedMedium" || d == "MediumInterface" || d == "Include") {
             throw Error("pbrt: directive " + d + " is outside the hot-path scope");
         } else {
             throw Error("pbrt: unknown directive " + d);
         }
     }
+    // scene_loader.rs:167-203: every top-level shape with the identity, then every instance's shapes with its matrix
+    for (auto &rs : top_shapes) emit_mesh(scene, rs, Mat4::identity(), use_shading_normal);
+    for (auto &in : instances)
+        for (auto &rs : objects[in.first]) emit_mesh(scene, rs, in.second, use_shading_normal);
     if (!have_camera) throw Error("The camera is not set!"); // scene_loader.rs:295
     auto c2w = world_to_camera.invert();                     // scene_loader.rs:288
     if (!c2w) throw Error("pbrt: camera transform is singular");

@@ -127,7 +127,8 @@ struct SceneLoader {
 };
 struct PBRTSceneLoader : SceneLoader {
     Scene load(const std::string &filename, bool use_shading_normal) const override;
-    Scene load_string(const std::string &text, bool use_shading_normal) const;
+    // base_dir: where `Shape "plymesh" "string filename"` paths are resolved (the scene file's directory)
+    Scene load_string(const std::string &text, bool use_shading_normal, const std::string &base_dir = "") const;
 };
 struct JSONSceneLoader : SceneLoader {
     Scene load(const std::string &filename, bool use_shading_normal) const override;

@@ -94,6 +94,43 @@ def test_pbrt_material_mapping():
     assert list(mats[5].kd) == [0.5] * 3 and list(mats[5].ks) == [0.5] * 3 and mats[5].alpha == pytest.approx(remap_roughness(0.1))
 
 
+def test_pbrt_objects_instances_and_plymesh(tmp_path):
+    """ObjectBegin / ObjectInstance (scene_loader.rs:183-203: instance.matrix * shape.matrix, instances after the top-level
+    shapes) and Shape "plymesh" (ascii and binary_little_endian, quads fanned) relative to the scene file."""
+    import struct
+    (tmp_path / "q.ply").write_text("ply\nformat ascii 1.0\nelement vertex 4\nproperty float x\nproperty float y\nproperty float z\n"
+                                    "property float nx\nproperty float ny\nproperty float nz\nelement face 1\n"
+                                    "property list uchar int vertex_indices\nend_header\n"
+                                    "0 0 0 0 0 1\n1 0 0 0 0 1\n1 1 0 0 0 1\n0 1 0 0 0 1\n4 0 1 2 3\n")
+    hdr = ("ply\nformat binary_little_endian 1.0\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\n"
+           "property float u\nproperty float v\nelement face 1\nproperty list uchar uint vertex_indices\nend_header\n").encode()
+    body = b"".join(struct.pack("<5f", *v) for v in [(0, 0, 0, 0, 0), (2, 0, 0, 1, 0), (0, 2, 0, 0, 1)]) + struct.pack("<B3I", 3, 0, 1, 2)
+    (tmp_path / "t.ply").write_bytes(hdr + body)
+    (tmp_path / "s.pbrt").write_text('''Camera "perspective" WorldBegin
+      ObjectBegin "quad"
+        Translate 0 0 1
+        Shape "plymesh" "string filename" "q.ply"
+      ObjectEnd
+      Shape "plymesh" "string filename" "t.ply"
+      AttributeBegin Translate 10 0 0 ObjectInstance "quad" AttributeEnd
+      AttributeBegin Scale 2 2 2 Material "mirror" ObjectInstance "quad" AttributeEnd
+    WorldEnd''')
+    sc = SceneLoaderManager().load(str(tmp_path / "s.pbrt"))
+    d = sc.desc.contents
+    assert d.nmeshes == 3
+    P = [np.ctypeslib.as_array(d.meshes[i].P, (3 * d.meshes[i].nverts,)).reshape(-1, 3) for i in range(3)]
+    idx = [list(np.ctypeslib.as_array(d.meshes[i].idx, (3 * d.meshes[i].ntris,))) for i in range(3)]
+    assert idx[0] == [0, 1, 2] and np.array_equal(P[0], [[0, 0, 0], [2, 0, 0], [0, 2, 0]]) and bool(d.meshes[0].UV) and not d.meshes[0].N
+    assert idx[1] == [0, 1, 2, 0, 2, 3] and np.array_equal(P[1], [[10, 0, 1], [11, 0, 1], [11, 1, 1], [10, 1, 1]])
+    assert np.array_equal(P[2], [[0, 0, 2], [2, 0, 2], [2, 2, 2], [0, 2, 2]])
+    assert bool(d.meshes[1].N) and list(np.ctypeslib.as_array(d.meshes[2].N, (12,))[:3]) == [0, 0, 1]  # renormalised after the scale
+    assert d.meshes[1].mat.kind == d.meshes[2].mat.kind == _abi.RL_BSDF_DIFFUSE  # material bound at definition, not at instantiation
+    with pytest.raises(SceneError, match="unknown object"):
+        SceneLoaderManager().load_string('Camera "perspective" WorldBegin ObjectInstance "nope" WorldEnd', "pbrt")
+    with pytest.raises(SceneError, match="cannot open"):
+        SceneLoaderManager().load_string('Camera "perspective" WorldBegin Shape "plymesh" "string filename" "missing.ply" WorldEnd', "pbrt")
+
+
 def test_pbrt_light_sources():
     """LightSource "point" / "distant" -> PointEmitter / DirectionalLight (scene_loader.rs:207-240): intensity * scale,
     direction = normalize(to - from), positions through the current transform; "infinite" stays outside the path."""
