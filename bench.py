@@ -301,7 +301,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": "cbox.pbrt path -n 128 -s 2 (1024x1024), independent:0 -> counter stream (mode B)",
                            "integrator": "path", "strategy": "all", "rr_depth": 0, "max_depth": "inf", "partition": f"16x16 tiles over {world} rank(s), 1 ncclReduce",
-                           "l2": "wavefront queues are 2.9 GB per batch, larger than the 126 MB L2"},
+                           "l2": "wavefront queues are 23.6 GB per batch (176 B x 134 M paths in flight), far larger than the 126 MB L2"},
                 "mpath_segments_per_s": tot_segs / (dev_ms * 1e-3) / 1e6,
                 "wall_ms_per_step": wall_ms / args.steps,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},

@@ -62,6 +62,7 @@ std::string g_create_error;
 
 struct rl_ctx {
     int device = 0, nranks = 1, rank = 0, sm_count = 148;
+    size_t mem_total = 0; // device memory (sizes the wavefront batches)
     cudaStream_t stream = nullptr;
     std::string err;
     bool profiling = false;
@@ -204,6 +205,7 @@ int rl_create(rl_ctx **out, int device, int nranks, int rank, const void *nccl_u
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->mem_total = prop.totalGlobalMem;
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CKC(cudaMalloc(&ctx->d_counts, 4 * sizeof(uint32_t)));
     CKC(cudaMalloc(&ctx->d_counters, sizeof(Counters)));
@@ -642,10 +644,23 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
         const uint32_t n_slots = direct ? 1u + nl + nbs : 1u;
         const uint32_t widest = std::max(std::max(nl, nbs), n_slots);
         uint32_t batch = o->batch_spp;
-        if (batch == 0) batch = (uint32_t)std::max<size_t>(1, ((size_t)1 << 24) / ((size_t)npix * widest));
+        if (batch == 0) {
+            // Auto: as many samples per pixel in flight as a quarter of the device memory holds (11 float4 queues = 176 B per
+            // path; 180 GB HBM3e -> 2^28 paths).  Every batch ends in a tail of ~25 nearly empty wavefront iterations that
+            // costs ~1 ms whatever the batch size, so fewer, larger batches are faster (measured, cbox 1024^2 x 128 spp:
+            // 16 spp/batch 49.5 ms, 32 45.9, 64 44.0, 128 43.0 ms per frame).
+            size_t budget = std::min<size_t>((size_t)1 << 28, std::max<size_t>((size_t)1 << 22, ctx->mem_total / 4 / 176));
+            batch = (uint32_t)std::max<size_t>(1, budget / ((size_t)npix * widest));
+        }
         batch = std::min(batch, o->spp);
-        const size_t batch_paths = (size_t)npix * batch;
-        rc = ensure_paths(ctx, batch_paths * std::max(1u, nbs), batch_paths * std::max(1u, nl), batch_paths * n_slots);
+        size_t batch_paths = (size_t)npix * batch;
+        for (;;) { // an automatic batch size shrinks when the device memory is shared with something else
+            rc = ensure_paths(ctx, batch_paths * std::max(1u, nbs), batch_paths * std::max(1u, nl), batch_paths * n_slots);
+            if (rc == RL_OK || o->batch_spp != 0 || batch == 1) break;
+            cudaGetLastError(); // clear the allocation error
+            batch = (batch + 1) / 2;
+            batch_paths = (size_t)npix * batch;
+        }
         if (rc != RL_OK) return rc;
         IntegParams ip{};
         ip.kind = I->kind, ip.min_depth = I->min_depth, ip.max_depth = I->max_depth, ip.rr_depth = I->rr_depth;
@@ -735,8 +750,11 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                 k_set_u32<<<1, 1, 0, st>>>(qc, (uint32_t)n_paths);
                 uint32_t k = 0, k_read = 0;
                 size_t n_ub = n_paths; // upper bound of the current queue length (lengths never grow)
-                const uint32_t group = prof ? 1u : (uint32_t)RL_SYNC_GROUP;
                 while (n_ub > 0) {
+                    // iterations launched between two reads of the queue lengths: few while the queues are long (an iteration
+                    // past the end of the longest path is three empty launches), more in the tail, where the host round trip
+                    // costs more than the launches
+                    const uint32_t group = prof ? 1u : (n_ub > ((size_t)1 << 20) ? (uint32_t)RL_SYNC_GROUP : 4u * (uint32_t)RL_SYNC_GROUP);
                     if (k + group >= kMaxIters) {
                         ctx->err = "rl_render: a path exceeded 4095 wavefront iterations (no Russian roulette in a closed scene?)";
                         return RL_ERR_UNSUPPORTED;
