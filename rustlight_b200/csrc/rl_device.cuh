@@ -1298,7 +1298,10 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, 
     float su0 = sqrtf(ux);
     float b0 = 1.0f - su0, b1 = uy * su0;
     V3 pos = v0 * b0 + v1 * b1 + v2 * (1.0f - b0 - b1);
-    V3 n_g = normalize(cross(v2 - v0, v1 - v0));
+    // sample_tri's normal is normalize(cross(v2 - v0, v1 - v0)) (geometry.rs:272-276): the operands of the hit path's
+    // normalize(cross(e1, e2)) swapped, i.e. exactly -n_geo (a cross product and |.| are exactly antisymmetric / even in f32),
+    // and n_geo is already in the shading table
+    V3 n_g = -xyz(sv.shade[4 * prim]);
     float4 s1 = sv.shade[4 * prim + 1];
     if (f2u(s1.w) != 0u) {
         V3 n0 = xyz(s1), n1 = xyz(sv.shade[4 * prim + 2]), n2 = xyz(sv.shade[4 * prim + 3]);
