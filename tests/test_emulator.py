@@ -4,6 +4,8 @@ This is the CPU-side half of the parity argument: the functions the kernels call
 discrete decisions, and produce the same radiance bits, as the oracle's stream estimator.  The
 GPU half (tests/test_gpu.py) checks that the kernels around them move the records correctly.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -200,3 +202,43 @@ def test_ao_render_bit_exact(dist, nc):
     io, so = ob.OracleScene(sc).render(integ, 8, seed=3, cfg=ob.config(**STREAM))
     assert se.segments == so.segments and np.array_equal(ie, io)
     assert 0.05 < io.mean() < 0.95 and set(np.unique(io * 8).tolist()) <= set(range(9))
+
+
+def test_prefilter_margins_carry_tenfold_slack(tmp_path):
+    """The group-table prefilter may only reject what the exact test rejects.  Rebuilding the emulator with every margin
+    scaled by 0.1 (RL_FLAT_MARGIN_SCALE) must still reproduce the oracle on the adversarial quads and on rays that start on
+    the Cornell box surfaces: the shipped margins carry at least 10x slack (first mismatches appear at 0.01x)."""
+    import ctypes
+    import subprocess
+    from conftest import ROOT, adversarial_pairs_case
+    so = str(tmp_path / "libemu_tight.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-DRL_FLAT_MARGIN_SCALE=0.1f",
+                           "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "rustlight_b200", "csrc"), "-shared", "-x", "c++",
+                           os.path.join(ROOT, "tests", "emu", "emu.cpp"), "-o", so], stderr=subprocess.DEVNULL)
+    L = ctypes.CDLL(so)
+    L.emu_scene_create.restype = ctypes.c_void_p
+    L.emu_scene_create.argtypes = [ctypes.POINTER(_abi.rl_scene_desc), ctypes.c_char_p, ctypes.c_size_t]
+    L.emu_trace.argtypes = [ctypes.c_void_p, ctypes.c_size_t, eb.FP, eb.FP, ctypes.POINTER(ctypes.c_uint32), eb.FP]
+    L.emu_scene_destroy.argtypes = [ctypes.c_void_p]
+
+    def trace(sc, o, d):
+        h = L.emu_scene_create(sc.desc, None, 0)
+        prim, tuv = np.zeros(len(o), np.uint32), np.zeros((len(o), 3), np.float32)
+        L.emu_trace(h, len(o), eb._f(o), eb._f(d), prim.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), eb._f(tuv))
+        L.emu_scene_destroy(h)
+        return prim, tuv
+    for seed in range(4):
+        sc, o, dd, _ = adversarial_pairs_case(seed)
+        pe, te = trace(sc, o, dd)
+        po, to = ob.OracleScene(sc).trace(o, dd, ob.ACCEL_NAIVE)
+        assert np.array_equal(pe, po) and np.array_equal(te, to)
+    sc = load_cbox()
+    osc = ob.OracleScene(sc)
+    o, d, _ = _rays(60000, 31)
+    po, to = osc.trace(o, d, ob.ACCEL_NAIVE)
+    hit = po != 0xFFFFFFFF
+    o2 = np.ascontiguousarray((o[hit] + d[hit] * to[hit, :1]).astype(np.float32))
+    d2 = np.ascontiguousarray(_rays(len(o2), 32)[1])
+    pe, te = trace(sc, o2, d2)
+    po2, to2 = osc.trace(o2, d2, ob.ACCEL_NAIVE)
+    assert np.array_equal(pe, po2) and np.array_equal(te, to2)
