@@ -57,7 +57,24 @@ typedef enum rl_microfacet { /* MicrofacetDistributionBSDF, src/bsdfs/distributi
     RL_MICROFACET_BECKMANN = 2
 } rl_microfacet;
 
-/* All colours are BSDFColor::Constant (bsdfs/mod.rs:11-41).  Fields used per kind:
+/* BSDFColor (bsdfs/mod.rs:11-101) other than Constant, for the DIFFUSE reflectance slot (kd) of DIFFUSE, PHONG and SUBSTRATE
+ * materials: rl_material.kd_texture = 1 + index into rl_scene_desc.textures (0 = BSDFColor::Constant(kd)).  A mesh without uv
+ * coordinates evaluates a texture to black ("Found a texture but no uv coordinate given", bsdfs/mod.rs:36-39). */
+typedef enum rl_texture_kind {
+    RL_TEX_BITMAP = 1,       /* nearest texel, Bitmap::pixel_uv (structure.rs:434-453)                         */
+    RL_TEX_CHECKERBOARD = 2, /* bsdfs/mod.rs:43-65                                                             */
+    RL_TEX_GRID = 3          /* bsdfs/mod.rs:66-99 (incl. its `uv.y + scale.y`)                                */
+} rl_texture_kind;
+typedef struct rl_texture {
+    uint32_t kind;
+    uint32_t width, height;     /* bitmap                                                                   */
+    const float *pixels;        /* bitmap: width*height*3 RGB floats, Bitmap.colors order (index y*width+x) */
+    float color0[3], color1[3]; /* checkerboard / grid                                                      */
+    float line_width;           /* grid                                                                     */
+    float offset[2], scale[2];  /* checkerboard / grid                                                      */
+} rl_texture;
+
+/* Other colours are BSDFColor::Constant.  Fields used per kind:
  *   DIFFUSE   kd
  *   PHONG     kd, ks, exponent, weight_specular
  *   METAL     ks = specular, eta, k, microfacet, alpha
@@ -74,6 +91,7 @@ typedef struct rl_material {
     float ior;             /* glass: relative index of refraction (!= 0, glass.rs:43-48)      */
     float alpha;           /* microfacet roughness alpha_u == alpha_v                          */
     uint32_t microfacet;   /* rl_microfacet                                                   */
+    uint32_t kd_texture;   /* 0 = constant kd, else 1 + index into rl_scene_desc.textures     */
 } rl_material;
 
 /* ---- geometry: Mesh, src/geometry.rs:107-119 ---------------------------------------------- */
@@ -117,6 +135,8 @@ typedef struct rl_scene_desc {
     uint32_t has_environment; /* must be 0: emitter_environment == None on this path          */
     uint32_t nlights;         /* Scene.emitters (EmittersState::Unbuild): sampled after the mesh lights, in this order */
     const rl_light_desc *lights;
+    uint32_t ntextures;
+    const rl_texture *textures;
 } rl_scene_desc;
 
 /* ---- integrators --------------------------------------------------------------------------- */

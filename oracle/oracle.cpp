@@ -374,6 +374,57 @@ struct Distribution1D { // :402-406
 // ============================================================================================
 // bsdfs
 // ============================================================================================
+struct UV { // Option<Vector2<f32>>
+    bool some = false;
+    P2 v{0.0f, 0.0f};
+};
+struct BitmapTex { // structure.rs:382-386 (the part pixel_uv needs)
+    uint32_t size_x = 0, size_y = 0;
+    std::vector<Color> colors;
+    Color pixel_uv(P2 uv) const { // :434-453
+        auto modulo = [](float x, float n) { return std::fmod(std::fmod(x, n) + n, n); }; // tools.rs:39-41
+        uv.x = modulo(uv.x, 1.0f);
+        uv.y = modulo(uv.y, 1.0f);
+        auto as_usize = [](float v) -> uint64_t { // `as usize`: saturating, NaN -> 0
+            if (!(v > 0.0f)) return 0;
+            if (v >= 18446744073709551616.0f) return ~(uint64_t)0;
+            return (uint64_t)v;
+        };
+        uint64_t x = as_usize(uv.x * (float)size_x), y = as_usize(uv.y * (float)size_y);
+        uint64_t i = (uint64_t)size_x * y + x;
+        if (i >= colors.size()) return Color::zero();
+        return colors[i];
+    }
+};
+struct BSDFColor { // bsdfs/mod.rs:11-101
+    enum Kind { Constant, Bitmap, Checkerbord, Grid } kind = Constant;
+    Color c{1, 1, 1};
+    std::shared_ptr<BitmapTex> img;
+    Color color0{}, color1{};
+    float line_width = 0.0f;
+    P2 offset{0, 0}, scale{1, 1};
+    static int32_t as_i32(float v) { // `as i32`: saturating, NaN -> 0
+        if (v != v) return 0;
+        if (v >= 2147483648.0f) return 2147483647;
+        if (v <= -2147483648.0f) return (int32_t)0x80000000u;
+        return (int32_t)v;
+    }
+    Color color(const UV &uv) const { // :32-101
+        if (kind == Constant) return c;
+        if (!uv.some) return Color::zero(); // "Found a texture but no uv coordinate given"
+        if (kind == Bitmap) return img->pixel_uv(uv.v);
+        if (kind == Checkerbord) {
+            P2 q{uv.v.x * scale.x + offset.x, uv.v.y * scale.y + offset.y};
+            int32_t x = 2 * (as_i32(q.x * 2.0f) % 2) - 1, y = 2 * (as_i32(q.y * 2.0f) % 2) - 1;
+            return x * y == 1 ? color0 : color1;
+        }
+        P2 q{uv.v.x * scale.x + offset.x, (uv.v.y + scale.y) + offset.y}; // Grid: `uv.y + scale.y` (:84)
+        float x = q.x - std::floor(q.x), y = q.y - std::floor(q.y);
+        if (x > 0.5f) x -= 1.0f;
+        if (y > 0.5f) y -= 1.0f;
+        return (std::fabs(x) < line_width || std::fabs(y) < line_width) ? color0 : color1;
+    }
+};
 struct SampledDirection { // bsdfs/mod.rs:129-137
     Color weight;
     V3 d;
@@ -383,37 +434,38 @@ inline V3 reflect(V3 d) { return V3{-d.x, -d.y, d.z}; } // bsdfs/mod.rs:124-126
 
 struct BSDF { // trait BSDF, bsdfs/mod.rs:163-199
     virtual ~BSDF() = default;
-    virtual bool sample(const Math &m, V3 d_in, P2 sample, SampledDirection *out) const = 0;
-    virtual PDF pdf(const Math &m, V3 d_in, V3 d_out) const = 0;
-    virtual Color eval(const Math &m, V3 d_in, V3 d_out) const = 0;
+    virtual bool sample(const Math &m, const UV &uv, V3 d_in, P2 sample, SampledDirection *out) const = 0;
+    virtual PDF pdf(const Math &m, const UV &uv, V3 d_in, V3 d_out) const = 0;
+    virtual Color eval(const Math &m, const UV &uv, V3 d_in, V3 d_out) const = 0;
     virtual bool is_twosided() const = 0;
     virtual bool is_smooth() const = 0; // bsdf_type().is_smooth(), bsdfs/mod.rs:157-161
 };
 struct BSDFDiffuse : BSDF { // bsdfs/diffuse.rs
-    Color diffuse;
-    bool sample(const Math &m, V3 d_in, P2 s, SampledDirection *out) const override { // :11-31
+    BSDFColor diffuse;
+    bool sample(const Math &m, const UV &uv, V3 d_in, P2 s, SampledDirection *out) const override { // :11-31
         if (d_in.z <= 0.0f) return false;
         V3 d_out = cosine_sample_hemisphere(m, s);
-        *out = SampledDirection{diffuse, d_out, PDF{PDF::SolidAngle, d_out.z * FRAC_1_PI}};
+        *out = SampledDirection{diffuse.color(uv), d_out, PDF{PDF::SolidAngle, d_out.z * FRAC_1_PI}};
         return true;
     }
-    PDF pdf(const Math &, V3 d_in, V3 d_out) const override { // :33-51
+    PDF pdf(const Math &, const UV &uv, V3 d_in, V3 d_out) const override { // :33-51
         if (d_in.z <= 0.0f) return PDF{PDF::SolidAngle, 0.0f};
         if (d_out.z <= 0.0f) return PDF{PDF::SolidAngle, 0.0f};
         return PDF{PDF::SolidAngle, d_out.z * FRAC_1_PI};
     }
-    Color eval(const Math &, V3 d_in, V3 d_out) const override { // :53-71
+    Color eval(const Math &, const UV &uv, V3 d_in, V3 d_out) const override { // :53-71
         if (d_in.z <= 0.0f) return Color::zero();
-        if (d_out.z > 0.0f) return diffuse * d_out.z * FRAC_1_PI;
+        if (d_out.z > 0.0f) return diffuse.color(uv) * d_out.z * FRAC_1_PI;
         return Color::zero();
     }
     bool is_twosided() const override { return true; }
     bool is_smooth() const override { return false; }
 };
 struct BSDFPhong : BSDF { // bsdfs/phong.rs
-    Color diffuse, specular;
+    BSDFColor diffuse;
+    Color specular;
     float exponent, weight_specular;
-    bool sample(const Math &m, V3 d_in, P2 s, SampledDirection *out) const override { // :14-63
+    bool sample(const Math &m, const UV &uv, V3 d_in, P2 s, SampledDirection *out) const override { // :14-63
         if (d_in.z <= 0.0f) return false;
         V3 d_out;
         if (s.x < weight_specular) {
@@ -431,12 +483,12 @@ struct BSDFPhong : BSDF { // bsdfs/phong.rs
             s.x = (s.x - weight_specular) / (1.0f - weight_specular);
             d_out = cosine_sample_hemisphere(m, s);
         }
-        PDF p = pdf(m, d_in, d_out);
+        PDF p = pdf(m, uv, d_in, d_out);
         if (p.value() == 0.0f) return false;
-        *out = SampledDirection{eval(m, d_in, d_out) / p.value(), d_out, p};
+        *out = SampledDirection{eval(m, uv, d_in, d_out) / p.value(), d_out, p};
         return true;
     }
-    PDF pdf(const Math &m, V3 d_in, V3 d_out) const override { // :65-91
+    PDF pdf(const Math &m, const UV &uv, V3 d_in, V3 d_out) const override { // :65-91
         if (d_in.z <= 0.0f || d_out.z <= 0.0f) return PDF{PDF::SolidAngle, 0.0f};
         float pdf_specular;
         float alpha = dot(reflect(d_in), d_out);
@@ -445,13 +497,13 @@ struct BSDFPhong : BSDF { // bsdfs/phong.rs
         float pdf_diffuse = (1.0f - weight_specular) * d_out.z * FRAC_1_PI;
         return PDF{PDF::SolidAngle, pdf_specular + pdf_diffuse};
     }
-    Color eval(const Math &m, V3 d_in, V3 d_out) const override { // :93-119
+    Color eval(const Math &m, const UV &uv, V3 d_in, V3 d_out) const override { // :93-119
         if (d_in.z <= 0.0f || d_out.z <= 0.0f) return Color::zero();
         Color specular_value;
         float alpha = dot(reflect(d_in), d_out);
         if (alpha > 0.0f) specular_value = specular * (m.powf(alpha, exponent) * (exponent + 2.0f) / (2.0f * PI));
         else specular_value = Color::zero();
-        Color diffuse_value = diffuse * d_out.z * FRAC_1_PI;
+        Color diffuse_value = diffuse.color(uv) * d_out.z * FRAC_1_PI;
         return specular_value + diffuse_value;
     }
     bool is_twosided() const override { return true; }
@@ -576,7 +628,7 @@ struct BSDFMetal : BSDF { // bsdfs/metal.rs
     Color specular, eta, k;
     bool has_distribution;
     MicrofacetDistribution distr;
-    bool sample(const Math &mm, V3 d_in, P2 s, SampledDirection *out) const override { // :15-73
+    bool sample(const Math &mm, const UV &uv, V3 d_in, P2 s, SampledDirection *out) const override { // :15-73
         if (d_in.z <= 0.0f) return false;
         if (!has_distribution) {
             *out = SampledDirection{specular * bu::fresnel_conductor(d_in.z, eta, k), reflect(d_in), PDF{PDF::Discrete, 1.0f}};
@@ -591,11 +643,11 @@ struct BSDFMetal : BSDF { // bsdfs/metal.rs
         *out = SampledDirection{w * f, wo, PDF{PDF::SolidAngle, pdf}};
         return true;
     }
-    PDF pdf(const Math &mm, V3 wi, V3 wo) const override { // :75-110 (Domain::SolidAngle; the Discrete arm is never asked)
+    PDF pdf(const Math &mm, const UV &uv, V3 wi, V3 wo) const override { // :75-110 (Domain::SolidAngle; the Discrete arm is never asked)
         V3 h = normalize(wi + wo);
         return PDF{PDF::SolidAngle, distr.pdf(mm, h) / (4.0f * std::fabs(dot(wo, h)))};
     }
-    Color eval(const Math &mm, V3 wi, V3 wo) const override { // :112-156
+    Color eval(const Math &mm, const UV &uv, V3 wi, V3 wo) const override { // :112-156
         V3 h = normalize(wi + wo);
         float d = distr.eval(mm, h);
         if (d == 0.0f) return Color::zero();
@@ -614,7 +666,7 @@ struct BSDFGlass : BSDF { // bsdfs/glass.rs
         float scale = cos_theta_t < 0.0f ? -inv_eta : -eta;
         return V3{scale * wi.x, scale * wi.y, cos_theta_t};
     }
-    bool sample(const Math &, V3 d_in, P2 s, SampledDirection *out) const override { // :75-121, transport == Importance
+    bool sample(const Math &, const UV &uv, V3 d_in, P2 s, SampledDirection *out) const override { // :75-121, transport == Importance
         auto [fresnel, cos_theta_trans] = bu::fresnel_dielectric(d_in.z, eta);
         if (s.x <= fresnel) {
             *out = SampledDirection{specular_reflectance, reflect(d_in), PDF{PDF::Discrete, fresnel}};
@@ -625,13 +677,14 @@ struct BSDFGlass : BSDF { // bsdfs/glass.rs
         return true;
     }
     // pdf() is todo!() and eval() asserts Domain::Discrete in the reference (:123-176): never reached because the BSDF is smooth
-    PDF pdf(const Math &, V3, V3) const override { std::abort(); }
-    Color eval(const Math &, V3, V3) const override { std::abort(); }
+    PDF pdf(const Math &, const UV &, V3, V3) const override { std::abort(); }
+    Color eval(const Math &, const UV &, V3, V3) const override { std::abort(); }
     bool is_twosided() const override { return false; }
     bool is_smooth() const override { return true; }
 };
 struct BSDFSubstrate : BSDF { // bsdfs/substrate.rs
-    Color specular, diffuse;
+    Color specular;
+    BSDFColor diffuse;
     bool has_distribution;
     MicrofacetDistribution distr;
     Color schlick_fresnel(float cos_theta) const { // :15-18
@@ -651,13 +704,13 @@ struct BSDFSubstrate : BSDF { // bsdfs/substrate.rs
         float pdf_specular = has_distribution ? distr.pdf(mm, m) / (4.0f * std::fabs(dot(wo, m))) : 0.0f;
         return PDF{PDF::SolidAngle, 0.5f * (pdf_diffuse + pdf_specular)};
     }
-    Color eval_domain(const Math &mm, V3 d_in, V3 d_out, PDF::Kind domain) const { // :149-206
+    Color eval_domain(const Math &mm, const UV &uv, V3 d_in, V3 d_out, PDF::Kind domain) const { // :149-206
         if (d_in.z <= 0.0f || d_out.z <= 0.0f) return Color::zero();
         V3 m = d_in + d_out;
         if (m.x == 0.0f && m.y == 0.0f && m.z == 0.0f) return Color::zero();
         m = normalize(m);
         if (domain == PDF::SolidAngle) {
-            Color diff = diffuse * (Color::one() - specular) * (28.0f / (23.0f * PI)) * (1.0f - powi(1.0f - 0.5f * bu::abs_cos_theta(d_in), 5)) *
+            Color diff = diffuse.color(uv) * (Color::one() - specular) * (28.0f / (23.0f * PI)) * (1.0f - powi(1.0f - 0.5f * bu::abs_cos_theta(d_in), 5)) *
                          (1.0f - powi(1.0f - 0.5f * bu::abs_cos_theta(d_out), 5));
             Color spec = Color::zero();
             if (has_distribution) {
@@ -669,7 +722,7 @@ struct BSDFSubstrate : BSDF { // bsdfs/substrate.rs
         if (bu::check_reflection_condition(d_in, d_out)) return schlick_fresnel(dot(d_in, m));
         std::abort(); // unimplemented!()
     }
-    bool sample(const Math &mm, V3 d_in, P2 s, SampledDirection *out) const override { // :22-90
+    bool sample(const Math &mm, const UV &uv, V3 d_in, P2 s, SampledDirection *out) const override { // :22-90
         if (d_in.z <= 0.0f) return false;
         V3 d_out;
         PDF::Kind domain;
@@ -694,16 +747,33 @@ struct BSDFSubstrate : BSDF { // bsdfs/substrate.rs
         }
         PDF p = pdf_domain(mm, d_in, d_out, domain);
         if (p.value() == 0.0f) return false;
-        Color f = eval_domain(mm, d_in, d_out, domain);
+        Color f = eval_domain(mm, uv, d_in, d_out, domain);
         *out = SampledDirection{f / p.value(), d_out, p};
         return true;
     }
-    PDF pdf(const Math &mm, V3 wi, V3 wo) const override { return pdf_domain(mm, wi, wo, PDF::SolidAngle); }
-    Color eval(const Math &mm, V3 wi, V3 wo) const override { return eval_domain(mm, wi, wo, PDF::SolidAngle); }
+    PDF pdf(const Math &mm, const UV &uv, V3 wi, V3 wo) const override { return pdf_domain(mm, wi, wo, PDF::SolidAngle); }
+    Color eval(const Math &mm, const UV &uv, V3 wi, V3 wo) const override { return eval_domain(mm, uv, wi, wo, PDF::SolidAngle); }
     bool is_twosided() const override { return true; }
     bool is_smooth() const override { return !has_distribution; } // DELTA | DIFFUSE without a distribution (:216-221)
 };
-std::unique_ptr<BSDF> make_bsdf(const rl_material &m) {
+std::unique_ptr<BSDF> make_bsdf(const rl_material &m, const rl_texture *textures = nullptr, uint32_t ntextures = 0) {
+    // the diffuse-reflectance slot: BSDFColor::Constant(kd) or one of the scene's textures
+    auto kd_color = [&]() {
+        BSDFColor c;
+        c.c = Color{m.kd[0], m.kd[1], m.kd[2]};
+        if (m.kd_texture != 0 && textures && m.kd_texture <= ntextures) {
+            const rl_texture &t = textures[m.kd_texture - 1];
+            c.kind = t.kind == RL_TEX_BITMAP ? BSDFColor::Bitmap : (t.kind == RL_TEX_GRID ? BSDFColor::Grid : BSDFColor::Checkerbord);
+            c.color0 = Color{t.color0[0], t.color0[1], t.color0[2]}, c.color1 = Color{t.color1[0], t.color1[1], t.color1[2]};
+            c.line_width = t.line_width, c.offset = P2{t.offset[0], t.offset[1]}, c.scale = P2{t.scale[0], t.scale[1]};
+            if (t.kind == RL_TEX_BITMAP) {
+                c.img = std::make_shared<BitmapTex>();
+                c.img->size_x = t.width, c.img->size_y = t.height;
+                for (size_t i = 0; i < (size_t)t.width * t.height; i++) c.img->colors.push_back(Color{t.pixels[3 * i], t.pixels[3 * i + 1], t.pixels[3 * i + 2]});
+            }
+        }
+        return c;
+    };
     auto distribution = [&](bool *has) {
         *has = m.microfacet != RL_MICROFACET_NONE;
         return MicrofacetDistribution{m.microfacet == RL_MICROFACET_BECKMANN ? MicrofacetDistribution::Beckmann : MicrofacetDistribution::GGX, m.alpha, m.alpha};
@@ -723,20 +793,20 @@ std::unique_ptr<BSDF> make_bsdf(const rl_material &m) {
     }
     if (m.kind == RL_BSDF_SUBSTRATE) {
         auto b = std::make_unique<BSDFSubstrate>();
-        b->diffuse = Color{m.kd[0], m.kd[1], m.kd[2]}, b->specular = Color{m.ks[0], m.ks[1], m.ks[2]};
+        b->diffuse = kd_color(), b->specular = Color{m.ks[0], m.ks[1], m.ks[2]};
         b->distr = distribution(&b->has_distribution);
         return b;
     }
     if (m.kind == RL_BSDF_PHONG) {
         auto b = std::make_unique<BSDFPhong>();
-        b->diffuse = Color{m.kd[0], m.kd[1], m.kd[2]};
+        b->diffuse = kd_color();
         b->specular = Color{m.ks[0], m.ks[1], m.ks[2]};
         b->exponent = m.exponent;
         b->weight_specular = m.weight_specular;
         return b;
     }
     auto b = std::make_unique<BSDFDiffuse>();
-    b->diffuse = Color{m.kd[0], m.kd[1], m.kd[2]};
+    b->diffuse = kd_color();
     return b;
 }
 
@@ -761,6 +831,8 @@ struct Mesh { // geometry.rs:107-119
     std::vector<Idx3> indices;
     bool has_normals = false;
     std::vector<V3> normals;
+    bool has_uv = false;
+    std::vector<P2> uv; // Mesh.uv: Option<Vec<Vector2<f32>>>
     std::unique_ptr<BSDF> bsdf;
     bool light = false; // emission != EmissionType::Zero
     Color emission = Color::zero();
@@ -856,6 +928,7 @@ struct Intersection {
     Frame frame;
     V3 wi;
     size_t primitive_id;
+    UV uv; // structure.rs:1015-1023
     float cos_theta() const { return wi.z; }
 };
 Intersection fill_intersection(const Mesh *mesh, size_t tri_id, float hit_u, float hit_v, const Ray &ray, V3 n_g, float dist, V3 p) {
@@ -879,6 +952,12 @@ Intersection fill_intersection(const Mesh *mesh, size_t tri_id, float hit_u, flo
     its.frame = Frame(n_s);
     its.wi = its.frame.to_local(-ray.d);
     its.primitive_id = tri_id;
+    if (mesh->has_uv) { // UV interpolation, structure.rs:1015-1023
+        P2 d0 = mesh->uv[index.x], d1 = mesh->uv[index.y], d2 = mesh->uv[index.z];
+        float w = 1.0f - hit_u - hit_v;
+        its.uv.some = true;
+        its.uv.v = P2{d0.x * w + d1.x * hit_u + d2.x * hit_v, d0.y * w + d1.y * hit_u + d2.y * hit_v};
+    }
     return its;
 }
 inline Ray spawn_ray(const Intersection &its, V3 d_out) { return Ray{its.p, d_out, EPSILON, F32_MAX}; } // structure.rs:717-731
@@ -1496,7 +1575,7 @@ struct DirectionalSamplingStrategy : SamplingStrategy { // strategies/directiona
             Intersection its = v.its; // copy: `path` is mutated below
             SampledDirection sb;
             P2 s2 = sampler.next2d();
-            if (!its.mesh->bsdf->sample(cx.math, its.wi, s2, &sb)) return;
+            if (!its.mesh->bsdf->sample(cx.math, its.uv, its.wi, s2, &sb)) return;
             V3 d_out_global = its.frame.to_world(sb.d);
             throughput = throughput * sb.weight; // *throughput *= &weight
             if (throughput.is_zero()) return;
@@ -1538,7 +1617,7 @@ struct DirectionalSamplingStrategy : SamplingStrategy { // strategies/directiona
         const Vertex &v = path.vertices[vertex_id];
         if (v.kind == Vertex::Surface) {
             if (v.its.mesh->bsdf->is_smooth()) return false;
-            *out = v.its.mesh->bsdf->pdf(cx.math, v.its.wi, v.its.frame.to_local(edge.d)).value();
+            *out = v.its.mesh->bsdf->pdf(cx.math, v.its.uv, v.its.wi, v.its.frame.to_local(edge.d)).value();
             return true;
         }
         if (v.kind == Vertex::Sensor) {
@@ -1562,7 +1641,7 @@ struct LightSamplingStrategy : SamplingStrategy { // strategies/emitters.rs
             Vertex nv;
             nv.kind = Vertex::Light;
             nv.pos = rec.p, nv.n = rec.n, nv.emitter = rec.emitter;
-            Color weight = its.mesh->bsdf->eval(cx.math, its.wi, its.frame.to_local(rec.d));
+            Color weight = its.mesh->bsdf->eval(cx.math, its.uv, its.wi, its.frame.to_local(rec.d));
             int nvid = path.register_vertex(nv);
             int eid = edge_from_vertex(path, vertex_id, rec.pdf, weight, rec.weight, 1.0f, nvid, id_strategy);
             path.vertices[vertex_id].edge_out.push_back(eid);
@@ -1755,7 +1834,7 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
         {
             SampledDirection sb;
             P2 s2 = sampler.next2d();
-            if (bsdf.sample(cx.math, its.wi, s2, &sb)) {
+            if (bsdf.sample(cx.math, its.uv, its.wi, s2, &sb)) {
                 V3 d_out_global = its.frame.to_world(sb.d);
                 Tn = T * sb.weight;
                 if (!Tn.is_zero()) {
@@ -1786,12 +1865,12 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
             bool visible = sc.visible(its.p, rec.p, cx.accel_mode, *cx.counters);
             if (rec.is_valid() && !mute && add_ok(vdepth) && I.strategy != RL_STRATEGY_BSDF) {
                 V3 wo = its.frame.to_local(rec.d);
-                Color f = bsdf.eval(cx.math, its.wi, wo);
+                Color f = bsdf.eval(cx.math, its.uv, its.wi, wo);
                 Color contrib = T * (rec.weight * f);
                 if (!contrib.is_zero()) {
                     float w = 1.0f;
                     if (I.strategy == RL_STRATEGY_ALL && rec.pdf.kind == PDF::SolidAngle) { // a Discrete light edge has no MIS (path.rs:80)
-                        float pb = bsdf.pdf(cx.math, its.wi, wo).value();
+                        float pb = bsdf.pdf(cx.math, its.uv, its.wi, wo).value();
                         float pl = rec.pdf.value();
                         w = pl / (pb + pl);
                     }
@@ -1833,16 +1912,16 @@ Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy
         LightSampling rec = sc.emitters.sample_light(its.p, r_sel, r, uv);
         V3 d_out_local = its.frame.to_local(rec.d);
         if (rec.is_valid() && sc.visible(its.p, rec.p, cx.accel_mode, *cx.counters) && !bsdf.is_smooth()) {
-            float pdf_bsdf = bsdf.pdf(cx.math, its.wi, d_out_local).value();
+            float pdf_bsdf = bsdf.pdf(cx.math, its.uv, its.wi, d_out_local).value();
             float weight_light = rec.pdf.kind == PDF::Discrete ? 1.0f // (PDF::Discrete(_), _) => 1.0, direct.rs:110
                                                                : mis_weight(rec.pdf.value() * weight_nb_light, pdf_bsdf * weight_nb_bsdf);
-            l_i = l_i + weight_light * bsdf.eval(cx.math, its.wi, d_out_local) * weight_nb_light * rec.weight;
+            l_i = l_i + weight_light * bsdf.eval(cx.math, its.uv, its.wi, d_out_local) * weight_nb_light * rec.weight;
         }
     }
     for (uint32_t i = 0; i < I.nb_bsdf_samples; i++) { // :135-230
         SampledDirection sb;
         P2 s2 = sampler.next2d();
-        if (!bsdf.sample(cx.math, its.wi, s2, &sb)) continue;
+        if (!bsdf.sample(cx.math, its.uv, its.wi, s2, &sb)) continue;
         V3 d_out_world = its.frame.to_world(sb.d);
         Ray r2 = spawn_ray(its, d_out_world);
         Intersection next_its;
@@ -1928,7 +2007,12 @@ orc_scene *orc_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
             m->has_normals = true;
             for (uint32_t v = 0; v < md.nverts; v++) m->normals.push_back(load3(md.N + 3 * v));
         }
-        m->bsdf = make_bsdf(md.mat);
+        if (md.UV) {
+            m->has_uv = true;
+            for (uint32_t v = 0; v < md.nverts; v++) m->uv.push_back(P2{md.UV[2 * v], md.UV[2 * v + 1]});
+        }
+        if (md.mat.kd_texture > desc->ntextures) return fail("kd_texture out of range");
+        m->bsdf = make_bsdf(md.mat, desc->textures, desc->ntextures);
         m->light = md.emission_kind != 0;
         m->emission = Color{md.emission[0], md.emission[1], md.emission[2]};
         m->first_prim = first;
@@ -2149,7 +2233,7 @@ float orc_mis_weight(float a, float b) { return mis_weight(a, b); }
 int orc_bsdf_sample(uint32_t math_mode, const rl_material *m, const float wi[3], float s0, float s1, float weight[3], float d[3], float *pdf) {
     auto b = make_bsdf(*m);
     SampledDirection sd;
-    if (!b->sample(Math{math_mode}, load3(wi), P2{s0, s1}, &sd)) return 0;
+    if (!b->sample(Math{math_mode}, UV{}, load3(wi), P2{s0, s1}, &sd)) return 0;
     weight[0] = sd.weight.r, weight[1] = sd.weight.g, weight[2] = sd.weight.b;
     store3(d, sd.d);
     *pdf = sd.pdf.value();
@@ -2160,10 +2244,10 @@ int orc_bsdf_flags(const rl_material *m) { // bit 0: is_twosided, bit 1: bsdf_ty
     return (b->is_twosided() ? 1 : 0) | (b->is_smooth() ? 2 : 0);
 }
 float orc_bsdf_pdf(uint32_t math_mode, const rl_material *m, const float wi[3], const float wo[3]) {
-    return make_bsdf(*m)->pdf(Math{math_mode}, load3(wi), load3(wo)).value();
+    return make_bsdf(*m)->pdf(Math{math_mode}, UV{}, load3(wi), load3(wo)).value();
 }
 void orc_bsdf_eval(uint32_t math_mode, const rl_material *m, const float wi[3], const float wo[3], float out[3]) {
-    Color c = make_bsdf(*m)->eval(Math{math_mode}, load3(wi), load3(wo));
+    Color c = make_bsdf(*m)->eval(Math{math_mode}, UV{}, load3(wi), load3(wo));
     out[0] = c.r, out[1] = c.g, out[2] = c.b;
 }
 int orc_sample_light(const orc_scene *os, const float x[3], float r_sel, float r, float u0, float u1, float p[3], float n[3], float d[3],

@@ -35,7 +35,7 @@ class rl_material(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("kd", C.c_float * 3), ("ks", C.c_float * 3),
                 ("exponent", C.c_float), ("weight_specular", C.c_float), ("kt", C.c_float * 3),
                 ("eta", C.c_float * 3), ("k", C.c_float * 3), ("ior", C.c_float), ("alpha", C.c_float),
-                ("microfacet", C.c_uint32)]
+                ("microfacet", C.c_uint32), ("kd_texture", C.c_uint32)]
 
 
 class rl_mesh_desc(C.Structure):
@@ -43,6 +43,17 @@ class rl_mesh_desc(C.Structure):
                 ("idx", C.POINTER(C.c_uint32)), ("ntris", C.c_uint32),
                 ("N", C.POINTER(C.c_float)), ("UV", C.POINTER(C.c_float)),
                 ("mat", rl_material), ("emission_kind", C.c_uint32), ("emission", C.c_float * 3)]
+
+
+RL_TEX_BITMAP = 1
+RL_TEX_CHECKERBOARD = 2
+RL_TEX_GRID = 3
+
+
+class rl_texture(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("width", C.c_uint32), ("height", C.c_uint32), ("pixels", C.POINTER(C.c_float)),
+                ("color0", C.c_float * 3), ("color1", C.c_float * 3), ("line_width", C.c_float),
+                ("offset", C.c_float * 2), ("scale", C.c_float * 2)]
 
 
 RL_LIGHT_POINT = 0
@@ -61,7 +72,8 @@ class rl_camera_desc(C.Structure):
 class rl_scene_desc(C.Structure):
     _fields_ = [("nmeshes", C.c_uint32), ("meshes", C.POINTER(rl_mesh_desc)),
                 ("camera", rl_camera_desc), ("has_volume", C.c_uint32), ("has_environment", C.c_uint32),
-                ("nlights", C.c_uint32), ("lights", C.POINTER(rl_light_desc))]
+                ("nlights", C.c_uint32), ("lights", C.POINTER(rl_light_desc)),
+                ("ntextures", C.c_uint32), ("textures", C.POINTER(rl_texture))]
 
 
 class rl_integrator_desc(C.Structure):

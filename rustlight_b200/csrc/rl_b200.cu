@@ -93,6 +93,8 @@ struct rl_scene {
     FlatTable flat;
     float4 *d_trav = nullptr, *d_nodes = nullptr, *d_shade = nullptr, *d_verts = nullptr, *d_mats = nullptr, *d_emit_info = nullptr;
     float *d_emit_cdf = nullptr, *d_area_cdf = nullptr;
+    float2 *d_uvs = nullptr;
+    float4 *d_tex = nullptr, *d_texels = nullptr;
     uint32_t n_node_f4 = 0, n_trav_f4 = 0;
     size_t smem_bytes = 0;
     bool smem_ok = false;
@@ -282,6 +284,7 @@ void rl_scene_destroy(rl_ctx *ctx, rl_scene *s) {
     if (ctx) cudaSetDevice(ctx->device);
     cudaFree(s->d_trav), cudaFree(s->d_nodes), cudaFree(s->d_shade), cudaFree(s->d_verts), cudaFree(s->d_mats);
     cudaFree(s->d_emit_info), cudaFree(s->d_emit_cdf), cudaFree(s->d_area_cdf), cudaFree(s->d_flat);
+    cudaFree(s->d_uvs), cudaFree(s->d_tex), cudaFree(s->d_texels);
     delete s;
 }
 
@@ -325,6 +328,9 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     CKS(upload(&s->d_emit_info, hs.emit_info, st));
     CKS(upload(&s->d_emit_cdf, hs.emit_cdf, st));
     CKS(upload(&s->d_area_cdf, hs.area_cdf, st));
+    if (!hs.uvs.empty()) CKS(upload(&s->d_uvs, hs.uvs, st));
+    if (!hs.tex.empty()) CKS(upload(&s->d_tex, hs.tex, st));
+    if (!hs.texels.empty()) CKS(upload(&s->d_texels, hs.texels, st));
     const uint32_t n_nodes = n > 1 ? n - 1 : 1;
     CKS(cudaMalloc(&s->d_trav, (size_t)n * RL_TRAV_F4 * sizeof(float4)));
     CKS(cudaMalloc(&s->d_nodes, (size_t)n_nodes * 4 * sizeof(float4)));
@@ -431,6 +437,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     SceneView &sv = s->sv;
     sv.trav = s->d_trav, sv.nodes = s->d_nodes, sv.shade = s->d_shade, sv.verts = s->d_verts, sv.mats = s->d_mats;
     sv.emit_info = s->d_emit_info, sv.emit_cdf = s->d_emit_cdf, sv.area_cdf = s->d_area_cdf;
+    sv.uvs = s->d_uvs, sv.tex = s->d_tex, sv.texels = s->d_texels;
     sv.ntris = n, sv.n_emitters = hs.n_emitters;
     sv.root_ref = root_ref;
     s->root_tree = root_ref;

@@ -287,7 +287,9 @@ RL_HD V3 cosine_sample_hemisphere(float ux, float uy) {
 // All tables are arrays of float4 so that every access is one 128-bit load.
 //   trav[4*s+0..3]   (Morton order s): {v0.xyz, det} {e1.xyz, prim} {e2.xyz, -} {n_geo.xyz, -}
 //   nodes[4*j+0..3]  wide LBVH node:   {lo0.xyz, hi0.x} {hi0.yz, lo1.xy} {lo1.z, hi1.xyz} {child0, child1, -, -}
-//   shade[4*p+0..3]  (original order p): {n_geo.xyz, mesh} {n0.xyz, has_normals} {n1.xyz, -} {n2.xyz, -}
+//   shade[4*p+0..3]  (original order p): {n_geo.xyz, mesh} {n0.xyz, flags: bit 0 normals, bit 1 uv} {n1.xyz, -} {n2.xyz, -}
+//   uvs[3*p+0..2]    per-corner texture coordinates (only when some mesh has uv)
+//   tex[4*t+0..3]    {color0, kind} {color1, line_width} {offset.xy, scale.xy} {width, height, texel offset, -};  texels[]
 //   verts[3*p+0..2]  (original order p): {v.xyz, -}
 //   mats[5*m+0..4]   {kd.rgb | metal eta | glass kt, kind} {ks.rgb, phong exponent | microfacet alpha} {Le.rgb, is_light}
 //                    {phong weight_specular | glass eta, 1/area, pdf_sel, microfacet} {metal k.rgb, glass 1/eta}
@@ -300,6 +302,9 @@ struct SceneView {
     const float4 *verts;
     const float4 *mats;
     const float4 *emit_info;
+    const float2 *uvs;    // nullptr when no mesh has uv
+    const float4 *tex;    // textures of the kd slot (BSDFColor::{Bitmap, Checkerbord, Grid})
+    const float4 *texels;
     const float *emit_cdf; // n_emitters+1
     const float *area_cdf; // concatenated per-emitter triangle-area cdfs (ntris+1 each)
     uint32_t ntris, n_emitters;
@@ -874,7 +879,7 @@ struct Material {
     float inv_area, pdf_sel;
     uint32_t kind, microfacet;
     bool is_light;
-    const float4 *ext;    // {metal k.rgb, glass 1/eta}: read only by the metal and glass branches
+    const float4 *ext;    // {metal k.rgb, glass 1/eta | kd_texture}: read only by the metal / glass branches and the texture lookup
 };
 RL_HD Material load_material(const float4 *mats, uint32_t mesh) {
     const float4 *row = mats + RL_MAT_F4 * mesh;
@@ -1203,6 +1208,56 @@ RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight
     return true;
 }
 
+// ---- BSDFColor::color for the kd slot (bsdfs/mod.rs:31-101) -----------------------------------------
+RL_HD uint64_t f32_as_usize(float v) { // Rust `as usize`: saturating, NaN -> 0
+    if (!(v > 0.0f)) return 0ull;
+    if (v >= 18446744073709551616.0f) return ~0ull;
+    return (uint64_t)v;
+}
+RL_HD int32_t f32_as_i32(float v) { // Rust `as i32`: saturating, NaN -> 0
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return 2147483647;
+    if (v <= -2147483648.0f) return (int32_t)0x80000000u;
+    return (int32_t)v;
+}
+RL_HD float modulo1(float x) { return fmodf(fmodf(x, 1.0f) + 1.0f, 1.0f); } // tools.rs:39-41 with n = 1.0
+// kd of a textured material at a hit: `flags` bit 1 = the mesh has uv; (hit_u, hit_v) barycentrics of the hit
+RL_HD Col texture_kd(const SceneView &sv, uint32_t tex_id, uint32_t prim, uint32_t flags, float hit_u, float hit_v) {
+    if (!(flags & 2u)) return Col{0.0f, 0.0f, 0.0f}; // "Found a texture but no uv coordinate given"
+    // uv interpolation, structure.rs:1015-1023: d0 * (1 - u - v) + d1 * u + d2 * v
+    const float2 d0 = sv.uvs[3 * prim], d1 = sv.uvs[3 * prim + 1], d2 = sv.uvs[3 * prim + 2];
+    const float w = 1.0f - hit_u - hit_v;
+    float ux = d0.x * w + d1.x * hit_u + d2.x * hit_v, uy = d0.y * w + d1.y * hit_u + d2.y * hit_v;
+    const float4 t0 = sv.tex[4 * tex_id], t1 = sv.tex[4 * tex_id + 1], t2 = sv.tex[4 * tex_id + 2];
+    const uint32_t kind = f2u(t0.w);
+    if (kind == 1u) { // Bitmap::pixel_uv, structure.rs:434-453
+        const float4 t3 = sv.tex[4 * tex_id + 3];
+        const uint32_t width = f2u(t3.x), height = f2u(t3.y), off = f2u(t3.z);
+        ux = modulo1(ux), uy = modulo1(uy);
+        const uint64_t x = f32_as_usize(ux * (float)width), y = f32_as_usize(uy * (float)height);
+        const uint64_t i = (uint64_t)width * y + x;
+        if (i >= (uint64_t)width * height) return Col{0.0f, 0.0f, 0.0f};
+        return xyz_col(sv.texels[off + i]);
+    }
+    if (kind == 2u) { // Checkerbord, bsdfs/mod.rs:43-65
+        ux = ux * t2.z + t2.x, uy = uy * t2.w + t2.y;
+        const int32_t x = 2 * (f32_as_i32(ux * 2.0f) % 2) - 1, y = 2 * (f32_as_i32(uy * 2.0f) % 2) - 1;
+        return x * y == 1 ? xyz_col(t0) : xyz_col(t1);
+    }
+    // Grid, bsdfs/mod.rs:66-99 (note `uv.y + scale.y`)
+    ux = ux * t2.z + t2.x, uy = (uy + t2.w) + t2.y;
+    float x = ux - floorf(ux), y = uy - floorf(uy);
+    if (x > 0.5f) x -= 1.0f;
+    if (y > 0.5f) y -= 1.0f;
+    return (fabsf(x) < t1.w || fabsf(y) < t1.w) ? xyz_col(t0) : xyz_col(t1);
+}
+// Replaces m.kd by the texture value when the material has one (DIFFUSE, PHONG, SUBSTRATE).
+RL_HD void apply_kd_texture(const SceneView &sv, Material &m, uint32_t prim, uint32_t flags, float hit_u, float hit_v) {
+    if (m.kind == 2u || m.kind == 3u) return;
+    const uint32_t t = f2u(m.ext[0].w);
+    if (t != 0u) m.kd = texture_kd(sv, t - 1u, prim, flags, hit_u, hit_v);
+}
+
 // ---- surface interaction (fill_intersection, structure.rs:965-1059) ---------------------------
 struct Surface {
     V3 p, n_g, n_s, wi;
@@ -1217,7 +1272,7 @@ RL_HD Surface fill_intersection(const SceneView &sv, const Material &mat, uint32
     s.p = o + t * d; // its.p as computed inside intersection_tri (geometry.rs:382)
     V3 n_g = xyz(s0);
     V3 n_s;
-    if (f2u(s1.w) != 0u) {
+    if (f2u(s1.w) & 1u) {
         V3 d0 = xyz(s1), d1 = xyz(s2), d2 = xyz(s3);
         V3 ns = d0 * (1.0f - hit_u - hit_v) + d1 * hit_u + d2 * hit_v;
         if (dot(n_g, ns) < 0.0f) n_g = -n_g;
@@ -1303,7 +1358,7 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, 
     // and n_geo is already in the shading table
     V3 n_g = -xyz(sv.shade[4 * prim]);
     float4 s1 = sv.shade[4 * prim + 1];
-    if (f2u(s1.w) != 0u) {
+    if (f2u(s1.w) & 1u) {
         V3 n0 = xyz(s1), n1 = xyz(sv.shade[4 * prim + 2]), n2 = xyz(sv.shade[4 * prim + 3]);
         V3 n = n0 * b0 + n1 * b1 + n2 * (1.0f - b0 - b1);
         float n_l = dot(n, n);
@@ -1413,6 +1468,7 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
     uint32_t mesh = f2u(s0.w);
     Material mat = load_material(sv.mats, mesh);
+    if (sv.tex) apply_kd_texture(sv, mat, hit.prim, f2u(s1.w), hit.u, hit.v);
     Surface its = fill_intersection<KM>(sv, mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
     const bool mute = ip.single_scattering != 0u;
     const bool smooth = mat_is_smooth<KM>(mat); // no light sampling at this vertex (emitters.rs:110-112), no draws either
@@ -1528,6 +1584,7 @@ RL_HD void direct_begin(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, 
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
     uint32_t mesh = f2u(s0.w);
     cx->mat = load_material(sv.mats, mesh);
+    if (sv.tex) apply_kd_texture(sv, cx->mat, hit.prim, f2u(s1.w), hit.u, hit.v);
     cx->its = fill_intersection(sv, cx->mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
     if (cx->its.wi.z <= 0.0f) return; // its.cos_theta() <= 0 (direct.rs:40-42)
     cx->ok = true;

@@ -20,7 +20,10 @@ struct HostScene {
     uint32_t ntris = 0, nmeshes = 0, n_emitters = 0;
     std::vector<float4> verts;     // 3 per prim
     std::vector<float4> shade;     // 4 per prim; [0].xyz (n_geo) filled by the device setup kernel
-    std::vector<float4> mats;      // 4 per mesh
+    std::vector<float4> mats;      // RL_MAT_F4 per mesh
+    std::vector<float2> uvs;       // 3 per prim (zeros for meshes without uv); empty when no mesh has uv
+    std::vector<float4> tex;       // 4 per texture: {color0, kind} {color1, line_width} {offset.xy, scale.xy} {width, height, texel offset, -}
+    std::vector<float4> texels;    // bitmap pixels {r, g, b, -}
     std::vector<float4> emit_info; // 1 per emitter
     std::vector<float> emit_cdf;   // n_emitters + 1
     std::vector<float> area_cdf;   // concatenated
@@ -92,6 +95,27 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
         float intensity[3] = {0, 0, 0}, v[3] = {0, 0, 0}, radius = 0.0f;
     };
     std::vector<EmitterTmp> emitters;
+    bool any_uv = false;
+    for (uint32_t mi = 0; mi < desc->nmeshes; mi++) any_uv = any_uv || desc->meshes[mi].UV != nullptr;
+    // textures (BSDFColor::{Bitmap, Checkerbord, Grid}) -> 4 rows each + the texel array
+    if (desc->ntextures > 0 && !desc->textures) {
+        err = "ntextures > 0 but textures is null";
+        return false;
+    }
+    for (uint32_t ti = 0; ti < desc->ntextures; ti++) {
+        const rl_texture &t = desc->textures[ti];
+        if (t.kind < RL_TEX_BITMAP || t.kind > RL_TEX_GRID || (t.kind == RL_TEX_BITMAP && (!t.pixels || t.width == 0 || t.height == 0))) {
+            err = "bad texture";
+            return false;
+        }
+        uint32_t off = (uint32_t)hs.texels.size();
+        hs.tex.push_back(f4(t.color0[0], t.color0[1], t.color0[2], u2f(t.kind)));
+        hs.tex.push_back(f4(t.color1[0], t.color1[1], t.color1[2], t.line_width));
+        hs.tex.push_back(f4(t.offset[0], t.offset[1], t.scale[0], t.scale[1]));
+        hs.tex.push_back(f4(u2f(t.width), u2f(t.height), u2f(off), 0.0f));
+        if (t.kind == RL_TEX_BITMAP)
+            for (size_t i = 0; i < (size_t)t.width * t.height; i++) hs.texels.push_back(f4(t.pixels[3 * i], t.pixels[3 * i + 1], t.pixels[3 * i + 2], 0.0f));
+    }
     std::vector<float> mesh_inv_area(desc->nmeshes, 0.0f);
     uint32_t first = 0;
     for (uint32_t mi = 0; mi < desc->nmeshes; mi++) {
@@ -102,7 +126,9 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
         }
         const bool has_mf = m.mat.kind == RL_BSDF_METAL || m.mat.kind == RL_BSDF_SUBSTRATE;
         if (m.mat.kind > RL_BSDF_SUBSTRATE || (has_mf && m.mat.microfacet > RL_MICROFACET_BECKMANN) ||
-            (has_mf && m.mat.microfacet != RL_MICROFACET_NONE && !(m.mat.alpha > 0.0f)) || (m.mat.kind == RL_BSDF_GLASS && m.mat.ior == 0.0f)) {
+            (has_mf && m.mat.microfacet != RL_MICROFACET_NONE && !(m.mat.alpha > 0.0f)) || (m.mat.kind == RL_BSDF_GLASS && m.mat.ior == 0.0f) ||
+            m.mat.kd_texture > desc->ntextures ||
+            (m.mat.kd_texture != 0 && m.mat.kind != RL_BSDF_DIFFUSE && m.mat.kind != RL_BSDF_PHONG && m.mat.kind != RL_BSDF_SUBSTRATE)) {
             err = "unsupported BSDF kind or parameters";
             return false;
         }
@@ -118,12 +144,19 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
                 v[k] = V3{m.P[3 * id[k]], m.P[3 * id[k] + 1], m.P[3 * id[k] + 2]};
                 hs.verts.push_back(f4(v[k].x, v[k].y, v[k].z, 0.0f));
             }
-            // shading record: n_geo slot (device fills xyz), mesh id, vertex normals
+            // shading record: n_geo slot (device fills xyz), mesh id, vertex normals; flags: bit 0 normals, bit 1 uv
+            const uint32_t flags = (m.N ? 1u : 0u) | (m.UV ? 2u : 0u);
             hs.shade.push_back(f4(0.0f, 0.0f, 0.0f, u2f(mi)));
             for (int k = 0; k < 3; k++) {
-                if (m.N) hs.shade.push_back(f4(m.N[3 * id[k]], m.N[3 * id[k] + 1], m.N[3 * id[k] + 2], k == 0 ? u2f(1u) : 0.0f));
-                else hs.shade.push_back(f4(0.0f, 0.0f, 0.0f, 0.0f));
+                if (m.N) hs.shade.push_back(f4(m.N[3 * id[k]], m.N[3 * id[k] + 1], m.N[3 * id[k] + 2], k == 0 ? u2f(flags) : 0.0f));
+                else hs.shade.push_back(f4(0.0f, 0.0f, 0.0f, k == 0 ? u2f(flags) : 0.0f));
             }
+            if (any_uv)
+                for (int k = 0; k < 3; k++) {
+                    float2 q;
+                    q.x = m.UV ? m.UV[2 * id[k]] : 0.0f, q.y = m.UV ? m.UV[2 * id[k] + 1] : 0.0f;
+                    hs.uvs.push_back(q);
+                }
             // bounds: compute_aabb_tri (geometry.rs:423-439) for the reference root box
             float lo[3], hi[3];
             for (int a = 0; a < 3; a++) {
@@ -239,7 +272,8 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
         hs.mats.push_back(f4(m.emission_kind ? m.emission[0] : 0.0f, m.emission_kind ? m.emission[1] : 0.0f,
                              m.emission_kind ? m.emission[2] : 0.0f, u2f(m.emission_kind ? 1u : 0u)));
         hs.mats.push_back(f4(mt.kind == RL_BSDF_GLASS ? mt.ior : mt.weight_specular, mesh_inv_area[mi], pdf_sel[mi], u2f(has_mf ? mt.microfacet : 0u)));
-        hs.mats.push_back(f4(mt.k[0], mt.k[1], mt.k[2], mt.kind == RL_BSDF_GLASS ? 1.0f / mt.ior : 0.0f)); // BSDFGlass::eta(): inv_eta = 1.0 / eta
+        // row 4: {metal k, glass 1/eta (BSDFGlass::eta(): inv_eta = 1.0 / eta) | kd_texture as uint bits}
+        hs.mats.push_back(f4(mt.k[0], mt.k[1], mt.k[2], mt.kind == RL_BSDF_GLASS ? 1.0f / mt.ior : u2f(mt.kd_texture)));
     }
     float am = 0.0f;
     for (int a = 0; a < 3; a++) am = fmaxf(am, fmaxf(fabsf(hs.raw_min[a]), fabsf(hs.raw_max[a])));

@@ -41,6 +41,10 @@ def lib():
         L.rlh_material_substrate.argtypes = [f3, f3, C.c_uint32, C.c_float, C.POINTER(_abi.rl_material)]
         L.rlh_remap_roughness.restype = C.c_float
         L.rlh_remap_roughness.argtypes = [C.c_float, C.c_int]
+        L.rlh_scene_add_texture.restype = C.c_uint32
+        L.rlh_scene_add_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        L.rlh_scene_add_texture_file.restype = C.c_uint32
+        L.rlh_scene_add_texture_file.argtypes = [C.c_void_p, C.c_char_p]
         L.rlh_scene_add_light.argtypes = [C.c_void_p, C.c_uint32, C.c_float * 3, C.c_float * 3]
         L.rlh_scene_set_material.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_abi.rl_material)]
         L.rlh_material_phong.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
@@ -106,6 +110,30 @@ class Scene:
         if lib().rlh_scene_set_material(self._h, int(mesh), C.byref(material)) != 0:
             raise SceneError("bad mesh index")
         return self
+
+    def add_bitmap_texture(self, rgb):
+        """BSDFColor::Bitmap from an (h, w, 3) float array (Bitmap.colors order: index y*w + x).  Returns the id for
+        rl_material.kd_texture."""
+        a = np.ascontiguousarray(rgb, dtype=np.float32)
+        h, w, _ = a.shape
+        t = lib().rlh_scene_add_texture(self._h, _abi.RL_TEX_BITMAP, w, h, a.ctypes.data_as(C.POINTER(C.c_float)), None)
+        if not t:
+            raise SceneError("bad bitmap texture")
+        return t
+
+    def add_texture_file(self, filename):
+        t = lib().rlh_scene_add_texture_file(self._h, os.fsencode(filename))
+        if not t:
+            raise SceneError(f"cannot read texture {filename}")
+        return t
+
+    def add_checkerboard_texture(self, color0, color1, offset=(0, 0), scale=(1, 1)):
+        p = (C.c_float * 11)(*color0, *color1, *offset, *scale, 0.0)
+        return lib().rlh_scene_add_texture(self._h, _abi.RL_TEX_CHECKERBOARD, 0, 0, None, p)
+
+    def add_grid_texture(self, color0, color1, line_width=0.01, offset=(0, 0), scale=(1, 1)):
+        p = (C.c_float * 11)(*color0, *color1, *offset, *scale, float(line_width))
+        return lib().rlh_scene_add_texture(self._h, _abi.RL_TEX_GRID, 0, 0, None, p)
 
     def add_point_light(self, intensity, position):
         """PointEmitter (emitter.rs:186-250), appended to Scene.emitters."""
@@ -197,10 +225,11 @@ def remap_roughness(v, remap=True):
     return lib().rlh_remap_roughness(float(v), 1 if remap else 0)
 
 
-def material_diffuse(kd):
+def material_diffuse(kd=(0.0, 0.0, 0.0), kd_texture=0):
     m = _abi.rl_material()
     m.kind = _abi.RL_BSDF_DIFFUSE
     m.kd[:] = kd
+    m.kd_texture = kd_texture
     return m
 
 

@@ -102,6 +102,27 @@ int rlh_scene_add_light(rlh_scene *s, uint32_t kind, const float intensity[3], c
     }
 }
 
+// BSDFColor::{Bitmap, Checkerbord, Grid}: returns the 1-based id for rl_material.kd_texture, 0 on error.
+// kind: rl_texture_kind; bitmap: (w, h, rgb[3*w*h]); checkerboard / grid: params = {color0[3], color1[3], offset[2], scale[2], line_width}
+uint32_t rlh_scene_add_texture(rlh_scene *s, uint32_t kind, uint32_t w, uint32_t h, const float *rgb, const float *params) {
+    try {
+        if (kind == RL_TEX_BITMAP) return s->scene.add_texture(Texture::bitmap(w, h, std::vector<float>(rgb, rgb + (size_t)3 * w * h)));
+        Color c0{params[0], params[1], params[2]}, c1{params[3], params[4], params[5]};
+        if (kind == RL_TEX_CHECKERBOARD) return s->scene.add_texture(Texture::checkerboard(c0, c1, params[6], params[7], params[8], params[9]));
+        if (kind == RL_TEX_GRID) return s->scene.add_texture(Texture::grid(c0, c1, params[10], params[6], params[7], params[8], params[9]));
+        return 0;
+    } catch (const std::exception &) {
+        return 0;
+    }
+}
+uint32_t rlh_scene_add_texture_file(rlh_scene *s, const char *filename) {
+    try {
+        return s->scene.add_texture(Texture::bitmap_file(filename));
+    } catch (const std::exception &) {
+        return 0;
+    }
+}
+
 // Material::metal / glass / substrate (bsdfs/metal.rs, glass.rs, substrate.rs); microfacet is an rl_microfacet
 int rlh_material_metal(const float specular[3], const float eta[3], const float k[3], uint32_t microfacet, float alpha, rl_material *out) {
     try {

@@ -365,9 +365,21 @@ void read_ply(const std::string &filename, RawShape &out) {
         if (v >= nv) throw Error("ply: face index out of range in " + filename);
 }
 
-Material material_from_params(const std::string &type, const ParamSet &ps) {
+// "texture Kd" "name" -> BSDFColor::Bitmap (bsdf_texture_match_pbrt, bsdfs/mod.rs:224-236); 0 when Kd is not a texture
+uint32_t kd_texture_of(const ParamSet &ps, const std::map<std::string, uint32_t> &texture_ids) {
+    const Param *p = ps.find("Kd");
+    if (!p || p->type != "texture") return 0;
+    if (p->strs.empty() || !texture_ids.count(p->strs[0])) throw Error("pbrt: Kd refers to an unknown texture"); // the reference warns and falls back to diffuse 0.8
+    return texture_ids.at(p->strs[0]);
+}
+Material material_from_params(const std::string &type, const ParamSet &ps, const std::map<std::string, uint32_t> &texture_ids) {
     if (type == "matte") {
         // pbrt_rs::BSDF::Matte { kd } -> BSDFDiffuse (src/bsdfs/mod.rs:299-306); Kd default 0.5
+        if (uint32_t t = kd_texture_of(ps, texture_ids)) {
+            Material m = Material::diffuse(Color{0.0f, 0.0f, 0.0f});
+            m.m.kd_texture = t;
+            return m;
+        }
         return Material::diffuse(ps.rgb("Kd", Color{0.5f, 0.5f, 0.5f}));
     }
     if (type == "phong") { // extension, see file header
@@ -389,8 +401,13 @@ Material material_from_params(const std::string &type, const ParamSet &ps) {
                                RL_MICROFACET_GGX, ggx_alpha(0.01));
     if (type == "glass") // bsdfs/mod.rs:307-333: the distribution is ignored ("Pure glass instead"), .eta(eta, 1.0)
         return Material::glass(ps.rgb("Kr", Color{1.0f, 1.0f, 1.0f}), ps.rgb("Kt", Color{1.0f, 1.0f, 1.0f}), (float)ps.num("eta", ps.num("index", 1.5)), 1.0f);
-    if (type == "substrate") // bsdfs/mod.rs:358-374
-        return Material::substrate(ps.rgb("Kd", Color{0.5f, 0.5f, 0.5f}), ps.rgb("Ks", Color{0.5f, 0.5f, 0.5f}), RL_MICROFACET_GGX, ggx_alpha(0.1));
+    if (type == "substrate") { // bsdfs/mod.rs:358-374
+        uint32_t t = kd_texture_of(ps, texture_ids);
+        Material m = Material::substrate(t ? Color{0.0f, 0.0f, 0.0f} : ps.rgb("Kd", Color{0.5f, 0.5f, 0.5f}), ps.rgb("Ks", Color{0.5f, 0.5f, 0.5f}), RL_MICROFACET_GGX,
+                                         ggx_alpha(0.1));
+        m.m.kd_texture = t;
+        return m;
+    }
     throw Error("pbrt: material type \"" + type + "\" is not supported (matte, mirror, metal, glass, substrate, phong)");
 }
 } // namespace
@@ -406,6 +423,7 @@ Scene PBRTSceneLoader::load_string(const std::string &text, bool use_shading_nor
     std::vector<GState> stack;
     std::vector<Mat4> tstack;
     std::map<std::string, Material> materials;
+    std::map<std::string, uint32_t> texture_ids;            // pbrt_rs::Scene::textures -> 1-based ids of scene.textures
     std::vector<RawShape> top_shapes;                       // pbrt_rs::Scene::shapes
     std::map<std::string, std::vector<RawShape>> objects;   // pbrt_rs::Scene::objects
     std::vector<std::pair<std::string, Mat4>> instances;    // pbrt_rs::Scene::instances {name, matrix}
@@ -475,14 +493,14 @@ Scene PBRTSceneLoader::load_string(const std::string &text, bool use_shading_nor
         } else if (d == "MakeNamedMaterial") {
             std::string name = ps.expect_str();
             ParamSet p = ps.params();
-            materials[name] = material_from_params(p.str("type", "matte"), p);
+            materials[name] = material_from_params(p.str("type", "matte"), p, texture_ids);
         } else if (d == "NamedMaterial") {
             gs.named_material = ps.expect_str();
             gs.material.reset();
         } else if (d == "Material") {
             std::string type = ps.expect_str();
             ParamSet p = ps.params();
-            gs.material = material_from_params(type, p);
+            gs.material = material_from_params(type, p, texture_ids);
             gs.named_material.clear();
         } else if (d == "AreaLightSource") {
             std::string type = ps.expect_str();
@@ -561,7 +579,16 @@ Scene PBRTSceneLoader::load_string(const std::string &text, bool use_shading_nor
                 Vec3 from = pt("from", 0, 0, 0), to = pt("to", 0, 0, 1);
                 scene.add_directional_light(Color{L.r * scale.r, L.g * scale.g, L.b * scale.b}, to.x - from.x, to.y - from.y, to.z - from.z);
             } else throw Error("pbrt: LightSource \"" + type + "\" is outside the hot-path scope (point, distant)");
-        } else if (d == "Texture" || d == "MakeNamedMedium" || d == "MediumInterface" || d == "Include") {
+        } else if (d == "Texture") { // pbrt_rs::Texture {filename}: only image maps reach the BSDFs (bsdfs/mod.rs:219-241)
+            std::string name = ps.expect_str(), ttype = ps.expect_str(), tclass = ps.expect_str();
+            ParamSet p = ps.params();
+            if (tclass != "imagemap") throw Error("pbrt: Texture class \"" + tclass + "\" is outside the hot-path scope (imagemap)");
+            std::string fn = p.str("filename");
+            if (fn.empty()) throw Error("pbrt: imagemap needs a filename");
+            if (fn[0] != '/' && !base_dir.empty()) fn = base_dir + "/" + fn;
+            texture_ids[name] = scene.add_texture(Texture::bitmap_file(fn));
+            (void)ttype;
+        } else if (d == "MakeNamedMedium" || d == "MediumInterface" || d == "Include") {
             throw Error("pbrt: directive " + d + " is outside the hot-path scope");
         } else {
             throw Error("pbrt: unknown directive " + d);
@@ -716,10 +743,11 @@ Material jmaterial(const JVal &m) {
 } // namespace
 
 Scene JSONSceneLoader::load(const std::string &filename, bool use_shading_normal) const {
-    return load_string(read_file(filename), use_shading_normal);
+    size_t slash = filename.find_last_of('/');
+    return load_string(read_file(filename), use_shading_normal, slash == std::string::npos ? "" : filename.substr(0, slash));
 }
 
-Scene JSONSceneLoader::load_string(const std::string &text, bool use_shading_normal) const {
+Scene JSONSceneLoader::load_string(const std::string &text, bool use_shading_normal, const std::string &base_dir) const {
     JParser jp(text);
     JVal root = jp.parse();
     if (root.t != JVal::Obj) throw Error("json: root must be an object");
@@ -740,10 +768,52 @@ Scene JSONSceneLoader::load_string(const std::string &text, bool use_shading_nor
     }
     scene.camera = Camera::create(w, h, axis, fov, to_world, flip);
 
+    // "textures": {name: {"type": "checkerboard", color0, color1, offset, scale} | {"type": "grid", ..., line_width} |
+    //                      {"type": "bitmap", "filename": "x.pfm|x.ppm"} | {"type": "bitmap", "width", "height", "pixels": [r,g,b,...]}}
+    std::map<std::string, uint32_t> texture_ids;
+    if (const JVal *ts = root.get("textures")) {
+        if (ts->t != JVal::Obj) throw Error("json: textures must be an object");
+        for (auto &kv : ts->o) {
+            const JVal &t = kv.second;
+            const JVal *ty = t.get("type");
+            std::string type = (ty && ty->t == JVal::Str) ? ty->s : "";
+            auto f2 = [&](const char *k, float d0, float d1) {
+                const JVal *v = t.get(k);
+                if (!v) return std::vector<float>{d0, d1};
+                return jfloats(v, k, 2);
+            };
+            if (type == "bitmap") {
+                const JVal *fn = t.get("filename");
+                if (fn && fn->t == JVal::Str) {
+                    std::string path = fn->s;
+                    if (path[0] != '/' && !base_dir.empty()) path = base_dir + "/" + path;
+                    texture_ids[kv.first] = scene.add_texture(Texture::bitmap_file(path));
+                } else {
+                    const JVal *w = t.get("width"), *h = t.get("height");
+                    if (!w || !h) throw Error("json: bitmap texture needs filename or width/height/pixels");
+                    texture_ids[kv.first] = scene.add_texture(Texture::bitmap((uint32_t)w->n, (uint32_t)h->n, jfloats(t.get("pixels"), "pixels", 0)));
+                }
+            } else if (type == "checkerboard" || type == "grid") {
+                Color c0 = jcolor(t.get("color0"), "color0", Color{0.4f, 0.4f, 0.4f}), c1 = jcolor(t.get("color1"), "color1", Color{0.2f, 0.2f, 0.2f});
+                auto off = f2("offset", 0.0f, 0.0f), sc = f2("scale", 1.0f, 1.0f);
+                const JVal *lw = t.get("line_width");
+                texture_ids[kv.first] = scene.add_texture(type == "grid" ? Texture::grid(c0, c1, lw ? (float)lw->n : 0.01f, off[0], off[1], sc[0], sc[1])
+                                                                          : Texture::checkerboard(c0, c1, off[0], off[1], sc[0], sc[1]));
+            } else throw Error("json: unknown texture type \"" + type + "\"");
+        }
+    }
+    auto with_texture = [&](const JVal &m, Material mat) {
+        if (const JVal *kt = m.get("kd_texture")) {
+            if (kt->t != JVal::Str || !texture_ids.count(kt->s)) throw Error("json: unknown kd_texture");
+            if (mat.m.kind != RL_BSDF_DIFFUSE && mat.m.kind != RL_BSDF_PHONG && mat.m.kind != RL_BSDF_SUBSTRATE) throw Error("json: kd_texture on a material without a diffuse slot");
+            mat.m.kd_texture = texture_ids[kt->s];
+        }
+        return mat;
+    };
     std::map<std::string, Material> materials;
     if (const JVal *ms = root.get("materials")) {
         if (ms->t != JVal::Obj) throw Error("json: materials must be an object");
-        for (auto &kv : ms->o) materials[kv.first] = jmaterial(kv.second);
+        for (auto &kv : ms->o) materials[kv.first] = with_texture(kv.second, jmaterial(kv.second));
     }
     if (const JVal *ls = root.get("lights")) { // [{"type": "point", "intensity": [r,g,b], "position": [x,y,z]}, {"type": "directional", "intensity", "direction"}]
         if (ls->t != JVal::Arr) throw Error("json: lights must be an array");
@@ -794,7 +864,7 @@ Scene JSONSceneLoader::load_string(const std::string &text, bool use_shading_nor
         if (mat && mat->t == JVal::Str) {
             if (!materials.count(mat->s)) throw Error("json: unknown material " + mat->s);
             mesh->bsdf = materials[mat->s];
-        } else if (mat && mat->t == JVal::Obj) mesh->bsdf = jmaterial(*mat);
+        } else if (mat && mat->t == JVal::Obj) mesh->bsdf = with_texture(*mat, jmaterial(*mat));
         else mesh->bsdf = Material::diffuse(Color{0.5f, 0.5f, 0.5f});
         if (jm.get("emission")) {
             mesh->is_light = true;
@@ -837,6 +907,33 @@ std::string scene_to_json(const Scene &scene) {
         }
         o << "],\n";
     }
+    if (!scene.textures.empty()) {
+        o << "  \"textures\": {";
+        for (size_t i = 0; i < scene.textures.size(); i++) {
+            const Texture &t = scene.textures[i];
+            o << (i ? ", " : "") << "\"tex" << i + 1 << "\": {\"type\": \"" << (t.t.kind == RL_TEX_BITMAP ? "bitmap" : (t.t.kind == RL_TEX_GRID ? "grid" : "checkerboard")) << "\"";
+            if (t.t.kind == RL_TEX_BITMAP) {
+                o << ", \"width\": " << t.t.width << ", \"height\": " << t.t.height << ", \"pixels\": ";
+                put_floats(o, t.pixels.data(), t.pixels.size());
+            } else {
+                o << ", \"color0\": ";
+                put_floats(o, t.t.color0, 3);
+                o << ", \"color1\": ";
+                put_floats(o, t.t.color1, 3);
+                o << ", \"offset\": ";
+                put_floats(o, t.t.offset, 2);
+                o << ", \"scale\": ";
+                put_floats(o, t.t.scale, 2);
+                if (t.t.kind == RL_TEX_GRID) {
+                    char b1[32];
+                    std::snprintf(b1, sizeof(b1), "%.9g", (double)t.t.line_width);
+                    o << ", \"line_width\": " << b1;
+                }
+            }
+            o << "}";
+        }
+        o << "},\n";
+    }
     o << "  \"meshes\": [\n";
     for (size_t i = 0; i < scene.meshes.size(); i++) {
         const Mesh &m = *scene.meshes[i];
@@ -857,6 +954,7 @@ std::string scene_to_json(const Scene &scene) {
         if (mt.kind == RL_BSDF_PHONG) put("exponent", &mt.exponent, 1);
         if (mt.kind == RL_BSDF_METAL) put("eta", mt.eta, 3), put("k", mt.k, 3);
         if (mt.kind == RL_BSDF_GLASS) put("kt", mt.kt, 3), put("ior", &mt.ior, 1);
+        if (mt.kd_texture) o << ", \"kd_texture\": \"tex" << mt.kd_texture << "\"";
         if (mt.kind == RL_BSDF_METAL || mt.kind == RL_BSDF_SUBSTRATE) {
             o << ", \"microfacet\": \"" << mfs[mt.microfacet <= RL_MICROFACET_BECKMANN ? mt.microfacet : 0] << "\"";
             put("alpha", &mt.alpha, 1);

@@ -84,6 +84,16 @@ struct Material {
 // distribution_pbrt's roughness remapping (bsdfs/mod.rs:265-276)
 float remap_roughness(float v, bool remap);
 
+// BSDFColor other than Constant (bsdfs/mod.rs:11-30), usable on the diffuse-reflectance slot of a material
+struct Texture {
+    rl_texture t{};             // t.pixels points into `pixels`
+    std::vector<float> pixels;  // bitmap: 3 * width * height (Bitmap.colors)
+    static Texture bitmap(uint32_t w, uint32_t h, std::vector<float> rgb);
+    static Texture bitmap_file(const std::string &filename); // .pfm (Bitmap::read_pfm) or binary .ppm (P6, /255 like read_ldr_image)
+    static Texture checkerboard(Color c0, Color c1, float ox, float oy, float sx, float sy);
+    static Texture grid(Color c0, Color c1, float line_width, float ox, float oy, float sx, float sy);
+};
+
 // src/geometry.rs:107-119
 struct Mesh {
     std::string name;
@@ -106,6 +116,11 @@ struct Scene {
     bool has_volume = false, has_environment = false;
     // Scene.emitters before build_emitters (EmittersState::Unbuild): PointEmitter / DirectionalLight (scene_loader.rs:207-240)
     std::vector<rl_light_desc> lights;
+    std::vector<Texture> textures; // referenced by Material.m.kd_texture (1-based)
+    uint32_t add_texture(Texture t) { // returns the 1-based id to store in rl_material.kd_texture
+        textures.push_back(std::move(t));
+        return (uint32_t)textures.size();
+    }
     void add_point_light(Color intensity, float x, float y, float z);
     void add_directional_light(Color intensity, float dx, float dy, float dz); // direction = normalize(to - from)
 
@@ -116,6 +131,7 @@ struct Scene {
 
   private:
     std::vector<rl_mesh_desc> mesh_descs_;
+    std::vector<rl_texture> texture_descs_;
     rl_scene_desc desc_{};
 };
 
@@ -132,7 +148,7 @@ struct PBRTSceneLoader : SceneLoader {
 };
 struct JSONSceneLoader : SceneLoader {
     Scene load(const std::string &filename, bool use_shading_normal) const override;
-    Scene load_string(const std::string &text, bool use_shading_normal) const;
+    Scene load_string(const std::string &text, bool use_shading_normal, const std::string &base_dir = "") const;
 };
 struct SceneLoaderManager {
     std::map<std::string, std::shared_ptr<SceneLoader>> loader;

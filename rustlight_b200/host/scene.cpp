@@ -5,6 +5,7 @@
 #include <fstream>
 
 #include "rl_host.hpp"
+#include <cctype>
 
 namespace rlh {
 
@@ -248,6 +249,62 @@ size_t Scene::nb_triangles() const {
     for (auto &m : meshes) n += m->indices.size() / 3;
     return n;
 }
+Texture Texture::bitmap(uint32_t w, uint32_t h, std::vector<float> rgb) {
+    if (w == 0 || h == 0 || rgb.size() != (size_t)3 * w * h) throw Error("texture: bitmap size mismatch");
+    Texture t;
+    t.t.kind = RL_TEX_BITMAP, t.t.width = w, t.t.height = h;
+    t.pixels = std::move(rgb);
+    return t;
+}
+Texture Texture::bitmap_file(const std::string &filename) {
+    auto ends = [&](const char *e) { return filename.size() >= std::strlen(e) && filename.compare(filename.size() - std::strlen(e), std::string::npos, e) == 0; };
+    if (ends(".pfm")) {
+        Bitmap b = Bitmap::read_pfm(filename);
+        return bitmap(b.size_x, b.size_y, std::move(b.colors));
+    }
+    if (ends(".ppm")) { // binary P6, 8 bit: value / 255 (Bitmap::read_ldr_image, structure.rs:649-668)
+        std::ifstream f(filename, std::ios::binary);
+        if (!f) throw Error("cannot open " + filename);
+        std::string magic;
+        f >> magic;
+        auto next_int = [&]() {
+            for (;;) {
+                int c = f.peek();
+                if (c == '#') {
+                    std::string skip;
+                    std::getline(f, skip);
+                } else if (std::isspace(c)) f.get();
+                else break;
+            }
+            long v;
+            f >> v;
+            return v;
+        };
+        long w = next_int(), h = next_int(), maxv = next_int();
+        f.get();
+        if (magic != "P6" || w <= 0 || h <= 0 || maxv != 255) throw Error("ppm: only binary P6 with maxval 255: " + filename);
+        std::vector<unsigned char> raw((size_t)3 * w * h);
+        f.read(reinterpret_cast<char *>(raw.data()), (std::streamsize)raw.size());
+        if (!f) throw Error("ppm: truncated " + filename);
+        std::vector<float> rgb(raw.size());
+        for (size_t i = 0; i < raw.size(); i++) rgb[i] = (float)raw[i] / 255.0f;
+        return bitmap((uint32_t)w, (uint32_t)h, std::move(rgb));
+    }
+    throw Error("texture: only .pfm and .ppm images can be read here: " + filename);
+}
+Texture Texture::checkerboard(Color c0, Color c1, float ox, float oy, float sx, float sy) {
+    Texture t;
+    t.t.kind = RL_TEX_CHECKERBOARD;
+    set3(t.t.color0, c0), set3(t.t.color1, c1);
+    t.t.offset[0] = ox, t.t.offset[1] = oy, t.t.scale[0] = sx, t.t.scale[1] = sy;
+    return t;
+}
+Texture Texture::grid(Color c0, Color c1, float line_width, float ox, float oy, float sx, float sy) {
+    Texture t = checkerboard(c0, c1, ox, oy, sx, sy);
+    t.t.kind = RL_TEX_GRID;
+    t.t.line_width = line_width;
+    return t;
+}
 void Scene::add_point_light(Color intensity, float x, float y, float z) {
     rl_light_desc l{};
     l.kind = RL_LIGHT_POINT;
@@ -289,6 +346,14 @@ const rl_scene_desc *Scene::desc() {
     std::memcpy(desc_.camera.to_world, camera.to_world.m, sizeof(float) * 16);
     desc_.has_volume = has_volume ? 1u : 0u;
     desc_.has_environment = has_environment ? 1u : 0u;
+    texture_descs_.clear();
+    for (auto &t : textures) {
+        rl_texture d = t.t;
+        d.pixels = t.pixels.empty() ? nullptr : t.pixels.data();
+        texture_descs_.push_back(d);
+    }
+    desc_.ntextures = (uint32_t)texture_descs_.size();
+    desc_.textures = texture_descs_.empty() ? nullptr : texture_descs_.data();
     desc_.nlights = (uint32_t)lights.size();
     desc_.lights = lights.empty() ? nullptr : lights.data();
     return &desc_;

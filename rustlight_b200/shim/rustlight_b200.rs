@@ -15,7 +15,11 @@ use std::os::raw::{c_char, c_int, c_void};
 #[repr(C)] #[derive(Clone, Copy)]
 pub struct rl_material {
     pub kind: u32, pub kd: [f32; 3], pub ks: [f32; 3], pub exponent: f32, pub weight_specular: f32,
-    pub kt: [f32; 3], pub eta: [f32; 3], pub k: [f32; 3], pub ior: f32, pub alpha: f32, pub microfacet: u32,
+    pub kt: [f32; 3], pub eta: [f32; 3], pub k: [f32; 3], pub ior: f32, pub alpha: f32, pub microfacet: u32, pub kd_texture: u32,
+}
+#[repr(C)] pub struct rl_texture {
+    pub kind: u32, pub width: u32, pub height: u32, pub pixels: *const f32, pub color0: [f32; 3], pub color1: [f32; 3],
+    pub line_width: f32, pub offset: [f32; 2], pub scale: [f32; 2],
 }
 #[repr(C)]
 pub struct rl_mesh_desc {
@@ -26,7 +30,7 @@ pub struct rl_mesh_desc {
 #[repr(C)] pub struct rl_light_desc { pub kind: u32, pub intensity: [f32; 3], pub v: [f32; 3] }
 #[repr(C)] pub struct rl_scene_desc {
     pub nmeshes: u32, pub meshes: *const rl_mesh_desc, pub camera: rl_camera_desc, pub has_volume: u32, pub has_environment: u32,
-    pub nlights: u32, pub lights: *const rl_light_desc,
+    pub nlights: u32, pub lights: *const rl_light_desc, pub ntextures: u32, pub textures: *const rl_texture,
 }
 #[repr(C)] pub struct rl_integrator_desc {
     pub kind: u32, pub min_depth: i32, pub max_depth: i32, pub rr_depth: i32, pub strategy: u32,
@@ -64,10 +68,10 @@ use cgmath::{Matrix, Point2};
 fn opt(v: Option<u32>) -> i32 { v.map_or(-1, |x| x as i32) }
 
 /// Scene -> flat description.  Vectors are kept alive in `Flat` for the duration of the call.
-struct Flat { p: Vec<Vec<f32>>, n: Vec<Vec<f32>>, idx: Vec<Vec<u32>>, meshes: Vec<rl_mesh_desc>, lights: Vec<rl_light_desc> }
+struct Flat { p: Vec<Vec<f32>>, n: Vec<Vec<f32>>, idx: Vec<Vec<u32>>, meshes: Vec<rl_mesh_desc>, lights: Vec<rl_light_desc>, textures: Vec<rl_texture> }
 fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
     assert!(scene.volume.is_none(), "scene.volume must be None on the GPU path");
-    let mut f = Flat { p: vec![], n: vec![], idx: vec![], meshes: vec![], lights: vec![] };
+    let mut f = Flat { p: vec![], n: vec![], idx: vec![], meshes: vec![], lights: vec![], textures: vec![] };
     for m in &scene.meshes {
         f.p.push(m.vertices.iter().flat_map(|v| [v.x, v.y, v.z]).collect());
         f.n.push(m.normals.as_ref().map_or(vec![], |ns| ns.iter().flat_map(|v| [v.x, v.y, v.z]).collect()));
@@ -97,7 +101,9 @@ fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
         has_volume: 0, has_environment: scene.emitter_environment.is_some() as u32,
         // PointEmitter / DirectionalLight of EmittersState::Unbuild need a `describe() -> Option<rl_light_desc>` on the Emitter
         // trait; `f.lights` keeps them alive like the mesh vectors
-        nlights: f.lights.len() as u32, lights: f.lights.as_ptr() };
+        nlights: f.lights.len() as u32, lights: f.lights.as_ptr(),
+        // BSDFColor::{Bitmap, Checkerbord, Grid} on a diffuse slot -> rl_texture + rl_material.kd_texture (describe() fills both)
+        ntextures: f.textures.len() as u32, textures: f.textures.as_ptr() };
     (f, desc)
 }
 

@@ -104,6 +104,7 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
     SceneView &sv = s->sv;
     sv.trav = s->trav.data(), sv.nodes = s->nodes.data(), sv.shade = hs.shade.data(), sv.verts = hs.verts.data(), sv.mats = hs.mats.data();
     sv.emit_info = hs.emit_info.data(), sv.emit_cdf = hs.emit_cdf.data(), sv.area_cdf = hs.area_cdf.data();
+    sv.uvs = hs.uvs.empty() ? nullptr : hs.uvs.data(), sv.tex = hs.tex.empty() ? nullptr : hs.tex.data(), sv.texels = hs.texels.data();
     sv.ntris = hs.ntris, sv.n_emitters = hs.n_emitters;
     sv.root_ref = s->root_ref;
     sv.flat = s->flat.f4.data(), sv.n_groups = s->flat.n_groups, sv.flat_valid[0] = s->flat.valid[0], sv.flat_valid[1] = s->flat.valid[1];
@@ -211,7 +212,7 @@ static void emu_material_rows(const rl_material *mt, float4 rows[RL_MAT_F4]) {
     rows[1] = f4(mt->ks[0], mt->ks[1], mt->ks[2], has_mf ? mt->alpha : mt->exponent);
     rows[2] = f4(0, 0, 0, u2f(0u));
     rows[3] = f4(mt->kind == RL_BSDF_GLASS ? mt->ior : mt->weight_specular, 0.0f, 0.0f, u2f(has_mf ? mt->microfacet : 0u));
-    rows[4] = f4(mt->k[0], mt->k[1], mt->k[2], mt->kind == RL_BSDF_GLASS ? 1.0f / mt->ior : 0.0f);
+    rows[4] = f4(mt->k[0], mt->k[1], mt->k[2], mt->kind == RL_BSDF_GLASS ? 1.0f / mt->ior : u2f(0u));
 }
 // returns 0 = None, 1 = SolidAngle pdf, 2 = Discrete pdf
 int emu_bsdf_sample(const rl_material *mt, const float wi[3], float s0, float s1, float weight[3], float d[3], float *pdf) {

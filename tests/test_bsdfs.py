@@ -294,3 +294,132 @@ def test_point_light_only_scene_matches_inverse_square_law():
     assert np.allclose(img[..., 0].ravel(), want, rtol=0.03)
     ie, _ = eb.EmuScene(sc).render(_abi.direct_desc(0, 1), 64, seed=1)
     assert np.array_equal(ie, img)
+
+
+# ---- BSDFColor::{Bitmap, Checkerbord, Grid} on the diffuse slot (bsdfs/mod.rs:31-101) ----------------------------
+def _tex_expected(kind, uv, **kw):
+    """Independent numpy restatement of BSDFColor::color for an array of uv (float32 arithmetic where it matters)."""
+    u, v = uv[:, 0].astype(np.float32), uv[:, 1].astype(np.float32)
+    if kind == "bitmap":
+        img = kw["img"]
+        h, w, _ = img.shape
+        x = (np.mod(np.mod(u, 1) + 1, 1) * np.float32(w)).astype(np.int64)
+        y = (np.mod(np.mod(v, 1) + 1, 1) * np.float32(h)).astype(np.int64)
+        return img[np.clip(y, 0, h - 1), np.clip(x, 0, w - 1)]
+    c0, c1 = np.float32(kw["c0"]), np.float32(kw["c1"])
+    ox, oy, sx, sy = kw["offset"] + kw["scale"]
+    if kind == "checkerboard":
+        a, b = u * np.float32(sx) + np.float32(ox), v * np.float32(sy) + np.float32(oy)
+        x = 2 * (np.fmod(np.trunc(a * 2), 2)).astype(np.int64) - 1
+        y = 2 * (np.fmod(np.trunc(b * 2), 2)).astype(np.int64) - 1
+        return np.where((x * y == 1)[:, None], c0, c1)
+    a, b = u * np.float32(sx) + np.float32(ox), (v + np.float32(sy)) + np.float32(oy)  # grid: uv.y + scale.y (bsdfs/mod.rs:84)
+    x, y = a - np.floor(a), b - np.floor(b)
+    x, y = np.where(x > 0.5, x - 1, x), np.where(y > 0.5, y - 1, y)
+    return np.where(((np.abs(x) < kw["lw"]) | (np.abs(y) < kw["lw"]))[:, None], c0, c1)
+
+
+def _textured_floor(kind, **kw):
+    """A [-1,1]^2 floor with uv in [0,1]^2 under a point light, seen from above; returns (scene, uv of the pixel centres)."""
+    import json
+    from rustlight_b200 import SceneLoaderManager
+    tex = {"type": kind}
+    if kind == "bitmap":
+        img = kw["img"]
+        tex.update(width=img.shape[1], height=img.shape[0], pixels=[float(x) for x in img.ravel()])
+    else:
+        tex.update(color0=list(kw["c0"]), color1=list(kw["c1"]), offset=list(kw["offset"]), scale=list(kw["scale"]))
+        if kind == "grid":
+            tex["line_width"] = kw["lw"]
+    txt = json.dumps({"camera": {"width": 48, "height": 48, "fov": 28, "to_world": [1, 0, 0, 0, 0, 0, -1, 0, 0, -1, 0, 0, 0, 4, 0, 1]},
+                      "textures": {"t": tex}, "lights": [{"type": "point", "intensity": [3, 3, 3], "position": [0.0, 1.5, 0.0]}],
+                      "meshes": [{"material": {"type": "diffuse", "kd_texture": "t"}, "indices": [0, 1, 2, 0, 2, 3],
+                                  "P": [-1, 0, -1, 1, 0, -1, 1, 0, 1, -1, 0, 1], "uv": [0, 0, 1, 0, 1, 1, 0, 1]},
+                                 {"material": {"type": "diffuse", "kd": [0.5] * 3}, "indices": [0, 1, 2], "P": [40, 5, 40, 41, 5, 40, 40, 5, 41]}]})
+    return SceneLoaderManager().load_string(txt, "json")
+
+
+TEX_CASES = [("checkerboard", dict(c0=(0.9, 0.1, 0.1), c1=(0.1, 0.2, 0.9), offset=(0.13, 0.0), scale=(2.0, 1.5))),
+             ("grid", dict(c0=(0.05, 0.05, 0.05), c1=(0.8, 0.7, 0.6), offset=(0.0, 0.1), scale=(3.0, 0.25), lw=0.06)),
+             ("bitmap", dict(img=np.random.default_rng(5).random((5, 7, 3)).astype(np.float32)))]
+
+
+@pytest.mark.parametrize("kind,kw", TEX_CASES)
+def test_texture_lookup_semantics(kind, kw):
+    """Oracle image of the textured floor / image of the same floor with kd = 1 == the texture value at the pixel's uv,
+    for pixels whose footprint stays inside one texel / cell (checked against an independent numpy restatement)."""
+    sc = _textured_floor(kind, **kw)
+    osc = ob.OracleScene(sc)
+    integ = _abi.direct_desc(0, 1)
+    img, _ = osc.render(integ, 32, seed=3, cfg=ob.config(**STREAM))
+    pg, tg = osc.primary_hits(ob.ACCEL_NAIVE)
+    floor = (pg.ravel() <= 1)
+    assert floor.mean() > 0.5
+    ys, xs = np.mgrid[0:48, 0:48]
+    want = np.zeros((48 * 48, 3), np.float32)
+    stable = np.ones(48 * 48, bool)
+    probes = [(0.5, 0.5)] + [(a, b) for a in (0.01, 0.25, 0.5, 0.75, 0.99) for b in (0.01, 0.25, 0.5, 0.75, 0.99)]
+    for dx, dy in probes:  # centre first, then a 5 x 5 lattice over the pixel footprint
+        rays = np.array([osc.camera_generate(float(x) + dx, float(y) + dy)[1] for y, x in zip(ys.ravel(), xs.ravel())])
+        t = 4.0 / -rays[:, 1]
+        hit = np.float32([0, 4, 0]) + rays * t[:, None]
+        uv = np.stack([(hit[:, 0] + 1) / 2, (hit[:, 2] + 1) / 2], axis=1)
+        val = _tex_expected(kind, uv, **kw)
+        if (dx, dy) == (0.5, 0.5):
+            want = val
+        else:
+            stable &= (val == want).all(axis=1)
+    sel = floor & stable
+    assert sel.sum() > 400
+    # same geometry with a constant kd = 1: divide out the lighting
+    sc2 = _textured_floor("checkerboard", c0=(1, 1, 1), c1=(1, 1, 1), offset=(0, 0), scale=(1, 1))
+    base, _ = ob.OracleScene(sc2).render(integ, 32, seed=3, cfg=ob.config(**STREAM))
+    ratio = img.reshape(-1, 3)[sel] / base.reshape(-1, 3)[sel]
+    assert np.allclose(ratio, want[sel], rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind,kw", TEX_CASES)
+def test_textured_render_bit_exact(kind, kw):
+    sc = _textured_floor(kind, **kw)
+    for integ in (_abi.direct_desc(1, 1), _abi.path_desc(max_depth=3)):
+        ie, _ = eb.EmuScene(sc).render(integ, 4, seed=2)
+        io, _ = ob.OracleScene(sc).render(integ, 4, seed=2, cfg=ob.config(**STREAM))
+        assert np.array_equal(ie, io) and io.max() > 0
+
+
+def test_textured_cornell_box_bit_exact():
+    """Textures on the Cornell box (its meshes carry uv): checkerboard floor, bitmap back wall, grid on a substrate box."""
+    from rustlight_b200.host import material_diffuse
+    sc = load_cbox(48, 48)
+    t1 = sc.add_checkerboard_texture((0.8, 0.8, 0.8), (0.1, 0.1, 0.1), (0, 0), (2, 2))
+    t2 = sc.add_bitmap_texture(np.random.default_rng(9).random((8, 8, 3)).astype(np.float32))
+    t3 = sc.add_grid_texture((0.9, 0.2, 0.2), (0.3, 0.3, 0.3), 0.05, (0, 0), (4, 1))
+    sc.set_material(0, material_diffuse(kd_texture=t1))
+    sc.set_material(2, material_diffuse(kd_texture=t2))
+    m = material_substrate((0, 0, 0), (0.05, 0.05, 0.05), "ggx", 0.2)
+    m.kd_texture = t3
+    sc.set_material(5, m)
+    d = sc.desc.contents
+    assert bool(d.meshes[0].UV) and d.ntextures == 3
+    integ = _abi.path_desc()
+    ie, se = eb.EmuScene(sc).render(integ, 6, seed=4)
+    io, so = ob.OracleScene(sc).render(integ, 6, seed=4, cfg=ob.config(**STREAM))
+    assert se.segments == so.segments and np.array_equal(ie, io)
+    ig, _ = ob.OracleScene(sc).render(integ, 6, seed=4, cfg=ob.config(estimator=ob.EST_GRAPH, accel_mode=ob.ACCEL_NAIVE))
+    assert rel_l2(io, ig) < 1e-6
+
+
+def test_texture_without_uv_is_black():
+    """"Found a texture but no uv coordinate given" -> Color::zero() (bsdfs/mod.rs:36-39): the floor reflects nothing."""
+    import json
+    from rustlight_b200 import SceneLoaderManager
+    sc = _textured_floor("checkerboard", c0=(1, 1, 1), c1=(1, 1, 1), offset=(0, 0), scale=(1, 1))
+    j = json.loads(sc.to_json())
+    del j["meshes"][0]["uv"]
+    sc2 = SceneLoaderManager().load_string(json.dumps(j), "json")
+    assert not sc2.desc.contents.meshes[0].UV and sc2.desc.contents.meshes[0].mat.kd_texture == 1
+    io, _ = ob.OracleScene(sc2).render(_abi.direct_desc(1, 1), 4, seed=1, cfg=ob.config(**STREAM))
+    ie, _ = eb.EmuScene(sc2).render(_abi.direct_desc(1, 1), 4, seed=1)
+    assert not io.any() and np.array_equal(ie, io)
+    lit, _ = ob.OracleScene(sc).render(_abi.direct_desc(1, 1), 4, seed=1, cfg=ob.config(**STREAM))
+    assert lit.mean() > 0.01

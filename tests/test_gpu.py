@@ -425,6 +425,26 @@ def test_tessellated_cornell_box_through_the_lbvh(gpu_ctx, n):
     dev.close()
 
 
+def test_textured_materials_bit_exact(gpu_ctx):
+    """BSDFColor::{Checkerbord, Bitmap, Grid} on diffuse slots of the Cornell box: uv interpolation + lookups on the device."""
+    from rustlight_b200.host import material_diffuse, material_substrate
+    sc = load_cbox(96, 96)
+    t1 = sc.add_checkerboard_texture((0.8, 0.8, 0.8), (0.1, 0.1, 0.1), (0, 0), (2, 2))
+    t2 = sc.add_bitmap_texture(np.random.default_rng(9).random((8, 8, 3)).astype(np.float32))
+    t3 = sc.add_grid_texture((0.9, 0.2, 0.2), (0.3, 0.3, 0.3), 0.05, (0, 0), (4, 1))
+    sc.set_material(0, material_diffuse(kd_texture=t1))
+    sc.set_material(2, material_diffuse(kd_texture=t2))
+    m = material_substrate((0, 0, 0), (0.05, 0.05, 0.05), "ggx", 0.2)
+    m.kd_texture = t3
+    sc.set_material(5, m)
+    dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
+    for integ in (_abi.path_desc(), _abi.direct_desc(1, 1)):
+        img, st = dev.render(integ, 6, seed=4)
+        ref, so = osc.render(integ, 6, seed=4, cfg=ob.config(**STREAM))
+        assert st.segments == so.segments and np.array_equal(img, ref)
+    dev.close()
+
+
 def test_config_shapes_c3_c5(gpu_ctx):
     """BASELINE configs[2] (Phong walls, 512x512) and configs[4] (1920x1080, Fov::Y quirk, ragged 16x16 tiles,
     material sort on): sub-sampled spp, bit-exact against the oracle on the same stream."""

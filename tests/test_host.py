@@ -131,6 +131,41 @@ def test_pbrt_objects_instances_and_plymesh(tmp_path):
         SceneLoaderManager().load_string('Camera "perspective" WorldBegin Shape "plymesh" "string filename" "missing.ply" WorldEnd', "pbrt")
 
 
+def test_textures_pbrt_imagemap_and_json_round_trip(tmp_path):
+    """Texture "imagemap" + "texture Kd" -> BSDFColor::Bitmap on the matte / substrate diffuse slot (bsdfs/mod.rs:219-241,
+    299-306, 358-374); .pfm through Bitmap::read_pfm (rows flipped back), binary .ppm as value / 255; JSON keeps every texture."""
+    from rustlight_b200.host import save_pfm
+    img = np.random.default_rng(3).random((3, 4, 3)).astype(np.float32)
+    save_pfm(str(tmp_path / "a.pfm"), img)
+    ppm = (np.arange(2 * 2 * 3, dtype=np.uint8) * 20).reshape(2, 2, 3)
+    (tmp_path / "b.ppm").write_bytes(b"P6\n# comment\n2 2\n255\n" + ppm.tobytes())
+    tri = 'Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0] "float uv" [0 0 1 0 0 1]'
+    (tmp_path / "s.pbrt").write_text(f'''Camera "perspective" WorldBegin
+      Texture "ta" "spectrum" "imagemap" "string filename" "a.pfm"
+      Texture "tb" "color" "imagemap" "string filename" "b.ppm"
+      Material "matte" "texture Kd" "ta" {tri}
+      Material "substrate" "texture Kd" "tb" "rgb Ks" [0.1 0.1 0.1] {tri}
+      Material "matte" "rgb Kd" [0.3 0.3 0.3] {tri}
+    WorldEnd''')
+    sc = SceneLoaderManager().load(str(tmp_path / "s.pbrt"))
+    d = sc.desc.contents
+    assert d.ntextures == 2 and [d.meshes[i].mat.kd_texture for i in range(3)] == [1, 2, 0]
+    t = d.textures[0]
+    assert (t.kind, t.width, t.height) == (_abi.RL_TEX_BITMAP, 4, 3)
+    assert np.array_equal(np.ctypeslib.as_array(t.pixels, (36,)).reshape(3, 4, 3), img)
+    assert np.allclose(np.ctypeslib.as_array(d.textures[1].pixels, (12,)), ppm.ravel() / 255.0, rtol=1e-6)
+    sc.add_checkerboard_texture((1, 0, 0), (0, 1, 0), (0.1, 0.2), (3, 4))
+    sc.add_grid_texture((1, 1, 1), (0, 0, 0), 0.02, (0, 0), (2, 2))
+    back_scene = SceneLoaderManager().load_string(sc.to_json(), "json")
+    b = back_scene.desc.contents
+    assert b.ntextures == 4 and [b.meshes[i].mat.kd_texture for i in range(3)] == [1, 2, 0]
+    assert np.array_equal(np.ctypeslib.as_array(b.textures[0].pixels, (36,)), np.ctypeslib.as_array(t.pixels, (36,)))
+    assert (b.textures[2].kind, list(b.textures[2].offset), list(b.textures[2].scale)) == (_abi.RL_TEX_CHECKERBOARD, pytest.approx([0.1, 0.2]), [3, 4])
+    assert b.textures[3].kind == _abi.RL_TEX_GRID and b.textures[3].line_width == pytest.approx(0.02)
+    with pytest.raises(SceneError, match="unknown texture"):
+        SceneLoaderManager().load_string(f'Camera "perspective" WorldBegin Material "matte" "texture Kd" "zz" {tri} WorldEnd', "pbrt")
+
+
 def test_pbrt_light_sources():
     """LightSource "point" / "distant" -> PointEmitter / DirectionalLight (scene_loader.rs:207-240): intensity * scale,
     direction = normalize(to - from), positions through the current transform; "infinite" stays outside the path."""
