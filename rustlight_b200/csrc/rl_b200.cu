@@ -780,13 +780,19 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                                                                  ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1], ctx->state[cur ^ 1], qc + k + 1,     \
                                                                  ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc, ctx->d_counters)
                         // kernel specialised for the BSDF kinds of the scene: {diffuse}, {diffuse, phong}, everything
-                        if (sc->kind_mask == 0x1u) RL_LAUNCH_SHADE(false, 0x1u);
-                        else if ((sc->kind_mask & ~0x3u) == 0u) {
+                        // (textured scenes take the general kernel: bit 8 of the mask)
+                        if (sc->kind_mask == 0x1u && !sc->d_tex) RL_LAUNCH_SHADE(false, 0x1u);
+                        else if ((sc->kind_mask & ~0x3u) == 0u && !sc->d_tex) {
                             if (sort_on) RL_LAUNCH_SHADE(true, 0x3u);
                             else RL_LAUNCH_SHADE(false, 0x3u);
                         } else {
-                            if (sort_on) RL_LAUNCH_SHADE(true, RL_KM_ALL);
-                            else RL_LAUNCH_SHADE(false, RL_KM_ALL);
+                            if (sc->d_tex) {
+                                if (sort_on) RL_LAUNCH_SHADE(true, RL_KM_ALL);
+                                else RL_LAUNCH_SHADE(false, RL_KM_ALL);
+                            } else {
+                                if (sort_on) RL_LAUNCH_SHADE(true, 0xffu);
+                                else RL_LAUNCH_SHADE(false, 0xffu);
+                            }
                         }
 #undef RL_LAUNCH_SHADE
                         ctx->launches++;

