@@ -278,7 +278,14 @@ def main():
         tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per k_trace launch from the committed ncu --set full capture
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            traffic, traffic_src = tj.get("k_trace_dram_bytes_per_launch"), tj.get("source")
+            # the capture is of a smaller render (8 spp); its launch 1 traces exactly 8 Mi camera rays, which gives the measured
+            # DRAM bytes per algorithmic byte of the kernel; scaled to this run's average launch
+            ratio = tj.get("dram_bytes_per_algorithmic_byte")
+            if ratio is not None:
+                traffic = ratio * bytes_total / launches_trace
+                traffic_src = tj.get("source", "") + f"; {ratio:.3f} DRAM bytes per algorithmic byte, scaled to this run's launch size"
+            else:
+                traffic, traffic_src = tj.get("k_trace_dram_bytes_per_launch"), tj.get("source")
         roof = {"kernel": "k_trace_flat (closest hit: group-table scan + exact triangle tests)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_unit": TRACE_BYTES_PER_SEGMENT, "units": "path segments", "units_per_step": int(st.segments),

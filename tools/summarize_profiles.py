@@ -66,6 +66,8 @@ with open(os.path.join(out, f"{tag}_ncu_full_summary.md"), "w") as f:
             scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
             per = [float(r[ir]) * scale[u[ir]] + float(r[iw]) * scale[u[iw]] for r in rr[2:5]]
             traffic = {"k_trace_dram_bytes_per_launch": sum(per) / len(per), "per_launch": per,
+                       # launch 1 traces exactly 1024*1024*8 camera rays: measured DRAM bytes per algorithmic byte (48 B / ray)
+                       "launch1_rays": 1024 * 1024 * 8, "dram_bytes_per_algorithmic_byte": per[0] / (1024 * 1024 * 8 * 48.0),
                        "source": f"profiles/{tag}_ncu_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum, mean of the 3 captured k_trace launches; "
                                  "algorithmic bytes of those launches: 8.39M, ~7.0M, ~4.5M rays x 48 B)"}
 json.dump(traffic, open(os.path.join(out, "traffic.json"), "w"), indent=1)
