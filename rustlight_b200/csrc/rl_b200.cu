@@ -761,6 +761,11 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                 k_set_u32<<<1, 1, 0, st>>>(qc, (uint32_t)n_paths);
                 uint32_t k = 0, k_read = 0;
                 size_t n_ub = n_paths; // upper bound of the current queue length (lengths never grow)
+                // Group-table scenes outside profiling mode: two launches per iteration (k_trace_shadow_flat + k_shade).  The
+                // per-stage timings of profiling mode need the separate kernels.
+                const bool fuse = !prof && sc->flat_ok && sc->coherent_tree == 0 && getenv("RL_NO_FUSE") == nullptr;
+                size_t ub_prev = n_paths;
+                const uint32_t *zero_count = ctx->d_hist + 2 * kMaxIters - 1; // never written: k + group < kMaxIters
                 while (n_ub > 0) {
                     // iterations launched between two reads of the queue lengths: few while the queues are long (an iteration
                     // past the end of the longest path is three empty launches), more in the tail, where the host round trip
@@ -772,7 +777,16 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                     }
                     for (uint32_t g = 0; g < group; g++, k++) {
                         if (prof) CK(cudaEventRecord(ctx->ev[2], st));
-                        if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
+                        if (fuse) { // rays of iteration k + shadow segments of iteration k-1 in one launch (k_trace_shadow_flat)
+                            SceneView sv = sc->sv;
+                            sv.n_groups = sc->flat.n_groups;
+                            const int tb = grid_for(ctx, n_ub, trav_per_sm()), sb = k == 0 ? 0 : grid_for(ctx, ub_prev, trav_per_sm());
+                            k_trace_shadow_flat<<<tb + sb, kBlock, sc->smem_flat_bytes, st>>>(sv, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit,
+                                                                                              k == 0 ? zero_count : shc + k - 1, ctx->sh_a, ctx->sh_b, ctx->sh_c,
+                                                                                              ctx->lacc, ctx->d_counters, sc->n_trav_f4, (uint32_t)tb);
+                            ctx->launches++;
+                            ub_prev = n_ub;
+                        } else if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
                         else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
                         if (prof) CK(cudaEventRecord(ctx->ev[3], st));
 #define RL_LAUNCH_SHADE(SORT, KM)                                                                                                                   \
@@ -798,7 +812,9 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                         ctx->launches++;
                         if (prof) CK(cudaEventRecord(ctx->ev[4], st));
                         // the shadow queue can never be longer than the input queue: size the grid from n_ub
-                        if (sc->smem_ok) launch_shadow<true>(ctx, sc, shc + k, n_ub, k == 0);
+                        if (fuse) {
+                            // traced by the next iteration's launch (or by the trailing launch after the loop)
+                        } else if (sc->smem_ok) launch_shadow<true>(ctx, sc, shc + k, n_ub, k == 0);
                         else launch_shadow<false>(ctx, sc, shc + k, n_ub, k == 0);
                         if (prof) CK(cudaEventRecord(ctx->ev[5], st));
                         cur ^= 1;
@@ -822,6 +838,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                     k_read = k;
                     n_ub = ctx->h_hist[k];
                 }
+                if (fuse && k > 0) launch_shadow<true>(ctx, sc, shc + k - 1, ub_prev, false); // shadow segments of the last shaded iteration
             }
             S.max_depth_seen = std::max<uint64_t>(S.max_depth_seen, iter);
             if (prof) CK(cudaEventRecord(ctx->ev[2], st));

@@ -143,14 +143,10 @@ __device__ __forceinline__ void stage_flat(const SceneView &sv, float4 *smem, ui
     for (uint32_t i = threadIdx.x; i < n_trav_f4; i += blockDim.x) smem[n_flat_f4 + i] = ldg4(sv.trav + i);
     __syncthreads();
 }
-__global__ void __launch_bounds__(kBlock) k_trace_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
-                                                       const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t n_trav_f4) {
-    extern __shared__ float4 smem[];
-    const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
-    stage_flat(sv, smem, n_flat_f4, n_trav_f4);
-    const float4 *flat = smem, *trav = smem + n_flat_f4;
-    const uint32_t n = *count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+// The two loops as device functions over a virtual grid (bid of nblocks), so that one launch can run both (below).
+__device__ __forceinline__ void trace_flat_body(const SceneView &sv, const float4 *flat, const float4 *trav, uint32_t bid, uint32_t nblocks, uint32_t n,
+                                                const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d, float4 *__restrict__ hit) {
+    for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n; i += nblocks * blockDim.x) {
         const float4 ro = ray_o[i], rd = ray_d[i];
         const V3 o = xyz(ro), d = xyz(rd);
         const V3 inv = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
@@ -160,16 +156,11 @@ __global__ void __launch_bounds__(kBlock) k_trace_flat(SceneView sv, const uint3
         hit[i] = make_float4(h.t, h.u, h.v, u2f(h.prim));
     }
 }
-__global__ void __launch_bounds__(kBlock) k_shadow_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ sh_a,
-                                                        const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c, float4 *__restrict__ lacc,
-                                                        Counters *counters, uint32_t n_trav_f4) {
-    extern __shared__ float4 smem[];
-    const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
-    stage_flat(sv, smem, n_flat_f4, n_trav_f4);
-    const float4 *flat = smem, *trav = smem + n_flat_f4;
-    const uint32_t n = *count;
+__device__ __forceinline__ void shadow_flat_body(const SceneView &sv, const float4 *flat, const float4 *trav, uint32_t bid, uint32_t nblocks, uint32_t n,
+                                                 const float4 *__restrict__ sh_a, const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c,
+                                                 float4 *__restrict__ lacc, Counters *counters) {
     uint32_t c_vis = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n; i += nblocks * blockDim.x) {
         const float4 a = sh_a[i], b = sh_b[i];
         V3 d;
         float thr;
@@ -185,6 +176,36 @@ __global__ void __launch_bounds__(kBlock) k_shadow_flat(SceneView sv, const uint
     }
     for (int off = 16; off > 0; off >>= 1) c_vis += __shfl_down_sync(0xffffffffu, c_vis, off);
     if ((threadIdx.x & 31u) == 0 && c_vis) atomicAdd(&counters->shadow_visible, (unsigned long long)c_vis);
+}
+__global__ void __launch_bounds__(kBlock) k_trace_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
+                                                       const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t n_trav_f4) {
+    extern __shared__ float4 smem[];
+    const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
+    stage_flat(sv, smem, n_flat_f4, n_trav_f4);
+    trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, gridDim.x, *count, ray_o, ray_d, hit);
+}
+__global__ void __launch_bounds__(kBlock) k_shadow_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ sh_a,
+                                                        const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c, float4 *__restrict__ lacc,
+                                                        Counters *counters, uint32_t n_trav_f4) {
+    extern __shared__ float4 smem[];
+    const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
+    stage_flat(sv, smem, n_flat_f4, n_trav_f4);
+    shadow_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, gridDim.x, *count, sh_a, sh_b, sh_c, lacc, counters);
+}
+// Extension rays of wavefront iteration k+1 and shadow rays of iteration k are independent (the shadow kernel only adds
+// to the per-path accumulators, which the traversal does not touch): one launch runs both, CTAs [0, trace_blocks) on the
+// ray queue and the rest on the shadow queue.  Every kernel costs ~7 us whatever its queue length (launch + table staging
+// + one scan at minimal occupancy), and a frame has ~40 iterations: two launches per iteration instead of three.
+__global__ void __launch_bounds__(kBlock) k_trace_shadow_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
+                                                              const float4 *__restrict__ ray_d, float4 *__restrict__ hit,
+                                                              const uint32_t *__restrict__ sh_count, const float4 *__restrict__ sh_a,
+                                                              const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c, float4 *__restrict__ lacc,
+                                                              Counters *counters, uint32_t n_trav_f4, uint32_t trace_blocks) {
+    extern __shared__ float4 smem[];
+    const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
+    stage_flat(sv, smem, n_flat_f4, n_trav_f4);
+    if (blockIdx.x < trace_blocks) trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, trace_blocks, *count, ray_o, ray_d, hit);
+    else shadow_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x - trace_blocks, gridDim.x - trace_blocks, *sh_count, sh_a, sh_b, sh_c, lacc, counters);
 }
 
 // ---- block-level compaction helper ---------------------------------------------------------------
