@@ -292,7 +292,9 @@ def main():
                 "launches_per_step": launches_trace, "avg_launch_ms": st.ms_trace / launches_trace,
                 "share_of_step": st.ms_trace / st.ms_total if st.ms_total else None,
                 "algorithmic_bytes_per_launch": bytes_total / launches_trace,
-                "note": "group table + triangle records (5 KB) are shared-memory resident: the kernel is instruction-issue bound, not HBM bound (SURVEY.md F9; profiles/)"}
+                "note": "group table + triangle records (5 KB) are shared-memory resident: the kernel is instruction-issue bound, not HBM bound (SURVEY.md F9; profiles/). "
+                        "Timed alone (k_trace_flat) in the profiled step; the timed steps run it inside k_trace_shadow_flat together with the shadow segments "
+                        "of the previous iteration (one launch instead of two), so the ncu launch list shows that kernel with the sum of both shares"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

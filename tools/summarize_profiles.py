@@ -37,6 +37,8 @@ with open(os.path.join(out, f"{tag}_launches_summary.md"), "w") as f:
     for k, v in sorted(tot.items(), key=lambda x: -x[1]):
         f.write(f"| `{k}` | {cnt[k]} | {v:.3f} | {v / T * 100:.1f}% |\n")
     live = sm["ms_trace"] + sm["ms_shade"] + sm["ms_shadow"] + sm["ms_raygen"] + sm["ms_accum"]
+    f.write("\n`k_trace_shadow_flat` = closest-hit rays of iteration k+1 + shadow segments of iteration k in one launch: its share is "
+            "the sum of the trace and shadow stages below (the profiled step times them as separate kernels).\n")
     f.write(f"\nLive CUDA-event stage times of one profiled step of the same build ({bench}): "
             + ", ".join(f"{k[3:]} {sm[k]:.2f} ms ({sm[k] / live * 100:.1f}%)" for k in ("ms_trace", "ms_shade", "ms_shadow", "ms_raygen", "ms_accum")) + ".\n")
 
