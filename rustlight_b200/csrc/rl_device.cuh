@@ -209,6 +209,16 @@ RL_HD float spec_powf(float x, float y) {
     return (float)spec_exp2((double)y * spec_log2((double)x));
 }
 
+// spec_powf(x, y) with log2(x) supplied by the caller (same bits: the same log2 value enters the same product), so that
+// several powers of one base share the logarithm
+RL_HD float spec_powf_pre(float x, float y, double log2_x) {
+    if (y == 0.0f) return 1.0f;
+    if (x == 0.0f) return y > 0.0f ? 0.0f : u2f(0x7f800000u);
+    if (x == 1.0f) return 1.0f;
+    if (!(x > 0.0f)) return u2f(0x7fc00000u);
+    return (float)spec_exp2((double)y * log2_x);
+}
+
 // e^x and ln x (Beckmann distribution only), same construction: f64 kernels, one rounding to f32
 RL_HD float spec_expf(float x) { return (float)spec_exp2((double)x * 1.4426950408889634074); }
 RL_HD float spec_logf(float x) {
@@ -1107,6 +1117,36 @@ RL_HD Col bsdf_eval(const Material &m, V3 wi, V3 wo) {
     Col diffuse_value = mul_checked(mul_checked(m.kd, wo.z), RL_FRAC_1_PI);
     return specular_value + diffuse_value;
 }
+// Phong pdf and eval of one direction pair with ONE evaluation of alpha^n (phong.rs:65-119): identical bits to calling
+// bsdf_pdf and bsdf_eval separately, half the transcendental work
+RL_HD void phong_eval_pdf(const Material &m, V3 wi, V3 wo, Col *f, float *pdf) {
+    if (wi.z <= 0.0f || wo.z <= 0.0f) {
+        *f = Col{0.0f, 0.0f, 0.0f};
+        *pdf = 0.0f;
+        return;
+    }
+    float alpha = dot(reflect_local(wi), wo);
+    float pdf_specular = 0.0f;
+    Col specular_value = Col{0.0f, 0.0f, 0.0f};
+    if (alpha > 0.0f) {
+        const float p = spec_powf(alpha, m.exponent);
+        pdf_specular = m.weight_specular * p * (m.exponent + 1.0f) / (2.0f * RL_PI);
+        specular_value = mul_checked(m.ks, p * (m.exponent + 2.0f) / (2.0f * RL_PI));
+    }
+    float pdf_diffuse = (1.0f - m.weight_specular) * wo.z * RL_FRAC_1_PI;
+    *pdf = pdf_specular + pdf_diffuse;
+    *f = specular_value + mul_checked(mul_checked(m.kd, wo.z), RL_FRAC_1_PI);
+}
+// eval and pdf of one direction pair (what light sampling with MIS needs)
+template <uint32_t KM = RL_KM_ALL>
+RL_HD void bsdf_eval_pdf(const Material &m, V3 wi, V3 wo, Col *f, float *pdf) {
+    if (RL_HAS(KM, 1) && m.kind == 1u) {
+        phong_eval_pdf(m, wi, wo, f, pdf);
+        return;
+    }
+    *f = bsdf_eval<KM>(m, wi, wo);
+    *pdf = bsdf_pdf<KM>(m, wi, wo);
+}
 // BSDF::sample (diffuse.rs:11-31, phong.rs:14-63, metal.rs:15-73, glass.rs:75-121, substrate.rs:22-90).
 // *discrete: the sampled pdf is PDF::Discrete (delta lobe) -- no MIS for the edge it creates.
 template <uint32_t KM = RL_KM_ALL>
@@ -1187,8 +1227,9 @@ RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight
     V3 d_out;
     if (sx < m.weight_specular) {
         sx = sx / m.weight_specular;
-        float sin_alpha = sqrtf(1.0f - spec_powf(sy, 2.0f / (m.exponent + 1.0f)));
-        float cos_alpha = spec_powf(sy, 1.0f / (m.exponent + 1.0f));
+        const double log2_sy = (sy > 0.0f && sy != 1.0f) ? spec_log2((double)sy) : 0.0;
+        float sin_alpha = sqrtf(1.0f - spec_powf_pre(sy, 2.0f / (m.exponent + 1.0f), log2_sy));
+        float cos_alpha = spec_powf_pre(sy, 1.0f / (m.exponent + 1.0f), log2_sy);
         float phi = 2.0f * RL_PI * sx;
         float sp, cp;
         spec_sincos(phi, &sp, &cp);
@@ -1200,9 +1241,11 @@ RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight
         sx = (sx - m.weight_specular) / (1.0f - m.weight_specular);
         d_out = cosine_sample_hemisphere(sx, sy);
     }
-    float p = bsdf_pdf<KM>(m, wi, d_out);
+    float p;
+    Col f;
+    phong_eval_pdf(m, wi, d_out, &f, &p);
     if (p == 0.0f) return false;
-    *weight = div_checked(bsdf_eval<KM>(m, wi, d_out), p);
+    *weight = div_checked(f, p);
     *wo = d_out;
     *pdf = p;
     return true;
@@ -1543,14 +1586,13 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
         LightSample ls = sample_light(sv, its.p, r_sel, r, ux, uy);
         if (ls.valid && !mute && ip_add_ok(ip, st.depth) && ip.strategy != 1u) {
             V3 wo = to_local(its.frame, ls.d);
-            Col f = bsdf_eval<KM>(mat, its.wi, wo);
+            Col f;
+            float pb;
+            bsdf_eval_pdf<KM>(mat, its.wi, wo, &f, &pb);
             Col contrib = st.T * (ls.weight * f);
             if (!is_zero(contrib)) {
                 float w = 1.0f;
-                if (ip.strategy == 0u && !ls.discrete) { // a PDF::Discrete light edge has no MIS (path.rs:80)
-                    float pb = bsdf_pdf<KM>(mat, its.wi, wo);
-                    w = ls.pdf / (pb + ls.pdf);
-                }
+                if (ip.strategy == 0u && !ls.discrete) w = ls.pdf / (pb + ls.pdf); // a PDF::Discrete light edge has no MIS (path.rs:80)
                 out->shadow = true;
                 out->sh_p0 = its.p;
                 out->sh_p1 = ls.p;
@@ -1604,9 +1646,11 @@ RL_HD bool direct_light_sample(const SceneView &sv, DirectCtx *cx, V3 *p1, Col *
     if (!ls.valid) return false;
     if (mat_is_smooth(cx->mat)) return false; // direct.rs:74-77: visible() is still called (valid stays true), nothing is added
     V3 wo = to_local(cx->its.frame, ls.d);
-    float pdf_bsdf = bsdf_pdf(cx->mat, cx->its.wi, wo);
+    float pdf_bsdf;
+    Col f;
+    bsdf_eval_pdf(cx->mat, cx->its.wi, wo, &f, &pdf_bsdf);
     float weight_light = ls.discrete ? 1.0f : mis_weight_power(ls.pdf * cx->wl, pdf_bsdf * cx->wb); // direct.rs:106-110
-    Col c = mul_checked(mul_plain(weight_light, bsdf_eval(cx->mat, cx->its.wi, wo)), cx->wl) * ls.weight;
+    Col c = mul_checked(mul_plain(weight_light, f), cx->wl) * ls.weight;
     *p1 = ls.p;
     *contrib = c;
     return !is_zero(c);
