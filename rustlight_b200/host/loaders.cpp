@@ -4,7 +4,7 @@
 // use: Transform/ConcatTransform/LookAt/Translate/Scale/Rotate/Identity, Film, Camera
 // "perspective", MakeNamedMaterial/NamedMaterial/Material "matte" | "mirror" | "metal" | "glass" | "substrate",
 // Shape "trianglemesh" | "plymesh", ObjectBegin/ObjectEnd/ObjectInstance, AreaLightSource "diffuse",
-// LightSource "point" | "distant", AttributeBegin/End, TransformBegin/End, ReverseOrientation.
+// LightSource "point" | "distant", Texture "imagemap", Include, AttributeBegin/End, TransformBegin/End, ReverseOrientation.
 // The pbrt_rs crate that does the parsing for the reference is not vendored,
 // so the grammar follows the pbrt-v3 file format itself.
 // One labelled extension: material type "phong" (Kd, Ks, exponent) -> BSDFPhong, which the
@@ -417,7 +417,32 @@ Scene PBRTSceneLoader::load(const std::string &filename, bool use_shading_normal
     return load_string(read_file(filename), use_shading_normal, slash == std::string::npos ? "" : filename.substr(0, slash));
 }
 
-Scene PBRTSceneLoader::load_string(const std::string &text, bool use_shading_normal, const std::string &base_dir) const {
+// `Include "file"` (one per line, as pbrt files write it): spliced in textually, relative to base_dir, before parsing
+static std::string expand_includes(const std::string &text, const std::string &base_dir, int depth = 0) {
+    if (depth > 16) throw Error("pbrt: Include nested deeper than 16 levels");
+    if (text.find("Include") == std::string::npos) return text;
+    std::istringstream in(text);
+    std::string line, out;
+    while (std::getline(in, line)) {
+        std::string code = line.substr(0, line.find('#'));
+        size_t a = code.find_first_not_of(" \t\r");
+        if (a != std::string::npos && code.compare(a, 7, "Include") == 0) {
+            size_t q0 = code.find('"', a + 7), q1 = q0 == std::string::npos ? q0 : code.find('"', q0 + 1);
+            if (q1 == std::string::npos) throw Error("pbrt: Include needs a quoted file name");
+            std::string fn = code.substr(q0 + 1, q1 - q0 - 1);
+            if (!fn.empty() && fn[0] != '/' && !base_dir.empty()) fn = base_dir + "/" + fn;
+            size_t slash = fn.find_last_of('/');
+            out += expand_includes(read_file(fn), slash == std::string::npos ? base_dir : fn.substr(0, slash), depth + 1);
+            out += "\n";
+            out += code.substr(q1 + 1);
+        } else out += line;
+        out += "\n";
+    }
+    return out;
+}
+
+Scene PBRTSceneLoader::load_string(const std::string &text_in, bool use_shading_normal, const std::string &base_dir) const {
+    const std::string text = expand_includes(text_in, base_dir);
     Parser ps(text);
     GState gs;
     std::vector<GState> stack;
@@ -588,7 +613,7 @@ Scene PBRTSceneLoader::load_string(const std::string &text, bool use_shading_nor
             if (fn[0] != '/' && !base_dir.empty()) fn = base_dir + "/" + fn;
             texture_ids[name] = scene.add_texture(Texture::bitmap_file(fn));
             (void)ttype;
-        } else if (d == "MakeNamedMedium" || d == "MediumInterface" || d == "Include") {
+        } else if (d == "MakeNamedMedium" || d == "MediumInterface") {
             throw Error("pbrt: directive " + d + " is outside the hot-path scope");
         } else {
             throw Error("pbrt: unknown directive " + d);

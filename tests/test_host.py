@@ -125,6 +125,11 @@ def test_pbrt_objects_instances_and_plymesh(tmp_path):
     assert np.array_equal(P[2], [[0, 0, 2], [2, 0, 2], [2, 2, 2], [0, 2, 2]])
     assert bool(d.meshes[1].N) and list(np.ctypeslib.as_array(d.meshes[2].N, (12,))[:3]) == [0, 0, 1]  # renormalised after the scale
     assert d.meshes[1].mat.kind == d.meshes[2].mat.kind == _abi.RL_BSDF_DIFFUSE  # material bound at definition, not at instantiation
+    (tmp_path / "geo.pbrt").write_text('Shape "plymesh" "string filename" "t.ply"  # included geometry\n')
+    (tmp_path / "top.pbrt").write_text('Camera "perspective"\nWorldBegin\n  Include "geo.pbrt"\n  Translate 0 0 3\n  Include "geo.pbrt"\nWorldEnd\n')
+    inc = SceneLoaderManager().load(str(tmp_path / "top.pbrt"))
+    di = inc.desc.contents
+    assert di.nmeshes == 2 and np.ctypeslib.as_array(di.meshes[1].P, (9,))[2] == 3.0
     with pytest.raises(SceneError, match="unknown object"):
         SceneLoaderManager().load_string('Camera "perspective" WorldBegin ObjectInstance "nope" WorldEnd', "pbrt")
     with pytest.raises(SceneError, match="cannot open"):
