@@ -134,7 +134,7 @@ static int grid_for(const rl_ctx *ctx, size_t n, int per_sm) {
 
 // Grid sizes (measured on B200, cbox 1024^2 x 32 spp, per-stage CUDA events; tools/ab_env.py RL_GRID_PER_SM):
 //   group-table traversal kernels: grid-stride over the queue with kTravPerSm CTAs per SM (the tree kernels, which
-//   stage up to 96 KB per CTA, stay at 8).  Rays differ in cost, so MORE CTAs than
+//   walk per-warp chunks of the queue, use 16).  Rays differ in cost, so MORE CTAs than
 //   are resident (5 per SM for k_trace_flat) balance better through the hardware block scheduler: 4/SM 5.01 ms,
 //   resident (5) 4.93, 8 4.77, 16 4.68, 32 4.60, 64 4.56 ms -- 32 keeps the per-CTA scene staging (5 KB) negligible.
 //   k_shade: one wave of resident CTAs (4 per SM at 64 registers); 6/SM 5.52 ms vs 4.81 ms.
@@ -148,6 +148,14 @@ static int resident_per_sm(K kernel, size_t smem) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kBlock, smem) != cudaSuccess || nb < 1) nb = 1;
     cache.push_back({smem, nb});
     return nb;
+}
+static int tree_per_sm() {
+    static int v = 0;
+    if (!v) {
+        v = 16; // tess24 (20 736 triangles): 4 / 8 / 16 / 32 CTAs per SM: 27.7 / 27.3 / 26.7 / 26.8 ms
+        if (const char *e = getenv("RL_TREE_PER_SM")) v = std::max(1, atoi(e)); // A/B hook
+    }
+    return v;
 }
 static int trav_per_sm() {
     static int v = 0;
@@ -350,11 +358,9 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     CKS(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_keys_sorted, (int)n, 0, 64, st));
     k_tri_setup<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(s->d_verts, d_keys_sorted, n, bvh_box_eps(hs.abs_max), s->d_trav, s->d_shade, d_leaf_lo, d_leaf_hi);
     CKS(cudaGetLastError());
-    // Leaf size: scenes of up to 64 triangles become ONE leaf (every lane scans the same triangles in
-    // lockstep: no SIMT divergence, shared-memory broadcasts); larger scenes collapse subtrees of <= 4.
-    // The tree itself collapses subtrees of <= 2 (tiny scenes) or <= 4 triangles; scenes of <= 64 triangles
-    // additionally get a "flat" root (the whole scene as one leaf) used for incoherent rays.
-    int leaf_max = n <= (uint32_t)RL_LEAF_MAX_CAP ? 2 : 4;
+    // The tree collapses subtrees of <= 2 triangles into leaves.  Scenes of <= 64 triangles additionally get the group
+    // table (rl_flat_host.hpp), which every ray scans instead of walking the tree.
+    int leaf_max = 2; // measured on a 20 736-triangle scene (tools/tess_cbox.py 24): leaves of <= 1 / 2 / 4 / 8 / 16 triangles: 31.2 / 27.4 / 28.4 / 31.1 / 36.1 ms
     if (const char *e = getenv("RL_LEAF_MAX")) leaf_max = std::max(1, std::min(RL_LEAF_MAX_CAP, atoi(e)));
     bool flat_ok = n <= (uint32_t)RL_LEAF_MAX_CAP;
     if (const char *e = getenv("RL_FLAT")) flat_ok = flat_ok && atoi(e) != 0;
@@ -614,7 +620,7 @@ static void launch_trace(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_
         return;
     }
     sv.root_ref = tree ? sc->root_tree : sc->root_flat;
-    k_trace<SMEM><<<grid_for(ctx, n, 8), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_node_f4, sc->n_trav_f4);
+    k_trace<SMEM><<<grid_for(ctx, n, tree_per_sm()), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_node_f4, sc->n_trav_f4);
     ctx->launches++;
 }
 template <bool SMEM>
@@ -629,7 +635,7 @@ static void launch_shadow(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size
         return;
     }
     sv.root_ref = tree ? sc->root_tree : sc->root_flat;
-    k_shadow<SMEM><<<grid_for(ctx, n, 8), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc,
+    k_shadow<SMEM><<<grid_for(ctx, n, tree_per_sm()), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc,
                                                                                              ctx->d_counters, sc->n_node_f4, sc->n_trav_f4);
     ctx->launches++;
 }

@@ -74,7 +74,7 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         if (!build_flat_table(hs, prim_of_slot, s->flat)) s->flat = FlatTable{};
     }
     // k_karras + k_fit
-    int leaf_max = n <= RL_LEAF_MAX_CAP ? (mode == "leaf" ? RL_LEAF_MAX_CAP : 2) : 4;
+    int leaf_max = (n <= RL_LEAF_MAX_CAP && mode == "leaf") ? RL_LEAF_MAX_CAP : 2;
     if (const char *e = getenv("RL_LEAF_MAX")) leaf_max = std::max(1, std::min(RL_LEAF_MAX_CAP, atoi(e)));
     s->leaf_max = leaf_max;
     int n_nodes = n > 1 ? n - 1 : 1;
