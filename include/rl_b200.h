@@ -132,11 +132,13 @@ typedef struct rl_scene_desc {
     const rl_mesh_desc *meshes;
     rl_camera_desc camera;
     uint32_t has_volume;      /* must be 0: scene.volume == None on this path                 */
-    uint32_t has_environment; /* must be 0: emitter_environment == None on this path          */
+    uint32_t has_environment; /* 0: emitter_environment == None; 1: EnvironmentLight with EnvironmentLightColor::Constant(
+                                 environment) (emitter.rs:300-568); environment TEXTURES are outside this path             */
     uint32_t nlights;         /* Scene.emitters (EmittersState::Unbuild): sampled after the mesh lights, in this order */
     const rl_light_desc *lights;
     uint32_t ntextures;
     const rl_texture *textures;
+    float environment[3];     /* constant environment radiance when has_environment == 1 */
 } rl_scene_desc;
 
 /* ---- integrators --------------------------------------------------------------------------- */

@@ -984,7 +984,7 @@ struct BoundingSphere { // structure.rs:880-884
 struct Emitter { // trait Emitter, emitter.rs:46-94 (the methods this path calls)
     virtual ~Emitter() = default;
     virtual PDF direct_pdf(const LightSamplingPDF &ls) const = 0;
-    virtual LightSampling direct_sample(V3 p, float r, P2 uv) const = 0;
+    virtual LightSampling direct_sample(const Math &m, V3 p, float r, P2 uv) const = 0;
     virtual Color flux() const = 0;
     virtual Color eval() const = 0; // eval(d, uv) with constant emission
 };
@@ -997,7 +997,7 @@ struct MeshEmitter : Emitter { // impl Emitter for Mesh, emitter.rs:570-688
         float geom = cos_light / magnitude2(ls.p - ls.o);
         return PDF{PDF::SolidAngle, m->pdf() / geom};
     }
-    LightSampling direct_sample(V3 p, float r, P2 uv) const override { // :652-688
+    LightSampling direct_sample(const Math &, V3 p, float r, P2 uv) const override { // :652-688
         SampledPosition sp = m->sample(r, uv);
         V3 d = sp.p - p;
         float dist = magnitude(d);
@@ -1015,7 +1015,7 @@ struct PointEmitter : Emitter { // emitter.rs:186-250
     Color intensity;
     V3 position;
     PDF direct_pdf(const LightSamplingPDF &) const override { return PDF{PDF::Discrete, 1.0f}; }
-    LightSampling direct_sample(V3 v, float, P2) const override { // :197-215
+    LightSampling direct_sample(const Math &, V3 v, float, P2) const override { // :197-215
         V3 p = position;
         V3 d = p - v;
         float dist = magnitude(d);
@@ -1030,7 +1030,7 @@ struct DirectionalLight : Emitter { // emitter.rs:96-190
     Color intensity;
     BoundingSphere bsphere{}; // preprocess(): scene.bsphere with radius * 1.1 (:106-109)
     PDF direct_pdf(const LightSamplingPDF &) const override { return PDF{PDF::Discrete, 1.0f}; }
-    LightSampling direct_sample(V3 v, float, P2) const override { // :115-133
+    LightSampling direct_sample(const Math &, V3 v, float, P2) const override { // :115-133
         V3 p = v - bsphere.radius * direction;
         return LightSampling{this, PDF{PDF::Discrete, 1.0f}, p, direction, -direction, 0, intensity};
     }
@@ -1039,6 +1039,69 @@ struct DirectionalLight : Emitter { // emitter.rs:96-190
         return area * intensity;
     }
     Color eval() const override { return intensity; }
+};
+// math.rs:324-352
+inline bool solve_quadratic(float a, float b, float c, float *x0_out, float *x1_out) {
+    if (a == 0.0f) {
+        if (b != 0.0f) {
+            float v = -c / b;
+            *x0_out = v, *x1_out = v;
+            return true;
+        }
+        return false;
+    }
+    float d = b * b - 4.0f * a * c;
+    if (d < 0.0f) return false;
+    float d_sqrt = std::sqrt(d);
+    float tmp = b < 0.0f ? -0.5f * (b - d_sqrt) : -0.5f * (b + d_sqrt);
+    float x0 = tmp / a, x1 = c / tmp;
+    if (x0 > x1) *x0_out = x1, *x1_out = x0;
+    else *x0_out = x0, *x1_out = x1;
+    return true;
+}
+inline bool bsphere_intersect(const BoundingSphere &bs, const Ray &r, float *t) { // structure.rs:899-920 (b = +2 d_p.d, verbatim)
+    V3 d_p = bs.center - r.o;
+    float a = magnitude2(r.d);
+    float b = 2.0f * dot(d_p, r.d);
+    float c = magnitude2(d_p) - bs.radius * bs.radius;
+    float t0, t1;
+    if (!solve_quadratic(a, b, c, &t0, &t1)) return false;
+    if (t0 < r.tnear) {
+        if (t1 < r.tfar) {
+            *t = t1;
+            return true;
+        }
+        return false;
+    } else if (t0 < r.tfar) {
+        *t = t0;
+        return true;
+    }
+    return false;
+}
+inline V3 sample_uniform_sphere(const Math &m, P2 u) { // math.rs:67-72
+    float z = 1.0f - 2.0f * u.x;
+    float r = std::sqrt(rmax(1.0f - z * z, 0.0f));
+    float phi = 2.0f * PI * u.y;
+    float sp, cp;
+    m.sincos(phi, &sp, &cp);
+    return V3{r * cp, r * sp, z};
+}
+struct EnvironmentLight : Emitter { // emitter.rs:428-568 with EnvironmentLightColor::Constant
+    Color luminance;
+    BoundingSphere bsphere{}; // preprocess(): scene.bsphere, radius * 1.1
+    static float color_pdf() { return 1.0f / (PI * 4.0f); } // :406
+    PDF direct_pdf(const LightSamplingPDF &) const override { return PDF{PDF::SolidAngle, color_pdf()}; } // :470-473
+    LightSampling direct_sample(const Math &math, V3 v, float, P2 uv) const override { // :474-511
+        V3 d = sample_uniform_sphere(math, uv); // luminance.sample_direction, :369-373
+        float pdf = color_pdf();
+        float t;
+        if (!bsphere_intersect(bsphere, ray_new(v, d), &t)) return LightSampling{this, PDF{PDF::SolidAngle, pdf}, V3{0, 0, 0}, V3{0, 0, 0}, d, 0, Color::zero()};
+        V3 p = v + d * t;
+        V3 n = normalize(bsphere.center - p);
+        return LightSampling{this, PDF{PDF::SolidAngle, pdf}, p, n, d, 0, luminance / pdf};
+    }
+    Color flux() const override { return (PI * powi(bsphere.radius, 2)) * luminance; } // :512-516
+    Color eval() const override { return luminance; }
 };
 struct EmitterSampler { // :1491-1495 (ats == None on this path)
     std::vector<std::unique_ptr<Emitter>> emitters;
@@ -1056,10 +1119,10 @@ struct EmitterSampler { // :1491-1495 (ats == None on this path)
     }
     PDF direct_pdf(const Emitter *e, const LightSamplingPDF &ls) const { return e->direct_pdf(ls) * pdf(e); } // :1566-1575
     PDF direct_pdf(const Mesh *m, const LightSamplingPDF &ls) const { return direct_pdf(of_mesh(m), ls); }
-    LightSampling sample_light(V3 p, float r_sel, float r, P2 uv) const { // :1604-1620, :1641-1647
+    LightSampling sample_light(const Math &m, V3 p, float r_sel, float r, P2 uv) const { // :1604-1620, :1641-1647
         size_t id_light = emitters_cdf.sample_discrete(r_sel);
         float pdf_sel = emitters_cdf.pdf(id_light);
-        LightSampling res = emitters[id_light]->direct_sample(p, r, uv);
+        LightSampling res = emitters[id_light]->direct_sample(m, p, r, uv);
         div_assign(res.weight, pdf_sel);
         res.pdf = res.pdf * pdf_sel;
         return res;
@@ -1250,6 +1313,10 @@ struct Scene {
     std::vector<BVHNode> nodes;
 
     std::vector<rl_light_desc> lights; // Scene.emitters: EmittersState::Unbuild (point / directional), in file order
+    bool has_environment = false;      // Scene.emitter_environment: EnvironmentLight with a constant colour
+    Color environment{};
+    const EnvironmentLight *env_emitter = nullptr;
+    Color enviroment_luminance() const { return has_environment ? environment : Color::zero(); } // scene.rs:125-130
     BoundingSphere bsphere{};
     void build_emitters() { // scene.rs:53-123 (no env map, no ATS)
         // bounding sphere: union of Mesh::compute_aabb (all vertices, geometry.rs:441-456) and the camera position
@@ -1273,6 +1340,16 @@ struct Scene {
                 emitters.emitters.push_back(std::make_unique<MeshEmitter>(m.get()));
                 emitters.emitter_mesh.push_back(m.get());
             }
+        env_emitter = nullptr;
+        if (has_environment) { // scene.rs:69-81: preprocess, then pushed right after the mesh lights
+            auto e = std::make_unique<EnvironmentLight>();
+            e->luminance = environment;
+            e->bsphere = bsphere;
+            e->bsphere.radius *= 1.1f;
+            env_emitter = e.get();
+            emitters.emitters.push_back(std::move(e));
+            emitters.emitter_mesh.push_back(nullptr);
+        }
         for (auto &l : lights) { // e.preprocess(self); emitters.push(e)  (scene.rs:85-96)
             if (l.kind == RL_LIGHT_POINT) {
                 auto e = std::make_unique<PointEmitter>();
@@ -1509,16 +1586,16 @@ Color vertex_contribution(const Vertex &v, const Edge &edge) {
     return Color::zero();
 }
 // Edge::contribution, edge.rs:201-210 (environment luminance is zero on this path)
-Color edge_contribution(const Edge &e, const Path &path) {
+Color edge_contribution(const Edge &e, const Path &path, const Scene *scene) {
     if (e.v1 >= 0) {
         if (e.has_contrib) return e.contrib * e.weight * e.rr_weight;
         return e.weight * e.rr_weight * vertex_contribution(path.vertices[e.v1], e);
     }
-    return e.weight * e.rr_weight * Color::zero();
+    return e.weight * e.rr_weight * scene->enviroment_luminance(); // scene.enviroment_luminance(self.d), constant
 }
-bool edge_next_on_light_source(const Edge &e, const Path &path) { // edge.rs:191-197
+bool edge_next_on_light_source(const Edge &e, const Path &path, const Scene *scene) { // edge.rs:191-197
     if (e.v1 >= 0) return path.vertices[e.v1].on_light_source();
-    return false; // no environment emitter
+    return scene->has_environment;
 }
 // Edge::from_ray, edge.rs:65-189 (medium == None)
 std::pair<int, int> edge_from_ray(Path &path, const Ray &ray, int org, PDF pdf_direction, Color weight, float rr_weight, const Ctx &cx, size_t id_sampling) {
@@ -1613,7 +1690,7 @@ struct DirectionalSamplingStrategy : SamplingStrategy { // strategies/directiona
     }
     bool pdf(const Path &path, const Ctx &cx, int vertex_id, int edge_id, float *out) const override { // :258-304
         const Edge &edge = path.edges[edge_id];
-        if (!edge_next_on_light_source(edge, path)) return false;
+        if (!edge_next_on_light_source(edge, path, cx.scene)) return false;
         const Vertex &v = path.vertices[vertex_id];
         if (v.kind == Vertex::Surface) {
             if (v.its.mesh->bsdf->is_smooth()) return false;
@@ -1635,7 +1712,7 @@ struct LightSamplingStrategy : SamplingStrategy { // strategies/emitters.rs
         float r_sel = sampler.next();
         float r = sampler.next();
         P2 uv = sampler.next2d();
-        LightSampling rec = cx.scene->emitters.sample_light(its.p, r_sel, r, uv);
+        LightSampling rec = cx.scene->emitters.sample_light(cx.math, its.p, r_sel, r, uv);
         bool visible = cx.scene->visible(its.p, rec.p, cx.accel_mode, *cx.counters); // evaluated before the && (:125-126)
         if (rec.is_valid() && visible) {
             Vertex nv;
@@ -1649,7 +1726,17 @@ struct LightSamplingStrategy : SamplingStrategy { // strategies/emitters.rs
         return false; // "Finish the sampling here"
     }
     bool pdf_emitter(const Path &path, const Ctx &cx, const Ray &ray, int next_vertex_id, float *out) const { // :10-92
-        if (next_vertex_id < 0) return false;
+        if (next_vertex_id < 0) { // :18-46: the edge left the scene
+            const EnvironmentLight *env = cx.scene->env_emitter;
+            if (!env) return false;
+            float t;
+            if (!bsphere_intersect(env->bsphere, ray, &t)) std::abort(); // t.unwrap()
+            V3 p = ray.o + ray.d * t;
+            V3 n = normalize(env->bsphere.center - p);
+            PDF pdf = cx.scene->emitters.direct_pdf(env, LightSamplingPDF{ray.o, p, n, ray.d});
+            *out = pdf.value();
+            return true;
+        }
         const Vertex &nv = path.vertices[next_vertex_id];
         if (nv.kind == Vertex::Surface) {
             PDF p = cx.scene->emitters.direct_pdf(nv.its.mesh, LightSamplingPDF{ray.o, nv.its.p, nv.its.n_g, ray.d});
@@ -1665,7 +1752,7 @@ struct LightSamplingStrategy : SamplingStrategy { // strategies/emitters.rs
     }
     bool pdf(const Path &path, const Ctx &cx, int vertex_id, int edge_id, float *out) const override { // :250-282
         const Edge &edge = path.edges[edge_id];
-        if (!edge_next_on_light_source(edge, path)) return false;
+        if (!edge_next_on_light_source(edge, path, cx.scene)) return false;
         const Vertex &v = path.vertices[vertex_id];
         if (v.kind == Vertex::Surface) {
             if (v.its.mesh->bsdf->is_smooth()) return false;
@@ -1706,7 +1793,7 @@ void generate(Path &path, int root, const Ctx &cx, Sampler &sampler, const Techn
 // TechniquePathTracing::evalute_edge / evaluate, path.rs:37-185
 Color evalute_edge(const TechniquePathTracing &tq, uint32_t curr_depth, int32_t min_depth, const Path &path, const Ctx &cx, int vertex_id, int edge_id, uint32_t strategy) {
     const Edge &edge = path.edges[edge_id];
-    Color contrib = edge_contribution(edge, path);
+    Color contrib = edge_contribution(edge, path, cx.scene);
     if (strategy == RL_STRATEGY_BSDF && edge.id_sampling != 0) contrib = Color::zero();
     if (strategy == RL_STRATEGY_EMITTER && edge.id_sampling != 1) contrib = Color::zero();
     bool add_contrib = min_depth < 0 ? true : curr_depth >= (uint32_t)min_depth;
@@ -1742,7 +1829,7 @@ Color evaluate(const TechniquePathTracing &tq, uint32_t curr_depth, int32_t min_
     } else if (v.kind == Vertex::Sensor) {
         const Edge &edge = path.edges[v.edge_out.at(0)];
         bool add_contrib = min_depth < 0 ? true : curr_depth >= (uint32_t)min_depth;
-        Color contrib = edge_contribution(edge, path);
+        Color contrib = edge_contribution(edge, path, cx.scene);
         if (!contrib.is_zero() && add_contrib) l_i = l_i + contrib;
         if (edge.v1 >= 0) l_i = l_i + edge.weight * edge.rr_weight * evaluate(tq, curr_depth + 1, min_depth, path, cx, edge.v1, strategy);
     }
@@ -1803,7 +1890,25 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
     bool mis_prev = true;   // false: the edge is PDF::Discrete, or was sampled at a smooth vertex (the light strategy's pdf is None: v / (v + 0))
     for (;;) {
         Intersection its;
-        if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) break;
+        if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) {
+            // edge without a next vertex: weight * rr * environment luminance (edge.rs:208), same gates and MIS as an emitter hit
+            if (sc.has_environment) {
+                if (depth == 1) {
+                    if (add_ok(0) && !sc.environment.is_zero()) L = L + sc.environment;
+                } else if (!mute && add_ok(depth - 1) && I.strategy != RL_STRATEGY_EMITTER) {
+                    Color contrib = T * sc.environment;
+                    if (!contrib.is_zero()) {
+                        float w = 1.0f;
+                        if (I.strategy == RL_STRATEGY_ALL && mis_prev) { // pdf_emitter's environment arm (emitters.rs:18-46)
+                            float pl = sc.emitters.direct_pdf(sc.env_emitter, LightSamplingPDF{ray.o, V3{0, 0, 0}, V3{0, 0, 0}, ray.d}).value();
+                            w = pdf_prev / (pdf_prev + pl);
+                        }
+                        L = L + contrib * w;
+                    }
+                }
+            }
+            break;
+        }
         const BSDF &bsdf = *its.mesh->bsdf;
         // ---- emission carried by the arriving edge ----
         if (depth == 1) { // sensor edge: un-weighted (path.rs:152-165)
@@ -1861,7 +1966,7 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
             float r_sel = sampler.next();
             float r = sampler.next();
             P2 uv = sampler.next2d();
-            LightSampling rec = sc.emitters.sample_light(its.p, r_sel, r, uv);
+            LightSampling rec = sc.emitters.sample_light(cx.math, its.p, r_sel, r, uv);
             bool visible = sc.visible(its.p, rec.p, cx.accel_mode, *cx.counters);
             if (rec.is_valid() && !mute && add_ok(vdepth) && I.strategy != RL_STRATEGY_BSDF) {
                 V3 wo = its.frame.to_local(rec.d);
@@ -1870,7 +1975,11 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
                 if (!contrib.is_zero()) {
                     float w = 1.0f;
                     if (I.strategy == RL_STRATEGY_ALL && rec.pdf.kind == PDF::SolidAngle) { // a Discrete light edge has no MIS (path.rs:80)
-                        float pb = bsdf.pdf(cx.math, its.uv, its.wi, wo).value();
+                        // the graph evaluates the BSDF pdf along Edge::from_vertex's direction (p_light - p) / |.| (edge.rs:37-39):
+                        // bit-identical to rec.d for mesh lights, not for the environment (p = x + d t)
+                        V3 de = rec.p - its.p;
+                        de = de / magnitude(de);
+                        float pb = bsdf.pdf(cx.math, its.uv, its.wi, rec.emitter == sc.env_emitter ? its.frame.to_local(de) : wo).value();
                         float pl = rec.pdf.value();
                         w = pl / (pb + pl);
                     }
@@ -1899,7 +2008,7 @@ Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy
     Color l_i = Color::zero();
     if (1 > cx.counters->max_depth) cx.counters->max_depth = 1;
     Intersection its;
-    if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) return Color::zero();
+    if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) return sc.enviroment_luminance(); // direct.rs:33-36
     if (its.cos_theta() <= 0.0f) return l_i;
     l_i = l_i + its.mesh->emit();
     float weight_nb_bsdf = I.nb_bsdf_samples == 0 ? 0.0f : 1.0f / (float)I.nb_bsdf_samples;
@@ -1909,7 +2018,7 @@ Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy
         float r_sel = sampler.next();
         float r = sampler.next();
         P2 uv = sampler.next2d();
-        LightSampling rec = sc.emitters.sample_light(its.p, r_sel, r, uv);
+        LightSampling rec = sc.emitters.sample_light(cx.math, its.p, r_sel, r, uv);
         V3 d_out_local = its.frame.to_local(rec.d);
         if (rec.is_valid() && sc.visible(its.p, rec.p, cx.accel_mode, *cx.counters) && !bsdf.is_smooth()) {
             float pdf_bsdf = bsdf.pdf(cx.math, its.uv, its.wi, d_out_local).value();
@@ -1934,6 +2043,17 @@ Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy
                 }
                 l_i = l_i + weight_bsdf * sb.weight * next_its.mesh->emit() * weight_nb_bsdf;
             }
+        } else if (sc.has_environment) { // direct.rs:183-227
+            float weight_bsdf = 1.0f;
+            if (sb.pdf.kind == PDF::SolidAngle) {
+                float t;
+                if (!bsphere_intersect(sc.env_emitter->bsphere, r2, &t)) std::abort(); // t.unwrap()
+                V3 p = r2.o + r2.d * t;
+                V3 n = normalize(sc.env_emitter->bsphere.center - p);
+                float light_pdf = sc.emitters.direct_pdf(sc.env_emitter, LightSamplingPDF{r2.o, p, n, r2.d}).value();
+                weight_bsdf = mis_weight(sb.pdf.value() * weight_nb_bsdf, light_pdf * weight_nb_light);
+            }
+            l_i = l_i + weight_bsdf * sb.weight * sc.enviroment_luminance() * weight_nb_bsdf;
         }
     }
     return l_i;
@@ -1991,7 +2111,7 @@ orc_scene *orc_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         return nullptr;
     };
     if (!desc || !desc->meshes || desc->nmeshes == 0) return fail("empty scene");
-    if (desc->has_volume || desc->has_environment) return fail("volume / environment map are outside the hot path");
+    if (desc->has_volume || desc->has_environment > 1) return fail("volume / environment textures are outside the hot path");
     auto *os = new orc_scene;
     Scene &s = os->scene;
     s.camera.img_x = desc->camera.width, s.camera.img_y = desc->camera.height;
@@ -2020,6 +2140,7 @@ orc_scene *orc_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         m->build_cdf();
         s.meshes.push_back(std::move(m));
     }
+    if (desc->has_environment) s.has_environment = true, s.environment = Color{desc->environment[0], desc->environment[1], desc->environment[2]};
     for (uint32_t li = 0; li < desc->nlights; li++) {
         if (desc->lights[li].kind > RL_LIGHT_DIRECTIONAL) return fail("unknown light kind");
         s.lights.push_back(desc->lights[li]);
@@ -2254,7 +2375,7 @@ int orc_sample_light(const orc_scene *os, const float x[3], float r_sel, float r
                      float weight[3], float *pdf) {
     const Scene &sc = os->scene;
     if (sc.emitters.emitters.empty()) return -1;
-    LightSampling rec = sc.emitters.sample_light(load3(x), r_sel, r, P2{u0, u1});
+    LightSampling rec = sc.emitters.sample_light(Math{ORC_MATH_SPEC}, load3(x), r_sel, r, P2{u0, u1});
     store3(p, rec.p), store3(n, rec.n), store3(d, rec.d);
     weight[0] = rec.weight.r, weight[1] = rec.weight.g, weight[2] = rec.weight.b;
     *pdf = rec.pdf.value();

@@ -73,7 +73,7 @@ class rl_scene_desc(C.Structure):
     _fields_ = [("nmeshes", C.c_uint32), ("meshes", C.POINTER(rl_mesh_desc)),
                 ("camera", rl_camera_desc), ("has_volume", C.c_uint32), ("has_environment", C.c_uint32),
                 ("nlights", C.c_uint32), ("lights", C.POINTER(rl_light_desc)),
-                ("ntextures", C.c_uint32), ("textures", C.POINTER(rl_texture))]
+                ("ntextures", C.c_uint32), ("textures", C.POINTER(rl_texture)), ("environment", C.c_float * 3)]
 
 
 class rl_integrator_desc(C.Structure):

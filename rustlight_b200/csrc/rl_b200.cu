@@ -303,7 +303,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     std::string err;
     if (!build_host_scene(desc, s->hs, err)) {
         ctx->err = "rl_scene_create: " + err;
-        bool unsupported = desc && (desc->has_volume || desc->has_environment);
+        bool unsupported = desc && (desc->has_volume || desc->has_environment > 1);
         delete s;
         return unsupported ? RL_ERR_UNSUPPORTED : RL_ERR_INVALID;
     }
@@ -461,6 +461,8 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     sv.root_min = V3{hs.root_min[0], hs.root_min[1], hs.root_min[2]};
     sv.root_max = V3{hs.root_max[0], hs.root_max[1], hs.root_max[2]};
     sv.abs_max = hs.abs_max;
+    sv.env_on = hs.env_on ? 1u : 0u, sv.env_color = Col{hs.env_color[0], hs.env_color[1], hs.env_color[2]};
+    sv.bs_center = V3{hs.bs_center[0], hs.bs_center[1], hs.bs_center[2]}, sv.bs_radius = hs.bs_radius, sv.env_pdf_sel = hs.env_pdf_sel;
     std::memcpy(sv.s2c, hs.s2c, 64);
     std::memcpy(sv.c2w, hs.c2w, 64);
     sv.cam_pos = V3{hs.cam_pos[0], hs.cam_pos[1], hs.cam_pos[2]};

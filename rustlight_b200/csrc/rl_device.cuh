@@ -327,6 +327,12 @@ struct SceneView {
     // BVHAccel nodes[0].aabb (union of compute_aabb_tri boxes), for the reference's root test
     V3 root_min, root_max;
     float abs_max; // max |coordinate| of the scene, scales the conservative-culling epsilon
+    // EnvironmentLight with a constant colour (emitter.rs:428-568): 0 when absent
+    uint32_t env_on;
+    Col env_color;
+    V3 bs_center;      // Scene.bsphere (scene.rs:54-60) ...
+    float bs_radius;   // ... radius x 1.1 (EnvironmentLight::preprocess)
+    float env_pdf_sel; // probability of picking the environment in sample_light
     // camera
     float s2c[16], c2w[16];
     V3 cam_pos;
@@ -1349,12 +1355,62 @@ RL_HD uint32_t cdf_sample_discrete(const float *cdf, uint32_t n_plus_1, float v)
     }
     return lo - 1;
 }
+// math.rs:324-352
+RL_HD bool solve_quadratic(float a, float b, float c, float *x0_out, float *x1_out) {
+    if (a == 0.0f) {
+        if (b != 0.0f) {
+            float v = -c / b;
+            *x0_out = v, *x1_out = v;
+            return true;
+        }
+        return false;
+    }
+    float d = b * b - 4.0f * a * c;
+    if (d < 0.0f) return false;
+    float d_sqrt = sqrtf(d);
+    float tmp = b < 0.0f ? -0.5f * (b - d_sqrt) : -0.5f * (b + d_sqrt);
+    float x0 = tmp / a, x1 = c / tmp;
+    if (x0 > x1) *x0_out = x1, *x1_out = x0;
+    else *x0_out = x0, *x1_out = x1;
+    return true;
+}
+// BoundingSphere::intersect (structure.rs:899-920) for Ray::new(o, d) (tnear = EPSILON, tfar = f32::MAX).  Note the
+// reference's b = +2 d_p.d with d_p = center - o (the roots are those of the mirrored ray); kept verbatim.
+RL_HD bool bsphere_intersect(V3 center, float radius, V3 o, V3 d, float *t) {
+    V3 d_p = center - o;
+    float a = dot(d, d);
+    float b = 2.0f * dot(d_p, d);
+    float c = dot(d_p, d_p) - radius * radius;
+    float t0, t1;
+    if (!solve_quadratic(a, b, c, &t0, &t1)) return false;
+    if (t0 < RL_EPSILON) {
+        if (t1 < RL_F32_MAX) {
+            *t = t1;
+            return true;
+        }
+        return false;
+    } else if (t0 < RL_F32_MAX) {
+        *t = t0;
+        return true;
+    }
+    return false;
+}
+RL_HD V3 sample_uniform_sphere(float ux, float uy) { // math.rs:67-72
+    float z = 1.0f - 2.0f * ux;
+    float r = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+    float phi = 2.0f * RL_PI * uy;
+    float sp, cp;
+    spec_sincos(phi, &sp, &cp);
+    return V3{r * cp, r * sp, z};
+}
+#define RL_ENV_PDF (1.0f / (RL_PI * 4.0f)) // EnvironmentLightColor::Constant pdf (emitter.rs:406, 369-373)
 struct LightSample {
     V3 p, n, d;
     Col weight;
     float pdf;
     bool valid;
     bool discrete; // PDF::Discrete: point and directional lights (no MIS against BSDF sampling)
+    bool env;      // sampled on the environment: the MIS pdf of the BSDF uses the direction recomputed from p (edge.rs:37-39)
 };
 // EmitterSampler::sample_light -> Mesh::direct_sample -> Mesh::sample -> sample_tri
 // (emitter.rs:1604-1620, 652-688; geometry.rs:340-348, 261-337; math.rs:388-394)
@@ -1368,6 +1424,27 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, 
         Col intensity = Col{info.y, info.z, info.w};
         LightSample ls;
         Col weight;
+        ls.env = false;
+        if ((f2u(info.x) & 0xfu) == 2u) { // EnvironmentLight::direct_sample, emitter.rs:474-511
+            V3 dd = sample_uniform_sphere(ux, uy);
+            float t;
+            ls.d = dd;
+            ls.discrete = false;
+            ls.env = true;
+            if (!bsphere_intersect(xyz(geo), geo.w, x, dd, &t)) { // "Miss bSphere": dummy record with a zero weight
+                ls.p = V3{0.0f, 0.0f, 0.0f};
+                ls.n = V3{0.0f, 0.0f, 0.0f};
+                weight = Col{0.0f, 0.0f, 0.0f};
+            } else {
+                ls.p = x + dd * t;
+                ls.n = normalize(xyz(geo) - ls.p);
+                weight = div_checked(intensity, RL_ENV_PDF);
+            }
+            ls.weight = Col{weight.r / pdf_sel, weight.g / pdf_sel, weight.b / pdf_sel};
+            ls.pdf = RL_ENV_PDF * pdf_sel;
+            ls.valid = ls.pdf != 0.0f;
+            return ls;
+        }
         if ((f2u(info.x) & 0xfu) == 0u) {
             ls.p = xyz(geo);
             V3 dd = ls.p - x;
@@ -1417,6 +1494,7 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, 
     ls.n = n_g;
     ls.d = dd;
     ls.discrete = false;
+    ls.env = false;
     const float cosl = dist != 0.0f ? fmaxf(dot(n_g, -dd), 0.0f) : 0.0f;
     const float d2 = dist * dist;
     if ((dist == 0.0f || (cosl == 0.0f && d2 > 0.0f)) && pdf_sel > 0.0f) {
@@ -1506,7 +1584,30 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
     out->shadow = false;
     out->nee_sampled = false;
     out->add = Col{0.0f, 0.0f, 0.0f};
-    if (hit.prim == RL_MISS) return;
+    if (hit.prim == RL_MISS) {
+        // Edge without a next vertex (edge.rs:93-127): contributes weight * rr * environment luminance (edge.rs:208), with the
+        // same gates and MIS as an emitter hit (path.rs:37-111, 152-165); the light strategy's pdf is pdf_emitter's
+        // environment arm (emitters.rs:18-46): constant 1 / 4 pi times the selection probability.
+        if (!sv.env_on) return;
+        if (st.depth == 1u) {
+            if (ip_add_ok(ip, 0u) && !is_zero(sv.env_color)) {
+                out->add = sv.env_color;
+                out->has_add = true;
+            }
+        } else if (ip.single_scattering == 0u && ip_add_ok(ip, st.depth - 1u) && ip.strategy != 2u) {
+            Col contrib = st.T * sv.env_color;
+            if (!is_zero(contrib)) {
+                float w = 1.0f;
+                if (ip.strategy == 0u && !(f2u(st.pdf_prev) >> 31)) {
+                    float pl = RL_ENV_PDF * sv.env_pdf_sel;
+                    w = st.pdf_prev / (st.pdf_prev + pl);
+                }
+                out->add = mul_checked(contrib, w);
+                out->has_add = true;
+            }
+        }
+        return;
+    }
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
     uint32_t mesh = f2u(s0.w);
     Material mat = load_material(sv.mats, mesh);
@@ -1589,6 +1690,13 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
             Col f;
             float pb;
             bsdf_eval_pdf<KM>(mat, its.wi, wo, &f, &pb);
+            if (ls.env) { // the edge direction is recomputed from the two positions (Edge::from_vertex, edge.rs:37-39); for mesh lights
+                          // that IS ls.d, for the environment (p = x + d t) it differs in the last bits
+                V3 de = ls.p - its.p;
+                float dist = magnitude(de);
+                de = de / dist;
+                pb = bsdf_pdf<KM>(mat, its.wi, to_local(its.frame, de));
+            }
             Col contrib = st.T * (ls.weight * f);
             if (!is_zero(contrib)) {
                 float w = 1.0f;
@@ -1615,13 +1723,18 @@ struct DirectCtx {
     Sampler smp;
     float wb, wl; // weight_nb_bsdf, weight_nb_light (direct.rs:48-57)
     bool ok;      // primary ray hit a surface seen from its front side
+    bool env_primary; // the primary ray escaped into the environment: the sample's value is `emit`
     Col emit;
 };
 RL_HD void direct_begin(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, const HitRec &hit, uint32_t rng_n, uint32_t pixel, uint32_t sample,
                         DirectCtx *cx) {
     cx->ok = false;
     cx->emit = Col{0.0f, 0.0f, 0.0f};
-    if (hit.prim == RL_MISS) return; // environment luminance is zero on this path (direct.rs:35)
+    cx->env_primary = false;
+    if (hit.prim == RL_MISS) { // return scene.enviroment_luminance(ray.d) (direct.rs:33-36)
+        if (sv.env_on) cx->emit = sv.env_color, cx->env_primary = true;
+        return;
+    }
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
     uint32_t mesh = f2u(s0.w);
     cx->mat = load_material(sv.mats, mesh);
@@ -1660,6 +1773,7 @@ RL_HD bool direct_light_sample(const SceneView &sv, DirectCtx *cx, V3 *p1, Col *
 // or, with a max_distance, when the next surface is further away.
 RL_HD void ao_begin(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, const HitRec &hit, uint32_t rng_n, uint32_t pixel, uint32_t sample, DirectCtx *cx) {
     cx->ok = false;
+    cx->env_primary = false;
     cx->emit = Col{0.0f, 0.0f, 0.0f};
     if (hit.prim == RL_MISS) return;
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
@@ -1696,7 +1810,15 @@ RL_HD bool direct_bsdf_sample(DirectCtx *cx, V3 *dir, Col *weight, float *pdf) {
 }
 // Stage 2 (direct.rs:145-181): the extension ray hit something; contribution if it is a light.
 RL_HD bool direct_finish(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, const HitRec &hit, Col bsdf_weight, float bsdf_pdf_v, Col *contrib) {
-    if (hit.prim == RL_MISS) return false;
+    if (hit.prim == RL_MISS) { // direct.rs:183-227: the BSDF sample escaped: MIS against sampling the environment
+        if (!sv.env_on) return false;
+        float wb = ip.nb_bsdf_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_bsdf_samples;
+        float wl = ip.nb_light_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_light_samples;
+        float weight_bsdf = 1.0f;
+        if (!(f2u(bsdf_pdf_v) >> 31)) weight_bsdf = mis_weight_power(bsdf_pdf_v * wb, (RL_ENV_PDF * sv.env_pdf_sel) * wl);
+        *contrib = mul_checked(mul_plain(weight_bsdf, bsdf_weight) * sv.env_color, wb);
+        return true;
+    }
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
     uint32_t mesh = f2u(s0.w);
     Material mat = load_material(sv.mats, mesh);

@@ -391,6 +391,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct1(SceneView sv, IntegPar
         const uint32_t i = tile * kBlock + threadIdx.x;
         DirectCtx cx;
         cx.ok = false;
+        cx.env_primary = false;
         uint32_t pid = 0;
         if (i < n) {
             float4 ro = ray_o[i], rd = ray_d[i], st4 = state[i], h4 = hit[i];
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct1(SceneView sv, IntegPar
             if (ip.kind == 2u) ao_begin(sv, ip, xyz(ro), xyz(rd), h, f2u(st4.w) & 0xffffu, __ldg(pixel_list + lp), ip.sample_base + s_local, &cx);
             else direct_begin(sv, ip, xyz(ro), xyz(rd), h, f2u(st4.w) & 0xffffu, __ldg(pixel_list + lp), ip.sample_base + s_local, &cx);
             if (h.prim != RL_MISS) c_hits++;
-            if (cx.ok && !is_zero(cx.emit)) lacc[pid] = make_float4(cx.emit.r, cx.emit.g, cx.emit.b, 0.0f);
+            if ((cx.ok || cx.env_primary) && !is_zero(cx.emit)) lacc[pid] = make_float4(cx.emit.r, cx.emit.g, cx.emit.b, 0.0f);
         }
         for (uint32_t j = 0; j < ip.nb_light_samples; j++) {
             V3 p1 = V3{0.0f, 0.0f, 0.0f};

@@ -31,6 +31,9 @@ struct HostScene {
     float raw_min[3], raw_max[3];   // plain vertex bounds (Morton normalisation)
     float abs_max = 0;
     float s2c[16], c2w[16], cam_pos[3];
+    // EnvironmentLight (constant): colour, bounding sphere (radius already x 1.1), emitter-selection pdf
+    bool env_on = false;
+    float env_color[3] = {0, 0, 0}, bs_center[3] = {0, 0, 0}, bs_radius = 0.0f, env_pdf_sel = 0.0f;
     uint32_t img_w = 0, img_h = 0;
 };
 
@@ -64,8 +67,8 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
         err = "scene.volume must be None on this path";
         return false;
     }
-    if (desc->has_environment) {
-        err = "environment emitters are outside the hot path";
+    if (desc->has_environment > 1) {
+        err = "environment textures are outside the hot path";
         return false;
     }
     if (desc->camera.width == 0 || desc->camera.height == 0) {
@@ -197,11 +200,11 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
     // Non-mesh emitters follow the mesh lights (scene.rs:85-96).  Scene.bsphere (scene.rs:54-60): union of
     // Mesh::compute_aabb over ALL vertices of every mesh (geometry.rs:441-456) and the camera position, to_sphere
     // (structure.rs:871-877); DirectionalLight::preprocess enlarges the radius by 1.1 (emitter.rs:106-109).
-    if (desc->nlights > 0) {
-        if (!desc->lights) {
-            err = "nlights > 0 but lights is null";
-            return false;
-        }
+    if (desc->nlights > 0 && !desc->lights) {
+        err = "nlights > 0 but lights is null";
+        return false;
+    }
+    if (desc->nlights > 0 || desc->has_environment) {
         float bmin[3] = {RL_F32_MAX, RL_F32_MAX, RL_F32_MAX}, bmax[3] = {-RL_F32_MAX, -RL_F32_MAX, -RL_F32_MAX};
         for (uint32_t mi = 0; mi < desc->nmeshes; mi++) {
             const rl_mesh_desc &m = desc->meshes[mi];
@@ -217,6 +220,19 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
         V3 size = V3{bmax[0] - bmin[0], bmax[1] - bmin[1], bmax[2] - bmin[2]};
         V3 c = size * 0.5f + V3{bmin[0], bmin[1], bmin[2]}; // AABB::center, structure.rs:844-846
         float radius = magnitude(c - V3{bmax[0], bmax[1], bmax[2]});
+        if (desc->has_environment) { // scene.rs:69-81: the environment follows the mesh lights; flux = PI r^2 c (emitter.rs:512-516)
+            EmitterTmp e{};
+            e.light_kind = 2u;
+            e.radius = radius * 1.1f; // EnvironmentLight::preprocess, emitter.rs:436-439
+            for (int a = 0; a < 3; a++) e.intensity[a] = desc->environment[a];
+            e.v[0] = c.x, e.v[1] = c.y, e.v[2] = c.z;
+            e.flux_max = channel_max(mul_plain(RL_PI * (e.radius * e.radius), Col{e.intensity[0], e.intensity[1], e.intensity[2]}));
+            emitters.push_back(e);
+            hs.env_on = true;
+            for (int a = 0; a < 3; a++) hs.env_color[a] = desc->environment[a];
+            hs.bs_center[0] = c.x, hs.bs_center[1] = c.y, hs.bs_center[2] = c.z;
+            hs.bs_radius = e.radius;
+        }
         for (uint32_t li = 0; li < desc->nlights; li++) {
             const rl_light_desc &l = desc->lights[li];
             EmitterTmp e{};
@@ -225,7 +241,7 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
             Col I = Col{l.intensity[0], l.intensity[1], l.intensity[2]};
             if (l.kind == RL_LIGHT_POINT) {
                 e.flux_max = channel_max(mul_checked(mul_checked(I, 4.0f), RL_PI)); // emitter.rs:239-241
-            } else if (l.kind == RL_LIGHT_DIRECTIONAL) {
+            } else if (l.kind == RL_LIGHT_DIRECTIONAL) { // kinds 0 / 1 = rl_light_kind, 2 = the environment (above)
                 e.radius = radius * 1.1f;
                 float area = RL_PI * (e.radius * e.radius);
                 e.flux_max = channel_max(mul_plain(area, I)); // emitter.rs:164-168
@@ -253,6 +269,7 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
             } else {
                 hs.emit_info.push_back(f4(u2f(0xfffffff0u | e.light_kind), e.intensity[0], e.intensity[1], e.intensity[2]));
                 hs.emit_info.push_back(f4(e.v[0], e.v[1], e.v[2], e.radius));
+                if (e.light_kind == 2u) hs.env_pdf_sel = hs.emit_cdf[i + 1] - hs.emit_cdf[i];
             }
         }
     } else {

@@ -45,6 +45,7 @@ def lib():
         L.rlh_scene_add_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.rlh_scene_add_texture_file.restype = C.c_uint32
         L.rlh_scene_add_texture_file.argtypes = [C.c_void_p, C.c_char_p]
+        L.rlh_scene_set_environment.argtypes = [C.c_void_p, C.c_float * 3]
         L.rlh_scene_add_light.argtypes = [C.c_void_p, C.c_uint32, C.c_float * 3, C.c_float * 3]
         L.rlh_scene_set_material.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_abi.rl_material)]
         L.rlh_material_phong.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
@@ -134,6 +135,11 @@ class Scene:
     def add_grid_texture(self, color0, color1, line_width=0.01, offset=(0, 0), scale=(1, 1)):
         p = (C.c_float * 11)(*color0, *color1, *offset, *scale, float(line_width))
         return lib().rlh_scene_add_texture(self._h, _abi.RL_TEX_GRID, 0, 0, None, p)
+
+    def set_environment(self, rgb):
+        """Constant EnvironmentLight (emitter.rs:428-568, pbrt LightSource "infinite" "rgb L")."""
+        lib().rlh_scene_set_environment(self._h, (C.c_float * 3)(*rgb))
+        return self
 
     def add_point_light(self, intensity, position):
         """PointEmitter (emitter.rs:186-250), appended to Scene.emitters."""

@@ -603,7 +603,12 @@ Scene PBRTSceneLoader::load_string(const std::string &text_in, bool use_shading_
                 Color L = p.rgb("L", Color{1.0f, 1.0f, 1.0f});
                 Vec3 from = pt("from", 0, 0, 0), to = pt("to", 0, 0, 1);
                 scene.add_directional_light(Color{L.r * scale.r, L.g * scale.g, L.b * scale.b}, to.x - from.x, to.y - from.y, to.z - from.z);
-            } else throw Error("pbrt: LightSource \"" + type + "\" is outside the hot-path scope (point, distant)");
+            } else if (type == "infinite") { // scene_loader.rs:241-276: a constant RGB L (x scale); map names are textures: not here
+                if (p.find("mapname")) throw Error("pbrt: LightSource \"infinite\" with a mapname (environment texture) is outside the hot-path scope");
+                if (scene.has_environment) throw Error("Multiple env map is NOT supported"); // scene_loader.rs:247-249
+                Color L = p.rgb("L", Color{1.0f, 1.0f, 1.0f});
+                scene.set_environment(Color{L.r * scale.r, L.g * scale.g, L.b * scale.b});
+            } else throw Error("pbrt: LightSource \"" + type + "\" is outside the hot-path scope (point, distant, infinite)");
         } else if (d == "Texture") { // pbrt_rs::Texture {filename}: only image maps reach the BSDFs (bsdfs/mod.rs:219-241)
             std::string name = ps.expect_str(), ttype = ps.expect_str(), tclass = ps.expect_str();
             ParamSet p = ps.params();
@@ -840,6 +845,10 @@ Scene JSONSceneLoader::load_string(const std::string &text, bool use_shading_nor
         if (ms->t != JVal::Obj) throw Error("json: materials must be an object");
         for (auto &kv : ms->o) materials[kv.first] = with_texture(kv.second, jmaterial(kv.second));
     }
+    if (const JVal *env = root.get("environment")) { // "environment": [r, g, b]: constant EnvironmentLight
+        Color c = jcolor(env, "environment", Color{0.0f, 0.0f, 0.0f});
+        scene.set_environment(c);
+    }
     if (const JVal *ls = root.get("lights")) { // [{"type": "point", "intensity": [r,g,b], "position": [x,y,z]}, {"type": "directional", "intensity", "direction"}]
         if (ls->t != JVal::Arr) throw Error("json: lights must be an array");
         for (auto &l : ls->a) {
@@ -920,6 +929,12 @@ std::string scene_to_json(const Scene &scene) {
       << (c.flip ? "true" : "false") << ",\n             \"to_world\": ";
     put_floats(o, c.to_world.m, 16);
     o << "},\n";
+    if (scene.has_environment) {
+        float e[3] = {scene.environment.r, scene.environment.g, scene.environment.b};
+        o << "  \"environment\": ";
+        put_floats(o, e, 3);
+        o << ",\n";
+    }
     if (!scene.lights.empty()) {
         o << "  \"lights\": [";
         for (size_t i = 0; i < scene.lights.size(); i++) {

@@ -114,6 +114,8 @@ struct Scene {
     std::optional<size_t> nb_threads;
     std::string output_img_path = "out.pfm";
     bool has_volume = false, has_environment = false;
+    Color environment; // EnvironmentLight{EnvironmentLightColor::Constant(environment)} when has_environment (scene_loader.rs:241-258)
+    void set_environment(Color c) { has_environment = true, environment = c; }
     // Scene.emitters before build_emitters (EmittersState::Unbuild): PointEmitter / DirectionalLight (scene_loader.rs:207-240)
     std::vector<rl_light_desc> lights;
     std::vector<Texture> textures; // referenced by Material.m.kd_texture (1-based)

@@ -346,6 +346,7 @@ const rl_scene_desc *Scene::desc() {
     std::memcpy(desc_.camera.to_world, camera.to_world.m, sizeof(float) * 16);
     desc_.has_volume = has_volume ? 1u : 0u;
     desc_.has_environment = has_environment ? 1u : 0u;
+    desc_.environment[0] = environment.r, desc_.environment[1] = environment.g, desc_.environment[2] = environment.b;
     texture_descs_.clear();
     for (auto &t : textures) {
         rl_texture d = t.t;

@@ -30,7 +30,7 @@ pub struct rl_mesh_desc {
 #[repr(C)] pub struct rl_light_desc { pub kind: u32, pub intensity: [f32; 3], pub v: [f32; 3] }
 #[repr(C)] pub struct rl_scene_desc {
     pub nmeshes: u32, pub meshes: *const rl_mesh_desc, pub camera: rl_camera_desc, pub has_volume: u32, pub has_environment: u32,
-    pub nlights: u32, pub lights: *const rl_light_desc, pub ntextures: u32, pub textures: *const rl_texture,
+    pub nlights: u32, pub lights: *const rl_light_desc, pub ntextures: u32, pub textures: *const rl_texture, pub environment: [f32; 3],
 }
 #[repr(C)] pub struct rl_integrator_desc {
     pub kind: u32, pub min_depth: i32, pub max_depth: i32, pub rr_depth: i32, pub strategy: u32,
@@ -103,7 +103,9 @@ fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
         // trait; `f.lights` keeps them alive like the mesh vectors
         nlights: f.lights.len() as u32, lights: f.lights.as_ptr(),
         // BSDFColor::{Bitmap, Checkerbord, Grid} on a diffuse slot -> rl_texture + rl_material.kd_texture (describe() fills both)
-        ntextures: f.textures.len() as u32, textures: f.textures.as_ptr() };
+        ntextures: f.textures.len() as u32, textures: f.textures.as_ptr(),
+        // EnvironmentLightColor::Constant(c) -> has_environment = 1 + environment = c; a Texture environment must be rejected
+        environment: env_constant(scene) };
     (f, desc)
 }
 

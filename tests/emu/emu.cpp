@@ -112,6 +112,8 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
     sv.root_min = V3{hs.root_min[0], hs.root_min[1], hs.root_min[2]};
     sv.root_max = V3{hs.root_max[0], hs.root_max[1], hs.root_max[2]};
     sv.abs_max = hs.abs_max;
+    sv.env_on = hs.env_on ? 1u : 0u, sv.env_color = Col{hs.env_color[0], hs.env_color[1], hs.env_color[2]};
+    sv.bs_center = V3{hs.bs_center[0], hs.bs_center[1], hs.bs_center[2]}, sv.bs_radius = hs.bs_radius, sv.env_pdf_sel = hs.env_pdf_sel;
     std::memcpy(sv.s2c, hs.s2c, 64);
     std::memcpy(sv.c2w, hs.c2w, 64);
     sv.cam_pos = V3{hs.cam_pos[0], hs.cam_pos[1], hs.cam_pos[2]};
@@ -310,7 +312,7 @@ int emu_render(const emu_scene *s, const rl_integrator_desc *I, uint32_t spp, ui
                     if (h.prim != RL_MISS) S.hits++;
                     DirectCtx cx;
                     direct_begin(sv, ip, o, d, h, st.rng_n, pixel, sidx, &cx);
-                    if (cx.ok) slots[0] = cx.emit;
+                    if (cx.ok || cx.env_primary) slots[0] = cx.emit;
                     for (uint32_t j = 0; j < ip.nb_light_samples && cx.ok; j++) {
                         V3 p1;
                         Col c;

@@ -423,3 +423,69 @@ def test_texture_without_uv_is_black():
     assert not io.any() and np.array_equal(ie, io)
     lit, _ = ob.OracleScene(sc).render(_abi.direct_desc(1, 1), 4, seed=1, cfg=ob.config(**STREAM))
     assert lit.mean() > 0.01
+
+
+# ---- EnvironmentLight with a constant colour (emitter.rs:428-568) ---------------------------------------------------
+def _env_scene(w=32, h=32, with_area_light=False):
+    """A diffuse sphere-ish blob (an octahedron) floating in a constant environment, seen from outside."""
+    import json
+    from rustlight_b200 import SceneLoaderManager
+    P = [1, 0, 0, -1, 0, 0, 0, 1, 0, 0, -1, 0, 0, 0, 1, 0, 0, -1]
+    idx = [0, 2, 4, 2, 1, 4, 1, 3, 4, 3, 0, 4, 2, 0, 5, 1, 2, 5, 3, 1, 5, 0, 3, 5]
+    meshes = [{"material": {"type": "diffuse", "kd": [0.6, 0.5, 0.4]}, "indices": idx, "P": P}]
+    if with_area_light:
+        meshes.append({"material": {"type": "diffuse", "kd": [0, 0, 0]}, "emission": [5, 5, 5], "indices": [0, 1, 2, 0, 2, 3],
+                       "P": [-0.5, 2.5, -0.5, 0.5, 2.5, -0.5, 0.5, 2.5, 0.5, -0.5, 2.5, 0.5]})
+    txt = json.dumps({"camera": {"width": w, "height": h, "fov": 40, "to_world": [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 0, 0, 5, 1]},
+                      "environment": [0.8, 0.9, 1.0], "meshes": meshes})
+    return SceneLoaderManager().load_string(txt, "json")
+
+
+def test_environment_white_furnace():
+    """A convex diffuse body under a uniform environment L: every camera ray sees L on a miss and L * kd / (1 - 0) ... more
+    precisely radiance = L * kd after one bounce, because a convex body never sees itself: pixel = L * kd exactly in the
+    expectation, for BSDF sampling, light sampling and MIS alike."""
+    sc = _env_scene(24, 24)
+    osc = ob.OracleScene(sc)
+    pg, _ = osc.primary_hits(ob.ACCEL_NAIVE)
+    hit = (pg != 0xFFFFFFFF)
+    assert 0.05 < hit.mean() < 0.9
+    L, kd = np.float32([0.8, 0.9, 1.0]), np.float32([0.6, 0.5, 0.4])
+    for strat in (_abi.RL_STRATEGY_ALL, _abi.RL_STRATEGY_BSDF, _abi.RL_STRATEGY_EMITTER):
+        img, _ = osc.render(_abi.path_desc(strategy=strat, max_depth=3), 1500, seed=3, cfg=ob.config(**STREAM))
+        inner = np.zeros_like(hit)
+        inner[1:-1, 1:-1] = hit[1:-1, 1:-1] & hit[:-2, 1:-1] & hit[2:, 1:-1] & hit[1:-1, :-2] & hit[1:-1, 2:]
+        outer = ~hit
+        outer[1:-1, 1:-1] &= ~hit[:-2, 1:-1] & ~hit[2:, 1:-1] & ~hit[1:-1, :-2] & ~hit[1:-1, 2:]
+        assert np.allclose(img[outer], L, rtol=1e-4)  # the sensor edge is un-weighted in every strategy (path.rs:152-165); f32 sum of 1500 terms
+        assert np.allclose(img[inner].mean(axis=0), L * kd, rtol=0.03), strat
+
+
+@pytest.mark.parametrize("integ", [_abi.path_desc(), _abi.path_desc(strategy=_abi.RL_STRATEGY_BSDF, max_depth=4), _abi.path_desc(strategy=_abi.RL_STRATEGY_EMITTER, max_depth=3),
+                                   _abi.direct_desc(1, 1), _abi.direct_desc(2, 0), _abi.direct_desc(0, 2)])
+def test_environment_render_bit_exact(integ):
+    sc = _env_scene(32, 32, with_area_light=True)
+    ie, se = eb.EmuScene(sc).render(integ, 6, seed=5)
+    io, so = ob.OracleScene(sc).render(integ, 6, seed=5, cfg=ob.config(**STREAM))
+    assert (se.segments, se.hits, se.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+    assert np.array_equal(ie, io) and io.mean() > 0.3
+    if integ.kind == _abi.RL_INTEGRATOR_PATH:
+        ig, sg = ob.OracleScene(sc).render(integ, 6, seed=5, cfg=ob.config(estimator=ob.EST_GRAPH, accel_mode=ob.ACCEL_NAIVE))
+        assert sg.segments == so.segments and rel_l2(io, ig) < 1e-6
+
+
+def test_environment_in_the_cornell_box_keeps_the_reference_quirk():
+    """BoundingSphere::intersect solves with b = +2 d_p.d (structure.rs:899-903): the distance it returns is the one to the
+    sphere BEHIND the ray, so the shadow segment of an environment sample ends after that length and occluders beyond it are not
+    seen.  Mirrored verbatim (device == oracle bit for bit); consequence: inside the Cornell box the light-sampling estimator
+    leaks environment light through the walls and reads higher than the (unbiased) BSDF-sampling one."""
+    sc = load_cbox(24, 24)
+    sc.set_environment((0.3, 0.3, 0.4))
+    osc = ob.OracleScene(sc)
+    integ = _abi.path_desc(max_depth=4)
+    ie, se = eb.EmuScene(sc).render(integ, 8, seed=2)
+    io, so = osc.render(integ, 8, seed=2, cfg=ob.config(**STREAM))
+    assert se.segments == so.segments and np.array_equal(ie, io)
+    m = [float(osc.render(_abi.path_desc(strategy=s, max_depth=4), 600, seed=2, cfg=ob.config(**STREAM))[0].mean())
+         for s in (_abi.RL_STRATEGY_BSDF, _abi.RL_STRATEGY_EMITTER)]
+    assert m[1] > 1.1 * m[0]

@@ -445,6 +445,21 @@ def test_textured_materials_bit_exact(gpu_ctx):
     dev.close()
 
 
+def test_constant_environment_bit_exact(gpu_ctx):
+    """EnvironmentLight (constant): escaping rays add the environment with MIS, light sampling draws uniform directions and
+    ends its shadow segment where the reference's BoundingSphere::intersect says (quirk kept), `direct` handles both misses."""
+    sc = load_cbox(96, 96)
+    sc.set_environment((0.3, 0.3, 0.4))
+    sc.add_point_light((0.2, 0.2, 0.2), (0.0, 1.0, 0.5))
+    dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
+    for integ in (_abi.path_desc(), _abi.path_desc(strategy=_abi.RL_STRATEGY_EMITTER, max_depth=4), _abi.direct_desc(1, 1), _abi.direct_desc(2, 0)):
+        img, st = dev.render(integ, 6, seed=11)
+        ref, so = osc.render(integ, 6, seed=11, cfg=ob.config(**STREAM))
+        assert (st.segments, st.hits, st.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+        assert np.array_equal(img, ref)
+    dev.close()
+
+
 def test_config_shapes_c3_c5(gpu_ctx):
     """BASELINE configs[2] (Phong walls, 512x512) and configs[4] (1920x1080, Fov::Y quirk, ragged 16x16 tiles,
     material sort on): sub-sampled spp, bit-exact against the oracle on the same stream."""

@@ -190,8 +190,15 @@ def test_pbrt_light_sources():
     back = back_scene.desc.contents
     assert back.nlights == 3 and all(bytes(back.lights[i]) == bytes(d.lights[i]) for i in range(2))
     assert list(back.lights[2].v) == pytest.approx(list(d.lights[2].v), abs=1e-7)  # re-normalised on load
+    env = SceneLoaderManager().load_string('Camera "perspective" WorldBegin LightSource "infinite" "rgb L" [0.5 1 2] "rgb scale" [2 2 2] ' + tri + ' WorldEnd', "pbrt")
+    de = env.desc.contents
+    assert de.has_environment == 1 and list(de.environment) == [1, 2, 4]   # scene_loader.rs:241-258: L * scale
+    env_back = SceneLoaderManager().load_string(env.to_json(), "json")
+    assert env_back.desc.contents.has_environment == 1 and list(env_back.desc.contents.environment) == [1, 2, 4]
     with pytest.raises(SceneError, match="scope"):
-        SceneLoaderManager().load_string('Camera "perspective" WorldBegin LightSource "infinite" WorldEnd', "pbrt")
+        SceneLoaderManager().load_string('Camera "perspective" WorldBegin LightSource "infinite" "string mapname" "sky.exr" WorldEnd', "pbrt")
+    with pytest.raises(SceneError, match="scope"):
+        SceneLoaderManager().load_string('Camera "perspective" WorldBegin LightSource "spot" WorldEnd', "pbrt")
 
 
 def test_json_materials_round_trip():
