@@ -220,11 +220,12 @@ def main():
     if rank == 0:
         clocks.start()
     t0 = time.perf_counter()
-    dev_ms, segs, launches, samples = 0.0, 0, 0, 0
+    dev_ms, segs, launches, samples, shadows = 0.0, 0, 0, 0, 0
     for _ in range(args.steps):
         st = step_device()
         dev_ms += st.ms_total + st.ms_reduce
         segs += st.segments
+        shadows += st.shadow_rays
         launches += st.kernel_launches
         samples += st.samples
     wall_ms = (time.perf_counter() - t0) * 1e3
@@ -234,6 +235,7 @@ def main():
     wall_ms = max_over_ranks(wall_ms)
     tot_samples = sum_over_ranks(samples)
     tot_segs = sum_over_ranks(segs)
+    tot_shadows = sum_over_ranks(shadows)
     tot_launches = sum_over_ranks(launches)
     value = tot_samples / (dev_ms * 1e-3) / 1e6
 
@@ -312,6 +314,7 @@ def main():
                            "integrator": "path", "strategy": "all", "rr_depth": 0, "max_depth": "inf", "partition": f"16x16 tiles over {world} rank(s), 1 ncclReduce",
                            "l2": "wavefront queues are 23.6 GB per batch (176 B x 134 M paths in flight), far larger than the 126 MB L2"},
                 "mpath_segments_per_s": tot_segs / (dev_ms * 1e-3) / 1e6,
+                "mshadow_rays_per_s": tot_shadows / (dev_ms * 1e-3) / 1e6,  # Acceleration::visible calls of the reference
                 "wall_ms_per_step": wall_ms / args.steps,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(tot_launches), "clocks": clk, "roofline": roof, "stage_ms": stage_ms, "cpu_baseline": cpu}
