@@ -27,11 +27,14 @@ dev.primary_hits()
 dev.close()
 mx = mixed_cbox(48, 48)
 mx.add_point_light((0.5, 0.5, 0.5), (0.2, 1.0, 0.3))
+mx.add_directional_light((0.4, 0.4, 0.4), (0.2, -1.0, -0.1))
+mx.set_environment((0.2, 0.2, 0.3))
 t = mx.add_checkerboard_texture((0.8, 0.8, 0.8), (0.1, 0.1, 0.1), (0, 0), (2, 2))
 mx.set_material(1, material_diffuse(kd_texture=t))
 dev = DeviceScene(ctx, mx)
 for sort in (0, 1):
     dev.render(_abi.path_desc(), 3, seed=2, material_sort=sort)
+dev.render(_abi.direct_desc(2, 2), 2, seed=2)
 dev.close()
 ts = SceneLoaderManager().load_string(tessellated_cbox_json(3), "json")
 ts.set_resolution(32, 32)
