@@ -124,8 +124,8 @@ static constexpr uint32_t kMaxIters = 4096; // wavefront iterations per batch (p
 #define RL_SYNC_GROUP 4
 #endif
 
-static int grid_for(const rl_ctx *ctx, size_t n, int per_sm) {
-    size_t blocks = (n + kBlock - 1) / kBlock;
+static int grid_for(const rl_ctx *ctx, size_t n, int per_sm, int block = kBlock) {
+    size_t blocks = (n + block - 1) / block;
     size_t cap = (size_t)ctx->sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
@@ -140,12 +140,12 @@ static int grid_for(const rl_ctx *ctx, size_t n, int per_sm) {
 //   k_shade: one wave of resident CTAs (4 per SM at 64 registers); 6/SM 5.52 ms vs 4.81 ms.
 static constexpr int kTravPerSm = 32;
 template <typename K>
-static int resident_per_sm(K kernel, size_t smem) {
+static int resident_per_sm(K kernel, size_t smem, int block = kBlock) {
     static std::vector<std::pair<size_t, int>> cache; // one static per kernel type
     for (auto &c : cache)
         if (c.first == smem) return c.second;
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kBlock, smem) != cudaSuccess || nb < 1) nb = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, block, smem) != cudaSuccess || nb < 1) nb = 1;
     cache.push_back({smem, nb});
     return nb;
 }
@@ -798,7 +798,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                         else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
                         if (prof) CK(cudaEventRecord(ctx->ev[3], st));
 #define RL_LAUNCH_SHADE(SORT, KM)                                                                                                                   \
-    k_shade<SORT, KM><<<grid_for(ctx, n_ub, resident_per_sm(k_shade<SORT, KM>, 0)), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], \
+    k_shade<SORT, KM><<<grid_for(ctx, n_ub, resident_per_sm(k_shade<SORT, KM>, 0, shade_block(KM)), shade_block(KM)), shade_block(KM), 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], \
                                                                  ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1], ctx->state[cur ^ 1], qc + k + 1,     \
                                                                  ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc, ctx->d_counters)
                         // kernel specialised for the BSDF kinds of the scene: {diffuse}, {diffuse, phong}, everything

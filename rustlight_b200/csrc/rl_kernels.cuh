@@ -26,7 +26,10 @@
 
 namespace rl {
 
-constexpr int kBlock = 256;
+#ifndef RL_BLOCK
+#define RL_BLOCK 256 // threads per CTA of every kernel (A/B hook)
+#endif
+constexpr int kBlock = RL_BLOCK;
 
 struct Counters { // device-side statistics, 64-bit
     unsigned long long hits, nee_sampled, shadow_visible, pad;
@@ -233,9 +236,10 @@ __device__ __forceinline__ uint32_t block_compact(bool flag, uint32_t *global_co
 }
 
 // Two queues at once (survivors and shadow segments): one pair of barriers instead of three per queue.
-__device__ __forceinline__ void block_compact2(bool fa, bool fb, uint32_t *count_a, uint32_t *count_b, uint32_t *scratch /* 2*(kBlock/32)+2 */,
+template <int B>
+__device__ __forceinline__ void block_compact2(bool fa, bool fb, uint32_t *count_a, uint32_t *count_b, uint32_t *scratch /* 2*(B/32)+2 */,
                                                uint32_t *slot_a, uint32_t *slot_b) {
-    constexpr int W = kBlock / 32;
+    constexpr int W = B / 32;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned ma = __ballot_sync(0xffffffffu, fa), mb = __ballot_sync(0xffffffffu, fb);
     const uint32_t lt = (1u << lane) - 1u;
@@ -270,8 +274,9 @@ __device__ __forceinline__ void block_compact2(bool fa, bool fb, uint32_t *count
 // the record this thread should process, so that every warp shades one material kind (and rays that
 // missed are grouped into whole warps that exit at once).  `perm` is kBlock uint16, `cnt` kSortKeys*(kBlock/32).
 constexpr int kSortKeys = 8;
+template <int B>
 __device__ __forceinline__ uint32_t tile_sort_by_key(uint32_t key, unsigned short *perm, uint32_t *cnt) {
-    constexpr int W = kBlock / 32;
+    constexpr int W = B / 32;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, lt = (1u << lane) - 1u;
     const unsigned mine = __match_any_sync(0xffffffffu, key); // lanes of this warp with my key
 #pragma unroll
@@ -295,39 +300,47 @@ __device__ __forceinline__ uint32_t tile_sort_by_key(uint32_t key, unsigned shor
     return perm[threadIdx.x];
 }
 
-#ifndef RL_SHADE_MINBLOCKS
-#define RL_SHADE_MINBLOCKS 4
+// CTA shape of k_shade (measured, tools/ab_variants.py + ab_mixed.py + config_times.py): the diffuse-only kernel runs
+// 128 threads x 8 CTAs per SM (a tile barrier waits for 4 warps instead of 8: cbox shade 4.42 -> 4.27 ms per 80 M
+// vertices); kernels that carry Phong / microfacet code stay at 256 x 4 (Phong walls 55.9 vs 57.7 ms, the mixed scene
+// 13.9 vs 18.3 ms sorted: larger tiles sort into fuller warps, and the heavier kernels spill into L1).
+#ifndef RL_SHADE_BLOCK_DIFFUSE
+#define RL_SHADE_BLOCK_DIFFUSE 128
 #endif
+__host__ __device__ constexpr int shade_block(uint32_t km) { return km == 0x1u ? RL_SHADE_BLOCK_DIFFUSE : kBlock; }
+
 template <bool SORT, uint32_t KM>
-__global__ void __launch_bounds__(kBlock, RL_SHADE_MINBLOCKS) k_shade(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
+__global__ void __launch_bounds__(shade_block(KM), 1024 / shade_block(KM)) k_shade(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
                                                   const uint32_t *__restrict__ count_in, const float4 *__restrict__ ray_o,
                                                   const float4 *__restrict__ ray_d, const float4 *__restrict__ state,
                                                   const float4 *__restrict__ hit, float4 *__restrict__ out_o, float4 *__restrict__ out_d,
                                                   float4 *__restrict__ out_state, uint32_t *count_out, float4 *__restrict__ sh_a,
                                                   float4 *__restrict__ sh_b, float4 *__restrict__ sh_c, uint32_t *count_shadow,
                                                   float4 *__restrict__ lacc, Counters *counters) {
-    __shared__ uint32_t s_scratch[2 * (kBlock / 32) + 2];
-    __shared__ unsigned short s_perm[SORT ? kBlock : 1];
-    __shared__ uint32_t s_cnt[SORT ? kSortKeys * (kBlock / 32) : 1];
+    constexpr int B = shade_block(KM);
+    __shared__ uint32_t s_scratch[2 * (B / 32) + 2];
+    __shared__ unsigned short s_perm[SORT ? B : 1];
+    __shared__ uint32_t s_cnt[SORT ? kSortKeys * (B / 32) : 1];
     const uint32_t n = *count_in;
-    const uint32_t n_tiles = (n + kBlock - 1) / kBlock;
+    const uint32_t n_tiles = (n + B - 1) / B;
     uint32_t c_hits = 0, c_nee = 0;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        uint32_t i = tile * kBlock + threadIdx.x;
+        uint32_t i = tile * B + threadIdx.x;
         if (SORT) {
             uint32_t key = 6u;
             if (i < n) {
                 const uint32_t prim = f2u(hit[i].w);
                 key = prim == RL_MISS ? 5u : min(f2u(__ldg(&sv.mats[RL_MAT_F4 * f2u(__ldg(&sv.shade[4 * prim]).w)]).w), 4u);
             }
-            i = tile * kBlock + tile_sort_by_key(key, s_perm, s_cnt);
+            const uint32_t src = tile_sort_by_key<B>(key, s_perm, s_cnt);
+            i = tile * B + src;
         }
         StepOut so;
         so.alive = false;
         so.shadow = false;
         uint32_t pid = 0;
         if (i < n) {
-            float4 ro = ray_o[i], rd = ray_d[i], st4 = state[i], h4 = hit[i];
+            const float4 ro = ray_o[i], rd = ray_d[i], st4 = state[i], h4 = hit[i];
             HitRec h;
             h.t = h4.x, h.u = h4.y, h.v = h4.z, h.prim = f2u(h4.w);
             PathState st;
@@ -351,7 +364,7 @@ __global__ void __launch_bounds__(kBlock, RL_SHADE_MINBLOCKS) k_shade(SceneView 
             if (so.alive && (so.next.depth >= 0xfff0u || so.next.rng_n >= 0xfff0u)) so.alive = false; // packing guard
         }
         uint32_t slot, sslot;
-        block_compact2(so.alive, so.shadow, count_out, count_shadow, s_scratch, &slot, &sslot);
+        block_compact2<B>(so.alive, so.shadow, count_out, count_shadow, s_scratch, &slot, &sslot);
         if (so.alive) {
             out_o[slot] = make_float4(so.next_o.x, so.next_o.y, so.next_o.z, u2f(so.next.path_id));
             out_d[slot] = make_float4(so.next_d.x, so.next_d.y, so.next_d.z, so.next.pdf_prev);
