@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <cmath>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -156,6 +157,13 @@ static int tree_per_sm() {
         if (const char *e = getenv("RL_TREE_PER_SM")) v = std::max(1, atoi(e)); // A/B hook
     }
     return v;
+}
+// Queue length at which k_tail takes a batch over: one resident wave of its CTAs (4 x 128 threads per SM at 128 registers).
+// Measured (tools/tail_ab.sh, cbox 1024^2 x 32 spp / one rank of 8 at 128 spp): off 11.20 / 5.96 ms, 37 888 10.94, 75 776 10.95 / 5.67,
+// 151 552 10.97 / 5.74, 303 104 11.21 / 5.91 ms -- beyond one wave the 128-register kernel is no faster than the wavefront.
+static size_t tail_threshold(const rl_ctx *ctx) {
+    if (const char *e = getenv("RL_TAIL_MAX")) return (size_t)std::max(0L, atol(e)); // A/B + test hook, read per render; 0 = pure wavefront
+    return (size_t)ctx->sm_count * 512;
 }
 static int trav_per_sm() {
     static int v = 0;
@@ -772,13 +780,24 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                 // Group-table scenes outside profiling mode: two launches per iteration (k_trace_shadow_flat + k_shade).  The
                 // per-stage timings of profiling mode need the separate kernels.
                 const bool fuse = !prof && sc->flat_ok && sc->coherent_tree == 0 && getenv("RL_NO_FUSE") == nullptr;
+                // hand-over to k_tail (rl_kernels.cuh) once the queue is at most this long; profiling mode keeps the per-stage kernels
+                const size_t tail_max = prof ? 0 : tail_threshold(ctx);
+                bool tail_done = false;
                 size_t ub_prev = n_paths;
                 const uint32_t *zero_count = ctx->d_hist + 2 * kMaxIters - 1; // never written: k + group < kMaxIters
                 while (n_ub > 0) {
                     // iterations launched between two reads of the queue lengths: few while the queues are long (an iteration
                     // past the end of the longest path is three empty launches), more in the tail, where the host round trip
                     // costs more than the launches
-                    const uint32_t group = prof ? 1u : (n_ub > ((size_t)1 << 20) ? (uint32_t)RL_SYNC_GROUP : 4u * (uint32_t)RL_SYNC_GROUP);
+                    uint32_t group = prof ? 1u : (n_ub > ((size_t)1 << 20) ? (uint32_t)RL_SYNC_GROUP : 4u * (uint32_t)RL_SYNC_GROUP);
+                    if (tail_max && !prof) {
+                        // aim the next look at the queue length at the iteration where it is expected to fit k_tail: lengths shrink by
+                        // a near-constant factor per bounce (taken from the last two lengths read)
+                        double rate = 0.7;
+                        if (k >= 1 && ctx->h_hist[k - 1] > 0) rate = std::min(0.95, std::max(0.3, (double)ctx->h_hist[k] / (double)ctx->h_hist[k - 1]));
+                        const double g = std::ceil(std::log((double)n_ub / (double)tail_max) / std::log(1.0 / rate));
+                        group = (uint32_t)std::min<double>(k == 0 ? RL_SYNC_GROUP : 2 * RL_SYNC_GROUP, std::max(1.0, g));
+                    }
                     if (k + group >= kMaxIters) {
                         ctx->err = "rl_render: a path exceeded 4095 wavefront iterations (no Russian roulette in a closed scene?)";
                         return RL_ERR_UNSUPPORTED;
@@ -845,8 +864,26 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                     }
                     k_read = k;
                     n_ub = ctx->h_hist[k];
+                    if (tail_max && n_ub > 0 && n_ub <= tail_max) { // the queue fits one resident wave: k_tail finishes the batch
+                        if (fuse && k > 0) launch_shadow<true>(ctx, sc, shc + k - 1, ub_prev, false); // segments queued by the last k_shade
+                        SceneView sv = sc->sv;
+                        if (sc->flat_ok) sv.n_groups = sc->flat.n_groups;
+                        else sv.root_ref = sc->root_flat;
+                        const int tg = (int)((n_ub + kTailBlock - 1) / kTailBlock);
+                        const size_t tsm = sc->flat_ok ? sc->smem_flat_bytes : 0;
+#define RL_LAUNCH_TAIL(KM) \
+    k_tail<KM><<<tg, kTailBlock, tsm, st>>>(sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], ctx->lacc, ctx->d_counters, sc->n_trav_f4, k)
+                        if (sc->kind_mask == 0x1u && !sc->d_tex) RL_LAUNCH_TAIL(0x1u);
+                        else if ((sc->kind_mask & ~0x3u) == 0u && !sc->d_tex) RL_LAUNCH_TAIL(0x3u);
+                        else if (sc->d_tex) RL_LAUNCH_TAIL(RL_KM_ALL);
+                        else RL_LAUNCH_TAIL(0xffu);
+#undef RL_LAUNCH_TAIL
+                        ctx->launches++;
+                        tail_done = true;
+                        break;
+                    }
                 }
-                if (fuse && k > 0) launch_shadow<true>(ctx, sc, shc + k - 1, ub_prev, false); // shadow segments of the last shaded iteration
+                if (fuse && k > 0 && !tail_done) launch_shadow<true>(ctx, sc, shc + k - 1, ub_prev, false); // shadow segments of the last shaded iteration
             }
             S.max_depth_seen = std::max<uint64_t>(S.max_depth_seen, iter);
             if (prof) CK(cudaEventRecord(ctx->ev[2], st));
@@ -871,6 +908,8 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
     S.ms_total = ms_total;
     S.samples = (uint64_t)npix * o->spp;
     S.hits = ctx->h_counters->hits;
+    S.segments += ctx->h_counters->tail_segments;
+    S.max_depth_seen = std::max<uint64_t>(S.max_depth_seen, ctx->h_counters->tail_iters);
     S.shadow_rays = ctx->h_counters->nee_sampled;
     S.shadow_visible = ctx->h_counters->shadow_visible;
     S.kernel_launches = ctx->launches;

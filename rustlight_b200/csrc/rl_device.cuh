@@ -831,7 +831,7 @@ RL_HD void visible_begin(Trav &tr, const SceneView &sv, V3 p0, V3 p1, bool *deci
 
 // Serial drivers (used by the CPU emulator and the small batch kernels; the wavefront kernels
 // run the same steps inside a persistent while-while loop, rl_kernels.cuh).
-RL_HD HitRec trace_closest(const SceneView &sv, const float4 *nodes, const float4 *trav, V3 o, V3 d) {
+RL_HD HitRec trace_closest(const SceneView &sv, const float4 *flat, const float4 *nodes, const float4 *trav, V3 o, V3 d) {
     Trav tr;
     int stack[RL_STACK_SIZE];
     if (sv.n_groups) { // flat group table: root test, then scan + exact tests
@@ -841,7 +841,7 @@ RL_HD HitRec trace_closest(const SceneView &sv, const float4 *nodes, const float
             h.t = RL_F32_MAX, h.u = 0.0f, h.v = 0.0f, h.prim = RL_MISS;
             return h;
         }
-        return flat_closest(sv, sv.flat, trav, o, d);
+        return flat_closest(sv, flat, trav, o, d);
     }
     if (closest_begin(tr, sv, o, d)) {
         while (tr.cur != RL_TRAV_DONE) {
@@ -851,7 +851,7 @@ RL_HD HitRec trace_closest(const SceneView &sv, const float4 *nodes, const float
     }
     return closest_result(tr);
 }
-RL_HD bool trace_visible(const SceneView &sv, const float4 *nodes, const float4 *trav, V3 p0, V3 p1) {
+RL_HD bool trace_visible(const SceneView &sv, const float4 *flat, const float4 *nodes, const float4 *trav, V3 p0, V3 p1) {
     Trav tr;
     int stack[RL_STACK_SIZE];
     bool decided, vis;
@@ -859,7 +859,7 @@ RL_HD bool trace_visible(const SceneView &sv, const float4 *nodes, const float4 
         V3 d;
         float thr;
         if (!visible_setup(sv, p0, p1, &d, &thr)) return false; // accel.rs:338-340
-        return !flat_any(sv, sv.flat, trav, p0, d, thr);
+        return !flat_any(sv, flat, trav, p0, d, thr);
     }
     visible_begin(tr, sv, p0, p1, &decided, &vis);
     if (decided) return vis;
@@ -869,6 +869,9 @@ RL_HD bool trace_visible(const SceneView &sv, const float4 *nodes, const float4 
     }
     return true;
 }
+// the group table where the scene description says it is (global memory); kernels that stage it pass their copy
+RL_HD HitRec trace_closest(const SceneView &sv, const float4 *nodes, const float4 *trav, V3 o, V3 d) { return trace_closest(sv, sv.flat, nodes, trav, o, d); }
+RL_HD bool trace_visible(const SceneView &sv, const float4 *nodes, const float4 *trav, V3 p0, V3 p1) { return trace_visible(sv, sv.flat, nodes, trav, p0, p1); }
 
 // ---- Camera::generate (camera.rs:81-91) -------------------------------------------------------
 RL_HD void m4_mul_v4(const float *m, float x, float y, float z, float w, float *out) {

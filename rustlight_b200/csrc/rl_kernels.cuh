@@ -33,6 +33,7 @@ constexpr int kBlock = RL_BLOCK;
 
 struct Counters { // device-side statistics, 64-bit
     unsigned long long hits, nee_sampled, shadow_visible, pad;
+    unsigned long long tail_segments, tail_iters; // k_tail: closest-hit calls; deepest iteration reached (absolute)
 };
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
@@ -384,6 +385,78 @@ __global__ void __launch_bounds__(shade_block(KM), 1024 / shade_block(KM)) k_sha
     if ((threadIdx.x & 31u) == 0) {
         if (c_hits) atomicAdd(&counters->hits, (unsigned long long)c_hits);
         if (c_nee) atomicAdd(&counters->nee_sampled, (unsigned long long)c_nee);
+    }
+}
+
+// ---- tail of a batch: one thread follows one path to its end ----------------------------------------
+// Once the ray queue fits one resident wave of the device, a wavefront iteration is all fixed cost (two launches at
+// ~7 us each whatever the queue length, plus the host's look at the queue length every few iterations), and a batch still
+// has ~25 iterations to go before its longest path ends.  k_tail takes the queue over at that point: each thread runs
+// trace -> path_step -> shadow test for its path until the path dies, with the path's accumulator in registers.  Same
+// device functions, same per-path order of additions (arrival emission of vertex k, light sample of vertex k, ...), same
+// random numbers: images are bit-identical to the pure wavefront (tests/test_gpu_render.py::test_tail_kernel_*).
+// Shadow segments still queued by the last k_shade must be resolved before this kernel starts (the host launches
+// k_shadow_flat / k_shadow first, same stream).
+constexpr int kTailBlock = 128;
+template <uint32_t KM>
+__global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
+                                                     const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
+                                                     const float4 *__restrict__ ray_d, const float4 *__restrict__ state, float4 *__restrict__ lacc,
+                                                     Counters *counters, uint32_t n_trav_f4, uint32_t iter_base) {
+    extern __shared__ float4 smem[];
+    const float4 *nodes = sv.nodes, *trav = sv.trav, *flat = sv.flat;
+    if (sv.n_groups) { // group table + exact-test records in shared memory, as in k_trace_flat
+        const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
+        stage_flat(sv, smem, n_flat_f4, n_trav_f4);
+        flat = smem;
+        trav = smem + n_flat_f4;
+    }
+    const uint32_t n = *count;
+    uint32_t c_hits = 0, c_nee = 0, c_vis = 0, c_seg = 0, c_iters = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 ro = ray_o[i], rd = ray_d[i], st4 = state[i];
+        V3 o = xyz(ro), d = xyz(rd);
+        PathState st;
+        st.T = Col{st4.x, st4.y, st4.z};
+        st.pdf_prev = rd.w;
+        st.path_id = f2u(ro.w);
+        st.depth = f2u(st4.w) >> 16;
+        st.rng_n = f2u(st4.w) & 0xffffu;
+        const uint32_t s_local = st.path_id / ip.npix, lp = st.path_id - s_local * ip.npix;
+        const uint32_t pixel = __ldg(pixel_list + lp), sample = ip.sample_base + s_local;
+        float4 l = lacc[st.path_id];
+        for (uint32_t it = 1;; it++) {
+            const HitRec h = trace_closest(sv, flat, nodes, trav, o, d);
+            c_seg++;
+            StepOut so;
+            path_step<KM>(sv, ip, o, d, h, st, pixel, sample, &so);
+            if (h.prim != RL_MISS) c_hits++;
+            if (so.nee_sampled) c_nee++;
+            if (so.has_add) l.x += so.add.r, l.y += so.add.g, l.z += so.add.b;
+            if (so.shadow && trace_visible(sv, flat, nodes, trav, so.sh_p0, so.sh_p1)) {
+                l.x += so.sh_contrib.r, l.y += so.sh_contrib.g, l.z += so.sh_contrib.b;
+                c_vis++;
+            }
+            c_iters = max(c_iters, it);
+            if (!so.alive || so.next.depth >= 0xfff0u || so.next.rng_n >= 0xfff0u) break; // packing guard as in k_shade
+            o = so.next_o, d = so.next_d;
+            st = so.next;
+        }
+        lacc[st.path_id] = l;
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        c_hits += __shfl_down_sync(0xffffffffu, c_hits, off);
+        c_nee += __shfl_down_sync(0xffffffffu, c_nee, off);
+        c_vis += __shfl_down_sync(0xffffffffu, c_vis, off);
+        c_seg += __shfl_down_sync(0xffffffffu, c_seg, off);
+        c_iters = max(c_iters, __shfl_down_sync(0xffffffffu, c_iters, off));
+    }
+    if ((threadIdx.x & 31u) == 0) {
+        if (c_hits) atomicAdd(&counters->hits, (unsigned long long)c_hits);
+        if (c_nee) atomicAdd(&counters->nee_sampled, (unsigned long long)c_nee);
+        if (c_vis) atomicAdd(&counters->shadow_visible, (unsigned long long)c_vis);
+        if (c_seg) atomicAdd(&counters->tail_segments, (unsigned long long)c_seg);
+        if (c_iters) atomicMax(&counters->tail_iters, (unsigned long long)(iter_base + c_iters));
     }
 }
 

@@ -478,3 +478,52 @@ def test_config_shapes_c3_c5(gpu_ctx):
     ref, so = ob.OracleScene(wide).render(_abi.path_desc(), 1, seed=0, cfg=ob.config(**STREAM))
     assert img.shape == (1080, 1920, 3) and np.array_equal(img, ref) and st.segments == so.segments
     dev.close()
+
+
+def _with_tail(value, fn):
+    """Run fn() with the k_tail hand-over threshold set (RL_TAIL_MAX is read on every rl_render; "0" = pure wavefront)."""
+    old = os.environ.get("RL_TAIL_MAX")
+    if value is None:
+        os.environ.pop("RL_TAIL_MAX", None)
+    else:
+        os.environ["RL_TAIL_MAX"] = str(value)
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop("RL_TAIL_MAX", None)
+        else:
+            os.environ["RL_TAIL_MAX"] = old
+
+
+@pytest.mark.parametrize("scene", ["cbox", "tess2", "mixed", "env"])
+def test_tail_kernel_changes_nothing_but_the_schedule(gpu_ctx, scene):
+    """k_tail (one thread follows one path to its end once the queue is short) against the pure wavefront: same image bits,
+    same counters, fewer launches -- on the group table, the LBVH, every BSDF kind and the environment's miss edges.  The
+    default threshold and "hand over as early as possible" both go through it; the oracle pins the result."""
+    if scene == "cbox":
+        sc = load_cbox(200, 136)
+    elif scene == "tess2":
+        import sys
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+        from tess_cbox import tessellated_cbox_json
+        sc = SceneLoaderManager().load_string(tessellated_cbox_json(2), "json")
+        sc.set_resolution(96, 96)
+    elif scene == "mixed":
+        from conftest import mixed_cbox
+        sc = mixed_cbox(96, 96)
+    else:
+        sc = load_cbox(96, 96)
+        sc.set_environment((0.4, 0.5, 0.7))
+    dev = DeviceScene(gpu_ctx, sc)
+    integ = _abi.path_desc()
+    key = lambda st: (st.samples, st.segments, st.hits, st.shadow_rays, st.shadow_visible, st.max_depth_seen)
+    a, sa = _with_tail(0, lambda: dev.render(integ, 12, seed=3, batch_spp=8))
+    b, sb = _with_tail(None, lambda: dev.render(integ, 12, seed=3, batch_spp=8))
+    c, sc_ = _with_tail(1 << 30, lambda: dev.render(integ, 12, seed=3, batch_spp=8))
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert key(sa) == key(sb) == key(sc_)
+    assert sc_.kernel_launches <= sb.kernel_launches < sa.kernel_launches
+    ref, so = ob.OracleScene(sc).render(integ, 12, seed=3, cfg=ob.config(**STREAM))
+    assert np.array_equal(a, ref) and sa.segments == so.segments
+    dev.close()
