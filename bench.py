@@ -29,6 +29,7 @@ METRIC = "Msamples/sec (Cornell box path, 1024x1024, 128spp); Mpath-segments/sec
 UNIT = "Msamples/s"
 # closest-hit traversal reads one 32-byte ray and writes one 16-byte hit per segment
 TRACE_BYTES_PER_SEGMENT = 48
+SHADE_BYTES_PER_VERTEX = 192  # 64 R + 48 W + 48 W (shadow segment) + 32 RMW
 
 
 def measured_peaks():
@@ -262,6 +263,7 @@ def main():
 
     # ---- roofline of the dominant kernel (closest-hit traversal), per-stage CUDA events ----
     roof = None
+    roof_shade = None
     stage_ms = None
     # every rank runs the profiled step: rl_render contains the collective (ncclReduce)
     barrier()
@@ -298,6 +300,15 @@ def main():
                         "Timed alone (k_trace_flat) in the profiled step; the timed steps run it inside k_trace_shadow_flat together with the shadow segments "
                         "of the previous iteration (one launch instead of two), so the ncu launch list shows that kernel with the sum of both shares"}
 
+        # the second large stage, same method (north_star: "traversal and shade kernels"): one surface vertex = 64 B read (ray, state,
+        # hit) + 48 B next ray/state + 48 B shadow segment + 32 B accumulator RMW = 192 B
+        shade_bytes = st.hits * SHADE_BYTES_PER_VERTEX
+        shade_achieved = shade_bytes / (st.ms_shade * 1e-3) / 1e9 if st.ms_shade > 0 else 0.0
+        roof_shade = {"kernel": "k_shade (surface interaction, BSDF sample + RR, light sample)", "bound": "hbm", "achieved": shade_achieved, "peak": peak,
+                      "unit": "GB/s", "frac": shade_achieved / peak, "algorithmic_bytes_per_unit": SHADE_BYTES_PER_VERTEX,
+                      "units": "surface vertices (hits)", "units_per_step": int(st.hits), "launches_per_step": launches_trace,
+                      "avg_launch_ms": st.ms_shade / launches_trace, "share_of_step": st.ms_shade / st.ms_total if st.ms_total else None}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         stc = cpu_reference_run(args.ref_spp)
@@ -317,7 +328,7 @@ def main():
                 "mshadow_rays_per_s": tot_shadows / (dev_ms * 1e-3) / 1e6,  # Acceleration::visible calls of the reference
                 "wall_ms_per_step": wall_ms / args.steps,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": int(tot_launches), "clocks": clk, "roofline": roof, "stage_ms": stage_ms, "cpu_baseline": cpu}
+                "gpu_launches": int(tot_launches), "clocks": clk, "roofline": roof, "roofline_shade": roof_shade, "stage_ms": stage_ms, "cpu_baseline": cpu}
         print(json.dumps(line))
     dsc.close()
     ctx.close()
