@@ -461,7 +461,12 @@ __global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams i
 }
 
 // ---- `direct` integrator, stage 1: primary hit -> emission, light samples, BSDF samples ---------------
-__global__ void __launch_bounds__(kBlock) k_shade_direct1(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
+// 4 CTAs per SM (64 registers, 216 B of spills) beat the unconstrained 119 registers / 2 CTAs: direct -b 1 -l 1 at 2048^2 x 16 spp
+// shade 5.58 -> 4.85 ms, ao 3.72 -> 3.19 ms (tools/ab_direct.py); 3 CTAs (80 registers) were slower than both (6.47 ms).
+#ifndef RL_DIRECT1_MINBLOCKS
+#define RL_DIRECT1_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(kBlock, RL_DIRECT1_MINBLOCKS) k_shade_direct1(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
                                                           const uint32_t *__restrict__ count_in, uint32_t n_paths, const float4 *__restrict__ ray_o,
                                                           const float4 *__restrict__ ray_d, const float4 *__restrict__ state,
                                                           const float4 *__restrict__ hit, float4 *__restrict__ out_o, float4 *__restrict__ out_d,

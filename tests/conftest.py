@@ -229,3 +229,12 @@ def mixed_cbox(w=48, h=48):
 
 def rel_l2(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(np.linalg.norm(b.astype(np.float64)), 1e-30))
+
+
+def author_metrics(ref, test, eps=1e-2):
+    """The image metrics the reference's author uses (tests/interactive-viewer/tools/metric.py:18-45, compute_metric):
+    means over pixels and channels of l1, l2, mrse, mape, smape with eps = 1e-2."""
+    ref, test = ref.astype(np.float64), test.astype(np.float64)
+    diff = ref - test
+    return {"l1": float(np.abs(diff).mean()), "l2": float((diff * diff).mean()), "mrse": float((diff * diff / (ref * ref + eps)).mean()),
+            "mape": float((np.abs(diff) / (ref + eps)).mean()), "smape": float((2 * np.abs(diff) / (ref + test + eps)).mean())}

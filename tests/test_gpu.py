@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, load_cbox, rel_l2, soup_scene
+from conftest import GOLDEN, author_metrics, load_cbox, rel_l2, soup_scene
 from oracle import binding as ob
 from rustlight_b200 import SceneLoaderManager, _abi
 from rustlight_b200.device import Context, DeviceError, DeviceScene, IndependentSampler, IntegratorPathTracing, lib
@@ -136,6 +136,9 @@ def test_cbox_512_spp16_vs_faithful_oracle(cbox_dev, cbox_oracle):
     ref, so = cbox_oracle.render(integ, 16, seed=0, cfg=ob.config(math_mode=ob.MATH_LIBM, accel_mode=ob.ACCEL_BVH, estimator=ob.EST_GRAPH))
     r = rel_l2(img, ref)
     assert r < TOL, r
+    m = author_metrics(ref, img)  # the reference author's own metrics (metric.py:18-45, eps = 1e-2)
+    print("C1 GPU vs faithful oracle: rel_l2 %.3g, " % r + ", ".join("%s %.3g" % kv for kv in m.items()))
+    assert m["mape"] < TOL and m["smape"] < TOL and m["l1"] < TOL and m["mrse"] < TOL * TOL
     assert abs(int(st.segments) - int(so.segments)) <= 32 and abs(int(st.shadow_rays) - int(so.shadow_rays)) <= 32
     ex, se = cbox_oracle.render(integ, 16, seed=0, cfg=ob.config(**STREAM))
     assert np.array_equal(img, ex) and st.segments == se.segments
