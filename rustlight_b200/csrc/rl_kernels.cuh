@@ -310,8 +310,12 @@ __device__ __forceinline__ uint32_t tile_sort_by_key(uint32_t key, unsigned shor
 #endif
 __host__ __device__ constexpr int shade_block(uint32_t km) { return km == 0x1u ? RL_SHADE_BLOCK_DIFFUSE : kBlock; }
 
+// Resident CTAs per SM (= the register cap): {diffuse} 8 x 128 threads and {diffuse, phong} 4 x 256 at 64 registers (Phong walls,
+// 512^2 x 512 spp: 56.4 ms; 80 registers 59.0, 110 registers 62.8 ms); the kernels with the microfacet / Fresnel code run best
+// unconstrained at 2 x 256 (122 registers, no spills: mixed scene sorted 14.0 -> 13.3 ms, unsorted 21.3 -> 20.1 ms).
+__host__ __device__ constexpr int shade_minblocks(uint32_t km) { return km == 0x1u ? 1024 / RL_SHADE_BLOCK_DIFFUSE : (km == 0x3u ? 4 : 2); }
 template <bool SORT, uint32_t KM>
-__global__ void __launch_bounds__(shade_block(KM), 1024 / shade_block(KM)) k_shade(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
+__global__ void __launch_bounds__(shade_block(KM), shade_minblocks(KM)) k_shade(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
                                                   const uint32_t *__restrict__ count_in, const float4 *__restrict__ ray_o,
                                                   const float4 *__restrict__ ray_d, const float4 *__restrict__ state,
                                                   const float4 *__restrict__ hit, float4 *__restrict__ out_o, float4 *__restrict__ out_d,
