@@ -705,7 +705,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
             ip.sample_base = o->sample_offset + s0;
             if (prof) CK(cudaEventRecord(ctx->ev[2], st));
             k_raygen<<<grid_for(ctx, n_paths, 8), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, (uint32_t)n_paths, ctx->ray_o[0], ctx->ray_d[0],
-                                                                   ctx->state[0], ctx->lacc, n_slots);
+                                                                   direct ? ctx->state[0] : nullptr, ctx->lacc, n_slots);
             ctx->launches++;
             if (prof) {
                 CK(cudaEventRecord(ctx->ev[3], st));
@@ -819,7 +819,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
 #define RL_LAUNCH_SHADE(SORT, KM)                                                                                                                   \
     k_shade<SORT, KM><<<grid_for(ctx, n_ub, resident_per_sm(k_shade<SORT, KM>, 0, shade_block(KM)), shade_block(KM)), shade_block(KM), 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], \
                                                                  ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1], ctx->state[cur ^ 1], qc + k + 1,     \
-                                                                 ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc, ctx->d_counters)
+                                                                 ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc, ctx->d_counters, k == 0 ? 1u : 0u)
                         // kernel specialised for the BSDF kinds of the scene: {diffuse}, {diffuse, phong}, everything
                         // (textured scenes take the general kernel: bit 8 of the mask)
                         if (sc->kind_mask == 0x1u && !sc->d_tex) RL_LAUNCH_SHADE(false, 0x1u);

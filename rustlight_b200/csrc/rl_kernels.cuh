@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, IntegParams ip,
         camera_generate(sv, (float)px + jx, (float)py + jy, &o, &d);
         ray_o[id] = make_float4(o.x, o.y, o.z, u2f(id));
         ray_d[id] = make_float4(d.x, d.y, d.z, 1.0f);
-        state[id] = make_float4(1.0f, 1.0f, 1.0f, u2f((1u << 16) | smp.n));
+        // `path`: every camera ray starts with throughput 1, depth 1 and two draws taken; k_shade fills that in itself for the
+        // first iteration instead of moving 16 B per path through HBM twice (state == nullptr)
+        if (state) state[id] = make_float4(1.0f, 1.0f, 1.0f, u2f((1u << 16) | smp.n));
         for (uint32_t sl = 0; sl < n_slots; sl++) lacc[(size_t)sl * n_paths + id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(shade_block(KM), shade_minblocks(KM)) k_shade(
                                                   const float4 *__restrict__ hit, float4 *__restrict__ out_o, float4 *__restrict__ out_d,
                                                   float4 *__restrict__ out_state, uint32_t *count_out, float4 *__restrict__ sh_a,
                                                   float4 *__restrict__ sh_b, float4 *__restrict__ sh_c, uint32_t *count_shadow,
-                                                  float4 *__restrict__ lacc, Counters *counters) {
+                                                  float4 *__restrict__ lacc, Counters *counters, uint32_t primary) {
     constexpr int B = shade_block(KM);
     __shared__ uint32_t s_scratch[2 * (B / 32) + 2];
     __shared__ unsigned short s_perm[SORT ? B : 1];
@@ -345,7 +347,8 @@ __global__ void __launch_bounds__(shade_block(KM), shade_minblocks(KM)) k_shade(
         so.shadow = false;
         uint32_t pid = 0;
         if (i < n) {
-            const float4 ro = ray_o[i], rd = ray_d[i], st4 = state[i], h4 = hit[i];
+            const float4 ro = ray_o[i], rd = ray_d[i], h4 = hit[i];
+            const float4 st4 = primary ? make_float4(1.0f, 1.0f, 1.0f, u2f((1u << 16) | 2u)) : state[i]; // camera rays: see k_raygen
             HitRec h;
             h.t = h4.x, h.u = h4.y, h.v = h4.z, h.prim = f2u(h4.w);
             PathState st;
