@@ -620,12 +620,12 @@ static int validate(rl_ctx *ctx, const rl_scene *scene, const rl_integrator_desc
 
 template <bool SMEM>
 static void launch_trace(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_t n, const float4 *ro, const float4 *rd, float4 *hit,
-                         bool coherent = false) {
+                         bool coherent = false, bool camera_origin = false) {
     SceneView sv = sc->sv;
     const bool tree = coherent && sc->coherent_tree >= 1;
     if (!tree && sc->flat_ok) {
         sv.n_groups = sc->flat.n_groups;
-        k_trace_flat<<<grid_for(ctx, n, trav_per_sm()), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_trav_f4);
+        k_trace_flat<<<grid_for(ctx, n, trav_per_sm()), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_trav_f4, camera_origin ? 1u : 0u);
         ctx->launches++;
         return;
     }
@@ -704,8 +704,11 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
             const size_t n_paths = (size_t)npix * nb;
             ip.sample_base = o->sample_offset + s0;
             if (prof) CK(cudaEventRecord(ctx->ev[2], st));
-            k_raygen<<<grid_for(ctx, n_paths, 8), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, (uint32_t)n_paths, ctx->ray_o[0], ctx->ray_d[0],
-                                                                   direct ? ctx->state[0] : nullptr, ctx->lacc, n_slots);
+            // `path` on a group-table scene: the camera rays' origin (sv.cam_pos), path id (= queue index) and path state are constants
+            // that the first k_trace_flat / k_shade fill in themselves: raygen writes 32 B per path (direction, accumulator) instead of 80
+            const bool camera_o = !direct && sc->flat_ok && sc->coherent_tree == 0;
+            k_raygen<<<grid_for(ctx, n_paths, 8), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, (uint32_t)n_paths, camera_o ? nullptr : ctx->ray_o[0],
+                                                                   ctx->ray_d[0], direct ? ctx->state[0] : nullptr, ctx->lacc, n_slots);
             ctx->launches++;
             if (prof) {
                 CK(cudaEventRecord(ctx->ev[3], st));
@@ -810,16 +813,16 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                             const int tb = grid_for(ctx, n_ub, trav_per_sm()), sb = k == 0 ? 0 : grid_for(ctx, ub_prev, trav_per_sm());
                             k_trace_shadow_flat<<<tb + sb, kBlock, sc->smem_flat_bytes, st>>>(sv, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit,
                                                                                               k == 0 ? zero_count : shc + k - 1, ctx->sh_a, ctx->sh_b, ctx->sh_c,
-                                                                                              ctx->lacc, ctx->d_counters, sc->n_trav_f4, (uint32_t)tb);
+                                                                                              ctx->lacc, ctx->d_counters, sc->n_trav_f4, (uint32_t)tb, (k == 0 && camera_o) ? 1u : 0u);
                             ctx->launches++;
                             ub_prev = n_ub;
-                        } else if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
-                        else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0);
+                        } else if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0, k == 0 && camera_o);
+                        else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0, k == 0 && camera_o);
                         if (prof) CK(cudaEventRecord(ctx->ev[3], st));
 #define RL_LAUNCH_SHADE(SORT, KM)                                                                                                                   \
     k_shade<SORT, KM><<<grid_for(ctx, n_ub, resident_per_sm(k_shade<SORT, KM>, 0, shade_block(KM)), shade_block(KM)), shade_block(KM), 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], \
                                                                  ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1], ctx->state[cur ^ 1], qc + k + 1,     \
-                                                                 ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc, ctx->d_counters, k == 0 ? 1u : 0u)
+                                                                 ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc, ctx->d_counters, k == 0 ? (camera_o ? 3u : 1u) : 0u)
                         // kernel specialised for the BSDF kinds of the scene: {diffuse}, {diffuse, phong}, everything
                         // (textured scenes take the general kernel: bit 8 of the mask)
                         if (sc->kind_mask == 0x1u && !sc->d_tex) RL_LAUNCH_SHADE(false, 0x1u);

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, IntegParams ip,
         float jy = smp.next();
         V3 o, d;
         camera_generate(sv, (float)px + jx, (float)py + jy, &o, &d);
-        ray_o[id] = make_float4(o.x, o.y, o.z, u2f(id));
+        if (ray_o) ray_o[id] = make_float4(o.x, o.y, o.z, u2f(id)); // nullptr: every camera ray starts at sv.cam_pos with path_id == queue index
         ray_d[id] = make_float4(d.x, d.y, d.z, 1.0f);
         // `path`: every camera ray starts with throughput 1, depth 1 and two draws taken; k_shade fills that in itself for the
         // first iteration instead of moving 16 B per path through HBM twice (state == nullptr)
@@ -151,10 +151,10 @@ __device__ __forceinline__ void stage_flat(const SceneView &sv, float4 *smem, ui
 }
 // The two loops as device functions over a virtual grid (bid of nblocks), so that one launch can run both (below).
 __device__ __forceinline__ void trace_flat_body(const SceneView &sv, const float4 *flat, const float4 *trav, uint32_t bid, uint32_t nblocks, uint32_t n,
-                                                const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d, float4 *__restrict__ hit) {
+                                                const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d, float4 *__restrict__ hit, bool camera) {
     for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n; i += nblocks * blockDim.x) {
-        const float4 ro = ray_o[i], rd = ray_d[i];
-        const V3 o = xyz(ro), d = xyz(rd);
+        const float4 rd = ray_d[i];
+        const V3 o = camera ? sv.cam_pos : xyz(ray_o[i]), d = xyz(rd); // camera rays share their origin: it is not stored (k_raygen)
         const V3 inv = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
         HitRec h;
         h.t = RL_F32_MAX, h.u = 0.0f, h.v = 0.0f, h.prim = RL_MISS;
@@ -184,11 +184,11 @@ __device__ __forceinline__ void shadow_flat_body(const SceneView &sv, const floa
     if ((threadIdx.x & 31u) == 0 && c_vis) atomicAdd(&counters->shadow_visible, (unsigned long long)c_vis);
 }
 __global__ void __launch_bounds__(kBlock) k_trace_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
-                                                       const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t n_trav_f4) {
+                                                       const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t n_trav_f4, uint32_t camera) {
     extern __shared__ float4 smem[];
     const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
     stage_flat(sv, smem, n_flat_f4, n_trav_f4);
-    trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, gridDim.x, *count, ray_o, ray_d, hit);
+    trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, gridDim.x, *count, ray_o, ray_d, hit, camera != 0u);
 }
 __global__ void __launch_bounds__(kBlock) k_shadow_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ sh_a,
                                                         const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c, float4 *__restrict__ lacc,
@@ -206,11 +206,11 @@ __global__ void __launch_bounds__(kBlock) k_trace_shadow_flat(SceneView sv, cons
                                                               const float4 *__restrict__ ray_d, float4 *__restrict__ hit,
                                                               const uint32_t *__restrict__ sh_count, const float4 *__restrict__ sh_a,
                                                               const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c, float4 *__restrict__ lacc,
-                                                              Counters *counters, uint32_t n_trav_f4, uint32_t trace_blocks) {
+                                                              Counters *counters, uint32_t n_trav_f4, uint32_t trace_blocks, uint32_t camera) {
     extern __shared__ float4 smem[];
     const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
     stage_flat(sv, smem, n_flat_f4, n_trav_f4);
-    if (blockIdx.x < trace_blocks) trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, trace_blocks, *count, ray_o, ray_d, hit);
+    if (blockIdx.x < trace_blocks) trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, trace_blocks, *count, ray_o, ray_d, hit, camera != 0u);
     else shadow_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x - trace_blocks, gridDim.x - trace_blocks, *sh_count, sh_a, sh_b, sh_c, lacc, counters);
 }
 
@@ -347,8 +347,10 @@ __global__ void __launch_bounds__(shade_block(KM), shade_minblocks(KM)) k_shade(
         so.shadow = false;
         uint32_t pid = 0;
         if (i < n) {
-            const float4 ro = ray_o[i], rd = ray_d[i], h4 = hit[i];
-            const float4 st4 = primary ? make_float4(1.0f, 1.0f, 1.0f, u2f((1u << 16) | 2u)) : state[i]; // camera rays: see k_raygen
+            // camera rays (k_raygen): bit 0 = constant path state, bit 1 = origin sv.cam_pos and path_id == queue index, neither stored
+            const float4 rd = ray_d[i], h4 = hit[i];
+            const float4 ro = (primary & 2u) ? make_float4(sv.cam_pos.x, sv.cam_pos.y, sv.cam_pos.z, u2f(i)) : ray_o[i];
+            const float4 st4 = (primary & 1u) ? make_float4(1.0f, 1.0f, 1.0f, u2f((1u << 16) | 2u)) : state[i];
             HitRec h;
             h.t = h4.x, h.u = h4.y, h.v = h4.z, h.prim = f2u(h4.w);
             PathState st;
