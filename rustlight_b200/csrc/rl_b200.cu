@@ -875,7 +875,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                         const int tg = (int)((n_ub + kTailBlock - 1) / kTailBlock);
                         const size_t tsm = sc->flat_ok ? sc->smem_flat_bytes : 0;
 #define RL_LAUNCH_TAIL(KM) \
-    k_tail<KM><<<tg, kTailBlock, tsm, st>>>(sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], ctx->lacc, ctx->d_counters, sc->n_trav_f4, k)
+    k_tail<KM><<<tg, kTailBlock, tsm, st>>>(sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], ctx->lacc, ctx->d_counters, sc->n_trav_f4, k, kMaxIters - 1u)
                         if (sc->kind_mask == 0x1u && !sc->d_tex) RL_LAUNCH_TAIL(0x1u);
                         else if ((sc->kind_mask & ~0x3u) == 0u && !sc->d_tex) RL_LAUNCH_TAIL(0x3u);
                         else if (sc->d_tex) RL_LAUNCH_TAIL(RL_KM_ALL);
@@ -910,6 +910,10 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
     CK(cudaEventElapsedTime(&ms_total, ctx->ev[0], ctx->ev[1]));
     S.ms_total = ms_total;
     S.samples = (uint64_t)npix * o->spp;
+    if (ctx->h_counters->tail_overflow) { // same limit and message as the wavefront loop
+        ctx->err = "rl_render: a path exceeded 4095 wavefront iterations (no Russian roulette in a closed scene?)";
+        return RL_ERR_UNSUPPORTED;
+    }
     S.hits = ctx->h_counters->hits;
     S.segments += ctx->h_counters->tail_segments;
     S.max_depth_seen = std::max<uint64_t>(S.max_depth_seen, ctx->h_counters->tail_iters);

@@ -34,6 +34,7 @@ constexpr int kBlock = RL_BLOCK;
 struct Counters { // device-side statistics, 64-bit
     unsigned long long hits, nee_sampled, shadow_visible, pad;
     unsigned long long tail_segments, tail_iters; // k_tail: closest-hit calls; deepest iteration reached (absolute)
+    unsigned long long tail_overflow, pad2;       // a path reached the iteration limit inside k_tail
 };
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
@@ -411,7 +412,7 @@ template <uint32_t KM>
 __global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
                                                      const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
                                                      const float4 *__restrict__ ray_d, const float4 *__restrict__ state, float4 *__restrict__ lacc,
-                                                     Counters *counters, uint32_t n_trav_f4, uint32_t iter_base) {
+                                                     Counters *counters, uint32_t n_trav_f4, uint32_t iter_base, uint32_t iter_limit) {
     extern __shared__ float4 smem[];
     const float4 *nodes = sv.nodes, *trav = sv.trav, *flat = sv.flat;
     if (sv.n_groups) { // group table + exact-test records in shared memory, as in k_trace_flat
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams i
         trav = smem + n_flat_f4;
     }
     const uint32_t n = *count;
-    uint32_t c_hits = 0, c_nee = 0, c_vis = 0, c_seg = 0, c_iters = 0;
+    uint32_t c_hits = 0, c_nee = 0, c_vis = 0, c_seg = 0, c_iters = 0, c_over = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 ro = ray_o[i], rd = ray_d[i], st4 = state[i];
         V3 o = xyz(ro), d = xyz(rd);
@@ -448,6 +449,10 @@ __global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams i
             }
             c_iters = max(c_iters, it);
             if (!so.alive || so.next.depth >= 0xfff0u || so.next.rng_n >= 0xfff0u) break; // packing guard as in k_shade
+            if (iter_base + it >= iter_limit) { // the wavefront's iteration limit (rl_render reports it as an error)
+                c_over = 1u;
+                break;
+            }
             o = so.next_o, d = so.next_d;
             st = so.next;
         }
@@ -467,6 +472,7 @@ __global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams i
         if (c_seg) atomicAdd(&counters->tail_segments, (unsigned long long)c_seg);
         if (c_iters) atomicMax(&counters->tail_iters, (unsigned long long)(iter_base + c_iters));
     }
+    if (c_over) atomicMax(&counters->tail_overflow, 1ull);
 }
 
 // ---- `direct` integrator, stage 1: primary hit -> emission, light samples, BSDF samples ---------------

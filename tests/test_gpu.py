@@ -530,3 +530,25 @@ def test_tail_kernel_changes_nothing_but_the_schedule(gpu_ctx, scene):
     ref, so = ob.OracleScene(sc).render(integ, 12, seed=3, cfg=ob.config(**STREAM))
     assert np.array_equal(a, ref) and sa.segments == so.segments
     dev.close()
+
+
+def test_endless_paths_are_an_error_not_a_hang(gpu_ctx):
+    """Closed cube with albedo 1 and no Russian roulette: paths never end.  The wavefront loop gives up after 4095 iterations
+    with RL_ERR_UNSUPPORTED; k_tail keeps the same limit and the same answer (it must not spin to the 16-bit depth guard)."""
+    import json
+    c = [(-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1), (-1, -1, 1), (1, -1, 1), (1, 1, 1), (-1, 1, 1)]
+    quads = [((0, 1, 2, 3), (0, 0, 1)), ((5, 4, 7, 6), (0, 0, -1)), ((4, 0, 3, 7), (1, 0, 0)), ((1, 5, 6, 2), (-1, 0, 0)),
+             ((4, 5, 1, 0), (0, 1, 0)), ((3, 2, 6, 7), (0, -1, 0))]
+    faces = [{"material": {"type": "diffuse", "kd": [1.0] * 3}, "emission": [1.0] * 3, "indices": [0, 1, 2, 0, 2, 3],
+              "P": [x for i in q for x in c[i]], "N": list(n) * 4} for q, n in quads]
+    sc = SceneLoaderManager().load_string(json.dumps({
+        "camera": {"width": 8, "height": 8, "fov": 60, "to_world": [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 0, 0, 0.5, 1]}, "meshes": faces}), "json")
+    dev = DeviceScene(gpu_ctx, sc)
+    integ = _abi.path_desc(rr_depth=1 << 20)  # roulette starts at depth 2^20: never (rr_depth=None would mean "always")
+    for tail in (0, None):
+        with pytest.raises(DeviceError) as e:
+            _with_tail(tail, lambda: dev.render(integ, 1, seed=1))
+        assert e.value.code == _abi.RL_ERR_UNSUPPORTED and "4095" in str(e.value)
+    img, st = dev.render(_abi.path_desc(rr_depth=1 << 20, max_depth=40), 1, seed=1)  # bounded depth: fine
+    assert st.max_depth_seen == 39 and np.isfinite(img).all()
+    dev.close()
