@@ -200,7 +200,9 @@ def main():
     integ = integ_desc()
     spp, seed = WORKLOAD["spp"], WORKLOAD["seed"]
     W, H = scene.size
-    out = np.zeros((H, W, 3), np.float32)
+    from rustlight_b200.device import PinnedImage
+    pinned = PinnedImage(H, W)  # the step's result is read back into pinned host memory (rl_host_alloc)
+    out = pinned.array
     from rustlight_b200 import _abi
     import ctypes as C
     from rustlight_b200.device import lib
@@ -331,6 +333,8 @@ def main():
                 "gpu_launches": int(tot_launches), "clocks": clk, "roofline": roof, "roofline_shade": roof_shade, "stage_ms": stage_ms, "cpu_baseline": cpu}
         print(json.dumps(line))
     dsc.close()
+    out = None
+    pinned.close()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -210,6 +210,11 @@ void rl_destroy(rl_ctx *ctx);
 int rl_nccl_unique_id(void *out_128_bytes);
 const char *rl_last_error(const rl_ctx *ctx); /* ctx may be NULL: last error of rl_create */
 int rl_abi_version(void);
+/* Page-locked host memory for out_rgb (optional: rl_render accepts any host pointer; a pinned buffer lets the frame's
+ * device-to-host copy run at PCIe/C2C line rate without a staging copy).  The reference returns its BufferCollection by
+ * value (integrators/mod.rs:219-228); here the caller owns the buffer.  NULL on failure; rl_host_free(NULL) is a no-op. */
+void *rl_host_alloc(size_t bytes);
+void rl_host_free(void *p);
 /* Toggle per-stage CUDA-event timing (adds synchronisation; off by default). */
 int rl_set_profiling(rl_ctx *ctx, int on);
 

@@ -253,6 +253,18 @@ int rl_create(rl_ctx **out, int device, int nranks, int rank, const void *nccl_u
     return RL_OK;
 }
 
+void *rl_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void rl_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 void rl_destroy(rl_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);

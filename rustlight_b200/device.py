@@ -52,8 +52,30 @@ def lib():
         L.rl_visible.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, FP, FP, C.POINTER(C.c_uint8)]
         L.rl_primary_hits.argtypes = [C.c_void_p, C.c_void_p, U32P, FP]
         L.rl_layout.argtypes = [C.c_void_p, C.POINTER(_abi.rl_layout_info)]
+        L.rl_host_alloc.restype = C.c_void_p
+        L.rl_host_alloc.argtypes = [C.c_size_t]
+        L.rl_host_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
+
+
+class PinnedImage:
+    """H x W x 3 float32 frame in page-locked host memory (rl_host_alloc): `.array` is a numpy view, valid until close()."""
+
+    def __init__(self, h, w):
+        import numpy as np
+        nbytes = h * w * 3 * 4
+        self._p = lib().rl_host_alloc(nbytes)
+        if not self._p:
+            raise RuntimeError("rl_host_alloc failed")
+        self.array = np.ctypeslib.as_array((C.c_float * (h * w * 3)).from_address(self._p)).reshape(h, w, 3)
+        self.array[...] = 0.0
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib().rl_host_free(self._p)
+            self._p = None
 
 
 def nccl_unique_id():

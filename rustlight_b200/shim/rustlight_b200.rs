@@ -56,6 +56,8 @@ extern "C" {
                      opts: *const rl_render_opts, out_rgb: *mut f32, stats: *mut rl_stats) -> c_int;
     pub fn rl_trace(ctx: *mut rl_ctx, scene: *mut rl_scene, n: usize, o: *const f32, d: *const f32, prim: *mut u32, tuv: *mut f32) -> c_int;
     pub fn rl_visible(ctx: *mut rl_ctx, scene: *mut rl_scene, n: usize, p0: *const f32, p1: *const f32, out: *mut u8) -> c_int;
+    pub fn rl_host_alloc(bytes: usize) -> *mut c_void; // optional: pinned buffer for out_rgb
+    pub fn rl_host_free(p: *mut c_void);
 }
 
 use crate::bsdfs::BSDFType;

@@ -552,3 +552,15 @@ def test_endless_paths_are_an_error_not_a_hang(gpu_ctx):
     img, st = dev.render(_abi.path_desc(rr_depth=1 << 20, max_depth=40), 1, seed=1)  # bounded depth: fine
     assert st.max_depth_seen == 39 and np.isfinite(img).all()
     dev.close()
+
+
+def test_pinned_host_buffer(cbox_dev):
+    """rl_host_alloc / rl_host_free: rl_render into a page-locked buffer gives the same frame as into pageable memory."""
+    from rustlight_b200.device import PinnedImage
+    pin = PinnedImage(cbox_dev.height, cbox_dev.width)
+    a, _ = cbox_dev.render(_abi.path_desc(), 2, seed=4)
+    b, _ = cbox_dev.render(_abi.path_desc(), 2, seed=4, out=pin.array)
+    assert b is pin.array and np.array_equal(a, b) and a.max() > 0
+    b = None
+    pin.close()
+    lib().rl_host_free(None)
