@@ -716,11 +716,11 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
             const size_t n_paths = (size_t)npix * nb;
             ip.sample_base = o->sample_offset + s0;
             if (prof) CK(cudaEventRecord(ctx->ev[2], st));
-            // `path` on a group-table scene: the camera rays' origin (sv.cam_pos), path id (= queue index) and path state are constants
+            // group-table scenes: the camera rays' origin (sv.cam_pos), path id (= queue index) and path state are constants
             // that the first k_trace_flat / k_shade fill in themselves: raygen writes 32 B per path (direction, accumulator) instead of 80
-            const bool camera_o = !direct && sc->flat_ok && sc->coherent_tree == 0;
+            const bool camera_o = sc->flat_ok && sc->coherent_tree == 0;
             k_raygen<<<grid_for(ctx, n_paths, 8), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, (uint32_t)n_paths, camera_o ? nullptr : ctx->ray_o[0],
-                                                                   ctx->ray_d[0], direct ? ctx->state[0] : nullptr, ctx->lacc, n_slots);
+                                                                   ctx->ray_d[0], ctx->lacc, n_slots);
             ctx->launches++;
             if (prof) {
                 CK(cudaEventRecord(ctx->ev[3], st));
@@ -737,12 +737,12 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                 // primary rays -> stage 1 (emission, light samples, BSDF samples) -> shadow rays -> extension rays -> stage 2
                 uint32_t *c_in = ctx->d_counts, *c_out = ctx->d_counts + 1, *c_sh = ctx->d_counts + 2;
                 if (prof) CK(cudaEventRecord(ctx->ev[2], st));
-                if (sc->smem_ok) launch_trace<true>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, true);
-                else launch_trace<false>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, true);
+                if (sc->smem_ok) launch_trace<true>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, true, camera_o);
+                else launch_trace<false>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, true, camera_o);
                 if (prof) CK(cudaEventRecord(ctx->ev[3], st));
                 k_shade_direct1<<<grid_for(ctx, n, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, c_in, (uint32_t)n_paths, ctx->ray_o[0], ctx->ray_d[0],
                                                                         ctx->state[0], ctx->hit, ctx->ray_o[1], ctx->ray_d[1], ctx->state[1], c_out, ctx->sh_a,
-                                                                        ctx->sh_b, ctx->sh_c, c_sh, ctx->lacc, ctx->d_counters);
+                                                                        ctx->sh_b, ctx->sh_c, c_sh, ctx->lacc, ctx->d_counters, camera_o ? 3u : 1u);
                 ctx->launches++;
                 if (prof) CK(cudaEventRecord(ctx->ev[4], st));
                 if (sc->smem_ok) launch_shadow<true>(ctx, sc, c_sh, n * std::max(1u, nl), true);

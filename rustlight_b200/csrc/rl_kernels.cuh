@@ -49,8 +49,8 @@ __device__ __forceinline__ void stage_scene(const SceneView &sv, float4 *smem, u
 
 // ---- ray generation ------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list, uint32_t n_paths,
-                                                   float4 *__restrict__ ray_o, float4 *__restrict__ ray_d, float4 *__restrict__ state,
-                                                   float4 *__restrict__ lacc, uint32_t n_slots) {
+                                                   float4 *__restrict__ ray_o, float4 *__restrict__ ray_d, float4 *__restrict__ lacc,
+                                                   uint32_t n_slots) {
     for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n_paths; id += gridDim.x * blockDim.x) {
         uint32_t s_local = id / ip.npix, lp = id - s_local * ip.npix;
         uint32_t pixel = __ldg(pixel_list + lp);
@@ -62,9 +62,8 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, IntegParams ip,
         camera_generate(sv, (float)px + jx, (float)py + jy, &o, &d);
         if (ray_o) ray_o[id] = make_float4(o.x, o.y, o.z, u2f(id)); // nullptr: every camera ray starts at sv.cam_pos with path_id == queue index
         ray_d[id] = make_float4(d.x, d.y, d.z, 1.0f);
-        // `path`: every camera ray starts with throughput 1, depth 1 and two draws taken; k_shade fills that in itself for the
-        // first iteration instead of moving 16 B per path through HBM twice (state == nullptr)
-        if (state) state[id] = make_float4(1.0f, 1.0f, 1.0f, u2f((1u << 16) | smp.n));
+        // No path-state record: every camera ray starts with throughput 1, depth 1 and two draws taken (smp.n == 2); the first
+        // k_shade / k_shade_direct1 fill that in themselves instead of moving 16 B per path through HBM twice.
         for (uint32_t sl = 0; sl < n_slots; sl++) lacc[(size_t)sl * n_paths + id] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
@@ -487,7 +486,7 @@ __global__ void __launch_bounds__(kBlock, RL_DIRECT1_MINBLOCKS) k_shade_direct1(
                                                           const float4 *__restrict__ hit, float4 *__restrict__ out_o, float4 *__restrict__ out_d,
                                                           float4 *__restrict__ out_state, uint32_t *count_out, float4 *__restrict__ sh_a,
                                                           float4 *__restrict__ sh_b, float4 *__restrict__ sh_c, uint32_t *count_shadow,
-                                                          float4 *__restrict__ lacc, Counters *counters) {
+                                                          float4 *__restrict__ lacc, Counters *counters, uint32_t camera) {
     __shared__ uint32_t s_warp[kBlock / 32];
     __shared__ uint32_t s_base;
     const uint32_t n = *count_in;
@@ -500,7 +499,10 @@ __global__ void __launch_bounds__(kBlock, RL_DIRECT1_MINBLOCKS) k_shade_direct1(
         cx.env_primary = false;
         uint32_t pid = 0;
         if (i < n) {
-            float4 ro = ray_o[i], rd = ray_d[i], st4 = state[i], h4 = hit[i];
+            // camera-ray constants are not stored (k_raygen): bit 0 = two draws taken, bit 1 = origin sv.cam_pos and path_id == queue index
+            const float4 rd = ray_d[i], h4 = hit[i];
+            const float4 ro = (camera & 2u) ? make_float4(sv.cam_pos.x, sv.cam_pos.y, sv.cam_pos.z, u2f(i)) : ray_o[i];
+            const float4 st4 = (camera & 1u) ? make_float4(1.0f, 1.0f, 1.0f, u2f((1u << 16) | 2u)) : state[i];
             HitRec h;
             h.t = h4.x, h.u = h4.y, h.v = h4.z, h.prim = f2u(h4.w);
             pid = f2u(ro.w);
