@@ -447,6 +447,7 @@ Scene PBRTSceneLoader::load_string(const std::string &text_in, bool use_shading_
     GState gs;
     std::vector<GState> stack;
     std::vector<Mat4> tstack;
+    std::map<std::string, Mat4> named_cs;                   // CoordinateSystem "name"
     std::map<std::string, Material> materials;
     std::map<std::string, uint32_t> texture_ids;            // pbrt_rs::Scene::textures -> 1-based ids of scene.textures
     std::vector<RawShape> top_shapes;                       // pbrt_rs::Scene::shapes
@@ -494,6 +495,7 @@ Scene PBRTSceneLoader::load_string(const std::string &text_in, bool use_shading_
             if (type != "perspective") throw Error("pbrt: only Camera \"perspective\" is supported");
             fov = (float)p.num("fov", 90.0);
             world_to_camera = gs.ctm;
+            if (auto inv = gs.ctm.invert()) named_cs["camera"] = *inv; // pbrt-v3: camera space -> world
             have_camera = true;
         } else if (d == "Integrator" || d == "Sampler" || d == "PixelFilter" || d == "Accelerator") {
             ps.expect_str();
@@ -513,6 +515,13 @@ Scene PBRTSceneLoader::load_string(const std::string &text_in, bool use_shading_
             if (tstack.empty()) throw Error("pbrt: unbalanced TransformEnd");
             gs.ctm = tstack.back();
             tstack.pop_back();
+        } else if (d == "CoordinateSystem") { // pbrt-v3: name the current transformation ("camera" is set by Camera)
+            named_cs[ps.expect_str()] = gs.ctm;
+        } else if (d == "CoordSysTransform") {
+            const std::string name = ps.expect_str();
+            auto it = named_cs.find(name);
+            if (it == named_cs.end()) throw Error("pbrt: CoordSysTransform of unknown coordinate system " + name);
+            gs.ctm = it->second;
         } else if (d == "ReverseOrientation") {
             gs.reverse_orientation = !gs.reverse_orientation;
         } else if (d == "MakeNamedMaterial") {

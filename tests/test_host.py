@@ -243,6 +243,31 @@ def test_pbrt_transforms_and_defaults():
     assert np.allclose(tw[:3, 3], [0, 0, 5], atol=1e-6) and np.allclose(tw[:3, 2], [0, 0, -1], atol=1e-6)
 
 
+def test_pbrt_named_coordinate_systems():
+    """pbrt-v3 CoordinateSystem / CoordSysTransform: a saved CTM comes back by name; "camera" is camera space -> world."""
+    txt = '''LookAt 0 0 5  0 0 0  0 1 0
+    Camera "perspective" "float fov" [30]
+    WorldBegin
+      Translate 1 2 3
+      CoordinateSystem "shifted"
+      Identity
+      Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]
+      CoordSysTransform "shifted"
+      Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]
+      CoordSysTransform "camera"
+      Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 1 1 0 1 0 1 1]
+    WorldEnd'''
+    sc = SceneLoaderManager().load_string(txt, "pbrt")
+    d = sc.desc.contents
+    P = [np.ctypeslib.as_array(d.meshes[i].P, (9,)).reshape(3, 3) for i in range(3)]
+    assert np.array_equal(P[0], [[0, 0, 0], [1, 0, 0], [0, 1, 0]])
+    assert np.array_equal(P[1], [[1, 2, 3], [2, 2, 3], [1, 3, 3]])
+    # camera space (pbrt looks down +z): one unit in front of the camera at (0,0,5), which looks towards -z of the world
+    assert np.allclose(P[2][0], [0, 0, 4], atol=1e-5) and np.allclose(P[2][2], [0, 1, 4], atol=1e-5)
+    with pytest.raises(Exception, match="unknown coordinate system"):
+        SceneLoaderManager().load_string('WorldBegin CoordSysTransform "nope" WorldEnd', "pbrt")
+
+
 def test_scale_image_truncates_and_keeps_matrices():
     sc = load_cbox()
     before = bytes(sc.desc.contents.camera)[8:]
