@@ -141,11 +141,32 @@ def run_reference(args):
             "mpath_segments_per_s": segs / secs / 1e6,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
+_RESULT = None  # the process's real stdout, kept for the one JSON line
+
+
+def claim_stdout():
+    """Exactly ONE line may reach stdout (the contract): point fd 1 at stderr for everything libraries print there
+    (NCCL writes its version banner to stdout on communicator creation) and keep the real stdout for the result line."""
+    global _RESULT
+    if _RESULT is None:
+        sys.stdout.flush()
+        _RESULT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _RESULT
+
+
+def emit(line):
+    out = claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -331,7 +352,7 @@ def main():
                 "wall_ms_per_step": wall_ms / args.steps,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(tot_launches), "clocks": clk, "roofline": roof, "roofline_shade": roof_shade, "stage_ms": stage_ms, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(line)
     dsc.close()
     out = None
     pinned.close()
