@@ -90,40 +90,30 @@ inline V3 transform_vector(const M4 &m, V3 d) { // (m * d.extend(0)).truncate()
 // "spec" transcendental functions: f64 polynomials, identical op sequence on
 // the GPU.  Used when math_mode == ORC_MATH_SPEC; ORC_MATH_LIBM calls glibc like Rust does.
 // ============================================================================================
-inline void spec_sincos(float xf, float *s, float *c) {
-    const double TWO_OVER_PI = 0.63661977236758134308;
-    const double PIO2_HI = 1.57079632673412561417e+00; // first 33 bits of pi/2
-    const double PIO2_LO = 6.07710050650619224932e-11; // pi/2 - PIO2_HI
-    double x = (double)xf;
-    double fn = std::floor(x * TWO_OVER_PI + 0.5);
+inline void spec_sincos(float x, float *s, float *c) {
+    // f32: three-piece Cody-Waite reduction by pi/2, Cephes sinf / cosf kernels; one fmaf / mul per step
+    const float TWO_OVER_PI = 0.636619772f;
+    const float PIO2_A = 1.5703125f, PIO2_B = 4.837512969970703125e-4f, PIO2_C = 7.54978995489188e-8f;
+    float fn = std::rint(x * TWO_OVER_PI);
     int n = (int)fn;
-    double y = (x - fn * PIO2_HI) - fn * PIO2_LO;
-    double y2 = y * y;
-    // Taylor coefficients 1/3!, 1/5!, ... and 1/2!, 1/4!, ...
-    double ps = 1.0 / 6227020800.0;                // +1/13!
-    ps = ps * y2 + -1.0 / 39916800.0;              // -1/11!
-    ps = ps * y2 + 1.0 / 362880.0;                 // +1/9!
-    ps = ps * y2 + -1.0 / 5040.0;                  // -1/7!
-    ps = ps * y2 + 1.0 / 120.0;                    // +1/5!
-    ps = ps * y2 + -1.0 / 6.0;                     // -1/3!
-    double sy = y + y * (y2 * ps);
-    double pc = -1.0 / 87178291200.0;              // -1/14!
-    pc = pc * y2 + 1.0 / 479001600.0;              // +1/12!
-    pc = pc * y2 + -1.0 / 3628800.0;               // -1/10!
-    pc = pc * y2 + 1.0 / 40320.0;                  // +1/8!
-    pc = pc * y2 + -1.0 / 720.0;                   // -1/6!
-    pc = pc * y2 + 1.0 / 24.0;                     // +1/4!
-    pc = pc * y2 + -0.5;                           // -1/2!
-    double cy = 1.0 + y2 * pc;
-    double rs, rc;
+    float y = std::fma(fn, -PIO2_A, x);
+    y = std::fma(fn, -PIO2_B, y);
+    y = std::fma(fn, -PIO2_C, y);
+    float y2 = y * y;
+    float ps = -1.9515295891e-4f;
+    ps = std::fma(ps, y2, 8.3321608736e-3f);
+    ps = std::fma(ps, y2, -1.6666654611e-1f);
+    float sy = std::fma(y * y2, ps, y);
+    float pc = 2.443315711809948e-5f;
+    pc = std::fma(pc, y2, -1.388731625493765e-3f);
+    pc = std::fma(pc, y2, 4.166664568298827e-2f);
+    float cy = std::fma(y2 * y2, pc, std::fma(-0.5f, y2, 1.0f));
     switch (n & 3) {
-    case 0: rs = sy, rc = cy; break;
-    case 1: rs = cy, rc = -sy; break;
-    case 2: rs = -sy, rc = -cy; break;
-    default: rs = -cy, rc = sy; break;
+    case 0: *s = sy, *c = cy; break;
+    case 1: *s = cy, *c = -sy; break;
+    case 2: *s = -sy, *c = -cy; break;
+    default: *s = -cy, *c = sy; break;
     }
-    *s = (float)rs;
-    *c = (float)rc;
 }
 inline double spec_log2(double x) { // x > 0, normal
     uint64_t bits;
@@ -1279,10 +1269,12 @@ struct CounterSampler : Sampler {
         key = mix64(h ^ (((uint64_t)pixel << 32) | (uint64_t)sample));
     }
     float next() override {
+        // draw n (1-based) = one 24-bit half of hash (n + 1) / 2: bits 40..63 for odd n, bits 16..39 for even n
         draws++;
         n++;
-        uint64_t z = mix64(key + (uint64_t)n * 0x9e3779b97f4a7c15ULL);
-        return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+        uint64_t z = mix64(key + (uint64_t)((n + 1u) >> 1) * 0x9e3779b97f4a7c15ULL);
+        uint32_t bits = (n & 1u) ? (uint32_t)(z >> 40) : ((uint32_t)(z >> 16) & 0xffffffu);
+        return (float)bits * (1.0f / 16777216.0f);
     }
 };
 

@@ -78,6 +78,7 @@ struct rl_ctx {
     uint32_t *pixel_list = nullptr;
     float *frame = nullptr; // W*H*3 mean image of this rank (zeros outside its tiles)
     uint32_t pl_w = 0, pl_h = 0, pl_npix = 0;
+    uint64_t pl_gen = 0; // bumped whenever the pixel list changes (keys the per-scene camera masks)
     uint32_t *d_counts = nullptr; // [cur/next ping-pong x2, shadow, pad] (direct integrator, rl_trace)
     uint32_t *d_hist = nullptr, *h_hist = nullptr; // queue length per wavefront iteration [0,kMaxIters) and shadow-queue length [kMaxIters, 2*kMaxIters)
     Counters *d_counters = nullptr;
@@ -91,6 +92,10 @@ struct rl_scene {
     HostScene hs;
     SceneView sv{};
     float4 *d_flat = nullptr; // group table of small scenes (rl_flat_host.hpp), nullptr when absent
+    float4 *d_quad_verts = nullptr; // vertices of the table's quads (k_camera_cull)
+    uint32_t *d_cam_masks = nullptr; // per block of 32 local pixels: quads its camera rays can see
+    size_t cam_cap = 0;
+    uint64_t cam_gen = 0; // ctx->pl_gen the masks were computed for (0 = never)
     FlatTable flat;
     float4 *d_trav = nullptr, *d_nodes = nullptr, *d_shade = nullptr, *d_verts = nullptr, *d_mats = nullptr, *d_emit_info = nullptr;
     float *d_emit_cdf = nullptr, *d_area_cdf = nullptr;
@@ -313,6 +318,7 @@ void rl_scene_destroy(rl_ctx *ctx, rl_scene *s) {
     cudaFree(s->d_trav), cudaFree(s->d_nodes), cudaFree(s->d_shade), cudaFree(s->d_verts), cudaFree(s->d_mats);
     cudaFree(s->d_emit_info), cudaFree(s->d_emit_cdf), cudaFree(s->d_area_cdf), cudaFree(s->d_flat);
     cudaFree(s->d_uvs), cudaFree(s->d_tex), cudaFree(s->d_texels);
+    cudaFree(s->d_quad_verts), cudaFree(s->d_cam_masks);
     delete s;
 }
 
@@ -423,6 +429,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
         flat_ok = build_flat_table(hs, prim_of_slot, s->flat);
         if (flat_ok) {
             CKS(upload(&s->d_flat, s->flat.f4, st));
+            CKS(upload(&s->d_quad_verts, s->flat.quad_verts, st));
             CKS(cudaStreamSynchronize(st));
         }
     }
@@ -469,9 +476,9 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     s->root_tree = root_ref;
     s->root_flat = root_ref;
     s->flat_ok = flat_ok;
-    s->smem_flat_bytes = (size_t)(s->flat.n_groups * RL_FLAT_F4 + s->n_trav_f4) * sizeof(float4);
+    s->smem_flat_bytes = (size_t)(s->flat.n_groups * RL_FLAT_F4 + RL_FLAT_TAIL_F4 + s->n_trav_f4) * sizeof(float4);
     sv.flat = s->d_flat, sv.n_groups = 0; // n_groups is set per launch (launch_trace / launch_shadow)
-    sv.flat_valid[0] = s->flat.valid[0], sv.flat_valid[1] = s->flat.valid[1], sv.flat_delta = s->flat.delta;
+    sv.flat_valid_a = s->flat.valid_a, sv.flat_valid_b = s->flat.valid_b, sv.flat_delta = s->flat.delta;
     if (const char *e = getenv("RL_FLAT_LEAF")) // A/B: the pre-group-table flat path (whole scene as one leaf of single records)
         if (atoi(e) != 0 && n <= (uint32_t)RL_LEAF_MAX_CAP) s->root_flat = leaf_ref(0u, n), s->flat_ok = false;
     // With a group table every ray scans it (measured on B200, cbox 1024^2 x 32 spp: 13.6 ms vs 14.6 ms with camera rays
@@ -576,6 +583,7 @@ static int ensure_pixels(rl_ctx *ctx, uint32_t w, uint32_t h) {
     }
     if (!list.empty()) CK(cudaMemcpy(ctx->pixel_list, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     ctx->pl_w = w, ctx->pl_h = h, ctx->pl_npix = (uint32_t)list.size();
+    ctx->pl_gen++;
     return RL_OK;
 }
 
@@ -632,12 +640,12 @@ static int validate(rl_ctx *ctx, const rl_scene *scene, const rl_integrator_desc
 
 template <bool SMEM>
 static void launch_trace(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_t n, const float4 *ro, const float4 *rd, float4 *hit,
-                         bool coherent = false, bool camera_origin = false) {
+                         bool coherent = false, bool camera_origin = false, const uint32_t *cam_masks = nullptr) {
     SceneView sv = sc->sv;
     const bool tree = coherent && sc->coherent_tree >= 1;
     if (!tree && sc->flat_ok) {
         sv.n_groups = sc->flat.n_groups;
-        k_trace_flat<<<grid_for(ctx, n, trav_per_sm()), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_trav_f4, camera_origin ? 1u : 0u);
+        k_trace_flat<<<grid_for(ctx, n, trav_per_sm()), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_trav_f4, camera_origin ? 1u : 0u, cam_masks, ctx->pl_npix);
         ctx->launches++;
         return;
     }
@@ -660,6 +668,28 @@ static void launch_shadow(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size
     k_shadow<SMEM><<<grid_for(ctx, n, tree_per_sm()), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc,
                                                                                              ctx->d_counters, sc->n_node_f4, sc->n_trav_f4);
     ctx->launches++;
+}
+
+// Camera-ray culling masks of a group-table scene for the current pixel list (k_camera_cull), cached per scene.
+static int ensure_cam_masks(rl_ctx *ctx, rl_scene *sc) {
+    if (sc->cam_gen == ctx->pl_gen && sc->d_cam_masks) return RL_OK;
+    const uint32_t npix = ctx->pl_npix, nblk = (npix + 31u) / 32u;
+    if (nblk > sc->cam_cap) {
+        cudaFree(sc->d_cam_masks);
+        sc->d_cam_masks = nullptr, sc->cam_cap = 0;
+        CK(cudaMalloc(&sc->d_cam_masks, (size_t)std::max(nblk, 1u) * sizeof(uint32_t)));
+        sc->cam_cap = nblk;
+    }
+    const HostScene &hs = sc->hs;
+    const double ext = (double)hs.abs_max + std::max(std::max(std::fabs((double)hs.cam_pos[0]), std::fabs((double)hs.cam_pos[1])), std::fabs((double)hs.cam_pos[2]));
+    SceneView sv = sc->sv;
+    if (npix) {
+        k_camera_cull<<<grid_for(ctx, nblk, 8), kBlock, 0, ctx->stream>>>(sv, sc->d_quad_verts, sc->flat.valid_a, ctx->pixel_list, npix, hs.img_w, 1e-4 * ext, sc->d_cam_masks);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    sc->cam_gen = ctx->pl_gen;
+    return RL_OK;
 }
 
 static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, const rl_render_opts *o, rl_stats *stats) {
@@ -719,6 +749,12 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
             // group-table scenes: the camera rays' origin (sv.cam_pos), path id (= queue index) and path state are constants
             // that the first k_trace_flat / k_shade fill in themselves: raygen writes 32 B per path (direction, accumulator) instead of 80
             const bool camera_o = sc->flat_ok && sc->coherent_tree == 0;
+            const uint32_t *cam_masks = nullptr; // camera rays scan only the quads their block of 32 pixels can see
+            if (camera_o && getenv("RL_NO_CAM_CULL") == nullptr) { // (A/B hook)
+                rc = ensure_cam_masks(ctx, sc);
+                if (rc != RL_OK) return rc;
+                cam_masks = sc->d_cam_masks;
+            }
             k_raygen<<<grid_for(ctx, n_paths, 8), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, (uint32_t)n_paths, camera_o ? nullptr : ctx->ray_o[0],
                                                                    ctx->ray_d[0], ctx->lacc, n_slots);
             ctx->launches++;
@@ -737,8 +773,8 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                 // primary rays -> stage 1 (emission, light samples, BSDF samples) -> shadow rays -> extension rays -> stage 2
                 uint32_t *c_in = ctx->d_counts, *c_out = ctx->d_counts + 1, *c_sh = ctx->d_counts + 2;
                 if (prof) CK(cudaEventRecord(ctx->ev[2], st));
-                if (sc->smem_ok) launch_trace<true>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, true, camera_o);
-                else launch_trace<false>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, true, camera_o);
+                if (sc->smem_ok) launch_trace<true>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, true, camera_o, cam_masks);
+                else launch_trace<false>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, true, camera_o, cam_masks);
                 if (prof) CK(cudaEventRecord(ctx->ev[3], st));
                 k_shade_direct1<<<grid_for(ctx, n, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, c_in, (uint32_t)n_paths, ctx->ray_o[0], ctx->ray_d[0],
                                                                         ctx->state[0], ctx->hit, ctx->ray_o[1], ctx->ray_d[1], ctx->state[1], c_out, ctx->sh_a,
@@ -825,11 +861,11 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                             const int tb = grid_for(ctx, n_ub, trav_per_sm()), sb = k == 0 ? 0 : grid_for(ctx, ub_prev, trav_per_sm());
                             k_trace_shadow_flat<<<tb + sb, kBlock, sc->smem_flat_bytes, st>>>(sv, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit,
                                                                                               k == 0 ? zero_count : shc + k - 1, ctx->sh_a, ctx->sh_b, ctx->sh_c,
-                                                                                              ctx->lacc, ctx->d_counters, sc->n_trav_f4, (uint32_t)tb, (k == 0 && camera_o) ? 1u : 0u);
+                                                                                              ctx->lacc, ctx->d_counters, sc->n_trav_f4, (uint32_t)tb, (k == 0 && camera_o) ? 1u : 0u, k == 0 ? cam_masks : nullptr, npix);
                             ctx->launches++;
                             ub_prev = n_ub;
-                        } else if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0, k == 0 && camera_o);
-                        else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0, k == 0 && camera_o);
+                        } else if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0, k == 0 && camera_o, k == 0 ? cam_masks : nullptr);
+                        else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0, k == 0 && camera_o, k == 0 ? cam_masks : nullptr);
                         if (prof) CK(cudaEventRecord(ctx->ev[3], st));
 #define RL_LAUNCH_SHADE(SORT, KM)                                                                                                                   \
     k_shade<SORT, KM><<<grid_for(ctx, n_ub, resident_per_sm(k_shade<SORT, KM>, 0, shade_block(KM)), shade_block(KM)), shade_block(KM), 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], \

@@ -121,38 +121,32 @@ RL_HD Col xyz_col(float4 f) { return Col{f.x, f.y, f.z}; }
 
 // ---- "spec" transcendental functions: DESIGN.md §math.  f64 polynomials; the oracle carries
 // an independently typed copy with the same operation sequence (oracle.cpp spec_*). ----------
-RL_HD void spec_sincos(float xf, float *s, float *c) {
-    const double TWO_OVER_PI = 0.63661977236758134308;
-    const double PIO2_HI = 1.57079632673412561417e+00;
-    const double PIO2_LO = 6.07710050650619224932e-11;
-    double x = (double)xf;
-    double fn = floor(x * TWO_OVER_PI + 0.5);
-    int n = (int)fn;
-    double y = (x - fn * PIO2_HI) - fn * PIO2_LO;
-    double y2 = y * y;
-    double ps = 1.0 / 6227020800.0;
-    ps = ps * y2 + -1.0 / 39916800.0;
-    ps = ps * y2 + 1.0 / 362880.0;
-    ps = ps * y2 + -1.0 / 5040.0;
-    ps = ps * y2 + 1.0 / 120.0;
-    ps = ps * y2 + -1.0 / 6.0;
-    double sy = y + y * (y2 * ps);
-    double pc = -1.0 / 87178291200.0;
-    pc = pc * y2 + 1.0 / 479001600.0;
-    pc = pc * y2 + -1.0 / 3628800.0;
-    pc = pc * y2 + 1.0 / 40320.0;
-    pc = pc * y2 + -1.0 / 720.0;
-    pc = pc * y2 + 1.0 / 24.0;
-    pc = pc * y2 + -0.5;
-    double cy = 1.0 + y2 * pc;
-    double rs, rc;
-    int q = n & 3;
+// sin and cos in f32: Cody-Waite reduction by pi/2 in three exact pieces (valid far beyond the |x| <= 2 pi the callers
+// pass), then the Cephes sinf / cosf kernels on |y| <= pi/4, every step one fmaf / mul (identical on the device, in the
+// emulator and in the oracle).  Max error ~1 ulp: the LIBM-vs-SPEC gate (tests: test_math_modes_agree) stays below 1e-5.
+RL_HD void spec_sincos(float x, float *s, float *c) {
+    const float fn = rintf(x * 0.636619772f);
+    const int n = (int)fn;
+    float y = fmaf(fn, -1.5703125f, x);
+    y = fmaf(fn, -4.837512969970703125e-4f, y);
+    y = fmaf(fn, -7.54978995489188e-8f, y);
+    const float y2 = y * y;
+    float ps = -1.9515295891e-4f;
+    ps = fmaf(ps, y2, 8.3321608736e-3f);
+    ps = fmaf(ps, y2, -1.6666654611e-1f);
+    const float sy = fmaf(y * y2, ps, y);
+    float pc = 2.443315711809948e-5f;
+    pc = fmaf(pc, y2, -1.388731625493765e-3f);
+    pc = fmaf(pc, y2, 4.166664568298827e-2f);
+    const float cy = fmaf(y2 * y2, pc, fmaf(-0.5f, y2, 1.0f));
+    const int q = n & 3;
+    float rs, rc;
     if (q == 0) { rs = sy; rc = cy; }
     else if (q == 1) { rs = cy; rc = -sy; }
     else if (q == 2) { rs = -sy; rc = -cy; }
     else { rs = -cy; rc = sy; }
-    *s = (float)rs;
-    *c = (float)rc;
+    *s = rs;
+    *c = rc;
 }
 RL_HD double spec_log2(double x) {
     uint64_t bits = d2u(x);
@@ -235,19 +229,27 @@ RL_HD uint64_t mix64(uint64_t z) {
     return z ^ (z >> 31);
 }
 RL_HD uint64_t seed_hash(uint64_t seed) { return mix64(seed + 0x9e3779b97f4a7c15ULL); }
+// Draw number n (1-based) of a pixel sample is one 24-bit half of hash number h = (n + 1) / 2: bits 40..63 for odd n,
+// bits 16..39 for even n -- one SplitMix64 finaliser per TWO draws.  The sampler keeps the last hash.
 struct Sampler {
-    uint64_t key;
-    uint32_t n;
+    uint64_t key, z;
+    uint32_t n, zh;
     RL_HD float next() {
         n++;
-        uint64_t z = mix64(key + (uint64_t)n * 0x9e3779b97f4a7c15ULL);
-        return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+        const uint32_t h = (n + 1u) >> 1;
+        if (h != zh) {
+            z = mix64(key + (uint64_t)h * 0x9e3779b97f4a7c15ULL);
+            zh = h;
+        }
+        const uint32_t bits = (n & 1u) ? (uint32_t)(z >> 40) : ((uint32_t)(z >> 16) & 0xffffffu);
+        return (float)bits * (1.0f / 16777216.0f);
     }
 };
 RL_HD Sampler make_sampler(uint64_t seed_h, uint32_t pixel, uint32_t sample, uint32_t n) {
     Sampler s;
     s.key = mix64(seed_h ^ (((uint64_t)pixel << 32) | (uint64_t)sample));
     s.n = n;
+    s.z = 0ull, s.zh = 0u; // no hash yet (hash numbers start at 1)
     return s;
 }
 
@@ -321,7 +323,7 @@ struct SceneView {
     // flat group table (rl_build.cuh: build_flat_table) for scenes of a few dozen triangles: n_groups == 0 when absent
     const float4 *flat;
     uint32_t n_groups;
-    uint32_t flat_valid[2]; // candidate bits that refer to real triangles (bit order of flat_scan)
+    uint32_t flat_valid_a, flat_valid_b; // quad bits whose A / B triangle is real (bit order of flat_scan)
     float flat_delta;       // largest plane mismatch inside a triangle pair (world units), added to the t margin
     int root_ref; // inner node 0, or a leaf reference when the whole scene is one leaf
     // BVHAccel nodes[0].aabb (union of compute_aabb_tri boxes), for the reference's root test
@@ -582,26 +584,28 @@ RL_HD bool trav_leaf_any(Trav &tr, const int *stack, const float4 *trav) {
     return false;
 }
 
-// ---- flat group scan (scenes of a few dozen triangles) ----------------------------------------------
+// ---- flat quad scan (scenes of a few dozen triangles) -----------------------------------------------
 // Incoherent rays gain nothing from a hierarchy over ~36 triangles (every lane of a warp walks a different
-// branch), so they run the conservative prefilter over ALL triangles in lockstep and the exact test only on
-// the survivors.  To make the scan cheap the triangles are grouped at build time (rl_build.cuh):
-//   pair record  = two triangles A, B lying in one plane (a quad face): the ray/plane part of the prefilter
-//                  is computed once, with A's plane (B's vertices are within flat_delta of it; unpaired
-//                  triangles get a dummy B whose candidate bit is masked by flat_valid);
-//   group        = two pair records P, Q interleaved component-wise, so that every arithmetic step is one
+// branch), so they run a conservative prefilter over ALL triangles in lockstep and the exact test only on
+// the survivors.  To make the scan cheap the triangles are grouped at build time (rl_flat_host.hpp):
+//   quad record  = two triangles A, B lying in one plane (a quad face): ONE ray/plane intersection with A's plane
+//                  (B's vertices are within flat_delta of it), ONE point-in-parallelogram test with two affine
+//                  functionals U, V in [0, 1] over A u B, and -- when A and B lie on opposite sides of a shared
+//                  edge -- the functional D = k0 + kU U + kV V (>= 0 on A, <= 0 on B) that tells which of the two
+//                  the ray can hit; unpaired triangles get a record of their own (B's bit masked by flat_valid_b);
+//   group        = two quad records P, Q interleaved component-wise, so that every arithmetic step is one
 //                  packed fma.rn.f32x2 / add / mul (FFMA2 / FADD2 / FMUL2 on sm_100) over (P, Q).
-// Eleven float4 per group (four triangles):
+// Eight float4 per group (two quads = up to four triangles):
 //   [0] {n.x P,Q  n.y P,Q}   [1] {n.z P,Q  pn P,Q}            plane of A: n.p = pn
-//   [2] {MuA.x P,Q MuA.y P,Q} [3] {MuA.z P,Q cuA P,Q}          u_A(p) = MuA.p + cuA        [4],[5] the same for v_A
-//   [6],[7] u_B   [8],[9] v_B
-//   [10] {mn P, mn Q, slots P, slots Q}   mn = largest gradient norm of the four functionals of the pair,
-//                                         slots = Morton slot of A | slot of B << 8 (index into trav[])
-// The result is one REJECT bit per triangle, shifted into the mask in scan order (first triangle ends in the
-// highest bit).  Rejection is decided by the sign of min(min(u,v,w) + m, tp + mt, tmax + mt - tp): FMNMX drops
-// NaN operands and an all-NaN minimum is the canonical (positive) NaN, so degenerate cases (d.n == 0, inf
-// arithmetic) stay candidates exactly like in tri_prefilter.
-#define RL_FLAT_F4 11
+//   [2] {MU.x P,Q MU.y P,Q}  [3] {MU.z P,Q cU P,Q}             U(p) = MU.p + cU           [4],[5] the same for V
+//   [6] {mn P,Q  k0 P,Q}     [7] {kU P,Q  kV P,Q}              mn = largest gradient norm of U, V, D
+// followed (after the last group) by 64 bytes: Morton slot (index into trav[]) of A [bit] and of B [32 + bit].
+// The scan yields three sign bits per quad, shifted into three masks in scan order (first quad ends in the highest
+// bit): q = outside the parallelogram or outside the t range, dp = D + m < 0 (not A), dm = m - D < 0 (not B).
+// Rejection is decided by the sign of a minimum: FMNMX drops NaN operands and an all-NaN minimum is the canonical
+// (positive) NaN, so degenerate cases (d.n == 0, inf arithmetic, NaN functionals) stay candidates.
+#define RL_FLAT_F4 8
+#define RL_FLAT_TAIL_F4 4
 #define RL_FLAT_MAX_GROUPS 16
 #ifndef RL_FLAT_MARGIN_SCALE
 #define RL_FLAT_MARGIN_SCALE 1.0f // test hook: tests/ shrink the margins to measure how much slack they carry
@@ -683,98 +687,184 @@ RL_HD FlatRay flat_ray(const SceneView &sv, V3 o, V3 d, float tmax) {
     fr.rs8 = RL_FLAT_MARGIN_SCALE * 8e-6f * rs;
     return fr;
 }
-// Scan groups [g0, g1): returns the reject bits (4 per group, scan order from the top).
-RL_HD uint32_t flat_scan(const FlatRay &fr, const float4 *flat, uint32_t g0, uint32_t g1) {
-    uint32_t mask = 0;
+struct FlatMasks {
+    uint32_t q, dp, dm;
+};
+// The six sign values of one group (two quads P, Q): outside parallelogram / t range, not A, not B.
+struct FlatSigns {
+    float qP, qQ, dpP, dpQ, dmP, dmQ;
+};
+// TMAX = false: closest-hit rays (tmax = f32::MAX: the far end of the t range cannot reject).
+template <bool TMAX>
+RL_HD FlatSigns flat_group(const FlatRay &fr, const float4 *g, F2 dx, F2 dy, F2 dz, F2 ox, F2 oy, F2 oz, F2 nox, F2 noy, F2 noz) {
+    const float4 a0 = g[0], a1 = g[1];
+    const F2 nx = f2(a0.x, a0.y), ny = f2(a0.z, a0.w), nz = f2(a1.x, a1.y), pn = f2(a1.z, a1.w);
+    // plane: t' = (pn - o.n) / (d.n)
+    const F2 den = fma2(dx, nx, fma2(dy, ny, mul2(dz, nz)));
+    const F2 num = fma2(nox, nx, fma2(noy, ny, fma2(noz, nz, pn)));
+    const F2 rden = f2(rcp_fast(den.x), rcp_fast(den.y));
+    const F2 tp = mul2(num, rden);
+    const float ard0 = fabsf(rden.x), ard1 = fabsf(rden.y);
+    const F2 mt = f2(ard0 * fmaf(fabsf(num.x), fmaf(ard0, RL_FLAT_MARGIN_SCALE * 2e-6f, RL_FLAT_MARGIN_SCALE * 8e-6f), fr.rs2), ard1 * fmaf(fabsf(num.y), fmaf(ard1, RL_FLAT_MARGIN_SCALE * 2e-6f, RL_FLAT_MARGIN_SCALE * 8e-6f), fr.rs2));
+    const F2 px = fma2(tp, dx, ox), py = fma2(tp, dy, oy), pz = fma2(tp, dz, oz);
+    const float4 c6 = g[6], c7 = g[7];
+    // margin of the in-plane functionals: m >= |grad| (6 mt + 8e-6 rs) + 2e-6
+    const F2 m = fma2(f2(c6.x, c6.y), fma2(mt, f2b(6.0f), f2b(fr.rs8)), f2b(RL_FLAT_MARGIN_SCALE * 2e-6f));
+    const F2 onem = add2(f2b(1.0f), m);
+    const F2 q1 = add2(tp, mt);
+    const float4 b0 = g[2], b1 = g[3], b2 = g[4], b3 = g[5];
+    const F2 U = fma2(px, f2(b0.x, b0.y), fma2(py, f2(b0.z, b0.w), fma2(pz, f2(b1.x, b1.y), f2(b1.z, b1.w))));
+    const F2 V = fma2(px, f2(b2.x, b2.y), fma2(py, f2(b2.z, b2.w), fma2(pz, f2(b3.x, b3.y), f2(b3.z, b3.w))));
+    const F2 ua = add2(U, m), va = add2(V, m), ub = sub2(onem, U), vb = sub2(onem, V);
+    const F2 D = fma2(f2(c7.x, c7.y), U, fma2(f2(c7.z, c7.w), V, f2(c6.z, c6.w)));
+    const F2 Dp = add2(D, m), Dm = sub2(m, D);
+    FlatSigns sg;
+    if (TMAX) {
+        const F2 q2 = sub2(add2(f2b(fr.tmax), mt), tp);
+        sg.qP = fminf(min3f(ua.x, va.x, ub.x), min3f(vb.x, q1.x, q2.x));
+        sg.qQ = fminf(min3f(ua.y, va.y, ub.y), min3f(vb.y, q1.y, q2.y));
+    } else {
+        sg.qP = min3f(min3f(ua.x, va.x, ub.x), vb.x, q1.x);
+        sg.qQ = min3f(min3f(ua.y, va.y, ub.y), vb.y, q1.y);
+    }
+    sg.dpP = Dp.x, sg.dpQ = Dp.y, sg.dmP = Dm.x, sg.dmQ = Dm.y;
+    return sg;
+}
+RL_HD uint32_t sign_bit(float s) { return f2u(s) >> 31; } // canonical NaNs are positive
+// Scan the groups.  CULL (camera rays): `quads` = the quads that overlap the frustum of the warp's pixels (rl_kernels.cuh:
+// k_camera_cull), uniform over the warp: only groups with a quad in it are scanned, everything else counts as rejected.
+#ifndef RL_SCAN_UNROLL
+#define RL_SCAN_UNROLL 1
+#endif
+constexpr int kScanUnroll = RL_SCAN_UNROLL;
+template <bool CULL, bool TMAX>
+RL_HD FlatMasks flat_scan(const FlatRay &fr, const float4 *flat, uint32_t n_groups, uint32_t quads) {
+    FlatMasks mk;
     const F2 dx = f2b(fr.d.x), dy = f2b(fr.d.y), dz = f2b(fr.d.z);
     const F2 ox = f2b(fr.o.x), oy = f2b(fr.o.y), oz = f2b(fr.o.z);
     const F2 nox = f2b(-fr.o.x), noy = f2b(-fr.o.y), noz = f2b(-fr.o.z);
-    for (uint32_t gi = g0; gi < g1; gi++) {
-        const float4 *g = flat + RL_FLAT_F4 * gi;
-        const float4 a0 = g[0], a1 = g[1];
-        const F2 nx = f2(a0.x, a0.y), ny = f2(a0.z, a0.w), nz = f2(a1.x, a1.y), pn = f2(a1.z, a1.w);
-        // plane: t' = (pn - o.n) / (d.n)
-        const F2 den = fma2(dx, nx, fma2(dy, ny, mul2(dz, nz)));
-        const F2 num = fma2(nox, nx, fma2(noy, ny, fma2(noz, nz, pn)));
-        const F2 rden = f2(rcp_fast(den.x), rcp_fast(den.y));
-        const F2 tp = mul2(num, rden);
-        const float ard0 = fabsf(rden.x), ard1 = fabsf(rden.y);
-        const F2 mt = f2(ard0 * fmaf(fabsf(num.x), fmaf(ard0, RL_FLAT_MARGIN_SCALE * 2e-6f, RL_FLAT_MARGIN_SCALE * 8e-6f), fr.rs2), ard1 * fmaf(fabsf(num.y), fmaf(ard1, RL_FLAT_MARGIN_SCALE * 2e-6f, RL_FLAT_MARGIN_SCALE * 8e-6f), fr.rs2));
-        const F2 px = fma2(tp, dx, ox), py = fma2(tp, dy, oy), pz = fma2(tp, dz, oz);
-        const float4 c10 = g[10];
-        const F2 m = fma2(f2(c10.x, c10.y), fma2(mt, f2b(6.0f), f2b(fr.rs8)), f2b(RL_FLAT_MARGIN_SCALE * 2e-6f));
-        const F2 q1 = add2(tp, mt), q2 = sub2(add2(f2b(fr.tmax), mt), tp);
-        const float4 b0 = g[2], b1 = g[3], b2 = g[4], b3 = g[5];
-        const F2 uA = fma2(px, f2(b0.x, b0.y), fma2(py, f2(b0.z, b0.w), fma2(pz, f2(b1.x, b1.y), f2(b1.z, b1.w))));
-        const F2 vA = fma2(px, f2(b2.x, b2.y), fma2(py, f2(b2.z, b2.w), fma2(pz, f2(b3.x, b3.y), f2(b3.z, b3.w))));
-        const F2 wA = sub2(sub2(f2b(1.0f), uA), vA);
-        const float4 b4 = g[6], b5 = g[7], b6 = g[8], b7 = g[9];
-        const F2 uB = fma2(px, f2(b4.x, b4.y), fma2(py, f2(b4.z, b4.w), fma2(pz, f2(b5.x, b5.y), f2(b5.z, b5.w))));
-        const F2 vB = fma2(px, f2(b6.x, b6.y), fma2(py, f2(b6.z, b6.w), fma2(pz, f2(b7.x, b7.y), f2(b7.z, b7.w))));
-        const F2 wB = sub2(sub2(f2b(1.0f), uB), vB);
-        mask = push_reject(mask, min3f(min3f(uA.x, vA.x, wA.x) + m.x, q1.x, q2.x)); // P.A
-        mask = push_reject(mask, min3f(min3f(uB.x, vB.x, wB.x) + m.x, q1.x, q2.x)); // P.B
-        mask = push_reject(mask, min3f(min3f(uA.y, vA.y, wA.y) + m.y, q1.y, q2.y)); // Q.A
-        mask = push_reject(mask, min3f(min3f(uB.y, vB.y, wB.y) + m.y, q1.y, q2.y)); // Q.B
+    if (CULL) {
+        mk.q = 0xffffffffu, mk.dp = 0u, mk.dm = 0u;
+        uint32_t todo = (quads | (quads >> 1)) & 0x55555555u; // bit 2k: group with quad bits 2k, 2k+1 has work
+        while (todo) {
+            const uint32_t lo = (uint32_t)ffs64((uint64_t)todo) - 1u; // bit position of the group's Q quad (P = lo + 1)
+            todo &= todo - 1u;
+            const uint32_t gi = n_groups - 1u - (lo >> 1);
+            const FlatSigns sg = flat_group<TMAX>(fr, flat + RL_FLAT_F4 * gi, dx, dy, dz, ox, oy, oz, nox, noy, noz);
+            mk.q = (mk.q & ~(3u << lo)) | (((sign_bit(sg.qP) << 1) | sign_bit(sg.qQ)) << lo);
+            mk.dp |= ((sign_bit(sg.dpP) << 1) | sign_bit(sg.dpQ)) << lo;
+            mk.dm |= ((sign_bit(sg.dmP) << 1) | sign_bit(sg.dmQ)) << lo;
+        }
+        return mk;
     }
-    return mask;
+    mk.q = 0u, mk.dp = 0u, mk.dm = 0u;
+#pragma unroll kScanUnroll
+    for (uint32_t gi = 0; gi < n_groups; gi++) {
+        const FlatSigns sg = flat_group<TMAX>(fr, flat + RL_FLAT_F4 * gi, dx, dy, dz, ox, oy, oz, nox, noy, noz);
+        mk.q = push_reject(push_reject(mk.q, sg.qP), sg.qQ);
+        mk.dp = push_reject(push_reject(mk.dp, sg.dpP), sg.dpQ);
+        mk.dm = push_reject(push_reject(mk.dm, sg.dmP), sg.dmQ);
+    }
+    return mk;
 }
-// Candidate bits of one half (groups [g0, g1)): valid and not rejected.  Bit b <-> scan index 4*(g1-g0)-1-b.
-RL_HD uint32_t flat_candidates(const FlatRay &fr, const SceneView &sv, const float4 *flat, int half) {
-    const uint32_t g0 = half ? 8u : 0u, g1 = half ? sv.n_groups : (sv.n_groups < 8u ? sv.n_groups : 8u);
-    if (g0 >= g1) return 0u;
-    return ~flat_scan(fr, flat, g0, g1) & sv.flat_valid[half];
+// Candidate triangles: bits [0, 32) the A triangles, bits [32, 64) the B triangles of the quads (bit b <-> scan index 2 n_groups - 1 - b).
+template <bool CULL, bool TMAX>
+RL_HD uint64_t flat_candidates(const FlatRay &fr, const SceneView &sv, const float4 *flat, uint32_t quads) {
+    const FlatMasks mk = flat_scan<CULL, TMAX>(fr, flat, sv.n_groups, quads);
+    uint32_t ca = ~(mk.q | mk.dp) & sv.flat_valid_a, cb = ~(mk.q | mk.dm) & sv.flat_valid_b;
+    if (CULL) ca &= quads, cb &= quads;
+    return ((uint64_t)cb << 32) | (uint64_t)ca;
 }
-RL_HD int clz32(uint32_t x) {
-#if defined(__CUDA_ARCH__)
-    return __clz((int)x);
-#else
-    return x ? __builtin_clz(x) : 32;
-#endif
+RL_HD uint32_t flat_slot(const SceneView &sv, const float4 *flat, uint32_t bit) {
+    return (uint32_t)reinterpret_cast<const unsigned char *>(flat + RL_FLAT_F4 * sv.n_groups)[bit];
 }
-// Morton slot of the triangle behind candidate bit `b` of half `half`.
-RL_HD uint32_t flat_slot(const SceneView &sv, const float4 *flat, int half, uint32_t b) {
-    const uint32_t g0 = half ? 8u : 0u, g1 = half ? sv.n_groups : (sv.n_groups < 8u ? sv.n_groups : 8u);
-    const uint32_t idx = 4u * (g1 - g0) - 1u - b; // scan index inside this half
-    const float4 c10 = flat[RL_FLAT_F4 * (g0 + (idx >> 2)) + 10];
-    const uint32_t word = f2u((idx & 2u) ? c10.w : c10.z);
-    return (word >> ((idx & 1u) * 8u)) & 0xffu;
+// Mesh::intersection_tri with the square roots and divisions of (u, v) deferred.  All decisions of tri_test are taken,
+// in the same arithmetic, up to the last one (u + v <= 1, which also implies u, v <= 1): that one is decided from
+// alpha = (e1 x pv).n ~ det v and beta = (pv x e2).n ~ det u when alpha + beta is clear of det by the margin `ml`
+// (|u0| <= |alpha| / |n| + |e1| eta with eta the out-of-plane rounding of p, far below ml det: DESIGN.md section 6),
+// and by the reference's own (u, v) otherwise.  Returns 0 = rejected, 1 = accepted with (u, v) still to be computed
+// by tri_uv, 2 = accepted and (u, v) computed.
+RL_HD int tri_test_lazy(float4 r0, float4 r1, float4 r2, float4 r3, V3 o, V3 d, float t_bound, float rs8, float *t_out, float *u_out, float *v_out) {
+    V3 v0 = xyz(r0), e1 = xyz(r1), e2 = xyz(r2), n_geo = xyz(r3);
+    float det = r0.w;
+    float denom = dot(d, n_geo);
+    if (denom == 0.0f) return 0;
+    float t = -dot(o - v0, n_geo) / denom;
+    if (t < 0.0f) return 0;
+    if (!(t <= t_bound) || !(t > 0.00001f)) return 0;
+    V3 p = o + t * d;
+    V3 pv = p - v0;
+    V3 u0 = cross(e1, pv);
+    float alpha = dot(u0, n_geo);
+    if (alpha < 0.0f) return 0;
+    V3 v0c = cross(pv, e2);
+    float beta = dot(v0c, n_geo);
+    if (beta < 0.0f) return 0;
+    *t_out = t;
+    const float ml = fmaf(r2.w, rs8, RL_FLAT_MARGIN_SCALE * 2e-6f);
+    const float s = alpha + beta;
+    if (s <= det * (1.0f - ml)) return 1; // false for NaN
+    if (s > det * (1.0f + ml)) return 0;
+    float v = magnitude(u0) / det;
+    float u = magnitude(v0c) / det;
+    if (u < 0.0f || v < 0.0f || u > 1.0f || v > 1.0f) return 0;
+    if (!(u + v <= 1.0f)) return 0;
+    *u_out = u;
+    *v_out = v;
+    return 2;
+}
+// (u, v) of an accepted hit: the operations of tri_test on the same inputs, hence the same bits
+RL_HD void tri_uv(float4 r0, float4 r1, float4 r2, V3 o, V3 d, float t, float *u_out, float *v_out) {
+    V3 v0 = xyz(r0), e1 = xyz(r1), e2 = xyz(r2);
+    float det = r0.w;
+    V3 p = o + t * d;
+    V3 pv = p - v0;
+    V3 u0 = cross(e1, pv);
+    V3 v0c = cross(pv, e2);
+    *v_out = magnitude(u0) / det;
+    *u_out = magnitude(v0c) / det;
 }
 // Closest hit over the flat table: same result rule as trav_leaf_closest.
-RL_HD HitRec flat_closest(const SceneView &sv, const float4 *flat, const float4 *trav, V3 o, V3 d) {
+template <bool CULL = false>
+RL_HD HitRec flat_closest(const SceneView &sv, const float4 *flat, const float4 *trav, V3 o, V3 d, uint32_t quads = 0xffffffffu) {
     FlatRay fr = flat_ray(sv, o, d, RL_F32_MAX);
     HitRec h;
     h.t = RL_F32_MAX, h.u = 0.0f, h.v = 0.0f, h.prim = RL_MISS;
-    uint32_t c0 = flat_candidates(fr, sv, flat, 0), c1 = flat_candidates(fr, sv, flat, 1);
-    for (int half = 0; half < 2; half++) {
-        uint32_t c = half ? c1 : c0;
-        while (c) {
-            const uint32_t b = 31u - (uint32_t)clz32(c);
-            c &= ~(1u << b);
-            const float4 *r = trav + 6 * flat_slot(sv, flat, half, b);
-            float4 r1 = r[1];
-            float t_, u_, v_;
-            if (tri_test(r[0], r1, r[2], r[3], o, d, h.t, &t_, &u_, &v_)) {
-                uint32_t prim_ = f2u(r1.w);
-                if (t_ < h.t || (h.prim != RL_MISS && prim_ < h.prim)) h.t = t_, h.u = u_, h.v = v_, h.prim = prim_;
+    uint64_t c = flat_candidates<CULL, false>(fr, sv, flat, quads);
+    uint32_t best_slot = 0u;
+    bool need_uv = false;
+    while (c) {
+        const uint32_t b = (uint32_t)ffs64(c) - 1u;
+        c &= c - 1;
+        const uint32_t slot = flat_slot(sv, flat, b);
+        const float4 *r = trav + 6 * slot;
+        float4 r1 = r[1];
+        float t_, u_, v_;
+        const int k = tri_test_lazy(r[0], r1, r[2], r[3], o, d, h.t, fr.rs8, &t_, &u_, &v_);
+        if (k) {
+            uint32_t prim_ = f2u(r1.w);
+            if (t_ < h.t || (h.prim != RL_MISS && prim_ < h.prim)) {
+                h.t = t_, h.prim = prim_, best_slot = slot, need_uv = k == 1;
+                if (k == 2) h.u = u_, h.v = v_;
             }
         }
+    }
+    if (need_uv) {
+        const float4 *r = trav + 6 * best_slot;
+        tri_uv(r[0], r[1], r[2], o, d, h.t, &h.u, &h.v);
     }
     return h;
 }
 // Any hit with t < thr over the flat table (Acceleration::visible): true when the segment is blocked.
 RL_HD bool flat_any(const SceneView &sv, const float4 *flat, const float4 *trav, V3 o, V3 d, float thr) {
     FlatRay fr = flat_ray(sv, o, d, thr);
-    uint32_t c0 = flat_candidates(fr, sv, flat, 0), c1 = flat_candidates(fr, sv, flat, 1);
-    for (int half = 0; half < 2; half++) {
-        uint32_t c = half ? c1 : c0;
-        while (c) {
-            const uint32_t b = 31u - (uint32_t)clz32(c);
-            c &= ~(1u << b);
-            const float4 *r = trav + 6 * flat_slot(sv, flat, half, b);
-            float t_, u_, v_;
-            if (tri_test(r[0], r[1], r[2], r[3], o, d, thr, &t_, &u_, &v_) && t_ < thr) return true;
-        }
+    uint64_t c = flat_candidates<false, true>(fr, sv, flat, 0xffffffffu);
+    while (c) {
+        const uint32_t b = (uint32_t)ffs64(c) - 1u;
+        c &= c - 1;
+        const float4 *r = trav + 6 * flat_slot(sv, flat, b);
+        float t_, u_, v_;
+        if (tri_test_lazy(r[0], r[1], r[2], r[3], o, d, thr, fr.rs8, &t_, &u_, &v_) && t_ < thr) return true;
     }
     return false;
 }
@@ -887,6 +977,54 @@ RL_HD void camera_generate(const SceneView &sv, float px, float py, V3 *o, V3 *d
     m4_mul_v4(sv.c2w, dl.x, dl.y, dl.z, 0.0f, g);
     *o = sv.cam_pos;
     *d = V3{g[0], g[1], g[2]};
+}
+
+// ---- camera rays of group-table scenes: which quads can the pixels [x0, x1] x [y0, y1] see? ---------------------
+// The pixel-space rectangle (jitter included, grown by 0.05 px), the pyramid of its four corner rays through the camera
+// position (Camera::generate in double), and per quad of the table the classic conservative frustum test: a quad whose
+// vertices (A and B, quad_verts[6 bit ..]) all lie more than eps outside ONE side plane cannot contain a point of any ray of
+// the block.  eps = 1e-4 x (scene + camera extent) dominates the rounding of the float ray directions (~1e-7 t) and of the
+// exact test's own acceptance region (ulps of the barycentrics).
+RL_HD uint32_t camera_block_mask(const SceneView &sv, const float4 *quad_verts, uint32_t valid_quads, uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1,
+                                 double eps) {
+    const double rx[2] = {(double)x0 - 0.05, (double)x1 + 1.05}, ry[2] = {(double)y0 - 0.05, (double)y1 + 1.05};
+    double D[4][3];
+    for (int c = 0; c < 4; c++) { // corners in cyclic order
+        const double px = rx[(c == 1 || c == 2) ? 1 : 0] / (double)sv.img_w, py = ry[c >= 2 ? 1 : 0] / (double)sv.img_h;
+        double h[4], g[3];
+        for (int r = 0; r < 4; r++) h[r] = (double)sv.s2c[r] * px + (double)sv.s2c[4 + r] * py + (double)sv.s2c[12 + r];
+        for (int r = 0; r < 3; r++) h[r] /= h[3];
+        for (int r = 0; r < 3; r++) g[r] = (double)sv.c2w[r] * h[0] + (double)sv.c2w[4 + r] * h[1] + (double)sv.c2w[8 + r] * h[2];
+        const double l = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+        for (int r = 0; r < 3; r++) D[c][r] = g[r] / l;
+    }
+    const double ctr[3] = {D[0][0] + D[1][0] + D[2][0] + D[3][0], D[0][1] + D[1][1] + D[2][1] + D[3][1], D[0][2] + D[1][2] + D[2][2] + D[3][2]};
+    double N[4][3];
+    for (int c = 0; c < 4; c++) {
+        const double *a = D[c], *e = D[(c + 1) & 3];
+        double nx = a[1] * e[2] - a[2] * e[1], ny = a[2] * e[0] - a[0] * e[2], nz = a[0] * e[1] - a[1] * e[0];
+        const double l = sqrt(nx * nx + ny * ny + nz * nz);
+        if (!(l > 1e-12)) return valid_quads; // degenerate pyramid (or NaN): see everything
+        const double sgn = (nx * ctr[0] + ny * ctr[1] + nz * ctr[2]) < 0.0 ? -1.0 : 1.0;
+        N[c][0] = sgn * nx / l, N[c][1] = sgn * ny / l, N[c][2] = sgn * nz / l;
+    }
+    uint32_t m = valid_quads;
+    for (uint32_t bit = 0; bit < 32u; bit++) {
+        if (!((valid_quads >> bit) & 1u)) continue;
+        bool culled = false;
+        for (int c = 0; c < 4 && !culled; c++) {
+            bool all_out = true;
+            for (int k = 0; k < 6; k++) {
+                const float4 v = quad_verts[6u * bit + k];
+                const double dist = N[c][0] * ((double)v.x - (double)sv.cam_pos.x) + N[c][1] * ((double)v.y - (double)sv.cam_pos.y) +
+                                    N[c][2] * ((double)v.z - (double)sv.cam_pos.z);
+                if (!(dist < -eps)) all_out = false; // NaN vertices keep the quad
+            }
+            culled = all_out;
+        }
+        if (culled) m &= ~(1u << bit);
+    }
+    return m;
 }
 
 // ---- materials ---------------------------------------------------------------------------------

@@ -140,6 +140,25 @@ __global__ void __launch_bounds__(kBlock) k_trace(SceneView sv, const uint32_t *
     }
 }
 
+// ---- camera rays of group-table scenes: which quads can a block of 32 pixels see? -------------------------------
+// One thread per block of 32 consecutive local pixels (the unit a warp of k_trace_flat traces): the pixel-space bounding
+// rectangle of the block (jitter included, grown by 0.05 px), the pyramid of its four corner rays through the camera position
+// (Camera::generate in double), and per quad of the table the classic conservative frustum test (rl_device.cuh:
+// camera_block_mask).  Culling only removes exact tests that must fail: images are unchanged.
+__global__ void __launch_bounds__(kBlock) k_camera_cull(SceneView sv, const float4 *__restrict__ quad_verts, uint32_t valid_quads,
+                                                        const uint32_t *__restrict__ pixel_list, uint32_t npix, uint32_t img_w, double eps,
+                                                        uint32_t *__restrict__ masks) {
+    const uint32_t nblk = (npix + 31u) >> 5;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nblk; b += gridDim.x * blockDim.x) {
+        uint32_t x0 = 0xffffffffu, x1 = 0u, y0 = 0xffffffffu, y1 = 0u;
+        for (uint32_t k = 32u * b; k < min(32u * b + 32u, npix); k++) {
+            const uint32_t pixel = __ldg(pixel_list + k), px = pixel % img_w, py = pixel / img_w;
+            x0 = min(x0, px), x1 = max(x1, px), y0 = min(y0, py), y1 = max(y1, py);
+        }
+        masks[b] = camera_block_mask(sv, quad_verts, valid_quads, x0, x1, y0, y1, eps);
+    }
+}
+
 // ---- group-table variants (scenes of a few dozen triangles, incoherent rays) ------------------------
 // One ray per thread, grid-stride, no traversal state: the reference's root-box test, the lockstep scan of the
 // flat group table (rl_device.cuh: flat_scan, packed f32x2 arithmetic, no divergence), then the exact triangle
@@ -150,17 +169,30 @@ __device__ __forceinline__ void stage_flat(const SceneView &sv, float4 *smem, ui
     __syncthreads();
 }
 // The two loops as device functions over a virtual grid (bid of nblocks), so that one launch can run both (below).
-__device__ __forceinline__ void trace_flat_body(const SceneView &sv, const float4 *flat, const float4 *trav, uint32_t bid, uint32_t nblocks, uint32_t n,
-                                                const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d, float4 *__restrict__ hit, bool camera) {
+// `cam_masks` (camera rays only, else nullptr): per block of 32 consecutive local pixels the quads that overlap the frustum of
+// those pixels (k_camera_cull).  A warp traces 32 consecutive paths = 32 consecutive local pixels of one sample index, so the
+// OR over the warp is (nearly always) one block's mask and whole groups of the table are skipped by the whole warp.
+template <bool CULL>
+__device__ __forceinline__ void trace_flat_body_t(const SceneView &sv, const float4 *flat, const float4 *trav, uint32_t bid, uint32_t nblocks, uint32_t n,
+                                                const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d, float4 *__restrict__ hit, bool camera,
+                                                const uint32_t *__restrict__ cam_masks, uint32_t npix) {
     for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n; i += nblocks * blockDim.x) {
         const float4 rd = ray_d[i];
         const V3 o = camera ? sv.cam_pos : xyz(ray_o[i]), d = xyz(rd); // camera rays share their origin: it is not stored (k_raygen)
         const V3 inv = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+        uint32_t quads = 0xffffffffu;
+        if (CULL) quads = __reduce_or_sync(__activemask(), __ldg(cam_masks + ((i % npix) >> 5)));
         HitRec h;
         h.t = RL_F32_MAX, h.u = 0.0f, h.v = 0.0f, h.prim = RL_MISS;
-        if (aabb_intersect_ref(sv.root_min, sv.root_max, o, inv, RL_EPSILON, RL_F32_MAX)) h = flat_closest(sv, flat, trav, o, d);
+        if (aabb_intersect_ref(sv.root_min, sv.root_max, o, inv, RL_EPSILON, RL_F32_MAX)) h = flat_closest<CULL>(sv, flat, trav, o, d, quads);
         hit[i] = make_float4(h.t, h.u, h.v, u2f(h.prim));
     }
+}
+__device__ __forceinline__ void trace_flat_body(const SceneView &sv, const float4 *flat, const float4 *trav, uint32_t bid, uint32_t nblocks, uint32_t n,
+                                                const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d, float4 *__restrict__ hit, bool camera,
+                                                const uint32_t *__restrict__ cam_masks, uint32_t npix) {
+    if (cam_masks) trace_flat_body_t<true>(sv, flat, trav, bid, nblocks, n, ray_o, ray_d, hit, camera, cam_masks, npix);
+    else trace_flat_body_t<false>(sv, flat, trav, bid, nblocks, n, ray_o, ray_d, hit, camera, cam_masks, npix);
 }
 __device__ __forceinline__ void shadow_flat_body(const SceneView &sv, const float4 *flat, const float4 *trav, uint32_t bid, uint32_t nblocks, uint32_t n,
                                                  const float4 *__restrict__ sh_a, const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c,
@@ -183,18 +215,22 @@ __device__ __forceinline__ void shadow_flat_body(const SceneView &sv, const floa
     for (int off = 16; off > 0; off >>= 1) c_vis += __shfl_down_sync(0xffffffffu, c_vis, off);
     if ((threadIdx.x & 31u) == 0 && c_vis) atomicAdd(&counters->shadow_visible, (unsigned long long)c_vis);
 }
-__global__ void __launch_bounds__(kBlock) k_trace_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
-                                                       const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t n_trav_f4, uint32_t camera) {
+#ifndef RL_TRAV_MINBLOCKS
+#define RL_TRAV_MINBLOCKS 5 // resident CTAs per SM the group-table kernels are compiled for (register cap; A/B hook)
+#endif
+__global__ void __launch_bounds__(kBlock, RL_TRAV_MINBLOCKS) k_trace_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
+                                                       const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t n_trav_f4, uint32_t camera,
+                                                       const uint32_t *__restrict__ cam_masks, uint32_t npix) {
     extern __shared__ float4 smem[];
-    const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
+    const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4 + RL_FLAT_TAIL_F4;
     stage_flat(sv, smem, n_flat_f4, n_trav_f4);
-    trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, gridDim.x, *count, ray_o, ray_d, hit, camera != 0u);
+    trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, gridDim.x, *count, ray_o, ray_d, hit, camera != 0u, cam_masks, npix);
 }
-__global__ void __launch_bounds__(kBlock) k_shadow_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ sh_a,
+__global__ void __launch_bounds__(kBlock, RL_TRAV_MINBLOCKS) k_shadow_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ sh_a,
                                                         const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c, float4 *__restrict__ lacc,
                                                         Counters *counters, uint32_t n_trav_f4) {
     extern __shared__ float4 smem[];
-    const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
+    const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4 + RL_FLAT_TAIL_F4;
     stage_flat(sv, smem, n_flat_f4, n_trav_f4);
     shadow_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, gridDim.x, *count, sh_a, sh_b, sh_c, lacc, counters);
 }
@@ -202,15 +238,16 @@ __global__ void __launch_bounds__(kBlock) k_shadow_flat(SceneView sv, const uint
 // to the per-path accumulators, which the traversal does not touch): one launch runs both, CTAs [0, trace_blocks) on the
 // ray queue and the rest on the shadow queue.  Every kernel costs ~7 us whatever its queue length (launch + table staging
 // + one scan at minimal occupancy), and a frame has ~40 iterations: two launches per iteration instead of three.
-__global__ void __launch_bounds__(kBlock) k_trace_shadow_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
+__global__ void __launch_bounds__(kBlock, RL_TRAV_MINBLOCKS) k_trace_shadow_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
                                                               const float4 *__restrict__ ray_d, float4 *__restrict__ hit,
                                                               const uint32_t *__restrict__ sh_count, const float4 *__restrict__ sh_a,
                                                               const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c, float4 *__restrict__ lacc,
-                                                              Counters *counters, uint32_t n_trav_f4, uint32_t trace_blocks, uint32_t camera) {
+                                                              Counters *counters, uint32_t n_trav_f4, uint32_t trace_blocks, uint32_t camera,
+                                                              const uint32_t *__restrict__ cam_masks, uint32_t npix) {
     extern __shared__ float4 smem[];
-    const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
+    const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4 + RL_FLAT_TAIL_F4;
     stage_flat(sv, smem, n_flat_f4, n_trav_f4);
-    if (blockIdx.x < trace_blocks) trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, trace_blocks, *count, ray_o, ray_d, hit, camera != 0u);
+    if (blockIdx.x < trace_blocks) trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, trace_blocks, *count, ray_o, ray_d, hit, camera != 0u, cam_masks, npix);
     else shadow_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x - trace_blocks, gridDim.x - trace_blocks, *sh_count, sh_a, sh_b, sh_c, lacc, counters);
 }
 
@@ -415,7 +452,7 @@ __global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams i
     extern __shared__ float4 smem[];
     const float4 *nodes = sv.nodes, *trav = sv.trav, *flat = sv.flat;
     if (sv.n_groups) { // group table + exact-test records in shared memory, as in k_trace_flat
-        const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4;
+        const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4 + RL_FLAT_TAIL_F4;
         stage_flat(sv, smem, n_flat_f4, n_trav_f4);
         flat = smem;
         trav = smem + n_flat_f4;

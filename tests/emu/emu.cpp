@@ -8,6 +8,7 @@
 // that the device code takes the same discrete decisions as the oracle.  It is never built
 // into or loaded by the product library.
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -107,7 +108,7 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
     sv.uvs = hs.uvs.empty() ? nullptr : hs.uvs.data(), sv.tex = hs.tex.empty() ? nullptr : hs.tex.data(), sv.texels = hs.texels.data();
     sv.ntris = hs.ntris, sv.n_emitters = hs.n_emitters;
     sv.root_ref = s->root_ref;
-    sv.flat = s->flat.f4.data(), sv.n_groups = s->flat.n_groups, sv.flat_valid[0] = s->flat.valid[0], sv.flat_valid[1] = s->flat.valid[1];
+    sv.flat = s->flat.f4.data(), sv.n_groups = s->flat.n_groups, sv.flat_valid_a = s->flat.valid_a, sv.flat_valid_b = s->flat.valid_b;
     sv.flat_delta = s->flat.delta;
     sv.root_min = V3{hs.root_min[0], hs.root_min[1], hs.root_min[2]};
     sv.root_max = V3{hs.root_max[0], hs.root_max[1], hs.root_max[2]};
@@ -178,6 +179,21 @@ int emu_bvh_validate(const emu_scene *s) {
     return 0;
 }
 
+// Camera ray of pixel (px, py) the way k_trace_flat traces it on group-table scenes: only the quads the pixel's frustum overlaps
+// (camera_block_mask; here a block of ONE pixel, the tightest mask there is -- the device uses blocks of 32 pixels).
+static HitRec trace_camera(const emu_scene *s, uint32_t px, uint32_t py, V3 o, V3 d) {
+    const SceneView &sv = s->sv;
+    if (!sv.n_groups || getenv("RL_NO_CAM_CULL")) return trace_closest(sv, sv.nodes, sv.trav, o, d);
+    const HostScene &hs = s->hs;
+    const double ext = (double)hs.abs_max + std::max(std::max(std::fabs((double)hs.cam_pos[0]), std::fabs((double)hs.cam_pos[1])), std::fabs((double)hs.cam_pos[2]));
+    const uint32_t quads = camera_block_mask(sv, s->flat.quad_verts.data(), s->flat.valid_a, px, px, py, py, 1e-4 * ext);
+    HitRec h;
+    h.t = RL_F32_MAX, h.u = 0.0f, h.v = 0.0f, h.prim = RL_MISS;
+    V3 inv = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    if (aabb_intersect_ref(sv.root_min, sv.root_max, o, inv, RL_EPSILON, RL_F32_MAX)) h = flat_closest<true>(sv, sv.flat, sv.trav, o, d, quads);
+    return h;
+}
+
 int emu_trace(const emu_scene *s, size_t n, const float *o, const float *d, uint32_t *prim, float *tuv) {
     for (size_t i = 0; i < n; i++) {
         HitRec h = trace_closest(s->sv, s->sv.nodes, s->sv.trav, V3{o[3 * i], o[3 * i + 1], o[3 * i + 2]}, V3{d[3 * i], d[3 * i + 1], d[3 * i + 2]});
@@ -201,7 +217,12 @@ int emu_primary_hits(const emu_scene *s, uint32_t *prim, float *tuv) {
             V3 o, d;
             camera_generate(s->sv, (float)x + 0.5f, (float)y + 0.5f, &o, &d);
             size_t i = (size_t)y * W + x;
-            emu_trace(s, 1, &o.x, &d.x, prim + i, tuv ? tuv + 3 * i : nullptr);
+            HitRec h = trace_camera(s, x, y, o, d);
+            prim[i] = h.prim;
+            if (tuv) {
+                bool miss = h.prim == RL_MISS;
+                tuv[3 * i] = miss ? 0.0f : h.t, tuv[3 * i + 1] = miss ? 0.0f : h.u, tuv[3 * i + 2] = miss ? 0.0f : h.v;
+            }
         }
     return 0;
 }
@@ -286,7 +307,7 @@ int emu_render(const emu_scene *s, const rl_integrator_desc *I, uint32_t spp, ui
                 if (I->kind == RL_INTEGRATOR_AO) {
                     // k_trace -> k_shade_direct1 (ao_begin / ao_sample) -> k_trace -> k_shade_direct2 (ao_finish)
                     S.segments++;
-                    HitRec h = trace_closest(sv, sv.nodes, sv.trav, o, d);
+                    HitRec h = trace_camera(s, px, py, o, d);
                     if (h.prim != RL_MISS) S.hits++;
                     DirectCtx cx;
                     ao_begin(sv, ip, o, d, h, st.rng_n, pixel, sidx, &cx);
@@ -308,7 +329,7 @@ int emu_render(const emu_scene *s, const rl_integrator_desc *I, uint32_t spp, ui
                     // k_trace -> k_shade_direct1 -> k_shadow -> k_trace -> k_shade_direct2; slots summed in order (k_accum)
                     std::vector<Col> slots(1 + ip.nb_light_samples + ip.nb_bsdf_samples, Col{0.0f, 0.0f, 0.0f});
                     S.segments++;
-                    HitRec h = trace_closest(sv, sv.nodes, sv.trav, o, d);
+                    HitRec h = trace_camera(s, px, py, o, d);
                     if (h.prim != RL_MISS) S.hits++;
                     DirectCtx cx;
                     direct_begin(sv, ip, o, d, h, st.rng_n, pixel, sidx, &cx);
@@ -348,7 +369,7 @@ int emu_render(const emu_scene *s, const rl_integrator_desc *I, uint32_t spp, ui
                 for (;;) {
                     iter++;
                     S.segments++;
-                    HitRec h = trace_closest(sv, sv.nodes, sv.trav, o, d); // k_trace
+                    HitRec h = iter == 1 ? trace_camera(s, px, py, o, d) : trace_closest(sv, sv.nodes, sv.trav, o, d); // k_trace
                     if (h.prim != RL_MISS) S.hits++;
                     StepOut so;
                     path_step(sv, ip, o, d, h, st, pixel, sidx, &so); // k_shade
