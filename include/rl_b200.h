@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RL_B200_ABI_VERSION 2
+#define RL_B200_ABI_VERSION 3
 
 typedef struct rl_ctx rl_ctx;     /* one per GPU / per rank; single-owner, not thread-safe */
 typedef struct rl_scene rl_scene; /* device-resident scene: geometry, LBVH, emitters, camera */
@@ -198,6 +198,9 @@ typedef struct rl_stats {
     double ms_total;  /* CUDA-event time of the whole rl_render device work                    */
     double ms_raygen, ms_trace, ms_shade, ms_shadow, ms_accum; /* filled when profiling is on   */
     double ms_h2d, ms_d2h, ms_reduce;
+    double ms_tail;           /* k_tail launches (profiling on)                                 */
+    uint64_t shadow_traced;   /* shadow segments actually traced (valid light samples with a non-zero contribution) */
+    uint64_t launches_trace, launches_shade; /* launches behind ms_trace / ms_shade (profiling on) */
 } rl_stats;
 
 /* ---- context -------------------------------------------------------------------------------- */
@@ -215,7 +218,9 @@ int rl_abi_version(void);
  * value (integrators/mod.rs:219-228); here the caller owns the buffer.  NULL on failure; rl_host_free(NULL) is a no-op. */
 void *rl_host_alloc(size_t bytes);
 void rl_host_free(void *p);
-/* Toggle per-stage CUDA-event timing (adds synchronisation; off by default). */
+/* Per-launch CUDA-event timing (no synchronisation: events are read when the frame is complete).  0 = off; 1 = trace and
+ * shadow kernels launched separately, so that ms_trace / ms_shadow are per stage; 2 = exactly the kernels of an untimed frame
+ * (ms_trace then holds the fused closest-hit + shadow launches). */
 int rl_set_profiling(rl_ctx *ctx, int on);
 
 /* ---- scene ----------------------------------------------------------------------------------- */

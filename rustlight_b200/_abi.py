@@ -95,7 +95,8 @@ class rl_stats(C.Structure):
                 ("kernel_launches", C.c_uint64), ("ms_total", C.c_double), ("ms_raygen", C.c_double),
                 ("ms_trace", C.c_double), ("ms_shade", C.c_double), ("ms_shadow", C.c_double),
                 ("ms_accum", C.c_double), ("ms_h2d", C.c_double), ("ms_d2h", C.c_double),
-                ("ms_reduce", C.c_double)]
+                ("ms_reduce", C.c_double), ("ms_tail", C.c_double), ("shadow_traced", C.c_uint64),
+                ("launches_trace", C.c_uint64), ("launches_shade", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <string>
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -66,7 +67,7 @@ struct rl_ctx {
     size_t mem_total = 0; // device memory (sizes the wavefront batches)
     cudaStream_t stream = nullptr;
     std::string err;
-    bool profiling = false;
+    int profiling = 0; // 0 off, 1 per-stage kernels, 2 events around the kernels of an untimed frame
     ncclComm_t comm = nullptr;
     // wavefront buffers (grown on demand)
     size_t cap_paths = 0, cap_shadow = 0, cap_lacc = 0; // ray/hit queues, shadow queues, radiance slots (records)
@@ -86,6 +87,12 @@ struct rl_ctx {
     Counters *h_counters = nullptr;
     cudaEvent_t ev[8] = {};
     uint64_t launches = 0;
+    // per-launch events of a profiled frame (rl_set_profiling) and the queue-length prediction of the device-decided schedule
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<uint8_t> ev_kind;
+    size_t ev_used = 0;
+    std::vector<double> pred_ratio; // queue length of iteration k / paths of the batch, last frame
+    uint64_t pred_key = 0;
 };
 
 struct rl_scene {
@@ -111,6 +118,7 @@ struct rl_scene {
     uint32_t kind_mask = 1;    // bit k: some mesh has rl_bsdf_kind k (selects the k_shade specialisation)
     bool flat_ok = false; // group table present: incoherent rays use k_trace_flat / k_shadow_flat
     size_t smem_flat_bytes = 0;
+    uint32_t scene_gen = 0; // distinguishes scenes that reuse an address (queue-length prediction key)
 };
 
 #define CK(call)                                                                                                   \
@@ -145,14 +153,21 @@ static int grid_for(const rl_ctx *ctx, size_t n, int per_sm, int block = kBlock)
 //   resident (5) 4.93, 8 4.77, 16 4.68, 32 4.60, 64 4.56 ms -- 32 keeps the per-CTA scene staging (5 KB) negligible.
 //   k_shade: one wave of resident CTAs (4 per SM at 64 registers); 6/SM 5.52 ms vs 4.81 ms.
 static constexpr int kTravPerSm = 32;
-template <typename K>
-static int resident_per_sm(K kernel, size_t smem, int block = kBlock) {
-    static std::vector<std::pair<size_t, int>> cache; // one static per kernel type
+// Resident CTAs per SM of a kernel at a block size / dynamic shared memory size (occupancy API), cached per (kernel, block, smem).
+static int resident_per_sm(const void *kernel, size_t smem, int block = kBlock) {
+    struct Key {
+        const void *k;
+        size_t smem;
+        int block, nb;
+    };
+    static std::mutex mu;
+    static std::vector<Key> cache;
+    std::lock_guard<std::mutex> lock(mu);
     for (auto &c : cache)
-        if (c.first == smem) return c.second;
+        if (c.k == kernel && c.smem == smem && c.block == block) return c.nb;
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, block, smem) != cudaSuccess || nb < 1) nb = 1;
-    cache.push_back({smem, nb});
+    cache.push_back({kernel, smem, block, nb});
     return nb;
 }
 static int tree_per_sm() {
@@ -286,13 +301,14 @@ void rl_destroy(rl_ctx *ctx) {
     cudaFreeHost(ctx->h_counts), cudaFreeHost(ctx->h_counters);
     for (auto &ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 int rl_set_profiling(rl_ctx *ctx, int on) {
     if (!ctx) return RL_ERR_INVALID;
-    ctx->profiling = on != 0;
+    ctx->profiling = on < 0 ? 0 : (on > 2 ? 2 : on);
     return RL_OK;
 }
 
@@ -326,6 +342,8 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     if (!ctx || !desc || !out) return RL_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     rl_scene *s = new rl_scene;
+    static uint32_t scene_counter = 0;
+    s->scene_gen = ++scene_counter;
     std::string err;
     if (!build_host_scene(desc, s->hs, err)) {
         ctx->err = "rl_scene_create: " + err;
@@ -640,33 +658,33 @@ static int validate(rl_ctx *ctx, const rl_scene *scene, const rl_integrator_desc
 
 template <bool SMEM>
 static void launch_trace(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_t n, const float4 *ro, const float4 *rd, float4 *hit,
-                         bool coherent = false, bool camera_origin = false, const uint32_t *cam_masks = nullptr) {
+                         const uint32_t *done_at, uint32_t my_k, bool coherent = false, bool camera_origin = false, const uint32_t *cam_masks = nullptr) {
     SceneView sv = sc->sv;
     const bool tree = coherent && sc->coherent_tree >= 1;
     if (!tree && sc->flat_ok) {
         sv.n_groups = sc->flat.n_groups;
-        k_trace_flat<<<grid_for(ctx, n, trav_per_sm()), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_trav_f4, camera_origin ? 1u : 0u, cam_masks, ctx->pl_npix);
+        k_trace_flat<<<grid_for(ctx, n, trav_per_sm()), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_trav_f4, camera_origin ? 1u : 0u, cam_masks, ctx->pl_npix, done_at, my_k);
         ctx->launches++;
         return;
     }
     sv.root_ref = tree ? sc->root_tree : sc->root_flat;
-    k_trace<SMEM><<<grid_for(ctx, n, tree_per_sm()), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_node_f4, sc->n_trav_f4);
+    k_trace<SMEM><<<grid_for(ctx, n, tree_per_sm()), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_node_f4, sc->n_trav_f4, done_at, my_k);
     ctx->launches++;
 }
 template <bool SMEM>
-static void launch_shadow(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_t n, bool coherent = false) {
+static void launch_shadow(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_t n, const uint32_t *done_at, uint32_t my_k, bool coherent = false) {
     SceneView sv = sc->sv;
     const bool tree = coherent && sc->coherent_tree >= 2;
     if (!tree && sc->flat_ok) {
         sv.n_groups = sc->flat.n_groups;
         k_shadow_flat<<<grid_for(ctx, n, trav_per_sm()), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc, ctx->d_counters,
-                                                                                          sc->n_trav_f4);
+                                                                                          sc->n_trav_f4, done_at, my_k);
         ctx->launches++;
         return;
     }
     sv.root_ref = tree ? sc->root_tree : sc->root_flat;
     k_shadow<SMEM><<<grid_for(ctx, n, tree_per_sm()), kBlock, SMEM ? sc->smem_bytes : 0, ctx->stream>>>(sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc,
-                                                                                             ctx->d_counters, sc->n_node_f4, sc->n_trav_f4);
+                                                                                             ctx->d_counters, sc->n_node_f4, sc->n_trav_f4, done_at, my_k);
     ctx->launches++;
 }
 
@@ -692,6 +710,51 @@ static int ensure_cam_masks(rl_ctx *ctx, rl_scene *sc) {
     return RL_OK;
 }
 
+// ---- per-launch timing without synchronisation ---------------------------------------------------------
+// One CUDA event after every launch (and one at the start); the time between two consecutive events is the duration of
+// the kernel launched in between (plus its launch gap), attributed to that kernel's stage.  Nothing is read until the
+// frame is complete, so the timed kernels are exactly the ones of an untimed frame.
+enum EvKind : uint8_t { EV_START = 0, EV_RAYGEN, EV_TRACE, EV_SHADE, EV_SHADOW, EV_TAIL, EV_ACCUM, EV_OTHER };
+static void ev_reset(rl_ctx *ctx) { ctx->ev_used = 0; }
+static void ev_mark(rl_ctx *ctx, EvKind kind) {
+    if (!ctx->profiling) return;
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        ctx->ev_pool.push_back(e);
+        ctx->ev_kind.push_back(EV_OTHER);
+    }
+    cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream);
+    ctx->ev_kind[ctx->ev_used] = (uint8_t)kind;
+    ctx->ev_used++;
+}
+static void ev_collect(rl_ctx *ctx, rl_stats &S) {
+    for (size_t i = 1; i < ctx->ev_used; i++) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[i - 1], ctx->ev_pool[i]) != cudaSuccess) continue;
+        switch (ctx->ev_kind[i]) {
+        case EV_RAYGEN: S.ms_raygen += ms; break;
+        case EV_TRACE: S.ms_trace += ms, S.launches_trace++; break;
+        case EV_SHADE: S.ms_shade += ms, S.launches_shade++; break;
+        case EV_SHADOW: S.ms_shadow += ms; break;
+        case EV_TAIL: S.ms_tail += ms; break;
+        case EV_ACCUM: S.ms_accum += ms; break;
+        default: break;
+        }
+    }
+}
+
+// Queue length expected at wavefront iteration k of a batch of n_paths paths: the previous frame's lengths for the same scene and
+// integrator when there is one (averaging wrappers render the same thing again and again), else a geometric model.  Only grid
+// sizes and the position of the k_tail window depend on it -- never a result.
+static size_t predict_len(const rl_ctx *ctx, size_t n_paths, uint32_t k) {
+    double r;
+    if (k < ctx->pred_ratio.size()) r = ctx->pred_ratio[k];
+    else if (!ctx->pred_ratio.empty()) r = ctx->pred_ratio.back() * std::pow(0.6, (double)(k + 1 - ctx->pred_ratio.size()));
+    else r = std::pow(0.62, (double)k);
+    return (size_t)std::min<double>((double)n_paths, std::ceil(r * (double)n_paths));
+}
+
 static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, const rl_render_opts *o, rl_stats *stats) {
     int rc = validate(ctx, sc, I, o);
     if (rc != RL_OK) return rc;
@@ -703,9 +766,13 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
     cudaStream_t st = ctx->stream;
     rl_stats S{};
     ctx->launches = 0;
-    CK(cudaMemsetAsync(ctx->frame, 0, (size_t)W * H * 3 * sizeof(float), st));
+    ev_reset(ctx);
+    if (ctx->nranks > 1) CK(cudaMemsetAsync(ctx->frame, 0, (size_t)W * H * 3 * sizeof(float), st)); // one rank: k_finish writes every pixel
     CK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), st));
     CK(cudaEventRecord(ctx->ev[0], st));
+    ev_mark(ctx, EV_START);
+    uint32_t hist_iters = 0;       // iterations scheduled in the last batch (entries of d_hist worth reading back)
+    size_t hist_paths = 0;
     if (npix > 0) {
         const bool ao = I->kind == RL_INTEGRATOR_AO; // runs on the two stages of `direct`: no light samples, one extension ray
         const bool direct = I->kind == RL_INTEGRATOR_DIRECT || ao;
@@ -738,14 +805,25 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
         ip.ao_max_distance = I->ao_max_distance, ip.ao_normal_correction = I->ao_normal_correction;
         ip.seed_h = seed_hash(o->seed);
         ip.npix = npix, ip.img_w = W;
-        const bool prof = ctx->profiling;
+        ip.npix_mul = 0u, ip.npix_shift = 0u;
+        if (npix > 1u) { // division by the invariant npix as multiply-high + shift, exact for ids < 2^31 (checked per batch below)
+            uint32_t l = 0;
+            while (((uint64_t)1 << l) < npix) l++;
+            const uint64_t m = (((uint64_t)1 << (31 + l)) / npix) + 1u;
+            if (m <= 0xffffffffull && l >= 1) ip.npix_mul = (uint32_t)m, ip.npix_shift = l - 1u;
+        }
+        const int prof = ctx->profiling; // 0 off, 1 per-stage kernels (trace and shadow launched separately), 2 the kernels of an untimed frame
         const bool sort_on = o->material_sort == 1u || (o->material_sort >= 2u && sc->n_bsdf_kinds > 1u);
-        float ms;
+        // the prediction of the queue lengths belongs to (scene, integrator): forget it when either changes
+        const uint64_t pred_key = (uint64_t)(uintptr_t)sc ^ ((uint64_t)I->kind << 56) ^ ((uint64_t)(uint32_t)I->max_depth << 40) ^ ((uint64_t)(uint32_t)I->rr_depth << 24) ^
+                                  ((uint64_t)I->strategy << 20) ^ ((uint64_t)sc->scene_gen << 4);
+        if (ctx->pred_key != pred_key) ctx->pred_ratio.clear(), ctx->pred_key = pred_key;
+        uint32_t *done_at = ctx->d_counts + 3;
         for (uint32_t s0 = 0; s0 < o->spp; s0 += batch) {
             const uint32_t nb = std::min(batch, o->spp - s0);
             const size_t n_paths = (size_t)npix * nb;
             ip.sample_base = o->sample_offset + s0;
-            if (prof) CK(cudaEventRecord(ctx->ev[2], st));
+            if (n_paths >= ((size_t)1 << 31)) ip.npix_mul = 0u; // the multiply-high form is exact below 2^31 only
             // group-table scenes: the camera rays' origin (sv.cam_pos), path id (= queue index) and path state are constants
             // that the first k_trace_flat / k_shade fill in themselves: raygen writes 32 B per path (direction, accumulator) instead of 80
             const bool camera_o = sc->flat_ok && sc->coherent_tree == 0;
@@ -758,215 +836,183 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
             k_raygen<<<grid_for(ctx, n_paths, 8), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, (uint32_t)n_paths, camera_o ? nullptr : ctx->ray_o[0],
                                                                    ctx->ray_d[0], ctx->lacc, n_slots);
             ctx->launches++;
-            if (prof) {
-                CK(cudaEventRecord(ctx->ev[3], st));
-                CK(cudaEventSynchronize(ctx->ev[3]));
-                CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-                S.ms_raygen += ms;
-            }
-            uint32_t init[4] = {(uint32_t)n_paths, 0, 0, 0};
+            ev_mark(ctx, EV_RAYGEN);
+            uint32_t init[4] = {(uint32_t)n_paths, 0, 0, 0xffffffffu}; // [3] = done_at
             CK(cudaMemcpyAsync(ctx->d_counts, init, sizeof(init), cudaMemcpyHostToDevice, st));
-            size_t n = n_paths;
-            int cur = 0;
-            uint64_t iter = 0;
             if (direct) {
-                // primary rays -> stage 1 (emission, light samples, BSDF samples) -> shadow rays -> extension rays -> stage 2
+                // primary rays -> stage 1 (emission, light samples, BSDF samples) -> shadow rays -> extension rays -> stage 2; nothing is read
+                // back: the second stage's grid is sized from its upper bound (every primary ray spawns at most nbs extension rays)
                 uint32_t *c_in = ctx->d_counts, *c_out = ctx->d_counts + 1, *c_sh = ctx->d_counts + 2;
-                if (prof) CK(cudaEventRecord(ctx->ev[2], st));
-                if (sc->smem_ok) launch_trace<true>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, true, camera_o, cam_masks);
-                else launch_trace<false>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, true, camera_o, cam_masks);
-                if (prof) CK(cudaEventRecord(ctx->ev[3], st));
+                const size_t n = n_paths;
+                if (sc->smem_ok) launch_trace<true>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, done_at, 0u, true, camera_o, cam_masks);
+                else launch_trace<false>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, done_at, 0u, true, camera_o, cam_masks);
+                ev_mark(ctx, EV_TRACE);
                 k_shade_direct1<<<grid_for(ctx, n, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, c_in, (uint32_t)n_paths, ctx->ray_o[0], ctx->ray_d[0],
                                                                         ctx->state[0], ctx->hit, ctx->ray_o[1], ctx->ray_d[1], ctx->state[1], c_out, ctx->sh_a,
                                                                         ctx->sh_b, ctx->sh_c, c_sh, ctx->lacc, ctx->d_counters, camera_o ? 3u : 1u);
                 ctx->launches++;
-                if (prof) CK(cudaEventRecord(ctx->ev[4], st));
-                if (sc->smem_ok) launch_shadow<true>(ctx, sc, c_sh, n * std::max(1u, nl), true);
-                else launch_shadow<false>(ctx, sc, c_sh, n * std::max(1u, nl), true);
-                if (prof) CK(cudaEventRecord(ctx->ev[5], st));
-                CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                CK(cudaGetLastError());
-                if (prof) {
-                    CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-                    S.ms_trace += ms;
-                    CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
-                    S.ms_shade += ms;
-                    CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
-                    S.ms_shadow += ms;
+                ev_mark(ctx, EV_SHADE);
+                if (nl > 0) {
+                    if (sc->smem_ok) launch_shadow<true>(ctx, sc, c_sh, n * nl, done_at, 0u, true);
+                    else launch_shadow<false>(ctx, sc, c_sh, n * nl, done_at, 0u, true);
+                    ev_mark(ctx, EV_SHADOW);
                 }
-                S.segments += n;
-                iter = 1;
-                const size_t n2 = ctx->h_counts[1];
-                if (n2 > 0) {
-                    if (prof) CK(cudaEventRecord(ctx->ev[2], st));
-                    if (sc->smem_ok) launch_trace<true>(ctx, sc, c_out, n2, ctx->ray_o[1], ctx->ray_d[1], ctx->hit);
-                    else launch_trace<false>(ctx, sc, c_out, n2, ctx->ray_o[1], ctx->ray_d[1], ctx->hit);
-                    if (prof) CK(cudaEventRecord(ctx->ev[3], st));
+                if (nbs > 0) {
+                    const size_t n2 = n * nbs;
+                    if (sc->smem_ok) launch_trace<true>(ctx, sc, c_out, n2, ctx->ray_o[1], ctx->ray_d[1], ctx->hit, done_at, 0u);
+                    else launch_trace<false>(ctx, sc, c_out, n2, ctx->ray_o[1], ctx->ray_d[1], ctx->hit, done_at, 0u);
+                    ev_mark(ctx, EV_TRACE);
                     k_shade_direct2<<<grid_for(ctx, n2, 8), kBlock, 0, st>>>(sc->sv, ip, c_out, ctx->ray_o[1], ctx->ray_d[1], ctx->state[1], ctx->hit, ctx->lacc,
                                                                              ctx->d_counters);
                     ctx->launches++;
-                    if (prof) {
-                        CK(cudaEventRecord(ctx->ev[4], st));
-                        CK(cudaEventSynchronize(ctx->ev[4]));
-                        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-                        S.ms_trace += ms;
-                        CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
-                        S.ms_shade += ms;
-                    }
-                    S.segments += n2;
-                    iter = 2;
+                    ev_mark(ctx, EV_SHADE);
                 }
-                n = 0;
-            }
-            if (n > 0) {
-                // Queue lengths live in a per-iteration history on the device (iteration k reads hist[k] and
-                // appends to hist[k+1]), so the host launches RL_SYNC_GROUP iterations back to back and only
-                // then reads the lengths; launches past the end of the longest path see empty queues.
+                k_tally<<<1, 1, 0, st>>>(ctx->d_counts, nullptr, 2u, done_at, 0u, ctx->d_counters); // rays of the two stages: d_counts[0], d_counts[1]
+                ctx->launches++;
+            } else {
+                // `path`.  Queue lengths live in a per-iteration history on the device (iteration k reads hist[k] and appends to
+                // hist[k+1]); the whole batch is enqueued without reading anything back (see rl_kernels.cuh: device-decided schedule).
                 uint32_t *qc = ctx->d_hist, *shc = ctx->d_hist + kMaxIters;
                 CK(cudaMemsetAsync(ctx->d_hist, 0, 2 * kMaxIters * sizeof(uint32_t), st));
                 k_set_u32<<<1, 1, 0, st>>>(qc, (uint32_t)n_paths);
-                uint32_t k = 0, k_read = 0;
-                size_t n_ub = n_paths; // upper bound of the current queue length (lengths never grow)
-                // Group-table scenes outside profiling mode: two launches per iteration (k_trace_shadow_flat + k_shade).  The
-                // per-stage timings of profiling mode need the separate kernels.
-                const bool fuse = !prof && sc->flat_ok && sc->coherent_tree == 0 && getenv("RL_NO_FUSE") == nullptr;
-                // hand-over to k_tail (rl_kernels.cuh) once the queue is at most this long; profiling mode keeps the per-stage kernels
-                const size_t tail_max = prof ? 0 : tail_threshold(ctx);
-                bool tail_done = false;
+                const bool flat = sc->flat_ok && sc->coherent_tree == 0;
+                const bool fuse_ok = prof != 1 && flat && getenv("RL_NO_FUSE") == nullptr;
+                const size_t tail_max = tail_threshold(ctx); // 0: never hand over (pure wavefront; test / A-B hook)
+                // k_tail window: from two iterations before the predicted hand-over a launch after every iteration, the last one unconditional
+                uint32_t k_pred = 0;
+                while (k_pred < 200u && predict_len(ctx, n_paths, k_pred) > std::max<size_t>(tail_max, 1)) k_pred++;
+                uint32_t win_lo = k_pred > 2u ? k_pred - 2u : 1u, win_hi = k_pred + 6u; // queue indices a k_tail launch is scheduled for
+                if (I->max_depth >= 0) win_hi = std::min<uint32_t>(win_hi, (uint32_t)I->max_depth), win_lo = std::min(win_lo, win_hi);
+                const uint32_t *zero_count = ctx->d_hist + 2 * kMaxIters - 1; // never written
+                int cur = 0;
                 size_t ub_prev = n_paths;
-                const uint32_t *zero_count = ctx->d_hist + 2 * kMaxIters - 1; // never written: k + group < kMaxIters
-                while (n_ub > 0) {
-                    // iterations launched between two reads of the queue lengths: few while the queues are long (an iteration
-                    // past the end of the longest path is three empty launches), more in the tail, where the host round trip
-                    // costs more than the launches
-                    uint32_t group = prof ? 1u : (n_ub > ((size_t)1 << 20) ? (uint32_t)RL_SYNC_GROUP : 4u * (uint32_t)RL_SYNC_GROUP);
-                    if (tail_max && !prof) {
-                        // aim the next look at the queue length at the iteration where it is expected to fit k_tail: lengths shrink by
-                        // a near-constant factor per bounce (taken from the last two lengths read)
-                        double rate = 0.7;
-                        if (k >= 1 && ctx->h_hist[k - 1] > 0) rate = std::min(0.95, std::max(0.3, (double)ctx->h_hist[k] / (double)ctx->h_hist[k - 1]));
-                        const double g = std::ceil(std::log((double)n_ub / (double)tail_max) / std::log(1.0 / rate));
-                        group = (uint32_t)std::min<double>(k == 0 ? RL_SYNC_GROUP : 2 * RL_SYNC_GROUP, std::max(1.0, g));
-                    }
-                    if (k + group >= kMaxIters) {
+                uint32_t k = 0;
+                bool legacy = tail_max == 0;
+                uint32_t legacy_read = 0;
+                for (;; k++) {
+                    if (k + 2 >= kMaxIters) {
                         ctx->err = "rl_render: a path exceeded 4095 wavefront iterations (no Russian roulette in a closed scene?)";
                         return RL_ERR_UNSUPPORTED;
                     }
-                    for (uint32_t g = 0; g < group; g++, k++) {
-                        if (prof) CK(cudaEventRecord(ctx->ev[2], st));
-                        if (fuse) { // rays of iteration k + shadow segments of iteration k-1 in one launch (k_trace_shadow_flat)
-                            SceneView sv = sc->sv;
-                            sv.n_groups = sc->flat.n_groups;
-                            const int tb = grid_for(ctx, n_ub, trav_per_sm()), sb = k == 0 ? 0 : grid_for(ctx, ub_prev, trav_per_sm());
-                            k_trace_shadow_flat<<<tb + sb, kBlock, sc->smem_flat_bytes, st>>>(sv, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit,
-                                                                                              k == 0 ? zero_count : shc + k - 1, ctx->sh_a, ctx->sh_b, ctx->sh_c,
-                                                                                              ctx->lacc, ctx->d_counters, sc->n_trav_f4, (uint32_t)tb, (k == 0 && camera_o) ? 1u : 0u, k == 0 ? cam_masks : nullptr, npix);
-                            ctx->launches++;
-                            ub_prev = n_ub;
-                        } else if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0, k == 0 && camera_o, k == 0 ? cam_masks : nullptr);
-                        else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0, k == 0 && camera_o, k == 0 ? cam_masks : nullptr);
-                        if (prof) CK(cudaEventRecord(ctx->ev[3], st));
-#define RL_LAUNCH_SHADE(SORT, KM)                                                                                                                   \
-    k_shade<SORT, KM><<<grid_for(ctx, n_ub, resident_per_sm(k_shade<SORT, KM>, 0, shade_block(KM)), shade_block(KM)), shade_block(KM), 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], \
-                                                                 ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1], ctx->state[cur ^ 1], qc + k + 1,     \
-                                                                 ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc, ctx->d_counters, k == 0 ? (camera_o ? 3u : 1u) : 0u)
-                        // kernel specialised for the BSDF kinds of the scene: {diffuse}, {diffuse, phong}, everything
-                        // (textured scenes take the general kernel: bit 8 of the mask)
-                        if (sc->kind_mask == 0x1u && !sc->d_tex) RL_LAUNCH_SHADE(false, 0x1u);
-                        else if ((sc->kind_mask & ~0x3u) == 0u && !sc->d_tex) {
-                            if (sort_on) RL_LAUNCH_SHADE(true, 0x3u);
-                            else RL_LAUNCH_SHADE(false, 0x3u);
-                        } else {
-                            if (sc->d_tex) {
-                                if (sort_on) RL_LAUNCH_SHADE(true, RL_KM_ALL);
-                                else RL_LAUNCH_SHADE(false, RL_KM_ALL);
-                            } else {
-                                if (sort_on) RL_LAUNCH_SHADE(true, 0xffu);
-                                else RL_LAUNCH_SHADE(false, 0xffu);
-                            }
-                        }
-#undef RL_LAUNCH_SHADE
+                    const size_t n_ub = legacy ? ub_prev : std::min<size_t>(n_paths, predict_len(ctx, n_paths, k) + predict_len(ctx, n_paths, k) / 4 + 1024);
+                    const bool fused = fuse_ok && !legacy && k < win_lo; // rays of iteration k + shadow segments of iteration k-1 in one launch
+                    if (fused) {
+                        SceneView sv = sc->sv;
+                        sv.n_groups = sc->flat.n_groups;
+                        const int tb = grid_for(ctx, n_ub, trav_per_sm()), sb = k == 0 ? 0 : grid_for(ctx, ub_prev, trav_per_sm());
+                        k_trace_shadow_flat<<<tb + sb, kBlock, sc->smem_flat_bytes, st>>>(sv, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit,
+                                                                                          k == 0 ? zero_count : shc + k - 1, ctx->sh_a, ctx->sh_b, ctx->sh_c,
+                                                                                          ctx->lacc, ctx->d_counters, sc->n_trav_f4, (uint32_t)tb,
+                                                                                          (k == 0 && camera_o) ? 1u : 0u, k == 0 ? cam_masks : nullptr, npix, done_at, k);
                         ctx->launches++;
-                        if (prof) CK(cudaEventRecord(ctx->ev[4], st));
-                        // the shadow queue can never be longer than the input queue: size the grid from n_ub
-                        if (fuse) {
-                            // traced by the next iteration's launch (or by the trailing launch after the loop)
-                        } else if (sc->smem_ok) launch_shadow<true>(ctx, sc, shc + k, n_ub, k == 0);
-                        else launch_shadow<false>(ctx, sc, shc + k, n_ub, k == 0);
-                        if (prof) CK(cudaEventRecord(ctx->ev[5], st));
-                        cur ^= 1;
+                    } else if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, done_at, k, k == 0, k == 0 && camera_o, k == 0 ? cam_masks : nullptr);
+                    else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, done_at, k, k == 0, k == 0 && camera_o, k == 0 ? cam_masks : nullptr);
+                    ev_mark(ctx, EV_TRACE);
+#define RL_LAUNCH_SHADE(SORT, KM)                                                                                                                   \
+    k_shade<SORT, KM><<<grid_for(ctx, n_ub, resident_per_sm((const void *)k_shade<SORT, KM>, 0, shade_block(KM)), shade_block(KM)), shade_block(KM), 0, st>>>(sc->sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], \
+                                                                 ctx->hit, ctx->ray_o[cur ^ 1], ctx->ray_d[cur ^ 1], ctx->state[cur ^ 1], qc + k + 1,     \
+                                                                 ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc, ctx->d_counters, k == 0 ? (camera_o ? 3u : 1u) : 0u, done_at, k)
+                    // kernel specialised for the BSDF kinds of the scene: {diffuse}, {diffuse, phong}, everything
+                    // (textured scenes take the general kernel: bit 8 of the mask)
+                    if (sc->kind_mask == 0x1u && !sc->d_tex) RL_LAUNCH_SHADE(false, 0x1u);
+                    else if ((sc->kind_mask & ~0x3u) == 0u && !sc->d_tex) {
+                        if (sort_on) RL_LAUNCH_SHADE(true, 0x3u);
+                        else RL_LAUNCH_SHADE(false, 0x3u);
+                    } else {
+                        if (sc->d_tex) {
+                            if (sort_on) RL_LAUNCH_SHADE(true, RL_KM_ALL);
+                            else RL_LAUNCH_SHADE(false, RL_KM_ALL);
+                        } else {
+                            if (sort_on) RL_LAUNCH_SHADE(true, 0xffu);
+                            else RL_LAUNCH_SHADE(false, 0xffu);
+                        }
                     }
-                    CK(cudaMemcpyAsync(ctx->h_hist + k_read, qc + k_read, (k + 1 - k_read) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-                    CK(cudaStreamSynchronize(st));
-                    CK(cudaGetLastError());
-                    if (prof) {
-                        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-                        S.ms_trace += ms;
-                        CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]));
-                        S.ms_shade += ms;
-                        CK(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
-                        S.ms_shadow += ms;
+#undef RL_LAUNCH_SHADE
+                    ctx->launches++;
+                    ev_mark(ctx, EV_SHADE);
+                    // shadow segments of iteration k: traced by the next iteration's fused launch, or here
+                    const bool next_fused = fuse_ok && !legacy && k + 1 < win_lo;
+                    if (!next_fused) {
+                        if (sc->smem_ok) launch_shadow<true>(ctx, sc, shc + k, n_ub, done_at, k, k == 0);
+                        else launch_shadow<false>(ctx, sc, shc + k, n_ub, done_at, k, k == 0);
+                        ev_mark(ctx, EV_SHADOW);
                     }
-                    for (uint32_t j = k_read; j < k; j++) {
-                        if (ctx->h_hist[j] == 0) break;
-                        S.segments += ctx->h_hist[j];
-                        iter++;
+                    ub_prev = n_ub;
+                    cur ^= 1;
+                    if (legacy) { // pure wavefront: the host reads the queue lengths every 8 iterations and stops at an empty queue
+                        if ((k & 7u) == 7u) {
+                            CK(cudaMemcpyAsync(ctx->h_hist + legacy_read, qc + legacy_read, (k + 2 - legacy_read) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                            CK(cudaStreamSynchronize(st));
+                            legacy_read = k + 1;
+                            ub_prev = ctx->h_hist[k + 1];
+                            if (ub_prev == 0) break;
+                        }
+                        continue;
                     }
-                    k_read = k;
-                    n_ub = ctx->h_hist[k];
-                    if (tail_max && n_ub > 0 && n_ub <= tail_max) { // the queue fits one resident wave: k_tail finishes the batch
-                        if (fuse && k > 0) launch_shadow<true>(ctx, sc, shc + k - 1, ub_prev, false); // segments queued by the last k_shade
+                    if (k + 1 >= win_lo) { // queue k+1 may go to k_tail (shadow segments of iteration k are resolved: launched above)
+                        const bool last = k + 1 >= win_hi;
                         SceneView sv = sc->sv;
                         if (sc->flat_ok) sv.n_groups = sc->flat.n_groups;
                         else sv.root_ref = sc->root_flat;
-                        const int tg = (int)((n_ub + kTailBlock - 1) / kTailBlock);
+                        const size_t tn = last ? std::max<size_t>(predict_len(ctx, n_paths, k + 1), tail_max) : tail_max;
+                        const int tg = (int)std::min<size_t>((tn + kTailBlock - 1) / kTailBlock, (size_t)ctx->sm_count * 16);
                         const size_t tsm = sc->flat_ok ? sc->smem_flat_bytes : 0;
+                        const uint32_t take_max = last ? 0xffffffffu : (uint32_t)tail_max;
 #define RL_LAUNCH_TAIL(KM) \
-    k_tail<KM><<<tg, kTailBlock, tsm, st>>>(sv, ip, ctx->pixel_list, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], ctx->lacc, ctx->d_counters, sc->n_trav_f4, k, kMaxIters - 1u)
+    k_tail<KM><<<tg, kTailBlock, tsm, st>>>(sv, ip, ctx->pixel_list, qc + k + 1, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], ctx->lacc, ctx->d_counters, sc->n_trav_f4, k + 1, kMaxIters - 1u, done_at, take_max)
                         if (sc->kind_mask == 0x1u && !sc->d_tex) RL_LAUNCH_TAIL(0x1u);
                         else if ((sc->kind_mask & ~0x3u) == 0u && !sc->d_tex) RL_LAUNCH_TAIL(0x3u);
                         else if (sc->d_tex) RL_LAUNCH_TAIL(RL_KM_ALL);
                         else RL_LAUNCH_TAIL(0xffu);
 #undef RL_LAUNCH_TAIL
                         ctx->launches++;
-                        tail_done = true;
-                        break;
+                        ev_mark(ctx, EV_TAIL);
+                        if (last) break;
                     }
                 }
-                if (fuse && k > 0 && !tail_done) launch_shadow<true>(ctx, sc, shc + k - 1, ub_prev, false); // shadow segments of the last shaded iteration
+                hist_iters = std::min<uint32_t>(k + 2, kMaxIters - 1);
+                hist_paths = n_paths;
+                k_tally<<<1, 1, 0, st>>>(qc, shc, hist_iters, done_at, 0u, ctx->d_counters);
+                ctx->launches++;
             }
-            S.max_depth_seen = std::max<uint64_t>(S.max_depth_seen, iter);
-            if (prof) CK(cudaEventRecord(ctx->ev[2], st));
             k_accum<<<grid_for(ctx, npix, 8), kBlock, 0, st>>>(ctx->lacc, npix, nb, n_slots, ctx->img_sum, s0 == 0 ? 1 : 0);
             ctx->launches++;
-            if (prof) {
-                CK(cudaEventRecord(ctx->ev[3], st));
-                CK(cudaEventSynchronize(ctx->ev[3]));
-                CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
-                S.ms_accum += ms;
-            }
+            ev_mark(ctx, EV_ACCUM);
         }
         k_finish<<<grid_for(ctx, npix, 8), kBlock, 0, st>>>(ctx->img_sum, ctx->pixel_list, npix, 1.0f / (float)o->spp, ctx->frame);
         ctx->launches++;
+        ev_mark(ctx, EV_ACCUM);
     }
     CK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    if (hist_iters) CK(cudaMemcpyAsync(ctx->h_hist, ctx->d_hist, hist_iters * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_counts, ctx->d_counts, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[1], st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     float ms_total = 0;
     CK(cudaEventElapsedTime(&ms_total, ctx->ev[0], ctx->ev[1]));
     S.ms_total = ms_total;
+    ev_collect(ctx, S);
     S.samples = (uint64_t)npix * o->spp;
-    if (ctx->h_counters->tail_overflow) { // same limit and message as the wavefront loop
+    const Counters &C = *ctx->h_counters;
+    if (C.tail_overflow) { // same limit and message as the wavefront loop
         ctx->err = "rl_render: a path exceeded 4095 wavefront iterations (no Russian roulette in a closed scene?)";
         return RL_ERR_UNSUPPORTED;
     }
-    S.hits = ctx->h_counters->hits;
-    S.segments += ctx->h_counters->tail_segments;
-    S.max_depth_seen = std::max<uint64_t>(S.max_depth_seen, ctx->h_counters->tail_iters);
-    S.shadow_rays = ctx->h_counters->nee_sampled;
-    S.shadow_visible = ctx->h_counters->shadow_visible;
+    if (hist_iters && hist_paths) { // the last batch's queue lengths size the next frame's grids (up to the hand-over: later entries were never written)
+        const uint32_t done = ctx->h_counts[3];
+        ctx->pred_ratio.clear();
+        for (uint32_t k = 0; k < hist_iters && k <= done; k++) {
+            if (ctx->h_hist[k] == 0) break;
+            ctx->pred_ratio.push_back((double)ctx->h_hist[k] / (double)hist_paths);
+        }
+    }
+    S.hits = C.hits;
+    S.segments = C.wave_segments + C.tail_segments;
+    S.max_depth_seen = std::max<uint64_t>(C.wave_iters, C.tail_iters);
+    S.shadow_rays = C.nee_sampled;
+    S.shadow_visible = C.shadow_visible;
+    S.shadow_traced = C.shadow_traced + C.tail_shadow;
     S.kernel_launches = ctx->launches;
     if (stats) *stats = S;
     return RL_OK;
@@ -1021,10 +1067,10 @@ int rl_render(rl_ctx *ctx, rl_scene *scene, const rl_integrator_desc *integrator
 
 // ---- Acceleration::{trace, visible} batches -----------------------------------------------------------
 static int trace_device_rays(rl_ctx *ctx, rl_scene *sc, size_t n, uint32_t *prim, float *tuv, bool coherent = false) {
-    uint32_t cnt = (uint32_t)n;
-    CK(cudaMemcpyAsync(ctx->d_counts, &cnt, sizeof(cnt), cudaMemcpyHostToDevice, ctx->stream));
-    if (sc->smem_ok) launch_trace<true>(ctx, sc, ctx->d_counts, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, coherent);
-    else launch_trace<false>(ctx, sc, ctx->d_counts, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, coherent);
+    uint32_t cnt[4] = {(uint32_t)n, 0u, 0u, 0xffffffffu}; // [3] = done_at: never
+    CK(cudaMemcpyAsync(ctx->d_counts, cnt, sizeof(cnt), cudaMemcpyHostToDevice, ctx->stream));
+    if (sc->smem_ok) launch_trace<true>(ctx, sc, ctx->d_counts, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, ctx->d_counts + 3, 0u, coherent);
+    else launch_trace<false>(ctx, sc, ctx->d_counts, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, ctx->d_counts + 3, 0u, coherent);
     CK(cudaGetLastError());
     std::vector<float4> h(n);
     CK(cudaMemcpyAsync(h.data(), ctx->hit, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));

@@ -1688,6 +1688,7 @@ struct IntegParams {
     uint64_t seed_h;   // seed_hash(seed)
     uint32_t sample_base; // first sample index of this batch
     uint32_t npix;        // pixels owned by this rank
+    uint32_t npix_mul, npix_shift; // id / npix == umulhi(id, npix_mul) >> npix_shift for every path id of the batch (0: plain division)
     uint32_t img_w;
 };
 
@@ -1714,6 +1715,19 @@ struct StepOut {
     V3 sh_p0, sh_p1;
     Col sh_contrib;
 };
+RL_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+// path id = s_local * npix + local pixel
+RL_HD void ip_split(const IntegParams &ip, uint32_t id, uint32_t *s_local, uint32_t *lp) {
+    const uint32_t q = ip.npix_mul ? (umulhi32(id, ip.npix_mul) >> ip.npix_shift) : id / ip.npix;
+    *s_local = q;
+    *lp = id - q * ip.npix;
+}
 RL_HD bool ip_expand(const IntegParams &ip, uint32_t depth) { return ip.max_depth < 0 ? true : depth < (uint32_t)ip.max_depth; }
 RL_HD bool ip_add_ok(const IntegParams &ip, uint32_t curr_depth) { return ip.min_depth < 0 ? true : curr_depth >= (uint32_t)ip.min_depth; }
 

@@ -35,7 +35,17 @@ struct Counters { // device-side statistics, 64-bit
     unsigned long long hits, nee_sampled, shadow_visible, pad;
     unsigned long long tail_segments, tail_iters; // k_tail: closest-hit calls; deepest iteration reached (absolute)
     unsigned long long tail_overflow, pad2;       // a path reached the iteration limit inside k_tail
+    unsigned long long wave_segments, shadow_traced; // k_tally: rays / shadow segments the wavefront kernels traced
+    unsigned long long wave_iters, tail_shadow;      // deepest wavefront iteration that held a ray; shadow segments traced inside k_tail
 };
+
+// ---- device-decided schedule -------------------------------------------------------------------------
+// The host enqueues a whole batch without reading anything back: wavefront iterations k = 0, 1, ... with grids sized from
+// a prediction (the kernels grid-stride over the true queue lengths, which live in device memory), and from the iteration
+// where the queue is expected to fit one resident wave a k_tail launch after every iteration that takes the batch over
+// as soon as the queue is short enough (or unconditionally, for the last one).  `done_at` = the iteration whose queue a
+// tail kernel consumed (0xffffffff: none yet): every kernel of iteration k returns at once when *done_at <= k.
+__device__ __forceinline__ bool batch_done(const uint32_t *done_at, uint32_t my_k) { return *reinterpret_cast<const volatile uint32_t *>(done_at) <= my_k; }
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
 
@@ -52,7 +62,8 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, IntegParams ip,
                                                    float4 *__restrict__ ray_o, float4 *__restrict__ ray_d, float4 *__restrict__ lacc,
                                                    uint32_t n_slots) {
     for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n_paths; id += gridDim.x * blockDim.x) {
-        uint32_t s_local = id / ip.npix, lp = id - s_local * ip.npix;
+        uint32_t s_local, lp;
+        ip_split(ip, id, &s_local, &lp);
         uint32_t pixel = __ldg(pixel_list + lp);
         uint32_t px = pixel % ip.img_w, py = pixel / ip.img_w;
         Sampler smp = make_sampler(ip.seed_h, pixel, ip.sample_base + s_local, 0u);
@@ -95,8 +106,9 @@ __device__ __forceinline__ void warp_chunk(uint32_t n, uint32_t *begin, uint32_t
 template <bool SMEM>
 __global__ void __launch_bounds__(kBlock) k_trace(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
                                                   const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t n_node_f4,
-                                                  uint32_t n_trav_f4) {
+                                                  uint32_t n_trav_f4, const uint32_t *__restrict__ done_at, uint32_t my_k) {
     extern __shared__ float4 smem[];
+    if (batch_done(done_at, my_k)) return;
     const float4 *nodes = sv.nodes, *trav = sv.trav;
     if (SMEM) {
         stage_scene(sv, smem, n_node_f4, n_trav_f4);
@@ -220,16 +232,18 @@ __device__ __forceinline__ void shadow_flat_body(const SceneView &sv, const floa
 #endif
 __global__ void __launch_bounds__(kBlock, RL_TRAV_MINBLOCKS) k_trace_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
                                                        const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t n_trav_f4, uint32_t camera,
-                                                       const uint32_t *__restrict__ cam_masks, uint32_t npix) {
+                                                       const uint32_t *__restrict__ cam_masks, uint32_t npix, const uint32_t *__restrict__ done_at, uint32_t my_k) {
     extern __shared__ float4 smem[];
+    if (batch_done(done_at, my_k) || blockIdx.x * blockDim.x >= *count) return; // nothing for this CTA: skip the staging
     const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4 + RL_FLAT_TAIL_F4;
     stage_flat(sv, smem, n_flat_f4, n_trav_f4);
     trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, gridDim.x, *count, ray_o, ray_d, hit, camera != 0u, cam_masks, npix);
 }
 __global__ void __launch_bounds__(kBlock, RL_TRAV_MINBLOCKS) k_shadow_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ sh_a,
                                                         const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c, float4 *__restrict__ lacc,
-                                                        Counters *counters, uint32_t n_trav_f4) {
+                                                        Counters *counters, uint32_t n_trav_f4, const uint32_t *__restrict__ done_at, uint32_t my_k) {
     extern __shared__ float4 smem[];
+    if (batch_done(done_at, my_k) || blockIdx.x * blockDim.x >= *count) return;
     const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4 + RL_FLAT_TAIL_F4;
     stage_flat(sv, smem, n_flat_f4, n_trav_f4);
     shadow_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, gridDim.x, *count, sh_a, sh_b, sh_c, lacc, counters);
@@ -243,8 +257,11 @@ __global__ void __launch_bounds__(kBlock, RL_TRAV_MINBLOCKS) k_trace_shadow_flat
                                                               const uint32_t *__restrict__ sh_count, const float4 *__restrict__ sh_a,
                                                               const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c, float4 *__restrict__ lacc,
                                                               Counters *counters, uint32_t n_trav_f4, uint32_t trace_blocks, uint32_t camera,
-                                                              const uint32_t *__restrict__ cam_masks, uint32_t npix) {
+                                                              const uint32_t *__restrict__ cam_masks, uint32_t npix,
+                                                              const uint32_t *__restrict__ done_at, uint32_t my_k) {
     extern __shared__ float4 smem[];
+    if (batch_done(done_at, my_k)) return; // (fused launches are only scheduled before the first k_tail launch: both halves are live or neither)
+    if (blockIdx.x < trace_blocks ? blockIdx.x * blockDim.x >= *count : (blockIdx.x - trace_blocks) * blockDim.x >= *sh_count) return;
     const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4 + RL_FLAT_TAIL_F4;
     stage_flat(sv, smem, n_flat_f4, n_trav_f4);
     if (blockIdx.x < trace_blocks) trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, trace_blocks, *count, ray_o, ray_d, hit, camera != 0u, cam_masks, npix);
@@ -347,12 +364,15 @@ __device__ __forceinline__ uint32_t tile_sort_by_key(uint32_t key, unsigned shor
 #ifndef RL_SHADE_BLOCK_DIFFUSE
 #define RL_SHADE_BLOCK_DIFFUSE 128
 #endif
+#ifndef RL_SHADE_MINBLOCKS_DIFFUSE
+#define RL_SHADE_MINBLOCKS_DIFFUSE (1024 / RL_SHADE_BLOCK_DIFFUSE)
+#endif
 __host__ __device__ constexpr int shade_block(uint32_t km) { return km == 0x1u ? RL_SHADE_BLOCK_DIFFUSE : kBlock; }
 
 // Resident CTAs per SM (= the register cap): {diffuse} 8 x 128 threads and {diffuse, phong} 4 x 256 at 64 registers (Phong walls,
 // 512^2 x 512 spp: 56.4 ms; 80 registers 59.0, 110 registers 62.8 ms); the kernels with the microfacet / Fresnel code run best
 // unconstrained at 2 x 256 (122 registers, no spills: mixed scene sorted 14.0 -> 13.3 ms, unsorted 21.3 -> 20.1 ms).
-__host__ __device__ constexpr int shade_minblocks(uint32_t km) { return km == 0x1u ? 1024 / RL_SHADE_BLOCK_DIFFUSE : (km == 0x3u ? 4 : 2); }
+__host__ __device__ constexpr int shade_minblocks(uint32_t km) { return km == 0x1u ? RL_SHADE_MINBLOCKS_DIFFUSE : (km == 0x3u ? 4 : 2); }
 template <bool SORT, uint32_t KM>
 __global__ void __launch_bounds__(shade_block(KM), shade_minblocks(KM)) k_shade(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
                                                   const uint32_t *__restrict__ count_in, const float4 *__restrict__ ray_o,
@@ -360,8 +380,10 @@ __global__ void __launch_bounds__(shade_block(KM), shade_minblocks(KM)) k_shade(
                                                   const float4 *__restrict__ hit, float4 *__restrict__ out_o, float4 *__restrict__ out_d,
                                                   float4 *__restrict__ out_state, uint32_t *count_out, float4 *__restrict__ sh_a,
                                                   float4 *__restrict__ sh_b, float4 *__restrict__ sh_c, uint32_t *count_shadow,
-                                                  float4 *__restrict__ lacc, Counters *counters, uint32_t primary) {
+                                                  float4 *__restrict__ lacc, Counters *counters, uint32_t primary,
+                                                  const uint32_t *__restrict__ done_at, uint32_t my_k) {
     constexpr int B = shade_block(KM);
+    if (batch_done(done_at, my_k)) return;
     __shared__ uint32_t s_scratch[2 * (B / 32) + 2];
     __shared__ unsigned short s_perm[SORT ? B : 1];
     __shared__ uint32_t s_cnt[SORT ? kSortKeys * (B / 32) : 1];
@@ -398,7 +420,8 @@ __global__ void __launch_bounds__(shade_block(KM), shade_minblocks(KM)) k_shade(
             uint32_t packed = f2u(st4.w);
             st.depth = packed >> 16;
             st.rng_n = packed & 0xffffu;
-            uint32_t s_local = st.path_id / ip.npix, lp = st.path_id - s_local * ip.npix;
+            uint32_t s_local, lp;
+            ip_split(ip, st.path_id, &s_local, &lp);
             uint32_t pixel = __ldg(pixel_list + lp);
             path_step<KM>(sv, ip, xyz(ro), xyz(rd), h, st, pixel, ip.sample_base + s_local, &so);
             if (h.prim != RL_MISS) c_hits++;
@@ -448,8 +471,15 @@ template <uint32_t KM>
 __global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
                                                      const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
                                                      const float4 *__restrict__ ray_d, const float4 *__restrict__ state, float4 *__restrict__ lacc,
-                                                     Counters *counters, uint32_t n_trav_f4, uint32_t iter_base, uint32_t iter_limit) {
+                                                     Counters *counters, uint32_t n_trav_f4, uint32_t iter_base, uint32_t iter_limit,
+                                                     uint32_t *done_at, uint32_t take_max) {
     extern __shared__ float4 smem[];
+    // iter_base = the iteration whose queue this launch may consume.  It does when no earlier launch has and the queue holds at
+    // most take_max rays (0xffffffff: unconditionally -- the last launch of the schedule).
+    if (*reinterpret_cast<volatile uint32_t *>(done_at) < iter_base) return;
+    if (*count > take_max) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMin(done_at, iter_base); // CTAs of THIS launch that start later still see done_at == iter_base: not "<"
+    if (blockIdx.x * blockDim.x >= *count) return;
     const float4 *nodes = sv.nodes, *trav = sv.trav, *flat = sv.flat;
     if (sv.n_groups) { // group table + exact-test records in shared memory, as in k_trace_flat
         const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4 + RL_FLAT_TAIL_F4;
@@ -458,7 +488,7 @@ __global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams i
         trav = smem + n_flat_f4;
     }
     const uint32_t n = *count;
-    uint32_t c_hits = 0, c_nee = 0, c_vis = 0, c_seg = 0, c_iters = 0, c_over = 0;
+    uint32_t c_hits = 0, c_nee = 0, c_vis = 0, c_seg = 0, c_iters = 0, c_over = 0, c_sht = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 ro = ray_o[i], rd = ray_d[i], st4 = state[i];
         V3 o = xyz(ro), d = xyz(rd);
@@ -468,7 +498,8 @@ __global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams i
         st.path_id = f2u(ro.w);
         st.depth = f2u(st4.w) >> 16;
         st.rng_n = f2u(st4.w) & 0xffffu;
-        const uint32_t s_local = st.path_id / ip.npix, lp = st.path_id - s_local * ip.npix;
+        uint32_t s_local, lp;
+        ip_split(ip, st.path_id, &s_local, &lp);
         const uint32_t pixel = __ldg(pixel_list + lp), sample = ip.sample_base + s_local;
         float4 l = lacc[st.path_id];
         for (uint32_t it = 1;; it++) {
@@ -479,9 +510,12 @@ __global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams i
             if (h.prim != RL_MISS) c_hits++;
             if (so.nee_sampled) c_nee++;
             if (so.has_add) l.x += so.add.r, l.y += so.add.g, l.z += so.add.b;
-            if (so.shadow && trace_visible(sv, flat, nodes, trav, so.sh_p0, so.sh_p1)) {
-                l.x += so.sh_contrib.r, l.y += so.sh_contrib.g, l.z += so.sh_contrib.b;
-                c_vis++;
+            if (so.shadow) {
+                c_sht++;
+                if (trace_visible(sv, flat, nodes, trav, so.sh_p0, so.sh_p1)) {
+                    l.x += so.sh_contrib.r, l.y += so.sh_contrib.g, l.z += so.sh_contrib.b;
+                    c_vis++;
+                }
             }
             c_iters = max(c_iters, it);
             if (!so.alive || so.next.depth >= 0xfff0u || so.next.rng_n >= 0xfff0u) break; // packing guard as in k_shade
@@ -499,6 +533,7 @@ __global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams i
         c_nee += __shfl_down_sync(0xffffffffu, c_nee, off);
         c_vis += __shfl_down_sync(0xffffffffu, c_vis, off);
         c_seg += __shfl_down_sync(0xffffffffu, c_seg, off);
+        c_sht += __shfl_down_sync(0xffffffffu, c_sht, off);
         c_iters = max(c_iters, __shfl_down_sync(0xffffffffu, c_iters, off));
     }
     if ((threadIdx.x & 31u) == 0) {
@@ -506,6 +541,7 @@ __global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams i
         if (c_nee) atomicAdd(&counters->nee_sampled, (unsigned long long)c_nee);
         if (c_vis) atomicAdd(&counters->shadow_visible, (unsigned long long)c_vis);
         if (c_seg) atomicAdd(&counters->tail_segments, (unsigned long long)c_seg);
+        if (c_sht) atomicAdd(&counters->tail_shadow, (unsigned long long)c_sht);
         if (c_iters) atomicMax(&counters->tail_iters, (unsigned long long)(iter_base + c_iters));
     }
     if (c_over) atomicMax(&counters->tail_overflow, 1ull);
@@ -543,7 +579,8 @@ __global__ void __launch_bounds__(kBlock, RL_DIRECT1_MINBLOCKS) k_shade_direct1(
             HitRec h;
             h.t = h4.x, h.u = h4.y, h.v = h4.z, h.prim = f2u(h4.w);
             pid = f2u(ro.w);
-            uint32_t s_local = pid / ip.npix, lp = pid - s_local * ip.npix;
+            uint32_t s_local, lp;
+            ip_split(ip, pid, &s_local, &lp);
             if (ip.kind == 2u) ao_begin(sv, ip, xyz(ro), xyz(rd), h, f2u(st4.w) & 0xffffu, __ldg(pixel_list + lp), ip.sample_base + s_local, &cx);
             else direct_begin(sv, ip, xyz(ro), xyz(rd), h, f2u(st4.w) & 0xffffu, __ldg(pixel_list + lp), ip.sample_base + s_local, &cx);
             if (h.prim != RL_MISS) c_hits++;
@@ -608,8 +645,10 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct2(SceneView sv, IntegPar
 template <bool SMEM>
 __global__ void __launch_bounds__(kBlock) k_shadow(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ sh_a,
                                                    const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c,
-                                                   float4 *__restrict__ lacc, Counters *counters, uint32_t n_node_f4, uint32_t n_trav_f4) {
+                                                   float4 *__restrict__ lacc, Counters *counters, uint32_t n_node_f4, uint32_t n_trav_f4,
+                                                   const uint32_t *__restrict__ done_at, uint32_t my_k) {
     extern __shared__ float4 smem[];
+    if (batch_done(done_at, my_k)) return;
     const float4 *nodes = sv.nodes, *trav = sv.trav;
     if (SMEM) {
         stage_scene(sv, smem, n_node_f4, n_trav_f4);
@@ -697,6 +736,22 @@ __global__ void __launch_bounds__(kBlock) k_finish(const float4 *__restrict__ im
 }
 
 __global__ void k_set_u32(uint32_t *p, uint32_t v) { *p = v; }
+
+// End of a batch: what did the wavefront kernels trace?  Queue k was traced by them iff k < *done_at (queue *done_at went to k_tail).
+__global__ void k_tally(const uint32_t *__restrict__ qc, const uint32_t *__restrict__ shc, uint32_t n_iters, const uint32_t *__restrict__ done_at, uint32_t iter_offset,
+                        Counters *counters) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    unsigned long long seg = 0, sh = 0, deepest = 0;
+    const uint32_t lim = min(n_iters, *done_at);
+    for (uint32_t k = 0; k < lim; k++) {
+        seg += qc[k];
+        if (shc) sh += shc[k];
+        if (qc[k]) deepest = iter_offset + k + 1;
+    }
+    counters->wave_segments += seg;
+    counters->shadow_traced += sh;
+    if (deepest > counters->wave_iters) counters->wave_iters = deepest;
+}
 
 // ---- Acceleration::{trace, visible} on caller-provided rays (rl_trace / rl_visible) ---------------
 __global__ void __launch_bounds__(kBlock) k_pack_rays(const float *__restrict__ o, const float *__restrict__ d, uint32_t n, float4 *ray_o, float4 *ray_d) {

@@ -110,7 +110,7 @@ class Context:
             raise DeviceError(rc, lib().rl_last_error(self._h).decode())
 
     def set_profiling(self, on):
-        self._check(lib().rl_set_profiling(self._h, 1 if on else 0))
+        self._check(lib().rl_set_profiling(self._h, int(on)))  # False/0 off, True/1 per-stage kernels, 2 the kernels of an untimed frame
 
     def layout(self):
         li = _abi.rl_layout_info()
