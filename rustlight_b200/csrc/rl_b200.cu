@@ -18,6 +18,7 @@
 #include "rl_b200.h"
 #include "rl_flat_host.hpp"
 #include "rl_kernels.cuh"
+#include "rl_refbvh_host.hpp"
 #include "rl_scene_host.hpp"
 
 using namespace rl;
@@ -73,6 +74,7 @@ struct rl_ctx {
     size_t cap_paths = 0, cap_shadow = 0, cap_lacc = 0; // ray/hit queues, shadow queues, radiance slots (records)
     float4 *ray_o[2] = {nullptr, nullptr}, *ray_d[2] = {nullptr, nullptr}, *state[2] = {nullptr, nullptr};
     float4 *hit = nullptr, *sh_a = nullptr, *sh_b = nullptr, *sh_c = nullptr, *lacc = nullptr;
+    uint32_t *fix_trace = nullptr, *fix_shadow = nullptr; // queue indices of the rays / shadow segments k_fix_flat re-traces (sized like the queues)
     // per-image buffers
     size_t cap_pix = 0, cap_frame = 0;
     float4 *img_sum = nullptr;
@@ -100,6 +102,8 @@ struct rl_scene {
     SceneView sv{};
     float4 *d_flat = nullptr; // group table of small scenes (rl_flat_host.hpp), nullptr when absent
     float4 *d_quad_verts = nullptr; // vertices of the table's quads (k_camera_cull)
+    float4 *d_ref_nodes = nullptr;  // the reference's own BVH (rl_refbvh_host.hpp): visit order of tied hits
+    uint32_t *d_ref_prims = nullptr, *d_ref_up = nullptr;
     uint32_t *d_cam_masks = nullptr; // per block of 32 local pixels: quads its camera rays can see
     size_t cam_cap = 0;
     uint64_t cam_gen = 0; // ctx->pl_gen the masks were computed for (0 = never)
@@ -108,7 +112,7 @@ struct rl_scene {
     float *d_emit_cdf = nullptr, *d_area_cdf = nullptr;
     float2 *d_uvs = nullptr;
     float4 *d_tex = nullptr, *d_texels = nullptr;
-    uint32_t n_node_f4 = 0, n_trav_f4 = 0;
+    uint32_t n_node_f4 = 0, n_trav_f4 = 0, n_ref_f4 = 0;
     size_t smem_bytes = 0;
     bool smem_ok = false;
     rl_bvh_info info{};
@@ -249,7 +253,7 @@ int rl_create(rl_ctx **out, int device, int nranks, int rank, const void *nccl_u
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CKC(cudaMalloc(&ctx->d_counts, 4 * sizeof(uint32_t)));
     CKC(cudaMalloc(&ctx->d_counters, sizeof(Counters)));
-    CKC(cudaMalloc(&ctx->d_hist, 2 * kMaxIters * sizeof(uint32_t)));
+    CKC(cudaMalloc(&ctx->d_hist, 4 * kMaxIters * sizeof(uint32_t))); // queue lengths, shadow-queue lengths, fix-list lengths (closest, shadow) per iteration
     CKC(cudaMallocHost(&ctx->h_hist, 2 * kMaxIters * sizeof(uint32_t)));
     CKC(cudaMallocHost(&ctx->h_counts, 4 * sizeof(uint32_t)));
     CKC(cudaMallocHost(&ctx->h_counters, sizeof(Counters)));
@@ -295,6 +299,7 @@ void rl_destroy(rl_ctx *ctx) {
         cudaFree(ctx->state[i]);
     }
     cudaFree(ctx->hit), cudaFree(ctx->sh_a), cudaFree(ctx->sh_b), cudaFree(ctx->sh_c), cudaFree(ctx->lacc);
+    cudaFree(ctx->fix_trace), cudaFree(ctx->fix_shadow);
     cudaFree(ctx->img_sum), cudaFree(ctx->pixel_list), cudaFree(ctx->frame);
     cudaFree(ctx->d_counts), cudaFree(ctx->d_counters), cudaFree(ctx->d_hist);
     cudaFreeHost(ctx->h_hist);
@@ -335,6 +340,7 @@ void rl_scene_destroy(rl_ctx *ctx, rl_scene *s) {
     cudaFree(s->d_emit_info), cudaFree(s->d_emit_cdf), cudaFree(s->d_area_cdf), cudaFree(s->d_flat);
     cudaFree(s->d_uvs), cudaFree(s->d_tex), cudaFree(s->d_texels);
     cudaFree(s->d_quad_verts), cudaFree(s->d_cam_masks);
+    cudaFree(s->d_ref_nodes), cudaFree(s->d_ref_prims), cudaFree(s->d_ref_up);
     delete s;
 }
 
@@ -417,10 +423,8 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     std::vector<int2> h_children;
     std::vector<int2v> h_ranges;
     std::vector<uint64_t> h_keys;
-    if (flat_ok) { // Morton order of the triangles, for the group table
-        h_keys.resize(n);
-        CKS(cudaMemcpyAsync(h_keys.data(), d_keys_sorted, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    }
+    h_keys.resize(n); // Morton order of the triangles: group table, and the slot of every primitive for the reference-order tree
+    CKS(cudaMemcpyAsync(h_keys.data(), d_keys_sorted, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     if (n > 1) {
         CKS(cudaMalloc(&d_children, (size_t)(n - 1) * sizeof(int2)));
         CKS(cudaMalloc(&d_ranges, (size_t)(n - 1) * sizeof(int2v)));
@@ -441,9 +445,32 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
         CKS(cudaMemcpyAsync(h_ranges.data(), d_ranges, (size_t)(n - 1) * sizeof(int2v), cudaMemcpyDeviceToHost, st));
     }
     CKS(cudaStreamSynchronize(st));
+    std::vector<uint32_t> prim_of_slot(n);
+    for (uint32_t i = 0; i < n; i++) prim_of_slot[i] = (uint32_t)(h_keys[i] & 0xffffffffull);
+    bool ref_ok = false;
+    if (getenv("RL_NO_REF_ORDER") == nullptr) { // (A/B + test hook: lowest-index tie rule of NaiveAcceleration instead)
+        RefBVH rb;
+        build_ref_bvh(hs, rb);
+        if (rb.depth + 2 <= (uint32_t)RL_STACK_SIZE) {
+            std::vector<uint32_t> slot_of_prim(n);
+            for (uint32_t i = 0; i < n; i++) slot_of_prim[prim_of_slot[i]] = i;
+            for (auto &p : rb.prims) p = slot_of_prim[p];
+            { // leaf of every triangle, indexed by Morton slot
+                const size_t nn = rb.nodes.size() / 2;
+                std::vector<uint32_t> leaf_of_slot(n);
+                for (uint32_t i = 0; i < n; i++) leaf_of_slot[rb.prims[i]] = rb.up[nn + i];
+                for (uint32_t i = 0; i < n; i++) rb.up[nn + i] = leaf_of_slot[i];
+                s->sv.ref_n_nodes = (uint32_t)nn;
+            }
+            CKS(upload(&s->d_ref_up, rb.up, st));
+            CKS(upload(&s->d_ref_nodes, rb.nodes, st));
+            CKS(upload(&s->d_ref_prims, rb.prims, st));
+            s->n_ref_f4 = (uint32_t)rb.nodes.size();
+            CKS(cudaStreamSynchronize(st)); // rb goes out of scope
+            ref_ok = true;
+        }
+    }
     if (flat_ok) {
-        std::vector<uint32_t> prim_of_slot(n);
-        for (uint32_t i = 0; i < n; i++) prim_of_slot[i] = (uint32_t)(h_keys[i] & 0xffffffffull);
         flat_ok = build_flat_table(hs, prim_of_slot, s->flat);
         if (flat_ok) {
             CKS(upload(&s->d_flat, s->flat.f4, st));
@@ -489,6 +516,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     sv.trav = s->d_trav, sv.nodes = s->d_nodes, sv.shade = s->d_shade, sv.verts = s->d_verts, sv.mats = s->d_mats;
     sv.emit_info = s->d_emit_info, sv.emit_cdf = s->d_emit_cdf, sv.area_cdf = s->d_area_cdf;
     sv.uvs = s->d_uvs, sv.tex = s->d_tex, sv.texels = s->d_texels;
+    sv.ref_nodes = ref_ok ? s->d_ref_nodes : nullptr, sv.ref_prims = ref_ok ? s->d_ref_prims : nullptr, sv.ref_up = ref_ok ? s->d_ref_up : nullptr;
     sv.ntris = n, sv.n_emitters = hs.n_emitters;
     sv.root_ref = root_ref;
     s->root_tree = root_ref;
@@ -543,8 +571,8 @@ static int ensure_paths(rl_ctx *ctx, size_t n_ray, size_t n_shadow = 0, size_t n
             cudaFree(ctx->ray_o[i]), cudaFree(ctx->ray_d[i]), cudaFree(ctx->state[i]);
             ctx->ray_o[i] = ctx->ray_d[i] = ctx->state[i] = nullptr;
         }
-        cudaFree(ctx->hit);
-        ctx->hit = nullptr;
+        cudaFree(ctx->hit), cudaFree(ctx->fix_trace);
+        ctx->hit = nullptr, ctx->fix_trace = nullptr;
         ctx->cap_paths = 0;
         size_t bytes = n_ray * sizeof(float4);
         for (int i = 0; i < 2; i++) {
@@ -553,15 +581,17 @@ static int ensure_paths(rl_ctx *ctx, size_t n_ray, size_t n_shadow = 0, size_t n
             CK(cudaMalloc(&ctx->state[i], bytes));
         }
         CK(cudaMalloc(&ctx->hit, bytes));
+        CK(cudaMalloc(&ctx->fix_trace, n_ray * sizeof(uint32_t)));
         ctx->cap_paths = n_ray;
     }
     if (n_shadow > ctx->cap_shadow) {
-        cudaFree(ctx->sh_a), cudaFree(ctx->sh_b), cudaFree(ctx->sh_c);
-        ctx->sh_a = ctx->sh_b = ctx->sh_c = nullptr;
+        cudaFree(ctx->sh_a), cudaFree(ctx->sh_b), cudaFree(ctx->sh_c), cudaFree(ctx->fix_shadow);
+        ctx->sh_a = ctx->sh_b = ctx->sh_c = nullptr, ctx->fix_shadow = nullptr;
         ctx->cap_shadow = 0;
         CK(cudaMalloc(&ctx->sh_a, n_shadow * sizeof(float4)));
         CK(cudaMalloc(&ctx->sh_b, n_shadow * sizeof(float4)));
         CK(cudaMalloc(&ctx->sh_c, n_shadow * sizeof(float4)));
+        CK(cudaMalloc(&ctx->fix_shadow, n_shadow * sizeof(uint32_t)));
         ctx->cap_shadow = n_shadow;
     }
     if (n_lacc > ctx->cap_lacc) {
@@ -656,6 +686,22 @@ static int validate(rl_ctx *ctx, const rl_scene *scene, const rl_integrator_desc
     return RL_OK;
 }
 
+// k_fix_flat over the lists a group-table kernel of iteration my_k has just filled (fixc_trace / fixc_shadow: their lengths; nullptr = none)
+static void launch_fix(rl_ctx *ctx, rl_scene *sc, const uint32_t *fixc_trace, const uint32_t *fixc_shadow, const float4 *ro, const float4 *rd, float4 *hit,
+                       bool camera_origin, const uint32_t *done_at, uint32_t my_k) {
+    if (!sc->sv.ref_nodes) return;
+    const uint32_t *zero = ctx->d_hist + 2 * kMaxIters - 1; // never written
+    SceneView sv = sc->sv;
+    const size_t smem = (size_t)(sc->n_ref_f4 + sc->n_trav_f4) * sizeof(float4) + (size_t)sc->hs.ntris * sizeof(uint32_t);
+    k_fix_flat<<<ctx->sm_count * 8, 128, smem, ctx->stream>>>(sv, fixc_trace ? fixc_trace : zero, ctx->fix_trace, ro, rd, hit, camera_origin ? 1u : 0u,
+                                                          fixc_shadow ? fixc_shadow : zero, ctx->fix_shadow, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc, ctx->d_counters,
+                                                          done_at, my_k, sc->n_ref_f4, sc->n_trav_f4);
+    ctx->launches++;
+}
+// fix-list lengths of iteration k live behind the queue-length history
+static uint32_t *fixc_trace_of(rl_ctx *ctx, uint32_t k) { return ctx->d_hist + 2 * kMaxIters + k; }
+static uint32_t *fixc_shadow_of(rl_ctx *ctx, uint32_t k) { return ctx->d_hist + 3 * kMaxIters + k; }
+
 template <bool SMEM>
 static void launch_trace(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_t n, const float4 *ro, const float4 *rd, float4 *hit,
                          const uint32_t *done_at, uint32_t my_k, bool coherent = false, bool camera_origin = false, const uint32_t *cam_masks = nullptr) {
@@ -663,8 +709,10 @@ static void launch_trace(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size_
     const bool tree = coherent && sc->coherent_tree >= 1;
     if (!tree && sc->flat_ok) {
         sv.n_groups = sc->flat.n_groups;
-        k_trace_flat<<<grid_for(ctx, n, trav_per_sm()), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_trav_f4, camera_origin ? 1u : 0u, cam_masks, ctx->pl_npix, done_at, my_k);
+        k_trace_flat<<<grid_for(ctx, n, trav_per_sm()), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ro, rd, hit, sc->n_trav_f4, camera_origin ? 1u : 0u, cam_masks,
+                                                                                         ctx->pl_npix, done_at, my_k, fixc_trace_of(ctx, my_k), ctx->fix_trace);
         ctx->launches++;
+        launch_fix(ctx, sc, fixc_trace_of(ctx, my_k), nullptr, ro, rd, hit, camera_origin, done_at, my_k);
         return;
     }
     sv.root_ref = tree ? sc->root_tree : sc->root_flat;
@@ -678,8 +726,9 @@ static void launch_shadow(rl_ctx *ctx, rl_scene *sc, const uint32_t *count, size
     if (!tree && sc->flat_ok) {
         sv.n_groups = sc->flat.n_groups;
         k_shadow_flat<<<grid_for(ctx, n, trav_per_sm()), kBlock, sc->smem_flat_bytes, ctx->stream>>>(sv, count, ctx->sh_a, ctx->sh_b, ctx->sh_c, ctx->lacc, ctx->d_counters,
-                                                                                          sc->n_trav_f4, done_at, my_k);
+                                                                                          sc->n_trav_f4, done_at, my_k, fixc_shadow_of(ctx, my_k), ctx->fix_shadow);
         ctx->launches++;
+        launch_fix(ctx, sc, nullptr, fixc_shadow_of(ctx, my_k), nullptr, nullptr, nullptr, false, done_at, my_k);
         return;
     }
     sv.root_ref = tree ? sc->root_tree : sc->root_flat;
@@ -840,6 +889,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
             uint32_t init[4] = {(uint32_t)n_paths, 0, 0, 0xffffffffu}; // [3] = done_at
             CK(cudaMemcpyAsync(ctx->d_counts, init, sizeof(init), cudaMemcpyHostToDevice, st));
             if (direct) {
+                CK(cudaMemsetAsync(ctx->d_hist + 2 * kMaxIters, 0, 2 * kMaxIters * sizeof(uint32_t), st)); // fix-list lengths
                 // primary rays -> stage 1 (emission, light samples, BSDF samples) -> shadow rays -> extension rays -> stage 2; nothing is read
                 // back: the second stage's grid is sized from its upper bound (every primary ray spawns at most nbs extension rays)
                 uint32_t *c_in = ctx->d_counts, *c_out = ctx->d_counts + 1, *c_sh = ctx->d_counts + 2;
@@ -859,8 +909,8 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                 }
                 if (nbs > 0) {
                     const size_t n2 = n * nbs;
-                    if (sc->smem_ok) launch_trace<true>(ctx, sc, c_out, n2, ctx->ray_o[1], ctx->ray_d[1], ctx->hit, done_at, 0u);
-                    else launch_trace<false>(ctx, sc, c_out, n2, ctx->ray_o[1], ctx->ray_d[1], ctx->hit, done_at, 0u);
+                    if (sc->smem_ok) launch_trace<true>(ctx, sc, c_out, n2, ctx->ray_o[1], ctx->ray_d[1], ctx->hit, done_at, 1u);
+                    else launch_trace<false>(ctx, sc, c_out, n2, ctx->ray_o[1], ctx->ray_d[1], ctx->hit, done_at, 1u);
                     ev_mark(ctx, EV_TRACE);
                     k_shade_direct2<<<grid_for(ctx, n2, 8), kBlock, 0, st>>>(sc->sv, ip, c_out, ctx->ray_o[1], ctx->ray_d[1], ctx->state[1], ctx->hit, ctx->lacc,
                                                                              ctx->d_counters);
@@ -873,7 +923,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                 // `path`.  Queue lengths live in a per-iteration history on the device (iteration k reads hist[k] and appends to
                 // hist[k+1]); the whole batch is enqueued without reading anything back (see rl_kernels.cuh: device-decided schedule).
                 uint32_t *qc = ctx->d_hist, *shc = ctx->d_hist + kMaxIters;
-                CK(cudaMemsetAsync(ctx->d_hist, 0, 2 * kMaxIters * sizeof(uint32_t), st));
+                CK(cudaMemsetAsync(ctx->d_hist, 0, 4 * kMaxIters * sizeof(uint32_t), st));
                 k_set_u32<<<1, 1, 0, st>>>(qc, (uint32_t)n_paths);
                 const bool flat = sc->flat_ok && sc->coherent_tree == 0;
                 const bool fuse_ok = prof != 1 && flat && getenv("RL_NO_FUSE") == nullptr;
@@ -881,7 +931,10 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                 // k_tail window: from two iterations before the predicted hand-over a launch after every iteration, the last one unconditional
                 uint32_t k_pred = 0;
                 while (k_pred < 200u && predict_len(ctx, n_paths, k_pred) > std::max<size_t>(tail_max, 1)) k_pred++;
-                uint32_t win_lo = k_pred > 2u ? k_pred - 2u : 1u, win_hi = k_pred + 6u; // queue indices a k_tail launch is scheduled for
+                // queue indices a k_tail launch is scheduled for: a wide window around the model's guess, a narrow one around last frame's hand-over
+                // (queue lengths of two frames of one scene differ by a fraction of a percent; every launch after the hand-over is a dead ~2 us)
+                const bool have_hist = !ctx->pred_ratio.empty();
+                uint32_t win_lo = have_hist ? (k_pred > 1u ? k_pred - 1u : 1u) : (k_pred > 2u ? k_pred - 2u : 1u), win_hi = k_pred + (have_hist ? 1u : 6u);
                 if (I->max_depth >= 0) win_hi = std::min<uint32_t>(win_hi, (uint32_t)I->max_depth), win_lo = std::min(win_lo, win_hi);
                 const uint32_t *zero_count = ctx->d_hist + 2 * kMaxIters - 1; // never written
                 int cur = 0;
@@ -903,8 +956,10 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                         k_trace_shadow_flat<<<tb + sb, kBlock, sc->smem_flat_bytes, st>>>(sv, qc + k, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit,
                                                                                           k == 0 ? zero_count : shc + k - 1, ctx->sh_a, ctx->sh_b, ctx->sh_c,
                                                                                           ctx->lacc, ctx->d_counters, sc->n_trav_f4, (uint32_t)tb,
-                                                                                          (k == 0 && camera_o) ? 1u : 0u, k == 0 ? cam_masks : nullptr, npix, done_at, k);
+                                                                                          (k == 0 && camera_o) ? 1u : 0u, k == 0 ? cam_masks : nullptr, npix, done_at, k,
+                                                                                          fixc_trace_of(ctx, k), ctx->fix_trace, fixc_shadow_of(ctx, k == 0 ? 0 : k - 1), ctx->fix_shadow); // shadow segments of iteration k-1
                         ctx->launches++;
+                        launch_fix(ctx, sc, fixc_trace_of(ctx, k), k == 0 ? nullptr : fixc_shadow_of(ctx, k - 1), ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, k == 0 && camera_o, done_at, k);
                     } else if (sc->smem_ok) launch_trace<true>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, done_at, k, k == 0, k == 0 && camera_o, k == 0 ? cam_masks : nullptr);
                     else launch_trace<false>(ctx, sc, qc + k, n_ub, ctx->ray_o[cur], ctx->ray_d[cur], ctx->hit, done_at, k, k == 0, k == 0 && camera_o, k == 0 ? cam_masks : nullptr);
                     ev_mark(ctx, EV_TRACE);
@@ -1069,6 +1124,7 @@ int rl_render(rl_ctx *ctx, rl_scene *scene, const rl_integrator_desc *integrator
 static int trace_device_rays(rl_ctx *ctx, rl_scene *sc, size_t n, uint32_t *prim, float *tuv, bool coherent = false) {
     uint32_t cnt[4] = {(uint32_t)n, 0u, 0u, 0xffffffffu}; // [3] = done_at: never
     CK(cudaMemcpyAsync(ctx->d_counts, cnt, sizeof(cnt), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_hist + 2 * kMaxIters, 0, 2 * kMaxIters * sizeof(uint32_t), ctx->stream)); // fix-list lengths
     if (sc->smem_ok) launch_trace<true>(ctx, sc, ctx->d_counts, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, ctx->d_counts + 3, 0u, coherent);
     else launch_trace<false>(ctx, sc, ctx->d_counts, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, ctx->d_counts + 3, 0u, coherent);
     CK(cudaGetLastError());

@@ -52,8 +52,16 @@ RL_HD void tri_bounds_inflated(const float4 *verts, uint32_t prim, float eps, V3
 // affine barycentric functionals u(p) = Mu.p + cu, v(p) = Mv.p + cv.  Six float4 per triangle,
 // written to Morton slot s; n_geo also goes to the shading table.
 #define RL_TRAV_F4 6
-RL_HD void tri_setup(const float4 *verts, uint32_t prim, uint32_t s, float4 *trav, float4 *shade) {
+// `box_eps` = bvh_box_eps(abs_max): a triangle whose box is thin (< 30 box_eps ~ 1e-3 of the scene, or padded) along two axes is
+// flagged RL_PRIM_NEEDLE in the prim word: the reference's slab test can fail on such a box even for interior hits (rl_device.cuh: hit_unsafe).
+RL_HD void tri_setup(const float4 *verts, uint32_t prim, uint32_t s, float box_eps, float4 *trav, float4 *shade) {
     V3 v0 = xyz(verts[3 * prim]), v1 = xyz(verts[3 * prim + 1]), v2 = xyz(verts[3 * prim + 2]);
+    const float ext[3] = {fmaxf(fmaxf(v0.x, v1.x), v2.x) - fminf(fminf(v0.x, v1.x), v2.x), fmaxf(fmaxf(v0.y, v1.y), v2.y) - fminf(fminf(v0.y, v1.y), v2.y),
+                          fmaxf(fmaxf(v0.z, v1.z), v2.z) - fminf(fminf(v0.z, v1.z), v2.z)};
+    int thin = 0;
+    for (int a = 0; a < 3; a++)
+        if (!(ext[a] >= fmaxf(RL_EPSILON, 30.0f * box_eps))) thin++;
+    const uint32_t prim_word = prim | (thin >= 2 ? RL_PRIM_NEEDLE : 0u);
     V3 e1 = v1 - v0, e2 = v2 - v0;
     V3 cr = cross(e1, e2);
     V3 n_geo = normalize(cr);
@@ -62,7 +70,7 @@ RL_HD void tri_setup(const float4 *verts, uint32_t prim, uint32_t s, float4 *tra
     V3 mu = cross(e2, n_geo) * idet, mv = cross(n_geo, e1) * idet;
     float mn = fmaxf(magnitude(mu), magnitude(mv));
     trav[RL_TRAV_F4 * s + 0] = make_float4(v0.x, v0.y, v0.z, det);
-    trav[RL_TRAV_F4 * s + 1] = make_float4(e1.x, e1.y, e1.z, u2f(prim));
+    trav[RL_TRAV_F4 * s + 1] = make_float4(e1.x, e1.y, e1.z, u2f(prim_word));
     trav[RL_TRAV_F4 * s + 2] = make_float4(e2.x, e2.y, e2.z, mn);
     trav[RL_TRAV_F4 * s + 3] = make_float4(n_geo.x, n_geo.y, n_geo.z, dot(v0, n_geo));
     trav[RL_TRAV_F4 * s + 4] = make_float4(mu.x, mu.y, mu.z, -dot(v0, mu));

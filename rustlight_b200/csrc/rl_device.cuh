@@ -26,8 +26,10 @@
 
 #if defined(__CUDACC__)
 #define RL_HD __host__ __device__ __forceinline__
+#define RL_HD_NOINLINE __host__ __device__ __noinline__ // rare slow paths: keep their registers and local arrays out of the callers
 #else
 #define RL_HD inline
+#define RL_HD_NOINLINE inline
 struct float4 {
     float x, y, z, w;
 };
@@ -46,6 +48,8 @@ namespace rl {
 #define RL_FRAC_PI_4 0.785398163397448309615660845819875721f
 #define RL_FRAC_1_PI 0.318309886183790671537767526745028724f
 #define RL_MISS 0xFFFFFFFFu
+#define RL_PRIM_NEEDLE 0x40000000u // flag in the prim word of a trav[] record (rl_build.cuh: tri_setup)
+#define RL_PRIM_MASK 0x01ffffffu   // triangle index (< 2^25)
 
 RL_HD uint32_t f2u(float f) {
 #if defined(__CUDA_ARCH__)
@@ -325,6 +329,11 @@ struct SceneView {
     uint32_t n_groups;
     uint32_t flat_valid_a, flat_valid_b; // quad bits whose A / B triangle is real (bit order of flat_scan)
     float flat_delta;       // largest plane mismatch inside a triangle pair (world units), added to the t margin
+    // the reference's own BVH (rl_refbvh_host.hpp), walked only by rays whose two nearest accepted hits (nearly) tie: nullptr = absent
+    const float4 *ref_nodes;   // 2 per node: {p_min, info} {p_max, count}
+    const uint32_t *ref_prims; // leaf contents as Morton slots (indices into trav[])
+    const uint32_t *ref_up;    // [node] parent; [ref_n_nodes + Morton slot] the leaf that holds the triangle
+    uint32_t ref_n_nodes;
     int root_ref; // inner node 0, or a leaf reference when the whole scene is one leaf
     // BVHAccel nodes[0].aabb (union of compute_aabb_tri boxes), for the reference's root test
     V3 root_min, root_max;
@@ -400,6 +409,66 @@ RL_HD bool tri_test(float4 r0, float4 r1, float4 r2, float4 r3, V3 o, V3 d, floa
     return true;
 }
 
+// ---- exact ties: the reference's visit order ------------------------------------------------------
+// Two accepted hits whose t differ by at most RL_TIE_WINDOW (relative) are "tied": which one the reference returns depends on
+// the order in which BVHAccel::intersect visits its leaves and on its `d < its.t` culling (accel.rs:243-288), far beyond what
+// a distance comparison can tell.  Hits further apart than the window are ordered identically by every correct traversal
+// (a box that holds the nearer triangle is entered before the farther hit's t, rounding is ~1e-7 t).
+#define RL_TIE_WINDOW 2e-5f
+#ifndef RL_REF_ORDER
+#define RL_REF_ORDER 1 // 0 compiles the reference-order slow path out (A/B hook: what does carrying it cost?)
+#endif
+#ifndef RL_FLAT_MARGIN_SCALE
+#define RL_FLAT_MARGIN_SCALE 1.0f // test hook: tests/ shrink the margins to measure how much slack they carry
+#endif
+RL_HD float tie_bound(float t) { return t + t * RL_TIE_WINDOW; } // t >= 0; F32_MAX -> inf
+RL_HD bool tie_window(float a, float b) { return fabsf(a - b) <= RL_TIE_WINDOW * fmaxf(a, b); }
+// AABB::intersect returning the entry distance (structure.rs:849-869)
+RL_HD bool aabb_entry_ref(V3 pmin, V3 pmax, V3 o, V3 inv, float tnear, float tfar, float *t_entry) {
+    float t_max = tfar, t_min = tnear;
+    {
+        float t0 = (pmin.x - o.x) * inv.x, t1 = (pmax.x - o.x) * inv.x;
+        if (inv.x < 0.0f) { float t = t0; t0 = t1; t1 = t; }
+        t_min = t0 > t_min ? t0 : t_min;
+        t_max = t1 < t_max ? t1 : t_max;
+        if (t_max <= t_min) return false;
+    }
+    {
+        float t0 = (pmin.y - o.y) * inv.y, t1 = (pmax.y - o.y) * inv.y;
+        if (inv.y < 0.0f) { float t = t0; t0 = t1; t1 = t; }
+        t_min = t0 > t_min ? t0 : t_min;
+        t_max = t1 < t_max ? t1 : t_max;
+        if (t_max <= t_min) return false;
+    }
+    {
+        float t0 = (pmin.z - o.z) * inv.z, t1 = (pmax.z - o.z) * inv.z;
+        if (inv.z < 0.0f) { float t = t0; t0 = t1; t1 = t; }
+        t_min = t0 > t_min ? t0 : t_min;
+        t_max = t1 < t_max ? t1 : t_max;
+        if (t_max <= t_min) return false;
+    }
+    *t_entry = t_min;
+    return true;
+}
+// Is the accepted hit (u, v) within the rounding-safe margin of the triangle's boundary?  The reference's boxes are the exact
+// vertex bounds: a hit on a vertex or edge that lies on a box face can fail BVHAccel's slab test by one ulp (t_max <= t_min),
+// so the reference MISSES it.  A hit further inside than rim_margin (in barycentrics; 2e-6 x the coordinate scale in space, ~10x the
+// rounding of the slab test) is strictly inside every box on its root-to-leaf path and is found by the reference too.
+RL_HD float rim_margin(float mn, float rs8) { return fmaf(mn, 0.25f * rs8, RL_FLAT_MARGIN_SCALE * 2e-6f); } // 2e-6 x coordinate scale in space
+RL_HD bool hit_near_edge(float u, float v, float mn, float rs8) { return !(fminf(fminf(u, v), 1.0f - u - v) >= rim_margin(mn, rs8)); }
+// The other ways BVHAccel can lose an interior hit, all of them properties of its boxes (geometry.rs:423-439: exact vertex bounds,
+// flat extents padded by 1e-4) and of its slab test with tnear = 1e-4 (structure.rs:849-869):
+//   * t <= 1e-4: a box the ray leaves before tnear fails `t_max <= t_min`;
+//   * a box that is thin along two axes (RL_PRIM_NEEDLE): the chord of the ray inside it can be shorter than the rounding of the test;
+//   * the 1e-4 padding itself is no longer large against that rounding, ~3 ulp of (2 |o| + t + scene extent).
+// A hit that is none of these (and neither tied nor on the rim) lies inside every box on its root-to-leaf path with a chord far
+// longer than the rounding, so the reference finds it: the device's answer IS the reference's.  Everything else is re-traced by
+// ref_bvh_closest / ref_bvh_any, i.e. by the reference's own algorithm.
+RL_HD bool hit_unsafe(uint32_t prim_word, float t, float omax, float abs_max) {
+    const float R = 2e-7f * (2.0f * omax + t + abs_max);
+    return (prim_word & RL_PRIM_NEEDLE) != 0u || !(t > 1.001e-4f) || !(8.0f * R <= RL_EPSILON);
+}
+
 // ---- LBVH traversal state -----------------------------------------------------------------------
 // The reference's BVH shape is not reproduced.  Culling is conservative:
 // node boxes are pre-inflated by 3e-5*abs_max at build time (rl_build.cuh), far more than the
@@ -430,7 +499,16 @@ struct Trav {
     V3 et;         // extra widening in t for far origins (0 otherwise)
     bool far;
     float rs2, rs8; // 2e-6 and 8e-6 times the coordinate scale of this ray (prefilter margins)
-    float tmax;    // closest: best t so far; shadow: the segment's threshold
+    float tmax;    // closest: best t so far widened by RL_TIE_WINDOW (culling bound); shadow: the segment's threshold
+    float best;    // closest: best t so far
+    bool amb;      // closest: two accepted hits within the tie window, or the best hit lies on the rim of its triangle -> the reference's
+                   // own traversal decides (ref_bvh_closest); shadow: the segment is blocked only by rim hits so far (ref_bvh_any decides)
+    bool edge;
+    uint32_t slot; // closest: Morton slot of the best triangle
+    uint32_t rim_slot; // shadow: Morton slot of the last rim blocker
+    float tie_t;   // closest: smallest t of a tie seen so far (-1: none); it matters only when it is within the window of the final hit
+    bool edge_checks; // the scene carries the reference's tree (sv.ref_nodes)
+    float omax, abs_max; // max |o|, scene extent (hit_unsafe)
     float u, v;
     uint32_t prim;
     int cur;       // >= 0 inner node, < 0 leaf ~cur, RL_TRAV_DONE
@@ -447,9 +525,15 @@ RL_HD void trav_begin(Trav &tr, const SceneView &sv, V3 o, V3 d, V3 inv, float t
     tr.ood = V3{o.x * tr.inv.x, o.y * tr.inv.y, o.z * tr.inv.z};
     float m = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
     tr.far = m > 8.0f * sv.abs_max;
+    tr.omax = m, tr.abs_max = sv.abs_max;
     float eps = tr.far ? 1e-5f * m : 0.0f;
     tr.et = V3{eps * fabsf(tr.inv.x), eps * fabsf(tr.inv.y), eps * fabsf(tr.inv.z)};
     tr.tmax = tmax;
+    tr.best = tmax;
+    tr.amb = false;
+    tr.edge = false;
+    tr.tie_t = -1.0f;
+    tr.edge_checks = RL_REF_ORDER && sv.ref_nodes != nullptr;
     tr.u = 0.0f;
     tr.v = 0.0f;
     tr.prim = RL_MISS;
@@ -554,10 +638,14 @@ RL_HD void trav_leaf_closest(Trav &tr, const int *stack, const float4 *trav) {
         float4 r1 = r[1];
         float t_, u_, v_;
         if (tri_test(r[0], r1, r[2], r[3], tr.o, tr.d, tr.tmax, &t_, &u_, &v_)) {
-            uint32_t prim_ = f2u(r1.w);
-            // reference: strict `t < its.t` in mesh-major order => on exact ties the lowest index wins
-            if (t_ < tr.tmax || (tr.prim != RL_MISS && prim_ < tr.prim)) {
-                tr.tmax = t_;
+            const uint32_t pw = f2u(r1.w), prim_ = pw & RL_PRIM_MASK;
+            if (tr.prim != RL_MISS && prim_ != tr.prim && tie_window(t_, tr.best)) tr.tie_t = tr.tie_t < 0.0f ? fminf(t_, tr.best) : fminf(tr.tie_t, fminf(t_, tr.best));
+            // without the reference's tree (sv.ref_nodes == nullptr): strict `t < its.t` in mesh-major order => on exact ties the lowest index wins
+            if (t_ < tr.best || (t_ == tr.best && tr.prim != RL_MISS && prim_ < tr.prim)) {
+                tr.best = t_;
+                tr.slot = first + k;
+                tr.edge = hit_near_edge(u_, v_, r[2].w, tr.rs8) || hit_unsafe(pw, t_, tr.omax, tr.abs_max);
+                tr.tmax = tie_bound(t_);
                 tr.u = u_;
                 tr.v = v_;
                 tr.prim = prim_;
@@ -575,7 +663,13 @@ RL_HD bool trav_leaf_any(Trav &tr, const int *stack, const float4 *trav) {
         mask &= mask - 1;
         const float4 *r = trav + 6 * (first + k);
         float t_, u_, v_;
-        if (tri_test(r[0], r[1], r[2], r[3], tr.o, tr.d, tr.tmax, &t_, &u_, &v_) && t_ < tr.tmax) {
+        const float4 r1 = r[1];
+        if (tri_test(r[0], r1, r[2], r[3], tr.o, tr.d, tr.tmax, &t_, &u_, &v_) && t_ < tr.tmax) {
+            if (tr.edge_checks && (hit_near_edge(u_, v_, r[2].w, tr.rs8) || hit_unsafe(f2u(r1.w), t_, tr.omax, tr.abs_max))) {
+                tr.rim_slot = first + k; // a rim hit: the caller checks whether the reference reaches it (ref_path_ok) ...
+                tr.amb = true;           // ... meanwhile keep looking for a blocker the reference cannot miss
+                continue;
+            }
             tr.cur = RL_TRAV_DONE;
             return true;
         }
@@ -584,6 +678,103 @@ RL_HD bool trav_leaf_any(Trav &tr, const int *stack, const float4 *trav) {
     return false;
 }
 
+// BVHAccel::intersect (accel.rs:243-288) over the reference's own tree, for a ray that passed the root test (tnear = 1e-4; `tfar`
+// and the initial its.t are f32::MAX for trace(), the shadow threshold for visible()).  The recursion becomes a stack of
+// (node, entry distance): the far child waits on the stack and its `d2 < its.t` test runs when it is popped, i.e. after the near
+// subtree has finished -- exactly where the reference evaluates it.  Leaves test their (<= 2) primitives in order with the
+// reference's strict `t < its.t`.  ANY: stop at the first accepted triangle (visible() only asks whether there is one).  The
+// tree's depth is checked against RL_STACK_SIZE when the scene is built.  Returns true when a triangle was accepted.
+template <bool ANY>
+RL_HD bool ref_bvh_walk(const float4 *ref_nodes, const uint32_t *ref_prims, const float4 *trav, V3 o, V3 d, float tfar, float *t_io, float *u_io, float *v_io, uint32_t *prim_io) {
+    const V3 inv = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    float best = tfar, bu = 0.0f, bv = 0.0f;
+    uint32_t bprim = RL_MISS;
+    int st_node[RL_STACK_SIZE];
+    float st_dist[RL_STACK_SIZE];
+    int sp = 0;
+    int node = 0;
+    for (;;) {
+        const float4 n0 = ref_nodes[2 * node], n1 = ref_nodes[2 * node + 1];
+        const uint32_t info = f2u(n0.w), count = f2u(n1.w);
+        if (count != 0u) {
+            for (uint32_t k = 0; k < count; k++) {
+                const float4 *r = trav + 6 * ref_prims[info + k];
+                const float4 r1 = r[1];
+                float t_, u_, v_;
+                if (tri_test(r[0], r1, r[2], r[3], o, d, best, &t_, &u_, &v_) && t_ < best) {
+                    best = t_, bu = u_, bv = v_, bprim = f2u(r1.w) & RL_PRIM_MASK;
+                    if (ANY) return true;
+                }
+            }
+        } else {
+            int id1 = (int)info, id2 = (int)info + 1;
+            float d1, d2;
+            const float4 a0 = ref_nodes[2 * id1], a1 = ref_nodes[2 * id1 + 1], b0 = ref_nodes[2 * id2], b1 = ref_nodes[2 * id2 + 1];
+            if (!aabb_entry_ref(xyz(a0), xyz(a1), o, inv, RL_EPSILON, tfar, &d1)) d1 = u2f(0x7f800000u);
+            if (!aabb_entry_ref(xyz(b0), xyz(b1), o, inv, RL_EPSILON, tfar, &d2)) d2 = u2f(0x7f800000u);
+            if (d1 > d2) {
+                const float td = d1;
+                d1 = d2, d2 = td;
+                const int ti = id1;
+                id1 = id2, id2 = ti;
+            }
+            if (sp < RL_STACK_SIZE) st_node[sp] = id2, st_dist[sp] = d2, sp++;
+            if (d1 < best) {
+                node = id1;
+                continue;
+            }
+        }
+        bool found = false;
+        while (sp > 0) {
+            sp--;
+            if (st_dist[sp] < best) {
+                node = st_node[sp];
+                found = true;
+                break;
+            }
+        }
+        if (!found) break;
+    }
+    if (!ANY) *t_io = bprim == RL_MISS ? RL_F32_MAX : best, *u_io = bu, *v_io = bv, *prim_io = bprim;
+    return bprim != RL_MISS;
+}
+RL_HD_NOINLINE void ref_bvh_closest_impl(const float4 *ref_nodes, const uint32_t *ref_prims, const float4 *trav, V3 o, V3 d, float *t_io, float *u_io, float *v_io,
+                                         uint32_t *prim_io) {
+    ref_bvh_walk<false>(ref_nodes, ref_prims, trav, o, d, RL_F32_MAX, t_io, u_io, v_io, prim_io);
+}
+RL_HD_NOINLINE bool ref_bvh_any_impl(const float4 *ref_nodes, const uint32_t *ref_prims, const float4 *trav, V3 o, V3 d, float thr) {
+    float t_, u_, v_;
+    uint32_t p_;
+    return ref_bvh_walk<true>(ref_nodes, ref_prims, trav, o, d, thr, &t_, &u_, &v_, &p_);
+}
+RL_HD void ref_bvh_closest(const SceneView &sv, const float4 *trav, V3 o, V3 d, float *t_io, float *u_io, float *v_io, uint32_t *prim_io) {
+#ifdef RL_REF_NOCALL
+    *t_io = *t_io + 0.0f * (float)(uintptr_t)sv.ref_nodes;
+    return;
+#endif
+    ref_bvh_closest_impl(sv.ref_nodes, sv.ref_prims, trav, o, d, t_io, u_io, v_io, prim_io);
+}
+// Does the reference reach the leaf of the triangle at Morton slot `slot`?  It does when every box on the way up to the root
+// passes its slab test (the caller has tested the root): the hit lies in all of them, so their entry distances are <= t (1 + ulps),
+// below any its.t the reference can hold before it finds this hit (the hit is the nearest by more than the tie window).  This settles
+// rim hits and hit_unsafe hits without a full walk; what fails here goes to ref_bvh_closest / ref_bvh_any.
+RL_HD bool ref_path_ok(const SceneView &sv, uint32_t slot, V3 o, V3 d, float tfar) {
+    const V3 inv = V3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+    uint32_t node = sv.ref_up[sv.ref_n_nodes + slot];
+    while (node != 0u) {
+        const float4 n0 = sv.ref_nodes[2 * node], n1 = sv.ref_nodes[2 * node + 1];
+        float t_entry;
+        if (!aabb_entry_ref(xyz(n0), xyz(n1), o, inv, RL_EPSILON, tfar, &t_entry)) return false;
+        node = sv.ref_up[node];
+    }
+    return true;
+}
+RL_HD bool ref_bvh_any(const SceneView &sv, const float4 *trav, V3 o, V3 d, float thr) {
+#ifdef RL_REF_NOCALL
+    return thr > 1e30f;
+#endif
+    return ref_bvh_any_impl(sv.ref_nodes, sv.ref_prims, trav, o, d, thr);
+}
 // ---- flat quad scan (scenes of a few dozen triangles) -----------------------------------------------
 // Incoherent rays gain nothing from a hierarchy over ~36 triangles (every lane of a warp walks a different
 // branch), so they run a conservative prefilter over ALL triangles in lockstep and the exact test only on
@@ -607,9 +798,6 @@ RL_HD bool trav_leaf_any(Trav &tr, const int *stack, const float4 *trav) {
 #define RL_FLAT_F4 8
 #define RL_FLAT_TAIL_F4 4
 #define RL_FLAT_MAX_GROUPS 16
-#ifndef RL_FLAT_MARGIN_SCALE
-#define RL_FLAT_MARGIN_SCALE 1.0f // test hook: tests/ shrink the margins to measure how much slack they carry
-#endif
 struct F2 {
     float x, y;
 };
@@ -677,12 +865,14 @@ struct FlatRay {
     V3 o, d;
     float tmax;
     float rs2, rs8; // margins scaled by the coordinate magnitude of this ray (as in trav_begin) + flat_delta
+    float omax;     // max |o|
 };
 RL_HD FlatRay flat_ray(const SceneView &sv, V3 o, V3 d, float tmax) {
     FlatRay fr;
     fr.o = o, fr.d = d, fr.tmax = tmax;
     float m = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
     const float rs = 4.0f * fmaxf(m, sv.abs_max);
+    fr.omax = m;
     fr.rs2 = RL_FLAT_MARGIN_SCALE * (3e-6f * rs + 2.0f * sv.flat_delta);
     fr.rs8 = RL_FLAT_MARGIN_SCALE * 8e-6f * rs;
     return fr;
@@ -784,7 +974,7 @@ RL_HD uint32_t flat_slot(const SceneView &sv, const float4 *flat, uint32_t bit) 
 // (|u0| <= |alpha| / |n| + |e1| eta with eta the out-of-plane rounding of p, far below ml det: DESIGN.md section 6),
 // and by the reference's own (u, v) otherwise.  Returns 0 = rejected, 1 = accepted with (u, v) still to be computed
 // by tri_uv, 2 = accepted and (u, v) computed.
-RL_HD int tri_test_lazy(float4 r0, float4 r1, float4 r2, float4 r3, V3 o, V3 d, float t_bound, float rs8, float *t_out, float *u_out, float *v_out) {
+RL_HD int tri_test_lazy(float4 r0, float4 r1, float4 r2, float4 r3, V3 o, V3 d, float t_bound, float rs8, float *t_out, float *u_out, float *v_out, bool *near_edge) {
     V3 v0 = xyz(r0), e1 = xyz(r1), e2 = xyz(r2), n_geo = xyz(r3);
     float det = r0.w;
     float denom = dot(d, n_geo);
@@ -803,6 +993,10 @@ RL_HD int tri_test_lazy(float4 r0, float4 r1, float4 r2, float4 r3, V3 o, V3 d, 
     *t_out = t;
     const float ml = fmaf(r2.w, rs8, RL_FLAT_MARGIN_SCALE * 2e-6f);
     const float s = alpha + beta;
+    if (near_edge) { // not strictly interior by the rim margin (see hit_near_edge)
+        const float mr = rim_margin(r2.w, rs8);
+        *near_edge = !(fminf(alpha, beta) >= det * mr && s <= det * (1.0f - mr));
+    }
     if (s <= det * (1.0f - ml)) return 1; // false for NaN
     if (s > det * (1.0f + ml)) return 0;
     float v = magnitude(u0) / det;
@@ -824,15 +1018,20 @@ RL_HD void tri_uv(float4 r0, float4 r1, float4 r2, V3 o, V3 d, float t, float *u
     *v_out = magnitude(u0) / det;
     *u_out = magnitude(v0c) / det;
 }
-// Closest hit over the flat table: same result rule as trav_leaf_closest.
-template <bool CULL = false>
-RL_HD HitRec flat_closest(const SceneView &sv, const float4 *flat, const float4 *trav, V3 o, V3 d, uint32_t quads = 0xffffffffu) {
+// Closest hit over the flat table: same result rule as trav_leaf_closest.  The loop only keeps the best and the second-best accepted
+// t; whether the winner is one the reference finds for certain (not tied, not on the rim, not hit_unsafe) is decided once, after it.
+// DEFER: do not walk the reference's tree here; report the ray in *needs_ref instead (the wavefront kernels collect such rays in a list
+// that k_fix_flat re-traces right after: a call to the slow path inside the hot kernels costs them 10-20 % through register allocation
+// alone, measured).
+template <bool CULL = false, bool DEFER = false>
+RL_HD HitRec flat_closest(const SceneView &sv, const float4 *flat, const float4 *trav, V3 o, V3 d, uint32_t quads = 0xffffffffu, bool *needs_ref = nullptr) {
     FlatRay fr = flat_ray(sv, o, d, RL_F32_MAX);
     HitRec h;
     h.t = RL_F32_MAX, h.u = 0.0f, h.v = 0.0f, h.prim = RL_MISS;
     uint64_t c = flat_candidates<CULL, false>(fr, sv, flat, quads);
     uint32_t best_slot = 0u;
     bool need_uv = false;
+    float t2 = u2f(0x7f800000u); // second smallest accepted t (a different triangle than the best)
     while (c) {
         const uint32_t b = (uint32_t)ffs64(c) - 1u;
         c &= c - 1;
@@ -840,31 +1039,59 @@ RL_HD HitRec flat_closest(const SceneView &sv, const float4 *flat, const float4 
         const float4 *r = trav + 6 * slot;
         float4 r1 = r[1];
         float t_, u_, v_;
-        const int k = tri_test_lazy(r[0], r1, r[2], r[3], o, d, h.t, fr.rs8, &t_, &u_, &v_);
+        const int k = tri_test_lazy(r[0], r1, r[2], r[3], o, d, tie_bound(h.t), fr.rs8, &t_, &u_, &v_, nullptr);
         if (k) {
-            uint32_t prim_ = f2u(r1.w);
-            if (t_ < h.t || (h.prim != RL_MISS && prim_ < h.prim)) {
+            const uint32_t prim_ = f2u(r1.w) & RL_PRIM_MASK;
+            if (t_ < h.t || (t_ == h.t && h.prim != RL_MISS && prim_ < h.prim)) {
+                if (h.prim != RL_MISS) t2 = h.t;
                 h.t = t_, h.prim = prim_, best_slot = slot, need_uv = k == 1;
                 if (k == 2) h.u = u_, h.v = v_;
-            }
+            } else t2 = fminf(t2, t_);
         }
     }
-    if (need_uv) {
-        const float4 *r = trav + 6 * best_slot;
-        tri_uv(r[0], r[1], r[2], o, d, h.t, &h.u, &h.v);
+    if (h.prim == RL_MISS) return h;
+    const float4 *rb = trav + 6 * best_slot;
+    const float4 rb1 = rb[1], rb2 = rb[2];
+    if (need_uv) tri_uv(rb[0], rb1, rb2, o, d, h.t, &h.u, &h.v);
+    if (RL_REF_ORDER && sv.ref_nodes) {
+        // (nearly) tied hits, a hit on the rim of its triangle or one the reference's boxes may lose: the reference's own traversal decides
+        // ties, and hits nearer than the reference's tnear = 1e-4 (every box entry distance is clamped to tnear there, so `d < its.t` culls
+        // whole subtrees as soon as ANY such hit is found): the full walk.  Rim / hit_unsafe hits: only when the reference misses the leaf.
+        bool walk = t2 <= tie_bound(h.t) || !(h.t > 1.001e-4f);
+        if (!walk && (hit_near_edge(h.u, h.v, rb2.w, fr.rs8) || hit_unsafe(f2u(rb1.w), h.t, fr.omax, sv.abs_max))) walk = !ref_path_ok(sv, best_slot, o, d, RL_F32_MAX);
+        if (walk) {
+            if (DEFER) *needs_ref = true;
+            else ref_bvh_closest(sv, trav, o, d, &h.t, &h.u, &h.v, &h.prim);
+        }
     }
     return h;
 }
 // Any hit with t < thr over the flat table (Acceleration::visible): true when the segment is blocked.
-RL_HD bool flat_any(const SceneView &sv, const float4 *flat, const float4 *trav, V3 o, V3 d, float thr) {
+template <bool DEFER = false>
+RL_HD bool flat_any(const SceneView &sv, const float4 *flat, const float4 *trav, V3 o, V3 d, float thr, bool *needs_ref = nullptr) {
     FlatRay fr = flat_ray(sv, o, d, thr);
     uint64_t c = flat_candidates<false, true>(fr, sv, flat, 0xffffffffu);
+    bool rim = false; // blocked only by hits on the rim of their triangle: the reference's boxes may cull them
     while (c) {
         const uint32_t b = (uint32_t)ffs64(c) - 1u;
         c &= c - 1;
-        const float4 *r = trav + 6 * flat_slot(sv, flat, b);
+        const uint32_t slot = flat_slot(sv, flat, b);
+        const float4 *r = trav + 6 * slot;
         float t_, u_, v_;
-        if (tri_test_lazy(r[0], r[1], r[2], r[3], o, d, thr, fr.rs8, &t_, &u_, &v_) && t_ < thr) return true;
+        bool ne;
+        const float4 r1 = r[1];
+        if (tri_test_lazy(r[0], r1, r[2], r[3], o, d, thr, fr.rs8, &t_, &u_, &v_, &ne) && t_ < thr) {
+            if (!RL_REF_ORDER || !sv.ref_nodes || !(ne || hit_unsafe(f2u(r1.w), t_, fr.omax, sv.abs_max))) return true;
+            if (ref_path_ok(sv, slot, o, d, thr)) return true; // the reference reaches this blocker
+            rim = true;
+        }
+    }
+    if (rim) {
+        if (DEFER) {
+            *needs_ref = true; // undecided: k_fix_flat walks the reference's tree and adds the contribution when the segment is visible
+            return true;
+        }
+        return ref_bvh_any(sv, trav, o, d, thr);
     }
     return false;
 }
@@ -880,9 +1107,15 @@ RL_HD bool closest_begin(Trav &tr, const SceneView &sv, V3 o, V3 d) {
     }
     return true;
 }
+// Must the reference's own walk decide this ray?  Ties: yes.  Rim / hit_unsafe hits: only when the reference does not reach the leaf.
+RL_HD bool closest_ambiguous(const Trav &tr, const SceneView &sv) {
+    if (tr.prim == RL_MISS) return false;
+    if ((tr.tie_t >= 0.0f && tie_window(tr.tie_t, tr.best)) || !(tr.best > 1.001e-4f)) return true; // (see flat_closest)
+    return tr.edge && !ref_path_ok(sv, tr.slot, tr.o, tr.d, RL_F32_MAX);
+}
 RL_HD HitRec closest_result(const Trav &tr) {
     HitRec h;
-    h.t = tr.prim == RL_MISS ? RL_F32_MAX : tr.tmax;
+    h.t = tr.prim == RL_MISS ? RL_F32_MAX : tr.best;
     h.u = tr.u;
     h.v = tr.v;
     h.prim = tr.prim;
@@ -939,7 +1172,9 @@ RL_HD HitRec trace_closest(const SceneView &sv, const float4 *flat, const float4
             else trav_leaf_closest(tr, stack, trav);
         }
     }
-    return closest_result(tr);
+    HitRec h = closest_result(tr);
+    if (RL_REF_ORDER && sv.ref_nodes && closest_ambiguous(tr, sv)) ref_bvh_closest(sv, trav, o, d, &h.t, &h.u, &h.v, &h.prim);
+    return h;
 }
 RL_HD bool trace_visible(const SceneView &sv, const float4 *flat, const float4 *nodes, const float4 *trav, V3 p0, V3 p1) {
     Trav tr;
@@ -957,6 +1192,7 @@ RL_HD bool trace_visible(const SceneView &sv, const float4 *flat, const float4 *
         if (tr.cur >= 0) trav_node_step(tr, stack, nodes);
         else if (trav_leaf_any(tr, stack, trav)) return false;
     }
+    if (tr.amb) return !(ref_path_ok(sv, tr.rim_slot, tr.o, tr.d, tr.tmax) || ref_bvh_any(sv, trav, tr.o, tr.d, tr.tmax)); // blocked by rim hits only
     return true;
 }
 // the group table where the scene description says it is (global memory); kernels that stage it pass their copy

@@ -57,7 +57,7 @@ inline bool build_flat_table(const HostScene &hs, const std::vector<uint32_t> &p
     out = FlatTable{};
     if (n == 0 || n > 64 || prim_of_slot.size() != n) return false;
     std::vector<float4> rec((size_t)RL_TRAV_F4 * n), shade_tmp(hs.shade);
-    for (uint32_t s = 0; s < n; s++) tri_setup(hs.verts.data(), prim_of_slot[s], s, rec.data(), shade_tmp.data());
+    for (uint32_t s = 0; s < n; s++) tri_setup(hs.verts.data(), prim_of_slot[s], s, bvh_box_eps(hs.abs_max), rec.data(), shade_tmp.data());
     const double cap = 1e-6 * (double)hs.abs_max;
     auto vert = [&](uint32_t slot, int k) { return hs.verts[3 * (size_t)prim_of_slot[slot] + k]; };
     auto mismatch = [&](uint32_t a, uint32_t b) { // vertices of slot b against the float plane of slot a

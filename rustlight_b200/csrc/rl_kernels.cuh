@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(kBlock) k_trace(SceneView sv, const uint32_t *
 #endif
         if (tr.cur == RL_TRAV_DONE && my != RL_MISS) {
             HitRec h = closest_result(tr);
+            if (RL_REF_ORDER && sv.ref_nodes && closest_ambiguous(tr, sv)) ref_bvh_closest(sv, trav, tr.o, tr.d, &h.t, &h.u, &h.v, &h.prim); // tied / rim hits: the reference's own traversal
             hit[my] = make_float4(h.t, h.u, h.v, u2f(h.prim));
             my = RL_MISS;
         }
@@ -187,7 +188,7 @@ __device__ __forceinline__ void stage_flat(const SceneView &sv, float4 *smem, ui
 template <bool CULL>
 __device__ __forceinline__ void trace_flat_body_t(const SceneView &sv, const float4 *flat, const float4 *trav, uint32_t bid, uint32_t nblocks, uint32_t n,
                                                 const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d, float4 *__restrict__ hit, bool camera,
-                                                const uint32_t *__restrict__ cam_masks, uint32_t npix) {
+                                                const uint32_t *__restrict__ cam_masks, uint32_t npix, uint32_t *fix_count, uint32_t *fix_list) {
     for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n; i += nblocks * blockDim.x) {
         const float4 rd = ray_d[i];
         const V3 o = camera ? sv.cam_pos : xyz(ray_o[i]), d = xyz(rd); // camera rays share their origin: it is not stored (k_raygen)
@@ -196,26 +197,31 @@ __device__ __forceinline__ void trace_flat_body_t(const SceneView &sv, const flo
         if (CULL) quads = __reduce_or_sync(__activemask(), __ldg(cam_masks + ((i % npix) >> 5)));
         HitRec h;
         h.t = RL_F32_MAX, h.u = 0.0f, h.v = 0.0f, h.prim = RL_MISS;
-        if (aabb_intersect_ref(sv.root_min, sv.root_max, o, inv, RL_EPSILON, RL_F32_MAX)) h = flat_closest<CULL>(sv, flat, trav, o, d, quads);
+        bool needs_ref = false;
+        if (aabb_intersect_ref(sv.root_min, sv.root_max, o, inv, RL_EPSILON, RL_F32_MAX)) h = flat_closest<CULL, true>(sv, flat, trav, o, d, quads, &needs_ref);
         hit[i] = make_float4(h.t, h.u, h.v, u2f(h.prim));
+        if (needs_ref) fix_list[atomicAdd(fix_count, 1u)] = i; // a few rays in 10^4 (ties, rim hits): re-traced over the reference's tree by k_fix_flat
     }
 }
 __device__ __forceinline__ void trace_flat_body(const SceneView &sv, const float4 *flat, const float4 *trav, uint32_t bid, uint32_t nblocks, uint32_t n,
                                                 const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d, float4 *__restrict__ hit, bool camera,
-                                                const uint32_t *__restrict__ cam_masks, uint32_t npix) {
-    if (cam_masks) trace_flat_body_t<true>(sv, flat, trav, bid, nblocks, n, ray_o, ray_d, hit, camera, cam_masks, npix);
-    else trace_flat_body_t<false>(sv, flat, trav, bid, nblocks, n, ray_o, ray_d, hit, camera, cam_masks, npix);
+                                                const uint32_t *__restrict__ cam_masks, uint32_t npix, uint32_t *fix_count, uint32_t *fix_list) {
+    if (cam_masks) trace_flat_body_t<true>(sv, flat, trav, bid, nblocks, n, ray_o, ray_d, hit, camera, cam_masks, npix, fix_count, fix_list);
+    else trace_flat_body_t<false>(sv, flat, trav, bid, nblocks, n, ray_o, ray_d, hit, camera, cam_masks, npix, fix_count, fix_list);
 }
 __device__ __forceinline__ void shadow_flat_body(const SceneView &sv, const float4 *flat, const float4 *trav, uint32_t bid, uint32_t nblocks, uint32_t n,
                                                  const float4 *__restrict__ sh_a, const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c,
-                                                 float4 *__restrict__ lacc, Counters *counters) {
+                                                 float4 *__restrict__ lacc, Counters *counters, uint32_t *fix_count, uint32_t *fix_list) {
     uint32_t c_vis = 0;
     for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n; i += nblocks * blockDim.x) {
         const float4 a = sh_a[i], b = sh_b[i];
         V3 d;
         float thr;
+        bool needs_ref = false;
         // root test failed => "not visible" (accel.rs:338-340): nothing to add
-        if (visible_setup(sv, xyz(a), xyz(b), &d, &thr) && !flat_any(sv, flat, trav, xyz(a), d, thr)) {
+        const bool vis = visible_setup(sv, xyz(a), xyz(b), &d, &thr) && !flat_any<true>(sv, flat, trav, xyz(a), d, thr, &needs_ref);
+        if (needs_ref) fix_list[atomicAdd(fix_count, 1u)] = i; // blocked by rim hits only: k_fix_flat decides (and adds the contribution)
+        if (vis) {
             const float4 c = sh_c[i];
             const uint32_t pid = f2u(a.w);
             float4 l = lacc[pid];
@@ -232,21 +238,23 @@ __device__ __forceinline__ void shadow_flat_body(const SceneView &sv, const floa
 #endif
 __global__ void __launch_bounds__(kBlock, RL_TRAV_MINBLOCKS) k_trace_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
                                                        const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t n_trav_f4, uint32_t camera,
-                                                       const uint32_t *__restrict__ cam_masks, uint32_t npix, const uint32_t *__restrict__ done_at, uint32_t my_k) {
+                                                       const uint32_t *__restrict__ cam_masks, uint32_t npix, const uint32_t *__restrict__ done_at, uint32_t my_k,
+                                                       uint32_t *fix_count, uint32_t *fix_list) {
     extern __shared__ float4 smem[];
     if (batch_done(done_at, my_k) || blockIdx.x * blockDim.x >= *count) return; // nothing for this CTA: skip the staging
     const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4 + RL_FLAT_TAIL_F4;
     stage_flat(sv, smem, n_flat_f4, n_trav_f4);
-    trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, gridDim.x, *count, ray_o, ray_d, hit, camera != 0u, cam_masks, npix);
+    trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, gridDim.x, *count, ray_o, ray_d, hit, camera != 0u, cam_masks, npix, fix_count, fix_list);
 }
 __global__ void __launch_bounds__(kBlock, RL_TRAV_MINBLOCKS) k_shadow_flat(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ sh_a,
                                                         const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c, float4 *__restrict__ lacc,
-                                                        Counters *counters, uint32_t n_trav_f4, const uint32_t *__restrict__ done_at, uint32_t my_k) {
+                                                        Counters *counters, uint32_t n_trav_f4, const uint32_t *__restrict__ done_at, uint32_t my_k,
+                                                        uint32_t *fix_count, uint32_t *fix_list) {
     extern __shared__ float4 smem[];
     if (batch_done(done_at, my_k) || blockIdx.x * blockDim.x >= *count) return;
     const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4 + RL_FLAT_TAIL_F4;
     stage_flat(sv, smem, n_flat_f4, n_trav_f4);
-    shadow_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, gridDim.x, *count, sh_a, sh_b, sh_c, lacc, counters);
+    shadow_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, gridDim.x, *count, sh_a, sh_b, sh_c, lacc, counters, fix_count, fix_list);
 }
 // Extension rays of wavefront iteration k+1 and shadow rays of iteration k are independent (the shadow kernel only adds
 // to the per-path accumulators, which the traversal does not touch): one launch runs both, CTAs [0, trace_blocks) on the
@@ -258,14 +266,66 @@ __global__ void __launch_bounds__(kBlock, RL_TRAV_MINBLOCKS) k_trace_shadow_flat
                                                               const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c, float4 *__restrict__ lacc,
                                                               Counters *counters, uint32_t n_trav_f4, uint32_t trace_blocks, uint32_t camera,
                                                               const uint32_t *__restrict__ cam_masks, uint32_t npix,
-                                                              const uint32_t *__restrict__ done_at, uint32_t my_k) {
+                                                              const uint32_t *__restrict__ done_at, uint32_t my_k, uint32_t *fix_count_trace,
+                                                              uint32_t *fix_list_trace, uint32_t *fix_count_shadow, uint32_t *fix_list_shadow) {
     extern __shared__ float4 smem[];
     if (batch_done(done_at, my_k)) return; // (fused launches are only scheduled before the first k_tail launch: both halves are live or neither)
     if (blockIdx.x < trace_blocks ? blockIdx.x * blockDim.x >= *count : (blockIdx.x - trace_blocks) * blockDim.x >= *sh_count) return;
     const uint32_t n_flat_f4 = sv.n_groups * RL_FLAT_F4 + RL_FLAT_TAIL_F4;
     stage_flat(sv, smem, n_flat_f4, n_trav_f4);
-    if (blockIdx.x < trace_blocks) trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, trace_blocks, *count, ray_o, ray_d, hit, camera != 0u, cam_masks, npix);
-    else shadow_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x - trace_blocks, gridDim.x - trace_blocks, *sh_count, sh_a, sh_b, sh_c, lacc, counters);
+    if (blockIdx.x < trace_blocks) trace_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x, trace_blocks, *count, ray_o, ray_d, hit, camera != 0u, cam_masks, npix, fix_count_trace, fix_list_trace);
+    else shadow_flat_body(sv, smem, smem + n_flat_f4, blockIdx.x - trace_blocks, gridDim.x - trace_blocks, *sh_count, sh_a, sh_b, sh_c, lacc, counters, fix_count_shadow, fix_list_shadow);
+}
+
+// ---- the rays the hot kernels could not decide for certain ------------------------------------------------
+// A few rays in 10^4: two accepted hits within the tie window, a hit on the rim of its triangle, or one the reference's boxes may
+// lose (rl_device.cuh: hit_unsafe).  For them the reference's answer is whatever BVHAccel::intersect does, so they are re-traced
+// over the reference's own tree (ref_bvh_closest / ref_bvh_any): closest-hit rays get their hit record rewritten, shadow segments
+// are decided here and their contribution added.  Runs right after the kernel that filled the lists, before anything reads the hits.
+__global__ void __launch_bounds__(128) k_fix_flat(SceneView sv, const uint32_t *__restrict__ n_trace, const uint32_t *__restrict__ list_trace,
+                                                  const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t camera,
+                                                  const uint32_t *__restrict__ n_shadow, const uint32_t *__restrict__ list_shadow, const float4 *__restrict__ sh_a,
+                                                  const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c, float4 *__restrict__ lacc, Counters *counters,
+                                                  const uint32_t *__restrict__ done_at, uint32_t my_k, uint32_t n_ref_f4, uint32_t n_trav_f4) {
+    extern __shared__ float4 smem[];
+    if (batch_done(done_at, my_k)) return;
+    // ONE ray per warp (lane 0): the walk is irregular, 32 different walks in one warp would execute one after the other
+    // (measured: 25-50 us per launch whatever the list length, against ~10 us like this)
+    const uint32_t nt = *n_trace, ns = *n_shadow;
+    const uint32_t warps_per_cta = blockDim.x >> 5, warp0 = blockIdx.x * warps_per_cta, n_warps = gridDim.x * warps_per_cta;
+    if (warp0 >= max(nt, ns)) return; // (usually: the lists hold a handful of rays)
+    // the reference's tree, its leaf contents and the triangle records in shared memory: the walk is a chain of dependent loads
+    float4 *s_nodes = smem, *s_trav = smem + n_ref_f4;
+    uint32_t *s_prims = reinterpret_cast<uint32_t *>(smem + n_ref_f4 + n_trav_f4);
+    for (uint32_t i = threadIdx.x; i < n_ref_f4; i += blockDim.x) s_nodes[i] = ldg4(sv.ref_nodes + i);
+    for (uint32_t i = threadIdx.x; i < n_trav_f4; i += blockDim.x) s_trav[i] = ldg4(sv.trav + i);
+    for (uint32_t i = threadIdx.x; i < sv.ntris; i += blockDim.x) s_prims[i] = __ldg(sv.ref_prims + i);
+    __syncthreads();
+    sv.ref_nodes = s_nodes, sv.ref_prims = s_prims;
+    if ((threadIdx.x & 31u) != 0u) return;
+    const uint32_t w = warp0 + (threadIdx.x >> 5);
+    for (uint32_t j = w; j < nt; j += n_warps) {
+        const uint32_t i = list_trace[j];
+        const float4 rd = ray_d[i];
+        const V3 o = camera ? sv.cam_pos : xyz(ray_o[i]), d = xyz(rd);
+        HitRec h;
+        ref_bvh_closest(sv, s_trav, o, d, &h.t, &h.u, &h.v, &h.prim); // the ray passed the root test (it had a hit)
+        hit[i] = make_float4(h.t, h.u, h.v, u2f(h.prim));
+    }
+    for (uint32_t j = w; j < ns; j += n_warps) {
+        const uint32_t i = list_shadow[j];
+        const float4 a = sh_a[i], b = sh_b[i];
+        V3 d;
+        float thr;
+        if (visible_setup(sv, xyz(a), xyz(b), &d, &thr) && !ref_bvh_any(sv, s_trav, xyz(a), d, thr)) {
+            const float4 c = sh_c[i];
+            const uint32_t pid = f2u(a.w);
+            float4 l = lacc[pid];
+            l.x += c.x, l.y += c.y, l.z += c.z;
+            lacc[pid] = l;
+            atomicAdd(&counters->shadow_visible, 1ull);
+        }
+    }
 }
 
 // ---- block-level compaction helper ---------------------------------------------------------------
@@ -689,6 +749,7 @@ __global__ void __launch_bounds__(kBlock) k_shadow(SceneView sv, const uint32_t 
         else if (tr.cur < 0) blocked = trav_leaf_any(tr, stack, trav) || blocked;
 #endif
         if (tr.cur == RL_TRAV_DONE && my != RL_MISS) {
+            if (!blocked && tr.amb) blocked = ref_path_ok(sv, tr.rim_slot, tr.o, tr.d, tr.tmax) || ref_bvh_any(sv, trav, tr.o, tr.d, tr.tmax); // only rim hits block the segment: the reference's boxes decide
             if (!blocked) { // visible: add the light-sampling contribution to the path's accumulator
                 float4 c = sh_c[my];
                 uint32_t pid = f2u(sh_a[my].w);
@@ -746,6 +807,7 @@ __global__ void k_tally(const uint32_t *__restrict__ qc, const uint32_t *__restr
     for (uint32_t k = 0; k < lim; k++) {
         seg += qc[k];
         if (shc) sh += shc[k];
+        else if (k == 1) sh += qc[2]; // `direct`: d_counts = {primary rays, extension rays, shadow segments, done_at}
         if (qc[k]) deepest = iter_offset + k + 1;
     }
     counters->wave_segments += seg;
@@ -790,7 +852,7 @@ __global__ void __launch_bounds__(kBlock) k_tri_setup(const float4 *__restrict__
                                                       float4 *shade, float4 *leaf_lo, float4 *leaf_hi) {
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < ntris; s += gridDim.x * blockDim.x) {
         uint32_t prim = (uint32_t)(keys[s] & 0xffffffffull);
-        tri_setup(verts, prim, s, trav, shade);
+        tri_setup(verts, prim, s, box_eps, trav, shade);
         V3 lo, hi;
         tri_bounds_inflated(verts, prim, box_eps, &lo, &hi);
         leaf_lo[s] = make_float4(lo.x, lo.y, lo.z, 0.0f);

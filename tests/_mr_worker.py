@@ -32,7 +32,7 @@ def main():
     for integ in (_abi.path_desc(), _abi.direct_desc(1, 1)):
         part, st = eb.EmuScene(sc).render(integ, 3, seed=7, rank=rank, nranks=world)
         opart, ost = ob.OracleScene(sc).render(integ, 3, seed=7, cfg=ob.config(
-            estimator=ob.EST_STREAM, accel_mode=ob.ACCEL_NAIVE, rank=rank, nranks=world))
+            estimator=ob.EST_STREAM, accel_mode=ob.ACCEL_BVH, rank=rank, nranks=world))
         assert np.array_equal(part, opart) and st.segments == ost.segments
         t = torch.from_numpy(part.copy())
         dist.all_reduce(t, op=dist.ReduceOp.SUM)

@@ -18,6 +18,7 @@
 #include "rl_build.cuh"
 #include "rl_device.cuh"
 #include "rl_flat_host.hpp"
+#include "rl_refbvh_host.hpp"
 #include "rl_scene_host.hpp"
 
 using namespace rl;
@@ -26,6 +27,7 @@ struct emu_scene {
     HostScene hs;
     std::vector<float4> trav, nodes;
     FlatTable flat;
+    RefBVH ref;
     SceneView sv{};
     uint32_t max_depth = 0;
     int root_ref = 0, leaf_max = 1;
@@ -62,7 +64,7 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
     std::vector<V3> leaf_lo(n), leaf_hi(n);
     for (int i = 0; i < n; i++) {
         uint32_t prim = (uint32_t)(keys[i] & 0xffffffffull);
-        tri_setup(hs.verts.data(), prim, i, s->trav.data(), hs.shade.data());
+        tri_setup(hs.verts.data(), prim, i, bvh_box_eps(hs.abs_max), s->trav.data(), hs.shade.data());
         tri_bounds_inflated(hs.verts.data(), prim, bvh_box_eps(hs.abs_max), &leaf_lo[i], &leaf_hi[i]);
     }
     // Traversal mode (the device uses all three: group table for incoherent rays of small scenes, tree otherwise;
@@ -102,7 +104,22 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         };
         Rec::fit(0, cl, cr, ranges, leaf_max, leaf_lo, leaf_hi, nlo, nhi, s->nodes.data());
     }
+    // reference-order tree (tie rule), leaf contents as Morton slots
+    if (!getenv("RL_NO_REF_ORDER")) {
+        build_ref_bvh(hs, s->ref);
+        if (s->ref.depth + 2 <= (uint32_t)RL_STACK_SIZE) {
+            std::vector<uint32_t> slot_of_prim(n);
+            for (int i = 0; i < n; i++) slot_of_prim[(uint32_t)(keys[i] & 0xffffffffull)] = (uint32_t)i;
+            for (auto &p : s->ref.prims) p = slot_of_prim[p];
+            const size_t nn = s->ref.nodes.size() / 2;
+            std::vector<uint32_t> leaf_of_slot(n);
+            for (int i = 0; i < n; i++) leaf_of_slot[s->ref.prims[i]] = s->ref.up[nn + i];
+            for (int i = 0; i < n; i++) s->ref.up[nn + i] = leaf_of_slot[i];
+        } else s->ref = RefBVH{};
+    }
     SceneView &sv = s->sv;
+    sv.ref_nodes = s->ref.nodes.empty() ? nullptr : s->ref.nodes.data(), sv.ref_prims = s->ref.prims.empty() ? nullptr : s->ref.prims.data();
+    sv.ref_up = s->ref.up.empty() ? nullptr : s->ref.up.data(), sv.ref_n_nodes = (uint32_t)(s->ref.nodes.size() / 2);
     sv.trav = s->trav.data(), sv.nodes = s->nodes.data(), sv.shade = hs.shade.data(), sv.verts = hs.verts.data(), sv.mats = hs.mats.data();
     sv.emit_info = hs.emit_info.data(), sv.emit_cdf = hs.emit_cdf.data(), sv.area_cdf = hs.area_cdf.data();
     sv.uvs = hs.uvs.empty() ? nullptr : hs.uvs.data(), sv.tex = hs.tex.empty() ? nullptr : hs.tex.data(), sv.texels = hs.texels.data();

@@ -34,7 +34,7 @@ def main():
         out[name + "_counts"] = np.array([st.segments, st.shadow_rays, st.hits], np.uint64)
     np.savez_compressed(os.path.join(HERE, "cbox64_spp16_seed0.npz"), **out)
     full = ob.OracleScene(load_cbox())
-    prim, tuv = full.primary_hits(ob.ACCEL_NAIVE)
+    prim, tuv = full.primary_hits(ob.ACCEL_BVH)  # the reference's default accelerator (visit order decides exact ties)
     prim8 = np.where(prim == 0xFFFFFFFF, 255, prim).astype(np.uint8)  # 36 triangles; 255 = miss
     np.savez_compressed(os.path.join(HERE, "cbox512_primary_hits.npz"), prim=prim8, t_sub8=tuv[::8, ::8, 0])
     print({k: (v.shape, float(v.mean())) for k, v in out.items()})

@@ -14,7 +14,7 @@ from oracle import binding as ob
 from rustlight_b200 import _abi
 from rustlight_b200.host import (material_glass, material_metal, material_mirror, material_phong, material_substrate)
 
-STREAM = dict(estimator=ob.EST_STREAM, accel_mode=ob.ACCEL_NAIVE)
+STREAM = dict(estimator=ob.EST_STREAM, accel_mode=ob.ACCEL_BVH)
 
 MIRROR = material_mirror((0.9, 0.8, 0.7))
 GOLD = material_metal((1, 1, 1), (0.143, 0.375, 1.442), (3.983, 2.386, 1.603), "ggx", 0.12)
@@ -203,7 +203,7 @@ def test_mixed_scene_stream_estimator_equals_graph():
     osc = ob.OracleScene(sc)
     for kw in (dict(), dict(strategy=_abi.RL_STRATEGY_BSDF), dict(strategy=_abi.RL_STRATEGY_EMITTER)):
         integ = _abi.path_desc(**kw)
-        a, sa = osc.render(integ, 8, seed=2, cfg=ob.config(estimator=ob.EST_GRAPH, accel_mode=ob.ACCEL_NAIVE))
+        a, sa = osc.render(integ, 8, seed=2, cfg=ob.config(estimator=ob.EST_GRAPH, accel_mode=ob.ACCEL_BVH))
         b, sb = osc.render(integ, 8, seed=2, cfg=ob.config(**STREAM))
         assert (sa.segments, sa.shadow_rays) == (sb.segments, sb.shadow_rays)
         assert rel_l2(b, a) < 1e-6
@@ -260,7 +260,7 @@ def test_delta_lights_render_bit_exact(integ):
     assert (se.segments, se.hits, se.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
     assert np.array_equal(ie, io) and io.mean() > 0.05
     if integ.kind == _abi.RL_INTEGRATOR_PATH:
-        ig, sg = ob.OracleScene(sc).render(integ, 6, seed=7, cfg=ob.config(estimator=ob.EST_GRAPH, accel_mode=ob.ACCEL_NAIVE))
+        ig, sg = ob.OracleScene(sc).render(integ, 6, seed=7, cfg=ob.config(estimator=ob.EST_GRAPH, accel_mode=ob.ACCEL_BVH))
         assert rel_l2(io, ig) < 1e-6 and sg.segments == so.segments
 
 
@@ -282,7 +282,7 @@ def test_point_light_only_scene_matches_inverse_square_law():
     assert sc.desc.contents.nlights == 1
     osc = ob.OracleScene(sc)
     img, st = osc.render(_abi.direct_desc(0, 1), 64, seed=1, cfg=ob.config(**STREAM))
-    pg, tg = osc.primary_hits(ob.ACCEL_NAIVE)
+    pg, tg = osc.primary_hits(ob.ACCEL_BVH)
     assert (pg != 0xFFFFFFFF).all()
     # hit points of the pixel centres: camera at (0,4,0) looking down
     o = np.float32([0, 4, 0])
@@ -352,7 +352,7 @@ def test_texture_lookup_semantics(kind, kw):
     osc = ob.OracleScene(sc)
     integ = _abi.direct_desc(0, 1)
     img, _ = osc.render(integ, 32, seed=3, cfg=ob.config(**STREAM))
-    pg, tg = osc.primary_hits(ob.ACCEL_NAIVE)
+    pg, tg = osc.primary_hits(ob.ACCEL_BVH)
     floor = (pg.ravel() <= 1)
     assert floor.mean() > 0.5
     ys, xs = np.mgrid[0:48, 0:48]
@@ -405,7 +405,7 @@ def test_textured_cornell_box_bit_exact():
     ie, se = eb.EmuScene(sc).render(integ, 6, seed=4)
     io, so = ob.OracleScene(sc).render(integ, 6, seed=4, cfg=ob.config(**STREAM))
     assert se.segments == so.segments and np.array_equal(ie, io)
-    ig, _ = ob.OracleScene(sc).render(integ, 6, seed=4, cfg=ob.config(estimator=ob.EST_GRAPH, accel_mode=ob.ACCEL_NAIVE))
+    ig, _ = ob.OracleScene(sc).render(integ, 6, seed=4, cfg=ob.config(estimator=ob.EST_GRAPH, accel_mode=ob.ACCEL_BVH))
     assert rel_l2(io, ig) < 1e-6
 
 
@@ -447,7 +447,7 @@ def test_environment_white_furnace():
     expectation, for BSDF sampling, light sampling and MIS alike."""
     sc = _env_scene(24, 24)
     osc = ob.OracleScene(sc)
-    pg, _ = osc.primary_hits(ob.ACCEL_NAIVE)
+    pg, _ = osc.primary_hits(ob.ACCEL_BVH)
     hit = (pg != 0xFFFFFFFF)
     assert 0.05 < hit.mean() < 0.9
     L, kd = np.float32([0.8, 0.9, 1.0]), np.float32([0.6, 0.5, 0.4])
@@ -470,7 +470,7 @@ def test_environment_render_bit_exact(integ):
     assert (se.segments, se.hits, se.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
     assert np.array_equal(ie, io) and io.mean() > 0.3
     if integ.kind == _abi.RL_INTEGRATOR_PATH:
-        ig, sg = ob.OracleScene(sc).render(integ, 6, seed=5, cfg=ob.config(estimator=ob.EST_GRAPH, accel_mode=ob.ACCEL_NAIVE))
+        ig, sg = ob.OracleScene(sc).render(integ, 6, seed=5, cfg=ob.config(estimator=ob.EST_GRAPH, accel_mode=ob.ACCEL_BVH))
         assert sg.segments == so.segments and rel_l2(io, ig) < 1e-6
 
 

@@ -15,7 +15,7 @@ from oracle import binding as ob
 from rustlight_b200 import SceneLoaderManager, _abi
 from rustlight_b200.host import material_phong
 
-STREAM = dict(estimator=ob.EST_STREAM, accel_mode=ob.ACCEL_NAIVE)
+STREAM = dict(estimator=ob.EST_STREAM, accel_mode=ob.ACCEL_BVH)
 
 
 def _rays(n, seed, lo=-0.99, hi=0.99, shift=(0, 1, 0)):
@@ -45,19 +45,19 @@ def test_accel_modes_agree_with_the_oracle(cbox, cbox_oracle, accel):
     assert (esc.flat_info()["groups"] > 0) == (accel == "flat")
     o, d, p1 = _rays(20000, 3)
     pe, te = esc.trace(o, d)
-    po, to = cbox_oracle.trace(o, d, ob.ACCEL_NAIVE)
+    po, to = cbox_oracle.trace(o, d, ob.ACCEL_BVH)
     assert np.array_equal(pe, po) and np.array_equal(te, to)
-    assert np.array_equal(esc.visible(o, p1), cbox_oracle.visible(o, p1, ob.ACCEL_NAIVE))
+    assert np.array_equal(esc.visible(o, p1), cbox_oracle.visible(o, p1, ob.ACCEL_BVH))
     # rays that start ON the surfaces (what the path tracer actually traces), incl. toward the light
     hit = po != 0xFFFFFFFF
     o2 = (o[hit] + d[hit] * to[hit, :1]).astype(np.float32)
     d2 = _rays(len(o2), 4)[1]
     pe, te = esc.trace(o2, d2)
-    po2, to2 = cbox_oracle.trace(o2, d2, ob.ACCEL_NAIVE)
+    po2, to2 = cbox_oracle.trace(o2, d2, ob.ACCEL_BVH)
     assert np.array_equal(pe, po2) and np.array_equal(te, to2)
     light = np.tile(np.array([[0.0, 1.98, 0.0]], np.float32), (len(o2), 1)) + _rays(len(o2), 5)[0] * np.float32(0.2) * [1, 0, 1]
     light = light.astype(np.float32)
-    assert np.array_equal(esc.visible(o2, light), cbox_oracle.visible(o2, light, ob.ACCEL_NAIVE))
+    assert np.array_equal(esc.visible(o2, light), cbox_oracle.visible(o2, light, ob.ACCEL_BVH))
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
@@ -68,15 +68,15 @@ def test_pair_records_are_conservative_on_adversarial_quads(seed):
     info = esc.flat_info()
     assert info["groups"] > 0 and info["pairs"] >= 3, info
     pe, te = esc.trace(o, dd)
-    po, to = osc.trace(o, dd, ob.ACCEL_NAIVE)
+    po, to = osc.trace(o, dd, ob.ACCEL_BVH)
     assert (po != 0xFFFFFFFF).mean() > 0.3
     assert np.array_equal(pe, po) and np.array_equal(te, to)
-    assert np.array_equal(esc.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))
+    assert np.array_equal(esc.visible(o, p1), osc.visible(o, p1, ob.ACCEL_BVH))
 
 
 def test_primary_hits_exact(cbox, cbox_oracle):
     pe, te = eb.EmuScene(cbox).primary_hits()
-    po, to = cbox_oracle.primary_hits(ob.ACCEL_NAIVE)
+    po, to = cbox_oracle.primary_hits(ob.ACCEL_BVH)
     assert np.array_equal(pe, po) and np.array_equal(te, to)
 
 
@@ -84,9 +84,9 @@ def test_random_rays_and_segments_exact(cbox, cbox_oracle):
     esc = eb.EmuScene(cbox)
     o, d, p1 = _rays(30000, 1)
     pe, te = esc.trace(o, d)
-    po, to = cbox_oracle.trace(o, d, ob.ACCEL_NAIVE)
+    po, to = cbox_oracle.trace(o, d, ob.ACCEL_BVH)
     assert np.array_equal(pe, po) and np.array_equal(te, to)
-    assert np.array_equal(esc.visible(o, p1), cbox_oracle.visible(o, p1, ob.ACCEL_NAIVE))
+    assert np.array_equal(esc.visible(o, p1), cbox_oracle.visible(o, p1, ob.ACCEL_BVH))
 
 
 @pytest.mark.parametrize("ntris,seed", [(50, 0), (600, 1), (3000, 2)])
@@ -97,9 +97,9 @@ def test_soup_lbvh_equals_brute_force(ntris, seed):
     assert esc.bvh_validate() == 0
     o, d, p1 = _rays(6000, seed + 10, -1.2, 1.2, (0, 0, 0))
     pe, te = esc.trace(o, d)
-    po, to = osc.trace(o, d, ob.ACCEL_NAIVE)
+    po, to = osc.trace(o, d, ob.ACCEL_BVH)
     assert np.array_equal(pe, po) and np.array_equal(te, to)
-    assert np.array_equal(esc.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))
+    assert np.array_equal(esc.visible(o, p1), osc.visible(o, p1, ob.ACCEL_BVH))
 
 
 def test_far_origin_rays_exact(cbox, cbox_oracle):
@@ -111,7 +111,7 @@ def test_far_origin_rays_exact(cbox, cbox_oracle):
     d = tgt - o
     d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
     pe, te = esc.trace(o, d)
-    po, to = cbox_oracle.trace(o, d, ob.ACCEL_NAIVE)
+    po, to = cbox_oracle.trace(o, d, ob.ACCEL_BVH)
     assert np.array_equal(pe, po) and np.array_equal(te, to)
 
 
@@ -122,7 +122,7 @@ def test_axis_aligned_rays_exact(cbox, cbox_oracle):
     o = (rng.uniform(-0.9, 0.9, (3000, 3)) + [0, 1, 0]).astype(np.float32)
     axes = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 3000)] * rng.choice([-1, 1], (3000, 1)).astype(np.float32)
     pe, te = esc.trace(o, axes)
-    po, to = cbox_oracle.trace(o, axes, ob.ACCEL_NAIVE)
+    po, to = cbox_oracle.trace(o, axes, ob.ACCEL_BVH)
     assert np.array_equal(pe, po) and np.array_equal(te, to)
 
 
@@ -173,7 +173,7 @@ def test_direct_render_bit_exact(nb, nl):
     sc = load_cbox(96, 80)
     integ = _abi.direct_desc(nb, nl)
     ie, se = eb.EmuScene(sc).render(integ, 5, seed=4)
-    io, so = ob.OracleScene(sc).render(integ, 5, seed=4, cfg=ob.config(accel_mode=ob.ACCEL_NAIVE))
+    io, so = ob.OracleScene(sc).render(integ, 5, seed=4, cfg=ob.config(accel_mode=ob.ACCEL_BVH))
     assert (se.segments, se.hits, se.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
     assert np.array_equal(ie, io)
 
@@ -186,10 +186,10 @@ def test_prefilter_is_conservative_on_adversarial_scenes(seed):
     sc, o, dd, p1 = adversarial_case(seed)
     esc, osc = eb.EmuScene(sc), ob.OracleScene(sc)
     pe, te = esc.trace(o, dd)
-    po, to = osc.trace(o, dd, ob.ACCEL_NAIVE)
+    po, to = osc.trace(o, dd, ob.ACCEL_BVH)
     assert np.array_equal(pe, po) and np.array_equal(te, to)
     assert (po != 0xFFFFFFFF).mean() > 0.2  # the rays do hit things
-    assert np.array_equal(esc.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))
+    assert np.array_equal(esc.visible(o, p1), osc.visible(o, p1, ob.ACCEL_BVH))
 
 
 @pytest.mark.parametrize("dist,nc", [(1.0, False), (None, False), (0.3, True)])
@@ -230,15 +230,15 @@ def test_prefilter_margins_carry_tenfold_slack(tmp_path):
     for seed in range(4):
         sc, o, dd, _ = adversarial_pairs_case(seed)
         pe, te = trace(sc, o, dd)
-        po, to = ob.OracleScene(sc).trace(o, dd, ob.ACCEL_NAIVE)
+        po, to = ob.OracleScene(sc).trace(o, dd, ob.ACCEL_BVH)
         assert np.array_equal(pe, po) and np.array_equal(te, to)
     sc = load_cbox()
     osc = ob.OracleScene(sc)
     o, d, _ = _rays(60000, 31)
-    po, to = osc.trace(o, d, ob.ACCEL_NAIVE)
+    po, to = osc.trace(o, d, ob.ACCEL_BVH)
     hit = po != 0xFFFFFFFF
     o2 = np.ascontiguousarray((o[hit] + d[hit] * to[hit, :1]).astype(np.float32))
     d2 = np.ascontiguousarray(_rays(len(o2), 32)[1])
     pe, te = trace(sc, o2, d2)
-    po2, to2 = osc.trace(o2, d2, ob.ACCEL_NAIVE)
+    po2, to2 = osc.trace(o2, d2, ob.ACCEL_BVH)
     assert np.array_equal(pe, po2) and np.array_equal(te, to2)

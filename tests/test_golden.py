@@ -29,13 +29,13 @@ def test_oracle_reproduces_golden(golden, name):
 def test_gpu_configuration_of_the_oracle_is_within_tolerance_of_golden(golden, name):
     """spec math + brute-force tie order + stream estimator (what the GPU computes) vs the faithful one."""
     osc = ob.OracleScene(load_cbox(64, 64))
-    img, st = osc.render(INTEGS[name], 16, seed=0, cfg=ob.config(math_mode=ob.MATH_SPEC, accel_mode=ob.ACCEL_NAIVE, estimator=ob.EST_STREAM))
+    img, st = osc.render(INTEGS[name], 16, seed=0, cfg=ob.config(math_mode=ob.MATH_SPEC, accel_mode=ob.ACCEL_BVH, estimator=ob.EST_STREAM))
     assert rel_l2(img, golden[name]) < 1e-3      # north_star tolerance; typically ~1e-6
     assert abs(int(st.segments) - int(golden[name + "_counts"][0])) <= 4
 
 
 def test_primary_hits_golden():
     g = np.load(os.path.join(GOLDEN, "cbox512_primary_hits.npz"))
-    prim, tuv = ob.OracleScene(load_cbox()).primary_hits(ob.ACCEL_NAIVE)
+    prim, tuv = ob.OracleScene(load_cbox()).primary_hits(ob.ACCEL_BVH)
     assert np.array_equal(np.where(prim == 0xFFFFFFFF, 255, prim).astype(np.uint8), g["prim"])
     assert np.array_equal(tuv[::8, ::8, 0], g["t_sub8"])

@@ -17,7 +17,7 @@ from rustlight_b200.host import material_phong
 
 pytestmark = pytest.mark.gpu
 
-STREAM = dict(estimator=ob.EST_STREAM, accel_mode=ob.ACCEL_NAIVE)
+STREAM = dict(estimator=ob.EST_STREAM, accel_mode=ob.ACCEL_BVH)
 TOL = 1e-3  # north_star: image within 1e-3 relative L2 of the CPU reference at matched spp
 
 
@@ -50,7 +50,7 @@ def test_native_library_is_the_one_running(gpu_ctx, cbox_dev):
 def test_primary_ray_grid_exact(cbox_dev, cbox_oracle):
     """north_star: exact match on ray/triangle hit indices for the fixed primary-ray test."""
     pg, tg = cbox_dev.primary_hits()
-    po, to = cbox_oracle.primary_hits(ob.ACCEL_NAIVE)
+    po, to = cbox_oracle.primary_hits(ob.ACCEL_BVH)
     assert np.array_equal(pg, po) and np.array_equal(tg, to)
     g = np.load(os.path.join(GOLDEN, "cbox512_primary_hits.npz"))
     assert np.array_equal(np.where(pg == 0xFFFFFFFF, 255, pg).astype(np.uint8), g["prim"])
@@ -64,9 +64,9 @@ def test_primary_ray_grid_exact(cbox_dev, cbox_oracle):
 def test_random_rays_exact(cbox_dev, cbox_oracle):
     o, d, p1 = _rays(300000, 1)
     pg, tg = cbox_dev.trace(o, d)
-    po, to = cbox_oracle.trace(o, d, ob.ACCEL_NAIVE)
+    po, to = cbox_oracle.trace(o, d, ob.ACCEL_BVH)
     assert np.array_equal(pg, po) and np.array_equal(tg, to)
-    assert np.array_equal(cbox_dev.visible(o, p1), cbox_oracle.visible(o, p1, ob.ACCEL_NAIVE))
+    assert np.array_equal(cbox_dev.visible(o, p1), cbox_oracle.visible(o, p1, ob.ACCEL_BVH))
 
 
 def test_edge_case_rays(cbox_dev, cbox_oracle):
@@ -79,13 +79,13 @@ def test_edge_case_rays(cbox_dev, cbox_oracle):
     dfar = (dfar / np.linalg.norm(dfar, axis=1, keepdims=True)).astype(np.float32)
     for oo, dd in ((o, axes), (far, dfar)):
         pg, tg = cbox_dev.trace(oo, dd)
-        po, to = cbox_oracle.trace(oo, dd, ob.ACCEL_NAIVE)
+        po, to = cbox_oracle.trace(oo, dd, ob.ACCEL_BVH)
         assert np.array_equal(pg, po) and np.array_equal(tg, to)
     # empty input, zero-length segment, segment shorter than tnear
     assert cbox_dev.trace(np.zeros((0, 3)), np.zeros((0, 3)))[0].size == 0
     p = np.float32([[0, 1, 0], [0, 1, 0]])
     q = np.float32([[0, 1, 0], [0, 1, 5e-5]])
-    assert np.array_equal(cbox_dev.visible(p, q), cbox_oracle.visible(p, q, ob.ACCEL_NAIVE))
+    assert np.array_equal(cbox_dev.visible(p, q), cbox_oracle.visible(p, q, ob.ACCEL_BVH))
 
 
 @pytest.mark.parametrize("ntris,seed", [(1, 0), (2, 1), (50, 2), (600, 3), (4000, 4)])
@@ -104,11 +104,11 @@ def test_soup_scenes_exact(gpu_ctx, ntris, seed):
     assert bi.ntris == sc.nb_triangles and bi.smem_resident == (1 if ntris < 200 else 0)
     o, d, p1 = _rays(50000, seed + 20, -1.2, 1.2, (0, 0, 0))
     pg, tg = dev.trace(o, d)
-    po, to = osc.trace(o, d, ob.ACCEL_NAIVE)
+    po, to = osc.trace(o, d, ob.ACCEL_BVH)
     assert np.array_equal(pg, po) and np.array_equal(tg, to)
-    assert np.array_equal(dev.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))
+    assert np.array_equal(dev.visible(o, p1), osc.visible(o, p1, ob.ACCEL_BVH))
     pg, tg = dev.primary_hits()
-    po, to = osc.primary_hits(ob.ACCEL_NAIVE)
+    po, to = osc.primary_hits(ob.ACCEL_BVH)
     assert np.array_equal(pg, po) and np.array_equal(tg, to)
     dev.close()
 
@@ -268,7 +268,7 @@ def test_direct_render_bit_exact_vs_oracle(gpu_ctx, nb, nl):
     dev = DeviceScene(gpu_ctx, sc)
     integ = _abi.direct_desc(nb, nl)
     img, st = dev.render(integ, 6, seed=4, batch_spp=4)
-    ref, so = ob.OracleScene(sc).render(integ, 6, seed=4, cfg=ob.config(accel_mode=ob.ACCEL_NAIVE))
+    ref, so = ob.OracleScene(sc).render(integ, 6, seed=4, cfg=ob.config(accel_mode=ob.ACCEL_BVH))
     assert (st.samples, st.segments, st.hits, st.shadow_rays) == (so.samples, so.segments, so.hits, so.shadow_rays)
     assert np.array_equal(img, ref)
     faithful, _ = ob.OracleScene(sc).render(integ, 6, seed=4, cfg=ob.config(math_mode=ob.MATH_LIBM, accel_mode=ob.ACCEL_BVH))
@@ -319,9 +319,9 @@ def test_adversarial_scenes_exact(gpu_ctx, seed):
     sc, o, dd, p1 = adversarial_case(seed)
     dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
     pg, tg = dev.trace(o, dd)
-    po, to = osc.trace(o, dd, ob.ACCEL_NAIVE)
+    po, to = osc.trace(o, dd, ob.ACCEL_BVH)
     assert np.array_equal(pg, po) and np.array_equal(tg, to)
-    assert np.array_equal(dev.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))
+    assert np.array_equal(dev.visible(o, p1), osc.visible(o, p1, ob.ACCEL_BVH))
     dev.close()
 
 
@@ -335,9 +335,9 @@ def test_adversarial_quads_exact(gpu_ctx, seed):
     bi = dev.bvh_info()
     assert bi.flat_groups > 0 and bi.flat_pairs >= 3
     pg, tg = dev.trace(o, dd)
-    po, to = osc.trace(o, dd, ob.ACCEL_NAIVE)
+    po, to = osc.trace(o, dd, ob.ACCEL_BVH)
     assert np.array_equal(pg, po) and np.array_equal(tg, to)
-    assert np.array_equal(dev.visible(o, p1), osc.visible(o, p1, ob.ACCEL_NAIVE))
+    assert np.array_equal(dev.visible(o, p1), osc.visible(o, p1, ob.ACCEL_BVH))
     dev.close()
 
 
@@ -345,18 +345,18 @@ def test_group_table_on_surface_rays_and_degenerate_directions(cbox_dev, cbox_or
     """What the wavefront actually traces: rays leaving the surfaces (origins ON planes of the table: num == 0 for the
     own quad), axis-parallel directions (d.n == 0: inf/NaN arithmetic in the scan must stay a candidate), segments to the light."""
     o, d, _ = _rays(300000, 21)
-    po, to = cbox_oracle.trace(o, d, ob.ACCEL_NAIVE)
+    po, to = cbox_oracle.trace(o, d, ob.ACCEL_BVH)
     hit = po != 0xFFFFFFFF
     o2 = (o[hit] + d[hit] * to[hit, :1]).astype(np.float32)
     d2 = _rays(len(o2), 22)[1]
     axes = np.eye(3, dtype=np.float32)[np.arange(len(o2)) % 3] * np.where(np.arange(len(o2)) % 2, 1, -1).astype(np.float32)[:, None]
     d2[::7] = axes[::7]
     pg, tg = cbox_dev.trace(o2, d2)
-    po2, to2 = cbox_oracle.trace(o2, d2, ob.ACCEL_NAIVE)
+    po2, to2 = cbox_oracle.trace(o2, d2, ob.ACCEL_BVH)
     assert np.array_equal(pg, po2) and np.array_equal(tg, to2)
     light = (np.array([[0.0, 1.98, -0.03]]) + (_rays(len(o2), 23)[0] - [0, 1, 0]) * [0.24, 0, 0.2]).astype(np.float32)
     vg = cbox_dev.visible(o2, light)
-    assert np.array_equal(vg, cbox_oracle.visible(o2, light, ob.ACCEL_NAIVE)) and 0.2 < vg.mean() < 0.9
+    assert np.array_equal(vg, cbox_oracle.visible(o2, light, ob.ACCEL_BVH)) and 0.2 < vg.mean() < 0.9
 
 
 @pytest.mark.parametrize("sort", [0, 1])

@@ -23,7 +23,7 @@ def main():
     print("scene create %.1f ms; bvh: ntris=%d nnodes=%d depth=%d smem=%d" % ((time.time() - t0) * 1e3, bi.ntris, bi.nnodes, bi.max_depth, bi.smem_resident))
     osc = ob.OracleScene(scene)
     pg, tg = dsc.primary_hits()
-    po, to = osc.primary_hits(ob.ACCEL_NAIVE)
+    po, to = osc.primary_hits(ob.ACCEL_BVH)
     print("primary hits: prim mismatches", int((pg != po).sum()), "tuv bit-exact", bool(np.array_equal(tg, to)))
     rng = np.random.default_rng(0)
     n = 200000
@@ -32,15 +32,15 @@ def main():
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     d = d.astype(np.float32)
     pg, tg = dsc.trace(o, d)
-    po, to = osc.trace(o, d, ob.ACCEL_NAIVE)
+    po, to = osc.trace(o, d, ob.ACCEL_BVH)
     print("random rays: prim mismatches", int((pg != po).sum()), "tuv bit-exact", bool(np.array_equal(tg, to)))
     p1 = rng.uniform(-0.99, 0.99, (n, 3)).astype(np.float32) + np.array([0, 1, 0], np.float32)
     vg = dsc.visible(o, p1)
-    vo = osc.visible(o, p1, ob.ACCEL_NAIVE)
+    vo = osc.visible(o, p1, ob.ACCEL_BVH)
     print("visible: mismatches", int((vg != vo).sum()), "visible frac", float(vg.mean()))
     integ = _abi.path_desc()
     img, st = dsc.render(integ, 4, seed=0)
-    ref, ost = osc.render(integ, 4, seed=0, cfg=ob.config(estimator=ob.EST_STREAM, accel_mode=ob.ACCEL_NAIVE))
+    ref, ost = osc.render(integ, 4, seed=0, cfg=ob.config(estimator=ob.EST_STREAM, accel_mode=ob.ACCEL_BVH))
     print("render 512x512x4: gpu", {k: v for k, v in st.as_dict().items() if not k.startswith("ms_") or v})
     print("                  orc", ost.as_dict())
     print("  bit-exact:", bool(np.array_equal(img, ref)), "ndiff px", int((img != ref).any(axis=2).sum()), "rel_l2", float(np.linalg.norm(img - ref) / np.linalg.norm(ref)))
