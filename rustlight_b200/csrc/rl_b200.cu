@@ -232,9 +232,9 @@ int rl_create(rl_ctx **out, int device, int nranks, int rank, const void *nccl_u
     }
     rl_ctx *ctx = new rl_ctx;
     ctx->device = device, ctx->nranks = nranks, ctx->rank = rank;
-    auto fail = [&](int code) {
+    auto fail = [&](int code) { // everything created so far goes through the same teardown as a live context
         g_create_error = ctx->err;
-        delete ctx;
+        rl_destroy(ctx);
         return code;
     };
 #define CKC(call)                                                                                                  \
@@ -626,7 +626,7 @@ static int ensure_pixels(rl_ctx *ctx, uint32_t w, uint32_t h) {
     if (frame > ctx->cap_frame) {
         cudaFree(ctx->frame);
         ctx->frame = nullptr, ctx->cap_frame = 0;
-        CK(cudaMalloc(&ctx->frame, frame * sizeof(float)));
+        CK(cudaMalloc(&ctx->frame, (frame + 1) * sizeof(float))); // + 1: the "a rank failed" flag that travels with the reduce
         ctx->cap_frame = frame;
     }
     if (!list.empty()) CK(cudaMemcpy(ctx->pixel_list, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -1091,22 +1091,45 @@ int rl_render_device(rl_ctx *ctx, rl_scene *scene, const rl_integrator_desc *int
 int rl_render(rl_ctx *ctx, rl_scene *scene, const rl_integrator_desc *integrator, const rl_render_opts *opts, float *out_rgb, rl_stats *stats) {
     if (!ctx) return RL_ERR_INVALID;
     rl_stats S{};
-    int rc = render_impl(ctx, scene, integrator, opts, &S);
-    if (rc != RL_OK) return rc;
+    const int rc = render_impl(ctx, scene, integrator, opts, &S);
+    // Argument errors (validate) are the same on every rank: nobody enters the collective.  Anything later (out of memory, a path
+    // over the iteration limit on THIS rank's tiles, a CUDA error) must not leave the peers waiting in ncclReduce: the failing rank
+    // contributes a zero frame and raises the flag that travels behind the frame; rank 0 reports it.
+    const bool collective = ctx->nranks > 1 && ctx->comm && scene && ctx->frame && (rc == RL_OK || rc != RL_ERR_INVALID);
+    if (rc != RL_OK && !collective) return rc;
     const size_t count = (size_t)scene->hs.img_w * scene->hs.img_h * 3;
     float ms = 0;
-    if (ctx->nranks > 1 && ctx->comm) {
+    if (collective) {
+        if (count > ctx->cap_frame) return rc != RL_OK ? rc : RL_ERR_CUDA; // (the frame of this size was never allocated: the failure came first)
+        const std::string own_err = ctx->err;
+        if (rc != RL_OK) {
+            cudaGetLastError();
+            CK(cudaMemsetAsync(ctx->frame, 0, count * sizeof(float), ctx->stream));
+        }
+        const float flag = rc != RL_OK ? 1.0f : 0.0f;
+        CK(cudaMemcpyAsync(ctx->frame + count, &flag, sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         // one ncclReduce(sum, f32) of the framebuffer: tiles are disjoint, so the sum is exact
         CK(cudaEventRecord(ctx->ev[6], ctx->stream));
-        int nrc = g_nccl.Reduce(ctx->frame, ctx->frame, count, /*ncclFloat32*/ 7, /*ncclSum*/ 0, 0, ctx->comm, ctx->stream);
+        int nrc = g_nccl.Reduce(ctx->frame, ctx->frame, count + 1, /*ncclFloat32*/ 7, /*ncclSum*/ 0, 0, ctx->comm, ctx->stream);
         if (nrc != 0) {
             ctx->err = std::string("ncclReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error");
             return RL_ERR_NCCL;
         }
         CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+        float failed = 0.0f;
+        if (ctx->rank == 0) CK(cudaMemcpyAsync(&failed, ctx->frame + count, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaEventSynchronize(ctx->ev[7]));
+        CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]));
         S.ms_reduce = ms;
+        if (rc != RL_OK) {
+            ctx->err = own_err;
+            return rc;
+        }
+        if (failed > 0.0f) {
+            ctx->err = "rl_render: " + std::to_string((int)failed) + " peer rank(s) failed to render their tiles; the reduced frame is incomplete";
+            return RL_ERR_NCCL;
+        }
     }
     if (out_rgb && (ctx->rank == 0 || !ctx->comm)) {
         CK(cudaEventRecord(ctx->ev[6], ctx->stream));
@@ -1143,6 +1166,16 @@ static int trace_device_rays(rl_ctx *ctx, rl_scene *sc, size_t n, uint32_t *prim
     return RL_OK;
 }
 
+namespace {
+struct DevBuf { // freed on every path out of the call
+    void *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    template <typename T>
+    T *as() { return static_cast<T *>(p); }
+};
+} // namespace
+
 int rl_trace(rl_ctx *ctx, rl_scene *sc, size_t n, const float *o, const float *d, uint32_t *prim, float *tuv) {
     if (!ctx || !sc || !o || !d || !prim) return RL_ERR_INVALID;
     if (n == 0) return RL_OK;
@@ -1150,15 +1183,14 @@ int rl_trace(rl_ctx *ctx, rl_scene *sc, size_t n, const float *o, const float *d
     CK(cudaSetDevice(ctx->device));
     int rc = ensure_paths(ctx, n);
     if (rc != RL_OK) return rc;
-    float *d_o = nullptr, *d_d = nullptr;
-    CK(cudaMalloc(&d_o, n * 12));
-    CK(cudaMalloc(&d_d, n * 12));
-    cudaMemcpyAsync(d_o, o, n * 12, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(d_d, d, n * 12, cudaMemcpyHostToDevice, ctx->stream);
-    k_pack_rays<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(d_o, d_d, (uint32_t)n, ctx->ray_o[0], ctx->ray_d[0]);
-    rc = trace_device_rays(ctx, sc, n, prim, tuv);
-    cudaFree(d_o), cudaFree(d_d);
-    return rc;
+    DevBuf d_o, d_d;
+    CK(d_o.alloc(n * 12));
+    CK(d_d.alloc(n * 12));
+    CK(cudaMemcpyAsync(d_o.p, o, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_d.p, d, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    k_pack_rays<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(d_o.as<float>(), d_d.as<float>(), (uint32_t)n, ctx->ray_o[0], ctx->ray_d[0]);
+    CK(cudaGetLastError());
+    return trace_device_rays(ctx, sc, n, prim, tuv); // synchronises the stream before the buffers go
 }
 
 int rl_primary_hits(rl_ctx *ctx, rl_scene *sc, uint32_t *prim, float *tuv) {
@@ -1176,19 +1208,20 @@ int rl_visible(rl_ctx *ctx, rl_scene *sc, size_t n, const float *p0, const float
     if (n == 0) return RL_OK;
     if (n > 0x7fffffffu) return RL_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    float *d_a = nullptr, *d_b = nullptr;
-    unsigned char *d_out = nullptr;
-    CK(cudaMalloc(&d_a, n * 12));
-    CK(cudaMalloc(&d_b, n * 12));
-    CK(cudaMalloc(&d_out, n));
-    cudaMemcpyAsync(d_a, p0, n * 12, cudaMemcpyHostToDevice, ctx->stream);
-    cudaMemcpyAsync(d_b, p1, n * 12, cudaMemcpyHostToDevice, ctx->stream);
+    DevBuf b_a, b_b, b_out;
+    CK(b_a.alloc(n * 12));
+    CK(b_b.alloc(n * 12));
+    CK(b_out.alloc(n));
+    float *d_a = b_a.as<float>(), *d_b = b_b.as<float>();
+    unsigned char *d_out = b_out.as<unsigned char>();
+    CK(cudaMemcpyAsync(d_a, p0, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_b, p1, n * 12, cudaMemcpyHostToDevice, ctx->stream));
     SceneView sv = sc->sv;
     if (sc->flat_ok) sv.n_groups = sc->flat.n_groups; // group table read through L1 (no staging in this small-batch kernel)
     k_visible_batch<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(sv, d_a, d_b, (uint32_t)n, d_out);
     cudaError_t e = cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_a), cudaFree(d_b), cudaFree(d_out);
+    else cudaStreamSynchronize(ctx->stream); // nothing may still read the buffers when they are freed
     if (e != cudaSuccess) {
         ctx->err = std::string("rl_visible: ") + cudaGetErrorString(e);
         return RL_ERR_CUDA;

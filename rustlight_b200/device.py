@@ -188,6 +188,7 @@ class IndependentSampler:
 
     def __init__(self, seed=0):
         self.seed = int(seed)
+        self.passes = 0  # compute() calls so far: pass p renders samples [p * spp, (p + 1) * spp), like rl_integrators.hpp
 
 
 class BufferCollection:
@@ -208,7 +209,12 @@ class _IntegratorBase:
         if not isinstance(scene, DeviceScene):
             scene = DeviceScene(ctx or Context(), scene)
         spp = kw.pop("spp", None) or scene.host_scene.nb_samples
+        # the reference's master sampler moves on with every compute() (generate_img_blocks clones it per block, mod.rs:351-374), so the
+        # passes of an averaging wrapper (avg.rs:45-65) never repeat a sample; here the sample offset advances instead
+        kw.setdefault("sample_offset", getattr(sampler, "passes", 0) * spp)
         img, st = scene.render(self.desc(), spp, seed=sampler.seed, **kw)
+        if hasattr(sampler, "passes"):
+            sampler.passes += 1
         return BufferCollection(img, st)
 
 

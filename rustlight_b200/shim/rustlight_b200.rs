@@ -1,25 +1,38 @@
-//! rustlight_b200.rs -- the binding a rustlight maintainer would add (UNCOMPILED here: this image
-//! has no Rust toolchain).  It declares the C ABI of include/rl_b200.h and
-//! implements `Integrator` for the two integrators by flattening `Scene` into `rl_scene_desc`,
-//! calling `rl_render` and wrapping the result into a `BufferCollection` -- replacing the
-//! one-line `compute_mc(self, sampler, accel, scene)` bodies of
-//! src/integrators/explicit/path.rs:187-196 and src/integrators/direct.rs:10-19.
-//! The `accel` argument is ignored: the GPU library builds its own LBVH.
+//! rustlight_b200.rs -- the binding a rustlight maintainer adds as `src/b200.rs` (+ `pub mod b200;` in lib.rs, feature "b200").
+//! UNCOMPILED here: this image has no Rust toolchain.  tests/test_shim_matches_header.py checks every
+//! `#[repr(C)]` struct and every `extern "C"` declaration below against include/rl_b200.h, field by field.
+//!
+//! It declares the whole C ABI of include/rl_b200.h and implements `Integrator` for `path`, `direct` and `ao` by flattening
+//! `Scene` into `rl_scene_desc`, calling `rl_render` and wrapping the result into a `BufferCollection` -- replacing the one-line
+//! `compute_mc(self, sampler, accel, scene)` bodies of src/integrators/explicit/path.rs:187-196, src/integrators/direct.rs:10-19
+//! and src/integrators/ao.rs.  The `accel` argument is ignored (the library builds its own structures).
+//!
+//! The context and the device scene stay alive across `compute()` calls (keyed on the `Scene` address), so the averaging
+//! wrappers (`-a`, `-e`: src/integrators/avg.rs:45-65, equal_time.rs:21-47) re-render a resident scene, and every call advances
+//! the sample offset by `nb_samples`, so successive passes draw fresh samples -- what the reference gets from the master
+//! sampler's state moving on in `generate_img_blocks` (src/integrators/mod.rs:351-374).
+//!
+//! Everything the reference does not expose yet is in `mod patch` at the end of this file, as the (small) additions a maintainer
+//! applies: `BSDF::describe`, `Emitter::describe`, two `Camera` accessors and `IndependentSampler::seed`.
 #![allow(non_camel_case_types, dead_code)]
 use std::ffi::CStr;
 use std::os::raw::{c_char, c_int, c_void};
+use std::sync::Mutex;
 
 #[repr(C)] pub struct rl_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct rl_scene { _p: [u8; 0] }
 
+pub const RL_B200_ABI_VERSION: c_int = 3;
+
+#[repr(C)] #[derive(Clone, Copy)]
+pub struct rl_texture {
+    pub kind: u32, pub width: u32, pub height: u32, pub pixels: *const f32, pub color0: [f32; 3], pub color1: [f32; 3],
+    pub line_width: f32, pub offset: [f32; 2], pub scale: [f32; 2],
+}
 #[repr(C)] #[derive(Clone, Copy)]
 pub struct rl_material {
     pub kind: u32, pub kd: [f32; 3], pub ks: [f32; 3], pub exponent: f32, pub weight_specular: f32,
     pub kt: [f32; 3], pub eta: [f32; 3], pub k: [f32; 3], pub ior: f32, pub alpha: f32, pub microfacet: u32, pub kd_texture: u32,
-}
-#[repr(C)] pub struct rl_texture {
-    pub kind: u32, pub width: u32, pub height: u32, pub pixels: *const f32, pub color0: [f32; 3], pub color1: [f32; 3],
-    pub line_width: f32, pub offset: [f32; 2], pub scale: [f32; 2],
 }
 #[repr(C)]
 pub struct rl_mesh_desc {
@@ -27,7 +40,7 @@ pub struct rl_mesh_desc {
     pub n: *const f32, pub uv: *const f32, pub mat: rl_material, pub emission_kind: u32, pub emission: [f32; 3],
 }
 #[repr(C)] pub struct rl_camera_desc { pub width: u32, pub height: u32, pub sample_to_camera: [f32; 16], pub to_world: [f32; 16] }
-#[repr(C)] pub struct rl_light_desc { pub kind: u32, pub intensity: [f32; 3], pub v: [f32; 3] }
+#[repr(C)] #[derive(Clone, Copy)] pub struct rl_light_desc { pub kind: u32, pub intensity: [f32; 3], pub v: [f32; 3] }
 #[repr(C)] pub struct rl_scene_desc {
     pub nmeshes: u32, pub meshes: *const rl_mesh_desc, pub camera: rl_camera_desc, pub has_volume: u32, pub has_environment: u32,
     pub nlights: u32, pub lights: *const rl_light_desc, pub ntextures: u32, pub textures: *const rl_texture, pub environment: [f32; 3],
@@ -42,101 +55,174 @@ pub struct rl_mesh_desc {
 pub struct rl_stats {
     pub samples: u64, pub segments: u64, pub shadow_rays: u64, pub shadow_visible: u64, pub hits: u64, pub max_depth_seen: u64,
     pub kernel_launches: u64, pub ms_total: f64, pub ms_raygen: f64, pub ms_trace: f64, pub ms_shade: f64, pub ms_shadow: f64,
-    pub ms_accum: f64, pub ms_h2d: f64, pub ms_d2h: f64, pub ms_reduce: f64,
+    pub ms_accum: f64, pub ms_h2d: f64, pub ms_d2h: f64, pub ms_reduce: f64, pub ms_tail: f64, pub shadow_traced: u64,
+    pub launches_trace: u64, pub launches_shade: u64,
+}
+#[repr(C)] #[derive(Default)]
+pub struct rl_bvh_info {
+    pub ntris: u32, pub nnodes: u32, pub nleaves: u32, pub max_depth: u32, pub root_min: [f32; 3], pub root_max: [f32; 3],
+    pub smem_resident: u32, pub flat_groups: u32, pub flat_pairs: u32, pub flat_singles: u32, pub flat_delta: f32,
+}
+#[repr(C)] #[derive(Default)]
+pub struct rl_layout_info {
+    pub ray_bytes: u32, pub hit_bytes: u32, pub state_bytes: u32, pub shadow_bytes: u32, pub accum_bytes: u32, pub max_paths_in_flight: u64,
 }
 
 #[link(name = "rl_b200")]
 extern "C" {
     pub fn rl_create(out: *mut *mut rl_ctx, device: c_int, nranks: c_int, rank: c_int, nccl_unique_id: *const c_void) -> c_int;
     pub fn rl_destroy(ctx: *mut rl_ctx);
+    pub fn rl_nccl_unique_id(out_128_bytes: *mut c_void) -> c_int;
     pub fn rl_last_error(ctx: *const rl_ctx) -> *const c_char;
+    pub fn rl_abi_version() -> c_int;
+    pub fn rl_host_alloc(bytes: usize) -> *mut c_void;
+    pub fn rl_host_free(p: *mut c_void);
+    pub fn rl_set_profiling(ctx: *mut rl_ctx, on: c_int) -> c_int;
     pub fn rl_scene_create(ctx: *mut rl_ctx, desc: *const rl_scene_desc, out: *mut *mut rl_scene) -> c_int;
     pub fn rl_scene_destroy(ctx: *mut rl_ctx, scene: *mut rl_scene);
+    pub fn rl_scene_bvh_info(ctx: *mut rl_ctx, scene: *const rl_scene, out: *mut rl_bvh_info) -> c_int;
     pub fn rl_render(ctx: *mut rl_ctx, scene: *mut rl_scene, integrator: *const rl_integrator_desc,
                      opts: *const rl_render_opts, out_rgb: *mut f32, stats: *mut rl_stats) -> c_int;
+    pub fn rl_render_device(ctx: *mut rl_ctx, scene: *mut rl_scene, integrator: *const rl_integrator_desc,
+                            opts: *const rl_render_opts, out_rgb_device: *mut f32, stats: *mut rl_stats) -> c_int;
     pub fn rl_trace(ctx: *mut rl_ctx, scene: *mut rl_scene, n: usize, o: *const f32, d: *const f32, prim: *mut u32, tuv: *mut f32) -> c_int;
     pub fn rl_visible(ctx: *mut rl_ctx, scene: *mut rl_scene, n: usize, p0: *const f32, p1: *const f32, out: *mut u8) -> c_int;
-    pub fn rl_host_alloc(bytes: usize) -> *mut c_void; // optional: pinned buffer for out_rgb
-    pub fn rl_host_free(p: *mut c_void);
+    pub fn rl_primary_hits(ctx: *mut rl_ctx, scene: *mut rl_scene, prim: *mut u32, tuv: *mut f32) -> c_int;
+    pub fn rl_layout(ctx: *mut rl_ctx, out: *mut rl_layout_info) -> c_int;
 }
 
-use crate::bsdfs::BSDFType;
-use crate::integrators::{BufferCollection, Integrator};
+use crate::integrators::ao::IntegratorAO;
 use crate::integrators::direct::IntegratorDirect;
 use crate::integrators::explicit::path::{IntegratorPathTracing, IntegratorPathTracingStrategies};
+use crate::integrators::{BufferCollection, Integrator};
 use crate::{accel::Acceleration, samplers::Sampler, scene::Scene, structure::Color};
-use cgmath::{Matrix, Point2};
+use cgmath::{Matrix4, Point2};
 
 fn opt(v: Option<u32>) -> i32 { v.map_or(-1, |x| x as i32) }
+unsafe fn last_error(ctx: *const rl_ctx) -> String { CStr::from_ptr(rl_last_error(ctx)).to_string_lossy().into_owned() }
+fn col(c: &Color) -> [f32; 3] { [c.r, c.g, c.b] }
+fn mat16(m: &Matrix4<f32>) -> [f32; 16] { *AsRef::<[f32; 16]>::as_ref(m) } // cgmath matrices are column-major, like the ABI
 
-/// Scene -> flat description.  Vectors are kept alive in `Flat` for the duration of the call.
-struct Flat { p: Vec<Vec<f32>>, n: Vec<Vec<f32>>, idx: Vec<Vec<u32>>, meshes: Vec<rl_mesh_desc>, lights: Vec<rl_light_desc>, textures: Vec<rl_texture> }
+/// Host arrays the flat description points into; they live until `rl_scene_create` has returned (the library copies everything).
+#[derive(Default)]
+pub struct Flat {
+    p: Vec<Vec<f32>>, n: Vec<Vec<f32>>, uv: Vec<Vec<f32>>, idx: Vec<Vec<u32>>, texels: Vec<Vec<f32>>,
+    meshes: Vec<rl_mesh_desc>, lights: Vec<rl_light_desc>, textures: Vec<rl_texture>,
+}
+impl Flat {
+    /// BSDFColor -> (constant colour, 0) or (black, 1 + texture index); `describe()` of a BSDF calls this for its diffuse slot.
+    pub fn color_slot(&mut self, c: &crate::bsdfs::BSDFColor) -> ([f32; 3], u32) {
+        use crate::bsdfs::BSDFColor::*;
+        let tex = match c {
+            Constant(v) => return (col(v), 0),
+            Bitmap { img } => {
+                self.texels.push(img.colors.iter().flat_map(|c| [c.r, c.g, c.b]).collect());
+                rl_texture { kind: 1, width: img.size.x, height: img.size.y, pixels: self.texels.last().unwrap().as_ptr(), color0: [0.0; 3],
+                             color1: [0.0; 3], line_width: 0.0, offset: [0.0; 2], scale: [1.0; 2] }
+            }
+            Checkerbord { color0, color1, offset, scale } => rl_texture { kind: 2, width: 0, height: 0, pixels: std::ptr::null(), color0: col(color0),
+                color1: col(color1), line_width: 0.0, offset: [offset.x, offset.y], scale: [scale.x, scale.y] },
+            Grid { color0, color1, line_width, offset, scale } => rl_texture { kind: 3, width: 0, height: 0, pixels: std::ptr::null(), color0: col(color0),
+                color1: col(color1), line_width: *line_width, offset: [offset.x, offset.y], scale: [scale.x, scale.y] },
+        };
+        self.textures.push(tex);
+        ([0.0; 3], self.textures.len() as u32)
+    }
+}
+
+/// Scene -> flat description (scene.rs:16-30, geometry.rs:107-119).  Panics where the reference offers something outside
+/// the GPU path (media, textured emission, environment maps, BSDFs without `describe`), like the reference panics on
+/// unsupported input (scene_loader.rs:40-43).
 fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
     assert!(scene.volume.is_none(), "scene.volume must be None on the GPU path");
-    let mut f = Flat { p: vec![], n: vec![], idx: vec![], meshes: vec![], lights: vec![], textures: vec![] };
+    let mut f = Flat::default();
     for m in &scene.meshes {
         f.p.push(m.vertices.iter().flat_map(|v| [v.x, v.y, v.z]).collect());
         f.n.push(m.normals.as_ref().map_or(vec![], |ns| ns.iter().flat_map(|v| [v.x, v.y, v.z]).collect()));
+        f.uv.push(m.uv.as_ref().map_or(vec![], |uv| uv.iter().flat_map(|v| [v.x, v.y]).collect()));
         f.idx.push(m.indices.iter().flat_map(|i| [i.x as u32, i.y as u32, i.z as u32]).collect());
     }
     for (k, m) in scene.meshes.iter().enumerate() {
-        // BSDFDiffuse / BSDFPhong -> rl_material: needs a small `fn describe(&self) -> rl_material`
-        // on the BSDF trait (or a downcast); everything else on this path is rejected up front.
-        let mat = m.bsdf.describe();
+        let mat = m.bsdf.describe(&mut f).unwrap_or_else(|| panic!("mesh {}: this BSDF has no GPU description (BSDFBlend?)", m.name));
         let (kind, e) = match &m.emission {
             crate::geometry::EmissionType::Zero => (0, Color::zero()),
             crate::geometry::EmissionType::Color { v } => (1, *v),
-            _ => panic!("textured emission is outside the GPU path"),
+            _ => panic!("mesh {}: HSV / textured emission is outside the GPU path", m.name),
         };
+        let (n, uv) = (&f.n[k], &f.uv[k]);
         f.meshes.push(rl_mesh_desc {
             p: f.p[k].as_ptr(), nverts: m.vertices.len() as u32, idx: f.idx[k].as_ptr(), ntris: m.indices.len() as u32,
-            n: if f.n[k].is_empty() { std::ptr::null() } else { f.n[k].as_ptr() }, uv: std::ptr::null(),
-            mat, emission_kind: kind, emission: [e.r, e.g, e.b],
+            n: if n.is_empty() { std::ptr::null() } else { n.as_ptr() }, uv: if uv.is_empty() { std::ptr::null() } else { uv.as_ptr() },
+            mat, emission_kind: kind, emission: col(&e),
         });
     }
+    // Non-mesh emitters in the order of Scene.emitters (scene.rs:85-96): mesh lights and the environment are rebuilt by the
+    // library from the meshes / `environment`; every other emitter must describe itself (PointEmitter, DirectionalLight).
+    if let Some(crate::scene::EmittersState::Build(sampler)) = &scene.emitters {
+        for e in &sampler.emitters {
+            if e.is_surface() || e.is_environment() { continue; }
+            f.lights.push(e.describe().expect("this emitter has no GPU description (PointNormalEmitter?)"));
+        }
+    }
+    let (has_env, env) = match scene.emitter_environment.as_ref().map(|e| &e.luminance) {
+        None => (0, [0.0; 3]),
+        Some(crate::emitter::EnvironmentLightColor::Constant(c)) => (1, col(c)),
+        Some(_) => panic!("environment textures are outside the GPU path"),
+    };
     let cam = &scene.camera;
-    let mut s2c = [0f32; 16]; let mut c2w = [0f32; 16];
-    s2c.copy_from_slice(AsRef::<[f32; 16]>::as_ref(cam.sample_to_camera()));   // needs pub accessors in camera.rs
-    c2w.copy_from_slice(AsRef::<[f32; 16]>::as_ref(cam.to_world()));
-    let desc = rl_scene_desc { nmeshes: f.meshes.len() as u32, meshes: f.meshes.as_ptr(),
-        camera: rl_camera_desc { width: cam.size().x, height: cam.size().y, sample_to_camera: s2c, to_world: c2w },
-        has_volume: 0, has_environment: scene.emitter_environment.is_some() as u32,
-        // PointEmitter / DirectionalLight of EmittersState::Unbuild need a `describe() -> Option<rl_light_desc>` on the Emitter
-        // trait; `f.lights` keeps them alive like the mesh vectors
-        nlights: f.lights.len() as u32, lights: f.lights.as_ptr(),
-        // BSDFColor::{Bitmap, Checkerbord, Grid} on a diffuse slot -> rl_texture + rl_material.kd_texture (describe() fills both)
-        ntextures: f.textures.len() as u32, textures: f.textures.as_ptr(),
-        // EnvironmentLightColor::Constant(c) -> has_environment = 1 + environment = c; a Texture environment must be rejected
-        environment: env_constant(scene) };
+    let desc = rl_scene_desc {
+        nmeshes: f.meshes.len() as u32, meshes: f.meshes.as_ptr(),
+        camera: rl_camera_desc { width: cam.size().x, height: cam.size().y, sample_to_camera: mat16(cam.sample_to_camera()), to_world: mat16(cam.to_world()) },
+        has_volume: 0, has_environment: has_env, nlights: f.lights.len() as u32, lights: f.lights.as_ptr(),
+        ntextures: f.textures.len() as u32, textures: f.textures.as_ptr(), environment: env,
+    };
     (f, desc)
 }
 
+/// One context + one resident device scene per process, rebuilt when `compute()` sees another `Scene`.
+struct Resident { ctx: *mut rl_ctx, dev: *mut rl_scene, scene_addr: usize, seed: u64, passes: u32 }
+unsafe impl Send for Resident {}
+impl Drop for Resident {
+    fn drop(&mut self) { unsafe { rl_scene_destroy(self.ctx, self.dev); rl_destroy(self.ctx); } }
+}
+static RESIDENT: Mutex<Option<Resident>> = Mutex::new(None);
+
 fn render(scene: &Scene, integ: rl_integrator_desc, seed: u64) -> BufferCollection {
     unsafe {
-        let mut ctx = std::ptr::null_mut();
-        assert_eq!(rl_create(&mut ctx, 0, 1, 0, std::ptr::null()), 0, "{:?}", CStr::from_ptr(rl_last_error(std::ptr::null())));
-        let (_keep, desc) = flatten(scene);
-        let mut dev = std::ptr::null_mut();
-        if rl_scene_create(ctx, &desc, &mut dev) != 0 { panic!("{:?}", CStr::from_ptr(rl_last_error(ctx))); }
+        assert_eq!(rl_abi_version(), RL_B200_ABI_VERSION, "librl_b200.so and this binding disagree on the ABI");
+        let mut guard = RESIDENT.lock().unwrap();
+        let addr = scene as *const Scene as usize;
+        if guard.as_ref().map_or(true, |r| r.scene_addr != addr) {
+            *guard = None; // drops the previous context and scene
+            let mut ctx = std::ptr::null_mut();
+            if rl_create(&mut ctx, 0, 1, 0, std::ptr::null()) != 0 { panic!("rl_create: {}", last_error(std::ptr::null())); }
+            let (_keep, desc) = flatten(scene);
+            let mut dev = std::ptr::null_mut();
+            if rl_scene_create(ctx, &desc, &mut dev) != 0 { let e = last_error(ctx); rl_destroy(ctx); panic!("rl_scene_create: {}", e); }
+            *guard = Some(Resident { ctx, dev, scene_addr: addr, seed, passes: 0 });
+        }
+        let r = guard.as_mut().unwrap();
+        if r.seed != seed { r.seed = seed; r.passes = 0; }
         let size = *scene.camera.size();
+        let spp = scene.nb_samples as u32;
+        assert_ne!(spp, 0); // integrators/mod.rs:410
         let mut rgb = vec![0f32; (size.x * size.y * 3) as usize];
-        let opts = rl_render_opts { struct_size: std::mem::size_of::<rl_render_opts>() as u32, spp: scene.nb_samples as u32,
-            seed, sampler_mode: 1, batch_spp: 0, material_sort: 0, sample_offset: 0 };
+        // pass p renders samples [p * spp, (p + 1) * spp): an averaging wrapper never sees the same sample twice
+        let opts = rl_render_opts { struct_size: std::mem::size_of::<rl_render_opts>() as u32, spp, seed, sampler_mode: 1, batch_spp: 0,
+                                    material_sort: 2, sample_offset: r.passes.wrapping_mul(spp) };
         let mut st = rl_stats::default();
-        if rl_render(ctx, dev, &integ, &opts, rgb.as_mut_ptr(), &mut st) != 0 { panic!("{:?}", CStr::from_ptr(rl_last_error(ctx))); }
-        info!("Elapsed Integrator: {} ms", st.ms_total as u64);   // same log line as integrators/mod.rs:334
+        if rl_render(r.ctx, r.dev, &integ, &opts, rgb.as_mut_ptr(), &mut st) != 0 { panic!("rl_render: {}", last_error(r.ctx)); }
+        r.passes += 1;
+        log::info!("Elapsed Integrator: {} ms", st.ms_total as u64); // same log line as integrators/mod.rs:334
         let mut img = BufferCollection::new(Point2::new(0, 0), size, &["primal".to_string()]);
         for y in 0..size.y { for x in 0..size.x {
             let i = ((y * size.x + x) * 3) as usize;
-            img.accumulate(Point2::new(x, y), Color::new(rgb[i], rgb[i + 1], rgb[i + 2]), &"primal".to_string());
+            img.accumulate(Point2::new(x, y), Color::new(rgb[i], rgb[i + 1], rgb[i + 2]), "primal");
         } }
-        rl_scene_destroy(ctx, dev);
-        rl_destroy(ctx);
         img
     }
 }
 
-/// `-r independent:<seed>`: the sampler only contributes its seed (Sampler gains `fn seed(&self) -> u64`).
 #[cfg(feature = "b200")]
 impl Integrator for IntegratorPathTracing {
     fn compute(&mut self, sampler: &mut dyn Sampler, _accel: &dyn Acceleration, scene: &Scene) -> BufferCollection {
@@ -156,10 +242,90 @@ impl Integrator for IntegratorDirect {
     }
 }
 #[cfg(feature = "b200")]
-impl Integrator for crate::integrators::ao::IntegratorAO {
+impl Integrator for IntegratorAO {
     fn compute(&mut self, sampler: &mut dyn Sampler, _accel: &dyn Acceleration, scene: &Scene) -> BufferCollection {
         render(scene, rl_integrator_desc { kind: 2, min_depth: 0, max_depth: -1, rr_depth: 0, strategy: 0, single_scattering: 0,
             nb_bsdf_samples: 1, nb_light_samples: 0, ao_max_distance: self.max_distance.unwrap_or(-1.0),
             ao_normal_correction: self.normal_correction as u32 }, sampler.seed())
     }
+}
+
+/// The additions to the reference's own files, as the code a maintainer pastes in (each block names its file).
+mod patch {
+    use super::{col, rl_light_desc, rl_material, Flat};
+    use crate::bsdfs::distribution::{MicrofacetDistributionBSDF, MicrofacetType};
+    use crate::bsdfs::{diffuse::BSDFDiffuse, glass::BSDFGlass, metal::BSDFMetal, phong::BSDFPhong, substrate::BSDFSubstrate, BSDFColor};
+    use crate::structure::Color;
+
+    // ---- src/bsdfs/mod.rs, inside `pub trait BSDF`:
+    //     /// Flat description for the GPU backend; None = not supported there (BSDFBlend).
+    //     fn describe(&self, _flat: &mut crate::b200::Flat) -> Option<crate::b200::rl_material> { None }
+    fn blank(kind: u32) -> rl_material {
+        rl_material { kind, kd: [0.0; 3], ks: [0.0; 3], exponent: 0.0, weight_specular: 0.0, kt: [0.0; 3], eta: [0.0; 3], k: [0.0; 3],
+                      ior: 1.0, alpha: 0.0, microfacet: 0, kd_texture: 0 }
+    }
+    /// Colour slots other than the diffuse one must be constants on the GPU path.
+    fn constant(c: &BSDFColor, what: &str) -> [f32; 3] {
+        match c { BSDFColor::Constant(v) => col(v), _ => panic!("{}: only the diffuse slot may carry a texture on the GPU path", what) }
+    }
+    fn microfacet(d: &Option<MicrofacetDistributionBSDF>) -> (u32, f32) {
+        match d {
+            None => (0, 0.0),
+            Some(d) => {
+                assert_eq!(d.alpha_u, d.alpha_v); // distribution.rs:62
+                (match d.microfacet_type { MicrofacetType::GGX => 1, MicrofacetType::Beckmann => 2 }, d.alpha_u)
+            }
+        }
+    }
+    // ---- src/bsdfs/diffuse.rs, inside `impl BSDF for BSDFDiffuse`:
+    pub fn describe_diffuse(b: &BSDFDiffuse, flat: &mut Flat) -> Option<rl_material> {
+        let (kd, kd_texture) = flat.color_slot(&b.diffuse);
+        Some(rl_material { kd, kd_texture, ..blank(0) })
+    }
+    // ---- src/bsdfs/phong.rs, inside `impl BSDF for BSDFPhong`:
+    pub fn describe_phong(b: &BSDFPhong, flat: &mut Flat) -> Option<rl_material> {
+        let (kd, kd_texture) = flat.color_slot(&b.diffuse);
+        Some(rl_material { kd, kd_texture, ks: constant(&b.specular, "phong specular"), exponent: b.exponent, weight_specular: b.weight_specular, ..blank(1) })
+    }
+    // ---- src/bsdfs/metal.rs, inside `impl BSDF for BSDFMetal`:
+    pub fn describe_metal(b: &BSDFMetal, _flat: &mut Flat) -> Option<rl_material> {
+        let (microfacet, alpha) = microfacet(&b.distribution);
+        Some(rl_material { ks: constant(&b.specular, "metal specular"), eta: constant(&b.eta, "metal eta"), k: constant(&b.k, "metal k"), microfacet, alpha, ..blank(2) })
+    }
+    // ---- src/bsdfs/glass.rs, inside `impl BSDF for BSDFGlass`:
+    pub fn describe_glass(b: &BSDFGlass, _flat: &mut Flat) -> Option<rl_material> {
+        Some(rl_material { ks: constant(&b.specular_reflectance, "glass reflectance"), kt: constant(&b.specular_transmittance, "glass transmittance"),
+                           ior: b.eta, ..blank(3) })
+    }
+    // ---- src/bsdfs/substrate.rs, inside `impl BSDF for BSDFSubstrate`:
+    pub fn describe_substrate(b: &BSDFSubstrate, flat: &mut Flat) -> Option<rl_material> {
+        let (kd, kd_texture) = flat.color_slot(&b.diffuse);
+        let (microfacet, alpha) = microfacet(&b.distribution);
+        Some(rl_material { kd, kd_texture, ks: constant(&b.specular, "substrate specular"), microfacet, alpha, ..blank(4) })
+    }
+    // (each `impl BSDF for X` gains `fn describe(&self, flat: &mut Flat) -> Option<rl_material> { crate::b200::patch::describe_x(self, flat) }`)
+
+    // ---- src/emitter.rs, inside `pub trait Emitter`:
+    //     fn describe(&self) -> Option<crate::b200::rl_light_desc> { None }
+    //     fn is_environment(&self) -> bool { false }        // EnvironmentLight returns true
+    // ---- inside `impl Emitter for PointEmitter`:
+    pub fn describe_point(e: &crate::emitter::PointEmitter) -> Option<rl_light_desc> {
+        Some(rl_light_desc { kind: 0, intensity: col(&e.intensity), v: [e.position.x, e.position.y, e.position.z] })
+    }
+    // ---- inside `impl Emitter for DirectionalLight` (its bounding sphere is rebuilt by the library, scene.rs:54-60):
+    pub fn describe_directional(e: &crate::emitter::DirectionalLight) -> Option<rl_light_desc> {
+        Some(rl_light_desc { kind: 1, intensity: col(&e.intensity), v: [e.direction.x, e.direction.y, e.direction.z] })
+    }
+
+    // ---- src/camera.rs, inside `impl Camera` (the matrices built by Camera::new, camera.rs:31-67, are private fields):
+    //     pub fn sample_to_camera(&self) -> &Matrix4<f32> { &self.sample_to_camera }
+    //     pub fn to_world(&self) -> &Matrix4<f32> { &self.to_world }
+
+    // ---- src/samplers/mod.rs, inside `pub trait Sampler`:
+    //     /// Seed of `-r independent:<seed>` (cli.rs:886-890); the GPU backend keys its counter streams on it.
+    //     fn seed(&self) -> u64 { 0 }
+    // ---- src/samplers/independent.rs: `pub struct IndependentSampler { pub rnd: SmallRng, pub seed: u64 }`, set where the CLI
+    //      builds it (`IndependentSampler { rnd: SmallRng::seed_from_u64(s), seed: s }`), and `fn seed(&self) -> u64 { self.seed }`.
+    #[allow(unused)]
+    fn _unused(_: Color) {}
 }

@@ -294,3 +294,90 @@ def test_bsdf_below_horizon():
 def test_phong_weight_specular():
     m = material_phong((0.2, 0.2, 0.2), (0.6, 0.6, 0.6), 10.0)
     assert m.weight_specular == pytest.approx(0.75, rel=1e-6)  # lum(ks)/(lum(kd)+lum(ks)), bsdfs/mod.rs:518-523
+
+
+# ---- outside pins of the third-party arithmetic the oracle restates -----------------------------
+def _pcg32_fill(state, nbytes):
+    """rand_core 0.6.4 SeedableRng::seed_from_u64 (the default SmallRng 0.8.5 inherits): PCG32 steps, output XSH-RR, little endian."""
+    MUL, INC = 6364136223846793005, 11634580027462260723
+    out = b""
+    while len(out) < nbytes:
+        state = (state * MUL + INC) & M64
+        xorshifted = (((state >> 18) ^ state) >> 27) & 0xFFFFFFFF
+        rot = state >> 59
+        x = ((xorshifted >> rot) | (xorshifted << ((32 - rot) & 31))) & 0xFFFFFFFF
+        out += x.to_bytes(4, "little")
+    return out[:nbytes]
+
+
+def _splitmix_fill(state, nbytes):
+    """Xoshiro256PlusPlus::seed_from_u64 (rand_xoshiro / rand 0.8.5 xoshiro256plusplus.rs): SplitMix64 outputs, little endian."""
+    PHI = 0x9e3779b97f4a7c15
+    out = b""
+    while len(out) < nbytes:
+        state = (state + PHI) & M64
+        out += _mix64(state).to_bytes(8, "little")
+    return out[:nbytes]
+
+
+def _seed_from_u64_py(seed, seeding):
+    raw = _pcg32_fill(seed, 32) if seeding == ob.SEED_PCG32 else _splitmix_fill(seed, 32)
+    return [int.from_bytes(raw[8 * i:8 * i + 8], "little") for i in range(4)]  # Xoshiro256PlusPlus::from_seed: read_u64_into
+
+
+def test_pcg32_known_answer():
+    """PCG32 (XSH-RR 64/32) with rand_core's constants: state 0 -> first outputs, computed by hand from the definition."""
+    raw = _pcg32_fill(0, 8)
+    # state1 = INC; xorshifted = ((INC >> 18) ^ INC) >> 27; rot = INC >> 59
+    INC = 11634580027462260723
+    xs = (((INC >> 18) ^ INC) >> 27) & 0xFFFFFFFF
+    rot = INC >> 59
+    assert int.from_bytes(raw[:4], "little") == ((xs >> rot) | (xs << (32 - rot))) & 0xFFFFFFFF
+    assert rot == 20 and len(set(raw)) > 4
+
+
+@pytest.mark.parametrize("seeding", [ob.SEED_PCG32, ob.SEED_SPLITMIX64])
+@pytest.mark.parametrize("seed", [0, 1, 0xDEADBEEFCAFEF00D])
+def test_block_stream_against_an_independent_python_implementation(seeding, seed):
+    """Sampler mode A end to end (samplers/independent.rs:10-22, integrators/mod.rs:351-374): master = SmallRng::seed_from_u64(seed);
+    block k's sampler = SmallRng::seed_from_u64(master.next_u64()) cloned in block order; next() = (next_u64() >> 32 >> 8) * 2^-24.
+    Every step re-typed here in Python from the published algorithms (PCG32 fill / SplitMix64 fill, xoshiro256++)."""
+    master = _seed_from_u64_py(seed, seeding)
+    for block in range(3):
+        r, master = _xoshiro_py(master)
+        st = _seed_from_u64_py(r, seeding)
+        exp = []
+        for _ in range(16):
+            v, st = _xoshiro_py(st)
+            exp.append(np.float32((v >> 32) >> 8) * np.float32(2.0**-24))
+        got = ob.sampler_block_stream(seed, block, 16, seeding)
+        assert np.array_equal(got, np.array(exp, np.float32)), (seeding, seed, block)
+
+
+def test_cgmath_perspective_and_invert_against_numpy_f64():
+    """Camera::new (camera.rs:31-67) = (S(-1/2, -a/2, 1) T(-1, -1/a, 0) perspective(fov, 1, 1e-2, 1000) S(x_v, 1, -1))^-1 with cgmath 0.18's
+    perspective (c0r0 = cot(f/2)/aspect, c1r1 = cot(f/2), c2r2 = (far+near)/(near-far), c2r3 = -1, c3r2 = 2 far near/(near-far)) and
+    Matrix4::invert: rebuilt in float64 with numpy.linalg.inv and compared entry by entry."""
+    def scale(x, y, z):
+        return np.diag([x, y, z, 1.0])
+
+    def trans(x, y, z):
+        m = np.eye(4)
+        m[:3, 3] = [x, y, z]
+        return m
+
+    def perspective(fovy_deg, aspect, near, far):
+        f = 1.0 / math.tan(math.radians(fovy_deg) / 2.0)
+        m = np.zeros((4, 4))
+        m[0, 0], m[1, 1] = f / aspect, f
+        m[2, 2], m[2, 3] = (far + near) / (near - far), 2.0 * far * near / (near - far)
+        m[3, 2] = -1.0
+        return m
+    for (w, h, fov, axis, flip) in [(512, 512, 19.5, "y", False), (1920, 1080, 30.0, "y", False), (640, 480, 45.0, "x", True), (64, 128, 60.0, "y", True)]:
+        a = w / h
+        fovy = fov * a if axis == "y" else fov  # the Fov::Y quirk (camera.rs:41-44): v * aspect, Fov::X(v): v
+        c2s = scale(-0.5, -0.5 * a, 1.0) @ trans(-1.0, -1.0 / a, 0.0) @ perspective(fovy, 1.0, 1e-2, 1000.0) @ scale(1.0 if flip else -1.0, 1.0, -1.0)
+        expect = np.linalg.inv(c2s)
+        got = ob.camera_new(w, h, fov, np.eye(4, dtype=np.float32), fov_axis=axis, flip=flip).reshape(4, 4).T.astype(np.float64)  # column-major
+        scale_ = np.abs(expect).max()
+        assert np.allclose(got, expect, rtol=2e-5, atol=2e-6 * scale_), (w, h, fov, axis, flip, np.abs(got - expect).max())
