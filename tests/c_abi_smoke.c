@@ -14,6 +14,7 @@
 int rlh_camera_create(uint32_t w, uint32_t h, int fov_axis, float fov_deg, const float to_world[16], int flip, float out_sample_to_camera[16],
                       float out_camera_to_sample[16]);
 
+#define FAIL() do { fprintf(stderr, "c_abi_smoke: check failed at line %d\n", __LINE__); return 1; } while (0)
 #define CHECK(call)                                                                    \
     do {                                                                               \
         int rc_ = (call);                                                              \
@@ -34,7 +35,7 @@ int main(void) {
         fprintf(stderr, "rl_create: %s\n", rl_last_error(NULL));
         return 3;
     }
-    if (rc != RL_OK) return 1;
+    if (rc != RL_OK) FAIL();
 
     /* floor y = 0 (4 x 4), lamp y = 2 (1 x 1, facing down) */
     static const float floor_p[] = {-2, 0, -2, 2, 0, -2, 2, 0, 2, -2, 0, 2};
@@ -52,16 +53,17 @@ int main(void) {
     memset(&desc, 0, sizeof(desc));
     desc.nmeshes = 2, desc.meshes = meshes;
     desc.camera.width = 16, desc.camera.height = 16;
-    /* camera at (0, 1, 5) looking down -z: column-major camera-to-world */
-    const float to_world[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 1, 5, 1};
+    /* camera at (0, 1, 5); Camera::new looks along +z of camera space (camera.rs:50: "undo gluPerspective"), so camera z maps to world -z.
+     * Column-major camera-to-world. */
+    const float to_world[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, -1, 0, 0, 1, 5, 1};
     memcpy(desc.camera.to_world, to_world, sizeof(to_world));
-    if (rlh_camera_create(16, 16, 0, 40.0f, to_world, 0, desc.camera.sample_to_camera, NULL) != 0) return 1;
+    if (rlh_camera_create(16, 16, 0, 40.0f, to_world, 0, desc.camera.sample_to_camera, NULL) != 0) FAIL();
 
     rl_scene *scene = NULL;
     CHECK(rl_scene_create(ctx, &desc, &scene));
     rl_bvh_info info;
     CHECK(rl_scene_bvh_info(ctx, scene, &info));
-    if (info.ntris != 4) return 1;
+    if (info.ntris != 4) FAIL();
 
     rl_integrator_desc path;
     memset(&path, 0, sizeof(path));
@@ -73,12 +75,12 @@ int main(void) {
     static float img[2][16 * 16 * 3], dimg[16 * 16 * 3];
     rl_stats st;
     CHECK(rl_render(ctx, scene, &path, &opts, img[0], &st));
-    if (st.samples != 16u * 16u * 32u || st.segments < st.samples) return 1;
+    if (st.samples != 16u * 16u * 32u || st.segments < st.samples) FAIL();
     opts.sample_offset = 32; /* pass 2 of an averaging wrapper */
     CHECK(rl_render(ctx, scene, &path, &opts, img[1], &st));
     double sum = 0.0, diff = 0.0;
     for (int i = 0; i < 16 * 16 * 3; i++) {
-        if (!(img[0][i] >= 0.0f) || !isfinite(img[0][i])) return 1;
+        if (!(img[0][i] >= 0.0f) || !isfinite(img[0][i])) FAIL();
         sum += img[0][i], diff += fabs((double)img[0][i] - (double)img[1][i]);
     }
     if (!(sum > 1.0) || !(diff > 0.0)) {
@@ -89,22 +91,22 @@ int main(void) {
     direct.kind = RL_INTEGRATOR_DIRECT;
     opts.sample_offset = 0;
     CHECK(rl_render(ctx, scene, &direct, &opts, dimg, &st));
-    if (st.segments > 2 * st.samples) return 1;
+    if (st.segments > 2 * st.samples) FAIL();
 
     /* Acceleration::trace / visible: straight down onto the floor from y = 1; floor point <-> lamp centre */
     const float o[3] = {0.25f, 1.0f, 0.25f}, d[3] = {0, -1, 0};
     uint32_t prim = 0;
     float tuv[3];
     CHECK(rl_trace(ctx, scene, 1, o, d, &prim, tuv));
-    if (prim > 1 || fabsf(tuv[0] - 1.0f) > 1e-6f) return 1;
+    if (prim > 1 || fabsf(tuv[0] - 1.0f) > 1e-6f) FAIL();
     const float p0[6] = {0.25f, 0.0f, 0.25f, 0.25f, 0.0f, 0.25f}, p1[6] = {0.0f, 2.0f, 0.0f, 0.0f, -3.0f, 0.0f};
     uint8_t vis[2];
     CHECK(rl_visible(ctx, scene, 2, p0, p1, vis));
-    if (vis[0] != 1) return 1;
+    if (vis[0] != 1) FAIL();
 
     /* errors are status codes, never aborts */
     opts.spp = 0;
-    if (rl_render(ctx, scene, &path, &opts, img[0], &st) != RL_ERR_INVALID) return 1;
+    if (rl_render(ctx, scene, &path, &opts, img[0], &st) != RL_ERR_INVALID) FAIL();
     rl_scene_destroy(ctx, scene);
     rl_destroy(ctx);
     printf("c_abi_smoke ok: path mean %.5f\n", sum / (16 * 16 * 3));
