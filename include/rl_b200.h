@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RL_B200_ABI_VERSION 3
+#define RL_B200_ABI_VERSION 4
 
 typedef struct rl_ctx rl_ctx;     /* one per GPU / per rank; single-owner, not thread-safe */
 typedef struct rl_scene rl_scene; /* device-resident scene: geometry, LBVH, emitters, camera */
@@ -57,9 +57,10 @@ typedef enum rl_microfacet { /* MicrofacetDistributionBSDF, src/bsdfs/distributi
     RL_MICROFACET_BECKMANN = 2
 } rl_microfacet;
 
-/* BSDFColor (bsdfs/mod.rs:11-101) other than Constant, for the DIFFUSE reflectance slot (kd) of DIFFUSE, PHONG and SUBSTRATE
- * materials: rl_material.kd_texture = 1 + index into rl_scene_desc.textures (0 = BSDFColor::Constant(kd)).  A mesh without uv
- * coordinates evaluates a texture to black ("Found a texture but no uv coordinate given", bsdfs/mod.rs:36-39). */
+/* BSDFColor (bsdfs/mod.rs:11-101) other than Constant, for any colour slot of a material: rl_material.<slot>_texture = 1 + index
+ * into rl_scene_desc.textures (0 = BSDFColor::Constant(<slot>)).  A mesh without uv coordinates evaluates a texture to black
+ * ("Found a texture but no uv coordinate given", bsdfs/mod.rs:36-39).  BSDFPhong's weight_specular stays the constant the
+ * caller computed (the reference computes it once from constant colours too, bsdfs/mod.rs:518-523). */
 typedef enum rl_texture_kind {
     RL_TEX_BITMAP = 1,       /* nearest texel, Bitmap::pixel_uv (structure.rs:434-453)                         */
     RL_TEX_CHECKERBOARD = 2, /* bsdfs/mod.rs:43-65                                                             */
@@ -92,6 +93,11 @@ typedef struct rl_material {
     float alpha;           /* microfacet roughness alpha_u == alpha_v                          */
     uint32_t microfacet;   /* rl_microfacet                                                   */
     uint32_t kd_texture;   /* 0 = constant kd, else 1 + index into rl_scene_desc.textures     */
+    /* the other colour slots bsdf_pbrt runs through bsdf_texture_match_pbrt (bsdfs/mod.rs:294-386): same encoding            */
+    uint32_t ks_texture;   /* phong / substrate Ks, metal specular (mirror Kr), glass Kr      */
+    uint32_t kt_texture;   /* glass Kt                                                        */
+    uint32_t eta_texture;  /* metal eta                                                       */
+    uint32_t k_texture;    /* metal k                                                         */
 } rl_material;
 
 /* ---- geometry: Mesh, src/geometry.rs:107-119 ---------------------------------------------- */

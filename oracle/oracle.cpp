@@ -453,7 +453,7 @@ struct BSDFDiffuse : BSDF { // bsdfs/diffuse.rs
 };
 struct BSDFPhong : BSDF { // bsdfs/phong.rs
     BSDFColor diffuse;
-    Color specular;
+    BSDFColor specular;
     float exponent, weight_specular;
     bool sample(const Math &m, const UV &uv, V3 d_in, P2 s, SampledDirection *out) const override { // :14-63
         if (d_in.z <= 0.0f) return false;
@@ -491,7 +491,7 @@ struct BSDFPhong : BSDF { // bsdfs/phong.rs
         if (d_in.z <= 0.0f || d_out.z <= 0.0f) return Color::zero();
         Color specular_value;
         float alpha = dot(reflect(d_in), d_out);
-        if (alpha > 0.0f) specular_value = specular * (m.powf(alpha, exponent) * (exponent + 2.0f) / (2.0f * PI));
+        if (alpha > 0.0f) specular_value = specular.color(uv) * (m.powf(alpha, exponent) * (exponent + 2.0f) / (2.0f * PI));
         else specular_value = Color::zero();
         Color diffuse_value = diffuse.color(uv) * d_out.z * FRAC_1_PI;
         return specular_value + diffuse_value;
@@ -615,20 +615,20 @@ struct MicrofacetDistribution {
 };
 
 struct BSDFMetal : BSDF { // bsdfs/metal.rs
-    Color specular, eta, k;
+    BSDFColor specular, eta, k;
     bool has_distribution;
     MicrofacetDistribution distr;
     bool sample(const Math &mm, const UV &uv, V3 d_in, P2 s, SampledDirection *out) const override { // :15-73
         if (d_in.z <= 0.0f) return false;
         if (!has_distribution) {
-            *out = SampledDirection{specular * bu::fresnel_conductor(d_in.z, eta, k), reflect(d_in), PDF{PDF::Discrete, 1.0f}};
+            *out = SampledDirection{specular.color(uv) * bu::fresnel_conductor(d_in.z, eta.color(uv), k.color(uv)), reflect(d_in), PDF{PDF::Discrete, 1.0f}};
             return true;
         }
         auto [m, pdf] = distr.sample(mm, s);
         if (pdf == 0.0f) return false;
         V3 wo = bu::reflect_vector(d_in, m);
         if (bu::cos_theta(wo) <= 0.0f) return false;
-        Color f = bu::fresnel_conductor(dot(d_in, m), eta, k) * specular;
+        Color f = bu::fresnel_conductor(dot(d_in, m), eta.color(uv), k.color(uv)) * specular.color(uv);
         float w = distr.eval(mm, m) * distr.g(d_in, wo, m) * dot(d_in, m) / (pdf * bu::cos_theta(d_in));
         *out = SampledDirection{w * f, wo, PDF{PDF::SolidAngle, pdf}};
         return true;
@@ -641,7 +641,7 @@ struct BSDFMetal : BSDF { // bsdfs/metal.rs
         V3 h = normalize(wi + wo);
         float d = distr.eval(mm, h);
         if (d == 0.0f) return Color::zero();
-        Color f = specular * bu::fresnel_conductor(dot(wi, h), eta, k);
+        Color f = specular.color(uv) * bu::fresnel_conductor(dot(wi, h), eta.color(uv), k.color(uv));
         float g = distr.g(wi, wo, h);
         float model = d * g / (4.0f * bu::cos_theta(wi));
         return f * model;
@@ -650,7 +650,7 @@ struct BSDFMetal : BSDF { // bsdfs/metal.rs
     bool is_smooth() const override { return !has_distribution; } // DELTA without a distribution, GLOSSY with one (:166-171)
 };
 struct BSDFGlass : BSDF { // bsdfs/glass.rs
-    Color specular_transmittance, specular_reflectance;
+    BSDFColor specular_transmittance, specular_reflectance;
     float eta, inv_eta;
     V3 refract(V3 wi, float cos_theta_t) const { // :50-58
         float scale = cos_theta_t < 0.0f ? -inv_eta : -eta;
@@ -659,10 +659,10 @@ struct BSDFGlass : BSDF { // bsdfs/glass.rs
     bool sample(const Math &, const UV &uv, V3 d_in, P2 s, SampledDirection *out) const override { // :75-121, transport == Importance
         auto [fresnel, cos_theta_trans] = bu::fresnel_dielectric(d_in.z, eta);
         if (s.x <= fresnel) {
-            *out = SampledDirection{specular_reflectance, reflect(d_in), PDF{PDF::Discrete, fresnel}};
+            *out = SampledDirection{specular_reflectance.color(uv), reflect(d_in), PDF{PDF::Discrete, fresnel}};
         } else {
             float factor = 1.0f;
-            *out = SampledDirection{specular_transmittance * factor * factor, refract(d_in, cos_theta_trans), PDF{PDF::Discrete, fresnel}};
+            *out = SampledDirection{specular_transmittance.color(uv) * factor * factor, refract(d_in, cos_theta_trans), PDF{PDF::Discrete, fresnel}};
         }
         return true;
     }
@@ -673,12 +673,12 @@ struct BSDFGlass : BSDF { // bsdfs/glass.rs
     bool is_smooth() const override { return true; }
 };
 struct BSDFSubstrate : BSDF { // bsdfs/substrate.rs
-    Color specular;
+    BSDFColor specular;
     BSDFColor diffuse;
     bool has_distribution;
     MicrofacetDistribution distr;
-    Color schlick_fresnel(float cos_theta) const { // :15-18
-        Color rs = specular;
+    Color schlick_fresnel(const UV &uv, float cos_theta) const { // :15-18
+        Color rs = specular.color(uv);
         return rs + (Color::one() - rs) * powi(1.0f - cos_theta, 5);
     }
     PDF pdf_domain(const Math &mm, V3 wi, V3 wo, PDF::Kind domain) const { // :92-147
@@ -700,16 +700,16 @@ struct BSDFSubstrate : BSDF { // bsdfs/substrate.rs
         if (m.x == 0.0f && m.y == 0.0f && m.z == 0.0f) return Color::zero();
         m = normalize(m);
         if (domain == PDF::SolidAngle) {
-            Color diff = diffuse.color(uv) * (Color::one() - specular) * (28.0f / (23.0f * PI)) * (1.0f - powi(1.0f - 0.5f * bu::abs_cos_theta(d_in), 5)) *
+            Color diff = diffuse.color(uv) * (Color::one() - specular.color(uv)) * (28.0f / (23.0f * PI)) * (1.0f - powi(1.0f - 0.5f * bu::abs_cos_theta(d_in), 5)) *
                          (1.0f - powi(1.0f - 0.5f * bu::abs_cos_theta(d_out), 5));
             Color spec = Color::zero();
             if (has_distribution) {
                 float model = distr.eval(mm, m) / (4.0f * std::fabs(dot(d_in, m)) * rmax(std::fabs(bu::cos_theta(d_in)), std::fabs(bu::cos_theta(d_out))));
-                spec = model * schlick_fresnel(dot(d_in, m));
+                spec = model * schlick_fresnel(uv, dot(d_in, m));
             }
             return (diff + spec) * d_out.z;
         }
-        if (bu::check_reflection_condition(d_in, d_out)) return schlick_fresnel(dot(d_in, m));
+        if (bu::check_reflection_condition(d_in, d_out)) return schlick_fresnel(uv, dot(d_in, m));
         std::abort(); // unimplemented!()
     }
     bool sample(const Math &mm, const UV &uv, V3 d_in, P2 s, SampledDirection *out) const override { // :22-90
@@ -747,12 +747,12 @@ struct BSDFSubstrate : BSDF { // bsdfs/substrate.rs
     bool is_smooth() const override { return !has_distribution; } // DELTA | DIFFUSE without a distribution (:216-221)
 };
 std::unique_ptr<BSDF> make_bsdf(const rl_material &m, const rl_texture *textures = nullptr, uint32_t ntextures = 0) {
-    // the diffuse-reflectance slot: BSDFColor::Constant(kd) or one of the scene's textures
-    auto kd_color = [&]() {
+    // a colour slot: BSDFColor::Constant(rgb) or one of the scene's textures (bsdf_texture_match_pbrt, bsdfs/mod.rs:218-240)
+    auto slot = [&](const float *rgb, uint32_t tex) {
         BSDFColor c;
-        c.c = Color{m.kd[0], m.kd[1], m.kd[2]};
-        if (m.kd_texture != 0 && textures && m.kd_texture <= ntextures) {
-            const rl_texture &t = textures[m.kd_texture - 1];
+        c.c = Color{rgb[0], rgb[1], rgb[2]};
+        if (tex != 0 && textures && tex <= ntextures) {
+            const rl_texture &t = textures[tex - 1];
             c.kind = t.kind == RL_TEX_BITMAP ? BSDFColor::Bitmap : (t.kind == RL_TEX_GRID ? BSDFColor::Grid : BSDFColor::Checkerbord);
             c.color0 = Color{t.color0[0], t.color0[1], t.color0[2]}, c.color1 = Color{t.color1[0], t.color1[1], t.color1[2]};
             c.line_width = t.line_width, c.offset = P2{t.offset[0], t.offset[1]}, c.scale = P2{t.scale[0], t.scale[1]};
@@ -764,33 +764,34 @@ std::unique_ptr<BSDF> make_bsdf(const rl_material &m, const rl_texture *textures
         }
         return c;
     };
+    auto kd_color = [&]() { return slot(m.kd, m.kd_texture); };
     auto distribution = [&](bool *has) {
         *has = m.microfacet != RL_MICROFACET_NONE;
         return MicrofacetDistribution{m.microfacet == RL_MICROFACET_BECKMANN ? MicrofacetDistribution::Beckmann : MicrofacetDistribution::GGX, m.alpha, m.alpha};
     };
     if (m.kind == RL_BSDF_METAL) {
         auto b = std::make_unique<BSDFMetal>();
-        b->specular = Color{m.ks[0], m.ks[1], m.ks[2]}, b->eta = Color{m.eta[0], m.eta[1], m.eta[2]}, b->k = Color{m.k[0], m.k[1], m.k[2]};
+        b->specular = slot(m.ks, m.ks_texture), b->eta = slot(m.eta, m.eta_texture), b->k = slot(m.k, m.k_texture);
         b->distr = distribution(&b->has_distribution);
         return b;
     }
     if (m.kind == RL_BSDF_GLASS) {
         auto b = std::make_unique<BSDFGlass>();
-        b->specular_reflectance = Color{m.ks[0], m.ks[1], m.ks[2]}, b->specular_transmittance = Color{m.kt[0], m.kt[1], m.kt[2]};
+        b->specular_reflectance = slot(m.ks, m.ks_texture), b->specular_transmittance = slot(m.kt, m.kt_texture);
         b->eta = m.ior;
         b->inv_eta = 1.0f / b->eta; // glass.rs:46
         return b;
     }
     if (m.kind == RL_BSDF_SUBSTRATE) {
         auto b = std::make_unique<BSDFSubstrate>();
-        b->diffuse = kd_color(), b->specular = Color{m.ks[0], m.ks[1], m.ks[2]};
+        b->diffuse = kd_color(), b->specular = slot(m.ks, m.ks_texture);
         b->distr = distribution(&b->has_distribution);
         return b;
     }
     if (m.kind == RL_BSDF_PHONG) {
         auto b = std::make_unique<BSDFPhong>();
         b->diffuse = kd_color();
-        b->specular = Color{m.ks[0], m.ks[1], m.ks[2]};
+        b->specular = slot(m.ks, m.ks_texture);
         b->exponent = m.exponent;
         b->weight_specular = m.weight_specular;
         return b;
@@ -2123,7 +2124,9 @@ orc_scene *orc_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
             m->has_uv = true;
             for (uint32_t v = 0; v < md.nverts; v++) m->uv.push_back(P2{md.UV[2 * v], md.UV[2 * v + 1]});
         }
-        if (md.mat.kd_texture > desc->ntextures) return fail("kd_texture out of range");
+        if (md.mat.kd_texture > desc->ntextures || md.mat.ks_texture > desc->ntextures || md.mat.kt_texture > desc->ntextures ||
+            md.mat.eta_texture > desc->ntextures || md.mat.k_texture > desc->ntextures)
+            return fail("texture index out of range");
         m->bsdf = make_bsdf(md.mat, desc->textures, desc->ntextures);
         m->light = md.emission_kind != 0;
         m->emission = Color{md.emission[0], md.emission[1], md.emission[2]};

@@ -35,7 +35,8 @@ class rl_material(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("kd", C.c_float * 3), ("ks", C.c_float * 3),
                 ("exponent", C.c_float), ("weight_specular", C.c_float), ("kt", C.c_float * 3),
                 ("eta", C.c_float * 3), ("k", C.c_float * 3), ("ior", C.c_float), ("alpha", C.c_float),
-                ("microfacet", C.c_uint32), ("kd_texture", C.c_uint32)]
+                ("microfacet", C.c_uint32), ("kd_texture", C.c_uint32), ("ks_texture", C.c_uint32),
+                ("kt_texture", C.c_uint32), ("eta_texture", C.c_uint32), ("k_texture", C.c_uint32)]
 
 
 class rl_mesh_desc(C.Structure):

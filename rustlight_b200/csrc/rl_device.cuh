@@ -1264,7 +1264,7 @@ RL_HD uint32_t camera_block_mask(const SceneView &sv, const float4 *quad_verts, 
 }
 
 // ---- materials ---------------------------------------------------------------------------------
-#define RL_MAT_F4 5
+#define RL_MAT_F4 6
 struct Material {
     Col kd, ks, le;       // kd: diffuse | metal eta | glass transmittance;  ks: specular / reflectance
     float exponent;       // phong exponent | microfacet alpha
@@ -1272,7 +1272,9 @@ struct Material {
     float inv_area, pdf_sel;
     uint32_t kind, microfacet;
     bool is_light;
-    const float4 *ext;    // {metal k.rgb, glass 1/eta | kd_texture}: read only by the metal / glass branches and the texture lookup
+    bool k_textured;      // metal k comes from a texture (k_tex) instead of ext[0]
+    Col k_tex;
+    const float4 *ext;    // row 4 {metal k.rgb, glass 1/eta}, row 5 {textures of the colour slots}: read only by the metal / glass branches and the texture lookup
 };
 RL_HD Material load_material(const float4 *mats, uint32_t mesh) {
     const float4 *row = mats + RL_MAT_F4 * mesh;
@@ -1289,8 +1291,11 @@ RL_HD Material load_material(const float4 *mats, uint32_t mesh) {
     m.pdf_sel = e.z;
     m.microfacet = f2u(e.w);
     m.ext = row + 4;
+    m.k_textured = false;
+    m.k_tex = Col{0.0f, 0.0f, 0.0f};
     return m;
 }
+RL_HD Col metal_k(const Material &m) { return m.k_textured ? m.k_tex : xyz_col(m.ext[0]); } // BSDFMetal.k: constant or texture (apply_textures)
 // bsdf_type().is_smooth() (bsdfs/mod.rs:157-161): DELTA in the type -> no light sampling, no MIS at this vertex
 // KM (here and below): compile-time mask of the rl_bsdf_kind values present in the scene (bit k = kind k).  The shade
 // kernel is instantiated for the masks {diffuse}, {diffuse, phong} and "all", so that a Cornell box does not carry the
@@ -1427,7 +1432,7 @@ RL_HD Col metal_eval(const Material &mt, V3 wi, V3 wo) {
     V3 h = normalize(wi + wo);
     float d = mf_eval(mt.microfacet, mt.exponent, h);
     if (d == 0.0f) return Col{0.0f, 0.0f, 0.0f};
-    Col f = mt.ks * fresnel_conductor(dot(wi, h), mt.kd, xyz_col(mt.ext[0]));
+    Col f = mt.ks * fresnel_conductor(dot(wi, h), mt.kd, metal_k(mt));
     float g = mf_g(mt.microfacet, mt.exponent, wi, wo, h);
     float model = d * g / (4.0f * wi.z);
     return mul_checked(f, model);
@@ -1552,7 +1557,7 @@ RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight
     }
     if (wi.z <= 0.0f) return false;
     if (RL_HAS(KM, 2) && m.kind == 2u) { // metal
-        Col k = xyz_col(m.ext[0]);
+        Col k = metal_k(m);
         if (m.microfacet == 0u) {
             *weight = m.ks * fresnel_conductor(wi.z, m.kd, k);
             *wo = reflect_local(wi);
@@ -1677,11 +1682,14 @@ RL_HD Col texture_kd(const SceneView &sv, uint32_t tex_id, uint32_t prim, uint32
     if (y > 0.5f) y -= 1.0f;
     return (fabsf(x) < t1.w || fabsf(y) < t1.w) ? xyz_col(t0) : xyz_col(t1);
 }
-// Replaces m.kd by the texture value when the material has one (DIFFUSE, PHONG, SUBSTRATE).
-RL_HD void apply_kd_texture(const SceneView &sv, Material &m, uint32_t prim, uint32_t flags, float hit_u, float hit_v) {
-    if (m.kind == 2u || m.kind == 3u) return;
-    const uint32_t t = f2u(m.ext[0].w);
-    if (t != 0u) m.kd = texture_kd(sv, t - 1u, prim, flags, hit_u, hit_v);
+// BSDFColor::color(uv) of every textured colour slot of the material at this hit: slot a (kd | metal eta | glass kt) and slot b (ks)
+// replace the constants loaded by load_material; slot c (metal k) goes to m.k_tex (the metal branches read k through metal_k()).
+RL_HD void apply_textures(const SceneView &sv, Material &m, uint32_t prim, uint32_t flags, float hit_u, float hit_v) {
+    const float4 t = m.ext[1];
+    const uint32_t ta = f2u(t.x), tb = f2u(t.y), tc = f2u(t.z);
+    if (ta != 0u) m.kd = texture_kd(sv, ta - 1u, prim, flags, hit_u, hit_v);
+    if (tb != 0u) m.ks = texture_kd(sv, tb - 1u, prim, flags, hit_u, hit_v);
+    if (tc != 0u) m.k_tex = texture_kd(sv, tc - 1u, prim, flags, hit_u, hit_v), m.k_textured = true;
 }
 
 // ---- surface interaction (fill_intersection, structure.rs:965-1059) ---------------------------
@@ -2002,7 +2010,7 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
     uint32_t mesh = f2u(s0.w);
     Material mat = load_material(sv.mats, mesh);
-    if (RL_HAS(KM, 8) && sv.tex) apply_kd_texture(sv, mat, hit.prim, f2u(s1.w), hit.u, hit.v);
+    if (RL_HAS(KM, 8) && sv.tex) apply_textures(sv, mat, hit.prim, f2u(s1.w), hit.u, hit.v);
     Surface its = fill_intersection<KM>(sv, mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
     const bool mute = ip.single_scattering != 0u;
     const bool smooth = mat_is_smooth<KM>(mat); // no light sampling at this vertex (emitters.rs:110-112), no draws either
@@ -2129,7 +2137,7 @@ RL_HD void direct_begin(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, 
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
     uint32_t mesh = f2u(s0.w);
     cx->mat = load_material(sv.mats, mesh);
-    if (sv.tex) apply_kd_texture(sv, cx->mat, hit.prim, f2u(s1.w), hit.u, hit.v);
+    if (sv.tex) apply_textures(sv, cx->mat, hit.prim, f2u(s1.w), hit.u, hit.v);
     cx->its = fill_intersection(sv, cx->mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
     if (cx->its.wi.z <= 0.0f) return; // its.cos_theta() <= 0 (direct.rs:40-42)
     cx->ok = true;

@@ -130,8 +130,11 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
         const bool has_mf = m.mat.kind == RL_BSDF_METAL || m.mat.kind == RL_BSDF_SUBSTRATE;
         if (m.mat.kind > RL_BSDF_SUBSTRATE || (has_mf && m.mat.microfacet > RL_MICROFACET_BECKMANN) ||
             (has_mf && m.mat.microfacet != RL_MICROFACET_NONE && !(m.mat.alpha > 0.0f)) || (m.mat.kind == RL_BSDF_GLASS && m.mat.ior == 0.0f) ||
-            m.mat.kd_texture > desc->ntextures ||
-            (m.mat.kd_texture != 0 && m.mat.kind != RL_BSDF_DIFFUSE && m.mat.kind != RL_BSDF_PHONG && m.mat.kind != RL_BSDF_SUBSTRATE)) {
+            m.mat.kd_texture > desc->ntextures || m.mat.ks_texture > desc->ntextures || m.mat.kt_texture > desc->ntextures ||
+            m.mat.eta_texture > desc->ntextures || m.mat.k_texture > desc->ntextures ||
+            (m.mat.kd_texture != 0 && m.mat.kind != RL_BSDF_DIFFUSE && m.mat.kind != RL_BSDF_PHONG && m.mat.kind != RL_BSDF_SUBSTRATE) ||
+            (m.mat.ks_texture != 0 && m.mat.kind == RL_BSDF_DIFFUSE) || (m.mat.kt_texture != 0 && m.mat.kind != RL_BSDF_GLASS) ||
+            ((m.mat.eta_texture != 0 || m.mat.k_texture != 0) && m.mat.kind != RL_BSDF_METAL)) {
             err = "unsupported BSDF kind or parameters";
             return false;
         }
@@ -289,8 +292,11 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
         hs.mats.push_back(f4(m.emission_kind ? m.emission[0] : 0.0f, m.emission_kind ? m.emission[1] : 0.0f,
                              m.emission_kind ? m.emission[2] : 0.0f, u2f(m.emission_kind ? 1u : 0u)));
         hs.mats.push_back(f4(mt.kind == RL_BSDF_GLASS ? mt.ior : mt.weight_specular, mesh_inv_area[mi], pdf_sel[mi], u2f(has_mf ? mt.microfacet : 0u)));
-        // row 4: {metal k, glass 1/eta (BSDFGlass::eta(): inv_eta = 1.0 / eta) | kd_texture as uint bits}
-        hs.mats.push_back(f4(mt.k[0], mt.k[1], mt.k[2], mt.kind == RL_BSDF_GLASS ? 1.0f / mt.ior : u2f(mt.kd_texture)));
+        // row 4: {metal k, glass 1/eta (BSDFGlass::eta(): inv_eta = 1.0 / eta)}
+        hs.mats.push_back(f4(mt.k[0], mt.k[1], mt.k[2], mt.kind == RL_BSDF_GLASS ? 1.0f / mt.ior : 0.0f));
+        // row 5: textures of the three colour slots as uint bits: {slot a = kd | metal eta | glass kt, slot b = ks, slot c = metal k, -}
+        const uint32_t ta = mt.kind == RL_BSDF_METAL ? mt.eta_texture : (mt.kind == RL_BSDF_GLASS ? mt.kt_texture : mt.kd_texture);
+        hs.mats.push_back(f4(u2f(ta), u2f(mt.ks_texture), u2f(mt.kind == RL_BSDF_METAL ? mt.k_texture : 0u), 0.0f));
     }
     float am = 0.0f;
     for (int a = 0; a < 3; a++) am = fmaxf(am, fmaxf(fabsf(hs.raw_min[a]), fabsf(hs.raw_max[a])));

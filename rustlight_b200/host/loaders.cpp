@@ -365,13 +365,15 @@ void read_ply(const std::string &filename, RawShape &out) {
         if (v >= nv) throw Error("ply: face index out of range in " + filename);
 }
 
-// "texture Kd" "name" -> BSDFColor::Bitmap (bsdf_texture_match_pbrt, bsdfs/mod.rs:224-236); 0 when Kd is not a texture
-uint32_t kd_texture_of(const ParamSet &ps, const std::map<std::string, uint32_t> &texture_ids) {
-    const Param *p = ps.find("Kd");
+// "texture <name>" "tex" -> BSDFColor::Bitmap (bsdf_texture_match_pbrt, bsdfs/mod.rs:224-236, applied to every colour parameter of
+// bsdf_pbrt: Kd, Ks, Kr, Kt, eta, k); 0 when the parameter is not a texture
+uint32_t texture_of(const ParamSet &ps, const char *name, const std::map<std::string, uint32_t> &texture_ids) {
+    const Param *p = ps.find(name);
     if (!p || p->type != "texture") return 0;
-    if (p->strs.empty() || !texture_ids.count(p->strs[0])) throw Error("pbrt: Kd refers to an unknown texture"); // the reference warns and falls back to diffuse 0.8
+    if (p->strs.empty() || !texture_ids.count(p->strs[0])) throw Error(std::string("pbrt: ") + name + " refers to an unknown texture"); // the reference warns / unwraps
     return texture_ids.at(p->strs[0]);
 }
+uint32_t kd_texture_of(const ParamSet &ps, const std::map<std::string, uint32_t> &texture_ids) { return texture_of(ps, "Kd", texture_ids); }
 Material material_from_params(const std::string &type, const ParamSet &ps, const std::map<std::string, uint32_t> &texture_ids) {
     if (type == "matte") {
         // pbrt_rs::BSDF::Matte { kd } -> BSDFDiffuse (src/bsdfs/mod.rs:299-306); Kd default 0.5
@@ -394,18 +396,37 @@ Material material_from_params(const std::string &type, const ParamSet &ps, const
         if (u != v) throw Error("pbrt: anisotropic roughness panics in the reference (distribution.rs:62)");
         return remap_roughness((float)u, remap);
     };
-    if (type == "mirror") // bsdfs/mod.rs:349-357
-        return Material::metal(ps.rgb("Kr", Color{0.9f, 0.9f, 0.9f}), Color{1.0f, 1.0f, 1.0f}, Color{0.0f, 0.0f, 0.0f}, RL_MICROFACET_NONE, 0.0f);
-    if (type == "metal") // bsdfs/mod.rs:334-348; defaults: pbrt-v3's copper as RGB (pbrt_rs is not vendored: unpinned)
-        return Material::metal(Color{1.0f, 1.0f, 1.0f}, ps.rgb("eta", Color{0.2004f, 0.9240f, 1.1022f}), ps.rgb("k", Color{3.9129f, 2.4528f, 2.1421f}),
-                               RL_MICROFACET_GGX, ggx_alpha(0.01));
-    if (type == "glass") // bsdfs/mod.rs:307-333: the distribution is ignored ("Pure glass instead"), .eta(eta, 1.0)
-        return Material::glass(ps.rgb("Kr", Color{1.0f, 1.0f, 1.0f}), ps.rgb("Kt", Color{1.0f, 1.0f, 1.0f}), (float)ps.num("eta", ps.num("index", 1.5)), 1.0f);
+    const Color black{0.0f, 0.0f, 0.0f};
+    auto rgb_or_tex = [&](const char *name, Color def, uint32_t *tex) { // a textured slot keeps a black constant (it is never read)
+        *tex = texture_of(ps, name, texture_ids);
+        return *tex ? black : ps.rgb(name, def);
+    };
+    if (type == "mirror") { // bsdfs/mod.rs:349-357
+        uint32_t t;
+        Color kr = rgb_or_tex("Kr", Color{0.9f, 0.9f, 0.9f}, &t);
+        Material m = Material::metal(kr, Color{1.0f, 1.0f, 1.0f}, Color{0.0f, 0.0f, 0.0f}, RL_MICROFACET_NONE, 0.0f);
+        m.m.ks_texture = t;
+        return m;
+    }
+    if (type == "metal") { // bsdfs/mod.rs:334-348; defaults: pbrt-v3's copper as RGB (pbrt_rs is not vendored: unpinned)
+        uint32_t te, tk;
+        Color eta = rgb_or_tex("eta", Color{0.2004f, 0.9240f, 1.1022f}, &te), k = rgb_or_tex("k", Color{3.9129f, 2.4528f, 2.1421f}, &tk);
+        Material m = Material::metal(Color{1.0f, 1.0f, 1.0f}, eta, k, RL_MICROFACET_GGX, ggx_alpha(0.01));
+        m.m.eta_texture = te, m.m.k_texture = tk;
+        return m;
+    }
+    if (type == "glass") { // bsdfs/mod.rs:307-333: the distribution is ignored ("Pure glass instead"), .eta(eta, 1.0)
+        uint32_t tr, tt;
+        Color kr = rgb_or_tex("Kr", Color{1.0f, 1.0f, 1.0f}, &tr), kt = rgb_or_tex("Kt", Color{1.0f, 1.0f, 1.0f}, &tt);
+        Material m = Material::glass(kr, kt, (float)ps.num("eta", ps.num("index", 1.5)), 1.0f);
+        m.m.ks_texture = tr, m.m.kt_texture = tt;
+        return m;
+    }
     if (type == "substrate") { // bsdfs/mod.rs:358-374
-        uint32_t t = kd_texture_of(ps, texture_ids);
-        Material m = Material::substrate(t ? Color{0.0f, 0.0f, 0.0f} : ps.rgb("Kd", Color{0.5f, 0.5f, 0.5f}), ps.rgb("Ks", Color{0.5f, 0.5f, 0.5f}), RL_MICROFACET_GGX,
-                                         ggx_alpha(0.1));
-        m.m.kd_texture = t;
+        uint32_t t, ts;
+        Color kd = rgb_or_tex("Kd", Color{0.5f, 0.5f, 0.5f}, &t), ks = rgb_or_tex("Ks", Color{0.5f, 0.5f, 0.5f}, &ts);
+        Material m = Material::substrate(kd, ks, RL_MICROFACET_GGX, ggx_alpha(0.1));
+        m.m.kd_texture = t, m.m.ks_texture = ts;
         return m;
     }
     throw Error("pbrt: material type \"" + type + "\" is not supported (matte, mirror, metal, glass, substrate, phong)");
@@ -847,6 +868,20 @@ Scene JSONSceneLoader::load_string(const std::string &text, bool use_shading_nor
             if (mat.m.kind != RL_BSDF_DIFFUSE && mat.m.kind != RL_BSDF_PHONG && mat.m.kind != RL_BSDF_SUBSTRATE) throw Error("json: kd_texture on a material without a diffuse slot");
             mat.m.kd_texture = texture_ids[kt->s];
         }
+        struct Slot {
+            const char *key;
+            uint32_t rl_material::*field;
+            bool ok;
+        } slots[] = {{"ks_texture", &rl_material::ks_texture, mat.m.kind != RL_BSDF_DIFFUSE},
+                     {"kt_texture", &rl_material::kt_texture, mat.m.kind == RL_BSDF_GLASS},
+                     {"eta_texture", &rl_material::eta_texture, mat.m.kind == RL_BSDF_METAL},
+                     {"k_texture", &rl_material::k_texture, mat.m.kind == RL_BSDF_METAL}};
+        for (const Slot &sl : slots)
+            if (const JVal *kt = m.get(sl.key)) {
+                if (kt->t != JVal::Str || !texture_ids.count(kt->s)) throw Error(std::string("json: unknown ") + sl.key);
+                if (!sl.ok) throw Error(std::string("json: ") + sl.key + " on a material without that slot");
+                mat.m.*(sl.field) = texture_ids[kt->s];
+            }
         return mat;
     };
     std::map<std::string, Material> materials;
@@ -1004,6 +1039,10 @@ std::string scene_to_json(const Scene &scene) {
         if (mt.kind == RL_BSDF_METAL) put("eta", mt.eta, 3), put("k", mt.k, 3);
         if (mt.kind == RL_BSDF_GLASS) put("kt", mt.kt, 3), put("ior", &mt.ior, 1);
         if (mt.kd_texture) o << ", \"kd_texture\": \"tex" << mt.kd_texture << "\"";
+        if (mt.ks_texture) o << ", \"ks_texture\": \"tex" << mt.ks_texture << "\"";
+        if (mt.kt_texture) o << ", \"kt_texture\": \"tex" << mt.kt_texture << "\"";
+        if (mt.eta_texture) o << ", \"eta_texture\": \"tex" << mt.eta_texture << "\"";
+        if (mt.k_texture) o << ", \"k_texture\": \"tex" << mt.k_texture << "\"";
         if (mt.kind == RL_BSDF_METAL || mt.kind == RL_BSDF_SUBSTRATE) {
             o << ", \"microfacet\": \"" << mfs[mt.microfacet <= RL_MICROFACET_BECKMANN ? mt.microfacet : 0] << "\"";
             put("alpha", &mt.alpha, 1);

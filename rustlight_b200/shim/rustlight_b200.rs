@@ -22,7 +22,7 @@ use std::sync::Mutex;
 #[repr(C)] pub struct rl_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct rl_scene { _p: [u8; 0] }
 
-pub const RL_B200_ABI_VERSION: c_int = 3;
+pub const RL_B200_ABI_VERSION: c_int = 4;
 
 #[repr(C)] #[derive(Clone, Copy)]
 pub struct rl_texture {
@@ -33,6 +33,7 @@ pub struct rl_texture {
 pub struct rl_material {
     pub kind: u32, pub kd: [f32; 3], pub ks: [f32; 3], pub exponent: f32, pub weight_specular: f32,
     pub kt: [f32; 3], pub eta: [f32; 3], pub k: [f32; 3], pub ior: f32, pub alpha: f32, pub microfacet: u32, pub kd_texture: u32,
+    pub ks_texture: u32, pub kt_texture: u32, pub eta_texture: u32, pub k_texture: u32,
 }
 #[repr(C)]
 pub struct rl_mesh_desc {
@@ -110,7 +111,7 @@ pub struct Flat {
     meshes: Vec<rl_mesh_desc>, lights: Vec<rl_light_desc>, textures: Vec<rl_texture>,
 }
 impl Flat {
-    /// BSDFColor -> (constant colour, 0) or (black, 1 + texture index); `describe()` of a BSDF calls this for its diffuse slot.
+    /// BSDFColor -> (constant colour, 0) or (black, 1 + texture index); `describe()` of a BSDF calls this for each of its colour slots.
     pub fn color_slot(&mut self, c: &crate::bsdfs::BSDFColor) -> ([f32; 3], u32) {
         use crate::bsdfs::BSDFColor::*;
         let tex = match c {
@@ -262,11 +263,7 @@ mod patch {
     //     fn describe(&self, _flat: &mut crate::b200::Flat) -> Option<crate::b200::rl_material> { None }
     fn blank(kind: u32) -> rl_material {
         rl_material { kind, kd: [0.0; 3], ks: [0.0; 3], exponent: 0.0, weight_specular: 0.0, kt: [0.0; 3], eta: [0.0; 3], k: [0.0; 3],
-                      ior: 1.0, alpha: 0.0, microfacet: 0, kd_texture: 0 }
-    }
-    /// Colour slots other than the diffuse one must be constants on the GPU path.
-    fn constant(c: &BSDFColor, what: &str) -> [f32; 3] {
-        match c { BSDFColor::Constant(v) => col(v), _ => panic!("{}: only the diffuse slot may carry a texture on the GPU path", what) }
+                      ior: 1.0, alpha: 0.0, microfacet: 0, kd_texture: 0, ks_texture: 0, kt_texture: 0, eta_texture: 0, k_texture: 0 }
     }
     fn microfacet(d: &Option<MicrofacetDistributionBSDF>) -> (u32, f32) {
         match d {
@@ -285,23 +282,29 @@ mod patch {
     // ---- src/bsdfs/phong.rs, inside `impl BSDF for BSDFPhong`:
     pub fn describe_phong(b: &BSDFPhong, flat: &mut Flat) -> Option<rl_material> {
         let (kd, kd_texture) = flat.color_slot(&b.diffuse);
-        Some(rl_material { kd, kd_texture, ks: constant(&b.specular, "phong specular"), exponent: b.exponent, weight_specular: b.weight_specular, ..blank(1) })
+        let (ks, ks_texture) = flat.color_slot(&b.specular);
+        Some(rl_material { kd, kd_texture, ks, ks_texture, exponent: b.exponent, weight_specular: b.weight_specular, ..blank(1) })
     }
     // ---- src/bsdfs/metal.rs, inside `impl BSDF for BSDFMetal`:
-    pub fn describe_metal(b: &BSDFMetal, _flat: &mut Flat) -> Option<rl_material> {
+    pub fn describe_metal(b: &BSDFMetal, flat: &mut Flat) -> Option<rl_material> {
         let (microfacet, alpha) = microfacet(&b.distribution);
-        Some(rl_material { ks: constant(&b.specular, "metal specular"), eta: constant(&b.eta, "metal eta"), k: constant(&b.k, "metal k"), microfacet, alpha, ..blank(2) })
+        let (ks, ks_texture) = flat.color_slot(&b.specular);
+        let (eta, eta_texture) = flat.color_slot(&b.eta);
+        let (k, k_texture) = flat.color_slot(&b.k);
+        Some(rl_material { ks, ks_texture, eta, eta_texture, k, k_texture, microfacet, alpha, ..blank(2) })
     }
     // ---- src/bsdfs/glass.rs, inside `impl BSDF for BSDFGlass`:
-    pub fn describe_glass(b: &BSDFGlass, _flat: &mut Flat) -> Option<rl_material> {
-        Some(rl_material { ks: constant(&b.specular_reflectance, "glass reflectance"), kt: constant(&b.specular_transmittance, "glass transmittance"),
-                           ior: b.eta, ..blank(3) })
+    pub fn describe_glass(b: &BSDFGlass, flat: &mut Flat) -> Option<rl_material> {
+        let (ks, ks_texture) = flat.color_slot(&b.specular_reflectance);
+        let (kt, kt_texture) = flat.color_slot(&b.specular_transmittance);
+        Some(rl_material { ks, ks_texture, kt, kt_texture, ior: b.eta, ..blank(3) })
     }
     // ---- src/bsdfs/substrate.rs, inside `impl BSDF for BSDFSubstrate`:
     pub fn describe_substrate(b: &BSDFSubstrate, flat: &mut Flat) -> Option<rl_material> {
         let (kd, kd_texture) = flat.color_slot(&b.diffuse);
+        let (ks, ks_texture) = flat.color_slot(&b.specular);
         let (microfacet, alpha) = microfacet(&b.distribution);
-        Some(rl_material { kd, kd_texture, ks: constant(&b.specular, "substrate specular"), microfacet, alpha, ..blank(4) })
+        Some(rl_material { kd, kd_texture, ks, ks_texture, microfacet, alpha, ..blank(4) })
     }
     // (each `impl BSDF for X` gains `fn describe(&self, flat: &mut Flat) -> Option<rl_material> { crate::b200::patch::describe_x(self, flat) }`)
 

@@ -252,7 +252,8 @@ static void emu_material_rows(const rl_material *mt, float4 rows[RL_MAT_F4]) {
     rows[1] = f4(mt->ks[0], mt->ks[1], mt->ks[2], has_mf ? mt->alpha : mt->exponent);
     rows[2] = f4(0, 0, 0, u2f(0u));
     rows[3] = f4(mt->kind == RL_BSDF_GLASS ? mt->ior : mt->weight_specular, 0.0f, 0.0f, u2f(has_mf ? mt->microfacet : 0u));
-    rows[4] = f4(mt->k[0], mt->k[1], mt->k[2], mt->kind == RL_BSDF_GLASS ? 1.0f / mt->ior : u2f(0u));
+    rows[4] = f4(mt->k[0], mt->k[1], mt->k[2], mt->kind == RL_BSDF_GLASS ? 1.0f / mt->ior : 0.0f);
+    rows[5] = f4(0.0f, 0.0f, 0.0f, 0.0f); // no textures in the per-material unit tests
 }
 // returns 0 = None, 1 = SolidAngle pdf, 2 = Discrete pdf
 int emu_bsdf_sample(const rl_material *mt, const float wi[3], float s0, float s1, float weight[3], float d[3], float *pdf) {

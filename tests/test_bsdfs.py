@@ -489,3 +489,58 @@ def test_environment_in_the_cornell_box_keeps_the_reference_quirk():
     m = [float(osc.render(_abi.path_desc(strategy=s, max_depth=4), 600, seed=2, cfg=ob.config(**STREAM))[0].mean())
          for s in (_abi.RL_STRATEGY_BSDF, _abi.RL_STRATEGY_EMITTER)]
     assert m[1] > 1.1 * m[0]
+
+
+def _cbox_textured_on_every_slot(w=48, h=48):
+    """Cornell box whose materials carry a texture on every colour slot bsdf_pbrt runs through bsdf_texture_match_pbrt
+    (bsdfs/mod.rs:294-386): phong Ks, substrate Ks (+ Kd), mirror Kr, metal eta and k, glass Kr and Kt."""
+    from rustlight_b200.host import material_glass, material_metal, material_mirror, material_phong, material_substrate
+    sc = load_cbox(w, h)
+    rng = np.random.default_rng(21)
+    chk = sc.add_checkerboard_texture((0.9, 0.6, 0.3), (0.2, 0.2, 0.25), (0, 0), (3, 3))
+    bmp = sc.add_bitmap_texture((0.2 + 0.7 * rng.random((6, 6, 3))).astype(np.float32))
+    grid = sc.add_grid_texture((0.95, 0.95, 0.9), (0.4, 0.5, 0.6), 0.08, (0, 0), (3, 2))
+    eta_t = sc.add_bitmap_texture((0.1 + 1.4 * rng.random((4, 4, 3))).astype(np.float32))
+    k_t = sc.add_bitmap_texture((2.0 + 3.0 * rng.random((4, 4, 3))).astype(np.float32))
+    m = material_phong((0.3, 0.3, 0.3), (0.0, 0.0, 0.0), 30.0)
+    m.ks_texture = chk
+    m.weight_specular = 0.4  # the caller's constant: the reference computes it once from constant colours (bsdfs/mod.rs:518-523)
+    sc.set_material(0, m)                                        # floor: phong with a textured Ks
+    m = material_substrate((0.0, 0.0, 0.0), (0.0, 0.0, 0.0), "ggx", 0.15)
+    m.kd_texture, m.ks_texture = bmp, grid
+    sc.set_material(1, m)                                        # ceiling: substrate, both slots textured
+    m = material_mirror((0.0, 0.0, 0.0))
+    m.ks_texture = grid
+    sc.set_material(3, m)                                        # a side wall: mirror with a textured Kr
+    m = material_metal((1, 1, 1), (0, 0, 0), (0, 0, 0), "ggx", 0.2)
+    m.eta_texture, m.k_texture = eta_t, k_t
+    sc.set_material(2, m)                                        # back wall: rough metal, eta and k from bitmaps
+    m = material_glass((0, 0, 0), (0, 0, 0), 1.5, 1.0)
+    m.ks_texture, m.kt_texture = chk, bmp
+    sc.set_material(5, m)                                        # short box: glass with textured Kr and Kt
+    return sc
+
+
+def test_textures_on_every_colour_slot_bit_exact():
+    """Device arithmetic (emulator) == oracle with a texture on Ks / Kr / Kt / eta / k, and the stream estimator still equals the
+    reference's graph estimator there."""
+    sc = _cbox_textured_on_every_slot()
+    d = sc.desc.contents
+    assert d.ntextures == 5 and d.meshes[2].mat.eta_texture == 4 and d.meshes[5].mat.kt_texture == 2
+    stream = {}
+    for name, integ in (("path", _abi.path_desc()), ("direct", _abi.direct_desc(1, 1))):
+        ie, se = eb.EmuScene(sc).render(integ, 6, seed=9)
+        io, so = ob.OracleScene(sc).render(integ, 6, seed=9, cfg=ob.config(**STREAM))
+        assert se.segments == so.segments and np.array_equal(ie, io) and io.max() > 0
+        stream[name] = io
+    ig, _ = ob.OracleScene(sc).render(_abi.path_desc(), 6, seed=9, cfg=ob.config(estimator=ob.EST_GRAPH, accel_mode=ob.ACCEL_BVH))
+    assert rel_l2(stream["path"], ig) < 1e-6
+    # the textures matter: constant-colour materials give another image
+    plain = load_cbox(48, 48)
+    ip, _ = ob.OracleScene(plain).render(_abi.path_desc(), 6, seed=9, cfg=ob.config(**STREAM))
+    assert rel_l2(ig, ip) > 0.05
+    # and they survive the JSON round trip
+    from rustlight_b200 import SceneLoaderManager
+    sc2 = SceneLoaderManager().load_string(sc.to_json(), "json")
+    m2 = sc2.desc.contents.meshes[5].mat
+    assert (m2.ks_texture, m2.kt_texture) == (1, 2) and sc2.desc.contents.meshes[2].mat.k_texture == 5

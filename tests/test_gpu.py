@@ -580,3 +580,18 @@ def test_consecutive_compute_calls_continue_the_sample_sequence(gpu_ctx):
     full, _ = dev.render(integ.desc(), 16, seed=5)
     assert np.allclose(0.5 * (a + b), full, rtol=2e-6, atol=1e-7)
     dev.close()
+
+
+def test_textures_on_every_colour_slot_bit_exact(gpu_ctx):
+    """Ks / Kr / Kt / eta / k textures (bsdfs/mod.rs:218-253 applies bsdf_texture_match_pbrt to every colour parameter): the general
+    shade kernel against the oracle, with and without the material sort."""
+    from test_bsdfs import _cbox_textured_on_every_slot
+    sc = _cbox_textured_on_every_slot(64, 64)
+    dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
+    for integ in (_abi.path_desc(), _abi.direct_desc(1, 1)):
+        ref, so = osc.render(integ, 6, seed=9, cfg=ob.config(**STREAM))
+        for sort in (0, 1):
+            img, st = dev.render(integ, 6, seed=9, material_sort=sort)
+            assert (st.segments, st.hits, st.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+            assert np.array_equal(img, ref)
+    dev.close()
