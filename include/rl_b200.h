@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RL_B200_ABI_VERSION 4
+#define RL_B200_ABI_VERSION 5
 
 typedef struct rl_ctx rl_ctx;     /* one per GPU / per rank; single-owner, not thread-safe */
 typedef struct rl_scene rl_scene; /* device-resident scene: geometry, LBVH, emitters, camera */
@@ -49,7 +49,9 @@ typedef enum rl_bsdf_kind {
     RL_BSDF_PHONG = 1,     /* BSDFPhong     src/bsdfs/phong.rs:6-136                                      */
     RL_BSDF_METAL = 2,     /* BSDFMetal     src/bsdfs/metal.rs:6-177 (microfacet == NONE: pbrt "mirror")  */
     RL_BSDF_GLASS = 3,     /* BSDFGlass     src/bsdfs/glass.rs:35-192 (DELTA, not two-sided)              */
-    RL_BSDF_SUBSTRATE = 4  /* BSDFSubstrate src/bsdfs/substrate.rs:8-225                                  */
+    RL_BSDF_SUBSTRATE = 4, /* BSDFSubstrate src/bsdfs/substrate.rs:8-225                                  */
+    RL_BSDF_BLEND = 5      /* BSDFBlend     src/bsdfs/blend.rs:3-95: weight * bsdf1 + (1 - weight) * bsdf2; both rough (the reference asserts
+                              !is_smooth()), two-sided, constant colours, not themselves blends                                       */
 } rl_bsdf_kind;
 typedef enum rl_microfacet { /* MicrofacetDistributionBSDF, src/bsdfs/distribution.rs:5-17; isotropic only (:62) */
     RL_MICROFACET_NONE = 0, /* distribution: None -> pure specular lobe (BSDFType::DELTA)                */
@@ -98,6 +100,8 @@ typedef struct rl_material {
     uint32_t kt_texture;   /* glass Kt                                                        */
     uint32_t eta_texture;  /* metal eta                                                       */
     uint32_t k_texture;    /* metal k                                                         */
+    uint32_t blend_a, blend_b; /* BLEND: bsdf1, bsdf2 as 1 + index into rl_scene_desc.submaterials */
+    float blend_weight;        /* BLEND: BSDFBlend.weight in [0, 1]                                */
 } rl_material;
 
 /* ---- geometry: Mesh, src/geometry.rs:107-119 ---------------------------------------------- */
@@ -145,6 +149,8 @@ typedef struct rl_scene_desc {
     uint32_t ntextures;
     const rl_texture *textures;
     float environment[3];     /* constant environment radiance when has_environment == 1 */
+    uint32_t nsubmaterials;   /* the bsdf1 / bsdf2 of RL_BSDF_BLEND materials */
+    const rl_material *submaterials;
 } rl_scene_desc;
 
 /* ---- integrators --------------------------------------------------------------------------- */

@@ -29,6 +29,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -746,7 +747,53 @@ struct BSDFSubstrate : BSDF { // bsdfs/substrate.rs
     bool is_twosided() const override { return true; }
     bool is_smooth() const override { return !has_distribution; } // DELTA | DIFFUSE without a distribution (:216-221)
 };
-std::unique_ptr<BSDF> make_bsdf(const rl_material &m, const rl_texture *textures = nullptr, uint32_t ntextures = 0) {
+struct BSDFBlend : BSDF { // bsdfs/blend.rs
+    std::unique_ptr<BSDF> bsdf1, bsdf2;
+    float weight;
+    bool sample(const Math &m, const UV &uv, V3 d_in, P2 s, SampledDirection *out) const override { // :10-45
+        // assert!(!bsdf1.is_smooth() && !bsdf2.is_smooth()) (:17) is enforced when the scene is built
+        SampledDirection sd;
+        bool some;
+        if (s.x < weight) {
+            P2 scaled{s.x * (1.0f / weight), s.y};
+            some = bsdf1->sample(m, uv, d_in, scaled, &sd);
+        } else {
+            P2 scaled{(s.x - weight) * (1.0f / (1.0f - weight)), s.y};
+            some = bsdf2->sample(m, uv, d_in, scaled, &sd);
+        }
+        if (!some) return false;
+        sd.pdf = pdf(m, uv, d_in, sd.d);
+        if (sd.pdf.value() == 0.0f) return false;
+        sd.weight = eval(m, uv, d_in, sd.d) / sd.pdf.value();
+        *out = sd;
+        return true;
+    }
+    PDF pdf(const Math &m, const UV &uv, V3 d_in, V3 d_out) const override { // :47-62 (`PDF * f32`, structure.rs:85-94)
+        PDF pdf_1 = bsdf1->pdf(m, uv, d_in, d_out), pdf_2 = bsdf2->pdf(m, uv, d_in, d_out);
+        pdf_1.v = pdf_1.v * weight, pdf_2.v = pdf_2.v * (1.0f - weight);
+        if (pdf_1.kind != PDF::SolidAngle || pdf_2.kind != PDF::SolidAngle) throw std::runtime_error("get wrong type of BSDF");
+        return PDF{PDF::SolidAngle, pdf_1.v + pdf_2.v};
+    }
+    Color eval(const Math &m, const UV &uv, V3 d_in, V3 d_out) const override { // :64-76 (`f32 * Color`, structure.rs:294-303: plain products)
+        Color a = bsdf1->eval(m, uv, d_in, d_out), b = bsdf2->eval(m, uv, d_in, d_out);
+        const float w2 = 1.0f - weight;
+        return Color{a.r * weight, a.g * weight, a.b * weight} + Color{b.r * w2, b.g * w2, b.b * w2};
+    }
+    bool is_twosided() const override { return true; } // :84-89 (panics unless both parts are two-sided; all rough BSDFs are)
+    bool is_smooth() const override { return bsdf1->is_smooth() || bsdf2->is_smooth(); } // bsdf_type() = bsdf1 | bsdf2 (:91-93)
+};
+std::unique_ptr<BSDF> make_bsdf(const rl_material &m, const rl_texture *textures = nullptr, uint32_t ntextures = 0, const rl_material *subs = nullptr,
+                                uint32_t nsubs = 0) {
+    if (m.kind == RL_BSDF_BLEND) {
+        if (!subs || m.blend_a == 0 || m.blend_b == 0 || m.blend_a > nsubs || m.blend_b > nsubs || subs[m.blend_a - 1].kind == RL_BSDF_BLEND ||
+            subs[m.blend_b - 1].kind == RL_BSDF_BLEND)
+            throw std::runtime_error("blend: bad submaterial reference");
+        auto b = std::make_unique<BSDFBlend>();
+        b->bsdf1 = make_bsdf(subs[m.blend_a - 1], textures, ntextures), b->bsdf2 = make_bsdf(subs[m.blend_b - 1], textures, ntextures);
+        b->weight = m.blend_weight;
+        if (b->bsdf1->is_smooth() || b->bsdf2->is_smooth()) throw std::runtime_error("blend: smooth part (blend.rs:17)");
+        return b;
+    }
     // a colour slot: BSDFColor::Constant(rgb) or one of the scene's textures (bsdf_texture_match_pbrt, bsdfs/mod.rs:218-240)
     auto slot = [&](const float *rgb, uint32_t tex) {
         BSDFColor c;
@@ -2127,7 +2174,12 @@ orc_scene *orc_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         if (md.mat.kd_texture > desc->ntextures || md.mat.ks_texture > desc->ntextures || md.mat.kt_texture > desc->ntextures ||
             md.mat.eta_texture > desc->ntextures || md.mat.k_texture > desc->ntextures)
             return fail("texture index out of range");
-        m->bsdf = make_bsdf(md.mat, desc->textures, desc->ntextures);
+        try {
+            m->bsdf = make_bsdf(md.mat, desc->textures, desc->ntextures, desc->submaterials, desc->nsubmaterials);
+        } catch (const std::exception &e) {
+            delete os;
+            return fail(e.what());
+        }
         m->light = md.emission_kind != 0;
         m->emission = Color{md.emission[0], md.emission[1], md.emission[2]};
         m->first_prim = first;
@@ -2346,8 +2398,10 @@ uint32_t orc_dist1d_sample_discrete(const float *cdf, uint32_t n_plus_1, float v
     return (uint32_t)d.sample_discrete(v);
 }
 float orc_mis_weight(float a, float b) { return mis_weight(a, b); }
+// one material; a blend is passed as an array of three materials {blend, bsdf1, bsdf2} with blend_a = 1, blend_b = 2
+static std::unique_ptr<BSDF> make_bsdf1(const rl_material *m) { return make_bsdf(*m, nullptr, 0, m + 1, m->kind == RL_BSDF_BLEND ? 2u : 0u); }
 int orc_bsdf_sample(uint32_t math_mode, const rl_material *m, const float wi[3], float s0, float s1, float weight[3], float d[3], float *pdf) {
-    auto b = make_bsdf(*m);
+    auto b = make_bsdf1(m);
     SampledDirection sd;
     if (!b->sample(Math{math_mode}, UV{}, load3(wi), P2{s0, s1}, &sd)) return 0;
     weight[0] = sd.weight.r, weight[1] = sd.weight.g, weight[2] = sd.weight.b;
@@ -2356,14 +2410,14 @@ int orc_bsdf_sample(uint32_t math_mode, const rl_material *m, const float wi[3],
     return sd.pdf.kind == PDF::Discrete ? 2 : 1; // 2: PDF::Discrete
 }
 int orc_bsdf_flags(const rl_material *m) { // bit 0: is_twosided, bit 1: bsdf_type().is_smooth()
-    auto b = make_bsdf(*m);
+    auto b = make_bsdf1(m);
     return (b->is_twosided() ? 1 : 0) | (b->is_smooth() ? 2 : 0);
 }
 float orc_bsdf_pdf(uint32_t math_mode, const rl_material *m, const float wi[3], const float wo[3]) {
-    return make_bsdf(*m)->pdf(Math{math_mode}, UV{}, load3(wi), load3(wo)).value();
+    return make_bsdf1(m)->pdf(Math{math_mode}, UV{}, load3(wi), load3(wo)).value();
 }
 void orc_bsdf_eval(uint32_t math_mode, const rl_material *m, const float wi[3], const float wo[3], float out[3]) {
-    Color c = make_bsdf(*m)->eval(Math{math_mode}, UV{}, load3(wi), load3(wo));
+    Color c = make_bsdf1(m)->eval(Math{math_mode}, UV{}, load3(wi), load3(wo));
     out[0] = c.r, out[1] = c.g, out[2] = c.b;
 }
 int orc_sample_light(const orc_scene *os, const float x[3], float r_sel, float r, float u0, float u1, float p[3], float n[3], float d[3],

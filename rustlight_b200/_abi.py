@@ -13,6 +13,7 @@ RL_BSDF_PHONG = 1
 RL_BSDF_METAL = 2
 RL_BSDF_GLASS = 3
 RL_BSDF_SUBSTRATE = 4
+RL_BSDF_BLEND = 5
 RL_MICROFACET_NONE = 0
 RL_MICROFACET_GGX = 1
 RL_MICROFACET_BECKMANN = 2
@@ -36,7 +37,8 @@ class rl_material(C.Structure):
                 ("exponent", C.c_float), ("weight_specular", C.c_float), ("kt", C.c_float * 3),
                 ("eta", C.c_float * 3), ("k", C.c_float * 3), ("ior", C.c_float), ("alpha", C.c_float),
                 ("microfacet", C.c_uint32), ("kd_texture", C.c_uint32), ("ks_texture", C.c_uint32),
-                ("kt_texture", C.c_uint32), ("eta_texture", C.c_uint32), ("k_texture", C.c_uint32)]
+                ("kt_texture", C.c_uint32), ("eta_texture", C.c_uint32), ("k_texture", C.c_uint32),
+                ("blend_a", C.c_uint32), ("blend_b", C.c_uint32), ("blend_weight", C.c_float)]
 
 
 class rl_mesh_desc(C.Structure):
@@ -74,7 +76,8 @@ class rl_scene_desc(C.Structure):
     _fields_ = [("nmeshes", C.c_uint32), ("meshes", C.POINTER(rl_mesh_desc)),
                 ("camera", rl_camera_desc), ("has_volume", C.c_uint32), ("has_environment", C.c_uint32),
                 ("nlights", C.c_uint32), ("lights", C.POINTER(rl_light_desc)),
-                ("ntextures", C.c_uint32), ("textures", C.POINTER(rl_texture)), ("environment", C.c_float * 3)]
+                ("ntextures", C.c_uint32), ("textures", C.POINTER(rl_texture)), ("environment", C.c_float * 3),
+                ("nsubmaterials", C.c_uint32), ("submaterials", C.POINTER(rl_material))]
 
 
 class rl_integrator_desc(C.Structure):

@@ -1300,7 +1300,7 @@ RL_HD Col metal_k(const Material &m) { return m.k_textured ? m.k_tex : xyz_col(m
 // KM (here and below): compile-time mask of the rl_bsdf_kind values present in the scene (bit k = kind k).  The shade
 // kernel is instantiated for the masks {diffuse}, {diffuse, phong} and "all", so that a Cornell box does not carry the
 // microfacet / Fresnel code (registers, instruction cache) it never runs; every other caller uses the default "all".
-#define RL_KM_ALL 0x1ffu  // bits 0-7: BSDF kinds, bit 8: the scene has textures
+#define RL_KM_ALL 0x1ffu  // bits 0-7: BSDF kinds (bit 5: BSDFBlend), bit 8: the scene has textures
 #define RL_HAS(KM, k) (((KM) >> (k)) & 1u)
 template <uint32_t KM = RL_KM_ALL>
 RL_HD bool mat_is_smooth(const Material &m) {
@@ -1471,7 +1471,7 @@ RL_HD Col substrate_eval(const Material &mt, V3 d_in, V3 d_out, bool discrete) {
 
 // BSDF::pdf (diffuse.rs:33-51, phong.rs:65-91)
 template <uint32_t KM = RL_KM_ALL>
-RL_HD float bsdf_pdf(const Material &m, V3 wi, V3 wo) {
+RL_HD float bsdf_pdf_leaf(const Material &m, V3 wi, V3 wo) {
     if (RL_HAS(KM, 2) && m.kind == 2u) return metal_pdf(m, wi, wo);               // only reached with a distribution (not smooth)
     if (RL_HAS(KM, 4) && m.kind == 4u) return substrate_pdf(m, wi, wo, false);
     if (!RL_HAS(KM, 1) || m.kind == 0u) {
@@ -1489,7 +1489,7 @@ RL_HD float bsdf_pdf(const Material &m, V3 wi, V3 wo) {
 }
 // BSDF::eval (diffuse.rs:53-71, phong.rs:93-119); includes the cosine for the diffuse lobe
 template <uint32_t KM = RL_KM_ALL>
-RL_HD Col bsdf_eval(const Material &m, V3 wi, V3 wo) {
+RL_HD Col bsdf_eval_leaf(const Material &m, V3 wi, V3 wo) {
     if (RL_HAS(KM, 2) && m.kind == 2u) return metal_eval(m, wi, wo);
     if (RL_HAS(KM, 4) && m.kind == 4u) return substrate_eval(m, wi, wo, false);
     if (!RL_HAS(KM, 1) || m.kind == 0u) {
@@ -1527,18 +1527,60 @@ RL_HD void phong_eval_pdf(const Material &m, V3 wi, V3 wo, Col *f, float *pdf) {
 }
 // eval and pdf of one direction pair (what light sampling with MIS needs)
 template <uint32_t KM = RL_KM_ALL>
-RL_HD void bsdf_eval_pdf(const Material &m, V3 wi, V3 wo, Col *f, float *pdf) {
+RL_HD void bsdf_eval_pdf_leaf(const Material &m, V3 wi, V3 wo, Col *f, float *pdf) {
     if (RL_HAS(KM, 1) && m.kind == 1u) {
         phong_eval_pdf(m, wi, wo, f, pdf);
         return;
     }
-    *f = bsdf_eval<KM>(m, wi, wo);
-    *pdf = bsdf_pdf<KM>(m, wi, wo);
+    *f = bsdf_eval_leaf<KM>(m, wi, wo);
+    *pdf = bsdf_pdf_leaf<KM>(m, wi, wo);
+}
+// BSDFBlend (bsdfs/blend.rs): kind 5, m.weight_specular = weight, ext[0].xy = row distance to the two parts (rl_scene_host.hpp: material_rows)
+#define RL_KM_NOBLEND(KM) ((KM) & ~(1u << 5))
+RL_HD Material blend_part(const Material &m, uint32_t which) {
+    const float4 e = m.ext[0];
+    return load_material(m.ext - 4 + (int32_t)f2u(which == 0u ? e.x : e.y), 0u);
+}
+// eval: weight * bsdf1.eval + (1 - weight) * bsdf2.eval (`f32 * Color`, structure.rs:294-303: plain products); pdf: pdf_1 * weight + pdf_2 * (1 - weight)
+template <uint32_t KM = RL_KM_ALL>
+RL_HD void bsdf_eval_pdf(const Material &m, V3 wi, V3 wo, Col *f, float *pdf) {
+    if (RL_HAS(KM, 5) && m.kind == 5u) {
+        const Material a = blend_part(m, 0u), b = blend_part(m, 1u);
+        Col fa, fb;
+        float pa, pb;
+        bsdf_eval_pdf_leaf<RL_KM_NOBLEND(KM)>(a, wi, wo, &fa, &pa);
+        bsdf_eval_pdf_leaf<RL_KM_NOBLEND(KM)>(b, wi, wo, &fb, &pb);
+        const float w = m.weight_specular;
+        *pdf = pa * w + pb * (1.0f - w);
+        *f = mul_plain(w, fa) + mul_plain(1.0f - w, fb);
+        return;
+    }
+    bsdf_eval_pdf_leaf<KM>(m, wi, wo, f, pdf);
+}
+template <uint32_t KM = RL_KM_ALL>
+RL_HD float bsdf_pdf(const Material &m, V3 wi, V3 wo) {
+    if (RL_HAS(KM, 5) && m.kind == 5u) {
+        Col f;
+        float p;
+        bsdf_eval_pdf<KM>(m, wi, wo, &f, &p);
+        return p;
+    }
+    return bsdf_pdf_leaf<KM>(m, wi, wo);
+}
+template <uint32_t KM = RL_KM_ALL>
+RL_HD Col bsdf_eval(const Material &m, V3 wi, V3 wo) {
+    if (RL_HAS(KM, 5) && m.kind == 5u) {
+        Col f;
+        float p;
+        bsdf_eval_pdf<KM>(m, wi, wo, &f, &p);
+        return f;
+    }
+    return bsdf_eval_leaf<KM>(m, wi, wo);
 }
 // BSDF::sample (diffuse.rs:11-31, phong.rs:14-63, metal.rs:15-73, glass.rs:75-121, substrate.rs:22-90).
 // *discrete: the sampled pdf is PDF::Discrete (delta lobe) -- no MIS for the edge it creates.
 template <uint32_t KM = RL_KM_ALL>
-RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight, V3 *wo, float *pdf, bool *discrete) {
+RL_HD bool bsdf_sample_leaf(const Material &m, V3 wi, float sx, float sy, Col *weight, V3 *wo, float *pdf, bool *discrete) {
     *discrete = false;
     if (RL_HAS(KM, 3) && m.kind == 3u) { // glass: no wi.z test (not two-sided), transport == Importance -> factor 1
         float fresnel, cos_theta_trans;
@@ -1637,6 +1679,29 @@ RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight
     *wo = d_out;
     *pdf = p;
     return true;
+}
+template <uint32_t KM = RL_KM_ALL>
+RL_HD bool bsdf_sample(const Material &m, V3 wi, float sx, float sy, Col *weight, V3 *wo, float *pdf, bool *discrete) {
+    if (RL_HAS(KM, 5) && m.kind == 5u) { // BSDFBlend::sample, blend.rs:10-45: pick a part by sample.x, then pdf and eval of the whole blend
+        const float w = m.weight_specular;
+        const bool first = sx < w;
+        const Material part = blend_part(m, first ? 0u : 1u);
+        const float sx2 = first ? sx * (1.0f / w) : (sx - w) * (1.0f / (1.0f - w));
+        Col w_part;
+        float p_part;
+        V3 d_out;
+        if (!bsdf_sample_leaf<RL_KM_NOBLEND(KM)>(part, wi, sx2, sy, &w_part, &d_out, &p_part, discrete)) return false;
+        Col f;
+        float p;
+        bsdf_eval_pdf<KM>(m, wi, d_out, &f, &p);
+        if (p == 0.0f) return false;
+        *weight = div_checked(f, p);
+        *wo = d_out;
+        *pdf = p;
+        *discrete = false;
+        return true;
+    }
+    return bsdf_sample_leaf<KM>(m, wi, sx, sy, weight, wo, pdf, discrete);
 }
 
 // ---- BSDFColor::color for the kd slot (bsdfs/mod.rs:31-101) -----------------------------------------

@@ -386,7 +386,7 @@ __device__ __forceinline__ void block_compact2(bool fa, bool fb, uint32_t *count
 
 // ---- shade: surface interaction, arrival emission, BSDF sample + RR, NEE sample ------------------
 // ---- material sort inside a CTA tile ------------------------------------------------------------
-// Counting sort of the tile's 256 records by key (0..4 = rl_bsdf_kind of the surface hit, 5 miss, 6 = past the end
+// Counting sort of the tile's 256 records by key (0..5 = rl_bsdf_kind of the surface hit, 6 miss, 7 = past the end
 // of the queue) with warp ballots + per-warp prefix sums in shared memory.  Returns the tile-local index of
 // the record this thread should process, so that every warp shades one material kind (and rays that
 // missed are grouped into whole warps that exit at once).  `perm` is kBlock uint16, `cnt` kSortKeys*(kBlock/32).
@@ -453,10 +453,10 @@ __global__ void __launch_bounds__(shade_block(KM), shade_minblocks(KM)) k_shade(
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint32_t i = tile * B + threadIdx.x;
         if (SORT) {
-            uint32_t key = 6u;
+            uint32_t key = 7u;
             if (i < n) {
                 const uint32_t prim = f2u(hit[i].w);
-                key = prim == RL_MISS ? 5u : min(f2u(__ldg(&sv.mats[RL_MAT_F4 * f2u(__ldg(&sv.shade[4 * prim]).w)]).w), 4u);
+                key = prim == RL_MISS ? 6u : min(f2u(__ldg(&sv.mats[RL_MAT_F4 * f2u(__ldg(&sv.shade[4 * prim]).w)]).w), 5u);
             }
             const uint32_t src = tile_sort_by_key<B>(key, s_perm, s_cnt);
             i = tile * B + src;

@@ -58,6 +58,44 @@ inline float dist1d_normalize(const std::vector<float> &elements, std::vector<fl
     return cur; // func_int
 }
 
+// BSDF parameters the device supports (sub = one of the two parts of a BSDFBlend: rough, constant colours, not a blend itself)
+inline bool material_ok(const rl_material &mt, const rl_scene_desc *desc, bool sub) {
+    if (mt.kind == RL_BSDF_BLEND) {
+        if (sub || !desc->submaterials || mt.blend_a == 0 || mt.blend_b == 0 || mt.blend_a > desc->nsubmaterials || mt.blend_b > desc->nsubmaterials) return false;
+        if (!(mt.blend_weight >= 0.0f && mt.blend_weight <= 1.0f)) return false;
+        return material_ok(desc->submaterials[mt.blend_a - 1], desc, true) && material_ok(desc->submaterials[mt.blend_b - 1], desc, true);
+    }
+    const bool has_mf = mt.kind == RL_BSDF_METAL || mt.kind == RL_BSDF_SUBSTRATE;
+    if (mt.kind > RL_BSDF_SUBSTRATE || (has_mf && mt.microfacet > RL_MICROFACET_BECKMANN) || (has_mf && mt.microfacet != RL_MICROFACET_NONE && !(mt.alpha > 0.0f)) ||
+        (mt.kind == RL_BSDF_GLASS && mt.ior == 0.0f))
+        return false;
+    if (mt.kd_texture > desc->ntextures || mt.ks_texture > desc->ntextures || mt.kt_texture > desc->ntextures || mt.eta_texture > desc->ntextures ||
+        mt.k_texture > desc->ntextures || (mt.kd_texture != 0 && mt.kind != RL_BSDF_DIFFUSE && mt.kind != RL_BSDF_PHONG && mt.kind != RL_BSDF_SUBSTRATE) ||
+        (mt.ks_texture != 0 && mt.kind == RL_BSDF_DIFFUSE) || (mt.kt_texture != 0 && mt.kind != RL_BSDF_GLASS) ||
+        ((mt.eta_texture != 0 || mt.k_texture != 0) && mt.kind != RL_BSDF_METAL))
+        return false;
+    if (sub) { // blend.rs:17 asserts !is_smooth() on both parts
+        const bool smooth = mt.kind == RL_BSDF_GLASS || (has_mf && mt.microfacet == RL_MICROFACET_NONE);
+        if (smooth || mt.kd_texture || mt.ks_texture || mt.kt_texture || mt.eta_texture || mt.k_texture) return false;
+    }
+    return true;
+}
+// The BSDF part of the RL_MAT_F4 rows of one material (rl_device.cuh: load_material); the caller adds the emitter fields (row 2, row 3 .y .z).
+// delta_a / delta_b: distance in float4 rows from this material's first row to the first row of the two parts of a blend.
+inline void material_rows(const rl_material &mt, float4 rows[6], int delta_a, int delta_b) {
+    const float *ca = mt.kind == RL_BSDF_METAL ? mt.eta : (mt.kind == RL_BSDF_GLASS ? mt.kt : mt.kd);
+    const bool has_mf = mt.kind == RL_BSDF_METAL || mt.kind == RL_BSDF_SUBSTRATE;
+    const bool blend = mt.kind == RL_BSDF_BLEND;
+    rows[0] = f4(ca[0], ca[1], ca[2], u2f(mt.kind));
+    rows[1] = f4(mt.ks[0], mt.ks[1], mt.ks[2], has_mf ? mt.alpha : mt.exponent);
+    rows[2] = f4(0.0f, 0.0f, 0.0f, u2f(0u));
+    rows[3] = f4(mt.kind == RL_BSDF_GLASS ? mt.ior : (blend ? mt.blend_weight : mt.weight_specular), 0.0f, 0.0f, u2f(has_mf ? mt.microfacet : 0u));
+    // row 4: {metal k, glass 1/eta (BSDFGlass::eta(): inv_eta = 1.0 / eta)} | blend: {row delta of bsdf1, row delta of bsdf2} as int bits
+    rows[4] = blend ? f4(u2f((uint32_t)delta_a), u2f((uint32_t)delta_b), 0.0f, 0.0f) : f4(mt.k[0], mt.k[1], mt.k[2], mt.kind == RL_BSDF_GLASS ? 1.0f / mt.ior : 0.0f);
+    // row 5: textures of the three colour slots as uint bits: {slot a = kd | metal eta | glass kt, slot b = ks, slot c = metal k, -}
+    const uint32_t ta = mt.kind == RL_BSDF_METAL ? mt.eta_texture : (mt.kind == RL_BSDF_GLASS ? mt.kt_texture : mt.kd_texture);
+    rows[5] = blend ? f4(0.0f, 0.0f, 0.0f, 0.0f) : f4(u2f(ta), u2f(mt.ks_texture), u2f(mt.kind == RL_BSDF_METAL ? mt.k_texture : 0u), 0.0f);
+}
 inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::string &err) {
     if (!desc || !desc->meshes || desc->nmeshes == 0) {
         err = "empty scene";
@@ -127,14 +165,7 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
             err = "mesh without geometry";
             return false;
         }
-        const bool has_mf = m.mat.kind == RL_BSDF_METAL || m.mat.kind == RL_BSDF_SUBSTRATE;
-        if (m.mat.kind > RL_BSDF_SUBSTRATE || (has_mf && m.mat.microfacet > RL_MICROFACET_BECKMANN) ||
-            (has_mf && m.mat.microfacet != RL_MICROFACET_NONE && !(m.mat.alpha > 0.0f)) || (m.mat.kind == RL_BSDF_GLASS && m.mat.ior == 0.0f) ||
-            m.mat.kd_texture > desc->ntextures || m.mat.ks_texture > desc->ntextures || m.mat.kt_texture > desc->ntextures ||
-            m.mat.eta_texture > desc->ntextures || m.mat.k_texture > desc->ntextures ||
-            (m.mat.kd_texture != 0 && m.mat.kind != RL_BSDF_DIFFUSE && m.mat.kind != RL_BSDF_PHONG && m.mat.kind != RL_BSDF_SUBSTRATE) ||
-            (m.mat.ks_texture != 0 && m.mat.kind == RL_BSDF_DIFFUSE) || (m.mat.kt_texture != 0 && m.mat.kind != RL_BSDF_GLASS) ||
-            ((m.mat.eta_texture != 0 || m.mat.k_texture != 0) && m.mat.kind != RL_BSDF_METAL)) {
+        if (!material_ok(m.mat, desc, false)) {
             err = "unsupported BSDF kind or parameters";
             return false;
         }
@@ -283,20 +314,18 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
     }
     for (uint32_t mi = 0; mi < desc->nmeshes; mi++) {
         const rl_mesh_desc &m = desc->meshes[mi];
-        // rows of rl_device.cuh: load_material
-        const rl_material &mt = m.mat;
-        const float *ca = mt.kind == RL_BSDF_METAL ? mt.eta : (mt.kind == RL_BSDF_GLASS ? mt.kt : mt.kd);
-        const bool has_mf = mt.kind == RL_BSDF_METAL || mt.kind == RL_BSDF_SUBSTRATE;
-        hs.mats.push_back(f4(ca[0], ca[1], ca[2], u2f(mt.kind)));
-        hs.mats.push_back(f4(mt.ks[0], mt.ks[1], mt.ks[2], has_mf ? mt.alpha : mt.exponent));
-        hs.mats.push_back(f4(m.emission_kind ? m.emission[0] : 0.0f, m.emission_kind ? m.emission[1] : 0.0f,
-                             m.emission_kind ? m.emission[2] : 0.0f, u2f(m.emission_kind ? 1u : 0u)));
-        hs.mats.push_back(f4(mt.kind == RL_BSDF_GLASS ? mt.ior : mt.weight_specular, mesh_inv_area[mi], pdf_sel[mi], u2f(has_mf ? mt.microfacet : 0u)));
-        // row 4: {metal k, glass 1/eta (BSDFGlass::eta(): inv_eta = 1.0 / eta)}
-        hs.mats.push_back(f4(mt.k[0], mt.k[1], mt.k[2], mt.kind == RL_BSDF_GLASS ? 1.0f / mt.ior : 0.0f));
-        // row 5: textures of the three colour slots as uint bits: {slot a = kd | metal eta | glass kt, slot b = ks, slot c = metal k, -}
-        const uint32_t ta = mt.kind == RL_BSDF_METAL ? mt.eta_texture : (mt.kind == RL_BSDF_GLASS ? mt.kt_texture : mt.kd_texture);
-        hs.mats.push_back(f4(u2f(ta), u2f(mt.ks_texture), u2f(mt.kind == RL_BSDF_METAL ? mt.k_texture : 0u), 0.0f));
+        // rows of rl_device.cuh: load_material; the submaterials of blends follow the meshes
+        float4 rows[6];
+        const int base = 6 * ((int)desc->nmeshes - (int)mi);
+        material_rows(m.mat, rows, base + 6 * ((int)m.mat.blend_a - 1), base + 6 * ((int)m.mat.blend_b - 1));
+        rows[2] = f4(m.emission_kind ? m.emission[0] : 0.0f, m.emission_kind ? m.emission[1] : 0.0f, m.emission_kind ? m.emission[2] : 0.0f, u2f(m.emission_kind ? 1u : 0u));
+        rows[3].y = mesh_inv_area[mi], rows[3].z = pdf_sel[mi];
+        hs.mats.insert(hs.mats.end(), rows, rows + 6);
+    }
+    for (uint32_t si = 0; si < desc->nsubmaterials; si++) {
+        float4 rows[6];
+        material_rows(desc->submaterials[si], rows, 0, 0);
+        hs.mats.insert(hs.mats.end(), rows, rows + 6);
     }
     float am = 0.0f;
     for (int a = 0; a < 3; a++) am = fmaxf(am, fmaxf(fabsf(hs.raw_min[a]), fabsf(hs.raw_max[a])));

@@ -48,6 +48,7 @@ def lib():
         L.rlh_scene_set_environment.argtypes = [C.c_void_p, C.c_float * 3]
         L.rlh_scene_add_light.argtypes = [C.c_void_p, C.c_uint32, C.c_float * 3, C.c_float * 3]
         L.rlh_scene_set_material.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_abi.rl_material)]
+        L.rlh_scene_set_material_blend.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_abi.rl_material), C.POINTER(_abi.rl_material), C.c_float]
         L.rlh_material_phong.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float,
                                          C.POINTER(_abi.rl_material)]
         L.rlh_scene_to_json.restype = C.c_size_t
@@ -110,6 +111,12 @@ class Scene:
     def set_material(self, mesh, material):
         if lib().rlh_scene_set_material(self._h, int(mesh), C.byref(material)) != 0:
             raise SceneError("bad mesh index")
+        return self
+
+    def set_material_blend(self, mesh, a, b, weight):
+        """BSDFBlend { bsdf1: a, bsdf2: b, weight } (bsdfs/blend.rs): both parts rough (blend.rs:17), constant colours."""
+        if lib().rlh_scene_set_material_blend(self._h, int(mesh), C.byref(a), C.byref(b), float(weight)) != 0:
+            raise SceneError("blend: bad mesh index, a smooth / textured / nested part, or weight outside [0, 1]")
         return self
 
     def add_bitmap_texture(self, rgb):

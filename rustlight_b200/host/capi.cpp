@@ -74,9 +74,22 @@ int rlh_scene_set_resolution(rlh_scene *s, uint32_t w, uint32_t h, char *err, si
 }
 
 int rlh_scene_set_material(rlh_scene *s, uint32_t mesh, const rl_material *m) {
-    if (!s || !m || mesh >= s->scene.meshes.size()) return -1;
+    if (!s || !m || mesh >= s->scene.meshes.size() || m->kind == RL_BSDF_BLEND) return -1; // blends: rlh_scene_set_material_blend
     s->scene.meshes[mesh]->bsdf.m = *m;
+    s->scene.meshes[mesh]->bsdf.subs.clear();
     return 0;
+}
+// BSDFBlend { bsdf1: a, bsdf2: b, weight } (bsdfs/blend.rs)
+int rlh_scene_set_material_blend(rlh_scene *s, uint32_t mesh, const rl_material *a, const rl_material *b, float weight) {
+    if (!s || !a || !b || mesh >= s->scene.meshes.size()) return -1;
+    try {
+        Material ma, mb;
+        ma.m = *a, mb.m = *b;
+        s->scene.meshes[mesh]->bsdf = Material::blend(ma, mb, weight);
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
 }
 
 // Material::phong incl. weight_specular, src/bsdfs/mod.rs:518-523

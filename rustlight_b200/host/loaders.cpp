@@ -798,7 +798,12 @@ Material jmaterial(const JVal &m) {
     }
     if (type == "substrate")
         return Material::substrate(jcolor(m.get("kd"), "kd", Color{0.5f, 0.5f, 0.5f}), jcolor(m.get("ks"), "ks", Color{0.5f, 0.5f, 0.5f}), jmicrofacet(), (float)jnum("alpha", 0.1));
-    throw Error("json: material type \"" + type + "\" is not supported (diffuse, phong, mirror, metal, glass, substrate)");
+    if (type == "blend") { // BSDFBlend (bsdfs/blend.rs): {"type": "blend", "a": {...}, "b": {...}, "weight": w}
+        const JVal *a = m.get("a"), *b = m.get("b");
+        if (!a || !b || a->t != JVal::Obj || b->t != JVal::Obj) throw Error("json: blend needs two material objects \"a\" and \"b\"");
+        return Material::blend(jmaterial(*a), jmaterial(*b), (float)jnum("weight", 0.5));
+    }
+    throw Error("json: material type \"" + type + "\" is not supported (diffuse, phong, mirror, metal, glass, substrate, blend)");
 }
 } // namespace
 
@@ -1021,10 +1026,8 @@ std::string scene_to_json(const Scene &scene) {
     o << "  \"meshes\": [\n";
     for (size_t i = 0; i < scene.meshes.size(); i++) {
         const Mesh &m = *scene.meshes[i];
-        const rl_material &mt = m.bsdf.m;
-        static const char *kinds[] = {"diffuse", "phong", "metal", "glass", "substrate"};
+        static const char *kinds[] = {"diffuse", "phong", "metal", "glass", "substrate", "blend"};
         static const char *mfs[] = {"none", "ggx", "beckmann"};
-        o << "    {\"name\": \"" << m.name << "\", \"material\": {\"type\": \"" << kinds[mt.kind <= RL_BSDF_SUBSTRATE ? mt.kind : 0] << "\"";
         auto put = [&](const char *key, const float *v, size_t n) {
             o << ", \"" << key << "\": ";
             if (n == 1) { // scalars are bare numbers
@@ -1033,19 +1036,32 @@ std::string scene_to_json(const Scene &scene) {
                 o << b1;
             } else put_floats(o, v, n);
         };
-        if (mt.kind == RL_BSDF_DIFFUSE || mt.kind == RL_BSDF_PHONG || mt.kind == RL_BSDF_SUBSTRATE) put("kd", mt.kd, 3);
-        if (mt.kind != RL_BSDF_DIFFUSE) put("ks", mt.ks, 3);
-        if (mt.kind == RL_BSDF_PHONG) put("exponent", &mt.exponent, 1);
-        if (mt.kind == RL_BSDF_METAL) put("eta", mt.eta, 3), put("k", mt.k, 3);
-        if (mt.kind == RL_BSDF_GLASS) put("kt", mt.kt, 3), put("ior", &mt.ior, 1);
-        if (mt.kd_texture) o << ", \"kd_texture\": \"tex" << mt.kd_texture << "\"";
-        if (mt.ks_texture) o << ", \"ks_texture\": \"tex" << mt.ks_texture << "\"";
-        if (mt.kt_texture) o << ", \"kt_texture\": \"tex" << mt.kt_texture << "\"";
-        if (mt.eta_texture) o << ", \"eta_texture\": \"tex" << mt.eta_texture << "\"";
-        if (mt.k_texture) o << ", \"k_texture\": \"tex" << mt.k_texture << "\"";
-        if (mt.kind == RL_BSDF_METAL || mt.kind == RL_BSDF_SUBSTRATE) {
-            o << ", \"microfacet\": \"" << mfs[mt.microfacet <= RL_MICROFACET_BECKMANN ? mt.microfacet : 0] << "\"";
-            put("alpha", &mt.alpha, 1);
+        auto put_material = [&](const rl_material &mt) {
+            o << "{\"type\": \"" << kinds[mt.kind <= RL_BSDF_BLEND ? mt.kind : 0] << "\"";
+            if (mt.kind == RL_BSDF_DIFFUSE || mt.kind == RL_BSDF_PHONG || mt.kind == RL_BSDF_SUBSTRATE) put("kd", mt.kd, 3);
+            if (mt.kind != RL_BSDF_DIFFUSE && mt.kind != RL_BSDF_BLEND) put("ks", mt.ks, 3);
+            if (mt.kind == RL_BSDF_PHONG) put("exponent", &mt.exponent, 1);
+            if (mt.kind == RL_BSDF_METAL) put("eta", mt.eta, 3), put("k", mt.k, 3);
+            if (mt.kind == RL_BSDF_GLASS) put("kt", mt.kt, 3), put("ior", &mt.ior, 1);
+            if (mt.kd_texture) o << ", \"kd_texture\": \"tex" << mt.kd_texture << "\"";
+            if (mt.ks_texture) o << ", \"ks_texture\": \"tex" << mt.ks_texture << "\"";
+            if (mt.kt_texture) o << ", \"kt_texture\": \"tex" << mt.kt_texture << "\"";
+            if (mt.eta_texture) o << ", \"eta_texture\": \"tex" << mt.eta_texture << "\"";
+            if (mt.k_texture) o << ", \"k_texture\": \"tex" << mt.k_texture << "\"";
+            if (mt.kind == RL_BSDF_METAL || mt.kind == RL_BSDF_SUBSTRATE) {
+                o << ", \"microfacet\": \"" << mfs[mt.microfacet <= RL_MICROFACET_BECKMANN ? mt.microfacet : 0] << "\"";
+                put("alpha", &mt.alpha, 1);
+            }
+        };
+        o << "    {\"name\": \"" << m.name << "\", \"material\": ";
+        put_material(m.bsdf.m);
+        if (m.bsdf.m.kind == RL_BSDF_BLEND && m.bsdf.subs.size() == 2) { // BSDFBlend { bsdf1: a, bsdf2: b, weight }
+            o << ", \"a\": ";
+            put_material(m.bsdf.subs[0]);
+            o << "}, \"b\": ";
+            put_material(m.bsdf.subs[1]);
+            o << "}";
+            put("weight", &m.bsdf.m.blend_weight, 1);
         }
         o << "}";
         if (m.is_light) {

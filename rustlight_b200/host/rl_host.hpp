@@ -70,6 +70,9 @@ struct Camera {
 // BSDF description; only what the hot path supports (src/bsdfs/{diffuse,phong}.rs).
 struct Material {
     rl_material m{};
+    std::vector<rl_material> subs; // BSDFBlend: {bsdf1, bsdf2} (m.blend_a / m.blend_b are filled in by Scene::desc)
+    // BSDFBlend (bsdfs/blend.rs): weight * a + (1 - weight) * b; both parts rough, neither a blend
+    static Material blend(const Material &a, const Material &b, float weight);
     static Material diffuse(Color kd);
     // weight_specular per src/bsdfs/mod.rs:518-523
     static Material phong(Color kd, Color ks, float exponent);
@@ -134,6 +137,7 @@ struct Scene {
   private:
     std::vector<rl_mesh_desc> mesh_descs_;
     std::vector<rl_texture> texture_descs_;
+    std::vector<rl_material> submaterial_descs_;
     rl_scene_desc desc_{};
 };
 

@@ -235,6 +235,20 @@ Material Material::substrate(Color diffuse, Color specular, uint32_t microfacet,
     r.m.alpha = microfacet == RL_MICROFACET_NONE ? 0.0f : alpha;
     return r;
 }
+static bool blend_part_ok(const rl_material &m) { // blend.rs:17 asserts !is_smooth() on both parts; here also: no nested blend, no textures
+    const bool rough = m.kind == RL_BSDF_DIFFUSE || m.kind == RL_BSDF_PHONG ||
+                       ((m.kind == RL_BSDF_METAL || m.kind == RL_BSDF_SUBSTRATE) && m.microfacet != RL_MICROFACET_NONE);
+    return rough && !m.kd_texture && !m.ks_texture && !m.kt_texture && !m.eta_texture && !m.k_texture;
+}
+Material Material::blend(const Material &a, const Material &b, float weight) {
+    if (!blend_part_ok(a.m) || !blend_part_ok(b.m)) throw Error("blend: both parts must be rough BSDFs with constant colours (bsdfs/blend.rs:17)");
+    if (!(weight >= 0.0f && weight <= 1.0f)) throw Error("blend: weight outside [0, 1]");
+    Material r;
+    r.m.kind = RL_BSDF_BLEND;
+    r.m.blend_weight = weight;
+    r.subs = {a.m, b.m};
+    return r;
+}
 float remap_roughness(float v, bool remap) {
     if (!remap) return v;
     float x = std::log(std::max(v, 1e-3f));
@@ -324,6 +338,7 @@ void Scene::add_directional_light(Color intensity, float dx, float dy, float dz)
 }
 const rl_scene_desc *Scene::desc() {
     mesh_descs_.clear();
+    submaterial_descs_.clear();
     for (auto &mp : meshes) {
         const Mesh &m = *mp;
         rl_mesh_desc d{};
@@ -334,6 +349,11 @@ const rl_scene_desc *Scene::desc() {
         d.N = m.normals.empty() ? nullptr : m.normals.data();
         d.UV = m.uv.empty() ? nullptr : m.uv.data();
         d.mat = m.bsdf.m;
+        if (d.mat.kind == RL_BSDF_BLEND && m.bsdf.subs.size() == 2) {
+            submaterial_descs_.push_back(m.bsdf.subs[0]);
+            submaterial_descs_.push_back(m.bsdf.subs[1]);
+            d.mat.blend_a = (uint32_t)submaterial_descs_.size() - 1u, d.mat.blend_b = (uint32_t)submaterial_descs_.size();
+        }
         d.emission_kind = m.is_light ? 1u : 0u;
         d.emission[0] = m.emission.r, d.emission[1] = m.emission.g, d.emission[2] = m.emission.b;
         mesh_descs_.push_back(d);
@@ -355,6 +375,8 @@ const rl_scene_desc *Scene::desc() {
     }
     desc_.ntextures = (uint32_t)texture_descs_.size();
     desc_.textures = texture_descs_.empty() ? nullptr : texture_descs_.data();
+    desc_.nsubmaterials = (uint32_t)submaterial_descs_.size();
+    desc_.submaterials = submaterial_descs_.empty() ? nullptr : submaterial_descs_.data();
     desc_.nlights = (uint32_t)lights.size();
     desc_.lights = lights.empty() ? nullptr : lights.data();
     return &desc_;

@@ -22,7 +22,7 @@ use std::sync::Mutex;
 #[repr(C)] pub struct rl_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct rl_scene { _p: [u8; 0] }
 
-pub const RL_B200_ABI_VERSION: c_int = 4;
+pub const RL_B200_ABI_VERSION: c_int = 5;
 
 #[repr(C)] #[derive(Clone, Copy)]
 pub struct rl_texture {
@@ -34,6 +34,7 @@ pub struct rl_material {
     pub kind: u32, pub kd: [f32; 3], pub ks: [f32; 3], pub exponent: f32, pub weight_specular: f32,
     pub kt: [f32; 3], pub eta: [f32; 3], pub k: [f32; 3], pub ior: f32, pub alpha: f32, pub microfacet: u32, pub kd_texture: u32,
     pub ks_texture: u32, pub kt_texture: u32, pub eta_texture: u32, pub k_texture: u32,
+    pub blend_a: u32, pub blend_b: u32, pub blend_weight: f32,
 }
 #[repr(C)]
 pub struct rl_mesh_desc {
@@ -45,6 +46,7 @@ pub struct rl_mesh_desc {
 #[repr(C)] pub struct rl_scene_desc {
     pub nmeshes: u32, pub meshes: *const rl_mesh_desc, pub camera: rl_camera_desc, pub has_volume: u32, pub has_environment: u32,
     pub nlights: u32, pub lights: *const rl_light_desc, pub ntextures: u32, pub textures: *const rl_texture, pub environment: [f32; 3],
+    pub nsubmaterials: u32, pub submaterials: *const rl_material,
 }
 #[repr(C)] pub struct rl_integrator_desc {
     pub kind: u32, pub min_depth: i32, pub max_depth: i32, pub rr_depth: i32, pub strategy: u32,
@@ -108,7 +110,7 @@ fn mat16(m: &Matrix4<f32>) -> [f32; 16] { *AsRef::<[f32; 16]>::as_ref(m) } // cg
 #[derive(Default)]
 pub struct Flat {
     p: Vec<Vec<f32>>, n: Vec<Vec<f32>>, uv: Vec<Vec<f32>>, idx: Vec<Vec<u32>>, texels: Vec<Vec<f32>>,
-    meshes: Vec<rl_mesh_desc>, lights: Vec<rl_light_desc>, textures: Vec<rl_texture>,
+    meshes: Vec<rl_mesh_desc>, lights: Vec<rl_light_desc>, textures: Vec<rl_texture>, submaterials: Vec<rl_material>,
 }
 impl Flat {
     /// BSDFColor -> (constant colour, 0) or (black, 1 + texture index); `describe()` of a BSDF calls this for each of its colour slots.
@@ -144,7 +146,7 @@ fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
         f.idx.push(m.indices.iter().flat_map(|i| [i.x as u32, i.y as u32, i.z as u32]).collect());
     }
     for (k, m) in scene.meshes.iter().enumerate() {
-        let mat = m.bsdf.describe(&mut f).unwrap_or_else(|| panic!("mesh {}: this BSDF has no GPU description (BSDFBlend?)", m.name));
+        let mat = m.bsdf.describe(&mut f).unwrap_or_else(|| panic!("mesh {}: this BSDF has no GPU description", m.name));
         let (kind, e) = match &m.emission {
             crate::geometry::EmissionType::Zero => (0, Color::zero()),
             crate::geometry::EmissionType::Color { v } => (1, *v),
@@ -176,6 +178,7 @@ fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
         camera: rl_camera_desc { width: cam.size().x, height: cam.size().y, sample_to_camera: mat16(cam.sample_to_camera()), to_world: mat16(cam.to_world()) },
         has_volume: 0, has_environment: has_env, nlights: f.lights.len() as u32, lights: f.lights.as_ptr(),
         ntextures: f.textures.len() as u32, textures: f.textures.as_ptr(), environment: env,
+        nsubmaterials: f.submaterials.len() as u32, submaterials: f.submaterials.as_ptr(),
     };
     (f, desc)
 }
@@ -263,7 +266,7 @@ mod patch {
     //     fn describe(&self, _flat: &mut crate::b200::Flat) -> Option<crate::b200::rl_material> { None }
     fn blank(kind: u32) -> rl_material {
         rl_material { kind, kd: [0.0; 3], ks: [0.0; 3], exponent: 0.0, weight_specular: 0.0, kt: [0.0; 3], eta: [0.0; 3], k: [0.0; 3],
-                      ior: 1.0, alpha: 0.0, microfacet: 0, kd_texture: 0, ks_texture: 0, kt_texture: 0, eta_texture: 0, k_texture: 0 }
+                      ior: 1.0, alpha: 0.0, microfacet: 0, kd_texture: 0, ks_texture: 0, kt_texture: 0, eta_texture: 0, k_texture: 0, blend_a: 0, blend_b: 0, blend_weight: 0.0 }
     }
     fn microfacet(d: &Option<MicrofacetDistributionBSDF>) -> (u32, f32) {
         match d {
@@ -305,6 +308,14 @@ mod patch {
         let (ks, ks_texture) = flat.color_slot(&b.specular);
         let (microfacet, alpha) = microfacet(&b.distribution);
         Some(rl_material { kd, kd_texture, ks, ks_texture, microfacet, alpha, ..blank(4) })
+    }
+    // ---- src/bsdfs/blend.rs, inside `impl BSDF for BSDFBlend` (both parts must describe themselves and be rough, blend.rs:17):
+    pub fn describe_blend(b: &crate::bsdfs::blend::BSDFBlend, flat: &mut Flat) -> Option<rl_material> {
+        let (a, c) = (b.bsdf1.describe(flat)?, b.bsdf2.describe(flat)?);
+        flat.submaterials.push(a);
+        flat.submaterials.push(c);
+        let n = flat.submaterials.len() as u32;
+        Some(rl_material { blend_a: n - 1, blend_b: n, blend_weight: b.weight, ..blank(5) })
     }
     // (each `impl BSDF for X` gains `fn describe(&self, flat: &mut Flat) -> Option<rl_material> { crate::b200::patch::describe_x(self, flat) }`)
 

@@ -238,3 +238,37 @@ def author_metrics(ref, test, eps=1e-2):
     diff = ref - test
     return {"l1": float(np.abs(diff).mean()), "l2": float((diff * diff).mean()), "mrse": float((diff * diff / (ref * ref + eps)).mean()),
             "mape": float((np.abs(diff) / (ref + eps)).mean()), "smape": float((2 * np.abs(diff) / (ref + test + eps)).mean())}
+
+
+def blend_triple(a, b, weight):
+    """One BSDFBlend as the per-material test entry points of the oracle and the emulator take it: the first element of an array
+    {blend, bsdf1, bsdf2} with blend_a = 1, blend_b = 2 (the returned struct is a view into that array and keeps it alive)."""
+    import ctypes as C
+    from rustlight_b200 import _abi
+    arr = (_abi.rl_material * 3)()
+    C.memmove(C.byref(arr, C.sizeof(_abi.rl_material)), C.byref(a), C.sizeof(_abi.rl_material))
+    C.memmove(C.byref(arr, 2 * C.sizeof(_abi.rl_material)), C.byref(b), C.sizeof(_abi.rl_material))
+    arr[0].kind = _abi.RL_BSDF_BLEND
+    arr[0].blend_a, arr[0].blend_b, arr[0].blend_weight = 1, 2, weight
+    return arr[0]
+
+
+def blended_cbox(w=48, h=48):
+    """Cornell box with BSDFBlend on four meshes (every rough kind appears as a part), the other meshes as in the file."""
+    from rustlight_b200.host import material_metal, material_phong, material_substrate
+    sc = load_cbox(w, h)
+    diffuse = _diffuse((0.6, 0.5, 0.2))
+    sc.set_material_blend(0, diffuse, material_phong((0.2, 0.2, 0.2), (0.5, 0.5, 0.5), 30.0), 0.35)
+    sc.set_material_blend(2, material_metal((1, 1, 1), (0.143, 0.375, 1.442), (3.983, 2.386, 1.603), "ggx", 0.2), _diffuse((0.1, 0.3, 0.6)), 0.5)
+    sc.set_material_blend(5, material_substrate((0.4, 0.25, 0.1), (0.05, 0.05, 0.05), "beckmann", 0.3), material_phong((0.1, 0.1, 0.1), (0.6, 0.6, 0.6), 80.0), 0.75)
+    sc.set_material_blend(6, _diffuse((0.7, 0.7, 0.7)), _diffuse((0.1, 0.6, 0.1)), 0.25)
+    return sc
+
+
+def _diffuse(kd):
+    from rustlight_b200 import _abi
+    m = _abi.rl_material()
+    m.kind = _abi.RL_BSDF_DIFFUSE
+    m.kd[0], m.kd[1], m.kd[2] = kd
+    m.ior = 1.0
+    return m

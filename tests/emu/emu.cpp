@@ -244,20 +244,19 @@ int emu_primary_hits(const emu_scene *s, uint32_t *prim, float *tuv) {
     return 0;
 }
 
-// Device BSDF arithmetic on one material (rows built exactly like build_host_scene builds them).
-static void emu_material_rows(const rl_material *mt, float4 rows[RL_MAT_F4]) {
-    const float *ca = mt->kind == RL_BSDF_METAL ? mt->eta : (mt->kind == RL_BSDF_GLASS ? mt->kt : mt->kd);
-    const bool has_mf = mt->kind == RL_BSDF_METAL || mt->kind == RL_BSDF_SUBSTRATE;
-    rows[0] = f4(ca[0], ca[1], ca[2], u2f(mt->kind));
-    rows[1] = f4(mt->ks[0], mt->ks[1], mt->ks[2], has_mf ? mt->alpha : mt->exponent);
-    rows[2] = f4(0, 0, 0, u2f(0u));
-    rows[3] = f4(mt->kind == RL_BSDF_GLASS ? mt->ior : mt->weight_specular, 0.0f, 0.0f, u2f(has_mf ? mt->microfacet : 0u));
-    rows[4] = f4(mt->k[0], mt->k[1], mt->k[2], mt->kind == RL_BSDF_GLASS ? 1.0f / mt->ior : 0.0f);
-    rows[5] = f4(0.0f, 0.0f, 0.0f, 0.0f); // no textures in the per-material unit tests
+// Device BSDF arithmetic on one material (rows built by the function build_host_scene uses).  A blend is passed as an array of
+// three materials {blend, bsdf1, bsdf2} with blend_a = 1, blend_b = 2.
+#define EMU_MAT_ROWS (3 * RL_MAT_F4)
+static void emu_material_rows(const rl_material *mt, float4 rows[EMU_MAT_ROWS]) {
+    material_rows(mt[0], rows, RL_MAT_F4, 2 * RL_MAT_F4);
+    if (mt->kind == RL_BSDF_BLEND) {
+        material_rows(mt[1], rows + RL_MAT_F4, 0, 0);
+        material_rows(mt[2], rows + 2 * RL_MAT_F4, 0, 0);
+    }
 }
 // returns 0 = None, 1 = SolidAngle pdf, 2 = Discrete pdf
 int emu_bsdf_sample(const rl_material *mt, const float wi[3], float s0, float s1, float weight[3], float d[3], float *pdf) {
-    float4 rows[RL_MAT_F4];
+    float4 rows[EMU_MAT_ROWS];
     emu_material_rows(mt, rows);
     Material m = load_material(rows, 0);
     Col w;
@@ -269,18 +268,18 @@ int emu_bsdf_sample(const rl_material *mt, const float wi[3], float s0, float s1
     return discrete ? 2 : 1;
 }
 float emu_bsdf_pdf(const rl_material *mt, const float wi[3], const float wo[3]) {
-    float4 rows[RL_MAT_F4];
+    float4 rows[EMU_MAT_ROWS];
     emu_material_rows(mt, rows);
     return bsdf_pdf(load_material(rows, 0), V3{wi[0], wi[1], wi[2]}, V3{wo[0], wo[1], wo[2]});
 }
 void emu_bsdf_eval(const rl_material *mt, const float wi[3], const float wo[3], float out[3]) {
-    float4 rows[RL_MAT_F4];
+    float4 rows[EMU_MAT_ROWS];
     emu_material_rows(mt, rows);
     Col c = bsdf_eval(load_material(rows, 0), V3{wi[0], wi[1], wi[2]}, V3{wo[0], wo[1], wo[2]});
     out[0] = c.r, out[1] = c.g, out[2] = c.b;
 }
 int emu_bsdf_flags(const rl_material *mt) {
-    float4 rows[RL_MAT_F4];
+    float4 rows[EMU_MAT_ROWS];
     emu_material_rows(mt, rows);
     Material m = load_material(rows, 0);
     return (mat_is_twosided(m) ? 1 : 0) | (mat_is_smooth(m) ? 2 : 0);

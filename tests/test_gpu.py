@@ -382,6 +382,27 @@ def test_mixed_material_scene_bit_exact(gpu_ctx, sort):
     dev.close()
 
 
+@pytest.mark.parametrize("sort", [0, 1])
+def test_blended_materials_bit_exact(gpu_ctx, sort):
+    """BSDFBlend (bsdfs/blend.rs) on four meshes of the Cornell box, every rough kind as a part: `path` (all strategies' MIS terms go
+    through the blend's pdf / eval), `direct`, the tail kernel and the material sort (blend = its own key)."""
+    from conftest import blended_cbox
+    sc = blended_cbox(96, 96)
+    dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
+    for kw in (dict(), dict(strategy=_abi.RL_STRATEGY_BSDF), dict(max_depth=6, rr_depth=2)):
+        integ = _abi.path_desc(**kw)
+        img, st = dev.render(integ, 8, seed=12, material_sort=sort)
+        ref, so = osc.render(integ, 8, seed=12, cfg=ob.config(**STREAM))
+        assert (st.segments, st.hits, st.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+        assert np.array_equal(img, ref)
+    if sort == 0:
+        integ = _abi.direct_desc(1, 2)
+        img, st = dev.render(integ, 4, seed=5)
+        ref, so = osc.render(integ, 4, seed=5, cfg=ob.config(**STREAM))
+        assert np.array_equal(img, ref) and st.segments == so.segments
+    dev.close()
+
+
 @pytest.mark.parametrize("dist,nc", [(1.0, False), (None, True), (0.25, False)])
 def test_ao_bit_exact(gpu_ctx, cbox, dist, nc):
     dev, osc = DeviceScene(gpu_ctx, cbox), ob.OracleScene(cbox)
