@@ -20,6 +20,7 @@
 #include "rl_kernels.cuh"
 #include "rl_refbvh_host.hpp"
 #include "rl_scene_host.hpp"
+#include "rl_wide_host.hpp"
 
 using namespace rl;
 
@@ -391,23 +392,10 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     if (!hs.texels.empty()) CKS(upload(&s->d_texels, hs.texels, st));
     const uint32_t n_nodes = n > 1 ? n - 1 : 1;
     CKS(cudaMalloc(&s->d_trav, (size_t)n * RL_TRAV_F4 * sizeof(float4)));
-    CKS(cudaMalloc(&s->d_nodes, (size_t)n_nodes * 4 * sizeof(float4)));
     CKS(cudaMalloc(&d_keys, (size_t)n * 8));
     CKS(cudaMalloc(&d_keys_sorted, (size_t)n * 8));
     CKS(cudaMalloc(&d_leaf_lo, (size_t)n * sizeof(float4)));
     CKS(cudaMalloc(&d_leaf_hi, (size_t)n * sizeof(float4)));
-    // Morton keys over the raw vertex bounds
-    V3 smin = V3{hs.raw_min[0], hs.raw_min[1], hs.raw_min[2]};
-    V3 ext = V3{hs.raw_max[0] - hs.raw_min[0], hs.raw_max[1] - hs.raw_min[1], hs.raw_max[2] - hs.raw_min[2]};
-    V3 sinv = V3{ext.x > 0.0f ? 1.0f / ext.x : 0.0f, ext.y > 0.0f ? 1.0f / ext.y : 0.0f, ext.z > 0.0f ? 1.0f / ext.z : 0.0f};
-    k_morton<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(s->d_verts, n, smin, sinv, d_keys);
-    CKS(cudaGetLastError());
-    size_t tmp_bytes = 0;
-    CKS(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_keys_sorted, (int)n, 0, 64, st));
-    CKS(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
-    CKS(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_keys_sorted, (int)n, 0, 64, st));
-    k_tri_setup<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(s->d_verts, d_keys_sorted, n, bvh_box_eps(hs.abs_max), s->d_trav, s->d_shade, d_leaf_lo, d_leaf_hi);
-    CKS(cudaGetLastError());
     // The tree collapses subtrees of <= 2 triangles into leaves.  Scenes of <= 64 triangles additionally get the group
     // table (rl_flat_host.hpp), which every ray scans instead of walking the tree.
     int leaf_max = 2; // measured on a 20 736-triangle scene (tools/tess_cbox.py 24): leaves of <= 1 / 2 / 4 / 8 / 16 triangles: 31.2 / 27.4 / 28.4 / 31.1 / 36.1 ms
@@ -420,12 +408,54 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
         rl_scene_destroy(ctx, s);
         return RL_ERR_UNSUPPORTED;
     }
+    // The reference's own tree (BVHAccel::new: full SAH sweep, leaves of <= 2 primitives), rebuilt on the host.  It decides ties and rim
+    // hits (rl_refbvh_host.hpp) and -- for scenes without a group table -- its TOPOLOGY is also the tree the traversal kernels walk:
+    // a sweep-SAH tree costs incoherent rays far fewer node visits than the Morton-order LBVH (measured below), and the build is host work
+    // the reference pays too.  The device boxes stay conservative (the reference's boxes grown by bvh_box_eps), so results do not change.
+    RefBVH rb;
+    bool have_rb = false;
+    if (getenv("RL_NO_REF_ORDER") == nullptr) { // (A/B + test hook: lowest-index tie rule of NaiveAcceleration instead)
+        build_ref_bvh(hs, rb);
+        have_rb = rb.depth + 2 <= (uint32_t)RL_STACK_SIZE;
+    }
+    bool use_sah = have_rb && n > (uint32_t)RL_LEAF_MAX_CAP && n > (uint32_t)leaf_max;
+    if (const char *e = getenv("RL_TREE")) use_sah = have_rb && n > 2u && n > (uint32_t)leaf_max && std::strcmp(e, "lbvh") != 0; // A/B: lbvh | sah
+    if (use_sah) leaf_max = std::max(leaf_max, 2);
+    // Morton keys over the raw vertex bounds
+    V3 smin = V3{hs.raw_min[0], hs.raw_min[1], hs.raw_min[2]};
+    V3 ext = V3{hs.raw_max[0] - hs.raw_min[0], hs.raw_max[1] - hs.raw_min[1], hs.raw_max[2] - hs.raw_min[2]};
+    V3 sinv = V3{ext.x > 0.0f ? 1.0f / ext.x : 0.0f, ext.y > 0.0f ? 1.0f / ext.y : 0.0f, ext.z > 0.0f ? 1.0f / ext.z : 0.0f};
+    std::vector<uint64_t> h_keys; // slot order of the triangles (Morton order, or the leaf order of the reference's tree)
+    if (use_sah) {
+        h_keys.resize(n);
+        for (uint32_t i = 0; i < n; i++) h_keys[i] = ((uint64_t)i << 32) | (uint64_t)rb.prims[i];
+        CKS(cudaMemcpyAsync(d_keys_sorted, h_keys.data(), (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    } else {
+        k_morton<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(s->d_verts, n, smin, sinv, d_keys);
+        CKS(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        CKS(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_keys_sorted, (int)n, 0, 64, st));
+        CKS(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+        CKS(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_keys_sorted, (int)n, 0, 64, st));
+    }
+    k_tri_setup<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(s->d_verts, d_keys_sorted, n, bvh_box_eps(hs.abs_max), s->d_trav, s->d_shade, d_leaf_lo, d_leaf_hi);
+    CKS(cudaGetLastError());
     std::vector<int2> h_children;
     std::vector<int2v> h_ranges;
-    std::vector<uint64_t> h_keys;
-    h_keys.resize(n); // Morton order of the triangles: group table, and the slot of every primitive for the reference-order tree
-    CKS(cudaMemcpyAsync(h_keys.data(), d_keys_sorted, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-    if (n > 1) {
+    WideTree wt;
+    if (use_sah) { // wide nodes from the reference's topology (rl_wide_host.hpp)
+        uint32_t width = 4;
+        if (const char *e = getenv("RL_TREE")) width = std::strcmp(e, "sah2") == 0 ? 2u : 4u; // A/B: lbvh | sah2 | sah (= 4-wide)
+        build_wide_tree(rb, bvh_box_eps(hs.abs_max), width, wt);
+        if (wt.max_stack > (uint32_t)RL_STACK_SIZE) build_wide_tree(rb, bvh_box_eps(hs.abs_max), 2u, wt); // (rb.depth + 2 <= RL_STACK_SIZE was checked)
+        CKS(cudaMalloc(&s->d_nodes, wt.nodes.size() * sizeof(float4)));
+        CKS(cudaMemcpyAsync(s->d_nodes, wt.nodes.data(), wt.nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    } else {
+        CKS(cudaMalloc(&s->d_nodes, (size_t)n_nodes * 4 * sizeof(float4)));
+        h_keys.resize(n); // Morton order of the triangles: group table, and the slot of every primitive for the reference-order tree
+        CKS(cudaMemcpyAsync(h_keys.data(), d_keys_sorted, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (n > 1 && !use_sah) {
         CKS(cudaMalloc(&d_children, (size_t)(n - 1) * sizeof(int2)));
         CKS(cudaMalloc(&d_ranges, (size_t)(n - 1) * sizeof(int2v)));
         CKS(cudaMalloc(&d_parent_node, (size_t)(n - 1) * sizeof(int)));
@@ -448,10 +478,8 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     std::vector<uint32_t> prim_of_slot(n);
     for (uint32_t i = 0; i < n; i++) prim_of_slot[i] = (uint32_t)(h_keys[i] & 0xffffffffull);
     bool ref_ok = false;
-    if (getenv("RL_NO_REF_ORDER") == nullptr) { // (A/B + test hook: lowest-index tie rule of NaiveAcceleration instead)
-        RefBVH rb;
-        build_ref_bvh(hs, rb);
-        if (rb.depth + 2 <= (uint32_t)RL_STACK_SIZE) {
+    {
+        if (have_rb) {
             std::vector<uint32_t> slot_of_prim(n);
             for (uint32_t i = 0; i < n; i++) slot_of_prim[prim_of_slot[i]] = i;
             for (auto &p : rb.prims) p = slot_of_prim[p];
@@ -483,7 +511,10 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     // tree statistics over the live part of the tree (and the traversal-stack bound)
     uint32_t max_depth = 1, live_nodes = 0, live_leaves = 0;
     int root_ref;
-    if (n <= (uint32_t)leaf_max) {
+    if (use_sah) {
+        root_ref = 0;
+        live_nodes = wt.n_nodes, live_leaves = wt.n_leaves, max_depth = wt.depth;
+    } else if (n <= (uint32_t)leaf_max) {
         root_ref = leaf_ref(0u, n);
         live_leaves = 1;
     } else {
@@ -506,7 +537,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
         rl_scene_destroy(ctx, s);
         return RL_ERR_UNSUPPORTED;
     }
-    s->n_node_f4 = n_nodes * 4;
+    s->n_node_f4 = use_sah ? (uint32_t)wt.nodes.size() : n_nodes * 4;
     s->n_trav_f4 = n * RL_TRAV_F4;
     s->smem_bytes = (size_t)(s->n_node_f4 + s->n_trav_f4) * sizeof(float4);
     size_t smem_limit = kMaxSmemScene;
@@ -519,6 +550,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     sv.ref_nodes = ref_ok ? s->d_ref_nodes : nullptr, sv.ref_prims = ref_ok ? s->d_ref_prims : nullptr, sv.ref_up = ref_ok ? s->d_ref_up : nullptr;
     sv.ntris = n, sv.n_emitters = hs.n_emitters;
     sv.root_ref = root_ref;
+    sv.wide4 = use_sah && wt.width == 4u ? 1u : 0u;
     s->root_tree = root_ref;
     s->root_flat = root_ref;
     s->flat_ok = flat_ok;

@@ -335,6 +335,7 @@ struct SceneView {
     const uint32_t *ref_up;    // [node] parent; [ref_n_nodes + Morton slot] the leaf that holds the triangle
     uint32_t ref_n_nodes;
     int root_ref; // inner node 0, or a leaf reference when the whole scene is one leaf
+    uint32_t wide4; // nodes[] holds 4-wide nodes (seven float4 each, rl_wide_host.hpp) instead of the 64-byte two-child nodes
     // BVHAccel nodes[0].aabb (union of compute_aabb_tri boxes), for the reference's root test
     V3 root_min, root_max;
     float abs_max; // max |coordinate| of the scene, scales the conservative-culling epsilon
@@ -480,6 +481,7 @@ RL_HD bool hit_unsafe(uint32_t prim_word, float t, float omax, float abs_max) {
 #define RL_STACK_SIZE 64
 #endif
 #define RL_TRAV_DONE 0x7fffffff
+#define RL_TRAV_EMPTY 0x7ffffffe // unused child slot of a 4-wide node (rl_wide_host.hpp)
 #define RL_LEAF_MAX_CAP 64
 struct int2v {
     int x, y;
@@ -508,6 +510,7 @@ struct Trav {
     uint32_t rim_slot; // shadow: Morton slot of the last rim blocker
     float tie_t;   // closest: smallest t of a tie seen so far (-1: none); it matters only when it is within the window of the final hit
     bool edge_checks; // the scene carries the reference's tree (sv.ref_nodes)
+    bool wide4;       // sv.wide4
     float omax, abs_max; // max |o|, scene extent (hit_unsafe)
     float u, v;
     uint32_t prim;
@@ -534,6 +537,7 @@ RL_HD void trav_begin(Trav &tr, const SceneView &sv, V3 o, V3 d, V3 inv, float t
     tr.edge = false;
     tr.tie_t = -1.0f;
     tr.edge_checks = RL_REF_ORDER && sv.ref_nodes != nullptr;
+    tr.wide4 = sv.wide4 != 0u;
     tr.u = 0.0f;
     tr.v = 0.0f;
     tr.prim = RL_MISS;
@@ -560,8 +564,44 @@ RL_HD float box_entry(const Trav &tr, float lox, float loy, float loz, float hix
     return tmin <= tend ? tmin : -1.0f;
 }
 RL_HD int trav_pop(Trav &tr, const int *stack) { return tr.sp > 0 ? stack[--tr.sp] : RL_TRAV_DONE; }
+// 4-wide node (rl_wide_host.hpp): four slab tests per visit.  The children that are hit are ordered by entry distance with a
+// sorting network over keys (distance bits with the child number in the two lowest bits: the order is a heuristic, two mantissa
+// bits do not matter); the nearest becomes tr.cur, the others go on the stack farthest first.
+RL_HD void sort2u(uint32_t &a, uint32_t &b) {
+    const uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo, b = hi;
+}
+RL_HD void trav_node_step4(Trav &tr, int *stack, const float4 *nodes) {
+    const float4 *nd = nodes + 7 * tr.cur;
+    const float4 lx = nd[0], ly = nd[1], lz = nd[2], hx = nd[3], hy = nd[4], hz = nd[5], rf = nd[6];
+    const float d0 = box_entry(tr, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x);
+    const float d1 = box_entry(tr, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y);
+    const float d2 = f2u(rf.z) == (uint32_t)RL_TRAV_EMPTY ? -1.0f : box_entry(tr, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z);
+    const float d3 = f2u(rf.w) == (uint32_t)RL_TRAV_EMPTY ? -1.0f : box_entry(tr, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w);
+    // d >= 0 on a hit (float bits are monotonic), -1 on a miss -> key 0xffffffff
+    uint32_t k0 = d0 >= 0.0f ? (f2u(d0) & ~3u) : 0xffffffffu;
+    uint32_t k1 = d1 >= 0.0f ? ((f2u(d1) & ~3u) | 1u) : 0xffffffffu;
+    uint32_t k2 = d2 >= 0.0f ? ((f2u(d2) & ~3u) | 2u) : 0xffffffffu;
+    uint32_t k3 = d3 >= 0.0f ? ((f2u(d3) & ~3u) | 3u) : 0xffffffffu;
+    sort2u(k0, k1), sort2u(k2, k3), sort2u(k0, k2), sort2u(k1, k3), sort2u(k1, k2);
+    const uint32_t c0 = f2u(rf.x), c1 = f2u(rf.y), c2 = f2u(rf.z), c3 = f2u(rf.w);
+#define RL_PICK4(k) (int)(((k) & 2u) ? (((k) & 1u) ? c3 : c2) : (((k) & 1u) ? c1 : c0))
+    if (k0 == 0xffffffffu) {
+        tr.cur = trav_pop(tr, stack);
+        return;
+    }
+    if (k3 != 0xffffffffu && tr.sp < RL_STACK_SIZE) stack[tr.sp++] = RL_PICK4(k3);
+    if (k2 != 0xffffffffu && tr.sp < RL_STACK_SIZE) stack[tr.sp++] = RL_PICK4(k2);
+    if (k1 != 0xffffffffu && tr.sp < RL_STACK_SIZE) stack[tr.sp++] = RL_PICK4(k1);
+    tr.cur = RL_PICK4(k0);
+#undef RL_PICK4
+}
 // Phase A: one inner-node step (tr.cur >= 0).  Leaves tr.cur at a child, a popped entry or DONE.
 RL_HD void trav_node_step(Trav &tr, int *stack, const float4 *nodes) {
+    if (tr.wide4) {
+        trav_node_step4(tr, stack, nodes);
+        return;
+    }
     const int node = tr.cur;
     float4 a = nodes[4 * node + 0], b = nodes[4 * node + 1], c = nodes[4 * node + 2], k = nodes[4 * node + 3];
     float d0 = box_entry(tr, a.x, a.y, a.z, a.w, b.x, b.y);

@@ -92,6 +92,9 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, IntegParams ip,
 #define RL_WHILE_WHILE 1
 #endif
 constexpr int kRefillIdle = RL_REFILL_IDLE;
+#ifndef RL_TREE_MINBLOCKS
+#define RL_TREE_MINBLOCKS 4 // resident CTAs per SM the tree kernels are compiled for (64 registers; tess24 x 16 spp, 1 / 4 / 5 / 6 / 8: 24.0 / 21.6 / 24.0 / 27.9 / 32.0 ms)
+#endif
 
 __device__ __forceinline__ void warp_chunk(uint32_t n, uint32_t *begin, uint32_t *end) {
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
@@ -104,7 +107,7 @@ __device__ __forceinline__ void warp_chunk(uint32_t n, uint32_t *begin, uint32_t
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(kBlock) k_trace(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
+__global__ void __launch_bounds__(kBlock, RL_TREE_MINBLOCKS) k_trace(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
                                                   const float4 *__restrict__ ray_d, float4 *__restrict__ hit, uint32_t n_node_f4,
                                                   uint32_t n_trav_f4, const uint32_t *__restrict__ done_at, uint32_t my_k) {
     extern __shared__ float4 smem[];
@@ -703,7 +706,7 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct2(SceneView sv, IntegPar
 
 // ---- shadow rays + NEE resolve ---------------------------------------------------------------------
 template <bool SMEM>
-__global__ void __launch_bounds__(kBlock) k_shadow(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ sh_a,
+__global__ void __launch_bounds__(kBlock, RL_TREE_MINBLOCKS) k_shadow(SceneView sv, const uint32_t *__restrict__ count, const float4 *__restrict__ sh_a,
                                                    const float4 *__restrict__ sh_b, const float4 *__restrict__ sh_c,
                                                    float4 *__restrict__ lacc, Counters *counters, uint32_t n_node_f4, uint32_t n_trav_f4,
                                                    const uint32_t *__restrict__ done_at, uint32_t my_k) {

@@ -20,6 +20,7 @@
 #include "rl_flat_host.hpp"
 #include "rl_refbvh_host.hpp"
 #include "rl_scene_host.hpp"
+#include "rl_wide_host.hpp"
 
 using namespace rl;
 
@@ -59,6 +60,17 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         keys[p] = morton_key(lo, hi, smin, sinv, (uint32_t)p);
     }
     std::sort(keys.begin(), keys.end()); // cub::DeviceRadixSort on the device
+    // Traversal mode (the device uses: group table for small scenes, the 4-wide tree over the reference's topology otherwise; LBVH as
+    // the fallback; the single big leaf is the pre-group-table flat path, kept as a cross-check):
+    // RL_EMU_ACCEL = flat | leaf | tree (Morton LBVH) | sah2 | sah4 (rl_wide_host.hpp)
+    std::string mode = "flat";
+    if (const char *e = getenv("RL_EMU_ACCEL")) mode = e;
+    RefBVH rb_tree;
+    const bool use_sah = (mode == "sah2" || mode == "sah4") && n > 2;
+    if (use_sah) { // slot order = the reference's primitive order
+        build_ref_bvh(hs, rb_tree);
+        for (int i = 0; i < n; i++) keys[i] = ((uint64_t)i << 32) | (uint64_t)rb_tree.prims[i];
+    }
     // k_tri_setup
     s->trav.resize((size_t)RL_TRAV_F4 * n);
     std::vector<V3> leaf_lo(n), leaf_hi(n);
@@ -67,10 +79,6 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         tri_setup(hs.verts.data(), prim, i, bvh_box_eps(hs.abs_max), s->trav.data(), hs.shade.data());
         tri_bounds_inflated(hs.verts.data(), prim, bvh_box_eps(hs.abs_max), &leaf_lo[i], &leaf_hi[i]);
     }
-    // Traversal mode (the device uses all three: group table for incoherent rays of small scenes, tree otherwise;
-    // the single big leaf is the pre-group-table flat path, kept as a cross-check): RL_EMU_ACCEL = flat | leaf | tree
-    std::string mode = "flat";
-    if (const char *e = getenv("RL_EMU_ACCEL")) mode = e;
     if (mode == "flat" && n <= RL_LEAF_MAX_CAP) {
         std::vector<uint32_t> prim_of_slot(n);
         for (int i = 0; i < n; i++) prim_of_slot[i] = (uint32_t)(keys[i] & 0xffffffffull);
@@ -84,7 +92,15 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
     s->nodes.resize((size_t)4 * n_nodes);
     s->root_ref = n <= leaf_max ? leaf_ref(0u, (uint32_t)n) : 0;
     s->max_depth = 1;
-    if (n > 1) {
+    if (use_sah) {
+        WideTree wt;
+        build_wide_tree(rb_tree, bvh_box_eps(hs.abs_max), mode == "sah4" ? 4u : 2u, wt);
+        if (wt.max_stack > (uint32_t)RL_STACK_SIZE) build_wide_tree(rb_tree, bvh_box_eps(hs.abs_max), 2u, wt);
+        s->nodes = wt.nodes;
+        s->root_ref = 0;
+        s->sv.wide4 = wt.width == 4u ? 1u : 0u;
+        s->max_depth = wt.depth;
+    } else if (n > 1) {
         std::vector<int> cl(n - 1), cr(n - 1);
         std::vector<int2v> ranges(n - 1);
         for (int i = 0; i < n - 1; i++) karras_node(keys.data(), n, i, &cl[i], &cr[i], &ranges[i].x, &ranges[i].y);
@@ -170,19 +186,36 @@ int emu_bvh_validate(const emu_scene *s) {
         }
         static bool walk(const emu_scene *s, int node, V3 *lo, V3 *hi, std::vector<int> &seen, uint32_t depth, uint32_t *max_depth) {
             *max_depth = std::max(*max_depth, depth);
-            const float4 *nd = &s->nodes[4 * node];
-            int ch[2] = {(int)f2u(nd[3].x), (int)f2u(nd[3].y)};
-            V3 blo[2] = {V3{nd[0].x, nd[0].y, nd[0].z}, V3{nd[1].z, nd[1].w, nd[2].x}};
-            V3 bhi[2] = {V3{nd[0].w, nd[1].x, nd[1].y}, V3{nd[2].y, nd[2].z, nd[2].w}};
-            for (int q = 0; q < 2; q++) {
+            int ch[4], nq = 2;
+            V3 blo[4], bhi[4];
+            if (s->sv.wide4) {
+                const float4 *nd = &s->nodes[7 * node];
+                const float *f = &nd[0].x;
+                nq = 0;
+                for (int q = 0; q < 4; q++) {
+                    const int c = (int)f2u(f[24 + q]);
+                    if (c == RL_TRAV_EMPTY) continue;
+                    ch[nq] = c, blo[nq] = V3{f[q], f[4 + q], f[8 + q]}, bhi[nq] = V3{f[12 + q], f[16 + q], f[20 + q]};
+                    nq++;
+                }
+            } else {
+                const float4 *nd = &s->nodes[4 * node];
+                ch[0] = (int)f2u(nd[3].x), ch[1] = (int)f2u(nd[3].y);
+                blo[0] = V3{nd[0].x, nd[0].y, nd[0].z}, blo[1] = V3{nd[1].z, nd[1].w, nd[2].x};
+                bhi[0] = V3{nd[0].w, nd[1].x, nd[1].y}, bhi[1] = V3{nd[2].y, nd[2].z, nd[2].w};
+            }
+            for (int q = 0; q < nq; q++) {
                 V3 clo, chi;
                 if (ch[q] < 0) {
                     if (!leaf(s, ch[q], &clo, &chi, seen)) return false;
                 } else if (!walk(s, ch[q], &clo, &chi, seen, depth + 1, max_depth)) return false;
                 if (clo.x < blo[q].x || clo.y < blo[q].y || clo.z < blo[q].z || chi.x > bhi[q].x || chi.y > bhi[q].y || chi.z > bhi[q].z) return false;
             }
-            *lo = V3{fminf(blo[0].x, blo[1].x), fminf(blo[0].y, blo[1].y), fminf(blo[0].z, blo[1].z)};
-            *hi = V3{fmaxf(bhi[0].x, bhi[1].x), fmaxf(bhi[0].y, bhi[1].y), fmaxf(bhi[0].z, bhi[1].z)};
+            *lo = blo[0], *hi = bhi[0];
+            for (int q = 1; q < nq; q++) {
+                *lo = V3{fminf(lo->x, blo[q].x), fminf(lo->y, blo[q].y), fminf(lo->z, blo[q].z)};
+                *hi = V3{fmaxf(hi->x, bhi[q].x), fmaxf(hi->y, bhi[q].y), fmaxf(hi->z, bhi[q].z)};
+            }
             return true;
         }
     };

@@ -38,9 +38,10 @@ def test_cbox_group_table_pairs_every_quad(cbox):
     assert info["groups"] == 9 and info["pairs"] == 18 and info["singles"] == 0 and info["delta"] < 1e-6
 
 
-@pytest.mark.parametrize("accel", ["flat", "leaf", "tree"])
+@pytest.mark.parametrize("accel", ["flat", "leaf", "tree", "sah2", "sah4"])
 def test_accel_modes_agree_with_the_oracle(cbox, cbox_oracle, accel):
-    """The three traversal modes of the device (group table, one big leaf, LBVH) give the oracle's hits bit for bit."""
+    """The traversal modes of the device (group table, one big leaf, Morton LBVH, 2- and 4-wide tree over the reference's topology)
+    give the oracle's hits bit for bit."""
     esc = eb.EmuScene(cbox, accel)
     assert (esc.flat_info()["groups"] > 0) == (accel == "flat")
     o, d, p1 = _rays(20000, 3)
@@ -89,12 +90,15 @@ def test_random_rays_and_segments_exact(cbox, cbox_oracle):
     assert np.array_equal(esc.visible(o, p1), cbox_oracle.visible(o, p1, ob.ACCEL_BVH))
 
 
+@pytest.mark.parametrize("accel", ["tree", "sah2", "sah4"])
 @pytest.mark.parametrize("ntris,seed", [(50, 0), (600, 1), (3000, 2)])
-def test_soup_lbvh_equals_brute_force(ntris, seed):
-    """Conservative culling: the LBVH never loses a triangle the exact test accepts."""
+def test_soup_trees_equal_the_oracle(ntris, seed, accel):
+    """Conservative culling: neither the Morton LBVH nor the 2- / 4-wide trees built over the reference's topology (rl_wide_host.hpp:
+    what the device walks on scenes without a group table) lose a triangle the exact test accepts; every triangle sits in exactly
+    one leaf and every child box contains its subtree."""
     sc = SceneLoaderManager().load_string(soup_scene(ntris, seed), "json")
-    esc, osc = eb.EmuScene(sc), ob.OracleScene(sc)
-    assert esc.bvh_validate() == 0
+    esc, osc = eb.EmuScene(sc, accel), ob.OracleScene(sc)
+    assert esc.bvh_validate() == 0 and esc.bvh_max_depth() >= 2
     o, d, p1 = _rays(6000, seed + 10, -1.2, 1.2, (0, 0, 0))
     pe, te = esc.trace(o, d)
     po, to = osc.trace(o, d, ob.ACCEL_BVH)
