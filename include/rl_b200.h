@@ -143,7 +143,8 @@ typedef struct rl_scene_desc {
     rl_camera_desc camera;
     uint32_t has_volume;      /* must be 0: scene.volume == None on this path                 */
     uint32_t has_environment; /* 0: emitter_environment == None; 1: EnvironmentLight with EnvironmentLightColor::Constant(
-                                 environment) (emitter.rs:300-568); environment TEXTURES are outside this path             */
+                                 environment); 2: EnvironmentLightColor::Texture { image = textures[environment_texture - 1] }
+                                 (lat-long map, importance-sampled through its Distribution2D; emitter.rs:300-568)           */
     uint32_t nlights;         /* Scene.emitters (EmittersState::Unbuild): sampled after the mesh lights, in this order */
     const rl_light_desc *lights;
     uint32_t ntextures;
@@ -151,6 +152,7 @@ typedef struct rl_scene_desc {
     float environment[3];     /* constant environment radiance when has_environment == 1 */
     uint32_t nsubmaterials;   /* the bsdf1 / bsdf2 of RL_BSDF_BLEND materials */
     const rl_material *submaterials;
+    uint32_t environment_texture; /* has_environment == 2: 1 + index into textures[] of an RL_TEX_BITMAP (EnvironmentLightColor::new_texture) */
 } rl_scene_desc;
 
 /* ---- integrators --------------------------------------------------------------------------- */

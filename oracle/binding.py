@@ -91,6 +91,12 @@ def lib():
     L.orc_xoshiro_next_u64.restype = C.c_uint64
     L.orc_xoshiro_next_u64.argtypes = [C.POINTER(C.c_uint64)]
     L.orc_spec_sincos.argtypes = [C.c_float, FP, FP]
+    L.orc_spec_atan2.restype = C.c_float
+    L.orc_spec_atan2.argtypes = [C.c_float, C.c_float]
+    L.orc_spec_acos.restype = C.c_float
+    L.orc_spec_acos.argtypes = [C.c_float]
+    L.orc_env_eval_pdf.argtypes = [C.c_void_p, C.c_uint32, FP, FP, FP]
+    L.orc_env_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, FP, FP, FP]
     L.orc_spec_powf.restype = C.c_float
     L.orc_spec_powf.argtypes = [C.c_float, C.c_float]
     L.orc_path_sample.argtypes = [C.c_void_p, C.POINTER(_abi.rl_integrator_desc), C.c_uint64, C.c_uint32, C.c_uint32,
@@ -133,6 +139,20 @@ class OracleScene:
         if rc != 0:
             raise ValueError(f"orc_render failed: {rc}")
         return img, st
+
+    def env_eval_pdf(self, d, math_mode=MATH_SPEC):
+        """EnvironmentLightColor::{eval, pdf} of the scene's environment for the direction d."""
+        rgb, pdf = np.zeros(3, np.float32), C.c_float()
+        if lib().orc_env_eval_pdf(self._h, math_mode, _f(np.ascontiguousarray(d, np.float32)), _f(rgb), C.byref(pdf)) != 0:
+            raise ValueError("no environment")
+        return rgb, pdf.value
+
+    def env_sample(self, u0, u1, math_mode=MATH_SPEC):
+        """EnvironmentLightColor::sample_direction((u0, u1)) -> (d, colour, pdf)."""
+        d, rgb, pdf = np.zeros(3, np.float32), np.zeros(3, np.float32), C.c_float()
+        if lib().orc_env_sample(self._h, math_mode, float(u0), float(u1), _f(d), _f(rgb), C.byref(pdf)) != 0:
+            raise ValueError("no environment")
+        return d, rgb, pdf.value
 
     def trace(self, o, d, accel_mode=ACCEL_BVH, full=False):
         o, d = f32(o).reshape(-1, 3), f32(d).reshape(-1, 3)
@@ -300,6 +320,14 @@ def xoshiro_next_u64(state):
     st = (C.c_uint64 * 4)(*state)
     r = lib().orc_xoshiro_next_u64(st)
     return r, list(st)
+
+
+def spec_atan2(y, x):
+    return lib().orc_spec_atan2(float(y), float(x))
+
+
+def spec_acos(x):
+    return lib().orc_spec_acos(float(x))
 
 
 def spec_sincos(x):

@@ -177,8 +177,58 @@ inline float spec_powf(float x, float y) { // x >= 0
     if (!(x > 0.0f)) return std::numeric_limits<float>::quiet_NaN();
     return (float)spec_exp2((double)y * spec_log2((double)x));
 }
+// atan2 / acos of the SPEC math mode: Cephes atanf / asinf kernels in f32, one fmaf / mul / div / sqrt per step;
+// typed independently of rl_device.cuh, same operation sequence.
+inline float spec_atan_nonneg(float x) {
+    float base, z;
+    if (x > 2.414213562373095f) base = 1.5707963267948966f, z = -(1.0f / x);
+    else if (x > 0.4142135623730950f) base = 0.7853981633974483f, z = (x - 1.0f) / (x + 1.0f);
+    else base = 0.0f, z = x;
+    const float zz = z * z;
+    float poly = std::fmaf(8.05374449538e-2f, zz, -1.38776856032e-1f);
+    poly = std::fmaf(poly, zz, 1.99777106478e-1f);
+    poly = std::fmaf(poly, zz, -3.33329491539e-1f);
+    return base + std::fmaf(poly * zz, z, z);
+}
+inline float spec_atan2(float y, float x) {
+    if (x != x || y != y) return x + y;
+    if (x == 0.0f) return y > 0.0f ? 1.5707963267948966f : (y < 0.0f ? -1.5707963267948966f : 0.0f);
+    const float q = y / x;
+    const float a = spec_atan_nonneg(std::fabs(q));
+    const float at = q < 0.0f ? -a : a;
+    if (x > 0.0f) return at;
+    return std::signbit(y) ? at - 3.14159265358979323846f : at + 3.14159265358979323846f; // atan2(-0, x < 0) = -pi
+}
+inline float spec_asin_nonneg(float a) {
+    if (a < 1e-4f) return a;
+    const bool big = a > 0.5f;
+    float z, x;
+    if (big) z = 0.5f * (1.0f - a), x = std::sqrt(z);
+    else x = a, z = x * x;
+    float poly = std::fmaf(4.2163199048e-2f, z, 2.4181311049e-2f);
+    poly = std::fmaf(poly, z, 4.5470025998e-2f);
+    poly = std::fmaf(poly, z, 7.4953002686e-2f);
+    poly = std::fmaf(poly, z, 1.6666752422e-1f);
+    float r = std::fmaf(poly * z, x, x);
+    if (big) r = 1.5707963267948966f - (r + r);
+    return r;
+}
+inline float spec_acos(float x) {
+    if (x != x) return x;
+    if (x < -0.5f) return 3.14159265358979323846f - 2.0f * spec_asin_nonneg(std::sqrt(0.5f * (1.0f + x)));
+    if (x > 0.5f) return 2.0f * spec_asin_nonneg(std::sqrt(0.5f * (1.0f - x)));
+    const float a = spec_asin_nonneg(std::fabs(x));
+    return 1.5707963267948966f - (x < 0.0f ? -a : a);
+}
 struct Math {
     uint32_t mode;
+    float atan2(float y, float x) const { return mode == ORC_MATH_LIBM ? std::atan2(y, x) : spec_atan2(y, x); }
+    float acos(float x) const { return mode == ORC_MATH_LIBM ? std::acos(x) : spec_acos(x); }
+    float sin(float x) const {
+        float sn, cs;
+        sincos(x, &sn, &cs);
+        return sn;
+    }
     void sincos(float x, float *s, float *c) const {
         if (mode == ORC_MATH_LIBM) {
             *s = std::sin(x);
@@ -1014,6 +1064,7 @@ struct LightSampling { // :10-24
 };
 struct LightSamplingPDF { // :26-44
     V3 o, p, n, dir;
+    uint32_t math_mode = ORC_MATH_SPEC; // (not in the reference: which sin / atan2 / acos EnvironmentLightColor::pdf evaluates with)
 };
 struct BoundingSphere { // structure.rs:880-884
     V3 center;
@@ -1124,22 +1175,126 @@ inline V3 sample_uniform_sphere(const Math &m, P2 u) { // math.rs:67-72
     m.sincos(phi, &sp, &cp);
     return V3{r * cp, r * sp, z};
 }
-struct EnvironmentLight : Emitter { // emitter.rs:428-568 with EnvironmentLightColor::Constant
-    Color luminance;
+constexpr float ONE_MINUS_EPSILON = 0.9999999403953552f; // lib.rs:52
+inline float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); } // lib.rs:59-67
+inline uint64_t as_usize(float v) { // `as usize` / `as u32` on the values used here: saturating, NaN -> 0
+    if (!(v > 0.0f)) return 0;
+    if (v >= 18446744073709551616.0f) return ~(uint64_t)0;
+    return (uint64_t)v;
+}
+inline float dist1d_sample_continuous(const Distribution1D &d, float v) { // math.rs:459-478
+    size_t i = d.sample_discrete(v);
+    float dv = v - d.cdf[i];
+    float pdf = d.pdf(i);
+    if (pdf > 0.0f) dv = dv / pdf;
+    return (float)i + dv;
+}
+struct Distribution2D { // math.rs:489-532
+    Distribution1D marginal;
+    std::vector<Distribution1D> conditionals;
+    static Distribution2D from_bitmap(const BitmapTex &image) { // :495-521
+        Distribution2D d;
+        std::vector<float> marg;
+        for (uint32_t y = 0; y < image.size_y; y++) {
+            std::vector<float> cond;
+            for (uint32_t x = 0; x < image.size_x; x++) {
+                const Color p = image.colors[(size_t)y * image.size_x + x];
+                cond.push_back(p.r * 0.212671f + p.g * 0.715160f + p.b * 0.072169f); // Color::luminance, structure.rs:173-176
+            }
+            d.conditionals.push_back(Distribution1D::normalize(cond));
+            marg.push_back(d.conditionals.back().func_int);
+        }
+        d.marginal = Distribution1D::normalize(marg);
+        return d;
+    }
+    P2 sample_continuous(P2 uv) const { // :523-527
+        float y = dist1d_sample_continuous(marginal, uv.y);
+        float x = dist1d_sample_continuous(conditionals[as_usize(y)], uv.x);
+        return P2{x, y};
+    }
+    float pdf(size_t x, size_t y) const { return conditionals[y].func[x] / marginal.func_int; } // :529-531
+};
+inline P2 to_spherical_coordinates(const Math &m, V3 d) { // emitter.rs:320-338
+    float p = m.atan2(d.y, d.x);
+    if (p < 0.0f) p = p + 2.0f * PI;
+    P2 uv{p * FRAC_1_PI * 0.5f, m.acos(clampf(d.z, -1.0f, 1.0f)) * FRAC_1_PI};
+    uv.x = clampf(uv.x, 0.0f, ONE_MINUS_EPSILON);
+    uv.y = clampf(uv.y, 0.0f, ONE_MINUS_EPSILON);
+    return uv;
+}
+struct EnvironmentLightColor { // emitter.rs:300-427
+    bool is_texture = false;
+    Color constant{};
+    BitmapTex image;
+    Distribution2D image_cdf[2]; // [math mode]: new_texture weights the rows by sin((y + 0.5) PI / size.y) (:341-353)
+    void new_texture(const BitmapTex &img) {
+        is_texture = true;
+        image = img;
+        for (uint32_t mode = 0; mode < 2; mode++) {
+            BitmapTex image_pdf = img;
+            for (uint32_t y = 0; y < img.size_y; y++) {
+                float w = Math{mode}.sin(((float)y + 0.5f) * PI / (float)img.size_y);
+                for (uint32_t x = 0; x < img.size_x; x++) {
+                    Color &c = image_pdf.colors[(size_t)y * img.size_x + x];
+                    c.r *= w, c.g *= w, c.b *= w; // MulAssign<f32>, structure.rs:225-231
+                }
+            }
+            image_cdf[mode] = Distribution2D::from_bitmap(image_pdf);
+        }
+    }
+    void sample_direction(const Math &m, P2 uv, V3 *d, Color *color, float *pdf) const { // :354-391
+        if (!is_texture) {
+            *d = sample_uniform_sphere(m, uv), *color = constant, *pdf = 1.0f / (PI * 4.0f);
+            return;
+        }
+        const Distribution2D &cdf = image_cdf[m.mode == ORC_MATH_LIBM ? ORC_MATH_LIBM : ORC_MATH_SPEC];
+        P2 q = cdf.sample_continuous(uv);
+        q.x = clampf(q.x, 0.0f, (float)image.size_x - 1.0f);
+        q.y = clampf(q.y, 0.0f, (float)image.size_y - 1.0f);
+        Color value = image.colors[(size_t)as_usize(q.y) * image.size_x + (size_t)as_usize(q.x)];
+        float p = cdf.pdf((size_t)as_usize(q.x), (size_t)as_usize(q.y));
+        float sin_phi, cos_phi, sin_theta, cos_theta;
+        m.sincos((2.0f * PI / (float)image.size_x) * q.x, &sin_phi, &cos_phi);
+        m.sincos((PI / (float)image.size_y) * q.y, &sin_theta, &cos_theta);
+        *d = V3{sin_theta * cos_phi, sin_theta * sin_phi, cos_theta};
+        if (sin_theta == 0.0f) *color = Color::zero(), *pdf = 0.0f;
+        else *color = value, *pdf = p / (2.0f * (PI * PI) * sin_theta);
+    }
+    Color eval(const Math &m, V3 d) const { // :393-401
+        if (!is_texture) return constant;
+        return image.pixel_uv(to_spherical_coordinates(m, d));
+    }
+    float pdf(const Math &m, V3 d) const { // :403-425
+        if (!is_texture) return 1.0f / (PI * 4.0f);
+        P2 uv = to_spherical_coordinates(m, d);
+        const Distribution2D &cdf = image_cdf[m.mode == ORC_MATH_LIBM ? ORC_MATH_LIBM : ORC_MATH_SPEC];
+        float p = cdf.pdf((size_t)as_usize(uv.x * (float)image.size_x), (size_t)as_usize(uv.y * (float)image.size_y));
+        float sin_theta = m.sin(PI * uv.y);
+        if (sin_theta == 0.0f) return 0.0f;
+        return p / (2.0f * (PI * PI) * sin_theta);
+    }
+};
+struct EnvironmentLight : Emitter { // emitter.rs:428-568
+    EnvironmentLightColor luminance;
     BoundingSphere bsphere{}; // preprocess(): scene.bsphere, radius * 1.1
-    static float color_pdf() { return 1.0f / (PI * 4.0f); } // :406
-    PDF direct_pdf(const LightSamplingPDF &) const override { return PDF{PDF::SolidAngle, color_pdf()}; } // :470-473
+    PDF direct_pdf(const LightSamplingPDF &ls) const override { return PDF{PDF::SolidAngle, luminance.pdf(Math{ls.math_mode}, ls.dir)}; } // :470-473
     LightSampling direct_sample(const Math &math, V3 v, float, P2 uv) const override { // :474-511
-        V3 d = sample_uniform_sphere(math, uv); // luminance.sample_direction, :369-373
-        float pdf = color_pdf();
+        V3 d;
+        Color color;
+        float pdf;
+        luminance.sample_direction(math, uv, &d, &color, &pdf);
         float t;
         if (!bsphere_intersect(bsphere, ray_new(v, d), &t)) return LightSampling{this, PDF{PDF::SolidAngle, pdf}, V3{0, 0, 0}, V3{0, 0, 0}, d, 0, Color::zero()};
         V3 p = v + d * t;
         V3 n = normalize(bsphere.center - p);
-        return LightSampling{this, PDF{PDF::SolidAngle, pdf}, p, n, d, 0, luminance / pdf};
+        return LightSampling{this, PDF{PDF::SolidAngle, pdf}, p, n, d, 0, color / pdf};
     }
-    Color flux() const override { return (PI * powi(bsphere.radius, 2)) * luminance; } // :512-516
-    Color eval() const override { return luminance; }
+    Color flux() const override { // :512-524
+        if (!luminance.is_texture) return (PI * powi(bsphere.radius, 2)) * luminance.constant;
+        float v = PI * powi(bsphere.radius, 2) * luminance.image_cdf[ORC_MATH_SPEC].marginal.func_int; // (the SPEC table: what the device builds)
+        return Color{v, v, v};
+    }
+    Color eval() const override { return luminance.constant; }
 };
 struct EmitterSampler { // :1491-1495 (ats == None on this path)
     std::vector<std::unique_ptr<Emitter>> emitters;
@@ -1356,7 +1511,8 @@ struct Scene {
     bool has_environment = false;      // Scene.emitter_environment: EnvironmentLight with a constant colour
     Color environment{};
     const EnvironmentLight *env_emitter = nullptr;
-    Color enviroment_luminance() const { return has_environment ? environment : Color::zero(); } // scene.rs:125-130
+    BitmapTex environment_image; // EnvironmentLightColor::Texture when size_x != 0
+    Color enviroment_luminance(const Math &m, V3 d) const { return env_emitter ? env_emitter->luminance.eval(m, d) : Color::zero(); } // scene.rs:125-130
     BoundingSphere bsphere{};
     void build_emitters() { // scene.rs:53-123 (no env map, no ATS)
         // bounding sphere: union of Mesh::compute_aabb (all vertices, geometry.rs:441-456) and the camera position
@@ -1383,7 +1539,8 @@ struct Scene {
         env_emitter = nullptr;
         if (has_environment) { // scene.rs:69-81: preprocess, then pushed right after the mesh lights
             auto e = std::make_unique<EnvironmentLight>();
-            e->luminance = environment;
+            if (environment_image.size_x != 0) e->luminance.new_texture(environment_image);
+            else e->luminance.constant = environment;
             e->bsphere = bsphere;
             e->bsphere.radius *= 1.1f;
             env_emitter = e.get();
@@ -1626,12 +1783,12 @@ Color vertex_contribution(const Vertex &v, const Edge &edge) {
     return Color::zero();
 }
 // Edge::contribution, edge.rs:201-210 (environment luminance is zero on this path)
-Color edge_contribution(const Edge &e, const Path &path, const Scene *scene) {
+Color edge_contribution(const Edge &e, const Path &path, const Scene *scene, const Math &math) {
     if (e.v1 >= 0) {
         if (e.has_contrib) return e.contrib * e.weight * e.rr_weight;
         return e.weight * e.rr_weight * vertex_contribution(path.vertices[e.v1], e);
     }
-    return e.weight * e.rr_weight * scene->enviroment_luminance(); // scene.enviroment_luminance(self.d), constant
+    return e.weight * e.rr_weight * scene->enviroment_luminance(math, e.d); // scene.enviroment_luminance(self.d)
 }
 bool edge_next_on_light_source(const Edge &e, const Path &path, const Scene *scene) { // edge.rs:191-197
     if (e.v1 >= 0) return path.vertices[e.v1].on_light_source();
@@ -1773,7 +1930,7 @@ struct LightSamplingStrategy : SamplingStrategy { // strategies/emitters.rs
             if (!bsphere_intersect(env->bsphere, ray, &t)) std::abort(); // t.unwrap()
             V3 p = ray.o + ray.d * t;
             V3 n = normalize(env->bsphere.center - p);
-            PDF pdf = cx.scene->emitters.direct_pdf(env, LightSamplingPDF{ray.o, p, n, ray.d});
+            PDF pdf = cx.scene->emitters.direct_pdf(env, LightSamplingPDF{ray.o, p, n, ray.d, cx.math.mode});
             *out = pdf.value();
             return true;
         }
@@ -1833,7 +1990,7 @@ void generate(Path &path, int root, const Ctx &cx, Sampler &sampler, const Techn
 // TechniquePathTracing::evalute_edge / evaluate, path.rs:37-185
 Color evalute_edge(const TechniquePathTracing &tq, uint32_t curr_depth, int32_t min_depth, const Path &path, const Ctx &cx, int vertex_id, int edge_id, uint32_t strategy) {
     const Edge &edge = path.edges[edge_id];
-    Color contrib = edge_contribution(edge, path, cx.scene);
+    Color contrib = edge_contribution(edge, path, cx.scene, cx.math);
     if (strategy == RL_STRATEGY_BSDF && edge.id_sampling != 0) contrib = Color::zero();
     if (strategy == RL_STRATEGY_EMITTER && edge.id_sampling != 1) contrib = Color::zero();
     bool add_contrib = min_depth < 0 ? true : curr_depth >= (uint32_t)min_depth;
@@ -1869,7 +2026,7 @@ Color evaluate(const TechniquePathTracing &tq, uint32_t curr_depth, int32_t min_
     } else if (v.kind == Vertex::Sensor) {
         const Edge &edge = path.edges[v.edge_out.at(0)];
         bool add_contrib = min_depth < 0 ? true : curr_depth >= (uint32_t)min_depth;
-        Color contrib = edge_contribution(edge, path, cx.scene);
+        Color contrib = edge_contribution(edge, path, cx.scene, cx.math);
         if (!contrib.is_zero() && add_contrib) l_i = l_i + contrib;
         if (edge.v1 >= 0) l_i = l_i + edge.weight * edge.rr_weight * evaluate(tq, curr_depth + 1, min_depth, path, cx, edge.v1, strategy);
     }
@@ -1933,14 +2090,15 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
         if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) {
             // edge without a next vertex: weight * rr * environment luminance (edge.rs:208), same gates and MIS as an emitter hit
             if (sc.has_environment) {
+                const Color env_l = sc.enviroment_luminance(cx.math, ray.d);
                 if (depth == 1) {
-                    if (add_ok(0) && !sc.environment.is_zero()) L = L + sc.environment;
+                    if (add_ok(0) && !env_l.is_zero()) L = L + env_l;
                 } else if (!mute && add_ok(depth - 1) && I.strategy != RL_STRATEGY_EMITTER) {
-                    Color contrib = T * sc.environment;
+                    Color contrib = T * env_l;
                     if (!contrib.is_zero()) {
                         float w = 1.0f;
                         if (I.strategy == RL_STRATEGY_ALL && mis_prev) { // pdf_emitter's environment arm (emitters.rs:18-46)
-                            float pl = sc.emitters.direct_pdf(sc.env_emitter, LightSamplingPDF{ray.o, V3{0, 0, 0}, V3{0, 0, 0}, ray.d}).value();
+                            float pl = sc.emitters.direct_pdf(sc.env_emitter, LightSamplingPDF{ray.o, V3{0, 0, 0}, V3{0, 0, 0}, ray.d, cx.math.mode}).value();
                             w = pdf_prev / (pdf_prev + pl);
                         }
                         L = L + contrib * w;
@@ -2048,7 +2206,7 @@ Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy
     Color l_i = Color::zero();
     if (1 > cx.counters->max_depth) cx.counters->max_depth = 1;
     Intersection its;
-    if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) return sc.enviroment_luminance(); // direct.rs:33-36
+    if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) return sc.enviroment_luminance(cx.math, ray.d); // direct.rs:33-36
     if (its.cos_theta() <= 0.0f) return l_i;
     l_i = l_i + its.mesh->emit();
     float weight_nb_bsdf = I.nb_bsdf_samples == 0 ? 0.0f : 1.0f / (float)I.nb_bsdf_samples;
@@ -2090,10 +2248,10 @@ Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy
                 if (!bsphere_intersect(sc.env_emitter->bsphere, r2, &t)) std::abort(); // t.unwrap()
                 V3 p = r2.o + r2.d * t;
                 V3 n = normalize(sc.env_emitter->bsphere.center - p);
-                float light_pdf = sc.emitters.direct_pdf(sc.env_emitter, LightSamplingPDF{r2.o, p, n, r2.d}).value();
+                float light_pdf = sc.emitters.direct_pdf(sc.env_emitter, LightSamplingPDF{r2.o, p, n, r2.d, cx.math.mode}).value();
                 weight_bsdf = mis_weight(sb.pdf.value() * weight_nb_bsdf, light_pdf * weight_nb_light);
             }
-            l_i = l_i + weight_bsdf * sb.weight * sc.enviroment_luminance() * weight_nb_bsdf;
+            l_i = l_i + weight_bsdf * sb.weight * sc.enviroment_luminance(cx.math, r2.d) * weight_nb_bsdf;
         }
     }
     return l_i;
@@ -2151,7 +2309,10 @@ orc_scene *orc_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         return nullptr;
     };
     if (!desc || !desc->meshes || desc->nmeshes == 0) return fail("empty scene");
-    if (desc->has_volume || desc->has_environment > 1) return fail("volume / environment textures are outside the hot path");
+    if (desc->has_volume || desc->has_environment > 2) return fail("volumes are outside the hot path");
+    if (desc->has_environment == 2 && (desc->environment_texture == 0 || desc->environment_texture > desc->ntextures || !desc->textures ||
+                                        desc->textures[desc->environment_texture - 1].kind != RL_TEX_BITMAP))
+        return fail("has_environment == 2 needs environment_texture = 1 + index of a bitmap texture");
     auto *os = new orc_scene;
     Scene &s = os->scene;
     s.camera.img_x = desc->camera.width, s.camera.img_y = desc->camera.height;
@@ -2188,6 +2349,11 @@ orc_scene *orc_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         s.meshes.push_back(std::move(m));
     }
     if (desc->has_environment) s.has_environment = true, s.environment = Color{desc->environment[0], desc->environment[1], desc->environment[2]};
+    if (desc->has_environment == 2) { // EnvironmentLightColor::new_texture(image)
+        const rl_texture &t = desc->textures[desc->environment_texture - 1];
+        s.environment_image.size_x = t.width, s.environment_image.size_y = t.height;
+        for (size_t i = 0; i < (size_t)t.width * t.height; i++) s.environment_image.colors.push_back(Color{t.pixels[3 * i], t.pixels[3 * i + 1], t.pixels[3 * i + 2]});
+    }
     for (uint32_t li = 0; li < desc->nlights; li++) {
         if (desc->lights[li].kind > RL_LIGHT_DIRECTIONAL) return fail("unknown light kind");
         s.lights.push_back(desc->lights[li]);
@@ -2467,6 +2633,26 @@ uint64_t orc_xoshiro_next_u64(uint64_t state[4]) {
     return r;
 }
 void orc_spec_sincos(float x, float *s, float *c) { spec_sincos(x, s, c); }
+float orc_spec_atan2(float y, float x) { return spec_atan2(y, x); }
+float orc_spec_acos(float x) { return spec_acos(x); }
+int orc_env_eval_pdf(const orc_scene *os, uint32_t math_mode, const float d[3], float rgb[3], float *pdf) {
+    const EnvironmentLight *env = os->scene.env_emitter;
+    if (!env) return -1;
+    Color c = env->luminance.eval(Math{math_mode}, load3(d));
+    rgb[0] = c.r, rgb[1] = c.g, rgb[2] = c.b;
+    *pdf = env->luminance.pdf(Math{math_mode}, load3(d));
+    return 0;
+}
+int orc_env_sample(const orc_scene *os, uint32_t math_mode, float u0, float u1, float d[3], float rgb[3], float *pdf) {
+    const EnvironmentLight *env = os->scene.env_emitter;
+    if (!env) return -1;
+    V3 dd;
+    Color c;
+    env->luminance.sample_direction(Math{math_mode}, P2{u0, u1}, &dd, &c, pdf);
+    store3(d, dd);
+    rgb[0] = c.r, rgb[1] = c.g, rgb[2] = c.b;
+    return 0;
+}
 float orc_spec_powf(float x, float y) { return spec_powf(x, y); }
 
 } // extern "C"

@@ -101,6 +101,11 @@ void orc_sampler_block_stream(uint64_t seed, uint32_t seeding, uint32_t block, u
 void orc_sampler_counter(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float *out);
 uint64_t orc_xoshiro_next_u64(uint64_t state[4]); /* xoshiro256++ step (KAT against the published algorithm) */
 void orc_spec_sincos(float x, float *s, float *c);
+float orc_spec_atan2(float y, float x);
+float orc_spec_acos(float x);
+/* EnvironmentLightColor of the scene's environment (emitter.rs:354-425): eval / pdf of a direction, sample_direction(uv) -> d, colour, pdf */
+int orc_env_eval_pdf(const orc_scene *s, uint32_t math_mode, const float d[3], float rgb[3], float *pdf);
+int orc_env_sample(const orc_scene *s, uint32_t math_mode, float u0, float u1, float d[3], float rgb[3], float *pdf);
 float orc_spec_powf(float x, float y);
 /* A single path sample with full trace of what happened (for debugging parity):
  * returns radiance, and writes up to cap (segments, shadow rays) counters. */

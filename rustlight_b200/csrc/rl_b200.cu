@@ -113,6 +113,7 @@ struct rl_scene {
     float *d_emit_cdf = nullptr, *d_area_cdf = nullptr;
     float2 *d_uvs = nullptr;
     float4 *d_tex = nullptr, *d_texels = nullptr;
+    float *d_env_dist = nullptr; // Distribution2D of an environment texture
     uint32_t n_node_f4 = 0, n_trav_f4 = 0, n_ref_f4 = 0;
     size_t smem_bytes = 0;
     bool smem_ok = false;
@@ -339,7 +340,7 @@ void rl_scene_destroy(rl_ctx *ctx, rl_scene *s) {
     if (ctx) cudaSetDevice(ctx->device);
     cudaFree(s->d_trav), cudaFree(s->d_nodes), cudaFree(s->d_shade), cudaFree(s->d_verts), cudaFree(s->d_mats);
     cudaFree(s->d_emit_info), cudaFree(s->d_emit_cdf), cudaFree(s->d_area_cdf), cudaFree(s->d_flat);
-    cudaFree(s->d_uvs), cudaFree(s->d_tex), cudaFree(s->d_texels);
+    cudaFree(s->d_uvs), cudaFree(s->d_tex), cudaFree(s->d_texels), cudaFree(s->d_env_dist);
     cudaFree(s->d_quad_verts), cudaFree(s->d_cam_masks);
     cudaFree(s->d_ref_nodes), cudaFree(s->d_ref_prims), cudaFree(s->d_ref_up);
     delete s;
@@ -390,6 +391,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     if (!hs.uvs.empty()) CKS(upload(&s->d_uvs, hs.uvs, st));
     if (!hs.tex.empty()) CKS(upload(&s->d_tex, hs.tex, st));
     if (!hs.texels.empty()) CKS(upload(&s->d_texels, hs.texels, st));
+    if (!hs.env_dist.empty()) CKS(upload(&s->d_env_dist, hs.env_dist, st));
     const uint32_t n_nodes = n > 1 ? n - 1 : 1;
     CKS(cudaMalloc(&s->d_trav, (size_t)n * RL_TRAV_F4 * sizeof(float4)));
     CKS(cudaMalloc(&d_keys, (size_t)n * 8));
@@ -568,6 +570,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     sv.abs_max = hs.abs_max;
     sv.env_on = hs.env_on ? 1u : 0u, sv.env_color = Col{hs.env_color[0], hs.env_color[1], hs.env_color[2]};
     sv.bs_center = V3{hs.bs_center[0], hs.bs_center[1], hs.bs_center[2]}, sv.bs_radius = hs.bs_radius, sv.env_pdf_sel = hs.env_pdf_sel;
+    sv.env_w = hs.env_w, sv.env_h = hs.env_h, sv.env_texel_off = hs.env_texel_off, sv.env_dist = s->d_env_dist, sv.env_func_int = hs.env_func_int;
     std::memcpy(sv.s2c, hs.s2c, 64);
     std::memcpy(sv.c2w, hs.c2w, 64);
     sv.cam_pos = V3{hs.cam_pos[0], hs.cam_pos[1], hs.cam_pos[2]};

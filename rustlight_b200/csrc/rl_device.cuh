@@ -152,6 +152,63 @@ RL_HD void spec_sincos(float x, float *s, float *c) {
     *s = rs;
     *c = rc;
 }
+// atan2 and acos in f32 (EnvironmentLightColor::Texture: to_spherical_coordinates, emitter.rs:320-338): the Cephes atanf / asinf
+// kernels, every step one fmaf / mul / div / sqrt, identical on the device, in the emulator and in the oracle.  ~2 ulp.
+RL_HD float spec_atanf_pos(float x) { // x >= 0
+    float y0, z;
+    if (x > 2.414213562373095f) {
+        y0 = 1.5707963267948966f;
+        z = -(1.0f / x);
+    } else if (x > 0.4142135623730950f) {
+        y0 = 0.7853981633974483f;
+        z = (x - 1.0f) / (x + 1.0f);
+    } else {
+        y0 = 0.0f;
+        z = x;
+    }
+    const float z2 = z * z;
+    float p = 8.05374449538e-2f;
+    p = fmaf(p, z2, -1.38776856032e-1f);
+    p = fmaf(p, z2, 1.99777106478e-1f);
+    p = fmaf(p, z2, -3.33329491539e-1f);
+    return y0 + fmaf(p * z2, z, z);
+}
+RL_HD float spec_atan2f(float y, float x) { // result in (-pi, pi]; (0, 0) -> 0
+    if (x != x || y != y) return x + y;
+    if (x == 0.0f) return y > 0.0f ? 1.5707963267948966f : (y < 0.0f ? -1.5707963267948966f : 0.0f);
+    const float q = y / x;
+    const float a = spec_atanf_pos(fabsf(q));
+    const float at = q < 0.0f ? -a : a;
+    if (x > 0.0f) return at;
+    return (f2u(y) >> 31) ? at - 3.14159265358979323846f : at + 3.14159265358979323846f; // sign bit: atan2(-0, x < 0) = -pi
+}
+RL_HD float spec_asinf_pos(float a) { // 0 <= a <= 1
+    if (a < 1e-4f) return a;
+    const bool big = a > 0.5f;
+    float z, x;
+    if (big) {
+        z = 0.5f * (1.0f - a);
+        x = sqrtf(z);
+    } else {
+        x = a;
+        z = x * x;
+    }
+    float p = 4.2163199048e-2f;
+    p = fmaf(p, z, 2.4181311049e-2f);
+    p = fmaf(p, z, 4.5470025998e-2f);
+    p = fmaf(p, z, 7.4953002686e-2f);
+    p = fmaf(p, z, 1.6666752422e-1f);
+    float r = fmaf(p * z, x, x);
+    if (big) r = 1.5707963267948966f - (r + r);
+    return r;
+}
+RL_HD float spec_acosf(float x) { // |x| <= 1 (callers clamp); NaN in, NaN out
+    if (x != x) return x;
+    if (x < -0.5f) return 3.14159265358979323846f - 2.0f * spec_asinf_pos(sqrtf(0.5f * (1.0f + x)));
+    if (x > 0.5f) return 2.0f * spec_asinf_pos(sqrtf(0.5f * (1.0f - x)));
+    const float a = spec_asinf_pos(fabsf(x));
+    return 1.5707963267948966f - (x < 0.0f ? -a : a);
+}
 RL_HD double spec_log2(double x) {
     uint64_t bits = d2u(x);
     int e = (int)((bits >> 52) & 0x7ff) - 1023;
@@ -345,6 +402,11 @@ struct SceneView {
     V3 bs_center;      // Scene.bsphere (scene.rs:54-60) ...
     float bs_radius;   // ... radius x 1.1 (EnvironmentLight::preprocess)
     float env_pdf_sel; // probability of picking the environment in sample_light
+    // EnvironmentLightColor::Texture (emitter.rs:300-427): env_w == 0 when the environment is constant.  env_dist = the Distribution2D
+    // (math.rs:489-532) as one float array: marginal cdf [env_h + 1], conditional cdfs [env_h][env_w + 1], conditional funcs [env_h][env_w]
+    uint32_t env_w, env_h, env_texel_off; // image size and its offset in texels[]
+    const float *env_dist;
+    float env_func_int; // marginal.func_int
     // camera
     float s2c[16], c2w[16];
     V3 cam_pos;
@@ -1894,6 +1956,67 @@ RL_HD V3 sample_uniform_sphere(float ux, float uy) { // math.rs:67-72
     return V3{r * cp, r * sp, z};
 }
 #define RL_ENV_PDF (1.0f / (RL_PI * 4.0f)) // EnvironmentLightColor::Constant pdf (emitter.rs:406, 369-373)
+// ---- EnvironmentLightColor::Texture (emitter.rs:300-427) over sv.env_dist / sv.texels ---------------------------------
+RL_HD float clamp_ref(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); } // lib.rs:59-67 (NaN passes through)
+#define RL_ONE_MINUS_EPSILON 0.9999999403953552f // lib.rs:52
+RL_HD void to_spherical_coordinates(V3 d, float *u, float *v) { // emitter.rs:320-338
+    float p = spec_atan2f(d.y, d.x);
+    if (p < 0.0f) p = p + 2.0f * RL_PI;
+    const float ux = p * RL_FRAC_1_PI * 0.5f;
+    const float uy = spec_acosf(clamp_ref(d.z, -1.0f, 1.0f)) * RL_FRAC_1_PI;
+    *u = clamp_ref(ux, 0.0f, RL_ONE_MINUS_EPSILON);
+    *v = clamp_ref(uy, 0.0f, RL_ONE_MINUS_EPSILON);
+}
+RL_HD const float *env_cond_cdf(const SceneView &sv, uint64_t y) { return sv.env_dist + (sv.env_h + 1u) + y * (uint64_t)(sv.env_w + 1u); }
+RL_HD float env_cdf_pdf(const SceneView &sv, uint64_t x, uint64_t y) { // Distribution2D::pdf, math.rs:529-531
+    const float *func = sv.env_dist + (sv.env_h + 1u) + (uint64_t)sv.env_h * (sv.env_w + 1u);
+    return func[y * sv.env_w + x] / sv.env_func_int;
+}
+RL_HD float dist1d_sample_continuous(const float *cdf, uint32_t n_plus_1, float v) { // math.rs:459-478
+    const uint32_t i = cdf_sample_discrete(cdf, n_plus_1, v);
+    float dv = v - cdf[i];
+    const float pdf = cdf[i + 1] - cdf[i];
+    if (pdf > 0.0f) dv = dv / pdf;
+    return (float)i + dv;
+}
+RL_HD Col env_eval(const SceneView &sv, V3 d) { // EnvironmentLightColor::eval -> Bitmap::pixel_uv (structure.rs:434-453)
+    float ux, uy;
+    to_spherical_coordinates(d, &ux, &uy);
+    ux = modulo1(ux), uy = modulo1(uy);
+    const uint64_t x = f32_as_usize(ux * (float)sv.env_w), y = f32_as_usize(uy * (float)sv.env_h);
+    const uint64_t i = (uint64_t)sv.env_w * y + x;
+    if (i >= (uint64_t)sv.env_w * sv.env_h) return Col{0.0f, 0.0f, 0.0f};
+    return xyz_col(sv.texels[sv.env_texel_off + i]);
+}
+RL_HD float env_pdf(const SceneView &sv, V3 d) { // EnvironmentLightColor::pdf, emitter.rs:403-425
+    float ux, uy;
+    to_spherical_coordinates(d, &ux, &uy);
+    const float pdf = env_cdf_pdf(sv, f32_as_usize(ux * (float)sv.env_w), f32_as_usize(uy * (float)sv.env_h));
+    float st, ct;
+    spec_sincos(RL_PI * uy, &st, &ct);
+    if (st == 0.0f) return 0.0f;
+    return pdf / (2.0f * (RL_PI * RL_PI) * st);
+}
+RL_HD void env_sample_direction(const SceneView &sv, float sx, float sy, V3 *d, Col *color, float *pdf) { // emitter.rs:354-391
+    float y = dist1d_sample_continuous(sv.env_dist, sv.env_h + 1u, sy); // Distribution2D::sample_continuous, math.rs:523-527
+    float x = dist1d_sample_continuous(env_cond_cdf(sv, f32_as_usize(y)), sv.env_w + 1u, sx);
+    x = clamp_ref(x, 0.0f, (float)sv.env_w - 1.0f);
+    y = clamp_ref(y, 0.0f, (float)sv.env_h - 1.0f);
+    const uint64_t xi = f32_as_usize(x), yi = f32_as_usize(y);
+    const Col value = xyz_col(sv.texels[sv.env_texel_off + yi * sv.env_w + xi]);
+    const float p = env_cdf_pdf(sv, xi, yi);
+    float sp, cp, st, ct;
+    spec_sincos((2.0f * RL_PI / (float)sv.env_w) * x, &sp, &cp);
+    spec_sincos((RL_PI / (float)sv.env_h) * y, &st, &ct);
+    *d = V3{st * cp, st * sp, ct};
+    if (st == 0.0f) {
+        *color = Col{0.0f, 0.0f, 0.0f};
+        *pdf = 0.0f;
+    } else {
+        *color = value;
+        *pdf = p / (2.0f * (RL_PI * RL_PI) * st);
+    }
+}
 struct LightSample {
     V3 p, n, d;
     Col weight;
@@ -1904,6 +2027,7 @@ struct LightSample {
 };
 // EmitterSampler::sample_light -> Mesh::direct_sample -> Mesh::sample -> sample_tri
 // (emitter.rs:1604-1620, 652-688; geometry.rs:340-348, 261-337; math.rs:388-394)
+template <bool ENVTEX = true>
 RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, float ux, float uy) {
     // one emitter: the cdf is {0, 1} and r_sel < 1, so the search returns 0
     uint32_t id_light = sv.n_emitters == 1u ? 0u : cdf_sample_discrete(sv.emit_cdf, sv.n_emitters + 1, r_sel);
@@ -1916,7 +2040,11 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, 
         Col weight;
         ls.env = false;
         if ((f2u(info.x) & 0xfu) == 2u) { // EnvironmentLight::direct_sample, emitter.rs:474-511
-            V3 dd = sample_uniform_sphere(ux, uy);
+            V3 dd;
+            Col color = intensity;
+            float pdf_dir = RL_ENV_PDF;
+            if (ENVTEX && sv.env_w) env_sample_direction(sv, ux, uy, &dd, &color, &pdf_dir); // luminance.sample_direction(uv), texture arm
+            else dd = sample_uniform_sphere(ux, uy);
             float t;
             ls.d = dd;
             ls.discrete = false;
@@ -1928,10 +2056,10 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, 
             } else {
                 ls.p = x + dd * t;
                 ls.n = normalize(xyz(geo) - ls.p);
-                weight = div_checked(intensity, RL_ENV_PDF);
+                weight = div_checked(color, pdf_dir);
             }
             ls.weight = Col{weight.r / pdf_sel, weight.g / pdf_sel, weight.b / pdf_sel};
-            ls.pdf = RL_ENV_PDF * pdf_sel;
+            ls.pdf = pdf_dir * pdf_sel;
             ls.valid = ls.pdf != 0.0f;
             return ls;
         }
@@ -2093,17 +2221,19 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
         // same gates and MIS as an emitter hit (path.rs:37-111, 152-165); the light strategy's pdf is pdf_emitter's
         // environment arm (emitters.rs:18-46): constant 1 / 4 pi times the selection probability.
         if (!sv.env_on) return;
+        const bool envtex = RL_HAS(KM, 8) && sv.env_w != 0u; // scene.enviroment_luminance(d) = env.eval(d): constant, or the texel d points at
+        const Col env_l = envtex ? env_eval(sv, d) : sv.env_color;
         if (st.depth == 1u) {
-            if (ip_add_ok(ip, 0u) && !is_zero(sv.env_color)) {
-                out->add = sv.env_color;
+            if (ip_add_ok(ip, 0u) && !is_zero(env_l)) {
+                out->add = env_l;
                 out->has_add = true;
             }
         } else if (ip.single_scattering == 0u && ip_add_ok(ip, st.depth - 1u) && ip.strategy != 2u) {
-            Col contrib = st.T * sv.env_color;
+            Col contrib = st.T * env_l;
             if (!is_zero(contrib)) {
                 float w = 1.0f;
                 if (ip.strategy == 0u && !(f2u(st.pdf_prev) >> 31)) {
-                    float pl = RL_ENV_PDF * sv.env_pdf_sel;
+                    float pl = (envtex ? env_pdf(sv, d) : RL_ENV_PDF) * sv.env_pdf_sel;
                     w = st.pdf_prev / (st.pdf_prev + pl);
                 }
                 out->add = mul_checked(contrib, w);
@@ -2188,7 +2318,7 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
         float ux = smp.next();
         float uy = smp.next();
         out->nee_sampled = true;
-        LightSample ls = sample_light(sv, its.p, r_sel, r, ux, uy);
+        LightSample ls = sample_light<RL_HAS(KM, 8) != 0u>(sv, its.p, r_sel, r, ux, uy);
         if (ls.valid && !mute && ip_add_ok(ip, st.depth) && ip.strategy != 1u) {
             V3 wo = to_local(its.frame, ls.d);
             Col f;
@@ -2236,7 +2366,7 @@ RL_HD void direct_begin(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, 
     cx->emit = Col{0.0f, 0.0f, 0.0f};
     cx->env_primary = false;
     if (hit.prim == RL_MISS) { // return scene.enviroment_luminance(ray.d) (direct.rs:33-36)
-        if (sv.env_on) cx->emit = sv.env_color, cx->env_primary = true;
+        if (sv.env_on) cx->emit = sv.env_w ? env_eval(sv, d) : sv.env_color, cx->env_primary = true;
         return;
     }
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
@@ -2319,8 +2449,8 @@ RL_HD bool direct_finish(const SceneView &sv, const IntegParams &ip, V3 o, V3 d,
         float wb = ip.nb_bsdf_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_bsdf_samples;
         float wl = ip.nb_light_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_light_samples;
         float weight_bsdf = 1.0f;
-        if (!(f2u(bsdf_pdf_v) >> 31)) weight_bsdf = mis_weight_power(bsdf_pdf_v * wb, (RL_ENV_PDF * sv.env_pdf_sel) * wl);
-        *contrib = mul_checked(mul_plain(weight_bsdf, bsdf_weight) * sv.env_color, wb);
+        if (!(f2u(bsdf_pdf_v) >> 31)) weight_bsdf = mis_weight_power(bsdf_pdf_v * wb, ((sv.env_w ? env_pdf(sv, d) : RL_ENV_PDF) * sv.env_pdf_sel) * wl);
+        *contrib = mul_checked(mul_plain(weight_bsdf, bsdf_weight) * (sv.env_w ? env_eval(sv, d) : sv.env_color), wb);
         return true;
     }
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];

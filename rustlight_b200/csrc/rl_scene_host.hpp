@@ -34,6 +34,10 @@ struct HostScene {
     // EnvironmentLight (constant): colour, bounding sphere (radius already x 1.1), emitter-selection pdf
     bool env_on = false;
     float env_color[3] = {0, 0, 0}, bs_center[3] = {0, 0, 0}, bs_radius = 0.0f, env_pdf_sel = 0.0f;
+    // EnvironmentLightColor::Texture: the image (in texels[] at env_texel_off) and its Distribution2D (rl_device.cuh: SceneView::env_dist)
+    uint32_t env_w = 0, env_h = 0, env_texel_off = 0;
+    std::vector<float> env_dist;
+    float env_func_int = 0.0f;
     uint32_t img_w = 0, img_h = 0;
 };
 
@@ -105,8 +109,9 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
         err = "scene.volume must be None on this path";
         return false;
     }
-    if (desc->has_environment > 1) {
-        err = "environment textures are outside the hot path";
+    if (desc->has_environment > 2 || (desc->has_environment == 2 && (desc->environment_texture == 0 || desc->environment_texture > desc->ntextures ||
+                                                                         !desc->textures || desc->textures[desc->environment_texture - 1].kind != RL_TEX_BITMAP))) {
+        err = "has_environment == 2 needs environment_texture = 1 + index of a bitmap texture";
         return false;
     }
     if (desc->camera.width == 0 || desc->camera.height == 0) {
@@ -258,12 +263,35 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
             EmitterTmp e{};
             e.light_kind = 2u;
             e.radius = radius * 1.1f; // EnvironmentLight::preprocess, emitter.rs:436-439
-            for (int a = 0; a < 3; a++) e.intensity[a] = desc->environment[a];
+            for (int a = 0; a < 3; a++) e.intensity[a] = desc->has_environment == 2 ? 0.0f : desc->environment[a];
             e.v[0] = c.x, e.v[1] = c.y, e.v[2] = c.z;
             e.flux_max = channel_max(mul_plain(RL_PI * (e.radius * e.radius), Col{e.intensity[0], e.intensity[1], e.intensity[2]}));
+            if (desc->has_environment == 2) { // EnvironmentLightColor::new_texture (emitter.rs:341-353) + Distribution2D::from_bitmap (math.rs:495-521)
+                const uint32_t ti = desc->environment_texture - 1;
+                const uint32_t W = f2u(hs.tex[4 * ti + 3].x), H = f2u(hs.tex[4 * ti + 3].y), off = f2u(hs.tex[4 * ti + 3].z);
+                hs.env_w = W, hs.env_h = H, hs.env_texel_off = off;
+                std::vector<float> marginal_elems, cond_cdfs, cond_funcs, row(W), cdf;
+                for (uint32_t y = 0; y < H; y++) {
+                    float sw, cw; // w = ((y + 0.5) * PI / size.y).sin(): the spec sine, like every sine of the device
+                    spec_sincos(((float)y + 0.5f) * RL_PI / (float)H, &sw, &cw);
+                    for (uint32_t x = 0; x < W; x++) {
+                        const float4 px = hs.texels[off + (size_t)y * W + x];
+                        const float r = px.x * sw, g = px.y * sw, b = px.z * sw;            // image_pdf pixel *= w (MulAssign<f32>, structure.rs:225-231)
+                        row[x] = r * 0.212671f + g * 0.715160f + b * 0.072169f;              // Color::luminance, structure.rs:173-176
+                    }
+                    marginal_elems.push_back(dist1d_normalize(row, cdf));
+                    cond_cdfs.insert(cond_cdfs.end(), cdf.begin(), cdf.end());
+                    cond_funcs.insert(cond_funcs.end(), row.begin(), row.end());
+                }
+                hs.env_func_int = dist1d_normalize(marginal_elems, cdf);
+                hs.env_dist = cdf;
+                hs.env_dist.insert(hs.env_dist.end(), cond_cdfs.begin(), cond_cdfs.end());
+                hs.env_dist.insert(hs.env_dist.end(), cond_funcs.begin(), cond_funcs.end());
+                e.flux_max = RL_PI * (e.radius * e.radius) * hs.env_func_int; // Color::value(PI r^2 func_int), emitter.rs:517-523
+            }
             emitters.push_back(e);
             hs.env_on = true;
-            for (int a = 0; a < 3; a++) hs.env_color[a] = desc->environment[a];
+            for (int a = 0; a < 3; a++) hs.env_color[a] = e.intensity[a];
             hs.bs_center[0] = c.x, hs.bs_center[1] = c.y, hs.bs_center[2] = c.z;
             hs.bs_radius = e.radius;
         }

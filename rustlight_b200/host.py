@@ -46,6 +46,7 @@ def lib():
         L.rlh_scene_add_texture_file.restype = C.c_uint32
         L.rlh_scene_add_texture_file.argtypes = [C.c_void_p, C.c_char_p]
         L.rlh_scene_set_environment.argtypes = [C.c_void_p, C.c_float * 3]
+        L.rlh_scene_set_environment_texture.argtypes = [C.c_void_p, C.c_uint32]
         L.rlh_scene_add_light.argtypes = [C.c_void_p, C.c_uint32, C.c_float * 3, C.c_float * 3]
         L.rlh_scene_set_material.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_abi.rl_material)]
         L.rlh_scene_set_material_blend.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_abi.rl_material), C.POINTER(_abi.rl_material), C.c_float]
@@ -146,6 +147,13 @@ class Scene:
     def set_environment(self, rgb):
         """Constant EnvironmentLight (emitter.rs:428-568, pbrt LightSource "infinite" "rgb L")."""
         lib().rlh_scene_set_environment(self._h, (C.c_float * 3)(*rgb))
+        return self
+
+    def set_environment_texture(self, tex_id):
+        """EnvironmentLightColor::new_texture(image) (emitter.rs:341-353; pbrt LightSource "infinite" "string mapname"): a lat-long
+        bitmap texture id from add_bitmap_texture."""
+        if lib().rlh_scene_set_environment_texture(self._h, int(tex_id)) != 0:
+            raise SceneError("environment texture: not a bitmap texture id")
         return self
 
     def add_point_light(self, intensity, position):

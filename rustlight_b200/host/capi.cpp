@@ -117,6 +117,15 @@ int rlh_scene_add_light(rlh_scene *s, uint32_t kind, const float intensity[3], c
 
 // Scene.emitter_environment = EnvironmentLight with a constant colour
 void rlh_scene_set_environment(rlh_scene *s, const float rgb[3]) { s->scene.set_environment(Color{rgb[0], rgb[1], rgb[2]}); }
+// EnvironmentLightColor::new_texture(image): `tex_id` = a bitmap texture id from rlh_scene_add_texture / rlh_scene_add_texture_file
+int rlh_scene_set_environment_texture(rlh_scene *s, uint32_t tex_id) {
+    try {
+        s->scene.set_environment_texture(tex_id);
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
 
 // BSDFColor::{Bitmap, Checkerbord, Grid}: returns the 1-based id for rl_material.kd_texture, 0 on error.
 // kind: rl_texture_kind; bitmap: (w, h, rgb[3*w*h]); checkerboard / grid: params = {color0[3], color1[3], offset[2], scale[2], line_width}

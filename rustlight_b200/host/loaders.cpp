@@ -633,11 +633,18 @@ Scene PBRTSceneLoader::load_string(const std::string &text_in, bool use_shading_
                 Color L = p.rgb("L", Color{1.0f, 1.0f, 1.0f});
                 Vec3 from = pt("from", 0, 0, 0), to = pt("to", 0, 0, 1);
                 scene.add_directional_light(Color{L.r * scale.r, L.g * scale.g, L.b * scale.b}, to.x - from.x, to.y - from.y, to.z - from.z);
-            } else if (type == "infinite") { // scene_loader.rs:241-276: a constant RGB L (x scale); map names are textures: not here
-                if (p.find("mapname")) throw Error("pbrt: LightSource \"infinite\" with a mapname (environment texture) is outside the hot-path scope");
+            } else if (type == "infinite") { // scene_loader.rs:239-276: a constant RGB L (x scale), or a lat-long image ("mapname")
                 if (scene.has_environment) throw Error("Multiple env map is NOT supported"); // scene_loader.rs:247-249
-                Color L = p.rgb("L", Color{1.0f, 1.0f, 1.0f});
-                scene.set_environment(Color{L.r * scale.r, L.g * scale.g, L.b * scale.b});
+                if (p.find("mapname")) { // Spectrum::Mapname: EnvironmentLightColor::new_texture(Bitmap::read(file)); the reference asserts scale == 1
+                    if (scale.r != 1.0f || scale.g != 1.0f || scale.b != 1.0f) throw Error("pbrt: LightSource \"infinite\" with a mapname needs scale 1 (scene_loader.rs:260-262)");
+                    std::string fn = p.str("mapname");
+                    if (fn.empty()) throw Error("pbrt: empty mapname");
+                    if (fn[0] != '/' && !base_dir.empty()) fn = base_dir + "/" + fn;
+                    scene.set_environment_texture(scene.add_texture(Texture::bitmap_file(fn)));
+                } else {
+                    Color L = p.rgb("L", Color{1.0f, 1.0f, 1.0f});
+                    scene.set_environment(Color{L.r * scale.r, L.g * scale.g, L.b * scale.b});
+                }
             } else throw Error("pbrt: LightSource \"" + type + "\" is outside the hot-path scope (point, distant, infinite)");
         } else if (d == "Texture") { // pbrt_rs::Texture {filename}: only image maps reach the BSDFs (bsdfs/mod.rs:219-241)
             std::string name = ps.expect_str(), ttype = ps.expect_str(), tclass = ps.expect_str();
@@ -894,9 +901,15 @@ Scene JSONSceneLoader::load_string(const std::string &text, bool use_shading_nor
         if (ms->t != JVal::Obj) throw Error("json: materials must be an object");
         for (auto &kv : ms->o) materials[kv.first] = with_texture(kv.second, jmaterial(kv.second));
     }
-    if (const JVal *env = root.get("environment")) { // "environment": [r, g, b]: constant EnvironmentLight
-        Color c = jcolor(env, "environment", Color{0.0f, 0.0f, 0.0f});
-        scene.set_environment(c);
+    if (const JVal *env = root.get("environment")) { // "environment": [r, g, b]: constant EnvironmentLight; {"texture": name}: a lat-long bitmap of "textures"
+        if (env->t == JVal::Obj) {
+            const JVal *tn = env->get("texture");
+            if (!tn || tn->t != JVal::Str || !texture_ids.count(tn->s)) throw Error("json: environment.texture must name a bitmap texture");
+            scene.set_environment_texture(texture_ids[tn->s]);
+        } else {
+            Color c = jcolor(env, "environment", Color{0.0f, 0.0f, 0.0f});
+            scene.set_environment(c);
+        }
     }
     if (const JVal *ls = root.get("lights")) { // [{"type": "point", "intensity": [r,g,b], "position": [x,y,z]}, {"type": "directional", "intensity", "direction"}]
         if (ls->t != JVal::Arr) throw Error("json: lights must be an array");
@@ -978,7 +991,8 @@ std::string scene_to_json(const Scene &scene) {
       << (c.flip ? "true" : "false") << ",\n             \"to_world\": ";
     put_floats(o, c.to_world.m, 16);
     o << "},\n";
-    if (scene.has_environment) {
+    if (scene.has_environment && scene.environment_texture) o << "  \"environment\": {\"texture\": \"tex" << scene.environment_texture << "\"},\n";
+    else if (scene.has_environment) {
         float e[3] = {scene.environment.r, scene.environment.g, scene.environment.b};
         o << "  \"environment\": ";
         put_floats(o, e, 3);

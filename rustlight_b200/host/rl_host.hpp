@@ -118,7 +118,9 @@ struct Scene {
     std::string output_img_path = "out.pfm";
     bool has_volume = false, has_environment = false;
     Color environment; // EnvironmentLight{EnvironmentLightColor::Constant(environment)} when has_environment (scene_loader.rs:241-258)
-    void set_environment(Color c) { has_environment = true, environment = c; }
+    void set_environment(Color c) { has_environment = true, environment = c, environment_texture = 0; }
+    uint32_t environment_texture = 0; // EnvironmentLightColor::Texture: 1-based id of a bitmap texture (add_texture), 0 = constant
+    void set_environment_texture(uint32_t id); // EnvironmentLightColor::new_texture(image) (scene_loader.rs:259-270)
     // Scene.emitters before build_emitters (EmittersState::Unbuild): PointEmitter / DirectionalLight (scene_loader.rs:207-240)
     std::vector<rl_light_desc> lights;
     std::vector<Texture> textures; // referenced by Material.m.kd_texture (1-based)

@@ -336,6 +336,10 @@ void Scene::add_directional_light(Color intensity, float dx, float dy, float dz)
     l.v[0] = dx * inv, l.v[1] = dy * inv, l.v[2] = dz * inv;
     lights.push_back(l);
 }
+void Scene::set_environment_texture(uint32_t id) {
+    if (id == 0 || id > textures.size() || textures[id - 1].t.kind != RL_TEX_BITMAP) throw Error("environment texture: not a bitmap texture id");
+    has_environment = true, environment = Color{0.0f, 0.0f, 0.0f}, environment_texture = id;
+}
 const rl_scene_desc *Scene::desc() {
     mesh_descs_.clear();
     submaterial_descs_.clear();
@@ -365,7 +369,8 @@ const rl_scene_desc *Scene::desc() {
     std::memcpy(desc_.camera.sample_to_camera, camera.sample_to_camera.m, sizeof(float) * 16);
     std::memcpy(desc_.camera.to_world, camera.to_world.m, sizeof(float) * 16);
     desc_.has_volume = has_volume ? 1u : 0u;
-    desc_.has_environment = has_environment ? 1u : 0u;
+    desc_.has_environment = has_environment ? (environment_texture ? 2u : 1u) : 0u;
+    desc_.environment_texture = environment_texture;
     desc_.environment[0] = environment.r, desc_.environment[1] = environment.g, desc_.environment[2] = environment.b;
     texture_descs_.clear();
     for (auto &t : textures) {

@@ -46,7 +46,7 @@ pub struct rl_mesh_desc {
 #[repr(C)] pub struct rl_scene_desc {
     pub nmeshes: u32, pub meshes: *const rl_mesh_desc, pub camera: rl_camera_desc, pub has_volume: u32, pub has_environment: u32,
     pub nlights: u32, pub lights: *const rl_light_desc, pub ntextures: u32, pub textures: *const rl_texture, pub environment: [f32; 3],
-    pub nsubmaterials: u32, pub submaterials: *const rl_material,
+    pub nsubmaterials: u32, pub submaterials: *const rl_material, pub environment_texture: u32,
 }
 #[repr(C)] pub struct rl_integrator_desc {
     pub kind: u32, pub min_depth: i32, pub max_depth: i32, pub rr_depth: i32, pub strategy: u32,
@@ -134,7 +134,7 @@ impl Flat {
 }
 
 /// Scene -> flat description (scene.rs:16-30, geometry.rs:107-119).  Panics where the reference offers something outside
-/// the GPU path (media, textured emission, environment maps, BSDFs without `describe`), like the reference panics on
+/// the GPU path (media, textured emission, BSDFs without `describe`), like the reference panics on
 /// unsupported input (scene_loader.rs:40-43).
 fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
     assert!(scene.volume.is_none(), "scene.volume must be None on the GPU path");
@@ -167,10 +167,16 @@ fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
             f.lights.push(e.describe().expect("this emitter has no GPU description (PointNormalEmitter?)"));
         }
     }
-    let (has_env, env) = match scene.emitter_environment.as_ref().map(|e| &e.luminance) {
-        None => (0, [0.0; 3]),
-        Some(crate::emitter::EnvironmentLightColor::Constant(c)) => (1, col(c)),
-        Some(_) => panic!("environment textures are outside the GPU path"),
+    let (has_env, env, env_tex) = match scene.emitter_environment.as_ref().map(|e| &e.luminance) {
+        None => (0, [0.0; 3], 0),
+        Some(crate::emitter::EnvironmentLightColor::Constant(c)) => (1, col(c), 0),
+        // the library rebuilds the Distribution2D from the image (EnvironmentLightColor::new_texture, emitter.rs:341-353)
+        Some(crate::emitter::EnvironmentLightColor::Texture { image, .. }) => {
+            f.texels.push(image.colors.iter().flat_map(|c| [c.r, c.g, c.b]).collect());
+            f.textures.push(rl_texture { kind: 1, width: image.size.x, height: image.size.y, pixels: f.texels.last().unwrap().as_ptr(), color0: [0.0; 3],
+                                         color1: [0.0; 3], line_width: 0.0, offset: [0.0; 2], scale: [1.0; 2] });
+            (2, [0.0; 3], f.textures.len() as u32)
+        }
     };
     let cam = &scene.camera;
     let desc = rl_scene_desc {
@@ -178,7 +184,7 @@ fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
         camera: rl_camera_desc { width: cam.size().x, height: cam.size().y, sample_to_camera: mat16(cam.sample_to_camera()), to_world: mat16(cam.to_world()) },
         has_volume: 0, has_environment: has_env, nlights: f.lights.len() as u32, lights: f.lights.as_ptr(),
         ntextures: f.textures.len() as u32, textures: f.textures.as_ptr(), environment: env,
-        nsubmaterials: f.submaterials.len() as u32, submaterials: f.submaterials.as_ptr(),
+        nsubmaterials: f.submaterials.len() as u32, submaterials: f.submaterials.as_ptr(), environment_texture: env_tex,
     };
     (f, desc)
 }

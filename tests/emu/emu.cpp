@@ -148,6 +148,7 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
     sv.abs_max = hs.abs_max;
     sv.env_on = hs.env_on ? 1u : 0u, sv.env_color = Col{hs.env_color[0], hs.env_color[1], hs.env_color[2]};
     sv.bs_center = V3{hs.bs_center[0], hs.bs_center[1], hs.bs_center[2]}, sv.bs_radius = hs.bs_radius, sv.env_pdf_sel = hs.env_pdf_sel;
+    sv.env_w = hs.env_w, sv.env_h = hs.env_h, sv.env_texel_off = hs.env_texel_off, sv.env_dist = hs.env_dist.data(), sv.env_func_int = hs.env_func_int;
     std::memcpy(sv.s2c, hs.s2c, 64);
     std::memcpy(sv.c2w, hs.c2w, 64);
     sv.cam_pos = V3{hs.cam_pos[0], hs.cam_pos[1], hs.cam_pos[2]};
@@ -310,6 +311,25 @@ void emu_bsdf_eval(const rl_material *mt, const float wi[3], const float wo[3], 
     emu_material_rows(mt, rows);
     Col c = bsdf_eval(load_material(rows, 0), V3{wi[0], wi[1], wi[2]}, V3{wo[0], wo[1], wo[2]});
     out[0] = c.r, out[1] = c.g, out[2] = c.b;
+}
+// EnvironmentLightColor::Texture on the device side (rl_device.cuh: env_*)
+float emu_spec_atan2(float y, float x) { return spec_atan2f(y, x); }
+float emu_spec_acos(float x) { return spec_acosf(x); }
+int emu_env_eval_pdf(const emu_scene *s, const float d[3], float rgb[3], float *pdf) {
+    if (!s->sv.env_w) return -1;
+    Col c = env_eval(s->sv, V3{d[0], d[1], d[2]});
+    rgb[0] = c.r, rgb[1] = c.g, rgb[2] = c.b;
+    *pdf = env_pdf(s->sv, V3{d[0], d[1], d[2]});
+    return 0;
+}
+int emu_env_sample(const emu_scene *s, float u0, float u1, float d[3], float rgb[3], float *pdf) {
+    if (!s->sv.env_w) return -1;
+    V3 dd;
+    Col c;
+    env_sample_direction(s->sv, u0, u1, &dd, &c, pdf);
+    d[0] = dd.x, d[1] = dd.y, d[2] = dd.z;
+    rgb[0] = c.r, rgb[1] = c.g, rgb[2] = c.b;
+    return 0;
 }
 int emu_bsdf_flags(const rl_material *mt) {
     float4 rows[EMU_MAT_ROWS];

@@ -44,6 +44,12 @@ def lib():
         L.emu_bsdf_pdf.argtypes = [C.POINTER(_abi.rl_material), FP, FP]
         L.emu_bsdf_eval.argtypes = [C.POINTER(_abi.rl_material), FP, FP, FP]
         L.emu_bsdf_flags.argtypes = [C.POINTER(_abi.rl_material)]
+        L.emu_spec_atan2.restype = C.c_float
+        L.emu_spec_atan2.argtypes = [C.c_float, C.c_float]
+        L.emu_spec_acos.restype = C.c_float
+        L.emu_spec_acos.argtypes = [C.c_float]
+        L.emu_env_eval_pdf.argtypes = [C.c_void_p, FP, FP, FP]
+        L.emu_env_sample.argtypes = [C.c_void_p, C.c_float, C.c_float, FP, FP, FP]
         _lib = L
     return _lib
 
@@ -113,6 +119,18 @@ class EmuScene:
 
     def bvh_validate(self):
         return lib().emu_bvh_validate(self._h)
+
+    def env_eval_pdf(self, d):
+        rgb, pdf = np.zeros(3, np.float32), C.c_float()
+        if lib().emu_env_eval_pdf(self._h, _f(np.ascontiguousarray(d, np.float32)), _f(rgb), C.byref(pdf)) != 0:
+            raise ValueError("no environment texture")
+        return rgb, pdf.value
+
+    def env_sample(self, u0, u1):
+        d, rgb, pdf = np.zeros(3, np.float32), np.zeros(3, np.float32), C.c_float()
+        if lib().emu_env_sample(self._h, float(u0), float(u1), _f(d), _f(rgb), C.byref(pdf)) != 0:
+            raise ValueError("no environment texture")
+        return d, rgb, pdf.value
 
     def trace(self, o, d):
         o = np.ascontiguousarray(o, np.float32).reshape(-1, 3)

@@ -382,6 +382,33 @@ def test_mixed_material_scene_bit_exact(gpu_ctx, sort):
     dev.close()
 
 
+@pytest.mark.parametrize("tail", [None, "0"])
+def test_environment_texture_bit_exact(gpu_ctx, tail, monkeypatch):
+    """EnvironmentLightColor::Texture (emitter.rs:300-427): a lat-long HDR image with a sun texel, a black row and a black texel as the
+    environment of an open scene (octahedron over a glossy floor + an area light) and of the Cornell box; `path` with every strategy,
+    `direct`; with the tail kernel and as a pure wavefront."""
+    from test_envmap import env_scene, sky_image
+    if tail is not None:
+        monkeypatch.setenv("RL_TAIL_MAX", tail)
+    sc = env_scene(sky_image(), 96, 96, area_light=True, floor=True)
+    dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
+    for integ in (_abi.path_desc(), _abi.path_desc(strategy=_abi.RL_STRATEGY_BSDF), _abi.path_desc(strategy=_abi.RL_STRATEGY_EMITTER),
+                  _abi.path_desc(max_depth=4, rr_depth=2), _abi.direct_desc(1, 1), _abi.direct_desc(0, 2), _abi.direct_desc(2, 0)):
+        img, st = dev.render(integ, 8, seed=12)
+        ref, so = osc.render(integ, 8, seed=12, cfg=ob.config(**STREAM))
+        assert (st.segments, st.hits, st.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+        assert np.array_equal(img, ref)
+    dev.close()
+    if tail is None:
+        box = load_cbox(64, 64)
+        box.set_environment_texture(box.add_bitmap_texture(sky_image(seed=3)))
+        dev, osc = DeviceScene(gpu_ctx, box), ob.OracleScene(box)
+        img, st = dev.render(_abi.path_desc(), 8, seed=2)
+        ref, so = osc.render(_abi.path_desc(), 8, seed=2, cfg=ob.config(**STREAM))
+        assert st.segments == so.segments and np.array_equal(img, ref)
+        dev.close()
+
+
 @pytest.mark.parametrize("sort", [0, 1])
 def test_blended_materials_bit_exact(gpu_ctx, sort):
     """BSDFBlend (bsdfs/blend.rs) on four meshes of the Cornell box, every rough kind as a part: `path` (all strategies' MIS terms go

@@ -195,7 +195,7 @@ def test_pbrt_light_sources():
     assert de.has_environment == 1 and list(de.environment) == [1, 2, 4]   # scene_loader.rs:241-258: L * scale
     env_back = SceneLoaderManager().load_string(env.to_json(), "json")
     assert env_back.desc.contents.has_environment == 1 and list(env_back.desc.contents.environment) == [1, 2, 4]
-    with pytest.raises(SceneError, match="scope"):
+    with pytest.raises(SceneError, match="pfm"):  # environment textures are read from .pfm / .ppm (test_envmap.py); no EXR reader here
         SceneLoaderManager().load_string('Camera "perspective" WorldBegin LightSource "infinite" "string mapname" "sky.exr" WorldEnd', "pbrt")
     with pytest.raises(SceneError, match="scope"):
         SceneLoaderManager().load_string('Camera "perspective" WorldBegin LightSource "spot" WorldEnd', "pbrt")
