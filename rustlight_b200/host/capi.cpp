@@ -39,6 +39,7 @@ rlh_scene *rlh_load_scene_string(const char *text, const char *fmt, int use_shad
         std::string f(fmt ? fmt : "");
         if (f == "pbrt") s->scene = PBRTSceneLoader().load_string(text, use_shading_normal != 0);
         else if (f == "json") s->scene = JSONSceneLoader().load_string(text, use_shading_normal != 0);
+        else if (f == "xml") s->scene = MTSSceneLoader().load_string(text, use_shading_normal != 0);
         else {
             delete s;
             throw Error("Impossible to found scene loader for " + f + " extension");

@@ -12,6 +12,7 @@
 //
 // JSONSceneLoader reads the new format documented in DESIGN.md ("scene JSON"); the reference
 // has no JSON loader at this commit.
+#include <array>
 #include <cctype>
 #include <cmath>
 #include <cstdio>
@@ -1102,11 +1103,481 @@ std::string scene_to_json(const Scene &scene) {
 }
 
 // ------------------------------------------------------------------------------------------
+// MTSSceneLoader, src/scene_loader.rs:318-795 + bsdf_mts, src/bsdfs/mod.rs:395-612 (Mitsuba 0.x XML subset)
+//
+// The reference parses the file with the mitsuba_rs crate (git dependency, not vendored: its defaults are restated from the
+// Mitsuba 0.5/0.6 documentation and are UNPINNED) and maps the result as follows, which is what this loader reproduces:
+//   sensor "perspective": film width / height, fov + fovAxis x | y, toWorld -> Camera::new(size, fov, mat, flip = true)   (:327-338)
+//   shapes "rectangle" (two triangles, normals, uv; :538-594), "sphere" (32 x 32 lat-long tessellation; :596-665), "ply", "obj";
+//     toWorld applied to points (transform_point) and normals (transform_vector, renormalised) (:341-376); bsdf (inline or <ref>),
+//     default BSDFDiffuse 0.8; <emitter type="area"> radiance -> EmissionType::Color; faceNormals discards normals
+//   bsdfs: twosided (ignored wrapper), diffuse, phong (weight_specular from the average luminances), dielectric -> BSDFGlass.eta(int, ext),
+//     plastic / roughplastic -> BSDFSubstrate, conductor / roughconductor -> BSDFMetal (eta, k divided by extEta), distribution
+//     "beckmann" | "ggx" with an isotropic alpha; anything else -> BSDFDiffuse 0.8                                           (mod.rs:499-612)
+//   colours: <rgb>/<spectrum> constants, <texture type="bitmap" | "checkerboard" | "gridtexture">                           (mod.rs:395-452)
+//   emitters "point" -> PointEmitter (:680-697).  The reference's "PointNormal" emitter cannot be sampled by `path` / `direct`
+//     (PointNormalEmitter::direct_sample is todo!(), emitter.rs:262-264): rejected here instead of panicking at the first light sample.
+//   media -> outside the hot path.  Shapes "serialized" (zlib-compressed binary) are not read.
+// ------------------------------------------------------------------------------------------
+namespace {
+struct XNode {
+    std::string tag;
+    std::map<std::string, std::string> attr;
+    std::vector<XNode> kids;
+    const XNode *child(const std::string &tag_, const std::string &name) const {
+        for (auto &k : kids)
+            if (k.tag == tag_ && k.get("name") == name) return &k;
+        return nullptr;
+    }
+    const XNode *named(const std::string &name) const {
+        for (auto &k : kids)
+            if (k.get("name") == name) return &k;
+        return nullptr;
+    }
+    std::string get(const std::string &k, const std::string &def = "") const {
+        auto it = attr.find(k);
+        return it == attr.end() ? def : it->second;
+    }
+};
+struct XParser {
+    const std::string &t;
+    size_t i = 0;
+    std::map<std::string, std::string> defaults; // <default name= value=> for $name substitution
+    explicit XParser(const std::string &text) : t(text) {}
+    [[noreturn]] void fail(const std::string &m) const { throw Error("xml: " + m + " at offset " + std::to_string(i)); }
+    void skip_misc() {
+        for (;;) {
+            while (i < t.size() && std::isspace((unsigned char)t[i])) i++;
+            if (t.compare(i, 4, "<!--") == 0) {
+                size_t e = t.find("-->", i);
+                if (e == std::string::npos) fail("unterminated comment");
+                i = e + 3;
+            } else if (t.compare(i, 2, "<?") == 0) {
+                size_t e = t.find("?>", i);
+                if (e == std::string::npos) fail("unterminated declaration");
+                i = e + 2;
+            } else break;
+        }
+    }
+    std::string subst(std::string v) const {
+        for (auto &d : defaults) {
+            const std::string key = "$" + d.first;
+            for (size_t p = v.find(key); p != std::string::npos; p = v.find(key, p + d.second.size())) v.replace(p, key.size(), d.second);
+        }
+        return v;
+    }
+    XNode element() {
+        skip_misc();
+        if (i >= t.size() || t[i] != '<') fail("expected an element");
+        i++;
+        XNode n;
+        while (i < t.size() && (std::isalnum((unsigned char)t[i]) || t[i] == '_' || t[i] == ':')) n.tag += t[i++];
+        if (n.tag.empty()) fail("empty tag name");
+        for (;;) {
+            while (i < t.size() && std::isspace((unsigned char)t[i])) i++;
+            if (i >= t.size()) fail("unterminated tag");
+            if (t[i] == '/') {
+                if (t.compare(i, 2, "/>") != 0) fail("bad tag end");
+                i += 2;
+                finish(n);
+                return n;
+            }
+            if (t[i] == '>') {
+                i++;
+                break;
+            }
+            std::string key;
+            while (i < t.size() && t[i] != '=' && !std::isspace((unsigned char)t[i])) key += t[i++];
+            while (i < t.size() && std::isspace((unsigned char)t[i])) i++;
+            if (i >= t.size() || t[i] != '=') fail("attribute without a value");
+            i++;
+            while (i < t.size() && std::isspace((unsigned char)t[i])) i++;
+            const char q = i < t.size() ? t[i] : 0;
+            if (q != '"' && q != '\'') fail("attribute value must be quoted");
+            size_t e = t.find(q, i + 1);
+            if (e == std::string::npos) fail("unterminated attribute value");
+            n.attr[key] = subst(t.substr(i + 1, e - i - 1));
+            i = e + 1;
+        }
+        for (;;) {
+            skip_misc();
+            if (i >= t.size()) fail("unterminated element <" + n.tag + ">");
+            if (t.compare(i, 2, "</") == 0) {
+                size_t e = t.find('>', i);
+                if (e == std::string::npos) fail("unterminated end tag");
+                i = e + 1;
+                finish(n);
+                return n;
+            }
+            if (t[i] != '<') { // text content: not used by the format
+                i++;
+                continue;
+            }
+            n.kids.push_back(element());
+        }
+    }
+    void finish(const XNode &n) {
+        if (n.tag == "default") defaults[n.get("name")] = n.get("value");
+    }
+};
+std::vector<float> xfloats(const std::string &v) {
+    std::vector<float> out;
+    std::string cur;
+    auto flush = [&]() {
+        if (!cur.empty()) out.push_back(std::strtof(cur.c_str(), nullptr)), cur.clear();
+    };
+    for (char c : v) {
+        if (std::isspace((unsigned char)c) || c == ',') flush();
+        else cur += c;
+    }
+    flush();
+    return out;
+}
+float xfloat(const XNode &n, const std::string &name, float def) {
+    const XNode *c = n.child("float", name);
+    if (!c) c = n.child("integer", name);
+    return c ? std::strtof(c->get("value").c_str(), nullptr) : def;
+}
+bool xbool(const XNode &n, const std::string &name, bool def) {
+    const XNode *c = n.child("boolean", name);
+    return c ? c->get("value") == "true" : def;
+}
+std::string xstring(const XNode &n, const std::string &name, const std::string &def) {
+    const XNode *c = n.child("string", name);
+    return c ? c->get("value") : def;
+}
+// Spectrum::as_rgb(): <rgb value="r, g, b"> | <rgb value="v"> | <spectrum value="v"> (a constant; wavelength lists are not converted)
+Color xrgb_value(const XNode &c) {
+    if (c.tag != "rgb" && c.tag != "spectrum" && c.tag != "srgb") throw Error("xml: <" + c.tag + " name=\"" + c.get("name") + "\"> is not a colour");
+    std::vector<float> v = xfloats(c.get("value"));
+    if (c.get("value").find(':') != std::string::npos) throw Error("xml: spectra given as wavelength:value lists are not supported");
+    if (v.size() == 1) return Color{v[0], v[0], v[0]};
+    if (v.size() == 3) return Color{v[0], v[1], v[2]};
+    throw Error("xml: a colour needs 1 or 3 values");
+}
+Color xrgb(const XNode &n, const std::string &name, Color def) {
+    const XNode *c = n.named(name);
+    return c ? xrgb_value(*c) : def;
+}
+// to_world.as_matrix(): the children of <transform> in order, each applied AFTER the previous ones (M = op * M)
+Mat4 xtransform(const XNode *tr) {
+    Mat4 m = Mat4::identity();
+    if (!tr) return m;
+    for (auto &op : tr->kids) {
+        Mat4 o = Mat4::identity();
+        auto f = [&](const char *k, float d) { return op.attr.count(k) ? std::strtof(op.get(k).c_str(), nullptr) : d; };
+        if (op.tag == "matrix") { // row-major in the file
+            std::vector<float> v = xfloats(op.get("value"));
+            if (v.size() != 16) throw Error("xml: <matrix> needs 16 values");
+            for (int r = 0; r < 4; r++)
+                for (int c = 0; c < 4; c++) o.at(c, r) = v[4 * r + c];
+        } else if (op.tag == "translate") o = Mat4::from_translation(f("x", 0), f("y", 0), f("z", 0));
+        else if (op.tag == "scale") {
+            const float u = f("value", 1.0f);
+            o = Mat4::from_nonuniform_scale(f("x", u), f("y", u), f("z", u));
+        } else if (op.tag == "rotate") o = Mat4::rotate_deg(f("angle", 0), Vec3{f("x", 0), f("y", 0), f("z", 0)});
+        else if (op.tag == "lookat" || op.tag == "lookAt") { // camera-to-world: columns left, up, dir, origin (Mitsuba's Transform::lookAt)
+            std::vector<float> e = xfloats(op.get("origin")), a = xfloats(op.get("target")), u = xfloats(op.get("up", "0, 1, 0"));
+            if (e.size() != 3 || a.size() != 3 || u.size() != 3) throw Error("xml: <lookat> needs origin, target (and up) with 3 values");
+            auto norm = [](Vec3 v) {
+                float l = std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+                return Vec3{v.x / l, v.y / l, v.z / l};
+            };
+            auto cross = [](Vec3 p, Vec3 q) { return Vec3{p.y * q.z - p.z * q.y, p.z * q.x - p.x * q.z, p.x * q.y - p.y * q.x}; };
+            Vec3 dir = norm(Vec3{a[0] - e[0], a[1] - e[1], a[2] - e[2]});
+            Vec3 left = norm(cross(Vec3{u[0], u[1], u[2]}, dir));
+            Vec3 up = cross(dir, left);
+            const float cols[4][4] = {{left.x, left.y, left.z, 0}, {up.x, up.y, up.z, 0}, {dir.x, dir.y, dir.z, 0}, {e[0], e[1], e[2], 1}};
+            for (int c = 0; c < 4; c++)
+                for (int r = 0; r < 4; r++) o.at(c, r) = cols[c][r];
+        } else throw Error("xml: transform operation <" + op.tag + "> is not supported");
+        m = o * m;
+    }
+    return m;
+}
+struct MtsCtx {
+    Scene *scene;
+    std::string base_dir;
+    std::map<std::string, const XNode *> ids; // id -> bsdf / texture node
+};
+// bsdf_texture_match_mts (mod.rs:395-452): constant -> (colour, 0); texture -> (black, 1-based texture id)
+std::pair<Color, uint32_t> mts_color(MtsCtx &cx, const XNode &owner, const std::string &name, Color def) {
+    const XNode *c = owner.named(name);
+    if (!c) return {def, 0u};
+    if (c->tag == "ref") {
+        auto it = cx.ids.find(c->get("id"));
+        if (it == cx.ids.end()) throw Error("xml: <ref id=\"" + c->get("id") + "\"> refers to nothing");
+        c = it->second;
+    }
+    if (c->tag != "texture") return {xrgb_value(*c), 0u};
+    const std::string type = c->get("type");
+    if (type == "bitmap") {
+        std::string fn = xstring(*c, "filename", "");
+        if (fn.empty()) throw Error("xml: bitmap texture without a filename");
+        if (fn[0] != '/' && !cx.base_dir.empty()) fn = cx.base_dir + "/" + fn;
+        Texture t = Texture::bitmap_file(fn);
+        const float gamma = xfloat(*c, "gamma", 1.0f);
+        if (gamma != 1.0f) // img.gamma(1.0 / gamma): per channel powf (structure.rs:416-422)
+            for (float &v : t.pixels) v = std::pow(v, 1.0f / gamma);
+        t.t.pixels = t.pixels.data();
+        return {Color{0, 0, 0}, cx.scene->add_texture(std::move(t))};
+    }
+    if (type == "checkerboard" || type == "gridtexture") {
+        Color c0 = xrgb(*c, "color0", type == "checkerboard" ? Color{0.4f, 0.4f, 0.4f} : Color{0.2f, 0.2f, 0.2f});
+        Color c1 = xrgb(*c, "color1", type == "checkerboard" ? Color{0.2f, 0.2f, 0.2f} : Color{0.4f, 0.4f, 0.4f});
+        const float ox = xfloat(*c, "uoffset", 0.0f), oy = xfloat(*c, "voffset", 0.0f), sx = xfloat(*c, "uscale", 1.0f), sy = xfloat(*c, "vscale", 1.0f);
+        if (type == "checkerboard") return {Color{0, 0, 0}, cx.scene->add_texture(Texture::checkerboard(c0, c1, ox, oy, sx, sy))};
+        return {Color{0, 0, 0}, cx.scene->add_texture(Texture::grid(c0, c1, xfloat(*c, "lineWidth", 0.01f), ox, oy, sx, sy))};
+    }
+    throw Error("Mitsuba texture type not supported: " + type); // mod.rs:450
+}
+uint32_t mts_distribution(const XNode &b, bool rough, float *alpha) { // distribution_mts, mod.rs:462-497
+    *alpha = 0.0f;
+    if (!rough) return RL_MICROFACET_NONE;
+    if (b.child("float", "alphaU") || b.child("float", "alphaV")) {
+        const float au = xfloat(b, "alphaU", 0.1f), av = xfloat(b, "alphaV", 0.1f);
+        if (au != av) throw Error("xml: anisotropic roughness is not supported (the reference asserts alpha_u == alpha_v, mod.rs:476)");
+        *alpha = au;
+    } else *alpha = xfloat(b, "alpha", 0.1f);
+    const std::string d = xstring(b, "distribution", "beckmann");
+    return d == "ggx" ? RL_MICROFACET_GGX : RL_MICROFACET_BECKMANN; // unknown names: "Unsupported microfacet type" -> Beckmann (mod.rs:484-487)
+}
+Material mts_bsdf(MtsCtx &cx, const XNode *b) { // bsdf_mts, mod.rs:499-612
+    const Material fallback = Material::diffuse(Color{0.8f, 0.8f, 0.8f});
+    if (!b) return fallback;
+    if (b->tag == "ref") {
+        auto it = cx.ids.find(b->get("id"));
+        if (it == cx.ids.end()) throw Error("xml: <ref id=\"" + b->get("id") + "\"> refers to nothing");
+        b = it->second;
+    }
+    const std::string type = b->get("type");
+    auto textured = [](Material m, uint32_t kd_t, uint32_t ks_t) {
+        m.m.kd_texture = kd_t, m.m.ks_texture = ks_t;
+        return m;
+    };
+    if (type == "twosided") { // "Rustlight automatically apply twosided"
+        for (auto &k : b->kids)
+            if (k.tag == "bsdf" || k.tag == "ref") return mts_bsdf(cx, &k);
+        return fallback;
+    }
+    if (type == "diffuse") {
+        auto r = mts_color(cx, *b, "reflectance", Color{0.5f, 0.5f, 0.5f});
+        return textured(Material::diffuse(r.first), r.second, 0u);
+    }
+    if (type == "phong") {
+        auto kd = mts_color(cx, *b, "diffuseReflectance", Color{0.5f, 0.5f, 0.5f}), ks = mts_color(cx, *b, "specularReflectance", Color{0.2f, 0.2f, 0.2f});
+        if (kd.second || ks.second) throw Error("xml: textured phong reflectances are not supported (weight_specular needs BSDFColor::avg)");
+        return Material::phong(kd.first, ks.first, xfloat(*b, "exponent", 30.0f));
+    }
+    if (type == "dielectric" || type == "thindielectric" || type == "roughdielectric") { // "Thin material are ignored / Impossible to do rough glass"
+        auto kr = mts_color(cx, *b, "specularReflectance", Color{1, 1, 1}), kt = mts_color(cx, *b, "specularTransmittance", Color{1, 1, 1});
+        Material m = Material::glass(kr.first, kt.first, xfloat(*b, "intIOR", 1.5046f), xfloat(*b, "extIOR", 1.000277f));
+        m.m.ks_texture = kr.second, m.m.kt_texture = kt.second;
+        return m;
+    }
+    if (type == "plastic" || type == "roughplastic") {
+        auto ks = mts_color(cx, *b, "specularReflectance", Color{1, 1, 1}), kd = mts_color(cx, *b, "diffuseReflectance", Color{0.5f, 0.5f, 0.5f});
+        float alpha;
+        const uint32_t mf = mts_distribution(*b, type == "roughplastic", &alpha);
+        return textured(Material::substrate(kd.first, ks.first, mf, alpha), kd.second, ks.second);
+    }
+    if (type == "conductor" || type == "roughconductor") {
+        auto ks = mts_color(cx, *b, "specularReflectance", Color{1, 1, 1});
+        const float ext = xfloat(*b, "extEta", 1.000277f);
+        Color eta = xrgb(*b, "eta", Color{0.2004f, 0.9240f, 1.1022f}), k = xrgb(*b, "k", Color{3.9129f, 2.4528f, 2.1421f}); // copper, as for pbrt "metal"
+        float alpha;
+        const uint32_t mf = mts_distribution(*b, type == "roughconductor", &alpha);
+        return textured(Material::metal(ks.first, Color{eta.r / ext, eta.g / ext, eta.b / ext}, Color{k.r / ext, k.g / ext, k.b / ext}, mf, alpha), 0u, ks.second);
+    }
+    return fallback; // `_ => None` -> BSDFDiffuse 0.8 (mod.rs:599-611)
+}
+// Wavefront OBJ, triangulated by fanning; one vertex per distinct (v, vt, vn) corner (tobj is not vendored: unpinned)
+void read_obj(const std::string &filename, RawShape &out) {
+    const std::string text = read_file(filename);
+    std::vector<float> P, T, N;
+    std::map<std::array<int, 3>, uint32_t> corner_ids;
+    std::istringstream in(text);
+    std::string line;
+    bool any_n = false, any_t = false;
+    std::vector<std::array<int, 3>> corners;
+    while (std::getline(in, line)) {
+        std::istringstream ls(line);
+        std::string kw;
+        if (!(ls >> kw)) continue;
+        if (kw == "v" || kw == "vn") {
+            float x, y, z;
+            if (!(ls >> x >> y >> z)) throw Error("obj: bad " + kw + " line");
+            auto &dst = kw == "v" ? P : N;
+            dst.insert(dst.end(), {x, y, z});
+        } else if (kw == "vt") {
+            float u, v = 0.0f;
+            if (!(ls >> u)) throw Error("obj: bad vt line");
+            ls >> v;
+            T.insert(T.end(), {u, v});
+        } else if (kw == "f") {
+            std::vector<uint32_t> face;
+            std::string tok;
+            while (ls >> tok) {
+                std::array<int, 3> c{0, 0, 0};
+                size_t a = tok.find('/');
+                c[0] = std::atoi(tok.substr(0, a).c_str());
+                if (a != std::string::npos) {
+                    size_t b2 = tok.find('/', a + 1);
+                    const std::string st = tok.substr(a + 1, b2 == std::string::npos ? std::string::npos : b2 - a - 1);
+                    if (!st.empty()) c[1] = std::atoi(st.c_str());
+                    if (b2 != std::string::npos) c[2] = std::atoi(tok.substr(b2 + 1).c_str());
+                }
+                if (c[0] < 0) c[0] = (int)(P.size() / 3) + 1 + c[0];
+                if (c[1] < 0) c[1] = (int)(T.size() / 2) + 1 + c[1];
+                if (c[2] < 0) c[2] = (int)(N.size() / 3) + 1 + c[2];
+                if (c[0] <= 0 || (size_t)c[0] > P.size() / 3 || (size_t)c[1] > T.size() / 2 || (size_t)c[2] > N.size() / 3) throw Error("obj: index out of range");
+                any_t = any_t || c[1] != 0, any_n = any_n || c[2] != 0;
+                auto it = corner_ids.find(c);
+                if (it == corner_ids.end()) {
+                    it = corner_ids.emplace(c, (uint32_t)corners.size()).first;
+                    corners.push_back(c);
+                }
+                face.push_back(it->second);
+            }
+            if (face.size() < 3) throw Error("obj: face with fewer than 3 vertices");
+            for (size_t k = 1; k + 1 < face.size(); k++) out.idx.insert(out.idx.end(), {face[0], face[k], face[k + 1]});
+        }
+    }
+    for (auto &c : corners) {
+        out.P.insert(out.P.end(), {P[3 * (c[0] - 1)], P[3 * (c[0] - 1) + 1], P[3 * (c[0] - 1) + 2]});
+        if (any_t) {
+            if (c[1]) out.uv.insert(out.uv.end(), {T[2 * (c[1] - 1)], T[2 * (c[1] - 1) + 1]});
+            else out.uv.insert(out.uv.end(), {0.0f, 0.0f});
+        }
+        if (any_n) {
+            if (c[2]) out.N.insert(out.N.end(), {N[3 * (c[2] - 1)], N[3 * (c[2] - 1) + 1], N[3 * (c[2] - 1) + 2]});
+            else out.N.insert(out.N.end(), {0.0f, 0.0f, 0.0f});
+        }
+    }
+}
+} // namespace
+
+Scene MTSSceneLoader::load(const std::string &filename, bool use_shading_normal) const {
+    size_t slash = filename.find_last_of('/');
+    return load_string(read_file(filename), use_shading_normal, slash == std::string::npos ? "" : filename.substr(0, slash));
+}
+Scene MTSSceneLoader::load_string(const std::string &text, bool use_shading_normal, const std::string &base_dir) const {
+    XParser xp(text);
+    const XNode root = xp.element();
+    if (root.tag != "scene") throw Error("xml: the root element must be <scene>");
+    Scene scene;
+    MtsCtx cx{&scene, base_dir, {}};
+    std::vector<const XNode *> sensors, shapes_id, shapes_unnamed, emitters;
+    for (auto &k : root.kids) {
+        if ((k.tag == "bsdf" || k.tag == "texture") && k.attr.count("id")) cx.ids[k.get("id")] = &k;
+        else if (k.tag == "sensor") sensors.push_back(&k);
+        else if (k.tag == "shape") (k.attr.count("id") ? shapes_id : shapes_unnamed).push_back(&k);
+        else if (k.tag == "emitter") emitters.push_back(&k);
+        else if (k.tag == "medium") throw Error("xml: participating media are outside the hot-path scope");
+    }
+    if (sensors.size() != 1) throw Error("xml: exactly one sensor is expected (assert_eq!(mts.sensors.len(), 1), scene_loader.rs:328)");
+    { // scene_loader.rs:327-338
+        const XNode &se = *sensors[0];
+        if (se.get("type") != "perspective") throw Error("xml: sensor type \"" + se.get("type") + "\" is not supported (perspective)");
+        uint32_t w = 768, h = 576;
+        for (auto &k : se.kids)
+            if (k.tag == "film") w = (uint32_t)xfloat(k, "width", 768.0f), h = (uint32_t)xfloat(k, "height", 576.0f);
+        const std::string axis = xstring(se, "fovAxis", "x");
+        if (axis != "x" && axis != "y") throw Error("Unsupport Fov axis definition: " + axis); // :335
+        const float fov = xfloat(se, "fov", 39.5978f); // Mitsuba's default focal length (50 mm on 36 mm film)
+        scene.camera = Camera::create(w, h, axis == "x" ? Fov::X : Fov::Y, fov, xtransform(se.child("transform", "toWorld")), true);
+    }
+    auto emit = [&](const XNode &sh, RawShape &rs, bool keep_normals) { // option.{bsdf, emitter, to_world} + apply_transform (:341-376)
+        const XNode *b = nullptr;
+        for (auto &k : sh.kids) {
+            if (k.tag == "ref" && !cx.ids.count(k.get("id"))) throw Error("xml: <ref id=\"" + k.get("id") + "\"> refers to nothing");
+            if (k.tag == "bsdf" || (k.tag == "ref" && cx.ids[k.get("id")]->tag == "bsdf")) b = &k;
+        }
+        rs.bsdf = mts_bsdf(cx, b);
+        for (auto &k : sh.kids)
+            if (k.tag == "emitter") {
+                if (k.get("type") != "area") throw Error("xml: a shape can only carry an area emitter");
+                rs.is_light = true;
+                rs.emission = xrgb(k, "radiance", Color{1, 1, 1});
+            }
+        if (!keep_normals) rs.N.clear();
+        emit_mesh(scene, rs, xtransform(sh.child("transform", "toWorld")), true);
+    };
+    auto load_shape = [&](const XNode &sh) {
+        const std::string type = sh.get("type");
+        RawShape rs;
+        const bool face_normal = xbool(sh, "faceNormals", false);
+        if (type == "rectangle") { // :538-594
+            rs.P = {-1, -1, 0, 1, -1, 0, 1, 1, 0, -1, 1, 0};
+            rs.uv = {0, 0, 1, 0, 1, 1, 0, 1};
+            rs.N = {0, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0, 1};
+            rs.idx = {0, 1, 2, 2, 3, 0};
+            emit(sh, rs, true);
+            scene.meshes.back()->name = "rectangle";
+        } else if (type == "sphere") { // :596-665: 32 x 32 vertices, f32 sin / cos of the host (LIBM: the loader is host code in the reference too)
+            Vec3 c{0, 0, 0};
+            if (const XNode *p = sh.child("point", "center")) c = Vec3{std::strtof(p->get("x", "0").c_str(), nullptr), std::strtof(p->get("y", "0").c_str(), nullptr), std::strtof(p->get("z", "0").c_str(), nullptr)};
+            const float radius = xfloat(sh, "radius", 1.0f);
+            const int NB = 32;
+            const float PI_F = 3.14159265358979323846f;
+            for (int i = 0; i < NB; i++) {
+                const float theta = (float)i / (float)(NB - 1) * PI_F;
+                for (int j = 0; j < NB; j++) {
+                    const float phi = (float)j / (float)(NB - 1) * 2.0f * PI_F;
+                    const float x = radius * std::sin(theta) * std::cos(phi), y = radius * std::sin(theta) * std::sin(phi), z = radius * std::cos(theta);
+                    rs.P.insert(rs.P.end(), {x + c.x, y + c.y, z + c.z});
+                    const float il = 1.0f / std::sqrt(x * x + y * y + z * z); // normalize = v * (1 / |v|)
+                    rs.N.insert(rs.N.end(), {x * il, y * il, z * il});
+                    rs.uv.insert(rs.uv.end(), {theta / PI_F, phi / (2.0f * PI_F)});
+                }
+            }
+            for (uint32_t i = 0; i + 1 < (uint32_t)NB; i++)
+                for (uint32_t j = 0; j + 1 < (uint32_t)NB; j++) {
+                    const uint32_t i0 = i * NB + j, i1 = i0 + 1, i2 = (i + 1) * NB + j + 1, i3 = (i + 1) * NB + j;
+                    rs.idx.insert(rs.idx.end(), {i0, i1, i2, i2, i3, i0});
+                }
+            emit(sh, rs, true);
+            scene.meshes.back()->name = "rectangle"; // (sic, :628)
+        } else if (type == "ply" || type == "obj") {
+            std::string fn = xstring(sh, "filename", "");
+            if (fn.empty()) throw Error("xml: shape \"" + type + "\" needs a filename");
+            if (fn[0] != '/' && !base_dir.empty()) fn = base_dir + "/" + fn;
+            if (type == "ply") read_ply(fn, rs);
+            else {
+                read_obj(fn, rs);
+                if (xbool(sh, "flipTexCoords", true)) // "Only v coordinate" (:482-491)
+                    for (size_t k = 1; k < rs.uv.size(); k += 2) rs.uv[k] = 1.0f - rs.uv[k];
+            }
+            emit(sh, rs, !face_normal && (type == "obj" || use_shading_normal)); // ply: `face_normal || !use_shading_normal` -> None (:399-403)
+        } else if (type == "serialized") {
+            throw Error("xml: shape \"serialized\" (zlib-compressed binary meshes) is not read by this loader");
+        } // anything else: "Ignoring shape" (:666-669)
+    };
+    for (const XNode *sh : shapes_id) load_shape(*sh);
+    for (const XNode *sh : shapes_unnamed) load_shape(*sh);
+    for (const XNode *e : emitters) { // :676-724
+        const std::string type = e->get("type");
+        if (type == "point") {
+            Vec3 p{0, 0, 0};
+            if (const XNode *q = e->child("point", "position")) p = Vec3{std::strtof(q->get("x", "0").c_str(), nullptr), std::strtof(q->get("y", "0").c_str(), nullptr), std::strtof(q->get("z", "0").c_str(), nullptr)};
+            p = xtransform(e->child("transform", "toWorld")).transform_point(p);
+            Color I = xrgb(*e, "intensity", Color{1, 1, 1});
+            scene.add_point_light(I, p.x, p.y, p.z);
+        } else if (type == "pointnormal" || type == "PointNormal")
+            throw Error("xml: the PointNormal emitter cannot be light-sampled (PointNormalEmitter::direct_sample is todo!() in the reference, emitter.rs:262-264)");
+        // anything else: "Ignoring emitter" (:720-722)
+    }
+    if (scene.meshes.empty()) throw Error("xml: the scene has no shape this loader reads");
+    return scene;
+}
+
+// ------------------------------------------------------------------------------------------
 // SceneLoaderManager, src/scene_loader.rs:21-58
 // ------------------------------------------------------------------------------------------
 SceneLoaderManager::SceneLoaderManager() {
     loader["pbrt"] = std::make_shared<PBRTSceneLoader>();
     loader["json"] = std::make_shared<JSONSceneLoader>();
+    loader["xml"] = std::make_shared<MTSSceneLoader>(); // scene_loader.rs:52-56 (feature "mitsuba")
 }
 Scene SceneLoaderManager::load(const std::string &filename, bool use_shading_normal) const {
     size_t dot = filename.find_last_of('.');

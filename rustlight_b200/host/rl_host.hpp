@@ -158,9 +158,14 @@ struct JSONSceneLoader : SceneLoader {
     Scene load(const std::string &filename, bool use_shading_normal) const override;
     Scene load_string(const std::string &text, bool use_shading_normal, const std::string &base_dir = "") const;
 };
+// Mitsuba 0.x XML subset (scene_loader.rs:318-795, bsdfs/mod.rs:395-612): the reference's only route to BSDFPhong
+struct MTSSceneLoader : SceneLoader {
+    Scene load(const std::string &filename, bool use_shading_normal) const override;
+    Scene load_string(const std::string &text, bool use_shading_normal, const std::string &base_dir = "") const;
+};
 struct SceneLoaderManager {
     std::map<std::string, std::shared_ptr<SceneLoader>> loader;
-    SceneLoaderManager(); // registers "pbrt" and "json"
+    SceneLoaderManager(); // registers "pbrt", "json" and "xml"
     Scene load(const std::string &filename, bool use_shading_normal) const;
 };
 std::string scene_to_json(const Scene &scene);

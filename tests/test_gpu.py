@@ -382,6 +382,25 @@ def test_mixed_material_scene_bit_exact(gpu_ctx, sort):
     dev.close()
 
 
+def test_mitsuba_xml_scene_bit_exact(gpu_ctx):
+    """The Mitsuba-XML route (the reference's only way to a BSDFPhong): Phong walls, checkerboard floor, rough plastic, a rough-conductor
+    sphere of 1922 triangles (4-wide tree over the reference's topology), area + point light."""
+    from test_mitsuba import BOX
+    sc = SceneLoaderManager().load_string(BOX, "xml")
+    sc.set_resolution(120, 96)
+    dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
+    assert dev.bvh_info().flat_groups == 0 and dev.bvh_info().ntris == 1934
+    for integ in (_abi.path_desc(), _abi.path_desc(max_depth=5, rr_depth=2), _abi.direct_desc(2, 2)):
+        img, st = dev.render(integ, 8, seed=7)
+        ref, so = osc.render(integ, 8, seed=7, cfg=ob.config(**STREAM))
+        assert (st.segments, st.hits, st.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+        assert np.array_equal(img, ref)
+    pg, tg = dev.primary_hits()
+    po, to = osc.primary_hits(ob.ACCEL_BVH)
+    assert np.array_equal(pg, po) and np.array_equal(tg, to)
+    dev.close()
+
+
 @pytest.mark.parametrize("tail", [None, "0"])
 def test_environment_texture_bit_exact(gpu_ctx, tail, monkeypatch):
     """EnvironmentLightColor::Texture (emitter.rs:300-427): a lat-long HDR image with a sun texel, a black row and a black texel as the
