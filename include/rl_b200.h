@@ -153,6 +153,9 @@ typedef struct rl_scene_desc {
     uint32_t nsubmaterials;   /* the bsdf1 / bsdf2 of RL_BSDF_BLEND materials */
     const rl_material *submaterials;
     uint32_t environment_texture; /* has_environment == 2: 1 + index into textures[] of an RL_TEX_BITMAP (EnvironmentLightColor::new_texture) */
+    uint32_t use_ats;             /* Scene::build_emitters(true) (`-x ats`, examples/cli.rs:325,432): light sampling through the light tree
+                                     LightSamplerATS (emitter.rs:1130-1400).  Mesh emitters only (the reference asserts is_surface()); `direct` only
+                                     with nb_bsdf_samples == 0 */
 } rl_scene_desc;
 
 /* ---- integrators --------------------------------------------------------------------------- */

@@ -91,6 +91,8 @@ def lib():
     L.orc_xoshiro_next_u64.restype = C.c_uint64
     L.orc_xoshiro_next_u64.argtypes = [C.POINTER(C.c_uint64)]
     L.orc_spec_sincos.argtypes = [C.c_float, FP, FP]
+    L.orc_ats_sample.argtypes = [C.c_void_p, C.c_float, FP, FP, C.c_int, C.POINTER(C.c_uint32), FP]
+    L.orc_ats_pdf.argtypes = [C.c_void_p, C.c_uint32, FP, FP, C.c_int, FP]
     L.orc_spec_atan2.restype = C.c_float
     L.orc_spec_atan2.argtypes = [C.c_float, C.c_float]
     L.orc_spec_acos.restype = C.c_float
@@ -139,6 +141,21 @@ class OracleScene:
         if rc != 0:
             raise ValueError(f"orc_render failed: {rc}")
         return img, st
+
+    def ats_sample(self, r, p, n=None):
+        """LightSamplerATS::sample(r, importance_point(p, n)) -> (global triangle index, pdf)."""
+        prim, pdf = C.c_uint32(), C.c_float()
+        nn = np.zeros(3, np.float32) if n is None else np.ascontiguousarray(n, np.float32)
+        if lib().orc_ats_sample(self._h, float(r), _f(np.ascontiguousarray(p, np.float32)), _f(nn), 0 if n is None else 1, C.byref(prim), C.byref(pdf)) != 0:
+            raise ValueError("no light tree")
+        return prim.value, pdf.value
+
+    def ats_pdf(self, prim, p, n=None):
+        pdf = C.c_float()
+        nn = np.zeros(3, np.float32) if n is None else np.ascontiguousarray(n, np.float32)
+        if lib().orc_ats_pdf(self._h, int(prim), _f(np.ascontiguousarray(p, np.float32)), _f(nn), 0 if n is None else 1, C.byref(pdf)) != 0:
+            raise ValueError("no light tree / not a light")
+        return pdf.value
 
     def env_eval_pdf(self, d, math_mode=MATH_SPEC):
         """EnvironmentLightColor::{eval, pdf} of the scene's environment for the direction d."""

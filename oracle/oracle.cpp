@@ -997,6 +997,12 @@ struct Mesh { // geometry.rs:107-119
         float area_tri = magnitude(cross(v1 - v0, v2 - v0)) * 0.5f;
         return SampledPosition{pos, n_g, PDF{PDF::Area, 1.0f / area_tri}, primitive_id};
     }
+    float pdf_tri(size_t primitive_id) const { // :226-234
+        Idx3 id = indices[primitive_id];
+        V3 v0 = vertices[id.x], v1 = vertices[id.y], v2 = vertices[id.z];
+        float area_tri = magnitude(cross(v1 - v0, v2 - v0)) * 0.5f;
+        return 1.0f / area_tri;
+    }
     SampledPosition sample(float s, P2 v) const { // :340-348
         size_t primitive_id = cdf.sample_discrete(s);
         SampledPosition res = sample_tri(primitive_id, v);
@@ -1072,6 +1078,9 @@ struct BoundingSphere { // structure.rs:880-884
 };
 struct Emitter { // trait Emitter, emitter.rs:46-94 (the methods this path calls)
     virtual ~Emitter() = default;
+    virtual bool is_surface() const { return false; }                                                    // :70-72
+    virtual PDF direct_pdf_tri(const LightSamplingPDF &, size_t) const { std::abort(); }                 // unimplemented!() (:84-86)
+    virtual LightSampling direct_sample_tri(V3, size_t, P2) const { std::abort(); }                      // unimplemented!() (:76-83)
     virtual PDF direct_pdf(const LightSamplingPDF &ls) const = 0;
     virtual LightSampling direct_sample(const Math &m, V3 p, float r, P2 uv) const = 0;
     virtual Color flux() const = 0;
@@ -1099,6 +1108,24 @@ struct MeshEmitter : Emitter { // impl Emitter for Mesh, emitter.rs:570-688
     }
     Color flux() const override { return m->flux(); }
     Color eval() const override { return m->emit(); }
+    bool is_surface() const override { return true; } // :727-729
+    PDF direct_pdf_tri(const LightSamplingPDF &ls, size_t id_primitive) const override { // :581-589
+        float cos_light = rmax(dot(ls.n, -ls.dir), 0.0f);
+        if (cos_light == 0.0f) return PDF{PDF::SolidAngle, 0.0f};
+        float geom = cos_light / magnitude2(ls.p - ls.o);
+        return PDF{PDF::SolidAngle, m->pdf_tri(id_primitive) / geom};
+    }
+    LightSampling direct_sample_tri(V3 p, size_t primitive_id, P2 uv) const override { // :608-649
+        SampledPosition sp = m->sample_tri(primitive_id, uv);
+        V3 d = sp.p - p;
+        float dist = magnitude(d);
+        if (dist != 0.0f) d = d / dist;
+        float geom = dist != 0.0f ? rmax(dot(sp.n, -d), 0.0f) / (dist * dist) : 0.0f;
+        float pdf_area = sp.pdf.value();
+        PDF pdf = sp.pdf.as_solid_angle_geom(geom);
+        Color weight = pdf.is_zero() ? Color::zero() : m->emit() * geom / pdf_area;
+        return LightSampling{this, pdf, sp.p, sp.n, d, 0, weight}; // primitive_id: None ("Not sampled a particular primitive")
+    }
 };
 struct PointEmitter : Emitter { // emitter.rs:186-250
     Color intensity;
@@ -1296,7 +1323,256 @@ struct EnvironmentLight : Emitter { // emitter.rs:428-568
     }
     Color eval() const override { return luminance.constant; }
 };
-struct EmitterSampler { // :1491-1495 (ats == None on this path)
+// ---- the light tree of `-x ats`: emitter.rs:782-1400 ------------------------------------------------------------------------
+inline float safe_acos(float v) { return std::acos(rmin(rmax(v, -1.0f), 1.0f)); } // :789-791
+inline float safe_asin(float v) { return std::asin(rmin(rmax(v, -1.0f), 1.0f)); } // :792-794
+inline float angle_between(V3 v1, V3 v2) { // :796-802
+    if (dot(v1, v2) < 0.0f) return PI - 2.0f * safe_asin(magnitude(v2 + v1) / 2.0f);
+    return 2.0f * safe_asin(magnitude(v2 - v1) / 2.0f);
+}
+inline V3 rotate_vector(float sin_theta, float cos_theta, V3 axis, V3 v) { // rotate(..).transform_vector(v), :804-824
+    V3 a = normalize(axis);
+    float c0r0 = a.x * a.x + (1.0f - a.x * a.x) * cos_theta;
+    float c0r1 = a.x * a.y * (1.0f - cos_theta) - a.z * sin_theta;
+    float c0r2 = a.x * a.z * (1.0f - cos_theta) + a.y * sin_theta;
+    float c1r0 = a.x * a.y * (1.0f - cos_theta) + a.z * sin_theta;
+    float c1r1 = a.y * a.y + (1.0f - a.y * a.y) * cos_theta;
+    float c1r2 = a.y * a.z * (1.0f - cos_theta) - a.x * sin_theta;
+    float c2r0 = a.x * a.z * (1.0f - cos_theta) - a.y * sin_theta;
+    float c2r1 = a.y * a.z * (1.0f - cos_theta) + a.x * sin_theta;
+    float c2r2 = a.z * a.z + (1.0f - a.z * a.z) * cos_theta;
+    // Matrix4::new(..) lists columns; .transpose() makes (c0r0, c0r1, c0r2) the first ROW; M * (v, 0) = col0 v.x + col1 v.y + col2 v.z + col3 0
+    return V3{c0r0 * v.x + c0r1 * v.y + c0r2 * v.z + 0.0f, c1r0 * v.x + c1r1 * v.y + c1r2 * v.z + 0.0f, c2r0 * v.x + c2r1 * v.y + c2r2 * v.z + 0.0f};
+}
+struct DirectionCone { // :782-900
+    V3 w{0.0f, 0.0f, 1.0f};
+    float cos_theta = -1.0f;
+    bool empty = false;
+    static DirectionCone entire_sphere() { return DirectionCone{}; }
+    static DirectionCone subtended_directions(const AABB &b, V3 p) { // :840-855
+        V3 c = b.center();
+        float radius = magnitude(c - b.p_max); // to_sphere
+        if (magnitude2(p - c) < radius * radius) return entire_sphere();
+        DirectionCone r;
+        r.w = normalize(c - p);
+        float sin_theta_max_2 = radius * radius / magnitude2(c - p);
+        r.cos_theta = std::sqrt(rmax(1.0f - sin_theta_max_2, 0.0f));
+        return r;
+    }
+    static DirectionCone union_(const DirectionCone &a, const DirectionCone &b) { // :857-899
+        if (a.empty) return b;
+        if (b.empty) return a;
+        float theta_a = safe_acos(a.cos_theta), theta_b = safe_acos(b.cos_theta), theta_d = angle_between(a.w, b.w);
+        if (rmin(theta_d + theta_b, PI) <= theta_a) return a;
+        if (rmin(theta_d + theta_a, PI) <= theta_b) return b;
+        float theta_o = (theta_a + theta_d + theta_b) / 2.0f;
+        if (theta_o >= PI) return entire_sphere();
+        float theta_r = theta_o - theta_a;
+        V3 wr = cross(a.w, b.w);
+        if (magnitude2(wr) == 0.0f) return entire_sphere();
+        float degrees = theta_r * 57.2957795130823208767981548141051703f; // f32::to_degrees
+        float radians = degrees * (PI / 180.0f);                          // f32::to_radians
+        DirectionCone r;
+        r.w = rotate_vector(std::sin(radians), std::cos(radians), wr, a.w);
+        r.cos_theta = std::cos(theta_o);
+        return r;
+    }
+};
+constexpr float EPSILON_ATS = 0.0001f;
+struct LightBounds { // :902-1108
+    AABB aabb;
+    V3 w{0.0f, 0.0f, 1.0f};
+    float phi = 0.0f, theta_o = 0.0f, theta_e = 0.0f, cos_theta_o = 1.0f, cos_theta_e = 1.0f;
+    bool two_sided = false;
+    static LightBounds union_(const LightBounds &a, const LightBounds &b) { // :948-973
+        if (a.phi == 0.0f) return b;
+        if (b.phi == 0.0f) return a;
+        DirectionCone ca, cb;
+        ca.w = a.w, ca.cos_theta = a.cos_theta_o, cb.w = b.w, cb.cos_theta = b.cos_theta_o;
+        DirectionCone c = DirectionCone::union_(ca, cb);
+        LightBounds r;
+        r.theta_o = safe_acos(c.cos_theta);
+        r.theta_e = rmax(a.theta_e, b.theta_e);
+        r.aabb = a.aabb.union_aabb(b.aabb);
+        r.w = c.w;
+        r.phi = a.phi + b.phi;
+        r.cos_theta_o = std::cos(r.theta_o);
+        r.cos_theta_e = std::cos(r.theta_e);
+        r.two_sided = a.two_sided | b.two_sided;
+        return r;
+    }
+    float importance_point(V3 p, const V3 *n) const { // :1034-1108
+        V3 pc = aabb.center();
+        float d2 = rmax(magnitude2(p - pc), EPSILON_ATS);
+        V3 wi = normalize(p - pc);
+        float cos_theta = dot(w, wi);
+        if (two_sided) cos_theta = std::fabs(cos_theta);
+        float sin_theta = std::sqrt(rmax(1.0f - cos_theta * cos_theta, 0.0f));
+        auto cos_sub_clamped = [](float sin_a, float cos_a, float sin_b, float cos_b) { return cos_a > cos_b ? 1.0f : cos_a * cos_b + sin_a * sin_b; };
+        auto sin_sub_clamped = [](float sin_a, float cos_a, float sin_b, float cos_b) { return cos_a > cos_b ? 1.0f : sin_a * cos_b - cos_a * sin_b; };
+        float cos_theta_u = DirectionCone::subtended_directions(aabb, p).cos_theta;
+        float sin_theta_u = std::sqrt(rmax(1.0f - cos_theta_u * cos_theta_u, 0.0f));
+        float sin_theta_o = std::sqrt(rmax(1.0f - cos_theta_o * cos_theta_o, 0.0f));
+        float cos_theta_x = cos_sub_clamped(sin_theta, cos_theta, sin_theta_o, cos_theta_o);
+        float sin_theta_x = sin_sub_clamped(sin_theta, cos_theta, sin_theta_o, cos_theta_o);
+        float cos_theta_p = cos_sub_clamped(sin_theta_x, cos_theta_x, sin_theta_u, cos_theta_u);
+        if (cos_theta_p <= cos_theta_e) return 0.0f;
+        float imp = phi * cos_theta_p / d2;
+        if (n) {
+            float cos_theta_i = std::fabs(dot(wi, *n));
+            float sin_theta_i = std::sqrt(rmax(1.0f - cos_theta_i * cos_theta_i, 0.0f));
+            imp *= cos_sub_clamped(sin_theta_i, cos_theta_i, sin_theta_u, cos_theta_u);
+        }
+        return rmax(imp, 0.0f);
+    }
+};
+struct LightProxy { // :1110-1114
+    size_t emitter_id, primitive_idx;
+    LightBounds bounds;
+};
+struct LightBVHNode { // :1116-1129
+    int left = -1, right = -1, parent = -1;
+    LightBounds bounds;
+    int light = -1;
+    bool is_leaf() const { return left < 0 && right < 0; }
+};
+struct LightSamplerATS { // :1130-1400
+    int root = -1;
+    std::vector<LightBVHNode> nodes;
+    std::vector<LightProxy> lights;
+    std::vector<std::pair<std::pair<size_t, size_t>, size_t>> query_to_nodes; // (emitter, primitive) -> node
+    bool failed = false; // a slice came out empty: unimplemented!() in the reference
+    size_t node_of(size_t emitter, size_t prim) const {
+        for (auto &q : query_to_nodes)
+            if (q.first.first == emitter && q.first.second == prim) return q.second;
+        std::abort(); // .unwrap()
+    }
+    size_t build_bvh(size_t index, LightProxy *ls, size_t n) { // :1145-1287
+        if (n == 0) {
+            failed = true;
+            return 0;
+        }
+        if (n == 1) {
+            LightBVHNode leaf;
+            leaf.bounds = ls[0].bounds, leaf.light = (int)index;
+            nodes.push_back(leaf);
+            query_to_nodes.push_back({{ls[0].emitter_id, ls[0].primitive_idx}, nodes.size() - 1});
+            return nodes.size() - 1;
+        }
+        AABB bounds, centroid_bounds;
+        for (size_t i = 0; i < n; i++) {
+            bounds = bounds.union_aabb(ls[i].bounds.aabb);
+            centroid_bounds = centroid_bounds.union_vec(ls[i].bounds.aabb.center());
+        }
+        auto offset = [&](V3 v, int dim) { // AABB::offset, structure.rs:809-818
+            float o = comp(v - centroid_bounds.p_min, dim), sz = comp(centroid_bounds.size(), dim);
+            return sz != 0.0f ? o / sz : 0.0f;
+        };
+        constexpr size_t NBUCKETS = 12;
+        auto bucket_of = [&](const LightProxy &l, int dim) {
+            size_t i = (size_t)as_usize((float)NBUCKETS * offset(l.bounds.aabb.center(), dim));
+            return i < NBUCKETS - 1 ? i : NBUCKETS - 1;
+        };
+        float min_cost = F32_MAX;
+        int min_cost_bucket = -1, min_cost_dim = -1;
+        for (int dim = 0; dim < 3; dim++) {
+            if (comp(centroid_bounds.p_max, dim) == comp(centroid_bounds.p_min, dim)) continue;
+            std::vector<LightBounds> buckets(NBUCKETS);
+            for (size_t i = 0; i < n; i++) {
+                size_t b = bucket_of(ls[i], dim);
+                buckets[b] = LightBounds::union_(buckets[b], ls[i].bounds);
+            }
+            auto momega = [](const LightBounds &b) {
+                float theta_w = rmin(b.theta_o + b.theta_e, PI);
+                return 2.0f * PI * (1.0f - std::cos(b.theta_o)) +
+                       FRAC_PI_2 * (2.0f * theta_w * std::sin(b.theta_o) - std::cos(b.theta_o - 2.0f * theta_w) - 2.0f * b.theta_o * std::sin(b.theta_o) + std::cos(b.theta_o));
+            };
+            for (size_t i = 0; i + 1 < NBUCKETS; i++) {
+                LightBounds b0, b1;
+                for (size_t j = 0; j < i + 1; j++) b0 = LightBounds::union_(b0, buckets[j]);
+                for (size_t j = i + 1; j < NBUCKETS; j++) b1 = LightBounds::union_(b1, buckets[j]);
+                V3 sz = bounds.size();
+                float kr = rmax(rmax(sz.x, sz.y), sz.z) / comp(sz, dim);
+                float c = kr * (b0.phi * momega(b0) * b0.aabb.surface_area() + b1.phi * momega(b1) * b1.aabb.surface_area());
+                if (c > 0.0f && c < min_cost) min_cost = c, min_cost_bucket = (int)i, min_cost_dim = dim;
+            }
+        }
+        size_t mid;
+        if (min_cost_dim == -1) mid = n / 2;
+        else { // itertools::partition(lights.iter_mut(), pred)
+            auto pred = [&](const LightProxy &l) { return bucket_of(l, min_cost_dim) <= (size_t)min_cost_bucket; };
+            size_t split_index = 0, lo = 0, hi = n; // the iterator covers [lo, hi)
+            while (lo < hi) {
+                LightProxy &front = ls[lo++];
+                if (!pred(front)) {
+                    bool swapped = false;
+                    while (lo < hi) {
+                        LightProxy &back = ls[--hi];
+                        if (pred(back)) {
+                            std::swap(front, back);
+                            swapped = true;
+                            break;
+                        }
+                    }
+                    if (!swapped) break; // next_back() returned None: break 'main
+                }
+                split_index++;
+            }
+            mid = split_index;
+        }
+        size_t left = build_bvh(index, ls, mid);
+        if (failed) return 0;
+        size_t right = build_bvh(index + mid, ls + mid, n - mid);
+        if (failed) return 0;
+        LightBVHNode inner;
+        inner.left = (int)left, inner.right = (int)right;
+        inner.bounds = LightBounds::union_(nodes[left].bounds, nodes[right].bounds);
+        nodes.push_back(inner);
+        size_t id = nodes.size() - 1;
+        nodes[left].parent = (int)id, nodes[right].parent = (int)id;
+        return id;
+    }
+    float prob_left(const LightBVHNode &node, V3 p, const V3 *n) const {
+        float imp_left = nodes[node.left].bounds.importance_point(p, n), imp_right = nodes[node.right].bounds.importance_point(p, n);
+        float imp_total = imp_left + imp_right;
+        return (imp_left == 0.0f && imp_right == 0.0f) ? 0.5f : imp_left / imp_total;
+    }
+    float pdf(size_t id_emitter, size_t id_primitive, V3 p, const V3 *n) const { // :1319-1359
+        size_t id = node_of(id_emitter, id_primitive);
+        float pdf = 1.0f;
+        while (nodes[id].parent >= 0) {
+            size_t id_parent = (size_t)nodes[id].parent;
+            float pl = prob_left(nodes[id_parent], p, n);
+            if ((size_t)nodes[id_parent].left == id) pdf *= pl;
+            else pdf *= 1.0f - pl;
+            id = id_parent;
+        }
+        return pdf;
+    }
+    const LightProxy &sample(float r, V3 p, const V3 *n, float *pdf_sel_out) const { // :1361-1399
+        float pdf_sel = 1.0f;
+        size_t node_index = (size_t)root;
+        for (;;) {
+            const LightBVHNode &node = nodes[node_index];
+            if (node.is_leaf()) {
+                *pdf_sel_out = pdf_sel;
+                return lights[node.light];
+            }
+            float pl = prob_left(node, p, n);
+            if (r < pl) {
+                r = r / pl;
+                node_index = (size_t)node.left;
+                pdf_sel *= pl;
+            } else {
+                r = (r - pl) / (1.0f - pl);
+                node_index = (size_t)node.right;
+                pdf_sel *= 1.0f - pl;
+            }
+        }
+    }
+};
+struct EmitterSampler { // :1491-1495
+    std::unique_ptr<LightSamplerATS> ats; // Some(..) after build_ats (`-x ats`)
     std::vector<std::unique_ptr<Emitter>> emitters;
     std::vector<const Mesh *> emitter_mesh; // the mesh behind emitters[i], or null
     Distribution1D emitters_cdf;
@@ -1310,9 +1586,29 @@ struct EmitterSampler { // :1491-1495 (ats == None on this path)
             if (emitters[i].get() == e) return emitters_cdf.pdf(i);
         return 0.0f; // the reference panics here; unreachable (only listed emitters are queried)
     }
-    PDF direct_pdf(const Emitter *e, const LightSamplingPDF &ls) const { return e->direct_pdf(ls) * pdf(e); } // :1566-1575
-    PDF direct_pdf(const Mesh *m, const LightSamplingPDF &ls) const { return direct_pdf(of_mesh(m), ls); }
-    LightSampling sample_light(const Math &m, V3 p, float r_sel, float r, P2 uv) const { // :1604-1620, :1641-1647
+    // :1566-1602.  With the light tree: direct_pdf_tri * ats.pdf(emitter, primitive, importance_point(ls.o, n))
+    PDF direct_pdf(const Emitter *e, const LightSamplingPDF &ls, const V3 *n = nullptr, long id_primitive = -1) const {
+        if (!ats) return e->direct_pdf(ls) * pdf(e);
+        size_t id_emitter = emitters.size();
+        for (size_t i = 0; i < emitters.size(); i++)
+            if (emitters[i].get() == e) {
+                id_emitter = i;
+                break;
+            }
+        if (id_emitter == emitters.size()) return PDF{PDF::SolidAngle, 0.0f}; // "PDF emitter without intersecting an emitter"
+        if (id_primitive < 0) std::abort();                                   // id_primitive.unwrap()
+        return e->direct_pdf_tri(ls, (size_t)id_primitive) * ats->pdf(id_emitter, (size_t)id_primitive, ls.o, n);
+    }
+    PDF direct_pdf(const Mesh *m, const LightSamplingPDF &ls, const V3 *n = nullptr, long id_primitive = -1) const { return direct_pdf(of_mesh(m), ls, n, id_primitive); }
+    LightSampling sample_light(const Math &m, V3 p, const V3 *n, float r_sel, float r, P2 uv) const { // :1604-1639, :1641-1647
+        if (ats) {
+            float pdf_sel;
+            const LightProxy &light_info = ats->sample(r_sel, p, n, &pdf_sel);
+            LightSampling res = emitters[light_info.emitter_id]->direct_sample_tri(p, light_info.primitive_idx, uv);
+            div_assign(res.weight, pdf_sel);
+            res.pdf = res.pdf * pdf_sel;
+            return res;
+        }
         size_t id_light = emitters_cdf.sample_discrete(r_sel);
         float pdf_sel = emitters_cdf.pdf(id_light);
         LightSampling res = emitters[id_light]->direct_sample(m, p, r, uv);
@@ -1514,7 +1810,9 @@ struct Scene {
     BitmapTex environment_image; // EnvironmentLightColor::Texture when size_x != 0
     Color enviroment_luminance(const Math &m, V3 d) const { return env_emitter ? env_emitter->luminance.eval(m, d) : Color::zero(); } // scene.rs:125-130
     BoundingSphere bsphere{};
-    void build_emitters() { // scene.rs:53-123 (no env map, no ATS)
+    bool build_ats = false; // Scene::build_emitters(build_ats), scene.rs:53, 118-120
+    std::string ats_error;
+    void build_emitters() { // scene.rs:53-123
         // bounding sphere: union of Mesh::compute_aabb (all vertices, geometry.rs:441-456) and the camera position
         AABB aabb;
         for (auto &m : meshes) {
@@ -1565,6 +1863,40 @@ struct Scene {
         std::vector<float> fl;
         for (auto &e : emitters.emitters) fl.push_back(e->flux().channel_max());
         emitters.emitters_cdf = Distribution1D::normalize(fl);
+        emitters.ats.reset();
+        if (build_ats) { // EmitterSampler::build_ats -> LightSamplerATS::new (emitter.rs:1290-1317, 1505-1508)
+            auto ats = std::make_unique<LightSamplerATS>();
+            for (size_t i = 0; i < emitters.emitters.size(); i++) {
+                if (!emitters.emitters[i]->is_surface()) { // assert!(e.is_surface())
+                    ats_error = "ats: every emitter must be a surface (assert!(e.is_surface()), emitter.rs:1292-1294)";
+                    return;
+                }
+                const Mesh *m = emitters.emitter_mesh[i];
+                for (size_t t = 0; t < m->indices.size(); t++) { // Mesh::convert_light_proxy, emitter.rs:730-779
+                    Idx3 idx = m->indices[t];
+                    V3 v0 = m->vertices[idx.x], v1 = m->vertices[idx.y], v2 = m->vertices[idx.z];
+                    V3 n = cross(v1 - v0, v2 - v0);
+                    LightProxy lp;
+                    lp.emitter_id = i, lp.primitive_idx = t;
+                    lp.bounds.w = normalize(n);
+                    lp.bounds.theta_o = 0.0f, lp.bounds.theta_e = FRAC_PI_2;
+                    lp.bounds.phi = m->emit().channel_max() * magnitude(n) * 0.5f;
+                    lp.bounds.aabb = AABB{}.union_vec(v0).union_vec(v1).union_vec(v2);
+                    lp.bounds.cos_theta_o = std::cos(lp.bounds.theta_o), lp.bounds.cos_theta_e = std::cos(lp.bounds.theta_e);
+                    ats->lights.push_back(lp);
+                }
+            }
+            if (ats->lights.empty()) {
+                ats_error = "ats: no emissive triangle (LightSamplerATS::new(..).unwrap())";
+                return;
+            }
+            ats->root = (int)ats->build_bvh(0, ats->lights.data(), ats->lights.size());
+            if (ats->failed) {
+                ats_error = "ats: a split left one side empty (unimplemented!() in build_bvh)";
+                return;
+            }
+            emitters.ats = std::move(ats);
+        }
     }
 
     // ---- BVHAccel::new, accel.rs:201-240 -----------------------------------------------
@@ -1909,7 +2241,7 @@ struct LightSamplingStrategy : SamplingStrategy { // strategies/emitters.rs
         float r_sel = sampler.next();
         float r = sampler.next();
         P2 uv = sampler.next2d();
-        LightSampling rec = cx.scene->emitters.sample_light(cx.math, its.p, r_sel, r, uv);
+        LightSampling rec = cx.scene->emitters.sample_light(cx.math, its.p, &its.n_s, r_sel, r, uv);
         bool visible = cx.scene->visible(its.p, rec.p, cx.accel_mode, *cx.counters); // evaluated before the && (:125-126)
         if (rec.is_valid() && visible) {
             Vertex nv;
@@ -1936,7 +2268,7 @@ struct LightSamplingStrategy : SamplingStrategy { // strategies/emitters.rs
         }
         const Vertex &nv = path.vertices[next_vertex_id];
         if (nv.kind == Vertex::Surface) {
-            PDF p = cx.scene->emitters.direct_pdf(nv.its.mesh, LightSamplingPDF{ray.o, nv.its.p, nv.its.n_g, ray.d});
+            PDF p = cx.scene->emitters.direct_pdf(nv.its.mesh, LightSamplingPDF{ray.o, nv.its.p, nv.its.n_g, ray.d}, nullptr, (long)nv.its.primitive_id);
             *out = p.value();
             return true;
         }
@@ -2117,7 +2449,7 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
                 if (!contrib.is_zero()) {
                     float w = 1.0f;
                     if (I.strategy == RL_STRATEGY_ALL && mis_prev) { // balance heuristic (path.rs:78-99)
-                        float pl = sc.emitters.direct_pdf(its.mesh, LightSamplingPDF{ray.o, its.p, its.n_g, ray.d}).value();
+                        float pl = sc.emitters.direct_pdf(its.mesh, LightSamplingPDF{ray.o, its.p, its.n_g, ray.d}, nullptr, (long)its.primitive_id).value();
                         w = pdf_prev / (pdf_prev + pl);
                     }
                     L = L + contrib * w;
@@ -2164,7 +2496,7 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
             float r_sel = sampler.next();
             float r = sampler.next();
             P2 uv = sampler.next2d();
-            LightSampling rec = sc.emitters.sample_light(cx.math, its.p, r_sel, r, uv);
+            LightSampling rec = sc.emitters.sample_light(cx.math, its.p, &its.n_s, r_sel, r, uv);
             bool visible = sc.visible(its.p, rec.p, cx.accel_mode, *cx.counters);
             if (rec.is_valid() && !mute && add_ok(vdepth) && I.strategy != RL_STRATEGY_BSDF) {
                 V3 wo = its.frame.to_local(rec.d);
@@ -2216,7 +2548,7 @@ Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy
         float r_sel = sampler.next();
         float r = sampler.next();
         P2 uv = sampler.next2d();
-        LightSampling rec = sc.emitters.sample_light(cx.math, its.p, r_sel, r, uv);
+        LightSampling rec = sc.emitters.sample_light(cx.math, its.p, &its.n_s, r_sel, r, uv);
         V3 d_out_local = its.frame.to_local(rec.d);
         if (rec.is_valid() && sc.visible(its.p, rec.p, cx.accel_mode, *cx.counters) && !bsdf.is_smooth()) {
             float pdf_bsdf = bsdf.pdf(cx.math, its.uv, its.wi, d_out_local).value();
@@ -2236,7 +2568,7 @@ Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy
             if (next_its.mesh->is_light() && dot(next_its.n_g, -r2.d) > 0.0f) {
                 float weight_bsdf = 1.0f; // PDF::Discrete(_v) => 1.0 (direct.rs:170)
                 if (sb.pdf.kind == PDF::SolidAngle) {
-                    float light_pdf = sc.emitters.direct_pdf(next_its.mesh, LightSamplingPDF{r2.o, next_its.p, next_its.n_g, r2.d}).value();
+                    float light_pdf = sc.emitters.direct_pdf(next_its.mesh, LightSamplingPDF{r2.o, next_its.p, next_its.n_g, r2.d}, &its.n_s, (long)next_its.primitive_id).value();
                     weight_bsdf = mis_weight(sb.pdf.value() * weight_nb_bsdf, light_pdf * weight_nb_light);
                 }
                 l_i = l_i + weight_bsdf * sb.weight * next_its.mesh->emit() * weight_nb_bsdf;
@@ -2358,7 +2690,13 @@ orc_scene *orc_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         if (desc->lights[li].kind > RL_LIGHT_DIRECTIONAL) return fail("unknown light kind");
         s.lights.push_back(desc->lights[li]);
     }
+    s.build_ats = desc->use_ats != 0;
     s.build_emitters();
+    if (!s.ats_error.empty()) {
+        std::string m = s.ats_error;
+        delete os;
+        return fail(m.c_str());
+    }
     s.build_bvh();
     return os;
 }
@@ -2590,7 +2928,7 @@ int orc_sample_light(const orc_scene *os, const float x[3], float r_sel, float r
                      float weight[3], float *pdf) {
     const Scene &sc = os->scene;
     if (sc.emitters.emitters.empty()) return -1;
-    LightSampling rec = sc.emitters.sample_light(Math{ORC_MATH_SPEC}, load3(x), r_sel, r, P2{u0, u1});
+    LightSampling rec = sc.emitters.sample_light(Math{ORC_MATH_SPEC}, load3(x), nullptr, r_sel, r, P2{u0, u1});
     store3(p, rec.p), store3(n, rec.n), store3(d, rec.d);
     weight[0] = rec.weight.r, weight[1] = rec.weight.g, weight[2] = rec.weight.b;
     *pdf = rec.pdf.value();
@@ -2633,6 +2971,32 @@ uint64_t orc_xoshiro_next_u64(uint64_t state[4]) {
     return r;
 }
 void orc_spec_sincos(float x, float *s, float *c) { spec_sincos(x, s, c); }
+static bool ats_locate(const Scene &sc, uint32_t prim, size_t *emitter, size_t *tri) { // global triangle index -> (emitter id, triangle of its mesh)
+    for (size_t e = 0; e < sc.emitters.emitters.size(); e++) {
+        const Mesh *m = sc.emitters.emitter_mesh[e];
+        if (m && prim >= m->first_prim && prim < m->first_prim + m->indices.size()) {
+            *emitter = e, *tri = prim - m->first_prim;
+            return true;
+        }
+    }
+    return false;
+}
+int orc_ats_sample(const orc_scene *os, float r, const float p[3], const float n[3], int has_n, uint32_t *prim, float *pdf) {
+    const Scene &sc = os->scene;
+    if (!sc.emitters.ats) return -1;
+    V3 nn = load3(n);
+    const LightProxy &lp = sc.emitters.ats->sample(r, load3(p), has_n ? &nn : nullptr, pdf);
+    *prim = (uint32_t)(sc.emitters.emitter_mesh[lp.emitter_id]->first_prim + lp.primitive_idx);
+    return 0;
+}
+int orc_ats_pdf(const orc_scene *os, uint32_t prim, const float p[3], const float n[3], int has_n, float *pdf) {
+    const Scene &sc = os->scene;
+    size_t e, t;
+    if (!sc.emitters.ats || !ats_locate(sc, prim, &e, &t)) return -1;
+    V3 nn = load3(n);
+    *pdf = sc.emitters.ats->pdf(e, t, load3(p), has_n ? &nn : nullptr);
+    return 0;
+}
 float orc_spec_atan2(float y, float x) { return spec_atan2(y, x); }
 float orc_spec_acos(float x) { return spec_acos(x); }
 int orc_env_eval_pdf(const orc_scene *os, uint32_t math_mode, const float d[3], float rgb[3], float *pdf) {

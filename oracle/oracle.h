@@ -101,6 +101,10 @@ void orc_sampler_block_stream(uint64_t seed, uint32_t seeding, uint32_t block, u
 void orc_sampler_counter(uint64_t seed, uint32_t pixel, uint32_t sample, uint32_t n, float *out);
 uint64_t orc_xoshiro_next_u64(uint64_t state[4]); /* xoshiro256++ step (KAT against the published algorithm) */
 void orc_spec_sincos(float x, float *s, float *c);
+/* LightSamplerATS of a scene created with use_ats (emitter.rs:1319-1399): sample(r) -> global triangle index + pdf; pdf of a triangle.
+ * has_n = 0 passes None for the normal.  -1 when the scene has no light tree. */
+int orc_ats_sample(const orc_scene *s, float r, const float p[3], const float n[3], int has_n, uint32_t *prim, float *pdf);
+int orc_ats_pdf(const orc_scene *s, uint32_t prim, const float p[3], const float n[3], int has_n, float *pdf);
 float orc_spec_atan2(float y, float x);
 float orc_spec_acos(float x);
 /* EnvironmentLightColor of the scene's environment (emitter.rs:354-425): eval / pdf of a direction, sample_direction(uv) -> d, colour, pdf */

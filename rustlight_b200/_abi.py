@@ -77,7 +77,7 @@ class rl_scene_desc(C.Structure):
                 ("camera", rl_camera_desc), ("has_volume", C.c_uint32), ("has_environment", C.c_uint32),
                 ("nlights", C.c_uint32), ("lights", C.POINTER(rl_light_desc)),
                 ("ntextures", C.c_uint32), ("textures", C.POINTER(rl_texture)), ("environment", C.c_float * 3),
-                ("nsubmaterials", C.c_uint32), ("submaterials", C.POINTER(rl_material)), ("environment_texture", C.c_uint32)]
+                ("nsubmaterials", C.c_uint32), ("submaterials", C.POINTER(rl_material)), ("environment_texture", C.c_uint32), ("use_ats", C.c_uint32)]
 
 
 class rl_integrator_desc(C.Structure):

@@ -114,6 +114,8 @@ struct rl_scene {
     float2 *d_uvs = nullptr;
     float4 *d_tex = nullptr, *d_texels = nullptr;
     float *d_env_dist = nullptr; // Distribution2D of an environment texture
+    float4 *d_ats_nodes = nullptr; // LightSamplerATS (rl_ats_host.hpp)
+    uint32_t *d_ats_leaf = nullptr;
     uint32_t n_node_f4 = 0, n_trav_f4 = 0, n_ref_f4 = 0;
     size_t smem_bytes = 0;
     bool smem_ok = false;
@@ -340,7 +342,7 @@ void rl_scene_destroy(rl_ctx *ctx, rl_scene *s) {
     if (ctx) cudaSetDevice(ctx->device);
     cudaFree(s->d_trav), cudaFree(s->d_nodes), cudaFree(s->d_shade), cudaFree(s->d_verts), cudaFree(s->d_mats);
     cudaFree(s->d_emit_info), cudaFree(s->d_emit_cdf), cudaFree(s->d_area_cdf), cudaFree(s->d_flat);
-    cudaFree(s->d_uvs), cudaFree(s->d_tex), cudaFree(s->d_texels), cudaFree(s->d_env_dist);
+    cudaFree(s->d_uvs), cudaFree(s->d_tex), cudaFree(s->d_texels), cudaFree(s->d_env_dist), cudaFree(s->d_ats_nodes), cudaFree(s->d_ats_leaf);
     cudaFree(s->d_quad_verts), cudaFree(s->d_cam_masks);
     cudaFree(s->d_ref_nodes), cudaFree(s->d_ref_prims), cudaFree(s->d_ref_up);
     delete s;
@@ -392,6 +394,10 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     if (!hs.tex.empty()) CKS(upload(&s->d_tex, hs.tex, st));
     if (!hs.texels.empty()) CKS(upload(&s->d_texels, hs.texels, st));
     if (!hs.env_dist.empty()) CKS(upload(&s->d_env_dist, hs.env_dist, st));
+    if (!hs.ats_nodes.empty()) {
+        CKS(upload(&s->d_ats_nodes, hs.ats_nodes, st));
+        CKS(upload(&s->d_ats_leaf, hs.ats_leaf_of_prim, st));
+    }
     const uint32_t n_nodes = n > 1 ? n - 1 : 1;
     CKS(cudaMalloc(&s->d_trav, (size_t)n * RL_TRAV_F4 * sizeof(float4)));
     CKS(cudaMalloc(&d_keys, (size_t)n * 8));
@@ -571,6 +577,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     sv.env_on = hs.env_on ? 1u : 0u, sv.env_color = Col{hs.env_color[0], hs.env_color[1], hs.env_color[2]};
     sv.bs_center = V3{hs.bs_center[0], hs.bs_center[1], hs.bs_center[2]}, sv.bs_radius = hs.bs_radius, sv.env_pdf_sel = hs.env_pdf_sel;
     sv.env_w = hs.env_w, sv.env_h = hs.env_h, sv.env_texel_off = hs.env_texel_off, sv.env_dist = s->d_env_dist, sv.env_func_int = hs.env_func_int;
+    sv.ats_nodes = s->d_ats_nodes, sv.ats_leaf_of_prim = s->d_ats_leaf, sv.ats_root = hs.ats_root;
     std::memcpy(sv.s2c, hs.s2c, 64);
     std::memcpy(sv.c2w, hs.c2w, 64);
     sv.cam_pos = V3{hs.cam_pos[0], hs.cam_pos[1], hs.cam_pos[2]};
@@ -704,6 +711,10 @@ static int validate(rl_ctx *ctx, const rl_scene *scene, const rl_integrator_desc
         if (scene->hs.n_emitters == 0 && I->nb_light_samples > 0) {
             ctx->err = "rl_render: no emitter in the scene but light samples requested";
             return RL_ERR_INVALID;
+        }
+        if (scene->d_ats_nodes && I->nb_bsdf_samples > 0) { // EmitterSampler::direct_pdf(.., Some(&its.n_s), ..) of a BSDF-sampled hit (direct.rs:158-165)
+            ctx->err = "rl_render: `direct` with BSDF samples and the light tree (use_ats) is not supported: the light-tree pdf of the second hit needs the first vertex' shading normal, which stage 2 does not carry";
+            return RL_ERR_UNSUPPORTED;
         }
         if (I->nb_bsdf_samples > 64 || I->nb_light_samples > 64) {
             ctx->err = "rl_render: more than 64 bsdf/light samples per pixel sample";
@@ -898,6 +909,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
         }
         const int prof = ctx->profiling; // 0 off, 1 per-stage kernels (trace and shadow launched separately), 2 the kernels of an untimed frame
         const bool sort_on = o->material_sort == 1u || (o->material_sort >= 2u && sc->n_bsdf_kinds > 1u);
+        const bool extra = sc->d_tex != nullptr || sc->d_ats_nodes != nullptr; // textures (incl. an environment texture) or the light tree: the kernels with KM bit 8
         // the prediction of the queue lengths belongs to (scene, integrator): forget it when either changes
         const uint64_t pred_key = (uint64_t)(uintptr_t)sc ^ ((uint64_t)I->kind << 56) ^ ((uint64_t)(uint32_t)I->max_depth << 40) ^ ((uint64_t)(uint32_t)I->rr_depth << 24) ^
                                   ((uint64_t)I->strategy << 20) ^ ((uint64_t)sc->scene_gen << 4);
@@ -1004,12 +1016,12 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                                                                  ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc, ctx->d_counters, k == 0 ? (camera_o ? 3u : 1u) : 0u, done_at, k)
                     // kernel specialised for the BSDF kinds of the scene: {diffuse}, {diffuse, phong}, everything
                     // (textured scenes take the general kernel: bit 8 of the mask)
-                    if (sc->kind_mask == 0x1u && !sc->d_tex) RL_LAUNCH_SHADE(false, 0x1u);
-                    else if ((sc->kind_mask & ~0x3u) == 0u && !sc->d_tex) {
+                    if (sc->kind_mask == 0x1u && !extra) RL_LAUNCH_SHADE(false, 0x1u);
+                    else if ((sc->kind_mask & ~0x3u) == 0u && !extra) {
                         if (sort_on) RL_LAUNCH_SHADE(true, 0x3u);
                         else RL_LAUNCH_SHADE(false, 0x3u);
                     } else {
-                        if (sc->d_tex) {
+                        if (extra) {
                             if (sort_on) RL_LAUNCH_SHADE(true, RL_KM_ALL);
                             else RL_LAUNCH_SHADE(false, RL_KM_ALL);
                         } else {
@@ -1050,9 +1062,9 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                         const uint32_t take_max = last ? 0xffffffffu : (uint32_t)tail_max;
 #define RL_LAUNCH_TAIL(KM) \
     k_tail<KM><<<tg, kTailBlock, tsm, st>>>(sv, ip, ctx->pixel_list, qc + k + 1, ctx->ray_o[cur], ctx->ray_d[cur], ctx->state[cur], ctx->lacc, ctx->d_counters, sc->n_trav_f4, k + 1, kMaxIters - 1u, done_at, take_max)
-                        if (sc->kind_mask == 0x1u && !sc->d_tex) RL_LAUNCH_TAIL(0x1u);
-                        else if ((sc->kind_mask & ~0x3u) == 0u && !sc->d_tex) RL_LAUNCH_TAIL(0x3u);
-                        else if (sc->d_tex) RL_LAUNCH_TAIL(RL_KM_ALL);
+                        if (sc->kind_mask == 0x1u && !extra) RL_LAUNCH_TAIL(0x1u);
+                        else if ((sc->kind_mask & ~0x3u) == 0u && !extra) RL_LAUNCH_TAIL(0x3u);
+                        else if (extra) RL_LAUNCH_TAIL(RL_KM_ALL);
                         else RL_LAUNCH_TAIL(0xffu);
 #undef RL_LAUNCH_TAIL
                         ctx->launches++;

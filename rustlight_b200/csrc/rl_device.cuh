@@ -407,6 +407,10 @@ struct SceneView {
     uint32_t env_w, env_h, env_texel_off; // image size and its offset in texels[]
     const float *env_dist;
     float env_func_int; // marginal.func_int
+    // LightSamplerATS (emitter.rs:1130-1400; rl_ats_host.hpp): four float4 per node, nullptr without `-x ats`
+    const float4 *ats_nodes;
+    const uint32_t *ats_leaf_of_prim; // [global triangle] -> leaf node (0xffffffff: not a light)
+    uint32_t ats_root;
     // camera
     float s2c[16], c2w[16];
     V3 cam_pos;
@@ -2017,6 +2021,85 @@ RL_HD void env_sample_direction(const SceneView &sv, float sx, float sy, V3 *d, 
         *pdf = p / (2.0f * (RL_PI * RL_PI) * st);
     }
 }
+// ---- LightSamplerATS: importance-driven descent of the light tree (emitter.rs:1034-1108, 1319-1399) ----------------------------
+#define RL_EPSILON_ATS 0.0001f
+RL_HD float ats_cos_sub_clamped(float sin_a, float cos_a, float sin_b, float cos_b) { return cos_a > cos_b ? 1.0f : cos_a * cos_b + sin_a * sin_b; }
+RL_HD float ats_sin_sub_clamped(float sin_a, float cos_a, float sin_b, float cos_b) { return cos_a > cos_b ? 1.0f : sin_a * cos_b - cos_a * sin_b; } // (1.0, sic: :1061-1067)
+// LightBounds::importance_point(p, n) of node `id`
+RL_HD float ats_importance_point(const float4 *nodes, uint32_t id, V3 p, V3 n, bool has_n) {
+    const float4 c4 = nodes[4 * id], w4 = nodes[4 * id + 1], k4 = nodes[4 * id + 2];
+    const V3 pc = xyz(c4), w = xyz(w4);
+    const float radius = c4.w, phi = w4.w, cos_theta_o = k4.x, cos_theta_e = k4.y;
+    const V3 pv = p - pc;
+    const float d2 = fmaxf(dot(pv, pv), RL_EPSILON_ATS);
+    const V3 wi = normalize(pv);
+    float cos_theta = dot(w, wi);
+    if (k4.z != 0.0f) cos_theta = fabsf(cos_theta);
+    const float sin_theta = sqrtf(fmaxf(1.0f - cos_theta * cos_theta, 0.0f));
+    // DirectionCone::subtended_directions(&aabb, p).cos_theta (:840-855)
+    float cos_theta_u;
+    if (dot(pv, pv) < radius * radius) cos_theta_u = -1.0f;
+    else {
+        const V3 cp = pc - p;
+        const float sin_theta_max_2 = radius * radius / dot(cp, cp);
+        cos_theta_u = sqrtf(fmaxf(1.0f - sin_theta_max_2, 0.0f));
+    }
+    const float sin_theta_u = sqrtf(fmaxf(1.0f - cos_theta_u * cos_theta_u, 0.0f));
+    const float sin_theta_o = sqrtf(fmaxf(1.0f - cos_theta_o * cos_theta_o, 0.0f));
+    const float cos_theta_x = ats_cos_sub_clamped(sin_theta, cos_theta, sin_theta_o, cos_theta_o);
+    const float sin_theta_x = ats_sin_sub_clamped(sin_theta, cos_theta, sin_theta_o, cos_theta_o);
+    const float cos_theta_p = ats_cos_sub_clamped(sin_theta_x, cos_theta_x, sin_theta_u, cos_theta_u);
+    if (cos_theta_p <= cos_theta_e) return 0.0f;
+    float imp = phi * cos_theta_p / d2;
+    if (has_n) {
+        const float cos_theta_i = fabsf(dot(wi, n));
+        const float sin_theta_i = sqrtf(fmaxf(1.0f - cos_theta_i * cos_theta_i, 0.0f));
+        imp *= ats_cos_sub_clamped(sin_theta_i, cos_theta_i, sin_theta_u, cos_theta_u);
+    }
+    return fmaxf(imp, 0.0f);
+}
+RL_HD float ats_prob_left(const float4 *nodes, uint32_t left, uint32_t right, V3 p, V3 n, bool has_n) {
+    const float imp_left = ats_importance_point(nodes, left, p, n, has_n), imp_right = ats_importance_point(nodes, right, p, n, has_n);
+    const float imp_total = imp_left + imp_right;
+    return (imp_left == 0.0f && imp_right == 0.0f) ? 0.5f : imp_left / imp_total;
+}
+// LightSamplerATS::sample (:1361-1399): returns the global triangle index of the chosen proxy
+RL_HD uint32_t ats_sample(const SceneView &sv, float r, V3 p, V3 n, float *pdf_sel_out) {
+    float pdf_sel = 1.0f;
+    uint32_t id = sv.ats_root;
+    for (;;) {
+        const float4 t = sv.ats_nodes[4 * id + 3];
+        const uint32_t left = f2u(t.x), right = f2u(t.y);
+        if (left == 0xffffffffu && right == 0xffffffffu) {
+            *pdf_sel_out = pdf_sel;
+            return f2u(t.w);
+        }
+        const float prob_left = ats_prob_left(sv.ats_nodes, left, right, p, n, true);
+        if (r < prob_left) {
+            r = r / prob_left;
+            id = left;
+            pdf_sel *= prob_left;
+        } else {
+            r = (r - prob_left) / (1.0f - prob_left);
+            id = right;
+            pdf_sel *= 1.0f - prob_left;
+        }
+    }
+}
+// LightSamplerATS::pdf (:1319-1359): the product of the branch probabilities from the proxy's leaf up to the root
+RL_HD float ats_pdf(const SceneView &sv, uint32_t prim, V3 p, V3 n, bool has_n) {
+    uint32_t id = sv.ats_leaf_of_prim[prim];
+    float pdf = 1.0f;
+    for (;;) {
+        const uint32_t parent = f2u(sv.ats_nodes[4 * id + 3].z);
+        if (parent == 0xffffffffu) return pdf;
+        const float4 t = sv.ats_nodes[4 * parent + 3];
+        const uint32_t left = f2u(t.x), right = f2u(t.y);
+        const float prob_left = ats_prob_left(sv.ats_nodes, left, right, p, n, has_n);
+        pdf *= left == id ? prob_left : 1.0f - prob_left;
+        id = parent;
+    }
+}
 struct LightSample {
     V3 p, n, d;
     Col weight;
@@ -2027,13 +2110,19 @@ struct LightSample {
 };
 // EmitterSampler::sample_light -> Mesh::direct_sample -> Mesh::sample -> sample_tri
 // (emitter.rs:1604-1620, 652-688; geometry.rs:340-348, 261-337; math.rs:388-394)
-template <bool ENVTEX = true>
-RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, float ux, float uy) {
+// `ns`: the shading normal at x (what the strategies pass as Some(&its.n_s); only the light tree uses it).  EXTRA = the kernel carries the
+// rarely used branches (environment texture, light tree): KM bit 8.
+template <bool EXTRA = true>
+RL_HD LightSample sample_light(const SceneView &sv, V3 x, V3 ns, float r_sel, float r, float ux, float uy) {
+    const bool ats = EXTRA && sv.ats_nodes != nullptr;
+    uint32_t ats_prim = 0u;
+    float ats_pdf_sel = 1.0f;
+    if (ats) ats_prim = ats_sample(sv, r_sel, x, ns, &ats_pdf_sel); // EmitterSampler::sample_light, ATS arm (emitter.rs:1621-1638)
     // one emitter: the cdf is {0, 1} and r_sel < 1, so the search returns 0
-    uint32_t id_light = sv.n_emitters == 1u ? 0u : cdf_sample_discrete(sv.emit_cdf, sv.n_emitters + 1, r_sel);
-    float pdf_sel = sv.emit_cdf[id_light + 1] - sv.emit_cdf[id_light];
-    float4 info = sv.emit_info[2 * id_light];
-    if (f2u(info.x) >= 0xfffffff0u) { // PointEmitter / DirectionalLight::direct_sample (emitter.rs:197-215, 115-133)
+    uint32_t id_light = (sv.n_emitters == 1u || ats) ? 0u : cdf_sample_discrete(sv.emit_cdf, sv.n_emitters + 1, r_sel);
+    float pdf_sel = ats ? ats_pdf_sel : sv.emit_cdf[id_light + 1] - sv.emit_cdf[id_light];
+    float4 info = ats ? make_float4(u2f(f2u(sv.shade[4 * ats_prim].w)), 0.0f, 0.0f, 0.0f) : sv.emit_info[2 * id_light];
+    if (!ats && f2u(info.x) >= 0xfffffff0u) { // PointEmitter / DirectionalLight::direct_sample (emitter.rs:197-215, 115-133)
         float4 geo = sv.emit_info[2 * id_light + 1];
         Col intensity = Col{info.y, info.z, info.w};
         LightSample ls;
@@ -2043,7 +2132,7 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, 
             V3 dd;
             Col color = intensity;
             float pdf_dir = RL_ENV_PDF;
-            if (ENVTEX && sv.env_w) env_sample_direction(sv, ux, uy, &dd, &color, &pdf_dir); // luminance.sample_direction(uv), texture arm
+            if (EXTRA && sv.env_w) env_sample_direction(sv, ux, uy, &dd, &color, &pdf_dir); // luminance.sample_direction(uv), texture arm
             else dd = sample_uniform_sphere(ux, uy);
             float t;
             ls.d = dd;
@@ -2085,8 +2174,12 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, 
     }
     uint32_t mesh = f2u(info.x), first_prim = f2u(info.y), ntris = f2u(info.z), cdf_off = f2u(info.w);
     Material mat = load_material(sv.mats, mesh);
-    uint32_t tri = cdf_sample_discrete(sv.area_cdf + cdf_off, ntris + 1, r);
-    uint32_t prim = first_prim + tri;
+    uint32_t prim;
+    if (ats) prim = ats_prim; // direct_sample_tri(p, light_info.primitive_idx, uv) (emitter.rs:608-649)
+    else {
+        uint32_t tri = cdf_sample_discrete(sv.area_cdf + cdf_off, ntris + 1, r);
+        prim = first_prim + tri;
+    }
     V3 v0 = xyz(sv.verts[3 * prim]), v1 = xyz(sv.verts[3 * prim + 1]), v2 = xyz(sv.verts[3 * prim + 2]);
     float su0 = sqrtf(ux);
     float b0 = 1.0f - su0, b1 = uy * su0;
@@ -2104,6 +2197,7 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, 
         if (dot(n_g, n) < 0.0f) n_g = -n_g;
     }
     float pdf_area = mat.inv_area; // 1 / cdf.total()
+    if (ats) pdf_area = 1.0f / (magnitude(cross(v1 - v0, v2 - v0)) * 0.5f); // sample_tri: PDF::Area(1.0 / area_tri) (geometry.rs:328-334)
     V3 dd = pos - x;
     float dist = magnitude(dd);
     if (dist != 0.0f) dd = dd / dist;
@@ -2133,16 +2227,25 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, float r_sel, float r, 
     return ls;
 }
 // EmitterSampler::direct_pdf (emitter.rs:1566-1575) -> Mesh::direct_pdf (emitter.rs:571-579)
-RL_HD float direct_pdf(const Material &light_mat, V3 o, V3 p, V3 n, V3 dir) {
+// With the light tree (emitter.rs:1573-1601): Mesh::direct_pdf_tri (:581-589, the TRIANGLE's area pdf) times LightSamplerATS::pdf evaluated
+// from `o` with the normal the caller has (`path`: None, emitters.rs:52-57; `direct`: Some(&its.n_s), direct.rs:158-165).
+template <bool EXTRA = true>
+RL_HD float direct_pdf(const SceneView &sv, const Material &light_mat, uint32_t prim, V3 o, V3 p, V3 n, V3 dir, V3 ns, bool has_ns) {
+    const bool ats = EXTRA && sv.ats_nodes != nullptr;
     float cos_light = fmaxf(dot(n, -dir), 0.0f);
     float v;
     if (cos_light == 0.0f) v = 0.0f;
     else {
         V3 po = p - o;
         float geom = cos_light / dot(po, po);
-        v = light_mat.inv_area / geom;
+        float pdf_area = light_mat.inv_area;
+        if (ats) { // Mesh::pdf_tri, geometry.rs:226-234
+            const V3 v0 = xyz(sv.verts[3 * prim]), v1 = xyz(sv.verts[3 * prim + 1]), v2 = xyz(sv.verts[3 * prim + 2]);
+            pdf_area = 1.0f / (magnitude(cross(v1 - v0, v2 - v0)) * 0.5f);
+        }
+        v = pdf_area / geom;
     }
-    return v * light_mat.pdf_sel;
+    return v * (ats ? ats_pdf(sv, prim, o, ns, has_ns) : light_mat.pdf_sel);
 }
 
 // mis_weight, integrators/mod.rs:462-478 (power heuristic, `direct` only)
@@ -2264,7 +2367,7 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
                 // balance heuristic against light sampling (path.rs:78-99); a negative pdf_prev marks an edge without
                 // MIS: PDF::Discrete (delta lobe), or sampled at a smooth vertex where the light strategy has no pdf
                 if (ip.strategy == 0u && !(f2u(st.pdf_prev) >> 31)) {
-                    float pl = direct_pdf(mat, o, its.p, its.n_g, d);
+                    float pl = direct_pdf<RL_HAS(KM, 8) != 0u>(sv, mat, hit.prim, o, its.p, its.n_g, d, V3{0.0f, 0.0f, 0.0f}, false);
                     w = st.pdf_prev / (st.pdf_prev + pl);
                 }
                 out->add = mul_checked(contrib, w);
@@ -2318,7 +2421,7 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
         float ux = smp.next();
         float uy = smp.next();
         out->nee_sampled = true;
-        LightSample ls = sample_light<RL_HAS(KM, 8) != 0u>(sv, its.p, r_sel, r, ux, uy);
+        LightSample ls = sample_light<RL_HAS(KM, 8) != 0u>(sv, its.p, its.n_s, r_sel, r, ux, uy);
         if (ls.valid && !mute && ip_add_ok(ip, st.depth) && ip.strategy != 1u) {
             V3 wo = to_local(its.frame, ls.d);
             Col f;
@@ -2388,7 +2491,7 @@ RL_HD bool direct_light_sample(const SceneView &sv, DirectCtx *cx, V3 *p1, Col *
     float r = cx->smp.next();
     float ux = cx->smp.next();
     float uy = cx->smp.next();
-    LightSample ls = sample_light(sv, cx->its.p, r_sel, r, ux, uy);
+    LightSample ls = sample_light(sv, cx->its.p, cx->its.n_s, r_sel, r, ux, uy);
     *valid = ls.valid;
     if (!ls.valid) return false;
     if (mat_is_smooth(cx->mat)) return false; // direct.rs:74-77: visible() is still called (valid stays true), nothing is added
@@ -2463,7 +2566,7 @@ RL_HD bool direct_finish(const SceneView &sv, const IntegParams &ip, V3 o, V3 d,
     float wl = ip.nb_light_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_light_samples;
     float weight_bsdf = 1.0f;
     if (!(f2u(bsdf_pdf_v) >> 31)) {
-        float light_pdf = direct_pdf(mat, o, nx.p, nx.n_g, d);
+        float light_pdf = direct_pdf(sv, mat, hit.prim, o, nx.p, nx.n_g, d, V3{0.0f, 0.0f, 0.0f}, false); // (light tree + BSDF samples of `direct`: refused by rl_render, the first vertex' normal is not carried)
         weight_bsdf = mis_weight_power(bsdf_pdf_v * wb, light_pdf * wl);
     }
     *contrib = mul_checked(mul_plain(weight_bsdf, bsdf_weight) * mat.le, wb);

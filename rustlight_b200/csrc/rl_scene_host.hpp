@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "rl_b200.h"
+#include "rl_ats_host.hpp"
 #include "rl_device.cuh"
 
 namespace rl {
@@ -38,6 +39,10 @@ struct HostScene {
     uint32_t env_w = 0, env_h = 0, env_texel_off = 0;
     std::vector<float> env_dist;
     float env_func_int = 0.0f;
+    // LightSamplerATS (rl_ats_host.hpp): filled by build_host_scene when desc->use_ats
+    std::vector<float4> ats_nodes;
+    std::vector<uint32_t> ats_leaf_of_prim;
+    uint32_t ats_root = 0, ats_depth = 0;
     uint32_t img_w = 0, img_h = 0;
 };
 
@@ -358,6 +363,24 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
     float am = 0.0f;
     for (int a = 0; a < 3; a++) am = fmaxf(am, fmaxf(fabsf(hs.raw_min[a]), fabsf(hs.raw_max[a])));
     hs.abs_max = am;
+    if (desc->use_ats) { // Scene::build_emitters(true) -> LightSamplerATS::new (emitter.rs:1290-1317): every emitter must be a surface
+        if (desc->nlights > 0 || desc->has_environment) {
+            err = "use_ats: the light tree takes mesh emitters only (assert!(e.is_surface()), emitter.rs:1292-1294)";
+            return false;
+        }
+        std::vector<uint8_t> emissive(hs.ntris, 0);
+        std::vector<float> le(3 * (size_t)hs.ntris, 0.0f);
+        uint32_t p = 0;
+        for (uint32_t mi = 0; mi < desc->nmeshes; mi++)
+            for (uint32_t t = 0; t < desc->meshes[mi].ntris; t++, p++)
+                if (desc->meshes[mi].emission_kind) {
+                    emissive[p] = 1;
+                    for (int a = 0; a < 3; a++) le[3 * (size_t)p + a] = desc->meshes[mi].emission[a];
+                }
+        AtsTree tree;
+        if (!build_ats_tree(hs.verts, hs.ntris, emissive, le, tree, err)) return false;
+        hs.ats_nodes = tree.nodes, hs.ats_leaf_of_prim = tree.leaf_of_prim, hs.ats_root = tree.root, hs.ats_depth = tree.depth;
+    }
     return true;
 }
 

@@ -47,6 +47,8 @@ def lib():
         L.rlh_scene_add_texture_file.argtypes = [C.c_void_p, C.c_char_p]
         L.rlh_scene_set_environment.argtypes = [C.c_void_p, C.c_float * 3]
         L.rlh_scene_set_environment_texture.argtypes = [C.c_void_p, C.c_uint32]
+        L.rlh_scene_set_ats.argtypes = [C.c_void_p, C.c_int]
+        L.rlh_scene_set_ats.restype = None
         L.rlh_scene_add_light.argtypes = [C.c_void_p, C.c_uint32, C.c_float * 3, C.c_float * 3]
         L.rlh_scene_set_material.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_abi.rl_material)]
         L.rlh_scene_set_material_blend.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_abi.rl_material), C.POINTER(_abi.rl_material), C.c_float]
@@ -147,6 +149,11 @@ class Scene:
     def set_environment(self, rgb):
         """Constant EnvironmentLight (emitter.rs:428-568, pbrt LightSource "infinite" "rgb L")."""
         lib().rlh_scene_set_environment(self._h, (C.c_float * 3)(*rgb))
+        return self
+
+    def set_ats(self, on=True):
+        """Scene::build_emitters(build_ats) (`-x ats`): sample lights through the light tree LightSamplerATS (emitter.rs:1130-1400)."""
+        lib().rlh_scene_set_ats(self._h, 1 if on else 0)
         return self
 
     def set_environment_texture(self, tex_id):

@@ -26,7 +26,7 @@ static std::optional<uint32_t> match_infinity(const std::string &s) { // cli.rs:
     return (uint32_t)std::stoul(s);
 }
 [[noreturn]] static void usage(const char *msg) {
-    std::fprintf(stderr, "error: %s\nusage: rustlight-b200 [-n N] [-a A] [-e SECS] [-r independent[:SEED]] [-s SCALE] -o OUT.pfm [-x no-shading] SCENE "
+    std::fprintf(stderr, "error: %s\nusage: rustlight-b200 [-n N] [-a A] [-e SECS] [-r independent[:SEED]] [-s SCALE] -o OUT.pfm [-x no-shading|ats] SCENE "
                          "(path [-m MAX] [-n MIN] [-r RR] [-x] [-s all|bsdf|emitter] | direct [-b NB] [-l NL] | ao [-d DIST|inf] [-n])\n", msg);
     std::exit(2);
 }
@@ -37,7 +37,7 @@ int main(int argc, char **argv) {
     std::optional<std::string> average, equal_time;
     std::string rng = "independent", output, scene_path, medium = "0.0";
     float scale_image = 1.0f;
-    bool shading_normals = true;
+    bool shading_normals = true, use_ats = false;
     size_t i = 0;
     auto need = [&](const char *flag) -> std::string {
         if (i + 1 >= a.size()) usage((std::string("missing value for ") + flag).c_str());
@@ -62,6 +62,7 @@ int main(int argc, char **argv) {
         else if (t == "-x" || t == "--xtra-options") {
             std::string x = need("-x");
             if (x == "no-shading") shading_normals = false;
+            else if (x == "ats") use_ats = true; // Scene::build_emitters(true), cli.rs:325, 432
             else usage(("-x " + x + " is outside the GPU path").c_str());
         } else if (t == "-h" || t == "--help") usage("help");
         else if (!t.empty() && t[0] == '-') usage(("unknown option " + t).c_str());
@@ -115,6 +116,7 @@ int main(int argc, char **argv) {
     }
     try {
         Scene scene = SceneLoaderManager().load(scene_path, shading_normals);
+        scene.use_ats = use_ats;
         scene.nb_samples = nbsamples;
         scene.output_img_path = output;
         if (scale_image != 1.0f) {

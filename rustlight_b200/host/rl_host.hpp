@@ -119,6 +119,7 @@ struct Scene {
     bool has_volume = false, has_environment = false;
     Color environment; // EnvironmentLight{EnvironmentLightColor::Constant(environment)} when has_environment (scene_loader.rs:241-258)
     void set_environment(Color c) { has_environment = true, environment = c, environment_texture = 0; }
+    bool use_ats = false; // Scene::build_emitters(build_ats) (scene.rs:53, 118-120): `-x ats`
     uint32_t environment_texture = 0; // EnvironmentLightColor::Texture: 1-based id of a bitmap texture (add_texture), 0 = constant
     void set_environment_texture(uint32_t id); // EnvironmentLightColor::new_texture(image) (scene_loader.rs:259-270)
     // Scene.emitters before build_emitters (EmittersState::Unbuild): PointEmitter / DirectionalLight (scene_loader.rs:207-240)

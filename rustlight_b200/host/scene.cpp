@@ -371,6 +371,7 @@ const rl_scene_desc *Scene::desc() {
     desc_.has_volume = has_volume ? 1u : 0u;
     desc_.has_environment = has_environment ? (environment_texture ? 2u : 1u) : 0u;
     desc_.environment_texture = environment_texture;
+    desc_.use_ats = use_ats ? 1u : 0u;
     desc_.environment[0] = environment.r, desc_.environment[1] = environment.g, desc_.environment[2] = environment.b;
     texture_descs_.clear();
     for (auto &t : textures) {

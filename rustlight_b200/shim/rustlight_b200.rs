@@ -46,7 +46,7 @@ pub struct rl_mesh_desc {
 #[repr(C)] pub struct rl_scene_desc {
     pub nmeshes: u32, pub meshes: *const rl_mesh_desc, pub camera: rl_camera_desc, pub has_volume: u32, pub has_environment: u32,
     pub nlights: u32, pub lights: *const rl_light_desc, pub ntextures: u32, pub textures: *const rl_texture, pub environment: [f32; 3],
-    pub nsubmaterials: u32, pub submaterials: *const rl_material, pub environment_texture: u32,
+    pub nsubmaterials: u32, pub submaterials: *const rl_material, pub environment_texture: u32, pub use_ats: u32,
 }
 #[repr(C)] pub struct rl_integrator_desc {
     pub kind: u32, pub min_depth: i32, pub max_depth: i32, pub rr_depth: i32, pub strategy: u32,
@@ -185,6 +185,7 @@ fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
         has_volume: 0, has_environment: has_env, nlights: f.lights.len() as u32, lights: f.lights.as_ptr(),
         ntextures: f.textures.len() as u32, textures: f.textures.as_ptr(), environment: env,
         nsubmaterials: f.submaterials.len() as u32, submaterials: f.submaterials.as_ptr(), environment_texture: env_tex,
+        use_ats: matches!(&scene.emitters, Some(crate::scene::EmittersState::Build(s)) if s.ats.is_some()) as u32, // build_emitters(true): `-x ats`
     };
     (f, desc)
 }

@@ -149,6 +149,7 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
     sv.env_on = hs.env_on ? 1u : 0u, sv.env_color = Col{hs.env_color[0], hs.env_color[1], hs.env_color[2]};
     sv.bs_center = V3{hs.bs_center[0], hs.bs_center[1], hs.bs_center[2]}, sv.bs_radius = hs.bs_radius, sv.env_pdf_sel = hs.env_pdf_sel;
     sv.env_w = hs.env_w, sv.env_h = hs.env_h, sv.env_texel_off = hs.env_texel_off, sv.env_dist = hs.env_dist.data(), sv.env_func_int = hs.env_func_int;
+    sv.ats_nodes = hs.ats_nodes.empty() ? nullptr : hs.ats_nodes.data(), sv.ats_leaf_of_prim = hs.ats_leaf_of_prim.data(), sv.ats_root = hs.ats_root;
     std::memcpy(sv.s2c, hs.s2c, 64);
     std::memcpy(sv.c2w, hs.c2w, 64);
     sv.cam_pos = V3{hs.cam_pos[0], hs.cam_pos[1], hs.cam_pos[2]};
@@ -311,6 +312,17 @@ void emu_bsdf_eval(const rl_material *mt, const float wi[3], const float wo[3], 
     emu_material_rows(mt, rows);
     Col c = bsdf_eval(load_material(rows, 0), V3{wi[0], wi[1], wi[2]}, V3{wo[0], wo[1], wo[2]});
     out[0] = c.r, out[1] = c.g, out[2] = c.b;
+}
+// LightSamplerATS on the device side (rl_device.cuh: ats_*)
+int emu_ats_sample(const emu_scene *s, float r, const float p[3], const float n[3], uint32_t *prim, float *pdf) {
+    if (!s->sv.ats_nodes) return -1;
+    *prim = ats_sample(s->sv, r, V3{p[0], p[1], p[2]}, V3{n[0], n[1], n[2]}, pdf);
+    return 0;
+}
+int emu_ats_pdf(const emu_scene *s, uint32_t prim, const float p[3], const float n[3], int has_n, float *pdf) {
+    if (!s->sv.ats_nodes || s->sv.ats_leaf_of_prim[prim] == 0xffffffffu) return -1;
+    *pdf = ats_pdf(s->sv, prim, V3{p[0], p[1], p[2]}, V3{n[0], n[1], n[2]}, has_n != 0);
+    return 0;
 }
 // EnvironmentLightColor::Texture on the device side (rl_device.cuh: env_*)
 float emu_spec_atan2(float y, float x) { return spec_atan2f(y, x); }

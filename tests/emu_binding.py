@@ -44,6 +44,8 @@ def lib():
         L.emu_bsdf_pdf.argtypes = [C.POINTER(_abi.rl_material), FP, FP]
         L.emu_bsdf_eval.argtypes = [C.POINTER(_abi.rl_material), FP, FP, FP]
         L.emu_bsdf_flags.argtypes = [C.POINTER(_abi.rl_material)]
+        L.emu_ats_sample.argtypes = [C.c_void_p, C.c_float, FP, FP, C.POINTER(C.c_uint32), FP]
+        L.emu_ats_pdf.argtypes = [C.c_void_p, C.c_uint32, FP, FP, C.c_int, FP]
         L.emu_spec_atan2.restype = C.c_float
         L.emu_spec_atan2.argtypes = [C.c_float, C.c_float]
         L.emu_spec_acos.restype = C.c_float
@@ -119,6 +121,19 @@ class EmuScene:
 
     def bvh_validate(self):
         return lib().emu_bvh_validate(self._h)
+
+    def ats_sample(self, r, p, n):
+        prim, pdf = C.c_uint32(), C.c_float()
+        if lib().emu_ats_sample(self._h, float(r), _f(np.ascontiguousarray(p, np.float32)), _f(np.ascontiguousarray(n, np.float32)), C.byref(prim), C.byref(pdf)) != 0:
+            raise ValueError("no light tree")
+        return prim.value, pdf.value
+
+    def ats_pdf(self, prim, p, n=None):
+        pdf = C.c_float()
+        nn = np.zeros(3, np.float32) if n is None else np.ascontiguousarray(n, np.float32)
+        if lib().emu_ats_pdf(self._h, int(prim), _f(np.ascontiguousarray(p, np.float32)), _f(nn), 0 if n is None else 1, C.byref(pdf)) != 0:
+            raise ValueError("no light tree / not a light")
+        return pdf.value
 
     def env_eval_pdf(self, d):
         rgb, pdf = np.zeros(3, np.float32), C.c_float()

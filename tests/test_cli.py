@@ -22,10 +22,10 @@ def test_cli_argument_errors():
     assert run("-o", "x.png", CBOX, "path").returncode == 2               # unsupported output type
     assert run(CBOX, "path").returncode == 2                              # missing -o
     assert run("-o", "x.pfm", "-m", "0.5", CBOX, "path").returncode == 2  # media are out of scope
-    assert run("-o", "x.pfm", "-x", "ats", CBOX, "path").returncode == 2
+    assert run("-o", "x.pfm", "-x", "vpl", CBOX, "path").returncode == 2  # an extra option outside the GPU path (`-x ats` and `-x no-shading` are accepted)
     assert run("-o", "x.pfm", CBOX, "path", "-s", "nope").returncode == 2  # "invalid strategy", cli.rs:536-541
     assert run("-o", "x.pfm", CBOX, "ao", "-q").returncode == 2
-    r = run("-o", "x.pfm", "nothing.xml", "path")
+    r = run("-o", "x.pfm", "nothing.obj", "path")
     assert r.returncode == 1 and "scene loader" in r.stderr               # scene_loader.rs:40-43
 
 

@@ -52,7 +52,7 @@ def test_use_shading_normal_flag():
 def test_loader_errors():
     m = SceneLoaderManager()
     with pytest.raises(SceneError, match="extension"):
-        m.load("scene.xml")            # no such loader registered (scene_loader.rs:40-43)
+        m.load("scene.obj")            # no such loader registered (scene_loader.rs:40-43)
     with pytest.raises(SceneError, match="No file extension"):
         m.load("scene")
     with pytest.raises(SceneError, match="camera"):
