@@ -1016,6 +1016,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                                                                  ctx->sh_a, ctx->sh_b, ctx->sh_c, shc + k, ctx->lacc, ctx->d_counters, k == 0 ? (camera_o ? 3u : 1u) : 0u, done_at, k)
                     // kernel specialised for the BSDF kinds of the scene: {diffuse}, {diffuse, phong}, everything
                     // (textured scenes take the general kernel: bit 8 of the mask)
+                    // (one BSDF kind: no sort.  Gathering the ~11 % of rays that missed into whole warps with the tile sort was measured: shade 3.95 -> 4.48 ms per 80 M vertices)
                     if (sc->kind_mask == 0x1u && !extra) RL_LAUNCH_SHADE(false, 0x1u);
                     else if ((sc->kind_mask & ~0x3u) == 0u && !extra) {
                         if (sort_on) RL_LAUNCH_SHADE(true, 0x3u);
