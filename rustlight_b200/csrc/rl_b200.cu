@@ -255,6 +255,13 @@ int rl_create(rl_ctx **out, int device, int nranks, int rank, const void *nccl_u
     ctx->sm_count = prop.multiProcessorCount;
     ctx->mem_total = prop.totalGlobalMem;
     CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    { // keep up to 512 MB of freed scene memory in the stream-ordered pool instead of returning it to the driver at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thr = 512ull << 20;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     CKC(cudaMalloc(&ctx->d_counts, 4 * sizeof(uint32_t)));
     CKC(cudaMalloc(&ctx->d_counters, sizeof(Counters)));
     CKC(cudaMalloc(&ctx->d_hist, 4 * kMaxIters * sizeof(uint32_t))); // queue lengths, shadow-queue lengths, fix-list lengths (closest, shadow) per iteration
@@ -331,20 +338,22 @@ int rl_layout(rl_ctx *ctx, rl_layout_info *out) {
 // ---- scene -------------------------------------------------------------------------------------------
 template <typename T>
 static cudaError_t upload(T **dst, const std::vector<T> &src, cudaStream_t st) {
-    cudaError_t e = cudaMalloc(dst, std::max<size_t>(src.size(), 1) * sizeof(T));
+    cudaError_t e = cudaMallocAsync(dst, std::max<size_t>(src.size(), 1) * sizeof(T), st); // stream-ordered pool: no device-wide synchronisation (e2e rebuilds the scene every step)
     if (e != cudaSuccess) return e;
     if (!src.empty()) e = cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, st);
     return e;
 }
 
+// scene memory comes from the device's stream-ordered pool (cudaMallocAsync on the context's stream; release threshold raised in rl_create)
+#define SFREE(p) ((p) == nullptr ? cudaSuccess : (ctx ? cudaFreeAsync((p), ctx->stream) : cudaFree(p)))
 void rl_scene_destroy(rl_ctx *ctx, rl_scene *s) {
     if (!s) return;
     if (ctx) cudaSetDevice(ctx->device);
-    cudaFree(s->d_trav), cudaFree(s->d_nodes), cudaFree(s->d_shade), cudaFree(s->d_verts), cudaFree(s->d_mats);
-    cudaFree(s->d_emit_info), cudaFree(s->d_emit_cdf), cudaFree(s->d_area_cdf), cudaFree(s->d_flat);
-    cudaFree(s->d_uvs), cudaFree(s->d_tex), cudaFree(s->d_texels), cudaFree(s->d_env_dist), cudaFree(s->d_ats_nodes), cudaFree(s->d_ats_leaf);
-    cudaFree(s->d_quad_verts), cudaFree(s->d_cam_masks);
-    cudaFree(s->d_ref_nodes), cudaFree(s->d_ref_prims), cudaFree(s->d_ref_up);
+    SFREE(s->d_trav), SFREE(s->d_nodes), SFREE(s->d_shade), SFREE(s->d_verts), SFREE(s->d_mats);
+    SFREE(s->d_emit_info), SFREE(s->d_emit_cdf), SFREE(s->d_area_cdf), SFREE(s->d_flat);
+    SFREE(s->d_uvs), SFREE(s->d_tex), SFREE(s->d_texels), SFREE(s->d_env_dist), SFREE(s->d_ats_nodes), SFREE(s->d_ats_leaf);
+    SFREE(s->d_quad_verts), SFREE(s->d_cam_masks);
+    SFREE(s->d_ref_nodes), SFREE(s->d_ref_prims), SFREE(s->d_ref_up);
     delete s;
 }
 
@@ -371,8 +380,8 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     float4 *d_leaf_lo = nullptr, *d_leaf_hi = nullptr, *d_node_lo = nullptr, *d_node_hi = nullptr;
     void *d_tmp = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_keys), cudaFree(d_keys_sorted), cudaFree(d_children), cudaFree(d_ranges), cudaFree(d_parent_node), cudaFree(d_parent_leaf);
-        cudaFree(d_flags), cudaFree(d_leaf_lo), cudaFree(d_leaf_hi), cudaFree(d_node_lo), cudaFree(d_node_hi), cudaFree(d_tmp);
+        SFREE(d_keys), SFREE(d_keys_sorted), SFREE(d_children), SFREE(d_ranges), SFREE(d_parent_node), SFREE(d_parent_leaf);
+        SFREE(d_flags), SFREE(d_leaf_lo), SFREE(d_leaf_hi), SFREE(d_node_lo), SFREE(d_node_hi), SFREE(d_tmp);
     };
 #define CKS(call)                                                                                                  \
     do {                                                                                                           \
@@ -399,11 +408,11 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
         CKS(upload(&s->d_ats_leaf, hs.ats_leaf_of_prim, st));
     }
     const uint32_t n_nodes = n > 1 ? n - 1 : 1;
-    CKS(cudaMalloc(&s->d_trav, (size_t)n * RL_TRAV_F4 * sizeof(float4)));
-    CKS(cudaMalloc(&d_keys, (size_t)n * 8));
-    CKS(cudaMalloc(&d_keys_sorted, (size_t)n * 8));
-    CKS(cudaMalloc(&d_leaf_lo, (size_t)n * sizeof(float4)));
-    CKS(cudaMalloc(&d_leaf_hi, (size_t)n * sizeof(float4)));
+    CKS(cudaMallocAsync(&s->d_trav, (size_t)n * RL_TRAV_F4 * sizeof(float4), st));
+    CKS(cudaMallocAsync(&d_keys, (size_t)n * 8, st));
+    CKS(cudaMallocAsync(&d_keys_sorted, (size_t)n * 8, st));
+    CKS(cudaMallocAsync(&d_leaf_lo, (size_t)n * sizeof(float4), st));
+    CKS(cudaMallocAsync(&d_leaf_hi, (size_t)n * sizeof(float4), st));
     // The tree collapses subtrees of <= 2 triangles into leaves.  Scenes of <= 64 triangles additionally get the group
     // table (rl_flat_host.hpp), which every ray scans instead of walking the tree.
     int leaf_max = 2; // measured on a 20 736-triangle scene (tools/tess_cbox.py 24): leaves of <= 1 / 2 / 4 / 8 / 16 triangles: 31.2 / 27.4 / 28.4 / 31.1 / 36.1 ms
@@ -443,7 +452,7 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
         CKS(cudaGetLastError());
         size_t tmp_bytes = 0;
         CKS(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, d_keys, d_keys_sorted, (int)n, 0, 64, st));
-        CKS(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+        CKS(cudaMallocAsync(&d_tmp, std::max<size_t>(tmp_bytes, 16), st));
         CKS(cub::DeviceRadixSort::SortKeys(d_tmp, tmp_bytes, d_keys, d_keys_sorted, (int)n, 0, 64, st));
     }
     k_tri_setup<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(s->d_verts, d_keys_sorted, n, bvh_box_eps(hs.abs_max), s->d_trav, s->d_shade, d_leaf_lo, d_leaf_hi);
@@ -456,21 +465,21 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
         if (const char *e = getenv("RL_TREE")) width = std::strcmp(e, "sah2") == 0 ? 2u : 4u; // A/B: lbvh | sah2 | sah (= 4-wide)
         build_wide_tree(rb, bvh_box_eps(hs.abs_max), width, wt);
         if (wt.max_stack > (uint32_t)RL_STACK_SIZE) build_wide_tree(rb, bvh_box_eps(hs.abs_max), 2u, wt); // (rb.depth + 2 <= RL_STACK_SIZE was checked)
-        CKS(cudaMalloc(&s->d_nodes, wt.nodes.size() * sizeof(float4)));
+        CKS(cudaMallocAsync(&s->d_nodes, wt.nodes.size() * sizeof(float4), st));
         CKS(cudaMemcpyAsync(s->d_nodes, wt.nodes.data(), wt.nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
     } else {
-        CKS(cudaMalloc(&s->d_nodes, (size_t)n_nodes * 4 * sizeof(float4)));
+        CKS(cudaMallocAsync(&s->d_nodes, (size_t)n_nodes * 4 * sizeof(float4), st));
         h_keys.resize(n); // Morton order of the triangles: group table, and the slot of every primitive for the reference-order tree
         CKS(cudaMemcpyAsync(h_keys.data(), d_keys_sorted, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     }
     if (n > 1 && !use_sah) {
-        CKS(cudaMalloc(&d_children, (size_t)(n - 1) * sizeof(int2)));
-        CKS(cudaMalloc(&d_ranges, (size_t)(n - 1) * sizeof(int2v)));
-        CKS(cudaMalloc(&d_parent_node, (size_t)(n - 1) * sizeof(int)));
-        CKS(cudaMalloc(&d_parent_leaf, (size_t)n * sizeof(int)));
-        CKS(cudaMalloc(&d_flags, (size_t)(n - 1) * sizeof(int)));
-        CKS(cudaMalloc(&d_node_lo, (size_t)(n - 1) * sizeof(float4)));
-        CKS(cudaMalloc(&d_node_hi, (size_t)(n - 1) * sizeof(float4)));
+        CKS(cudaMallocAsync(&d_children, (size_t)(n - 1) * sizeof(int2), st));
+        CKS(cudaMallocAsync(&d_ranges, (size_t)(n - 1) * sizeof(int2v), st));
+        CKS(cudaMallocAsync(&d_parent_node, (size_t)(n - 1) * sizeof(int), st));
+        CKS(cudaMallocAsync(&d_parent_leaf, (size_t)n * sizeof(int), st));
+        CKS(cudaMallocAsync(&d_flags, (size_t)(n - 1) * sizeof(int), st));
+        CKS(cudaMallocAsync(&d_node_lo, (size_t)(n - 1) * sizeof(float4), st));
+        CKS(cudaMallocAsync(&d_node_hi, (size_t)(n - 1) * sizeof(float4), st));
         CKS(cudaMemsetAsync(d_flags, 0, (size_t)(n - 1) * sizeof(int), st));
         k_karras<<<grid_for(ctx, n - 1, 8), kBlock, 0, st>>>(d_keys_sorted, (int)n, d_children, d_ranges, d_parent_node, d_parent_leaf);
         CKS(cudaGetLastError());
@@ -788,9 +797,9 @@ static int ensure_cam_masks(rl_ctx *ctx, rl_scene *sc) {
     if (sc->cam_gen == ctx->pl_gen && sc->d_cam_masks) return RL_OK;
     const uint32_t npix = ctx->pl_npix, nblk = (npix + 31u) / 32u;
     if (nblk > sc->cam_cap) {
-        cudaFree(sc->d_cam_masks);
+        if (sc->d_cam_masks) cudaFreeAsync(sc->d_cam_masks, ctx->stream);
         sc->d_cam_masks = nullptr, sc->cam_cap = 0;
-        CK(cudaMalloc(&sc->d_cam_masks, (size_t)std::max(nblk, 1u) * sizeof(uint32_t)));
+        CK(cudaMallocAsync(&sc->d_cam_masks, (size_t)std::max(nblk, 1u) * sizeof(uint32_t), ctx->stream));
         sc->cam_cap = nblk;
     }
     const HostScene &hs = sc->hs;
