@@ -953,9 +953,13 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                 if (sc->smem_ok) launch_trace<true>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, done_at, 0u, true, camera_o, cam_masks);
                 else launch_trace<false>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, done_at, 0u, true, camera_o, cam_masks);
                 ev_mark(ctx, EV_TRACE);
-                k_shade_direct1<<<grid_for(ctx, n, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, c_in, (uint32_t)n_paths, ctx->ray_o[0], ctx->ray_d[0],
-                                                                        ctx->state[0], ctx->hit, ctx->ray_o[1], ctx->ray_d[1], ctx->state[1], c_out, ctx->sh_a,
-                                                                        ctx->sh_b, ctx->sh_c, c_sh, ctx->lacc, ctx->d_counters, camera_o ? 3u : 1u);
+#define RL_LAUNCH_DIRECT1(KM) k_shade_direct1<KM><<<grid_for(ctx, n, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, c_in, (uint32_t)n_paths, ctx->ray_o[0], ctx->ray_d[0], \
+        ctx->state[0], ctx->hit, ctx->ray_o[1], ctx->ray_d[1], ctx->state[1], c_out, ctx->sh_a, \
+        ctx->sh_b, ctx->sh_c, c_sh, ctx->lacc, ctx->d_counters, camera_o ? 3u : 1u)
+                if (sc->kind_mask == 0x1u && !extra) RL_LAUNCH_DIRECT1(0x1u);
+                else RL_LAUNCH_DIRECT1(RL_KM_ALL);
+#undef RL_LAUNCH_DIRECT1
+
                 ctx->launches++;
                 ev_mark(ctx, EV_SHADE);
                 if (nl > 0) {

@@ -2459,20 +2459,21 @@ struct DirectCtx {
     bool env_primary; // the primary ray escaped into the environment: the sample's value is `emit`
     Col emit;
 };
+template <uint32_t KM = RL_KM_ALL>
 RL_HD void direct_begin(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, const HitRec &hit, uint32_t rng_n, uint32_t pixel, uint32_t sample,
                         DirectCtx *cx) {
     cx->ok = false;
     cx->emit = Col{0.0f, 0.0f, 0.0f};
     cx->env_primary = false;
     if (hit.prim == RL_MISS) { // return scene.enviroment_luminance(ray.d) (direct.rs:33-36)
-        if (sv.env_on) cx->emit = sv.env_w ? env_eval(sv, d) : sv.env_color, cx->env_primary = true;
+        if (sv.env_on) cx->emit = (RL_HAS(KM, 8) && sv.env_w) ? env_eval(sv, d) : sv.env_color, cx->env_primary = true;
         return;
     }
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
     uint32_t mesh = f2u(s0.w);
     cx->mat = load_material(sv.mats, mesh);
-    if (sv.tex) apply_textures(sv, cx->mat, hit.prim, f2u(s1.w), hit.u, hit.v);
-    cx->its = fill_intersection(sv, cx->mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
+    if (RL_HAS(KM, 8) && sv.tex) apply_textures(sv, cx->mat, hit.prim, f2u(s1.w), hit.u, hit.v);
+    cx->its = fill_intersection<KM>(sv, cx->mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
     if (cx->its.wi.z <= 0.0f) return; // its.cos_theta() <= 0 (direct.rs:40-42)
     cx->ok = true;
     if (cx->mat.is_light) cx->emit = cx->mat.le;
@@ -2482,19 +2483,20 @@ RL_HD void direct_begin(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, 
 }
 // One light sample (direct.rs:63-129).  Returns true when a shadow segment must be traced;
 // *valid tells whether the reference would have called Acceleration::visible.
+template <uint32_t KM = RL_KM_ALL>
 RL_HD bool direct_light_sample(const SceneView &sv, DirectCtx *cx, V3 *p1, Col *contrib, bool *valid) {
     float r_sel = cx->smp.next();
     float r = cx->smp.next();
     float ux = cx->smp.next();
     float uy = cx->smp.next();
-    LightSample ls = sample_light(sv, cx->its.p, cx->its.n_s, r_sel, r, ux, uy);
+    LightSample ls = sample_light<RL_HAS(KM, 8) != 0u>(sv, cx->its.p, cx->its.n_s, r_sel, r, ux, uy);
     *valid = ls.valid;
     if (!ls.valid) return false;
-    if (mat_is_smooth(cx->mat)) return false; // direct.rs:74-77: visible() is still called (valid stays true), nothing is added
+    if (mat_is_smooth<KM>(cx->mat)) return false; // direct.rs:74-77: visible() is still called (valid stays true), nothing is added
     V3 wo = to_local(cx->its.frame, ls.d);
     float pdf_bsdf;
     Col f;
-    bsdf_eval_pdf(cx->mat, cx->its.wi, wo, &f, &pdf_bsdf);
+    bsdf_eval_pdf<KM>(cx->mat, cx->its.wi, wo, &f, &pdf_bsdf);
     float weight_light = ls.discrete ? 1.0f : mis_weight_power(ls.pdf * cx->wl, pdf_bsdf * cx->wb); // direct.rs:106-110
     Col c = mul_checked(mul_plain(weight_light, f), cx->wl) * ls.weight;
     *p1 = ls.p;
@@ -2531,12 +2533,13 @@ RL_HD bool ao_finish(const IntegParams &ip, const HitRec &hit, Col *contrib) {
     return open;
 }
 // One BSDF sample (direct.rs:135-144): the extension ray and what stage 2 needs (weight, pdf).
+template <uint32_t KM = RL_KM_ALL>
 RL_HD bool direct_bsdf_sample(DirectCtx *cx, V3 *dir, Col *weight, float *pdf) {
     float sx = cx->smp.next();
     float sy = cx->smp.next();
     V3 wo;
     bool discrete;
-    if (!bsdf_sample(cx->mat, cx->its.wi, sx, sy, weight, &wo, pdf, &discrete)) return false;
+    if (!bsdf_sample<KM>(cx->mat, cx->its.wi, sx, sy, weight, &wo, pdf, &discrete)) return false;
     if (discrete) *pdf = u2f(f2u(*pdf) | 0x80000000u); // PDF::Discrete -> weight_bsdf = 1 in stage 2 (direct.rs:170)
     *dir = to_world(cx->its.frame, wo);
     return true;

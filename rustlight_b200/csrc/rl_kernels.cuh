@@ -616,6 +616,9 @@ __global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams i
 #ifndef RL_DIRECT1_MINBLOCKS
 #define RL_DIRECT1_MINBLOCKS 4
 #endif
+// KM: the BSDF kinds of the scene as for k_shade ({diffuse} and "everything" are instantiated): the Cornell-box kernel carries no Phong / microfacet /
+// blend / texture / light-tree code (826 -> see profiles bytes of spills when everything is compiled in).
+template <uint32_t KM>
 __global__ void __launch_bounds__(kBlock, RL_DIRECT1_MINBLOCKS) k_shade_direct1(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
                                                           const uint32_t *__restrict__ count_in, uint32_t n_paths, const float4 *__restrict__ ray_o,
                                                           const float4 *__restrict__ ray_d, const float4 *__restrict__ state,
@@ -645,7 +648,7 @@ __global__ void __launch_bounds__(kBlock, RL_DIRECT1_MINBLOCKS) k_shade_direct1(
             uint32_t s_local, lp;
             ip_split(ip, pid, &s_local, &lp);
             if (ip.kind == 2u) ao_begin(sv, ip, xyz(ro), xyz(rd), h, f2u(st4.w) & 0xffffu, __ldg(pixel_list + lp), ip.sample_base + s_local, &cx);
-            else direct_begin(sv, ip, xyz(ro), xyz(rd), h, f2u(st4.w) & 0xffffu, __ldg(pixel_list + lp), ip.sample_base + s_local, &cx);
+            else direct_begin<KM>(sv, ip, xyz(ro), xyz(rd), h, f2u(st4.w) & 0xffffu, __ldg(pixel_list + lp), ip.sample_base + s_local, &cx);
             if (h.prim != RL_MISS) c_hits++;
             if ((cx.ok || cx.env_primary) && !is_zero(cx.emit)) lacc[pid] = make_float4(cx.emit.r, cx.emit.g, cx.emit.b, 0.0f);
         }
@@ -653,7 +656,7 @@ __global__ void __launch_bounds__(kBlock, RL_DIRECT1_MINBLOCKS) k_shade_direct1(
             V3 p1 = V3{0.0f, 0.0f, 0.0f};
             Col c = Col{0.0f, 0.0f, 0.0f};
             bool valid = false;
-            bool emit_sh = cx.ok && direct_light_sample(sv, &cx, &p1, &c, &valid);
+            bool emit_sh = cx.ok && direct_light_sample<KM>(sv, &cx, &p1, &c, &valid);
             if (valid) c_nee++;
             uint32_t slot = block_compact(emit_sh, count_shadow, s_warp, &s_base);
             if (emit_sh) {
@@ -666,7 +669,7 @@ __global__ void __launch_bounds__(kBlock, RL_DIRECT1_MINBLOCKS) k_shade_direct1(
             V3 dir = V3{0.0f, 0.0f, 0.0f};
             Col w = Col{0.0f, 0.0f, 0.0f};
             float pdf = 0.0f;
-            bool go = cx.ok && (ip.kind == 2u ? ao_sample(ip, &cx, &dir) : direct_bsdf_sample(&cx, &dir, &w, &pdf));
+            bool go = cx.ok && (ip.kind == 2u ? ao_sample(ip, &cx, &dir) : direct_bsdf_sample<KM>(&cx, &dir, &w, &pdf));
             uint32_t slot = block_compact(go, count_out, s_warp, &s_base);
             if (go) {
                 out_o[slot] = make_float4(cx.its.p.x, cx.its.p.y, cx.its.p.z, u2f(pid));
