@@ -625,43 +625,88 @@ RL_HD float box_entry(const Trav &tr, float lox, float loy, float loz, float hix
     float tend = fminf(fminf(fx, fy), fminf(fz, tr.tmax));
     return tmin <= tend ? tmin : -1.0f;
 }
-RL_HD int trav_pop(Trav &tr, const int *stack) { return tr.sp > 0 ? stack[--tr.sp] : RL_TRAV_DONE; }
+#ifndef RL_TREE_DIST
+#define RL_TREE_DIST 1 // closest-hit rays keep the entry distance of every stacked node and drop it at the pop once a nearer hit is known (A/B hook)
+#endif
+#ifndef RL_TREE_ANY_NOSORT
+#define RL_TREE_ANY_NOSORT 1 // shadow segments do not order the children of a node (A/B hook)
+#endif
+// Next node from the stack.  sdist (closest-hit rays): the entry distances of the stacked nodes (rounded down) -- an entry behind the
+// culling bound tr.tmax, which has shrunk since the push, would only be visited to find all its children culled.
+RL_HD int trav_pop(Trav &tr, const int *stack, const float *sdist = nullptr) {
+    if (RL_TREE_DIST && sdist) {
+        while (tr.sp > 0) {
+            --tr.sp;
+            if (sdist[tr.sp] <= tr.tmax) return stack[tr.sp];
+        }
+        return RL_TRAV_DONE;
+    }
+    return tr.sp > 0 ? stack[--tr.sp] : RL_TRAV_DONE;
+}
 // 4-wide node (rl_wide_host.hpp): four slab tests per visit.  The children that are hit are ordered by entry distance with a
 // sorting network over keys (distance bits with the child number in the two lowest bits: the order is a heuristic, two mantissa
 // bits do not matter); the nearest becomes tr.cur, the others go on the stack farthest first.
+// ANY (shadow segments: every node the segment crosses is visited unless a blocker ends the walk, so the order is worth nothing):
+// the first child hit becomes tr.cur, the others are pushed as they come.
 RL_HD void sort2u(uint32_t &a, uint32_t &b) {
     const uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
     a = lo, b = hi;
 }
-RL_HD void trav_node_step4(Trav &tr, int *stack, const float4 *nodes) {
+template <bool ANY>
+RL_HD void trav_node_step4(Trav &tr, int *stack, const float4 *nodes, float *sdist) {
     const float4 *nd = nodes + 7 * tr.cur;
     const float4 lx = nd[0], ly = nd[1], lz = nd[2], hx = nd[3], hy = nd[4], hz = nd[5], rf = nd[6];
     const float d0 = box_entry(tr, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x);
     const float d1 = box_entry(tr, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y);
     const float d2 = f2u(rf.z) == (uint32_t)RL_TRAV_EMPTY ? -1.0f : box_entry(tr, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z);
     const float d3 = f2u(rf.w) == (uint32_t)RL_TRAV_EMPTY ? -1.0f : box_entry(tr, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w);
+    const uint32_t c0 = f2u(rf.x), c1 = f2u(rf.y), c2 = f2u(rf.z), c3 = f2u(rf.w);
+    if (ANY && RL_TREE_ANY_NOSORT) {
+        int next = RL_TRAV_DONE;
+        if (d3 >= 0.0f) next = (int)c3;
+        if (d2 >= 0.0f) {
+            if (next != RL_TRAV_DONE && tr.sp < RL_STACK_SIZE) stack[tr.sp++] = next;
+            next = (int)c2;
+        }
+        if (d1 >= 0.0f) {
+            if (next != RL_TRAV_DONE && tr.sp < RL_STACK_SIZE) stack[tr.sp++] = next;
+            next = (int)c1;
+        }
+        if (d0 >= 0.0f) {
+            if (next != RL_TRAV_DONE && tr.sp < RL_STACK_SIZE) stack[tr.sp++] = next;
+            next = (int)c0;
+        }
+        tr.cur = next != RL_TRAV_DONE ? next : trav_pop(tr, stack);
+        return;
+    }
     // d >= 0 on a hit (float bits are monotonic), -1 on a miss -> key 0xffffffff
     uint32_t k0 = d0 >= 0.0f ? (f2u(d0) & ~3u) : 0xffffffffu;
     uint32_t k1 = d1 >= 0.0f ? ((f2u(d1) & ~3u) | 1u) : 0xffffffffu;
     uint32_t k2 = d2 >= 0.0f ? ((f2u(d2) & ~3u) | 2u) : 0xffffffffu;
     uint32_t k3 = d3 >= 0.0f ? ((f2u(d3) & ~3u) | 3u) : 0xffffffffu;
     sort2u(k0, k1), sort2u(k2, k3), sort2u(k0, k2), sort2u(k1, k3), sort2u(k1, k2);
-    const uint32_t c0 = f2u(rf.x), c1 = f2u(rf.y), c2 = f2u(rf.z), c3 = f2u(rf.w);
 #define RL_PICK4(k) (int)(((k) & 2u) ? (((k) & 1u) ? c3 : c2) : (((k) & 1u) ? c1 : c0))
+#define RL_PUSH4(k)                                                             \
+    if ((k) != 0xffffffffu && tr.sp < RL_STACK_SIZE) {                          \
+        if (RL_TREE_DIST && sdist) sdist[tr.sp] = u2f((k) & ~3u); /* <= d */    \
+        stack[tr.sp++] = RL_PICK4(k);                                           \
+    }
     if (k0 == 0xffffffffu) {
-        tr.cur = trav_pop(tr, stack);
+        tr.cur = trav_pop(tr, stack, sdist);
         return;
     }
-    if (k3 != 0xffffffffu && tr.sp < RL_STACK_SIZE) stack[tr.sp++] = RL_PICK4(k3);
-    if (k2 != 0xffffffffu && tr.sp < RL_STACK_SIZE) stack[tr.sp++] = RL_PICK4(k2);
-    if (k1 != 0xffffffffu && tr.sp < RL_STACK_SIZE) stack[tr.sp++] = RL_PICK4(k1);
+    RL_PUSH4(k3)
+    RL_PUSH4(k2)
+    RL_PUSH4(k1)
     tr.cur = RL_PICK4(k0);
+#undef RL_PUSH4
 #undef RL_PICK4
 }
 // Phase A: one inner-node step (tr.cur >= 0).  Leaves tr.cur at a child, a popped entry or DONE.
-RL_HD void trav_node_step(Trav &tr, int *stack, const float4 *nodes) {
+template <bool ANY = false>
+RL_HD void trav_node_step(Trav &tr, int *stack, const float4 *nodes, float *sdist = nullptr) {
     if (tr.wide4) {
-        trav_node_step4(tr, stack, nodes);
+        trav_node_step4<ANY>(tr, stack, nodes, sdist);
         return;
     }
     const int node = tr.cur;
@@ -672,11 +717,14 @@ RL_HD void trav_node_step(Trav &tr, int *stack, const float4 *nodes) {
     if (d0 >= 0.0f && d1 >= 0.0f) {
         bool swap = d1 < d0;
         int nearc = swap ? c1 : c0, farc = swap ? c0 : c1;
-        if (tr.sp < RL_STACK_SIZE) stack[tr.sp++] = farc;
+        if (tr.sp < RL_STACK_SIZE) {
+            if (RL_TREE_DIST && sdist) sdist[tr.sp] = swap ? d0 : d1;
+            stack[tr.sp++] = farc;
+        }
         tr.cur = nearc;
     } else if (d0 >= 0.0f) tr.cur = c0;
     else if (d1 >= 0.0f) tr.cur = c1;
-    else tr.cur = trav_pop(tr, stack);
+    else tr.cur = trav_pop(tr, stack, sdist);
 }
 // Conservative prefilter in front of the exact triangle test: approximate hit parameter and
 // barycentrics from the precomputed plane / affine functionals (fma, reciprocal), with error
@@ -730,7 +778,7 @@ RL_HD uint64_t leaf_scan(const Trav &tr, const float4 *trav, uint32_t first, uin
     }
     return mask;
 }
-RL_HD void trav_leaf_closest(Trav &tr, const int *stack, const float4 *trav) {
+RL_HD void trav_leaf_closest(Trav &tr, const int *stack, const float4 *trav, const float *sdist = nullptr) {
     const uint32_t first = leaf_first(tr.cur), count = leaf_count(tr.cur);
     uint64_t mask = leaf_scan(tr, trav, first, count);
     while (mask) {
@@ -754,7 +802,7 @@ RL_HD void trav_leaf_closest(Trav &tr, const int *stack, const float4 *trav) {
             }
         }
     }
-    tr.cur = trav_pop(tr, stack);
+    tr.cur = trav_pop(tr, stack, sdist);
 }
 // Phase B (any hit): returns true when the segment is blocked.
 RL_HD bool trav_leaf_any(Trav &tr, const int *stack, const float4 *trav) {
@@ -1269,9 +1317,14 @@ RL_HD HitRec trace_closest(const SceneView &sv, const float4 *flat, const float4
         return flat_closest(sv, flat, trav, o, d);
     }
     if (closest_begin(tr, sv, o, d)) {
+#if RL_TREE_DIST
+        float sdist[RL_STACK_SIZE];
+#else
+        float *sdist = nullptr;
+#endif
         while (tr.cur != RL_TRAV_DONE) {
-            if (tr.cur >= 0) trav_node_step(tr, stack, nodes);
-            else trav_leaf_closest(tr, stack, trav);
+            if (tr.cur >= 0) trav_node_step<false>(tr, stack, nodes, sdist);
+            else trav_leaf_closest(tr, stack, trav, sdist);
         }
     }
     HitRec h = closest_result(tr);
@@ -1291,7 +1344,7 @@ RL_HD bool trace_visible(const SceneView &sv, const float4 *flat, const float4 *
     visible_begin(tr, sv, p0, p1, &decided, &vis);
     if (decided) return vis;
     while (tr.cur != RL_TRAV_DONE) {
-        if (tr.cur >= 0) trav_node_step(tr, stack, nodes);
+        if (tr.cur >= 0) trav_node_step<true>(tr, stack, nodes);
         else if (trav_leaf_any(tr, stack, trav)) return false;
     }
     if (tr.amb) return !(ref_path_ok(sv, tr.rim_slot, tr.o, tr.d, tr.tmax) || ref_bvh_any(sv, trav, tr.o, tr.d, tr.tmax)); // blocked by rim hits only

@@ -123,6 +123,11 @@ __global__ void __launch_bounds__(kBlock, RL_TREE_MINBLOCKS) k_trace(SceneView s
     warp_chunk(*count, &cursor, &chunk_end);
     Trav tr;
     int stack[RL_STACK_SIZE];
+#if RL_TREE_DIST
+    float sdist[RL_STACK_SIZE]; // entry distances of the stacked nodes (trav_pop)
+#else
+    float *sdist = nullptr;
+#endif
     tr.cur = RL_TRAV_DONE;
     uint32_t my = RL_MISS; // queue index of the ray this lane is tracing
     for (;;) {
@@ -141,11 +146,11 @@ __global__ void __launch_bounds__(kBlock, RL_TREE_MINBLOCKS) k_trace(SceneView s
         }
         if (idle == 0xffffffffu) break; // chunk exhausted and every lane finished
 #if RL_WHILE_WHILE
-        while ((uint32_t)tr.cur < (uint32_t)RL_TRAV_DONE) trav_node_step(tr, stack, nodes); // descend: inner nodes
-        if (tr.cur < 0) trav_leaf_closest(tr, stack, trav);                                  // one leaf
+        while ((uint32_t)tr.cur < (uint32_t)RL_TRAV_DONE) trav_node_step<false>(tr, stack, nodes, sdist); // descend: inner nodes
+        if (tr.cur < 0) trav_leaf_closest(tr, stack, trav, sdist);                                         // one leaf
 #else
-        if ((uint32_t)tr.cur < (uint32_t)RL_TRAV_DONE) trav_node_step(tr, stack, nodes);
-        else if (tr.cur < 0) trav_leaf_closest(tr, stack, trav);
+        if ((uint32_t)tr.cur < (uint32_t)RL_TRAV_DONE) trav_node_step<false>(tr, stack, nodes, sdist);
+        else if (tr.cur < 0) trav_leaf_closest(tr, stack, trav, sdist);
 #endif
         if (tr.cur == RL_TRAV_DONE && my != RL_MISS) {
             HitRec h = closest_result(tr);
@@ -748,10 +753,10 @@ __global__ void __launch_bounds__(kBlock, RL_TREE_MINBLOCKS) k_shadow(SceneView 
         }
         if (idle == 0xffffffffu) break;
 #if RL_WHILE_WHILE
-        while ((uint32_t)tr.cur < (uint32_t)RL_TRAV_DONE) trav_node_step(tr, stack, nodes);
+        while ((uint32_t)tr.cur < (uint32_t)RL_TRAV_DONE) trav_node_step<true>(tr, stack, nodes);
         if (tr.cur < 0) blocked = trav_leaf_any(tr, stack, trav) || blocked;
 #else
-        if ((uint32_t)tr.cur < (uint32_t)RL_TRAV_DONE) trav_node_step(tr, stack, nodes);
+        if ((uint32_t)tr.cur < (uint32_t)RL_TRAV_DONE) trav_node_step<true>(tr, stack, nodes);
         else if (tr.cur < 0) blocked = trav_leaf_any(tr, stack, trav) || blocked;
 #endif
         if (tr.cur == RL_TRAV_DONE && my != RL_MISS) {

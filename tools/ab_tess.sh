@@ -1,1 +1,3 @@
-for v in base mb4 mb5 mb6 mb8; do echo "== $v"; RL_B200_LIB=build/variants/librl_$v.so timeout 300 python tools/tess_cbox.py 24 16 2>&1 | grep tess24 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_total'], d['trace'], d['shadow'], d['mean'])"; done
+#!/bin/bash
+# Tessellated Cornell box (tree kernels) through each variant in build/variants: tools/ab_tess.sh "<variants>" "<N list>" [spp]   (development aid)
+for v in $1; do for n in $2; do echo -n "$v "; RL_B200_LIB=build/variants/librl_$v.so timeout 300 python tools/tess_cbox.py $n ${3:-16} 2>&1 | grep "tess$n"; done; done
