@@ -576,6 +576,8 @@ struct Trav {
     float tie_t;   // closest: smallest t of a tie seen so far (-1: none); it matters only when it is within the window of the final hit
     bool edge_checks; // the scene carries the reference's tree (sv.ref_nodes)
     bool wide4;       // sv.wide4
+    uint32_t near_off; // 4-wide nodes: which of the float4 rows {lo.x lo.y lo.z hi.x hi.y hi.z} holds the NEAR plane of each axis (2 bits per axis: 0 / 3 + axis);
+                       // the far plane is the other one (rl_wide_host.hpp)
     float omax, abs_max; // max |o|, scene extent (hit_unsafe)
     float u, v;
     uint32_t prim;
@@ -604,6 +606,7 @@ RL_HD void trav_begin(Trav &tr, const SceneView &sv, V3 o, V3 d, V3 inv, float t
     tr.tie_t = -1.0f;
     tr.edge_checks = RL_REF_ORDER && sv.ref_nodes != nullptr;
     tr.wide4 = sv.wide4 != 0u;
+    tr.near_off = (tr.inv.x < 0.0f ? 3u : 0u) | (tr.inv.y < 0.0f ? 3u << 2 : 0u) | (tr.inv.z < 0.0f ? 3u << 4 : 0u);
     tr.u = 0.0f;
     tr.v = 0.0f;
     tr.prim = RL_MISS;
@@ -633,6 +636,12 @@ RL_HD float box_entry(const Trav &tr, float lox, float loy, float loz, float hix
 #endif
 // Next node from the stack.  sdist (closest-hit rays): the entry distances of the stacked nodes (rounded down) -- an entry behind the
 // culling bound tr.tmax, which has shrunk since the push, would only be visited to find all its children culled.
+// box_entry with the near / far planes already picked
+RL_HD float box_entry_nf(const Trav &tr, float nxp, float nyp, float nzp, float fxp, float fyp, float fzp) {
+    const float tn = fmaxf(fmaxf(fmaf(nxp, tr.inv.x, -tr.ood_n.x), fmaf(nyp, tr.inv.y, -tr.ood_n.y)), fmaxf(fmaf(nzp, tr.inv.z, -tr.ood_n.z), 0.0f));
+    const float tf = fminf(fminf(fmaf(fxp, tr.inv.x, -tr.ood_f.x), fmaf(fyp, tr.inv.y, -tr.ood_f.y)), fminf(fmaf(fzp, tr.inv.z, -tr.ood_f.z), tr.tmax));
+    return tn <= tf ? tn : -1.0f;
+}
 RL_HD int trav_pop(Trav &tr, const int *stack, const float *sdist = nullptr) {
     if (RL_TREE_DIST && sdist) {
         while (tr.sp > 0) {
@@ -655,11 +664,13 @@ RL_HD void sort2u(uint32_t &a, uint32_t &b) {
 template <bool ANY>
 RL_HD void trav_node_step4(Trav &tr, int *stack, const float4 *nodes, float *sdist) {
     const float4 *nd = nodes + 7 * tr.cur;
-    const float4 lx = nd[0], ly = nd[1], lz = nd[2], hx = nd[3], hy = nd[4], hz = nd[5], rf = nd[6];
-    const float d0 = box_entry(tr, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x);
-    const float d1 = box_entry(tr, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y);
-    const float d2 = f2u(rf.z) == (uint32_t)RL_TRAV_EMPTY ? -1.0f : box_entry(tr, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z);
-    const float d3 = f2u(rf.w) == (uint32_t)RL_TRAV_EMPTY ? -1.0f : box_entry(tr, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w);
+    // The near / far plane of each axis is picked by the sign of the direction (box_entry) -- the same for every node of a ray, so the
+    // choice sits in the ADDRESS of the row (rows 0-2 lo, 3-5 hi): 6 fma per box and no selects.  Unused slots hold an inverted
+    // infinite box and fail the test by themselves.
+    const uint32_t ox = tr.near_off & 3u, oy = (tr.near_off >> 2) & 3u, oz = tr.near_off >> 4;
+    const float4 nx = nd[ox], ny = nd[1u + oy], nz = nd[2u + oz], fx = nd[3u - ox], fy = nd[4u - oy], fz = nd[5u - oz], rf = nd[6];
+    const float d0 = box_entry_nf(tr, nx.x, ny.x, nz.x, fx.x, fy.x, fz.x), d1 = box_entry_nf(tr, nx.y, ny.y, nz.y, fx.y, fy.y, fz.y);
+    const float d2 = box_entry_nf(tr, nx.z, ny.z, nz.z, fx.z, fy.z, fz.z), d3 = box_entry_nf(tr, nx.w, ny.w, nz.w, fx.w, fy.w, fz.w);
     const uint32_t c0 = f2u(rf.x), c1 = f2u(rf.y), c2 = f2u(rf.z), c3 = f2u(rf.w);
     if (ANY && RL_TREE_ANY_NOSORT) {
         int next = RL_TRAV_DONE;

@@ -11,10 +11,11 @@
 //            children or only leaves): seven float4 per node in SoA form
 //              [0] lo.x of children 0-3   [1] lo.y   [2] lo.z   [3] hi.x   [4] hi.y   [5] hi.z   [6] child references (int bits)
 //            One visit = seven 128-bit loads for four slab tests instead of two dependent visits of four loads each: half the
-//            dependent memory round trips per ray on incoherent rays.  Unused child slots hold RL_TRAV_EMPTY.
+//            dependent memory round trips per ray on incoherent rays.  Unused child slots hold RL_TRAV_EMPTY and an inverted infinite box.
 // Child references as in rl_device.cuh: >= 0 inner node index, bit 31 set = leaf_ref(first slot, count).  Slot order = the
 // reference's primitive order (RefBVH::prims), so every leaf covers consecutive slots.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <vector>
 
@@ -72,7 +73,9 @@ inline void build_wide_tree(const RefBVH &rb, float eps, uint32_t width, WideTre
         V3 lo[4], hi[4];
         for (uint32_t k = 0; k < 4; k++) {
             refs[k] = RL_TRAV_EMPTY;
-            lo[k] = hi[k] = V3{0.0f, 0.0f, 0.0f};
+            // an inverted, infinite box: the slab test of an unused slot fails by itself (entry +inf, exit -inf whatever the direction;
+            // inf x (1/d clamped to a finite non-zero value) is never NaN)
+            lo[k] = V3{INFINITY, INFINITY, INFINITY}, hi[k] = V3{-INFINITY, -INFINITY, -INFINITY};
         }
         for (uint32_t k = 0; k < nk; k++) {
             const float4 a = rb.nodes[2 * kids[k]], b = rb.nodes[2 * kids[k] + 1];
