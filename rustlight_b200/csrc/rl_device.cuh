@@ -306,6 +306,47 @@ struct Sampler {
         return (float)bits * (1.0f / 16777216.0f);
     }
 };
+// The same stream read in (even, odd) slot order from a start n0 that is only known at run time, with every hash at a fixed place in
+// the code: no "is the hash still valid" test and no branch per draw (k_shade: the generic next() was 7 % of the kernel's
+// instructions).  With s = n0 & 1, slot j of this reader is half j + s of the hash sequence that starts at hash number n0 / 2 + 1:
+// an even slot reads the current hash (upper half when s = 0, lower when s = 1), an odd slot computes the next hash and reads its
+// upper half (s = 1) or the current hash's lower half (s = 0).  Calls must alternate even(), odd(), even(), ...; after a draw that is
+// taken conditionally the caller re-begins at the new count (one more hash).
+#ifndef RL_PAIR_SAMPLER
+#define RL_PAIR_SAMPLER 1
+#endif
+struct PairSampler {
+    uint64_t key, zc;
+    uint32_t h, n;
+    bool s;
+    RL_HD static uint32_t hi24(uint64_t z) { return (uint32_t)(z >> 40); }
+    RL_HD static uint32_t lo24(uint64_t z) { return (uint32_t)(z >> 16) & 0xffffffu; }
+    RL_HD static float unit(uint32_t bits) { return (float)bits * (1.0f / 16777216.0f); }
+    RL_HD void begin(uint32_t n0) {
+        n = n0;
+        s = (n0 & 1u) != 0u;
+        h = (n0 >> 1) + 1u;
+        zc = mix64(key + (uint64_t)h * 0x9e3779b97f4a7c15ULL);
+    }
+    RL_HD float even() {
+        n++;
+        return unit(s ? lo24(zc) : hi24(zc));
+    }
+    RL_HD float odd() {
+        n++;
+        h++;
+        const uint64_t zn = mix64(key + (uint64_t)h * 0x9e3779b97f4a7c15ULL);
+        const uint32_t bits = s ? hi24(zn) : lo24(zc);
+        zc = zn;
+        return unit(bits);
+    }
+};
+RL_HD PairSampler make_pair_sampler(uint64_t seed_h, uint32_t pixel, uint32_t sample, uint32_t n) {
+    PairSampler p;
+    p.key = mix64(seed_h ^ (((uint64_t)pixel << 32) | (uint64_t)sample));
+    p.begin(n);
+    return p;
+}
 RL_HD Sampler make_sampler(uint64_t seed_h, uint32_t pixel, uint32_t sample, uint32_t n) {
     Sampler s;
     s.key = mix64(seed_h ^ (((uint64_t)pixel << 32) | (uint64_t)sample));
@@ -2438,11 +2479,20 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
     // ---- expand this vertex ----------------------------------------------------------------------
     uint32_t depth = st.depth + 1u;
     if (!ip_expand(ip, depth)) return;
+#if RL_PAIR_SAMPLER
+    PairSampler smp = make_pair_sampler(ip.seed_h, pixel, sample, st.rng_n);
+#else
     Sampler smp = make_sampler(ip.seed_h, pixel, sample, st.rng_n);
+#endif
     // directional strategy: BSDF sample + Russian roulette (directional.rs:44-107)
     {
+#if RL_PAIR_SAMPLER
+        float sx = smp.even();
+        float sy = smp.odd();
+#else
         float sx = smp.next();
         float sy = smp.next();
+#endif
         Col bw;
         V3 wo;
         float bpdf;
@@ -2456,7 +2506,11 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
                 float rr_weight = 1.0f;
                 if (do_rr) {
                     float q = fminf(channel_max(Tn), 0.95f);
+#if RL_PAIR_SAMPLER
+                    if (q < smp.even()) survive = false;
+#else
                     if (q < smp.next()) survive = false;
+#endif
                     else rr_weight = 1.0f / q;
                 }
                 if (survive) {
@@ -2476,10 +2530,18 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
     }
     // light sampling strategy (emitters.rs:108-175); runs even when the bounce died
     if (use_nee) {
+#if RL_PAIR_SAMPLER
+        smp.begin(smp.n); // the roulette draw above is conditional: re-begin at the count reached
+        float r_sel = smp.even();
+        float r = smp.odd();
+        float ux = smp.even();
+        float uy = smp.odd();
+#else
         float r_sel = smp.next();
         float r = smp.next();
         float ux = smp.next();
         float uy = smp.next();
+#endif
         out->nee_sampled = true;
         LightSample ls = sample_light<RL_HAS(KM, 8) != 0u>(sv, its.p, its.n_s, r_sel, r, ux, uy);
         if (ls.valid && !mute && ip_add_ok(ip, st.depth) && ip.strategy != 1u) {

@@ -361,6 +361,9 @@ __device__ __forceinline__ uint32_t block_compact(bool flag, uint32_t *global_co
 }
 
 // Two queues at once (survivors and shadow segments): one pair of barriers instead of three per queue.
+#ifndef RL_COMPACT_2BUF
+#define RL_COMPACT_2BUF 1
+#endif
 template <int B>
 __device__ __forceinline__ void block_compact2(bool fa, bool fb, uint32_t *count_a, uint32_t *count_b, uint32_t *scratch /* 2*(B/32)+2 */,
                                                uint32_t *slot_a, uint32_t *slot_b) {
@@ -386,10 +389,12 @@ __device__ __forceinline__ void block_compact2(bool fa, bool fb, uint32_t *count
     __syncthreads();
     *slot_a = scratch[2 * W] + scratch[warp] + __popc(ma & lt);
     *slot_b = scratch[2 * W + 1] + scratch[W + warp] + __popc(mb & lt);
-    // no trailing barrier: the next call writes scratch only after its own ballots, and every thread
-    // reads its slots before it can reach the next call's first barrier... but a fast warp could
-    // overwrite scratch[warp] of the NEXT tile before a slow warp has read this tile's values:
+#if !RL_COMPACT_2BUF
+    // a fast warp could overwrite scratch[warp] with the NEXT tile's count before a slow warp has read this tile's values:
     __syncthreads();
+#endif
+    // RL_COMPACT_2BUF: the caller alternates between two scratch areas from tile to tile instead.  A warp can write area A again (tile
+    // t + 2) only after the second barrier of tile t + 1, which every thread reaches after it has read its slots of tile t.
 }
 
 // ---- shade: surface interaction, arrival emission, BSDF sample + RR, NEE sample ------------------
@@ -452,12 +457,13 @@ __global__ void __launch_bounds__(shade_block(KM), shade_minblocks(KM)) k_shade(
                                                   const uint32_t *__restrict__ done_at, uint32_t my_k) {
     constexpr int B = shade_block(KM);
     if (batch_done(done_at, my_k)) return;
-    __shared__ uint32_t s_scratch[2 * (B / 32) + 2];
+    __shared__ uint32_t s_scratch[2 * (2 * (B / 32) + 2)]; // two areas, used alternately (block_compact2)
     __shared__ unsigned short s_perm[SORT ? B : 1];
     __shared__ uint32_t s_cnt[SORT ? kSortKeys * (B / 32) : 1];
     const uint32_t n = *count_in;
     const uint32_t n_tiles = (n + B - 1) / B;
     uint32_t c_hits = 0, c_nee = 0;
+    bool flip = false;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint32_t i = tile * B + threadIdx.x;
         if (SORT) {
@@ -502,7 +508,8 @@ __global__ void __launch_bounds__(shade_block(KM), shade_minblocks(KM)) k_shade(
             if (so.alive && (so.next.depth >= 0xfff0u || so.next.rng_n >= 0xfff0u)) so.alive = false; // packing guard
         }
         uint32_t slot, sslot;
-        block_compact2<B>(so.alive, so.shadow, count_out, count_shadow, s_scratch, &slot, &sslot);
+        block_compact2<B>(so.alive, so.shadow, count_out, count_shadow, s_scratch + (flip ? 2 * (B / 32) + 2 : 0), &slot, &sslot);
+        flip = !flip;
         if (so.alive) {
             out_o[slot] = make_float4(so.next_o.x, so.next_o.y, so.next_o.z, u2f(so.next.path_id));
             out_d[slot] = make_float4(so.next_d.x, so.next_d.y, so.next_d.z, so.next.pdf_prev);
