@@ -61,6 +61,8 @@ def lib():
         L.rlh_save_pfm.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
         L.rlh_read_pfm.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                    C.POINTER(C.c_float), C.c_size_t]
+        L.rlh_save_image.argtypes = L.rlh_save_pfm.argtypes
+        L.rlh_read_image.argtypes = L.rlh_read_pfm.argtypes
         _lib = L
     return _lib
 
@@ -276,6 +278,24 @@ def save_pfm(path, img):
     h, w, _ = img.shape
     if lib().rlh_save_pfm(os.fsencode(path), w, h, img.ctypes.data_as(C.POINTER(C.c_float))) != 0:
         raise SceneError(f"cannot write {path}")
+
+
+def save_image(path, img):
+    """Bitmap::save (structure.rs:528-545): by extension, .pfm or .png (gamma 2.2, 8 bit)."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    h, w = img.shape[:2]
+    if lib().rlh_save_image(os.fsencode(path), w, h, img.ctypes.data_as(C.POINTER(C.c_float))) != 0:
+        raise SceneError(f"cannot write {path}")
+
+
+def read_image(path):
+    """Bitmap::read (structure.rs:670-683): by extension, .pfm or .png (8-bit RGB / 255)."""
+    w, h = C.c_uint32(), C.c_uint32()
+    if lib().rlh_read_image(os.fsencode(path), C.byref(w), C.byref(h), None, 0) != 0:
+        raise SceneError(f"cannot read {path}")
+    img = np.zeros((h.value, w.value, 3), dtype=np.float32)
+    lib().rlh_read_image(os.fsencode(path), C.byref(w), C.byref(h), img.ctypes.data_as(C.POINTER(C.c_float)), img.size)
+    return img
 
 
 def read_pfm(path):

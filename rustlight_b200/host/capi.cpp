@@ -231,4 +231,30 @@ int rlh_read_pfm(const char *path, uint32_t *w, uint32_t *h, float *rgb, size_t 
     }
 }
 
+// Bitmap::save / Bitmap::read by extension (structure.rs:528-545, 670-683): .pfm, .png
+int rlh_save_image(const char *path, uint32_t w, uint32_t h, const float *rgb) {
+    try {
+        Bitmap b;
+        b.size_x = w, b.size_y = h;
+        b.colors.assign(rgb, rgb + 3 * (size_t)w * h);
+        b.save(path);
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+int rlh_read_image(const char *path, uint32_t *w, uint32_t *h, float *rgb, size_t capacity_floats) {
+    try {
+        Bitmap b = Bitmap::read(path);
+        *w = b.size_x, *h = b.size_y;
+        if (rgb) {
+            if (capacity_floats < b.colors.size()) return -2;
+            std::memcpy(rgb, b.colors.data(), b.colors.size() * sizeof(float));
+        }
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+
 } // extern "C"

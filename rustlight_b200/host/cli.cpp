@@ -9,7 +9,7 @@
 //
 // Differences from the reference, all forced by scope: only `path`, `direct` and `ao`; `-m` must be 0
 // (no medium); `-x ats|hvs-light|texture-light` are rejected; `-t` is accepted and ignored (the GPU replaces
-// the Rayon pool); output must be .pfm.  `-a N` averages N passes (the reference's argument is a time-out in
+// the Rayon pool); output is .pfm or .png (gamma 2.2, 8 bit, as Bitmap::save_ldr_image).  `-a N` averages N passes (the reference's argument is a time-out in
 // seconds or `inf`; both spellings are accepted: `-a 30s` / `-a inf` / `-a 8`).
 #include <cstdio>
 #include <cstdlib>
@@ -26,7 +26,7 @@ static std::optional<uint32_t> match_infinity(const std::string &s) { // cli.rs:
     return (uint32_t)std::stoul(s);
 }
 [[noreturn]] static void usage(const char *msg) {
-    std::fprintf(stderr, "error: %s\nusage: rustlight-b200 [-n N] [-a A] [-e SECS] [-r independent[:SEED]] [-s SCALE] -o OUT.pfm [-x no-shading|ats] SCENE "
+    std::fprintf(stderr, "error: %s\nusage: rustlight-b200 [-n N] [-a A] [-e SECS] [-r independent[:SEED]] [-s SCALE] -o OUT.pfm|OUT.png [-x no-shading|ats] SCENE "
                          "(path [-m MAX] [-n MIN] [-r RR] [-x] [-s all|bsdf|emitter] | direct [-b NB] [-l NL] | ao [-d DIST|inf] [-n])\n", msg);
     std::exit(2);
 }
@@ -72,7 +72,10 @@ int main(int argc, char **argv) {
     if (scene_path.empty()) usage("missing scene file");
     if (output.empty()) usage("missing -o output");
     if (std::stof(medium) != 0.0f) usage("participating media are outside the GPU path (-m must be 0)");
-    if (output.size() < 4 || output.substr(output.size() - 4) != ".pfm") usage("output must be a .pfm file");
+    {
+        const std::string ext = output.size() >= 4 ? output.substr(output.size() - 4) : std::string();
+        if (ext != ".pfm" && ext != ".png") usage("output must be a .pfm or .png file (Bitmap::save, structure.rs:528-545; .exr needs the reference's optional openexr feature)");
+    }
 
     std::unique_ptr<Integrator> integ;
     if (command == "path") {

@@ -92,7 +92,7 @@ struct Texture {
     rl_texture t{};             // t.pixels points into `pixels`
     std::vector<float> pixels;  // bitmap: 3 * width * height (Bitmap.colors)
     static Texture bitmap(uint32_t w, uint32_t h, std::vector<float> rgb);
-    static Texture bitmap_file(const std::string &filename); // .pfm (Bitmap::read_pfm) or binary .ppm (P6, /255 like read_ldr_image)
+    static Texture bitmap_file(const std::string &filename); // .pfm (Bitmap::read_pfm), .png (Bitmap::read_ldr_image) or binary .ppm (P6, /255 like read_ldr_image)
     static Texture checkerboard(Color c0, Color c1, float ox, float oy, float sx, float sy);
     static Texture grid(Color c0, Color c1, float line_width, float ox, float oy, float sx, float sy);
 };
@@ -177,11 +177,15 @@ struct Bitmap {
     std::vector<float> colors; // 3*size_x*size_y, row-major y*W+x
     void save_pfm(const std::string &path) const; // rows bottom-to-top, abs(), LE f32
     static Bitmap read_pfm(const std::string &path);
+    void save_png(const std::string &path) const;    // Bitmap::save_ldr_image + Color::to_rgba: (min(c, 1)^(1/2.2) * 255) as u8
+    static Bitmap read_png(const std::string &path); // Bitmap::read_ldr_image: to_rgb8() / 255
+    void save(const std::string &path) const;        // by extension (structure.rs:528-545): pfm | png
+    static Bitmap read(const std::string &path);     // by extension (structure.rs:670-683): pfm | png
 };
 // src/integrators/mod.rs:48-52; only the "primal" buffer exists on this path.
 struct BufferCollection {
     std::map<std::string, Bitmap> values;
-    void save(const std::string &name, const std::string &filename) const { values.at(name).save_pfm(filename); }
+    void save(const std::string &name, const std::string &filename) const { values.at(name).save(filename); }
 };
 
 struct Error : std::runtime_error {

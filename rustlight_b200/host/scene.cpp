@@ -3,9 +3,12 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <iterator>
+#include <algorithm>
 
 #include "rl_host.hpp"
 #include <cctype>
+#include <zlib.h> // inflate / deflate / crc32 of the PNG container (the reference reads and writes PNG through the `image` crate)
 
 namespace rlh {
 
@@ -304,7 +307,11 @@ Texture Texture::bitmap_file(const std::string &filename) {
         for (size_t i = 0; i < raw.size(); i++) rgb[i] = (float)raw[i] / 255.0f;
         return bitmap((uint32_t)w, (uint32_t)h, std::move(rgb));
     }
-    throw Error("texture: only .pfm and .ppm images can be read here: " + filename);
+    if (ends(".png")) { // Bitmap::read -> read_ldr_image (structure.rs:649-668): image::open(..).to_rgb8(), value / 255, no gamma
+        Bitmap b = Bitmap::read_png(filename);
+        return bitmap(b.size_x, b.size_y, std::move(b.colors));
+    }
+    throw Error("texture: only .pfm, .png and .ppm images can be read here: " + filename);
 }
 Texture Texture::checkerboard(Color c0, Color c1, float ox, float oy, float sx, float sy) {
     Texture t;
@@ -419,6 +426,165 @@ Bitmap Bitmap::read_pfm(const std::string &path) {
     for (uint32_t y = 0; y < h; y++)
         f.read(reinterpret_cast<char *>(&b.colors[3 * (size_t)(h - y - 1) * w]), (std::streamsize)(3 * w * sizeof(float)));
     return b;
+}
+
+// ------------------------------------------------------------------------------------------
+// PNG (the `image` feature of the reference, on by default: Bitmap::read_ldr_image / save_ldr_image, structure.rs:471-485, 649-668)
+// ------------------------------------------------------------------------------------------
+// Reader: what `image::open(path).to_rgb8()` yields for a PNG, then value / 255 (no gamma, alpha dropped, gAMA / tRNS ignored):
+// colour types 0 / 2 / 3 / 4 / 6, bit depths 1-16, the five row filters; sub-byte grey samples are scaled to 8 bits (x 255 / 85 / 17) and
+// 16-bit samples narrowed as image 0.24 does, (v + 128) / 257.  Interlaced (Adam7) files are refused loudly.
+namespace {
+uint32_t be32(const unsigned char *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3]; }
+void put_be32(std::vector<unsigned char> &v, uint32_t x) {
+    v.push_back((unsigned char)(x >> 24)), v.push_back((unsigned char)(x >> 16)), v.push_back((unsigned char)(x >> 8)), v.push_back((unsigned char)x);
+}
+int paeth(int a, int b, int c) {
+    const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+} // namespace
+Bitmap Bitmap::read_png(const std::string &path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw Error("cannot open " + path);
+    std::vector<unsigned char> file((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (file.size() < 8 || std::memcmp(file.data(), sig, 8) != 0) throw Error("not a PNG file: " + path);
+    uint32_t w = 0, h = 0;
+    int depth = 0, ctype = -1;
+    std::vector<unsigned char> idat, plte;
+    bool end = false;
+    for (size_t pos = 8; !end;) {
+        if (pos + 12 > file.size()) throw Error("png: truncated " + path);
+        const uint32_t len = be32(&file[pos]);
+        if ((size_t)len > file.size() - pos - 12) throw Error("png: truncated chunk in " + path);
+        const unsigned char *type = &file[pos + 4], *data = &file[pos + 8];
+        if (be32(data + len) != (uint32_t)crc32(crc32(0L, type, 4), data, len)) throw Error("png: CRC mismatch in " + path);
+        if (std::memcmp(type, "IHDR", 4) == 0) {
+            if (len != 13) throw Error("png: bad IHDR in " + path);
+            w = be32(data), h = be32(data + 4), depth = data[8], ctype = data[9];
+            if (data[10] != 0 || data[11] != 0) throw Error("png: unknown compression / filter method in " + path);
+            if (data[12] != 0) throw Error("png: interlaced (Adam7) files are not supported: " + path);
+        } else if (std::memcmp(type, "PLTE", 4) == 0) plte.assign(data, data + len);
+        else if (std::memcmp(type, "IDAT", 4) == 0) idat.insert(idat.end(), data, data + len);
+        else if (std::memcmp(type, "IEND", 4) == 0) end = true;
+        pos += (size_t)len + 12;
+    }
+    int channels;
+    switch (ctype) {
+    case 0: channels = 1; break;
+    case 2: channels = 3; break;
+    case 3: channels = 1; break;
+    case 4: channels = 2; break;
+    case 6: channels = 4; break;
+    default: throw Error("png: bad colour type in " + path);
+    }
+    const bool depth_ok = ctype == 0 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)
+                          : ctype == 3 ? (depth == 1 || depth == 2 || depth == 4 || depth == 8) : (depth == 8 || depth == 16);
+    if (w == 0 || h == 0 || !depth_ok || (uint64_t)w * h > (1ull << 28)) throw Error("png: bad header in " + path);
+    const size_t row_bytes = ((size_t)w * channels * depth + 7) / 8, bpp = std::max<size_t>(1, (size_t)channels * depth / 8);
+    std::vector<unsigned char> raw((row_bytes + 1) * h);
+    uLongf got = (uLongf)raw.size();
+    if (uncompress(raw.data(), &got, idat.data(), (uLong)idat.size()) != Z_OK || got != raw.size()) throw Error("png: corrupt image data in " + path);
+    std::vector<unsigned char> prev(row_bytes, 0), cur(row_bytes);
+    Bitmap b;
+    b.size_x = w, b.size_y = h;
+    b.colors.resize((size_t)3 * w * h);
+    auto narrow16 = [](uint32_t v) { return (v + 128u) / 257u; }; // image 0.24: u16 -> u8
+    for (uint32_t y = 0; y < h; y++) {
+        const unsigned char *src = &raw[(row_bytes + 1) * y];
+        const int ft = src[0];
+        if (ft > 4) throw Error("png: bad row filter in " + path);
+        for (size_t i = 0; i < row_bytes; i++) {
+            const int a = i >= bpp ? cur[i - bpp] : 0, up = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+            const int pred = ft == 0 ? 0 : ft == 1 ? a : ft == 2 ? up : ft == 3 ? (a + up) / 2 : paeth(a, up, c);
+            cur[i] = (unsigned char)(src[1 + i] + pred);
+        }
+        for (uint32_t x = 0; x < w; x++) {
+            uint32_t px[4] = {0, 0, 0, 0};
+            for (int c = 0; c < channels; c++) {
+                if (depth == 8) px[c] = cur[(size_t)x * channels + c];
+                else if (depth == 16) px[c] = ((uint32_t)cur[((size_t)x * channels + c) * 2] << 8) | cur[((size_t)x * channels + c) * 2 + 1];
+                else { // 1 / 2 / 4 bits, one channel, most significant bits first
+                    const size_t bit = (size_t)x * depth;
+                    px[c] = (cur[bit / 8] >> (8 - depth - (bit % 8))) & ((1u << depth) - 1u);
+                }
+            }
+            uint32_t r, g, bl;
+            if (ctype == 3) {
+                if ((size_t)px[0] * 3 + 2 >= plte.size()) throw Error("png: palette index out of range in " + path);
+                r = plte[px[0] * 3], g = plte[px[0] * 3 + 1], bl = plte[px[0] * 3 + 2];
+            } else {
+                for (int c = 0; c < channels; c++) {
+                    if (depth == 16) px[c] = narrow16(px[c]);
+                    else if (depth < 8) px[c] *= 255u / ((1u << depth) - 1u);
+                }
+                if (channels <= 2) r = g = bl = px[0];
+                else r = px[0], g = px[1], bl = px[2];
+            }
+            float *dst = &b.colors[3 * ((size_t)y * w + x)];
+            dst[0] = (float)r / 255.0f, dst[1] = (float)g / 255.0f, dst[2] = (float)bl / 255.0f;
+        }
+        prev.swap(cur);
+    }
+    return b;
+}
+// Writer: Bitmap::save_ldr_image with Color::to_rgba (structure.rs:160-167, 471-485): (min(c, 1) ^ (1 / 2.2) * 255) as u8 -- truncation,
+// f32::min semantics (a NaN channel becomes 1), Rust's saturating cast (the NaN of a negative base -> 0) -- as 8-bit RGB.  The bytes of the file differ from the `image` crate's encoder (filter
+// and deflate choices), the decoded pixels do not.
+void Bitmap::save_png(const std::string &path) const {
+    auto to_u8 = [](float c) -> unsigned char {
+        const float v = std::pow(std::fmin(c, 1.0f), 1.0f / 2.2f) * 255.0f; // fmin: f32::min returns the non-NaN operand
+        if (!(v > 0.0f)) return 0;                                          // NaN (negative base) and 0
+        return v >= 255.0f ? 255 : (unsigned char)v;
+    };
+    std::vector<unsigned char> raw(((size_t)3 * size_x + 1) * size_y);
+    for (uint32_t y = 0; y < size_y; y++) {
+        unsigned char *row = &raw[((size_t)3 * size_x + 1) * y];
+        row[0] = 0; // filter: none
+        for (size_t i = 0; i < (size_t)3 * size_x; i++) row[1 + i] = to_u8(colors[(size_t)3 * size_x * y + i]);
+    }
+    uLongf zlen = compressBound((uLong)raw.size());
+    std::vector<unsigned char> z(zlen);
+    if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 6) != Z_OK) throw Error("png: deflate failed for " + path);
+    std::vector<unsigned char> out = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    auto chunk = [&](const char *type, const unsigned char *data, size_t len) {
+        put_be32(out, (uint32_t)len);
+        const size_t at = out.size();
+        out.insert(out.end(), type, type + 4);
+        if (len) out.insert(out.end(), data, data + len);
+        put_be32(out, (uint32_t)crc32(0L, &out[at], (uInt)(len + 4)));
+    };
+    std::vector<unsigned char> ihdr;
+    put_be32(ihdr, size_x), put_be32(ihdr, size_y);
+    ihdr.insert(ihdr.end(), {8, 2, 0, 0, 0}); // 8 bits, RGB, deflate, adaptive filtering, no interlace
+    chunk("IHDR", ihdr.data(), ihdr.size());
+    chunk("IDAT", z.data(), zlen);
+    chunk("IEND", nullptr, 0);
+    std::ofstream f(path, std::ios::binary);
+    if (!f) throw Error("cannot open " + path);
+    f.write(reinterpret_cast<const char *>(out.data()), (std::streamsize)out.size());
+    if (!f) throw Error("cannot write " + path);
+}
+// Bitmap::save / Bitmap::read (structure.rs:528-545, 670-683): by extension.  .exr needs the reference's optional `openexr` feature
+// (off by default: it panics there) and is refused here.
+static std::string extension_of(const std::string &path) {
+    const size_t dot = path.find_last_of('.'), slash = path.find_last_of('/');
+    if (dot == std::string::npos || (slash != std::string::npos && dot < slash)) throw Error("No file extension provided: " + path);
+    return path.substr(dot + 1);
+}
+void Bitmap::save(const std::string &path) const {
+    const std::string ext = extension_of(path);
+    if (ext == "pfm") save_pfm(path);
+    else if (ext == "png") save_png(path);
+    else if (ext == "exr") throw Error("OpenEXR output is not built (the reference's optional `openexr` feature): " + path);
+    else throw Error("Unknow output file extension: " + path);
+}
+Bitmap Bitmap::read(const std::string &path) {
+    const std::string ext = extension_of(path);
+    if (ext == "pfm") return read_pfm(path);
+    if (ext == "png") return read_png(path);
+    throw Error("image: only .pfm and .png can be read: " + path);
 }
 
 } // namespace rlh
