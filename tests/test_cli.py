@@ -19,7 +19,7 @@ def run(*args):
 
 def test_cli_argument_errors():
     assert run("-o", "x.pfm", CBOX).returncode == 2                       # no subcommand
-    assert run("-o", "x.png", CBOX, "path").returncode == 2               # unsupported output type
+    assert run("-o", "x.exr", CBOX, "path").returncode == 2               # unsupported output type (.pfm and .png are written)
     assert run(CBOX, "path").returncode == 2                              # missing -o
     assert run("-o", "x.pfm", "-m", "0.5", CBOX, "path").returncode == 2  # media are out of scope
     assert run("-o", "x.pfm", "-x", "vpl", CBOX, "path").returncode == 2  # an extra option outside the GPU path (`-x ats` and `-x no-shading` are accepted)
@@ -54,6 +54,13 @@ def test_cli_matches_library(tmp_path, gpu_ctx):
     assert run("-n", "2", "-s", "0.25", "-o", out2, os.path.join(DATA, "cbox.json"), "direct", "-b", "2", "-l", "1").returncode == 0
     img, _ = DeviceScene(gpu_ctx, sc).render(_abi.direct_desc(2, 1), 2, seed=0)
     assert np.array_equal(read_pfm(out2), np.abs(img))
+    # -o x.png: Bitmap::save_ldr_image (gamma 2.2, 8 bit); reading it back gives value / 255 of what the library's own writer produces
+    from rustlight_b200.host import read_image, save_image
+    outp, refp = str(tmp_path / "d.png"), str(tmp_path / "ref.png")
+    assert run("-n", "2", "-s", "0.25", "-o", outp, os.path.join(DATA, "cbox.json"), "direct", "-b", "2", "-l", "1").returncode == 0
+    save_image(refp, img)
+    got = read_image(outp)
+    assert got.shape == img.shape and np.array_equal(got, read_image(refp)) and 0.05 < got.mean() < 0.9
 
 
 @pytest.mark.gpu
