@@ -21,6 +21,7 @@
 #include <fstream>
 #include <map>
 #include <sstream>
+#include <zlib.h> // Mitsuba "serialized" meshes are deflate streams
 
 #include "rl_host.hpp"
 
@@ -1108,7 +1109,7 @@ std::string scene_to_json(const Scene &scene) {
 // The reference parses the file with the mitsuba_rs crate (git dependency, not vendored: its defaults are restated from the
 // Mitsuba 0.5/0.6 documentation and are UNPINNED) and maps the result as follows, which is what this loader reproduces:
 //   sensor "perspective": film width / height, fov + fovAxis x | y, toWorld -> Camera::new(size, fov, mat, flip = true)   (:327-338)
-//   shapes "rectangle" (two triangles, normals, uv; :538-594), "sphere" (32 x 32 lat-long tessellation; :596-665), "ply", "obj";
+//   shapes "rectangle" (two triangles, normals, uv; :538-594), "sphere" (32 x 32 lat-long tessellation; :596-665), "ply", "obj", "serialized";
 //     toWorld applied to points (transform_point) and normals (transform_vector, renormalised) (:341-376); bsdf (inline or <ref>),
 //     default BSDFDiffuse 0.8; <emitter type="area"> radiance -> EmissionType::Color; faceNormals discards normals
 //   bsdfs: twosided (ignored wrapper), diffuse, phong (weight_specular from the average luminances), dielectric -> BSDFGlass.eta(int, ext),
@@ -1117,7 +1118,7 @@ std::string scene_to_json(const Scene &scene) {
 //   colours: <rgb>/<spectrum> constants, <texture type="bitmap" | "checkerboard" | "gridtexture">                           (mod.rs:395-452)
 //   emitters "point" -> PointEmitter (:680-697).  The reference's "PointNormal" emitter cannot be sampled by `path` / `direct`
 //     (PointNormalEmitter::direct_sample is todo!(), emitter.rs:262-264): rejected here instead of panicking at the first light sample.
-//   media -> outside the hot path.  Shapes "serialized" (zlib-compressed binary) are not read.
+//   media -> outside the hot path.  Shapes "serialized" (:499-538): read_serialized below (deflate through zlib).
 // ------------------------------------------------------------------------------------------
 namespace {
 struct XNode {
@@ -1391,6 +1392,104 @@ Material mts_bsdf(MtsCtx &cx, const XNode *b) { // bsdf_mts, mod.rs:499-612
     }
     return fallback; // `_ => None` -> BSDFDiffuse 0.8 (mod.rs:599-611)
 }
+// Mitsuba 0.5 / 0.6 ".serialized" mesh (mitsuba_rs::serialized::read_serialized, crate not vendored: the published format, UNPINNED):
+//   [u16 0x041C][u16 version 3 | 4][zlib stream: u32 flags, (v4) UTF-8 name + NUL, u64 vertices, u64 triangles, positions 3 n,
+//   normals 3 n if flags & 1, texcoords 2 n if flags & 2, colours 3 n if flags & 8 (skipped), indices 3 t (u32; u64 above 2^32 - 1 vertices)],
+//   reals f32 (flag 0x1000) or f64 (0x2000, narrowed).  A file may hold several shapes: its last u32 is their count, preceded by the
+//   table of their start offsets (u64 in version 4, u32 in version 3); shape 0 starts the file.
+void read_serialized(const std::string &filename, uint32_t shape_index, RawShape &out, std::string *name_out) {
+    const std::string file = read_file(filename);
+    const unsigned char *fp = reinterpret_cast<const unsigned char *>(file.data());
+    auto le = [&](size_t at, int bytes) {
+        if (at + (size_t)bytes > file.size()) throw Error("serialized: truncated " + filename);
+        uint64_t v = 0;
+        for (int k = bytes - 1; k >= 0; k--) v = (v << 8) | fp[at + k];
+        return v;
+    };
+    if (le(0, 2) != 0x041Cu) throw Error("serialized: bad magic in " + filename);
+    size_t start = 0;
+    if (shape_index > 0) {
+        const uint64_t ver0 = le(2, 2), count = le(file.size() - 4, 4), osz = ver0 == 4 ? 8 : 4;
+        if (shape_index >= count || file.size() < 4 + osz * count) throw Error("serialized: shape index out of range in " + filename);
+        start = (size_t)le(file.size() - 4 - (size_t)(osz * (count - shape_index)), (int)osz);
+        if (le(start, 2) != 0x041Cu) throw Error("serialized: bad shape offset in " + filename);
+    }
+    const uint64_t version = le(start + 2, 2);
+    if (version != 3 && version != 4) throw Error("serialized: unknown version in " + filename);
+    std::vector<unsigned char> data;
+    {
+        z_stream zs{};
+        if (inflateInit(&zs) != Z_OK) throw Error("serialized: zlib");
+        zs.next_in = const_cast<Bytef *>(fp + start + 4);
+        zs.avail_in = (uInt)std::min<size_t>(file.size() - start - 4, 0xffffffffu);
+        unsigned char buf[1 << 16];
+        int rc = Z_OK;
+        while (rc != Z_STREAM_END) {
+            zs.next_out = buf, zs.avail_out = sizeof(buf);
+            rc = inflate(&zs, Z_NO_FLUSH);
+            if (rc != Z_OK && rc != Z_STREAM_END) {
+                inflateEnd(&zs);
+                throw Error("serialized: corrupt deflate stream in " + filename);
+            }
+            data.insert(data.end(), buf, buf + (sizeof(buf) - zs.avail_out));
+            if (rc == Z_OK && zs.avail_in == 0 && zs.avail_out != 0) {
+                inflateEnd(&zs);
+                throw Error("serialized: truncated deflate stream in " + filename);
+            }
+        }
+        inflateEnd(&zs);
+    }
+    size_t pos = 0;
+    auto need = [&](size_t n) {
+        if (n > data.size() - pos) throw Error("serialized: short mesh record in " + filename);
+    };
+    auto get = [&](int bytes) {
+        need((size_t)bytes);
+        uint64_t v = 0;
+        for (int k = bytes - 1; k >= 0; k--) v = (v << 8) | data[pos + k];
+        pos += (size_t)bytes;
+        return v;
+    };
+    const uint32_t flags = (uint32_t)get(4);
+    std::string name;
+    if (version == 4) {
+        while (true) {
+            need(1);
+            const char c = (char)data[pos++];
+            if (!c) break;
+            name.push_back(c);
+        }
+    }
+    if (name_out) *name_out = name;
+    const uint64_t nv = get(8), nt = get(8);
+    const bool dbl = (flags & 0x2000u) != 0;
+    if (!dbl && !(flags & 0x1000u)) throw Error("serialized: neither single nor double precision flagged in " + filename);
+    if (nv == 0 || nt == 0 || nv > (1ull << 31) || nt > (1ull << 31)) throw Error("serialized: bad counts in " + filename);
+    auto reals = [&](std::vector<float> *dst, size_t n) {
+        const size_t sz = dbl ? 8 : 4;
+        if (n > (data.size() - pos) / sz) throw Error("serialized: short mesh record in " + filename);
+        if (dst) dst->resize(n);
+        for (size_t i = 0; i < n; i++, pos += sz) {
+            if (!dst) continue;
+            if (dbl) {
+                double d;
+                std::memcpy(&d, &data[pos], 8);
+                (*dst)[i] = (float)d;
+            } else std::memcpy(&(*dst)[i], &data[pos], 4);
+        }
+    };
+    reals(&out.P, (size_t)nv * 3);
+    if (flags & 0x0001u) reals(&out.N, (size_t)nv * 3);
+    if (flags & 0x0002u) reals(&out.uv, (size_t)nv * 2);
+    if (flags & 0x0008u) reals(nullptr, (size_t)nv * 3);
+    const int isz = nv > 0xffffffffull ? 8 : 4;
+    out.idx.resize((size_t)nt * 3);
+    for (size_t i = 0; i < out.idx.size(); i++) {
+        const uint64_t v = get(isz);
+        if (v >= nv) throw Error("serialized: vertex index out of range in " + filename);
+        out.idx[i] = (uint32_t)v;
+    }
+}
 // Wavefront OBJ, triangulated by fanning; one vertex per distinct (v, vt, vn) corner (tobj is not vendored: unpinned)
 void read_obj(const std::string &filename, RawShape &out) {
     const std::string text = read_file(filename);
@@ -1549,8 +1648,14 @@ Scene MTSSceneLoader::load_string(const std::string &text, bool use_shading_norm
                     for (size_t k = 1; k < rs.uv.size(); k += 2) rs.uv[k] = 1.0f - rs.uv[k];
             }
             emit(sh, rs, !face_normal && (type == "obj" || use_shading_normal)); // ply: `face_normal || !use_shading_normal` -> None (:399-403)
-        } else if (type == "serialized") {
-            throw Error("xml: shape \"serialized\" (zlib-compressed binary meshes) is not read by this loader");
+        } else if (type == "serialized") { // :499-538: normals unless faceNormals (use_shading_normal is not consulted), texcoords as stored
+            std::string fn = xstring(sh, "filename", "");
+            if (fn.empty()) throw Error("xml: shape \"serialized\" needs a filename");
+            if (fn[0] != '/' && !base_dir.empty()) fn = base_dir + "/" + fn;
+            std::string mesh_name;
+            read_serialized(fn, (uint32_t)xfloat(sh, "shapeIndex", 0.0f), rs, &mesh_name);
+            emit(sh, rs, !face_normal);
+            scene.meshes.back()->name = mesh_name; // (:502)
         } // anything else: "Ignoring shape" (:666-669)
     };
     for (const XNode *sh : shapes_id) load_shape(*sh);

@@ -157,6 +157,58 @@ def test_obj_and_ply_shapes(tmp_path):
     assert np.allclose(np.ctypeslib.as_array(d.meshes[6].P, (3, 3))[:, 2], -0.5)
 
 
+def _serialized_shape(P, idx, N=None, UV=None, version=4, double=False, name="quad"):
+    """One shape of a Mitsuba .serialized file, packed with struct + zlib only."""
+    import struct
+    import zlib
+    real = "<f8" if double else "<f4"
+    flags = (0x2000 if double else 0x1000) | (1 if N is not None else 0) | (2 if UV is not None else 0)
+    body = struct.pack("<I", flags)
+    if version == 4:
+        body += name.encode() + b"\0"
+    body += struct.pack("<QQ", len(P), len(idx))
+    body += np.asarray(P, real).tobytes()
+    if N is not None:
+        body += np.asarray(N, real).tobytes()
+    if UV is not None:
+        body += np.asarray(UV, real).tobytes()
+    body += np.asarray(idx, "<u4").tobytes()
+    return struct.pack("<HH", 0x041C, version) + zlib.compress(body)
+
+
+def test_serialized_shapes(tmp_path):
+    """<shape type="serialized"> (scene_loader.rs:499-538): normals kept unless faceNormals, texcoords as stored, shapeIndex through the
+    offset table at the end of the file, f64 records narrowed; versions 3 and 4."""
+    import struct
+    P = [[-1, 0, -1], [1, 0, -1], [1, 0, 1], [-1, 0, 1]]
+    N = [[0, 1, 0]] * 4
+    UV = [[0, 0], [1, 0], [1, 1], [0, 1]]
+    for version in (3, 4):
+        s0 = _serialized_shape(P, [[0, 1, 2], [0, 2, 3]], N, UV, version=version)
+        s1 = _serialized_shape([[0, 0, 0], [1, 0, 0], [0, 1, 0]], [[0, 1, 2]], version=version, double=True, name="tri")
+        table = struct.pack("<QQ" if version == 4 else "<II", 0, len(s0)) + struct.pack("<I", 2)
+        (tmp_path / "m.serialized").write_bytes(s0 + s1 + table)
+        xml = BOX.replace('<shape type="sphere">', '<shape type="serialized"><string name="filename" value="m.serialized"/></shape>\n'
+                          '<shape type="serialized"><string name="filename" value="m.serialized"/><integer name="shapeIndex" value="1"/>'
+                          '<boolean name="faceNormals" value="true"/><transform name="toWorld"><translate z="-0.5"/></transform></shape>\n<shape type="sphere">')
+        (tmp_path / "s.xml").write_text(xml)
+        sc = SceneLoaderManager().load(str(tmp_path / "s.xml"))
+        d = sc.desc.contents
+        assert d.nmeshes == 9 and d.meshes[5].ntris == 2 and d.meshes[6].ntris == 1
+        assert np.array_equal(np.ctypeslib.as_array(d.meshes[5].P, (4, 3)), np.array(P, np.float32))
+        assert np.array_equal(np.ctypeslib.as_array(d.meshes[5].N, (4, 3)), np.array(N, np.float32))
+        assert np.array_equal(np.ctypeslib.as_array(d.meshes[5].UV, (4, 2)), np.array(UV, np.float32))  # no flip
+        assert not d.meshes[6].N and not d.meshes[6].UV
+        assert np.allclose(np.ctypeslib.as_array(d.meshes[6].P, (3, 3))[:, 2], -0.5)
+    bad = s0[:-7]
+    (tmp_path / "m.serialized").write_bytes(bad)
+    with pytest.raises(SceneError, match="serialized"):
+        SceneLoaderManager().load(str(tmp_path / "s.xml"))
+    (tmp_path / "m.serialized").write_bytes(b"\x1c\x05" + s0[2:])
+    with pytest.raises(SceneError, match="magic"):
+        SceneLoaderManager().load(str(tmp_path / "s.xml"))
+
+
 def test_rejected_inputs():
     with pytest.raises(SceneError, match="sensor"):
         _load(BOX.replace("<sensor", "<zsensor").replace("</sensor>", "</zsensor>"))
