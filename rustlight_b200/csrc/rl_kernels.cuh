@@ -542,8 +542,11 @@ __global__ void __launch_bounds__(shade_block(KM), shade_minblocks(KM)) k_shade(
 // Shadow segments still queued by the last k_shade must be resolved before this kernel starts (the host launches
 // k_shadow_flat / k_shadow first, same stream).
 constexpr int kTailBlock = 128;
+#ifndef RL_TAIL_MINBLOCKS
+#define RL_TAIL_MINBLOCKS 1 // resident CTAs per SM k_tail is compiled for (register cap; A/B hook)
+#endif
 template <uint32_t KM>
-__global__ void __launch_bounds__(kTailBlock) k_tail(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
+__global__ void __launch_bounds__(kTailBlock, RL_TAIL_MINBLOCKS) k_tail(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
                                                      const uint32_t *__restrict__ count, const float4 *__restrict__ ray_o,
                                                      const float4 *__restrict__ ray_d, const float4 *__restrict__ state, float4 *__restrict__ lacc,
                                                      Counters *counters, uint32_t n_trav_f4, uint32_t iter_base, uint32_t iter_limit,
