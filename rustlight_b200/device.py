@@ -199,8 +199,9 @@ class BufferCollection:
         self.stats = stats
 
     def save(self, name, filename):
-        from .host import save_pfm
-        save_pfm(filename, self.values[name])
+        """BufferCollection::save -> Bitmap::save (structure.rs:528-545): .pfm or .png by extension."""
+        from .host import save_image
+        save_image(filename, self.values[name])
 
 
 class _IntegratorBase:

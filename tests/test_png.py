@@ -186,3 +186,19 @@ def test_png_texture_and_cli_output(tmp_path):
     cli = os.path.join(ROOT, "rustlight_b200", "rustlight-b200")
     r = subprocess.run([cli, "-o", str(tmp_path / "out.exr"), os.path.join(ROOT, "data", "cbox.pbrt"), "path"], capture_output=True, text=True)
     assert r.returncode != 0 and ".png" in r.stderr
+
+
+def test_buffer_collection_saves_by_extension(tmp_path):
+    """BufferCollection::save -> Bitmap::save (structure.rs:528-545): the extension picks the writer; anything else is refused."""
+    from rustlight_b200.device import BufferCollection
+    from rustlight_b200.host import read_pfm
+    img = np.random.default_rng(1).random((6, 7, 3), dtype=np.float32)
+    bc = BufferCollection(img)
+    bc.save("primal", str(tmp_path / "a.pfm"))
+    bc.save("primal", str(tmp_path / "a.png"))
+    assert np.array_equal(read_pfm(str(tmp_path / "a.pfm")), img)
+    assert np.abs(read_image(str(tmp_path / "a.png")) - np.minimum(img, 1.0) ** (1 / 2.2)).max() < 1.0 / 255.0 + 1e-6
+    with pytest.raises(SceneError):
+        bc.save("primal", str(tmp_path / "a.exr"))
+    with pytest.raises(SceneError):
+        bc.save("primal", str(tmp_path / "a.bmp"))
