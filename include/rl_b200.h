@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RL_B200_ABI_VERSION 5
+#define RL_B200_ABI_VERSION 6
 
 typedef struct rl_ctx rl_ctx;     /* one per GPU / per rank; single-owner, not thread-safe */
 typedef struct rl_scene rl_scene; /* device-resident scene: geometry, LBVH, emitters, camera */
@@ -105,6 +105,15 @@ typedef struct rl_material {
 } rl_material;
 
 /* ---- geometry: Mesh, src/geometry.rs:107-119 ---------------------------------------------- */
+/* EmissionType (geometry.rs:99-104) and Mesh::emit(uv) (:184-206).  HSV and TEXTURE are what the CLI's `-x hvs-light` /
+ * `-x texture-light` turn every mesh light into (examples/cli.rs:410-429, scale = luminance of its colour); they need uv
+ * coordinates on the mesh (the reference unwraps them).  Mesh::flux uses Color::value(scale) for both (emitter.rs:591-599). */
+typedef enum rl_emission_kind {
+    RL_EMISSION_ZERO = 0,
+    RL_EMISSION_COLOR = 1,  /* emit = v                                                                       */
+    RL_EMISSION_HSV = 2,    /* emit = (x, 1 - x, 0) * scale with x = |uv.x| % 1 (a red-to-green ramp; sic)    */
+    RL_EMISSION_TEXTURE = 3 /* emit = img.pixel_uv(uv) * scale                                                */
+} rl_emission_kind;
 typedef struct rl_mesh_desc {
     const float *P;      /* 3*nverts                                                          */
     uint32_t nverts;
@@ -113,8 +122,9 @@ typedef struct rl_mesh_desc {
     const float *N;  /* 3*nverts shading normals or NULL (Mesh.normals: Option)               */
     const float *UV; /* 2*nverts or NULL (Mesh.uv: Option)                                    */
     rl_material mat;
-    uint32_t emission_kind; /* 0 = EmissionType::Zero, 1 = EmissionType::Color (is_light())   */
-    float emission[3];
+    uint32_t emission_kind; /* rl_emission_kind                                               */
+    float emission[3];      /* COLOR: v; HSV / TEXTURE: emission[0] = scale                   */
+    uint32_t emission_texture; /* TEXTURE: 1 + index into rl_scene_desc.textures (a RL_TEX_BITMAP) */
 } rl_mesh_desc;
 
 /* ---- camera: src/camera.rs:5-15; matrices as built by Camera::new (camera.rs:31-67) ------- */

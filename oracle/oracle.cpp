@@ -910,6 +910,7 @@ struct SampledPosition { // structure.rs:96-102
     V3 p, n;
     PDF pdf;
     size_t primitive_id;
+    UV uv{}; // Option<Vector2<f32>>
 };
 struct Idx3 {
     uint32_t x, y, z;
@@ -924,6 +925,10 @@ struct Mesh { // geometry.rs:107-119
     std::unique_ptr<BSDF> bsdf;
     bool light = false; // emission != EmissionType::Zero
     Color emission = Color::zero();
+    // EmissionType (:99-104): Color { v } | HSV { scale } | Texture { scale, img }
+    enum EmissionType { EColor = 1, EHsv = 2, ETexture = 3 } emission_type = EColor;
+    float emission_scale = 0.0f;
+    std::shared_ptr<BitmapTex> emission_img;
     Distribution1D cdf;
     uint32_t first_prim = 0; // global index of triangle 0 (mesh-major numbering)
 
@@ -935,7 +940,21 @@ struct Mesh { // geometry.rs:107-119
         }
         cdf = Distribution1D::normalize(areas);
     }
-    Color emit() const { return light ? emission : Color::zero(); } // :184-206 (Zero | Color)
+    Color emit(const UV &uv) const { // :184-206
+        if (!light) return Color::zero();
+        if (emission_type == EHsv) {
+            Color c1{1.0f, 0.0f, 0.0f}, c2{0.0f, 1.0f, 0.0f};
+            if (!uv.some) std::abort(); // uv.unwrap()
+            float x = std::fmod(std::fabs(uv.v.x), 1.0f); // uv.x.abs() % 1.0
+            Color c = x * c1 + (1.0f - x) * c2;
+            return c * emission_scale;
+        }
+        if (emission_type == ETexture) {
+            if (!uv.some) std::abort();
+            return emission_img->pixel_uv(uv.v) * emission_scale;
+        }
+        return emission;
+    }
     bool is_light() const { return light; }                         // :412-417
     float pdf() const { return 1.0f / cdf.total(); }                // :223-225
 
@@ -994,8 +1013,16 @@ struct Mesh { // geometry.rs:107-119
             else if (n_l != 1.0f) n = n / std::sqrt(n_l);
             if (dot(n_g, n) < 0.0f) n_g = -n_g;
         }
+        UV suv;
+        if (has_uv) { // :316-325: the interpolated uv, normalized as a 2-vector (sic)
+            P2 n0 = uv[id.x], n1 = uv[id.y], n2 = uv[id.z];
+            float b2 = 1.0f - b.x - b.y;
+            P2 q{n0.x * b.x + n1.x * b.y + n2.x * b2, n0.y * b.x + n1.y * b.y + n2.y * b2};
+            float il = 1.0f / std::sqrt(q.x * q.x + q.y * q.y); // normalize = v * (1 / |v|)
+            suv.some = true, suv.v = P2{q.x * il, q.y * il};
+        }
         float area_tri = magnitude(cross(v1 - v0, v2 - v0)) * 0.5f;
-        return SampledPosition{pos, n_g, PDF{PDF::Area, 1.0f / area_tri}, primitive_id};
+        return SampledPosition{pos, n_g, PDF{PDF::Area, 1.0f / area_tri}, primitive_id, suv};
     }
     float pdf_tri(size_t primitive_id) const { // :226-234
         Idx3 id = indices[primitive_id];
@@ -1009,7 +1036,10 @@ struct Mesh { // geometry.rs:107-119
         res.pdf = PDF{PDF::Area, 1.0f / cdf.total()};
         return res;
     }
-    Color flux() const { return cdf.total() * emit() * PI; } // emitter.rs:591-599 (f32*Color then Color*f32)
+    Color flux() const { // emitter.rs:591-599 (f32*Color then Color*f32); HSV / Texture: Color::value(scale), "TODO" there
+        Color e = !light ? Color::zero() : (emission_type == EColor ? emission : Color{emission_scale, emission_scale, emission_scale});
+        return cdf.total() * e * PI;
+    }
 };
 
 // ============================================================================================
@@ -1066,6 +1096,7 @@ struct LightSampling { // :10-24
     V3 p, n, d;
     size_t primitive_id;
     Color weight;
+    UV uv{}; // uv of the sampled position (mesh emitters)
     bool is_valid() const { return !pdf.is_zero(); }
 };
 struct LightSamplingPDF { // :26-44
@@ -1084,7 +1115,7 @@ struct Emitter { // trait Emitter, emitter.rs:46-94 (the methods this path calls
     virtual PDF direct_pdf(const LightSamplingPDF &ls) const = 0;
     virtual LightSampling direct_sample(const Math &m, V3 p, float r, P2 uv) const = 0;
     virtual Color flux() const = 0;
-    virtual Color eval() const = 0; // eval(d, uv) with constant emission
+    virtual Color eval(const UV &uv) const = 0; // eval(d, uv)
 };
 struct MeshEmitter : Emitter { // impl Emitter for Mesh, emitter.rs:570-688
     const Mesh *m;
@@ -1103,11 +1134,11 @@ struct MeshEmitter : Emitter { // impl Emitter for Mesh, emitter.rs:570-688
         float geom = dist != 0.0f ? rmax(dot(sp.n, -d), 0.0f) / (dist * dist) : 0.0f;
         float pdf_area = sp.pdf.value();
         PDF pdf = sp.pdf.as_solid_angle_geom(geom);
-        Color weight = pdf.is_zero() ? Color::zero() : m->emit() * geom / pdf_area;
-        return LightSampling{this, pdf, sp.p, sp.n, d, sp.primitive_id, weight};
+        Color weight = pdf.is_zero() ? Color::zero() : m->emit(sp.uv) * geom / pdf_area;
+        return LightSampling{this, pdf, sp.p, sp.n, d, sp.primitive_id, weight, sp.uv};
     }
     Color flux() const override { return m->flux(); }
-    Color eval() const override { return m->emit(); }
+    Color eval(const UV &uv) const override { return m->emit(uv); }
     bool is_surface() const override { return true; } // :727-729
     PDF direct_pdf_tri(const LightSamplingPDF &ls, size_t id_primitive) const override { // :581-589
         float cos_light = rmax(dot(ls.n, -ls.dir), 0.0f);
@@ -1123,8 +1154,8 @@ struct MeshEmitter : Emitter { // impl Emitter for Mesh, emitter.rs:570-688
         float geom = dist != 0.0f ? rmax(dot(sp.n, -d), 0.0f) / (dist * dist) : 0.0f;
         float pdf_area = sp.pdf.value();
         PDF pdf = sp.pdf.as_solid_angle_geom(geom);
-        Color weight = pdf.is_zero() ? Color::zero() : m->emit() * geom / pdf_area;
-        return LightSampling{this, pdf, sp.p, sp.n, d, 0, weight}; // primitive_id: None ("Not sampled a particular primitive")
+        Color weight = pdf.is_zero() ? Color::zero() : m->emit(sp.uv) * geom / pdf_area;
+        return LightSampling{this, pdf, sp.p, sp.n, d, 0, weight, sp.uv}; // primitive_id: None ("Not sampled a particular primitive")
     }
 };
 struct PointEmitter : Emitter { // emitter.rs:186-250
@@ -1139,7 +1170,7 @@ struct PointEmitter : Emitter { // emitter.rs:186-250
         return LightSampling{this, PDF{PDF::Discrete, 1.0f}, p, V3{0.0f, 0.0f, 0.0f}, d, 0, intensity / powi(dist, 2)};
     }
     Color flux() const override { return intensity * 4.0f * PI; } // :239-241
-    Color eval() const override { return intensity; }
+    Color eval(const UV &) const override { return intensity; }
 };
 struct DirectionalLight : Emitter { // emitter.rs:96-190
     V3 direction; // from the light to the world
@@ -1154,7 +1185,7 @@ struct DirectionalLight : Emitter { // emitter.rs:96-190
         float area = PI * powi(bsphere.radius, 2);
         return area * intensity;
     }
-    Color eval() const override { return intensity; }
+    Color eval(const UV &) const override { return intensity; }
 };
 // math.rs:324-352
 inline bool solve_quadratic(float a, float b, float c, float *x0_out, float *x1_out) {
@@ -1321,7 +1352,7 @@ struct EnvironmentLight : Emitter { // emitter.rs:428-568
         float v = PI * powi(bsphere.radius, 2) * luminance.image_cdf[ORC_MATH_SPEC].marginal.func_int; // (the SPEC table: what the device builds)
         return Color{v, v, v};
     }
-    Color eval() const override { return luminance.constant; }
+    Color eval(const UV &) const override { return luminance.constant; }
 };
 // ---- the light tree of `-x ats`: emitter.rs:782-1400 ------------------------------------------------------------------------
 inline float safe_acos(float v) { return std::acos(rmin(rmax(v, -1.0f), 1.0f)); } // :789-791
@@ -1880,7 +1911,12 @@ struct Scene {
                     lp.emitter_id = i, lp.primitive_idx = t;
                     lp.bounds.w = normalize(n);
                     lp.bounds.theta_o = 0.0f, lp.bounds.theta_e = FRAC_PI_2;
-                    lp.bounds.phi = m->emit().channel_max() * magnitude(n) * 0.5f;
+                    UV cuv; // "For now we interpolate at the middle" (:742-750)
+                    if (m->has_uv) {
+                        P2 a = m->uv[idx.x], b = m->uv[idx.y], c = m->uv[idx.z];
+                        cuv.some = true, cuv.v = P2{((a.x + b.x) + c.x) / 3.0f, ((a.y + b.y) + c.y) / 3.0f};
+                    }
+                    lp.bounds.phi = m->emit(cuv).channel_max() * magnitude(n) * 0.5f;
                     lp.bounds.aabb = AABB{}.union_vec(v0).union_vec(v1).union_vec(v2);
                     lp.bounds.cos_theta_o = std::cos(lp.bounds.theta_o), lp.bounds.cos_theta_e = std::cos(lp.bounds.theta_e);
                     ats->lights.push_back(lp);
@@ -2074,6 +2110,7 @@ struct Vertex {
     Intersection its{};
     // Light
     V3 n{};
+    UV light_uv{};
     const Emitter *emitter = nullptr;
     // edges
     int edge_in = -1;
@@ -2108,10 +2145,10 @@ struct Path {
 // Vertex::contribution, vertex.rs:69-82
 Color vertex_contribution(const Vertex &v, const Edge &edge) {
     if (v.kind == Vertex::Surface) {
-        if (dot(v.its.n_s, -edge.d) >= 0.0f) return v.its.mesh->emit();
+        if (dot(v.its.n_s, -edge.d) >= 0.0f) return v.its.mesh->emit(v.its.uv);
         return Color::zero();
     }
-    if (v.kind == Vertex::Light) return v.emitter->eval(); // emitter.eval(-edge.d, uv), emitter.rs:605-607
+    if (v.kind == Vertex::Light) return v.emitter->eval(v.light_uv); // emitter.eval(-edge.d, uv), emitter.rs:605-607
     return Color::zero();
 }
 // Edge::contribution, edge.rs:201-210 (environment luminance is zero on this path)
@@ -2246,7 +2283,7 @@ struct LightSamplingStrategy : SamplingStrategy { // strategies/emitters.rs
         if (rec.is_valid() && visible) {
             Vertex nv;
             nv.kind = Vertex::Light;
-            nv.pos = rec.p, nv.n = rec.n, nv.emitter = rec.emitter;
+            nv.pos = rec.p, nv.n = rec.n, nv.emitter = rec.emitter, nv.light_uv = rec.uv;
             Color weight = its.mesh->bsdf->eval(cx.math, its.uv, its.wi, its.frame.to_local(rec.d));
             int nvid = path.register_vertex(nv);
             int eid = edge_from_vertex(path, vertex_id, rec.pdf, weight, rec.weight, 1.0f, nvid, id_strategy);
@@ -2442,10 +2479,10 @@ Color path_compute_pixel_stream(const rl_integrator_desc &I, uint32_t ix, uint32
         const BSDF &bsdf = *its.mesh->bsdf;
         // ---- emission carried by the arriving edge ----
         if (depth == 1) { // sensor edge: un-weighted (path.rs:152-165)
-            if (add_ok(0) && dot(its.n_s, -ray.d) >= 0.0f && its.mesh->is_light() && !its.mesh->emit().is_zero()) L = L + its.mesh->emit();
+            if (add_ok(0) && dot(its.n_s, -ray.d) >= 0.0f && its.mesh->is_light() && !its.mesh->emit(its.uv).is_zero()) L = L + its.mesh->emit(its.uv);
         } else if (!mute && add_ok(depth - 1) && I.strategy != RL_STRATEGY_EMITTER) {
             if (dot(its.n_s, -ray.d) >= 0.0f && its.mesh->is_light()) {
-                Color contrib = T * its.mesh->emit();
+                Color contrib = T * its.mesh->emit(its.uv);
                 if (!contrib.is_zero()) {
                     float w = 1.0f;
                     if (I.strategy == RL_STRATEGY_ALL && mis_prev) { // balance heuristic (path.rs:78-99)
@@ -2540,7 +2577,7 @@ Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy
     Intersection its;
     if (!sc.trace(ray, cx.accel_mode, *cx.counters, &its)) return sc.enviroment_luminance(cx.math, ray.d); // direct.rs:33-36
     if (its.cos_theta() <= 0.0f) return l_i;
-    l_i = l_i + its.mesh->emit();
+    l_i = l_i + its.mesh->emit(its.uv);
     float weight_nb_bsdf = I.nb_bsdf_samples == 0 ? 0.0f : 1.0f / (float)I.nb_bsdf_samples;
     float weight_nb_light = I.nb_light_samples == 0 ? 0.0f : 1.0f / (float)I.nb_light_samples;
     const BSDF &bsdf = *its.mesh->bsdf;
@@ -2571,7 +2608,7 @@ Color direct_compute_pixel(const rl_integrator_desc &I, uint32_t ix, uint32_t iy
                     float light_pdf = sc.emitters.direct_pdf(next_its.mesh, LightSamplingPDF{r2.o, next_its.p, next_its.n_g, r2.d}, &its.n_s, (long)next_its.primitive_id).value();
                     weight_bsdf = mis_weight(sb.pdf.value() * weight_nb_bsdf, light_pdf * weight_nb_light);
                 }
-                l_i = l_i + weight_bsdf * sb.weight * next_its.mesh->emit() * weight_nb_bsdf;
+                l_i = l_i + weight_bsdf * sb.weight * next_its.mesh->emit(next_its.uv) * weight_nb_bsdf;
             }
         } else if (sc.has_environment) { // direct.rs:183-227
             float weight_bsdf = 1.0f;
@@ -2675,6 +2712,20 @@ orc_scene *orc_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
         }
         m->light = md.emission_kind != 0;
         m->emission = Color{md.emission[0], md.emission[1], md.emission[2]};
+        if (md.emission_kind > RL_EMISSION_TEXTURE) return fail("unknown emission kind");
+        if (md.emission_kind >= RL_EMISSION_HSV) { // EmissionType::HSV { scale } | Texture { scale, img }
+            if (!md.UV) return fail("HSV / textured emission needs uv coordinates (uv.unwrap(), geometry.rs:197)");
+            m->emission_type = md.emission_kind == RL_EMISSION_HSV ? Mesh::EHsv : Mesh::ETexture;
+            m->emission_scale = md.emission[0];
+            if (md.emission_kind == RL_EMISSION_TEXTURE) {
+                if (md.emission_texture == 0 || md.emission_texture > desc->ntextures || desc->textures[md.emission_texture - 1].kind != RL_TEX_BITMAP)
+                    return fail("emission_texture must be 1 + index of a bitmap texture");
+                const rl_texture &t = desc->textures[md.emission_texture - 1];
+                m->emission_img = std::make_shared<BitmapTex>();
+                m->emission_img->size_x = t.width, m->emission_img->size_y = t.height;
+                for (size_t i = 0; i < (size_t)t.width * t.height; i++) m->emission_img->colors.push_back(Color{t.pixels[3 * i], t.pixels[3 * i + 1], t.pixels[3 * i + 2]});
+            }
+        }
         m->first_prim = first;
         first += md.ntris;
         m->build_cdf();

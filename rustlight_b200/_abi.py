@@ -45,9 +45,10 @@ class rl_mesh_desc(C.Structure):
     _fields_ = [("P", C.POINTER(C.c_float)), ("nverts", C.c_uint32),
                 ("idx", C.POINTER(C.c_uint32)), ("ntris", C.c_uint32),
                 ("N", C.POINTER(C.c_float)), ("UV", C.POINTER(C.c_float)),
-                ("mat", rl_material), ("emission_kind", C.c_uint32), ("emission", C.c_float * 3)]
+                ("mat", rl_material), ("emission_kind", C.c_uint32), ("emission", C.c_float * 3), ("emission_texture", C.c_uint32)]
 
 
+RL_EMISSION_ZERO, RL_EMISSION_COLOR, RL_EMISSION_HSV, RL_EMISSION_TEXTURE = 0, 1, 2, 3  # rl_emission_kind (geometry.rs:99-104)
 RL_TEX_BITMAP = 1
 RL_TEX_CHECKERBOARD = 2
 RL_TEX_GRID = 3

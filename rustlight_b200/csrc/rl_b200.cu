@@ -113,6 +113,7 @@ struct rl_scene {
     float *d_emit_cdf = nullptr, *d_area_cdf = nullptr;
     float2 *d_uvs = nullptr;
     float4 *d_tex = nullptr, *d_texels = nullptr;
+    bool emit_var = false; // a mesh light with EmissionType::HSV / Texture
     float *d_env_dist = nullptr; // Distribution2D of an environment texture
     float4 *d_ats_nodes = nullptr; // LightSamplerATS (rl_ats_host.hpp)
     uint32_t *d_ats_leaf = nullptr;
@@ -564,6 +565,8 @@ int rl_scene_create(rl_ctx *ctx, const rl_scene_desc *desc, rl_scene **out) {
     sv.trav = s->d_trav, sv.nodes = s->d_nodes, sv.shade = s->d_shade, sv.verts = s->d_verts, sv.mats = s->d_mats;
     sv.emit_info = s->d_emit_info, sv.emit_cdf = s->d_emit_cdf, sv.area_cdf = s->d_area_cdf;
     sv.uvs = s->d_uvs, sv.tex = s->d_tex, sv.texels = s->d_texels;
+    sv.emit_var = hs.emit_var ? 1u : 0u;
+    s->emit_var = hs.emit_var;
     sv.ref_nodes = ref_ok ? s->d_ref_nodes : nullptr, sv.ref_prims = ref_ok ? s->d_ref_prims : nullptr, sv.ref_up = ref_ok ? s->d_ref_up : nullptr;
     sv.ntris = n, sv.n_emitters = hs.n_emitters;
     sv.root_ref = root_ref;
@@ -918,7 +921,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
         }
         const int prof = ctx->profiling; // 0 off, 1 per-stage kernels (trace and shadow launched separately), 2 the kernels of an untimed frame
         const bool sort_on = o->material_sort == 1u || (o->material_sort >= 2u && sc->n_bsdf_kinds > 1u);
-        const bool extra = sc->d_tex != nullptr || sc->d_ats_nodes != nullptr; // textures (incl. an environment texture) or the light tree: the kernels with KM bit 8
+        const bool extra = sc->d_tex != nullptr || sc->d_ats_nodes != nullptr || sc->emit_var; // textures (incl. an environment texture), the light tree or uv-dependent emission: the kernels with KM bit 8
         // the prediction of the queue lengths belongs to (scene, integrator): forget it when either changes
         const uint64_t pred_key = (uint64_t)(uintptr_t)sc ^ ((uint64_t)I->kind << 56) ^ ((uint64_t)(uint32_t)I->max_depth << 40) ^ ((uint64_t)(uint32_t)I->rr_depth << 24) ^
                                   ((uint64_t)I->strategy << 20) ^ ((uint64_t)sc->scene_gen << 4);

@@ -418,6 +418,7 @@ struct SceneView {
     const float4 *emit_info;
     const float2 *uvs;    // nullptr when no mesh has uv
     const float4 *tex;    // textures of the kd slot (BSDFColor::{Bitmap, Checkerbord, Grid})
+    uint32_t emit_var;    // some mesh light has EmissionType::HSV / Texture (mesh_emit)
     const float4 *texels;
     const float *emit_cdf; // n_emitters+1
     const float *area_cdf; // concatenated per-emitter triangle-area cdfs (ntris+1 each)
@@ -1479,6 +1480,7 @@ struct Material {
     float inv_area, pdf_sel;
     uint32_t kind, microfacet;
     bool is_light;
+    uint32_t emit_kind;   // rl_emission_kind; HSV / TEXTURE: le = {scale, texture index (bits), -} until mesh_emit has replaced it (apply_textures, sample_light)
     bool k_textured;      // metal k comes from a texture (k_tex) instead of ext[0]
     Col k_tex;
     const float4 *ext;    // row 4 {metal k.rgb, glass 1/eta}, row 5 {textures of the colour slots}: read only by the metal / glass branches and the texture lookup
@@ -1492,7 +1494,8 @@ RL_HD Material load_material(const float4 *mats, uint32_t mesh) {
     m.ks = xyz_col(b);
     m.exponent = b.w;
     m.le = xyz_col(c);
-    m.is_light = f2u(c.w) != 0u;
+    m.emit_kind = f2u(c.w);
+    m.is_light = m.emit_kind != 0u;
     m.weight_specular = e.x;
     m.inv_area = e.y;
     m.pdf_sel = e.z;
@@ -1924,6 +1927,27 @@ RL_HD int32_t f32_as_i32(float v) { // Rust `as i32`: saturating, NaN -> 0
     return (int32_t)v;
 }
 RL_HD float modulo1(float x) { return fmodf(fmodf(x, 1.0f) + 1.0f, 1.0f); } // tools.rs:39-41 with n = 1.0
+// Bitmap::pixel_uv (structure.rs:434-453) of bitmap texture tex_id
+RL_HD Col bitmap_pixel_uv(const SceneView &sv, uint32_t tex_id, float ux, float uy) {
+    const float4 t3 = sv.tex[4 * tex_id + 3];
+    const uint32_t width = f2u(t3.x), height = f2u(t3.y), off = f2u(t3.z);
+    ux = modulo1(ux), uy = modulo1(uy);
+    const uint64_t x = f32_as_usize(ux * (float)width), y = f32_as_usize(uy * (float)height);
+    const uint64_t i = (uint64_t)width * y + x;
+    if (i >= (uint64_t)width * height) return Col{0.0f, 0.0f, 0.0f};
+    return xyz_col(sv.texels[off + i]);
+}
+// Mesh::emit(uv) for EmissionType::HSV / Texture (geometry.rs:184-206): `m.le` still holds {scale, texture index}.
+// HSV: c = x * (1, 0, 0) + (1 - x) * (0, 1, 0) with x = uv.x.abs() % 1.0 (`f32 * Color`: plain products), then Color * scale.
+RL_HD Col mesh_emit(const SceneView &sv, const Material &m, float ux, float uy) {
+    const float scale = m.le.r;
+    Col c;
+    if (m.emit_kind == 2u) {
+        const float x = fmodf(fabsf(ux), 1.0f);
+        c = Col{x * 1.0f + (1.0f - x) * 0.0f, x * 0.0f + (1.0f - x) * 1.0f, x * 0.0f + (1.0f - x) * 0.0f};
+    } else c = bitmap_pixel_uv(sv, f2u(m.le.g), ux, uy);
+    return mul_checked(c, scale);
+}
 // kd of a textured material at a hit: `flags` bit 1 = the mesh has uv; (hit_u, hit_v) barycentrics of the hit
 RL_HD Col texture_kd(const SceneView &sv, uint32_t tex_id, uint32_t prim, uint32_t flags, float hit_u, float hit_v) {
     if (!(flags & 2u)) return Col{0.0f, 0.0f, 0.0f}; // "Found a texture but no uv coordinate given"
@@ -1933,15 +1957,7 @@ RL_HD Col texture_kd(const SceneView &sv, uint32_t tex_id, uint32_t prim, uint32
     float ux = d0.x * w + d1.x * hit_u + d2.x * hit_v, uy = d0.y * w + d1.y * hit_u + d2.y * hit_v;
     const float4 t0 = sv.tex[4 * tex_id], t1 = sv.tex[4 * tex_id + 1], t2 = sv.tex[4 * tex_id + 2];
     const uint32_t kind = f2u(t0.w);
-    if (kind == 1u) { // Bitmap::pixel_uv, structure.rs:434-453
-        const float4 t3 = sv.tex[4 * tex_id + 3];
-        const uint32_t width = f2u(t3.x), height = f2u(t3.y), off = f2u(t3.z);
-        ux = modulo1(ux), uy = modulo1(uy);
-        const uint64_t x = f32_as_usize(ux * (float)width), y = f32_as_usize(uy * (float)height);
-        const uint64_t i = (uint64_t)width * y + x;
-        if (i >= (uint64_t)width * height) return Col{0.0f, 0.0f, 0.0f};
-        return xyz_col(sv.texels[off + i]);
-    }
+    if (kind == 1u) return bitmap_pixel_uv(sv, tex_id, ux, uy); // Bitmap::pixel_uv, structure.rs:434-453
     if (kind == 2u) { // Checkerbord, bsdfs/mod.rs:43-65
         ux = ux * t2.z + t2.x, uy = uy * t2.w + t2.y;
         const int32_t x = 2 * (f32_as_i32(ux * 2.0f) % 2) - 1, y = 2 * (f32_as_i32(uy * 2.0f) % 2) - 1;
@@ -1962,6 +1978,12 @@ RL_HD void apply_textures(const SceneView &sv, Material &m, uint32_t prim, uint3
     if (ta != 0u) m.kd = texture_kd(sv, ta - 1u, prim, flags, hit_u, hit_v);
     if (tb != 0u) m.ks = texture_kd(sv, tb - 1u, prim, flags, hit_u, hit_v);
     if (tc != 0u) m.k_tex = texture_kd(sv, tc - 1u, prim, flags, hit_u, hit_v), m.k_textured = true;
+    if (m.emit_kind >= 2u) { // its.mesh.emit(&its.uv): the uv of the hit (structure.rs:1015-1023); such meshes always carry uv (scene build)
+        const float2 d0 = sv.uvs[3 * prim], d1 = sv.uvs[3 * prim + 1], d2 = sv.uvs[3 * prim + 2];
+        const float w = 1.0f - hit_u - hit_v;
+        m.le = mesh_emit(sv, m, d0.x * w + d1.x * hit_u + d2.x * hit_v, d0.y * w + d1.y * hit_u + d2.y * hit_v);
+        m.emit_kind = 1u;
+    }
 }
 
 // ---- surface interaction (fill_intersection, structure.rs:965-1059) ---------------------------
@@ -2321,7 +2343,15 @@ RL_HD LightSample sample_light(const SceneView &sv, V3 x, V3 ns, float r_sel, fl
     }
     float geom = dist != 0.0f ? cosl / d2 : 0.0f;
     float pdf = geom == 0.0f ? 0.0f : pdf_area / geom;
-    Col weight = pdf == 0.0f ? Col{0.0f, 0.0f, 0.0f} : div_checked(mul_checked(mat.le, geom), pdf_area);
+    Col le = mat.le;
+    if (EXTRA && mat.emit_kind >= 2u) { // self.emit(&sampled_pos.uv): sample_tri's uv (geometry.rs:316-325), the interpolation NORMALIZED as a 2-vector (sic)
+        const float2 q0 = sv.uvs[3 * prim], q1 = sv.uvs[3 * prim + 1], q2 = sv.uvs[3 * prim + 2];
+        const float b2 = 1.0f - b0 - b1;
+        const float qx = q0.x * b0 + q1.x * b1 + q2.x * b2, qy = q0.y * b0 + q1.y * b1 + q2.y * b2;
+        const float il = 1.0f / sqrtf(qx * qx + qy * qy);
+        le = mesh_emit(sv, mat, qx * il, qy * il);
+    }
+    Col weight = pdf == 0.0f ? Col{0.0f, 0.0f, 0.0f} : div_checked(mul_checked(le, geom), pdf_area);
     ls.weight = pdf_sel == 1.0f ? weight : Col{weight.r / pdf_sel, weight.g / pdf_sel, weight.b / pdf_sel}; // x / 1 == x
     ls.pdf = pdf * pdf_sel;
     ls.valid = ls.pdf != 0.0f;
@@ -2449,7 +2479,7 @@ RL_HD void path_step(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, con
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
     uint32_t mesh = f2u(s0.w);
     Material mat = load_material(sv.mats, mesh);
-    if (RL_HAS(KM, 8) && sv.tex) apply_textures(sv, mat, hit.prim, f2u(s1.w), hit.u, hit.v);
+    if (RL_HAS(KM, 8) && (sv.tex || sv.emit_var)) apply_textures(sv, mat, hit.prim, f2u(s1.w), hit.u, hit.v);
     Surface its = fill_intersection<KM>(sv, mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
     const bool mute = ip.single_scattering != 0u;
     const bool smooth = mat_is_smooth<KM>(mat); // no light sampling at this vertex (emitters.rs:110-112), no draws either
@@ -2598,7 +2628,7 @@ RL_HD void direct_begin(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, 
     float4 s0 = sv.shade[4 * hit.prim], s1 = sv.shade[4 * hit.prim + 1], s2 = sv.shade[4 * hit.prim + 2], s3 = sv.shade[4 * hit.prim + 3];
     uint32_t mesh = f2u(s0.w);
     cx->mat = load_material(sv.mats, mesh);
-    if (RL_HAS(KM, 8) && sv.tex) apply_textures(sv, cx->mat, hit.prim, f2u(s1.w), hit.u, hit.v);
+    if (RL_HAS(KM, 8) && (sv.tex || sv.emit_var)) apply_textures(sv, cx->mat, hit.prim, f2u(s1.w), hit.u, hit.v);
     cx->its = fill_intersection<KM>(sv, cx->mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
     if (cx->its.wi.z <= 0.0f) return; // its.cos_theta() <= 0 (direct.rs:40-42)
     cx->ok = true;
@@ -2685,6 +2715,7 @@ RL_HD bool direct_finish(const SceneView &sv, const IntegParams &ip, V3 o, V3 d,
     uint32_t mesh = f2u(s0.w);
     Material mat = load_material(sv.mats, mesh);
     if (!mat.is_light) return false;
+    if (mat.emit_kind >= 2u) apply_textures(sv, mat, hit.prim, f2u(s1.w), hit.u, hit.v); // next_its.mesh.emit(&next_its.uv) (direct.rs:179)
     Surface nx = fill_intersection(sv, mat, hit.prim, mesh, s0, s1, s2, s3, hit.t, hit.u, hit.v, o, d);
     if (!(dot(nx.n_g, -d) > 0.0f)) return false;
     float wb = ip.nb_bsdf_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_bsdf_samples;

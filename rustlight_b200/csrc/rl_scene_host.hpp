@@ -19,6 +19,7 @@ namespace rl {
 
 struct HostScene {
     uint32_t ntris = 0, nmeshes = 0, n_emitters = 0;
+    bool emit_var = false;         // a mesh light with EmissionType::HSV / Texture: emission depends on uv (kernels with KM bit 8)
     std::vector<float4> verts;     // 3 per prim
     std::vector<float4> shade;     // 4 per prim; [0].xyz (n_geo) filled by the device setup kernel
     std::vector<float4> mats;      // RL_MAT_F4 per mesh
@@ -105,6 +106,24 @@ inline void material_rows(const rl_material &mt, float4 rows[6], int delta_a, in
     const uint32_t ta = mt.kind == RL_BSDF_METAL ? mt.eta_texture : (mt.kind == RL_BSDF_GLASS ? mt.kt_texture : mt.kd_texture);
     rows[5] = blend ? f4(0.0f, 0.0f, 0.0f, 0.0f) : f4(u2f(ta), u2f(mt.ks_texture), u2f(mt.kind == RL_BSDF_METAL ? mt.k_texture : 0u), 0.0f);
 }
+// Mesh::emit(uv) for EmissionType::HSV / Texture on the host (the light tree's proxies, emitter.rs:742-756); the operations of
+// rl_device.cuh: mesh_emit.  `out` = three floats.
+inline void host_mesh_emit(const rl_scene_desc *desc, const rl_mesh_desc &m, float u, float v, float *out) {
+    const float scale = m.emission[0];
+    Col c;
+    if (m.emission_kind == RL_EMISSION_HSV) {
+        const float x = fmodf(fabsf(u), 1.0f); // uv.x.abs() % 1.0
+        c = Col{x * 1.0f + (1.0f - x) * 0.0f, x * 0.0f + (1.0f - x) * 1.0f, x * 0.0f + (1.0f - x) * 0.0f};
+    } else { // img.pixel_uv(uv), structure.rs:434-453
+        const rl_texture &t = desc->textures[m.emission_texture - 1];
+        auto modulo1 = [](float a) { return fmodf(fmodf(a, 1.0f) + 1.0f, 1.0f); };
+        auto as_usize = [](float a) -> uint64_t { return !(a > 0.0f) ? 0ull : (a >= 18446744073709551616.0f ? ~0ull : (uint64_t)a); };
+        const uint64_t x = as_usize(modulo1(u) * (float)t.width), y = as_usize(modulo1(v) * (float)t.height), i = (uint64_t)t.width * y + x;
+        c = i >= (uint64_t)t.width * t.height ? Col{0.0f, 0.0f, 0.0f} : Col{t.pixels[3 * i], t.pixels[3 * i + 1], t.pixels[3 * i + 2]};
+    }
+    c = mul_checked(c, scale);
+    out[0] = c.r, out[1] = c.g, out[2] = c.b;
+}
 inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::string &err) {
     if (!desc || !desc->meshes || desc->nmeshes == 0) {
         err = "empty scene";
@@ -179,6 +198,22 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
             err = "unsupported BSDF kind or parameters";
             return false;
         }
+        if (m.emission_kind > RL_EMISSION_TEXTURE) {
+            err = "unknown emission kind";
+            return false;
+        }
+        if (m.emission_kind >= RL_EMISSION_HSV) { // Mesh::emit unwraps the uv of the hit / of the sampled point (geometry.rs:197, 204)
+            if (!m.UV) {
+                err = "HSV / textured emission on a mesh without uv coordinates (the reference panics: uv.unwrap(), geometry.rs:197)";
+                return false;
+            }
+            if (m.emission_kind == RL_EMISSION_TEXTURE &&
+                (m.emission_texture == 0 || m.emission_texture > desc->ntextures || desc->textures[m.emission_texture - 1].kind != RL_TEX_BITMAP)) {
+                err = "emission_texture must be 1 + index of a bitmap texture";
+                return false;
+            }
+            hs.emit_var = true;
+        }
         std::vector<float> areas;
         for (uint32_t t = 0; t < m.ntris; t++) {
             uint32_t id[3] = {m.idx[3 * t], m.idx[3 * t + 1], m.idx[3 * t + 2]};
@@ -232,7 +267,9 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
             EmitterTmp e;
             e.mesh = mi, e.first_prim = first, e.ntris = m.ntris, e.cdf_off = (uint32_t)hs.area_cdf.size();
             // Mesh::flux = total * Le * PI, emitter.rs:591-599; channel_max for the emitter CDF, scene.rs:103-111
-            float fr = (m.emission[0] * total), fg = (m.emission[1] * total), fb = (m.emission[2] * total);
+            // (HSV / Texture: e = Color::value(scale), "TODO" in the reference)
+            const bool var = m.emission_kind >= RL_EMISSION_HSV;
+            float fr = (m.emission[0] * total), fg = ((var ? m.emission[0] : m.emission[1]) * total), fb = ((var ? m.emission[0] : m.emission[2]) * total);
             Col fl = mul_checked(Col{fr, fg, fb}, RL_PI);
             e.flux_max = channel_max(fl);
             emitters.push_back(e);
@@ -351,7 +388,9 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
         float4 rows[6];
         const int base = 6 * ((int)desc->nmeshes - (int)mi);
         material_rows(m.mat, rows, base + 6 * ((int)m.mat.blend_a - 1), base + 6 * ((int)m.mat.blend_b - 1));
-        rows[2] = f4(m.emission_kind ? m.emission[0] : 0.0f, m.emission_kind ? m.emission[1] : 0.0f, m.emission_kind ? m.emission[2] : 0.0f, u2f(m.emission_kind ? 1u : 0u));
+        // {Le.rgb, 1} | HSV {scale, -, -, 2} | Texture {scale, texture index (bits), -, 3}: rl_device.cuh: mesh_emit
+        if (m.emission_kind >= RL_EMISSION_HSV) rows[2] = f4(m.emission[0], u2f(m.emission_kind == RL_EMISSION_TEXTURE ? m.emission_texture - 1u : 0u), 0.0f, u2f(m.emission_kind));
+        else rows[2] = f4(m.emission_kind ? m.emission[0] : 0.0f, m.emission_kind ? m.emission[1] : 0.0f, m.emission_kind ? m.emission[2] : 0.0f, u2f(m.emission_kind ? 1u : 0u));
         rows[3].y = mesh_inv_area[mi], rows[3].z = pdf_sel[mi];
         hs.mats.insert(hs.mats.end(), rows, rows + 6);
     }
@@ -375,7 +414,14 @@ inline bool build_host_scene(const rl_scene_desc *desc, HostScene &hs, std::stri
             for (uint32_t t = 0; t < desc->meshes[mi].ntris; t++, p++)
                 if (desc->meshes[mi].emission_kind) {
                     emissive[p] = 1;
-                    for (int a = 0; a < 3; a++) le[3 * (size_t)p + a] = desc->meshes[mi].emission[a];
+                    const rl_mesh_desc &m = desc->meshes[mi];
+                    if (m.emission_kind >= RL_EMISSION_HSV) { // self.emit(&uv) at the centroid uv, (uv0 + uv1 + uv2) / 3.0 (emitter.rs:742-756)
+                        const uint32_t *ix = m.idx + 3 * (size_t)t;
+                        const float cu = ((m.UV[2 * ix[0]] + m.UV[2 * ix[1]]) + m.UV[2 * ix[2]]) / 3.0f;
+                        const float cv = ((m.UV[2 * ix[0] + 1] + m.UV[2 * ix[1] + 1]) + m.UV[2 * ix[2] + 1]) / 3.0f;
+                        host_mesh_emit(desc, m, cu, cv, &le[3 * (size_t)p]);
+                    } else
+                        for (int a = 0; a < 3; a++) le[3 * (size_t)p + a] = m.emission[a];
                 }
         AtsTree tree;
         if (!build_ats_tree(hs.verts, hs.ntris, emissive, le, tree, err)) return false;

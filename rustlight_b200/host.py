@@ -47,6 +47,7 @@ def lib():
         L.rlh_scene_add_texture_file.argtypes = [C.c_void_p, C.c_char_p]
         L.rlh_scene_set_environment.argtypes = [C.c_void_p, C.c_float * 3]
         L.rlh_scene_set_environment_texture.argtypes = [C.c_void_p, C.c_uint32]
+        L.rlh_scene_override_lights.argtypes = [C.c_void_p, C.c_uint32]
         L.rlh_scene_set_ats.argtypes = [C.c_void_p, C.c_int]
         L.rlh_scene_set_ats.restype = None
         L.rlh_scene_add_light.argtypes = [C.c_void_p, C.c_uint32, C.c_float * 3, C.c_float * 3]
@@ -156,6 +157,17 @@ class Scene:
     def set_ats(self, on=True):
         """Scene::build_emitters(build_ats) (`-x ats`): sample lights through the light tree LightSamplerATS (emitter.rs:1130-1400)."""
         lib().rlh_scene_set_ats(self._h, 1 if on else 0)
+        return self
+
+    def override_lights_hsv(self):
+        """`-x hvs-light` (examples/cli.rs:410-421): every mesh light becomes EmissionType::HSV { scale = luminance of its colour }."""
+        lib().rlh_scene_override_lights(self._h, 0)
+        return self
+
+    def override_lights_texture(self, tex_id):
+        """`-x texture-light` (examples/cli.rs:421-427): EmissionType::Texture { scale, img } with a bitmap texture id from add_bitmap_texture."""
+        if lib().rlh_scene_override_lights(self._h, int(tex_id)) != 0:
+            raise SceneError("texture lights: not a bitmap texture id")
         return self
 
     def set_environment_texture(self, tex_id):

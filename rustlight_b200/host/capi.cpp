@@ -120,6 +120,16 @@ int rlh_scene_add_light(rlh_scene *s, uint32_t kind, const float intensity[3], c
 void rlh_scene_set_environment(rlh_scene *s, const float rgb[3]) { s->scene.set_environment(Color{rgb[0], rgb[1], rgb[2]}); }
 // Scene::build_emitters(build_ats): light sampling through LightSamplerATS (`-x ats`)
 void rlh_scene_set_ats(rlh_scene *s, int on) { s->scene.use_ats = on != 0; }
+// `-x hvs-light` (tex_id == 0) / `-x texture-light` (tex_id = a bitmap texture id): examples/cli.rs:410-429
+int rlh_scene_override_lights(rlh_scene *s, uint32_t tex_id) {
+    try {
+        if (tex_id == 0) s->scene.override_lights_hsv();
+        else s->scene.override_lights_texture(tex_id);
+        return 0;
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
 // EnvironmentLightColor::new_texture(image): `tex_id` = a bitmap texture id from rlh_scene_add_texture / rlh_scene_add_texture_file
 int rlh_scene_set_environment_texture(rlh_scene *s, uint32_t tex_id) {
     try {

@@ -8,12 +8,13 @@
 //                | ao     [-d distance|inf] [-n]
 //
 // Differences from the reference, all forced by scope: only `path`, `direct` and `ao`; `-m` must be 0
-// (no medium); `-x ats|hvs-light|texture-light` are rejected; `-t` is accepted and ignored (the GPU replaces
+// (no medium); `-x ats|hvs-light|texture-light|no-shading` as in the reference (texture-light reads butterfly.png / .pfm instead of butterfly.jpg); `-t` is accepted and ignored (the GPU replaces
 // the Rayon pool); output is .pfm or .png (gamma 2.2, 8 bit, as Bitmap::save_ldr_image).  `-a N` averages N passes (the reference's argument is a time-out in
 // seconds or `inf`; both spellings are accepted: `-a 30s` / `-a inf` / `-a 8`).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fstream>
 #include <string>
 #include <vector>
 
@@ -37,7 +38,7 @@ int main(int argc, char **argv) {
     std::optional<std::string> average, equal_time;
     std::string rng = "independent", output, scene_path, medium = "0.0";
     float scale_image = 1.0f;
-    bool shading_normals = true, use_ats = false;
+    bool shading_normals = true, use_ats = false, hsv_lights = false, texture_lights = false;
     size_t i = 0;
     auto need = [&](const char *flag) -> std::string {
         if (i + 1 >= a.size()) usage((std::string("missing value for ") + flag).c_str());
@@ -63,6 +64,8 @@ int main(int argc, char **argv) {
             std::string x = need("-x");
             if (x == "no-shading") shading_normals = false;
             else if (x == "ats") use_ats = true; // Scene::build_emitters(true), cli.rs:325, 432
+            else if (x == "hvs-light") hsv_lights = true;         // EmissionType::HSV on every mesh light, cli.rs:410-421
+            else if (x == "texture-light") texture_lights = true; // EmissionType::Texture { img: Bitmap::read("butterfly.jpg") }, cli.rs:421-427
             else usage(("-x " + x + " is outside the GPU path").c_str());
         } else if (t == "-h" || t == "--help") usage("help");
         else if (!t.empty() && t[0] == '-') usage(("unknown option " + t).c_str());
@@ -120,6 +123,20 @@ int main(int argc, char **argv) {
     try {
         Scene scene = SceneLoaderManager().load(scene_path, shading_normals);
         scene.use_ats = use_ats;
+        if (hsv_lights) scene.override_lights_hsv(); // (hvs wins when both are given, cli.rs:419)
+        else if (texture_lights) {
+            // the reference reads "butterfly.jpg" from the working directory; JPEG is not decoded here: the same picture as
+            // butterfly.png / butterfly.pfm is taken instead, and its absence is an error like the reference's panic
+            uint32_t id = 0;
+            for (const char *fn : {"butterfly.png", "butterfly.pfm"}) {
+                if (std::ifstream(fn).good()) {
+                    id = scene.add_texture(Texture::bitmap_file(fn));
+                    break;
+                }
+            }
+            if (!id) throw Error("-x texture-light: butterfly.png (or .pfm) not found in the working directory (the reference reads butterfly.jpg; JPEG is not decoded here)");
+            scene.override_lights_texture(id);
+        }
         scene.nb_samples = nbsamples;
         scene.output_img_path = output;
         if (scale_image != 1.0f) {

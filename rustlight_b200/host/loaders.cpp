@@ -968,6 +968,18 @@ Scene JSONSceneLoader::load_string(const std::string &text, bool use_shading_nor
             mesh->is_light = true;
             mesh->emission = jcolor(jm.get("emission"), "mesh.emission", Color{});
         }
+        // EmissionType::HSV / Texture (geometry.rs:99-104): "emission_hsv": scale | "emission_texture": {"texture": name, "scale": s}
+        if (const JVal *h = jm.get("emission_hsv")) {
+            const float sc = jfloats(h, "mesh.emission_hsv", 1)[0];
+            mesh->is_light = true, mesh->emission_kind = RL_EMISSION_HSV, mesh->emission = Color{sc, sc, sc};
+        } else if (const JVal *t = jm.get("emission_texture")) {
+            const JVal *tn = t->get("texture"), *ts = t->get("scale");
+            if (!tn || tn->t != JVal::Str || !texture_ids.count(tn->s)) throw Error("json: mesh.emission_texture needs {\"texture\": <name of a texture>, \"scale\": s}");
+            const uint32_t id = texture_ids[tn->s];
+            if (scene.textures[id - 1].t.kind != RL_TEX_BITMAP) throw Error("json: mesh.emission_texture must name a bitmap texture");
+            const float sc = ts ? jfloats(ts, "mesh.emission_texture.scale", 1)[0] : 1.0f;
+            mesh->is_light = true, mesh->emission_kind = RL_EMISSION_TEXTURE, mesh->emission = Color{sc, sc, sc}, mesh->emission_texture = id;
+        }
         if (!mesh->indices.empty()) scene.meshes.push_back(mesh);
     }
     return scene;
@@ -1080,7 +1092,14 @@ std::string scene_to_json(const Scene &scene) {
             put("weight", &m.bsdf.m.blend_weight, 1);
         }
         o << "}";
-        if (m.is_light) {
+        if (m.is_light && m.emission_kind == RL_EMISSION_HSV) {
+            o << ", \"emission_hsv\": ";
+            put_floats(o, &m.emission.r, 1);
+        } else if (m.is_light && m.emission_kind == RL_EMISSION_TEXTURE) {
+            o << ", \"emission_texture\": {\"texture\": \"tex" << m.emission_texture << "\", \"scale\": ";
+            put_floats(o, &m.emission.r, 1);
+            o << "}";
+        } else if (m.is_light) {
             float e[3] = {m.emission.r, m.emission.g, m.emission.b};
             o << ", \"emission\": ";
             put_floats(o, e, 3);

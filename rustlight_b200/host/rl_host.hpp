@@ -107,6 +107,10 @@ struct Mesh {
     Material bsdf;
     bool is_light = false; // emission != EmissionType::Zero
     Color emission;
+    // EmissionType::HSV / Texture (geometry.rs:99-104; what `-x hvs-light` / `-x texture-light` make of every mesh light, cli.rs:410-429):
+    // emission_kind = RL_EMISSION_HSV | RL_EMISSION_TEXTURE, emission.r = scale, emission_texture = 1 + index into Scene::textures
+    uint32_t emission_kind = 0; // 0: Zero / Color according to is_light
+    uint32_t emission_texture = 0;
 };
 
 // src/scene.rs:16-30 (the fields this path consumes)
@@ -129,6 +133,11 @@ struct Scene {
         textures.push_back(std::move(t));
         return (uint32_t)textures.size();
     }
+    // `-x hvs-light` / `-x texture-light` (examples/cli.rs:410-429): every mesh light becomes EmissionType::HSV { scale } or
+    // EmissionType::Texture { scale, img } with scale = luminance of its colour (a light that already is one of the two keeps scale 1);
+    // tex_id = a bitmap texture id from add_texture (the reference reads "butterfly.jpg").
+    void override_lights_hsv();
+    void override_lights_texture(uint32_t tex_id);
     void add_point_light(Color intensity, float x, float y, float z);
     void add_directional_light(Color intensity, float dx, float dy, float dz); // direction = normalize(to - from)
 

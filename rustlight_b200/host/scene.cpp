@@ -347,6 +347,28 @@ void Scene::set_environment_texture(uint32_t id) {
     if (id == 0 || id > textures.size() || textures[id - 1].t.kind != RL_TEX_BITMAP) throw Error("environment texture: not a bitmap texture id");
     has_environment = true, environment = Color{0.0f, 0.0f, 0.0f}, environment_texture = id;
 }
+// examples/cli.rs:410-429 (Color::luminance, structure.rs:173-176)
+static float light_scale(const Mesh &m) {
+    if (m.emission_kind == RL_EMISSION_HSV || m.emission_kind == RL_EMISSION_TEXTURE) return 1.0f; // `_ => 1.0`
+    return m.emission.r * 0.212671f + m.emission.g * 0.715160f + m.emission.b * 0.072169f;
+}
+void Scene::override_lights_hsv() {
+    for (auto &mp : meshes) {
+        Mesh &m = *mp;
+        if (!m.is_light) continue;
+        const float scale = light_scale(m);
+        m.emission_kind = RL_EMISSION_HSV, m.emission = Color{scale, scale, scale}, m.emission_texture = 0;
+    }
+}
+void Scene::override_lights_texture(uint32_t tex_id) {
+    if (tex_id == 0 || tex_id > textures.size() || textures[tex_id - 1].t.kind != RL_TEX_BITMAP) throw Error("texture lights: not a bitmap texture id");
+    for (auto &mp : meshes) {
+        Mesh &m = *mp;
+        if (!m.is_light) continue;
+        const float scale = light_scale(m);
+        m.emission_kind = RL_EMISSION_TEXTURE, m.emission = Color{scale, scale, scale}, m.emission_texture = tex_id;
+    }
+}
 const rl_scene_desc *Scene::desc() {
     mesh_descs_.clear();
     submaterial_descs_.clear();
@@ -365,8 +387,9 @@ const rl_scene_desc *Scene::desc() {
             submaterial_descs_.push_back(m.bsdf.subs[1]);
             d.mat.blend_a = (uint32_t)submaterial_descs_.size() - 1u, d.mat.blend_b = (uint32_t)submaterial_descs_.size();
         }
-        d.emission_kind = m.is_light ? 1u : 0u;
+        d.emission_kind = m.is_light ? (m.emission_kind ? m.emission_kind : 1u) : 0u;
         d.emission[0] = m.emission.r, d.emission[1] = m.emission.g, d.emission[2] = m.emission.b;
+        d.emission_texture = m.emission_texture;
         mesh_descs_.push_back(d);
     }
     desc_.nmeshes = (uint32_t)mesh_descs_.size();

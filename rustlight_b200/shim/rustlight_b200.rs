@@ -22,7 +22,7 @@ use std::sync::Mutex;
 #[repr(C)] pub struct rl_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct rl_scene { _p: [u8; 0] }
 
-pub const RL_B200_ABI_VERSION: c_int = 5;
+pub const RL_B200_ABI_VERSION: c_int = 6;
 
 #[repr(C)] #[derive(Clone, Copy)]
 pub struct rl_texture {
@@ -39,7 +39,7 @@ pub struct rl_material {
 #[repr(C)]
 pub struct rl_mesh_desc {
     pub p: *const f32, pub nverts: u32, pub idx: *const u32, pub ntris: u32,
-    pub n: *const f32, pub uv: *const f32, pub mat: rl_material, pub emission_kind: u32, pub emission: [f32; 3],
+    pub n: *const f32, pub uv: *const f32, pub mat: rl_material, pub emission_kind: u32, pub emission: [f32; 3], pub emission_texture: u32,
 }
 #[repr(C)] pub struct rl_camera_desc { pub width: u32, pub height: u32, pub sample_to_camera: [f32; 16], pub to_world: [f32; 16] }
 #[repr(C)] #[derive(Clone, Copy)] pub struct rl_light_desc { pub kind: u32, pub intensity: [f32; 3], pub v: [f32; 3] }
@@ -131,10 +131,17 @@ impl Flat {
         self.textures.push(tex);
         ([0.0; 3], self.textures.len() as u32)
     }
+    /// The image of an `EmissionType::Texture` as a bitmap texture: 1 + texture index (rl_mesh_desc.emission_texture).
+    pub fn bitmap(&mut self, img: &crate::structure::Bitmap) -> u32 {
+        self.texels.push(img.colors.iter().flat_map(|c| [c.r, c.g, c.b]).collect());
+        self.textures.push(rl_texture { kind: 1, width: img.size.x, height: img.size.y, pixels: self.texels.last().unwrap().as_ptr(), color0: [0.0; 3],
+                                        color1: [0.0; 3], line_width: 0.0, offset: [0.0; 2], scale: [1.0; 2] });
+        self.textures.len() as u32
+    }
 }
 
 /// Scene -> flat description (scene.rs:16-30, geometry.rs:107-119).  Panics where the reference offers something outside
-/// the GPU path (media, textured emission, BSDFs without `describe`), like the reference panics on
+/// the GPU path (media, BSDFs without `describe`), like the reference panics on
 /// unsupported input (scene_loader.rs:40-43).
 fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
     assert!(scene.volume.is_none(), "scene.volume must be None on the GPU path");
@@ -147,16 +154,17 @@ fn flatten(scene: &Scene) -> (Flat, rl_scene_desc) {
     }
     for (k, m) in scene.meshes.iter().enumerate() {
         let mat = m.bsdf.describe(&mut f).unwrap_or_else(|| panic!("mesh {}: this BSDF has no GPU description", m.name));
-        let (kind, e) = match &m.emission {
-            crate::geometry::EmissionType::Zero => (0, Color::zero()),
-            crate::geometry::EmissionType::Color { v } => (1, *v),
-            _ => panic!("mesh {}: HSV / textured emission is outside the GPU path", m.name),
+        let (kind, e, etex) = match &m.emission {
+            crate::geometry::EmissionType::Zero => (0, Color::zero(), 0),
+            crate::geometry::EmissionType::Color { v } => (1, *v, 0),
+            crate::geometry::EmissionType::HSV { scale } => (2, Color::value(*scale), 0), // -x hvs-light (cli.rs:419-420)
+            crate::geometry::EmissionType::Texture { scale, img } => (3, Color::value(*scale), f.bitmap(img)), // -x texture-light: 1 + texture index
         };
         let (n, uv) = (&f.n[k], &f.uv[k]);
         f.meshes.push(rl_mesh_desc {
             p: f.p[k].as_ptr(), nverts: m.vertices.len() as u32, idx: f.idx[k].as_ptr(), ntris: m.indices.len() as u32,
             n: if n.is_empty() { std::ptr::null() } else { n.as_ptr() }, uv: if uv.is_empty() { std::ptr::null() } else { uv.as_ptr() },
-            mat, emission_kind: kind, emission: col(&e),
+            mat, emission_kind: kind, emission: col(&e), emission_texture: etex,
         });
     }
     // Non-mesh emitters in the order of Scene.emitters (scene.rs:85-96): mesh lights and the environment are rebuilt by the

@@ -139,6 +139,7 @@ emu_scene *emu_scene_create(const rl_scene_desc *desc, char *err, size_t errlen)
     sv.trav = s->trav.data(), sv.nodes = s->nodes.data(), sv.shade = hs.shade.data(), sv.verts = hs.verts.data(), sv.mats = hs.mats.data();
     sv.emit_info = hs.emit_info.data(), sv.emit_cdf = hs.emit_cdf.data(), sv.area_cdf = hs.area_cdf.data();
     sv.uvs = hs.uvs.empty() ? nullptr : hs.uvs.data(), sv.tex = hs.tex.empty() ? nullptr : hs.tex.data(), sv.texels = hs.texels.data();
+    sv.emit_var = hs.emit_var ? 1u : 0u;
     sv.ntris = hs.ntris, sv.n_emitters = hs.n_emitters;
     sv.root_ref = s->root_ref;
     sv.flat = s->flat.f4.data(), sv.n_groups = s->flat.n_groups, sv.flat_valid_a = s->flat.valid_a, sv.flat_valid_b = s->flat.valid_b;

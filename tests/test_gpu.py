@@ -405,6 +405,37 @@ def test_light_tree_bit_exact(gpu_ctx):
     dev.close()
 
 
+def test_varying_emission_bit_exact(gpu_ctx):
+    """`-x hvs-light` / `-x texture-light` (EmissionType::HSV / Texture, geometry.rs:99-104, 184-206): the lamp's emission depends on the uv
+    of the hit (arrival emission) and on the normalized uv of the sampled point (light sampling); `path` in all three strategies, `direct`,
+    the light tree, the tail kernel and the tessellated box (tree kernels)."""
+    from test_emission import hsv_box, texture_box
+    for make in (hsv_box, texture_box):
+        sc = make(96, 96)
+        dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
+        for integ in (_abi.path_desc(), _abi.path_desc(strategy=_abi.RL_STRATEGY_EMITTER), _abi.path_desc(strategy=_abi.RL_STRATEGY_BSDF, max_depth=4),
+                      _abi.direct_desc(2, 2), _abi.direct_desc(0, 1)):
+            img, st = dev.render(integ, 8, seed=21)
+            ref, so = osc.render(integ, 8, seed=21, cfg=ob.config(**STREAM))
+            assert (st.segments, st.hits, st.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
+            assert np.array_equal(img, ref)
+        dev.close()
+    sc = hsv_box(64, 64).set_ats(True)
+    dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
+    img, st = dev.render(_abi.path_desc(), 8, seed=5)
+    ref, so = osc.render(_abi.path_desc(), 8, seed=5, cfg=ob.config(**STREAM))
+    assert st.segments == so.segments and np.array_equal(img, ref)
+    dev.close()
+    # a lamp of one colour changes nothing: the kernels with the emission lookup equal the plain ones
+    plain = load_cbox(64, 64)
+    a, _ = DeviceScene(gpu_ctx, plain).render(_abi.path_desc(), 4, seed=9)
+    const = load_cbox(64, 64)
+    const.override_lights_texture(const.add_bitmap_texture(np.ones((2, 2, 3), np.float32)))
+    b, _ = DeviceScene(gpu_ctx, const).render(_abi.path_desc(), 4, seed=9)
+    lum = np.float32(17.0) * np.float32(0.212671) + np.float32(12.0) * np.float32(0.715160) + np.float32(4.0) * np.float32(0.072169)
+    assert a.mean() > 0 and abs(b[..., 0].mean() / a[..., 0].mean() - lum / 17.0) < 0.05  # same picture up to the lamp's colour
+
+
 def test_mitsuba_xml_scene_bit_exact(gpu_ctx):
     """The Mitsuba-XML route (the reference's only way to a BSDFPhong): Phong walls, checkerboard floor, rough plastic, a rough-conductor
     sphere of 1922 triangles (4-wide tree over the reference's topology), area + point light."""
