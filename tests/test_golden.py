@@ -39,3 +39,15 @@ def test_primary_hits_golden():
     prim, tuv = ob.OracleScene(load_cbox()).primary_hits(ob.ACCEL_BVH)
     assert np.array_equal(np.where(prim == 0xFFFFFFFF, 255, prim).astype(np.uint8), g["prim"])
     assert np.array_equal(tuv[::8, ::8, 0], g["t_sub8"])
+
+
+@pytest.mark.parametrize("name", ["hsv_path", "hsv_direct", "texture_path", "texture_direct"])
+def test_oracle_reproduces_emission_golden(name):
+    """uv-dependent emission (EmissionType::HSV / Texture): tests/golden/make_golden.py emission."""
+    from test_emission import hsv_box, texture_box
+    g = np.load(os.path.join(GOLDEN, "cbox48_emission_spp8_seed0.npz"))
+    make = hsv_box if name.startswith("hsv") else texture_box
+    integ = _abi.path_desc() if name.endswith("path") else _abi.direct_desc(1, 1)
+    img, st = ob.OracleScene(make(48, 48)).render(integ, 8, seed=0, cfg=ob.config(math_mode=ob.MATH_LIBM, accel_mode=ob.ACCEL_BVH, estimator=ob.EST_GRAPH))
+    assert np.array_equal(img, g[name])
+    assert [st.segments, st.shadow_rays, st.hits] == list(g[name + "_counts"])
