@@ -724,10 +724,6 @@ static int validate(rl_ctx *ctx, const rl_scene *scene, const rl_integrator_desc
             ctx->err = "rl_render: no emitter in the scene but light samples requested";
             return RL_ERR_INVALID;
         }
-        if (scene->d_ats_nodes && I->nb_bsdf_samples > 0) { // EmitterSampler::direct_pdf(.., Some(&its.n_s), ..) of a BSDF-sampled hit (direct.rs:158-165)
-            ctx->err = "rl_render: `direct` with BSDF samples and the light tree (use_ats) is not supported: the light-tree pdf of the second hit needs the first vertex' shading normal, which stage 2 does not carry";
-            return RL_ERR_UNSUPPORTED;
-        }
         if (I->nb_bsdf_samples > 64 || I->nb_light_samples > 64) {
             ctx->err = "rl_render: more than 64 bsdf/light samples per pixel sample";
             return RL_ERR_INVALID;
@@ -956,9 +952,12 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                 if (sc->smem_ok) launch_trace<true>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, done_at, 0u, true, camera_o, cam_masks);
                 else launch_trace<false>(ctx, sc, c_in, n, ctx->ray_o[0], ctx->ray_d[0], ctx->hit, done_at, 0u, true, camera_o, cam_masks);
                 ev_mark(ctx, EV_TRACE);
+                // light-tree scenes: the first vertex' shading normal travels with every extension ray (EmitterSampler::direct_pdf(.., Some(&its.n_s), ..),
+                // direct.rs:158-165) in the stage-1 state queue, which camera rays do not use (their state is a constant)
+                float4 *ns_buf = (sc->d_ats_nodes && nbs > 0 && !ao) ? ctx->state[0] : nullptr;
 #define RL_LAUNCH_DIRECT1(KM) k_shade_direct1<KM><<<grid_for(ctx, n, 4), kBlock, 0, st>>>(sc->sv, ip, ctx->pixel_list, c_in, (uint32_t)n_paths, ctx->ray_o[0], ctx->ray_d[0], \
         ctx->state[0], ctx->hit, ctx->ray_o[1], ctx->ray_d[1], ctx->state[1], c_out, ctx->sh_a, \
-        ctx->sh_b, ctx->sh_c, c_sh, ctx->lacc, ctx->d_counters, camera_o ? 3u : 1u)
+        ctx->sh_b, ctx->sh_c, c_sh, ctx->lacc, ctx->d_counters, camera_o ? 3u : 1u, ns_buf)
                 if (sc->kind_mask == 0x1u && !extra) RL_LAUNCH_DIRECT1(0x1u);
                 else RL_LAUNCH_DIRECT1(RL_KM_ALL);
 #undef RL_LAUNCH_DIRECT1
@@ -976,7 +975,7 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                     else launch_trace<false>(ctx, sc, c_out, n2, ctx->ray_o[1], ctx->ray_d[1], ctx->hit, done_at, 1u);
                     ev_mark(ctx, EV_TRACE);
                     k_shade_direct2<<<grid_for(ctx, n2, 8), kBlock, 0, st>>>(sc->sv, ip, c_out, ctx->ray_o[1], ctx->ray_d[1], ctx->state[1], ctx->hit, ctx->lacc,
-                                                                             ctx->d_counters);
+                                                                             ctx->d_counters, ns_buf);
                     ctx->launches++;
                     ev_mark(ctx, EV_SHADE);
                 }

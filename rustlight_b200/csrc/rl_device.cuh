@@ -2701,7 +2701,9 @@ RL_HD bool direct_bsdf_sample(DirectCtx *cx, V3 *dir, Col *weight, float *pdf) {
     return true;
 }
 // Stage 2 (direct.rs:145-181): the extension ray hit something; contribution if it is a light.
-RL_HD bool direct_finish(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, const HitRec &hit, Col bsdf_weight, float bsdf_pdf_v, Col *contrib) {
+// (ns, has_ns: the first vertex' shading normal, which the light tree's pdf of the second hit takes: Some(&its.n_s), direct.rs:158-165)
+RL_HD bool direct_finish(const SceneView &sv, const IntegParams &ip, V3 o, V3 d, const HitRec &hit, Col bsdf_weight, float bsdf_pdf_v, Col *contrib,
+                         V3 ns = V3{0.0f, 0.0f, 0.0f}, bool has_ns = false) {
     if (hit.prim == RL_MISS) { // direct.rs:183-227: the BSDF sample escaped: MIS against sampling the environment
         if (!sv.env_on) return false;
         float wb = ip.nb_bsdf_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_bsdf_samples;
@@ -2722,7 +2724,7 @@ RL_HD bool direct_finish(const SceneView &sv, const IntegParams &ip, V3 o, V3 d,
     float wl = ip.nb_light_samples == 0u ? 0.0f : 1.0f / (float)ip.nb_light_samples;
     float weight_bsdf = 1.0f;
     if (!(f2u(bsdf_pdf_v) >> 31)) {
-        float light_pdf = direct_pdf(sv, mat, hit.prim, o, nx.p, nx.n_g, d, V3{0.0f, 0.0f, 0.0f}, false); // (light tree + BSDF samples of `direct`: refused by rl_render, the first vertex' normal is not carried)
+        float light_pdf = direct_pdf(sv, mat, hit.prim, o, nx.p, nx.n_g, d, ns, has_ns);
         weight_bsdf = mis_weight_power(bsdf_pdf_v * wb, light_pdf * wl);
     }
     *contrib = mul_checked(mul_plain(weight_bsdf, bsdf_weight) * mat.le, wb);

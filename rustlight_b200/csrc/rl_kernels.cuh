@@ -640,7 +640,8 @@ __global__ void __launch_bounds__(kBlock, RL_DIRECT1_MINBLOCKS) k_shade_direct1(
                                                           const float4 *__restrict__ hit, float4 *__restrict__ out_o, float4 *__restrict__ out_d,
                                                           float4 *__restrict__ out_state, uint32_t *count_out, float4 *__restrict__ sh_a,
                                                           float4 *__restrict__ sh_b, float4 *__restrict__ sh_c, uint32_t *count_shadow,
-                                                          float4 *__restrict__ lacc, Counters *counters, uint32_t camera) {
+                                                          float4 *__restrict__ lacc, Counters *counters, uint32_t camera, float4 *__restrict__ out_ns) {
+    // out_ns (light-tree scenes, else nullptr): the shading normal of the first vertex per extension ray, for the tree's pdf in stage 2
     __shared__ uint32_t s_warp[kBlock / 32];
     __shared__ uint32_t s_base;
     const uint32_t n = *count_in;
@@ -690,6 +691,7 @@ __global__ void __launch_bounds__(kBlock, RL_DIRECT1_MINBLOCKS) k_shade_direct1(
                 out_o[slot] = make_float4(cx.its.p.x, cx.its.p.y, cx.its.p.z, u2f(pid));
                 out_d[slot] = make_float4(dir.x, dir.y, dir.z, pdf);
                 out_state[slot] = make_float4(w.r, w.g, w.b, u2f((1u + ip.nb_light_samples + k) * n_paths + pid));
+                if (out_ns) out_ns[slot] = make_float4(cx.its.n_s.x, cx.its.n_s.y, cx.its.n_s.z, 0.0f);
             }
         }
     }
@@ -706,7 +708,7 @@ __global__ void __launch_bounds__(kBlock, RL_DIRECT1_MINBLOCKS) k_shade_direct1(
 __global__ void __launch_bounds__(kBlock) k_shade_direct2(SceneView sv, IntegParams ip, const uint32_t *__restrict__ count_in,
                                                           const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d,
                                                           const float4 *__restrict__ state, const float4 *__restrict__ hit, float4 *__restrict__ lacc,
-                                                          Counters *counters) {
+                                                          Counters *counters, const float4 *__restrict__ ns_in) {
     const uint32_t n = *count_in;
     uint32_t c_hits = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -715,7 +717,8 @@ __global__ void __launch_bounds__(kBlock) k_shade_direct2(SceneView sv, IntegPar
         h.t = h4.x, h.u = h4.y, h.v = h4.z, h.prim = f2u(h4.w);
         if (h.prim != RL_MISS) c_hits++;
         Col c;
-        const bool add = ip.kind == 2u ? ao_finish(ip, h, &c) : direct_finish(sv, ip, xyz(ro), xyz(rd), h, Col{st4.x, st4.y, st4.z}, rd.w, &c);
+        const V3 ns = ns_in ? xyz(ns_in[i]) : V3{0.0f, 0.0f, 0.0f};
+        const bool add = ip.kind == 2u ? ao_finish(ip, h, &c) : direct_finish(sv, ip, xyz(ro), xyz(rd), h, Col{st4.x, st4.y, st4.z}, rd.w, &c, ns, ns_in != nullptr);
         if (add) lacc[f2u(st4.w)] = make_float4(c.r, c.g, c.b, 0.0f);
     }
     for (int off = 16; off > 0; off >>= 1) c_hits += __shfl_down_sync(0xffffffffu, c_hits, off);

@@ -440,7 +440,7 @@ int emu_render(const emu_scene *s, const rl_integrator_desc *I, uint32_t spp, ui
                         HitRec h2 = trace_closest(sv, sv.nodes, sv.trav, cx.its.p, dir);
                         if (h2.prim != RL_MISS) S.hits++;
                         Col c;
-                        if (direct_finish(sv, ip, cx.its.p, dir, h2, w, pdf, &c)) slots[1 + ip.nb_light_samples + k] = c;
+                        if (direct_finish(sv, ip, cx.its.p, dir, h2, w, pdf, &c, cx.its.n_s, sv.ats_nodes != nullptr)) slots[1 + ip.nb_light_samples + k] = c;
                     }
                     Col tot = slots[0];
                     for (size_t q = 1; q < slots.size(); q++) tot = tot + slots[q];

@@ -121,7 +121,8 @@ def test_device_tree_functions_bit_exact():
 
 
 @pytest.mark.parametrize("integ", [_abi.path_desc(), _abi.path_desc(strategy=_abi.RL_STRATEGY_EMITTER), _abi.path_desc(max_depth=4, rr_depth=2),
-                                   _abi.direct_desc(0, 2)], ids=["path", "path-emitter", "path-d4", "direct02"])
+                                   _abi.direct_desc(0, 2), _abi.direct_desc(1, 1), _abi.direct_desc(2, 3)],
+                         ids=["path", "path-emitter", "path-d4", "direct02", "direct11", "direct23"])
 def test_light_tree_render_bit_exact(integ):
     sc = many_lights_scene(32, 32)
     ie, se = eb.EmuScene(sc, "sah4").render(integ, 4, seed=4)

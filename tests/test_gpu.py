@@ -385,17 +385,17 @@ def test_mixed_material_scene_bit_exact(gpu_ctx, sort):
 def test_light_tree_bit_exact(gpu_ctx):
     """`-x ats` (LightSamplerATS, emitter.rs:782-1400): 26 emissive triangles in 10 meshes, light sampling through the importance-driven
     descent of the light tree; `path` (tree with Some(n_s) for light samples, with None for the MIS pdf of BSDF-sampled hits), `direct`
-    with light samples; the unsupported combination is refused."""
+    with light and BSDF samples."""
     from test_ats import many_lights_scene
     sc = many_lights_scene(96, 96)
     dev, osc = DeviceScene(gpu_ctx, sc), ob.OracleScene(sc)
-    for integ in (_abi.path_desc(), _abi.path_desc(strategy=_abi.RL_STRATEGY_EMITTER), _abi.path_desc(max_depth=4, rr_depth=2), _abi.direct_desc(0, 2)):
+    # (`direct` with BSDF samples: the tree's pdf of the second hit takes the FIRST vertex' shading normal, Some(&its.n_s), direct.rs:158-165)
+    for integ in (_abi.path_desc(), _abi.path_desc(strategy=_abi.RL_STRATEGY_EMITTER), _abi.path_desc(max_depth=4, rr_depth=2), _abi.direct_desc(0, 2),
+                  _abi.direct_desc(1, 1), _abi.direct_desc(2, 1)):
         img, st = dev.render(integ, 8, seed=12)
         ref, so = osc.render(integ, 8, seed=12, cfg=ob.config(**STREAM))
         assert (st.segments, st.hits, st.shadow_rays) == (so.segments, so.hits, so.shadow_rays)
         assert np.array_equal(img, ref)
-    with pytest.raises(DeviceError, match="light tree"):
-        dev.render(_abi.direct_desc(1, 1), 1)
     dev.close()
     box = load_cbox(64, 64).set_ats(True)  # the plain Cornell box: a tree of two leaves
     dev, osc = DeviceScene(gpu_ctx, box), ob.OracleScene(box)
