@@ -626,13 +626,13 @@ __global__ void __launch_bounds__(kTailBlock, RL_TAIL_MINBLOCKS) k_tail(SceneVie
 }
 
 // ---- `direct` integrator, stage 1: primary hit -> emission, light samples, BSDF samples ---------------
-// 4 CTAs per SM (64 registers, 216 B of spills) beat the unconstrained 119 registers / 2 CTAs: direct -b 1 -l 1 at 2048^2 x 16 spp
+// 4 CTAs per SM (64 registers) beat the unconstrained 119 registers / 2 CTAs for the general kernel: direct -b 1 -l 1 at 2048^2 x 16 spp
 // shade 5.58 -> 4.85 ms, ao 3.72 -> 3.19 ms (tools/ab_direct.py); 3 CTAs (80 registers) were slower than both (6.47 ms).
 #ifndef RL_DIRECT1_MINBLOCKS
 #define RL_DIRECT1_MINBLOCKS 4
 #endif
 // KM: the BSDF kinds of the scene as for k_shade ({diffuse} and "everything" are instantiated): the Cornell-box kernel carries no Phong / microfacet /
-// blend / texture / light-tree code (826 -> see profiles bytes of spills when everything is compiled in).
+// blend / texture / light-tree code and fits its 64 registers without spills (stack frame 216 -> 0 B; shade 5.35 -> 3.63 ms per 2048^2 x 16 spp).
 template <uint32_t KM>
 __global__ void __launch_bounds__(kBlock, RL_DIRECT1_MINBLOCKS) k_shade_direct1(SceneView sv, IntegParams ip, const uint32_t *__restrict__ pixel_list,
                                                           const uint32_t *__restrict__ count_in, uint32_t n_paths, const float4 *__restrict__ ray_o,
