@@ -8,7 +8,7 @@
 //                | ao     [-d distance|inf] [-n]
 //
 // Differences from the reference, all forced by scope: only `path`, `direct` and `ao`; `-m` must be 0
-// (no medium); `-x ats|hvs-light|texture-light|no-shading` as in the reference (texture-light reads butterfly.png / .pfm instead of butterfly.jpg); `-t` is accepted and ignored (the GPU replaces
+// (no medium); `-x ats|hvs-light|texture-light|no-shading` as in the reference (texture-light reads butterfly.jpg like the reference, or butterfly.png / .pfm); `-t` is accepted and ignored (the GPU replaces
 // the Rayon pool); output is .pfm or .png (gamma 2.2, 8 bit, as Bitmap::save_ldr_image).  `-a N` averages N passes (the reference's argument is a time-out in
 // seconds or `inf`; both spellings are accepted: `-a 30s` / `-a inf` / `-a 8`).
 #include <cstdio>
@@ -125,16 +125,16 @@ int main(int argc, char **argv) {
         scene.use_ats = use_ats;
         if (hsv_lights) scene.override_lights_hsv(); // (hvs wins when both are given, cli.rs:419)
         else if (texture_lights) {
-            // the reference reads "butterfly.jpg" from the working directory; JPEG is not decoded here: the same picture as
-            // butterfly.png / butterfly.pfm is taken instead, and its absence is an error like the reference's panic
+            // the reference reads "butterfly.jpg" from the working directory (Bitmap::read, cli.rs:424); the same picture as .png / .pfm is
+            // accepted too, and its absence is an error like the reference's panic
             uint32_t id = 0;
-            for (const char *fn : {"butterfly.png", "butterfly.pfm"}) {
+            for (const char *fn : {"butterfly.jpg", "butterfly.png", "butterfly.pfm"}) {
                 if (std::ifstream(fn).good()) {
                     id = scene.add_texture(Texture::bitmap_file(fn));
                     break;
                 }
             }
-            if (!id) throw Error("-x texture-light: butterfly.png (or .pfm) not found in the working directory (the reference reads butterfly.jpg; JPEG is not decoded here)");
+            if (!id) throw Error("-x texture-light: butterfly.jpg (or .png / .pfm) not found in the working directory");
             scene.override_lights_texture(id);
         }
         scene.nb_samples = nbsamples;

@@ -92,7 +92,7 @@ struct Texture {
     rl_texture t{};             // t.pixels points into `pixels`
     std::vector<float> pixels;  // bitmap: 3 * width * height (Bitmap.colors)
     static Texture bitmap(uint32_t w, uint32_t h, std::vector<float> rgb);
-    static Texture bitmap_file(const std::string &filename); // .pfm (Bitmap::read_pfm), .png (Bitmap::read_ldr_image) or binary .ppm (P6, /255 like read_ldr_image)
+    static Texture bitmap_file(const std::string &filename); // .pfm (Bitmap::read_pfm), .png / .jpg (Bitmap::read_ldr_image) or binary .ppm (P6, /255 like read_ldr_image)
     static Texture checkerboard(Color c0, Color c1, float ox, float oy, float sx, float sy);
     static Texture grid(Color c0, Color c1, float line_width, float ox, float oy, float sx, float sy);
 };
@@ -188,8 +188,9 @@ struct Bitmap {
     static Bitmap read_pfm(const std::string &path);
     void save_png(const std::string &path) const;    // Bitmap::save_ldr_image + Color::to_rgba: (min(c, 1)^(1/2.2) * 255) as u8
     static Bitmap read_png(const std::string &path); // Bitmap::read_ldr_image: to_rgb8() / 255
+    static Bitmap read_jpeg(const std::string &path); // Bitmap::read_ldr_image for .jpg / .jpeg (host/jpeg.cpp: baseline + progressive Huffman JPEG)
     void save(const std::string &path) const;        // by extension (structure.rs:528-545): pfm | png
-    static Bitmap read(const std::string &path);     // by extension (structure.rs:670-683): pfm | png
+    static Bitmap read(const std::string &path);     // by extension (structure.rs:670-683): pfm | png | jpg
 };
 // src/integrators/mod.rs:48-52; only the "primal" buffer exists on this path.
 struct BufferCollection {

@@ -311,7 +311,11 @@ Texture Texture::bitmap_file(const std::string &filename) {
         Bitmap b = Bitmap::read_png(filename);
         return bitmap(b.size_x, b.size_y, std::move(b.colors));
     }
-    throw Error("texture: only .pfm, .png and .ppm images can be read here: " + filename);
+    if (ends(".jpg") || ends(".jpeg") || ends(".JPG")) {
+        Bitmap b = Bitmap::read_jpeg(filename);
+        return bitmap(b.size_x, b.size_y, std::move(b.colors));
+    }
+    throw Error("texture: only .pfm, .png, .jpg and .ppm images can be read here: " + filename);
 }
 Texture Texture::checkerboard(Color c0, Color c1, float ox, float oy, float sx, float sy) {
     Texture t;
@@ -607,7 +611,8 @@ Bitmap Bitmap::read(const std::string &path) {
     const std::string ext = extension_of(path);
     if (ext == "pfm") return read_pfm(path);
     if (ext == "png") return read_png(path);
-    throw Error("image: only .pfm and .png can be read: " + path);
+    if (ext == "jpg" || ext == "jpeg" || ext == "JPG") return read_jpeg(path);
+    throw Error("image: only .pfm, .png and .jpg can be read: " + path);
 }
 
 } // namespace rlh
