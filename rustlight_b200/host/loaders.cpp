@@ -12,6 +12,7 @@
 //
 // JSONSceneLoader reads the new format documented in DESIGN.md ("scene JSON"); the reference
 // has no JSON loader at this commit.
+#include <algorithm>
 #include <array>
 #include <cctype>
 #include <cmath>
@@ -264,7 +265,7 @@ void read_ply(const std::string &filename, RawShape &out) {
         std::vector<Prop> props;
     };
     std::vector<Elem> elems;
-    bool binary = false;
+    bool binary = false, big_endian = false;
     while (std::getline(f, line)) {
         if (!line.empty() && line.back() == '\r') line.pop_back();
         std::istringstream ls(line);
@@ -274,6 +275,7 @@ void read_ply(const std::string &filename, RawShape &out) {
             std::string fmt;
             ls >> fmt;
             if (fmt == "binary_little_endian") binary = true;
+            else if (fmt == "binary_big_endian") binary = true, big_endian = true;
             else if (fmt != "ascii") throw Error("ply: unsupported format " + fmt);
         } else if (w == "element") {
             Elem e;
@@ -307,6 +309,7 @@ void read_ply(const std::string &filename, RawShape &out) {
         size_t n = size_of(t);
         f.read(reinterpret_cast<char *>(b), (std::streamsize)n);
         if (!f) throw Error("ply: truncated binary data");
+        if (big_endian) std::reverse(b, b + n);
         if (t == "float" || t == "float32") { float v; std::memcpy(&v, b, 4); return v; }
         if (t == "double" || t == "float64") { double v; std::memcpy(&v, b, 8); return v; }
         if (t == "char" || t == "int8") return (signed char)b[0];

@@ -130,6 +130,12 @@ def test_pbrt_objects_instances_and_plymesh(tmp_path):
     inc = SceneLoaderManager().load(str(tmp_path / "top.pbrt"))
     di = inc.desc.contents
     assert di.nmeshes == 2 and np.ctypeslib.as_array(di.meshes[1].P, (9,))[2] == 3.0
+    # binary_big_endian: the same triangle
+    hdr_be = hdr.replace(b"binary_little_endian", b"binary_big_endian")
+    body_be = b"".join(struct.pack(">5f", *v) for v in [(0, 0, 0, 0, 0), (2, 0, 0, 1, 0), (0, 2, 0, 0, 1)]) + struct.pack(">B3I", 3, 0, 1, 2)
+    (tmp_path / "t.ply").write_bytes(hdr_be + body_be)
+    be = SceneLoaderManager().load(str(tmp_path / "top.pbrt"))
+    assert np.array_equal(np.ctypeslib.as_array(be.desc.contents.meshes[0].P, (9,)), [0, 0, 0, 2, 0, 0, 0, 2, 0])
     with pytest.raises(SceneError, match="unknown object"):
         SceneLoaderManager().load_string('Camera "perspective" WorldBegin ObjectInstance "nope" WorldEnd', "pbrt")
     with pytest.raises(SceneError, match="cannot open"):
