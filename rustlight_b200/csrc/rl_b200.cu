@@ -996,7 +996,10 @@ static int render_impl(rl_ctx *ctx, rl_scene *sc, const rl_integrator_desc *I, c
                 // queue indices a k_tail launch is scheduled for: a wide window around the model's guess, a narrow one around last frame's hand-over
                 // (queue lengths of two frames of one scene differ by a fraction of a percent; every launch after the hand-over is a dead ~2 us)
                 const bool have_hist = !ctx->pred_ratio.empty();
-                uint32_t win_lo = have_hist ? (k_pred > 1u ? k_pred - 1u : 1u) : (k_pred > 2u ? k_pred - 2u : 1u), win_hi = k_pred + (have_hist ? 1u : 6u);
+                // (*r03*: with the previous frame's lengths the window is ONE unconditional launch at the iteration that frame handed over at --
+                // k_tail strides over whatever the queue holds, so a queue 1 % above the threshold costs nothing, whereas every window
+                // iteration runs trace and shadow unfused and the iteration after the hand-over is six dead launches: ~40 us per frame)
+                uint32_t win_lo = have_hist ? std::max(k_pred, 1u) : (k_pred > 2u ? k_pred - 2u : 1u), win_hi = have_hist ? win_lo : k_pred + 6u;
                 if (I->max_depth >= 0) win_hi = std::min<uint32_t>(win_hi, (uint32_t)I->max_depth), win_lo = std::min(win_lo, win_hi);
                 const uint32_t *zero_count = ctx->d_hist + 2 * kMaxIters - 1; // never written
                 int cur = 0;
