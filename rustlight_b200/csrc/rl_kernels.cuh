@@ -91,6 +91,9 @@ __global__ void __launch_bounds__(kBlock) k_raygen(SceneView sv, IntegParams ip,
 #ifndef RL_WHILE_WHILE
 #define RL_WHILE_WHILE 1
 #endif
+#ifndef RL_SELF_FIX
+#define RL_SELF_FIX 1 // group-table closest-hit kernels re-trace a thread's first ambiguous ray themselves, after the loop; 0 = every one goes to k_fix_flat (A/B hook)
+#endif
 constexpr int kRefillIdle = RL_REFILL_IDLE;
 #ifndef RL_TREE_MINBLOCKS
 #define RL_TREE_MINBLOCKS 4 // resident CTAs per SM the tree kernels are compiled for (64 registers; tess24 x 16 spp, 1 / 4 / 5 / 6 / 8: 24.0 / 21.6 / 24.0 / 27.9 / 32.0 ms)
@@ -197,6 +200,9 @@ template <bool CULL>
 __device__ __forceinline__ void trace_flat_body_t(const SceneView &sv, const float4 *flat, const float4 *trav, uint32_t bid, uint32_t nblocks, uint32_t n,
                                                 const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d, float4 *__restrict__ hit, bool camera,
                                                 const uint32_t *__restrict__ cam_masks, uint32_t npix, uint32_t *fix_count, uint32_t *fix_list) {
+#if RL_SELF_FIX
+    uint32_t pend = RL_MISS; // a ray of this thread whose answer the reference's own traversal must give (ties, rim hits: a few in 10^4)
+#endif
     for (uint32_t i = bid * blockDim.x + threadIdx.x; i < n; i += nblocks * blockDim.x) {
         const float4 rd = ray_d[i];
         const V3 o = camera ? sv.cam_pos : xyz(ray_o[i]), d = xyz(rd); // camera rays share their origin: it is not stored (k_raygen)
@@ -208,8 +214,28 @@ __device__ __forceinline__ void trace_flat_body_t(const SceneView &sv, const flo
         bool needs_ref = false;
         if (aabb_intersect_ref(sv.root_min, sv.root_max, o, inv, RL_EPSILON, RL_F32_MAX)) h = flat_closest<CULL, true>(sv, flat, trav, o, d, quads, &needs_ref);
         hit[i] = make_float4(h.t, h.u, h.v, u2f(h.prim));
+#if RL_SELF_FIX
+        if (needs_ref) { // the thread re-traces its first such ray itself once its share of the queue is done; a second one goes to k_fix_flat's list
+            if (pend == RL_MISS) pend = i;
+            else fix_list[atomicAdd(fix_count, 1u)] = i;
+        }
+#else
         if (needs_ref) fix_list[atomicAdd(fix_count, 1u)] = i; // a few rays in 10^4 (ties, rim hits): re-traced over the reference's tree by k_fix_flat
+#endif
     }
+#if RL_SELF_FIX
+    // *r03*: k_fix_flat's single-lane walks of a short list are pure latency (12-15 us per wavefront iteration: 3 % of one rank's frame on 8
+    // GPUs, 10 % of config 1).  Here the walk of the thread's own ray runs while other warps are still scanning and k_fix_flat, still launched
+    // for what is left (shadow segments blocked by rim hits only, second rays), finds its lists empty (~4 us).  Only the walk AFTER the loop is
+    // free: a call inside the loop, or one that takes the SceneView by reference (shadow segments), costs every ray ~10 % (measured: trace 3.29 ->
+    // 3.56-3.64 ms, shadow 2.33 -> 2.74-2.79 ms per 80 M segments).  The reference's tree is read through L1; the triangle records are the staged ones.
+    if (pend != RL_MISS) {
+        const V3 o = camera ? sv.cam_pos : xyz(ray_o[pend]), d = xyz(ray_d[pend]);
+        HitRec h;
+        ref_bvh_closest(sv, trav, o, d, &h.t, &h.u, &h.v, &h.prim); // the ray passed the root test (it had a hit)
+        hit[pend] = make_float4(h.t, h.u, h.v, u2f(h.prim));
+    }
+#endif
 }
 __device__ __forceinline__ void trace_flat_body(const SceneView &sv, const float4 *flat, const float4 *trav, uint32_t bid, uint32_t nblocks, uint32_t n,
                                                 const float4 *__restrict__ ray_o, const float4 *__restrict__ ray_d, float4 *__restrict__ hit, bool camera,
