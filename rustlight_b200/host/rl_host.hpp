@@ -188,6 +188,7 @@ struct Bitmap {
     static Bitmap read_pfm(const std::string &path);
     void save_png(const std::string &path) const;    // Bitmap::save_ldr_image + Color::to_rgba: (min(c, 1)^(1/2.2) * 255) as u8
     static Bitmap read_png(const std::string &path); // Bitmap::read_ldr_image: to_rgb8() / 255
+    static Bitmap read_tga(const std::string &path);  // Truevision TGA (true colour / grey / colour-mapped, raw or RLE)
     static Bitmap read_jpeg(const std::string &path); // Bitmap::read_ldr_image for .jpg / .jpeg (host/jpeg.cpp: baseline + progressive Huffman JPEG)
     void save(const std::string &path) const;        // by extension (structure.rs:528-545): pfm | png
     static Bitmap read(const std::string &path);     // by extension (structure.rs:670-683): pfm | png | jpg

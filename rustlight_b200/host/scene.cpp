@@ -315,7 +315,11 @@ Texture Texture::bitmap_file(const std::string &filename) {
         Bitmap b = Bitmap::read_jpeg(filename);
         return bitmap(b.size_x, b.size_y, std::move(b.colors));
     }
-    throw Error("texture: only .pfm, .png, .jpg and .ppm images can be read here: " + filename);
+    if (ends(".tga") || ends(".TGA")) {
+        Bitmap b = Bitmap::read_tga(filename);
+        return bitmap(b.size_x, b.size_y, std::move(b.colors));
+    }
+    throw Error("texture: only .pfm, .png, .jpg, .tga and .ppm images can be read here: " + filename);
 }
 Texture Texture::checkerboard(Color c0, Color c1, float ox, float oy, float sx, float sy) {
     Texture t;
@@ -593,6 +597,68 @@ void Bitmap::save_png(const std::string &path) const {
     f.write(reinterpret_cast<const char *>(out.data()), (std::streamsize)out.size());
     if (!f) throw Error("cannot write " + path);
 }
+// Truevision TGA (textures of the pbrt-v3 scenes; read by the `image` crate in the reference): types 2 / 10 (true colour, raw / RLE, 24 or 32 bits: BGR(A),
+// alpha dropped), 3 / 11 (grey 8 bits), 1 / 9 (colour-mapped 8-bit indices over a 24 / 32-bit map); bottom-up rows unless bit 5 of the descriptor says
+// top-down, right-to-left columns when bit 4 is set.  value / 255 like every LDR image (structure.rs:649-668).
+Bitmap Bitmap::read_tga(const std::string &path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw Error("cannot open " + path);
+    std::vector<unsigned char> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (d.size() < 18) throw Error("tga: truncated header in " + path);
+    const int id_len = d[0], cmap_type = d[1], type = d[2], cmap_first = d[3] | (d[4] << 8), cmap_len = d[5] | (d[6] << 8), cmap_bits = d[7];
+    const int w = d[12] | (d[13] << 8), h = d[14] | (d[15] << 8), bpp = d[16], desc = d[17];
+    const bool rle = type >= 9;
+    const int base = type & 7;
+    if ((base != 1 && base != 2 && base != 3) || w <= 0 || h <= 0) throw Error("tga: unsupported image type in " + path);
+    if ((base == 2 && bpp != 24 && bpp != 32) || (base == 3 && bpp != 8) || (base == 1 && (bpp != 8 || cmap_type != 1 || (cmap_bits != 24 && cmap_bits != 32))))
+        throw Error("tga: unsupported pixel format in " + path);
+    size_t pos = 18 + (size_t)id_len;
+    const size_t cmap_bytes = cmap_type ? (size_t)cmap_len * ((cmap_bits + 7) / 8) : 0;
+    if (pos + cmap_bytes > d.size()) throw Error("tga: truncated colour map in " + path);
+    const unsigned char *cmap = &d[pos];
+    pos += cmap_bytes;
+    const int px = bpp / 8;
+    std::vector<unsigned char> raw((size_t)w * h * px);
+    if (!rle) {
+        if (pos + raw.size() > d.size()) throw Error("tga: truncated pixel data in " + path);
+        std::memcpy(raw.data(), &d[pos], raw.size());
+    } else {
+        size_t o = 0;
+        while (o < raw.size()) {
+            if (pos >= d.size()) throw Error("tga: truncated RLE data in " + path);
+            const int hd = d[pos++], n = (hd & 127) + 1;
+            if (o + (size_t)n * px > raw.size()) throw Error("tga: RLE packet past the end of the image in " + path);
+            if (hd & 128) {
+                if (pos + px > d.size()) throw Error("tga: truncated RLE data in " + path);
+                for (int k = 0; k < n; k++, o += px) std::memcpy(&raw[o], &d[pos], px);
+                pos += px;
+            } else {
+                if (pos + (size_t)n * px > d.size()) throw Error("tga: truncated RLE data in " + path);
+                std::memcpy(&raw[o], &d[pos], (size_t)n * px);
+                o += (size_t)n * px, pos += (size_t)n * px;
+            }
+        }
+    }
+    Bitmap b;
+    b.size_x = (uint32_t)w, b.size_y = (uint32_t)h;
+    b.colors.resize((size_t)3 * w * h);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const int sy = (desc & 0x20) ? y : h - 1 - y, sx = (desc & 0x10) ? w - 1 - x : x;
+            const unsigned char *p = &raw[((size_t)sy * w + sx) * px];
+            unsigned char r, g, bl;
+            if (base == 3) r = g = bl = p[0];
+            else if (base == 2) bl = p[0], g = p[1], r = p[2];
+            else {
+                const int idx = (int)p[0] - cmap_first, eb = (cmap_bits + 7) / 8;
+                if (idx < 0 || idx >= cmap_len) throw Error("tga: colour index out of range in " + path);
+                bl = cmap[idx * eb], g = cmap[idx * eb + 1], r = cmap[idx * eb + 2];
+            }
+            float *dst = &b.colors[3 * ((size_t)y * w + x)];
+            dst[0] = (float)r / 255.0f, dst[1] = (float)g / 255.0f, dst[2] = (float)bl / 255.0f;
+        }
+    return b;
+}
 // Bitmap::save / Bitmap::read (structure.rs:528-545, 670-683): by extension.  .exr needs the reference's optional `openexr` feature
 // (off by default: it panics there) and is refused here.
 static std::string extension_of(const std::string &path) {
@@ -612,7 +678,8 @@ Bitmap Bitmap::read(const std::string &path) {
     if (ext == "pfm") return read_pfm(path);
     if (ext == "png") return read_png(path);
     if (ext == "jpg" || ext == "jpeg" || ext == "JPG") return read_jpeg(path);
-    throw Error("image: only .pfm, .png and .jpg can be read: " + path);
+    if (ext == "tga" || ext == "TGA") return read_tga(path);
+    throw Error("image: only .pfm, .png, .jpg and .tga can be read: " + path);
 }
 
 } // namespace rlh

@@ -76,3 +76,18 @@ def test_jpeg_texture_and_refusals(tmp_path):
     (tmp_path / "cmyk.jpg").write_bytes(cmyk.getvalue())
     with pytest.raises(SceneError):
         read_image(str(tmp_path / "cmyk.jpg"))  # 4 components: refused
+
+
+@pytest.mark.parametrize("mode,rle", [("RGB", False), ("RGB", True), ("RGBA", False), ("RGBA", True), ("L", False), ("L", True), ("P", False)])
+def test_tga_equals_pil(tmp_path, mode, rle):
+    """Truevision TGA (textures of the pbrt-v3 scenes): true colour / grey / colour-mapped, raw and RLE, bottom-up and top-down rows."""
+    src = picture(23, 17, 4)
+    src[5:9, 3:20] = (200, 10, 30)  # runs for the RLE packets
+    im = PIL.fromarray(src)
+    im = im.convert("RGBA") if mode == "RGBA" else im.convert("L") if mode == "L" else im.quantize(64) if mode == "P" else im
+    for orientation in (1, -1):
+        path = tmp_path / "t.tga"
+        im.save(path, "TGA", compression="tga_rle" if rle else None, orientation=orientation)
+        want = np.asarray(PIL.open(path).convert("RGB"), np.uint8)
+        got = read_image(str(path))
+        assert np.array_equal(got, want.astype(np.float32) / np.float32(255.0))
